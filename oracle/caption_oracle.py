@@ -1,0 +1,404 @@
+"""CPU oracle for the caption-decode hot path (TEST INFRASTRUCTURE ONLY).
+
+This file is a from-scratch, functional restatement (torch fp32 on CPU, no nn.Module) of the
+reference algorithm on the path BASELINE.json names.  It is the *checker*: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` leg may import it.
+The product package (``imagecaptioning.pytorch_b200``) never does.
+
+Parity pin: ``oracle/make_golden.py`` imports the live reference from ``/root/reference`` (in the build
+container only) and writes ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks every function
+here against those vectors, so this restatement is pinned to outputs of the reference itself.
+
+Reference lines each function follows (paths relative to /root/reference/captioning):
+  linear / lstm_cell        torch.nn.Linear / torch.nn.LSTMCell call sites models/AttModel.py:620-621
+  updown_prepare            models/AttModel.py:114-124  (_prepare_feature; fc_embed/att_embed/ctx2att :74-95)
+  additive_attention        models/AttModel.py:728-748  (Attention.forward)
+  updown_core               models/AttModel.py:624-640  (UpDownCore.forward)
+  newfc_prepare/newfc_core  models/AttModel.py:915-945, models/FCModel.py:25-42 (maxout LSTMCore)
+  logprobs_state            models/AttModel.py:166-176  (get_logprobs_state)
+  beam_search               models/CaptionModel.py:35-209 (group_size == 1 path)
+  sample_beam               models/AttModel.py:218-256
+  sample                    models/AttModel.py:258-352 + models/CaptionModel.py:370-407 (greedy / multinomial)
+  forward_teacher           models/AttModel.py:126-164
+  reward_criterion          modules/losses.py:22-37
+
+Weights are passed as a plain dict keyed by the reference ``state_dict`` names.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+Weights = Dict[str, Tensor]
+
+
+# --------------------------------------------------------------------------------------------------
+# primitive ops
+# --------------------------------------------------------------------------------------------------
+
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None) -> Tensor:
+    y = x @ w.t()
+    return y if b is None else y + b
+
+
+def lstm_cell(x: Tensor, h: Tensor, c: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh: Tensor):
+    """nn.LSTMCell arithmetic, gate order (i, f, g, o)."""
+    gates = linear(x, w_ih, b_ih) + linear(h, w_hh, b_hh)
+    hs = h.shape[1]
+    gi, gf, gg, go = gates[:, :hs], gates[:, hs:2 * hs], gates[:, 2 * hs:3 * hs], gates[:, 3 * hs:]
+    c_new = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gg)
+    h_new = torch.sigmoid(go) * torch.tanh(c_new)
+    return h_new, c_new
+
+
+def repeat_rows(x: Optional[Tensor], n: int) -> Optional[Tensor]:
+    """Row i*n+j of the result is row i of x (models/utils.py:3-15)."""
+    if x is None or n == 1:
+        return x
+    return x.unsqueeze(1).expand(x.shape[0], n, *x.shape[1:]).reshape(x.shape[0] * n, *x.shape[1:])
+
+
+# --------------------------------------------------------------------------------------------------
+# UpDown (TopDown attention LSTM)
+# --------------------------------------------------------------------------------------------------
+
+def clip_att(att: Tensor, masks: Optional[Tensor]):
+    if masks is None:
+        return att, None
+    max_len = int(masks.long().sum(1).max())
+    return att[:, :max_len].contiguous(), masks[:, :max_len].contiguous()
+
+
+def updown_prepare(W: Weights, fc: Tensor, att: Tensor, masks: Optional[Tensor] = None):
+    """fc_embed, att_embed (Linear+ReLU; dropout is identity in eval) and ctx2att."""
+    att, masks = clip_att(att, masks)
+    fc_e = torch.relu(linear(fc, W['fc_embed.0.weight'], W['fc_embed.0.bias']))
+    att_e = torch.relu(linear(att, W['att_embed.0.weight'], W['att_embed.0.bias']))
+    if masks is not None:
+        # pack_wrapper runs the module on valid rows only and zero-pads the rest
+        att_e = att_e * masks.unsqueeze(-1).to(att_e)
+    p_att = linear(att_e, W['ctx2att.weight'], W['ctx2att.bias'])
+    return fc_e, att_e, p_att, masks
+
+
+def additive_attention(W: Weights, h: Tensor, att_e: Tensor, p_att: Tensor, masks: Optional[Tensor], prefix='core.attention.'):
+    att_h = linear(h, W[prefix + 'h2att.weight'], W[prefix + 'h2att.bias'])          # [N, A]
+    dot = torch.tanh(p_att + att_h.unsqueeze(1))                                     # [N, R, A]
+    score = linear(dot, W[prefix + 'alpha_net.weight'], W[prefix + 'alpha_net.bias']).squeeze(-1)   # [N, R]
+    weight = F.softmax(score, dim=1)
+    if masks is not None:
+        weight = weight * masks.to(weight)
+        weight = weight / weight.sum(1, keepdim=True)
+    return torch.bmm(weight.unsqueeze(1), att_e).squeeze(1)
+
+
+def updown_core(W: Weights, xt: Tensor, fc_e: Tensor, att_e: Tensor, p_att: Tensor, state, masks=None):
+    h, c = state                                   # each [2, N, H]
+    x1 = torch.cat([h[1], fc_e, xt], 1)
+    h_att, c_att = lstm_cell(x1, h[0], c[0], W['core.att_lstm.weight_ih'], W['core.att_lstm.weight_hh'],
+                             W['core.att_lstm.bias_ih'], W['core.att_lstm.bias_hh'])
+    att = additive_attention(W, h_att, att_e, p_att, masks)
+    x2 = torch.cat([att, h_att], 1)
+    h_lang, c_lang = lstm_cell(x2, h[1], c[1], W['core.lang_lstm.weight_ih'], W['core.lang_lstm.weight_hh'],
+                               W['core.lang_lstm.bias_ih'], W['core.lang_lstm.bias_hh'])
+    return h_lang, (torch.stack([h_att, h_lang]), torch.stack([c_att, c_lang]))
+
+
+# --------------------------------------------------------------------------------------------------
+# NewFC (maxout LSTM fed with the image embedding at the first step)
+# --------------------------------------------------------------------------------------------------
+
+def newfc_prepare(W: Weights, fc: Tensor, att: Tensor, masks=None):
+    return linear(fc, W['fc_embed.weight'], W['fc_embed.bias']), att, att, masks
+
+
+def maxout_lstm(W: Weights, x: Tensor, state):
+    h, c = state                                   # [1, N, H]
+    hs = h.shape[2]
+    s = linear(x, W['_core.i2h.weight'], W['_core.i2h.bias']) + linear(h[-1], W['_core.h2h.weight'], W['_core.h2h.bias'])
+    sig = torch.sigmoid(s[:, :3 * hs])
+    i_g, f_g, o_g = sig[:, :hs], sig[:, hs:2 * hs], sig[:, 2 * hs:3 * hs]
+    g = torch.max(s[:, 3 * hs:4 * hs], s[:, 4 * hs:5 * hs])
+    c_new = f_g * c[-1] + i_g * g
+    h_new = o_g * torch.tanh(c_new)
+    return h_new, (h_new.unsqueeze(0), c_new.unsqueeze(0))
+
+
+def newfc_core(W: Weights, xt: Tensor, fc_e: Tensor, att_e, p_att, state, masks=None):
+    first = (state[0] == 0).all(2).all(0)          # rows whose state is exactly zero
+    if bool(first.all()):
+        _, state = maxout_lstm(W, fc_e, state)
+    elif bool(first.any()):
+        _, st2 = maxout_lstm(W, fc_e, state)
+        state = (torch.where(first[None, :, None], st2[0], state[0]), torch.where(first[None, :, None], st2[1], state[1]))
+    return maxout_lstm(W, xt, state)
+
+
+# --------------------------------------------------------------------------------------------------
+# family dispatch
+# --------------------------------------------------------------------------------------------------
+
+class Family:
+    def __init__(self, name: str, W: Weights, seq_length: int):
+        self.name = name
+        self.W = W
+        self.seq_length = seq_length
+        if name == 'updown':
+            self.num_layers = 2
+            self.rnn_size = W['core.att_lstm.weight_hh'].shape[1]
+            self.vocab1 = W['logit.weight'].shape[0]
+        elif name == 'newfc':
+            self.num_layers = 1
+            self.rnn_size = W['_core.h2h.weight'].shape[1]
+            self.vocab1 = W['logit.weight'].shape[0]
+        else:
+            raise ValueError(name)
+
+    def prepare(self, fc, att, masks=None):
+        return (updown_prepare if self.name == 'updown' else newfc_prepare)(self.W, fc, att, masks)
+
+    def init_state(self, n: int):
+        z = torch.zeros(self.num_layers, n, self.rnn_size)
+        return (z, z.clone())
+
+    def embed(self, it: Tensor) -> Tensor:
+        if self.name == 'updown':
+            return torch.relu(self.W['embed.0.weight'][it])
+        return self.W['embed.weight'][it]
+
+    def logprobs_state(self, it, fc_e, att_e, p_att, masks, state, output_logsoftmax=True):
+        xt = self.embed(it)
+        core = updown_core if self.name == 'updown' else newfc_core
+        out, state = core(self.W, xt, fc_e, att_e, p_att, state, masks)
+        logits = linear(out, self.W['logit.weight'], self.W['logit.bias'])
+        return (F.log_softmax(logits, dim=1) if output_logsoftmax else logits), state
+
+
+# --------------------------------------------------------------------------------------------------
+# beam search
+# --------------------------------------------------------------------------------------------------
+
+def _length_penalty(cfg: str):
+    if cfg == '':
+        return lambda length, lp: lp
+    kind, alpha = cfg.split('_')
+    alpha = float(alpha)
+    if kind == 'wu':
+        return lambda length, lp: lp / (((5 + length) ** alpha) / ((5 + 1) ** alpha))
+    if kind == 'avg':
+        return lambda length, lp: lp / length
+    raise ValueError(cfg)
+
+
+def beam_search(fam: Family, init_state, init_logprobs: Tensor, fc_e, att_e, p_att, masks, beam_size: int,
+                length_penalty: str = '', temperature: float = 1.0, eos_idx: int = 0, record_margin: Optional[list] = None):
+    """Classical batched beam search, one group.  Returns list[B] of list[<=beam] records.
+
+    State/feature rows are image-major: row i*beam+j is beam j of image i.  The first step works on B rows
+    (one live beam per image).  A beam that emits EOS, or any beam at the last step, is recorded and its
+    running sum is lowered by 1000 -- but it stays in the beam and keeps being expanded, fed token 0.
+    """
+    pen = _length_penalty(length_penalty)
+    B, V1 = init_logprobs.shape
+    T = fam.seq_length
+    seqs = torch.zeros(B, beam_size, 0, dtype=torch.long)
+    hist = torch.zeros(B, beam_size, 0, V1)
+    sums = torch.zeros(B, beam_size)
+    state = [s.clone() for s in init_state]
+    logprobs = init_logprobs.clone()
+    done: List[List[dict]] = [[] for _ in range(B)]
+    for t in range(T):
+        lp = logprobs.reshape(B, -1, V1)                      # [B, live, V1]
+        live = lp.shape[1]
+        cand = (sums[:, :live].unsqueeze(-1) + lp).reshape(B, -1)
+        ys, ix = torch.sort(cand, -1, True)
+        if record_margin is not None:
+            record_margin.append(float((ys[:, :beam_size] - ys[:, 1:beam_size + 1]).min()))
+        ys, ix = ys[:, :beam_size], ix[:, :beam_size]
+        parent = ix // V1
+        word = ix % V1
+        rows = (parent + torch.arange(B).unsqueeze(-1) * live).reshape(-1)
+        if t > 0:
+            seqs = seqs.gather(1, parent.unsqueeze(-1).expand_as(seqs))
+            hist = hist.gather(1, parent.unsqueeze(-1).unsqueeze(-1).expand_as(hist))
+        seqs = torch.cat([seqs, word.unsqueeze(-1)], -1)
+        sums = sums[:, :live].gather(1, parent) + lp.reshape(B, -1).gather(1, ix)
+        hist = torch.cat([hist, lp.gather(1, parent.unsqueeze(-1).expand(-1, -1, V1)).unsqueeze(2)], 2)
+        state = [s[:, rows] for s in state]
+        ended = (word == eos_idx) if t < T - 1 else torch.ones_like(word, dtype=torch.bool)
+        for b in range(B):
+            for v in range(beam_size):
+                if ended[b, v]:
+                    done[b].append({'seq': seqs[b, v].clone(), 'logps': hist[b, v].clone(),
+                                    'unaug_p': float(hist[b, v].sum()), 'p': pen(t + 1, float(sums[b, v]))})
+        sums = sums - 1000.0 * ended.to(sums)
+        it = word.reshape(-1)
+        logprobs, state = fam.logprobs_state(it, fc_e, att_e, p_att, masks, state)
+        state = list(state)
+        logprobs = F.log_softmax(logprobs / temperature, dim=-1)
+    return [sorted(d, key=lambda r: -r['p'])[:beam_size] for d in done]
+
+
+def sample_beam(fam: Family, fc: Tensor, att: Tensor, masks: Optional[Tensor] = None, beam_size: int = 5, sample_n: int = 1,
+                length_penalty: str = '', record_margin: Optional[list] = None):
+    assert sample_n in (1, beam_size)
+    B = fc.shape[0]
+    T, V1 = fam.seq_length, fam.vocab1
+    fc_e, att_e, p_att, masks = fam.prepare(fc, att, masks)
+    state = fam.init_state(B)
+    it = torch.zeros(B, dtype=torch.long)
+    logprobs, state = fam.logprobs_state(it, fc_e, att_e, p_att, masks, state)
+    fc_r, att_r, p_att_r, masks_r = (repeat_rows(x, beam_size) for x in (fc_e, att_e, p_att, masks))
+    done = beam_search(fam, state, logprobs, fc_r, att_r, p_att_r, masks_r, beam_size, length_penalty, record_margin=record_margin)
+    seq = torch.zeros(B * sample_n, T, dtype=torch.long)
+    seq_lp = torch.zeros(B * sample_n, T, V1)
+    for k in range(B):
+        for n in range(sample_n):
+            rec = done[k][n]
+            L = rec['seq'].shape[0]
+            seq[k * sample_n + n, :L] = rec['seq']
+            seq_lp[k * sample_n + n, :L] = rec['logps']
+    return seq, seq_lp, done
+
+
+# --------------------------------------------------------------------------------------------------
+# greedy / multinomial sampling
+# --------------------------------------------------------------------------------------------------
+
+def sample(fam: Family, fc: Tensor, att: Tensor, masks: Optional[Tensor] = None, sample_method: str = 'greedy',
+           sample_n: int = 1, temperature: float = 1.0, forced_tokens: Optional[Tensor] = None, eos_idx: int = 0,
+           record_margin: Optional[list] = None):
+    """Returns (seq [N,T] int64, seqLogprobs [N,T,V1]).  ``forced_tokens`` replays a given sample (used to compare
+    log-prob rows when the sampler's random stream differs)."""
+    B = fc.shape[0]
+    N = B * sample_n
+    T, V1 = fam.seq_length, fam.vocab1
+    fc_e, att_e, p_att, masks = fam.prepare(fc, att, masks)
+    fc_e, att_e, p_att, masks = (repeat_rows(x, sample_n) for x in (fc_e, att_e, p_att, masks))
+    state = fam.init_state(N)
+    seq = torch.zeros(N, T, dtype=torch.long)
+    seq_lp = torch.zeros(N, T, V1)
+    it = torch.zeros(N, dtype=torch.long)
+    unfinished = None
+    for t in range(T):
+        logprobs, state = fam.logprobs_state(it, fc_e, att_e, p_att, masks, state)
+        if forced_tokens is not None:
+            it = forced_tokens[:, t].clone()
+        elif sample_method == 'greedy':
+            top2 = logprobs.topk(2, dim=1).values
+            if record_margin is not None:
+                live = torch.ones(N, dtype=torch.bool) if unfinished is None else unfinished
+                if bool(live.any()):
+                    record_margin.append(float((top2[:, 0] - top2[:, 1])[live].min()))
+            it = logprobs.argmax(1)
+        else:
+            # the temperature only shapes the sampling distribution; the stored row stays unscaled
+            it = torch.distributions.Categorical(logits=logprobs / temperature).sample()
+        if t == 0:
+            unfinished = it != eos_idx
+        else:
+            it = it * unfinished.to(it)
+            logprobs = logprobs * unfinished.unsqueeze(1).to(logprobs)
+            unfinished = unfinished & (it != eos_idx)
+        seq[:, t] = it
+        seq_lp[:, t] = logprobs
+        if int(unfinished.sum()) == 0:
+            break
+    return seq, seq_lp
+
+
+# --------------------------------------------------------------------------------------------------
+# teacher forcing and the SCST criterion
+# --------------------------------------------------------------------------------------------------
+
+def forward_teacher(fam: Family, fc: Tensor, att: Tensor, seq: Tensor, masks: Optional[Tensor] = None):
+    B = fc.shape[0]
+    if seq.dim() == 3:
+        seq = seq.reshape(-1, seq.shape[2])
+    spi = seq.shape[0] // B
+    N = B * spi
+    fc_e, att_e, p_att, masks = fam.prepare(fc, att, masks)
+    fc_e, att_e, p_att, masks = (repeat_rows(x, spi) for x in (fc_e, att_e, p_att, masks))
+    state = fam.init_state(N)
+    out = torch.zeros(N, seq.shape[1], fam.vocab1)
+    for i in range(seq.shape[1]):
+        if i >= 1 and int(seq[:, i].sum()) == 0:
+            break
+        lp, state = fam.logprobs_state(seq[:, i].clone(), fc_e, att_e, p_att, masks, state)
+        out[:, i] = lp
+    return out
+
+
+def reward_criterion(logprobs: Tensor, seq: Tensor, reward: Tensor, reduction: str = 'mean') -> Tensor:
+    N, L = seq.shape
+    picked = logprobs.gather(2, seq.unsqueeze(2)).squeeze(2)
+    mask = (seq > 0).to(picked)
+    mask = torch.cat([torch.ones(N, 1), mask[:, :-1]], 1)
+    out = -picked * reward * mask
+    if reduction == 'none':
+        return out.sum(1) / mask.sum(1)
+    return out.sum() / mask.sum()
+
+
+def reward_criterion_grad(seq: Tensor, reward: Tensor, V1: int) -> Tensor:
+    """d(loss_mean)/d(logprobs): -reward*mask/sum(mask) scattered at the sampled ids."""
+    N, L = seq.shape
+    mask = torch.cat([torch.ones(N, 1), (seq > 0).float()[:, :-1]], 1)
+    g = torch.zeros(N, L, V1)
+    g.scatter_(2, seq.unsqueeze(2), (-(reward * mask) / mask.sum()).unsqueeze(2))
+    return g
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic weights (shared by tests, bench and the golden generator)
+# --------------------------------------------------------------------------------------------------
+
+def _uniform(gen, shape, bound):
+    return (torch.rand(shape, generator=gen) * 2 - 1) * bound
+
+
+def make_weights(family: str, V: int, E: int, H: int, A: int, F_fc: int, F_att: int, seed: int = 1234,
+                 logit_scale: float = 12.0) -> Weights:
+    """Deterministic synthetic weights with torch-default-like ranges; ``logit.weight`` is scaled so the
+    next-word distribution is peaked (top-1/top-2 margins far above the 1e-4 log-prob tolerance)."""
+    g = torch.Generator().manual_seed(seed)
+    V1 = V + 1
+    W: Weights = {}
+
+    def lin(name, out_f, in_f, scale=1.0):
+        b = 1.0 / math.sqrt(in_f)
+        W[name + '.weight'] = _uniform(g, (out_f, in_f), b) * scale
+        W[name + '.bias'] = _uniform(g, (out_f,), b)
+
+    if family == 'updown':
+        W['embed.0.weight'] = torch.randn(V1, E, generator=g)
+        lin('fc_embed.0', H, F_fc)
+        lin('att_embed.0', H, F_att)
+        lin('logit', V1, H, logit_scale)
+        lin('ctx2att', A, H)
+        b = 1.0 / math.sqrt(H)
+        for cell, in_f in (('core.att_lstm', E + 2 * H), ('core.lang_lstm', 2 * H)):
+            W[cell + '.weight_ih'] = _uniform(g, (4 * H, in_f), b)
+            W[cell + '.weight_hh'] = _uniform(g, (4 * H, H), b)
+            W[cell + '.bias_ih'] = _uniform(g, (4 * H,), b)
+            W[cell + '.bias_hh'] = _uniform(g, (4 * H,), b)
+        lin('core.attention.h2att', A, H)
+        lin('core.attention.alpha_net', 1, A)
+    elif family == 'newfc':
+        W['embed.weight'] = torch.randn(V1, E, generator=g)
+        lin('fc_embed', E, F_fc)
+        lin('logit', V1, H, logit_scale)
+        lin('_core.i2h', 5 * H, E)
+        lin('_core.h2h', 5 * H, H)
+    else:
+        raise ValueError(family)
+    return W
+
+
+def make_inputs(B: int, R: int, F_fc: int, F_att: int, seed: int = 1234):
+    g = torch.Generator().manual_seed(seed + 1)
+    return torch.randn(B, F_fc, generator=g), torch.randn(B, R, F_att, generator=g)

@@ -1,0 +1,237 @@
+"""Generate tests/golden/*.npz by running the LIVE reference (build container only; /root/reference is read-only).
+
+    python oracle/make_golden.py            # needs /root/reference; writes tests/golden/
+
+The reference modules are imported unmodified from /root/reference with a scratch cwd that holds the
+``cider`` / ``coco-caption`` symlinks and a writable ``data/<name>.p`` document-frequency pickle, because
+captioning/utils/rewards.py:12,15 and cider/pyciderevalcap/ciderD/ciderD_scorer.py:109 use cwd-relative paths.
+Synthetic weights come from oracle.caption_oracle.make_weights (seeded) and are loaded into the reference's own
+nn.Modules with load_state_dict, so each golden file records what the reference computes on exactly the inputs the
+tests regenerate from the same seeds.  Nothing here is imported at test time on the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import pickle
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = '/root/reference'
+sys.path.insert(0, REPO)
+
+from oracle import caption_oracle as co          # noqa: E402
+from oracle import ciderd_oracle as cdo          # noqa: E402
+
+
+def _enter_scratch():
+    d = tempfile.mkdtemp(prefix='refcwd_')
+    os.symlink(os.path.join(REF, 'cider'), os.path.join(d, 'cider'))
+    os.symlink(os.path.join(REF, 'coco-caption'), os.path.join(d, 'coco-caption'))
+    os.makedirs(os.path.join(d, 'data'))
+    os.chdir(d)
+    sys.path.insert(0, REF)
+    sys.dont_write_bytecode = True
+    return d
+
+
+def ref_model(family, V, E, H, A, F_fc, F_att, T, W):
+    import captioning.models as M
+    opt = argparse.Namespace(vocab_size=V, input_encoding_size=E, rnn_size=H, num_layers=1, drop_prob_lm=0.5,
+                             max_length=T, seq_length=T, fc_feat_size=F_fc, att_feat_size=F_att, att_hid_size=A,
+                             vocab={str(i): 'w%d' % i for i in range(1, V + 1)}, caption_model=family, use_bn=0,
+                             logit_layers=1)
+    m = M.setup(opt)
+    missing = m.load_state_dict(W, strict=True)
+    m.eval()
+    return m
+
+
+def beams_to_arrays(done_beams, b, T):
+    B = len(done_beams)
+    seqs = np.zeros((B, b, T), np.int64)
+    lens = np.zeros((B, b), np.int64)
+    ps = np.zeros((B, b), np.float64)
+    for i, lst in enumerate(done_beams):
+        for j, rec in enumerate(lst):
+            L = rec['seq'].shape[0]
+            seqs[i, j, :L] = rec['seq'].numpy()
+            lens[i, j] = L
+            ps[i, j] = rec['p']
+    return seqs, lens, ps
+
+
+def gen_updown_small(out_dir):
+    cfg = dict(V=60, E=32, H=32, A=16, F_fc=48, F_att=48, T=8)
+    B, R, b = 4, 7, 3
+    W = co.make_weights('updown', cfg['V'], cfg['E'], cfg['H'], cfg['A'], cfg['F_fc'], cfg['F_att'], seed=11, logit_scale=20.0)
+    fc, att = co.make_inputs(B, R, cfg['F_fc'], cfg['F_att'], seed=11)
+    m = ref_model('updown', W=W, **cfg)
+    res = {}
+    with torch.no_grad():
+        seq, lp = m(fc, att, None, opt={'sample_method': 'greedy', 'beam_size': 1}, mode='sample')
+        res['greedy_seq'], res['greedy_lp'] = seq.numpy(), lp.numpy()
+        seq, lp = m(fc, att, None, opt={'beam_size': b, 'sample_n': 1}, mode='sample')
+        res['beam_seq'], res['beam_lp'] = seq.numpy(), lp.numpy()
+        res['done_seq'], res['done_len'], res['done_p'] = beams_to_arrays(m.done_beams, b, cfg['T'])
+        seq, lp = m(fc, att, None, opt={'beam_size': b, 'sample_n': b}, mode='sample')
+        res['beamn_seq'] = seq.numpy()
+        # variable region counts (prefix masks)
+        masks = torch.ones(B, R)
+        masks[1, 5:] = 0
+        masks[3, 3:] = 0
+        seq, lp = m(fc, att, masks, opt={'sample_method': 'greedy', 'beam_size': 1}, mode='sample')
+        res['masked_greedy_seq'], res['masked_greedy_lp'] = seq.numpy(), lp.numpy()
+        seq, lp = m(fc, att, masks, opt={'beam_size': b, 'sample_n': 1}, mode='sample')
+        res['masked_beam_seq'] = seq.numpy()
+        res['masks'] = masks.numpy()
+        # teacher forcing on the greedy result, 2 captions per image
+        labels = torch.from_numpy(np.concatenate([np.zeros((B, 1), np.int64), res['greedy_seq'][:, :-1]], 1))
+        labels2 = torch.stack([labels, labels.flip(0)], 1)                      # [B, 2, T]
+        res['teacher_in'] = labels2.numpy()
+        res['teacher_lp'] = m(fc, att, labels2, None).numpy()
+        # sampled run, replayed by the oracle with forced tokens
+        torch.manual_seed(5)
+        seq, lp = m(fc, att, None, opt={'sample_method': 'sample', 'beam_size': 1, 'sample_n': 3, 'temperature': 1.0}, mode='sample')
+        res['sample_seq'], res['sample_lp'] = seq.numpy(), lp.numpy()
+    np.savez_compressed(os.path.join(out_dir, 'updown_small.npz'), cfg=np.array([cfg[k] for k in ('V', 'E', 'H', 'A', 'F_fc', 'F_att', 'T')]),
+                        meta=np.array([B, R, b, 11]), **res)
+    print('updown_small', {k: v.shape for k, v in res.items()})
+
+
+def gen_newfc(out_dir):
+    """BASELINE.json configs[0]: newfc greedy, batch 4, 2048-d fc feats, seq_len 16 (opts.py defaults E=H=512)."""
+    cfg = dict(V=9487, E=512, H=512, A=512, F_fc=2048, F_att=2048, T=16)
+    B = 4
+    W = co.make_weights('newfc', cfg['V'], cfg['E'], cfg['H'], cfg['A'], cfg['F_fc'], cfg['F_att'], seed=1234, logit_scale=12.0)
+    fc, att = co.make_inputs(B, 1, cfg['F_fc'], cfg['F_att'], seed=1234)
+    m = ref_model('newfc', W=W, **cfg)
+    with torch.no_grad():
+        seq, lp = m(fc, att, None, opt={'sample_method': 'greedy', 'beam_size': 1}, mode='sample')
+        seqb, lpb = m(fc, att, None, opt={'beam_size': 3, 'sample_n': 1}, mode='sample')
+    picked = lp.gather(2, seq.unsqueeze(2)).squeeze(2)
+    top2 = lp.topk(2, dim=2).values
+    np.savez_compressed(os.path.join(out_dir, 'newfc_cfg1.npz'), cfg=np.array([cfg[k] for k in ('V', 'E', 'H', 'A', 'F_fc', 'F_att', 'T')]),
+                        meta=np.array([B, 1, 1, 1234]), greedy_seq=seq.numpy(), greedy_picked_lp=picked.numpy(),
+                        greedy_margin=(top2[..., 0] - top2[..., 1]).numpy(), greedy_row_sum=lp.sum(2).numpy(),
+                        beam_seq=seqb.numpy(), done_p=beams_to_arrays(m.done_beams, 3, cfg['T'])[2])
+    print('newfc_cfg1 greedy', seq[0].tolist())
+
+
+def gen_updown_full(out_dir):
+    """Full model dimensions of configs/updown/updown.yml (E=H=1000, A=512, V=9487), small batch; weights are
+    regenerated from the seed at test time, only outputs are stored."""
+    cfg = dict(V=9487, E=1000, H=1000, A=512, F_fc=2048, F_att=2048, T=20)
+    B, R, b = 6, 36, 5
+    W = co.make_weights('updown', cfg['V'], cfg['E'], cfg['H'], cfg['A'], cfg['F_fc'], cfg['F_att'], seed=1234, logit_scale=12.0)
+    fc, att = co.make_inputs(B, R, cfg['F_fc'], cfg['F_att'], seed=1234)
+    m = ref_model('updown', W=W, **cfg)
+    with torch.no_grad():
+        seq, lp = m(fc, att, None, opt={'sample_method': 'greedy', 'beam_size': 1}, mode='sample')
+        picked = lp.gather(2, seq.unsqueeze(2)).squeeze(2)
+        top2 = lp.topk(2, dim=2).values
+        seqb, lpb = m(fc, att, None, opt={'beam_size': b, 'sample_n': 1}, mode='sample')
+        pickedb = lpb.gather(2, seqb.unsqueeze(2)).squeeze(2)
+        dseq, dlen, dp = beams_to_arrays(m.done_beams, b, cfg['T'])
+    np.savez_compressed(os.path.join(out_dir, 'updown_full.npz'), cfg=np.array([cfg[k] for k in ('V', 'E', 'H', 'A', 'F_fc', 'F_att', 'T')]),
+                        meta=np.array([B, R, b, 1234]), greedy_seq=seq.numpy(), greedy_picked_lp=picked.numpy(),
+                        greedy_margin=(top2[..., 0] - top2[..., 1]).numpy(), beam_seq=seqb.numpy(), beam_picked_lp=pickedb.numpy(),
+                        done_seq=dseq, done_len=dlen, done_p=dp)
+    print('updown_full greedy', seq[0].tolist(), 'beam', seqb[0].tolist())
+
+
+def gen_ciderd(out_dir, scratch):
+    """CIDEr-D scores and the self-critical reward from the reference's own scorer (df from a pickle)."""
+    from captioning.utils import rewards as R
+    V, B, n, T = 40, 6, 5, 12
+    df_imgs = cdo.make_refs(300, V, seed=3)
+    df, ref_len = cdo.build_document_frequency(df_imgs)
+    # pickle in the prepro_ngrams.py format: keys are tuples of *strings*
+    from collections import defaultdict
+    dd = defaultdict(float)                              # the reference indexes a defaultdict (ciderD_scorer.py:169)
+    dd.update({tuple(str(t) for t in k): v for k, v in df.items()})
+    pk = {'document_frequency': dd, 'ref_len': ref_len}
+    with open(os.path.join(scratch, 'data', 'golden-df.p'), 'wb') as f:
+        pickle.dump(pk, f, protocol=2)
+    # cross-check the DF builder against the reference's CiderScorer.compute_doc_freq
+    sys.path.append('cider')
+    from pyciderevalcap.ciderD.ciderD_scorer import CiderScorer
+    cs = CiderScorer(df_mode='corpus')
+    for rows in df_imgs:
+        cs.cook_append(None, [R.array_to_str(r) for r in rows])
+    cs.compute_doc_freq()
+    assert {tuple(int(t) for t in k): v for k, v in cs.document_frequency.items()} == df
+    R.init_scorer('golden-df')
+    gts = cdo.make_refs(B, V, seed=9)
+    rng = np.random.RandomState(1)
+
+    def hyp_rows(nrows):
+        rows = np.zeros((nrows, T), np.int64)
+        for i in range(nrows):
+            ln = rng.randint(0, T + 1)
+            rows[i, :ln] = np.minimum(rng.zipf(1.3, size=ln), V)
+        return rows
+    sampled = hyp_rows(B * n)
+    greedy = hyp_rows(B)
+    # make some hypotheses copy pieces of their references so the scores are not all ~0
+    for i in range(B):
+        sampled[i * n, :8] = gts[i][0][:8]
+        greedy[i, :6] = gts[i][1][:6]
+    sampled[3] = 0                                      # empty caption (just EOS)
+    opt = argparse.Namespace(cider_reward_weight=1.0, bleu_reward_weight=0.0)
+    reward = R.get_self_critical_reward(torch.from_numpy(greedy), gts, torch.from_numpy(sampled), opt)
+    # raw scores through the scorer API
+    res_ = [{'image_id': i, 'caption': [R.array_to_str(sampled[i])]} for i in range(B * n)]
+    gts_ = {i: [R.array_to_str(r) for r in gts[i // n]] for i in range(B * n)}
+    _, scores = R.CiderD_scorer.compute_score(gts_, res_)
+    keys = np.array([list(k) + [-1] * (4 - len(k)) for k in df.keys()], np.int64)
+    vals = np.array(list(df.values()), np.float64)
+    np.savez_compressed(os.path.join(out_dir, 'ciderd.npz'), df_keys=keys, df_vals=vals, ref_len=np.array(ref_len),
+                        gts=np.stack(gts), sampled=sampled, greedy=greedy, reward=reward, sample_scores=scores,
+                        meta=np.array([V, B, n, T]))
+    print('ciderd scores', np.round(scores[:6], 4), 'reward', np.round(reward[:3, 0], 4))
+
+
+def gen_reward_criterion(out_dir):
+    from captioning.modules.losses import RewardCriterion
+    g = torch.Generator().manual_seed(3)
+    N, L, V1 = 10, 7, 23
+    lp = torch.log_softmax(torch.randn(N, L, V1, generator=g), 2).requires_grad_(True)
+    seq = torch.randint(1, V1, (N, L), generator=g)
+    seq[0, 3:] = 0
+    seq[4, 0:] = 0
+    seq[7, 6:] = 0
+    reward = torch.randn(N, 1, generator=g).expand(N, L).contiguous()
+    crit = RewardCriterion()
+    loss = crit(lp, seq, reward)
+    loss.backward()
+    loss_none = crit(lp.detach(), seq, reward, reduction='none')
+    np.savez_compressed(os.path.join(out_dir, 'reward_criterion.npz'), lp=lp.detach().numpy(), seq=seq.numpy(), reward=reward.numpy(),
+                        loss=loss.detach().numpy(), grad=lp.grad.numpy(), loss_none=loss_none.numpy())
+    print('reward_criterion loss', float(loss))
+
+
+def main():
+    out_dir = os.path.join(REPO, 'tests', 'golden')
+    os.makedirs(out_dir, exist_ok=True)
+    scratch = _enter_scratch()
+    torch.set_num_threads(os.cpu_count())
+    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc']
+    if 'small' in which:
+        gen_updown_small(out_dir)
+    if 'newfc' in which:
+        gen_newfc(out_dir)
+    if 'full' in which:
+        gen_updown_full(out_dir)
+    if 'ciderd' in which:
+        gen_ciderd(out_dir, scratch)
+    if 'rc' in which:
+        gen_reward_criterion(out_dir)
+
+
+if __name__ == '__main__':
+    main()

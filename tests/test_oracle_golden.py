@@ -1,0 +1,111 @@
+"""CPU: the oracle restatement must reproduce the vectors the live reference produced (tests/golden, made by
+oracle/make_golden.py).  This is what pins the oracle; every GPU parity test then compares against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import caption_oracle as co
+from oracle import ciderd_oracle as cdo
+
+TOL = 1e-4   # north_star: log-probs and CIDEr-D rewards within 1e-4 fp32
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _family(g, name, scale):
+    V, E, H, A, F_fc, F_att, T = (int(x) for x in g['cfg'])
+    B, R, b, seed = (int(x) for x in g['meta'])
+    W = co.make_weights(name, V, E, H, A, F_fc, F_att, seed=seed, logit_scale=scale)
+    fc, att = co.make_inputs(B, R, F_fc, F_att, seed=seed)
+    return co.Family(name, W, T), fc, att, b
+
+
+def test_updown_small_greedy_and_beam(golden_dir):
+    g = _load(golden_dir, 'updown_small.npz')
+    fam, fc, att, b = _family(g, 'updown', 20.0)
+    seq, lp = co.sample(fam, fc, att)
+    assert np.array_equal(seq.numpy(), g['greedy_seq'])
+    assert np.abs(lp.numpy() - g['greedy_lp']).max() < TOL
+    seq, lp, done = co.sample_beam(fam, fc, att, beam_size=b)
+    assert np.array_equal(seq.numpy(), g['beam_seq'])
+    assert np.abs(lp.numpy() - g['beam_lp']).max() < TOL
+    for i, lst in enumerate(done):
+        for j, rec in enumerate(lst):
+            L = int(g['done_len'][i, j])
+            assert rec['seq'].tolist() == g['done_seq'][i, j, :L].tolist()
+            assert abs(rec['p'] - g['done_p'][i, j]) < 1e-3
+    seq, _, _ = co.sample_beam(fam, fc, att, beam_size=b, sample_n=b)
+    assert np.array_equal(seq.numpy(), g['beamn_seq'])
+
+
+def test_updown_small_masks_teacher_sample(golden_dir):
+    g = _load(golden_dir, 'updown_small.npz')
+    fam, fc, att, b = _family(g, 'updown', 20.0)
+    masks = torch.from_numpy(g['masks'])
+    seq, lp = co.sample(fam, fc, att, masks)
+    assert np.array_equal(seq.numpy(), g['masked_greedy_seq'])
+    assert np.abs(lp.numpy() - g['masked_greedy_lp']).max() < TOL
+    seq, _, _ = co.sample_beam(fam, fc, att, masks, beam_size=b)
+    assert np.array_equal(seq.numpy(), g['masked_beam_seq'])
+    out = co.forward_teacher(fam, fc, att, torch.from_numpy(g['teacher_in']))
+    assert np.abs(out.numpy() - g['teacher_lp']).max() < TOL
+    # the reference's random stream is torch.multinomial's; replay its tokens and compare the stored rows
+    forced = torch.from_numpy(g['sample_seq'])
+    seq, lp = co.sample(fam, fc, att, sample_method='sample', sample_n=3, forced_tokens=forced)
+    assert np.array_equal(seq.numpy(), g['sample_seq'])
+    assert np.abs(lp.numpy() - g['sample_lp']).max() < TOL
+
+
+def test_newfc_config1(golden_dir):
+    """BASELINE.json configs[0]: newfc greedy, batch 4, 2048-d fc feats, seq_len 16, CPU."""
+    g = _load(golden_dir, 'newfc_cfg1.npz')
+    fam, fc, att, _ = _family(g, 'newfc', 12.0)
+    seq, lp = co.sample(fam, fc, att)
+    assert np.array_equal(seq.numpy(), g['greedy_seq'])
+    picked = lp.gather(2, seq.unsqueeze(2)).squeeze(2)
+    assert np.abs(picked.numpy() - g['greedy_picked_lp']).max() < TOL
+    seq, _, done = co.sample_beam(fam, fc, att, beam_size=3)
+    assert np.array_equal(seq.numpy(), g['beam_seq'])
+    assert np.abs(np.array([[r['p'] for r in d] for d in done]) - g['done_p']).max() < 1e-3
+
+
+@pytest.mark.slow
+def test_updown_full_dims(golden_dir):
+    g = _load(golden_dir, 'updown_full.npz')
+    fam, fc, att, b = _family(g, 'updown', 12.0)
+    seq, lp = co.sample(fam, fc, att)
+    assert np.array_equal(seq.numpy(), g['greedy_seq'])
+    picked = lp.gather(2, seq.unsqueeze(2)).squeeze(2)
+    assert np.abs(picked.numpy() - g['greedy_picked_lp']).max() < TOL
+    seq, lp, done = co.sample_beam(fam, fc, att, beam_size=b)
+    assert np.array_equal(seq.numpy(), g['beam_seq'])
+    assert np.abs(np.array([[r['p'] for r in d] for d in done]) - g['done_p']).max() < 1e-3
+
+
+def _df_from_golden(g):
+    return {tuple(int(t) for t in k if t >= 0): float(v) for k, v in zip(g['df_keys'], g['df_vals'])}
+
+
+def test_ciderd_scores_and_reward(golden_dir):
+    g = _load(golden_dir, 'ciderd.npz')
+    df = _df_from_golden(g)
+    V, B, n, T = (int(x) for x in g['meta'])
+    gts = [g['gts'][i] for i in range(B)]
+    reward, scores = cdo.self_critical_reward(g['greedy'], gts, g['sampled'], df, float(g['ref_len']))
+    assert np.abs(reward - g['reward']).max() < 1e-9
+    assert np.abs(scores[:B * n] - g['sample_scores']).max() < 1e-9
+    # the DF builder reproduces the table the reference's compute_doc_freq produced
+    df2, n_img = cdo.build_document_frequency(cdo.make_refs(300, V, seed=3))
+    assert df2 == df and n_img == int(g['ref_len'])
+
+
+def test_reward_criterion(golden_dir):
+    g = _load(golden_dir, 'reward_criterion.npz')
+    lp, seq, reward = (torch.from_numpy(g[k]) for k in ('lp', 'seq', 'reward'))
+    assert abs(float(co.reward_criterion(lp, seq, reward)) - float(g['loss'])) < 1e-6
+    assert np.abs(co.reward_criterion(lp, seq, reward, 'none').numpy() - g['loss_none']).max() < 1e-6
+    assert np.abs(co.reward_criterion_grad(seq, reward, lp.shape[2]).numpy() - g['grad']).max() < 1e-7
