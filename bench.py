@@ -1,0 +1,232 @@
+"""Headline benchmark: captions/sec at beam=5, seq_len=20 (BASELINE.json metric), UpDown, 36x2048 bottom-up features.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (one process per GPU; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+A "step" = one pass of the hot path (AttModel._sample_beam: prologue + 20 timesteps + beam bookkeeping) over one batch of
+synthetic inputs (configs[1]: batch 256 per GPU).  Images are independent, so ranks shard the work with no data-path
+collective ("scaling": "weak"); the only collectives are the timing barrier and the max-over-ranks reduction.
+
+  value   captions/s with the step's inputs already resident in HBM (CUDA events, max over ranks)
+  e2e     the same metric through the public model(...) call with HOST (pinned) inputs: H2D copy of the features and the
+          D2H read of the caption ids are inside the timed region, every step
+  roofline the dominant kernel (attention-LSTM gate GEMM, tcgen05): algorithmic FLOPs / CUDA-event time vs the measured bf16
+          tensor peak in MEASURED_PEAKS.json (see DESIGN.md for why the parity-grade 3-pass kernel tops out at 1/3 of it)
+  cpu_baseline  the oracle port of the reference's CPU path, timed on this box's host cores on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, 'tests'))
+
+CFG = dict(V=9487, E=1000, H=1000, A=512, F_fc=2048, F_att=2048, T=20)     # configs/updown/updown.yml + opts.py defaults
+R = 36
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument('--gpus', type=int, default=1)
+    p.add_argument('--steps', type=int, default=10)
+    p.add_argument('--warmup', type=int, default=3)
+    p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    p.add_argument('--batch', type=int, default=256, help='images per GPU per step')
+    p.add_argument('--beam', type=int, default=5)
+    p.add_argument('--mode', default='tc_f16x3', choices=['tc_f16x3', 'tc_f16x1', 'simt_fp32'])
+    p.add_argument('--cpu-batch', type=int, default=32, help='images per CPU-baseline step (bounded sample)')
+    p.add_argument('--no-cpu-baseline', action='store_true')
+    return p.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        names = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'hw_power_brake': 0x80}
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                bits = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(self.nv, 'nvmlDeviceGetCurrentClocksEventReasons') \
+                    else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, b in names.items():
+                    if bits & b:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        return {'sm_mhz': statistics.median(self.samples) if self.samples else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+def cpu_reference_rate(batch, beam, steps, warmup):
+    """The oracle port (torch fp32 on all host cores) of AttModel._sample_beam on the same model / feature shapes."""
+    import torch
+    from oracle import caption_oracle as co
+    torch.set_num_threads(os.cpu_count())
+    W = co.make_weights('updown', CFG['V'], CFG['E'], CFG['H'], CFG['A'], CFG['F_fc'], CFG['F_att'], seed=1234, logit_scale=12.0)
+    fam = co.Family('updown', W, CFG['T'])
+    fc, att = co.make_inputs(batch, R, CFG['F_fc'], CFG['F_att'], seed=1234)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            co.sample_beam(fam, fc, att, beam_size=beam)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    dt = statistics.median(times)
+    return batch / dt, dt, os.cpu_count()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    workload = 'UpDown beam=%d, %dx2048 bottom-up feats, batch=%d per GPU, seq_len=20, V=9487' % (args.beam, R, args.batch)
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 5))
+        rate, dt, cores = cpu_reference_rate(args.cpu_batch, args.beam, steps, 1)
+        line = {'impl': 'reference', 'metric': 'captions/sec at beam=5 seq_len=20', 'value': rate, 'unit': 'captions/s', 'n_gpus': args.gpus,
+                'steps': steps, 'warmup': 1, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic', 'config': {'workload': workload, 'sample': 'batch=%d per step on the host cores' % args.cpu_batch},
+                'cpu_baseline': {'value': rate, 'unit': 'captions/s', 'cores': cores, 'kind': 'port',
+                                 'sample': '%d steps of batch %d (oracle port of the reference CPU path, torch fp32, all host threads)' % (steps, args.cpu_batch)},
+                'e2e': {'value': rate, 'unit': 'captions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    if local_rank == 0:
+        ge.build()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        dist.barrier()
+    from helpers import build_pair
+    from oracle import caption_oracle as co
+    dev = torch.device('cuda', local_rank)
+    model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode=args.mode, device=dev, **CFG)
+    B, T = args.batch, CFG['T']
+    opt = {'beam_size': args.beam, 'sample_n': 1}
+    n_rot = 3                                         # rotate input batches; per-step working set (features, weights, 1 GB slab) >> 126 MB L2
+    host = [co.make_inputs(B, R, CFG['F_fc'], CFG['F_att'], seed=1234 + 17 * rank + i) for i in range(n_rot)]
+    host = [(a.pin_memory(), b.pin_memory()) for a, b in host]
+    devin = [(a.to(dev), b.to(dev)) for a, b in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        fc, att = devin[i % n_rot]
+        with torch.no_grad():
+            return model(fc, att, None, opt=opt, mode='sample')
+
+    def step_e2e(i):
+        fc_h, att_h = host[i % n_rot]
+        fc = fc_h.to(dev, non_blocking=True)
+        att = att_h.to(dev, non_blocking=True)
+        with torch.no_grad():
+            seq, _ = model(fc, att, None, opt=opt, mode='sample')
+        return seq.cpu()                                   # the captions (ids) are the step's result
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        l0 = model.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        sampler.stop_flag = True
+        sampler.join()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), sampler.summary(), model.launch_count - l0
+
+    ms, clocks, launches = timed(step_resident, args.steps, args.warmup)
+    value = world * B * args.steps / (ms / 1e3)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup - 1))
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+
+    # roofline of the dominant kernel, timed live with CUDA events on the launching stream over a few more steps
+    model.set_profiling(True)
+    for i in range(3):
+        step_resident(i)
+    prof = model.read_profile()
+    model.set_profiling(False)
+    peaks_path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))['bf16_tflops_sustained']), 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)'
+    else:
+        peak, peak_src = 1400.0, 'fallback 1.4 PFLOP/s sustained (of fallback)'
+    dom_ms, dom_fl, dom_calls = prof['att_lstm']
+    achieved = dom_fl / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else 0.0
+    all_ms = sum(v[0] for v in prof.values())
+    all_fl = sum(v[1] for v in prof.values())
+    roofline = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel<128,%d> (att_lstm gates, M=%d N=4000 K=3000)' % (3 if args.mode == 'tc_f16x3' else 1, B * args.beam),
+                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'mma_passes': 3 if args.mode == 'tc_f16x3' else 1, 'launches_timed': dom_calls, 'avg_launch_ms': dom_ms / max(dom_calls, 1),
+                'all_gemms': {'tflops': all_fl / (all_ms / 1e3) / 1e12 if all_ms > 0 else 0.0, 'ms_per_step': all_ms / 3,
+                              'share_of_step': (all_ms / 3) / (ms / args.steps)},
+                'per_gemm_ms_per_step': {k: v[0] / 3 for k, v in prof.items() if v[2] > 0}}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {'metric': 'captions/sec at beam=5 seq_len=20', 'value': value, 'unit': 'captions/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 (fp32-grade: split-fp16 x3 tensor-core passes, fp32 accumulate)' if args.mode == 'tc_f16x3' else args.mode, 'data': 'synthetic',
+            'config': {'workload': workload, 'numeric_mode': args.mode, 'global_batch': B * world, 'parallelism': 'dp%d (independent images, no collective)' % world,
+                       'l2': 'inputs rotated over %d batches; per-step working set ~1.3 GB >> 126 MB L2' % n_rot},
+            'clocks': clocks,
+            'e2e': {'value': e2e, 'unit': 'captions/s', 'h2d_bytes_per_step': B * (CFG['F_fc'] + R * CFG['F_att']) * 4, 'd2h_bytes_per_step': B * T * 8,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': launches, 'roofline': roofline}
+    if not args.no_cpu_baseline and world == 1:
+        rate, dt, cores = cpu_reference_rate(args.cpu_batch, args.beam, 2, 1)
+        line['cpu_baseline'] = {'value': rate, 'unit': 'captions/s', 'cores': cores, 'kind': 'port',
+                                'sample': '2 steps of batch %d through the oracle port of the reference CPU path (torch fp32, all host threads)' % args.cpu_batch}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,108 @@
+"""ctypes binding of libcapb200.so (C ABI: include/capb200.h).  There is no CPU fallback: if the library is missing
+or a call fails the error surfaces as a RuntimeError, which the reference's training loop already turns into a
+checkpoint-and-exit (tools/train.py:287-292)."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_long, c_longlong, c_ulonglong, c_void_p
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, 'libcapb200.so')
+
+MODE_SIMT_FP32, MODE_TC_F16X3, MODE_TC_F16X1 = 0, 1, 2
+MODES = {'simt_fp32': MODE_SIMT_FP32, 'tc_f16x3': MODE_TC_F16X3, 'tc_f16x1': MODE_TC_F16X1}
+FAMILY_UPDOWN, FAMILY_NEWFC = 0, 1
+SAMPLE_GREEDY, SAMPLE_MULTINOMIAL, SAMPLE_FORCED, SAMPLE_TEACHER = 0, 1, 2, 3
+
+
+class ModelCfg(Structure):
+    _fields_ = [('family', c_int), ('vocab_size', c_int), ('input_encoding_size', c_int), ('rnn_size', c_int), ('att_hid_size', c_int),
+                ('fc_feat_size', c_int), ('att_feat_size', c_int), ('seq_length', c_int), ('numeric_mode', c_int)]
+
+
+WEIGHT_FIELDS = ['embed', 'fc_embed_w', 'fc_embed_b', 'att_embed_w', 'att_embed_b', 'ctx2att_w', 'ctx2att_b', 'logit_w', 'logit_b',
+                 'att_lstm_w_ih', 'att_lstm_w_hh', 'att_lstm_b_ih', 'att_lstm_b_hh', 'lang_lstm_w_ih', 'lang_lstm_w_hh', 'lang_lstm_b_ih',
+                 'lang_lstm_b_hh', 'h2att_w', 'h2att_b', 'alpha_w', 'alpha_b', 'i2h_w', 'i2h_b', 'h2h_w', 'h2h_b']
+
+
+class Weights(Structure):
+    _fields_ = [(f, c_void_p) for f in WEIGHT_FIELDS]
+
+
+class BeamOpts(Structure):
+    _fields_ = [('beam_size', c_int), ('sample_n', c_int), ('penalty_kind', c_int), ('penalty_alpha', c_float)]
+
+
+class SampleOpts(Structure):
+    _fields_ = [('sample_n', c_int), ('method', c_int), ('temperature', c_float), ('seed', c_ulonglong), ('steps', c_int)]
+
+
+# every exported symbol of include/capb200.h: (restype, argtypes)
+SIGNATURES = {
+    'capb200_last_error': (c_char_p, []),
+    'capb200_abi_version': (c_int, []),
+    'capb200_linear': (c_int, [c_void_p, c_long, c_void_p, c_long, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'capb200_lstm_cell': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                  c_int, c_void_p]),
+    'capb200_additive_attention': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                           c_void_p]),
+    'capb200_log_softmax_topk': (c_int, [c_void_p, c_long, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'capb200_engine_create': (c_void_p, [POINTER(ModelCfg)]),
+    'capb200_engine_destroy': (None, [c_void_p]),
+    'capb200_engine_bind_weights': (c_int, [c_void_p, POINTER(Weights), c_void_p]),
+    'capb200_decode_beam': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(BeamOpts), c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]),
+    'capb200_beam_record_logprobs': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    'capb200_decode_sample': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(SampleOpts), c_void_p, c_long, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
+    'capb200_engine_launch_count': (c_long, [c_void_p]),
+    'capb200_engine_set_profiling': (c_int, [c_void_p, c_int]),
+    'capb200_engine_read_profile': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int]),
+    'capb200_cider_table_create': (c_void_p, [c_void_p, c_void_p, c_long, c_double, c_void_p]),
+    'capb200_cider_table_destroy': (None, [c_void_p]),
+    'capb200_self_critical_reward': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                             c_void_p]),
+    'capb200_reward_criterion_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'capb200_reward_criterion_backward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Loads the shared library (building is the job of __graft_entry__.build / build.py) and types every symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError('capb200: %s is missing -- run `python imagecaptioning.pytorch_b200/build.py`; there is no CPU fallback' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError here means the library and the header disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.capb200_abi_version() != 1:
+        raise RuntimeError('capb200: ABI version mismatch')
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = '') -> None:
+    if rc != 0:
+        msg = load().capb200_last_error()
+        raise RuntimeError('capb200 %s failed: %s' % (what, msg.decode() if msg else 'unknown error'))
+
+
+def ptr(t) -> int:
+    """Device (or host) address of a torch tensor / numpy array, or None."""
+    if t is None:
+        return None
+    if hasattr(t, 'data_ptr'):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,213 @@
+// Device-resident beam search bookkeeping (group_size == 1 path of CaptionModel.beam_search).
+//
+// The reference (captioning/models/CaptionModel.py:60-110,148-207) sorts all b*(V+1) candidates per image, gathers and
+// re-concatenates the whole [B,b,t,V+1] log-prob history every step, runs three .all() host syncs and a Python loop with
+// .item() per finished beam.  Here hypotheses stay on the device for all T steps:
+//   * vocab.cu leaves the per-row top-b (value, word) pairs; beam_step merges live*b candidates per image in registers,
+//   * token / slab-row histories are b*T ints per image, reordered by parent pointer,
+//   * finished beams are appended to a per-image record list (<= b*T entries), exactly mirroring the reference's
+//     quirks: a beam that emits EOS (or any beam at the last step) is recorded with its current sum, then its running sum
+//     is lowered by 1000 but it stays in the beam and keeps being expanded (CaptionModel.py:183-198),
+//   * the full log-prob rows are never copied while searching: each step's [rows, V+1] slab stays where the vocab kernel
+//     wrote it and the winner's rows are gathered once at the end (AttModel.py:245-254 semantics).
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace capb200 {
+
+namespace {
+
+constexpr int MAXB = 16;
+
+__device__ __forceinline__ double apply_penalty(int kind, float alpha, int length, double p) {
+    if (kind == 1) return p / (pow(5.0 + length, (double)alpha) / pow(6.0, (double)alpha));   // 'wu_<alpha>'  misc.py:137-145
+    if (kind == 2) return p / (double)length;                                                  // 'avg_<alpha>' misc.py:147-151
+    return p;
+}
+
+// one warp per image
+__global__ void __launch_bounds__(32) beam_step_kernel(BeamState s, int t, int live, const float* __restrict__ top_val,
+                                                       const int* __restrict__ top_idx, int penalty_kind, float penalty_alpha,
+                                                       double* __restrict__ done_p) {
+    const int img = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int b = s.beam, T = s.T;
+    const int ncand = live * b;
+    // each lane owns candidates lane, lane+32, ... (ncand <= 256)
+    float cv[8];
+    int cf[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int c = lane + 32 * u;
+        cv[u] = -INFINITY;
+        cf[u] = 0x7fffffff;
+        if (c < ncand) {
+            const int pb = c / b, k = c % b;
+            const long row = (long)img * live + pb;
+            cv[u] = s.sums[(long)img * b + pb] + top_val[row * b + k];      // same fp32 add as CaptionModel.py:79
+            cf[u] = pb * s.V1 + top_idx[row * b + k];                       // flat index into the [live*(V+1)] candidate list
+        }
+    }
+    const int* seq_old = (t & 1) ? s.seq_b : s.seq_a;
+    int* seq_new = (t & 1) ? s.seq_a : s.seq_b;
+    const int* hist_old = (t & 1) ? s.hist_b : s.hist_a;
+    int* hist_new = (t & 1) ? s.hist_a : s.hist_b;
+
+    for (int j = 0; j < b; ++j) {
+        // arg-max over the remaining candidates; ties -> lowest flat index
+        float bv = -INFINITY;
+        int bf = 0x7fffffff, bu = -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (cv[u] > bv || (cv[u] == bv && cf[u] < bf)) { bv = cv[u]; bf = cf[u]; bu = u; }
+        float wv = bv;
+        int wf = bf;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+            const int of = __shfl_xor_sync(0xffffffffu, wf, o);
+            if (ov > wv || (ov == wv && of < wf)) { wv = ov; wf = of; }
+        }
+        if (bu >= 0 && bf == wf && bv == wv) {       // the owning lane retires the winner
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (u == bu) { cv[u] = -INFINITY; cf[u] = 0x7fffffff; }
+        }
+        const int parent = wf / s.V1;
+        const int word = wf % s.V1;
+        float new_sum = wv;
+        const long dst = ((long)img * b + j) * T;
+        const long src = ((long)img * b + parent) * T;
+        for (int q = lane; q < t; q += 32) {
+            seq_new[dst + q] = seq_old[src + q];
+            hist_new[dst + q] = hist_old[src + q];
+        }
+        if (lane == 0) {
+            seq_new[dst + t] = word;
+            hist_new[dst + t] = img * live + parent;
+        }
+        __syncwarp();
+        const bool ended = (word == 0) || (t == T - 1);
+        if (ended) {
+            int slot = 0;
+            if (lane == 0) {
+                slot = s.done_cnt[img];
+                s.done_cnt[img] = slot + 1;
+                const long rec = (long)img * b * T + slot;
+                s.done_len[rec] = t + 1;
+                s.done_raw[rec] = new_sum;
+                done_p[rec] = apply_penalty(penalty_kind, penalty_alpha, t + 1, (double)new_sum);
+            }
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            const long rec = ((long)img * b * T + slot) * T;
+            for (int q = lane; q <= t; q += 32) {
+                s.done_seq[rec + q] = seq_new[dst + q];
+                s.done_hist[rec + q] = hist_new[dst + q];
+            }
+            new_sum -= 1000.0f;
+        }
+        if (lane == 0) {
+            s.sums[(long)img * b + j] = new_sum;
+            s.tokens[(long)img * b + j] = word;
+            s.src_row[(long)img * b + j] = img * live + parent;
+        }
+        __syncwarp();
+    }
+}
+
+// one warp per image: stable selection of the `keep` best records by penalised score (CaptionModel.py:207)
+__global__ void __launch_bounds__(32) beam_finalize_kernel(BeamState s, int keep, const double* __restrict__ done_p, long long* __restrict__ out_seq,
+                                                           int* __restrict__ out_len, float* __restrict__ out_p, float* __restrict__ out_raw,
+                                                           int* __restrict__ out_hist) {
+    const int img = blockIdx.x, lane = threadIdx.x;
+    const int b = s.beam, T = s.T;
+    const int cnt = s.done_cnt[img];
+    const long base = (long)img * b * T;
+    __shared__ unsigned char taken[MAXB * 64];
+    for (int i = lane; i < cnt; i += 32) taken[i] = 0;
+    __syncwarp();
+    for (int k = 0; k < keep; ++k) {
+        double bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int i = lane; i < cnt; i += 32) {
+            if (!taken[i]) {
+                const double v = done_p[base + i];
+                if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        const long o = (long)img * keep + k;
+        if (bi == 0x7fffffff) {          // fewer records than requested (cannot happen after T steps; keep outputs defined)
+            if (lane == 0) { out_len[o] = 0; out_p[o] = -INFINITY; out_raw[o] = -INFINITY; }
+            for (int q = lane; q < T; q += 32) { out_seq[o * T + q] = 0; out_hist[o * T + q] = -1; }
+            continue;
+        }
+        if (lane == 0) {
+            taken[bi] = 1;
+            out_len[o] = s.done_len[base + bi];
+            out_p[o] = (float)bv;
+            out_raw[o] = s.done_raw[base + bi];
+        }
+        const int len = s.done_len[base + bi];
+        for (int q = lane; q < T; q += 32) {
+            out_seq[o * T + q] = (q < len) ? (long long)s.done_seq[(base + bi) * T + q] : 0;
+            out_hist[o * T + q] = (q < len) ? s.done_hist[(base + bi) * T + q] : -1;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ slab, long step_stride, long ld_slab, const int* __restrict__ hist, int T, int V1,
+                                   float* __restrict__ dst) {
+    const long item = blockIdx.x;          // item = k * T + s
+    const int sidx = (int)(item % T);
+    const int row = hist[item];
+    float* d = dst + item * V1;
+    if (row < 0) {
+        for (int v = threadIdx.x; v < V1; v += blockDim.x) d[v] = 0.f;
+        return;
+    }
+    const float* src = slab + (long)sidx * step_stride + (long)row * ld_slab;
+    const bool vec = ((V1 & 3) == 0) && ((ld_slab & 3) == 0) && ((step_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(slab) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    if (vec) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(d);
+        for (int v = threadIdx.x; v < V1 / 4; v += blockDim.x) d4[v] = __ldg(s4 + v);
+    } else {
+        for (int v = threadIdx.x; v < V1; v += blockDim.x) d[v] = src[v];
+    }
+}
+
+}  // namespace
+
+int beam_step_launch(const BeamState& s, int t, int live, const float* top_val, const int* top_idx, int penalty_kind, float penalty_alpha,
+                     cudaStream_t stream) {
+    CAPB_REQUIRE(s.beam >= 1 && s.beam <= MAXB, "beam size 1..16");
+    CAPB_REQUIRE(s.beam * s.T <= MAXB * 64, "beam*T record capacity");
+    beam_step_kernel<<<s.B, 32, 0, stream>>>(s, t, live, top_val, top_idx, penalty_kind, penalty_alpha, s.done_p);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int beam_finalize_launch(const BeamState& s, int keep, long long* out_seq, int* out_len, float* out_p, float* out_raw, int* out_hist,
+                         cudaStream_t stream) {
+    CAPB_REQUIRE(keep >= 1 && keep <= s.beam, "keep must be in 1..beam");
+    beam_finalize_kernel<<<s.B, 32, 0, stream>>>(s, keep, s.done_p, out_seq, out_len, out_p, out_raw, out_hist);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gather_logprob_rows_launch(const float* slab, long step_stride, long ld_slab, const int* hist, int nseq, int T, int V1, float* dst,
+                               cudaStream_t stream) {
+    if (nseq <= 0) return 0;
+    gather_rows_kernel<<<nseq * T, 256, 0, stream>>>(slab, step_stride, ld_slab, hist, T, V1, dst);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace capb200

@@ -1,0 +1,97 @@
+// Shared host/device helpers for the capb200 kernels.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace capb200 {
+
+// ---- error plumbing: every C-ABI entry point returns 0 or stores a message retrievable with capb200_last_error()
+void set_error(const std::string& msg);
+#define CAPB_CHECK_CUDA(expr)                                                                          \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            capb200::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " +    \
+                               __FILE__ + ":" + std::to_string(__LINE__));                            \
+            return 1;                                                                                  \
+        }                                                                                              \
+    } while (0)
+#define CAPB_REQUIRE(cond, msg)                                                                        \
+    do {                                                                                               \
+        if (!(cond)) {                                                                                 \
+            capb200::set_error(std::string("requirement failed: ") + #cond + " -- " + (msg));          \
+            return 1;                                                                                  \
+        }                                                                                              \
+    } while (0)
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline long round_up(long a, long b) { return (a + b - 1) / b * b; }
+
+// ---- split-fp16 representation of an fp32 value: x ~= hi + lo, |x - hi - lo| <= 2^-22 |x| + 2^-25
+__device__ __forceinline__ void split_f32(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+
+// ---- GEMM problem description shared by the SIMT and the tcgen05 back ends ------------------------
+// C[M,N] = sum_s A_s[M,K_s] * W_s[N,K_s]^T  (+ bias[N]) (+ row_bias[row / rows_per_group, N]) ; optional ReLU.
+// Each K-segment has its own activation and weight views so concatenated LSTM inputs are never materialised
+// (the reference builds torch.cat([prev_h, fc_feats, xt]) every step, AttModel.py:626).
+constexpr int kMaxSeg = 3;
+struct GemmSeg {
+    const float* A = nullptr;      // fp32 activations [M, K], row pitch lda   (SIMT path)
+    long lda = 0;
+    const float* W = nullptr;      // fp32 weights [N, K], row pitch ldw       (SIMT path)
+    long ldw = 0;
+    const __half* A_hi = nullptr;  // split planes of A, pitch lda_h (multiple of 8 elements)   (tcgen05 path)
+    const __half* A_lo = nullptr;
+    long lda_h = 0;
+    const __half* W_hi = nullptr;  // split planes of W, pitch ldw_h
+    const __half* W_lo = nullptr;
+    long ldw_h = 0;
+    int K = 0;
+};
+struct GemmEpilogue {
+    const float* bias = nullptr;        // [N]
+    const float* row_bias = nullptr;    // [M / rows_per_group, N], pitch ld_row_bias
+    long ld_row_bias = 0;
+    int rows_per_group = 1;
+    int relu = 0;
+    float* C = nullptr;                 // fp32 result, pitch ldc (may be null when only the split planes are wanted)
+    long ldc = 0;
+    __half* C_hi = nullptr;             // optional split planes of the result, pitch ldcs
+    __half* C_lo = nullptr;
+    long ldcs = 0;
+};
+struct GemmProblem {
+    int M = 0, N = 0, nseg = 0;
+    GemmSeg seg[kMaxSeg];
+    GemmEpilogue epi;
+};
+
+enum NumericMode : int {
+    kModeSimtFp32 = 0,   // plain fp32 FFMA on CUDA cores (exact reference arithmetic up to summation order)
+    kModeTcF16x3 = 1,    // tcgen05 kind::f16, split-fp16 operands, 3 MMA passes (hi*hi + hi*lo + lo*hi), fp32 accumulate
+    kModeTcF16x1 = 2,    // tcgen05 kind::f16, hi plane only (throughput mode; NOT parity grade)
+};
+
+int gemm_simt_launch(const GemmProblem& p, cudaStream_t stream);
+
+// tcgen05 path: a plan owns the encoded TMA tensor maps; build once per buffer set, launch many times.
+struct GemmTcPlan;
+GemmTcPlan* gemm_tc_plan_create(const GemmProblem& p, int passes);   // nullptr on failure (see last_error)
+void gemm_tc_plan_destroy(GemmTcPlan* plan);
+// Launch-time overrides: C/ldc (<= 0 keeps the planned pitch), M (rows actually valid, <= planned rows; 0 keeps) and the
+// row-bias group size (0 keeps).  The tensor maps keep the planned extents; rows beyond M are computed but never stored.
+int gemm_tc_plan_launch(GemmTcPlan* plan, float* C_override, long ldc_override, int M_override, int rows_per_group_override,
+                        cudaStream_t stream);
+bool gemm_tc_supported(const GemmProblem& p, std::string* why);
+
+int split_planes_launch(const float* x, long ldx, int rows, int cols, __half* hi, __half* lo, long ldh, cudaStream_t stream);
+
+}  // namespace capb200

@@ -1,0 +1,842 @@
+// Engine: owns packed weights + workspaces and drives the whole decode (prologue, T timesteps, beam bookkeeping) as a
+// host-sync-free sequence of kernel launches on the caller's stream.  C ABI declared in include/capb200.h.
+//
+// Reference call stack this replaces:
+//   AttModel._sample_beam  AttModel.py:218-256  -> _prepare_feature :114-124, get_logprobs_state :166-176,
+//                                                  CaptionModel.beam_search CaptionModel.py:35-209
+//   AttModel._sample       AttModel.py:258-352  -> sample_next_word CaptionModel.py:370-407
+//   AttModel._forward      AttModel.py:126-164
+// Differences that matter for speed, none for results:
+//   * image features (fc', att', p_att) are indexed per image, never replicated per beam (repeat_tensors, AttModel.py:241),
+//   * the fc' contribution to the attention-LSTM gates is constant over time, so it is contracted once per image in the
+//     prologue and enters every step as a per-image row bias (the reference re-multiplies it every step, AttModel.py:626),
+//   * no per-step host synchronisation: EOS handling, finished-beam records and history live on the device.
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "../../include/capb200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace capb200 {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
+__global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = a[i] + b[i];
+}
+__global__ void fill_int_kernel(int* p, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void iota_div_kernel(int* p, int n, int div) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i / div;
+}
+__global__ void load_token_column_kernel(const long long* src, long ld, int col, int n, int* dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (int)src[(long)i * ld + col];
+}
+
+struct Planes {
+    __half* hi = nullptr;
+    __half* lo = nullptr;
+    long ld = 0;
+};
+
+// bump allocator over one cudaMalloc'ed block; a dry run (base == nullptr) measures the size
+struct Arena {
+    char* base = nullptr;
+    size_t off = 0;
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+struct Act {
+    ActView v;
+    void carve(Arena& a, long rows, long cols, bool planes) {
+        v.ld = round_up(cols, 8);
+        v.f = a.take<float>(rows * v.ld);
+        if (planes) {
+            v.hi = a.take<__half>(rows * v.ld);
+            v.lo = a.take<__half>(rows * v.ld);
+        } else {
+            v.hi = v.lo = nullptr;
+        }
+    }
+};
+
+enum GemmId { G_FC = 0, G_ATT, G_CTX, G_GFC, G_LSTM1, G_H2ATT, G_LSTM2, G_LOGIT, G_CORE, G_COUNT };
+
+}  // namespace
+}  // namespace capb200
+
+using namespace capb200;
+
+struct capb200_cider_table {
+    CiderTable* t = nullptr;
+};
+
+struct capb200_engine {
+    capb200_model_cfg cfg{};
+    capb200_weights w{};
+    int V1 = 0, E = 0, H = 0, A = 0, T = 0;
+    int mode = 0;
+    bool tc = false;
+    bool bound = false;
+    long launches = 0;
+
+    // bind-time buffers (owned)
+    char* wblock = nullptr;
+    size_t wblock_bytes = 0;
+    float *bsum_att = nullptr, *bsum_lang = nullptr, *bsum_core = nullptr;
+    Planes p_fc, p_attw, p_ctx, p_logit, p_a_ih_h, p_a_ih_fc, p_a_ih_x, p_a_hh, p_l_ih_a, p_l_ih_h, p_l_hh, p_h2att, p_i2h, p_h2h;
+
+    // workspace (owned)
+    char* ws = nullptr;
+    size_t ws_bytes = 0;
+    int capB = 0, capRows = 0, capR = 0, capBeam = 0;
+    Planes in_fc, in_att;                        // split copies of the user inputs (tensor-core modes)
+    Act fc_e, att_e, p_att, g_fc, xt, h0_in, h1_in, h0_out, h1_out, att_res, att_h, gates;
+    float *c0[2] = {nullptr, nullptr}, *c1[2] = {nullptr, nullptr};
+    long ld_c = 0;
+    int *tokens = nullptr, *src_row = nullptr, *neg1 = nullptr, *img_of_row = nullptr, *unfinished = nullptr, *forced = nullptr;
+    float* top_val = nullptr;
+    int* top_idx = nullptr;
+    BeamState bs;
+    long long* rec_seq = nullptr;   // [B, beam, T] sorted records of the last beam decode
+    int *rec_len = nullptr, *rec_hist = nullptr, *out_hist = nullptr;
+    float *rec_p = nullptr, *rec_raw = nullptr;
+    int *tmp_len = nullptr;
+    float *tmp_p = nullptr, *tmp_raw = nullptr;
+    // slab of per-step log-prob rows for beam search (owned, grown on demand)
+    float* slab = nullptr;
+    size_t slab_bytes = 0;
+    long slab_step_stride = 0;
+    int last_B = 0, last_beam = 0;
+
+    GemmTcPlan* plans[G_COUNT] = {nullptr};
+    int core_cur = 0;   // which c buffer currently holds the state
+
+    // optional per-GEMM device timing (cudaEvent pairs on the launching stream), off by default
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_ids;          // GEMM id of each recorded pair
+    std::vector<double> ev_flops;     // algorithmic FLOPs of each recorded launch
+    size_t ev_used = 0;
+    double prof_ms[G_COUNT] = {0};
+    double prof_flops[G_COUNT] = {0};
+    long prof_calls[G_COUNT] = {0};
+};
+
+namespace {
+
+void destroy_plans(capb200_engine* e) {
+    for (int i = 0; i < G_COUNT; ++i) {
+        if (e->plans[i]) { gemm_tc_plan_destroy(e->plans[i]); e->plans[i] = nullptr; }
+    }
+}
+
+Planes carve_planes(Arena& a, long rows, long cols) {
+    Planes p;
+    p.ld = round_up(cols, 8);
+    p.hi = a.take<__half>(rows * p.ld);
+    p.lo = a.take<__half>(rows * p.ld);
+    return p;
+}
+
+void layout_weights(capb200_engine* e, Arena& a) {
+    const int H = e->H, E = e->E, A = e->A, V1 = e->V1;
+    const bool updown = e->cfg.family == CAPB200_FAMILY_UPDOWN;
+    e->bsum_att = a.take<float>(4 * H);
+    e->bsum_lang = a.take<float>(4 * H);
+    e->bsum_core = a.take<float>(5 * H);
+    if (!e->tc) return;
+    e->p_logit = carve_planes(a, V1, H);
+    if (updown) {
+        e->p_fc = carve_planes(a, H, e->cfg.fc_feat_size);
+        e->p_attw = carve_planes(a, H, e->cfg.att_feat_size);
+        e->p_ctx = carve_planes(a, A, H);
+        e->p_a_ih_h = carve_planes(a, 4 * H, H);
+        e->p_a_ih_fc = carve_planes(a, 4 * H, H);
+        e->p_a_ih_x = carve_planes(a, 4 * H, E);
+        e->p_a_hh = carve_planes(a, 4 * H, H);
+        e->p_l_ih_a = carve_planes(a, 4 * H, H);
+        e->p_l_ih_h = carve_planes(a, 4 * H, H);
+        e->p_l_hh = carve_planes(a, 4 * H, H);
+        e->p_h2att = carve_planes(a, A, H);
+    } else {
+        e->p_fc = carve_planes(a, E, e->cfg.fc_feat_size);
+        e->p_i2h = carve_planes(a, 5 * H, E);
+        e->p_h2h = carve_planes(a, 5 * H, H);
+    }
+}
+
+int pack(capb200_engine* e, const float* w, long ldw, int rows, int cols, const Planes& p, cudaStream_t st) {
+    e->launches++;
+    return split_planes_launch(w, ldw, rows, cols, p.hi, p.lo, p.ld, st);
+}
+
+void layout_workspace(capb200_engine* e, Arena& a, int B, int rows, int R, int beam) {
+    const int H = e->H, E = e->E, A = e->A, T = e->T;
+    const bool updown = e->cfg.family == CAPB200_FAMILY_UPDOWN;
+    const bool tc = e->tc;
+    if (tc) {
+        e->in_fc = carve_planes(a, B, e->cfg.fc_feat_size);
+        if (updown) e->in_att = carve_planes(a, (long)B * R, e->cfg.att_feat_size);
+    }
+    e->fc_e.carve(a, B, updown ? H : E, tc);
+    if (updown) {
+        e->att_e.carve(a, (long)B * R, H, tc);
+        e->p_att.carve(a, (long)B * R, A, false);
+        e->g_fc.carve(a, B, 4 * H, false);
+        e->h1_in.carve(a, rows, H, tc);
+        e->h1_out.carve(a, rows, H, tc);
+        e->att_res.carve(a, rows, H, tc);
+        e->att_h.carve(a, rows, A, false);
+    }
+    e->xt.carve(a, rows, E, tc);
+    e->h0_in.carve(a, rows, H, tc);
+    e->h0_out.carve(a, rows, H, tc);
+    e->gates.carve(a, rows, 5 * H, false);
+    e->ld_c = round_up(H, 8);
+    for (int i = 0; i < 2; ++i) {
+        e->c0[i] = a.take<float>((long)rows * e->ld_c);
+        e->c1[i] = a.take<float>((long)rows * e->ld_c);
+    }
+    e->tokens = a.take<int>(rows);
+    e->src_row = a.take<int>(rows);
+    e->neg1 = a.take<int>(rows);
+    e->img_of_row = a.take<int>(rows);
+    e->unfinished = a.take<int>(rows);
+    e->forced = a.take<int>(rows);
+    e->top_val = a.take<float>((long)rows * 16);
+    e->top_idx = a.take<int>((long)rows * 16);
+    BeamState& s = e->bs;
+    const long rec = (long)B * beam * T;
+    s.sums = a.take<float>((long)B * beam);
+    s.seq_a = a.take<int>(rec);
+    s.seq_b = a.take<int>(rec);
+    s.hist_a = a.take<int>(rec);
+    s.hist_b = a.take<int>(rec);
+    s.done_cnt = a.take<int>(B);
+    s.done_seq = a.take<int>(rec * T);
+    s.done_hist = a.take<int>(rec * T);
+    s.done_len = a.take<int>(rec);
+    s.done_p = a.take<double>(rec);
+    s.done_raw = a.take<float>(rec);
+    s.tokens = e->tokens;
+    s.src_row = e->src_row;
+    e->rec_seq = a.take<long long>(rec);
+    e->rec_hist = a.take<int>(rec);
+    e->out_hist = a.take<int>(rec);
+    e->rec_len = a.take<int>((long)B * beam);
+    e->rec_p = a.take<float>((long)B * beam);
+    e->rec_raw = a.take<float>((long)B * beam);
+    e->tmp_len = a.take<int>((long)B * beam);
+    e->tmp_p = a.take<float>((long)B * beam);
+    e->tmp_raw = a.take<float>((long)B * beam);
+}
+
+int ensure_workspace(capb200_engine* e, int B, int rows, int R, int beam, cudaStream_t st) {
+    if (B <= e->capB && rows <= e->capRows && R <= e->capR && beam <= e->capBeam && e->ws != nullptr) return 0;
+    const int nB = B > e->capB ? B : e->capB, nRows = rows > e->capRows ? rows : e->capRows;
+    const int nR = R > e->capR ? R : e->capR, nBeam = beam > e->capBeam ? beam : e->capBeam;
+    Arena dry;
+    layout_workspace(e, dry, nB, nRows, nR, nBeam);
+    const size_t need = dry.off + 256;
+    CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
+    destroy_plans(e);
+    if (e->ws) CAPB_CHECK_CUDA(cudaFree(e->ws));
+    e->ws = nullptr;
+    CAPB_CHECK_CUDA(cudaMalloc(&e->ws, need));
+    e->ws_bytes = need;
+    Arena real;
+    real.base = e->ws;
+    layout_workspace(e, real, nB, nRows, nR, nBeam);
+    e->capB = nB; e->capRows = nRows; e->capR = nR; e->capBeam = nBeam;
+    CAPB_CHECK_CUDA(cudaMemsetAsync(e->ws, 0, need, st));
+    fill_int_kernel<<<cdiv(nRows, 256), 256, 0, st>>>(e->neg1, nRows, -1);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- GEMM dispatch ------------------------------------------------------------------------------------------------
+GemmSeg seg_of(const ActView& a, const float* w, long ldw, const Planes& wp, int K) {
+    GemmSeg s;
+    s.A = a.f; s.lda = a.ld; s.W = w; s.ldw = ldw;
+    s.A_hi = a.hi; s.A_lo = a.lo; s.lda_h = a.ld;
+    s.W_hi = wp.hi; s.W_lo = wp.lo; s.ldw_h = wp.ld;
+    s.K = K;
+    return s;
+}
+
+// `plan_rows` is the row capacity the tensor maps are encoded for; M the rows valid in this launch.
+int run_gemm_inner(capb200_engine* e, int id, GemmProblem& g, int plan_rows, cudaStream_t st) {
+    e->launches++;
+    if (!e->tc) return gemm_simt_launch(g, st);
+    if (e->plans[id] == nullptr) {
+        GemmProblem planned = g;
+        planned.M = plan_rows;
+        e->plans[id] = gemm_tc_plan_create(planned, e->mode == CAPB200_MODE_TC_F16X3 ? 3 : 1);
+        if (e->plans[id] == nullptr) return 1;
+    }
+    return gemm_tc_plan_launch(e->plans[id], g.epi.C, g.epi.ldc, g.M, g.epi.rows_per_group, st);
+}
+
+int run_gemm(capb200_engine* e, int id, GemmProblem& g, int plan_rows, cudaStream_t st) {
+    if (!e->profiling) return run_gemm_inner(e, id, g, plan_rows, st);
+    if (e->ev_used + 2 > e->ev_pool.size()) {
+        for (int i = 0; i < 64; ++i) {
+            cudaEvent_t ev;
+            CAPB_CHECK_CUDA(cudaEventCreate(&ev));
+            e->ev_pool.push_back(ev);
+        }
+    }
+    double k_total = 0;
+    for (int s = 0; s < g.nseg; ++s) k_total += g.seg[s].K;
+    CAPB_CHECK_CUDA(cudaEventRecord(e->ev_pool[e->ev_used], st));
+    const int rc = run_gemm_inner(e, id, g, plan_rows, st);
+    CAPB_CHECK_CUDA(cudaEventRecord(e->ev_pool[e->ev_used + 1], st));
+    e->ev_used += 2;
+    e->ev_ids.push_back(id);
+    e->ev_flops.push_back(2.0 * g.M * g.N * k_total);
+    return rc;
+}
+
+// ---- prologue: _prepare_feature ---------------------------------------------------------------------------------------
+int prepare(capb200_engine* e, const float* fc, const float* att, const float* mask, int B, int R, cudaStream_t st) {
+    const int H = e->H, E = e->E, A = e->A;
+    const bool updown = e->cfg.family == CAPB200_FAMILY_UPDOWN;
+    const capb200_weights& w = e->w;
+    ActView fc_in;  fc_in.f = const_cast<float*>(fc);  fc_in.ld = e->cfg.fc_feat_size;
+    if (e->tc) {
+        e->launches++;
+        if (split_planes_launch(fc, e->cfg.fc_feat_size, B, e->cfg.fc_feat_size, e->in_fc.hi, e->in_fc.lo, e->in_fc.ld, st)) return 1;
+    }
+    {   // fc_embed: Linear (+ReLU for the attention models; NewFC has a bare Linear, AttModel.py:907)
+        GemmProblem g;
+        g.M = B; g.N = updown ? H : E; g.nseg = 1;
+        g.seg[0] = seg_of(fc_in, w.fc_embed_w, e->cfg.fc_feat_size, e->p_fc, e->cfg.fc_feat_size);
+        g.seg[0].A_hi = e->in_fc.hi; g.seg[0].A_lo = e->in_fc.lo; g.seg[0].lda_h = e->in_fc.ld;
+        g.epi.bias = w.fc_embed_b; g.epi.relu = updown ? 1 : 0;
+        g.epi.C = e->fc_e.v.f; g.epi.ldc = e->fc_e.v.ld; g.epi.C_hi = e->fc_e.v.hi; g.epi.C_lo = e->fc_e.v.lo; g.epi.ldcs = e->fc_e.v.ld;
+        if (run_gemm(e, G_FC, g, e->capB, st)) return 1;
+    }
+    if (!updown) return 0;
+    ActView att_in; att_in.f = const_cast<float*>(att); att_in.ld = e->cfg.att_feat_size;
+    if (e->tc) {
+        e->launches++;
+        if (split_planes_launch(att, e->cfg.att_feat_size, B * R, e->cfg.att_feat_size, e->in_att.hi, e->in_att.lo, e->in_att.ld, st)) return 1;
+    }
+    {   // att_embed: the one consumer of the [B,R,2048] bottom-up tile (AttModel.py:119)
+        GemmProblem g;
+        g.M = B * R; g.N = H; g.nseg = 1;
+        g.seg[0] = seg_of(att_in, w.att_embed_w, e->cfg.att_feat_size, e->p_attw, e->cfg.att_feat_size);
+        g.seg[0].A_hi = e->in_att.hi; g.seg[0].A_lo = e->in_att.lo; g.seg[0].lda_h = e->in_att.ld;
+        g.epi.bias = w.att_embed_b; g.epi.relu = 1;
+        g.epi.C = e->att_e.v.f; g.epi.ldc = e->att_e.v.ld; g.epi.C_hi = e->att_e.v.hi; g.epi.C_lo = e->att_e.v.lo; g.epi.ldcs = e->att_e.v.ld;
+        if (run_gemm(e, G_ATT, g, e->capB * e->capR, st)) return 1;
+    }
+    if (mask != nullptr) {   // pack_wrapper zero-pads the rows of invalid regions (AttModel.py:44-49)
+        e->launches++;
+        if (mask_rows_launch(e->att_e.v, B, R, H, mask, R, st)) return 1;
+    }
+    {   // ctx2att
+        GemmProblem g;
+        g.M = B * R; g.N = A; g.nseg = 1;
+        g.seg[0] = seg_of(e->att_e.v, w.ctx2att_w, H, e->p_ctx, H);
+        g.epi.bias = w.ctx2att_b;
+        g.epi.C = e->p_att.v.f; g.epi.ldc = e->p_att.v.ld;
+        if (run_gemm(e, G_CTX, g, e->capB * e->capR, st)) return 1;
+    }
+    {   // time-invariant part of the attention-LSTM gates: fc' * W_ih[:, H:2H]^T + b_ih + b_hh
+        GemmProblem g;
+        g.M = B; g.N = 4 * H; g.nseg = 1;
+        g.seg[0] = seg_of(e->fc_e.v, w.att_lstm_w_ih + H, E + 2 * H, e->p_a_ih_fc, H);
+        g.epi.bias = e->bsum_att;
+        g.epi.C = e->g_fc.v.f; g.epi.ldc = e->g_fc.v.ld;
+        if (run_gemm(e, G_GFC, g, e->capB, st)) return 1;
+    }
+    return 0;
+}
+
+// ---- one application of the recurrent core on `rows` rows (rpi rows per image) -----------------------------------------
+// tokens: input word per row; src_row: parent row per row (nullptr = identity, e->neg1 = fresh zero state)
+int core_step(capb200_engine* e, int rows, int rpi, const int* tokens, const int* src_row, float* logits, long ld_logits, int n_images, int R,
+              const float* mask, cudaStream_t st) {
+    const int H = e->H, E = e->E, A = e->A, V1 = e->V1;
+    const capb200_weights& w = e->w;
+    if (e->cfg.family == CAPB200_FAMILY_UPDOWN) {
+        StateCopy s0, s1;
+        s0.src = e->h0_out.v.f; s0.ld_src = e->h0_out.v.ld; s0.dst = e->h0_in.v;
+        s1.src = e->h1_out.v.f; s1.ld_src = e->h1_out.v.ld; s1.dst = e->h1_in.v;
+        e->launches++;
+        if (state_gather_embed_launch(rows, tokens, src_row, w.embed, E, E, 1, e->xt.v, H, 2, s0, s1, st)) return 1;
+        const int cur = e->core_cur, nxt = cur ^ 1;
+        {   // attention LSTM gates: [h_lang_prev | xt | h_att_prev] segments + per-image fc' term
+            GemmProblem g;
+            g.M = rows; g.N = 4 * H; g.nseg = 3;
+            g.seg[0] = seg_of(e->h1_in.v, w.att_lstm_w_ih, E + 2 * H, e->p_a_ih_h, H);
+            g.seg[1] = seg_of(e->xt.v, w.att_lstm_w_ih + 2 * H, E + 2 * H, e->p_a_ih_x, E);
+            g.seg[2] = seg_of(e->h0_in.v, w.att_lstm_w_hh, H, e->p_a_hh, H);
+            g.epi.row_bias = e->g_fc.v.f; g.epi.ld_row_bias = e->g_fc.v.ld; g.epi.rows_per_group = rpi;
+            g.epi.C = e->gates.v.f; g.epi.ldc = e->gates.v.ld;
+            if (run_gemm(e, G_LSTM1, g, e->capRows, st)) return 1;
+        }
+        e->launches++;
+        if (lstm_pointwise_launch(rows, H, e->gates.v.f, e->gates.v.ld, src_row, e->c0[cur], e->ld_c, e->c0[nxt], e->ld_c, e->h0_out.v, st)) return 1;
+        {   // h2att
+            GemmProblem g;
+            g.M = rows; g.N = A; g.nseg = 1;
+            g.seg[0] = seg_of(e->h0_out.v, w.h2att_w, H, e->p_h2att, H);
+            g.epi.bias = w.h2att_b;
+            g.epi.C = e->att_h.v.f; g.epi.ldc = e->att_h.v.ld;
+            if (run_gemm(e, G_H2ATT, g, e->capRows, st)) return 1;
+        }
+        e->launches++;
+        if (additive_attention_launch(n_images, rpi, R, A, H, e->att_h.v.f, e->att_h.v.ld, e->p_att.v.f, e->p_att.v.ld, e->att_e.v.f, e->att_e.v.ld,
+                                      mask, R, w.alpha_w, w.alpha_b, e->att_res.v, st)) return 1;
+        {   // language LSTM gates: [att_res | h_att | h_lang_prev]
+            GemmProblem g;
+            g.M = rows; g.N = 4 * H; g.nseg = 3;
+            g.seg[0] = seg_of(e->att_res.v, w.lang_lstm_w_ih, 2 * H, e->p_l_ih_a, H);
+            g.seg[1] = seg_of(e->h0_out.v, w.lang_lstm_w_ih + H, 2 * H, e->p_l_ih_h, H);
+            g.seg[2] = seg_of(e->h1_in.v, w.lang_lstm_w_hh, H, e->p_l_hh, H);
+            g.epi.bias = e->bsum_lang;
+            g.epi.C = e->gates.v.f; g.epi.ldc = e->gates.v.ld;
+            if (run_gemm(e, G_LSTM2, g, e->capRows, st)) return 1;
+        }
+        e->launches++;
+        if (lstm_pointwise_launch(rows, H, e->gates.v.f, e->gates.v.ld, src_row, e->c1[cur], e->ld_c, e->c1[nxt], e->ld_c, e->h1_out.v, st)) return 1;
+        e->core_cur = nxt;
+        {   // vocabulary projection straight into the caller's log-prob storage
+            GemmProblem g;
+            g.M = rows; g.N = V1; g.nseg = 1;
+            g.seg[0] = seg_of(e->h1_out.v, w.logit_w, H, e->p_logit, H);
+            g.epi.bias = w.logit_b;
+            g.epi.C = logits; g.epi.ldc = ld_logits;
+            if (run_gemm(e, G_LOGIT, g, e->capRows, st)) return 1;
+        }
+        return 0;
+    }
+    // ---- NewFC: maxout LSTM; a fresh state first consumes the image embedding (AttModel.py:925-936)
+    const bool fresh = (src_row == e->neg1);
+    for (int pass = fresh ? 0 : 1; pass < 2; ++pass) {
+        StateCopy s0, s1;
+        s0.src = e->h0_out.v.f; s0.ld_src = e->h0_out.v.ld; s0.dst = e->h0_in.v;
+        const int* srcs = (pass == 0) ? e->neg1 : (fresh ? nullptr : src_row);
+        e->launches++;
+        if (pass == 0) {
+            if (state_gather_embed_launch(rows, e->img_of_row, srcs, e->fc_e.v.f, e->fc_e.v.ld, E, 0, e->xt.v, H, 1, s0, s1, st)) return 1;
+        } else {
+            if (state_gather_embed_launch(rows, tokens, srcs, w.embed, E, E, 0, e->xt.v, H, 1, s0, s1, st)) return 1;
+        }
+        const int cur = e->core_cur, nxt = cur ^ 1;
+        GemmProblem g;
+        g.M = rows; g.N = 5 * H; g.nseg = 2;
+        g.seg[0] = seg_of(e->xt.v, w.i2h_w, E, e->p_i2h, E);
+        g.seg[1] = seg_of(e->h0_in.v, w.h2h_w, H, e->p_h2h, H);
+        g.epi.bias = e->bsum_core;
+        g.epi.C = e->gates.v.f; g.epi.ldc = e->gates.v.ld;
+        if (run_gemm(e, G_CORE, g, e->capRows, st)) return 1;
+        e->launches++;
+        if (maxout_pointwise_launch(rows, H, e->gates.v.f, e->gates.v.ld, srcs, e->c0[cur], e->ld_c, e->c0[nxt], e->ld_c, e->h0_out.v, st)) return 1;
+        e->core_cur = nxt;
+    }
+    GemmProblem g;
+    g.M = rows; g.N = V1; g.nseg = 1;
+    g.seg[0] = seg_of(e->h0_out.v, w.logit_w, H, e->p_logit, H);
+    g.epi.bias = w.logit_b;
+    g.epi.C = logits; g.epi.ldc = ld_logits;
+    return run_gemm(e, G_LOGIT, g, e->capRows, st);
+}
+
+int check_ready(capb200_engine* e) {
+    CAPB_REQUIRE(e != nullptr, "null engine");
+    CAPB_REQUIRE(e->bound, "capb200_engine_bind_weights has not been called");
+    return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+extern "C" {
+
+const char* capb200_last_error(void) { return g_last_error.c_str(); }
+int capb200_abi_version(void) { return CAPB200_ABI_VERSION; }
+
+capb200_engine* capb200_engine_create(const capb200_model_cfg* cfg) {
+    if (cfg == nullptr) { set_error("null cfg"); return nullptr; }
+    if (cfg->family != CAPB200_FAMILY_UPDOWN && cfg->family != CAPB200_FAMILY_NEWFC) { set_error("unknown model family"); return nullptr; }
+    if (cfg->numeric_mode < 0 || cfg->numeric_mode > 2) { set_error("unknown numeric mode"); return nullptr; }
+    if (cfg->seq_length < 1 || cfg->seq_length > 64) { set_error("seq_length must be in 1..64"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: the capb200 engine has no CPU fallback");
+        return nullptr;
+    }
+    capb200_engine* e = new capb200_engine();
+    e->cfg = *cfg;
+    e->V1 = cfg->vocab_size + 1;
+    e->E = cfg->input_encoding_size;
+    e->H = cfg->rnn_size;
+    e->A = cfg->att_hid_size;
+    e->T = cfg->seq_length;
+    e->mode = cfg->numeric_mode;
+    e->tc = cfg->numeric_mode != CAPB200_MODE_SIMT_FP32;
+    return e;
+}
+
+void capb200_engine_destroy(capb200_engine* e) {
+    if (e == nullptr) return;
+    destroy_plans(e);
+    for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+    cudaFree(e->wblock);
+    cudaFree(e->ws);
+    cudaFree(e->slab);
+    delete e;
+}
+
+long capb200_engine_launch_count(const capb200_engine* e) { return e ? e->launches : 0; }
+
+int capb200_engine_set_profiling(capb200_engine* e, int enable) {
+    CAPB_REQUIRE(e != nullptr, "null engine");
+    e->profiling = enable != 0;
+    return 0;
+}
+
+int capb200_engine_read_profile(capb200_engine* e, int reset, double* ms, double* flops, long* calls, int n) {
+    CAPB_REQUIRE(e != nullptr && n >= G_COUNT, "need room for 9 GEMM ids");
+    CAPB_CHECK_CUDA(cudaDeviceSynchronize());
+    for (size_t i = 0; i < e->ev_ids.size(); ++i) {
+        float t = 0.f;
+        CAPB_CHECK_CUDA(cudaEventElapsedTime(&t, e->ev_pool[2 * i], e->ev_pool[2 * i + 1]));
+        e->prof_ms[e->ev_ids[i]] += t;
+        e->prof_flops[e->ev_ids[i]] += e->ev_flops[i];
+        e->prof_calls[e->ev_ids[i]] += 1;
+    }
+    e->ev_ids.clear();
+    e->ev_flops.clear();
+    e->ev_used = 0;
+    for (int i = 0; i < G_COUNT; ++i) {
+        if (ms) ms[i] = e->prof_ms[i];
+        if (flops) flops[i] = e->prof_flops[i];
+        if (calls) calls[i] = e->prof_calls[i];
+        if (reset) { e->prof_ms[i] = 0; e->prof_flops[i] = 0; e->prof_calls[i] = 0; }
+    }
+    return 0;
+}
+
+int capb200_engine_bind_weights(capb200_engine* e, const capb200_weights* w, void* stream) {
+    CAPB_REQUIRE(e != nullptr && w != nullptr, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool updown = e->cfg.family == CAPB200_FAMILY_UPDOWN;
+    CAPB_REQUIRE(w->embed && w->fc_embed_w && w->fc_embed_b && w->logit_w && w->logit_b, "missing shared weights");
+    if (updown) {
+        CAPB_REQUIRE(w->att_embed_w && w->att_embed_b && w->ctx2att_w && w->ctx2att_b && w->att_lstm_w_ih && w->att_lstm_w_hh && w->att_lstm_b_ih &&
+                         w->att_lstm_b_hh && w->lang_lstm_w_ih && w->lang_lstm_w_hh && w->lang_lstm_b_ih && w->lang_lstm_b_hh && w->h2att_w &&
+                         w->h2att_b && w->alpha_w && w->alpha_b, "missing UpDown weights");
+    } else {
+        CAPB_REQUIRE(w->i2h_w && w->i2h_b && w->h2h_w && w->h2h_b, "missing NewFC weights");
+    }
+    e->w = *w;
+    const int H = e->H, E = e->E, A = e->A, V1 = e->V1;
+    if (e->wblock == nullptr) {
+        Arena dry;
+        layout_weights(e, dry);
+        e->wblock_bytes = dry.off + 256;
+        CAPB_CHECK_CUDA(cudaMalloc(&e->wblock, e->wblock_bytes));
+        CAPB_CHECK_CUDA(cudaMemsetAsync(e->wblock, 0, e->wblock_bytes, st));
+        Arena real;
+        real.base = e->wblock;
+        layout_weights(e, real);
+    }
+    if (updown) {
+        add_vec_kernel<<<cdiv(4 * H, 256), 256, 0, st>>>(w->att_lstm_b_ih, w->att_lstm_b_hh, e->bsum_att, 4 * H);
+        add_vec_kernel<<<cdiv(4 * H, 256), 256, 0, st>>>(w->lang_lstm_b_ih, w->lang_lstm_b_hh, e->bsum_lang, 4 * H);
+        e->launches += 2;
+    } else {
+        add_vec_kernel<<<cdiv(5 * H, 256), 256, 0, st>>>(w->i2h_b, w->h2h_b, e->bsum_core, 5 * H);
+        e->launches += 1;
+    }
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    if (e->tc) {
+        int rc = pack(e, w->logit_w, H, V1, H, e->p_logit, st);
+        if (updown) {
+            rc |= pack(e, w->fc_embed_w, e->cfg.fc_feat_size, H, e->cfg.fc_feat_size, e->p_fc, st);
+            rc |= pack(e, w->att_embed_w, e->cfg.att_feat_size, H, e->cfg.att_feat_size, e->p_attw, st);
+            rc |= pack(e, w->ctx2att_w, H, A, H, e->p_ctx, st);
+            rc |= pack(e, w->att_lstm_w_ih, E + 2 * H, 4 * H, H, e->p_a_ih_h, st);
+            rc |= pack(e, w->att_lstm_w_ih + H, E + 2 * H, 4 * H, H, e->p_a_ih_fc, st);
+            rc |= pack(e, w->att_lstm_w_ih + 2 * H, E + 2 * H, 4 * H, E, e->p_a_ih_x, st);
+            rc |= pack(e, w->att_lstm_w_hh, H, 4 * H, H, e->p_a_hh, st);
+            rc |= pack(e, w->lang_lstm_w_ih, 2 * H, 4 * H, H, e->p_l_ih_a, st);
+            rc |= pack(e, w->lang_lstm_w_ih + H, 2 * H, 4 * H, H, e->p_l_ih_h, st);
+            rc |= pack(e, w->lang_lstm_w_hh, H, 4 * H, H, e->p_l_hh, st);
+            rc |= pack(e, w->h2att_w, H, A, H, e->p_h2att, st);
+        } else {
+            rc |= pack(e, w->fc_embed_w, e->cfg.fc_feat_size, E, e->cfg.fc_feat_size, e->p_fc, st);
+            rc |= pack(e, w->i2h_w, E, 5 * H, E, e->p_i2h, st);
+            rc |= pack(e, w->h2h_w, H, 5 * H, H, e->p_h2h, st);
+        }
+        if (rc) return 1;
+    }
+    e->bound = true;
+    return 0;
+}
+
+int capb200_decode_beam(capb200_engine* e, const float* fc, const float* att, const float* mask, int B, int R, const capb200_beam_opts* opts,
+                        long long* seq, float* seq_logprobs, long long* done_seq, int* done_len, float* done_p, float* done_raw, void* stream) {
+    if (check_ready(e)) return 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CAPB_REQUIRE(opts != nullptr && fc != nullptr && seq != nullptr, "null argument");
+    const int beam = opts->beam_size, keep = opts->sample_n;
+    CAPB_REQUIRE(beam >= 1 && beam <= 16 && beam <= e->V1, "beam_size must be in 1..16 and <= V+1");
+    CAPB_REQUIRE(keep == 1 || keep == beam, "sample_n must be 1 or beam_size (AttModel.py:223)");
+    CAPB_REQUIRE(B >= 1, "empty batch");
+    const bool updown = e->cfg.family == CAPB200_FAMILY_UPDOWN;
+    if (updown) CAPB_REQUIRE(att != nullptr && R >= 1, "attention features required");
+    if (!updown) R = 1;
+    const int T = e->T, V1 = e->V1;
+    const int rows = B * beam;
+    if (ensure_workspace(e, B, rows, R, beam, st)) return 1;
+    const size_t slab_need = (size_t)T * rows * V1 * sizeof(float);
+    if (slab_need > e->slab_bytes) {
+        CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
+        if (e->slab) CAPB_CHECK_CUDA(cudaFree(e->slab));
+        e->slab = nullptr;
+        CAPB_CHECK_CUDA(cudaMalloc(&e->slab, slab_need));
+        e->slab_bytes = slab_need;
+    }
+    e->slab_step_stride = (long)rows * V1;
+    e->last_B = B;
+    e->last_beam = beam;
+    BeamState s = e->bs;
+    s.B = B; s.beam = beam; s.T = T; s.V1 = V1;
+    CAPB_CHECK_CUDA(cudaMemsetAsync(s.sums, 0, sizeof(float) * B * beam, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(s.done_cnt, 0, sizeof(int) * B, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(e->tokens, 0, sizeof(int) * rows, st));      // <bos> = 0
+    if (!updown) { iota_div_kernel<<<cdiv(rows, 256), 256, 0, st>>>(e->img_of_row, rows, 1); e->launches++; }
+    if (prepare(e, fc, att, mask, B, R, st)) return 1;
+    e->core_cur = 0;
+    for (int t = 0; t < T; ++t) {
+        const int live = (t == 0) ? 1 : beam;
+        const int nrows = B * live;
+        float* logits = e->slab + (long)t * e->slab_step_stride;
+        if (core_step(e, nrows, live, e->tokens, t == 0 ? e->neg1 : e->src_row, logits, V1, B, R, mask, st)) return 1;
+        VocabStepArgs va;
+        va.rows = nrows; va.V1 = V1; va.logits = logits; va.ld = V1;
+        va.twice = (t > 0) ? 1 : 0;      // init_logprobs went through one log_softmax only (AttModel.py:239, CaptionModel.py:204)
+        va.topk = beam; va.top_val = e->top_val; va.top_idx = e->top_idx;
+        e->launches++;
+        if (vocab_step_launch(va, st)) return 1;
+        e->launches++;
+        if (beam_step_launch(s, t, live, e->top_val, e->top_idx, opts->penalty_kind, opts->penalty_alpha, st)) return 1;
+    }
+    // all finished beams of every image, best first
+    e->launches++;
+    if (beam_finalize_launch(s, beam, e->rec_seq, e->rec_len, e->rec_p, e->rec_raw, e->rec_hist, st)) return 1;
+    if (keep == beam) {
+        CAPB_CHECK_CUDA(cudaMemcpyAsync(seq, e->rec_seq, sizeof(long long) * B * beam * T, cudaMemcpyDeviceToDevice, st));
+        if (seq_logprobs) {
+            e->launches++;
+            if (gather_logprob_rows_launch(e->slab, e->slab_step_stride, V1, e->rec_hist, B * beam, T, V1, seq_logprobs, st)) return 1;
+        }
+    } else {
+        e->launches++;
+        if (beam_finalize_launch(s, 1, seq, e->tmp_len, e->tmp_p, e->tmp_raw, e->out_hist, st)) return 1;
+        if (seq_logprobs) {
+            e->launches++;
+            if (gather_logprob_rows_launch(e->slab, e->slab_step_stride, V1, e->out_hist, B, T, V1, seq_logprobs, st)) return 1;
+        }
+    }
+    if (done_seq) CAPB_CHECK_CUDA(cudaMemcpyAsync(done_seq, e->rec_seq, sizeof(long long) * B * beam * T, cudaMemcpyDeviceToDevice, st));
+    if (done_len) CAPB_CHECK_CUDA(cudaMemcpyAsync(done_len, e->rec_len, sizeof(int) * B * beam, cudaMemcpyDeviceToDevice, st));
+    if (done_p) CAPB_CHECK_CUDA(cudaMemcpyAsync(done_p, e->rec_p, sizeof(float) * B * beam, cudaMemcpyDeviceToDevice, st));
+    if (done_raw) CAPB_CHECK_CUDA(cudaMemcpyAsync(done_raw, e->rec_raw, sizeof(float) * B * beam, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int capb200_beam_record_logprobs(capb200_engine* e, int image, int rank, float* dst, void* stream) {
+    if (check_ready(e)) return 1;
+    CAPB_REQUIRE(e->slab != nullptr && image >= 0 && image < e->last_B && rank >= 0 && rank < e->last_beam, "no such finished beam");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    e->launches++;
+    return gather_logprob_rows_launch(e->slab, e->slab_step_stride, e->V1, e->rec_hist + ((long)image * e->last_beam + rank) * e->T, 1, e->T, e->V1,
+                                      dst, st);
+}
+
+int capb200_decode_sample(capb200_engine* e, const float* fc, const float* att, const float* mask, int B, int R, const capb200_sample_opts* opts,
+                          const long long* tokens_in, long ld_tok, long long* seq, float* seq_logprobs, float* picked, void* stream) {
+    if (check_ready(e)) return 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CAPB_REQUIRE(opts != nullptr && fc != nullptr && seq_logprobs != nullptr, "null argument");
+    const int n = opts->sample_n;
+    CAPB_REQUIRE(n >= 1 && B >= 1, "empty batch");
+    const bool updown = e->cfg.family == CAPB200_FAMILY_UPDOWN;
+    if (updown) CAPB_REQUIRE(att != nullptr && R >= 1, "attention features required");
+    if (!updown) R = 1;
+    const int method = opts->method;
+    CAPB_REQUIRE(method >= 0 && method <= 3, "unknown sampling method");
+    if (method == CAPB200_SAMPLE_FORCED || method == CAPB200_SAMPLE_TEACHER) CAPB_REQUIRE(tokens_in != nullptr && ld_tok >= 1, "token matrix required");
+    if (method != CAPB200_SAMPLE_TEACHER) CAPB_REQUIRE(seq != nullptr, "seq output required");
+    if (method == CAPB200_SAMPLE_MULTINOMIAL) CAPB_REQUIRE(opts->temperature > 0.f, "temperature must be positive");
+    const int T = e->T, V1 = e->V1;
+    const int rows = B * n;
+    const int steps = (method == CAPB200_SAMPLE_TEACHER) ? opts->steps : T;
+    const long t_out = (method == CAPB200_SAMPLE_TEACHER) ? ld_tok : T;
+    CAPB_REQUIRE(steps >= 0 && steps <= t_out, "steps out of range");
+    if (ensure_workspace(e, B, rows, R, 1, st)) return 1;
+    CAPB_CHECK_CUDA(cudaMemsetAsync(e->tokens, 0, sizeof(int) * rows, st));
+    if (!updown) { iota_div_kernel<<<cdiv(rows, 256), 256, 0, st>>>(e->img_of_row, rows, n); e->launches++; }
+    if (prepare(e, fc, att, mask, B, R, st)) return 1;
+    e->core_cur = 0;
+    for (int t = 0; t < steps; ++t) {
+        if (method == CAPB200_SAMPLE_TEACHER) {
+            load_token_column_kernel<<<cdiv(rows, 256), 256, 0, st>>>(tokens_in, ld_tok, t, rows, e->tokens);
+            e->launches++;
+        } else if (method == CAPB200_SAMPLE_FORCED) {
+            load_token_column_kernel<<<cdiv(rows, 256), 256, 0, st>>>(tokens_in, ld_tok, t, rows, e->forced);
+            e->launches++;
+        }
+        float* logits = seq_logprobs + (long)t * V1;
+        if (core_step(e, rows, n, e->tokens, t == 0 ? e->neg1 : nullptr, logits, t_out * V1, B, R, mask, st)) return 1;
+        VocabStepArgs va;
+        va.rows = rows; va.V1 = V1; va.logits = logits; va.ld = t_out * V1;
+        va.twice = 0;
+        if (method != CAPB200_SAMPLE_TEACHER) {
+            va.select = (method == CAPB200_SAMPLE_GREEDY) ? 1 : (method == CAPB200_SAMPLE_MULTINOMIAL ? 2 : 3);
+            va.temperature = opts->temperature;
+            va.seed = opts->seed;
+            va.step = (unsigned long long)t;
+            va.forced = e->forced;
+            va.unfinished = e->unfinished;
+            va.first_step = (t == 0);
+            va.tokens_out = e->tokens;
+            va.seq_out = seq; va.ld_seq = T; va.t = t;
+            va.picked_lp = picked ? picked + t : nullptr;      // picked is [N,T]
+            va.ld_picked = T;
+        }
+        e->launches++;
+        if (vocab_step_launch(va, st)) return 1;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// operator-level entry points
+// ---------------------------------------------------------------------------------------------------------------------
+int capb200_linear(const float* x, long ldx, const float* w, long ldw, const float* b, float* y, long ldy, int M, int N, int K, int relu, int mode,
+                   void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CAPB_REQUIRE(x && w && y && M > 0 && N > 0 && K > 0, "bad argument");
+    GemmProblem g;
+    g.M = M; g.N = N; g.nseg = 1;
+    g.seg[0].A = x; g.seg[0].lda = ldx; g.seg[0].W = w; g.seg[0].ldw = ldw; g.seg[0].K = K;
+    g.epi.bias = b; g.epi.relu = relu; g.epi.C = y; g.epi.ldc = ldy;
+    if (mode == CAPB200_MODE_SIMT_FP32) return gemm_simt_launch(g, st);
+    CAPB_REQUIRE(mode == CAPB200_MODE_TC_F16X3 || mode == CAPB200_MODE_TC_F16X1, "unknown mode");
+    const long ldh = round_up(K, 8);
+    __half* scratch = nullptr;
+    const size_t elems = (size_t)(M + N) * ldh * 2;
+    CAPB_CHECK_CUDA(cudaMallocAsync(&scratch, elems * sizeof(__half), st));
+    __half* xh = scratch; __half* xl = xh + (size_t)M * ldh;
+    __half* wh = xl + (size_t)M * ldh; __half* wl = wh + (size_t)N * ldh;
+    int rc = split_planes_launch(x, ldx, M, K, xh, xl, ldh, st) | split_planes_launch(w, ldw, N, K, wh, wl, ldh, st);
+    g.seg[0].A_hi = xh; g.seg[0].A_lo = xl; g.seg[0].lda_h = ldh;
+    g.seg[0].W_hi = wh; g.seg[0].W_lo = wl; g.seg[0].ldw_h = ldh;
+    GemmTcPlan* plan = rc ? nullptr : gemm_tc_plan_create(g, mode == CAPB200_MODE_TC_F16X3 ? 3 : 1);
+    if (plan == nullptr) rc = 1;
+    if (!rc) rc = gemm_tc_plan_launch(plan, nullptr, 0, 0, 0, st);
+    if (plan) gemm_tc_plan_destroy(plan);
+    cudaFreeAsync(scratch, st);
+    return rc;
+}
+
+int capb200_lstm_cell(const float* x, int Kx, const float* h, const float* c, const float* w_ih, const float* w_hh, const float* b_ih,
+                      const float* b_hh, float* h_out, float* c_out, int M, int H, int mode, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CAPB_REQUIRE(x && h && c && w_ih && w_hh && b_ih && b_hh && h_out && c_out, "null argument");
+    float* gates = nullptr;
+    CAPB_CHECK_CUDA(cudaMallocAsync(&gates, sizeof(float) * ((size_t)M * 4 * H + 4 * H), st));
+    float* bsum = gates + (size_t)M * 4 * H;
+    add_vec_kernel<<<cdiv(4 * H, 256), 256, 0, st>>>(b_ih, b_hh, bsum, 4 * H);
+    int rc = capb200_linear(x, Kx, w_ih, Kx, bsum, gates, 4 * H, M, 4 * H, Kx, 0, mode, stream);
+    float* g2 = nullptr;
+    if (!rc) {
+        // second contraction accumulated through a temporary: gates += h * w_hh^T
+        CAPB_CHECK_CUDA(cudaMallocAsync(&g2, sizeof(float) * (size_t)M * 4 * H, st));
+        rc = capb200_linear(h, H, w_hh, H, nullptr, g2, 4 * H, M, 4 * H, H, 0, mode, stream);
+        if (!rc) add_vec_kernel<<<cdiv(M * 4 * H, 256), 256, 0, st>>>(gates, g2, gates, M * 4 * H);
+    }
+    if (!rc) {
+        ActView ho; ho.f = h_out; ho.ld = H;
+        rc = lstm_pointwise_launch(M, H, gates, 4 * H, nullptr, c, H, c_out, H, ho, st);
+    }
+    if (g2) cudaFreeAsync(g2, st);
+    cudaFreeAsync(gates, st);
+    return rc;
+}
+
+int capb200_additive_attention(const float* att_h, const float* p_att, const float* att, const float* mask, const float* alpha_w,
+                               const float* alpha_b, float* out, int n_images, int rows_per_image, int R, int A, int H, void* stream) {
+    CAPB_REQUIRE(att_h && p_att && att && alpha_w && alpha_b && out, "null argument");
+    ActView o; o.f = out; o.ld = H;
+    return additive_attention_launch(n_images, rows_per_image, R, A, H, att_h, A, p_att, A, att, H, mask, R, alpha_w, alpha_b, o,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+int capb200_log_softmax_topk(float* logits, long ld, int rows, int V1, int twice, int k, float* top_val, int* top_idx, void* stream) {
+    CAPB_REQUIRE(logits != nullptr && rows > 0 && V1 > 0, "bad argument");
+    VocabStepArgs va;
+    va.rows = rows; va.V1 = V1; va.logits = logits; va.ld = ld; va.twice = twice; va.topk = k; va.top_val = top_val; va.top_idx = top_idx;
+    return vocab_step_launch(va, static_cast<cudaStream_t>(stream));
+}
+
+capb200_cider_table* capb200_cider_table_create(const int* keys, const double* df, long n, double ref_len, void* stream) {
+    if (keys == nullptr || df == nullptr || n < 0 || ref_len <= 0) { set_error("bad CIDEr-D table arguments"); return nullptr; }
+    CiderTable* t = cider_table_create(keys, df, n, ref_len, static_cast<cudaStream_t>(stream));
+    if (t == nullptr) return nullptr;
+    capb200_cider_table* h = new capb200_cider_table();
+    h->t = t;
+    return h;
+}
+
+void capb200_cider_table_destroy(capb200_cider_table* t) {
+    if (t == nullptr) return;
+    cider_table_destroy(t->t);
+    delete t;
+}
+
+int capb200_self_critical_reward(const capb200_cider_table* t, const long long* sampled, int S, const long long* greedy, int B, int T,
+                                 const int* refs, const int* ref_offsets, int L, double* scores, float* reward, void* stream) {
+    CAPB_REQUIRE(t != nullptr && sampled && greedy && refs && ref_offsets && scores, "null argument");
+    return cider_reward_launch(t->t, sampled, S, greedy, B, T, refs, ref_offsets, L, scores, reward, T, T, static_cast<cudaStream_t>(stream));
+}
+
+int capb200_reward_criterion_forward(const float* logprobs, const long long* seq, const float* reward, int N, int T, int V1, float* loss_mean,
+                                     float* loss_rows, float* mask_sum, void* stream) {
+    CAPB_REQUIRE(logprobs && seq && reward && N > 0 && T > 0, "bad argument");
+    return reward_criterion_fwd_launch(logprobs, (long)T * V1, V1, seq, reward, N, T, loss_mean, loss_rows, mask_sum, static_cast<cudaStream_t>(stream));
+}
+
+int capb200_reward_criterion_backward(const long long* seq, const float* reward, int N, int T, int V1, const float* mask_sum, float upstream,
+                                      float* grad, void* stream) {
+    CAPB_REQUIRE(seq && reward && mask_sum && grad, "null argument");
+    return reward_criterion_bwd_launch(seq, reward, N, T, mask_sum, upstream, grad, (long)T * V1, V1, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,348 @@
+// tcgen05 GEMM for the caption-decode path:  C[M,N] = sum_s A_s * W_s^T (+bias, +per-group row bias, ReLU)
+//
+// Replaces the cuBLAS SGEMMs behind nn.Linear / nn.LSTMCell on the hot path (reference call sites:
+// captioning/models/AttModel.py:119 att_embed, :172 logit, :628/:635 LSTMCell, :733 h2att).
+//
+// Numerics.  The reference computes in fp32; parity demands log-probs within 1e-4 and bit-exact greedy ids, which
+// single-pass fp16/bf16/tf32 tensor-core products do not deliver.  Operands are therefore kept in HBM as two fp16
+// planes (hi = fp16(x), lo = fp16(x - hi): same bytes as fp32) and every K-block issues three kind::f16 MMAs into
+// one fp32 TMEM accumulator:  hi*lo + lo*hi + hi*hi  (the lo*lo term, <= 2^-22 relative, is dropped).
+// PASSES == 1 is the throughput mode (hi plane only) and is never used for parity claims.
+//
+// Structure (one 128 x BN output tile per CTA, 256 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes [64 k x 128 rows] (128B swizzle) for A_hi, A_lo, W_hi,
+//               W_lo of the current K-block into a STAGES-deep shared-memory ring, mbarrier complete_tx signalling.
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) straight from
+//               shared-memory descriptors; tcgen05.commit releases ring slots and finally signals the epilogue.
+//   warp 2      allocates / frees the TMEM accumulator columns.
+//   warps 4..7  epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused bias / row-bias / ReLU, fp32 store and
+//               (optionally) a split-fp16 copy so the next GEMM can consume the result without a conversion pass.
+// K-segments (up to 3 activation/weight pairs) are walked back to back so concatenated LSTM inputs are never built.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace capb200 {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;   // fp16 elements: one 128-byte swizzle row
+
+struct TcParams {
+    CUtensorMap a_hi[kMaxSeg];
+    CUtensorMap a_lo[kMaxSeg];
+    CUtensorMap w_hi[kMaxSeg];
+    CUtensorMap w_lo[kMaxSeg];
+    int kblocks[kMaxSeg];
+    int nseg;
+    int M, N;
+    float* C;
+    long ldc;
+    __half* C_hi;
+    __half* C_lo;
+    long ldcs;
+    const float* bias;
+    const float* row_bias;
+    long ld_row_bias;
+    int rows_per_group;
+    int relu;
+};
+
+template <int BN, int PASSES>
+struct TcCfg {
+    static constexpr int kPlanes = (PASSES == 3) ? 2 : 1;
+    static constexpr uint32_t kABytes = BM * BK * 2;
+    static constexpr uint32_t kWBytes = BN * BK * 2;
+    static constexpr uint32_t kStageBytes = kPlanes * (kABytes + kWBytes);
+    static constexpr int kStages = (200 * 1024) / kStageBytes >= 8 ? 8 : (200 * 1024) / kStageBytes;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+    static_assert((kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be a power of two");
+    static_assert(kStages >= 2, "need at least a double buffer");
+};
+
+template <int BN, int PASSES>
+__global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+    using Cfg = TcCfg<BN, PASSES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + Cfg::kStages;
+    uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM;
+    const int n0 = blockIdx.x * BN;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.nseg; ++s) {
+            ptx::prefetch_tmap(&p.a_hi[s]);
+            ptx::prefetch_tmap(&p.w_hi[s]);
+            if (PASSES == 3) {
+                ptx::prefetch_tmap(&p.a_lo[s]);
+                ptx::prefetch_tmap(&p.w_lo[s]);
+            }
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < Cfg::kStages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        ptx::mbar_init(tmem_full_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_holder, Cfg::kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int s = 0; s < p.nseg; ++s) {
+                for (int kb = 0; kb < p.kblocks[s]; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* st = smem + stage * Cfg::kStageBytes;
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    ptx::tma_load_2d(st, &p.a_hi[s], &full_bar[stage], kb * BK, m0);
+                    ptx::tma_load_2d(st + Cfg::kABytes * Cfg::kPlanes, &p.w_hi[s], &full_bar[stage], kb * BK, n0);
+                    if (PASSES == 3) {
+                        ptx::tma_load_2d(st + Cfg::kABytes, &p.a_lo[s], &full_bar[stage], kb * BK, m0);
+                        ptx::tma_load_2d(st + Cfg::kABytes * 2 + Cfg::kWBytes, &p.w_lo[s], &full_bar[stage], kb * BK, n0);
+                    }
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16_f32(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t accumulate = 0;
+            for (int s = 0; s < p.nseg; ++s) {
+                for (int kb = 0; kb < p.kblocks[s]; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after_sync();
+                    const uint32_t st = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint32_t a_hi = st;
+                    const uint32_t a_lo = st + Cfg::kABytes;                          // only valid when PASSES == 3
+                    const uint32_t w_hi = st + Cfg::kABytes * Cfg::kPlanes;
+                    const uint32_t w_lo = st + Cfg::kABytes * 2 + Cfg::kWBytes;       // only valid when PASSES == 3
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint32_t koff = k * 32;   // 16 fp16 = 32 bytes inside the 128-byte swizzle row
+                        if (PASSES == 3) {
+                            ptx::umma_f16(tmem_base, ptx::make_smem_desc_sw128(a_hi + koff), ptx::make_smem_desc_sw128(w_lo + koff), idesc, accumulate);
+                            ptx::umma_f16(tmem_base, ptx::make_smem_desc_sw128(a_lo + koff), ptx::make_smem_desc_sw128(w_hi + koff), idesc, 1);
+                            ptx::umma_f16(tmem_base, ptx::make_smem_desc_sw128(a_hi + koff), ptx::make_smem_desc_sw128(w_hi + koff), idesc, 1);
+                        } else {
+                            ptx::umma_f16(tmem_base, ptx::make_smem_desc_sw128(a_hi + koff), ptx::make_smem_desc_sw128(w_hi + koff), idesc, accumulate);
+                        }
+                        accumulate = 1;
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+            ptx::umma_commit(tmem_full_bar);
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+        const int row = m0 + q * 32 + lane;
+        ptx::mbar_wait(tmem_full_bar, 0);
+        ptx::tc_fence_after_sync();
+        const bool row_ok = row < p.M;
+        const float* rb = (p.row_bias != nullptr && row_ok) ? p.row_bias + (long)(row / p.rows_per_group) * p.ld_row_bias : nullptr;
+        const bool vec4 = p.C != nullptr && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
+        const bool vec2h = p.C_hi != nullptr && (p.ldcs & 7) == 0 && (reinterpret_cast<uintptr_t>(p.C_hi) & 15) == 0 &&
+                           (reinterpret_cast<uintptr_t>(p.C_lo) & 15) == 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the guarded stores of the previous chunk
+            ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+            ptx::tmem_ld_wait();
+            const int col0 = n0 + c0;
+            if (!row_ok || col0 >= p.N) continue;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = col0 + j;
+                float x = __uint_as_float(r[j]);
+                if (col < p.N) {
+                    if (p.bias != nullptr) x += __ldg(p.bias + col);
+                    if (rb != nullptr) x += __ldg(rb + col);
+                    if (p.relu) x = fmaxf(x, 0.0f);
+                }
+                v[j] = x;
+            }
+            const bool full = col0 + 32 <= p.N;
+            if (p.C != nullptr) {
+                float* dst = p.C + (long)row * p.ldc + col0;
+                if (full && vec4) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+                    for (int j = 0; j < 32; ++j) if (col0 + j < p.N) dst[j] = v[j];
+                }
+            }
+            if (p.C_hi != nullptr) {
+                __half* dh = p.C_hi + (long)row * p.ldcs + col0;
+                __half* dl = p.C_lo + (long)row * p.ldcs + col0;
+                if (full && vec2h) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        __align__(16) __half h[8];
+                        __align__(16) __half l[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) split_f32(v[j + u], h[u], l[u]);
+                        *reinterpret_cast<uint4*>(dh + j) = *reinterpret_cast<const uint4*>(h);
+                        *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(l);
+                    }
+                } else {
+                    for (int j = 0; j < 32; ++j) {
+                        if (col0 + j < p.N) {
+                            __half h, l;
+                            split_f32(v[j], h, l);
+                            dh[j] = h;
+                            dl[j] = l;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || sym == nullptr) {
+            return nullptr;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// fp16 plane [rows, K] with row pitch `pitch` elements; box = 64 (K) x box_rows, 128-byte swizzle, zero OOB fill.
+bool encode_plane(CUtensorMap* map, const __half* base, long rows, long K, long pitch, int box_rows, std::string* err) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(pitch) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r); return false; }
+    return true;
+}
+
+template <int BN, int PASSES>
+int launch_cfg(const TcParams& prm, cudaStream_t stream) {
+    using Cfg = TcCfg<BN, PASSES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    dim3 grid(cdiv(prm.N, BN), cdiv(prm.M, BM));
+    gemm_tc_kernel<BN, PASSES><<<grid, 256, Cfg::kSmemBytes, stream>>>(prm);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+struct GemmTcPlan {
+    TcParams prm;
+    int passes;
+    int bn;
+};
+
+bool gemm_tc_supported(const GemmProblem& p, std::string* why) {
+    auto bad = [&](const char* m) { if (why) *why = m; return false; };
+    if (p.nseg < 1 || p.nseg > kMaxSeg) return bad("1..3 K-segments");
+    for (int s = 0; s < p.nseg; ++s) {
+        const GemmSeg& g = p.seg[s];
+        if (g.A_hi == nullptr || g.W_hi == nullptr) return bad("split planes missing");
+        if ((g.lda_h & 7) || (g.ldw_h & 7)) return bad("plane pitch must be a multiple of 8 elements (16 bytes)");
+        if ((reinterpret_cast<uintptr_t>(g.A_hi) & 15) || (reinterpret_cast<uintptr_t>(g.W_hi) & 15)) return bad("plane base must be 16-byte aligned");
+        if (g.K < 1) return bad("empty K-segment");
+    }
+    return true;
+}
+
+GemmTcPlan* gemm_tc_plan_create(const GemmProblem& p, int passes) {
+    std::string why;
+    if (!gemm_tc_supported(p, &why)) { set_error("gemm_tc: unsupported problem: " + why); return nullptr; }
+    if (passes != 1 && passes != 3) { set_error("gemm_tc: passes must be 1 or 3"); return nullptr; }
+    GemmTcPlan* plan = new GemmTcPlan();
+    memset(&plan->prm, 0, sizeof(TcParams));
+    plan->passes = passes;
+    plan->bn = 128;
+    TcParams& t = plan->prm;
+    t.nseg = p.nseg;
+    t.M = p.M;
+    t.N = p.N;
+    std::string err;
+    for (int s = 0; s < p.nseg; ++s) {
+        const GemmSeg& g = p.seg[s];
+        t.kblocks[s] = cdiv(g.K, BK);
+        bool ok = encode_plane(&t.a_hi[s], g.A_hi, p.M, g.K, g.lda_h, BM, &err) &&
+                  encode_plane(&t.w_hi[s], g.W_hi, p.N, g.K, g.ldw_h, plan->bn, &err);
+        if (ok && passes == 3) {
+            if (g.A_lo == nullptr || g.W_lo == nullptr) { err = "lo planes missing for 3-pass mode"; ok = false; }
+            ok = ok && encode_plane(&t.a_lo[s], g.A_lo, p.M, g.K, g.lda_h, BM, &err) &&
+                 encode_plane(&t.w_lo[s], g.W_lo, p.N, g.K, g.ldw_h, plan->bn, &err);
+        }
+        if (!ok) { set_error("gemm_tc: " + err); delete plan; return nullptr; }
+    }
+    t.C = p.epi.C; t.ldc = p.epi.ldc;
+    t.C_hi = p.epi.C_hi; t.C_lo = p.epi.C_lo; t.ldcs = p.epi.ldcs;
+    t.bias = p.epi.bias; t.row_bias = p.epi.row_bias; t.ld_row_bias = p.epi.ld_row_bias;
+    t.rows_per_group = p.epi.rows_per_group < 1 ? 1 : p.epi.rows_per_group;
+    t.relu = p.epi.relu;
+    return plan;
+}
+
+void gemm_tc_plan_destroy(GemmTcPlan* plan) { delete plan; }
+
+int gemm_tc_plan_launch(GemmTcPlan* plan, float* C_override, long ldc_override, int M_override, int rows_per_group_override,
+                        cudaStream_t stream) {
+    TcParams prm = plan->prm;
+    if (C_override != nullptr) prm.C = C_override;
+    if (ldc_override > 0) prm.ldc = ldc_override;
+    if (M_override > 0) {
+        if (M_override > prm.M) { set_error("gemm_tc: M override exceeds the planned row count"); return 1; }
+        prm.M = M_override;
+    }
+    if (rows_per_group_override > 0) prm.rows_per_group = rows_per_group_override;
+    if (prm.M <= 0 || prm.N <= 0) return 0;
+    if (plan->passes == 3) return launch_cfg<128, 3>(prm, stream);
+    return launch_cfg<128, 1>(prm, stream);
+}
+
+}  // namespace capb200

@@ -1,0 +1,100 @@
+// Internal launch prototypes shared by the kernel translation units and the engine.
+#pragma once
+#include "common.cuh"
+
+namespace capb200 {
+
+// An activation matrix [rows, cols] kept as fp32 and (tensor-core modes) as split-fp16 planes, common pitch `ld`.
+struct ActView {
+    float* f = nullptr;
+    __half* hi = nullptr;
+    __half* lo = nullptr;
+    long ld = 0;
+};
+
+// One state tensor to reorder by parent row: dst[r, :] = src[src_row[r], :]
+struct StateCopy {
+    const float* src = nullptr;
+    long ld_src = 0;
+    ActView dst;
+};
+
+// ---- pointwise.cu
+int state_gather_embed_launch(int rows, const int* tokens, const int* src_row, const float* emb, long ld_emb, int E, int relu,
+                              ActView xt, int H, int nstate, StateCopy sc0, StateCopy sc1, cudaStream_t stream);
+int lstm_pointwise_launch(int rows, int H, const float* gates, long ld_g, const int* src_row, const float* c_prev, long ld_cp,
+                          float* c_out, long ld_co, ActView h_out, cudaStream_t stream);
+int maxout_pointwise_launch(int rows, int H, const float* sums, long ld_s, const int* src_row, const float* c_prev, long ld_cp,
+                            float* c_out, long ld_co, ActView h_out, cudaStream_t stream);
+int additive_attention_launch(int n_images, int rpi, int R, int A, int H, const float* att_h, long ld_ah, const float* p_att, long ld_pa,
+                              const float* att, long ld_at, const float* mask, long ld_mask, const float* alpha_w, const float* alpha_b,
+                              ActView out, cudaStream_t stream);
+int mask_rows_launch(ActView x, int n_images, int R, int cols, const float* mask, long ld_mask, cudaStream_t stream);
+
+// ---- vocab.cu : log-softmax over the vocabulary + candidate selection
+struct VocabStepArgs {
+    int rows = 0;
+    int V1 = 0;
+    float* logits = nullptr;      // [rows, V1] in/out: overwritten with log-probs (pitch ld)
+    long ld = 0;
+    int twice = 0;                // beam search renormalises the log-probs a second time (CaptionModel.py:204)
+    // top-k output for beam search (k <= 16)
+    int topk = 0;
+    float* top_val = nullptr;     // [rows, topk]
+    int* top_idx = nullptr;       // [rows, topk]
+    // greedy / multinomial selection for _sample
+    int select = 0;               // 0 none, 1 greedy argmax, 2 multinomial (Gumbel-max on logp / temperature), 3 forced tokens
+    float temperature = 1.0f;
+    unsigned long long seed = 0;
+    unsigned long long step = 0;  // Philox offset: one independent stream per (row, step)
+    const int* forced = nullptr;  // [rows] when select == 3
+    int* unfinished = nullptr;    // [rows] in/out (nullptr at beam search); rows already finished emit pad and a zero row
+    int first_step = 0;
+    int* tokens_out = nullptr;    // [rows] next input token
+    long long* seq_out = nullptr; // seq[row * ld_seq + t] = token (int64, reference dtype)
+    long ld_seq = 0;
+    int t = 0;
+    float* picked_lp = nullptr;   // optional: picked_lp[row * ld_picked] = log-prob of the chosen token
+    long ld_picked = 1;
+};
+int vocab_step_launch(const VocabStepArgs& a, cudaStream_t stream);
+
+// ---- beam.cu
+struct BeamState {
+    int B = 0, beam = 0, T = 0, V1 = 0;
+    float* sums = nullptr;        // [B, beam]
+    int* seq_a = nullptr;         // [B, beam, T] ping
+    int* seq_b = nullptr;         // [B, beam, T] pong
+    int* hist_a = nullptr;        // [B, beam, T] row index into the step-s log-prob slab, ping
+    int* hist_b = nullptr;
+    int* done_cnt = nullptr;      // [B]
+    int* done_seq = nullptr;      // [B, beam*T, T]
+    int* done_hist = nullptr;     // [B, beam*T, T]
+    int* done_len = nullptr;      // [B, beam*T]
+    double* done_p = nullptr;     // [B, beam*T]  length-penalised score (the reference keeps Python floats)
+    float* done_raw = nullptr;    // [B, beam*T]  raw sum of log-probs
+    int* tokens = nullptr;        // [B*beam] next input tokens
+    int* src_row = nullptr;       // [B*beam] parent row (index into the previous step's rows)
+};
+int beam_step_launch(const BeamState& s, int t, int live, const float* top_val, const int* top_idx, int penalty_kind, float penalty_alpha,
+                     cudaStream_t stream);
+// sorts each image's finished beams by score, writes the best `keep` records:
+//   out_seq [B*keep, T] int64, out_len/out_p [B*keep], out_hist [B*keep, T] (slab rows, -1 beyond length)
+int beam_finalize_launch(const BeamState& s, int keep, long long* out_seq, int* out_len, float* out_p, float* out_raw, int* out_hist,
+                         cudaStream_t stream);
+// dst[k, s, :] = slab[s][hist[k, s], :] (zeros where hist < 0); slab step stride `step_stride` elements
+int gather_logprob_rows_launch(const float* slab, long step_stride, long ld_slab, const int* hist, int nseq, int T, int V1, float* dst,
+                               cudaStream_t stream);
+
+// ---- reward.cu (CIDEr-D) and criterion
+struct CiderTable;   // device hash table of n-gram -> idf
+CiderTable* cider_table_create(const int* keys, const double* df, long n, double ref_len, cudaStream_t stream);
+void cider_table_destroy(CiderTable* t);
+int cider_reward_launch(const CiderTable* t, const long long* sampled, int S, const long long* greedy, int B, int T, const int* refs,
+                        const int* ref_offsets, int L, double* scores, float* reward, long ld_reward, int reward_cols, cudaStream_t stream);
+int reward_criterion_fwd_launch(const float* logprobs, long ld_row, long ld_t, const long long* seq, const float* reward, int N, int T,
+                                float* loss_mean, float* loss_rows, float* mask_sum, cudaStream_t stream);
+int reward_criterion_bwd_launch(const long long* seq, const float* reward, int N, int T, const float* mask_sum, float upstream,
+                                float* grad, long ld_row, long ld_t, cudaStream_t stream);
+
+}  // namespace capb200

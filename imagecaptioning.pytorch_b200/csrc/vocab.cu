@@ -1,0 +1,197 @@
+// Vocabulary epilogue: log-softmax (once for _sample, twice for beam search) and candidate selection.
+//
+// Replaces, per decode step:  F.log_softmax(self.logit(output))            AttModel.py:172
+//                             F.log_softmax(logprobs / temperature)        CaptionModel.py:204   (beam search only; T = 1)
+//                             torch.sort(b*(V+1) candidates)[:b]           CaptionModel.py:80-81 (per-row top-b, merged in beam.cu)
+//                             torch.max / Categorical(logits).sample()     CaptionModel.py:372,405
+//                             finished-row masking                         AttModel.py:340-347
+// One CTA per row; the row lives in shared memory between the passes so HBM sees one read and one write.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace capb200 {
+
+namespace {
+
+constexpr int VT = 256;   // threads per row
+
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = scratch[0];
+#pragma unroll
+    for (int w = 1; w < VT / 32; ++w) r = fmaxf(r, scratch[w]);
+    return r;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < VT / 32; ++w) r += scratch[w];
+    return r;
+}
+
+// arg-max with lowest-index tie-break; result broadcast to all threads
+__device__ __forceinline__ void block_argmax(float v, int i, float* sval, int* sidx, float& out_v, int& out_i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { sval[threadIdx.x >> 5] = v; sidx[threadIdx.x >> 5] = i; }
+    __syncthreads();
+    out_v = sval[0];
+    out_i = sidx[0];
+#pragma unroll
+    for (int w = 1; w < VT / 32; ++w) {
+        const float ov = sval[w];
+        const int oi = sidx[w];
+        if (ov > out_v || (ov == out_v && oi < out_i)) { out_v = ov; out_i = oi; }
+    }
+}
+
+// Philox4x32-10 counter-based generator (Salmon et al. 2011): one 128-bit block per (element, row, step).
+__device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+
+__global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
+    extern __shared__ float row[];                // [V1]
+    __shared__ float s_red[VT / 32];
+    __shared__ int s_idx[VT / 32];
+    const int r = blockIdx.x;
+    const int V1 = a.V1;
+    float* g = a.logits + (long)r * a.ld;
+
+    if (a.unfinished != nullptr && !a.first_step && a.unfinished[r] == 0) {
+        // sequence already ended: emit pad and a zero log-prob row (AttModel.py:342-344)
+        for (int v = threadIdx.x; v < V1; v += VT) g[v] = 0.f;
+        if (threadIdx.x == 0) {
+            if (a.tokens_out) a.tokens_out[r] = 0;
+            if (a.seq_out) a.seq_out[(long)r * a.ld_seq + a.t] = 0;
+            if (a.picked_lp) a.picked_lp[(long)r * a.ld_picked] = 0.f;
+        }
+        return;
+    }
+
+    float mx = -INFINITY;
+    for (int v = threadIdx.x; v < V1; v += VT) { const float x = g[v]; row[v] = x; mx = fmaxf(mx, x); }
+    mx = block_max(mx, s_red);
+    float sum = 0.f;
+    for (int v = threadIdx.x; v < V1; v += VT) sum += expf(row[v] - mx);
+    sum = block_sum(sum, s_red);
+    const float lsum = logf(sum);
+    if (a.twice) {
+        // log_softmax of log-probs: max is (mx - mx) - lsum
+        const float m2 = (mx - mx) - lsum;
+        float sum2 = 0.f;
+        for (int v = threadIdx.x; v < V1; v += VT) { const float lp = (row[v] - mx) - lsum; row[v] = lp; sum2 += expf(lp - m2); }
+        sum2 = block_sum(sum2, s_red);
+        const float l2 = logf(sum2);
+        for (int v = threadIdx.x; v < V1; v += VT) { const float lp = (row[v] - m2) - l2; row[v] = lp; g[v] = lp; }
+    } else {
+        for (int v = threadIdx.x; v < V1; v += VT) { const float lp = (row[v] - mx) - lsum; row[v] = lp; g[v] = lp; }
+    }
+    __syncthreads();
+
+    if (a.topk > 0) {
+        for (int k = 0; k < a.topk; ++k) {
+            float bv = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int v = threadIdx.x; v < V1; v += VT) { const float x = row[v]; if (x > bv) { bv = x; bi = v; } }
+            float ov; int oi;
+            block_argmax(bv, bi, s_red, s_idx, ov, oi);
+            if (threadIdx.x == 0) {
+                a.top_val[(long)r * a.topk + k] = ov;
+                a.top_idx[(long)r * a.topk + k] = oi;
+                if (oi < V1) row[oi] = -INFINITY;
+            }
+            __syncthreads();
+        }
+    }
+
+    if (a.select != 0) {
+        int tok;
+        if (a.select == 3) {
+            tok = a.forced[r];
+        } else {
+            float bv = -INFINITY;
+            int bi = 0x7fffffff;
+            if (a.select == 1) {
+                for (int v = threadIdx.x; v < V1; v += VT) { const float x = row[v]; if (x > bv) { bv = x; bi = v; } }
+            } else {
+                const float inv_t = 1.0f / a.temperature;
+                const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+                for (int v = threadIdx.x; v < V1; v += VT) {
+                    const uint32_t bits = philox_first((uint32_t)v, (uint32_t)r, (uint32_t)a.step, (uint32_t)(a.step >> 32), k0, k1);
+                    const float u = ((float)(bits >> 9) + 0.5f) * (1.0f / 8388608.0f);      // (0,1), 23 bits
+                    const float x = row[v] * inv_t - logf(-logf(u));                         // Gumbel-max sample of softmax(logp / T)
+                    if (x > bv) { bv = x; bi = v; }
+                }
+            }
+            float ov;
+            block_argmax(bv, bi, s_red, s_idx, ov, tok);
+        }
+        if (threadIdx.x == 0) {
+            if (a.unfinished) a.unfinished[r] = (tok != 0) ? 1 : 0;
+            if (a.tokens_out) a.tokens_out[r] = tok;
+            if (a.seq_out) a.seq_out[(long)r * a.ld_seq + a.t] = tok;
+            if (a.picked_lp) a.picked_lp[(long)r * a.ld_picked] = row[tok];
+        }
+    }
+}
+
+__global__ void mask_rows_kernel(ActView x, int R, int cols, const float* __restrict__ mask, long ld_mask) {
+    const int row = blockIdx.x;              // row = img * R + r
+    const int img = row / R, r = row % R;
+    if (mask[(long)img * ld_mask + r] != 0.f) return;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        x.f[(long)row * x.ld + c] = 0.f;
+        if (x.hi) { x.hi[(long)row * x.ld + c] = __float2half(0.f); x.lo[(long)row * x.ld + c] = __float2half(0.f); }
+    }
+}
+
+}  // namespace
+
+int vocab_step_launch(const VocabStepArgs& a, cudaStream_t stream) {
+    if (a.rows <= 0) return 0;
+    CAPB_REQUIRE(a.topk <= 16, "beam size up to 16");
+    const size_t smem = sizeof(float) * (size_t)a.V1;
+    CAPB_REQUIRE(smem <= 200 * 1024, "vocabulary larger than 51200 entries needs the multi-pass variant");
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        CAPB_CHECK_CUDA(cudaFuncSetAttribute(vocab_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        configured = 200 * 1024;
+    }
+    vocab_step_kernel<<<a.rows, VT, smem, stream>>>(a);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int mask_rows_launch(ActView x, int n_images, int R, int cols, const float* mask, long ld_mask, cudaStream_t stream) {
+    if (n_images <= 0 || mask == nullptr) return 0;
+    mask_rows_kernel<<<n_images * R, 128, 0, stream>>>(x, R, cols, mask, ld_mask);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace capb200

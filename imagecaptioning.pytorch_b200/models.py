@@ -1,0 +1,401 @@
+"""Host-side mirror of the reference's model surface for the decode hot path.
+
+``B200UpDownModel`` / ``B200NewFCModel`` present exactly what ``captioning.models.setup(opt)`` returns for
+``caption_model in ('updown', 'topdown', 'newfc')`` (captioning/models/__init__.py:20-73):
+
+  * the same constructor argument (``opt`` namespace) and attributes (vocab_size, seq_length, bos/eos/pad/unk_idx,
+    vocab, bad_endings_ix, ss_prob, done_beams)                                   AttModel.py:52-97
+  * the same ``state_dict`` keys and tensor layouts, so reference checkpoints load unchanged (tools/train.py:79-80)
+  * ``forward(*args, mode=...)`` dispatching to ``_forward`` / ``_sample`` (/ ``_sample_beam``)   CaptionModel.py:29-33
+  * ``_sample(fc_feats, att_feats, att_masks=None, opt={})`` -> (seq int64 [B*n, T], seqLogprobs fp32 [B*n, T, V+1])
+    and ``self.done_beams`` after beam search                                      AttModel.py:218-352
+
+The parameters are ordinary ``nn.Parameter``s owned by PyTorch; every timestep of every decode runs in the hand-written
+sm_100a kernels behind the C ABI (include/capb200.h).  Nothing here computes on the CPU and nothing falls back to
+PyTorch ops: unsupported decode options raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections.abc import Mapping
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+BAD_ENDINGS = ['a', 'an', 'the', 'in', 'for', 'at', 'of', 'with', 'before', 'after', 'on', 'upon', 'near', 'to', 'is', 'are', 'am', 'the']
+
+_PENALTY = {'': 0, 'wu': 1, 'avg': 2}
+
+
+class _DoneBeam(Mapping):
+    """One finished hypothesis, dict-compatible with CaptionModel.py:190-195.  ``logps`` ([len, V+1]) is gathered from the
+    engine's per-step slab on first access instead of being copied for every beam of every image."""
+
+    def __init__(self, owner, image, rank, seq, p, raw):
+        self._owner, self._image, self._rank = owner, image, rank
+        self._seq, self._p, self._raw = seq, p, raw
+        self._logps = None
+
+    def _materialise(self):
+        if self._logps is None:
+            self._logps = self._owner._beam_logps(self._image, self._rank)[: self._seq.shape[0]]
+        return self._logps
+
+    def __getitem__(self, key):
+        if key == 'seq':
+            return self._seq
+        if key == 'p':
+            return self._p
+        if key == 'logps':
+            return self._materialise()
+        if key == 'unaug_p':
+            return float(self._materialise().sum().item())
+        if key == 'sum_logp':          # extension: the raw (un-penalised) running sum
+            return self._raw
+        raise KeyError(key)
+
+    def __iter__(self):
+        return iter(('seq', 'logps', 'unaug_p', 'p'))
+
+    def __len__(self):
+        return 4
+
+
+class B200CaptionModel(nn.Module):
+    """Common machinery: engine life-cycle, weight binding and the three call surfaces."""
+
+    family = None           # _lib.FAMILY_*
+    family_name = ''
+
+    def __init__(self, opt, numeric_mode: Optional[str] = None):
+        super().__init__()
+        self.vocab_size = opt.vocab_size
+        self.input_encoding_size = opt.input_encoding_size
+        self.rnn_size = opt.rnn_size
+        self.num_layers = getattr(opt, 'num_layers', 1)
+        self.drop_prob_lm = getattr(opt, 'drop_prob_lm', 0.5)
+        self.seq_length = getattr(opt, 'max_length', 20) or opt.seq_length
+        self.fc_feat_size = opt.fc_feat_size
+        self.att_feat_size = opt.att_feat_size
+        self.att_hid_size = opt.att_hid_size
+        self.bos_idx = getattr(opt, 'bos_idx', 0)
+        self.eos_idx = getattr(opt, 'eos_idx', 0)
+        self.pad_idx = getattr(opt, 'pad_idx', 0)
+        self.unk_idx = getattr(opt, 'unk_idx', None)
+        if (self.bos_idx, self.eos_idx, self.pad_idx) != (0, 0, 0):
+            raise NotImplementedError('capb200 engine assumes bos = eos = pad = 0 (AttModel.py:65-67 defaults)')
+        if getattr(opt, 'use_bn', 0):
+            raise NotImplementedError('use_bn is not on the B200 decode path')
+        if getattr(opt, 'logit_layers', 1) != 1:
+            raise NotImplementedError('logit_layers > 1 is not on the B200 decode path')
+        self.ss_prob = 0.0
+        self.vocab = opt.vocab
+        self.bad_endings_ix = [int(k) for k, v in self.vocab.items() if v in BAD_ENDINGS]
+        self.numeric_mode = numeric_mode or getattr(opt, 'b200_numeric_mode', 'tc_f16x3')
+        if self.numeric_mode not in _lib.MODES:
+            raise ValueError('numeric_mode must be one of %s' % sorted(_lib.MODES))
+        self.done_beams = []
+        self._engine = None
+        self._engine_key = None
+        self._bound_versions = None
+        self._keepalive = None
+
+    # ---- engine plumbing --------------------------------------------------------------------------------------------
+    def _weight_table(self):
+        raise NotImplementedError
+
+    def _ensure_engine(self, device):
+        if device.type != 'cuda':
+            raise RuntimeError('capb200: the decode engine runs on CUDA devices only (no CPU fallback); got %s' % device)
+        lib = _lib.load()
+        key = (device.index, self.numeric_mode)
+        if self._engine is None or self._engine_key != key:
+            self._destroy_engine()
+            cfg = _lib.ModelCfg(self.family, self.vocab_size, self.input_encoding_size, self.rnn_size, self.att_hid_size, self.fc_feat_size,
+                                self.att_feat_size, self.seq_length, _lib.MODES[self.numeric_mode])
+            with torch.cuda.device(device):
+                eng = lib.capb200_engine_create(ctypes.byref(cfg))
+            if not eng:
+                raise RuntimeError('capb200 engine_create failed: %s' % lib.capb200_last_error().decode())
+            self._engine, self._engine_key, self._bound_versions = eng, key, None
+        table = self._weight_table()
+        versions = tuple((t.data_ptr(), t._version) for t in table.values())
+        if versions != self._bound_versions:
+            w = _lib.Weights()
+            keep = []
+            for name, t in table.items():
+                if t.device != device or t.dtype != torch.float32:
+                    raise RuntimeError('capb200: parameter %s must be a float32 tensor on %s' % (name, device))
+                tc = t.detach().contiguous()
+                keep.append(tc)
+                setattr(w, name, tc.data_ptr())
+            _lib.check(lib.capb200_engine_bind_weights(self._engine, ctypes.byref(w), _lib.current_stream()), 'bind_weights')
+            self._keepalive = keep
+            self._bound_versions = versions
+        return lib
+
+    def _destroy_engine(self):
+        if self._engine is not None:
+            _lib.load().capb200_engine_destroy(self._engine)
+            self._engine = None
+
+    def __del__(self):
+        try:
+            self._destroy_engine()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return 0 if self._engine is None else int(_lib.load().capb200_engine_launch_count(self._engine))
+
+    GEMM_IDS = ('fc_embed', 'att_embed', 'ctx2att', 'fc_gate_bias', 'att_lstm', 'h2att', 'lang_lstm', 'logit', 'newfc_core')
+
+    def set_profiling(self, enable: bool):
+        _lib.check(_lib.load().capb200_engine_set_profiling(self._engine, int(enable)), 'set_profiling')
+
+    def read_profile(self, reset=True):
+        """{gemm name: (milliseconds, algorithmic FLOPs, launches)} accumulated since the last reset (device-side cudaEvents)."""
+        import numpy as np
+        ms, fl, calls = np.zeros(9), np.zeros(9), np.zeros(9, dtype=np.int64)
+        _lib.check(_lib.load().capb200_engine_read_profile(self._engine, int(reset), ms.ctypes.data, fl.ctypes.data, calls.ctypes.data, 9), 'read_profile')
+        return {n: (float(ms[i]), float(fl[i]), int(calls[i])) for i, n in enumerate(self.GEMM_IDS)}
+
+    # ---- reference surface ------------------------------------------------------------------------------------------
+    def forward(self, *args, **kwargs):
+        mode = kwargs.pop('mode', 'forward')
+        return getattr(self, '_' + mode)(*args, **kwargs)
+
+    @staticmethod
+    def _f32(t):
+        return None if t is None else t.detach().to(torch.float32).contiguous()
+
+    def _clip(self, att_feats, att_masks):
+        """clip_att (AttModel.py:106-112): cut the region axis to the longest valid length (one host sync, as the reference)."""
+        if att_masks is not None:
+            max_len = int(att_masks.detach().long().sum(1).max().item())
+            att_feats = att_feats[:, :max_len]
+            att_masks = att_masks[:, :max_len]
+        return self._f32(att_feats), self._f32(att_masks)
+
+    def _check_opts(self, opt):
+        if opt.get('group_size', 1) != 1:
+            raise NotImplementedError('diverse beam search (group_size > 1) is out of scope of the B200 engine (SURVEY.md section 8f)')
+        for k in ('decoding_constraint', 'block_trigrams', 'remove_bad_endings'):
+            if opt.get(k, 0):
+                raise NotImplementedError('%s is out of scope of the B200 engine (SURVEY.md section 8f)' % k)
+        if opt.get('output_logsoftmax', 1) != 1:
+            raise NotImplementedError('output_logsoftmax=0 is out of scope of the B200 engine')
+
+    def _sample(self, fc_feats, att_feats, att_masks=None, opt={}, forced_tokens=None):
+        sample_method = opt.get('sample_method', 'greedy')
+        beam_size = opt.get('beam_size', 1)
+        temperature = float(opt.get('temperature', 1.0))
+        sample_n = int(opt.get('sample_n', 1))
+        self._check_opts(opt)
+        if beam_size > 1 and sample_method in ('greedy', 'beam_search'):
+            return self._sample_beam(fc_feats, att_feats, att_masks, opt)
+        if forced_tokens is not None:
+            method = _lib.SAMPLE_FORCED
+        elif sample_method == 'greedy':
+            method = _lib.SAMPLE_GREEDY
+        elif sample_method == 'sample':
+            method = _lib.SAMPLE_MULTINOMIAL
+        else:
+            raise NotImplementedError("sample_method %r is out of scope of the B200 engine (greedy / sample / beam search)" % sample_method)
+        lib = self._ensure_engine(fc_feats.device)
+        fc = self._f32(fc_feats)
+        att, masks = self._clip(att_feats, att_masks)
+        B = fc.shape[0]
+        R = att.shape[1] if att is not None and att.dim() == 3 else 1
+        N, T, V1 = B * sample_n, self.seq_length, self.vocab_size + 1
+        seq = torch.zeros(N, T, dtype=torch.long, device=fc.device)
+        logprobs = torch.zeros(N, T, V1, dtype=torch.float32, device=fc.device)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if method == _lib.SAMPLE_MULTINOMIAL else 0   # follows torch.manual_seed
+        so = _lib.SampleOpts(sample_n, method, temperature, seed, T)
+        tok = None
+        if forced_tokens is not None:
+            tok = forced_tokens.detach().to(torch.long).contiguous()
+            assert tok.shape == (N, T)
+        _lib.check(lib.capb200_decode_sample(self._engine, _lib.ptr(fc), _lib.ptr(att), _lib.ptr(masks), B, R, ctypes.byref(so), _lib.ptr(tok), T,
+                                             _lib.ptr(seq), _lib.ptr(logprobs), None, _lib.current_stream()), 'decode_sample')
+        return seq, logprobs
+
+    def _sample_beam(self, fc_feats, att_feats, att_masks=None, opt={}):
+        beam_size = opt.get('beam_size', 10)
+        sample_n = opt.get('sample_n', 10)
+        self._check_opts(opt)
+        if opt.get('suppress_UNK', 0) and self.vocab.get(str(self.vocab_size)) == 'UNK' or self.unk_idx is not None:
+            raise NotImplementedError('UNK suppression is out of scope of the B200 engine')
+        assert sample_n == 1 or sample_n == beam_size, 'when beam search, sample_n == 1 or beam search'
+        assert beam_size <= self.vocab_size + 1
+        cfg = opt.get('length_penalty', '')
+        kind, alpha = (cfg.split('_') + ['0'])[:2] if cfg else ('', '0')
+        lib = self._ensure_engine(fc_feats.device)
+        fc = self._f32(fc_feats)
+        att, masks = self._clip(att_feats, att_masks)
+        B = fc.shape[0]
+        R = att.shape[1] if att is not None and att.dim() == 3 else 1
+        T, V1 = self.seq_length, self.vocab_size + 1
+        dev = fc.device
+        seq = torch.zeros(B * sample_n, T, dtype=torch.long, device=dev)
+        logprobs = torch.zeros(B * sample_n, T, V1, dtype=torch.float32, device=dev)
+        d_seq = torch.zeros(B, beam_size, T, dtype=torch.long, device=dev)
+        d_len = torch.zeros(B, beam_size, dtype=torch.int32, device=dev)
+        d_p = torch.zeros(B, beam_size, dtype=torch.float32, device=dev)
+        d_raw = torch.zeros(B, beam_size, dtype=torch.float32, device=dev)
+        bo = _lib.BeamOpts(beam_size, sample_n, _PENALTY[kind], float(alpha))
+        _lib.check(lib.capb200_decode_beam(self._engine, _lib.ptr(fc), _lib.ptr(att), _lib.ptr(masks), B, R, ctypes.byref(bo), _lib.ptr(seq),
+                                           _lib.ptr(logprobs), _lib.ptr(d_seq), _lib.ptr(d_len), _lib.ptr(d_p), _lib.ptr(d_raw),
+                                           _lib.current_stream()), 'decode_beam')
+        self._last_beam = (d_seq, d_len, d_p, d_raw)
+        self.done_beams = _LazyDoneBeams(self, B, beam_size)
+        return seq, logprobs
+
+    def _beam_logps(self, image, rank):
+        dst = torch.zeros(self.seq_length, self.vocab_size + 1, dtype=torch.float32, device=self._last_beam[0].device)
+        _lib.check(_lib.load().capb200_beam_record_logprobs(self._engine, image, rank, _lib.ptr(dst), _lib.current_stream()), 'beam_record_logprobs')
+        return dst
+
+    def _forward(self, fc_feats, att_feats, seq, att_masks=None):
+        """Teacher forcing (AttModel.py:126-164).  Scheduled sampling (ss_prob > 0) is an XE-stage feature."""
+        if self.training and self.ss_prob > 0.0:
+            raise NotImplementedError('scheduled sampling is out of scope of the B200 engine')
+        lib = self._ensure_engine(fc_feats.device)
+        fc = self._f32(fc_feats)
+        att, masks = self._clip(att_feats, att_masks)
+        B = fc.shape[0]
+        if seq.dim() == 3:
+            seq = seq.reshape(-1, seq.shape[2])
+        seq = seq.detach().to(torch.long).contiguous()
+        spi = seq.shape[0] // B
+        L = seq.shape[1]
+        if L > self.seq_length + 2:
+            raise ValueError('label width %d exceeds what the engine was built for' % L)
+        # the reference stops at the first column i >= 1 whose labels are all pad (AttModel.py:158-159)
+        col_empty = (seq[:, 1:].sum(0) == 0).nonzero()
+        steps = int(col_empty[0].item()) + 1 if col_empty.numel() > 0 else L
+        R = att.shape[1] if att is not None and att.dim() == 3 else 1
+        out = torch.zeros(B * spi, L, self.vocab_size + 1, dtype=torch.float32, device=fc.device)
+        so = _lib.SampleOpts(spi, _lib.SAMPLE_TEACHER, 1.0, 0, steps)
+        _lib.check(lib.capb200_decode_sample(self._engine, _lib.ptr(fc), _lib.ptr(att), _lib.ptr(masks), B, R, ctypes.byref(so), _lib.ptr(seq), L,
+                                             None, _lib.ptr(out), None, _lib.current_stream()), 'forward_teacher')
+        return out
+
+
+class _LazyDoneBeams(list):
+    """list[B] of list[beam] of finished-beam records; host copies happen on first indexing (one D2H for the whole batch)."""
+
+    def __init__(self, owner, B, beam):
+        super().__init__()
+        self._owner, self._B, self._beam, self._built = owner, B, beam, False
+
+    def _build(self):
+        if self._built:
+            return
+        d_seq, d_len, d_p, d_raw = self._owner._last_beam
+        lens = d_len.cpu().tolist()
+        ps = d_p.double().cpu().tolist()
+        raws = d_raw.cpu().tolist()
+        for i in range(self._B):
+            super().append([_DoneBeam(self._owner, i, j, d_seq[i, j, :lens[i][j]], ps[i][j], raws[i][j]) for j in range(self._beam)])
+        self._built = True
+
+    def __getitem__(self, i):
+        self._build()
+        return super().__getitem__(i)
+
+    def __iter__(self):
+        self._build()
+        return super().__iter__()
+
+    def __len__(self):
+        return self._B
+
+
+class _UpDownCoreParams(nn.Module):
+    """Parameter container with the key names of UpDownCore + Attention (AttModel.py:615-622,719-726)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.att_lstm = nn.LSTMCell(opt.input_encoding_size + opt.rnn_size * 2, opt.rnn_size)
+        self.lang_lstm = nn.LSTMCell(opt.rnn_size * 2, opt.rnn_size)
+        self.attention = nn.Module()
+        self.attention.h2att = nn.Linear(opt.rnn_size, opt.att_hid_size)
+        self.attention.alpha_net = nn.Linear(opt.att_hid_size, 1)
+
+
+class B200UpDownModel(B200CaptionModel):
+    """Drop-in for captioning.models.AttModel.UpDownModel (AttModel.py:868-872)."""
+
+    family = _lib.FAMILY_UPDOWN
+    family_name = 'updown'
+
+    def __init__(self, opt, numeric_mode=None):
+        super().__init__(opt, numeric_mode)
+        self.num_layers = 2
+        V1 = self.vocab_size + 1
+        self.embed = nn.Sequential(nn.Embedding(V1, self.input_encoding_size), nn.ReLU(), nn.Dropout(self.drop_prob_lm))
+        self.fc_embed = nn.Sequential(nn.Linear(self.fc_feat_size, self.rnn_size), nn.ReLU(), nn.Dropout(self.drop_prob_lm))
+        self.att_embed = nn.Sequential(nn.Linear(self.att_feat_size, self.rnn_size), nn.ReLU(), nn.Dropout(self.drop_prob_lm))
+        self.logit = nn.Linear(self.rnn_size, V1)
+        self.ctx2att = nn.Linear(self.rnn_size, self.att_hid_size)
+        self.core = _UpDownCoreParams(opt)
+
+    def _weight_table(self):
+        c = self.core
+        return {
+            'embed': self.embed[0].weight, 'fc_embed_w': self.fc_embed[0].weight, 'fc_embed_b': self.fc_embed[0].bias,
+            'att_embed_w': self.att_embed[0].weight, 'att_embed_b': self.att_embed[0].bias,
+            'ctx2att_w': self.ctx2att.weight, 'ctx2att_b': self.ctx2att.bias, 'logit_w': self.logit.weight, 'logit_b': self.logit.bias,
+            'att_lstm_w_ih': c.att_lstm.weight_ih, 'att_lstm_w_hh': c.att_lstm.weight_hh, 'att_lstm_b_ih': c.att_lstm.bias_ih,
+            'att_lstm_b_hh': c.att_lstm.bias_hh, 'lang_lstm_w_ih': c.lang_lstm.weight_ih, 'lang_lstm_w_hh': c.lang_lstm.weight_hh,
+            'lang_lstm_b_ih': c.lang_lstm.bias_ih, 'lang_lstm_b_hh': c.lang_lstm.bias_hh,
+            'h2att_w': c.attention.h2att.weight, 'h2att_b': c.attention.h2att.bias,
+            'alpha_w': c.attention.alpha_net.weight, 'alpha_b': c.attention.alpha_net.bias,
+        }
+
+
+class _MaxoutCoreParams(nn.Module):
+    """Parameter container with the key names of FCModel.LSTMCore (FCModel.py:13-23)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.i2h = nn.Linear(opt.input_encoding_size, 5 * opt.rnn_size)
+        self.h2h = nn.Linear(opt.rnn_size, 5 * opt.rnn_size)
+
+
+class B200NewFCModel(B200CaptionModel):
+    """Drop-in for captioning.models.AttModel.NewFCModel (AttModel.py:904-945)."""
+
+    family = _lib.FAMILY_NEWFC
+    family_name = 'newfc'
+
+    def __init__(self, opt, numeric_mode=None):
+        super().__init__(opt, numeric_mode)
+        V1 = self.vocab_size + 1
+        self.embed = nn.Embedding(V1, self.input_encoding_size)
+        self.fc_embed = nn.Linear(self.fc_feat_size, self.input_encoding_size)
+        self.logit = nn.Linear(self.rnn_size, V1)
+        self._core = _MaxoutCoreParams(opt)
+
+    def _weight_table(self):
+        return {
+            'embed': self.embed.weight, 'fc_embed_w': self.fc_embed.weight, 'fc_embed_b': self.fc_embed.bias,
+            'logit_w': self.logit.weight, 'logit_b': self.logit.bias,
+            'i2h_w': self._core.i2h.weight, 'i2h_b': self._core.i2h.bias, 'h2h_w': self._core.h2h.weight, 'h2h_b': self._core.h2h.bias,
+        }
+
+
+def setup(opt, numeric_mode=None):
+    """Factory with the contract of captioning.models.setup (captioning/models/__init__.py:20-73) for the families on the
+    B200 hot path."""
+    name = opt.caption_model
+    if name in ('topdown', 'updown'):
+        return B200UpDownModel(opt, numeric_mode)
+    if name == 'newfc':
+        return B200NewFCModel(opt, numeric_mode)
+    raise NotImplementedError('caption_model %r is not on the B200 decode path yet (SURVEY.md section 8)' % name)

@@ -1,0 +1,122 @@
+"""Device-side mirror of captioning/utils/rewards.py for the SCST inner loop (CIDEr-D reward only).
+
+    init_scorer(cached_tokens)                                   rewards.py:25-31
+    get_self_critical_reward(greedy_res, data_gts, gen_result, opt)   rewards.py:41-81
+
+The reference moves both id tensors to the host, formats every id as a string and walks Python dicts; here the ids
+never leave the GPU: n-gram extraction, the document-frequency lookup (open-addressing hash table built once from the
+``scripts/prepro_ngrams.py`` pickle), the clipped tf-idf cosine and the self-critical difference run in csrc/reward.cu.
+``bleu_reward_weight`` must be 0 (its default, opts.py:171).
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class CiderDTable:
+    """Owns the device hash table n-gram -> idf (capb200_cider_table)."""
+
+    def __init__(self, document_frequency: Dict[Tuple, float], ref_len: float, device=None):
+        n = len(document_frequency)
+        keys = np.full((max(n, 1), 4), -1, dtype=np.int32)
+        vals = np.zeros((max(n, 1),), dtype=np.float64)
+        for i, (k, v) in enumerate(document_frequency.items()):
+            keys[i, :len(k)] = [int(t) for t in k]        # pickle keys are tuples of id strings (prepro_ngrams.py:42-45)
+            vals[i] = float(v)
+        self.ref_len = float(ref_len)
+        self.entries = n
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            self._h = lib.capb200_cider_table_create(keys.ctypes.data, vals.ctypes.data, n, self.ref_len, _lib.current_stream())
+        if not self._h:
+            raise RuntimeError('capb200 cider_table_create failed: %s' % lib.capb200_last_error().decode())
+
+    @classmethod
+    def from_pickle(cls, path: str, device=None):
+        with open(path, 'rb') as f:
+            pk = pickle.load(f, encoding='latin1')
+        return cls(pk['document_frequency'], pk['ref_len'], device)
+
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None):
+                _lib.load().capb200_cider_table_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+CiderD_scorer: Optional[CiderDTable] = None
+
+
+def init_scorer(cached_tokens, device=None):
+    """Same contract as the reference: ``cached_tokens`` names ``data/<cached_tokens>.p`` relative to the cwd
+    (ciderD_scorer.py:109); an existing path or an already built CiderDTable is accepted too.  Idempotent."""
+    global CiderD_scorer
+    if CiderD_scorer is not None:
+        return CiderD_scorer
+    if isinstance(cached_tokens, CiderDTable):
+        CiderD_scorer = cached_tokens
+    else:
+        path = cached_tokens if os.path.exists(str(cached_tokens)) else os.path.join('data', str(cached_tokens) + '.p')
+        CiderD_scorer = CiderDTable.from_pickle(path, device)
+    return CiderD_scorer
+
+
+def reset_scorer():
+    global CiderD_scorer
+    CiderD_scorer = None
+
+
+def pack_references(data_gts: Sequence, device) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """list[B] of int arrays [n_refs_i, L] (dataloader.py:213) -> (refs int32 [total, L], offsets int32 [B+1], L) on the device."""
+    L = max(int(np.asarray(g).shape[1]) for g in data_gts)
+    rows, offs = [], [0]
+    for g in data_gts:
+        g = np.asarray(g)
+        pad = np.zeros((g.shape[0], L), dtype=np.int32)
+        pad[:, :g.shape[1]] = g
+        rows.append(pad)
+        offs.append(offs[-1] + g.shape[0])
+    refs = torch.from_numpy(np.concatenate(rows, 0)).to(device, non_blocking=True)
+    offsets = torch.tensor(offs, dtype=torch.int32).to(device, non_blocking=True)
+    return refs, offsets, L
+
+
+def cider_scores_and_reward(greedy_res: torch.Tensor, data_gts: Sequence, gen_result: torch.Tensor, table: Optional[CiderDTable] = None):
+    table = table or CiderD_scorer
+    if table is None:
+        raise RuntimeError('init_scorer(cached_tokens) must be called before the SCST reward (tools/train.py:150-152)')
+    dev = gen_result.device
+    if dev.type != 'cuda':
+        raise RuntimeError('capb200: the reward kernel runs on CUDA tensors only')
+    B = len(data_gts)
+    S, T = gen_result.shape
+    assert greedy_res.shape[0] == B and S % B == 0
+    sampled = gen_result.detach().to(torch.long).contiguous()
+    greedy = greedy_res.detach().to(torch.long).contiguous()
+    refs, offsets, L = pack_references(data_gts, dev)
+    scores = torch.empty(S + B, dtype=torch.float64, device=dev)
+    reward = torch.empty(S, T, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.capb200_self_critical_reward(table._h, _lib.ptr(sampled), S, _lib.ptr(greedy), B, T, _lib.ptr(refs), _lib.ptr(offsets), L,
+                                                _lib.ptr(scores), _lib.ptr(reward), _lib.current_stream()), 'self_critical_reward')
+    return scores, reward
+
+
+def get_self_critical_reward(greedy_res, data_gts, gen_result, opt):
+    """reward[i*n+j, :] = CIDEr-D(sample j of image i) - CIDEr-D(greedy of image i), as a device fp32 tensor [S, T]
+    (the reference returns the same values as a host float64 array that LossWrapper immediately moves back to the GPU)."""
+    if getattr(opt, 'bleu_reward_weight', 0) > 0:
+        raise NotImplementedError('BLEU reward is out of scope of the B200 engine (bleu_reward_weight defaults to 0)')
+    w = float(getattr(opt, 'cider_reward_weight', 1))
+    _, reward = cider_scores_and_reward(greedy_res, data_gts, gen_result)
+    return reward if w == 1.0 else reward * w

@@ -1,0 +1,166 @@
+/* capb200 -- C ABI of the B200-native caption-decoding / SCST engine.
+ *
+ * Drop-in boundary.  The reference (ruotianluo/ImageCaptioning.pytorch) is pure Python and has no FFI layer; its boundary
+ * for this path is two Python call surfaces:
+ *     CaptionModel.forward(..., mode='sample'|'forward')            captioning/models/CaptionModel.py:29-33
+ *       -> AttModel._sample / _sample_beam / _forward              captioning/models/AttModel.py:258,218,126
+ *     LossWrapper.forward(..., sc_flag=True)                        captioning/modules/loss_wrapper.py:56-73
+ * The Python adapter in imagecaptioning.pytorch_b200 keeps those signatures and calls the entry points below through
+ * ctypes.  Every entry point takes plain device pointers and sizes (no torch types), an explicit cudaStream_t passed as
+ * void*, is asynchronous with respect to the host unless stated, returns 0 on success and non-zero on failure with a
+ * message available from capb200_last_error().  PyTorch owns all tensors; the engine owns only packed weight copies and
+ * workspaces.  One engine per device; different engines may be driven from different host threads.
+ *
+ * All matrices are row-major fp32 unless noted; token ids are int64 (the reference's torch.long) at the boundary.
+ */
+#ifndef CAPB200_H_
+#define CAPB200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAPB200_ABI_VERSION 1
+
+/* numeric modes of the dense contractions */
+#define CAPB200_MODE_SIMT_FP32 0 /* fp32 FFMA on CUDA cores */
+#define CAPB200_MODE_TC_F16X3 1  /* tcgen05 kind::f16, split-fp16 operands, 3 MMA passes, fp32 accumulate (parity grade) */
+#define CAPB200_MODE_TC_F16X1 2  /* tcgen05 kind::f16, single pass (throughput mode, not parity grade) */
+
+#define CAPB200_FAMILY_UPDOWN 0 /* UpDownModel  captioning/models/AttModel.py:868 */
+#define CAPB200_FAMILY_NEWFC 1  /* NewFCModel   captioning/models/AttModel.py:904 */
+
+typedef struct capb200_engine capb200_engine;
+typedef struct capb200_cider_table capb200_cider_table;
+
+const char* capb200_last_error(void);
+int capb200_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Operator level (each replaces one library call of the reference's per-timestep core; used by the parity tests)
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* y[M,N] = x[M,K] * w[N,K]^T + b[N] (optional ReLU)             nn.Linear call sites AttModel.py:74-95,172,733
+ * mode selects the arithmetic; the tensor-core modes split x and w into fp16 planes in scratch memory first. */
+int capb200_linear(const float* x, long ldx, const float* w, long ldw, const float* b, float* y, long ldy, int M, int N, int K,
+                   int relu, int mode, void* stream);
+
+/* nn.LSTMCell: gates = x*w_ih^T + b_ih + h*w_hh^T + b_hh; (i,f,g,o)           AttModel.py:628,635
+ * x[M,Kx], h/c[M,H] -> h_out/c_out[M,H] */
+int capb200_lstm_cell(const float* x, int Kx, const float* h, const float* c, const float* w_ih, const float* w_hh, const float* b_ih,
+                      const float* b_hh, float* h_out, float* c_out, int M, int H, int mode, void* stream);
+
+/* Attention.forward (AttModel.py:728-748) with per-image features: row r uses image r / rows_per_image.
+ * att_h[rows,A] = h2att(h) incl. bias; p_att[B,R,A]; att[B,R,H]; mask[B,R] or NULL; alpha_w[A], alpha_b[1] -> out[rows,H] */
+int capb200_additive_attention(const float* att_h, const float* p_att, const float* att, const float* mask, const float* alpha_w,
+                               const float* alpha_b, float* out, int n_images, int rows_per_image, int R, int A, int H, void* stream);
+
+/* In-place log_softmax over each row of logits[rows,V1] (twice != 0 applies it a second time, CaptionModel.py:204) and
+ * the per-row top-k (values and indices, descending, lowest index first on ties). top_val/top_idx may be NULL if k == 0. */
+int capb200_log_softmax_topk(float* logits, long ld, int rows, int V1, int twice, int k, float* top_val, int* top_idx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Engine level
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int family;              /* CAPB200_FAMILY_* */
+    int vocab_size;          /* V; logits have V+1 entries, id 0 = BOS = EOS = PAD (AttModel.py:65-67) */
+    int input_encoding_size; /* E */
+    int rnn_size;            /* H */
+    int att_hid_size;        /* A */
+    int fc_feat_size;        /* F_fc */
+    int att_feat_size;       /* F_att */
+    int seq_length;          /* T = max_length (AttModel.py:60) */
+    int numeric_mode;        /* CAPB200_MODE_* */
+} capb200_model_cfg;
+
+/* Borrowed fp32 device pointers in the reference's state_dict layouts (SURVEY.md section 8b key list). */
+typedef struct {
+    const float* embed;                                                           /* [V+1,E]  embed.0.weight | embed.weight */
+    const float *fc_embed_w, *fc_embed_b;                                         /* [H,F_fc] (newfc: [E,F_fc]) */
+    const float *att_embed_w, *att_embed_b;                                       /* [H,F_att] */
+    const float *ctx2att_w, *ctx2att_b;                                           /* [A,H] */
+    const float *logit_w, *logit_b;                                               /* [V+1,H] */
+    const float *att_lstm_w_ih, *att_lstm_w_hh, *att_lstm_b_ih, *att_lstm_b_hh;   /* [4H,E+2H] [4H,H] [4H] [4H] */
+    const float *lang_lstm_w_ih, *lang_lstm_w_hh, *lang_lstm_b_ih, *lang_lstm_b_hh; /* [4H,2H] [4H,H] [4H] [4H] */
+    const float *h2att_w, *h2att_b;                                               /* [A,H] */
+    const float *alpha_w, *alpha_b;                                               /* [1,A] [1] */
+    const float *i2h_w, *i2h_b, *h2h_w, *h2h_b;                                   /* newfc _core: [5H,E] [5H] [5H,H] [5H] */
+} capb200_weights;
+
+capb200_engine* capb200_engine_create(const capb200_model_cfg* cfg);
+void capb200_engine_destroy(capb200_engine* e);
+/* (Re)binds the parameter tensors; call again after every optimizer step.  Tensor-core modes repack the fp16 planes here. */
+int capb200_engine_bind_weights(capb200_engine* e, const capb200_weights* w, void* stream);
+
+typedef struct {
+    int beam_size;      /* b, 1..16 */
+    int sample_n;       /* 1 or beam_size (AttModel.py:223) */
+    int penalty_kind;   /* 0 '' (identity), 1 'wu_<alpha>', 2 'avg_<alpha>'   captioning/utils/misc.py:133-151 */
+    float penalty_alpha;
+} capb200_beam_opts;
+
+/* AttModel._sample_beam + CaptionModel.beam_search (group_size 1).
+ * fc[B,F_fc], att[B,R,F_att] contiguous, mask[B,R] or NULL.
+ * seq[B*sample_n,T] int64 zero padded; seq_logprobs[B*sample_n,T,V+1] (NULL to skip the gather);
+ * done_seq[B,b,T] int64, done_len[B,b], done_p[B,b], done_raw[B,b]: each image's finished beams sorted by score (may be NULL). */
+int capb200_decode_beam(capb200_engine* e, const float* fc, const float* att, const float* mask, int B, int R, const capb200_beam_opts* opts,
+                        long long* seq, float* seq_logprobs, long long* done_seq, int* done_len, float* done_p, float* done_raw, void* stream);
+/* Full log-prob rows [len, V+1] of finished beam `rank` of image `image` from the most recent capb200_decode_beam call
+ * (done_beams[image][rank]['logps'], CaptionModel.py:192); dst must hold T*(V+1) floats, rows beyond the length are zeroed. */
+int capb200_beam_record_logprobs(capb200_engine* e, int image, int rank, float* dst, void* stream);
+
+#define CAPB200_SAMPLE_GREEDY 0
+#define CAPB200_SAMPLE_MULTINOMIAL 1
+#define CAPB200_SAMPLE_FORCED 2  /* replay given tokens (parity checks against another sampler's draw) */
+#define CAPB200_SAMPLE_TEACHER 3 /* AttModel._forward: feed labels[:, t] at step t, no finished-row masking */
+typedef struct {
+    int sample_n;             /* rows per image */
+    int method;               /* CAPB200_SAMPLE_* */
+    float temperature;
+    unsigned long long seed;  /* Philox key for CAPB200_SAMPLE_MULTINOMIAL */
+    int steps;                /* TEACHER: number of label columns to run (<= the label width) */
+} capb200_sample_opts;
+
+/* AttModel._sample (greedy / multinomial) and AttModel._forward (teacher forcing).
+ * tokens_in[N,ld_tok] int64: forced tokens (FORCED) or labels (TEACHER), else NULL.  N = B*sample_n.
+ * seq[N,T] int64; seq_logprobs[N,T_out,V+1] where T_out = T (sampling) or ld_tok (TEACHER); picked[N,T] optional. */
+int capb200_decode_sample(capb200_engine* e, const float* fc, const float* att, const float* mask, int B, int R, const capb200_sample_opts* opts,
+                          const long long* tokens_in, long ld_tok, long long* seq, float* seq_logprobs, float* picked, void* stream);
+
+/* Number of this library's kernel launches issued through the engine since creation (bench.py reports it). */
+long capb200_engine_launch_count(const capb200_engine* e);
+
+/* Optional device-side timing of the dense contractions (cudaEvent pairs recorded on the launching stream around every
+ * GEMM launch).  ids: 0 fc_embed, 1 att_embed, 2 ctx2att, 3 fc->gate bias, 4 att_lstm gates, 5 h2att, 6 lang_lstm gates,
+ * 7 logit, 8 newfc core.  read_profile synchronises the device and returns accumulated milliseconds, algorithmic FLOPs
+ * (2*M*N*K) and launch counts per id; n must be >= 9. */
+int capb200_engine_set_profiling(capb200_engine* e, int enable);
+int capb200_engine_read_profile(capb200_engine* e, int reset, double* ms, double* flops, long* calls, int n);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * SCST reward and criterion
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* Document-frequency table in the scripts/prepro_ngrams.py format, flattened: keys[n,4] int32 token ids padded with -1,
+ * df[n] float64, ref_len = number of reference images (ciderD_scorer.py:108-111).  Host pointers; synchronous. */
+capb200_cider_table* capb200_cider_table_create(const int* keys, const double* df, long n, double ref_len, void* stream);
+void capb200_cider_table_destroy(capb200_cider_table* t);
+
+/* get_self_critical_reward (captioning/utils/rewards.py:41-81) with CIDEr-D only:
+ * sampled[S,T], greedy[B,T] int64 device; refs[n_refs_total,L] int32 device (0 padded), ref_offsets[B+1] int32 device;
+ * scores[S+B] float64 device (CIDEr-D of every hypothesis); reward[S,T] fp32 = score(sample) - score(greedy of its image). */
+int capb200_self_critical_reward(const capb200_cider_table* t, const long long* sampled, int S, const long long* greedy, int B, int T,
+                                 const int* refs, const int* ref_offsets, int L, double* scores, float* reward, void* stream);
+
+/* RewardCriterion.forward (captioning/modules/losses.py:22-37). logprobs[N,T,V1]; seq[N,T] int64; reward[N,T].
+ * loss_mean[1], loss_rows[N] (reduction 'none'), mask_sum[1]; any output may be NULL. */
+int capb200_reward_criterion_forward(const float* logprobs, const long long* seq, const float* reward, int N, int T, int V1, float* loss_mean,
+                                     float* loss_rows, float* mask_sum, void* stream);
+/* d loss_mean / d logprobs, scaled by `upstream`; grad[N,T,V1] must be zero-filled by the caller. */
+int capb200_reward_criterion_backward(const long long* seq, const float* reward, int N, int T, int V1, const float* mask_sum, float upstream,
+                                      float* grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAPB200_H_ */

@@ -215,12 +215,26 @@ def gen_reward_criterion(out_dir):
     print('reward_criterion loss', float(loss))
 
 
+def gen_state_dict_keys(out_dir):
+    """Names and shapes of the reference modules' parameters: the drop-in must expose exactly these."""
+    import json
+    res = {}
+    for fam in ('updown', 'newfc'):
+        cfg = dict(V=60, E=32, H=40, A=16, F_fc=48, F_att=56, T=8)
+        W = co.make_weights(fam, cfg['V'], cfg['E'], cfg['H'], cfg['A'], cfg['F_fc'], cfg['F_att'], seed=1)
+        m = ref_model(fam, W=W, **cfg)
+        res[fam] = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(out_dir, 'state_dict_keys.json'), 'w') as f:
+        json.dump({'cfg': cfg, 'keys': res}, f, indent=1, sort_keys=True)
+    print('state_dict_keys', {k: len(v) for k, v in res.items()})
+
+
 def main():
     out_dir = os.path.join(REPO, 'tests', 'golden')
     os.makedirs(out_dir, exist_ok=True)
     scratch = _enter_scratch()
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc']
+    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys']
     if 'small' in which:
         gen_updown_small(out_dir)
     if 'newfc' in which:
@@ -231,6 +245,8 @@ def main():
         gen_ciderd(out_dir, scratch)
     if 'rc' in which:
         gen_reward_criterion(out_dir)
+    if 'keys' in which:
+        gen_state_dict_keys(out_dir)
 
 
 if __name__ == '__main__':

@@ -1,0 +1,73 @@
+"""CPU-only checks of the boundary: the shared library loads, exports every symbol include/capb200.h declares, refuses
+to run without a GPU (no CPU fallback), and the host-side mirrors expose the reference's parameter names / shapes."""
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from helpers import REPO, make_opt
+
+
+@pytest.fixture(scope='module')
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    import imagecaptioning.pytorch_b200 as b200
+    return b200._lib.load()
+
+
+def test_header_symbols_exported(lib):
+    import imagecaptioning.pytorch_b200 as b200
+    header = open(os.path.join(REPO, 'include', 'capb200.h')).read()
+    declared = set(re.findall(r'\b(capb200_[a-z0-9_]+)\s*\(', header))
+    declared -= {'capb200_engine', 'capb200_cider_table'}
+    assert len(declared) >= 18
+    assert declared == set(b200._lib.SIGNATURES), declared ^ set(b200._lib.SIGNATURES)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.capb200_abi_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the behaviour of a box without a GPU')
+def test_no_cpu_fallback(lib):
+    import ctypes
+    import imagecaptioning.pytorch_b200 as b200
+    cfg = b200._lib.ModelCfg(0, 60, 32, 32, 16, 48, 48, 8, 1)
+    assert not lib.capb200_engine_create(ctypes.byref(cfg))
+    assert b'no CUDA device' in lib.capb200_last_error()
+    model = b200.setup(make_opt('updown', 60, 32, 32, 16, 48, 48, 8))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        model(torch.zeros(2, 48), torch.zeros(2, 3, 48), None, opt={'beam_size': 1}, mode='sample')
+
+
+def test_state_dict_keys_match_reference(golden_dir):
+    import imagecaptioning.pytorch_b200 as b200
+    g = json.load(open(os.path.join(golden_dir, 'state_dict_keys.json')))
+    c = g['cfg']
+    for fam, ref in g['keys'].items():
+        m = b200.setup(make_opt(fam, c['V'], c['E'], c['H'], c['A'], c['F_fc'], c['F_att'], c['T']))
+        mine = {k: list(v.shape) for k, v in m.state_dict().items()}
+        assert mine == ref, (fam, set(mine) ^ set(ref))
+
+
+def test_unsupported_options_raise():
+    import imagecaptioning.pytorch_b200 as b200
+    m = b200.setup(make_opt('updown', 60, 32, 32, 16, 48, 48, 8))
+    fc, att = torch.zeros(2, 48), torch.zeros(2, 3, 48)
+    for bad in ({'group_size': 2, 'beam_size': 2}, {'block_trigrams': 1}, {'sample_method': 'top5'}, {'decoding_constraint': 1}):
+        with pytest.raises(NotImplementedError):
+            m(fc, att, None, opt=bad, mode='sample')
+    with pytest.raises(NotImplementedError):
+        b200.setup(make_opt('adaatt', 60, 32, 32, 16, 48, 48, 8))
+
+
+def test_pack_references_layout():
+    import numpy as np
+    from oracle import ciderd_oracle as cdo
+    import imagecaptioning.pytorch_b200 as b200
+    gts = cdo.make_refs(3, 20, n_refs=4, L=16, seed=1) + [np.zeros((2, 7), dtype=np.int64)]
+    refs, offs, L = b200.rewards.pack_references(gts, 'cpu')
+    assert L == 16 and refs.shape == (14, 16) and offs.tolist() == [0, 4, 8, 12, 14]
+    assert refs[:4].tolist() == gts[0].tolist()

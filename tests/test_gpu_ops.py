@@ -1,0 +1,147 @@
+"""GPU parity of the operator-level C-ABI entry points against torch fp64/fp32 CPU references and the golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import LOGP_TOL, co
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def L():
+    import imagecaptioning.pytorch_b200 as b200
+    return b200._lib
+
+
+def _linear(L, x, w, b, relu, mode):
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, device='cuda')
+    L.check(L.load().capb200_linear(L.ptr(x), K, L.ptr(w), K, L.ptr(b), L.ptr(y), N, M, N, K, int(relu), L.MODES[mode], L.current_stream()), 'linear')
+    torch.cuda.synchronize()
+    return y
+
+
+@pytest.mark.parametrize('mode', ['simt_fp32', 'tc_f16x3', 'tc_f16x1'])
+@pytest.mark.parametrize('shape', [(5, 7, 24), (128, 128, 64), (130, 260, 1000), (1280, 512, 1000), (333, 9488, 1000), (36, 40, 2048)])
+def test_linear_matches_fp64(L, mode, shape):
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M * 7 + N)
+    x = torch.randn(M, K, generator=g)
+    w = (torch.rand(N, K, generator=g) * 2 - 1) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    ref = (x.double() @ w.double().t() + b.double())
+    y = _linear(L, x.cuda(), w.cuda(), b.cuda(), False, mode).cpu().double()
+    err = float((y - ref).abs().max())
+    fp32_err = float(((x @ w.t() + b).double() - ref).abs().max())
+    # fp32-grade modes must be as good as an fp32 GEMM (summation-order noise only); the single-pass mode is fp16-grade
+    tol = max(4 * fp32_err, 2e-6) if mode != 'tc_f16x1' else 2e-2
+    assert err < tol, (mode, shape, err, fp32_err)
+    yr = _linear(L, x.cuda(), w.cuda(), b.cuda(), True, mode).cpu().double()
+    assert float((yr - ref.clamp_min(0)).abs().max()) < tol
+
+
+@pytest.mark.parametrize('mode', ['simt_fp32', 'tc_f16x3'])
+def test_lstm_cell(L, mode):
+    g = torch.Generator().manual_seed(3)
+    M, Kx, H = 37, 72, 40
+    x, h, c = torch.randn(M, Kx, generator=g), torch.randn(M, H, generator=g), torch.randn(M, H, generator=g)
+    cell = torch.nn.LSTMCell(Kx, H)
+    with torch.no_grad():
+        h_ref, c_ref = cell(x, (h, c))
+    dev = [t.detach().cuda().contiguous() for t in (x, h, c, cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh)]
+    ho, c_o = torch.empty(M, H, device='cuda'), torch.empty(M, H, device='cuda')
+    L.check(L.load().capb200_lstm_cell(L.ptr(dev[0]), Kx, L.ptr(dev[1]), L.ptr(dev[2]), L.ptr(dev[3]), L.ptr(dev[4]), L.ptr(dev[5]), L.ptr(dev[6]),
+                                       L.ptr(ho), L.ptr(c_o), M, H, L.MODES[mode], L.current_stream()), 'lstm_cell')
+    torch.cuda.synchronize()
+    assert float((ho.cpu() - h_ref).abs().max()) < 2e-6 and float((c_o.cpu() - c_ref).abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize('rpi,masked', [(1, False), (5, False), (7, True), (10, False)])
+def test_additive_attention(L, rpi, masked):
+    g = torch.Generator().manual_seed(rpi)
+    B, R, A, H = 3, 36, 64, 100
+    N = B * rpi
+    W = {'core.attention.h2att.weight': torch.zeros(A, H), 'core.attention.h2att.bias': torch.zeros(A),
+         'core.attention.alpha_net.weight': torch.randn(1, A, generator=g), 'core.attention.alpha_net.bias': torch.randn(1, generator=g)}
+    att_h = torch.randn(N, A, generator=g)
+    p_att = torch.randn(B, R, A, generator=g)
+    att = torch.randn(B, R, H, generator=g)
+    mask = None
+    if masked:
+        mask = torch.ones(B, R)
+        mask[0, 20:] = 0
+        mask[2, 5:] = 0
+    # oracle: feed att_h through a zero h2att by adding it to p_att rows
+    rep = lambda t: co.repeat_rows(t, rpi)
+    dot = torch.tanh(rep(p_att) + att_h.unsqueeze(1))
+    score = (dot @ W['core.attention.alpha_net.weight'].t()).squeeze(-1) + W['core.attention.alpha_net.bias']
+    wgt = torch.softmax(score, 1)
+    if mask is not None:
+        wgt = wgt * rep(mask)
+        wgt = wgt / wgt.sum(1, keepdim=True)
+    ref = torch.bmm(wgt.unsqueeze(1), rep(att)).squeeze(1)
+    out = torch.empty(N, H, device='cuda')
+    d = [t.cuda().contiguous() if t is not None else None for t in (att_h, p_att, att, mask, W['core.attention.alpha_net.weight'], W['core.attention.alpha_net.bias'])]
+    L.check(L.load().capb200_additive_attention(L.ptr(d[0]), L.ptr(d[1]), L.ptr(d[2]), L.ptr(d[3]), L.ptr(d[4]), L.ptr(d[5]), L.ptr(out), B, rpi, R, A, H,
+                                                L.current_stream()), 'attention')
+    torch.cuda.synchronize()
+    assert float((out.cpu() - ref).abs().max()) < 5e-6
+
+
+@pytest.mark.parametrize('V1,twice,k', [(61, 0, 3), (9488, 1, 5), (9488, 0, 10), (1000, 1, 1)])
+def test_log_softmax_topk(L, V1, twice, k):
+    g = torch.Generator().manual_seed(V1 + k)
+    rows = 17
+    x = torch.randn(rows, V1, generator=g) * 4
+    ref = torch.log_softmax(x, 1)
+    if twice:
+        ref = torch.log_softmax(ref, 1)
+    tv, ti = ref.topk(k, dim=1)
+    xd = x.cuda()
+    top_val = torch.empty(rows, k, device='cuda')
+    top_idx = torch.empty(rows, k, dtype=torch.int32, device='cuda')
+    L.check(L.load().capb200_log_softmax_topk(L.ptr(xd), V1, rows, V1, twice, k, L.ptr(top_val), L.ptr(top_idx), L.current_stream()), 'log_softmax_topk')
+    torch.cuda.synchronize()
+    assert float((xd.cpu() - ref).abs().max()) < 1e-5
+    assert np.array_equal(top_idx.cpu().numpy(), ti.numpy().astype(np.int32))
+    assert float((top_val.cpu() - tv).abs().max()) < 1e-5
+
+
+def test_ciderd_reward_matches_golden(golden_dir):
+    import imagecaptioning.pytorch_b200 as b200
+    from oracle import ciderd_oracle as cdo
+    g = np.load(os.path.join(golden_dir, 'ciderd.npz'))
+    df = {tuple(int(t) for t in k if t >= 0): float(v) for k, v in zip(g['df_keys'], g['df_vals'])}
+    V, B, n, T = (int(v) for v in g['meta'])
+    table = b200.rewards.CiderDTable(df, float(g['ref_len']))
+    gts = [g['gts'][i] for i in range(B)]
+    scores, reward = b200.rewards.cider_scores_and_reward(torch.from_numpy(g['greedy']).cuda(), gts, torch.from_numpy(g['sampled']).cuda(), table)
+    torch.cuda.synchronize()
+    assert np.abs(scores.cpu().numpy()[:B * n] - g['sample_scores']).max() < 1e-9
+    assert np.abs(reward.cpu().numpy() - g['reward']).max() < LOGP_TOL
+    # ragged references + random hypotheses against the oracle
+    rng = np.random.RandomState(5)
+    gts2 = [cdo.make_refs(1, V, n_refs=int(rng.randint(1, 6)), seed=int(s))[0] for s in rng.randint(0, 1000, size=7)]
+    samp = np.minimum(rng.zipf(1.3, size=(7 * 3, 20)), V).astype(np.int64)
+    samp[rng.rand(*samp.shape) < 0.08] = 0
+    grd = np.minimum(rng.zipf(1.3, size=(7, 20)), V).astype(np.int64)
+    ref_reward, ref_scores = cdo.self_critical_reward(grd, gts2, samp, df, float(g['ref_len']))
+    scores, reward = b200.rewards.cider_scores_and_reward(torch.from_numpy(grd).cuda(), gts2, torch.from_numpy(samp).cuda(), table)
+    assert np.abs(scores.cpu().numpy() - ref_scores).max() < 1e-9
+    assert np.abs(reward.cpu().numpy() - ref_reward).max() < LOGP_TOL
+
+
+def test_reward_criterion_matches_golden(golden_dir):
+    import imagecaptioning.pytorch_b200 as b200
+    g = np.load(os.path.join(golden_dir, 'reward_criterion.npz'))
+    lp, seq, reward = (torch.from_numpy(g[k]).cuda() for k in ('lp', 'seq', 'reward'))
+    crit = b200.RewardCriterion()
+    loss = crit(lp, seq, reward)
+    assert abs(float(loss) - float(g['loss'])) < 1e-6
+    assert np.abs(crit(lp, seq, reward, reduction='none').cpu().numpy() - g['loss_none']).max() < 1e-6
+    grad = crit.backward_logprobs(seq, reward, lp.shape[2])
+    assert np.abs(grad.cpu().numpy() - g['grad']).max() < 1e-7
