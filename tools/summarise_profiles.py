@@ -1,0 +1,58 @@
+"""Summarise ncu outputs from gpurun_out/ into profiles/ (tracked).  Usage: python tools/summarise_profiles.py r01"""
+import collections
+import csv
+import io
+import os
+import subprocess
+import sys
+
+tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
+os.makedirs('profiles', exist_ok=True)
+
+# ---- launch list: per-kernel totals and shares
+rows = []
+with open('gpurun_out/%s_launches.csv' % tag) as f:
+    lines = [l for l in f if not l.startswith('==')]
+for r in csv.DictReader(io.StringIO(''.join(lines))):
+    if r.get('Metric Name') == 'gpu__time_duration.sum':
+        val = float(r['Metric Value'].replace(',', ''))
+        unit = r['Metric Unit']
+        ns = val * {'ns': 1, 'us': 1e3, 'ms': 1e6, 'nsecond': 1, 'usecond': 1e3, 'msecond': 1e6}.get(unit, 1)
+        rows.append((r['Kernel Name'], ns))
+tot = collections.defaultdict(lambda: [0, 0.0])
+for k, ns in rows:
+    name = k.split('(')[0]
+    tot[name][0] += 1
+    tot[name][1] += ns
+total = sum(v[1] for v in tot.values())
+with open('profiles/%s_launch_summary.md' % tag, 'w') as f:
+    f.write('# %s: ncu launch list of `python bench.py --steps 1 --warmup 1 --no-cpu-baseline` (first 1200 launches)\n\n' % tag)
+    f.write('`ncu --metrics gpu__time_duration.sum --clock-control none -c 1200` -- cold-cache, serialised: compare shares, not absolutes.\n\n')
+    f.write('| kernel | launches | total us | share |\n|---|---:|---:|---:|\n')
+    for name, (n, ns) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+        f.write('| `%s` | %d | %.1f | %.1f%% |\n' % (name[:110], n, ns / 1e3, 100 * ns / total))
+    f.write('\nTotal %.2f ms over %d launches.\n' % (total / 1e6, len(rows)))
+print(open('profiles/%s_launch_summary.md' % tag).read())
+
+# ---- full capture: key metrics per captured launch
+rep = 'gpurun_out/%s_gemm.ncu-rep' % tag
+if os.path.exists(rep):
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+            'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+            'launch__registers_per_thread', 'launch__grid_size', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+            'sm__inst_executed_pipe_tensor.sum', 'lts__t_bytes.sum', 'l1tex__data_bank_conflicts_pipe_lsu.sum',
+            'sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active', 'launch__shared_mem_per_block_dynamic']
+    rd = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rd[0], rd[1]
+    with open('profiles/%s_gemm_full.md' % tag, 'w') as f:
+        f.write('# %s: `ncu --set full --clock-control none -k regex:gemm_tc_kernel -s 8 -c 4` (one timestep: att_lstm, h2att, lang_lstm, logit)\n\n' % tag)
+        cols = [i for i, h in enumerate(hdr) if h in want or h in ('Kernel Name', 'Grid Size', 'Block Size')]
+        tens = [i for i, h in enumerate(hdr) if 'tensor' in h and 'pct' in h]
+        cols = sorted(set(cols + tens))
+        for r in rd[2:]:
+            f.write('## launch id %s\n\n' % r[0])
+            for i in cols:
+                f.write('- %s = %s %s\n' % (hdr[i], r[i], units[i]))
+            f.write('\n')
+    print(open('profiles/%s_gemm_full.md' % tag).read()[:6000])
