@@ -100,6 +100,9 @@ struct capb200_engine {
     char* wblock = nullptr;
     size_t wblock_bytes = 0;
     float *bsum_att = nullptr, *bsum_lang = nullptr, *bsum_core = nullptr;
+    float* xgate = nullptr;          // [V+1, 4H] relu(embed) * W_ih[:, 2H:]^T: per-token gate contribution (eval-mode decode)
+    long ld_xgate = 0;
+    bool use_xgate = true;
     Planes p_fc, p_attw, p_ctx, p_logit, p_a_ih_h, p_a_ih_fc, p_a_ih_x, p_a_hh, p_l_ih_a, p_l_ih_h, p_l_hh, p_h2att, p_i2h, p_h2h;
 
     // workspace (owned)
@@ -113,6 +116,7 @@ struct capb200_engine {
     int *tokens = nullptr, *src_row = nullptr, *neg1 = nullptr, *img_of_row = nullptr, *unfinished = nullptr, *forced = nullptr;
     float* top_val = nullptr;
     int* top_idx = nullptr;
+    float* att_score = nullptr;   // [rows, R] attention scores
     BeamState bs;
     long long* rec_seq = nullptr;   // [B, beam, T] sorted records of the last beam decode
     int *rec_len = nullptr, *rec_hist = nullptr, *out_hist = nullptr;
@@ -161,6 +165,7 @@ void layout_weights(capb200_engine* e, Arena& a) {
     e->bsum_att = a.take<float>(4 * H);
     e->bsum_lang = a.take<float>(4 * H);
     e->bsum_core = a.take<float>(5 * H);
+    if (updown) { e->ld_xgate = round_up(4 * H, 8); e->xgate = a.take<float>((long)V1 * e->ld_xgate); }
     if (!e->tc) return;
     e->p_logit = carve_planes(a, V1, H);
     if (updown) {
@@ -222,6 +227,7 @@ void layout_workspace(capb200_engine* e, Arena& a, int B, int rows, int R, int b
     e->forced = a.take<int>(rows);
     e->top_val = a.take<float>((long)rows * 16);
     e->top_idx = a.take<int>((long)rows * 16);
+    e->att_score = a.take<float>((long)rows * (R > 0 ? R : 1));
     BeamState& s = e->bs;
     const long rec = (long)B * beam * T;
     s.sums = a.take<float>((long)B * beam);
@@ -381,21 +387,24 @@ int core_step(capb200_engine* e, int rows, int rpi, const int* tokens, const int
         StateCopy s0, s1;
         s0.src = e->h0_out.v.f; s0.ld_src = e->h0_out.v.ld; s0.dst = e->h0_in.v;
         s1.src = e->h1_out.v.f; s1.ld_src = e->h1_out.v.ld; s1.dst = e->h1_in.v;
+        const bool xg = e->use_xgate;     // word contribution comes from the per-token table instead of a K-segment
         e->launches++;
-        if (state_gather_embed_launch(rows, tokens, src_row, w.embed, E, E, 1, e->xt.v, H, 2, s0, s1, st)) return 1;
+        if (state_gather_embed_launch(rows, tokens, src_row, w.embed, E, xg ? 0 : E, 1, e->xt.v, H, 2, s0, s1, st)) return 1;
         const int cur = e->core_cur, nxt = cur ^ 1;
-        {   // attention LSTM gates: [h_lang_prev | xt | h_att_prev] segments + per-image fc' term
+        {   // attention LSTM gates: [h_lang_prev | (xt) | h_att_prev] segments + per-image fc' term
             GemmProblem g;
-            g.M = rows; g.N = 4 * H; g.nseg = 3;
+            g.M = rows; g.N = 4 * H;
             g.seg[0] = seg_of(e->h1_in.v, w.att_lstm_w_ih, E + 2 * H, e->p_a_ih_h, H);
-            g.seg[1] = seg_of(e->xt.v, w.att_lstm_w_ih + 2 * H, E + 2 * H, e->p_a_ih_x, E);
-            g.seg[2] = seg_of(e->h0_in.v, w.att_lstm_w_hh, H, e->p_a_hh, H);
+            g.seg[1] = seg_of(e->h0_in.v, w.att_lstm_w_hh, H, e->p_a_hh, H);
+            g.nseg = 2;
+            if (!xg) { g.seg[2] = seg_of(e->xt.v, w.att_lstm_w_ih + 2 * H, E + 2 * H, e->p_a_ih_x, E); g.nseg = 3; }
             g.epi.row_bias = e->g_fc.v.f; g.epi.ld_row_bias = e->g_fc.v.ld; g.epi.rows_per_group = rpi;
             g.epi.C = e->gates.v.f; g.epi.ldc = e->gates.v.ld;
             if (run_gemm(e, G_LSTM1, g, e->capRows, st)) return 1;
         }
         e->launches++;
-        if (lstm_pointwise_launch(rows, H, e->gates.v.f, e->gates.v.ld, src_row, e->c0[cur], e->ld_c, e->c0[nxt], e->ld_c, e->h0_out.v, st)) return 1;
+        if (lstm_pointwise_launch(rows, H, e->gates.v.f, e->gates.v.ld, src_row, e->c0[cur], e->ld_c, e->c0[nxt], e->ld_c, e->h0_out.v,
+                                  xg ? e->xgate : nullptr, e->ld_xgate, tokens, st)) return 1;
         {   // h2att
             GemmProblem g;
             g.M = rows; g.N = A; g.nseg = 1;
@@ -404,9 +413,9 @@ int core_step(capb200_engine* e, int rows, int rpi, const int* tokens, const int
             g.epi.C = e->att_h.v.f; g.epi.ldc = e->att_h.v.ld;
             if (run_gemm(e, G_H2ATT, g, e->capRows, st)) return 1;
         }
-        e->launches++;
+        e->launches += 2;
         if (additive_attention_launch(n_images, rpi, R, A, H, e->att_h.v.f, e->att_h.v.ld, e->p_att.v.f, e->p_att.v.ld, e->att_e.v.f, e->att_e.v.ld,
-                                      mask, R, w.alpha_w, w.alpha_b, e->att_res.v, st)) return 1;
+                                      mask, R, w.alpha_w, w.alpha_b, e->att_score, e->att_res.v, st)) return 1;
         {   // language LSTM gates: [att_res | h_att | h_lang_prev]
             GemmProblem g;
             g.M = rows; g.N = 4 * H; g.nseg = 3;
@@ -418,7 +427,8 @@ int core_step(capb200_engine* e, int rows, int rpi, const int* tokens, const int
             if (run_gemm(e, G_LSTM2, g, e->capRows, st)) return 1;
         }
         e->launches++;
-        if (lstm_pointwise_launch(rows, H, e->gates.v.f, e->gates.v.ld, src_row, e->c1[cur], e->ld_c, e->c1[nxt], e->ld_c, e->h1_out.v, st)) return 1;
+        if (lstm_pointwise_launch(rows, H, e->gates.v.f, e->gates.v.ld, src_row, e->c1[cur], e->ld_c, e->c1[nxt], e->ld_c, e->h1_out.v,
+                                  nullptr, 0, nullptr, st)) return 1;
         e->core_cur = nxt;
         {   // vocabulary projection straight into the caller's log-prob storage
             GemmProblem g;
@@ -592,6 +602,48 @@ int capb200_engine_bind_weights(capb200_engine* e, const capb200_weights* w, voi
             rc |= pack(e, w->i2h_w, E, 5 * H, E, e->p_i2h, st);
             rc |= pack(e, w->h2h_w, H, 5 * H, H, e->p_h2h, st);
         }
+        if (rc) return 1;
+    }
+    if (updown) {
+        // per-token gate table: relu(embed)[V+1,E] * W_ih[:, 2H:2H+E]^T  (one GEMM per bind; replaces a K=E segment in every step)
+        const long n = (long)V1 * E;
+        const long ldE = round_up(E, 8);
+        char* tmp = nullptr;
+        const size_t tmp_bytes = (size_t)V1 * ldE * (sizeof(float) + (e->tc ? 2 * sizeof(__half) : 0)) + 1024;
+        CAPB_CHECK_CUDA(cudaMallocAsync(&tmp, tmp_bytes, st));
+        ActView ev;
+        ev.ld = ldE;
+        ev.f = reinterpret_cast<float*>(tmp);
+        if (e->tc) {
+            ev.hi = reinterpret_cast<__half*>(tmp + (size_t)V1 * ldE * sizeof(float));
+            ev.lo = ev.hi + (size_t)V1 * ldE;
+        }
+        int rc = 0;
+        if (ldE == E) {
+            rc = relu_copy_launch(w->embed, n, ev, st);
+        } else {
+            CAPB_CHECK_CUDA(cudaMemsetAsync(tmp, 0, tmp_bytes, st));
+            for (int v = 0; v < V1 && !rc; ++v) {     // ragged pitch (tiny test configs only): row by row
+                ActView rv = ev;
+                rv.f += (long)v * ldE; if (rv.hi) { rv.hi += (long)v * ldE; rv.lo += (long)v * ldE; }
+                rc = relu_copy_launch(w->embed + (long)v * E, E, rv, st);
+            }
+        }
+        GemmProblem g;
+        g.M = V1; g.N = 4 * H; g.nseg = 1;
+        g.seg[0] = seg_of(ev, w->att_lstm_w_ih + 2 * H, E + 2 * H, e->p_a_ih_x, E);
+        g.epi.C = e->xgate; g.epi.ldc = e->ld_xgate;
+        if (!rc) {
+            if (!e->tc) {
+                rc = gemm_simt_launch(g, st);
+            } else {
+                GemmTcPlan* plan = gemm_tc_plan_create(g, e->mode == CAPB200_MODE_TC_F16X3 ? 3 : 1);
+                rc = plan ? gemm_tc_plan_launch(plan, nullptr, 0, 0, 0, st) : 1;
+                if (plan) gemm_tc_plan_destroy(plan);
+            }
+        }
+        e->launches += 2;
+        cudaFreeAsync(tmp, st);
         if (rc) return 1;
     }
     e->bound = true;
@@ -784,7 +836,7 @@ int capb200_lstm_cell(const float* x, int Kx, const float* h, const float* c, co
     }
     if (!rc) {
         ActView ho; ho.f = h_out; ho.ld = H;
-        rc = lstm_pointwise_launch(M, H, gates, 4 * H, nullptr, c, H, c_out, H, ho, st);
+        rc = lstm_pointwise_launch(M, H, gates, 4 * H, nullptr, c, H, c_out, H, ho, nullptr, 0, nullptr, st);
     }
     if (g2) cudaFreeAsync(g2, st);
     cudaFreeAsync(gates, st);
@@ -795,8 +847,12 @@ int capb200_additive_attention(const float* att_h, const float* p_att, const flo
                                const float* alpha_b, float* out, int n_images, int rows_per_image, int R, int A, int H, void* stream) {
     CAPB_REQUIRE(att_h && p_att && att && alpha_w && alpha_b && out, "null argument");
     ActView o; o.f = out; o.ld = H;
-    return additive_attention_launch(n_images, rows_per_image, R, A, H, att_h, A, p_att, A, att, H, mask, R, alpha_w, alpha_b, o,
-                                     static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* scratch = nullptr;
+    CAPB_CHECK_CUDA(cudaMallocAsync(&scratch, sizeof(float) * (size_t)n_images * rows_per_image * R, st));
+    const int rc = additive_attention_launch(n_images, rows_per_image, R, A, H, att_h, A, p_att, A, att, H, mask, R, alpha_w, alpha_b, scratch, o, st);
+    cudaFreeAsync(scratch, st);
+    return rc;
 }
 
 int capb200_log_softmax_topk(float* logits, long ld, int rows, int V1, int twice, int k, float* top_val, int* top_idx, void* stream) {

@@ -23,12 +23,14 @@ struct StateCopy {
 int state_gather_embed_launch(int rows, const int* tokens, const int* src_row, const float* emb, long ld_emb, int E, int relu,
                               ActView xt, int H, int nstate, StateCopy sc0, StateCopy sc1, cudaStream_t stream);
 int lstm_pointwise_launch(int rows, int H, const float* gates, long ld_g, const int* src_row, const float* c_prev, long ld_cp,
-                          float* c_out, long ld_co, ActView h_out, cudaStream_t stream);
+                          float* c_out, long ld_co, ActView h_out, const float* gather_bias, long ld_gb, const int* gather_idx,
+                          cudaStream_t stream);
+int relu_copy_launch(const float* x, long n, ActView out_flat, cudaStream_t stream);   // out = relu(x) (+ split planes), flat
 int maxout_pointwise_launch(int rows, int H, const float* sums, long ld_s, const int* src_row, const float* c_prev, long ld_cp,
                             float* c_out, long ld_co, ActView h_out, cudaStream_t stream);
 int additive_attention_launch(int n_images, int rpi, int R, int A, int H, const float* att_h, long ld_ah, const float* p_att, long ld_pa,
                               const float* att, long ld_at, const float* mask, long ld_mask, const float* alpha_w, const float* alpha_b,
-                              ActView out, cudaStream_t stream);
+                              float* score_scratch /*[rows, R]*/, ActView out, cudaStream_t stream);
 int mask_rows_launch(ActView x, int n_images, int R, int cols, const float* mask, long ld_mask, cudaStream_t stream);
 
 // ---- vocab.cu : log-softmax over the vocabulary + candidate selection

@@ -74,6 +74,10 @@ __device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint3
     return c0;
 }
 
+// Passes over the shared-memory copy of the row: (1) load + max, (2) sum exp, (3) log-probs + second-normalisation sum +
+// per-thread sorted top-KMAX, (4) final values to HBM; then k block-wide arg-max rounds over the per-thread list heads.
+// The second log_softmax only shifts the row by a constant, so candidates are ranked on the first-pass values.
+template <int KMAX>
 __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
     extern __shared__ float row[];                // [V1]
     __shared__ float s_red[VT / 32];
@@ -100,32 +104,50 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
     for (int v = threadIdx.x; v < V1; v += VT) sum += expf(row[v] - mx);
     sum = block_sum(sum, s_red);
     const float lsum = logf(sum);
-    if (a.twice) {
-        // log_softmax of log-probs: max is (mx - mx) - lsum
-        const float m2 = (mx - mx) - lsum;
-        float sum2 = 0.f;
-        for (int v = threadIdx.x; v < V1; v += VT) { const float lp = (row[v] - mx) - lsum; row[v] = lp; sum2 += expf(lp - m2); }
-        sum2 = block_sum(sum2, s_red);
-        const float l2 = logf(sum2);
-        for (int v = threadIdx.x; v < V1; v += VT) { const float lp = (row[v] - m2) - l2; row[v] = lp; g[v] = lp; }
-    } else {
-        for (int v = threadIdx.x; v < V1; v += VT) { const float lp = (row[v] - mx) - lsum; row[v] = lp; g[v] = lp; }
-    }
-    __syncthreads();
-
-    if (a.topk > 0) {
-        for (int k = 0; k < a.topk; ++k) {
-            float bv = -INFINITY;
-            int bi = 0x7fffffff;
-            for (int v = threadIdx.x; v < V1; v += VT) { const float x = row[v]; if (x > bv) { bv = x; bi = v; } }
-            float ov; int oi;
-            block_argmax(bv, bi, s_red, s_idx, ov, oi);
-            if (threadIdx.x == 0) {
-                a.top_val[(long)r * a.topk + k] = ov;
-                a.top_idx[(long)r * a.topk + k] = oi;
-                if (oi < V1) row[oi] = -INFINITY;
+    const float m2 = (mx - mx) - lsum;            // max of the log-probs (second log_softmax)
+    const int k_eff = a.topk > 0 ? a.topk : (a.select == 1 ? 1 : 0);
+    float tv[KMAX];
+    int ti[KMAX];
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q) { tv[q] = -INFINITY; ti[q] = 0x7fffffff; }
+    float sum2 = 0.f;
+    for (int v = threadIdx.x; v < V1; v += VT) {
+        const float lp = (row[v] - mx) - lsum;
+        row[v] = lp;
+        if (a.twice) sum2 += expf(lp - m2);
+        if (k_eff > 0 && lp > tv[KMAX - 1]) {
+            float cv = lp;
+            int ci = v;
+#pragma unroll
+            for (int q = 0; q < KMAX; ++q) {
+                if (cv > tv[q]) { const float t0 = tv[q]; const int t1 = ti[q]; tv[q] = cv; ti[q] = ci; cv = t0; ci = t1; }
             }
-            __syncthreads();
+        }
+    }
+    float l2 = 0.f;
+    if (a.twice) {
+        sum2 = block_sum(sum2, s_red);
+        l2 = logf(sum2);
+        for (int v = threadIdx.x; v < V1; v += VT) g[v] = (row[v] - m2) - l2;
+    } else {
+        for (int v = threadIdx.x; v < V1; v += VT) g[v] = row[v];
+    }
+
+    int greedy_tok = 0;
+    for (int k = 0; k < k_eff; ++k) {
+        float ov;
+        int oi;
+        block_argmax(tv[0], ti[0], s_red, s_idx, ov, oi);
+        if (ti[0] == oi) {                        // the owner pops its head
+#pragma unroll
+            for (int q = 0; q + 1 < KMAX; ++q) { tv[q] = tv[q + 1]; ti[q] = ti[q + 1]; }
+            tv[KMAX - 1] = -INFINITY;
+            ti[KMAX - 1] = 0x7fffffff;
+        }
+        if (k == 0) greedy_tok = oi;
+        if (a.topk > 0 && threadIdx.x == 0) {
+            a.top_val[(long)r * a.topk + k] = a.twice ? (ov - m2) - l2 : ov;
+            a.top_idx[(long)r * a.topk + k] = oi;
         }
     }
 
@@ -133,24 +155,24 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
         int tok;
         if (a.select == 3) {
             tok = a.forced[r];
+        } else if (a.select == 1) {
+            tok = greedy_tok;
         } else {
+            __syncthreads();
             float bv = -INFINITY;
             int bi = 0x7fffffff;
-            if (a.select == 1) {
-                for (int v = threadIdx.x; v < V1; v += VT) { const float x = row[v]; if (x > bv) { bv = x; bi = v; } }
-            } else {
-                const float inv_t = 1.0f / a.temperature;
-                const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
-                for (int v = threadIdx.x; v < V1; v += VT) {
-                    const uint32_t bits = philox_first((uint32_t)v, (uint32_t)r, (uint32_t)a.step, (uint32_t)(a.step >> 32), k0, k1);
-                    const float u = ((float)(bits >> 9) + 0.5f) * (1.0f / 8388608.0f);      // (0,1), 23 bits
-                    const float x = row[v] * inv_t - logf(-logf(u));                         // Gumbel-max sample of softmax(logp / T)
-                    if (x > bv) { bv = x; bi = v; }
-                }
+            const float inv_t = 1.0f / a.temperature;
+            const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+            for (int v = threadIdx.x; v < V1; v += VT) {
+                const uint32_t bits = philox_first((uint32_t)v, (uint32_t)r, (uint32_t)a.step, (uint32_t)(a.step >> 32), k0, k1);
+                const float u = ((float)(bits >> 9) + 0.5f) * (1.0f / 8388608.0f);      // (0,1), 23 bits
+                const float x = row[v] * inv_t - logf(-logf(u));                         // Gumbel-max sample of softmax(logp / T)
+                if (x > bv) { bv = x; bi = v; }
             }
             float ov;
             block_argmax(bv, bi, s_red, s_idx, ov, tok);
         }
+        __syncthreads();
         if (threadIdx.x == 0) {
             if (a.unfinished) a.unfinished[r] = (tok != 0) ? 1 : 0;
             if (a.tokens_out) a.tokens_out[r] = tok;
@@ -177,12 +199,16 @@ int vocab_step_launch(const VocabStepArgs& a, cudaStream_t stream) {
     CAPB_REQUIRE(a.topk <= 16, "beam size up to 16");
     const size_t smem = sizeof(float) * (size_t)a.V1;
     CAPB_REQUIRE(smem <= 200 * 1024, "vocabulary larger than 51200 entries needs the multi-pass variant");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        CAPB_CHECK_CUDA(cudaFuncSetAttribute(vocab_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-        configured = 200 * 1024;
+    static bool configured = false;
+    if (!configured) {
+        CAPB_CHECK_CUDA(cudaFuncSetAttribute(vocab_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        CAPB_CHECK_CUDA(cudaFuncSetAttribute(vocab_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        CAPB_CHECK_CUDA(cudaFuncSetAttribute(vocab_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        configured = true;
     }
-    vocab_step_kernel<<<a.rows, VT, smem, stream>>>(a);
+    if (a.topk <= 2) vocab_step_kernel<2><<<a.rows, VT, smem, stream>>>(a);
+    else if (a.topk <= 8) vocab_step_kernel<8><<<a.rows, VT, smem, stream>>>(a);
+    else vocab_step_kernel<16><<<a.rows, VT, smem, stream>>>(a);
     CAPB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
