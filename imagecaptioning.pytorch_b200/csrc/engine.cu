@@ -818,6 +818,46 @@ int capb200_linear(const float* x, long ldx, const float* w, long ldw, const flo
     return rc;
 }
 
+int capb200_bench_linear(const float* x, const float* w, const float* b, float* y, int M, int N, int K, int mode, int iters, float* ms_per_launch,
+                         void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CAPB_REQUIRE(x && w && y && ms_per_launch && M > 0 && N > 0 && K > 0 && iters > 0, "bad argument");
+    GemmProblem g;
+    g.M = M; g.N = N; g.nseg = 1;
+    g.seg[0].A = x; g.seg[0].lda = K; g.seg[0].W = w; g.seg[0].ldw = K; g.seg[0].K = K;
+    g.epi.bias = b; g.epi.C = y; g.epi.ldc = N;
+    const long ldh = round_up(K, 8);
+    __half* scratch = nullptr;
+    GemmTcPlan* plan = nullptr;
+    int rc = 0;
+    if (mode != CAPB200_MODE_SIMT_FP32) {
+        CAPB_CHECK_CUDA(cudaMalloc(&scratch, (size_t)(M + N) * ldh * 2 * sizeof(__half)));
+        __half* xh = scratch; __half* xl = xh + (size_t)M * ldh;
+        __half* wh = xl + (size_t)M * ldh; __half* wl = wh + (size_t)N * ldh;
+        rc = split_planes_launch(x, K, M, K, xh, xl, ldh, st) | split_planes_launch(w, K, N, K, wh, wl, ldh, st);
+        g.seg[0].A_hi = xh; g.seg[0].A_lo = xl; g.seg[0].lda_h = ldh;
+        g.seg[0].W_hi = wh; g.seg[0].W_lo = wl; g.seg[0].ldw_h = ldh;
+        plan = rc ? nullptr : gemm_tc_plan_create(g, mode == CAPB200_MODE_TC_F16X3 ? 3 : 1);
+        if (plan == nullptr) rc = 1;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 3 + iters && !rc; ++i) {
+        if (i == 3) cudaEventRecord(e0, st);
+        rc = plan ? gemm_tc_plan_launch(plan, nullptr, 0, 0, 0, st) : gemm_simt_launch(g, st);
+    }
+    cudaEventRecord(e1, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("bench_linear: ") + cudaGetErrorString(cudaGetLastError())); rc = 1; }
+    float ms = 0.f;
+    if (!rc) { cudaEventElapsedTime(&ms, e0, e1); *ms_per_launch = ms / iters; }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (plan) gemm_tc_plan_destroy(plan);
+    if (scratch) cudaFree(scratch);
+    return rc;
+}
+
 int capb200_lstm_cell(const float* x, int Kx, const float* h, const float* c, const float* w_ih, const float* w_hh, const float* b_ih,
                       const float* b_hh, float* h_out, float* c_out, int M, int H, int mode, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -18,6 +18,8 @@
 //   warps 4..7  epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused bias / row-bias / ReLU, fp32 store and
 //               (optionally) a split-fp16 copy so the next GEMM can consume the result without a conversion pass.
 // K-segments (up to 3 activation/weight pairs) are walked back to back so concatenated LSTM inputs are never built.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -54,16 +56,23 @@ struct TcCfg {
     static constexpr uint32_t kABytes = BM * BK * 2;
     static constexpr uint32_t kWBytes = BN * BK * 2;
     static constexpr uint32_t kStageBytes = kPlanes * (kABytes + kWBytes);
-    static constexpr int kStages = (200 * 1024) / kStageBytes >= 8 ? 8 : (200 * 1024) / kStageBytes;
+    static constexpr int kStages = (206 * 1024) / kStageBytes >= 8 ? 8 : (206 * 1024) / kStageBytes;
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
-    static_assert((kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be a power of two");
+    static constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16, 256]");
+    static_assert(kWBytes % 1024 == 0, "operand tiles must keep the 1024-byte swizzle-atom alignment");
     static_assert(kStages >= 2, "need at least a double buffer");
 };
 
-template <int BN, int PASSES>
+// CX x CY thread-block cluster: the CX CTAs of a cluster row share their A row block, the CY CTAs of a cluster column share
+// their W column block.  Each CTA fetches 1/CX of its A tile and 1/CY of its W tile and TMA-multicasts it to the peers, so
+// L2->SM operand traffic per CTA drops to A/CX + W/CY (the r01 ncu capture shows that traffic is the limiter of the
+// single-CTA kernel).  Stage release is the mirror image: tcgen05.commit multicasts the "slot free" arrival to every CTA
+// that writes into this CTA's slot.
+template <int BN, int PASSES, int CX, int CY>
 __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
     using Cfg = TcCfg<BN, PASSES>;
+    constexpr bool kCluster = (CX * CY) > 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -75,6 +84,14 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     const int lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM;
     const int n0 = blockIdx.x * BN;
+    // position inside the cluster (cluster dims = (CX, CY, 1): rank = x + CX * y)
+    const uint32_t cx = kCluster ? ptx::cluster_ctaid_x() : 0;
+    const uint32_t cy = kCluster ? ptx::cluster_ctaid_y() : 0;
+    uint16_t mask_a = 0, mask_w = 0;          // CTAs that receive my A slice / my W slice
+    if (kCluster) {
+        for (int x = 0; x < CX; ++x) mask_a |= static_cast<uint16_t>(1u << (x + CX * cy));
+        for (int y = 0; y < CY; ++y) mask_w |= static_cast<uint16_t>(1u << (cx + CX * y));
+    }
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.nseg; ++s) {
@@ -89,7 +106,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < Cfg::kStages; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], CX + CY - 1);      // one release per CTA that writes into this slot
         }
         ptx::mbar_init(tmem_full_bar, 1);
         ptx::fence_mbar_init();
@@ -100,8 +117,14 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     }
     ptx::tc_fence_before_sync();
     __syncthreads();
+    if (kCluster) ptx::cluster_sync_all();                   // every CTA's barriers are initialised before any remote arrive
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_holder;
+
+    constexpr uint32_t kASlice = Cfg::kABytes / CX;           // bytes of my share of an A plane tile
+    constexpr uint32_t kWSlice = Cfg::kWBytes / CY;
+    constexpr int kARows = BM / CX, kWRows = BN / CY;
+    static_assert(kASlice % 1024 == 0 && kWSlice % 1024 == 0, "slices must stay swizzle-atom aligned");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -111,12 +134,25 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
                 for (int kb = 0; kb < p.kblocks[s]; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * Cfg::kStageBytes;
+                    uint8_t* a_hi = st + cx * kASlice;
+                    uint8_t* a_lo = st + Cfg::kABytes + cx * kASlice;
+                    uint8_t* w_hi = st + Cfg::kABytes * Cfg::kPlanes + cy * kWSlice;
+                    uint8_t* w_lo = st + Cfg::kABytes * 2 + Cfg::kWBytes + cy * kWSlice;
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                    ptx::tma_load_2d(st, &p.a_hi[s], &full_bar[stage], kb * BK, m0);
-                    ptx::tma_load_2d(st + Cfg::kABytes * Cfg::kPlanes, &p.w_hi[s], &full_bar[stage], kb * BK, n0);
-                    if (PASSES == 3) {
-                        ptx::tma_load_2d(st + Cfg::kABytes, &p.a_lo[s], &full_bar[stage], kb * BK, m0);
-                        ptx::tma_load_2d(st + Cfg::kABytes * 2 + Cfg::kWBytes, &p.w_lo[s], &full_bar[stage], kb * BK, n0);
+                    if (kCluster) {
+                        ptx::tma_load_2d_mcast(a_hi, &p.a_hi[s], &full_bar[stage], kb * BK, m0 + cx * kARows, mask_a);
+                        ptx::tma_load_2d_mcast(w_hi, &p.w_hi[s], &full_bar[stage], kb * BK, n0 + cy * kWRows, mask_w);
+                        if (PASSES == 3) {
+                            ptx::tma_load_2d_mcast(a_lo, &p.a_lo[s], &full_bar[stage], kb * BK, m0 + cx * kARows, mask_a);
+                            ptx::tma_load_2d_mcast(w_lo, &p.w_lo[s], &full_bar[stage], kb * BK, n0 + cy * kWRows, mask_w);
+                        }
+                    } else {
+                        ptx::tma_load_2d(a_hi, &p.a_hi[s], &full_bar[stage], kb * BK, m0);
+                        ptx::tma_load_2d(w_hi, &p.w_hi[s], &full_bar[stage], kb * BK, n0);
+                        if (PASSES == 3) {
+                            ptx::tma_load_2d(a_lo, &p.a_lo[s], &full_bar[stage], kb * BK, m0);
+                            ptx::tma_load_2d(w_lo, &p.w_lo[s], &full_bar[stage], kb * BK, n0);
+                        }
                     }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -125,6 +161,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_f16_f32(BM, BN);
+            const uint16_t release_mask = static_cast<uint16_t>(mask_a | mask_w);
             int stage = 0;
             uint32_t phase = 0;
             uint32_t accumulate = 0;
@@ -149,7 +186,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
                         }
                         accumulate = 1;
                     }
-                    ptx::umma_commit(&empty_bar[stage]);
+                    if (kCluster) ptx::umma_commit_mcast(&empty_bar[stage], release_mask);
+                    else ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -166,16 +204,16 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         const bool vec2h = p.C_hi != nullptr && (p.ldcs & 7) == 0 && (reinterpret_cast<uintptr_t>(p.C_hi) & 15) == 0 &&
                            (reinterpret_cast<uintptr_t>(p.C_lo) & 15) == 0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t r[16];
             __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the guarded stores of the previous chunk
-            ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+            ptx::tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
             ptx::tmem_ld_wait();
             const int col0 = n0 + c0;
             if (!row_ok || col0 >= p.N) continue;
-            float v[32];
+            float v[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 const int col = col0 + j;
                 float x = __uint_as_float(r[j]);
                 if (col < p.N) {
@@ -185,14 +223,14 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
                 }
                 v[j] = x;
             }
-            const bool full = col0 + 32 <= p.N;
+            const bool full = col0 + 16 <= p.N;
             if (p.C != nullptr) {
                 float* dst = p.C + (long)row * p.ldc + col0;
                 if (full && vec4) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 } else {
-                    for (int j = 0; j < 32; ++j) if (col0 + j < p.N) dst[j] = v[j];
+                    for (int j = 0; j < 16; ++j) if (col0 + j < p.N) dst[j] = v[j];
                 }
             }
             if (p.C_hi != nullptr) {
@@ -200,7 +238,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
                 __half* dl = p.C_lo + (long)row * p.ldcs + col0;
                 if (full && vec2h) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
+                    for (int j = 0; j < 16; j += 8) {
                         __align__(16) __half h[8];
                         __align__(16) __half l[8];
 #pragma unroll
@@ -209,7 +247,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
                         *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(l);
                     }
                 } else {
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < 16; ++j) {
                         if (col0 + j < p.N) {
                             __half h, l;
                             split_f32(v[j], h, l);
@@ -223,6 +261,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     }
     ptx::tc_fence_before_sync();
     __syncthreads();
+    if (kCluster) ptx::cluster_sync_all();                   // no CTA leaves while a peer may still write its slots / barriers
     ptx::tc_fence_after_sync();
     if (warp == 2) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
@@ -260,18 +299,43 @@ bool encode_plane(CUtensorMap* map, const __half* base, long rows, long K, long 
     return true;
 }
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, int CX, int CY>
 int launch_cfg(const TcParams& prm, cudaStream_t stream) {
     using Cfg = TcCfg<BN, PASSES>;
     static bool attr_set = false;
     if (!attr_set) {
-        CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, CX, CY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
-    dim3 grid(cdiv(prm.N, BN), cdiv(prm.M, BM));
-    gemm_tc_kernel<BN, PASSES><<<grid, 256, Cfg::kSmemBytes, stream>>>(prm);
-    CAPB_CHECK_CUDA(cudaGetLastError());
+    // grid padded to whole clusters; CTAs outside the matrix still run the pipeline (their TMA boxes are zero-filled) so
+    // that their cluster peers receive the multicast slices they wait for
+    dim3 grid(round_up(cdiv(prm.N, BN), CX), round_up(cdiv(prm.M, BM), CY));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CX;
+    attr[0].val.clusterDim.y = CY;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (CX * CY > 1) ? 1 : 0;
+    CAPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PASSES, CX, CY>, prm));
     return 0;
+}
+
+// Round count of a tiling on 148 SMs: clusters are placed whole, so only floor(148 / cluster size) of them run at once.
+double tiling_cost(int M, int N, int bn, int cx, int cy) {
+    const long tiles_n = round_up(cdiv(N, bn), cx), tiles_m = round_up(cdiv(M, BM), cy);
+    const long clusters = (tiles_n / cx) * (tiles_m / cy);
+    const long slots = (cx * cy == 4) ? 33 : 148 / (cx * cy);      // 4-CTA clusters strand SMs in GPCs of 18 (33 x 4 = 132 usable)
+    const long rounds = (clusters + slots - 1) / slots;
+    // per-round time ~ max(MMA time, operand delivery): operand bytes per CTA per K-block scale with BM/cx + bn/cy
+    const double mma = bn;                                         // cycles per k16 MMA ~ BM * bn / 256
+    const double bytes = (double)BM / cx + (double)bn / cy;        // rows fetched per K-block
+    return rounds * (mma > 0.75 * bytes ? mma : 0.75 * bytes);
 }
 
 }  // namespace
@@ -280,6 +344,7 @@ struct GemmTcPlan {
     TcParams prm;
     int passes;
     int bn;
+    int cx, cy;       // cluster shape (multicast of A across cx CTAs, of W across cy CTAs)
 };
 
 bool gemm_tc_supported(const GemmProblem& p, std::string* why) {
@@ -302,7 +367,29 @@ GemmTcPlan* gemm_tc_plan_create(const GemmProblem& p, int passes) {
     GemmTcPlan* plan = new GemmTcPlan();
     memset(&plan->prm, 0, sizeof(TcParams));
     plan->passes = passes;
-    plan->bn = 128;
+    // pick the tile width / cluster shape with the lowest modelled cost; tiny problems stay on the plain kernel
+    {
+        const int cand_bn[2] = {128, 144};
+        const int cand_c[4][2] = {{1, 1}, {2, 1}, {1, 2}, {2, 2}};
+        double best = 1e30;
+        plan->bn = 128;
+        plan->cx = plan->cy = 1;
+        for (int c = 0; c < 4; ++c) {
+            for (int b = 0; b < 2; ++b) {
+                const int cx = cand_c[c][0], cy = cand_c[c][1];
+                if (cdiv(p.M, BM) < cy || cdiv(p.N, cand_bn[b]) < cx) continue;
+                const double cost = tiling_cost(p.M, p.N, cand_bn[b], cx, cy);
+                if (cost < best) { best = cost; plan->bn = cand_bn[b]; plan->cx = cx; plan->cy = cy; }
+            }
+        }
+        const char* force = getenv("CAPB200_GEMM_TILING");      // "<BN>x<CX>x<CY>", e.g. "144x2x1" (debug / sweeps)
+        if (force != nullptr) {
+            int fb = 0, fx = 0, fy = 0;
+            if (sscanf(force, "%dx%dx%d", &fb, &fx, &fy) == 3 && (fb == 128 || fb == 144) && (fx == 1 || fx == 2) && (fy == 1 || fy == 2)) {
+                plan->bn = fb; plan->cx = fx; plan->cy = fy;
+            }
+        }
+    }
     TcParams& t = plan->prm;
     t.nseg = p.nseg;
     t.M = p.M;
@@ -311,12 +398,13 @@ GemmTcPlan* gemm_tc_plan_create(const GemmProblem& p, int passes) {
     for (int s = 0; s < p.nseg; ++s) {
         const GemmSeg& g = p.seg[s];
         t.kblocks[s] = cdiv(g.K, BK);
-        bool ok = encode_plane(&t.a_hi[s], g.A_hi, p.M, g.K, g.lda_h, BM, &err) &&
-                  encode_plane(&t.w_hi[s], g.W_hi, p.N, g.K, g.ldw_h, plan->bn, &err);
+        const int a_box = BM / plan->cx, w_box = plan->bn / plan->cy;     // each CTA fetches its slice of the tile
+        bool ok = encode_plane(&t.a_hi[s], g.A_hi, p.M, g.K, g.lda_h, a_box, &err) &&
+                  encode_plane(&t.w_hi[s], g.W_hi, p.N, g.K, g.ldw_h, w_box, &err);
         if (ok && passes == 3) {
             if (g.A_lo == nullptr || g.W_lo == nullptr) { err = "lo planes missing for 3-pass mode"; ok = false; }
-            ok = ok && encode_plane(&t.a_lo[s], g.A_lo, p.M, g.K, g.lda_h, BM, &err) &&
-                 encode_plane(&t.w_lo[s], g.W_lo, p.N, g.K, g.ldw_h, plan->bn, &err);
+            ok = ok && encode_plane(&t.a_lo[s], g.A_lo, p.M, g.K, g.lda_h, a_box, &err) &&
+                 encode_plane(&t.w_lo[s], g.W_lo, p.N, g.K, g.ldw_h, w_box, &err);
         }
         if (!ok) { set_error("gemm_tc: " + err); delete plan; return nullptr; }
     }
@@ -341,8 +429,17 @@ int gemm_tc_plan_launch(GemmTcPlan* plan, float* C_override, long ldc_override, 
     }
     if (rows_per_group_override > 0) prm.rows_per_group = rows_per_group_override;
     if (prm.M <= 0 || prm.N <= 0) return 0;
-    if (plan->passes == 3) return launch_cfg<128, 3>(prm, stream);
-    return launch_cfg<128, 1>(prm, stream);
+    const int key = plan->bn * 100 + plan->cx * 10 + plan->cy;
+#define CAPB_TC_CASE(BN_, CX_, CY_)                                                      \
+    case BN_ * 100 + CX_ * 10 + CY_:                                                     \
+        return plan->passes == 3 ? launch_cfg<BN_, 3, CX_, CY_>(prm, stream) : launch_cfg<BN_, 1, CX_, CY_>(prm, stream);
+    switch (key) {
+        CAPB_TC_CASE(128, 1, 1) CAPB_TC_CASE(128, 2, 1) CAPB_TC_CASE(128, 1, 2) CAPB_TC_CASE(128, 2, 2)
+        CAPB_TC_CASE(144, 1, 1) CAPB_TC_CASE(144, 2, 1) CAPB_TC_CASE(144, 1, 2) CAPB_TC_CASE(144, 2, 2)
+    }
+#undef CAPB_TC_CASE
+    set_error("gemm_tc: no kernel instance for the planned tiling");
+    return 1;
 }
 
 }  // namespace capb200

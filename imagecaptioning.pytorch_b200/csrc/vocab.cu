@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
     for (int v = threadIdx.x; v < V1; v += VT) { const float x = g[v]; row[v] = x; mx = fmaxf(mx, x); }
     mx = block_max(mx, s_red);
     float sum = 0.f;
-    for (int v = threadIdx.x; v < V1; v += VT) sum += expf(row[v] - mx);
+    for (int v = threadIdx.x; v < V1; v += VT) sum += __expf(row[v] - mx);      // ex2.approx path: relative error ~1e-7 on the sum
     sum = block_sum(sum, s_red);
     const float lsum = logf(sum);
     const float m2 = (mx - mx) - lsum;            // max of the log-probs (second log_softmax)
@@ -110,11 +110,9 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
     int ti[KMAX];
 #pragma unroll
     for (int q = 0; q < KMAX; ++q) { tv[q] = -INFINITY; ti[q] = 0x7fffffff; }
-    float sum2 = 0.f;
     for (int v = threadIdx.x; v < V1; v += VT) {
         const float lp = (row[v] - mx) - lsum;
         row[v] = lp;
-        if (a.twice) sum2 += expf(lp - m2);
         if (k_eff > 0 && lp > tv[KMAX - 1]) {
             float cv = lp;
             int ci = v;
@@ -124,10 +122,10 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
             }
         }
     }
-    float l2 = 0.f;
+    // Second log_softmax (beam search, CaptionModel.py:204): its max is m2 = -lsum, so exp(lp - m2) = exp(x - mx) term by term and
+    // its normaliser is the first pass's `sum` again (up to one rounding, ~1e-7 on the log-prob); no second exp pass is needed.
+    const float l2 = lsum;
     if (a.twice) {
-        sum2 = block_sum(sum2, s_red);
-        l2 = logf(sum2);
         for (int v = threadIdx.x; v < V1; v += VT) g[v] = (row[v] - m2) - l2;
     } else {
         for (int v = threadIdx.x; v < V1; v += VT) g[v] = row[v];

@@ -45,6 +45,11 @@ int capb200_abi_version(void);
 int capb200_linear(const float* x, long ldx, const float* w, long ldw, const float* b, float* y, long ldy, int M, int N, int K,
                    int relu, int mode, void* stream);
 
+/* Same contraction with the operands split once, then `iters` back-to-back launches timed with CUDA events on `stream`
+ * (synchronous; y holds the result afterwards).  Used by bench.py / the tiling sweeps. */
+int capb200_bench_linear(const float* x, const float* w, const float* b, float* y, int M, int N, int K, int mode, int iters, float* ms_per_launch,
+                         void* stream);
+
 /* nn.LSTMCell: gates = x*w_ih^T + b_ih + h*w_hh^T + b_hh; (i,f,g,o)           AttModel.py:628,635
  * x[M,Kx], h/c[M,H] -> h_out/c_out[M,H] */
 int capb200_lstm_cell(const float* x, int Kx, const float* h, const float* c, const float* w_ih, const float* w_hh, const float* b_ih,
