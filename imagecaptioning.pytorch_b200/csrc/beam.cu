@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(32) beam_finalize_kernel(BeamState s, int keep
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ slab, long step_stride, long ld_slab, const int* __restrict__ hist, int T, int V1,
-                                   float* __restrict__ dst) {
+                                   float* __restrict__ dst, const float2* __restrict__ stats, long stats_stride) {
     const long item = blockIdx.x;          // item = k * T + s
     const int sidx = (int)(item % T);
     const int row = hist[item];
@@ -172,6 +172,18 @@ __global__ void gather_rows_kernel(const float* __restrict__ slab, long step_str
         return;
     }
     const float* src = slab + (long)sidx * step_stride + (long)row * ld_slab;
+    if (stats != nullptr) {
+        // raw logits -> log-probs with the row statistics of the search step (second log_softmax from step 1 on)
+        const float2 st = stats[(long)sidx * stats_stride + row];
+        const float mx = st.x, lsum = st.y;
+        const float m2 = (mx - mx) - lsum, l2 = lsum;
+        const bool twice = sidx > 0;
+        for (int v = threadIdx.x; v < V1; v += blockDim.x) {
+            const float lp = (src[v] - mx) - lsum;
+            d[v] = twice ? (lp - m2) - l2 : lp;
+        }
+        return;
+    }
     const bool vec = ((V1 & 3) == 0) && ((ld_slab & 3) == 0) && ((step_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(slab) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
     if (vec) {
@@ -203,9 +215,9 @@ int beam_finalize_launch(const BeamState& s, int keep, long long* out_seq, int* 
 }
 
 int gather_logprob_rows_launch(const float* slab, long step_stride, long ld_slab, const int* hist, int nseq, int T, int V1, float* dst,
-                               cudaStream_t stream) {
+                               const float2* stats, long stats_stride, cudaStream_t stream) {
     if (nseq <= 0) return 0;
-    gather_rows_kernel<<<nseq * T, 256, 0, stream>>>(slab, step_stride, ld_slab, hist, T, V1, dst);
+    gather_rows_kernel<<<nseq * T, 256, 0, stream>>>(slab, step_stride, ld_slab, hist, T, V1, dst, stats, stats_stride);
     CAPB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

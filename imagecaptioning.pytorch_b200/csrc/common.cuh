@@ -67,7 +67,31 @@ struct GemmEpilogue {
     __half* C_hi = nullptr;             // optional split planes of the result, pitch ldcs
     __half* C_lo = nullptr;
     long ldcs = 0;
+    // Fused nn.LSTMCell epilogue (tensor-core path only).  N = 4H and the weight rows / bias / row-bias / gather-bias columns are
+    // gate-interleaved (column 4*j+g holds gate g in (i,f,g,o) of hidden unit j), so one epilogue thread owns all four gates
+    // of a unit: c' = sig(f)*c + sig(i)*tanh(g), h' = sig(o)*tanh(c').  C / C_hi / C_lo are unused in this mode.
+    int lstm = 0;
+    int H = 0;
+    const float* c_prev = nullptr;      // [*, H] pitch ld_cprev, read at row src_row[r] (nullptr src_row = identity, < 0 = zero state)
+    long ld_cprev = 0;
+    const int* src_row = nullptr;
+    float* c_out = nullptr;             // [M, H] pitch ld_cout
+    long ld_cout = 0;
+    const float* gather_bias = nullptr; // optional per-row gathered gate bias: gather_bias[gather_idx[r], 4H] (per-token table)
+    long ld_gb = 0;
+    const int* gather_idx = nullptr;
+    float* h_f = nullptr;               // h' as fp32 and split planes, common pitch ld_h
+    __half* h_hi = nullptr;
+    __half* h_lo = nullptr;
+    long ld_h = 0;
 };
+
+// SFU-based transcendental forms (ex2.approx + fast reciprocal): absolute error < 3e-7 on outputs in [-1, 1].
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float e = __expf(2.0f * x);
+    return 1.0f - __fdividef(2.0f, 1.0f + e);
+}
 struct GemmProblem {
     int M = 0, N = 0, nseg = 0;
     GemmSeg seg[kMaxSeg];
@@ -86,12 +110,14 @@ int gemm_simt_launch(const GemmProblem& p, cudaStream_t stream);
 struct GemmTcPlan;
 GemmTcPlan* gemm_tc_plan_create(const GemmProblem& p, int passes);   // nullptr on failure (see last_error)
 void gemm_tc_plan_destroy(GemmTcPlan* plan);
-// Launch-time overrides: C/ldc (<= 0 keeps the planned pitch), M (rows actually valid, <= planned rows; 0 keeps) and the
-// row-bias group size (0 keeps).  The tensor maps keep the planned extents; rows beyond M are computed but never stored.
-int gemm_tc_plan_launch(GemmTcPlan* plan, float* C_override, long ldc_override, int M_override, int rows_per_group_override,
-                        cudaStream_t stream);
+// Launch-time overrides: the whole epilogue (output pointers, biases, fused-LSTM state pointers change per decode step) and
+// M (rows actually valid, <= planned rows; 0 keeps).  The tensor maps keep the planned extents; rows beyond M are computed
+// but never stored.
+int gemm_tc_plan_launch(GemmTcPlan* plan, const GemmEpilogue* epi_override, int M_override, cudaStream_t stream);
 bool gemm_tc_supported(const GemmProblem& p, std::string* why);
 
 int split_planes_launch(const float* x, long ldx, int rows, int cols, __half* hi, __half* lo, long ldh, cudaStream_t stream);
+// gate-interleaving variant for LSTM weights [4H, cols]: destination row 4*j+g <- source row g*H + j
+int split_planes_interleave_launch(const float* x, long ldx, int H, int cols, __half* hi, __half* lo, long ldh, cudaStream_t stream);
 
 }  // namespace capb200

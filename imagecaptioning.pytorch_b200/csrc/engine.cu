@@ -30,6 +30,10 @@ __global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) o[i] = a[i] + b[i];
 }
+__global__ void interleave_gates_kernel(const float* src, float* dst, int H) {      // dst[4*j+g] = src[g*H + j]
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 4 * H) dst[i] = src[(i & 3) * H + (i >> 2)];
+}
 __global__ void fill_int_kernel(int* p, int n, int v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -100,6 +104,7 @@ struct capb200_engine {
     char* wblock = nullptr;
     size_t wblock_bytes = 0;
     float *bsum_att = nullptr, *bsum_lang = nullptr, *bsum_core = nullptr;
+    float *bsum_att_il = nullptr, *bsum_lang_il = nullptr;   // gate-interleaved copies for the fused LSTM epilogue (tensor-core modes)
     float* xgate = nullptr;          // [V+1, 4H] relu(embed) * W_ih[:, 2H:]^T: per-token gate contribution (eval-mode decode)
     long ld_xgate = 0;
     bool use_xgate = true;
@@ -117,6 +122,7 @@ struct capb200_engine {
     float* top_val = nullptr;
     int* top_idx = nullptr;
     float* att_score = nullptr;   // [rows, R] attention scores
+    float2* slab_stats = nullptr; // [T, rows] (max, log-sum-exp) of every slab row (beam search keeps raw logits in the slab)
     BeamState bs;
     long long* rec_seq = nullptr;   // [B, beam, T] sorted records of the last beam decode
     int *rec_len = nullptr, *rec_hist = nullptr, *out_hist = nullptr;
@@ -165,6 +171,8 @@ void layout_weights(capb200_engine* e, Arena& a) {
     e->bsum_att = a.take<float>(4 * H);
     e->bsum_lang = a.take<float>(4 * H);
     e->bsum_core = a.take<float>(5 * H);
+    e->bsum_att_il = a.take<float>(4 * H);
+    e->bsum_lang_il = a.take<float>(4 * H);
     if (updown) { e->ld_xgate = round_up(4 * H, 8); e->xgate = a.take<float>((long)V1 * e->ld_xgate); }
     if (!e->tc) return;
     e->p_logit = carve_planes(a, V1, H);
@@ -190,6 +198,11 @@ void layout_weights(capb200_engine* e, Arena& a) {
 int pack(capb200_engine* e, const float* w, long ldw, int rows, int cols, const Planes& p, cudaStream_t st) {
     e->launches++;
     return split_planes_launch(w, ldw, rows, cols, p.hi, p.lo, p.ld, st);
+}
+// LSTM weight blocks [4H, cols] are stored gate-interleaved (row 4*j+g) so the GEMM epilogue can apply the cell directly
+int pack_gates(capb200_engine* e, const float* w, long ldw, int H, int cols, const Planes& p, cudaStream_t st) {
+    e->launches++;
+    return split_planes_interleave_launch(w, ldw, H, cols, p.hi, p.lo, p.ld, st);
 }
 
 void layout_workspace(capb200_engine* e, Arena& a, int B, int rows, int R, int beam) {
@@ -228,6 +241,7 @@ void layout_workspace(capb200_engine* e, Arena& a, int B, int rows, int R, int b
     e->top_val = a.take<float>((long)rows * 16);
     e->top_idx = a.take<int>((long)rows * 16);
     e->att_score = a.take<float>((long)rows * (R > 0 ? R : 1));
+    e->slab_stats = a.take<float2>((long)rows * T);
     BeamState& s = e->bs;
     const long rec = (long)B * beam * T;
     s.sums = a.take<float>((long)B * beam);
@@ -297,7 +311,7 @@ int run_gemm_inner(capb200_engine* e, int id, GemmProblem& g, int plan_rows, cud
         e->plans[id] = gemm_tc_plan_create(planned, e->mode == CAPB200_MODE_TC_F16X3 ? 3 : 1);
         if (e->plans[id] == nullptr) return 1;
     }
-    return gemm_tc_plan_launch(e->plans[id], g.epi.C, g.epi.ldc, g.M, g.epi.rows_per_group, st);
+    return gemm_tc_plan_launch(e->plans[id], &g.epi, g.M, st);
 }
 
 int run_gemm(capb200_engine* e, int id, GemmProblem& g, int plan_rows, cudaStream_t st) {
@@ -370,7 +384,7 @@ int prepare(capb200_engine* e, const float* fc, const float* att, const float* m
         GemmProblem g;
         g.M = B; g.N = 4 * H; g.nseg = 1;
         g.seg[0] = seg_of(e->fc_e.v, w.att_lstm_w_ih + H, E + 2 * H, e->p_a_ih_fc, H);
-        g.epi.bias = e->bsum_att;
+        g.epi.bias = e->tc ? e->bsum_att_il : e->bsum_att;     // tensor-core modes keep every gate quantity interleaved
         g.epi.C = e->g_fc.v.f; g.epi.ldc = e->g_fc.v.ld;
         if (run_gemm(e, G_GFC, g, e->capB, st)) return 1;
     }
@@ -399,12 +413,22 @@ int core_step(capb200_engine* e, int rows, int rpi, const int* tokens, const int
             g.nseg = 2;
             if (!xg) { g.seg[2] = seg_of(e->xt.v, w.att_lstm_w_ih + 2 * H, E + 2 * H, e->p_a_ih_x, E); g.nseg = 3; }
             g.epi.row_bias = e->g_fc.v.f; g.epi.ld_row_bias = e->g_fc.v.ld; g.epi.rows_per_group = rpi;
-            g.epi.C = e->gates.v.f; g.epi.ldc = e->gates.v.ld;
+            if (e->tc) {     // cell applied in the GEMM epilogue: no gate buffer, no point-wise launch
+                g.epi.lstm = 1; g.epi.H = H;
+                g.epi.c_prev = e->c0[cur]; g.epi.ld_cprev = e->ld_c; g.epi.src_row = src_row;
+                g.epi.c_out = e->c0[nxt]; g.epi.ld_cout = e->ld_c;
+                g.epi.gather_bias = xg ? e->xgate : nullptr; g.epi.ld_gb = e->ld_xgate; g.epi.gather_idx = tokens;
+                g.epi.h_f = e->h0_out.v.f; g.epi.h_hi = e->h0_out.v.hi; g.epi.h_lo = e->h0_out.v.lo; g.epi.ld_h = e->h0_out.v.ld;
+            } else {
+                g.epi.C = e->gates.v.f; g.epi.ldc = e->gates.v.ld;
+            }
             if (run_gemm(e, G_LSTM1, g, e->capRows, st)) return 1;
         }
-        e->launches++;
-        if (lstm_pointwise_launch(rows, H, e->gates.v.f, e->gates.v.ld, src_row, e->c0[cur], e->ld_c, e->c0[nxt], e->ld_c, e->h0_out.v,
-                                  xg ? e->xgate : nullptr, e->ld_xgate, tokens, st)) return 1;
+        if (!e->tc) {
+            e->launches++;
+            if (lstm_pointwise_launch(rows, H, e->gates.v.f, e->gates.v.ld, src_row, e->c0[cur], e->ld_c, e->c0[nxt], e->ld_c, e->h0_out.v,
+                                      xg ? e->xgate : nullptr, e->ld_xgate, tokens, st)) return 1;
+        }
         {   // h2att
             GemmProblem g;
             g.M = rows; g.N = A; g.nseg = 1;
@@ -422,13 +446,23 @@ int core_step(capb200_engine* e, int rows, int rpi, const int* tokens, const int
             g.seg[0] = seg_of(e->att_res.v, w.lang_lstm_w_ih, 2 * H, e->p_l_ih_a, H);
             g.seg[1] = seg_of(e->h0_out.v, w.lang_lstm_w_ih + H, 2 * H, e->p_l_ih_h, H);
             g.seg[2] = seg_of(e->h1_in.v, w.lang_lstm_w_hh, H, e->p_l_hh, H);
-            g.epi.bias = e->bsum_lang;
-            g.epi.C = e->gates.v.f; g.epi.ldc = e->gates.v.ld;
+            if (e->tc) {
+                g.epi.bias = e->bsum_lang_il;
+                g.epi.lstm = 1; g.epi.H = H;
+                g.epi.c_prev = e->c1[cur]; g.epi.ld_cprev = e->ld_c; g.epi.src_row = src_row;
+                g.epi.c_out = e->c1[nxt]; g.epi.ld_cout = e->ld_c;
+                g.epi.h_f = e->h1_out.v.f; g.epi.h_hi = e->h1_out.v.hi; g.epi.h_lo = e->h1_out.v.lo; g.epi.ld_h = e->h1_out.v.ld;
+            } else {
+                g.epi.bias = e->bsum_lang;
+                g.epi.C = e->gates.v.f; g.epi.ldc = e->gates.v.ld;
+            }
             if (run_gemm(e, G_LSTM2, g, e->capRows, st)) return 1;
         }
-        e->launches++;
-        if (lstm_pointwise_launch(rows, H, e->gates.v.f, e->gates.v.ld, src_row, e->c1[cur], e->ld_c, e->c1[nxt], e->ld_c, e->h1_out.v,
-                                  nullptr, 0, nullptr, st)) return 1;
+        if (!e->tc) {
+            e->launches++;
+            if (lstm_pointwise_launch(rows, H, e->gates.v.f, e->gates.v.ld, src_row, e->c1[cur], e->ld_c, e->c1[nxt], e->ld_c, e->h1_out.v,
+                                      nullptr, 0, nullptr, st)) return 1;
+        }
         e->core_cur = nxt;
         {   // vocabulary projection straight into the caller's log-prob storage
             GemmProblem g;
@@ -577,7 +611,9 @@ int capb200_engine_bind_weights(capb200_engine* e, const capb200_weights* w, voi
     if (updown) {
         add_vec_kernel<<<cdiv(4 * H, 256), 256, 0, st>>>(w->att_lstm_b_ih, w->att_lstm_b_hh, e->bsum_att, 4 * H);
         add_vec_kernel<<<cdiv(4 * H, 256), 256, 0, st>>>(w->lang_lstm_b_ih, w->lang_lstm_b_hh, e->bsum_lang, 4 * H);
-        e->launches += 2;
+        interleave_gates_kernel<<<cdiv(4 * H, 256), 256, 0, st>>>(e->bsum_att, e->bsum_att_il, H);
+        interleave_gates_kernel<<<cdiv(4 * H, 256), 256, 0, st>>>(e->bsum_lang, e->bsum_lang_il, H);
+        e->launches += 4;
     } else {
         add_vec_kernel<<<cdiv(5 * H, 256), 256, 0, st>>>(w->i2h_b, w->h2h_b, e->bsum_core, 5 * H);
         e->launches += 1;
@@ -589,13 +625,13 @@ int capb200_engine_bind_weights(capb200_engine* e, const capb200_weights* w, voi
             rc |= pack(e, w->fc_embed_w, e->cfg.fc_feat_size, H, e->cfg.fc_feat_size, e->p_fc, st);
             rc |= pack(e, w->att_embed_w, e->cfg.att_feat_size, H, e->cfg.att_feat_size, e->p_attw, st);
             rc |= pack(e, w->ctx2att_w, H, A, H, e->p_ctx, st);
-            rc |= pack(e, w->att_lstm_w_ih, E + 2 * H, 4 * H, H, e->p_a_ih_h, st);
-            rc |= pack(e, w->att_lstm_w_ih + H, E + 2 * H, 4 * H, H, e->p_a_ih_fc, st);
-            rc |= pack(e, w->att_lstm_w_ih + 2 * H, E + 2 * H, 4 * H, E, e->p_a_ih_x, st);
-            rc |= pack(e, w->att_lstm_w_hh, H, 4 * H, H, e->p_a_hh, st);
-            rc |= pack(e, w->lang_lstm_w_ih, 2 * H, 4 * H, H, e->p_l_ih_a, st);
-            rc |= pack(e, w->lang_lstm_w_ih + H, 2 * H, 4 * H, H, e->p_l_ih_h, st);
-            rc |= pack(e, w->lang_lstm_w_hh, H, 4 * H, H, e->p_l_hh, st);
+            rc |= pack_gates(e, w->att_lstm_w_ih, E + 2 * H, H, H, e->p_a_ih_h, st);
+            rc |= pack_gates(e, w->att_lstm_w_ih + H, E + 2 * H, H, H, e->p_a_ih_fc, st);
+            rc |= pack_gates(e, w->att_lstm_w_ih + 2 * H, E + 2 * H, H, E, e->p_a_ih_x, st);
+            rc |= pack_gates(e, w->att_lstm_w_hh, H, H, H, e->p_a_hh, st);
+            rc |= pack_gates(e, w->lang_lstm_w_ih, 2 * H, H, H, e->p_l_ih_a, st);
+            rc |= pack_gates(e, w->lang_lstm_w_ih + H, 2 * H, H, H, e->p_l_ih_h, st);
+            rc |= pack_gates(e, w->lang_lstm_w_hh, H, H, H, e->p_l_hh, st);
             rc |= pack(e, w->h2att_w, H, A, H, e->p_h2att, st);
         } else {
             rc |= pack(e, w->fc_embed_w, e->cfg.fc_feat_size, E, e->cfg.fc_feat_size, e->p_fc, st);
@@ -638,7 +674,7 @@ int capb200_engine_bind_weights(capb200_engine* e, const capb200_weights* w, voi
                 rc = gemm_simt_launch(g, st);
             } else {
                 GemmTcPlan* plan = gemm_tc_plan_create(g, e->mode == CAPB200_MODE_TC_F16X3 ? 3 : 1);
-                rc = plan ? gemm_tc_plan_launch(plan, nullptr, 0, 0, 0, st) : 1;
+                rc = plan ? gemm_tc_plan_launch(plan, nullptr, 0, st) : 1;
                 if (plan) gemm_tc_plan_destroy(plan);
             }
         }
@@ -693,6 +729,7 @@ int capb200_decode_beam(capb200_engine* e, const float* fc, const float* att, co
         va.rows = nrows; va.V1 = V1; va.logits = logits; va.ld = V1;
         va.twice = (t > 0) ? 1 : 0;      // init_logprobs went through one log_softmax only (AttModel.py:239, CaptionModel.py:204)
         va.topk = beam; va.top_val = e->top_val; va.top_idx = e->top_idx;
+        va.stats = e->slab_stats + (long)t * rows;
         e->launches++;
         if (vocab_step_launch(va, st)) return 1;
         e->launches++;
@@ -705,14 +742,14 @@ int capb200_decode_beam(capb200_engine* e, const float* fc, const float* att, co
         CAPB_CHECK_CUDA(cudaMemcpyAsync(seq, e->rec_seq, sizeof(long long) * B * beam * T, cudaMemcpyDeviceToDevice, st));
         if (seq_logprobs) {
             e->launches++;
-            if (gather_logprob_rows_launch(e->slab, e->slab_step_stride, V1, e->rec_hist, B * beam, T, V1, seq_logprobs, st)) return 1;
+            if (gather_logprob_rows_launch(e->slab, e->slab_step_stride, V1, e->rec_hist, B * beam, T, V1, seq_logprobs, e->slab_stats, rows, st)) return 1;
         }
     } else {
         e->launches++;
         if (beam_finalize_launch(s, 1, seq, e->tmp_len, e->tmp_p, e->tmp_raw, e->out_hist, st)) return 1;
         if (seq_logprobs) {
             e->launches++;
-            if (gather_logprob_rows_launch(e->slab, e->slab_step_stride, V1, e->out_hist, B, T, V1, seq_logprobs, st)) return 1;
+            if (gather_logprob_rows_launch(e->slab, e->slab_step_stride, V1, e->out_hist, B, T, V1, seq_logprobs, e->slab_stats, rows, st)) return 1;
         }
     }
     if (done_seq) CAPB_CHECK_CUDA(cudaMemcpyAsync(done_seq, e->rec_seq, sizeof(long long) * B * beam * T, cudaMemcpyDeviceToDevice, st));
@@ -728,7 +765,7 @@ int capb200_beam_record_logprobs(capb200_engine* e, int image, int rank, float* 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     e->launches++;
     return gather_logprob_rows_launch(e->slab, e->slab_step_stride, e->V1, e->rec_hist + ((long)image * e->last_beam + rank) * e->T, 1, e->T, e->V1,
-                                      dst, st);
+                                      dst, e->slab_stats, (long)e->last_B * e->last_beam, st);
 }
 
 int capb200_decode_sample(capb200_engine* e, const float* fc, const float* att, const float* mask, int B, int R, const capb200_sample_opts* opts,
@@ -812,7 +849,7 @@ int capb200_linear(const float* x, long ldx, const float* w, long ldw, const flo
     g.seg[0].W_hi = wh; g.seg[0].W_lo = wl; g.seg[0].ldw_h = ldh;
     GemmTcPlan* plan = rc ? nullptr : gemm_tc_plan_create(g, mode == CAPB200_MODE_TC_F16X3 ? 3 : 1);
     if (plan == nullptr) rc = 1;
-    if (!rc) rc = gemm_tc_plan_launch(plan, nullptr, 0, 0, 0, st);
+    if (!rc) rc = gemm_tc_plan_launch(plan, nullptr, 0, st);
     if (plan) gemm_tc_plan_destroy(plan);
     cudaFreeAsync(scratch, st);
     return rc;
@@ -845,7 +882,7 @@ int capb200_bench_linear(const float* x, const float* w, const float* b, float* 
     cudaEventCreate(&e1);
     for (int i = 0; i < 3 + iters && !rc; ++i) {
         if (i == 3) cudaEventRecord(e0, st);
-        rc = plan ? gemm_tc_plan_launch(plan, nullptr, 0, 0, 0, st) : gemm_simt_launch(g, st);
+        rc = plan ? gemm_tc_plan_launch(plan, nullptr, 0, st) : gemm_simt_launch(g, st);
     }
     cudaEventRecord(e1, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("bench_linear: ") + cudaGetErrorString(cudaGetLastError())); rc = 1; }

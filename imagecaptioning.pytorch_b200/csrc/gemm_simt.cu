@@ -137,10 +137,34 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long ldx, int r
     }
 }
 
+__global__ void split_planes_interleave_kernel(const float* __restrict__ x, long ldx, int H, int cols, __half* __restrict__ hi,
+                                               __half* __restrict__ lo, long ldh) {
+    const long total = (long)4 * H * cols;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int rd = (int)(i / cols), c = (int)(i % cols);          // destination row 4*j+g
+        const int j = rd >> 2, g = rd & 3;
+        __half h, l;
+        split_f32(__ldg(x + (long)(g * H + j) * ldx + c), h, l);
+        hi[(long)rd * ldh + c] = h;
+        lo[(long)rd * ldh + c] = l;
+    }
+}
+
 }  // namespace
+
+int split_planes_interleave_launch(const float* x, long ldx, int H, int cols, __half* hi, __half* lo, long ldh, cudaStream_t stream) {
+    const long total = (long)4 * H * cols;
+    if (total <= 0) return 0;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    split_planes_interleave_kernel<<<blocks, 256, 0, stream>>>(x, ldx, H, cols, hi, lo, ldh);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int gemm_simt_launch(const GemmProblem& g, cudaStream_t stream) {
     CAPB_REQUIRE(g.nseg >= 1 && g.nseg <= kMaxSeg, "1..3 K-segments");
+    CAPB_REQUIRE(g.epi.lstm == 0, "the fused LSTM epilogue exists on the tensor-core path only");
     if (g.M <= 0 || g.N <= 0) return 0;
     SimtParams p;
     memset(&p, 0, sizeof(p));

@@ -48,6 +48,21 @@ struct TcParams {
     long ld_row_bias;
     int rows_per_group;
     int relu;
+    int tiles_m, tiles_n;       // CTA tiles, padded to whole clusters
+    // fused LSTM epilogue (see GemmEpilogue)
+    int lstm, H;
+    const float* c_prev;
+    long ld_cprev;
+    const int* src_row;
+    float* c_out;
+    long ld_cout;
+    const float* gather_bias;
+    long ld_gb;
+    const int* gather_idx;
+    float* h_f;
+    __half* h_hi;
+    __half* h_lo;
+    long ld_h;
 };
 
 template <int BN, int PASSES>
@@ -58,7 +73,7 @@ struct TcCfg {
     static constexpr uint32_t kStageBytes = kPlanes * (kABytes + kWBytes);
     static constexpr int kStages = (206 * 1024) / kStageBytes >= 8 ? 8 : (206 * 1024) / kStageBytes;
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    static constexpr uint32_t kTmemCols = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // two accumulators
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16, 256]");
     static_assert(kWBytes % 1024 == 0, "operand tiles must keep the 1024-byte swizzle-atom alignment");
     static_assert(kStages >= 2, "need at least a double buffer");
@@ -77,17 +92,21 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
     uint64_t* empty_bar = full_bar + Cfg::kStages;
-    uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;        // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;              // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM;
-    const int n0 = blockIdx.x * BN;
-    // position inside the cluster (cluster dims = (CX, CY, 1): rank = x + CX * y)
-    const uint32_t cx = kCluster ? ptx::cluster_ctaid_x() : 0;
-    const uint32_t cy = kCluster ? ptx::cluster_ctaid_y() : 0;
-    uint16_t mask_a = 0, mask_w = 0;          // CTAs that receive my A slice / my W slice
+    // Persistent schedule: gridDim = (CX * P, CY); cluster c walks cluster-tiles c, c + P, ... in n-major order so that
+    // concurrently running clusters share the same weight columns (W tile comes from HBM once, then from L2).
+    const uint32_t cx = blockIdx.x % CX;
+    const uint32_t cy = blockIdx.y;
+    const int cluster_id = blockIdx.x / CX;
+    const int num_clusters = gridDim.x / CX;
+    const int cl_m = p.tiles_m / CY;
+    const int n_ctiles = (p.tiles_n / CX) * cl_m;
+    uint16_t mask_a = 0, mask_w = 0;          // CTAs that receive my A slice / my W slice (cluster rank = x + CX * y)
     if (kCluster) {
         for (int x = 0; x < CX; ++x) mask_a |= static_cast<uint16_t>(1u << (x + CX * cy));
         for (int y = 0; y < CY; ++y) mask_w |= static_cast<uint16_t>(1u << (cx + CX * y));
@@ -108,7 +127,10 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             ptx::mbar_init(&full_bar[i], 1);
             ptx::mbar_init(&empty_bar[i], CX + CY - 1);      // one release per CTA that writes into this slot
         }
-        ptx::mbar_init(tmem_full_bar, 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tmem_full_bar[i], 1);
+            ptx::mbar_init(&tmem_empty_bar[i], 128);         // every epilogue thread releases the accumulator
+        }
         ptx::fence_mbar_init();
     }
     if (warp == 2) {
@@ -130,31 +152,35 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int s = 0; s < p.nseg; ++s) {
-                for (int kb = 0; kb < p.kblocks[s]; ++kb) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* st = smem + stage * Cfg::kStageBytes;
-                    uint8_t* a_hi = st + cx * kASlice;
-                    uint8_t* a_lo = st + Cfg::kABytes + cx * kASlice;
-                    uint8_t* w_hi = st + Cfg::kABytes * Cfg::kPlanes + cy * kWSlice;
-                    uint8_t* w_lo = st + Cfg::kABytes * 2 + Cfg::kWBytes + cy * kWSlice;
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                    if (kCluster) {
-                        ptx::tma_load_2d_mcast(a_hi, &p.a_hi[s], &full_bar[stage], kb * BK, m0 + cx * kARows, mask_a);
-                        ptx::tma_load_2d_mcast(w_hi, &p.w_hi[s], &full_bar[stage], kb * BK, n0 + cy * kWRows, mask_w);
-                        if (PASSES == 3) {
-                            ptx::tma_load_2d_mcast(a_lo, &p.a_lo[s], &full_bar[stage], kb * BK, m0 + cx * kARows, mask_a);
-                            ptx::tma_load_2d_mcast(w_lo, &p.w_lo[s], &full_bar[stage], kb * BK, n0 + cy * kWRows, mask_w);
+            for (int ct = cluster_id; ct < n_ctiles; ct += num_clusters) {
+                const int m0 = ((ct % cl_m) * CY + cy) * BM;
+                const int n0 = ((ct / cl_m) * CX + cx) * BN;
+                for (int s = 0; s < p.nseg; ++s) {
+                    for (int kb = 0; kb < p.kblocks[s]; ++kb) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* st = smem + stage * Cfg::kStageBytes;
+                        uint8_t* a_hi = st + cx * kASlice;
+                        uint8_t* a_lo = st + Cfg::kABytes + cx * kASlice;
+                        uint8_t* w_hi = st + Cfg::kABytes * Cfg::kPlanes + cy * kWSlice;
+                        uint8_t* w_lo = st + Cfg::kABytes * 2 + Cfg::kWBytes + cy * kWSlice;
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                        if (kCluster) {
+                            ptx::tma_load_2d_mcast(a_hi, &p.a_hi[s], &full_bar[stage], kb * BK, m0 + cx * kARows, mask_a);
+                            ptx::tma_load_2d_mcast(w_hi, &p.w_hi[s], &full_bar[stage], kb * BK, n0 + cy * kWRows, mask_w);
+                            if (PASSES == 3) {
+                                ptx::tma_load_2d_mcast(a_lo, &p.a_lo[s], &full_bar[stage], kb * BK, m0 + cx * kARows, mask_a);
+                                ptx::tma_load_2d_mcast(w_lo, &p.w_lo[s], &full_bar[stage], kb * BK, n0 + cy * kWRows, mask_w);
+                            }
+                        } else {
+                            ptx::tma_load_2d(a_hi, &p.a_hi[s], &full_bar[stage], kb * BK, m0);
+                            ptx::tma_load_2d(w_hi, &p.w_hi[s], &full_bar[stage], kb * BK, n0);
+                            if (PASSES == 3) {
+                                ptx::tma_load_2d(a_lo, &p.a_lo[s], &full_bar[stage], kb * BK, m0);
+                                ptx::tma_load_2d(w_lo, &p.w_lo[s], &full_bar[stage], kb * BK, n0);
+                            }
                         }
-                    } else {
-                        ptx::tma_load_2d(a_hi, &p.a_hi[s], &full_bar[stage], kb * BK, m0);
-                        ptx::tma_load_2d(w_hi, &p.w_hi[s], &full_bar[stage], kb * BK, n0);
-                        if (PASSES == 3) {
-                            ptx::tma_load_2d(a_lo, &p.a_lo[s], &full_bar[stage], kb * BK, m0);
-                            ptx::tma_load_2d(w_lo, &p.w_lo[s], &full_bar[stage], kb * BK, n0);
-                        }
+                        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                     }
-                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -164,99 +190,160 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             const uint16_t release_mask = static_cast<uint16_t>(mask_a | mask_w);
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t accumulate = 0;
-            for (int s = 0; s < p.nseg; ++s) {
-                for (int kb = 0; kb < p.kblocks[s]; ++kb) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
-                    ptx::tc_fence_after_sync();
-                    const uint32_t st = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
-                    const uint32_t a_hi = st;
-                    const uint32_t a_lo = st + Cfg::kABytes;                          // only valid when PASSES == 3
-                    const uint32_t w_hi = st + Cfg::kABytes * Cfg::kPlanes;
-                    const uint32_t w_lo = st + Cfg::kABytes * 2 + Cfg::kWBytes;       // only valid when PASSES == 3
+            int it = 0;
+            for (int ct = cluster_id; ct < n_ctiles; ct += num_clusters, ++it) {
+                const int buf = it & 1;
+                ptx::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);       // epilogue drained this accumulator
+                ptx::tc_fence_after_sync();
+                const uint32_t tmem_d = tmem_base + buf * BN;
+                uint32_t accumulate = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    for (int kb = 0; kb < p.kblocks[s]; ++kb) {
+                        ptx::mbar_wait(&full_bar[stage], phase);
+                        ptx::tc_fence_after_sync();
+                        const uint32_t st = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+                        const uint32_t a_hi = st;
+                        const uint32_t a_lo = st + Cfg::kABytes;                          // only valid when PASSES == 3
+                        const uint32_t w_hi = st + Cfg::kABytes * Cfg::kPlanes;
+                        const uint32_t w_lo = st + Cfg::kABytes * 2 + Cfg::kWBytes;       // only valid when PASSES == 3
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint32_t koff = k * 32;   // 16 fp16 = 32 bytes inside the 128-byte swizzle row
-                        if (PASSES == 3) {
-                            ptx::umma_f16(tmem_base, ptx::make_smem_desc_sw128(a_hi + koff), ptx::make_smem_desc_sw128(w_lo + koff), idesc, accumulate);
-                            ptx::umma_f16(tmem_base, ptx::make_smem_desc_sw128(a_lo + koff), ptx::make_smem_desc_sw128(w_hi + koff), idesc, 1);
-                            ptx::umma_f16(tmem_base, ptx::make_smem_desc_sw128(a_hi + koff), ptx::make_smem_desc_sw128(w_hi + koff), idesc, 1);
-                        } else {
-                            ptx::umma_f16(tmem_base, ptx::make_smem_desc_sw128(a_hi + koff), ptx::make_smem_desc_sw128(w_hi + koff), idesc, accumulate);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint32_t koff = k * 32;   // 16 fp16 = 32 bytes inside the 128-byte swizzle row
+                            if (PASSES == 3) {
+                                ptx::umma_f16(tmem_d, ptx::make_smem_desc_sw128(a_hi + koff), ptx::make_smem_desc_sw128(w_lo + koff), idesc, accumulate);
+                                ptx::umma_f16(tmem_d, ptx::make_smem_desc_sw128(a_lo + koff), ptx::make_smem_desc_sw128(w_hi + koff), idesc, 1);
+                                ptx::umma_f16(tmem_d, ptx::make_smem_desc_sw128(a_hi + koff), ptx::make_smem_desc_sw128(w_hi + koff), idesc, 1);
+                            } else {
+                                ptx::umma_f16(tmem_d, ptx::make_smem_desc_sw128(a_hi + koff), ptx::make_smem_desc_sw128(w_hi + koff), idesc, accumulate);
+                            }
+                            accumulate = 1;
                         }
-                        accumulate = 1;
+                        if (kCluster) ptx::umma_commit_mcast(&empty_bar[stage], release_mask);
+                        else ptx::umma_commit(&empty_bar[stage]);
+                        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                     }
-                    if (kCluster) ptx::umma_commit_mcast(&empty_bar[stage], release_mask);
-                    else ptx::umma_commit(&empty_bar[stage]);
-                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
+                ptx::umma_commit(&tmem_full_bar[buf]);
             }
-            ptx::umma_commit(tmem_full_bar);
         }
     } else if (warp >= 4) {
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read
-        const int row = m0 + q * 32 + lane;
-        ptx::mbar_wait(tmem_full_bar, 0);
-        ptx::tc_fence_after_sync();
-        const bool row_ok = row < p.M;
-        const float* rb = (p.row_bias != nullptr && row_ok) ? p.row_bias + (long)(row / p.rows_per_group) * p.ld_row_bias : nullptr;
         const bool vec4 = p.C != nullptr && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
         const bool vec2h = p.C_hi != nullptr && (p.ldcs & 7) == 0 && (reinterpret_cast<uintptr_t>(p.C_hi) & 15) == 0 &&
                            (reinterpret_cast<uintptr_t>(p.C_lo) & 15) == 0;
+        const bool lstm_vec = p.lstm && (p.ld_cout & 3) == 0 && (p.ld_h & 3) == 0;
+        int it = 0;
+        for (int ct = cluster_id; ct < n_ctiles; ct += num_clusters, ++it) {
+            const int buf = it & 1;
+            const int m0 = ((ct % cl_m) * CY + cy) * BM;
+            const int n0 = ((ct / cl_m) * CX + cx) * BN;
+            const int row = m0 + q * 32 + lane;
+            ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+            ptx::tc_fence_after_sync();
+            const bool row_ok = row < p.M;
+            const float* rb = (p.row_bias != nullptr && row_ok) ? p.row_bias + (long)(row / p.rows_per_group) * p.ld_row_bias : nullptr;
+            const float* gb = (p.gather_bias != nullptr && row_ok) ? p.gather_bias + (long)p.gather_idx[row] * p.ld_gb : nullptr;
+            int src = row;
+            if (p.lstm && row_ok && p.src_row != nullptr) src = p.src_row[row];
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            uint32_t r[16];
-            __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the guarded stores of the previous chunk
-            ptx::tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
-            ptx::tmem_ld_wait();
-            const int col0 = n0 + c0;
-            if (!row_ok || col0 >= p.N) continue;
-            float v[16];
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t r[16];
+                __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the guarded stores of the previous chunk
+                ptx::tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c0, r);
+                ptx::tmem_ld_wait();
+                const int col0 = n0 + c0;
+                if (!row_ok || col0 >= p.N) continue;
+                float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int col = col0 + j;
-                float x = __uint_as_float(r[j]);
-                if (col < p.N) {
-                    if (p.bias != nullptr) x += __ldg(p.bias + col);
-                    if (rb != nullptr) x += __ldg(rb + col);
-                    if (p.relu) x = fmaxf(x, 0.0f);
-                }
-                v[j] = x;
-            }
-            const bool full = col0 + 16 <= p.N;
-            if (p.C != nullptr) {
-                float* dst = p.C + (long)row * p.ldc + col0;
-                if (full && vec4) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-                    for (int j = 0; j < 16; ++j) if (col0 + j < p.N) dst[j] = v[j];
-                }
-            }
-            if (p.C_hi != nullptr) {
-                __half* dh = p.C_hi + (long)row * p.ldcs + col0;
-                __half* dl = p.C_lo + (long)row * p.ldcs + col0;
-                if (full && vec2h) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 8) {
-                        __align__(16) __half h[8];
-                        __align__(16) __half l[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) split_f32(v[j + u], h[u], l[u]);
-                        *reinterpret_cast<uint4*>(dh + j) = *reinterpret_cast<const uint4*>(h);
-                        *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(l);
+                for (int j = 0; j < 16; ++j) {
+                    const int col = col0 + j;
+                    float x = __uint_as_float(r[j]);
+                    if (col < p.N) {
+                        if (p.bias != nullptr) x += __ldg(p.bias + col);
+                        if (rb != nullptr) x += __ldg(rb + col);
+                        if (gb != nullptr) x += __ldg(gb + col);
+                        if (p.relu) x = fmaxf(x, 0.0f);
                     }
-                } else {
-                    for (int j = 0; j < 16; ++j) {
-                        if (col0 + j < p.N) {
-                            __half h, l;
-                            split_f32(v[j], h, l);
-                            dh[j] = h;
-                            dl[j] = l;
+                    v[j] = x;
+                }
+                if (p.lstm) {
+                    // columns col0 .. col0+15 = hidden units u0 .. u0+3, gates (i,f,g,o) interleaved
+                    const int u0 = col0 >> 2;
+                    float cn[4], hn[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int unit = u0 + u;
+                        float cp = 0.f;
+                        if (unit < p.H && src >= 0 && p.c_prev != nullptr) cp = p.c_prev[(long)src * p.ld_cprev + unit];
+                        cn[u] = fast_sigmoid(v[4 * u + 1]) * cp + fast_sigmoid(v[4 * u]) * fast_tanh(v[4 * u + 2]);
+                        hn[u] = fast_sigmoid(v[4 * u + 3]) * fast_tanh(cn[u]);
+                    }
+                    if (lstm_vec && u0 + 4 <= p.H) {
+                        *reinterpret_cast<float4*>(p.c_out + (long)row * p.ld_cout + u0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                        *reinterpret_cast<float4*>(p.h_f + (long)row * p.ld_h + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                        if (p.h_hi != nullptr) {
+                            __align__(8) __half h[4];
+                            __align__(8) __half l[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) split_f32(hn[u], h[u], l[u]);
+                            *reinterpret_cast<uint2*>(p.h_hi + (long)row * p.ld_h + u0) = *reinterpret_cast<const uint2*>(h);
+                            *reinterpret_cast<uint2*>(p.h_lo + (long)row * p.ld_h + u0) = *reinterpret_cast<const uint2*>(l);
+                        }
+                    } else {
+                        for (int u = 0; u < 4; ++u) {
+                            const int unit = u0 + u;
+                            if (unit < p.H) {
+                                p.c_out[(long)row * p.ld_cout + unit] = cn[u];
+                                p.h_f[(long)row * p.ld_h + unit] = hn[u];
+                                if (p.h_hi != nullptr) {
+                                    __half h, l;
+                                    split_f32(hn[u], h, l);
+                                    p.h_hi[(long)row * p.ld_h + unit] = h;
+                                    p.h_lo[(long)row * p.ld_h + unit] = l;
+                                }
+                            }
+                        }
+                    }
+                    continue;
+                }
+                const bool full = col0 + 16 <= p.N;
+                if (p.C != nullptr) {
+                    float* dst = p.C + (long)row * p.ldc + col0;
+                    if (full && vec4) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+                        for (int j = 0; j < 16; ++j) if (col0 + j < p.N) dst[j] = v[j];
+                    }
+                }
+                if (p.C_hi != nullptr) {
+                    __half* dh = p.C_hi + (long)row * p.ldcs + col0;
+                    __half* dl = p.C_lo + (long)row * p.ldcs + col0;
+                    if (full && vec2h) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 8) {
+                            __align__(16) __half h[8];
+                            __align__(16) __half l[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) split_f32(v[j + u], h[u], l[u]);
+                            *reinterpret_cast<uint4*>(dh + j) = *reinterpret_cast<const uint4*>(h);
+                            *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(l);
+                        }
+                    } else {
+                        for (int j = 0; j < 16; ++j) {
+                            if (col0 + j < p.N) {
+                                __half h, l;
+                                split_f32(v[j], h, l);
+                                dh[j] = h;
+                                dl[j] = l;
+                            }
                         }
                     }
                 }
             }
+            __syncwarp();
+            ptx::tc_fence_before_sync();
+            ptx::mbar_arrive(&tmem_empty_bar[buf]);            // accumulator drained: the MMA warp may reuse it
         }
     }
     ptx::tc_fence_before_sync();
@@ -309,7 +396,13 @@ int launch_cfg(const TcParams& prm, cudaStream_t stream) {
     }
     // grid padded to whole clusters; CTAs outside the matrix still run the pipeline (their TMA boxes are zero-filled) so
     // that their cluster peers receive the multicast slices they wait for
-    dim3 grid(round_up(cdiv(prm.N, BN), CX), round_up(cdiv(prm.M, BM), CY));
+    TcParams prm2 = prm;
+    prm2.tiles_n = (int)round_up(cdiv(prm.N, BN), CX);
+    prm2.tiles_m = (int)round_up(cdiv(prm.M, BM), CY);
+    const int n_ctiles = (prm2.tiles_n / CX) * (prm2.tiles_m / CY);
+    const int slots = (CX * CY == 4) ? 33 : 148 / (CX * CY);          // clusters resident at once
+    const int P = n_ctiles < slots ? n_ctiles : slots;
+    dim3 grid(CX * P, CY);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(256);
@@ -322,7 +415,7 @@ int launch_cfg(const TcParams& prm, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (CX * CY > 1) ? 1 : 0;
-    CAPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PASSES, CX, CY>, prm));
+    CAPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PASSES, CX, CY>, prm2));
     return 0;
 }
 
@@ -346,6 +439,19 @@ struct GemmTcPlan {
     int bn;
     int cx, cy;       // cluster shape (multicast of A across cx CTAs, of W across cy CTAs)
 };
+
+static void fill_epilogue(TcParams& t, const GemmEpilogue& e) {
+    t.C = e.C; t.ldc = e.ldc;
+    t.C_hi = e.C_hi; t.C_lo = e.C_lo; t.ldcs = e.ldcs;
+    t.bias = e.bias; t.row_bias = e.row_bias; t.ld_row_bias = e.ld_row_bias;
+    t.rows_per_group = e.rows_per_group < 1 ? 1 : e.rows_per_group;
+    t.relu = e.relu;
+    t.lstm = e.lstm; t.H = e.H;
+    t.c_prev = e.c_prev; t.ld_cprev = e.ld_cprev; t.src_row = e.src_row;
+    t.c_out = e.c_out; t.ld_cout = e.ld_cout;
+    t.gather_bias = e.gather_bias; t.ld_gb = e.ld_gb; t.gather_idx = e.gather_idx;
+    t.h_f = e.h_f; t.h_hi = e.h_hi; t.h_lo = e.h_lo; t.ld_h = e.ld_h;
+}
 
 bool gemm_tc_supported(const GemmProblem& p, std::string* why) {
     auto bad = [&](const char* m) { if (why) *why = m; return false; };
@@ -408,26 +514,23 @@ GemmTcPlan* gemm_tc_plan_create(const GemmProblem& p, int passes) {
         }
         if (!ok) { set_error("gemm_tc: " + err); delete plan; return nullptr; }
     }
-    t.C = p.epi.C; t.ldc = p.epi.ldc;
-    t.C_hi = p.epi.C_hi; t.C_lo = p.epi.C_lo; t.ldcs = p.epi.ldcs;
-    t.bias = p.epi.bias; t.row_bias = p.epi.row_bias; t.ld_row_bias = p.epi.ld_row_bias;
-    t.rows_per_group = p.epi.rows_per_group < 1 ? 1 : p.epi.rows_per_group;
-    t.relu = p.epi.relu;
+    fill_epilogue(t, p.epi);
     return plan;
 }
 
 void gemm_tc_plan_destroy(GemmTcPlan* plan) { delete plan; }
 
-int gemm_tc_plan_launch(GemmTcPlan* plan, float* C_override, long ldc_override, int M_override, int rows_per_group_override,
-                        cudaStream_t stream) {
+int gemm_tc_plan_launch(GemmTcPlan* plan, const GemmEpilogue* epi_override, int M_override, cudaStream_t stream) {
     TcParams prm = plan->prm;
-    if (C_override != nullptr) prm.C = C_override;
-    if (ldc_override > 0) prm.ldc = ldc_override;
+    if (epi_override != nullptr) fill_epilogue(prm, *epi_override);
     if (M_override > 0) {
         if (M_override > prm.M) { set_error("gemm_tc: M override exceeds the planned row count"); return 1; }
         prm.M = M_override;
     }
-    if (rows_per_group_override > 0) prm.rows_per_group = rows_per_group_override;
+    if (prm.lstm && (prm.N != 4 * prm.H || prm.c_out == nullptr || prm.h_f == nullptr)) {
+        set_error("gemm_tc: fused LSTM epilogue needs N == 4H, c_out and h_f");
+        return 1;
+    }
     if (prm.M <= 0 || prm.N <= 0) return 0;
     const int key = plan->bn * 100 + plan->cx * 10 + plan->cy;
 #define CAPB_TC_CASE(BN_, CX_, CY_)                                                      \

@@ -40,6 +40,7 @@ struct VocabStepArgs {
     float* logits = nullptr;      // [rows, V1] in/out: overwritten with log-probs (pitch ld)
     long ld = 0;
     int twice = 0;                // beam search renormalises the log-probs a second time (CaptionModel.py:204)
+    float2* stats = nullptr;      // beam search: keep the raw logits in place and write (max, log-sum-exp) per row here instead
     // top-k output for beam search (k <= 16)
     int topk = 0;
     float* top_val = nullptr;     // [rows, topk]
@@ -85,8 +86,10 @@ int beam_step_launch(const BeamState& s, int t, int live, const float* top_val, 
 int beam_finalize_launch(const BeamState& s, int keep, long long* out_seq, int* out_len, float* out_p, float* out_raw, int* out_hist,
                          cudaStream_t stream);
 // dst[k, s, :] = slab[s][hist[k, s], :] (zeros where hist < 0); slab step stride `step_stride` elements
+// `stats` (optional): the slab holds raw logits and stats[s * stats_stride + row] = (max, log-sum-exp); rows are normalised on the fly
+// (log_softmax once at s == 0, twice afterwards, exactly as the search scored them).
 int gather_logprob_rows_launch(const float* slab, long step_stride, long ld_slab, const int* hist, int nseq, int T, int V1, float* dst,
-                               cudaStream_t stream);
+                               const float2* stats, long stats_stride, cudaStream_t stream);
 
 // ---- reward.cu (CIDEr-D) and criterion
 struct CiderTable;   // device hash table of n-gram -> idf

@@ -19,12 +19,7 @@ static int pw_blocks(long total) {
 
 namespace {
 
-// SFU-based transcendental forms (ex2.approx + fast reciprocal): absolute error < 3e-7 on outputs in [-1, 1], far below the 1e-4 bar.
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) {
-    const float e = __expf(2.0f * x);
-    return 1.0f - __fdividef(2.0f, 1.0f + e);
-}
+__device__ __forceinline__ float sigmoidf_(float x) { return fast_sigmoid(x); }
 
 __device__ __forceinline__ void store_act(const ActView& o, long row, int col, float v) {
     o.f[row * o.ld + col] = v;
@@ -107,52 +102,54 @@ __global__ void maxout_pointwise_kernel(int rows, int H, const float* __restrict
 //                       out[row, c] = sum_r a[row, r] * att[img, r, c].
 // tanh is evaluated as 1 - 2 / (1 + exp(2x)) on the SFU (ex2.approx): absolute error < 3e-7, far below the 1e-4 log-prob bar.
 constexpr int ATT_JB = 5;       // rows handled per pass (beam 5 = one pass)
-constexpr int ATT_AMAX = 32;    // att_hid_size up to 32 * 32 = 1024 per lane-register tile
 constexpr int ATT_SW = 8;       // warps (= regions) per CTA
 // grid = (ceil(R / 8), B): the CTA stages the image's att_h rows in shared memory once (coalesced), then each warp scores one region.
+// NA = ceil(A / 32) rounded up to a power of two is a template parameter so the inner loops are branch-free and the
+// independent tanh chains of different k overlap (the runtime-bound version serialised them: 61 us -> see profiles/).
+template <int NA>
 __global__ void __launch_bounds__(ATT_SW * 32) att_score_kernel(int rpi, int R, int A, const float* __restrict__ att_h, long ld_ah,
                                                                 const float* __restrict__ p_att, long ld_pa, const float* __restrict__ alpha_w,
                                                                 const float* __restrict__ alpha_b_ptr, float* __restrict__ score) {
-    extern __shared__ float s_ah[];               // [ATT_JB][A]
+    extern __shared__ float s_ah[];               // [ATT_JB][NA * 32] (zero padded beyond A)
+    constexpr int AP = NA * 32;
     const int img = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * ATT_SW + warp;
     const float alpha_b = __ldg(alpha_b_ptr);
-    float pv[ATT_AMAX], wv[ATT_AMAX];
-    const int na = (A + 31) / 32;
-    if (r < R) {
-        const float* pr = p_att + ((long)img * R + r) * ld_pa;
+    float pv[NA], wv[NA];
+    const bool live = r < R;
+    const float* pr = p_att + ((long)img * R + (live ? r : 0)) * ld_pa;
 #pragma unroll
-        for (int k = 0; k < ATT_AMAX; ++k) {
-            const int a = lane + 32 * k;
-            const bool ok = (k < na) && (a < A);
-            pv[k] = ok ? __ldg(pr + a) : 0.f;
-            wv[k] = ok ? __ldg(alpha_w + a) : 0.f;      // zero weight kills padded lanes
-        }
+    for (int k = 0; k < NA; ++k) {
+        const int a = lane + 32 * k;
+        const bool ok = live && (a < A);
+        pv[k] = ok ? __ldg(pr + a) : 0.f;
+        wv[k] = ok ? __ldg(alpha_w + a) : 0.f;      // zero weight kills padded lanes
     }
     for (int j0 = 0; j0 < rpi; j0 += ATT_JB) {
         const int nj = min(ATT_JB, rpi - j0);
         __syncthreads();
-        for (int i = threadIdx.x; i < nj * A; i += ATT_SW * 32) {
-            const int j = i / A, a = i - j * A;
-            s_ah[j * A + a] = att_h[((long)img * rpi + j0 + j) * ld_ah + a];
+        for (int i = threadIdx.x; i < nj * AP; i += ATT_SW * 32) {
+            const int j = i / AP, a = i - j * AP;
+            s_ah[i] = (a < A) ? att_h[((long)img * rpi + j0 + j) * ld_ah + a] : 0.f;
         }
         __syncthreads();
-        if (r < R) {
-            for (int j = 0; j < nj; ++j) {
-                const float* ah = s_ah + j * A;
-                float part = 0.f;
+        if (live) {
+            float part[ATT_JB];
 #pragma unroll
-                for (int k = 0; k < ATT_AMAX; ++k) {
-                    if (k < na) {
-                        const int a = lane + 32 * k;
-                        const float hv = (a < A) ? ah[a] : 0.f;
-                        part = fmaf(wv[k], fast_tanh(pv[k] + hv), part);
-                    }
+            for (int j = 0; j < ATT_JB; ++j) {
+                part[j] = 0.f;
+                if (j < nj) {
+#pragma unroll
+                    for (int k = 0; k < NA; ++k) part[j] = fmaf(wv[k], fast_tanh(pv[k] + s_ah[j * AP + lane + 32 * k]), part[j]);
                 }
+            }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                if (lane == 0) score[((long)img * rpi + j0 + j) * R + r] = part + alpha_b;
+            for (int j = 0; j < ATT_JB; ++j) {
+                float v = part[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && j < nj) score[((long)img * rpi + j0 + j) * R + r] = v + alpha_b;
             }
         }
     }
@@ -258,11 +255,19 @@ int additive_attention_launch(int n_images, int rpi, int R, int A, int H, const 
                               const float* att, long ld_at, const float* mask, long ld_mask, const float* alpha_w, const float* alpha_b,
                               float* score_scratch, ActView out, cudaStream_t stream) {
     if (n_images <= 0 || rpi <= 0) return 0;
-    CAPB_REQUIRE(A <= 32 * ATT_AMAX, "attention: att_hid_size above 1024");
+    CAPB_REQUIRE(A <= 1024, "attention: att_hid_size above 1024");
     CAPB_REQUIRE(score_scratch != nullptr, "attention: score scratch missing");
-    const size_t smem_s = sizeof(float) * (size_t)ATT_JB * A;
     dim3 sgrid(cdiv(R, ATT_SW), n_images);
-    att_score_kernel<<<sgrid, ATT_SW * 32, smem_s, stream>>>(rpi, R, A, att_h, ld_ah, p_att, ld_pa, alpha_w, alpha_b, score_scratch);
+    const int na = cdiv(A, 32);
+#define CAPB_ATT_CASE(NA_)                                                                                                             \
+    att_score_kernel<NA_><<<sgrid, ATT_SW * 32, sizeof(float) * ATT_JB * NA_ * 32, stream>>>(rpi, R, A, att_h, ld_ah, p_att, ld_pa, alpha_w, \
+                                                                                               alpha_b, score_scratch)
+    if (na <= 2) CAPB_ATT_CASE(2);
+    else if (na <= 4) CAPB_ATT_CASE(4);
+    else if (na <= 8) CAPB_ATT_CASE(8);
+    else if (na <= 16) CAPB_ATT_CASE(16);
+    else CAPB_ATT_CASE(32);
+#undef CAPB_ATT_CASE
     CAPB_CHECK_CUDA(cudaGetLastError());
     const size_t smem = sizeof(float) * (size_t)ATT_JB * R;
     CAPB_REQUIRE(smem <= 48 * 1024, "attention: too many regions");

@@ -180,6 +180,72 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
     }
 }
 
+// Beam-search variant: the raw logits stay where the GEMM wrote them (they are normalised lazily, only for the rows that end up in
+// the output); this kernel streams each row twice from L2 (max, then sum-exp + per-thread top-k) and writes only the row statistics
+// and the top-k candidates.  Halves the HBM traffic of the step's vocabulary epilogue.
+template <int KMAX>
+__global__ void __launch_bounds__(VT) vocab_stats_kernel(const VocabStepArgs a) {
+    __shared__ float s_red[VT / 32];
+    __shared__ int s_idx[VT / 32];
+    const int r = blockIdx.x;
+    const int V1 = a.V1;
+    const float* g = a.logits + (long)r * a.ld;
+    const bool vec = ((V1 & 3) == 0) && ((a.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.logits) & 15) == 0);
+    float mx = -INFINITY;
+    if (vec) {
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        for (int v = threadIdx.x; v < V1 / 4; v += VT) { const float4 x = g4[v]; mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w))); }
+    } else {
+        for (int v = threadIdx.x; v < V1; v += VT) mx = fmaxf(mx, g[v]);
+    }
+    mx = block_max(mx, s_red);
+    float tv[KMAX];
+    int ti[KMAX];
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q) { tv[q] = -INFINITY; ti[q] = 0x7fffffff; }
+    float sum = 0.f;
+    auto visit = [&](float x, int v) {
+        sum += __expf(x - mx);
+        if (x > tv[KMAX - 1]) {
+            float cv = x;
+            int ci = v;
+#pragma unroll
+            for (int q = 0; q < KMAX; ++q) {
+                if (cv > tv[q]) { const float t0 = tv[q]; const int t1 = ti[q]; tv[q] = cv; ti[q] = ci; cv = t0; ci = t1; }
+            }
+        }
+    };
+    if (vec) {
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        for (int v = threadIdx.x; v < V1 / 4; v += VT) {
+            const float4 x = g4[v];
+            visit(x.x, 4 * v); visit(x.y, 4 * v + 1); visit(x.z, 4 * v + 2); visit(x.w, 4 * v + 3);
+        }
+    } else {
+        for (int v = threadIdx.x; v < V1; v += VT) visit(g[v], v);
+    }
+    sum = block_sum(sum, s_red);
+    const float lsum = logf(sum);
+    const float m2 = (mx - mx) - lsum, l2 = lsum;
+    if (threadIdx.x == 0) a.stats[r] = make_float2(mx, lsum);
+    for (int k = 0; k < a.topk; ++k) {
+        float ov;
+        int oi;
+        block_argmax(tv[0], ti[0], s_red, s_idx, ov, oi);
+        if (ti[0] == oi) {
+#pragma unroll
+            for (int q = 0; q + 1 < KMAX; ++q) { tv[q] = tv[q + 1]; ti[q] = ti[q + 1]; }
+            tv[KMAX - 1] = -INFINITY;
+            ti[KMAX - 1] = 0x7fffffff;
+        }
+        if (threadIdx.x == 0) {
+            const float lp = (ov - mx) - lsum;
+            a.top_val[(long)r * a.topk + k] = a.twice ? (lp - m2) - l2 : lp;
+            a.top_idx[(long)r * a.topk + k] = oi;
+        }
+    }
+}
+
 __global__ void mask_rows_kernel(ActView x, int R, int cols, const float* __restrict__ mask, long ld_mask) {
     const int row = blockIdx.x;              // row = img * R + r
     const int img = row / R, r = row % R;
@@ -195,6 +261,14 @@ __global__ void mask_rows_kernel(ActView x, int R, int cols, const float* __rest
 int vocab_step_launch(const VocabStepArgs& a, cudaStream_t stream) {
     if (a.rows <= 0) return 0;
     CAPB_REQUIRE(a.topk <= 16, "beam size up to 16");
+    if (a.stats != nullptr) {
+        CAPB_REQUIRE(a.select == 0 && a.topk > 0, "stats mode is the beam-search epilogue");
+        if (a.topk <= 2) vocab_stats_kernel<2><<<a.rows, VT, 0, stream>>>(a);
+        else if (a.topk <= 8) vocab_stats_kernel<8><<<a.rows, VT, 0, stream>>>(a);
+        else vocab_stats_kernel<16><<<a.rows, VT, 0, stream>>>(a);
+        CAPB_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     const size_t smem = sizeof(float) * (size_t)a.V1;
     CAPB_REQUIRE(smem <= 200 * 1024, "vocabulary larger than 51200 entries needs the multi-pass variant");
     static bool configured = false;

@@ -139,11 +139,143 @@ def newfc_core(W: Weights, xt: Tensor, fc_e: Tensor, att_e, p_att, state, masks=
 
 
 # --------------------------------------------------------------------------------------------------
+# Transformer (annotated-transformer encoder/decoder) and AoA (attention-on-attention) pieces
+#   layer_norm          models/TransformerModel.py:76-87   (unbiased std, eps added to the std)
+#   dot_attention       models/TransformerModel.py:152-162
+#   mha4                models/TransformerModel.py:164-195 (four Linears: q, k, v, out)
+#   transformer_encode  models/TransformerModel.py:305-338 + Encoder/EncoderLayer :64-115
+#   transformer_decode  models/TransformerModel.py:351-363 (stateless: re-runs all t tokens) + Decoder/DecoderLayer :117-144
+#   aoa_prepare         models/AoAModel.py:207-226 (+ AoA_Refiner_Core/Layer :100-126, MultiHeadedDotAttention :56-98)
+#   aoa_core            models/AoAModel.py:163-186
+# --------------------------------------------------------------------------------------------------
+
+def layer_norm(x: Tensor, a: Tensor, b: Tensor, eps: float = 1e-6) -> Tensor:
+    mean = x.mean(-1, keepdim=True)
+    std = x.std(-1, keepdim=True)
+    return a * (x - mean) / (std + eps) + b
+
+
+def dot_attention(q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor]) -> Tensor:
+    scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(q.shape[-1])
+    if mask is not None:
+        scores = scores.masked_fill(mask == 0, float('-inf'))
+    return torch.matmul(F.softmax(scores, dim=-1), v)
+
+
+def _heads(x: Tensor, h: int) -> Tensor:
+    n, t, d = x.shape
+    return x.view(n, t, h, d // h).transpose(1, 2)
+
+
+def mha4(W: Weights, pre: str, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor], h: int) -> Tensor:
+    if mask is not None:
+        mask = mask.unsqueeze(1)
+    qh, kh, vh = (_heads(linear(x, W[pre + 'linears.%d.weight' % i], W[pre + 'linears.%d.bias' % i]), h) for i, x in enumerate((q, k, v)))
+    x = dot_attention(qh, kh, vh, mask).transpose(1, 2).contiguous().view(q.shape[0], -1, q.shape[2])
+    return linear(x, W[pre + 'linears.3.weight'], W[pre + 'linears.3.bias'])
+
+
+def _ffn(W: Weights, pre: str, x: Tensor) -> Tensor:
+    return linear(torch.relu(linear(x, W[pre + 'w_1.weight'], W[pre + 'w_1.bias'])), W[pre + 'w_2.weight'], W[pre + 'w_2.bias'])
+
+
+def _ln(W: Weights, pre: str, x: Tensor) -> Tensor:
+    return layer_norm(x, W[pre + 'a_2'], W[pre + 'b_2'])
+
+
+def transformer_prepare(W: Weights, fc: Tensor, att: Tensor, masks: Optional[Tensor], n_layers: int, h: int):
+    att, masks = clip_att(att, masks)
+    x = torch.relu(linear(att, W['att_embed.0.weight'], W['att_embed.0.bias']))
+    if masks is not None:
+        x = x * masks.unsqueeze(-1).to(x)
+    else:
+        masks = torch.ones(att.shape[:2], dtype=torch.long)
+    m3 = masks.unsqueeze(-2)                                   # [B, 1, R]
+    for i in range(n_layers):
+        pre = 'model.encoder.layers.%d.' % i
+        y = _ln(W, pre + 'sublayer.0.norm.', x)
+        x = x + mha4(W, pre + 'self_attn.', y, y, y, m3, h)
+        x = x + _ffn(W, pre + 'feed_forward.', _ln(W, pre + 'sublayer.1.norm.', x))
+    memory = _ln(W, 'model.encoder.norm.', x)
+    return fc[..., :0], att[..., :0], memory, m3
+
+
+def transformer_decode(W: Weights, memory: Tensor, src_mask: Tensor, ys: Tensor, n_layers: int, h: int, tgt_mask: Optional[Tensor] = None) -> Tensor:
+    d = memory.shape[-1]
+    t = ys.shape[1]
+    x = W['model.tgt_embed.0.lut.weight'][ys] * math.sqrt(d) + W['model.tgt_embed.1.pe'][:, :t]
+    if tgt_mask is None:
+        tgt_mask = torch.tril(torch.ones(1, t, t, dtype=torch.bool))
+    for i in range(n_layers):
+        pre = 'model.decoder.layers.%d.' % i
+        y = _ln(W, pre + 'sublayer.0.norm.', x)
+        x = x + mha4(W, pre + 'self_attn.', y, y, y, tgt_mask, h)
+        y = _ln(W, pre + 'sublayer.1.norm.', x)
+        x = x + mha4(W, pre + 'src_attn.', y, memory, memory, src_mask, h)
+        x = x + _ffn(W, pre + 'feed_forward.', _ln(W, pre + 'sublayer.2.norm.', x))
+    return _ln(W, 'model.decoder.norm.', x)
+
+
+def aoa_mha(W: Weights, pre: str, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor], h: int, project_k_v: bool, norm_q: bool, do_aoa: bool):
+    """MultiHeadedDotAttention(query, value, key) -- note the reference's argument order is (query, value, key)."""
+    if mask is not None:
+        if mask.dim() == 2:
+            mask = mask.unsqueeze(-2)
+        mask = mask.unsqueeze(1)
+    single = q.dim() == 2
+    if single:
+        q = q.unsqueeze(1)
+    if norm_q:
+        q = layer_norm(q, W[pre + 'norm.a_2'], W[pre + 'norm.b_2'])
+    qh = _heads(linear(q, W[pre + 'linears.0.weight'], W[pre + 'linears.0.bias']), h)
+    if project_k_v:
+        kh = _heads(linear(k, W[pre + 'linears.1.weight'], W[pre + 'linears.1.bias']), h)
+        vh = _heads(linear(v, W[pre + 'linears.2.weight'], W[pre + 'linears.2.bias']), h)
+    else:
+        kh, vh = _heads(k, h), _heads(v, h)
+    x = dot_attention(qh, kh, vh, mask).transpose(1, 2).contiguous().view(q.shape[0], -1, qh.shape[1] * qh.shape[3])
+    if do_aoa:
+        x = F.glu(linear(torch.cat([x, q], -1), W[pre + 'aoa_layer.0.weight'], W[pre + 'aoa_layer.0.bias']), -1)
+    return x.squeeze(1) if single else x
+
+
+def aoa_prepare(W: Weights, fc: Tensor, att: Tensor, masks: Optional[Tensor], h: int):
+    att, masks = clip_att(att, masks)
+    x = torch.relu(linear(att, W['att_embed.0.weight'], W['att_embed.0.bias']))
+    if masks is not None:
+        x = x * masks.unsqueeze(-1).to(x)
+    for i in range(6):
+        pre = 'refiner.layers.%d.' % i
+        y = _ln(W, pre + 'sublayer.0.norm.', x)
+        # self_attn(x, x, x, mask): key = value = query source
+        x = x + aoa_mha(W, pre + 'self_attn.', y, y, y, masks, h, True, False, True)
+    x = _ln(W, 'refiner.norm.', x)
+    if masks is None:
+        mean = x.mean(1)
+    else:
+        mean = (x * masks.unsqueeze(-1)).sum(1) / masks.unsqueeze(-1).sum(1)
+    p_att = linear(x, W['ctx2att.weight'], W['ctx2att.bias'])
+    return mean, x, p_att, masks
+
+
+def aoa_core(W: Weights, xt: Tensor, mean: Tensor, att_e: Tensor, p_att: Tensor, state, masks, h: int):
+    hs, cs = state                                  # [2, N, H]; hs[1] carries the previous context vector
+    H = hs.shape[2]
+    x1 = torch.cat([xt, mean + hs[1]], 1)
+    h_att, c_att = lstm_cell(x1, hs[0], cs[0], W['core.att_lstm.weight_ih'], W['core.att_lstm.weight_hh'], W['core.att_lstm.bias_ih'],
+                             W['core.att_lstm.bias_hh'])
+    # attention(h_att, p_att[..., :H], p_att[..., H:], mask) with signature (query, value, key)
+    att = aoa_mha(W, 'core.attention.', h_att, p_att[..., H:], p_att[..., :H], masks, h, False, True, False)
+    out = F.glu(linear(torch.cat([att, h_att], 1), W['core.att2ctx.0.weight'], W['core.att2ctx.0.bias']), -1)
+    return out, (torch.stack([h_att, out]), torch.stack([c_att, cs[1]]))
+
+
+# --------------------------------------------------------------------------------------------------
 # family dispatch
 # --------------------------------------------------------------------------------------------------
 
 class Family:
-    def __init__(self, name: str, W: Weights, seq_length: int):
+    def __init__(self, name: str, W: Weights, seq_length: int, heads: int = 8):
         self.name = name
         self.W = W
         self.seq_length = seq_length
@@ -155,25 +287,50 @@ class Family:
             self.num_layers = 1
             self.rnn_size = W['_core.h2h.weight'].shape[1]
             self.vocab1 = W['logit.weight'].shape[0]
+        elif name == 'aoa':
+            self.num_layers = 2
+            self.rnn_size = W['core.att_lstm.weight_hh'].shape[1]
+            self.vocab1 = W['logit.weight'].shape[0]
+            self.heads = heads
+        elif name == 'transformer':
+            self.vocab1 = W['model.generator.proj.weight'].shape[0]
+            self.heads = heads
+            self.n_layers = 1 + max(int(k.split('.')[3]) for k in W if k.startswith('model.decoder.layers.'))
         else:
             raise ValueError(name)
 
     def prepare(self, fc, att, masks=None):
-        return (updown_prepare if self.name == 'updown' else newfc_prepare)(self.W, fc, att, masks)
+        if self.name == 'updown':
+            return updown_prepare(self.W, fc, att, masks)
+        if self.name == 'newfc':
+            return newfc_prepare(self.W, fc, att, masks)
+        if self.name == 'aoa':
+            return aoa_prepare(self.W, fc, att, masks, self.heads)
+        return transformer_prepare(self.W, fc, att, masks, self.n_layers, self.heads)
 
     def init_state(self, n: int):
+        if self.name == 'transformer':
+            return []
         z = torch.zeros(self.num_layers, n, self.rnn_size)
         return (z, z.clone())
 
     def embed(self, it: Tensor) -> Tensor:
-        if self.name == 'updown':
+        if self.name in ('updown', 'aoa'):
             return torch.relu(self.W['embed.0.weight'][it])
         return self.W['embed.weight'][it]
 
     def logprobs_state(self, it, fc_e, att_e, p_att, masks, state, output_logsoftmax=True):
+        if self.name == 'transformer':
+            ys = it.unsqueeze(1) if len(state) == 0 else torch.cat([state[0][0], it.unsqueeze(1)], 1)
+            out = transformer_decode(self.W, p_att, masks, ys, self.n_layers, self.heads)[:, -1]
+            logits = linear(out, self.W['model.generator.proj.weight'], self.W['model.generator.proj.bias'])
+            return (F.log_softmax(logits, dim=1) if output_logsoftmax else logits), [ys.unsqueeze(0)]
         xt = self.embed(it)
-        core = updown_core if self.name == 'updown' else newfc_core
-        out, state = core(self.W, xt, fc_e, att_e, p_att, state, masks)
+        if self.name == 'aoa':
+            out, state = aoa_core(self.W, xt, fc_e, att_e, p_att, state, masks, self.heads)
+        else:
+            core = updown_core if self.name == 'updown' else newfc_core
+            out, state = core(self.W, xt, fc_e, att_e, p_att, state, masks)
         logits = linear(out, self.W['logit.weight'], self.W['logit.bias'])
         return (F.log_softmax(logits, dim=1) if output_logsoftmax else logits), state
 
@@ -321,6 +478,15 @@ def forward_teacher(fam: Family, fc: Tensor, att: Tensor, seq: Tensor, masks: Op
         seq = seq.reshape(-1, seq.shape[2])
     spi = seq.shape[0] // B
     N = B * spi
+    if fam.name == 'transformer':        # one parallel pass with the pad/eos + causal mask (TransformerModel.py:324-348)
+        _, _, memory, m3 = fam.prepare(fc, att, masks)
+        memory, m3 = repeat_rows(memory, spi), repeat_rows(m3, spi)
+        seq_mask = (seq != 0)
+        seq_mask[:, 0] = True
+        t = seq.shape[1]
+        tgt_mask = seq_mask.unsqueeze(-2) & torch.tril(torch.ones(1, t, t, dtype=torch.bool))
+        out = transformer_decode(fam.W, memory, m3, seq, fam.n_layers, fam.heads, tgt_mask)
+        return F.log_softmax(linear(out, fam.W['model.generator.proj.weight'], fam.W['model.generator.proj.bias']), dim=-1)
     fc_e, att_e, p_att, masks = fam.prepare(fc, att, masks)
     fc_e, att_e, p_att, masks = (repeat_rows(x, spi) for x in (fc_e, att_e, p_att, masks))
     state = fam.init_state(N)
@@ -388,6 +554,62 @@ def make_weights(family: str, V: int, E: int, H: int, A: int, F_fc: int, F_att: 
             W[cell + '.bias_hh'] = _uniform(g, (4 * H,), b)
         lin('core.attention.h2att', A, H)
         lin('core.attention.alpha_net', 1, A)
+    elif family == 'aoa':
+        W['embed.0.weight'] = torch.randn(V1, E, generator=g)
+        lin('att_embed.0', H, F_att)
+        lin('logit', V1, H, logit_scale)
+        lin('ctx2att', 2 * H, H)
+        for i in range(6):
+            pre = 'refiner.layers.%d.' % i
+            for j in range(3):
+                lin(pre + 'self_attn.linears.%d' % j, H, H)
+            lin(pre + 'self_attn.aoa_layer.0', 2 * H, 2 * H)
+            W[pre + 'sublayer.0.norm.a_2'] = 1 + 0.1 * torch.randn(H, generator=g)
+            W[pre + 'sublayer.0.norm.b_2'] = 0.1 * torch.randn(H, generator=g)
+        W['refiner.norm.a_2'] = 1 + 0.1 * torch.randn(H, generator=g)
+        W['refiner.norm.b_2'] = 0.1 * torch.randn(H, generator=g)
+        b = 1.0 / math.sqrt(H)
+        W['core.att_lstm.weight_ih'] = _uniform(g, (4 * H, E + H), b)
+        W['core.att_lstm.weight_hh'] = _uniform(g, (4 * H, H), b)
+        W['core.att_lstm.bias_ih'] = _uniform(g, (4 * H,), b)
+        W['core.att_lstm.bias_hh'] = _uniform(g, (4 * H,), b)
+        lin('core.att2ctx.0', 2 * H, 2 * H)
+        W['core.attention.norm.a_2'] = 1 + 0.1 * torch.randn(H, generator=g)
+        W['core.attention.norm.b_2'] = 0.1 * torch.randn(H, generator=g)
+        lin('core.attention.linears.0', H, H)
+    elif family == 'transformer':
+        # here E = d_model, H = d_ff, A = number of layers (both stacks)
+        D, Dff, NL = E, H, A
+
+        def xav(name, out_f, in_f, scale=1.0):
+            bnd = math.sqrt(6.0 / (in_f + out_f))
+            W[name + '.weight'] = _uniform(g, (out_f, in_f), bnd) * scale
+            W[name + '.bias'] = _uniform(g, (out_f,), 1.0 / math.sqrt(in_f))
+
+        def norm(name):
+            W[name + '.a_2'] = 1 + 0.1 * torch.randn(D, generator=g)
+            W[name + '.b_2'] = 0.1 * torch.randn(D, generator=g)
+
+        xav('att_embed.0', D, F_att)
+        for stack, n_sub in (('encoder', 2), ('decoder', 3)):
+            for i in range(NL):
+                pre = 'model.%s.layers.%d.' % (stack, i)
+                for att_name in (('self_attn',) if stack == 'encoder' else ('self_attn', 'src_attn')):
+                    for j in range(4):
+                        xav(pre + att_name + '.linears.%d' % j, D, D)
+                xav(pre + 'feed_forward.w_1', Dff, D)
+                xav(pre + 'feed_forward.w_2', D, Dff)
+                for j in range(n_sub):
+                    norm(pre + 'sublayer.%d.norm' % j)
+            norm('model.%s.norm' % stack)
+        W['model.tgt_embed.0.lut.weight'] = torch.randn(V1, D, generator=g) * (1.0 / math.sqrt(D))
+        pe = torch.zeros(5000, D)
+        position = torch.arange(0, 5000).unsqueeze(1).float()
+        div_term = torch.exp(torch.arange(0, D, 2).float() * -(math.log(10000.0) / D))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        W['model.tgt_embed.1.pe'] = pe.unsqueeze(0)
+        xav('model.generator.proj', V1, D, logit_scale)
     elif family == 'newfc':
         W['embed.weight'] = torch.randn(V1, E, generator=g)
         lin('fc_embed', E, F_fc)
