@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
 // Beam-search variant: the raw logits stay where the GEMM wrote them (they are normalised lazily, only for the rows that end up in
 // the output); this kernel streams each row twice from L2 (max, then sum-exp + per-thread top-k) and writes only the row statistics
 // and the top-k candidates.  Halves the HBM traffic of the step's vocabulary epilogue.
-template <int KMAX>
+// Each thread sees only ~V1/256 elements, so it keeps just its two best; the k block-wide arg-max rounds pop list heads and a
+// thread whose list runs dry (it owned >= 3 of the global top-k: rare) rescans its elements for the next one.
 __global__ void __launch_bounds__(VT) vocab_stats_kernel(const VocabStepArgs a) {
     __shared__ float s_red[VT / 32];
     __shared__ int s_idx[VT / 32];
@@ -199,20 +200,14 @@ __global__ void __launch_bounds__(VT) vocab_stats_kernel(const VocabStepArgs a) 
         for (int v = threadIdx.x; v < V1; v += VT) mx = fmaxf(mx, g[v]);
     }
     mx = block_max(mx, s_red);
-    float tv[KMAX];
-    int ti[KMAX];
-#pragma unroll
-    for (int q = 0; q < KMAX; ++q) { tv[q] = -INFINITY; ti[q] = 0x7fffffff; }
+    float t0v = -INFINITY, t1v = -INFINITY;
+    int t0i = 0x7fffffff, t1i = 0x7fffffff;
     float sum = 0.f;
     auto visit = [&](float x, int v) {
         sum += __expf(x - mx);
-        if (x > tv[KMAX - 1]) {
-            float cv = x;
-            int ci = v;
-#pragma unroll
-            for (int q = 0; q < KMAX; ++q) {
-                if (cv > tv[q]) { const float t0 = tv[q]; const int t1 = ti[q]; tv[q] = cv; ti[q] = ci; cv = t0; ci = t1; }
-            }
+        if (x > t1v) {                              // strict: earlier (lower) indices win ties
+            if (x > t0v) { t1v = t0v; t1i = t0i; t0v = x; t0i = v; }
+            else { t1v = x; t1i = v; }
         }
     };
     if (vec) {
@@ -228,15 +223,32 @@ __global__ void __launch_bounds__(VT) vocab_stats_kernel(const VocabStepArgs a) 
     const float lsum = logf(sum);
     const float m2 = (mx - mx) - lsum, l2 = lsum;
     if (threadIdx.x == 0) a.stats[r] = make_float2(mx, lsum);
+    int popped = 0;
     for (int k = 0; k < a.topk; ++k) {
         float ov;
         int oi;
-        block_argmax(tv[0], ti[0], s_red, s_idx, ov, oi);
-        if (ti[0] == oi) {
-#pragma unroll
-            for (int q = 0; q + 1 < KMAX; ++q) { tv[q] = tv[q + 1]; ti[q] = ti[q + 1]; }
-            tv[KMAX - 1] = -INFINITY;
-            ti[KMAX - 1] = 0x7fffffff;
+        block_argmax(t0v, t0i, s_red, s_idx, ov, oi);
+        if (t0i == oi && oi != 0x7fffffff) {
+            const float lastv = t0v;
+            const int lasti = t0i;
+            t0v = t1v; t0i = t1i;
+            t1v = -INFINITY; t1i = 0x7fffffff;
+            if (++popped >= 2 && t0i == 0x7fffffff) {
+                // rescan my elements for the best one ordered after (lastv, lasti)
+                auto consider = [&](float x, int v) {
+                    const bool after = (x < lastv) || (x == lastv && v > lasti);
+                    if (after && (x > t0v || (x == t0v && v < t0i))) { t0v = x; t0i = v; }
+                };
+                if (vec) {
+                    const float4* g4 = reinterpret_cast<const float4*>(g);
+                    for (int v = threadIdx.x; v < V1 / 4; v += VT) {
+                        const float4 x = g4[v];
+                        consider(x.x, 4 * v); consider(x.y, 4 * v + 1); consider(x.z, 4 * v + 2); consider(x.w, 4 * v + 3);
+                    }
+                } else {
+                    for (int v = threadIdx.x; v < V1; v += VT) consider(g[v], v);
+                }
+            }
         }
         if (threadIdx.x == 0) {
             const float lp = (ov - mx) - lsum;
@@ -263,9 +275,7 @@ int vocab_step_launch(const VocabStepArgs& a, cudaStream_t stream) {
     CAPB_REQUIRE(a.topk <= 16, "beam size up to 16");
     if (a.stats != nullptr) {
         CAPB_REQUIRE(a.select == 0 && a.topk > 0, "stats mode is the beam-search epilogue");
-        if (a.topk <= 2) vocab_stats_kernel<2><<<a.rows, VT, 0, stream>>>(a);
-        else if (a.topk <= 8) vocab_stats_kernel<8><<<a.rows, VT, 0, stream>>>(a);
-        else vocab_stats_kernel<16><<<a.rows, VT, 0, stream>>>(a);
+        vocab_stats_kernel<<<a.rows, VT, 0, stream>>>(a);
         CAPB_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
