@@ -38,6 +38,32 @@ class SampleOpts(Structure):
     _fields_ = [('sample_n', c_int), ('method', c_int), ('temperature', c_float), ('seed', c_ulonglong), ('steps', c_int)]
 
 
+TFM_MAX_LAYERS = 8
+
+
+class TfmCfg(Structure):
+    _fields_ = [(f, c_int) for f in ('vocab_size', 'd_model', 'd_ff', 'heads', 'n_enc', 'n_dec', 'att_feat_size', 'seq_length', 'numeric_mode')]
+
+
+class MhaWeights(Structure):
+    _fields_ = [(f, c_void_p) for f in ('q_w', 'q_b', 'k_w', 'k_b', 'v_w', 'v_b', 'o_w', 'o_b')]
+
+
+class TfmEncLayer(Structure):
+    _fields_ = [('self_attn', MhaWeights)] + [(f, c_void_p) for f in ('w1_w', 'w1_b', 'w2_w', 'w2_b', 'ln0_a', 'ln0_b', 'ln1_a', 'ln1_b')]
+
+
+class TfmDecLayer(Structure):
+    _fields_ = [('self_attn', MhaWeights), ('src_attn', MhaWeights)] + \
+               [(f, c_void_p) for f in ('w1_w', 'w1_b', 'w2_w', 'w2_b', 'ln0_a', 'ln0_b', 'ln1_a', 'ln1_b', 'ln2_a', 'ln2_b')]
+
+
+class TfmWeights(Structure):
+    _fields_ = [('att_embed_w', c_void_p), ('att_embed_b', c_void_p), ('enc', TfmEncLayer * TFM_MAX_LAYERS), ('enc_norm_a', c_void_p),
+                ('enc_norm_b', c_void_p), ('dec', TfmDecLayer * TFM_MAX_LAYERS), ('dec_norm_a', c_void_p), ('dec_norm_b', c_void_p),
+                ('lut', c_void_p), ('pe', c_void_p), ('gen_w', c_void_p), ('gen_b', c_void_p)]
+
+
 # every exported symbol of include/capb200.h: (restype, argtypes)
 SIGNATURES = {
     'capb200_last_error': (c_char_p, []),
@@ -60,6 +86,15 @@ SIGNATURES = {
     'capb200_engine_launch_count': (c_long, [c_void_p]),
     'capb200_engine_set_profiling': (c_int, [c_void_p, c_int]),
     'capb200_engine_read_profile': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int]),
+    'capb200_tfm_create': (c_void_p, [POINTER(TfmCfg)]),
+    'capb200_tfm_destroy': (None, [c_void_p]),
+    'capb200_tfm_bind_weights': (c_int, [c_void_p, POINTER(TfmWeights), c_void_p]),
+    'capb200_tfm_decode_beam': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(BeamOpts), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
+    'capb200_tfm_beam_record_logprobs': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    'capb200_tfm_decode_sample': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(SampleOpts), c_void_p, c_long, c_void_p, c_void_p, c_void_p,
+                                          c_void_p]),
+    'capb200_tfm_launch_count': (c_long, [c_void_p]),
     'capb200_cider_table_create': (c_void_p, [c_void_p, c_void_p, c_long, c_double, c_void_p]),
     'capb200_cider_table_destroy': (None, [c_void_p]),
     'capb200_self_critical_reward': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,

@@ -61,6 +61,8 @@ struct GemmEpilogue {
     const float* row_bias = nullptr;    // [M / rows_per_group, N], pitch ld_row_bias
     long ld_row_bias = 0;
     int rows_per_group = 1;
+    const float* residual = nullptr;    // optional [M, N] added after the bias (pre-norm residual connections), pitch ld_res
+    long ld_res = 0;
     int relu = 0;
     float* C = nullptr;                 // fp32 result, pitch ldc (may be null when only the split planes are wanted)
     long ldc = 0;

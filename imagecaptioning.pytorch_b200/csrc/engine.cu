@@ -18,11 +18,34 @@
 #include "../../include/capb200.h"
 #include "common.cuh"
 #include "kernels.cuh"
+#include "engine_common.cuh"
 
 namespace capb200 {
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+const char* last_error_cstr() { return g_last_error.c_str(); }
+
+__global__ void capb_fill_int_kernel(int* p, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void capb_load_token_column_kernel(const long long* src, long ld, int col, int n, int* dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (int)src[(long)i * ld + col];
+}
+int fill_int_launch(int* p, int n, int v, cudaStream_t st) {
+    if (n <= 0) return 0;
+    capb_fill_int_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, n, v);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int load_token_column_launch(const long long* src, long ld, int col, int n, int* dst, cudaStream_t st) {
+    if (n <= 0) return 0;
+    capb_load_token_column_kernel<<<cdiv(n, 256), 256, 0, st>>>(src, ld, col, n, dst);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 
 namespace {
 
@@ -34,51 +57,12 @@ __global__ void interleave_gates_kernel(const float* src, float* dst, int H) {  
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 4 * H) dst[i] = src[(i & 3) * H + (i >> 2)];
 }
-__global__ void fill_int_kernel(int* p, int n, int v) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
+
 __global__ void iota_div_kernel(int* p, int n, int div) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i / div;
 }
-__global__ void load_token_column_kernel(const long long* src, long ld, int col, int n, int* dst) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = (int)src[(long)i * ld + col];
-}
 
-struct Planes {
-    __half* hi = nullptr;
-    __half* lo = nullptr;
-    long ld = 0;
-};
-
-// bump allocator over one cudaMalloc'ed block; a dry run (base == nullptr) measures the size
-struct Arena {
-    char* base = nullptr;
-    size_t off = 0;
-    template <typename T>
-    T* take(size_t n) {
-        off = (off + 255) & ~size_t(255);
-        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
-        off += n * sizeof(T);
-        return p;
-    }
-};
-
-struct Act {
-    ActView v;
-    void carve(Arena& a, long rows, long cols, bool planes) {
-        v.ld = round_up(cols, 8);
-        v.f = a.take<float>(rows * v.ld);
-        if (planes) {
-            v.hi = a.take<__half>(rows * v.ld);
-            v.lo = a.take<__half>(rows * v.ld);
-        } else {
-            v.hi = v.lo = nullptr;
-        }
-    }
-};
 
 enum GemmId { G_FC = 0, G_ATT, G_CTX, G_GFC, G_LSTM1, G_H2ATT, G_LSTM2, G_LOGIT, G_CORE, G_COUNT };
 
@@ -118,22 +102,9 @@ struct capb200_engine {
     Act fc_e, att_e, p_att, g_fc, xt, h0_in, h1_in, h0_out, h1_out, att_res, att_h, gates;
     float *c0[2] = {nullptr, nullptr}, *c1[2] = {nullptr, nullptr};
     long ld_c = 0;
-    int *tokens = nullptr, *src_row = nullptr, *neg1 = nullptr, *img_of_row = nullptr, *unfinished = nullptr, *forced = nullptr;
-    float* top_val = nullptr;
-    int* top_idx = nullptr;
+    int* img_of_row = nullptr;
     float* att_score = nullptr;   // [rows, R] attention scores
-    float2* slab_stats = nullptr; // [T, rows] (max, log-sum-exp) of every slab row (beam search keeps raw logits in the slab)
-    BeamState bs;
-    long long* rec_seq = nullptr;   // [B, beam, T] sorted records of the last beam decode
-    int *rec_len = nullptr, *rec_hist = nullptr, *out_hist = nullptr;
-    float *rec_p = nullptr, *rec_raw = nullptr;
-    int *tmp_len = nullptr;
-    float *tmp_p = nullptr, *tmp_raw = nullptr;
-    // slab of per-step log-prob rows for beam search (owned, grown on demand)
-    float* slab = nullptr;
-    size_t slab_bytes = 0;
-    long slab_step_stride = 0;
-    int last_B = 0, last_beam = 0;
+    DecodeBuffers d;              // tokens / beam state / slab shared with the other families' engines
 
     GemmTcPlan* plans[G_COUNT] = {nullptr};
     int core_cur = 0;   // which c buffer currently holds the state
@@ -155,14 +126,6 @@ void destroy_plans(capb200_engine* e) {
     for (int i = 0; i < G_COUNT; ++i) {
         if (e->plans[i]) { gemm_tc_plan_destroy(e->plans[i]); e->plans[i] = nullptr; }
     }
-}
-
-Planes carve_planes(Arena& a, long rows, long cols) {
-    Planes p;
-    p.ld = round_up(cols, 8);
-    p.hi = a.take<__half>(rows * p.ld);
-    p.lo = a.take<__half>(rows * p.ld);
-    return p;
 }
 
 void layout_weights(capb200_engine* e, Arena& a) {
@@ -232,40 +195,9 @@ void layout_workspace(capb200_engine* e, Arena& a, int B, int rows, int R, int b
         e->c0[i] = a.take<float>((long)rows * e->ld_c);
         e->c1[i] = a.take<float>((long)rows * e->ld_c);
     }
-    e->tokens = a.take<int>(rows);
-    e->src_row = a.take<int>(rows);
-    e->neg1 = a.take<int>(rows);
     e->img_of_row = a.take<int>(rows);
-    e->unfinished = a.take<int>(rows);
-    e->forced = a.take<int>(rows);
-    e->top_val = a.take<float>((long)rows * 16);
-    e->top_idx = a.take<int>((long)rows * 16);
     e->att_score = a.take<float>((long)rows * (R > 0 ? R : 1));
-    e->slab_stats = a.take<float2>((long)rows * T);
-    BeamState& s = e->bs;
-    const long rec = (long)B * beam * T;
-    s.sums = a.take<float>((long)B * beam);
-    s.seq_a = a.take<int>(rec);
-    s.seq_b = a.take<int>(rec);
-    s.hist_a = a.take<int>(rec);
-    s.hist_b = a.take<int>(rec);
-    s.done_cnt = a.take<int>(B);
-    s.done_seq = a.take<int>(rec * T);
-    s.done_hist = a.take<int>(rec * T);
-    s.done_len = a.take<int>(rec);
-    s.done_p = a.take<double>(rec);
-    s.done_raw = a.take<float>(rec);
-    s.tokens = e->tokens;
-    s.src_row = e->src_row;
-    e->rec_seq = a.take<long long>(rec);
-    e->rec_hist = a.take<int>(rec);
-    e->out_hist = a.take<int>(rec);
-    e->rec_len = a.take<int>((long)B * beam);
-    e->rec_p = a.take<float>((long)B * beam);
-    e->rec_raw = a.take<float>((long)B * beam);
-    e->tmp_len = a.take<int>((long)B * beam);
-    e->tmp_p = a.take<float>((long)B * beam);
-    e->tmp_raw = a.take<float>((long)B * beam);
+    e->d.carve(a, B, rows, beam, T);
 }
 
 int ensure_workspace(capb200_engine* e, int B, int rows, int R, int beam, cudaStream_t st) {
@@ -286,21 +218,10 @@ int ensure_workspace(capb200_engine* e, int B, int rows, int R, int beam, cudaSt
     layout_workspace(e, real, nB, nRows, nR, nBeam);
     e->capB = nB; e->capRows = nRows; e->capR = nR; e->capBeam = nBeam;
     CAPB_CHECK_CUDA(cudaMemsetAsync(e->ws, 0, need, st));
-    fill_int_kernel<<<cdiv(nRows, 256), 256, 0, st>>>(e->neg1, nRows, -1);
-    CAPB_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    return fill_int_launch(e->d.neg1, nRows, -1, st);
 }
 
 // ---- GEMM dispatch ------------------------------------------------------------------------------------------------
-GemmSeg seg_of(const ActView& a, const float* w, long ldw, const Planes& wp, int K) {
-    GemmSeg s;
-    s.A = a.f; s.lda = a.ld; s.W = w; s.ldw = ldw;
-    s.A_hi = a.hi; s.A_lo = a.lo; s.lda_h = a.ld;
-    s.W_hi = wp.hi; s.W_lo = wp.lo; s.ldw_h = wp.ld;
-    s.K = K;
-    return s;
-}
-
 // `plan_rows` is the row capacity the tensor maps are encoded for; M the rows valid in this launch.
 int run_gemm_inner(capb200_engine* e, int id, GemmProblem& g, int plan_rows, cudaStream_t st) {
     e->launches++;
@@ -475,11 +396,11 @@ int core_step(capb200_engine* e, int rows, int rpi, const int* tokens, const int
         return 0;
     }
     // ---- NewFC: maxout LSTM; a fresh state first consumes the image embedding (AttModel.py:925-936)
-    const bool fresh = (src_row == e->neg1);
+    const bool fresh = (src_row == e->d.neg1);
     for (int pass = fresh ? 0 : 1; pass < 2; ++pass) {
         StateCopy s0, s1;
         s0.src = e->h0_out.v.f; s0.ld_src = e->h0_out.v.ld; s0.dst = e->h0_in.v;
-        const int* srcs = (pass == 0) ? e->neg1 : (fresh ? nullptr : src_row);
+        const int* srcs = (pass == 0) ? e->d.neg1 : (fresh ? nullptr : src_row);
         e->launches++;
         if (pass == 0) {
             if (state_gather_embed_launch(rows, e->img_of_row, srcs, e->fc_e.v.f, e->fc_e.v.ld, E, 0, e->xt.v, H, 1, s0, s1, st)) return 1;
@@ -550,7 +471,7 @@ void capb200_engine_destroy(capb200_engine* e) {
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     cudaFree(e->wblock);
     cudaFree(e->ws);
-    cudaFree(e->slab);
+    cudaFree(e->d.slab);
     delete e;
 }
 
@@ -701,71 +622,19 @@ int capb200_decode_beam(capb200_engine* e, const float* fc, const float* att, co
     const int T = e->T, V1 = e->V1;
     const int rows = B * beam;
     if (ensure_workspace(e, B, rows, R, beam, st)) return 1;
-    const size_t slab_need = (size_t)T * rows * V1 * sizeof(float);
-    if (slab_need > e->slab_bytes) {
-        CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
-        if (e->slab) CAPB_CHECK_CUDA(cudaFree(e->slab));
-        e->slab = nullptr;
-        CAPB_CHECK_CUDA(cudaMalloc(&e->slab, slab_need));
-        e->slab_bytes = slab_need;
-    }
-    e->slab_step_stride = (long)rows * V1;
-    e->last_B = B;
-    e->last_beam = beam;
-    BeamState s = e->bs;
-    s.B = B; s.beam = beam; s.T = T; s.V1 = V1;
-    CAPB_CHECK_CUDA(cudaMemsetAsync(s.sums, 0, sizeof(float) * B * beam, st));
-    CAPB_CHECK_CUDA(cudaMemsetAsync(s.done_cnt, 0, sizeof(int) * B, st));
-    CAPB_CHECK_CUDA(cudaMemsetAsync(e->tokens, 0, sizeof(int) * rows, st));      // <bos> = 0
     if (!updown) { iota_div_kernel<<<cdiv(rows, 256), 256, 0, st>>>(e->img_of_row, rows, 1); e->launches++; }
     if (prepare(e, fc, att, mask, B, R, st)) return 1;
     e->core_cur = 0;
-    for (int t = 0; t < T; ++t) {
-        const int live = (t == 0) ? 1 : beam;
-        const int nrows = B * live;
-        float* logits = e->slab + (long)t * e->slab_step_stride;
-        if (core_step(e, nrows, live, e->tokens, t == 0 ? e->neg1 : e->src_row, logits, V1, B, R, mask, st)) return 1;
-        VocabStepArgs va;
-        va.rows = nrows; va.V1 = V1; va.logits = logits; va.ld = V1;
-        va.twice = (t > 0) ? 1 : 0;      // init_logprobs went through one log_softmax only (AttModel.py:239, CaptionModel.py:204)
-        va.topk = beam; va.top_val = e->top_val; va.top_idx = e->top_idx;
-        va.stats = e->slab_stats + (long)t * rows;
-        e->launches++;
-        if (vocab_step_launch(va, st)) return 1;
-        e->launches++;
-        if (beam_step_launch(s, t, live, e->top_val, e->top_idx, opts->penalty_kind, opts->penalty_alpha, st)) return 1;
-    }
-    // all finished beams of every image, best first
-    e->launches++;
-    if (beam_finalize_launch(s, beam, e->rec_seq, e->rec_len, e->rec_p, e->rec_raw, e->rec_hist, st)) return 1;
-    if (keep == beam) {
-        CAPB_CHECK_CUDA(cudaMemcpyAsync(seq, e->rec_seq, sizeof(long long) * B * beam * T, cudaMemcpyDeviceToDevice, st));
-        if (seq_logprobs) {
-            e->launches++;
-            if (gather_logprob_rows_launch(e->slab, e->slab_step_stride, V1, e->rec_hist, B * beam, T, V1, seq_logprobs, e->slab_stats, rows, st)) return 1;
-        }
-    } else {
-        e->launches++;
-        if (beam_finalize_launch(s, 1, seq, e->tmp_len, e->tmp_p, e->tmp_raw, e->out_hist, st)) return 1;
-        if (seq_logprobs) {
-            e->launches++;
-            if (gather_logprob_rows_launch(e->slab, e->slab_step_stride, V1, e->out_hist, B, T, V1, seq_logprobs, e->slab_stats, rows, st)) return 1;
-        }
-    }
-    if (done_seq) CAPB_CHECK_CUDA(cudaMemcpyAsync(done_seq, e->rec_seq, sizeof(long long) * B * beam * T, cudaMemcpyDeviceToDevice, st));
-    if (done_len) CAPB_CHECK_CUDA(cudaMemcpyAsync(done_len, e->rec_len, sizeof(int) * B * beam, cudaMemcpyDeviceToDevice, st));
-    if (done_p) CAPB_CHECK_CUDA(cudaMemcpyAsync(done_p, e->rec_p, sizeof(float) * B * beam, cudaMemcpyDeviceToDevice, st));
-    if (done_raw) CAPB_CHECK_CUDA(cudaMemcpyAsync(done_raw, e->rec_raw, sizeof(float) * B * beam, cudaMemcpyDeviceToDevice, st));
-    return 0;
+    auto core = [&](int nrows, int live, const int* tokens, const int* src_row, int /*t*/, float* logits, long ld) {
+        return core_step(e, nrows, live, tokens, src_row, logits, ld, B, R, mask, st);
+    };
+    return beam_decode_driver(e->d, V1, T, B, beam, keep, opts->penalty_kind, opts->penalty_alpha, seq, seq_logprobs, done_seq, done_len, done_p,
+                              done_raw, core, &e->launches, st);
 }
 
 int capb200_beam_record_logprobs(capb200_engine* e, int image, int rank, float* dst, void* stream) {
     if (check_ready(e)) return 1;
-    CAPB_REQUIRE(e->slab != nullptr && image >= 0 && image < e->last_B && rank >= 0 && rank < e->last_beam, "no such finished beam");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    e->launches++;
-    return gather_logprob_rows_launch(e->slab, e->slab_step_stride, e->V1, e->rec_hist + ((long)image * e->last_beam + rank) * e->T, 1, e->T, e->V1,
-                                      dst, e->slab_stats, (long)e->last_B * e->last_beam, st);
+    return beam_record_logprobs(e->d, e->V1, e->T, image, rank, dst, static_cast<cudaStream_t>(stream));
 }
 
 int capb200_decode_sample(capb200_engine* e, const float* fc, const float* att, const float* mask, int B, int R, const capb200_sample_opts* opts,
@@ -789,40 +658,14 @@ int capb200_decode_sample(capb200_engine* e, const float* fc, const float* att, 
     const long t_out = (method == CAPB200_SAMPLE_TEACHER) ? ld_tok : T;
     CAPB_REQUIRE(steps >= 0 && steps <= t_out, "steps out of range");
     if (ensure_workspace(e, B, rows, R, 1, st)) return 1;
-    CAPB_CHECK_CUDA(cudaMemsetAsync(e->tokens, 0, sizeof(int) * rows, st));
     if (!updown) { iota_div_kernel<<<cdiv(rows, 256), 256, 0, st>>>(e->img_of_row, rows, n); e->launches++; }
     if (prepare(e, fc, att, mask, B, R, st)) return 1;
     e->core_cur = 0;
-    for (int t = 0; t < steps; ++t) {
-        if (method == CAPB200_SAMPLE_TEACHER) {
-            load_token_column_kernel<<<cdiv(rows, 256), 256, 0, st>>>(tokens_in, ld_tok, t, rows, e->tokens);
-            e->launches++;
-        } else if (method == CAPB200_SAMPLE_FORCED) {
-            load_token_column_kernel<<<cdiv(rows, 256), 256, 0, st>>>(tokens_in, ld_tok, t, rows, e->forced);
-            e->launches++;
-        }
-        float* logits = seq_logprobs + (long)t * V1;
-        if (core_step(e, rows, n, e->tokens, t == 0 ? e->neg1 : nullptr, logits, t_out * V1, B, R, mask, st)) return 1;
-        VocabStepArgs va;
-        va.rows = rows; va.V1 = V1; va.logits = logits; va.ld = t_out * V1;
-        va.twice = 0;
-        if (method != CAPB200_SAMPLE_TEACHER) {
-            va.select = (method == CAPB200_SAMPLE_GREEDY) ? 1 : (method == CAPB200_SAMPLE_MULTINOMIAL ? 2 : 3);
-            va.temperature = opts->temperature;
-            va.seed = opts->seed;
-            va.step = (unsigned long long)t;
-            va.forced = e->forced;
-            va.unfinished = e->unfinished;
-            va.first_step = (t == 0);
-            va.tokens_out = e->tokens;
-            va.seq_out = seq; va.ld_seq = T; va.t = t;
-            va.picked_lp = picked ? picked + t : nullptr;      // picked is [N,T]
-            va.ld_picked = T;
-        }
-        e->launches++;
-        if (vocab_step_launch(va, st)) return 1;
-    }
-    return 0;
+    auto core = [&](int nrows, int /*live*/, const int* tokens, const int* src_row, int /*t*/, float* logits, long ld) {
+        return core_step(e, nrows, n, tokens, src_row, logits, ld, B, R, mask, st);
+    };
+    return sample_decode_driver(e->d, V1, T, rows, method, opts->temperature, opts->seed, steps, tokens_in, ld_tok, seq, seq_logprobs, picked, core,
+                                &e->launches, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,237 @@
+// Helpers shared by the engines (UpDown/NewFC in engine.cu, Transformer in tfm_engine.cu, AoA in aoa_engine.cu).
+#pragma once
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace capb200 {
+
+struct Planes {
+    __half* hi = nullptr;
+    __half* lo = nullptr;
+    long ld = 0;
+};
+
+// bump allocator over one cudaMalloc'ed block; a dry run (base == nullptr) measures the size
+struct Arena {
+    char* base = nullptr;
+    size_t off = 0;
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+struct Act {
+    ActView v;
+    void carve(Arena& a, long rows, long cols, bool planes) {
+        v.ld = round_up(cols, 8);
+        v.f = a.take<float>(rows * v.ld);
+        if (planes) {
+            v.hi = a.take<__half>(rows * v.ld);
+            v.lo = a.take<__half>(rows * v.ld);
+        } else {
+            v.hi = v.lo = nullptr;
+        }
+    }
+};
+
+inline Planes carve_planes(Arena& a, long rows, long cols) {
+    Planes p;
+    p.ld = round_up(cols, 8);
+    p.hi = a.take<__half>(rows * p.ld);
+    p.lo = a.take<__half>(rows * p.ld);
+    return p;
+}
+
+
+inline GemmSeg seg_of(const ActView& a, const float* w, long ldw, const Planes& wp, int K) {
+    GemmSeg s;
+    s.A = a.f; s.lda = a.ld; s.W = w; s.ldw = ldw;
+    s.A_hi = a.hi; s.A_lo = a.lo; s.lda_h = a.ld;
+    s.W_hi = wp.hi; s.W_lo = wp.lo; s.ldw_h = wp.ld;
+    s.K = K;
+    return s;
+}
+
+
+// Runs one GEMM in the engine's numeric mode.  `plan` caches the encoded TMA maps of this call site (tensor-core modes);
+// `plan_rows` is the row capacity the maps are encoded for, g.M the rows valid in this launch.
+inline int run_gemm_mode(int mode, GemmTcPlan** plan, GemmProblem& g, int plan_rows, cudaStream_t st) {
+    if (mode == 0) return gemm_simt_launch(g, st);
+    if (*plan == nullptr) {
+        GemmProblem planned = g;
+        planned.M = plan_rows;
+        *plan = gemm_tc_plan_create(planned, mode == 1 ? 3 : 1);
+        if (*plan == nullptr) return 1;
+    }
+    return gemm_tc_plan_launch(*plan, &g.epi, g.M, st);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Search / sampling state shared by every model family, and the two decode drivers.  A family supplies only its recurrent
+// core as a callable:  core(rows, rows_per_image, tokens, src_row, t, logits, ld_logits) -> 0 on success, which must leave the
+// step's raw logits [rows, V1] at `logits` (row pitch ld_logits).
+// ---------------------------------------------------------------------------------------------------------------------
+struct DecodeBuffers {
+    int *tokens = nullptr, *src_row = nullptr, *neg1 = nullptr, *unfinished = nullptr, *forced = nullptr;
+    float* top_val = nullptr;
+    int* top_idx = nullptr;
+    float2* slab_stats = nullptr;     // [T, rows]
+    BeamState bs;
+    long long* rec_seq = nullptr;     // [B, beam, T] sorted records of the last beam decode
+    int *rec_len = nullptr, *rec_hist = nullptr, *out_hist = nullptr, *tmp_len = nullptr;
+    float *rec_p = nullptr, *rec_raw = nullptr, *tmp_p = nullptr, *tmp_raw = nullptr;
+    float* slab = nullptr;            // separately allocated: [T, rows, V1] raw logits of a beam search
+    size_t slab_bytes = 0;
+    long slab_step_stride = 0;
+    int last_B = 0, last_beam = 0;
+
+    void carve(Arena& a, int B, int rows, int beam, int T) {
+        tokens = a.take<int>(rows);
+        src_row = a.take<int>(rows);
+        neg1 = a.take<int>(rows);
+        unfinished = a.take<int>(rows);
+        forced = a.take<int>(rows);
+        top_val = a.take<float>((long)rows * 16);
+        top_idx = a.take<int>((long)rows * 16);
+        slab_stats = a.take<float2>((long)rows * T);
+        const long rec = (long)B * beam * T;
+        bs.sums = a.take<float>((long)B * beam);
+        bs.seq_a = a.take<int>(rec);
+        bs.seq_b = a.take<int>(rec);
+        bs.hist_a = a.take<int>(rec);
+        bs.hist_b = a.take<int>(rec);
+        bs.done_cnt = a.take<int>(B);
+        bs.done_seq = a.take<int>(rec * T);
+        bs.done_hist = a.take<int>(rec * T);
+        bs.done_len = a.take<int>(rec);
+        bs.done_p = a.take<double>(rec);
+        bs.done_raw = a.take<float>(rec);
+        bs.tokens = tokens;
+        bs.src_row = src_row;
+        rec_seq = a.take<long long>(rec);
+        rec_hist = a.take<int>(rec);
+        out_hist = a.take<int>(rec);
+        rec_len = a.take<int>((long)B * beam);
+        rec_p = a.take<float>((long)B * beam);
+        rec_raw = a.take<float>((long)B * beam);
+        tmp_len = a.take<int>((long)B * beam);
+        tmp_p = a.take<float>((long)B * beam);
+        tmp_raw = a.take<float>((long)B * beam);
+    }
+};
+
+__global__ void capb_fill_int_kernel(int* p, int n, int v);
+__global__ void capb_load_token_column_kernel(const long long* src, long ld, int col, int n, int* dst);
+int fill_int_launch(int* p, int n, int v, cudaStream_t st);
+int load_token_column_launch(const long long* src, long ld, int col, int n, int* dst, cudaStream_t st);
+
+// ancestors of the current rows at step t of a beam search (valid for positions < t): the table beam_step(t-1) wrote
+inline const int* beam_ancestors(const BeamState& s, int t) { return ((t - 1) & 1) ? s.hist_a : s.hist_b; }
+
+// AttModel._sample_beam + CaptionModel.beam_search (see engine.cu header for the reference lines)
+template <class CoreFn>
+int beam_decode_driver(DecodeBuffers& d, int V1, int T, int B, int beam, int keep, int penalty_kind, float penalty_alpha, long long* seq,
+                       float* seq_logprobs, long long* done_seq, int* done_len, float* done_p, float* done_raw, CoreFn core, long* launches,
+                       cudaStream_t st) {
+    const int rows = B * beam;
+    const size_t slab_need = (size_t)T * rows * V1 * sizeof(float);
+    if (slab_need > d.slab_bytes) {
+        CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
+        if (d.slab) CAPB_CHECK_CUDA(cudaFree(d.slab));
+        d.slab = nullptr;
+        CAPB_CHECK_CUDA(cudaMalloc(&d.slab, slab_need));
+        d.slab_bytes = slab_need;
+    }
+    d.slab_step_stride = (long)rows * V1;
+    d.last_B = B;
+    d.last_beam = beam;
+    BeamState s = d.bs;
+    s.B = B; s.beam = beam; s.T = T; s.V1 = V1;
+    CAPB_CHECK_CUDA(cudaMemsetAsync(s.sums, 0, sizeof(float) * B * beam, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(s.done_cnt, 0, sizeof(int) * B, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(d.tokens, 0, sizeof(int) * rows, st));      // <bos> = 0
+    for (int t = 0; t < T; ++t) {
+        const int live = (t == 0) ? 1 : beam;
+        const int nrows = B * live;
+        float* logits = d.slab + (long)t * d.slab_step_stride;
+        if (core(nrows, live, d.tokens, t == 0 ? d.neg1 : d.src_row, t, logits, (long)V1)) return 1;
+        VocabStepArgs va;
+        va.rows = nrows; va.V1 = V1; va.logits = logits; va.ld = V1;
+        va.twice = (t > 0) ? 1 : 0;      // init_logprobs went through one log_softmax only (AttModel.py:239, CaptionModel.py:204)
+        va.topk = beam; va.top_val = d.top_val; va.top_idx = d.top_idx;
+        va.stats = d.slab_stats + (long)t * rows;
+        if (vocab_step_launch(va, st)) return 1;
+        if (beam_step_launch(s, t, live, d.top_val, d.top_idx, penalty_kind, penalty_alpha, st)) return 1;
+        *launches += 2;
+    }
+    // all finished beams of every image, best first
+    if (beam_finalize_launch(s, beam, d.rec_seq, d.rec_len, d.rec_p, d.rec_raw, d.rec_hist, st)) return 1;
+    *launches += 1;
+    if (keep == beam) {
+        CAPB_CHECK_CUDA(cudaMemcpyAsync(seq, d.rec_seq, sizeof(long long) * B * beam * T, cudaMemcpyDeviceToDevice, st));
+        if (seq_logprobs) {
+            *launches += 1;
+            if (gather_logprob_rows_launch(d.slab, d.slab_step_stride, V1, d.rec_hist, B * beam, T, V1, seq_logprobs, d.slab_stats, rows, st)) return 1;
+        }
+    } else {
+        *launches += 1;
+        if (beam_finalize_launch(s, 1, seq, d.tmp_len, d.tmp_p, d.tmp_raw, d.out_hist, st)) return 1;
+        if (seq_logprobs) {
+            *launches += 1;
+            if (gather_logprob_rows_launch(d.slab, d.slab_step_stride, V1, d.out_hist, B, T, V1, seq_logprobs, d.slab_stats, rows, st)) return 1;
+        }
+    }
+    if (done_seq) CAPB_CHECK_CUDA(cudaMemcpyAsync(done_seq, d.rec_seq, sizeof(long long) * B * beam * T, cudaMemcpyDeviceToDevice, st));
+    if (done_len) CAPB_CHECK_CUDA(cudaMemcpyAsync(done_len, d.rec_len, sizeof(int) * B * beam, cudaMemcpyDeviceToDevice, st));
+    if (done_p) CAPB_CHECK_CUDA(cudaMemcpyAsync(done_p, d.rec_p, sizeof(float) * B * beam, cudaMemcpyDeviceToDevice, st));
+    if (done_raw) CAPB_CHECK_CUDA(cudaMemcpyAsync(done_raw, d.rec_raw, sizeof(float) * B * beam, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+inline int beam_record_logprobs(DecodeBuffers& d, int V1, int T, int image, int rank, float* dst, cudaStream_t st) {
+    CAPB_REQUIRE(d.slab != nullptr && image >= 0 && image < d.last_B && rank >= 0 && rank < d.last_beam, "no such finished beam");
+    return gather_logprob_rows_launch(d.slab, d.slab_step_stride, V1, d.rec_hist + ((long)image * d.last_beam + rank) * T, 1, T, V1, dst,
+                                      d.slab_stats, (long)d.last_B * d.last_beam, st);
+}
+
+// AttModel._sample (greedy / multinomial / forced replay) and AttModel._forward (teacher forcing); method codes = CAPB200_SAMPLE_*
+template <class CoreFn>
+int sample_decode_driver(DecodeBuffers& d, int V1, int T, int rows, int method, float temperature, unsigned long long seed, int steps,
+                         const long long* tokens_in, long ld_tok, long long* seq, float* seq_logprobs, float* picked, CoreFn core, long* launches,
+                         cudaStream_t st) {
+    const bool teacher = method == 3, forced = method == 2;
+    const long t_out = teacher ? ld_tok : T;
+    CAPB_CHECK_CUDA(cudaMemsetAsync(d.tokens, 0, sizeof(int) * rows, st));
+    for (int t = 0; t < steps; ++t) {
+        if (teacher) { if (load_token_column_launch(tokens_in, ld_tok, t, rows, d.tokens, st)) return 1; *launches += 1; }
+        else if (forced) { if (load_token_column_launch(tokens_in, ld_tok, t, rows, d.forced, st)) return 1; *launches += 1; }
+        float* logits = seq_logprobs + (long)t * V1;
+        if (core(rows, 0, d.tokens, t == 0 ? d.neg1 : nullptr, t, logits, t_out * V1)) return 1;
+        VocabStepArgs va;
+        va.rows = rows; va.V1 = V1; va.logits = logits; va.ld = t_out * V1;
+        va.twice = 0;
+        if (!teacher) {
+            va.select = (method == 0) ? 1 : (method == 1 ? 2 : 3);
+            va.temperature = temperature;
+            va.seed = seed;
+            va.step = (unsigned long long)t;
+            va.forced = d.forced;
+            va.unfinished = d.unfinished;
+            va.first_step = (t == 0);
+            va.tokens_out = d.tokens;
+            va.seq_out = seq; va.ld_seq = T; va.t = t;
+            va.picked_lp = picked ? picked + t : nullptr;      // picked is [N,T]
+            va.ld_picked = T;
+        }
+        *launches += 1;
+        if (vocab_step_launch(va, st)) return 1;
+    }
+    return 0;
+}
+
+}  // namespace capb200

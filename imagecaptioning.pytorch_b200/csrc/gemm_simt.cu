@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(256, 2) gemm_simt_kernel(const SimtParams p) {
             float x = acc[i][j];
             if (e.bias) x += __ldg(e.bias + col);
             if (rb) x += __ldg(rb + col);
+            if (e.residual) x += e.residual[(long)row * e.ld_res + col];
             if (e.relu) x = fmaxf(x, 0.f);
             if (e.C) e.C[(long)row * e.ldc + col] = x;
             if (e.C_hi) {

@@ -48,6 +48,8 @@ struct TcParams {
     long ld_row_bias;
     int rows_per_group;
     int relu;
+    const float* residual;
+    long ld_res;
     int tiles_m, tiles_n;       // CTA tiles, padded to whole clusters
     // fused LSTM epilogue (see GemmEpilogue)
     int lstm, H;
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
                         if (p.bias != nullptr) x += __ldg(p.bias + col);
                         if (rb != nullptr) x += __ldg(rb + col);
                         if (gb != nullptr) x += __ldg(gb + col);
+                        if (p.residual != nullptr) x += p.residual[(long)row * p.ld_res + col];
                         if (p.relu) x = fmaxf(x, 0.0f);
                     }
                     v[j] = x;
@@ -446,6 +449,7 @@ static void fill_epilogue(TcParams& t, const GemmEpilogue& e) {
     t.bias = e.bias; t.row_bias = e.row_bias; t.ld_row_bias = e.ld_row_bias;
     t.rows_per_group = e.rows_per_group < 1 ? 1 : e.rows_per_group;
     t.relu = e.relu;
+    t.residual = e.residual; t.ld_res = e.ld_res;
     t.lstm = e.lstm; t.H = e.H;
     t.c_prev = e.c_prev; t.ld_cprev = e.ld_cprev; t.src_row = e.src_row;
     t.c_out = e.c_out; t.ld_cout = e.ld_cout;

@@ -91,6 +91,16 @@ int beam_finalize_launch(const BeamState& s, int keep, long long* out_seq, int* 
 int gather_logprob_rows_launch(const float* slab, long step_stride, long ld_slab, const int* hist, int nseq, int T, int V1, float* dst,
                                const float2* stats, long stats_stride, cudaStream_t stream);
 
+// ---- transformer.cu
+int layer_norm_launch(int rows, int D, const float* x, long ld_x, const float* a, const float* b, float eps, ActView out, cudaStream_t st);
+int embed_pe_launch(int rows, int D, const int* tokens, const float* lut, const float* pe_row, float scale, ActView out, cudaStream_t st);
+int enc_self_attention_launch(int B, int R, int heads, int dk, const float* q, const float* k, const float* v, long ld, const float* mask,
+                              long ld_mask, ActView out, cudaStream_t st);
+int dec_self_attention_launch(int rows, int heads, int dk, int t, const float* qkv, long ld_qkv, float* kcache, float* vcache, long step_stride,
+                              long ld_c, const int* anc, long ld_anc, const long long* labels, long ld_lab, ActView out, cudaStream_t st);
+int cross_attention_launch(int rows, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
+                           const float* mask, long ld_mask, ActView out, cudaStream_t st);
+
 // ---- reward.cu (CIDEr-D) and criterion
 struct CiderTable;   // device hash table of n-gram -> idf
 CiderTable* cider_table_create(const int* keys, const double* df, long n, double ref_len, cudaStream_t stream);

@@ -220,9 +220,25 @@ class B200CaptionModel(nn.Module):
         if forced_tokens is not None:
             tok = forced_tokens.detach().to(torch.long).contiguous()
             assert tok.shape == (N, T)
-        _lib.check(lib.capb200_decode_sample(self._engine, _lib.ptr(fc), _lib.ptr(att), _lib.ptr(masks), B, R, ctypes.byref(so), _lib.ptr(tok), T,
-                                             _lib.ptr(seq), _lib.ptr(logprobs), None, _lib.current_stream()), 'decode_sample')
+        _lib.check(self._call_sample(lib, fc, att, masks, B, R, so, tok, T, seq, logprobs), 'decode_sample')
         return seq, logprobs
+
+    # family-specific C-ABI entry points (overridden by the Transformer / AoA mirrors)
+    def _call_sample(self, lib, fc, att, masks, B, R, so, tok, ld_tok, seq, logprobs):
+        return lib.capb200_decode_sample(self._engine, _lib.ptr(fc), _lib.ptr(att), _lib.ptr(masks), B, R, ctypes.byref(so), _lib.ptr(tok), ld_tok,
+                                         _lib.ptr(seq), _lib.ptr(logprobs), None, _lib.current_stream())
+
+    def _call_beam(self, lib, fc, att, masks, B, R, bo, seq, logprobs, d_seq, d_len, d_p, d_raw):
+        return lib.capb200_decode_beam(self._engine, _lib.ptr(fc), _lib.ptr(att), _lib.ptr(masks), B, R, ctypes.byref(bo), _lib.ptr(seq),
+                                       _lib.ptr(logprobs), _lib.ptr(d_seq), _lib.ptr(d_len), _lib.ptr(d_p), _lib.ptr(d_raw), _lib.current_stream())
+
+    def _call_record(self, lib, image, rank, dst):
+        return lib.capb200_beam_record_logprobs(self._engine, image, rank, _lib.ptr(dst), _lib.current_stream())
+
+    def _teacher_steps(self, seq):
+        # the reference stops at the first column i >= 1 whose labels are all pad (AttModel.py:158-159)
+        col_empty = (seq[:, 1:].sum(0) == 0).nonzero()
+        return int(col_empty[0].item()) + 1 if col_empty.numel() > 0 else seq.shape[1]
 
     def _sample_beam(self, fc_feats, att_feats, att_masks=None, opt={}):
         beam_size = opt.get('beam_size', 10)
@@ -248,16 +264,14 @@ class B200CaptionModel(nn.Module):
         d_p = torch.zeros(B, beam_size, dtype=torch.float32, device=dev)
         d_raw = torch.zeros(B, beam_size, dtype=torch.float32, device=dev)
         bo = _lib.BeamOpts(beam_size, sample_n, _PENALTY[kind], float(alpha))
-        _lib.check(lib.capb200_decode_beam(self._engine, _lib.ptr(fc), _lib.ptr(att), _lib.ptr(masks), B, R, ctypes.byref(bo), _lib.ptr(seq),
-                                           _lib.ptr(logprobs), _lib.ptr(d_seq), _lib.ptr(d_len), _lib.ptr(d_p), _lib.ptr(d_raw),
-                                           _lib.current_stream()), 'decode_beam')
+        _lib.check(self._call_beam(lib, fc, att, masks, B, R, bo, seq, logprobs, d_seq, d_len, d_p, d_raw), 'decode_beam')
         self._last_beam = (d_seq, d_len, d_p, d_raw)
         self.done_beams = _LazyDoneBeams(self, B, beam_size)
         return seq, logprobs
 
     def _beam_logps(self, image, rank):
         dst = torch.zeros(self.seq_length, self.vocab_size + 1, dtype=torch.float32, device=self._last_beam[0].device)
-        _lib.check(_lib.load().capb200_beam_record_logprobs(self._engine, image, rank, _lib.ptr(dst), _lib.current_stream()), 'beam_record_logprobs')
+        _lib.check(self._call_record(_lib.load(), image, rank, dst), 'beam_record_logprobs')
         return dst
 
     def _forward(self, fc_feats, att_feats, seq, att_masks=None):
@@ -275,14 +289,11 @@ class B200CaptionModel(nn.Module):
         L = seq.shape[1]
         if L > self.seq_length + 2:
             raise ValueError('label width %d exceeds what the engine was built for' % L)
-        # the reference stops at the first column i >= 1 whose labels are all pad (AttModel.py:158-159)
-        col_empty = (seq[:, 1:].sum(0) == 0).nonzero()
-        steps = int(col_empty[0].item()) + 1 if col_empty.numel() > 0 else L
+        steps = self._teacher_steps(seq)
         R = att.shape[1] if att is not None and att.dim() == 3 else 1
         out = torch.zeros(B * spi, L, self.vocab_size + 1, dtype=torch.float32, device=fc.device)
         so = _lib.SampleOpts(spi, _lib.SAMPLE_TEACHER, 1.0, 0, steps)
-        _lib.check(lib.capb200_decode_sample(self._engine, _lib.ptr(fc), _lib.ptr(att), _lib.ptr(masks), B, R, ctypes.byref(so), _lib.ptr(seq), L,
-                                             None, _lib.ptr(out), None, _lib.current_stream()), 'forward_teacher')
+        _lib.check(self._call_sample(lib, fc, att, masks, B, R, so, seq, L, None, out), 'forward_teacher')
         return out
 
 
@@ -390,6 +401,160 @@ class B200NewFCModel(B200CaptionModel):
         }
 
 
+def _mha_params(d_model):
+    m = nn.Module()
+    m.linears = nn.ModuleList([nn.Linear(d_model, d_model) for _ in range(4)])
+    return m
+
+
+def _ln_params(d_model):
+    m = nn.Module()
+    m.a_2 = nn.Parameter(torch.ones(d_model))
+    m.b_2 = nn.Parameter(torch.zeros(d_model))
+    return m
+
+
+def _tfm_layer(d_model, d_ff, n_sub, with_src):
+    layer = nn.Module()
+    layer.self_attn = _mha_params(d_model)
+    if with_src:
+        layer.src_attn = _mha_params(d_model)
+    layer.feed_forward = nn.Module()
+    layer.feed_forward.w_1 = nn.Linear(d_model, d_ff)
+    layer.feed_forward.w_2 = nn.Linear(d_ff, d_model)
+    layer.sublayer = nn.ModuleList()
+    for _ in range(n_sub):
+        sub = nn.Module()
+        sub.norm = _ln_params(d_model)
+        layer.sublayer.append(sub)
+    return layer
+
+
+class B200TransformerModel(B200CaptionModel):
+    """Drop-in for captioning.models.TransformerModel.TransformerModel (TransformerModel.py:237-363): same opt fields (N_enc, N_dec,
+    d_model, d_ff, num_att_heads), same state_dict keys (att_embed.0.*, model.encoder/decoder.layers.*, model.tgt_embed.0.lut.weight,
+    model.tgt_embed.1.pe buffer, model.generator.proj.*).  Decoding keeps a per-layer K/V cache on the device."""
+
+    family_name = 'transformer'
+
+    def __init__(self, opt, numeric_mode=None):
+        super().__init__(opt, numeric_mode)
+        import math
+        self.N_enc = getattr(opt, 'N_enc', opt.num_layers)
+        self.N_dec = getattr(opt, 'N_dec', opt.num_layers)
+        self.d_model = getattr(opt, 'd_model', opt.input_encoding_size)
+        self.d_ff = getattr(opt, 'd_ff', opt.rnn_size)
+        self.h = getattr(opt, 'num_att_heads', 8)
+        if self.N_enc > _lib.TFM_MAX_LAYERS or self.N_dec > _lib.TFM_MAX_LAYERS:
+            raise NotImplementedError('at most %d layers per stack' % _lib.TFM_MAX_LAYERS)
+        V1, D = self.vocab_size + 1, self.d_model
+        self.att_embed = nn.Sequential(nn.Linear(self.att_feat_size, D), nn.ReLU(), nn.Dropout(self.drop_prob_lm))
+        self.model = nn.Module()
+        self.model.encoder = nn.Module()
+        self.model.encoder.layers = nn.ModuleList([_tfm_layer(D, self.d_ff, 2, False) for _ in range(self.N_enc)])
+        self.model.encoder.norm = _ln_params(D)
+        self.model.decoder = nn.Module()
+        self.model.decoder.layers = nn.ModuleList([_tfm_layer(D, self.d_ff, 3, True) for _ in range(self.N_dec)])
+        self.model.decoder.norm = _ln_params(D)
+        emb = nn.Module()
+        emb.lut = nn.Embedding(V1, D)
+        pos = nn.Module()
+        pe = torch.zeros(5000, D)
+        position = torch.arange(0, 5000).unsqueeze(1).float()
+        div_term = torch.exp(torch.arange(0, D, 2).float() * -(math.log(10000.0) / D))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        pos.register_buffer('pe', pe.unsqueeze(0))
+        self.model.tgt_embed = nn.Sequential(emb, pos)
+        self.model.generator = nn.Module()
+        self.model.generator.proj = nn.Linear(D, V1)
+        for p_ in self.model.parameters():        # Glorot init like make_model (TransformerModel.py:255-258)
+            if p_.dim() > 1:
+                nn.init.xavier_uniform_(p_)
+
+    # ---- engine plumbing (own C-ABI entry points: capb200_tfm_*) ------------------------------------------------------
+    def _tensors(self):
+        out = [self.att_embed[0].weight, self.att_embed[0].bias, self.model.tgt_embed[0].lut.weight, self.model.tgt_embed[1].pe,
+               self.model.generator.proj.weight, self.model.generator.proj.bias]
+        out += list(self.model.encoder.parameters()) + list(self.model.decoder.parameters())
+        return out
+
+    def _ensure_engine(self, device):
+        if device.type != 'cuda':
+            raise RuntimeError('capb200: the decode engine runs on CUDA devices only (no CPU fallback); got %s' % device)
+        lib = _lib.load()
+        key = (device.index, self.numeric_mode)
+        if self._engine is None or self._engine_key != key:
+            self._destroy_engine()
+            cfg = _lib.TfmCfg(self.vocab_size, self.d_model, self.d_ff, self.h, self.N_enc, self.N_dec, self.att_feat_size, self.seq_length,
+                              _lib.MODES[self.numeric_mode])
+            with torch.cuda.device(device):
+                eng = lib.capb200_tfm_create(ctypes.byref(cfg))
+            if not eng:
+                raise RuntimeError('capb200 tfm_create failed: %s' % lib.capb200_last_error().decode())
+            self._engine, self._engine_key, self._bound_versions = eng, key, None
+        tensors = self._tensors()
+        versions = tuple((t.data_ptr(), t._version) for t in tensors)
+        if versions != self._bound_versions:
+            for t in tensors:
+                if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise RuntimeError('capb200: parameters must be contiguous float32 tensors on %s' % device)
+            w = _lib.TfmWeights()
+            P = lambda t: t.data_ptr()
+
+            def mha(dst, src):
+                for name, lin in zip(('q', 'k', 'v', 'o'), src.linears):
+                    setattr(dst, name + '_w', P(lin.weight))
+                    setattr(dst, name + '_b', P(lin.bias))
+
+            def common(dst, layer, n_sub):
+                dst.w1_w, dst.w1_b = P(layer.feed_forward.w_1.weight), P(layer.feed_forward.w_1.bias)
+                dst.w2_w, dst.w2_b = P(layer.feed_forward.w_2.weight), P(layer.feed_forward.w_2.bias)
+                for j in range(n_sub):
+                    setattr(dst, 'ln%d_a' % j, P(layer.sublayer[j].norm.a_2))
+                    setattr(dst, 'ln%d_b' % j, P(layer.sublayer[j].norm.b_2))
+
+            w.att_embed_w, w.att_embed_b = P(self.att_embed[0].weight), P(self.att_embed[0].bias)
+            for i, layer in enumerate(self.model.encoder.layers):
+                mha(w.enc[i].self_attn, layer.self_attn)
+                common(w.enc[i], layer, 2)
+            for i, layer in enumerate(self.model.decoder.layers):
+                mha(w.dec[i].self_attn, layer.self_attn)
+                mha(w.dec[i].src_attn, layer.src_attn)
+                common(w.dec[i], layer, 3)
+            w.enc_norm_a, w.enc_norm_b = P(self.model.encoder.norm.a_2), P(self.model.encoder.norm.b_2)
+            w.dec_norm_a, w.dec_norm_b = P(self.model.decoder.norm.a_2), P(self.model.decoder.norm.b_2)
+            w.lut, w.pe = P(self.model.tgt_embed[0].lut.weight), P(self.model.tgt_embed[1].pe)
+            w.gen_w, w.gen_b = P(self.model.generator.proj.weight), P(self.model.generator.proj.bias)
+            _lib.check(lib.capb200_tfm_bind_weights(self._engine, ctypes.byref(w), _lib.current_stream()), 'tfm_bind_weights')
+            self._bound_versions = versions
+        return lib
+
+    def _destroy_engine(self):
+        if self._engine is not None:
+            _lib.load().capb200_tfm_destroy(self._engine)
+            self._engine = None
+
+    @property
+    def launch_count(self) -> int:
+        return 0 if self._engine is None else int(_lib.load().capb200_tfm_launch_count(self._engine))
+
+    # ---- calls: the transformer ignores fc_feats (TransformerModel.py:305-310) ---------------------------------------
+    def _call_sample(self, lib, fc, att, masks, B, R, so, tok, ld_tok, seq, logprobs):
+        return lib.capb200_tfm_decode_sample(self._engine, _lib.ptr(att), _lib.ptr(masks), B, R, ctypes.byref(so), _lib.ptr(tok), ld_tok,
+                                             _lib.ptr(seq), _lib.ptr(logprobs), None, _lib.current_stream())
+
+    def _call_beam(self, lib, fc, att, masks, B, R, bo, seq, logprobs, d_seq, d_len, d_p, d_raw):
+        return lib.capb200_tfm_decode_beam(self._engine, _lib.ptr(att), _lib.ptr(masks), B, R, ctypes.byref(bo), _lib.ptr(seq), _lib.ptr(logprobs),
+                                           _lib.ptr(d_seq), _lib.ptr(d_len), _lib.ptr(d_p), _lib.ptr(d_raw), _lib.current_stream())
+
+    def _call_record(self, lib, image, rank, dst):
+        return lib.capb200_tfm_beam_record_logprobs(self._engine, image, rank, _lib.ptr(dst), _lib.current_stream())
+
+    def _teacher_steps(self, seq):
+        return seq.shape[1]            # one parallel pass in the reference: every position is computed (TransformerModel.py:340-348)
+
+
 def setup(opt, numeric_mode=None):
     """Factory with the contract of captioning.models.setup (captioning/models/__init__.py:20-73) for the families on the
     B200 hot path."""
@@ -398,4 +563,8 @@ def setup(opt, numeric_mode=None):
         return B200UpDownModel(opt, numeric_mode)
     if name == 'newfc':
         return B200NewFCModel(opt, numeric_mode)
+    if name == 'transformer':
+        if getattr(opt, 'cached_transformer', False):
+            raise NotImplementedError('cachedTransformer is a reference-side variant; the B200 engine always caches K/V')
+        return B200TransformerModel(opt, numeric_mode)
     raise NotImplementedError('caption_model %r is not on the B200 decode path yet (SURVEY.md section 8)' % name)

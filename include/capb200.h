@@ -144,6 +144,48 @@ int capb200_engine_set_profiling(capb200_engine* e, int enable);
 int capb200_engine_read_profile(capb200_engine* e, int reset, double* ms, double* flops, long* calls, int n);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Transformer captioner (TransformerModel, captioning/models/TransformerModel.py:237-363)
+ *   prologue = att_embed + N_enc encoder layers (TransformerModel.py:305-338); decode keeps a K/V cache per layer instead of
+ *   re-running all t tokens each step (:351-363) -- identical results because the decoder mask is causal.
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define CAPB200_TFM_MAX_LAYERS 8
+typedef struct capb200_tfm_engine capb200_tfm_engine;
+typedef struct {
+    int vocab_size, d_model, d_ff, heads, n_enc, n_dec, att_feat_size, seq_length, numeric_mode;
+} capb200_tfm_cfg;
+typedef struct { const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b; } capb200_mha_weights;          /* linears.0..3 */
+typedef struct {
+    capb200_mha_weights self_attn;
+    const float *w1_w, *w1_b, *w2_w, *w2_b;                                                                   /* feed_forward.w_1 / w_2 */
+    const float *ln0_a, *ln0_b, *ln1_a, *ln1_b;                                                               /* sublayer.{0,1}.norm.{a_2,b_2} */
+} capb200_tfm_enc_layer;
+typedef struct {
+    capb200_mha_weights self_attn, src_attn;
+    const float *w1_w, *w1_b, *w2_w, *w2_b;
+    const float *ln0_a, *ln0_b, *ln1_a, *ln1_b, *ln2_a, *ln2_b;
+} capb200_tfm_dec_layer;
+typedef struct {
+    const float *att_embed_w, *att_embed_b;                     /* att_embed.0 [D, F_att] */
+    capb200_tfm_enc_layer enc[CAPB200_TFM_MAX_LAYERS];          /* model.encoder.layers.i */
+    const float *enc_norm_a, *enc_norm_b;                       /* model.encoder.norm */
+    capb200_tfm_dec_layer dec[CAPB200_TFM_MAX_LAYERS];          /* model.decoder.layers.i */
+    const float *dec_norm_a, *dec_norm_b;                       /* model.decoder.norm */
+    const float *lut, *pe;                                      /* model.tgt_embed.0.lut.weight [V+1, D]; model.tgt_embed.1.pe [1, 5000, D] */
+    const float *gen_w, *gen_b;                                 /* model.generator.proj [V+1, D] */
+} capb200_tfm_weights;
+
+capb200_tfm_engine* capb200_tfm_create(const capb200_tfm_cfg* cfg);
+void capb200_tfm_destroy(capb200_tfm_engine* e);
+int capb200_tfm_bind_weights(capb200_tfm_engine* e, const capb200_tfm_weights* w, void* stream);
+/* same contracts as capb200_decode_beam / capb200_beam_record_logprobs / capb200_decode_sample; fc features are unused */
+int capb200_tfm_decode_beam(capb200_tfm_engine* e, const float* att, const float* mask, int B, int R, const capb200_beam_opts* opts, long long* seq,
+                            float* seq_logprobs, long long* done_seq, int* done_len, float* done_p, float* done_raw, void* stream);
+int capb200_tfm_beam_record_logprobs(capb200_tfm_engine* e, int image, int rank, float* dst, void* stream);
+int capb200_tfm_decode_sample(capb200_tfm_engine* e, const float* att, const float* mask, int B, int R, const capb200_sample_opts* opts,
+                              const long long* tokens_in, long ld_tok, long long* seq, float* seq_logprobs, float* picked, void* stream);
+long capb200_tfm_launch_count(const capb200_tfm_engine* e);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * SCST reward and criterion
  * ---------------------------------------------------------------------------------------------------------------- */
 /* Document-frequency table in the scripts/prepro_ngrams.py format, flattened: keys[n,4] int32 token ids padded with -1,

@@ -577,6 +577,7 @@ def make_weights(family: str, V: int, E: int, H: int, A: int, F_fc: int, F_att: 
         W['core.attention.norm.a_2'] = 1 + 0.1 * torch.randn(H, generator=g)
         W['core.attention.norm.b_2'] = 0.1 * torch.randn(H, generator=g)
         lin('core.attention.linears.0', H, H)
+        W['logit.bias'][0] -= 4.0          # keep EOS from winning at the first steps so the synthetic captions have some length
     elif family == 'transformer':
         # here E = d_model, H = d_ff, A = number of layers (both stacks)
         D, Dff, NL = E, H, A

@@ -39,12 +39,14 @@ def _enter_scratch():
     return d
 
 
-def ref_model(family, V, E, H, A, F_fc, F_att, T, W):
+def ref_model(family, V, E, H, A, F_fc, F_att, T, W, **extra):
     import captioning.models as M
     opt = argparse.Namespace(vocab_size=V, input_encoding_size=E, rnn_size=H, num_layers=1, drop_prob_lm=0.5,
                              max_length=T, seq_length=T, fc_feat_size=F_fc, att_feat_size=F_att, att_hid_size=A,
                              vocab={str(i): 'w%d' % i for i in range(1, V + 1)}, caption_model=family, use_bn=0,
                              logit_layers=1)
+    for k, v in extra.items():
+        setattr(opt, k, v)
     m = M.setup(opt)
     missing = m.load_state_dict(W, strict=True)
     m.eval()
@@ -215,6 +217,52 @@ def gen_reward_criterion(out_dir):
     print('reward_criterion loss', float(loss))
 
 
+def _gen_family_small(out_dir, family, name, cfg, extra, heads, logit_scale):
+    """greedy / beam / masks / teacher forcing / sampled replay of a small model through the live reference."""
+    B, R, b, seed = 4, 7, 3, 17
+    W = co.make_weights(family, cfg['V'], cfg['E'], cfg['H'], cfg['A'], cfg['F_fc'], cfg['F_att'], seed=seed, logit_scale=logit_scale)
+    fc, att = co.make_inputs(B, R, cfg['F_fc'], cfg['F_att'], seed=seed)
+    m = ref_model(family, W=W, **cfg, **extra)
+    res = {}
+    with torch.no_grad():
+        seq, lp = m(fc, att, None, opt={'sample_method': 'greedy', 'beam_size': 1}, mode='sample')
+        res['greedy_seq'], res['greedy_lp'] = seq.numpy(), lp.numpy()
+        seq, lp = m(fc, att, None, opt={'beam_size': b, 'sample_n': 1}, mode='sample')
+        res['beam_seq'], res['beam_lp'] = seq.numpy(), lp.numpy()
+        res['done_seq'], res['done_len'], res['done_p'] = beams_to_arrays(m.done_beams, b, cfg['T'])
+        masks = torch.ones(B, R)
+        masks[1, 5:] = 0
+        masks[3, 3:] = 0
+        seq, lp = m(fc, att, masks, opt={'sample_method': 'greedy', 'beam_size': 1}, mode='sample')
+        res['masked_greedy_seq'], res['masked_greedy_lp'] = seq.numpy(), lp.numpy()
+        seq, lp = m(fc, att, masks, opt={'beam_size': b, 'sample_n': 1}, mode='sample')
+        res['masked_beam_seq'] = seq.numpy()
+        res['masks'] = masks.numpy()
+        labels = torch.from_numpy(np.concatenate([np.zeros((B, 1), np.int64), res['greedy_seq'][:, :-1]], 1))
+        labels2 = torch.stack([labels, labels.flip(0)], 1)
+        res['teacher_in'] = labels2.numpy()
+        res['teacher_lp'] = m(fc, att, labels2, None).numpy()
+        torch.manual_seed(5)
+        seq, lp = m(fc, att, None, opt={'sample_method': 'sample', 'beam_size': 1, 'sample_n': 3, 'temperature': 1.0}, mode='sample')
+        res['sample_seq'], res['sample_lp'] = seq.numpy(), lp.numpy()
+    np.savez_compressed(os.path.join(out_dir, name), cfg=np.array([cfg[k] for k in ('V', 'E', 'H', 'A', 'F_fc', 'F_att', 'T')]),
+                        meta=np.array([B, R, b, seed, heads]), **res)
+    print(name, 'greedy', res['greedy_seq'][0].tolist(), 'beam', res['beam_seq'][0].tolist())
+
+
+def gen_transformer_small(out_dir):
+    # make_weights('transformer'): E = d_model, H = d_ff, A = layers per stack
+    cfg = dict(V=60, E=32, H=64, A=2, F_fc=48, F_att=48, T=8)
+    _gen_family_small(out_dir, 'transformer', 'transformer_small.npz', cfg, dict(num_layers=2, N_enc=2, N_dec=2, d_model=32, d_ff=64,
+                                                                                 num_att_heads=4, dropout=0.1), 4, 10.0)
+
+
+def gen_aoa_small(out_dir):
+    cfg = dict(V=60, E=32, H=32, A=16, F_fc=48, F_att=48, T=8)
+    _gen_family_small(out_dir, 'aoa', 'aoa_small.npz', cfg, dict(num_layers=2, refine=1, refine_aoa=1, use_ff=0, decoder_type='AoA', use_multi_head=2,
+                                                                  num_heads=4, multi_head_scale=1, mean_feats=1, ctx_drop=1, dropout_aoa=0.3), 4, 20.0)
+
+
 def gen_state_dict_keys(out_dir):
     """Names and shapes of the reference modules' parameters: the drop-in must expose exactly these."""
     import json
@@ -224,6 +272,13 @@ def gen_state_dict_keys(out_dir):
         W = co.make_weights(fam, cfg['V'], cfg['E'], cfg['H'], cfg['A'], cfg['F_fc'], cfg['F_att'], seed=1)
         m = ref_model(fam, W=W, **cfg)
         res[fam] = {k: list(v.shape) for k, v in m.state_dict().items()}
+    W = co.make_weights('transformer', 60, 32, 64, 2, 48, 56, seed=1)
+    m = ref_model('transformer', 60, 32, 64, 2, 48, 56, 8, W, num_layers=2, N_enc=2, N_dec=2, d_model=32, d_ff=64, num_att_heads=4, dropout=0.1)
+    res['transformer'] = {k: list(v.shape) for k, v in m.state_dict().items()}
+    W = co.make_weights('aoa', 60, 32, 32, 16, 48, 56, seed=1)
+    m = ref_model('aoa', 60, 32, 32, 16, 48, 56, 8, W, num_layers=2, refine=1, refine_aoa=1, use_ff=0, decoder_type='AoA', use_multi_head=2,
+                  num_heads=4, multi_head_scale=1, mean_feats=1, ctx_drop=1, dropout_aoa=0.3)
+    res['aoa'] = {k: list(v.shape) for k, v in m.state_dict().items()}
     with open(os.path.join(out_dir, 'state_dict_keys.json'), 'w') as f:
         json.dump({'cfg': cfg, 'keys': res}, f, indent=1, sort_keys=True)
     print('state_dict_keys', {k: len(v) for k, v in res.items()})
@@ -234,7 +289,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     scratch = _enter_scratch()
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys']
+    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys', 'tfm', 'aoa']
     if 'small' in which:
         gen_updown_small(out_dir)
     if 'newfc' in which:
@@ -247,6 +302,10 @@ def main():
         gen_reward_criterion(out_dir)
     if 'keys' in which:
         gen_state_dict_keys(out_dir)
+    if 'tfm' in which:
+        gen_transformer_small(out_dir)
+    if 'aoa' in which:
+        gen_aoa_small(out_dir)
 
 
 if __name__ == '__main__':

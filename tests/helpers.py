@@ -22,14 +22,26 @@ def make_opt(family, V, E, H, A, F_fc, F_att, T):
                               caption_model=family, use_bn=0, logit_layers=1)
 
 
-def build_pair(family, V, E, H, A, F_fc, F_att, T, seed, logit_scale, mode, device='cuda'):
-    """Returns (B200 model on the GPU, oracle Family on the CPU) sharing the same synthetic weights."""
+def family_opt(family, V, E, H, A, F_fc, F_att, T, heads=8):
+    """opt namespace for a family; for 'transformer' E = d_model, H = d_ff, A = layers per stack (make_weights convention)."""
+    opt = make_opt(family, V, E, H, A, F_fc, F_att, T)
+    if family == 'transformer':
+        opt.num_layers, opt.N_enc, opt.N_dec, opt.d_model, opt.d_ff, opt.num_att_heads = A, A, A, E, H, heads
+    if family == 'aoa':
+        opt.num_layers, opt.refine, opt.refine_aoa, opt.use_ff, opt.decoder_type, opt.use_multi_head = 2, 1, 1, 0, 'AoA', 2
+        opt.num_heads, opt.multi_head_scale, opt.mean_feats, opt.ctx_drop = heads, 1, 1, 1
+    return opt
+
+
+def build_pair(family, V, E, H, A, F_fc, F_att, T, seed, logit_scale, mode, device='cuda', heads=8):
+    """Returns (B200 model on the GPU, oracle Family on the CPU) sharing the same synthetic weights.
+    For 'transformer': E = d_model, H = d_ff, A = layers per stack (the make_weights convention)."""
     import imagecaptioning.pytorch_b200 as b200
     W = co.make_weights(family, V, E, H, A, F_fc, F_att, seed=seed, logit_scale=logit_scale)
-    model = b200.setup(make_opt(family, V, E, H, A, F_fc, F_att, T), numeric_mode=mode)
+    model = b200.setup(family_opt(family, V, E, H, A, F_fc, F_att, T, heads), numeric_mode=mode)
     model.load_state_dict(W, strict=True)
     model = model.to(device).eval()
-    return model, co.Family(family, W, T)
+    return model, co.Family(family, W, T, heads=heads)
 
 
 def first_divergence(a, b):

@@ -109,3 +109,34 @@ def test_reward_criterion(golden_dir):
     assert abs(float(co.reward_criterion(lp, seq, reward)) - float(g['loss'])) < 1e-6
     assert np.abs(co.reward_criterion(lp, seq, reward, 'none').numpy() - g['loss_none']).max() < 1e-6
     assert np.abs(co.reward_criterion_grad(seq, reward, lp.shape[2]).numpy() - g['grad']).max() < 1e-7
+
+
+def _family_small(golden_dir, fname, family, scale):
+    g = _load(golden_dir, fname)
+    V, E, H, A, F_fc, F_att, T = (int(x) for x in g['cfg'])
+    B, R, b, seed, heads = (int(x) for x in g['meta'])
+    W = co.make_weights(family, V, E, H, A, F_fc, F_att, seed=seed, logit_scale=scale)
+    fc, att = co.make_inputs(B, R, F_fc, F_att, seed=seed)
+    return g, co.Family(family, W, T, heads=heads), fc, att, b
+
+
+@pytest.mark.parametrize('fname,family,scale', [('transformer_small.npz', 'transformer', 10.0), ('aoa_small.npz', 'aoa', 20.0)])
+def test_transformer_and_aoa_small(golden_dir, fname, family, scale):
+    g, fam, fc, att, b = _family_small(golden_dir, fname, family, scale)
+    seq, lp = co.sample(fam, fc, att)
+    assert np.array_equal(seq.numpy(), g['greedy_seq'])
+    assert np.abs(lp.numpy() - g['greedy_lp']).max() < TOL
+    seq, lp, done = co.sample_beam(fam, fc, att, beam_size=b)
+    assert np.array_equal(seq.numpy(), g['beam_seq'])
+    assert np.abs(lp.numpy() - g['beam_lp']).max() < TOL
+    assert np.abs(np.array([[r['p'] for r in d] for d in done]) - g['done_p']).max() < 1e-3
+    masks = torch.from_numpy(g['masks'])
+    seq, lp = co.sample(fam, fc, att, masks)
+    assert np.array_equal(seq.numpy(), g['masked_greedy_seq'])
+    assert np.abs(lp.numpy() - g['masked_greedy_lp']).max() < TOL
+    seq, _, _ = co.sample_beam(fam, fc, att, masks, beam_size=b)
+    assert np.array_equal(seq.numpy(), g['masked_beam_seq'])
+    out = co.forward_teacher(fam, fc, att, torch.from_numpy(g['teacher_in']))
+    assert np.abs(out.numpy() - g['teacher_lp']).max() < TOL
+    seq, lp = co.sample(fam, fc, att, sample_method='sample', sample_n=3, forced_tokens=torch.from_numpy(g['sample_seq']))
+    assert np.abs(lp.numpy() - g['sample_lp']).max() < TOL
