@@ -4,7 +4,7 @@ Only what the hot path needs lives here: ``csrc/`` (hand-written sm_100a kernels
 host-side mirrors of the reference interfaces (``models``, ``loss_wrapper``, ``rewards``).  See DESIGN.md.
 """
 from . import _lib                                    # noqa: F401
-from .models import B200UpDownModel, B200NewFCModel, B200TransformerModel, B200CaptionModel, setup      # noqa: F401
+from .models import B200UpDownModel, B200NewFCModel, B200TransformerModel, B200AoAModel, B200CaptionModel, setup      # noqa: F401
 from .loss_wrapper import B200LossWrapper, RewardCriterion                        # noqa: F401
 from . import rewards                                 # noqa: F401
 

@@ -64,6 +64,24 @@ class TfmWeights(Structure):
                 ('lut', c_void_p), ('pe', c_void_p), ('gen_w', c_void_p), ('gen_b', c_void_p)]
 
 
+AOA_REFINER_LAYERS = 6
+
+
+class AoaCfg(Structure):
+    _fields_ = [(f, c_int) for f in ('vocab_size', 'input_encoding_size', 'rnn_size', 'heads', 'att_feat_size', 'seq_length', 'numeric_mode')]
+
+
+class AoaRefinerLayer(Structure):
+    _fields_ = [(f, c_void_p) for f in ('q_w', 'q_b', 'k_w', 'k_b', 'v_w', 'v_b', 'aoa_w', 'aoa_b', 'ln_a', 'ln_b')]
+
+
+class AoaWeights(Structure):
+    _fields_ = [('embed', c_void_p), ('att_embed_w', c_void_p), ('att_embed_b', c_void_p), ('refiner', AoaRefinerLayer * AOA_REFINER_LAYERS)] + \
+               [(f, c_void_p) for f in ('refiner_norm_a', 'refiner_norm_b', 'ctx2att_w', 'ctx2att_b', 'att_lstm_w_ih', 'att_lstm_w_hh', 'att_lstm_b_ih',
+                                        'att_lstm_b_hh', 'attn_norm_a', 'attn_norm_b', 'attn_q_w', 'attn_q_b', 'att2ctx_w', 'att2ctx_b', 'logit_w',
+                                        'logit_b')]
+
+
 # every exported symbol of include/capb200.h: (restype, argtypes)
 SIGNATURES = {
     'capb200_last_error': (c_char_p, []),
@@ -95,6 +113,15 @@ SIGNATURES = {
     'capb200_tfm_decode_sample': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(SampleOpts), c_void_p, c_long, c_void_p, c_void_p, c_void_p,
                                           c_void_p]),
     'capb200_tfm_launch_count': (c_long, [c_void_p]),
+    'capb200_aoa_create': (c_void_p, [POINTER(AoaCfg)]),
+    'capb200_aoa_destroy': (None, [c_void_p]),
+    'capb200_aoa_bind_weights': (c_int, [c_void_p, POINTER(AoaWeights), c_void_p]),
+    'capb200_aoa_decode_beam': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(BeamOpts), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
+    'capb200_aoa_beam_record_logprobs': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    'capb200_aoa_decode_sample': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(SampleOpts), c_void_p, c_long, c_void_p, c_void_p, c_void_p,
+                                          c_void_p]),
+    'capb200_aoa_launch_count': (c_long, [c_void_p]),
     'capb200_cider_table_create': (c_void_p, [c_void_p, c_void_p, c_long, c_double, c_void_p]),
     'capb200_cider_table_destroy': (None, [c_void_p]),
     'capb200_self_critical_reward': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,

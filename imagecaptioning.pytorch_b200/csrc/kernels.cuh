@@ -101,6 +101,9 @@ int dec_self_attention_launch(int rows, int heads, int dk, int t, const float* q
 int cross_attention_launch(int rows, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
                            const float* mask, long ld_mask, ActView out, cudaStream_t st);
 
+int glu_launch(int rows, int H, const float* t, long ld_t, const float* residual, long ld_res, ActView out, cudaStream_t st);
+int masked_mean_launch(int B, int R, int H, const float* x, long ld_x, const float* mask, long ld_mask, ActView out, cudaStream_t st);
+
 // ---- reward.cu (CIDEr-D) and criterion
 struct CiderTable;   // device hash table of n-gram -> idf
 CiderTable* cider_table_create(const int* keys, const double* df, long n, double ref_len, cudaStream_t stream);

@@ -195,7 +195,50 @@ __global__ void __launch_bounds__(128) cross_attention_kernel(int rows, int rpi,
     }
 }
 
+// GLU over the last dimension (nn.GLU, AoAModel.py:41,143): out[r, j] = t[r, j] * sigmoid(t[r, H + j]) (+ residual[r, j])
+__global__ void glu_kernel(int rows, int H, const float* __restrict__ t, long ld_t, const float* __restrict__ residual, long ld_res, ActView out) {
+    const long total = (long)rows * H;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / H), j = (int)(i % H);
+        const float a = t[(long)r * ld_t + j], b = t[(long)r * ld_t + H + j];
+        float v = a * (1.0f / (1.0f + expf(-b)));
+        if (residual != nullptr) v += residual[(long)r * ld_res + j];
+        store_act2(out, r, j, v);
+    }
+}
+
+// mean over the (valid) regions of each image (AoAModel.py:214-219): one CTA per image
+__global__ void masked_mean_kernel(int R, int H, const float* __restrict__ x, long ld_x, const float* __restrict__ mask, long ld_mask, ActView out) {
+    const int img = blockIdx.x;
+    float cnt = 0.f;
+    if (mask != nullptr) { for (int r = 0; r < R; ++r) cnt += mask[(long)img * ld_mask + r]; } else cnt = (float)R;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < R; ++r) {
+            const float v = x[((long)img * R + r) * ld_x + c];
+            s += (mask != nullptr) ? v * mask[(long)img * ld_mask + r] : v;
+        }
+        store_act2(out, img, c, s / cnt);
+    }
+}
+
 }  // namespace
+
+int glu_launch(int rows, int H, const float* t, long ld_t, const float* residual, long ld_res, ActView out, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    long blocks = ((long)rows * H + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    glu_kernel<<<(int)blocks, 256, 0, st>>>(rows, H, t, ld_t, residual, ld_res, out);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int masked_mean_launch(int B, int R, int H, const float* x, long ld_x, const float* mask, long ld_mask, ActView out, cudaStream_t st) {
+    if (B <= 0) return 0;
+    masked_mean_kernel<<<B, 256, 0, st>>>(R, H, x, ld_x, mask, ld_mask, out);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int layer_norm_launch(int rows, int D, const float* x, long ld_x, const float* a, const float* b, float eps, ActView out, cudaStream_t st) {
     if (rows <= 0) return 0;
@@ -215,7 +258,12 @@ int enc_self_attention_launch(int B, int R, int heads, int dk, const float* q, c
                               long ld_mask, ActView out, cudaStream_t st) {
     if (B <= 0) return 0;
     const size_t smem = sizeof(float) * ((size_t)2 * R * (dk + 1) + 4 * R);
-    CAPB_REQUIRE(smem <= 48 * 1024, "self-attention: region count x head width too large for the shared-memory staging");
+    CAPB_REQUIRE(smem <= 200 * 1024, "self-attention: region count x head width too large for the shared-memory staging");
+    static bool configured = false;
+    if (!configured) {
+        CAPB_CHECK_CUDA(cudaFuncSetAttribute(enc_self_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
     enc_self_attention_kernel<<<dim3(B, heads), 128, smem, st>>>(R, dk, q, k, v, ld, mask, ld_mask, 1.0f / sqrtf((float)dk), out);
     CAPB_CHECK_CUDA(cudaGetLastError());
     return 0;

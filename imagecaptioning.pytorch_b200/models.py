@@ -555,6 +555,116 @@ class B200TransformerModel(B200CaptionModel):
         return seq.shape[1]            # one parallel pass in the reference: every position is computed (TransformerModel.py:340-348)
 
 
+class B200AoAModel(B200CaptionModel):
+    """Drop-in for captioning.models.AoAModel.AoAModel in the configs/aoa.yml configuration (refine=1, refine_aoa=1, use_ff=0,
+    decoder_type='AoA', use_multi_head=2, multi_head_scale=1, mean_feats=1): same state_dict keys (no fc_embed), same surfaces."""
+
+    family_name = 'aoa'
+
+    def __init__(self, opt, numeric_mode=None):
+        super().__init__(opt, numeric_mode)
+        need = dict(refine=1, refine_aoa=1, use_ff=0, decoder_type='AoA', use_multi_head=2, multi_head_scale=1)
+        for k, v in need.items():
+            if getattr(opt, k, v) != v:
+                raise NotImplementedError('AoA option %s=%r is outside the configs/aoa.yml configuration the B200 engine implements' % (k, getattr(opt, k)))
+        if not getattr(opt, 'mean_feats', 1):
+            raise NotImplementedError('mean_feats=0 is outside the configs/aoa.yml configuration')
+        if getattr(opt, 'out_res', 0):
+            raise NotImplementedError('out_res is outside the configs/aoa.yml configuration')
+        self.num_layers = 2
+        self.num_heads = opt.num_heads
+        H, E, V1 = self.rnn_size, self.input_encoding_size, self.vocab_size + 1
+        self.embed = nn.Sequential(nn.Embedding(V1, E), nn.ReLU(), nn.Dropout(self.drop_prob_lm))
+        self.att_embed = nn.Sequential(nn.Linear(self.att_feat_size, H), nn.ReLU(), nn.Dropout(self.drop_prob_lm))
+        self.logit = nn.Linear(H, V1)
+        self.ctx2att = nn.Linear(H, 2 * H)
+        self.refiner = nn.Module()
+        self.refiner.layers = nn.ModuleList()
+        for _ in range(_lib.AOA_REFINER_LAYERS):
+            layer = nn.Module()
+            layer.self_attn = nn.Module()
+            layer.self_attn.linears = nn.ModuleList([nn.Linear(H, H) for _ in range(3)])
+            layer.self_attn.aoa_layer = nn.Sequential(nn.Linear(2 * H, 2 * H), nn.GLU())
+            sub = nn.Module()
+            sub.norm = _ln_params(H)
+            layer.sublayer = nn.ModuleList([sub])
+            self.refiner.layers.append(layer)
+        self.refiner.norm = _ln_params(H)
+        self.core = nn.Module()
+        self.core.att_lstm = nn.LSTMCell(E + H, H)
+        self.core.att2ctx = nn.Sequential(nn.Linear(2 * H, 2 * H), nn.GLU())
+        self.core.attention = nn.Module()
+        self.core.attention.norm = _ln_params(H)
+        self.core.attention.linears = nn.ModuleList([nn.Linear(H, H)])
+
+    def _tensors(self):
+        return list(self.parameters())
+
+    def _ensure_engine(self, device):
+        if device.type != 'cuda':
+            raise RuntimeError('capb200: the decode engine runs on CUDA devices only (no CPU fallback); got %s' % device)
+        lib = _lib.load()
+        key = (device.index, self.numeric_mode)
+        if self._engine is None or self._engine_key != key:
+            self._destroy_engine()
+            cfg = _lib.AoaCfg(self.vocab_size, self.input_encoding_size, self.rnn_size, self.num_heads, self.att_feat_size, self.seq_length,
+                              _lib.MODES[self.numeric_mode])
+            with torch.cuda.device(device):
+                eng = lib.capb200_aoa_create(ctypes.byref(cfg))
+            if not eng:
+                raise RuntimeError('capb200 aoa_create failed: %s' % lib.capb200_last_error().decode())
+            self._engine, self._engine_key, self._bound_versions = eng, key, None
+        tensors = self._tensors()
+        versions = tuple((t.data_ptr(), t._version) for t in tensors)
+        if versions != self._bound_versions:
+            for t in tensors:
+                if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise RuntimeError('capb200: parameters must be contiguous float32 tensors on %s' % device)
+            P = lambda t: t.data_ptr()
+            w = _lib.AoaWeights()
+            w.embed = P(self.embed[0].weight)
+            w.att_embed_w, w.att_embed_b = P(self.att_embed[0].weight), P(self.att_embed[0].bias)
+            for i, layer in enumerate(self.refiner.layers):
+                r = w.refiner[i]
+                for name, lin in zip(('q', 'k', 'v'), layer.self_attn.linears):
+                    setattr(r, name + '_w', P(lin.weight))
+                    setattr(r, name + '_b', P(lin.bias))
+                r.aoa_w, r.aoa_b = P(layer.self_attn.aoa_layer[0].weight), P(layer.self_attn.aoa_layer[0].bias)
+                r.ln_a, r.ln_b = P(layer.sublayer[0].norm.a_2), P(layer.sublayer[0].norm.b_2)
+            w.refiner_norm_a, w.refiner_norm_b = P(self.refiner.norm.a_2), P(self.refiner.norm.b_2)
+            w.ctx2att_w, w.ctx2att_b = P(self.ctx2att.weight), P(self.ctx2att.bias)
+            c = self.core
+            w.att_lstm_w_ih, w.att_lstm_w_hh = P(c.att_lstm.weight_ih), P(c.att_lstm.weight_hh)
+            w.att_lstm_b_ih, w.att_lstm_b_hh = P(c.att_lstm.bias_ih), P(c.att_lstm.bias_hh)
+            w.attn_norm_a, w.attn_norm_b = P(c.attention.norm.a_2), P(c.attention.norm.b_2)
+            w.attn_q_w, w.attn_q_b = P(c.attention.linears[0].weight), P(c.attention.linears[0].bias)
+            w.att2ctx_w, w.att2ctx_b = P(c.att2ctx[0].weight), P(c.att2ctx[0].bias)
+            w.logit_w, w.logit_b = P(self.logit.weight), P(self.logit.bias)
+            _lib.check(lib.capb200_aoa_bind_weights(self._engine, ctypes.byref(w), _lib.current_stream()), 'aoa_bind_weights')
+            self._bound_versions = versions
+        return lib
+
+    def _destroy_engine(self):
+        if self._engine is not None:
+            _lib.load().capb200_aoa_destroy(self._engine)
+            self._engine = None
+
+    @property
+    def launch_count(self) -> int:
+        return 0 if self._engine is None else int(_lib.load().capb200_aoa_launch_count(self._engine))
+
+    def _call_sample(self, lib, fc, att, masks, B, R, so, tok, ld_tok, seq, logprobs):
+        return lib.capb200_aoa_decode_sample(self._engine, _lib.ptr(att), _lib.ptr(masks), B, R, ctypes.byref(so), _lib.ptr(tok), ld_tok,
+                                             _lib.ptr(seq), _lib.ptr(logprobs), None, _lib.current_stream())
+
+    def _call_beam(self, lib, fc, att, masks, B, R, bo, seq, logprobs, d_seq, d_len, d_p, d_raw):
+        return lib.capb200_aoa_decode_beam(self._engine, _lib.ptr(att), _lib.ptr(masks), B, R, ctypes.byref(bo), _lib.ptr(seq), _lib.ptr(logprobs),
+                                           _lib.ptr(d_seq), _lib.ptr(d_len), _lib.ptr(d_p), _lib.ptr(d_raw), _lib.current_stream())
+
+    def _call_record(self, lib, image, rank, dst):
+        return lib.capb200_aoa_beam_record_logprobs(self._engine, image, rank, _lib.ptr(dst), _lib.current_stream())
+
+
 def setup(opt, numeric_mode=None):
     """Factory with the contract of captioning.models.setup (captioning/models/__init__.py:20-73) for the families on the
     B200 hot path."""
@@ -563,6 +673,8 @@ def setup(opt, numeric_mode=None):
         return B200UpDownModel(opt, numeric_mode)
     if name == 'newfc':
         return B200NewFCModel(opt, numeric_mode)
+    if name == 'aoa':
+        return B200AoAModel(opt, numeric_mode)
     if name == 'transformer':
         if getattr(opt, 'cached_transformer', False):
             raise NotImplementedError('cachedTransformer is a reference-side variant; the B200 engine always caches K/V')

@@ -186,6 +186,43 @@ int capb200_tfm_decode_sample(capb200_tfm_engine* e, const float* att, const flo
 long capb200_tfm_launch_count(const capb200_tfm_engine* e);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * AoANet (AoAModel, captioning/models/AoAModel.py:188-226; configs/aoa.yml: refine=1, refine_aoa=1, use_ff=0,
+ * decoder_type=AoA, use_multi_head=2, multi_head_scale=1, mean_feats=1)
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define CAPB200_AOA_REFINER_LAYERS 6
+typedef struct capb200_aoa_engine capb200_aoa_engine;
+typedef struct {
+    int vocab_size, input_encoding_size, rnn_size, heads, att_feat_size, seq_length, numeric_mode;
+} capb200_aoa_cfg;
+typedef struct {
+    const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b;   /* refiner.layers.i.self_attn.linears.{0,1,2} [H,H] */
+    const float *aoa_w, *aoa_b;                       /* refiner.layers.i.self_attn.aoa_layer.0 [2H,2H] */
+    const float *ln_a, *ln_b;                         /* refiner.layers.i.sublayer.0.norm.{a_2,b_2} */
+} capb200_aoa_refiner_layer;
+typedef struct {
+    const float* embed;                               /* embed.0.weight [V+1,E] */
+    const float *att_embed_w, *att_embed_b;           /* att_embed.0 [H,F_att] */
+    capb200_aoa_refiner_layer refiner[CAPB200_AOA_REFINER_LAYERS];
+    const float *refiner_norm_a, *refiner_norm_b;     /* refiner.norm */
+    const float *ctx2att_w, *ctx2att_b;               /* ctx2att [2H,H] */
+    const float *att_lstm_w_ih, *att_lstm_w_hh, *att_lstm_b_ih, *att_lstm_b_hh;   /* core.att_lstm [4H,E+H] [4H,H] */
+    const float *attn_norm_a, *attn_norm_b;           /* core.attention.norm */
+    const float *attn_q_w, *attn_q_b;                 /* core.attention.linears.0 [H,H] */
+    const float *att2ctx_w, *att2ctx_b;               /* core.att2ctx.0 [2H,2H] */
+    const float *logit_w, *logit_b;                   /* logit [V+1,H] */
+} capb200_aoa_weights;
+
+capb200_aoa_engine* capb200_aoa_create(const capb200_aoa_cfg* cfg);
+void capb200_aoa_destroy(capb200_aoa_engine* e);
+int capb200_aoa_bind_weights(capb200_aoa_engine* e, const capb200_aoa_weights* w, void* stream);
+int capb200_aoa_decode_beam(capb200_aoa_engine* e, const float* att, const float* mask, int B, int R, const capb200_beam_opts* opts, long long* seq,
+                            float* seq_logprobs, long long* done_seq, int* done_len, float* done_p, float* done_raw, void* stream);
+int capb200_aoa_beam_record_logprobs(capb200_aoa_engine* e, int image, int rank, float* dst, void* stream);
+int capb200_aoa_decode_sample(capb200_aoa_engine* e, const float* att, const float* mask, int B, int R, const capb200_sample_opts* opts,
+                              const long long* tokens_in, long ld_tok, long long* seq, float* seq_logprobs, float* picked, void* stream);
+long capb200_aoa_launch_count(const capb200_aoa_engine* e);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * SCST reward and criterion
  * ---------------------------------------------------------------------------------------------------------------- */
 /* Document-frequency table in the scripts/prepro_ngrams.py format, flattened: keys[n,4] int32 token ids padded with -1,
