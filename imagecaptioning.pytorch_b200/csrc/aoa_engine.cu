@@ -264,7 +264,8 @@ int core_step(capb200_aoa_engine* e, int rows, int rpi, const int* tokens, const
         if (gemm(e, A_Q, g, e->capRows, st)) return 1;
     }
     e->launches++;
-    if (cross_attention_launch(rows, rpi, e->heads, e->dk, R, e->qproj.v.f, e->qproj.v.ld, e->p_att_kv.v.f, e->p_att_kv.v.f + H, e->p_att_kv.v.ld, mask, R,
+    // AoAModel.py:168 passes (query, value = p_att[..., :H], key = p_att[..., H:]): the first half of ctx2att's output is V, the second K
+    if (cross_attention_launch(rows, rpi, e->heads, e->dk, R, e->qproj.v.f, e->qproj.v.ld, e->p_att_kv.v.f + H, e->p_att_kv.v.f, e->p_att_kv.v.ld, mask, R,
                                e->att.v, st)) return 1;
     {   // att2ctx: GLU(Linear(cat[att, h_att]))
         GemmProblem g;

@@ -53,3 +53,32 @@ def first_divergence(a, b):
         if d.size:
             out[i] = d[0]
     return out
+
+
+def check_decode(fam, fc, att, seq, lp, oseq, olp, margins, masks=None, sample_n=1, done_p=None, odone=None):
+    """Non-vacuous decode comparison.
+    * decisions separated by more than 10x the log-prob tolerance -> token ids must be bit-exact and log-probs within 1e-4;
+    * always: the returned sequences, re-scored by the oracle with teacher forcing, must carry the log-probs the engine reported
+      (within 1e-4), and for beam search the winning score must match the oracle's best score within 1e-3 -- so a legitimately
+      ambiguous near-tie can change which hypothesis wins, but never produce a worse or mis-scored one."""
+    import torch
+    seq_c, lp_c = seq.cpu(), lp.cpu()
+    strict = min(margins) > 10 * LOGP_TOL
+    if strict:
+        assert np.array_equal(seq_c.numpy(), oseq.numpy()), (min(margins), first_divergence(seq_c.numpy(), oseq.numpy()))
+        picked = lp_c.gather(2, seq_c.unsqueeze(2)).squeeze(2)
+        opicked = olp.gather(2, oseq.unsqueeze(2)).squeeze(2)
+        assert float((picked - opicked).abs().max()) < LOGP_TOL
+        assert bool(((lp_c - olp).abs() <= LOGP_TOL + 1e-5 * olp.abs()).all())
+    N, T = seq_c.shape
+    labels = torch.cat([torch.zeros(N, 1, dtype=torch.long), seq_c[:, :-1]], 1)
+    B = fc.shape[0]
+    tf = co.forward_teacher(fam, fc, att, labels.reshape(B, N // B, T), masks)
+    valid = torch.cat([torch.ones(N, 1, dtype=torch.bool), (seq_c[:, :-1] > 0)], 1)       # tokens through the first EOS
+    mine = lp_c.gather(2, seq_c.unsqueeze(2)).squeeze(2)
+    theirs = tf.gather(2, seq_c.unsqueeze(2)).squeeze(2)
+    assert float(((mine - theirs).abs() * valid).max()) < 2 * LOGP_TOL, float(((mine - theirs).abs() * valid).max())
+    if done_p is not None and odone is not None:
+        best = np.array([d[0]['p'] for d in odone])
+        assert np.abs(np.asarray(done_p)[:, 0] - best).max() < 1e-3
+    return strict

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import LOGP_TOL, PARITY_MODES, build_pair, co, first_divergence
+from helpers import LOGP_TOL, PARITY_MODES, build_pair, check_decode, co, first_divergence
 
 pytestmark = pytest.mark.gpu
 
@@ -45,7 +45,7 @@ def test_aoa_small_golden(golden_dir, mode):
 def test_aoa_config_dims_vs_oracle(mode, B, R, n, beam):
     """configs/aoa.yml widths (E = H = 1024, 8 heads, 6 refiner layers) at the SCST shape (10 images x 5 samples) and a beam case."""
     cfg = dict(V=501, E=1024, H=1024, A=0, F_fc=16, F_att=2048, T=8)
-    model, fam = build_pair('aoa', seed=5, logit_scale=6.0, mode=mode, heads=8, **cfg)
+    model, fam = build_pair('aoa', seed=6, logit_scale=6.0, mode=mode, heads=8, **cfg)
     fc, att = co.make_inputs(B, R, cfg['F_fc'], cfg['F_att'], seed=B + R)
     margins = []
     with torch.no_grad():
@@ -55,9 +55,6 @@ def test_aoa_config_dims_vs_oracle(mode, B, R, n, beam):
         else:
             seq, lp = model(fc.cuda(), att.cuda(), None, opt={'sample_method': 'greedy', 'beam_size': 1, 'sample_n': n}, mode='sample')
             oseq, olp = co.sample(fam, fc, att, sample_n=n, record_margin=margins)
-    if min(margins) > 10 * LOGP_TOL:
-        assert np.array_equal(seq.cpu().numpy(), oseq.numpy()), (min(margins), first_divergence(seq.cpu().numpy(), oseq.numpy()))
-        picked = lp.cpu().gather(2, seq.cpu().unsqueeze(2)).squeeze(2)
-        opicked = olp.gather(2, oseq.unsqueeze(2)).squeeze(2)
-        assert float((picked - opicked).abs().max()) < LOGP_TOL
-        assert bool(((lp.cpu() - olp).abs() <= LOGP_TOL + 1e-5 * olp.abs()).all())
+    strict = check_decode(fam, fc, att, seq, lp, oseq, olp, margins, sample_n=n)
+    if beam == 1:
+        assert strict, 'the SCST-shape greedy case is seeded to have unambiguous decisions'

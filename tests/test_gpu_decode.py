@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import LOGP_TOL, PARITY_MODES, build_pair, co, first_divergence
+from helpers import LOGP_TOL, PARITY_MODES, build_pair, check_decode, co, first_divergence
 
 pytestmark = pytest.mark.gpu
 
@@ -106,9 +106,8 @@ def test_updown_random_shapes_vs_oracle(mode, B, R, beam):
         else:
             seq, lp = model(fc.cuda(), att.cuda(), None, opt={'sample_method': 'greedy', 'beam_size': 1}, mode='sample')
             oseq, olp = co.sample(fam, fc, att, record_margin=margins)
-    if min(margins) > 10 * LOGP_TOL:          # decisions closer than the tolerance are legitimately order-ambiguous
-        assert np.array_equal(seq.cpu().numpy(), oseq.numpy()), (min(margins), first_divergence(seq.cpu().numpy(), oseq.numpy()))
-        assert float((lp.cpu() - olp).abs().max()) < LOGP_TOL
+    done_p = [[model.done_beams[i][j]['p'] for j in range(beam)] for i in range(B)] if beam > 1 else None
+    check_decode(fam, fc, att, seq, lp, oseq, olp, margins, done_p=done_p, odone=odone if beam > 1 else None)
 
 
 def test_multinomial_sampler_distribution():
