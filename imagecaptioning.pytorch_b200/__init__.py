@@ -7,5 +7,6 @@ from . import _lib                                    # noqa: F401
 from .models import B200UpDownModel, B200NewFCModel, B200TransformerModel, B200AoAModel, B200CaptionModel, setup      # noqa: F401
 from .loss_wrapper import B200LossWrapper, RewardCriterion                        # noqa: F401
 from . import rewards                                 # noqa: F401
+from . import parallel                                # noqa: F401
 
-__all__ = ['setup', 'B200UpDownModel', 'B200NewFCModel', 'B200CaptionModel', 'B200LossWrapper', 'RewardCriterion', 'rewards']
+__all__ = ['setup', 'B200UpDownModel', 'B200NewFCModel', 'B200CaptionModel', 'B200LossWrapper', 'RewardCriterion', 'rewards', 'parallel']
