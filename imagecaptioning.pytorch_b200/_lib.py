@@ -38,6 +38,19 @@ class SampleOpts(Structure):
     _fields_ = [('sample_n', c_int), ('method', c_int), ('temperature', c_float), ('seed', c_ulonglong), ('steps', c_int)]
 
 
+class ScstOpts(Structure):
+    _fields_ = [('sample_n', c_int), ('temperature', c_float), ('seed', c_ulonglong), ('drop_prob', c_float), ('upstream', c_float)]
+
+
+GRAD_FIELDS = ['embed', 'fc_embed_w', 'fc_embed_b', 'att_embed_w', 'att_embed_b', 'ctx2att_w', 'ctx2att_b', 'logit_w', 'logit_b',
+               'att_lstm_w_ih', 'att_lstm_w_hh', 'att_lstm_b_ih', 'att_lstm_b_hh', 'lang_lstm_w_ih', 'lang_lstm_w_hh', 'lang_lstm_b_ih',
+               'lang_lstm_b_hh', 'h2att_w', 'h2att_b', 'alpha_w', 'alpha_b']
+
+
+class UpdownGrads(Structure):
+    _fields_ = [(f, c_void_p) for f in GRAD_FIELDS]
+
+
 TFM_MAX_LAYERS = 8
 
 
@@ -122,6 +135,9 @@ SIGNATURES = {
     'capb200_aoa_decode_sample': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(SampleOpts), c_void_p, c_long, c_void_p, c_void_p, c_void_p,
                                           c_void_p]),
     'capb200_aoa_launch_count': (c_long, [c_void_p]),
+    'capb200_updown_scst_step': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(ScstOpts), c_void_p, c_void_p, c_void_p, c_int,
+                                         POINTER(UpdownGrads), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'capb200_dropout_mask': (c_int, [c_void_p, c_long, c_ulonglong, c_int, c_int, c_float, c_void_p]),
     'capb200_cider_table_create': (c_void_p, [c_void_p, c_void_p, c_long, c_double, c_void_p]),
     'capb200_cider_table_destroy': (None, [c_void_p]),
     'capb200_self_critical_reward': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,

@@ -109,6 +109,10 @@ struct capb200_engine {
     GemmTcPlan* plans[G_COUNT] = {nullptr};
     int core_cur = 0;   // which c buffer currently holds the state
 
+    // SCST training tape (owned, grown on demand)
+    char* tape = nullptr;
+    size_t tape_bytes = 0;
+
     // optional per-GEMM device timing (cudaEvent pairs on the launching stream), off by default
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -472,6 +476,7 @@ void capb200_engine_destroy(capb200_engine* e) {
     cudaFree(e->wblock);
     cudaFree(e->ws);
     cudaFree(e->d.slab);
+    cudaFree(e->tape);
     delete e;
 }
 
@@ -780,6 +785,239 @@ int capb200_log_softmax_topk(float* logits, long ld, int rows, int V1, int twice
     VocabStepArgs va;
     va.rows = rows; va.V1 = V1; va.logits = logits; va.ld = ld; va.twice = twice; va.topk = k; va.top_val = top_val; va.top_idx = top_idx;
     return vocab_step_launch(va, static_cast<cudaStream_t>(stream));
+}
+
+// =====================================================================================================================
+// SCST training step (UpDown)
+// =====================================================================================================================
+namespace {
+
+struct Tape {
+    int* tok; float *xt, *g1, *h0, *c0, *atth, *alpha, *attres, *g2, *h1, *c1, *out;          // forward, [T][N][.] except out [N][T][H]
+    float *fc_e, *att_e, *p_att, *g_fc, *gl, *glp;                                              // prologue + greedy scratch
+    float *DL, *dOUT, *DG1, *DG2, *DATTH, *dh0, *dc0, *dh1, *dc1, *tmpH, *dX2, *dxt, *d_att_e, *d_p_att, *S, *d_fc_e, *dpre_att, *dpre_fc, *mask_sum;
+    double* scores;
+    long long* gseq_dummy;
+};
+
+void layout_tape(Tape& tp, Arena& a, int B, int R, int N, int T, int E, int H, int A, int V1, int F_att, int F_fc) {
+    const long TN = (long)T * N, BR = (long)B * R;
+    tp.tok = a.take<int>(TN);
+    tp.xt = a.take<float>(TN * E); tp.g1 = a.take<float>(TN * 4 * H); tp.h0 = a.take<float>(TN * H); tp.c0 = a.take<float>(TN * H);
+    tp.atth = a.take<float>(TN * A); tp.alpha = a.take<float>(TN * R); tp.attres = a.take<float>(TN * H);
+    tp.g2 = a.take<float>(TN * 4 * H); tp.h1 = a.take<float>(TN * H); tp.c1 = a.take<float>(TN * H); tp.out = a.take<float>(TN * H);
+    tp.fc_e = a.take<float>((long)B * H); tp.att_e = a.take<float>(BR * H); tp.p_att = a.take<float>(BR * A); tp.g_fc = a.take<float>((long)B * 4 * H);
+    tp.gl = a.take<float>((long)N * H); tp.glp = a.take<float>((long)B * T * V1);
+    tp.DL = a.take<float>(TN * V1); tp.dOUT = a.take<float>(TN * H); tp.DG1 = a.take<float>(TN * 4 * H); tp.DG2 = a.take<float>(TN * 4 * H);
+    tp.DATTH = a.take<float>(TN * A);
+    tp.dh0 = a.take<float>((long)N * H); tp.dc0 = a.take<float>((long)N * H); tp.dh1 = a.take<float>((long)N * H); tp.dc1 = a.take<float>((long)N * H);
+    tp.tmpH = a.take<float>((long)N * H); tp.dX2 = a.take<float>((long)N * 2 * H); tp.dxt = a.take<float>((long)N * E);
+    tp.d_att_e = a.take<float>(BR * H); tp.d_p_att = a.take<float>(BR * A); tp.S = a.take<float>((long)B * 4 * H); tp.d_fc_e = a.take<float>((long)B * H);
+    tp.dpre_att = a.take<float>(BR * H); tp.dpre_fc = a.take<float>((long)B * H); tp.mask_sum = a.take<float>(8);
+    tp.scores = a.take<double>((long)N + B);
+    (void)F_att; (void)F_fc;
+}
+
+// y = x * W^T (+ b): skinny fp32 GEMM on the raw PyTorch weights (always current, no repack after optimizer steps)
+int lin(const float* x, long ldx, const float* w, long ldw, const float* b, float* y, long ldy, int M, int N, int K, int accumulate, cudaStream_t st) {
+    return gemm_generic_launch(0, 1, M, N, K, x, ldx, w, ldw, y, ldy, accumulate, b, st);
+}
+
+}  // namespace
+
+extern "C" int capb200_dropout_mask(float* mask, long n, unsigned long long seed, int site, int step, float p, void* stream) {
+    CAPB_REQUIRE(mask != nullptr && n > 0, "bad argument");
+    return dropout_mask_launch(mask, n, seed, (unsigned)site, (unsigned)step, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, const float* att, int B, int R, const capb200_scst_opts* opts,
+                                        const capb200_cider_table* table, const int* refs, const int* ref_offsets, int L,
+                                        const capb200_updown_grads* grads, long long* sample_seq, long long* greedy_seq, float* sample_logprobs,
+                                        float* reward, float* loss, void* stream) {
+    if (check_ready(e)) return 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CAPB_REQUIRE(e->cfg.family == CAPB200_FAMILY_UPDOWN, "the SCST step is implemented for the UpDown family");
+    CAPB_REQUIRE(opts && fc && att && table && refs && ref_offsets && grads && sample_seq && greedy_seq && sample_logprobs && reward && loss, "null argument");
+    const int n = opts->sample_n, N = B * n, T = e->T, E = e->E, H = e->H, A = e->A, V1 = e->V1;
+    const int Fa = e->cfg.att_feat_size, Ff = e->cfg.fc_feat_size;
+    CAPB_REQUIRE(n >= 1 && n <= 16 && B >= 1 && R >= 1, "sample_n must be in 1..16");
+    const float p = opts->drop_prob;
+    CAPB_REQUIRE(p >= 0.f && p < 1.f, "drop_prob must be in [0, 1)");
+    const float keep_scale = 1.0f / (1.0f - p);
+    const unsigned long long seed = opts->seed;
+    const capb200_weights& w = e->w;
+
+    // ---- (1) greedy baseline, eval mode (no dropout): the regular decode path
+    {
+        Arena dry; Tape t0; layout_tape(t0, dry, B, R, N, T, E, H, A, V1, Fa, Ff);
+        if (dry.off + 256 > e->tape_bytes) {
+            CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
+            if (e->tape) CAPB_CHECK_CUDA(cudaFree(e->tape));
+            e->tape = nullptr;
+            CAPB_CHECK_CUDA(cudaMalloc(&e->tape, dry.off + 256));
+            e->tape_bytes = dry.off + 256;
+        }
+    }
+    Arena ar; ar.base = e->tape;
+    Tape tp; layout_tape(tp, ar, B, R, N, T, E, H, A, V1, Fa, Ff);
+    {
+        capb200_sample_opts so; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.seed = 0; so.steps = T;
+        CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, st));
+        CAPB_CHECK_CUDA(cudaMemsetAsync(greedy_seq, 0, sizeof(long long) * (size_t)B * T, st));
+        if (capb200_decode_sample(e, fc, att, nullptr, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, stream)) return 1;
+    }
+    if (ensure_workspace(e, B, N, R, 1, st)) return 1;        // DecodeBuffers (tokens, unfinished, ...) for N rows
+
+    // ---- (2) train-mode prologue: fc_embed / att_embed with dropout, ctx2att, per-image gate term
+    const long BR = (long)B * R;
+    if (lin(fc, Ff, w.fc_embed_w, Ff, w.fc_embed_b, tp.fc_e, H, B, H, Ff, 0, st)) return 1;
+    if (relu_copy_launch(tp.fc_e, (long)B * H, ActView{tp.fc_e, nullptr, nullptr, H}, st)) return 1;
+    if (dropout_apply_launch(tp.fc_e, B, H, H, seed, 0, 0, p, st)) return 1;
+    if (lin(att, Fa, w.att_embed_w, Fa, w.att_embed_b, tp.att_e, H, (int)BR, H, Fa, 0, st)) return 1;
+    if (relu_copy_launch(tp.att_e, BR * H, ActView{tp.att_e, nullptr, nullptr, H}, st)) return 1;
+    if (dropout_apply_launch(tp.att_e, (int)BR, H, H, seed, 1, 0, p, st)) return 1;
+    if (lin(tp.att_e, H, w.ctx2att_w, H, w.ctx2att_b, tp.p_att, A, (int)BR, A, H, 0, st)) return 1;
+    if (lin(tp.fc_e, H, w.att_lstm_w_ih + H, E + 2 * H, e->bsum_att, tp.g_fc, 4 * H, B, 4 * H, H, 0, st)) return 1;
+    e->launches += 8;
+
+    // ---- (3) T sampling steps with the tape
+    const long NH = (long)N * H;
+    CAPB_CHECK_CUDA(cudaMemsetAsync(e->d.tokens, 0, sizeof(int) * N, st));
+    for (int t = 0; t < T; ++t) {
+        int* tok = tp.tok + (long)t * N;
+        CAPB_CHECK_CUDA(cudaMemcpyAsync(tok, e->d.tokens, sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
+        float* xt = tp.xt + (long)t * N * E;
+        float* g1 = tp.g1 + (long)t * N * 4 * H;
+        float* g2 = tp.g2 + (long)t * N * 4 * H;
+        const float* h0p = t ? tp.h0 + (long)(t - 1) * NH : nullptr;
+        const float* h1p = t ? tp.h1 + (long)(t - 1) * NH : nullptr;
+        const float* c0p = t ? tp.c0 + (long)(t - 1) * NH : nullptr;
+        const float* c1p = t ? tp.c1 + (long)(t - 1) * NH : nullptr;
+        float *h0 = tp.h0 + (long)t * NH, *c0 = tp.c0 + (long)t * NH, *h1 = tp.h1 + (long)t * NH, *c1 = tp.c1 + (long)t * NH;
+        if (embed_relu_dropout_launch(N, E, tok, w.embed, xt, seed, (unsigned)t, p, st)) return 1;
+        // gates1 = g_fc[img] + xt W_x^T (+ h_lang_prev W_h^T + h_att_prev W_hh^T)
+        {
+            GemmProblem g; g.M = N; g.N = 4 * H; g.nseg = 1;
+            g.seg[0].A = xt; g.seg[0].lda = E; g.seg[0].W = w.att_lstm_w_ih + 2 * H; g.seg[0].ldw = E + 2 * H; g.seg[0].K = E;
+            if (t) {
+                g.seg[1].A = h1p; g.seg[1].lda = H; g.seg[1].W = w.att_lstm_w_ih; g.seg[1].ldw = E + 2 * H; g.seg[1].K = H;
+                g.seg[2].A = h0p; g.seg[2].lda = H; g.seg[2].W = w.att_lstm_w_hh; g.seg[2].ldw = H; g.seg[2].K = H;
+                g.nseg = 3;
+            }
+            g.epi.row_bias = tp.g_fc; g.epi.ld_row_bias = 4 * H; g.epi.rows_per_group = n;
+            g.epi.C = g1; g.epi.ldc = 4 * H;
+            if (gemm_simt_launch(g, st)) return 1;
+        }
+        if (lstm_pointwise_launch(N, H, g1, 4 * H, nullptr, c0p, H, c0, H, ActView{h0, nullptr, nullptr, H}, nullptr, 0, nullptr, st)) return 1;
+        float* atth = tp.atth + (long)t * N * A;
+        if (lin(h0, H, w.h2att_w, H, w.h2att_b, atth, A, N, A, H, 0, st)) return 1;
+        float* attres = tp.attres + (long)t * NH;
+        if (additive_attention_launch(B, n, R, A, H, atth, A, tp.p_att, A, tp.att_e, H, nullptr, R, w.alpha_w, w.alpha_b, e->att_score,
+                                      ActView{attres, nullptr, nullptr, H}, st, tp.alpha + (long)t * N * R)) return 1;
+        {
+            GemmProblem g; g.M = N; g.N = 4 * H; g.nseg = 2;
+            g.seg[0].A = attres; g.seg[0].lda = H; g.seg[0].W = w.lang_lstm_w_ih; g.seg[0].ldw = 2 * H; g.seg[0].K = H;
+            g.seg[1].A = h0; g.seg[1].lda = H; g.seg[1].W = w.lang_lstm_w_ih + H; g.seg[1].ldw = 2 * H; g.seg[1].K = H;
+            if (t) { g.seg[2].A = h1p; g.seg[2].lda = H; g.seg[2].W = w.lang_lstm_w_hh; g.seg[2].ldw = H; g.seg[2].K = H; g.nseg = 3; }
+            g.epi.bias = e->bsum_lang;
+            g.epi.C = g2; g.epi.ldc = 4 * H;
+            if (gemm_simt_launch(g, st)) return 1;
+        }
+        if (lstm_pointwise_launch(N, H, g2, 4 * H, nullptr, c1p, H, c1, H, ActView{h1, nullptr, nullptr, H}, nullptr, 0, nullptr, st)) return 1;
+        // core output = dropout(h_lang), stored in (n, t) order for the batched logit backward
+        float* out = tp.out + (long)t * H;
+        if (dropout_copy_launch(h1, H, out, (long)T * H, N, H, seed, 3, (unsigned)t, p, st)) return 1;
+        float* logits = sample_logprobs + (long)t * V1;
+        if (lin(out, (long)T * H, w.logit_w, H, w.logit_b, logits, (long)T * V1, N, V1, H, 0, st)) return 1;
+        VocabStepArgs va;
+        va.rows = N; va.V1 = V1; va.logits = logits; va.ld = (long)T * V1;
+        va.select = 2; va.temperature = opts->temperature; va.seed = seed; va.step = (unsigned long long)t;
+        va.unfinished = e->d.unfinished; va.first_step = (t == 0); va.tokens_out = e->d.tokens;
+        va.seq_out = sample_seq; va.ld_seq = T; va.t = t;
+        if (vocab_step_launch(va, st)) return 1;
+        e->launches += 12;
+    }
+
+    // ---- (4) reward and loss
+    if (cider_reward_launch(table->t, sample_seq, N, greedy_seq, B, T, refs, ref_offsets, L, tp.scores, reward, T, T, st)) return 1;
+    if (reward_criterion_fwd_launch(sample_logprobs, (long)T * V1, V1, sample_seq, reward, N, T, loss, nullptr, tp.mask_sum, st)) return 1;
+    e->launches += 3;
+
+    // ---- (5) backward
+    const long TN = (long)T * N;
+    const capb200_updown_grads& G = *grads;
+    // logit layer, batched over all (n, t)
+    if (scst_dlogits_launch(sample_logprobs, sample_seq, reward, tp.mask_sum, opts->upstream, N, T, V1, tp.DL, st)) return 1;
+    if (gemm_generic_launch(0, 0, (int)TN, H, V1, tp.DL, V1, w.logit_w, H, tp.dOUT, H, 0, nullptr, st)) return 1;          // dOUT = DL * W
+    if (gemm_generic_launch(1, 0, V1, H, (int)TN, tp.DL, V1, tp.out, H, G.logit_w, H, 0, nullptr, st)) return 1;            // dW = DL^T * OUT
+    if (colsum_launch((int)TN, V1, tp.DL, V1, G.logit_b, 0, st)) return 1;
+    CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dh0, 0, sizeof(float) * NH, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dc0, 0, sizeof(float) * NH, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dh1, 0, sizeof(float) * NH, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dc1, 0, sizeof(float) * NH, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(tp.d_att_e, 0, sizeof(float) * BR * H, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(tp.d_p_att, 0, sizeof(float) * BR * A, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(G.alpha_w, 0, sizeof(float) * A, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(G.alpha_b, 0, sizeof(float), st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(G.embed, 0, sizeof(float) * (size_t)V1 * E, st));
+    for (int t = T - 1; t >= 0; --t) {
+        const float* c0p = t ? tp.c0 + (long)(t - 1) * NH : nullptr;
+        const float* c1p = t ? tp.c1 + (long)(t - 1) * NH : nullptr;
+        float* dg1 = tp.DG1 + (long)t * N * 4 * H;
+        float* dg2 = tp.DG2 + (long)t * N * 4 * H;
+        // language LSTM: dh = carried dh1 + dropout-masked dOUT[:, t]
+        if (lstm_cell_backward_launch(N, H, tp.g2 + (long)t * N * 4 * H, c1p, tp.c1 + (long)t * NH, tp.dh1, tp.dOUT + (long)t * H, (long)T * H, 3, (unsigned)t,
+                                      seed, p, tp.dc1, dg2, st)) return 1;
+        if (gemm_generic_launch(0, 0, N, 2 * H, 4 * H, dg2, 4 * H, w.lang_lstm_w_ih, 2 * H, tp.dX2, 2 * H, 0, nullptr, st)) return 1;   // [d att_res | d h_att]
+        if (gemm_generic_launch(0, 0, N, H, 4 * H, dg2, 4 * H, w.lang_lstm_w_hh, H, tp.dh1, H, 0, nullptr, st)) return 1;              // carried dh_lang
+        // attention: needs a contiguous d att_res
+        CAPB_CHECK_CUDA(cudaMemcpy2DAsync(tp.tmpH, sizeof(float) * H, tp.dX2, sizeof(float) * 2 * H, sizeof(float) * H, N, cudaMemcpyDeviceToDevice, st));
+        float* datth = tp.DATTH + (long)t * N * A;
+        if (attention_backward_launch(B, n, R, A, H, tp.tmpH, tp.alpha + (long)t * N * R, tp.atth + (long)t * N * A, tp.p_att, tp.att_e, w.alpha_w, datth,
+                                      tp.d_att_e, tp.d_p_att, G.alpha_w, G.alpha_b, st)) return 1;
+        // dh_att = carried + d h_att from the language LSTM input + d att_h * W_h2att
+        if (add_strided_launch(tp.dh0, tp.dX2 + H, 2 * H, N, H, st)) return 1;
+        if (gemm_generic_launch(0, 0, N, H, A, datth, A, w.h2att_w, H, tp.dh0, H, 1, nullptr, st)) return 1;
+        if (lstm_cell_backward_launch(N, H, tp.g1 + (long)t * N * 4 * H, c0p, tp.c0 + (long)t * NH, tp.dh0, nullptr, 0, 0, 0, seed, p, tp.dc0, dg1, st)) return 1;
+        // inputs of the attention LSTM: [h_lang_prev | fc' | xt] and h_att_prev
+        if (gemm_generic_launch(0, 0, N, H, 4 * H, dg1, 4 * H, w.att_lstm_w_ih, E + 2 * H, tp.dh1, H, 1, nullptr, st)) return 1;         // += d h_lang_prev
+        if (gemm_generic_launch(0, 0, N, E, 4 * H, dg1, 4 * H, w.att_lstm_w_ih + 2 * H, E + 2 * H, tp.dxt, E, 0, nullptr, st)) return 1;
+        if (gemm_generic_launch(0, 0, N, H, 4 * H, dg1, 4 * H, w.att_lstm_w_hh, H, tp.dh0, H, 0, nullptr, st)) return 1;                // carried dh_att
+        if (embed_backward_launch(N, E, tp.tok + (long)t * N, tp.xt + (long)t * N * E, tp.dxt, E, keep_scale, G.embed, st)) return 1;
+        e->launches += 12;
+    }
+    // weight gradients, batched over time (K = T*N)
+    const int TN1 = (int)((long)(T - 1) * N);
+    const float* DG1s = tp.DG1 + (long)N * 4 * H;     // steps 1..T-1 pair with the previous step's hidden states
+    const float* DG2s = tp.DG2 + (long)N * 4 * H;
+    int rc = 0;
+    rc |= gemm_generic_launch(1, 0, 4 * H, H, (int)TN, tp.DG2, 4 * H, tp.attres, H, G.lang_lstm_w_ih, 2 * H, 0, nullptr, st);
+    rc |= gemm_generic_launch(1, 0, 4 * H, H, (int)TN, tp.DG2, 4 * H, tp.h0, H, G.lang_lstm_w_ih + H, 2 * H, 0, nullptr, st);
+    rc |= gemm_generic_launch(1, 0, 4 * H, H, TN1, DG2s, 4 * H, tp.h1, H, G.lang_lstm_w_hh, H, 0, nullptr, st);
+    rc |= colsum_launch((int)TN, 4 * H, tp.DG2, 4 * H, G.lang_lstm_b_ih, 0, st);
+    rc |= colsum_launch((int)TN, 4 * H, tp.DG2, 4 * H, G.lang_lstm_b_hh, 0, st);
+    rc |= gemm_generic_launch(1, 0, 4 * H, H, TN1, DG1s, 4 * H, tp.h1, H, G.att_lstm_w_ih, E + 2 * H, 0, nullptr, st);
+    rc |= gemm_generic_launch(1, 0, 4 * H, E, (int)TN, tp.DG1, 4 * H, tp.xt, E, G.att_lstm_w_ih + 2 * H, E + 2 * H, 0, nullptr, st);
+    rc |= gemm_generic_launch(1, 0, 4 * H, H, TN1, DG1s, 4 * H, tp.h0, H, G.att_lstm_w_hh, H, 0, nullptr, st);
+    rc |= colsum_launch((int)TN, 4 * H, tp.DG1, 4 * H, G.att_lstm_b_ih, 0, st);
+    rc |= colsum_launch((int)TN, 4 * H, tp.DG1, 4 * H, G.att_lstm_b_hh, 0, st);
+    rc |= per_image_sum_launch(T, N, n, 4 * H, tp.DG1, tp.S, st);
+    rc |= gemm_generic_launch(1, 0, 4 * H, H, B, tp.S, 4 * H, tp.fc_e, H, G.att_lstm_w_ih + H, E + 2 * H, 0, nullptr, st);               // fc' block
+    rc |= gemm_generic_launch(0, 0, B, H, 4 * H, tp.S, 4 * H, w.att_lstm_w_ih + H, E + 2 * H, tp.d_fc_e, H, 0, nullptr, st);             // d fc'
+    rc |= gemm_generic_launch(1, 0, A, H, (int)TN, tp.DATTH, A, tp.h0, H, G.h2att_w, H, 0, nullptr, st);
+    rc |= colsum_launch((int)TN, A, tp.DATTH, A, G.h2att_b, 0, st);
+    // prologue
+    rc |= gemm_generic_launch(0, 0, (int)BR, H, A, tp.d_p_att, A, w.ctx2att_w, H, tp.d_att_e, H, 1, nullptr, st);
+    rc |= gemm_generic_launch(1, 0, A, H, (int)BR, tp.d_p_att, A, tp.att_e, H, G.ctx2att_w, H, 0, nullptr, st);
+    rc |= colsum_launch((int)BR, A, tp.d_p_att, A, G.ctx2att_b, 0, st);
+    rc |= relu_dropout_backward_launch(BR * H, tp.att_e, tp.d_att_e, tp.dpre_att, keep_scale, st);
+    rc |= gemm_generic_launch(1, 0, H, Fa, (int)BR, tp.dpre_att, H, att, Fa, G.att_embed_w, Fa, 0, nullptr, st);
+    rc |= colsum_launch((int)BR, H, tp.dpre_att, H, G.att_embed_b, 0, st);
+    rc |= relu_dropout_backward_launch((long)B * H, tp.fc_e, tp.d_fc_e, tp.dpre_fc, keep_scale, st);
+    rc |= gemm_generic_launch(1, 0, H, Ff, B, tp.dpre_fc, H, fc, Ff, G.fc_embed_w, Ff, 0, nullptr, st);
+    rc |= colsum_launch(B, H, tp.dpre_fc, H, G.fc_embed_b, 0, st);
+    e->launches += 30;
+    return rc;
 }
 
 capb200_cider_table* capb200_cider_table_create(const int* keys, const double* df, long n, double ref_len, void* stream) {

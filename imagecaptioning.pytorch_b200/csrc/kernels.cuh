@@ -30,7 +30,7 @@ int maxout_pointwise_launch(int rows, int H, const float* sums, long ld_s, const
                             float* c_out, long ld_co, ActView h_out, cudaStream_t stream);
 int additive_attention_launch(int n_images, int rpi, int R, int A, int H, const float* att_h, long ld_ah, const float* p_att, long ld_pa,
                               const float* att, long ld_at, const float* mask, long ld_mask, const float* alpha_w, const float* alpha_b,
-                              float* score_scratch /*[rows, R]*/, ActView out, cudaStream_t stream);
+                              float* score_scratch /*[rows, R]*/, ActView out, cudaStream_t stream, float* alpha_out = nullptr /*[rows, R]*/);
 int mask_rows_launch(ActView x, int n_images, int R, int cols, const float* mask, long ld_mask, cudaStream_t stream);
 
 // ---- vocab.cu : log-softmax over the vocabulary + candidate selection
@@ -103,6 +103,29 @@ int cross_attention_launch(int rows, int rpi, int heads, int dk, int R, const fl
 
 int glu_launch(int rows, int H, const float* t, long ld_t, const float* residual, long ld_res, ActView out, cudaStream_t st);
 int masked_mean_launch(int B, int R, int H, const float* x, long ld_x, const float* mask, long ld_mask, ActView out, cudaStream_t st);
+
+// ---- gemm_generic.cu / scst_kernels.cu (training step)
+int gemm_generic_launch(int ta, int tb, int M, int N, int K, const float* A, long lda, const float* B, long ldb, float* C, long ldc, int accumulate,
+                        const float* bias, cudaStream_t st);
+int colsum_launch(int rows, int cols, const float* x, long ld, float* out, int accumulate, cudaStream_t st);
+int dropout_apply_launch(float* x, int rows, int cols, long ld, unsigned long long seed, unsigned site, unsigned step, float p, cudaStream_t st);
+int dropout_mask_launch(float* m, long n, unsigned long long seed, unsigned site, unsigned step, float p, cudaStream_t st);
+int dropout_copy_launch(const float* x, long ld_x, float* y, long ld_y, int rows, int cols, unsigned long long seed, unsigned site, unsigned step, float p,
+                        cudaStream_t st);
+int embed_relu_dropout_launch(int rows, int E, const int* tokens, const float* emb, float* xt, unsigned long long seed, unsigned step, float p,
+                              cudaStream_t st);
+int scst_dlogits_launch(const float* logp, const long long* seq, const float* reward, const float* mask_sum, float upstream, int N, int T, int V1,
+                        float* dl, cudaStream_t st);
+int lstm_cell_backward_launch(int rows, int H, const float* gates, const float* c_prev, const float* c_new, const float* dh, const float* dh_extra,
+                              long ld_extra, unsigned drop_site, unsigned drop_step, unsigned long long seed, float p, float* dc_carry, float* dgates,
+                              cudaStream_t st);
+int attention_backward_launch(int n_images, int rpi, int R, int A, int H, const float* d_out, const float* alpha, const float* att_h, const float* p_att,
+                              const float* att, const float* w, float* d_att_h, float* d_att, float* d_p_att, float* d_w, float* d_b, cudaStream_t st);
+int relu_dropout_backward_launch(long n, const float* x, const float* dy, float* dx, float scale, cudaStream_t st);
+int embed_backward_launch(int rows, int E, const int* tokens, const float* xt, const float* dxt, long ld_dxt, float scale, float* d_emb, cudaStream_t st);
+int per_image_sum_launch(int steps, int rows, int rpi, int cols, const float* x, float* out, cudaStream_t st);
+int add_inplace_launch(float* a, const float* b, long n, cudaStream_t st);
+int add_strided_launch(float* a, const float* b, long ld_b, int rows, int cols, cudaStream_t st);
 
 // ---- reward.cu (CIDEr-D) and criterion
 struct CiderTable;   // device hash table of n-gram -> idf

@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(ATT_SW * 32) att_score_kernel(int rpi, int R, 
 
 constexpr int ATT_CT = 256;
 __global__ void __launch_bounds__(ATT_CT) att_combine_kernel(int rpi, int R, int H, const float* __restrict__ score, const float* __restrict__ att,
-                                                             long ld_at, const float* __restrict__ mask, long ld_mask, ActView out) {
+                                                             long ld_at, const float* __restrict__ mask, long ld_mask, ActView out,
+                                                             float* __restrict__ alpha_out) {
     extern __shared__ float s_w[];                 // [ATT_JB][R]
     const int img = blockIdx.x;
     const int c = blockIdx.y * ATT_CT + threadIdx.x;
@@ -190,6 +191,9 @@ __global__ void __launch_bounds__(ATT_CT) att_combine_kernel(int rpi, int R, int
             }
         }
         __syncthreads();
+        if (alpha_out != nullptr && blockIdx.y == 0) {       // training keeps the attention weights for the backward pass
+            for (int i = threadIdx.x; i < nj * R; i += ATT_CT) alpha_out[((long)img * rpi + j0) * R + i] = s_w[i];
+        }
         if (c < H) {
             float acc[ATT_JB];
 #pragma unroll
@@ -253,7 +257,7 @@ int maxout_pointwise_launch(int rows, int H, const float* sums, long ld_s, const
 
 int additive_attention_launch(int n_images, int rpi, int R, int A, int H, const float* att_h, long ld_ah, const float* p_att, long ld_pa,
                               const float* att, long ld_at, const float* mask, long ld_mask, const float* alpha_w, const float* alpha_b,
-                              float* score_scratch, ActView out, cudaStream_t stream) {
+                              float* score_scratch, ActView out, cudaStream_t stream, float* alpha_out) {
     if (n_images <= 0 || rpi <= 0) return 0;
     CAPB_REQUIRE(A <= 1024, "attention: att_hid_size above 1024");
     CAPB_REQUIRE(score_scratch != nullptr, "attention: score scratch missing");
@@ -272,7 +276,7 @@ int additive_attention_launch(int n_images, int rpi, int R, int A, int H, const 
     const size_t smem = sizeof(float) * (size_t)ATT_JB * R;
     CAPB_REQUIRE(smem <= 48 * 1024, "attention: too many regions");
     dim3 grid(n_images, cdiv(H, ATT_CT));
-    att_combine_kernel<<<grid, ATT_CT, smem, stream>>>(rpi, R, H, score_scratch, att, ld_at, mask, ld_mask, out);
+    att_combine_kernel<<<grid, ATT_CT, smem, stream>>>(rpi, R, H, score_scratch, att, ld_at, mask, ld_mask, out, alpha_out);
     CAPB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,296 @@
+// Kernels of the SCST training step that have no counterpart in decoding: replayable dropout, the backward of
+// log-softmax + RewardCriterion, nn.LSTMCell, additive attention, ReLU/dropout, the embedding scatter and per-image sums.
+//
+// What they differentiate (reference, relative to /root/reference/captioning):
+//   dropout sites            models/AttModel.py:74-88 (embed / fc_embed / att_embed Sequentials), :637 (core output)
+//   dlogits                  modules/losses.py:22-37 (RewardCriterion) composed with F.log_softmax (AttModel.py:172)
+//   lstm_cell_backward       nn.LSTMCell (AttModel.py:628,635)
+//   attention_backward       models/AttModel.py:728-748
+// Dropout masks are never stored: keep(seed, site, step, element) is a pure function (Philox4x32-10), re-evaluated in the backward.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace capb200 {
+
+namespace {
+
+__device__ __forceinline__ uint32_t philox_word(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+
+// 0 (dropped) or 1/(1-p) (kept): inverted dropout like nn.Dropout
+__device__ __forceinline__ float drop_scale(unsigned long long seed, uint32_t site, uint32_t step, uint32_t idx, float p) {
+    if (p <= 0.f) return 1.f;
+    const uint32_t bits = philox_word(idx, site, step, 0x5C57u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);        // [0, 1)
+    return u < p ? 0.f : 1.0f / (1.0f - p);
+}
+
+__global__ void dropout_apply_kernel(float* x, long n, int cols, long ld, unsigned long long seed, uint32_t site, uint32_t step, float p) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / cols;
+        const int c = (int)(i % cols);
+        x[r * ld + c] *= drop_scale(seed, site, step, (uint32_t)i, p);
+    }
+}
+
+__global__ void dropout_mask_kernel(float* m, long n, unsigned long long seed, uint32_t site, uint32_t step, float p) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) m[i] = drop_scale(seed, site, step, (uint32_t)i, p);
+}
+
+// y[r, c] = x[r, c] * dropmask(site, step, r*cols + c)  with separate pitches (core output -> [N, T, H] tape slot)
+__global__ void dropout_copy_kernel(const float* __restrict__ x, long ld_x, float* __restrict__ y, long ld_y, int rows, int cols, unsigned long long seed,
+                                    uint32_t site, uint32_t step, float p) {
+    const long n = (long)rows * cols;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / cols;
+        const int c = (int)(i % cols);
+        y[r * ld_y + c] = x[r * ld_x + c] * drop_scale(seed, site, step, (uint32_t)i, p);
+    }
+}
+
+// xt[r, :] = relu(emb[tok[r], :]) * dropmask
+__global__ void embed_relu_dropout_kernel(int rows, int E, const int* __restrict__ tokens, const float* __restrict__ emb, float* __restrict__ xt,
+                                          unsigned long long seed, uint32_t step, float p) {
+    const int r = blockIdx.x;
+    const float* e = emb + (long)tokens[r] * E;
+    for (int c = threadIdx.x; c < E; c += blockDim.x) xt[(long)r * E + c] = fmaxf(__ldg(e + c), 0.f) * drop_scale(seed, 2u, step, (uint32_t)(r * E + c), p);
+}
+
+// d logits of  loss = sum_{n,t} -logp[n,t,seq] * reward[n] * mask[n,t] / sum(mask)  through log_softmax:
+//   dl[n,t,v] = coef * (1[v == seq] - exp(logp[n,t,v])),  coef = -reward[n,t] * mask[n,t] / mask_sum * upstream
+__global__ void scst_dlogits_kernel(const float* __restrict__ logp, const long long* __restrict__ seq, const float* __restrict__ reward,
+                                    const float* __restrict__ mask_sum, float upstream, int T, int V1, float* __restrict__ dl) {
+    const long item = blockIdx.x;                 // n * T + t
+    const int t = (int)(item % T);
+    const long n = item / T;
+    const float m = (t == 0 || seq[n * T + t - 1] > 0) ? 1.f : 0.f;
+    const float coef = -reward[item] * m / (*mask_sum) * upstream;
+    const long long tok = seq[item];
+    const float* lp = logp + item * V1;
+    float* d = dl + item * V1;
+    if (coef == 0.f) {
+        for (int v = threadIdx.x; v < V1; v += blockDim.x) d[v] = 0.f;
+        return;
+    }
+    for (int v = threadIdx.x; v < V1; v += blockDim.x) d[v] = coef * ((v == tok ? 1.f : 0.f) - expf(lp[v]));
+}
+
+// nn.LSTMCell backward (gate pre-activations saved): dgates [rows, 4H] (i,f,g,o) and dc_prev from dh, dc
+__global__ void lstm_cell_backward_kernel(int rows, int H, const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_new,
+                                          const float* __restrict__ dh, const float* __restrict__ dh_extra, long ld_extra, uint32_t drop_site,
+                                          uint32_t drop_step, unsigned long long seed, float p, float* __restrict__ dc_carry,
+                                          float* __restrict__ dgates) {
+    const long total = (long)rows * H;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / H), c = (int)(i % H);
+        const float* g = gates + (long)r * 4 * H;
+        const float ig = 1.f / (1.f + expf(-g[c])), fg = 1.f / (1.f + expf(-g[H + c])), gg = tanhf(g[2 * H + c]), og = 1.f / (1.f + expf(-g[3 * H + c]));
+        const float cp = c_prev ? c_prev[i] : 0.f;
+        const float tc = tanhf(c_new[i]);
+        float dht = dh[i];
+        if (dh_extra != nullptr) dht += dh_extra[(long)r * ld_extra + c] * (drop_site ? drop_scale(seed, drop_site, drop_step, (uint32_t)i, p) : 1.f);
+        const float dc = dc_carry[i] + dht * og * (1.f - tc * tc);
+        float* dg = dgates + (long)r * 4 * H;
+        dg[c] = dc * gg * ig * (1.f - ig);
+        dg[H + c] = dc * cp * fg * (1.f - fg);
+        dg[2 * H + c] = dc * ig * (1.f - gg * gg);
+        dg[3 * H + c] = dht * tc * og * (1.f - og);
+        dc_carry[i] = dc * fg;
+    }
+}
+
+// Additive attention backward, one CTA per image (rpi rows of it):
+//   in : d_out[rows,H] (grad of the attended vector), alpha[rows,R], att_h[rows,A], p_att[B,R,A], att[B,R,H], w[A]
+//   out: d_att_h[rows,A] (overwritten); accumulated: d_att[B,R,H], d_p_att[B,R,A]; atomically accumulated: d_w[A], d_b[1]
+constexpr int AB_MAX_RPI = 16;
+__global__ void __launch_bounds__(256) attention_backward_kernel(int rpi, int R, int A, int H, const float* __restrict__ d_out, const float* __restrict__ alpha,
+                                                                 const float* __restrict__ att_h, const float* __restrict__ p_att, const float* __restrict__ att,
+                                                                 const float* __restrict__ w, float* __restrict__ d_att_h, float* __restrict__ d_att,
+                                                                 float* __restrict__ d_p_att, float* __restrict__ d_w, float* __restrict__ d_b) {
+    extern __shared__ float sm[];
+    float* s_da = sm;                  // [rpi][R]  d alpha, then d score
+    float* s_al = s_da + rpi * R;      // [rpi][R]  alpha
+    const int img = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < rpi * R; i += 256) s_al[i] = alpha[(long)img * rpi * R + i];
+    // d alpha[j, r] = <d_out[row j], att[img, r, :]>
+    for (int item = warp; item < rpi * R; item += 8) {
+        const int j = item / R, r = item % R;
+        const float* dr = d_out + ((long)img * rpi + j) * H;
+        const float* ar = att + ((long)img * R + r) * H;
+        float s = 0.f;
+        for (int c = lane; c < H; c += 32) s = fmaf(dr[c], ar[c], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) s_da[item] = s;
+    }
+    __syncthreads();
+    // d att[img, r, c] += sum_j alpha[j, r] * d_out[j, c]
+    for (int i = threadIdx.x; i < R * H; i += 256) {
+        const int r = i / H, c = i % H;
+        float s = 0.f;
+        for (int j = 0; j < rpi; ++j) s = fmaf(s_al[j * R + r], d_out[((long)img * rpi + j) * H + c], s);
+        d_att[((long)img * R + r) * H + c] += s;
+    }
+    // softmax backward: d score = alpha * (d alpha - sum_r alpha * d alpha)
+    if (warp < rpi) {
+        float dot = 0.f;
+        for (int r = lane; r < R; r += 32) dot = fmaf(s_al[warp * R + r], s_da[warp * R + r], dot);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        float bsum = 0.f;
+        for (int r = lane; r < R; r += 32) {
+            const float ds = s_al[warp * R + r] * (s_da[warp * R + r] - dot);
+            s_da[warp * R + r] = ds;
+            bsum += ds;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+        if (lane == 0) atomicAdd(d_b, bsum);
+    }
+    __syncthreads();
+    // through w . tanh(p_att + att_h): thread per hidden index a
+    for (int a = threadIdx.x; a < A; a += 256) {
+        const float wa = w[a];
+        float dw = 0.f;
+        float dah[AB_MAX_RPI];
+#pragma unroll
+        for (int j = 0; j < AB_MAX_RPI; ++j) dah[j] = 0.f;
+        for (int r = 0; r < R; ++r) {
+            const float pv = p_att[((long)img * R + r) * A + a];
+            float dp = 0.f;
+#pragma unroll
+            for (int j = 0; j < AB_MAX_RPI; ++j) {
+                if (j < rpi) {
+                    const float th = tanhf(pv + att_h[((long)img * rpi + j) * A + a]);
+                    const float ds = s_da[j * R + r];
+                    dw = fmaf(ds, th, dw);
+                    const float dz = ds * wa * (1.f - th * th);
+                    dp += dz;
+                    dah[j] += dz;
+                }
+            }
+            d_p_att[((long)img * R + r) * A + a] += dp;
+        }
+#pragma unroll
+        for (int j = 0; j < AB_MAX_RPI; ++j)
+            if (j < rpi) d_att_h[((long)img * rpi + j) * A + a] = dah[j];
+        atomicAdd(d_w + a, dw);
+    }
+}
+
+// y = dy * (x > 0 ? scale : 0): backward of Dropout(ReLU(.)) given the saved post-dropout activation x
+__global__ void relu_dropout_backward_kernel(long n, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, float scale) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) dx[i] = x[i] > 0.f ? dy[i] * scale : 0.f;
+}
+
+// d_emb[tok[r], :] += d_xt[r, :] * (xt[r, :] > 0 ? scale : 0)
+__global__ void embed_backward_kernel(int rows, int E, const int* __restrict__ tokens, const float* __restrict__ xt, const float* __restrict__ dxt, long ld_dxt,
+                                      float scale, float* __restrict__ d_emb) {
+    const int r = blockIdx.x;
+    float* d = d_emb + (long)tokens[r] * E;
+    for (int c = threadIdx.x; c < E; c += blockDim.x) {
+        if (xt[(long)r * E + c] > 0.f) atomicAdd(d + c, dxt[(long)r * ld_dxt + c] * scale);
+    }
+}
+
+// out[img, c] (+)= sum over the image's rows and all steps of x[step][row, c]
+__global__ void per_image_sum_kernel(int steps, int rows, int rpi, int cols, const float* __restrict__ x, float* __restrict__ out) {
+    const int img = blockIdx.x;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        float s = 0.f;
+        for (int t = 0; t < steps; ++t)
+            for (int j = 0; j < rpi; ++j) s += x[((long)t * rows + (long)img * rpi + j) * cols + c];
+        out[(long)img * cols + c] = s;
+    }
+}
+
+__global__ void add_inplace_kernel(float* a, const float* b, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) a[i] += b[i];
+}
+__global__ void add_strided_kernel(float* a, const float* b, long ld_b, int rows, int cols) {
+    const long n = (long)rows * cols;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) a[i] += b[(i / cols) * ld_b + (i % cols)];
+}
+
+int nblocks(long n) {
+    long b = (n + 255) / 256;
+    return (int)(b > 148 * 8 ? 148 * 8 : (b < 1 ? 1 : b));
+}
+
+}  // namespace
+
+#define LAUNCH_OK()                         \
+    CAPB_CHECK_CUDA(cudaGetLastError());    \
+    return 0
+
+int dropout_apply_launch(float* x, int rows, int cols, long ld, unsigned long long seed, unsigned site, unsigned step, float p, cudaStream_t st) {
+    if (p <= 0.f || rows <= 0) return 0;
+    dropout_apply_kernel<<<nblocks((long)rows * cols), 256, 0, st>>>(x, (long)rows * cols, cols, ld, seed, site, step, p);
+    LAUNCH_OK();
+}
+int dropout_mask_launch(float* m, long n, unsigned long long seed, unsigned site, unsigned step, float p, cudaStream_t st) {
+    dropout_mask_kernel<<<nblocks(n), 256, 0, st>>>(m, n, seed, site, step, p);
+    LAUNCH_OK();
+}
+int dropout_copy_launch(const float* x, long ld_x, float* y, long ld_y, int rows, int cols, unsigned long long seed, unsigned site, unsigned step, float p,
+                        cudaStream_t st) {
+    dropout_copy_kernel<<<nblocks((long)rows * cols), 256, 0, st>>>(x, ld_x, y, ld_y, rows, cols, seed, site, step, p);
+    LAUNCH_OK();
+}
+int embed_relu_dropout_launch(int rows, int E, const int* tokens, const float* emb, float* xt, unsigned long long seed, unsigned step, float p,
+                              cudaStream_t st) {
+    embed_relu_dropout_kernel<<<rows, 128, 0, st>>>(rows, E, tokens, emb, xt, seed, step, p);
+    LAUNCH_OK();
+}
+int scst_dlogits_launch(const float* logp, const long long* seq, const float* reward, const float* mask_sum, float upstream, int N, int T, int V1,
+                        float* dl, cudaStream_t st) {
+    scst_dlogits_kernel<<<N * T, 256, 0, st>>>(logp, seq, reward, mask_sum, upstream, T, V1, dl);
+    LAUNCH_OK();
+}
+int lstm_cell_backward_launch(int rows, int H, const float* gates, const float* c_prev, const float* c_new, const float* dh, const float* dh_extra,
+                              long ld_extra, unsigned drop_site, unsigned drop_step, unsigned long long seed, float p, float* dc_carry, float* dgates,
+                              cudaStream_t st) {
+    lstm_cell_backward_kernel<<<nblocks((long)rows * H), 256, 0, st>>>(rows, H, gates, c_prev, c_new, dh, dh_extra, ld_extra, drop_site, drop_step, seed, p,
+                                                                        dc_carry, dgates);
+    LAUNCH_OK();
+}
+int attention_backward_launch(int n_images, int rpi, int R, int A, int H, const float* d_out, const float* alpha, const float* att_h, const float* p_att,
+                              const float* att, const float* w, float* d_att_h, float* d_att, float* d_p_att, float* d_w, float* d_b, cudaStream_t st) {
+    CAPB_REQUIRE(rpi <= AB_MAX_RPI, "attention backward handles up to 16 rows per image");
+    const size_t smem = sizeof(float) * 2 * rpi * R;
+    attention_backward_kernel<<<n_images, 256, smem, st>>>(rpi, R, A, H, d_out, alpha, att_h, p_att, att, w, d_att_h, d_att, d_p_att, d_w, d_b);
+    LAUNCH_OK();
+}
+int relu_dropout_backward_launch(long n, const float* x, const float* dy, float* dx, float scale, cudaStream_t st) {
+    relu_dropout_backward_kernel<<<nblocks(n), 256, 0, st>>>(n, x, dy, dx, scale);
+    LAUNCH_OK();
+}
+int embed_backward_launch(int rows, int E, const int* tokens, const float* xt, const float* dxt, long ld_dxt, float scale, float* d_emb, cudaStream_t st) {
+    embed_backward_kernel<<<rows, 128, 0, st>>>(rows, E, tokens, xt, dxt, ld_dxt, scale, d_emb);
+    LAUNCH_OK();
+}
+int per_image_sum_launch(int steps, int rows, int rpi, int cols, const float* x, float* out, cudaStream_t st) {
+    per_image_sum_kernel<<<rows / rpi, 256, 0, st>>>(steps, rows, rpi, cols, x, out);
+    LAUNCH_OK();
+}
+int add_inplace_launch(float* a, const float* b, long n, cudaStream_t st) {
+    add_inplace_kernel<<<nblocks(n), 256, 0, st>>>(a, b, n);
+    LAUNCH_OK();
+}
+int add_strided_launch(float* a, const float* b, long ld_b, int rows, int cols, cudaStream_t st) {
+    add_strided_kernel<<<nblocks((long)rows * cols), 256, 0, st>>>(a, b, ld_b, rows, cols);
+    LAUNCH_OK();
+}
+
+}  // namespace capb200

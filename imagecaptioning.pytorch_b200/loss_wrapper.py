@@ -45,6 +45,21 @@ class RewardCriterion(nn.Module):
         return grad
 
 
+class _ScstLoss(torch.autograd.Function):
+    """Connects the engine-computed loss to the parameters: the gradients were produced by the engine's own BPTT during the forward
+    call; backward hands them (scaled by the upstream gradient) to autograd, so loss.backward(), DDP hooks, clip_grad_value_ and the
+    optimizers of tools/train.py:189-196 work unchanged."""
+
+    @staticmethod
+    def forward(ctx, loss_value, grad_list, *params):
+        ctx.grad_list = grad_list
+        return loss_value.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return (None, None) + tuple(g * grad_out for g in ctx.grad_list)
+
+
 class B200LossWrapper(nn.Module):
     def __init__(self, model, opt):
         super().__init__()
@@ -60,6 +75,22 @@ class B200LossWrapper(nn.Module):
             raise NotImplementedError('structure losses are the next row of SURVEY.md section 8(f)')
         if not sc_flag:
             raise NotImplementedError('the XE stage is the next row of SURVEY.md section 8(f)')
+        fused = (hasattr(self.model, 'scst_step') and att_masks is None and not drop_worst_flag and torch.is_grad_enabled() and
+                 opt.sc_sample_method == 'greedy' and opt.sc_beam_size == 1 and opt.train_sample_method == 'sample' and opt.train_beam_size == 1 and
+                 getattr(opt, 'bleu_reward_weight', 0) == 0 and getattr(opt, 'cider_reward_weight', 1) == 1)
+        if fused:
+            # whole step on the device incl. back-propagation through time (UpDown); dropout as in model.train()
+            from . import rewards as _rw
+            if _rw.CiderD_scorer is None:
+                raise RuntimeError('init_scorer(cached_tokens) must be called before the SCST reward (tools/train.py:150-152)')
+            self.model.train()
+            gts = [gts[_] for _ in gt_indices.tolist()]
+            res = self.model.scst_step(fc_feats, att_feats, gts, _rw.CiderD_scorer, opt.train_sample_n, temperature=getattr(opt, 'temperature', 1.0))
+            params = list(res['grads'].keys())
+            out['loss'] = _ScstLoss.apply(res['loss'], [res['grads'][p_] for p_ in params], *params)
+            out['reward'] = res['reward'][:, 0].mean()
+            self.last_step = res
+            return out
         self.model.eval()
         with torch.no_grad():
             greedy_res, _ = self.model(fc_feats, att_feats, att_masks, mode='sample',

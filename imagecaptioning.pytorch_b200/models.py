@@ -370,6 +370,39 @@ class B200UpDownModel(B200CaptionModel):
         }
 
 
+    # ---- SCST training step (UpDown): greedy baseline + sampling with dropout + CIDEr-D reward + RewardCriterion + BPTT -----
+    def scst_step(self, fc_feats, att_feats, gts, table, sample_n, temperature=1.0, drop_prob=None, seed=None, upstream=1.0):
+        """Runs one self-critical step entirely on the device (capb200_updown_scst_step).  Returns a dict with 'loss' (0-dim),
+        'reward' [N, T], 'sample_seq', 'greedy_seq', 'sample_logprobs' and 'grads' {parameter: gradient tensor}."""
+        from .rewards import pack_references
+        lib = self._ensure_engine(fc_feats.device)
+        fc = self._f32(fc_feats)
+        att = self._f32(att_feats)
+        dev = fc.device
+        B, R = att.shape[0], att.shape[1]
+        N, T, V1 = B * sample_n, self.seq_length, self.vocab_size + 1
+        refs, offsets, L = pack_references(gts, dev)
+        table_params = self._weight_table()
+        grads = {name: torch.empty_like(t) for name, t in table_params.items()}
+        g = _lib.UpdownGrads()
+        for name, t in grads.items():
+            setattr(g, name, t.data_ptr())
+        sample_seq = torch.zeros(N, T, dtype=torch.long, device=dev)
+        greedy_seq = torch.zeros(B, T, dtype=torch.long, device=dev)
+        logprobs = torch.zeros(N, T, V1, dtype=torch.float32, device=dev)
+        reward = torch.empty(N, T, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        p = self.drop_prob_lm if drop_prob is None else drop_prob
+        so = _lib.ScstOpts(sample_n, float(temperature), seed, float(p), float(upstream))
+        _lib.check(lib.capb200_updown_scst_step(self._engine, _lib.ptr(fc), _lib.ptr(att), B, R, ctypes.byref(so), table._h, _lib.ptr(refs),
+                                                _lib.ptr(offsets), L, ctypes.byref(g), _lib.ptr(sample_seq), _lib.ptr(greedy_seq), _lib.ptr(logprobs),
+                                                _lib.ptr(reward), _lib.ptr(loss), _lib.current_stream()), 'updown_scst_step')
+        return {'loss': loss[0], 'reward': reward, 'sample_seq': sample_seq, 'greedy_seq': greedy_seq, 'sample_logprobs': logprobs,
+                'grads': {table_params[k]: v for k, v in grads.items()}, 'seed': seed}
+
+
 class _MaxoutCoreParams(nn.Module):
     """Parameter container with the key names of FCModel.LSTMCore (FCModel.py:13-23)."""
 

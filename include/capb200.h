@@ -244,6 +244,34 @@ int capb200_reward_criterion_forward(const float* logprobs, const long long* seq
 int capb200_reward_criterion_backward(const long long* seq, const float* reward, int N, int T, int V1, const float* mask_sum, float upstream,
                                       float* grad, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * One self-critical training step of the UpDown model (LossWrapper.forward with sc_flag, loss_wrapper.py:56-73, plus the
+ * loss.backward() of tools/train.py:189): eval-mode greedy baseline, train-mode multinomial samples (dropout on, AttModel.py:74-88,
+ * :637), CIDEr-D self-critical reward, RewardCriterion, then back-propagation through time into every parameter gradient.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int sample_n;              /* opt.train_sample_n */
+    float temperature;
+    unsigned long long seed;   /* Philox key of the sampler and of the dropout masks */
+    float drop_prob;           /* drop_prob_lm; 0 disables dropout */
+    float upstream;            /* d(total loss)/d(this loss), normally 1 */
+} capb200_scst_opts;
+/* Gradient buffers, one per capb200_weights field (same shapes, fp32, device); every one is OVERWRITTEN. */
+typedef struct {
+    float* embed;
+    float *fc_embed_w, *fc_embed_b, *att_embed_w, *att_embed_b, *ctx2att_w, *ctx2att_b, *logit_w, *logit_b;
+    float *att_lstm_w_ih, *att_lstm_w_hh, *att_lstm_b_ih, *att_lstm_b_hh, *lang_lstm_w_ih, *lang_lstm_w_hh, *lang_lstm_b_ih, *lang_lstm_b_hh;
+    float *h2att_w, *h2att_b, *alpha_w, *alpha_b;
+} capb200_updown_grads;
+/* fc[B,F_fc], att[B,R,F_att] (fixed region count: att_masks = None, dataloader.py:239-241); refs as in capb200_self_critical_reward.
+ * Outputs: sample_seq[B*n,T] int64, greedy_seq[B,T] int64, sample_logprobs[B*n,T,V+1] (caller zero-fills), reward[B*n,T], loss[1]. */
+int capb200_updown_scst_step(capb200_engine* e, const float* fc, const float* att, int B, int R, const capb200_scst_opts* opts,
+                             const capb200_cider_table* table, const int* refs, const int* ref_offsets, int L, const capb200_updown_grads* grads,
+                             long long* sample_seq, long long* greedy_seq, float* sample_logprobs, float* reward, float* loss, void* stream);
+/* The dropout keep/scale mask (0 or 1/(1-p)) of one site and step, for tests that replay it in the oracle:
+ * site 0 = fc_embed [B,H], 1 = att_embed [B*R,H], 2 = word embedding at `step` [N,E], 3 = core output at `step` [N,H]. */
+int capb200_dropout_mask(float* mask, long n, unsigned long long seed, int site, int step, float p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

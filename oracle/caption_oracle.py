@@ -73,11 +73,15 @@ def clip_att(att: Tensor, masks: Optional[Tensor]):
     return att[:, :max_len].contiguous(), masks[:, :max_len].contiguous()
 
 
-def updown_prepare(W: Weights, fc: Tensor, att: Tensor, masks: Optional[Tensor] = None):
-    """fc_embed, att_embed (Linear+ReLU; dropout is identity in eval) and ctx2att."""
+def updown_prepare(W: Weights, fc: Tensor, att: Tensor, masks: Optional[Tensor] = None, drop=None):
+    """fc_embed, att_embed (Linear+ReLU; dropout is identity in eval) and ctx2att.  ``drop`` (train mode) carries explicit inverted-
+    dropout masks {'fc': [B,H], 'att': [B,R,H], 'xt': [T,N,E], 'out': [T,N,H]} so a run can be replayed exactly."""
     att, masks = clip_att(att, masks)
     fc_e = torch.relu(linear(fc, W['fc_embed.0.weight'], W['fc_embed.0.bias']))
     att_e = torch.relu(linear(att, W['att_embed.0.weight'], W['att_embed.0.bias']))
+    if drop is not None:
+        fc_e = fc_e * drop['fc']
+        att_e = att_e * drop['att']
     if masks is not None:
         # pack_wrapper runs the module on valid rows only and zero-pads the rest
         att_e = att_e * masks.unsqueeze(-1).to(att_e)
@@ -96,7 +100,7 @@ def additive_attention(W: Weights, h: Tensor, att_e: Tensor, p_att: Tensor, mask
     return torch.bmm(weight.unsqueeze(1), att_e).squeeze(1)
 
 
-def updown_core(W: Weights, xt: Tensor, fc_e: Tensor, att_e: Tensor, p_att: Tensor, state, masks=None):
+def updown_core(W: Weights, xt: Tensor, fc_e: Tensor, att_e: Tensor, p_att: Tensor, state, masks=None, out_drop=None):
     h, c = state                                   # each [2, N, H]
     x1 = torch.cat([h[1], fc_e, xt], 1)
     h_att, c_att = lstm_cell(x1, h[0], c[0], W['core.att_lstm.weight_ih'], W['core.att_lstm.weight_hh'],
@@ -105,7 +109,8 @@ def updown_core(W: Weights, xt: Tensor, fc_e: Tensor, att_e: Tensor, p_att: Tens
     x2 = torch.cat([att, h_att], 1)
     h_lang, c_lang = lstm_cell(x2, h[1], c[1], W['core.lang_lstm.weight_ih'], W['core.lang_lstm.weight_hh'],
                                W['core.lang_lstm.bias_ih'], W['core.lang_lstm.bias_hh'])
-    return h_lang, (torch.stack([h_att, h_lang]), torch.stack([c_att, c_lang]))
+    out = h_lang if out_drop is None else h_lang * out_drop       # F.dropout on the output only; the state keeps h_lang (AttModel.py:637-638)
+    return out, (torch.stack([h_att, h_lang]), torch.stack([c_att, c_lang]))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -276,6 +281,7 @@ def aoa_core(W: Weights, xt: Tensor, mean: Tensor, att_e: Tensor, p_att: Tensor,
 
 class Family:
     def __init__(self, name: str, W: Weights, seq_length: int, heads: int = 8):
+        self.drop = None          # explicit dropout masks for a train-mode replay (UpDown only)
         self.name = name
         self.W = W
         self.seq_length = seq_length
@@ -301,7 +307,7 @@ class Family:
 
     def prepare(self, fc, att, masks=None):
         if self.name == 'updown':
-            return updown_prepare(self.W, fc, att, masks)
+            return updown_prepare(self.W, fc, att, masks, self.drop)
         if self.name == 'newfc':
             return newfc_prepare(self.W, fc, att, masks)
         if self.name == 'aoa':
@@ -319,7 +325,7 @@ class Family:
             return torch.relu(self.W['embed.0.weight'][it])
         return self.W['embed.weight'][it]
 
-    def logprobs_state(self, it, fc_e, att_e, p_att, masks, state, output_logsoftmax=True):
+    def logprobs_state(self, it, fc_e, att_e, p_att, masks, state, output_logsoftmax=True, t=None):
         if self.name == 'transformer':
             ys = it.unsqueeze(1) if len(state) == 0 else torch.cat([state[0][0], it.unsqueeze(1)], 1)
             out = transformer_decode(self.W, p_att, masks, ys, self.n_layers, self.heads)[:, -1]
@@ -328,9 +334,14 @@ class Family:
         xt = self.embed(it)
         if self.name == 'aoa':
             out, state = aoa_core(self.W, xt, fc_e, att_e, p_att, state, masks, self.heads)
+        elif self.name == 'updown':
+            od = None
+            if self.drop is not None and t is not None:
+                xt = xt * self.drop['xt'][t]
+                od = self.drop['out'][t]
+            out, state = updown_core(self.W, xt, fc_e, att_e, p_att, state, masks, od)
         else:
-            core = updown_core if self.name == 'updown' else newfc_core
-            out, state = core(self.W, xt, fc_e, att_e, p_att, state, masks)
+            out, state = newfc_core(self.W, xt, fc_e, att_e, p_att, state, masks)
         logits = linear(out, self.W['logit.weight'], self.W['logit.bias'])
         return (F.log_softmax(logits, dim=1) if output_logsoftmax else logits), state
 
@@ -442,7 +453,7 @@ def sample(fam: Family, fc: Tensor, att: Tensor, masks: Optional[Tensor] = None,
     it = torch.zeros(N, dtype=torch.long)
     unfinished = None
     for t in range(T):
-        logprobs, state = fam.logprobs_state(it, fc_e, att_e, p_att, masks, state)
+        logprobs, state = fam.logprobs_state(it, fc_e, att_e, p_att, masks, state, t=t)
         if forced_tokens is not None:
             it = forced_tokens[:, t].clone()
         elif sample_method == 'greedy':
