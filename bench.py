@@ -43,7 +43,7 @@ def parse():
     p.add_argument('--mode', default='tc_f16x3', choices=['tc_f16x3', 'tc_f16x1', 'simt_fp32'])
     p.add_argument('--cpu-batch', type=int, default=32, help='images per CPU-baseline step (bounded sample)')
     p.add_argument('--no-cpu-baseline', action='store_true')
-    p.add_argument('--workload', default='updown_beam', choices=['updown_beam', 'transformer_beam', 'aoa_beam'],
+    p.add_argument('--workload', default='updown_beam', choices=['updown_beam', 'transformer_beam', 'aoa_beam', 'updown_scst'],
                    help='updown_beam = BASELINE.json configs[1] (the headline); transformer_beam = configs[2] (use --batch 64); aoa_beam = AoANet decode')
     return p.parse_args()
 
@@ -119,6 +119,82 @@ def cpu_reference_rate(batch, beam, steps, warmup):
     return batch / dt, dt, best[0]
 
 
+def bench_scst(args, rank, world, local_rank, dev):
+    """SCST samples/sec: UpDown, per-GPU batch = --batch images (BASELINE configs[3] uses 10), train_sample_n = 5, CIDEr-D reward, greedy
+    baseline, BPTT, ONE gradient all-reduce (NCCL), Adam step.  value = 5 * batch * world / step time."""
+    import argparse as ap
+    import torch
+    import torch.distributed as dist
+    import imagecaptioning.pytorch_b200 as b200
+    from helpers import build_pair
+    from oracle import caption_oracle as co
+    from oracle import ciderd_oracle as cdo
+    B, n, T = args.batch, 5, CFG['T']
+    model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode=args.mode, device=dev, **CFG)
+    model.train()
+    df, ref_len = cdo.build_document_frequency(cdo.make_refs(1000, CFG['V'], seed=4))        # synthetic DF table (format of prepro_ngrams.py)
+    b200.rewards.reset_scorer()
+    b200.rewards.init_scorer(b200.rewards.CiderDTable(df, ref_len))
+    opt = ap.Namespace(sc_sample_method='greedy', sc_beam_size=1, train_sample_method='sample', train_beam_size=1, train_sample_n=n,
+                       cider_reward_weight=1, bleu_reward_weight=0)
+    lw = b200.B200LossWrapper(model, opt)
+    optim = torch.optim.Adam(model.parameters(), lr=5e-5)
+    host = [co.make_inputs(B, R, CFG['F_fc'], CFG['F_att'], seed=99 + 13 * rank + i) for i in range(3)]
+    host = [(a.pin_memory(), b.pin_memory()) for a, b in host]
+    gts = cdo.make_refs(B, CFG['V'], seed=5 + rank)
+    idx = torch.arange(B)
+    grad_bytes = [0]
+
+    def step(i):
+        fc_h, att_h = host[i % 3]
+        fc, att = fc_h.to(dev, non_blocking=True), att_h.to(dev, non_blocking=True)      # H2D every step (inputs start on the host)
+        out = lw(fc, att, None, None, None, gts, idx, True, False, False)
+        optim.zero_grad(set_to_none=True)
+        out['loss'].backward()
+        grad_bytes[0] = b200.parallel.allreduce_gradients(model.parameters())            # the one collective of the step
+        torch.nn.utils.clip_grad_value_(model.parameters(), 0.1)
+        optim.step()
+        return float(out['loss'])                                                        # D2H read of the loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = model.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    if rank == 0:
+        value = world * B * n * args.steps / (ms / 1e3)
+        line = {'metric': 'SCST samples/sec (UpDown, train_sample_n=5, CIDEr-D reward, greedy baseline, BPTT, Adam)', 'value': value, 'unit': 'samples/s',
+                'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': 'UpDown SCST step, per-GPU batch=%d images x %d samples, 36x2048 feats, seq_len=20, V=9487' % (B, n),
+                           'images_per_sec': value / n, 'parallelism': 'dp%d, one gradient all-reduce of %d bytes per step' % (world, grad_bytes[0]),
+                           'numeric_mode': 'greedy baseline %s; sampling + backward fp32 CUDA-core GEMMs' % args.mode},
+                'clocks': sampler.summary(),
+                'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': B * (CFG['F_fc'] + R * CFG['F_att']) * 4, 'd2h_bytes_per_step': 4},
+                'gpu_launches': model.launch_count - l0, 'roofline': None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get('RANK', '0'))
@@ -154,6 +230,8 @@ def main():
     from helpers import build_pair
     from oracle import caption_oracle as co
     dev = torch.device('cuda', local_rank)
+    if args.workload == 'updown_scst':
+        return bench_scst(args, rank, world, local_rank, dev)
     if args.workload == 'updown_beam':
         model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode=args.mode, device=dev, **CFG)
     elif args.workload == 'transformer_beam':     # configs/transformer/transformer.yml: d_model 512, d_ff 2048, 6 + 6 layers, 8 heads

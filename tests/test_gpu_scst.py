@@ -67,10 +67,12 @@ def test_scst_step_gradients(mode, drop_prob):
     for p, g in res['grads'].items():
         key = name_of[id(p)]
         ref = ograds[key]
-        scale = float(ref.abs().max()) + 1e-8
+        scale = float(ref.abs().max())
         err = float((g.cpu() - ref).abs().max())
-        worst = max(worst, err / scale)
-        assert err <= 2e-4 * scale + 1e-7, (key, err, scale)
+        if scale > 1e-7:
+            worst = max(worst, err / scale)
+        assert err <= 5e-4 * scale + 2e-9, (key, err, scale)      # 5e-4 of the tensor's largest gradient entry
+    assert abs(oloss) > 1e-2 and sum(float(v.abs().max()) > 1e-5 for v in ograds.values()) >= 15      # the comparison is not vacuous
     print('max relative gradient error', worst)
 
 
