@@ -38,14 +38,17 @@ def parse():
     p.add_argument('--steps', type=int, default=10)
     p.add_argument('--warmup', type=int, default=3)
     p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    p.add_argument('--batch', type=int, default=256, help='images per GPU per step')
+    p.add_argument('--batch', type=int, default=None, help='images per GPU per step (default 256; 10 for updown_scst = BASELINE configs[3])')
     p.add_argument('--beam', type=int, default=5)
     p.add_argument('--mode', default='tc_f16x3', choices=['tc_f16x3', 'tc_f16x1', 'simt_fp32'])
     p.add_argument('--cpu-batch', type=int, default=32, help='images per CPU-baseline step (bounded sample)')
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--workload', default='updown_beam', choices=['updown_beam', 'transformer_beam', 'aoa_beam', 'updown_scst'],
                    help='updown_beam = BASELINE.json configs[1] (the headline); transformer_beam = configs[2] (use --batch 64); aoa_beam = AoANet decode')
-    return p.parse_args()
+    args = p.parse_args()
+    if args.batch is None:
+        args.batch = 10 if args.workload == 'updown_scst' else 256
+    return args
 
 
 class ClockSampler(threading.Thread):
@@ -200,7 +203,7 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    names = {'updown_beam': 'UpDown', 'transformer_beam': 'Transformer 6+6/512/2048/8', 'aoa_beam': 'AoANet 1024'}
+    names = {'updown_beam': 'UpDown', 'transformer_beam': 'Transformer 6+6/512/2048/8', 'aoa_beam': 'AoANet 1024', 'updown_scst': 'UpDown SCST'}
     workload = '%s beam=%d, %dx2048 bottom-up feats, batch=%d per GPU, seq_len=20, V=9487' % (names[args.workload], args.beam, R, args.batch)
 
     if args.impl == 'reference':

@@ -795,7 +795,8 @@ namespace {
 struct Tape {
     int* tok; float *xt, *g1, *h0, *c0, *atth, *alpha, *attres, *g2, *h1, *c1, *out;          // forward, [T][N][.] except out [N][T][H]
     float *fc_e, *att_e, *p_att, *g_fc, *gl, *glp;                                              // prologue + greedy scratch
-    float *DL, *dOUT, *DG1, *DG2, *DATTH, *dh0, *dc0, *dh1, *dc1, *tmpH, *dX2, *dxt, *d_att_e, *d_p_att, *S, *d_fc_e, *dpre_att, *dpre_fc, *mask_sum;
+    float *DL, *dOUT, *DG1, *DG2, *DATTH, *dh0, *dc0, *dh1, *dc1, *tmpH, *dX2, *dxt, *d_att_e, *d_p_att, *S, *d_fc_e, *dpre_att, *dpre_fc, *mask_sum, *dalpha, *skinny;
+    size_t skinny_floats;
     double* scores;
     long long* gseq_dummy;
 };
@@ -815,13 +816,33 @@ void layout_tape(Tape& tp, Arena& a, int B, int R, int N, int T, int E, int H, i
     tp.d_att_e = a.take<float>(BR * H); tp.d_p_att = a.take<float>(BR * A); tp.S = a.take<float>((long)B * 4 * H); tp.d_fc_e = a.take<float>((long)B * H);
     tp.dpre_att = a.take<float>(BR * H); tp.dpre_fc = a.take<float>((long)B * H); tp.mask_sum = a.take<float>(8);
     tp.scores = a.take<double>((long)N + B);
+    tp.dalpha = a.take<float>((long)N * R);
+    tp.skinny_floats = (size_t)4 << 20;                       // split-K partial sums (16 MB)
+    tp.skinny = a.take<float>((long)tp.skinny_floats);
     (void)F_att; (void)F_fc;
 }
 
-// y = x * W^T (+ b): skinny fp32 GEMM on the raw PyTorch weights (always current, no repack after optimizer steps)
-int lin(const float* x, long ldx, const float* w, long ldw, const float* b, float* y, long ldy, int M, int N, int K, int accumulate, cudaStream_t st) {
-    return gemm_generic_launch(0, 1, M, N, K, x, ldx, w, ldw, y, ldy, accumulate, b, st);
-}
+// Skinny fp32 GEMMs on the raw PyTorch weights (always current, no repack after optimizer steps); split-K partials live in the tape.
+struct Skinny {
+    float* scratch; size_t cap; cudaStream_t st;
+    // y = x * W^T (+ b)          (nn.Linear forward; W stored [N, K])
+    int lin(const float* x, long ldx, const float* w, long ldw, const float* b, float* y, long ldy, int M, int N, int K, int accumulate) const {
+        const int tb = 1;
+        return gemm_skinny_launch(M, N, 1, &x, &ldx, &w, &ldw, &K, &tb, y, ldy, b, nullptr, 0, 1, accumulate, scratch, cap, st);
+    }
+    // dx = dy * W                (nn.Linear input gradient; W stored [K, N])
+    int dgrad(int M, int N, int K, const float* dy, long lddy, const float* w, long ldw, float* dx, long lddx, int accumulate) const {
+        const int tb = 0;
+        return gemm_skinny_launch(M, N, 1, &dy, &lddy, &w, &ldw, &K, &tb, dx, lddx, nullptr, nullptr, 0, 1, accumulate, scratch, cap, st);
+    }
+    // the K-segmented gate GEMM of the decode path, on fp32 weights
+    int gates(const GemmProblem& g) const {
+        const float* A[3]; const float* B[3]; long lda[3], ldb[3]; int K[3], tb[3];
+        for (int i = 0; i < g.nseg; ++i) { A[i] = g.seg[i].A; lda[i] = g.seg[i].lda; B[i] = g.seg[i].W; ldb[i] = g.seg[i].ldw; K[i] = g.seg[i].K; tb[i] = 1; }
+        return gemm_skinny_launch(g.M, g.N, g.nseg, A, lda, B, ldb, K, tb, g.epi.C, g.epi.ldc, g.epi.bias, g.epi.row_bias, g.epi.ld_row_bias,
+                                  g.epi.rows_per_group, 0, scratch, cap, st);
+    }
+};
 
 }  // namespace
 
@@ -867,17 +888,18 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
         if (capb200_decode_sample(e, fc, att, nullptr, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, stream)) return 1;
     }
     if (ensure_workspace(e, B, N, R, 1, st)) return 1;        // DecodeBuffers (tokens, unfinished, ...) for N rows
+    const Skinny sk{tp.skinny, tp.skinny_floats, st};
 
     // ---- (2) train-mode prologue: fc_embed / att_embed with dropout, ctx2att, per-image gate term
     const long BR = (long)B * R;
-    if (lin(fc, Ff, w.fc_embed_w, Ff, w.fc_embed_b, tp.fc_e, H, B, H, Ff, 0, st)) return 1;
+    if (sk.lin(fc, Ff, w.fc_embed_w, Ff, w.fc_embed_b, tp.fc_e, H, B, H, Ff, 0)) return 1;
     if (relu_copy_launch(tp.fc_e, (long)B * H, ActView{tp.fc_e, nullptr, nullptr, H}, st)) return 1;
     if (dropout_apply_launch(tp.fc_e, B, H, H, seed, 0, 0, p, st)) return 1;
-    if (lin(att, Fa, w.att_embed_w, Fa, w.att_embed_b, tp.att_e, H, (int)BR, H, Fa, 0, st)) return 1;
+    if (sk.lin(att, Fa, w.att_embed_w, Fa, w.att_embed_b, tp.att_e, H, (int)BR, H, Fa, 0)) return 1;
     if (relu_copy_launch(tp.att_e, BR * H, ActView{tp.att_e, nullptr, nullptr, H}, st)) return 1;
     if (dropout_apply_launch(tp.att_e, (int)BR, H, H, seed, 1, 0, p, st)) return 1;
-    if (lin(tp.att_e, H, w.ctx2att_w, H, w.ctx2att_b, tp.p_att, A, (int)BR, A, H, 0, st)) return 1;
-    if (lin(tp.fc_e, H, w.att_lstm_w_ih + H, E + 2 * H, e->bsum_att, tp.g_fc, 4 * H, B, 4 * H, H, 0, st)) return 1;
+    if (sk.lin(tp.att_e, H, w.ctx2att_w, H, w.ctx2att_b, tp.p_att, A, (int)BR, A, H, 0)) return 1;
+    if (sk.lin(tp.fc_e, H, w.att_lstm_w_ih + H, E + 2 * H, e->bsum_att, tp.g_fc, 4 * H, B, 4 * H, H, 0)) return 1;
     e->launches += 8;
 
     // ---- (3) T sampling steps with the tape
@@ -906,11 +928,11 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
             }
             g.epi.row_bias = tp.g_fc; g.epi.ld_row_bias = 4 * H; g.epi.rows_per_group = n;
             g.epi.C = g1; g.epi.ldc = 4 * H;
-            if (gemm_simt_launch(g, st)) return 1;
+            if (sk.gates(g)) return 1;
         }
         if (lstm_pointwise_launch(N, H, g1, 4 * H, nullptr, c0p, H, c0, H, ActView{h0, nullptr, nullptr, H}, nullptr, 0, nullptr, st)) return 1;
         float* atth = tp.atth + (long)t * N * A;
-        if (lin(h0, H, w.h2att_w, H, w.h2att_b, atth, A, N, A, H, 0, st)) return 1;
+        if (sk.lin(h0, H, w.h2att_w, H, w.h2att_b, atth, A, N, A, H, 0)) return 1;
         float* attres = tp.attres + (long)t * NH;
         if (additive_attention_launch(B, n, R, A, H, atth, A, tp.p_att, A, tp.att_e, H, nullptr, R, w.alpha_w, w.alpha_b, e->att_score,
                                       ActView{attres, nullptr, nullptr, H}, st, tp.alpha + (long)t * N * R)) return 1;
@@ -921,14 +943,14 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
             if (t) { g.seg[2].A = h1p; g.seg[2].lda = H; g.seg[2].W = w.lang_lstm_w_hh; g.seg[2].ldw = H; g.seg[2].K = H; g.nseg = 3; }
             g.epi.bias = e->bsum_lang;
             g.epi.C = g2; g.epi.ldc = 4 * H;
-            if (gemm_simt_launch(g, st)) return 1;
+            if (sk.gates(g)) return 1;
         }
         if (lstm_pointwise_launch(N, H, g2, 4 * H, nullptr, c1p, H, c1, H, ActView{h1, nullptr, nullptr, H}, nullptr, 0, nullptr, st)) return 1;
         // core output = dropout(h_lang), stored in (n, t) order for the batched logit backward
         float* out = tp.out + (long)t * H;
         if (dropout_copy_launch(h1, H, out, (long)T * H, N, H, seed, 3, (unsigned)t, p, st)) return 1;
         float* logits = sample_logprobs + (long)t * V1;
-        if (lin(out, (long)T * H, w.logit_w, H, w.logit_b, logits, (long)T * V1, N, V1, H, 0, st)) return 1;
+        if (sk.lin(out, (long)T * H, w.logit_w, H, w.logit_b, logits, (long)T * V1, N, V1, H, 0)) return 1;
         VocabStepArgs va;
         va.rows = N; va.V1 = V1; va.logits = logits; va.ld = (long)T * V1;
         va.select = 2; va.temperature = opts->temperature; va.seed = seed; va.step = (unsigned long long)t;
@@ -948,7 +970,7 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
     const capb200_updown_grads& G = *grads;
     // logit layer, batched over all (n, t)
     if (scst_dlogits_launch(sample_logprobs, sample_seq, reward, tp.mask_sum, opts->upstream, N, T, V1, tp.DL, st)) return 1;
-    if (gemm_generic_launch(0, 0, (int)TN, H, V1, tp.DL, V1, w.logit_w, H, tp.dOUT, H, 0, nullptr, st)) return 1;          // dOUT = DL * W
+    if (sk.dgrad((int)TN, H, V1, tp.DL, V1, w.logit_w, H, tp.dOUT, H, 0)) return 1;          // dOUT = DL * W
     if (gemm_generic_launch(1, 0, V1, H, (int)TN, tp.DL, V1, tp.out, H, G.logit_w, H, 0, nullptr, st)) return 1;            // dW = DL^T * OUT
     if (colsum_launch((int)TN, V1, tp.DL, V1, G.logit_b, 0, st)) return 1;
     CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dh0, 0, sizeof(float) * NH, st));
@@ -968,21 +990,21 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
         // language LSTM: dh = carried dh1 + dropout-masked dOUT[:, t]
         if (lstm_cell_backward_launch(N, H, tp.g2 + (long)t * N * 4 * H, c1p, tp.c1 + (long)t * NH, tp.dh1, tp.dOUT + (long)t * H, (long)T * H, 3, (unsigned)t,
                                       seed, p, tp.dc1, dg2, st)) return 1;
-        if (gemm_generic_launch(0, 0, N, 2 * H, 4 * H, dg2, 4 * H, w.lang_lstm_w_ih, 2 * H, tp.dX2, 2 * H, 0, nullptr, st)) return 1;   // [d att_res | d h_att]
-        if (gemm_generic_launch(0, 0, N, H, 4 * H, dg2, 4 * H, w.lang_lstm_w_hh, H, tp.dh1, H, 0, nullptr, st)) return 1;              // carried dh_lang
+        if (sk.dgrad(N, 2 * H, 4 * H, dg2, 4 * H, w.lang_lstm_w_ih, 2 * H, tp.dX2, 2 * H, 0)) return 1;   // [d att_res | d h_att]
+        if (sk.dgrad(N, H, 4 * H, dg2, 4 * H, w.lang_lstm_w_hh, H, tp.dh1, H, 0)) return 1;              // carried dh_lang
         // attention: needs a contiguous d att_res
         CAPB_CHECK_CUDA(cudaMemcpy2DAsync(tp.tmpH, sizeof(float) * H, tp.dX2, sizeof(float) * 2 * H, sizeof(float) * H, N, cudaMemcpyDeviceToDevice, st));
         float* datth = tp.DATTH + (long)t * N * A;
         if (attention_backward_launch(B, n, R, A, H, tp.tmpH, tp.alpha + (long)t * N * R, tp.atth + (long)t * N * A, tp.p_att, tp.att_e, w.alpha_w, datth,
-                                      tp.d_att_e, tp.d_p_att, G.alpha_w, G.alpha_b, st)) return 1;
+                                      tp.d_att_e, tp.d_p_att, G.alpha_w, G.alpha_b, tp.dalpha, st)) return 1;
         // dh_att = carried + d h_att from the language LSTM input + d att_h * W_h2att
         if (add_strided_launch(tp.dh0, tp.dX2 + H, 2 * H, N, H, st)) return 1;
-        if (gemm_generic_launch(0, 0, N, H, A, datth, A, w.h2att_w, H, tp.dh0, H, 1, nullptr, st)) return 1;
+        if (sk.dgrad(N, H, A, datth, A, w.h2att_w, H, tp.dh0, H, 1)) return 1;
         if (lstm_cell_backward_launch(N, H, tp.g1 + (long)t * N * 4 * H, c0p, tp.c0 + (long)t * NH, tp.dh0, nullptr, 0, 0, 0, seed, p, tp.dc0, dg1, st)) return 1;
         // inputs of the attention LSTM: [h_lang_prev | fc' | xt] and h_att_prev
-        if (gemm_generic_launch(0, 0, N, H, 4 * H, dg1, 4 * H, w.att_lstm_w_ih, E + 2 * H, tp.dh1, H, 1, nullptr, st)) return 1;         // += d h_lang_prev
-        if (gemm_generic_launch(0, 0, N, E, 4 * H, dg1, 4 * H, w.att_lstm_w_ih + 2 * H, E + 2 * H, tp.dxt, E, 0, nullptr, st)) return 1;
-        if (gemm_generic_launch(0, 0, N, H, 4 * H, dg1, 4 * H, w.att_lstm_w_hh, H, tp.dh0, H, 0, nullptr, st)) return 1;                // carried dh_att
+        if (sk.dgrad(N, H, 4 * H, dg1, 4 * H, w.att_lstm_w_ih, E + 2 * H, tp.dh1, H, 1)) return 1;         // += d h_lang_prev
+        if (sk.dgrad(N, E, 4 * H, dg1, 4 * H, w.att_lstm_w_ih + 2 * H, E + 2 * H, tp.dxt, E, 0)) return 1;
+        if (sk.dgrad(N, H, 4 * H, dg1, 4 * H, w.att_lstm_w_hh, H, tp.dh0, H, 0)) return 1;                // carried dh_att
         if (embed_backward_launch(N, E, tp.tok + (long)t * N, tp.xt + (long)t * N * E, tp.dxt, E, keep_scale, G.embed, st)) return 1;
         e->launches += 12;
     }
@@ -1003,11 +1025,11 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
     rc |= colsum_launch((int)TN, 4 * H, tp.DG1, 4 * H, G.att_lstm_b_hh, 0, st);
     rc |= per_image_sum_launch(T, N, n, 4 * H, tp.DG1, tp.S, st);
     rc |= gemm_generic_launch(1, 0, 4 * H, H, B, tp.S, 4 * H, tp.fc_e, H, G.att_lstm_w_ih + H, E + 2 * H, 0, nullptr, st);               // fc' block
-    rc |= gemm_generic_launch(0, 0, B, H, 4 * H, tp.S, 4 * H, w.att_lstm_w_ih + H, E + 2 * H, tp.d_fc_e, H, 0, nullptr, st);             // d fc'
+    rc |= sk.dgrad(B, H, 4 * H, tp.S, 4 * H, w.att_lstm_w_ih + H, E + 2 * H, tp.d_fc_e, H, 0);             // d fc'
     rc |= gemm_generic_launch(1, 0, A, H, (int)TN, tp.DATTH, A, tp.h0, H, G.h2att_w, H, 0, nullptr, st);
     rc |= colsum_launch((int)TN, A, tp.DATTH, A, G.h2att_b, 0, st);
     // prologue
-    rc |= gemm_generic_launch(0, 0, (int)BR, H, A, tp.d_p_att, A, w.ctx2att_w, H, tp.d_att_e, H, 1, nullptr, st);
+    rc |= sk.dgrad((int)BR, H, A, tp.d_p_att, A, w.ctx2att_w, H, tp.d_att_e, H, 1);
     rc |= gemm_generic_launch(1, 0, A, H, (int)BR, tp.d_p_att, A, tp.att_e, H, G.ctx2att_w, H, 0, nullptr, st);
     rc |= colsum_launch((int)BR, A, tp.d_p_att, A, G.ctx2att_b, 0, st);
     rc |= relu_dropout_backward_launch(BR * H, tp.att_e, tp.d_att_e, tp.dpre_att, keep_scale, st);

@@ -109,71 +109,90 @@ __global__ void lstm_cell_backward_kernel(int rows, int H, const float* __restri
     }
 }
 
-// Additive attention backward, one CTA per image (rpi rows of it):
+// Additive attention backward in two kernels (rpi rows per image):
 //   in : d_out[rows,H] (grad of the attended vector), alpha[rows,R], att_h[rows,A], p_att[B,R,A], att[B,R,H], w[A]
 //   out: d_att_h[rows,A] (overwritten); accumulated: d_att[B,R,H], d_p_att[B,R,A]; atomically accumulated: d_w[A], d_b[1]
+// (1) d alpha[row, r] = <d_out[row], att[img, r, :]>, one warp per (row, region)
 constexpr int AB_MAX_RPI = 16;
-__global__ void __launch_bounds__(256) attention_backward_kernel(int rpi, int R, int A, int H, const float* __restrict__ d_out, const float* __restrict__ alpha,
-                                                                 const float* __restrict__ att_h, const float* __restrict__ p_att, const float* __restrict__ att,
-                                                                 const float* __restrict__ w, float* __restrict__ d_att_h, float* __restrict__ d_att,
-                                                                 float* __restrict__ d_p_att, float* __restrict__ d_w, float* __restrict__ d_b) {
-    extern __shared__ float sm[];
-    float* s_da = sm;                  // [rpi][R]  d alpha, then d score
-    float* s_al = s_da + rpi * R;      // [rpi][R]  alpha
-    const int img = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < rpi * R; i += 256) s_al[i] = alpha[(long)img * rpi * R + i];
-    // d alpha[j, r] = <d_out[row j], att[img, r, :]>
-    for (int item = warp; item < rpi * R; item += 8) {
-        const int j = item / R, r = item % R;
-        const float* dr = d_out + ((long)img * rpi + j) * H;
-        const float* ar = att + ((long)img * R + r) * H;
-        float s = 0.f;
-        for (int c = lane; c < H; c += 32) s = fmaf(dr[c], ar[c], s);
+__global__ void __launch_bounds__(256) attention_dalpha_kernel(int items, int rpi, int R, int H, const float* __restrict__ d_out, const float* __restrict__ att,
+                                                               float* __restrict__ d_alpha) {
+    const int item = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (item >= items) return;
+    const int row = item / R, r = item % R, img = row / rpi;
+    const float4* dr = reinterpret_cast<const float4*>(d_out + (long)row * H);
+    const float4* ar = reinterpret_cast<const float4*>(att + ((long)img * R + r) * H);
+    float s = 0.f;
+    for (int c = lane; c < H / 4; c += 32) {
+        const float4 x = dr[c], y = ar[c];
+        s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+    }
+    for (int c = (H / 4) * 4 + lane; c < H; c += 32) s = fmaf(d_out[(long)row * H + c], att[((long)img * R + r) * H + c], s);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) s_da[item] = s;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) d_alpha[item] = s;
+}
+
+// (2) grid (image, chunk of 32 hidden indices): softmax backward re-derived per CTA (rpi*R values), then the tanh path with the
+// regions split over 8 thread groups and reduced through shared memory; the CTA also owns regions r = chunk, chunk + nchunks, ... for d_att.
+__global__ void __launch_bounds__(256) attention_backward_kernel(int rpi, int R, int A, int H, const float* __restrict__ d_out, const float* __restrict__ alpha,
+                                                                 const float* __restrict__ d_alpha, const float* __restrict__ att_h,
+                                                                 const float* __restrict__ p_att, const float* __restrict__ w, float* __restrict__ d_att_h,
+                                                                 float* __restrict__ d_att, float* __restrict__ d_p_att, float* __restrict__ d_w,
+                                                                 float* __restrict__ d_b) {
+    extern __shared__ float sm[];
+    float* s_ds = sm;                       // [rpi][R]  d alpha, then d score
+    float* s_al = s_ds + rpi * R;           // [rpi][R]  alpha
+    float* s_red = s_al + rpi * R;          // [8][32][rpi + 1]
+    const int img = blockIdx.x, chunk = blockIdx.y, nchunks = gridDim.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < rpi * R; i += 256) {
+        s_al[i] = alpha[(long)img * rpi * R + i];
+        s_ds[i] = d_alpha[(long)img * rpi * R + i];
     }
     __syncthreads();
-    // d att[img, r, c] += sum_j alpha[j, r] * d_out[j, c]
-    for (int i = threadIdx.x; i < R * H; i += 256) {
-        const int r = i / H, c = i % H;
-        float s = 0.f;
-        for (int j = 0; j < rpi; ++j) s = fmaf(s_al[j * R + r], d_out[((long)img * rpi + j) * H + c], s);
-        d_att[((long)img * R + r) * H + c] += s;
-    }
-    // softmax backward: d score = alpha * (d alpha - sum_r alpha * d alpha)
-    if (warp < rpi) {
+    for (int j = warp; j < rpi; j += 8) {
         float dot = 0.f;
-        for (int r = lane; r < R; r += 32) dot = fmaf(s_al[warp * R + r], s_da[warp * R + r], dot);
+        for (int r = lane; r < R; r += 32) dot = fmaf(s_al[j * R + r], s_ds[j * R + r], dot);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
         float bsum = 0.f;
         for (int r = lane; r < R; r += 32) {
-            const float ds = s_al[warp * R + r] * (s_da[warp * R + r] - dot);
-            s_da[warp * R + r] = ds;
+            const float ds = s_al[j * R + r] * (s_ds[j * R + r] - dot);
+            s_ds[j * R + r] = ds;
             bsum += ds;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
-        if (lane == 0) atomicAdd(d_b, bsum);
+        if (lane == 0 && chunk == 0) atomicAdd(d_b, bsum);
     }
     __syncthreads();
-    // through w . tanh(p_att + att_h): thread per hidden index a
-    for (int a = threadIdx.x; a < A; a += 256) {
-        const float wa = w[a];
-        float dw = 0.f;
-        float dah[AB_MAX_RPI];
+    // d att[img, r, c] += sum_j alpha[j, r] * d_out[j, c] for this CTA's regions
+    for (int r = chunk; r < R; r += nchunks) {
+        for (int c = threadIdx.x; c < H; c += 256) {
+            float s = 0.f;
+            for (int j = 0; j < rpi; ++j) s = fmaf(s_al[j * R + r], d_out[((long)img * rpi + j) * H + c], s);
+            d_att[((long)img * R + r) * H + c] += s;
+        }
+    }
+    // through w . tanh(p_att + att_h): lane = hidden index inside the chunk, warp = region group
+    const int a = chunk * 32 + lane;
+    float dw = 0.f;
+    float dah[AB_MAX_RPI];
 #pragma unroll
-        for (int j = 0; j < AB_MAX_RPI; ++j) dah[j] = 0.f;
-        for (int r = 0; r < R; ++r) {
+    for (int j = 0; j < AB_MAX_RPI; ++j) dah[j] = 0.f;
+    if (a < A) {
+        const float wa = w[a];
+        float ah[AB_MAX_RPI];
+#pragma unroll
+        for (int j = 0; j < AB_MAX_RPI; ++j) ah[j] = j < rpi ? att_h[((long)img * rpi + j) * A + a] : 0.f;
+        for (int r = warp; r < R; r += 8) {
             const float pv = p_att[((long)img * R + r) * A + a];
             float dp = 0.f;
 #pragma unroll
             for (int j = 0; j < AB_MAX_RPI; ++j) {
                 if (j < rpi) {
-                    const float th = tanhf(pv + att_h[((long)img * rpi + j) * A + a]);
-                    const float ds = s_da[j * R + r];
+                    const float th = tanhf(pv + ah[j]);
+                    const float ds = s_ds[j * R + r];
                     dw = fmaf(ds, th, dw);
                     const float dz = ds * wa * (1.f - th * th);
                     dp += dz;
@@ -182,10 +201,22 @@ __global__ void __launch_bounds__(256) attention_backward_kernel(int rpi, int R,
             }
             d_p_att[((long)img * R + r) * A + a] += dp;
         }
+    }
+    float* red = s_red + (warp * 32 + lane) * (rpi + 1);
 #pragma unroll
-        for (int j = 0; j < AB_MAX_RPI; ++j)
-            if (j < rpi) d_att_h[((long)img * rpi + j) * A + a] = dah[j];
-        atomicAdd(d_w + a, dw);
+    for (int j = 0; j < AB_MAX_RPI; ++j)
+        if (j < rpi) red[j] = dah[j];
+    red[rpi] = dw;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * (rpi + 1); i += 256) {
+        const int l = i / (rpi + 1), j = i % (rpi + 1);
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) s += s_red[(g * 32 + l) * (rpi + 1) + j];
+        const int aa = chunk * 32 + l;
+        if (aa >= A) continue;
+        if (j < rpi) d_att_h[((long)img * rpi + j) * A + aa] = s;
+        else atomicAdd(d_w + aa, s);
     }
 }
 
@@ -266,10 +297,16 @@ int lstm_cell_backward_launch(int rows, int H, const float* gates, const float* 
     LAUNCH_OK();
 }
 int attention_backward_launch(int n_images, int rpi, int R, int A, int H, const float* d_out, const float* alpha, const float* att_h, const float* p_att,
-                              const float* att, const float* w, float* d_att_h, float* d_att, float* d_p_att, float* d_w, float* d_b, cudaStream_t st) {
+                              const float* att, const float* w, float* d_att_h, float* d_att, float* d_p_att, float* d_w, float* d_b, float* d_alpha_scratch,
+                              cudaStream_t st) {
     CAPB_REQUIRE(rpi <= AB_MAX_RPI, "attention backward handles up to 16 rows per image");
-    const size_t smem = sizeof(float) * 2 * rpi * R;
-    attention_backward_kernel<<<n_images, 256, smem, st>>>(rpi, R, A, H, d_out, alpha, att_h, p_att, att, w, d_att_h, d_att, d_p_att, d_w, d_b);
+    CAPB_REQUIRE(H % 4 == 0, "attention backward needs rnn_size % 4 == 0");
+    const int items = n_images * rpi * R;
+    attention_dalpha_kernel<<<cdiv(items, 8), 256, 0, st>>>(items, rpi, R, H, d_out, att, d_alpha_scratch);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    const size_t smem = sizeof(float) * (2 * rpi * R + 256 * (rpi + 1));
+    attention_backward_kernel<<<dim3(n_images, cdiv(A, 32)), 256, smem, st>>>(rpi, R, A, H, d_out, alpha, d_alpha_scratch, att_h, p_att, w, d_att_h, d_att, d_p_att,
+                                                                             d_w, d_b);
     LAUNCH_OK();
 }
 int relu_dropout_backward_launch(long n, const float* x, const float* dy, float* dx, float scale, cudaStream_t st) {

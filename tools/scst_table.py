@@ -1,0 +1,30 @@
+"""GPU: warm per-kernel time table of one UpDown SCST training step (batch 10 x 5 samples)."""
+import argparse, os, sys
+import torch
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, 'tests'))
+import imagecaptioning.pytorch_b200 as b200
+from helpers import build_pair
+from oracle import caption_oracle as co, ciderd_oracle as cdo
+import bench
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode='tc_f16x3', **bench.CFG)
+model.train()
+df, ref_len = cdo.build_document_frequency(cdo.make_refs(500, 9487, seed=4))
+table = b200.rewards.CiderDTable(df, ref_len)
+fc, att = co.make_inputs(B, 36, 2048, 2048, seed=1)
+fc, att = fc.cuda(), att.cuda()
+gts = cdo.make_refs(B, 9487, seed=5)
+for _ in range(2):
+    model.scst_step(fc, att, gts, table, 5)
+torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(2):
+        model.scst_step(fc, att, gts, table, 5)
+    torch.cuda.synchronize()
+rows = [(e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0]
+tot = sum(r[2] for r in rows)
+print('SCST step (B=%d, n=5): total kernel time %.2f ms per step' % (B, tot / 2e3))
+for k, n, t in sorted(rows, key=lambda r: -r[2])[:22]:
+    print('%-100s n=%5d  %9.1f us/step  %7.1f us/launch  %5.1f%%' % (k[:100], n // 2, t / 2, t / n, 100 * t / tot))
