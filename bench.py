@@ -80,7 +80,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(float(os.environ.get('CAPB200_CLOCK_SAMPLE_S', '0.05')))
 
     def summary(self):
         return {'sm_mhz': statistics.median(self.samples) if self.samples else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
@@ -189,7 +189,7 @@ def bench_scst(args, rank, world, local_rank, dev):
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                 'config': {'workload': 'UpDown SCST step, per-GPU batch=%d images x %d samples, 36x2048 feats, seq_len=20, V=9487' % (B, n),
                            'images_per_sec': value / n, 'parallelism': 'dp%d, one gradient all-reduce of %d bytes per step' % (world, grad_bytes[0]),
-                           'numeric_mode': 'greedy baseline %s; sampling + backward fp32 CUDA-core GEMMs' % args.mode},
+                           'numeric_mode': 'greedy baseline %s (tcgen05); sampling + backward on 3xTF32 split-K tensor-core GEMMs over the fp32 weights, weight-gradient GEMMs fp32' % args.mode},
                 'clocks': sampler.summary(),
                 'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': B * (CFG['F_fc'] + R * CFG['F_att']) * 4, 'd2h_bytes_per_step': 4},
                 'gpu_launches': model.launch_count - l0, 'roofline': None}

@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(PKG, 'libcapb200.so')
 
 MODE_SIMT_FP32, MODE_TC_F16X3, MODE_TC_F16X1 = 0, 1, 2
 MODES = {'simt_fp32': MODE_SIMT_FP32, 'tc_f16x3': MODE_TC_F16X3, 'tc_f16x1': MODE_TC_F16X1}
+# capb200_linear additionally exposes the training step's split-K GEMM variants
+OP_MODES = dict(MODES, skinny_tf32x3=3, skinny_fp32=4)
 FAMILY_UPDOWN, FAMILY_NEWFC = 0, 1
 SAMPLE_GREEDY, SAMPLE_MULTINOMIAL, SAMPLE_FORCED, SAMPLE_TEACHER = 0, 1, 2, 3
 
@@ -39,7 +41,15 @@ class SampleOpts(Structure):
 
 
 class ScstOpts(Structure):
-    _fields_ = [('sample_n', c_int), ('temperature', c_float), ('seed', c_ulonglong), ('drop_prob', c_float), ('upstream', c_float)]
+    _fields_ = [('sample_n', c_int), ('temperature', c_float), ('seed', c_ulonglong), ('drop_prob', c_float), ('upstream', c_float), ('baseline', c_int)]
+
+
+BASELINE_GREEDY, BASELINE_LEAVE_ONE_OUT = 0, 1
+
+
+class XeOpts(Structure):
+    _fields_ = [('seq_per_img', c_int), ('steps', c_int), ('seed', c_ulonglong), ('drop_prob', c_float), ('label_smoothing', c_float),
+                ('upstream', c_float)]
 
 
 GRAD_FIELDS = ['embed', 'fc_embed_w', 'fc_embed_b', 'att_embed_w', 'att_embed_b', 'ctx2att_w', 'ctx2att_b', 'logit_w', 'logit_b',
@@ -140,6 +150,9 @@ SIGNATURES = {
     'capb200_dropout_mask': (c_int, [c_void_p, c_long, c_ulonglong, c_int, c_int, c_float, c_void_p]),
     'capb200_cider_table_create': (c_void_p, [c_void_p, c_void_p, c_long, c_double, c_void_p]),
     'capb200_cider_table_destroy': (None, [c_void_p]),
+    'capb200_cider_scores': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    'capb200_updown_xe_step': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(XeOpts), c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_void_p]),
     'capb200_self_critical_reward': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                              c_void_p]),
     'capb200_reward_criterion_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

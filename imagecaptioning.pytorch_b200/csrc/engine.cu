@@ -685,8 +685,19 @@ int capb200_linear(const float* x, long ldx, const float* w, long ldw, const flo
     g.seg[0].A = x; g.seg[0].lda = ldx; g.seg[0].W = w; g.seg[0].ldw = ldw; g.seg[0].K = K;
     g.epi.bias = b; g.epi.relu = relu; g.epi.C = y; g.epi.ldc = ldy;
     if (mode == CAPB200_MODE_SIMT_FP32) return gemm_simt_launch(g, st);
+    if (mode == CAPB200_MODE_SKINNY_TF32X3 || mode == CAPB200_MODE_SKINNY_FP32) {
+        // the training step's split-K GEMM (no relu epilogue); scratch for the partial sums is allocated per call here
+        CAPB_REQUIRE(!relu, "the skinny GEMM has no relu epilogue");
+        const size_t cap = (size_t)4 << 20;
+        float* part = nullptr;
+        CAPB_CHECK_CUDA(cudaMallocAsync(&part, cap * sizeof(float), st));
+        const int tb = 1;
+        const int rc = gemm_skinny_launch(M, N, 1, &x, &ldx, &w, &ldw, &K, &tb, y, ldy, b, nullptr, 0, 1, 0, part, cap, mode == CAPB200_MODE_SKINNY_TF32X3, st);
+        cudaFreeAsync(part, st);
+        return rc;
+    }
     CAPB_REQUIRE(mode == CAPB200_MODE_TC_F16X3 || mode == CAPB200_MODE_TC_F16X1, "unknown mode");
-    const long ldh = round_up(K, 8);
+    const long ldh = round_up(K, 64);
     __half* scratch = nullptr;
     const size_t elems = (size_t)(M + N) * ldh * 2;
     CAPB_CHECK_CUDA(cudaMallocAsync(&scratch, elems * sizeof(__half), st));
@@ -711,7 +722,7 @@ int capb200_bench_linear(const float* x, const float* w, const float* b, float* 
     g.M = M; g.N = N; g.nseg = 1;
     g.seg[0].A = x; g.seg[0].lda = K; g.seg[0].W = w; g.seg[0].ldw = K; g.seg[0].K = K;
     g.epi.bias = b; g.epi.C = y; g.epi.ldc = N;
-    const long ldh = round_up(K, 8);
+    const long ldh = round_up(K, 64);
     __half* scratch = nullptr;
     GemmTcPlan* plan = nullptr;
     int rc = 0;
@@ -795,7 +806,7 @@ namespace {
 struct Tape {
     int* tok; float *xt, *g1, *h0, *c0, *atth, *alpha, *attres, *g2, *h1, *c1, *out;          // forward, [T][N][.] except out [N][T][H]
     float *fc_e, *att_e, *p_att, *g_fc, *gl, *glp;                                              // prologue + greedy scratch
-    float *DL, *dOUT, *DG1, *DG2, *DATTH, *dh0, *dc0, *dh1, *dc1, *tmpH, *dX2, *dxt, *d_att_e, *d_p_att, *S, *d_fc_e, *dpre_att, *dpre_fc, *mask_sum, *dalpha, *skinny;
+    float *DL, *dOUT, *DG1, *DG2, *DATTH, *dh0, *dc0, *dh1, *dc1, *tmpH, *dX2, *dxt, *d_att_e, *d_p_att, *S, *d_fc_e, *dpre_att, *dpre_fc, *mask_sum, *dalpha, *skinny, *item_loss;
     size_t skinny_floats;
     double* scores;
     long long* gseq_dummy;
@@ -817,6 +828,7 @@ void layout_tape(Tape& tp, Arena& a, int B, int R, int N, int T, int E, int H, i
     tp.dpre_att = a.take<float>(BR * H); tp.dpre_fc = a.take<float>((long)B * H); tp.mask_sum = a.take<float>(8);
     tp.scores = a.take<double>((long)N + B);
     tp.dalpha = a.take<float>((long)N * R);
+    tp.item_loss = a.take<float>(TN);
     tp.skinny_floats = (size_t)4 << 20;                       // split-K partial sums (16 MB)
     tp.skinny = a.take<float>((long)tp.skinny_floats);
     (void)F_att; (void)F_fc;
@@ -824,23 +836,23 @@ void layout_tape(Tape& tp, Arena& a, int B, int R, int N, int T, int E, int H, i
 
 // Skinny fp32 GEMMs on the raw PyTorch weights (always current, no repack after optimizer steps); split-K partials live in the tape.
 struct Skinny {
-    float* scratch; size_t cap; cudaStream_t st;
+    float* scratch; size_t cap; int mode; cudaStream_t st;
     // y = x * W^T (+ b)          (nn.Linear forward; W stored [N, K])
     int lin(const float* x, long ldx, const float* w, long ldw, const float* b, float* y, long ldy, int M, int N, int K, int accumulate) const {
         const int tb = 1;
-        return gemm_skinny_launch(M, N, 1, &x, &ldx, &w, &ldw, &K, &tb, y, ldy, b, nullptr, 0, 1, accumulate, scratch, cap, st);
+        return gemm_skinny_launch(M, N, 1, &x, &ldx, &w, &ldw, &K, &tb, y, ldy, b, nullptr, 0, 1, accumulate, scratch, cap, mode, st);
     }
     // dx = dy * W                (nn.Linear input gradient; W stored [K, N])
     int dgrad(int M, int N, int K, const float* dy, long lddy, const float* w, long ldw, float* dx, long lddx, int accumulate) const {
         const int tb = 0;
-        return gemm_skinny_launch(M, N, 1, &dy, &lddy, &w, &ldw, &K, &tb, dx, lddx, nullptr, nullptr, 0, 1, accumulate, scratch, cap, st);
+        return gemm_skinny_launch(M, N, 1, &dy, &lddy, &w, &ldw, &K, &tb, dx, lddx, nullptr, nullptr, 0, 1, accumulate, scratch, cap, mode, st);
     }
     // the K-segmented gate GEMM of the decode path, on fp32 weights
     int gates(const GemmProblem& g) const {
         const float* A[3]; const float* B[3]; long lda[3], ldb[3]; int K[3], tb[3];
         for (int i = 0; i < g.nseg; ++i) { A[i] = g.seg[i].A; lda[i] = g.seg[i].lda; B[i] = g.seg[i].W; ldb[i] = g.seg[i].ldw; K[i] = g.seg[i].K; tb[i] = 1; }
         return gemm_skinny_launch(g.M, g.N, g.nseg, A, lda, B, ldb, K, tb, g.epi.C, g.epi.ldc, g.epi.bias, g.epi.row_bias, g.epi.ld_row_bias,
-                                  g.epi.rows_per_group, 0, scratch, cap, st);
+                                  g.epi.rows_per_group, 0, scratch, cap, mode, st);
     }
 };
 
@@ -851,22 +863,41 @@ extern "C" int capb200_dropout_mask(float* mask, long n, unsigned long long seed
     return dropout_mask_launch(mask, n, seed, (unsigned)site, (unsigned)step, p, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, const float* att, int B, int R, const capb200_scst_opts* opts,
-                                        const capb200_cider_table* table, const int* refs, const int* ref_offsets, int L,
-                                        const capb200_updown_grads* grads, long long* sample_seq, long long* greedy_seq, float* sample_logprobs,
-                                        float* reward, float* loss, void* stream) {
-    if (check_ready(e)) return 1;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CAPB_REQUIRE(e->cfg.family == CAPB200_FAMILY_UPDOWN, "the SCST step is implemented for the UpDown family");
-    CAPB_REQUIRE(opts && fc && att && table && refs && ref_offsets && grads && sample_seq && greedy_seq && sample_logprobs && reward && loss, "null argument");
-    const int n = opts->sample_n, N = B * n, T = e->T, E = e->E, H = e->H, A = e->A, V1 = e->V1;
+namespace {
+
+// One training step on the tape: SCST (sampled tokens, reward-weighted loss) or XE (teacher-forced tokens, cross-entropy).
+struct TrainArgs {
+    bool xe = false;
+    int n = 1;                 // rows per image: train_sample_n (SCST) or seq_per_img (XE)
+    int T = 0;                 // steps evaluated (and columns of the tape)
+    int Tl = 0;                // columns of the log-prob output [N, Tl, V1]
+    float p = 0.f, temperature = 1.f, upstream = 1.f, smoothing = 0.f;
+    unsigned long long seed = 0;
+    // SCST
+    bool greedy_baseline = true;
+    const capb200_cider_table* table = nullptr;
+    const int* refs = nullptr; const int* ref_offsets = nullptr; int L = 0;
+    long long* sample_seq = nullptr; long long* greedy_seq = nullptr; float* reward = nullptr;
+    // XE
+    const long long* labels = nullptr; long ld_labels = 0; const float* masks = nullptr; long ld_masks = 0;
+    float* logprobs = nullptr; float* loss = nullptr;
+};
+
+int updown_train_step(capb200_engine* e, const float* fc, const float* att, int B, int R, const TrainArgs& ta, const capb200_updown_grads* grads,
+                      cudaStream_t st) {
+    void* stream = static_cast<void*>(st);
+    const int n = ta.n, N = B * n, T = ta.T, E = e->E, H = e->H, A = e->A, V1 = e->V1;
     const int Fa = e->cfg.att_feat_size, Ff = e->cfg.fc_feat_size;
-    CAPB_REQUIRE(n >= 1 && n <= 16 && B >= 1 && R >= 1, "sample_n must be in 1..16");
-    const float p = opts->drop_prob;
-    CAPB_REQUIRE(p >= 0.f && p < 1.f, "drop_prob must be in [0, 1)");
+    const float p = ta.p;
     const float keep_scale = 1.0f / (1.0f - p);
-    const unsigned long long seed = opts->seed;
+    const unsigned long long seed = ta.seed;
     const capb200_weights& w = e->w;
+    float* const sample_logprobs = ta.logprobs;
+    const long ld_lp = (long)ta.Tl * V1;
+    long long* const sample_seq = ta.sample_seq;
+    long long* const greedy_seq = ta.greedy_seq;
+    float* const reward = ta.reward;
+    float* const loss = ta.loss;
 
     // ---- (1) greedy baseline, eval mode (no dropout): the regular decode path
     {
@@ -881,14 +912,14 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
     }
     Arena ar; ar.base = e->tape;
     Tape tp; layout_tape(tp, ar, B, R, N, T, E, H, A, V1, Fa, Ff);
-    {
+    if (!ta.xe && ta.greedy_baseline) {
         capb200_sample_opts so; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.seed = 0; so.steps = T;
         CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, st));
         CAPB_CHECK_CUDA(cudaMemsetAsync(greedy_seq, 0, sizeof(long long) * (size_t)B * T, st));
         if (capb200_decode_sample(e, fc, att, nullptr, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, stream)) return 1;
     }
     if (ensure_workspace(e, B, N, R, 1, st)) return 1;        // DecodeBuffers (tokens, unfinished, ...) for N rows
-    const Skinny sk{tp.skinny, tp.skinny_floats, st};
+    const Skinny sk{tp.skinny, tp.skinny_floats, e->tc ? 1 : 0, st};        // 3xTF32 tensor-core GEMMs unless the engine is in simt_fp32 mode
 
     // ---- (2) train-mode prologue: fc_embed / att_embed with dropout, ctx2att, per-image gate term
     const long BR = (long)B * R;
@@ -907,7 +938,8 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
     CAPB_CHECK_CUDA(cudaMemsetAsync(e->d.tokens, 0, sizeof(int) * N, st));
     for (int t = 0; t < T; ++t) {
         int* tok = tp.tok + (long)t * N;
-        CAPB_CHECK_CUDA(cudaMemcpyAsync(tok, e->d.tokens, sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
+        if (ta.xe) { if (load_token_column_launch(ta.labels, ta.ld_labels, t, N, tok, st)) return 1; }
+        else CAPB_CHECK_CUDA(cudaMemcpyAsync(tok, e->d.tokens, sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
         float* xt = tp.xt + (long)t * N * E;
         float* g1 = tp.g1 + (long)t * N * 4 * H;
         float* g2 = tp.g2 + (long)t * N * 4 * H;
@@ -950,26 +982,32 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
         float* out = tp.out + (long)t * H;
         if (dropout_copy_launch(h1, H, out, (long)T * H, N, H, seed, 3, (unsigned)t, p, st)) return 1;
         float* logits = sample_logprobs + (long)t * V1;
-        if (sk.lin(out, (long)T * H, w.logit_w, H, w.logit_b, logits, (long)T * V1, N, V1, H, 0)) return 1;
+        if (sk.lin(out, (long)T * H, w.logit_w, H, w.logit_b, logits, ld_lp, N, V1, H, 0)) return 1;
         VocabStepArgs va;
-        va.rows = N; va.V1 = V1; va.logits = logits; va.ld = (long)T * V1;
-        va.select = 2; va.temperature = opts->temperature; va.seed = seed; va.step = (unsigned long long)t;
-        va.unfinished = e->d.unfinished; va.first_step = (t == 0); va.tokens_out = e->d.tokens;
-        va.seq_out = sample_seq; va.ld_seq = T; va.t = t;
+        va.rows = N; va.V1 = V1; va.logits = logits; va.ld = ld_lp;
+        if (!ta.xe) {
+            va.select = 2; va.temperature = ta.temperature; va.seed = seed; va.step = (unsigned long long)t;
+            va.unfinished = e->d.unfinished; va.first_step = (t == 0); va.tokens_out = e->d.tokens;
+            va.seq_out = sample_seq; va.ld_seq = T; va.t = t;
+        }
         if (vocab_step_launch(va, st)) return 1;
         e->launches += 12;
     }
 
     // ---- (4) reward and loss
-    if (cider_reward_launch(table->t, sample_seq, N, greedy_seq, B, T, refs, ref_offsets, L, tp.scores, reward, T, T, st)) return 1;
-    if (reward_criterion_fwd_launch(sample_logprobs, (long)T * V1, V1, sample_seq, reward, N, T, loss, nullptr, tp.mask_sum, st)) return 1;
-    e->launches += 3;
-
-    // ---- (5) backward
     const long TN = (long)T * N;
     const capb200_updown_grads& G = *grads;
-    // logit layer, batched over all (n, t)
-    if (scst_dlogits_launch(sample_logprobs, sample_seq, reward, tp.mask_sum, opts->upstream, N, T, V1, tp.DL, st)) return 1;
+    if (ta.xe) {
+        if (xe_loss_backward_launch(sample_logprobs, ld_lp, ta.labels, ta.ld_labels, ta.masks, ta.ld_masks, N, T, ta.Tl, V1, ta.smoothing, ta.upstream,
+                                    tp.mask_sum, tp.item_loss, tp.DL, loss, st)) return 1;
+    } else {
+        if (cider_reward_launch(ta.table->t, sample_seq, N, ta.greedy_baseline ? greedy_seq : nullptr, B, T, ta.refs, ta.ref_offsets, ta.L, tp.scores, reward,
+                                T, T, st)) return 1;
+        if (reward_criterion_fwd_launch(sample_logprobs, ld_lp, V1, sample_seq, reward, N, T, loss, nullptr, tp.mask_sum, st)) return 1;
+        // ---- (5) backward: logit layer, batched over all (n, t)
+        if (scst_dlogits_launch(sample_logprobs, ld_lp, sample_seq, reward, tp.mask_sum, ta.upstream, N, T, V1, tp.DL, st)) return 1;
+    }
+    e->launches += 3;
     if (sk.dgrad((int)TN, H, V1, tp.DL, V1, w.logit_w, H, tp.dOUT, H, 0)) return 1;          // dOUT = DL * W
     if (gemm_generic_launch(1, 0, V1, H, (int)TN, tp.DL, V1, tp.out, H, G.logit_w, H, 0, nullptr, st)) return 1;            // dW = DL^T * OUT
     if (colsum_launch((int)TN, V1, tp.DL, V1, G.logit_b, 0, st)) return 1;
@@ -1042,6 +1080,48 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
     return rc;
 }
 
+}  // namespace
+
+extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, const float* att, int B, int R, const capb200_scst_opts* opts,
+                                        const capb200_cider_table* table, const int* refs, const int* ref_offsets, int L,
+                                        const capb200_updown_grads* grads, long long* sample_seq, long long* greedy_seq, float* sample_logprobs,
+                                        float* reward, float* loss, void* stream) {
+    if (check_ready(e)) return 1;
+    CAPB_REQUIRE(e->cfg.family == CAPB200_FAMILY_UPDOWN, "the SCST step is implemented for the UpDown family");
+    CAPB_REQUIRE(opts && fc && att && table && refs && ref_offsets && grads && sample_seq && sample_logprobs && reward && loss, "null argument");
+    const bool greedy_baseline = opts->baseline == CAPB200_BASELINE_GREEDY;
+    CAPB_REQUIRE(greedy_baseline || opts->baseline == CAPB200_BASELINE_LEAVE_ONE_OUT, "unknown baseline");
+    CAPB_REQUIRE(!greedy_baseline || greedy_seq != nullptr, "the greedy baseline needs greedy_seq");
+    CAPB_REQUIRE(greedy_baseline || opts->sample_n >= 2, "the leave-one-out baseline needs sample_n >= 2");
+    CAPB_REQUIRE(opts->sample_n >= 1 && opts->sample_n <= 16 && B >= 1 && R >= 1, "sample_n must be in 1..16");
+    CAPB_REQUIRE(opts->drop_prob >= 0.f && opts->drop_prob < 1.f, "drop_prob must be in [0, 1)");
+    TrainArgs ta;
+    ta.n = opts->sample_n; ta.T = e->T; ta.Tl = e->T; ta.p = opts->drop_prob; ta.temperature = opts->temperature; ta.upstream = opts->upstream;
+    ta.seed = opts->seed; ta.greedy_baseline = greedy_baseline; ta.table = table; ta.refs = refs; ta.ref_offsets = ref_offsets; ta.L = L;
+    ta.sample_seq = sample_seq; ta.greedy_seq = greedy_seq; ta.reward = reward; ta.logprobs = sample_logprobs; ta.loss = loss;
+    return updown_train_step(e, fc, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int capb200_updown_xe_step(capb200_engine* e, const float* fc, const float* att, int B, int R, const capb200_xe_opts* opts,
+                                      const long long* labels, const float* masks, int label_cols, const capb200_updown_grads* grads, float* logprobs,
+                                      float* loss, void* stream) {
+    if (check_ready(e)) return 1;
+    CAPB_REQUIRE(e->cfg.family == CAPB200_FAMILY_UPDOWN, "the XE step is implemented for the UpDown family");
+    CAPB_REQUIRE(opts && fc && att && labels && masks && grads && logprobs && loss, "null argument");
+    CAPB_REQUIRE(opts->seq_per_img >= 1 && opts->seq_per_img <= 16 && B >= 1 && R >= 1, "seq_per_img must be in 1..16");
+    CAPB_REQUIRE(opts->drop_prob >= 0.f && opts->drop_prob < 1.f, "drop_prob must be in [0, 1)");
+    CAPB_REQUIRE(opts->label_smoothing >= 0.f && opts->label_smoothing < 1.f, "label_smoothing must be in [0, 1)");
+    CAPB_REQUIRE(label_cols >= 2 && label_cols <= e->T + 2, "labels are [N, seq_length + 2] (BOS, words, EOS padding)");
+    CAPB_REQUIRE(opts->steps >= 1 && opts->steps <= label_cols - 1, "steps must be in 1..label_cols-1");
+    TrainArgs ta;
+    ta.xe = true;
+    ta.n = opts->seq_per_img; ta.T = opts->steps; ta.Tl = label_cols - 1; ta.p = opts->drop_prob; ta.upstream = opts->upstream; ta.seed = opts->seed;
+    ta.smoothing = opts->label_smoothing;
+    ta.labels = labels; ta.ld_labels = label_cols; ta.masks = masks; ta.ld_masks = label_cols; ta.logprobs = logprobs; ta.loss = loss;
+    return updown_train_step(e, fc, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
+}
+
+
 capb200_cider_table* capb200_cider_table_create(const int* keys, const double* df, long n, double ref_len, void* stream) {
     if (keys == nullptr || df == nullptr || n < 0 || ref_len <= 0) { set_error("bad CIDEr-D table arguments"); return nullptr; }
     CiderTable* t = cider_table_create(keys, df, n, ref_len, static_cast<cudaStream_t>(stream));
@@ -1061,6 +1141,12 @@ int capb200_self_critical_reward(const capb200_cider_table* t, const long long* 
                                  const int* refs, const int* ref_offsets, int L, double* scores, float* reward, void* stream) {
     CAPB_REQUIRE(t != nullptr && sampled && greedy && refs && ref_offsets && scores, "null argument");
     return cider_reward_launch(t->t, sampled, S, greedy, B, T, refs, ref_offsets, L, scores, reward, T, T, static_cast<cudaStream_t>(stream));
+}
+
+int capb200_cider_scores(const capb200_cider_table* t, const long long* sampled, int S, int B, int T, const int* refs, const int* ref_offsets,
+                         int L, double* scores, float* reward, void* stream) {
+    CAPB_REQUIRE(t != nullptr && sampled && refs && ref_offsets && scores, "null argument");
+    return cider_reward_launch(t->t, sampled, S, nullptr, B, T, refs, ref_offsets, L, scores, reward, T, T, static_cast<cudaStream_t>(stream));
 }
 
 int capb200_reward_criterion_forward(const float* logprobs, const long long* seq, const float* reward, int N, int T, int V1, float* loss_mean,

@@ -27,7 +27,7 @@ struct Arena {
 struct Act {
     ActView v;
     void carve(Arena& a, long rows, long cols, bool planes) {
-        v.ld = round_up(cols, 8);
+        v.ld = round_up(cols, 64);          // 128-byte plane rows: every TMA box row is one aligned L2 line
         v.f = a.take<float>(rows * v.ld);
         if (planes) {
             v.hi = a.take<__half>(rows * v.ld);
@@ -40,7 +40,7 @@ struct Act {
 
 inline Planes carve_planes(Arena& a, long rows, long cols) {
     Planes p;
-    p.ld = round_up(cols, 8);
+    p.ld = round_up(cols, 64);
     p.hi = a.take<__half>(rows * p.ld);
     p.lo = a.take<__half>(rows * p.ld);
     return p;

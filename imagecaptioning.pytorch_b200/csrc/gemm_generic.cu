@@ -200,6 +200,127 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const SkinnyParams p) 
     }
 }
 
+// Same problem on the tensor cores: 3xTF32 (hi*lo + lo*hi + hi*hi, fp32 accumulate) through mma.sync.m16n8k8, reading the fp32 weights
+// as they are (no repack after optimizer steps; TF32 keeps the fp32 exponent, so small gradients do not underflow the way fp16 planes
+// would).  The shapes are weight-streaming bound, so the legacy mma path is enough; tile 64 x 64 x 16, 8 warps as 2 (M) x 4 (N).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+constexpr int SA_LD = GK + 4;      // A / B^T tiles [64][16] padded: fragment loads hit 32 distinct banks
+constexpr int SB_LD = GT + 8;      // B tile [16][64] padded (TB = 0)
+
+template <int TB>
+__global__ void __launch_bounds__(256) gemm_skinny_tf32_kernel(const SkinnyParams p) {
+    __shared__ uint32_t As[2][GT * SA_LD];                              // [hi/lo][m][k]
+    __shared__ uint32_t Bs[2][TB ? GT * SA_LD : GK * SB_LD];            // TB: [n][k]   else [k][n]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;
+    const int n0 = blockIdx.x * GT, m0 = blockIdx.z * GT;
+    const int per = (p.ksteps_total + p.ksplit - 1) / p.ksplit;
+    const int ks0 = blockIdx.y * per, ks1 = min(p.ksteps_total, ks0 + per);
+    float acc[2][2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+    // global -> register staging: one float4 of A and one of B per thread
+    const int a_row = tid >> 2, a_k = (tid & 3) * 4;
+    const int b_r = TB ? (tid >> 2) : (tid >> 4), b_c = TB ? (tid & 3) * 4 : (tid & 15) * 4;          // TB: (n, k)   else (k, n)
+    float4 ra, rb;
+    int seg = 0, seg_first = 0;
+    auto fetch = [&](int ks) {
+        while (seg < p.nseg - 1 && ks >= seg_first + (p.K[seg] + GK - 1) / GK) { seg_first += (p.K[seg] + GK - 1) / GK; ++seg; }
+        const int k0 = (ks - seg_first) * GK, K = p.K[seg];
+        ra = make_float4(0.f, 0.f, 0.f, 0.f);
+        rb = ra;
+        if (m0 + a_row < p.M && k0 + a_k < K) ra = *reinterpret_cast<const float4*>(p.A[seg] + (long)(m0 + a_row) * p.lda[seg] + k0 + a_k);
+        if (TB) {
+            if (n0 + b_r < p.N && k0 + b_c < K) rb = *reinterpret_cast<const float4*>(p.B[seg] + (long)(n0 + b_r) * p.ldb[seg] + k0 + b_c);
+        } else {
+            if (k0 + b_r < K && n0 + b_c < p.N) rb = *reinterpret_cast<const float4*>(p.B[seg] + (long)(k0 + b_r) * p.ldb[seg] + n0 + b_c);
+        }
+    };
+    if (ks0 < ks1) fetch(ks0);
+    for (int ks = ks0; ks < ks1; ++ks) {
+        {
+            const float av[4] = {ra.x, ra.y, ra.z, ra.w}, bv[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t hi, lo;
+                split_tf32(av[q], hi, lo);
+                As[0][a_row * SA_LD + a_k + q] = hi; As[1][a_row * SA_LD + a_k + q] = lo;
+                split_tf32(bv[q], hi, lo);
+                const int o = TB ? b_r * SA_LD + b_c + q : b_r * SB_LD + b_c + q;
+                Bs[0][o] = hi; Bs[1][o] = lo;
+            }
+        }
+        __syncthreads();
+        if (ks + 1 < ks1) fetch(ks + 1);
+#pragma unroll
+        for (int kk = 0; kk < GK; kk += 8) {
+            uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = wm + i * 16 + g;
+                ah[i][0] = As[0][r * SA_LD + kk + tig];       ah[i][1] = As[0][(r + 8) * SA_LD + kk + tig];
+                ah[i][2] = As[0][r * SA_LD + kk + tig + 4];   ah[i][3] = As[0][(r + 8) * SA_LD + kk + tig + 4];
+                al[i][0] = As[1][r * SA_LD + kk + tig];       al[i][1] = As[1][(r + 8) * SA_LD + kk + tig];
+                al[i][2] = As[1][r * SA_LD + kk + tig + 4];   al[i][3] = As[1][(r + 8) * SA_LD + kk + tig + 4];
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = wn + j * 8 + g;
+                if (TB) {
+                    bh[j][0] = Bs[0][c * SA_LD + kk + tig]; bh[j][1] = Bs[0][c * SA_LD + kk + tig + 4];
+                    bl[j][0] = Bs[1][c * SA_LD + kk + tig]; bl[j][1] = Bs[1][c * SA_LD + kk + tig + 4];
+                } else {
+                    bh[j][0] = Bs[0][(kk + tig) * SB_LD + c]; bh[j][1] = Bs[0][(kk + tig + 4) * SB_LD + c];
+                    bl[j][0] = Bs[1][(kk + tig) * SB_LD + c]; bl[j][1] = Bs[1][(kk + tig + 4) * SB_LD + c];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    mma_tf32(acc[i][j], ah[i], bl[j]);
+                    mma_tf32(acc[i][j], al[i], bh[j]);
+                    mma_tf32(acc[i][j], ah[i], bh[j]);
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int row = m0 + wm + i * 16 + g + (q >> 1) * 8;
+                const int col = n0 + wn + j * 8 + 2 * tig + (q & 1);
+                if (row >= p.M || col >= p.N) continue;
+                float v = acc[i][j][q];
+                if (p.ksplit == 1) {
+                    if (p.bias) v += p.bias[col];
+                    if (p.row_bias) v += p.row_bias[(long)(row / p.rpg) * p.ld_rb + col];
+                    float* c = p.out + (long)row * p.ldo + col;
+                    *c = p.accumulate ? (*c + v) : v;
+                } else {
+                    p.out[((long)blockIdx.y * p.M + row) * p.N + col] = v;
+                }
+            }
+}
+
 __global__ void skinny_reduce_kernel(int M, int N, int ksplit, const float* __restrict__ part, float* __restrict__ C, long ldc, const float* __restrict__ bias,
                                      const float* __restrict__ row_bias, long ld_rb, int rpg, int accumulate) {
     const long total = (long)M * N;
@@ -218,7 +339,7 @@ __global__ void skinny_reduce_kernel(int M, int N, int ksplit, const float* __re
 
 int gemm_skinny_launch(int M, int N, int nseg, const float* const* A, const long* lda, const float* const* B, const long* ldb, const int* K, const int* tb,
                        float* C, long ldc, const float* bias, const float* row_bias, long ld_rb, int rpg, int accumulate, float* scratch,
-                       size_t scratch_floats, cudaStream_t st) {
+                       size_t scratch_floats, int mode, cudaStream_t st) {
     if (M <= 0 || N <= 0) return 0;
     CAPB_REQUIRE(nseg >= 1 && nseg <= 3, "1..3 segments");
     SkinnyParams p;
@@ -239,7 +360,15 @@ int gemm_skinny_launch(int M, int N, int nseg, const float* const* A, const long
     p.bias = bias; p.row_bias = row_bias; p.ld_rb = ld_rb; p.rpg = rpg < 1 ? 1 : rpg; p.accumulate = accumulate;
     if (ksplit == 1) { p.out = C; p.ldo = ldc; } else { p.out = scratch; p.ldo = N; }
     dim3 grid(cdiv(N, GT), ksplit, cdiv(M, GT));
-    gemm_skinny_kernel<<<grid, 256, 0, st>>>(p);
+    // tensor-core variant needs 16-byte aligned float4 rows and one storage order for all segments
+    bool tc = (mode != 0);
+    for (int s = 0; s < nseg; ++s) {
+        tc = tc && tb[s] == tb[0] && K[s] % 4 == 0 && lda[s] % 4 == 0 && ldb[s] % 4 == 0 && (reinterpret_cast<uintptr_t>(A[s]) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(B[s]) & 15) == 0 && (tb[s] || N % 4 == 0);
+    }
+    if (tc && tb[0]) gemm_skinny_tf32_kernel<1><<<grid, 256, 0, st>>>(p);
+    else if (tc) gemm_skinny_tf32_kernel<0><<<grid, 256, 0, st>>>(p);
+    else gemm_skinny_kernel<<<grid, 256, 0, st>>>(p);
     CAPB_CHECK_CUDA(cudaGetLastError());
     if (ksplit > 1) {
         long blocks = ((long)M * N + 255) / 256;

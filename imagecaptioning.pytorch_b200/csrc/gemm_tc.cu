@@ -81,6 +81,114 @@ struct TcCfg {
     static_assert(kStages >= 2, "need at least a double buffer");
 };
 
+// Drains one 128 x BN accumulator (TMEM columns tmem_acc .. tmem_acc + BN) into global memory: thread (q, lane) owns tile row q*32 + lane.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_acc, int m0, int n0, int q, int lane, bool vec4, bool vec2h, bool lstm_vec) {
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const float* rb = (p.row_bias != nullptr && row_ok) ? p.row_bias + (long)(row / p.rows_per_group) * p.ld_row_bias : nullptr;
+    const float* gb = (p.gather_bias != nullptr && row_ok) ? p.gather_bias + (long)p.gather_idx[row] * p.ld_gb : nullptr;
+    int src = row;
+    if (p.lstm && row_ok && p.src_row != nullptr) src = p.src_row[row];
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the guarded stores of the previous chunk
+        ptx::tmem_ld_32x32b_x16(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+        ptx::tmem_ld_wait();
+        const int col0 = n0 + c0;
+        if (!row_ok || col0 >= p.N) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int col = col0 + j;
+            float x = __uint_as_float(r[j]);
+            if (col < p.N) {
+                if (p.bias != nullptr) x += __ldg(p.bias + col);
+                if (rb != nullptr) x += __ldg(rb + col);
+                if (gb != nullptr) x += __ldg(gb + col);
+                if (p.residual != nullptr) x += p.residual[(long)row * p.ld_res + col];
+                if (p.relu) x = fmaxf(x, 0.0f);
+            }
+            v[j] = x;
+        }
+        if (p.lstm) {
+            // columns col0 .. col0+15 = hidden units u0 .. u0+3, gates (i,f,g,o) interleaved
+            const int u0 = col0 >> 2;
+            float cn[4], hn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int unit = u0 + u;
+                float cp = 0.f;
+                if (unit < p.H && src >= 0 && p.c_prev != nullptr) cp = p.c_prev[(long)src * p.ld_cprev + unit];
+                cn[u] = fast_sigmoid(v[4 * u + 1]) * cp + fast_sigmoid(v[4 * u]) * fast_tanh(v[4 * u + 2]);
+                hn[u] = fast_sigmoid(v[4 * u + 3]) * fast_tanh(cn[u]);
+            }
+            if (lstm_vec && u0 + 4 <= p.H) {
+                *reinterpret_cast<float4*>(p.c_out + (long)row * p.ld_cout + u0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                *reinterpret_cast<float4*>(p.h_f + (long)row * p.ld_h + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                if (p.h_hi != nullptr) {
+                    __align__(8) __half h[4];
+                    __align__(8) __half l[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) split_f32(hn[u], h[u], l[u]);
+                    *reinterpret_cast<uint2*>(p.h_hi + (long)row * p.ld_h + u0) = *reinterpret_cast<const uint2*>(h);
+                    *reinterpret_cast<uint2*>(p.h_lo + (long)row * p.ld_h + u0) = *reinterpret_cast<const uint2*>(l);
+                }
+            } else {
+                for (int u = 0; u < 4; ++u) {
+                    const int unit = u0 + u;
+                    if (unit < p.H) {
+                        p.c_out[(long)row * p.ld_cout + unit] = cn[u];
+                        p.h_f[(long)row * p.ld_h + unit] = hn[u];
+                        if (p.h_hi != nullptr) {
+                            __half h, l;
+                            split_f32(hn[u], h, l);
+                            p.h_hi[(long)row * p.ld_h + unit] = h;
+                            p.h_lo[(long)row * p.ld_h + unit] = l;
+                        }
+                    }
+                }
+            }
+            continue;
+        }
+        const bool full = col0 + 16 <= p.N;
+        if (p.C != nullptr) {
+            float* dst = p.C + (long)row * p.ldc + col0;
+            if (full && vec4) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+                for (int j = 0; j < 16; ++j) if (col0 + j < p.N) dst[j] = v[j];
+            }
+        }
+        if (p.C_hi != nullptr) {
+            __half* dh = p.C_hi + (long)row * p.ldcs + col0;
+            __half* dl = p.C_lo + (long)row * p.ldcs + col0;
+            if (full && vec2h) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 8) {
+                    __align__(16) __half h[8];
+                    __align__(16) __half l[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) split_f32(v[j + u], h[u], l[u]);
+                    *reinterpret_cast<uint4*>(dh + j) = *reinterpret_cast<const uint4*>(h);
+                    *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(l);
+                }
+            } else {
+                for (int j = 0; j < 16; ++j) {
+                    if (col0 + j < p.N) {
+                        __half h, l;
+                        split_f32(v[j], h, l);
+                        dh[j] = h;
+                        dl[j] = l;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // CX x CY thread-block cluster: the CX CTAs of a cluster row share their A row block, the CY CTAs of a cluster column share
 // their W column block.  Each CTA fetches 1/CX of its A tile and 1/CY of its W tile and TMA-multicasts it to the peers, so
 // L2->SM operand traffic per CTA drops to A/CX + W/CY (the r01 ncu capture shows that traffic is the limiter of the
@@ -239,111 +347,9 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             const int buf = it & 1;
             const int m0 = ((ct % cl_m) * CY + cy) * BM;
             const int n0 = ((ct / cl_m) * CX + cx) * BN;
-            const int row = m0 + q * 32 + lane;
             ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
             ptx::tc_fence_after_sync();
-            const bool row_ok = row < p.M;
-            const float* rb = (p.row_bias != nullptr && row_ok) ? p.row_bias + (long)(row / p.rows_per_group) * p.ld_row_bias : nullptr;
-            const float* gb = (p.gather_bias != nullptr && row_ok) ? p.gather_bias + (long)p.gather_idx[row] * p.ld_gb : nullptr;
-            int src = row;
-            if (p.lstm && row_ok && p.src_row != nullptr) src = p.src_row[row];
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t r[16];
-                __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the guarded stores of the previous chunk
-                ptx::tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c0, r);
-                ptx::tmem_ld_wait();
-                const int col0 = n0 + c0;
-                if (!row_ok || col0 >= p.N) continue;
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int col = col0 + j;
-                    float x = __uint_as_float(r[j]);
-                    if (col < p.N) {
-                        if (p.bias != nullptr) x += __ldg(p.bias + col);
-                        if (rb != nullptr) x += __ldg(rb + col);
-                        if (gb != nullptr) x += __ldg(gb + col);
-                        if (p.residual != nullptr) x += p.residual[(long)row * p.ld_res + col];
-                        if (p.relu) x = fmaxf(x, 0.0f);
-                    }
-                    v[j] = x;
-                }
-                if (p.lstm) {
-                    // columns col0 .. col0+15 = hidden units u0 .. u0+3, gates (i,f,g,o) interleaved
-                    const int u0 = col0 >> 2;
-                    float cn[4], hn[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int unit = u0 + u;
-                        float cp = 0.f;
-                        if (unit < p.H && src >= 0 && p.c_prev != nullptr) cp = p.c_prev[(long)src * p.ld_cprev + unit];
-                        cn[u] = fast_sigmoid(v[4 * u + 1]) * cp + fast_sigmoid(v[4 * u]) * fast_tanh(v[4 * u + 2]);
-                        hn[u] = fast_sigmoid(v[4 * u + 3]) * fast_tanh(cn[u]);
-                    }
-                    if (lstm_vec && u0 + 4 <= p.H) {
-                        *reinterpret_cast<float4*>(p.c_out + (long)row * p.ld_cout + u0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                        *reinterpret_cast<float4*>(p.h_f + (long)row * p.ld_h + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                        if (p.h_hi != nullptr) {
-                            __align__(8) __half h[4];
-                            __align__(8) __half l[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) split_f32(hn[u], h[u], l[u]);
-                            *reinterpret_cast<uint2*>(p.h_hi + (long)row * p.ld_h + u0) = *reinterpret_cast<const uint2*>(h);
-                            *reinterpret_cast<uint2*>(p.h_lo + (long)row * p.ld_h + u0) = *reinterpret_cast<const uint2*>(l);
-                        }
-                    } else {
-                        for (int u = 0; u < 4; ++u) {
-                            const int unit = u0 + u;
-                            if (unit < p.H) {
-                                p.c_out[(long)row * p.ld_cout + unit] = cn[u];
-                                p.h_f[(long)row * p.ld_h + unit] = hn[u];
-                                if (p.h_hi != nullptr) {
-                                    __half h, l;
-                                    split_f32(hn[u], h, l);
-                                    p.h_hi[(long)row * p.ld_h + unit] = h;
-                                    p.h_lo[(long)row * p.ld_h + unit] = l;
-                                }
-                            }
-                        }
-                    }
-                    continue;
-                }
-                const bool full = col0 + 16 <= p.N;
-                if (p.C != nullptr) {
-                    float* dst = p.C + (long)row * p.ldc + col0;
-                    if (full && vec4) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-                        for (int j = 0; j < 16; ++j) if (col0 + j < p.N) dst[j] = v[j];
-                    }
-                }
-                if (p.C_hi != nullptr) {
-                    __half* dh = p.C_hi + (long)row * p.ldcs + col0;
-                    __half* dl = p.C_lo + (long)row * p.ldcs + col0;
-                    if (full && vec2h) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 8) {
-                            __align__(16) __half h[8];
-                            __align__(16) __half l[8];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) split_f32(v[j + u], h[u], l[u]);
-                            *reinterpret_cast<uint4*>(dh + j) = *reinterpret_cast<const uint4*>(h);
-                            *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(l);
-                        }
-                    } else {
-                        for (int j = 0; j < 16; ++j) {
-                            if (col0 + j < p.N) {
-                                __half h, l;
-                                split_f32(v[j], h, l);
-                                dh[j] = h;
-                                dl[j] = l;
-                            }
-                        }
-                    }
-                }
-            }
+            epilogue_tile<BN>(p, tmem_base + buf * BN, m0, n0, q, lane, vec4, vec2h, lstm_vec);
             __syncwarp();
             ptx::tc_fence_before_sync();
             ptx::mbar_arrive(&tmem_empty_bar[buf]);            // accumulator drained: the MMA warp may reuse it
@@ -354,6 +360,172 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     if (kCluster) ptx::cluster_sync_all();                   // no CTA leaves while a peer may still write its slots / barriers
     ptx::tc_fence_after_sync();
     if (warp == 2) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a 1 x 2 cluster sit on the two SMs of one TPC and execute ONE
+// M = 256, N = BN MMA per instruction.  Each CTA stages its own 128 A rows and only HALF of the W tile (BN/2 rows), so the
+// operand bytes a CTA must pull through L2 -> shared memory per K-block drop from (128 + BN) to (128 + BN/2) rows, the stage
+// shrinks (one more pipeline stage fits) and the shared-memory read traffic of the MMA halves.  Both CTAs run a TMA producer
+// (complete_tx lands on the leader's "full" barrier) and an epilogue over their own 128 accumulator rows; only the leader
+// (cluster rank 0) issues MMAs, and its tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both CTAs.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int BN, int PASSES>
+struct TcPairCfg {
+    static constexpr int kPlanes = (PASSES == 3) ? 2 : 1;
+    static constexpr uint32_t kABytes = BM * BK * 2;
+    static constexpr uint32_t kWBytes = (BN / 2) * BK * 2;            // this CTA's half of the W tile
+    static constexpr uint32_t kStageBytes = kPlanes * (kABytes + kWBytes);
+    static constexpr int kStages = (206 * 1024) / kStageBytes >= 8 ? 8 : (206 * 1024) / kStageBytes;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
+    static constexpr uint32_t kTmemCols = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+    static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "UMMA N for M=256 must be a multiple of 16 in [32, 256]");
+    static_assert(kWBytes % 1024 == 0, "the half W tile must keep the 1024-byte swizzle-atom alignment");
+    static_assert(kStages >= 2, "need at least a double buffer");
+};
+
+template <int BN, int PASSES>
+__global__ void __launch_bounds__(256, 1) gemm_tc_pair_kernel(const __grid_constant__ TcParams p) {
+    using Cfg = TcPairCfg<BN, PASSES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + Cfg::kStages;
+    uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;        // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;              // [2]  (the leader's copy collects both CTAs' epilogue threads)
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = blockIdx.y;                          // cluster (1, 2): rank in the pair; 0 = leader
+    const int pair_id = blockIdx.x;
+    const int num_pairs = gridDim.x;
+    const int cl_m = p.tiles_m / 2;
+    const int n_ptiles = p.tiles_n * cl_m;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.nseg; ++s) {
+            ptx::prefetch_tmap(&p.a_hi[s]);
+            ptx::prefetch_tmap(&p.w_hi[s]);
+            if (PASSES == 3) {
+                ptx::prefetch_tmap(&p.a_lo[s]);
+                ptx::prefetch_tmap(&p.w_lo[s]);
+            }
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < Cfg::kStages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);                   // the leader's expect_tx arrive (+ the bytes of both CTAs)
+            ptx::mbar_init(&empty_bar[i], 1);                  // one multicast commit per use
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tmem_full_bar[i], 1);
+            ptx::mbar_init(&tmem_empty_bar[i], 256);           // 128 epilogue threads of each CTA
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc_pair(tmem_holder, Cfg::kTmemCols);
+        ptx::tmem_relinquish_pair();
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::cluster_sync_all();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int pt = pair_id; pt < n_ptiles; pt += num_pairs) {
+                const int m0 = ((pt % cl_m) * 2 + rank) * BM;
+                const int n0 = (pt / cl_m) * BN + rank * (BN / 2);
+                for (int s = 0; s < p.nseg; ++s) {
+                    for (int kb = 0; kb < p.kblocks[s]; ++kb) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* st = smem + stage * Cfg::kStageBytes;
+                        uint8_t* a_hi = st;
+                        uint8_t* a_lo = st + Cfg::kABytes;
+                        uint8_t* w_hi = st + Cfg::kABytes * Cfg::kPlanes;
+                        uint8_t* w_lo = st + Cfg::kABytes * 2 + Cfg::kWBytes;
+                        if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                        ptx::tma_load_2d_pair(a_hi, &p.a_hi[s], &full_bar[stage], kb * BK, m0);
+                        ptx::tma_load_2d_pair(w_hi, &p.w_hi[s], &full_bar[stage], kb * BK, n0);
+                        if (PASSES == 3) {
+                            ptx::tma_load_2d_pair(a_lo, &p.a_lo[s], &full_bar[stage], kb * BK, m0);
+                            ptx::tma_load_2d_pair(w_lo, &p.w_lo[s], &full_bar[stage], kb * BK, n0);
+                        }
+                        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16_f32(2 * BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int pt = pair_id; pt < n_ptiles; pt += num_pairs, ++it) {
+                const int buf = it & 1;
+                ptx::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);       // both CTAs drained this accumulator
+                ptx::tc_fence_after_sync();
+                const uint32_t tmem_d = tmem_base + buf * BN;
+                uint32_t accumulate = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    for (int kb = 0; kb < p.kblocks[s]; ++kb) {
+                        ptx::mbar_wait(&full_bar[stage], phase);
+                        ptx::tc_fence_after_sync();
+                        const uint32_t st = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+                        const uint32_t a_hi = st;
+                        const uint32_t a_lo = st + Cfg::kABytes;
+                        const uint32_t w_hi = st + Cfg::kABytes * Cfg::kPlanes;
+                        const uint32_t w_lo = st + Cfg::kABytes * 2 + Cfg::kWBytes;
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint32_t koff = k * 32;
+                            if (PASSES == 3) {
+                                ptx::umma_f16_pair(tmem_d, ptx::make_smem_desc_sw128(a_hi + koff), ptx::make_smem_desc_sw128(w_lo + koff), idesc, accumulate);
+                                ptx::umma_f16_pair(tmem_d, ptx::make_smem_desc_sw128(a_lo + koff), ptx::make_smem_desc_sw128(w_hi + koff), idesc, 1);
+                                ptx::umma_f16_pair(tmem_d, ptx::make_smem_desc_sw128(a_hi + koff), ptx::make_smem_desc_sw128(w_hi + koff), idesc, 1);
+                            } else {
+                                ptx::umma_f16_pair(tmem_d, ptx::make_smem_desc_sw128(a_hi + koff), ptx::make_smem_desc_sw128(w_hi + koff), idesc, accumulate);
+                            }
+                            accumulate = 1;
+                        }
+                        ptx::umma_commit_pair(&empty_bar[stage]);
+                        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+                ptx::umma_commit_pair(&tmem_full_bar[buf]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const bool vec4 = p.C != nullptr && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
+        const bool vec2h = p.C_hi != nullptr && (p.ldcs & 7) == 0 && (reinterpret_cast<uintptr_t>(p.C_hi) & 15) == 0 &&
+                           (reinterpret_cast<uintptr_t>(p.C_lo) & 15) == 0;
+        const bool lstm_vec = p.lstm && (p.ld_cout & 3) == 0 && (p.ld_h & 3) == 0;
+        int it = 0;
+        for (int pt = pair_id; pt < n_ptiles; pt += num_pairs, ++it) {
+            const int buf = it & 1;
+            const int m0 = ((pt % cl_m) * 2 + rank) * BM;
+            const int n0 = (pt / cl_m) * BN;
+            ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+            ptx::tc_fence_after_sync();
+            epilogue_tile<BN>(p, tmem_base + buf * BN, m0, n0, q, lane, vec4, vec2h, lstm_vec);
+            __syncwarp();
+            ptx::tc_fence_before_sync();
+            ptx::mbar_arrive_leader(&tmem_empty_bar[buf]);
+        }
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::cluster_sync_all();
+    ptx::tc_fence_after_sync();
+    if (warp == 2) ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -422,6 +594,36 @@ int launch_cfg(const TcParams& prm, cudaStream_t stream) {
     return 0;
 }
 
+
+template <int BN, int PASSES>
+int launch_pair(const TcParams& prm, cudaStream_t stream) {
+    using Cfg = TcPairCfg<BN, PASSES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    TcParams prm2 = prm;
+    prm2.tiles_n = (int)cdiv(prm.N, BN);
+    prm2.tiles_m = (int)round_up(cdiv(prm.M, BM), 2);
+    const int n_ptiles = prm2.tiles_n * (prm2.tiles_m / 2);
+    const int P = n_ptiles < 74 ? n_ptiles : 74;                       // one pair per TPC
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(P, 2);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 2;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CAPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BN, PASSES>, prm2));
+    return 0;
+}
+
 // Round count of a tiling on 148 SMs: clusters are placed whole, so only floor(148 / cluster size) of them run at once.
 double tiling_cost(int M, int N, int bn, int cx, int cy) {
     const long tiles_n = round_up(cdiv(N, bn), cx), tiles_m = round_up(cdiv(M, BM), cy);
@@ -441,6 +643,7 @@ struct GemmTcPlan {
     int passes;
     int bn;
     int cx, cy;       // cluster shape (multicast of A across cx CTAs, of W across cy CTAs)
+    int pair;         // 1: cta_group::2 kernel (cx = 1, cy = 2; W box = bn / 2 rows)
 };
 
 static void fill_epilogue(TcParams& t, const GemmEpilogue& e) {
@@ -477,6 +680,7 @@ GemmTcPlan* gemm_tc_plan_create(const GemmProblem& p, int passes) {
     GemmTcPlan* plan = new GemmTcPlan();
     memset(&plan->prm, 0, sizeof(TcParams));
     plan->passes = passes;
+    plan->pair = 0;
     // pick the tile width / cluster shape with the lowest modelled cost; tiny problems stay on the plain kernel
     {
         const int cand_bn[2] = {128, 144};
@@ -499,6 +703,9 @@ GemmTcPlan* gemm_tc_plan_create(const GemmProblem& p, int passes) {
             int fb = 0, fx = 0, fy = 0;
             if (sscanf(force, "%dx%dx%d", &fb, &fx, &fy) == 3 && (fb == 64 || fb == 128 || fb == 144) && (fx == 1 || fx == 2) && (fy == 1 || fy == 2)) {
                 plan->bn = fb; plan->cx = fx; plan->cy = fy;
+            }
+            if (sscanf(force, "pair%d", &fb) == 1 && (fb == 128 || fb == 144 || fb == 192 || fb == 256) && cdiv(p.M, BM) >= 2) {
+                plan->bn = fb; plan->cx = 1; plan->cy = 2; plan->pair = 1;
             }
         }
     }
@@ -538,6 +745,16 @@ int gemm_tc_plan_launch(GemmTcPlan* plan, const GemmEpilogue* epi_override, int 
         return 1;
     }
     if (prm.M <= 0 || prm.N <= 0) return 0;
+    if (plan->pair) {
+        switch (plan->bn) {
+            case 128: return plan->passes == 3 ? launch_pair<128, 3>(prm, stream) : launch_pair<128, 1>(prm, stream);
+            case 144: return plan->passes == 3 ? launch_pair<144, 3>(prm, stream) : launch_pair<144, 1>(prm, stream);
+            case 192: return plan->passes == 3 ? launch_pair<192, 3>(prm, stream) : launch_pair<192, 1>(prm, stream);
+            case 256: return plan->passes == 3 ? launch_pair<256, 3>(prm, stream) : launch_pair<256, 1>(prm, stream);
+        }
+        set_error("gemm_tc: no pair kernel instance for the planned tile width");
+        return 1;
+    }
     const int key = plan->bn * 100 + plan->cx * 10 + plan->cy;
 #define CAPB_TC_CASE(BN_, CX_, CY_)                                                      \
     case BN_ * 100 + CX_ * 10 + CY_:                                                     \

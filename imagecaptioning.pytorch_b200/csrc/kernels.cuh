@@ -109,7 +109,7 @@ int gemm_generic_launch(int ta, int tb, int M, int N, int K, const float* A, lon
                         const float* bias, cudaStream_t st);
 int gemm_skinny_launch(int M, int N, int nseg, const float* const* A, const long* lda, const float* const* B, const long* ldb, const int* K, const int* tb,
                        float* C, long ldc, const float* bias, const float* row_bias, long ld_rb, int rpg, int accumulate, float* scratch,
-                       size_t scratch_floats, cudaStream_t st);
+                       size_t scratch_floats, int mode, cudaStream_t st);   // mode 0 = fp32 CUDA cores, 1 = 3xTF32 mma.sync
 int colsum_launch(int rows, int cols, const float* x, long ld, float* out, int accumulate, cudaStream_t st);
 int dropout_apply_launch(float* x, int rows, int cols, long ld, unsigned long long seed, unsigned site, unsigned step, float p, cudaStream_t st);
 int dropout_mask_launch(float* m, long n, unsigned long long seed, unsigned site, unsigned step, float p, cudaStream_t st);
@@ -117,8 +117,10 @@ int dropout_copy_launch(const float* x, long ld_x, float* y, long ld_y, int rows
                         cudaStream_t st);
 int embed_relu_dropout_launch(int rows, int E, const int* tokens, const float* emb, float* xt, unsigned long long seed, unsigned step, float p,
                               cudaStream_t st);
-int scst_dlogits_launch(const float* logp, const long long* seq, const float* reward, const float* mask_sum, float upstream, int N, int T, int V1,
+int scst_dlogits_launch(const float* logp, long ld_row, const long long* seq, const float* reward, const float* mask_sum, float upstream, int N, int T, int V1,
                         float* dl, cudaStream_t st);
+int xe_loss_backward_launch(const float* logp, long ld_row, const long long* labels, long ld_l, const float* masks, long ld_m, int N, int steps, int Ls, int V1,
+                            float smoothing, float upstream, float* mask_sum, float* item_loss, float* dl, float* loss, cudaStream_t st);
 int lstm_cell_backward_launch(int rows, int H, const float* gates, const float* c_prev, const float* c_new, const float* dh, const float* dh_extra,
                               long ld_extra, unsigned drop_site, unsigned drop_step, unsigned long long seed, float p, float* dc_carry, float* dgates,
                               cudaStream_t st);

@@ -210,6 +210,17 @@ __global__ void cider_reward_kernel(const double* __restrict__ scores, int S, in
     for (int c = threadIdx.x; c < cols; c += blockDim.x) reward[(long)i * ld + c] = rwd;
 }
 
+// new_self_critical (losses.py:168-187): reward_i = s_i - mean of the image's other samples, in fp32 after scores.type_as(input) (:62)
+__global__ void cider_reward_loo_kernel(const double* __restrict__ scores, int n_per, float* __restrict__ reward, long ld, int cols) {
+    const int i = blockIdx.x;
+    const int first = (i / n_per) * n_per;
+    float sum = 0.f;
+    for (int j = 0; j < n_per; ++j) sum += (float)scores[first + j];
+    const float s = (float)scores[i];
+    const float rwd = s - (sum - s) / (float)(n_per - 1);
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) reward[(long)i * ld + c] = rwd;
+}
+
 // RewardCriterion (losses.py:22-37): single CTA, deterministic tree reduction
 __global__ void __launch_bounds__(256) reward_criterion_fwd_kernel(const float* __restrict__ lp, long ld_row, long ld_t, const long long* __restrict__ seq,
                                                                    const float* __restrict__ reward, int N, int T, float* loss_mean,
@@ -259,10 +270,18 @@ int cider_reward_launch(const CiderTable* t, const long long* sampled, int S, co
     CAPB_REQUIRE(t != nullptr, "CIDEr-D table not initialised (init_scorer)");
     CAPB_REQUIRE(B > 0 && S % B == 0, "sample rows must be a multiple of the image count");
     CAPB_REQUIRE(T <= CIDER_MAXL && L <= CIDER_MAXL, "caption length above 64 tokens");
-    cider_score_kernel<<<S + B, 256, 0, stream>>>(t->slots, t->mask, t->log_ref_len, sampled, S, greedy, B, T, refs, ref_offsets, L, scores);
+    // greedy == nullptr: score the samples only; the reward baseline is then the mean of the image's other samples
+    const int hyps = greedy != nullptr ? S + B : S;
+    if (hyps == 0) return 0;
+    cider_score_kernel<<<hyps, 256, 0, stream>>>(t->slots, t->mask, t->log_ref_len, sampled, S, greedy, B, T, refs, ref_offsets, L, scores);
     CAPB_CHECK_CUDA(cudaGetLastError());
     if (reward != nullptr && S > 0) {
-        cider_reward_kernel<<<S, 32, 0, stream>>>(scores, S, B, reward, ld_reward, reward_cols);
+        if (greedy != nullptr) {
+            cider_reward_kernel<<<S, 32, 0, stream>>>(scores, S, B, reward, ld_reward, reward_cols);
+        } else {
+            CAPB_REQUIRE(S / B >= 2, "the leave-one-out baseline needs at least two samples per image");
+            cider_reward_loo_kernel<<<S, 32, 0, stream>>>(scores, S / B, reward, ld_reward, reward_cols);
+        }
         CAPB_CHECK_CUDA(cudaGetLastError());
     }
     return 0;

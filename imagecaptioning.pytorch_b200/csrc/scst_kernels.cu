@@ -68,7 +68,7 @@ __global__ void embed_relu_dropout_kernel(int rows, int E, const int* __restrict
 
 // d logits of  loss = sum_{n,t} -logp[n,t,seq] * reward[n] * mask[n,t] / sum(mask)  through log_softmax:
 //   dl[n,t,v] = coef * (1[v == seq] - exp(logp[n,t,v])),  coef = -reward[n,t] * mask[n,t] / mask_sum * upstream
-__global__ void scst_dlogits_kernel(const float* __restrict__ logp, const long long* __restrict__ seq, const float* __restrict__ reward,
+__global__ void scst_dlogits_kernel(const float* __restrict__ logp, long ld_row, const long long* __restrict__ seq, const float* __restrict__ reward,
                                     const float* __restrict__ mask_sum, float upstream, int T, int V1, float* __restrict__ dl) {
     const long item = blockIdx.x;                 // n * T + t
     const int t = (int)(item % T);
@@ -76,13 +76,79 @@ __global__ void scst_dlogits_kernel(const float* __restrict__ logp, const long l
     const float m = (t == 0 || seq[n * T + t - 1] > 0) ? 1.f : 0.f;
     const float coef = -reward[item] * m / (*mask_sum) * upstream;
     const long long tok = seq[item];
-    const float* lp = logp + item * V1;
+    const float* lp = logp + n * ld_row + (long)t * V1;
     float* d = dl + item * V1;
     if (coef == 0.f) {
         for (int v = threadIdx.x; v < V1; v += blockDim.x) d[v] = 0.f;
         return;
     }
     for (int v = threadIdx.x; v < V1; v += blockDim.x) d[v] = coef * ((v == tok ? 1.f : 0.f) - expf(lp[v]));
+}
+
+// ---- cross-entropy stage (LanguageModelCriterion / LabelSmoothing, losses.py:204-265) on teacher-forced log-probs [N, Ls, V1]:
+// target[n, t] = labels[n, t + 1], mask[n, t] = masks[n, t + 1]; steps <= Ls columns were evaluated (the rest stay zero, AttModel.py:158-159).
+__global__ void xe_mask_sum_kernel(const float* __restrict__ masks, long ld_m, int N, int Ls, float* __restrict__ mask_sum) {
+    __shared__ float sh[256];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < N * Ls; i += 256) s += masks[(long)(i / Ls) * ld_m + (i % Ls) + 1];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *mask_sum = sh[0];
+}
+
+// one CTA per (n, t < steps): d logits = coef * (softmax - target_dist), coef = mask / mask_sum * upstream; item_loss = un-normalised loss term
+__global__ void __launch_bounds__(256) xe_dlogits_kernel(const float* __restrict__ logp, long ld_row, const long long* __restrict__ labels, long ld_l,
+                                                         const float* __restrict__ masks, long ld_m, const float* __restrict__ mask_sum, float upstream,
+                                                         float smoothing, int steps, int V1, float* __restrict__ dl, float* __restrict__ item_loss) {
+    __shared__ float sh[256];
+    const long item = blockIdx.x;                 // n * steps + t
+    const int t = (int)(item % steps);
+    const long n = item / steps;
+    const float m = masks[n * ld_m + t + 1];
+    const long long tgt = labels[n * ld_l + t + 1];
+    const float coef = m / (*mask_sum) * upstream;
+    const float* lp = logp + n * ld_row + (long)t * V1;
+    float* d = dl + item * V1;
+    const float off = smoothing > 0.f ? smoothing / (float)(V1 - 1) : 0.f, conf = 1.f - smoothing;
+    float lsum = 0.f;
+    for (int v = threadIdx.x; v < V1; v += 256) {
+        const float l = lp[v];
+        const float td = (v == tgt) ? conf : off;
+        d[v] = coef * (expf(l) - td);
+        if (smoothing > 0.f) lsum += (td > 0.f) ? td * (logf(td) - l) : 0.f;           // KLDivLoss pointwise term (xlogy convention)
+    }
+    sh[threadIdx.x] = lsum;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) item_loss[item] = (smoothing > 0.f ? sh[0] : -lp[tgt]) * m;
+}
+
+// loss = (sum of item terms + the terms of the never-evaluated columns, whose log-probs are zero) / mask_sum
+__global__ void xe_loss_kernel(const float* __restrict__ item_loss, int N, int steps, int Ls, const float* __restrict__ masks, long ld_m, float smoothing,
+                               int V1, const float* __restrict__ mask_sum, float* __restrict__ loss) {
+    __shared__ float sh[256];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < N * steps; i += 256) s += item_loss[i];
+    if (smoothing > 0.f && steps < Ls) {
+        const float off = smoothing / (float)(V1 - 1), conf = 1.f - smoothing;
+        const float zero_row = (float)(V1 - 1) * off * logf(off) + (conf > 0.f ? conf * logf(conf) : 0.f);
+        const int extra = Ls - steps;
+        for (int i = threadIdx.x; i < N * extra; i += 256) s += zero_row * masks[(long)(i / extra) * ld_m + steps + (i % extra) + 1];
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss = sh[0] / (*mask_sum);
 }
 
 // nn.LSTMCell backward (gate pre-activations saved): dgates [rows, 4H] (i,f,g,o) and dc_prev from dh, dc
@@ -284,9 +350,18 @@ int embed_relu_dropout_launch(int rows, int E, const int* tokens, const float* e
     embed_relu_dropout_kernel<<<rows, 128, 0, st>>>(rows, E, tokens, emb, xt, seed, step, p);
     LAUNCH_OK();
 }
-int scst_dlogits_launch(const float* logp, const long long* seq, const float* reward, const float* mask_sum, float upstream, int N, int T, int V1,
+int scst_dlogits_launch(const float* logp, long ld_row, const long long* seq, const float* reward, const float* mask_sum, float upstream, int N, int T, int V1,
                         float* dl, cudaStream_t st) {
-    scst_dlogits_kernel<<<N * T, 256, 0, st>>>(logp, seq, reward, mask_sum, upstream, T, V1, dl);
+    scst_dlogits_kernel<<<N * T, 256, 0, st>>>(logp, ld_row, seq, reward, mask_sum, upstream, T, V1, dl);
+    LAUNCH_OK();
+}
+int xe_loss_backward_launch(const float* logp, long ld_row, const long long* labels, long ld_l, const float* masks, long ld_m, int N, int steps, int Ls, int V1,
+                            float smoothing, float upstream, float* mask_sum, float* item_loss, float* dl, float* loss, cudaStream_t st) {
+    xe_mask_sum_kernel<<<1, 256, 0, st>>>(masks, ld_m, N, Ls, mask_sum);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    xe_dlogits_kernel<<<N * steps, 256, 0, st>>>(logp, ld_row, labels, ld_l, masks, ld_m, mask_sum, upstream, smoothing, steps, V1, dl, item_loss);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    xe_loss_kernel<<<1, 256, 0, st>>>(item_loss, N, steps, Ls, masks, ld_m, smoothing, V1, mask_sum, loss);
     LAUNCH_OK();
 }
 int lstm_cell_backward_launch(int rows, int H, const float* gates, const float* c_prev, const float* c_new, const float* dh, const float* dh_extra,

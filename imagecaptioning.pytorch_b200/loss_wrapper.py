@@ -4,8 +4,10 @@
                                         sc_flag, struc_flag, drop_worst_flag) -> {'loss', 'reward'}
 
 sc_flag=True follows loss_wrapper.py:56-73 exactly: eval-mode greedy baseline, train-mode multinomial samples, CIDEr-D
-self-critical reward and RewardCriterion -- every stage on the device through the C ABI.  The XE branch (sc_flag=False)
-and the structure-loss branch are the next rows of SURVEY.md section 8(f) and raise for now.
+self-critical reward and RewardCriterion -- every stage on the device through the C ABI.  sc_flag=False is the XE stage
+(loss_wrapper.py:54-55: teacher-forced forward + LanguageModelCriterion / LabelSmoothing) and struc_flag=True the structure-loss
+branch (loss_wrapper.py:25-53) with ``structure_loss_type='new_self_critical'`` (losses.py:168-187), the recipe of the reference's
+best models; both run as one fused device step incl. back-propagation through time (UpDown).
 """
 from __future__ import annotations
 
@@ -13,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .rewards import get_self_critical_reward
+from .rewards import cider_scores, get_self_critical_reward
 
 
 class RewardCriterion(nn.Module):
@@ -45,6 +47,71 @@ class RewardCriterion(nn.Module):
         return grad
 
 
+def _shifted_mask(seq):
+    # tokens up to and including the first EOS (losses.py:28-29, :57-58)
+    m = (seq > 0).to(torch.float32)
+    return torch.cat([m.new_ones(m.shape[0], 1), m[:, :-1]], 1)
+
+
+class LanguageModelCriterion(nn.Module):
+    """losses.py:204-225: masked negative log-likelihood of the target tokens (host-level torch ops; the training path uses the fused
+    kernel of capb200_updown_xe_step, this module serves evaluation and the parity tests)."""
+
+    def forward(self, input, target, mask, reduction='mean'):
+        if target.ndim == 3:
+            target, mask = target.reshape(-1, target.shape[2]), mask.reshape(-1, mask.shape[2])
+        L = input.shape[1]
+        target, mask = target[:, :L], mask[:, :L].to(input)
+        nll = -torch.gather(input, 2, target.unsqueeze(2)).squeeze(2) * mask
+        return nll.sum(1) / mask.sum(1) if reduction == 'none' else nll.sum() / mask.sum()
+
+
+class LabelSmoothing(nn.Module):
+    """losses.py:228-265: KL divergence to the smoothed target distribution (smoothing / (V1 - 1) off-target, 1 - smoothing on it)."""
+
+    def __init__(self, size=0, padding_idx=0, smoothing=0.0):
+        super().__init__()
+        self.smoothing, self.confidence = smoothing, 1.0 - smoothing
+
+    def forward(self, input, target, mask, reduction='mean'):
+        N, L, V1 = input.shape
+        target, mask = target[:, :L].reshape(-1), mask[:, :L].reshape(-1).to(input)
+        flat = input.reshape(-1, V1)
+        dist = torch.full_like(flat, self.smoothing / (V1 - 1))
+        dist.scatter_(1, target.unsqueeze(1), self.confidence)
+        kl = (torch.xlogy(dist, dist) - dist * flat).sum(1) * mask
+        if reduction == 'none':
+            return kl.view(N, L).sum(1) / mask.view(N, L).sum(1)
+        return kl.sum() / mask.sum()
+
+
+class StructureLosses(nn.Module):
+    """losses.py:38-200 for ``structure_loss_type='new_self_critical'``: every sample is rewarded with its CIDEr-D minus the mean CIDEr-D
+    of the image's other samples.  Scores come from the device kernel (rewards.get_scores)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.loss_type = opt.structure_loss_type
+        if self.loss_type != 'new_self_critical':
+            raise NotImplementedError("structure_loss_type %r: the B200 engine implements 'new_self_critical'" % self.loss_type)
+
+    def forward(self, input, seq, data_gts, reduction='mean'):
+        n = input.shape[0] // len(data_gts)
+        assert n == self.opt.train_sample_n, n
+        if getattr(self.opt, 'entropy_reward_weight', 0) > 0 or getattr(self.opt, 'self_cider_reward_weight', 0) > 0:
+            raise NotImplementedError('entropy / self-CIDEr rewards are out of scope of the B200 engine')
+        mask = _shifted_mask(seq)
+        w = float(getattr(self.opt, 'cider_reward_weight', 1))
+        scores = (cider_scores(data_gts, seq) * w).to(input).view(-1, n)
+        out = {'reward': scores}
+        adv = scores - (scores.sum(1, keepdim=True) - scores) / (n - 1)
+        picked = torch.gather(input, 2, seq.unsqueeze(2)).squeeze(2)
+        term = -picked * mask * adv.reshape(-1, 1)
+        out['loss'] = term.sum(1) / mask.sum(1) if reduction == 'none' else term.sum() / mask.sum()
+        return out
+
+
 class _ScstLoss(torch.autograd.Function):
     """Connects the engine-computed loss to the parameters: the gradients were produced by the engine's own BPTT during the forward
     call; backward hands them (scaled by the upstream gradient) to autograd, so loss.backward(), DDP hooks, clip_grad_value_ and the
@@ -65,31 +132,72 @@ class B200LossWrapper(nn.Module):
         super().__init__()
         self.opt = opt
         self.model = model
+        smoothing = getattr(opt, 'label_smoothing', 0)
+        self.crit = LabelSmoothing(smoothing=smoothing) if smoothing > 0 else LanguageModelCriterion()      # loss_wrapper.py:10-13
         self.rl_crit = RewardCriterion()
+        self.struc_crit = None
+
+    # -- fused device steps ------------------------------------------------------------------------------------------
+    def _bridge(self, res):
+        params = list(res['grads'].keys())
+        return _ScstLoss.apply(res['loss'], [res['grads'][p_] for p_ in params], *params)
+
+    def _scorer(self):
+        from . import rewards as _rw
+        if _rw.CiderD_scorer is None:
+            raise RuntimeError('init_scorer(cached_tokens) must be called before the SCST reward (tools/train.py:150-152)')
+        return _rw.CiderD_scorer
+
+    def _xe_loss(self, fc_feats, att_feats, labels, masks, att_masks, drop_worst_flag):
+        """loss_wrapper.py:54-55: crit(model(fc, att, labels[..., :-1], att_masks), labels[..., 1:], masks[..., 1:])."""
+        if torch.is_grad_enabled() and self.model.training:
+            if not hasattr(self.model, 'xe_step') or att_masks is not None or drop_worst_flag:
+                raise NotImplementedError('the fused XE step covers the UpDown family with att_masks=None and reduction="mean"')
+            res = self.model.xe_step(fc_feats, att_feats, labels, masks, label_smoothing=getattr(self.opt, 'label_smoothing', 0))
+            self.last_step = res
+            return self._bridge(res)
+        # evaluation (no gradients): the teacher-forced forward of the engine plus the criterion as host-level ops
+        reduction = 'none' if drop_worst_flag else 'mean'
+        return self.crit(self.model(fc_feats, att_feats, labels[..., :-1], att_masks), labels[..., 1:], masks[..., 1:], reduction=reduction)
+
+    def _sampled_step(self, fc_feats, att_feats, gts, baseline):
+        opt = self.opt
+        self.model.train()
+        res = self.model.scst_step(fc_feats, att_feats, gts, self._scorer(), opt.train_sample_n, temperature=getattr(opt, 'temperature', 1.0),
+                                   baseline=baseline)
+        self.last_step = res
+        return res
 
     def forward(self, fc_feats, att_feats, labels, masks, att_masks, gts, gt_indices, sc_flag, struc_flag, drop_worst_flag):
         opt = self.opt
         out = {}
         reduction = 'none' if drop_worst_flag else 'mean'
+        plain_reward = getattr(opt, 'bleu_reward_weight', 0) == 0 and getattr(opt, 'cider_reward_weight', 1) == 1
+        can_fuse = (hasattr(self.model, 'scst_step') and att_masks is None and not drop_worst_flag and torch.is_grad_enabled() and plain_reward and
+                    opt.train_sample_method == 'sample' and opt.train_beam_size == 1)
         if struc_flag:
-            raise NotImplementedError('structure losses are the next row of SURVEY.md section 8(f)')
+            w = opt.structure_loss_weight
+            lm_loss = self._xe_loss(fc_feats, att_feats, labels, masks, att_masks, drop_worst_flag) if w < 1 else torch.zeros((), device=fc_feats.device)
+            if w > 0:
+                if getattr(opt, 'use_ppo', 0) or opt.structure_loss_type != 'new_self_critical' or not can_fuse:
+                    raise NotImplementedError("the structure-loss branch covers structure_loss_type='new_self_critical' on the fused UpDown step")
+                gts = [gts[_] for _ in gt_indices.tolist()]
+                res = self._sampled_step(fc_feats, att_feats, gts, 'leave_one_out')
+                struc = {'loss': self._bridge(res), 'reward': cider_scores(gts, res['sample_seq']).float().view(-1, opt.train_sample_n)}
+            else:
+                struc = {'loss': torch.zeros((), device=fc_feats.device), 'reward': torch.zeros((), device=fc_feats.device)}
+            out['lm_loss'], out['struc_loss'], out['reward'] = lm_loss, struc['loss'], struc['reward']
+            out['loss'] = (1 - w) * lm_loss + w * struc['loss']
+            return out
         if not sc_flag:
-            raise NotImplementedError('the XE stage is the next row of SURVEY.md section 8(f)')
-        fused = (hasattr(self.model, 'scst_step') and att_masks is None and not drop_worst_flag and torch.is_grad_enabled() and
-                 opt.sc_sample_method == 'greedy' and opt.sc_beam_size == 1 and opt.train_sample_method == 'sample' and opt.train_beam_size == 1 and
-                 getattr(opt, 'bleu_reward_weight', 0) == 0 and getattr(opt, 'cider_reward_weight', 1) == 1)
-        if fused:
+            out['loss'] = self._xe_loss(fc_feats, att_feats, labels, masks, att_masks, drop_worst_flag)
+            return out
+        if can_fuse and opt.sc_sample_method == 'greedy' and opt.sc_beam_size == 1:
             # whole step on the device incl. back-propagation through time (UpDown); dropout as in model.train()
-            from . import rewards as _rw
-            if _rw.CiderD_scorer is None:
-                raise RuntimeError('init_scorer(cached_tokens) must be called before the SCST reward (tools/train.py:150-152)')
-            self.model.train()
             gts = [gts[_] for _ in gt_indices.tolist()]
-            res = self.model.scst_step(fc_feats, att_feats, gts, _rw.CiderD_scorer, opt.train_sample_n, temperature=getattr(opt, 'temperature', 1.0))
-            params = list(res['grads'].keys())
-            out['loss'] = _ScstLoss.apply(res['loss'], [res['grads'][p_] for p_ in params], *params)
+            res = self._sampled_step(fc_feats, att_feats, gts, 'greedy')
+            out['loss'] = self._bridge(res)
             out['reward'] = res['reward'][:, 0].mean()
-            self.last_step = res
             return out
         self.model.eval()
         with torch.no_grad():

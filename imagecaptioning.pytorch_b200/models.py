@@ -371,9 +371,12 @@ class B200UpDownModel(B200CaptionModel):
 
 
     # ---- SCST training step (UpDown): greedy baseline + sampling with dropout + CIDEr-D reward + RewardCriterion + BPTT -----
-    def scst_step(self, fc_feats, att_feats, gts, table, sample_n, temperature=1.0, drop_prob=None, seed=None, upstream=1.0):
+    def scst_step(self, fc_feats, att_feats, gts, table, sample_n, temperature=1.0, drop_prob=None, seed=None, upstream=1.0, baseline='greedy'):
         """Runs one self-critical step entirely on the device (capb200_updown_scst_step).  Returns a dict with 'loss' (0-dim),
-        'reward' [N, T], 'sample_seq', 'greedy_seq', 'sample_logprobs' and 'grads' {parameter: gradient tensor}."""
+        'reward' [N, T], 'sample_seq', 'greedy_seq', 'sample_logprobs' and 'grads' {parameter: gradient tensor}.
+        ``baseline='greedy'`` is the self-critical step (loss_wrapper.py:56-73); ``'leave_one_out'`` the 'new_self_critical' structure
+        loss (losses.py:168-187): no greedy decode, each sample is scored against the mean of the image's other samples, and the
+        result carries 'scores' [B, n] (the raw CIDEr-D values the reference reports as out['reward'])."""
         from .rewards import pack_references
         lib = self._ensure_engine(fc_feats.device)
         fc = self._f32(fc_feats)
@@ -395,12 +398,52 @@ class B200UpDownModel(B200CaptionModel):
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         p = self.drop_prob_lm if drop_prob is None else drop_prob
-        so = _lib.ScstOpts(sample_n, float(temperature), seed, float(p), float(upstream))
+        if baseline not in ('greedy', 'leave_one_out'):
+            raise ValueError("baseline must be 'greedy' or 'leave_one_out'")
+        loo = baseline == 'leave_one_out'
+        so = _lib.ScstOpts(sample_n, float(temperature), seed, float(p), float(upstream), _lib.BASELINE_LEAVE_ONE_OUT if loo else _lib.BASELINE_GREEDY)
         _lib.check(lib.capb200_updown_scst_step(self._engine, _lib.ptr(fc), _lib.ptr(att), B, R, ctypes.byref(so), table._h, _lib.ptr(refs),
                                                 _lib.ptr(offsets), L, ctypes.byref(g), _lib.ptr(sample_seq), _lib.ptr(greedy_seq), _lib.ptr(logprobs),
                                                 _lib.ptr(reward), _lib.ptr(loss), _lib.current_stream()), 'updown_scst_step')
-        return {'loss': loss[0], 'reward': reward, 'sample_seq': sample_seq, 'greedy_seq': greedy_seq, 'sample_logprobs': logprobs,
-                'grads': {table_params[k]: v for k, v in grads.items()}, 'seed': seed}
+        res = {'loss': loss[0], 'reward': reward, 'sample_seq': sample_seq, 'greedy_seq': None if loo else greedy_seq, 'sample_logprobs': logprobs,
+               'grads': {table_params[k]: v for k, v in grads.items()}, 'seed': seed}
+        return res
+
+    def xe_step(self, fc_feats, att_feats, labels, masks, label_smoothing=0.0, drop_prob=None, seed=None, upstream=1.0):
+        """One cross-entropy step on the device (capb200_updown_xe_step): teacher-forced forward over ``labels[..., :-1]`` in train mode,
+        LanguageModelCriterion / LabelSmoothing against ``labels[..., 1:]``, ``masks[..., 1:]`` (reduction 'mean'), BPTT.
+        Returns {'loss', 'logprobs' [N, L-1, V+1], 'grads' {parameter: gradient}, 'seed'}."""
+        if self.ss_prob > 0.0:
+            raise NotImplementedError('scheduled sampling is out of scope of the B200 engine')
+        lib = self._ensure_engine(fc_feats.device)
+        fc = self._f32(fc_feats)
+        att = self._f32(att_feats)
+        dev = fc.device
+        B, R = att.shape[0], att.shape[1]
+        if labels.dim() == 3:
+            labels = labels.reshape(-1, labels.shape[2])
+            masks = masks.reshape(-1, masks.shape[2])
+        labels = labels.detach().to(torch.long).contiguous()
+        masks = masks.detach().to(torch.float32).contiguous()
+        N, Lc = labels.shape
+        if N % B != 0 or Lc > self.seq_length + 2 or masks.shape != labels.shape:
+            raise ValueError('labels/masks must be [B * seq_per_img, <= seq_length + 2]')
+        steps = self._teacher_steps(labels[:, :-1])
+        V1 = self.vocab_size + 1
+        table_params = self._weight_table()
+        grads = {name: torch.empty_like(t) for name, t in table_params.items()}
+        g = _lib.UpdownGrads()
+        for name, t in grads.items():
+            setattr(g, name, t.data_ptr())
+        logprobs = torch.zeros(N, Lc - 1, V1, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        p = self.drop_prob_lm if drop_prob is None else drop_prob
+        xo = _lib.XeOpts(N // B, steps, seed, float(p), float(label_smoothing), float(upstream))
+        _lib.check(lib.capb200_updown_xe_step(self._engine, _lib.ptr(fc), _lib.ptr(att), B, R, ctypes.byref(xo), _lib.ptr(labels), _lib.ptr(masks), Lc,
+                                              ctypes.byref(g), _lib.ptr(logprobs), _lib.ptr(loss), _lib.current_stream()), 'updown_xe_step')
+        return {'loss': loss[0], 'logprobs': logprobs, 'grads': {table_params[k]: v for k, v in grads.items()}, 'seed': seed}
 
 
 class _MaxoutCoreParams(nn.Module):

@@ -2,6 +2,7 @@
 
     init_scorer(cached_tokens)                                   rewards.py:25-31
     get_self_critical_reward(greedy_res, data_gts, gen_result, opt)   rewards.py:41-81
+    get_scores(data_gts, gen_result, opt)                             rewards.py:83-114
 
 The reference moves both id tensors to the host, formats every id as a string and walks Python dicts; here the ids
 never leave the GPU: n-gram extraction, the document-frequency lookup (open-addressing hash table built once from the
@@ -120,3 +121,34 @@ def get_self_critical_reward(greedy_res, data_gts, gen_result, opt):
     w = float(getattr(opt, 'cider_reward_weight', 1))
     _, reward = cider_scores_and_reward(greedy_res, data_gts, gen_result)
     return reward if w == 1.0 else reward * w
+
+
+def cider_scores(data_gts: Sequence, gen_result: torch.Tensor, table: Optional[CiderDTable] = None, with_reward: bool = False):
+    """CIDEr-D of every sampled caption (float64 [S]) and, optionally, the leave-one-out reward [S, T] (capb200_cider_scores)."""
+    table = table or CiderD_scorer
+    if table is None:
+        raise RuntimeError('init_scorer(cached_tokens) must be called before the structure-loss scores (tools/train.py:150-152)')
+    dev = gen_result.device
+    if dev.type != 'cuda':
+        raise RuntimeError('capb200: the reward kernel runs on CUDA tensors only')
+    B = len(data_gts)
+    S, T = gen_result.shape
+    assert S % B == 0
+    sampled = gen_result.detach().to(torch.long).contiguous()
+    refs, offsets, L = pack_references(data_gts, dev)
+    scores = torch.empty(S, dtype=torch.float64, device=dev)
+    reward = torch.empty(S, T, dtype=torch.float32, device=dev) if with_reward else None
+    lib = _lib.load()
+    _lib.check(lib.capb200_cider_scores(table._h, _lib.ptr(sampled), S, B, T, _lib.ptr(refs), _lib.ptr(offsets), L, _lib.ptr(scores),
+                                        _lib.ptr(reward) if with_reward else None, _lib.current_stream()), 'cider_scores')
+    return (scores, reward) if with_reward else scores
+
+
+def get_scores(data_gts, gen_result, opt):
+    """rewards.py:83-114 with the CIDEr-D term only: ``cider_reward_weight * CIDEr-D`` per sampled caption, float64 [S] on the device
+    (the reference returns the same values as a host numpy array)."""
+    if getattr(opt, 'bleu_reward_weight', 0) > 0:
+        raise NotImplementedError('BLEU reward is out of scope of the B200 engine (bleu_reward_weight defaults to 0)')
+    w = float(getattr(opt, 'cider_reward_weight', 1))
+    scores = cider_scores(data_gts, gen_result)
+    return scores if w == 1.0 else scores * w

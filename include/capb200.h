@@ -26,6 +26,8 @@ extern "C" {
 #define CAPB200_MODE_SIMT_FP32 0 /* fp32 FFMA on CUDA cores */
 #define CAPB200_MODE_TC_F16X3 1  /* tcgen05 kind::f16, split-fp16 operands, 3 MMA passes, fp32 accumulate (parity grade) */
 #define CAPB200_MODE_TC_F16X1 2  /* tcgen05 kind::f16, single pass (throughput mode, not parity grade) */
+#define CAPB200_MODE_SKINNY_TF32X3 3 /* capb200_linear only: the training step's split-K GEMM, 3xTF32 mma.sync on the fp32 weights */
+#define CAPB200_MODE_SKINNY_FP32 4   /* capb200_linear only: same split-K GEMM on CUDA cores */
 
 #define CAPB200_FAMILY_UPDOWN 0 /* UpDownModel  captioning/models/AttModel.py:868 */
 #define CAPB200_FAMILY_NEWFC 1  /* NewFCModel   captioning/models/AttModel.py:904 */
@@ -236,6 +238,12 @@ void capb200_cider_table_destroy(capb200_cider_table* t);
 int capb200_self_critical_reward(const capb200_cider_table* t, const long long* sampled, int S, const long long* greedy, int B, int T,
                                  const int* refs, const int* ref_offsets, int L, double* scores, float* reward, void* stream);
 
+/* get_scores (captioning/utils/rewards.py:83-114) with cider_reward_weight = 1: CIDEr-D of S = B*n sampled captions against their
+ * image's references -> scores[S] float64.  reward (optional, [S,T] fp32): score minus the mean score of the image's other samples,
+ * the per-token weight of the 'new_self_critical' structure loss (losses.py:168-187). */
+int capb200_cider_scores(const capb200_cider_table* t, const long long* sampled, int S, int B, int T, const int* refs, const int* ref_offsets,
+                         int L, double* scores, float* reward, void* stream);
+
 /* RewardCriterion.forward (captioning/modules/losses.py:22-37). logprobs[N,T,V1]; seq[N,T] int64; reward[N,T].
  * loss_mean[1], loss_rows[N] (reduction 'none'), mask_sum[1]; any output may be NULL. */
 int capb200_reward_criterion_forward(const float* logprobs, const long long* seq, const float* reward, int N, int T, int V1, float* loss_mean,
@@ -255,7 +263,11 @@ typedef struct {
     unsigned long long seed;   /* Philox key of the sampler and of the dropout masks */
     float drop_prob;           /* drop_prob_lm; 0 disables dropout */
     float upstream;            /* d(total loss)/d(this loss), normally 1 */
+    int baseline;              /* CAPB200_BASELINE_GREEDY (self-critical, loss_wrapper.py:56-73) or CAPB200_BASELINE_LEAVE_ONE_OUT
+                                  (structure loss 'new_self_critical', losses.py:168-187: no greedy decode, greedy_seq may be NULL) */
 } capb200_scst_opts;
+#define CAPB200_BASELINE_GREEDY 0
+#define CAPB200_BASELINE_LEAVE_ONE_OUT 1
 /* Gradient buffers, one per capb200_weights field (same shapes, fp32, device); every one is OVERWRITTEN. */
 typedef struct {
     float* embed;
@@ -268,6 +280,24 @@ typedef struct {
 int capb200_updown_scst_step(capb200_engine* e, const float* fc, const float* att, int B, int R, const capb200_scst_opts* opts,
                              const capb200_cider_table* table, const int* refs, const int* ref_offsets, int L, const capb200_updown_grads* grads,
                              long long* sample_seq, long long* greedy_seq, float* sample_logprobs, float* reward, float* loss, void* stream);
+/* ------------------------------------------------------------------------------------------------------------------
+ * One cross-entropy (XE) training step of the UpDown model: the teacher-forced AttModel._forward (AttModel.py:126-164; train mode,
+ * dropout on, no scheduled sampling) over labels[..., :-1], LanguageModelCriterion or LabelSmoothing (losses.py:204-265) against
+ * labels[..., 1:] / masks[..., 1:] with reduction 'mean' (loss_wrapper.py:54-55), and back-propagation through time.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int seq_per_img;           /* label rows per image (the reference repeats the features, utils.repeat_tensors) */
+    int steps;                 /* columns actually evaluated: the reference stops at the first column i >= 1 whose tokens are all 0 */
+    unsigned long long seed;   /* Philox key of the dropout masks */
+    float drop_prob;
+    float label_smoothing;     /* 0 = LanguageModelCriterion, > 0 = LabelSmoothing(smoothing) */
+    float upstream;
+} capb200_xe_opts;
+/* labels[N, label_cols] int64 (column 0 = BOS = 0), masks[N, label_cols] fp32, N = B * seq_per_img.
+ * Outputs: logprobs[N, label_cols-1, V+1] (caller zero-fills; columns >= steps stay zero), loss[1], every grads buffer overwritten. */
+int capb200_updown_xe_step(capb200_engine* e, const float* fc, const float* att, int B, int R, const capb200_xe_opts* opts, const long long* labels,
+                           const float* masks, int label_cols, const capb200_updown_grads* grads, float* logprobs, float* loss, void* stream);
+
 /* The dropout keep/scale mask (0 or 1/(1-p)) of one site and step, for tests that replay it in the oracle:
  * site 0 = fc_embed [B,H], 1 = att_embed [B*R,H], 2 = word embedding at `step` [N,E], 3 = core output at `step` [N,H]. */
 int capb200_dropout_mask(float* mask, long n, unsigned long long seed, int site, int step, float p, void* stream);

@@ -505,7 +505,7 @@ def forward_teacher(fam: Family, fc: Tensor, att: Tensor, seq: Tensor, masks: Op
     for i in range(seq.shape[1]):
         if i >= 1 and int(seq[:, i].sum()) == 0:
             break
-        lp, state = fam.logprobs_state(seq[:, i].clone(), fc_e, att_e, p_att, masks, state)
+        lp, state = fam.logprobs_state(seq[:, i].clone(), fc_e, att_e, p_att, masks, state, t=i if fam.drop is not None else None)
         out[:, i] = lp
     return out
 
@@ -516,6 +516,48 @@ def reward_criterion(logprobs: Tensor, seq: Tensor, reward: Tensor, reduction: s
     mask = (seq > 0).to(picked)
     mask = torch.cat([torch.ones(N, 1), mask[:, :-1]], 1)
     out = -picked * reward * mask
+    if reduction == 'none':
+        return out.sum(1) / mask.sum(1)
+    return out.sum() / mask.sum()
+
+
+def language_model_criterion(logprobs: Tensor, target: Tensor, mask: Tensor, reduction: str = 'mean') -> Tensor:
+    """captioning/modules/losses.py:204-225: masked NLL of the targets; target/mask are cut to the log-prob width."""
+    if target.dim() == 3:
+        target, mask = target.reshape(-1, target.shape[2]), mask.reshape(-1, mask.shape[2])
+    L = logprobs.shape[1]
+    target, mask = target[:, :L], mask[:, :L].to(logprobs)
+    out = -logprobs.gather(2, target.unsqueeze(2)).squeeze(2) * mask
+    if reduction == 'none':
+        return out.sum(1) / mask.sum(1)
+    return out.sum() / mask.sum()
+
+
+def label_smoothing_loss(logprobs: Tensor, target: Tensor, mask: Tensor, smoothing: float, reduction: str = 'mean') -> Tensor:
+    """captioning/modules/losses.py:228-265: KLDiv(logp, smoothed one-hot) summed over the vocabulary, masked; the smoothed
+    distribution puts ``smoothing / (V1 - 1)`` everywhere and ``1 - smoothing`` on the target (:251-253)."""
+    N, L, V1 = logprobs.shape
+    if target.dim() == 3:
+        target, mask = target.reshape(-1, target.shape[2]), mask.reshape(-1, mask.shape[2])
+    target, mask = target[:, :L].reshape(-1), mask[:, :L].reshape(-1).to(logprobs)
+    lp = logprobs.reshape(-1, V1)
+    dist = torch.full_like(lp, smoothing / (V1 - 1))
+    dist.scatter_(1, target.unsqueeze(1), 1.0 - smoothing)
+    kl = (dist * (torch.log(dist) - lp)).sum(1) * mask
+    if reduction == 'none':
+        return kl.view(N, L).sum(1) / mask.view(N, L).sum(1)
+    return kl.sum() / mask.sum()
+
+
+def new_self_critical_loss(logprobs: Tensor, seq: Tensor, scores: Tensor, sample_n: int, reduction: str = 'mean') -> Tensor:
+    """StructureLosses, loss_type 'new_self_critical' (captioning/modules/losses.py:46-67, :168-187): ``scores`` [N] are the CIDEr-D
+    values of get_scores cast to the log-prob dtype; each sample's weight is its score minus the mean of the image's other samples."""
+    N, L = seq.shape
+    mask = torch.cat([torch.ones(N, 1), (seq > 0).to(logprobs)[:, :-1]], 1)
+    sc = scores.to(logprobs).view(-1, sample_n)
+    sc = sc - (sc.sum(1, keepdim=True) - sc) / (sample_n - 1)
+    picked = logprobs.gather(2, seq.unsqueeze(2)).squeeze(2)
+    out = -picked * mask * sc.reshape(-1, 1)
     if reduction == 'none':
         return out.sum(1) / mask.sum(1)
     return out.sum() / mask.sum()

@@ -111,6 +111,16 @@ def self_critical_reward(greedy: np.ndarray, gts: Sequence[np.ndarray], sampled:
     return np.repeat(diff.reshape(S)[:, None], sampled.shape[1], 1), scores
 
 
+def get_scores(gts: Sequence[np.ndarray], sampled: np.ndarray, df: Dict[Tuple[int, ...], float], ref_len: float,
+               cider_weight: float = 1.0) -> np.ndarray:
+    """captioning/utils/rewards.py:83-114 (CIDEr-D term): one score per sampled caption against its image's references."""
+    B, S = len(gts), sampled.shape[0]
+    n = S // B
+    ref_tok = [[tokens_through_eos(r) for r in gts[i]] for i in range(B)]
+    hyps = [tokens_through_eos(sampled[i]) for i in range(S)]
+    return cider_weight * ciderd_scores(hyps, [ref_tok[i // n] for i in range(S)], df, ref_len)
+
+
 def make_refs(B: int, V: int, n_refs: int = 5, L: int = 16, seed: int = 7, zipf: bool = True) -> List[np.ndarray]:
     """Synthetic references: per image n_refs rows, lengths U[6,15], 0-padded to L.  Ids follow a Zipf-like law so
     n-grams repeat (otherwise every similarity would be 0)."""

@@ -198,6 +198,81 @@ def gen_ciderd(out_dir, scratch):
     print('ciderd scores', np.round(scores[:6], 4), 'reward', np.round(reward[:3, 0], 4))
 
 
+def gen_xe_struct(out_dir, scratch):
+    """LanguageModelCriterion, LabelSmoothing and StructureLosses('new_self_critical') of the live reference on fixed inputs, plus the XE
+    loss and a few parameter gradients of the reference UpDown model (train mode, drop_prob_lm = 0 so no RNG is involved)."""
+    from captioning.modules import losses as RL
+    from captioning.utils import rewards as R
+    g = torch.Generator().manual_seed(8)
+    res = {}
+    # (1) criteria on random log-probs; labels [N, L+1] with EOS padding, masks through the EOS
+    N, L, V1 = 9, 7, 31
+    lp = torch.log_softmax(torch.randn(N, L, V1, generator=g) * 2, 2)
+    labels = torch.zeros(N, L + 1, dtype=torch.long)
+    masks = torch.zeros(N, L + 1)
+    for i in range(N):
+        ln = int(torch.randint(1, L, (1,), generator=g))
+        labels[i, 1:1 + ln] = torch.randint(1, V1, (ln,), generator=g)
+        masks[i, :ln + 2] = 1
+    for name, crit in (('lm', RL.LanguageModelCriterion()), ('ls', RL.LabelSmoothing(smoothing=0.2))):
+        x = lp.clone().requires_grad_(True)
+        loss = crit(x, labels[:, 1:], masks[:, 1:])
+        loss.backward()
+        res[name + '_loss'], res[name + '_grad'] = loss.detach().numpy(), x.grad.numpy()
+        res[name + '_loss_none'] = crit(lp, labels[:, 1:], masks[:, 1:], reduction='none').numpy()
+    res['crit_lp'], res['crit_labels'], res['crit_masks'] = lp.numpy(), labels.numpy(), masks.numpy()
+    # (2) structure loss with the scorer of the ciderd golden (same document-frequency pickle and hypotheses)
+    z = np.load(os.path.join(out_dir, 'ciderd.npz'))
+    V, B, n, T = [int(v) for v in z['meta']]
+    R.init_scorer('golden-df')
+    gts = [z['gts'][i] for i in range(B)]
+    sampled = torch.from_numpy(z['sampled'])
+    opt = argparse.Namespace(structure_loss_type='new_self_critical', train_sample_n=n, cider_reward_weight=1.0, bleu_reward_weight=0.0,
+                             entropy_reward_weight=0.0, self_cider_reward_weight=0.0)
+    slp = torch.log_softmax(torch.randn(B * n, T, V + 1, generator=g), 2).requires_grad_(True)
+    out = RL.StructureLosses(opt)(slp, sampled, gts)
+    out['loss'].backward()
+    res['struc_lp'], res['struc_loss'], res['struc_grad'], res['struc_reward'] = slp.detach().numpy(), out['loss'].detach().numpy(), slp.grad.numpy(), \
+        out['reward'].numpy()
+    res['struc_scores'] = R.get_scores(gts, sampled, opt)
+    # (3) XE step of the reference UpDown model
+    cfg = dict(V=60, E=32, H=32, A=16, F_fc=48, F_att=48, T=8)
+    Bm, Rm, spi = 4, 7, 2
+    W = co.make_weights('updown', cfg['V'], cfg['E'], cfg['H'], cfg['A'], cfg['F_fc'], cfg['F_att'], seed=11, logit_scale=20.0)
+    fc, att = co.make_inputs(Bm, Rm, cfg['F_fc'], cfg['F_att'], seed=11)
+    m = ref_model('updown', W=W, **cfg)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    m.drop_prob_lm = 0.0
+    m.core.drop_prob_lm = 0.0                         # F.dropout on the core output (AttModel.py:637)
+    m.train()
+    xl = torch.zeros(Bm, spi, cfg['T'] + 2, dtype=torch.long)
+    xm = torch.zeros(Bm, spi, cfg['T'] + 2)
+    for i in range(Bm):
+        for j in range(spi):
+            ln = int(torch.randint(2, cfg['T'] - 1, (1,), generator=g))          # every caption ends before the last column: early break
+            xl[i, j, 1:1 + ln] = torch.randint(1, cfg['V'] + 1, (ln,), generator=g)
+            xm[i, j, :ln + 2] = 1
+    for name, crit in (('xe', RL.LanguageModelCriterion()), ('xels', RL.LabelSmoothing(smoothing=0.1))):
+        m.zero_grad()
+        lpm = m(fc, att, xl[..., :-1], None)
+        loss = crit(lpm, xl[..., 1:].reshape(Bm * spi, -1), xm[..., 1:].reshape(Bm * spi, -1))
+        loss.backward()
+        res[name + '_loss'] = loss.detach().numpy()
+        sd = dict(m.named_parameters())
+        for k in ('logit.weight', 'core.att_lstm.weight_ih', 'core.lang_lstm.weight_hh', 'embed.0.weight', 'att_embed.0.weight', 'core.attention.alpha_net.bias',
+                  'ctx2att.weight', 'fc_embed.0.bias'):
+            res[name + '_grad_' + k] = sd[k].grad.numpy().copy()
+        if name == 'xe':
+            res['xe_logprobs'] = lpm.detach().numpy()
+    res['xe_labels'], res['xe_masks'] = xl.numpy(), xm.numpy()
+    res['xe_cfg'] = np.array([cfg[k] for k in ('V', 'E', 'H', 'A', 'F_fc', 'F_att', 'T')] + [Bm, Rm, spi, 11])
+    np.savez_compressed(os.path.join(out_dir, 'xe_struct.npz'), **res)
+    print('xe_struct: lm', float(res['lm_loss']), 'ls', float(res['ls_loss']), 'struc', float(res['struc_loss']), 'xe', float(res['xe_loss']),
+          'xels', float(res['xels_loss']))
+
+
 def gen_reward_criterion(out_dir):
     from captioning.modules.losses import RewardCriterion
     g = torch.Generator().manual_seed(3)
@@ -289,7 +364,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     scratch = _enter_scratch()
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys', 'tfm', 'aoa']
+    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys', 'tfm', 'aoa', 'xe']
     if 'small' in which:
         gen_updown_small(out_dir)
     if 'newfc' in which:
@@ -300,6 +375,8 @@ def main():
         gen_ciderd(out_dir, scratch)
     if 'rc' in which:
         gen_reward_criterion(out_dir)
+    if 'xe' in which:
+        gen_xe_struct(out_dir, scratch)            # needs the scratch pickle written by gen_ciderd in the same run
     if 'keys' in which:
         gen_state_dict_keys(out_dir)
     if 'tfm' in which:

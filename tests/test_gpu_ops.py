@@ -20,7 +20,7 @@ def _linear(L, x, w, b, relu, mode):
     M, K = x.shape
     N = w.shape[0]
     y = torch.empty(M, N, device='cuda')
-    L.check(L.load().capb200_linear(L.ptr(x), K, L.ptr(w), K, L.ptr(b), L.ptr(y), N, M, N, K, int(relu), L.MODES[mode], L.current_stream()), 'linear')
+    L.check(L.load().capb200_linear(L.ptr(x), K, L.ptr(w), K, L.ptr(b), L.ptr(y), N, M, N, K, int(relu), L.OP_MODES[mode], L.current_stream()), 'linear')
     torch.cuda.synchronize()
     return y
 
@@ -49,6 +49,24 @@ def test_linear_matches_fp64(L, mode, shape):
     assert err < tol, (mode, shape, err, fp32_err)
     yr = _linear(L, x.cuda(), w.cuda(), b.cuda(), True, mode).cpu().double()
     assert float((yr - ref.clamp_min(0)).abs().max()) < tol
+
+
+@pytest.mark.parametrize('mode', ['skinny_tf32x3', 'skinny_fp32'])
+@pytest.mark.parametrize('shape', [(5, 7, 24), (50, 4000, 1000), (50, 1000, 4000), (50, 9488, 1000), (360, 1000, 2048), (1000, 1000, 9488), (37, 52, 100)])
+def test_skinny_linear_matches_fp64(L, mode, shape):
+    """The training step's split-K GEMM: fp32 CUDA-core and 3xTF32 tensor-core variants, fp32-grade against float64; the inputs
+    include tiny magnitudes (gradient-like rows) that fp16 planes would flush."""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M * 11 + N)
+    x = torch.randn(M, K, generator=g)
+    x[M // 2:] *= 1e-7
+    w = (torch.rand(N, K, generator=g) * 2 - 1) / K ** 0.5
+    b = torch.randn(N, generator=g) * 1e-3
+    ref = x.double() @ w.double().t() + b.double()
+    y = _linear(L, x.cuda(), w.cuda(), b.cuda(), False, mode).cpu().double()
+    scale = (x.double().abs() @ w.double().abs().t() + b.double().abs())          # per-element condition scale
+    rel = float(((y - ref).abs() / scale).max())
+    assert rel < (4e-6 if mode == 'skinny_tf32x3' else 2e-6), (mode, shape, rel)
 
 
 @pytest.mark.parametrize('mode', ['simt_fp32', 'tc_f16x3'])

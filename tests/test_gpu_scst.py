@@ -100,3 +100,165 @@ def test_loss_wrapper_backward_sets_param_grads():
     out2 = lw(fc.cuda(), att.cuda(), None, None, None, gts, torch.arange(B), True, False, False)
     assert torch.isfinite(out2['loss'])
     b200.rewards.reset_scorer()
+
+
+def _dropout_masks(b200, seed, p, B, R, N, T, E, H):
+    L, lib = b200._lib, b200._lib.load()
+
+    def mask(site, step, rows, cols):
+        m = torch.empty(rows * cols, device='cuda')
+        L.check(lib.capb200_dropout_mask(L.ptr(m), rows * cols, seed, site, step, p, L.current_stream()), 'dropout_mask')
+        return m.cpu().reshape(rows, cols)
+    return {'fc': mask(0, 0, B, H), 'att': mask(1, 0, B * R, H).reshape(B, R, H),
+            'xt': torch.stack([mask(2, t, N, E) for t in range(T)]), 'out': torch.stack([mask(3, t, N, H) for t in range(T)])}
+
+
+def _check_grads(model, grads, ograds, rel=5e-4):
+    name_of = {id(p): k for k, p in model.state_dict(keep_vars=True).items()}
+    largest = max(float(v.abs().max()) for v in ograds.values())
+    for p, g in grads.items():
+        key = name_of[id(p)]
+        ref = ograds[key]
+        scale = float(ref.abs().max())
+        err = float((g.cpu() - ref).abs().max())
+        # 5e-4 of the tensor's largest entry; tensors whose true gradient is zero (alpha_net.bias: softmax shift invariance) are held to
+        # 1e-7 of the largest gradient of the step
+        assert err <= rel * scale + 1e-7 * largest, (key, err, scale)
+    assert sum(float(v.abs().max()) > 1e-5 for v in ograds.values()) >= 15
+
+
+def _labels(B, spi, V, cols, seed, short=False):
+    g = torch.Generator().manual_seed(seed)
+    labels = torch.zeros(B, spi, cols, dtype=torch.long)
+    masks = torch.zeros(B, spi, cols)
+    for i in range(B):
+        for j in range(spi):
+            ln = int(torch.randint(1, cols - (4 if short else 1), (1,), generator=g))
+            labels[i, j, 1:1 + ln] = torch.randint(1, V + 1, (ln,), generator=g)
+            masks[i, j, :ln + 2] = 1
+    return labels, masks
+
+
+@pytest.mark.parametrize('smoothing', [0.0, 0.1])
+@pytest.mark.parametrize('mode,drop_prob,short', [('tc_f16x3', 0.0, False), ('tc_f16x3', 0.5, True), ('simt_fp32', 0.5, False)])
+def test_xe_step_gradients(mode, drop_prob, short, smoothing):
+    """Teacher-forced XE step (AttModel._forward + LanguageModelCriterion / LabelSmoothing + backward) against autograd through the
+    oracle, with the engine's dropout masks replayed; ``short`` labels end early so the data-dependent break is exercised."""
+    import imagecaptioning.pytorch_b200 as b200
+    model, _ = build_pair('updown', seed=31, logit_scale=5.0, mode=mode, **CFG)
+    W = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    B, R, spi, T = 4, 9, 3, CFG['T']
+    fc, att = co.make_inputs(B, R, CFG['F_fc'], CFG['F_att'], seed=6)
+    labels, masks = _labels(B, spi, CFG['V'], T + 2, seed=9, short=short)
+    model.train()
+    res = model.xe_step(fc.cuda(), att.cuda(), labels.cuda(), masks.cuda(), label_smoothing=smoothing, drop_prob=drop_prob, seed=77)
+    torch.cuda.synchronize()
+    Wg = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    fam = co.Family('updown', Wg, T)
+    if drop_prob > 0:
+        fam.drop = _dropout_masks(b200, 77, drop_prob, B, R, B * spi, T + 1, CFG['E'], CFG['H'])
+    lp = co.forward_teacher(fam, fc, att, labels[..., :-1])
+    if short:
+        assert float(lp[:, -1].abs().max()) == 0.0
+    tl, tm = labels[..., 1:].reshape(B * spi, -1), masks[..., 1:].reshape(B * spi, -1)
+    loss = co.language_model_criterion(lp, tl, tm) if smoothing == 0 else co.label_smoothing_loss(lp, tl, tm, smoothing)
+    loss.backward()
+    assert float((res['logprobs'].cpu() - lp.detach()).abs().max()) < LOGP_TOL
+    assert abs(float(res['loss']) - float(loss)) < LOGP_TOL
+    _check_grads(model, res['grads'], {k: v.grad for k, v in Wg.items()})
+
+
+def test_xe_step_matches_reference_golden():
+    """The XE loss and parameter gradients the live reference produced (tests/golden/xe_struct.npz), straight against the engine."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'xe_struct.npz'))
+    V, E, H, A, F_fc, F_att, T, B, R, spi, seed = (int(x) for x in g['xe_cfg'])
+    model, _ = build_pair('updown', V=V, E=E, H=H, A=A, F_fc=F_fc, F_att=F_att, T=T, seed=seed, logit_scale=20.0, mode='tc_f16x3')
+    fc, att = co.make_inputs(B, R, F_fc, F_att, seed=seed)
+    model.train()
+    name_of = {id(p): k for k, p in model.state_dict(keep_vars=True).items()}
+    for name, smoothing in (('xe', 0.0), ('xels', 0.1)):
+        res = model.xe_step(fc.cuda(), att.cuda(), torch.from_numpy(g['xe_labels']).cuda(), torch.from_numpy(g['xe_masks']).cuda(),
+                            label_smoothing=smoothing, drop_prob=0.0, seed=1)
+        assert abs(float(res['loss']) - float(g[name + '_loss'])) < LOGP_TOL
+        if smoothing == 0:
+            assert np.abs(res['logprobs'].cpu().numpy() - g['xe_logprobs']).max() < LOGP_TOL
+        checked = 0
+        largest = max(float(np.abs(g[k]).max()) for k in g.files if k.startswith(name + '_grad_'))
+        for p, grad in res['grads'].items():
+            key = name + '_grad_' + name_of[id(p)]
+            if key in g.files:
+                ref = g[key]
+                # alpha_net.bias has a mathematically zero gradient (softmax shift invariance): absolute floor relative to the step
+                assert np.abs(grad.cpu().numpy() - ref).max() <= 5e-4 * np.abs(ref).max() + 1e-7 * largest, key
+                checked += 1
+        assert checked == 8
+
+
+@pytest.mark.parametrize('drop_prob', [0.0, 0.5])
+def test_new_self_critical_step(drop_prob):
+    """Structure loss 'new_self_critical' (losses.py:168-187): leave-one-out CIDEr-D baseline, no greedy decode."""
+    import imagecaptioning.pytorch_b200 as b200
+    from oracle import ciderd_oracle as cdo
+    model, _ = build_pair('updown', seed=31, logit_scale=5.0, mode='tc_f16x3', **CFG)
+    W = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    B, R, n, T = 5, 11, 4, CFG['T']
+    fc, att = co.make_inputs(B, R, CFG['F_fc'], CFG['F_att'], seed=4)
+    gts = cdo.make_refs(B, CFG['V'], seed=2)
+    df, ref_len = cdo.build_document_frequency(cdo.make_refs(200, CFG['V'], seed=4))
+    table = b200.rewards.CiderDTable(df, ref_len)
+    model.train()
+    res = model.scst_step(fc.cuda(), att.cuda(), gts, table, n, drop_prob=drop_prob, seed=99, baseline='leave_one_out')
+    torch.cuda.synchronize()
+    assert res['greedy_seq'] is None
+    seq = res['sample_seq'].cpu()
+    Wg = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    fam = co.Family('updown', Wg, T)
+    if drop_prob > 0:
+        fam.drop = _dropout_masks(b200, 99, drop_prob, B, R, B * n, T, CFG['E'], CFG['H'])
+    _, lp = co.sample(fam, fc, att, sample_method='sample', sample_n=n, forced_tokens=seq)
+    scores = torch.from_numpy(cdo.get_scores(gts, seq.numpy(), df, ref_len))
+    loss = co.new_self_critical_loss(lp, seq, scores, n)
+    loss.backward()
+    dev_scores = b200.rewards.cider_scores(gts, res['sample_seq'], table)
+    assert float((dev_scores.cpu() - scores).abs().max()) < 1e-9
+    sc = scores.float().view(B, n)
+    adv = (sc - (sc.sum(1, keepdim=True) - sc) / (n - 1)).reshape(-1)
+    assert float((res['reward'][:, 0].cpu() - adv).abs().max()) < LOGP_TOL
+    assert abs(float(res['loss']) - float(loss)) < LOGP_TOL
+    assert float(adv.abs().max()) > 1e-3
+    _check_grads(model, res['grads'], {k: v.grad for k, v in Wg.items()})
+
+
+def test_loss_wrapper_xe_and_structure_branches():
+    """B200LossWrapper: sc_flag=False (XE) and struc_flag=True with structure_loss_weight in {1, 0.5} produce losses wired to autograd."""
+    import imagecaptioning.pytorch_b200 as b200
+    from oracle import ciderd_oracle as cdo
+    model, _ = build_pair('updown', seed=31, logit_scale=5.0, mode='tc_f16x3', **CFG)
+    B, R, n, spi, T = 4, 7, 3, 2, CFG['T']
+    fc, att = co.make_inputs(B, R, CFG['F_fc'], CFG['F_att'], seed=5)
+    labels, masks = _labels(B, spi, CFG['V'], T + 2, seed=3)
+    gts = cdo.make_refs(B, CFG['V'], seed=3)
+    df, ref_len = cdo.build_document_frequency(cdo.make_refs(100, CFG['V'], seed=4))
+    b200.rewards.reset_scorer()
+    b200.rewards.init_scorer(b200.rewards.CiderDTable(df, ref_len))
+    opt = argparse.Namespace(sc_sample_method='greedy', sc_beam_size=1, train_sample_method='sample', train_beam_size=1, train_sample_n=n,
+                             cider_reward_weight=1, bleu_reward_weight=0, label_smoothing=0.0, structure_loss_weight=1.0,
+                             structure_loss_type='new_self_critical', use_ppo=0)
+    lw = b200.B200LossWrapper(model, opt)
+    model.train()
+    args = (fc.cuda(), att.cuda(), labels.cuda(), masks.cuda(), None, gts, torch.arange(B))
+    out = lw(*args, False, False, False)
+    ref = lw.crit(model(fc.cuda(), att.cuda(), labels.cuda()[..., :-1], None), labels.cuda()[..., 1:], masks.cuda()[..., 1:])
+    out['loss'].backward()
+    assert all(p.grad is not None for p in model.parameters())
+    assert torch.isfinite(ref) and float(ref) > 0                       # eval-mode teacher forcing of the engine + host criterion
+    out = lw(*args, False, True, False)
+    assert out['reward'].shape == (B, n) and float(out['lm_loss']) == 0.0 and out['loss'].requires_grad
+    opt.structure_loss_weight = 0.5
+    model.zero_grad()
+    out = lw(*args, False, True, False)
+    assert abs(float(out['loss']) - 0.5 * float(out['lm_loss']) - 0.5 * float(out['struc_loss'])) < 1e-6
+    out['loss'].backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    b200.rewards.reset_scorer()

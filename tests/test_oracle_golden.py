@@ -140,3 +140,53 @@ def test_transformer_and_aoa_small(golden_dir, fname, family, scale):
     assert np.abs(out.numpy() - g['teacher_lp']).max() < TOL
     seq, lp = co.sample(fam, fc, att, sample_method='sample', sample_n=3, forced_tokens=torch.from_numpy(g['sample_seq']))
     assert np.abs(lp.numpy() - g['sample_lp']).max() < TOL
+
+
+def test_xe_criteria_and_structure_loss(golden_dir):
+    """LanguageModelCriterion, LabelSmoothing and StructureLosses('new_self_critical') restatements against the live reference's values."""
+    g = _load(golden_dir, 'xe_struct.npz')
+    labels, masks = torch.from_numpy(g['crit_labels']), torch.from_numpy(g['crit_masks'])
+    for name, fn in (('lm', co.language_model_criterion), ('ls', lambda a, b, c, r='mean': co.label_smoothing_loss(a, b, c, 0.2, r))):
+        x = torch.from_numpy(g['crit_lp']).clone().requires_grad_(True)
+        loss = fn(x, labels[:, 1:], masks[:, 1:])
+        loss.backward()
+        assert abs(float(loss) - float(g[name + '_loss'])) < 1e-6
+        assert np.abs(x.grad.numpy() - g[name + '_grad']).max() < 1e-7
+        assert np.abs(fn(x.detach(), labels[:, 1:], masks[:, 1:], 'none').numpy() - g[name + '_loss_none']).max() < 1e-6
+    c = _load(golden_dir, 'ciderd.npz')
+    V, B, n, T = (int(x) for x in c['meta'])
+    gts = [c['gts'][i] for i in range(B)]
+    scores = cdo.get_scores(gts, c['sampled'], _df_from_golden(c), float(c['ref_len']))
+    assert np.abs(scores - g['struc_scores']).max() < 1e-9
+    x = torch.from_numpy(g['struc_lp']).clone().requires_grad_(True)
+    loss = co.new_self_critical_loss(x, torch.from_numpy(c['sampled']), torch.from_numpy(scores), n)
+    loss.backward()
+    assert abs(float(loss) - float(g['struc_loss'])) < 1e-6
+    assert np.abs(x.grad.numpy() - g['struc_grad']).max() < 1e-7
+    assert np.abs(scores.reshape(B, n) - g['struc_reward']).max() < 1e-6
+
+
+@pytest.mark.parametrize('name,smoothing', [('xe', 0.0), ('xels', 0.1)])
+def test_xe_step_of_the_reference_model(golden_dir, name, smoothing):
+    """Teacher-forced forward (train mode, no dropout) + criterion + autograd through the oracle reproduce the reference model's XE loss
+    and parameter gradients; the labels end before the last column, so the data-dependent early break (AttModel.py:158-159) is covered."""
+    g = _load(golden_dir, 'xe_struct.npz')
+    V, E, H, A, F_fc, F_att, T, B, R, spi, seed = (int(x) for x in g['xe_cfg'])
+    W = co.make_weights('updown', V, E, H, A, F_fc, F_att, seed=seed, logit_scale=20.0)
+    Wg = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    fc, att = co.make_inputs(B, R, F_fc, F_att, seed=seed)
+    labels, masks = torch.from_numpy(g['xe_labels']), torch.from_numpy(g['xe_masks'])
+    lp = co.forward_teacher(co.Family('updown', Wg, T), fc, att, labels[..., :-1])
+    if smoothing == 0:
+        assert np.abs(lp.detach().numpy() - g['xe_logprobs']).max() < TOL
+        assert float(lp[:, -1].abs().max()) == 0.0                       # columns after the early break stay zero
+        loss = co.language_model_criterion(lp, labels[..., 1:], masks[..., 1:])
+    else:
+        loss = co.label_smoothing_loss(lp, labels[..., 1:], masks[..., 1:], smoothing)
+    loss.backward()
+    assert abs(float(loss) - float(g[name + '_loss'])) < 1e-5
+    for k in g.files:
+        if k.startswith(name + '_grad_'):
+            ref = g[k]
+            got = Wg[k[len(name) + 6:]].grad.numpy()
+            assert np.abs(got - ref).max() < 1e-5 * max(1.0, np.abs(ref).max()), k

@@ -23,8 +23,9 @@ for (M, N, K) in [(1280, 4000, 2000), (1280, 4000, 3000), (1280, 9488, 1000), (9
     print('  M=%%5d N=%%5d K=%%5d rc=%%d  %%.1f us  %%.0f TFLOP/s alg  max|err|=%%.2e' %% (M, N, K, rc, ms.value * 1e3, 2.0 * M * N * K / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0, err), flush=True)
 ''' % REPO
 
+TILINGS = sys.argv[1:] or ['128x1x1', '144x1x1', '128x2x1', '144x2x1', '128x1x2', '144x1x2', '128x2x2', '144x2x2', 'pair128', 'pair144', 'pair192', 'pair256', 'auto']
 for mode in ['tc_f16x3', 'tc_f16x1']:
-    for tiling in ['128x1x1', '144x1x1', '128x2x1', '144x2x1', '128x1x2', '144x1x2', '128x2x2', '144x2x2', 'auto']:
+    for tiling in TILINGS:
         env = dict(os.environ)
         if tiling != 'auto':
             env['CAPB200_GEMM_TILING'] = tiling

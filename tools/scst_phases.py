@@ -1,0 +1,49 @@
+"""GPU: wall-clock phases of one SCST training step as bench.py runs it (weights change every step)."""
+import argparse, os, sys, time
+import torch
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, 'tests'))
+import imagecaptioning.pytorch_b200 as b200
+from helpers import build_pair
+from oracle import caption_oracle as co, ciderd_oracle as cdo
+import bench
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode='tc_f16x3', **bench.CFG)
+model.train()
+df, ref_len = cdo.build_document_frequency(cdo.make_refs(500, 9487, seed=4))
+b200.rewards.reset_scorer(); b200.rewards.init_scorer(b200.rewards.CiderDTable(df, ref_len))
+opt = argparse.Namespace(sc_sample_method='greedy', sc_beam_size=1, train_sample_method='sample', train_beam_size=1, train_sample_n=5,
+                         cider_reward_weight=1, bleu_reward_weight=0)
+lw = b200.B200LossWrapper(model, opt)
+optim = torch.optim.Adam(model.parameters(), lr=5e-5)
+fc, att = co.make_inputs(B, 36, 2048, 2048, seed=1)
+fc, att = fc.cuda(), att.cuda()
+gts = cdo.make_refs(B, 9487, seed=5)
+idx = torch.arange(B)
+acc = {}
+def tick(name, t0):
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    acc[name] = acc.get(name, 0.0) + (t1 - t0)
+    return t1
+for it in range(6):
+    if it == 2:
+        acc.clear()
+    torch.cuda.synchronize(); t = time.perf_counter()
+    out = lw(fc, att, None, None, None, gts, idx, True, False, False); t = tick('loss_wrapper (greedy + sample + reward + BPTT)', t)
+    optim.zero_grad(set_to_none=True); t = tick('zero_grad', t)
+    out['loss'].backward(); t = tick('autograd bridge backward', t)
+    b200.parallel.allreduce_gradients(model.parameters()); t = tick('allreduce_gradients', t)
+    torch.nn.utils.clip_grad_value_(model.parameters(), 0.1); t = tick('clip_grad_value_', t)
+    optim.step(); t = tick('optimizer step', t)
+for k, v in acc.items():
+    print('%-55s %8.2f ms/step' % (k, v / 4 * 1e3))
+# inside the wrapper: engine rebind vs the C call
+import cProfile, pstats
+pr = cProfile.Profile()
+optim.step()
+pr.enable()
+out = lw(fc, att, None, None, None, gts, idx, True, False, False)
+torch.cuda.synchronize()
+pr.disable()
+pstats.Stats(pr).sort_stats('cumulative').print_stats(18)
