@@ -90,6 +90,11 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
     const float* gb = (p.gather_bias != nullptr && row_ok) ? p.gather_bias + (long)p.gather_idx[row] * p.ld_gb : nullptr;
     int src = row;
     if (p.lstm && row_ok && p.src_row != nullptr) src = p.src_row[row];
+    // 128-bit operand loads need 16-byte aligned rows of every additive term
+    const bool vec_in = (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
+                        (p.row_bias == nullptr || ((reinterpret_cast<uintptr_t>(p.row_bias) & 15) == 0 && (p.ld_row_bias & 3) == 0)) &&
+                        (p.gather_bias == nullptr || ((reinterpret_cast<uintptr_t>(p.gather_bias) & 15) == 0 && (p.ld_gb & 3) == 0)) &&
+                        (p.residual == nullptr || ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 && (p.ld_res & 3) == 0));
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
         uint32_t r[16];
@@ -100,27 +105,54 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
         if (!row_ok || col0 >= p.N) continue;
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int col = col0 + j;
-            float x = __uint_as_float(r[j]);
-            if (col < p.N) {
-                if (p.bias != nullptr) x += __ldg(p.bias + col);
-                if (rb != nullptr) x += __ldg(rb + col);
-                if (gb != nullptr) x += __ldg(gb + col);
-                if (p.residual != nullptr) x += p.residual[(long)row * p.ld_res + col];
-                if (p.relu) x = fmaxf(x, 0.0f);
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (col0 + 16 <= p.N && vec_in) {
+            // each lane reads a different row: 128-bit loads keep the number of distinct-line wavefronts per chunk at 4 per operand
+            // (scalar loads cost 16 and made this epilogue, not the MMA main loop, the critical path of the LSTM GEMMs)
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                if (p.bias != nullptr) { const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j)); v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w; }
+                if (rb != nullptr) { const float4 b = __ldg(reinterpret_cast<const float4*>(rb + col0 + j)); v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w; }
+                if (gb != nullptr) { const float4 b = __ldg(reinterpret_cast<const float4*>(gb + col0 + j)); v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w; }
+                if (p.residual != nullptr) {
+                    const float4 b = *reinterpret_cast<const float4*>(p.residual + (long)row * p.ld_res + col0 + j);
+                    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                }
             }
-            v[j] = x;
+            if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int col = col0 + j;
+                float x = v[j];
+                if (col < p.N) {
+                    if (p.bias != nullptr) x += __ldg(p.bias + col);
+                    if (rb != nullptr) x += __ldg(rb + col);
+                    if (gb != nullptr) x += __ldg(gb + col);
+                    if (p.residual != nullptr) x += p.residual[(long)row * p.ld_res + col];
+                    if (p.relu) x = fmaxf(x, 0.0f);
+                }
+                v[j] = x;
+            }
         }
         if (p.lstm) {
             // columns col0 .. col0+15 = hidden units u0 .. u0+3, gates (i,f,g,o) interleaved
             const int u0 = col0 >> 2;
-            float cn[4], hn[4];
+            float cn[4], hn[4], cpv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (src >= 0 && p.c_prev != nullptr) {
+                if (lstm_vec && (p.ld_cprev & 3) == 0 && u0 + 4 <= p.H) {
+                    const float4 c4 = *reinterpret_cast<const float4*>(p.c_prev + (long)src * p.ld_cprev + u0);
+                    cpv[0] = c4.x; cpv[1] = c4.y; cpv[2] = c4.z; cpv[3] = c4.w;
+                } else {
+                    for (int u = 0; u < 4; ++u) if (u0 + u < p.H) cpv[u] = p.c_prev[(long)src * p.ld_cprev + u0 + u];
+                }
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int unit = u0 + u;
-                float cp = 0.f;
-                if (unit < p.H && src >= 0 && p.c_prev != nullptr) cp = p.c_prev[(long)src * p.ld_cprev + unit];
+                const float cp = cpv[u];
                 cn[u] = fast_sigmoid(v[4 * u + 1]) * cp + fast_sigmoid(v[4 * u]) * fast_tanh(v[4 * u + 2]);
                 hn[u] = fast_sigmoid(v[4 * u + 3]) * fast_tanh(cn[u]);
             }
@@ -364,7 +396,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a 1 x 2 cluster sit on the two SMs of one TPC and execute ONE
+// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a 2 x 1 cluster sit on the two SMs of one TPC and execute ONE
 // M = 256, N = BN MMA per instruction.  Each CTA stages its own 128 A rows and only HALF of the W tile (BN/2 rows), so the
 // operand bytes a CTA must pull through L2 -> shared memory per K-block drop from (128 + BN) to (128 + BN/2) rows, the stage
 // shrinks (one more pipeline stage fits) and the shared-memory read traffic of the MMA halves.  Both CTAs run a TMA producer
@@ -398,9 +430,9 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_pair_kernel(const __grid_const
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = blockIdx.y;                          // cluster (1, 2): rank in the pair; 0 = leader
-    const int pair_id = blockIdx.x;
-    const int num_pairs = gridDim.x;
+    const uint32_t rank = blockIdx.x & 1;                      // cluster (2, 1, 1): rank in the pair; 0 = leader
+    const int pair_id = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
     const int cl_m = p.tiles_m / 2;
     const int n_ptiles = p.tiles_n * cl_m;
 
@@ -609,14 +641,14 @@ int launch_pair(const TcParams& prm, cudaStream_t stream) {
     const int n_ptiles = prm2.tiles_n * (prm2.tiles_m / 2);
     const int P = n_ptiles < 74 ? n_ptiles : 74;                       // one pair per TPC
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(P, 2);
+    cfg.gridDim = dim3(2 * P, 1);                                      // the pair must be adjacent in x (clusterDim.x = 2)
     cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = 2;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
@@ -698,11 +730,23 @@ GemmTcPlan* gemm_tc_plan_create(const GemmProblem& p, int passes) {
         }
         // small problems (fewer 128-wide tiles than half the SMs) are latency-bound: halve the tile width to double the CTAs
         if (cdiv(p.M, BM) * cdiv(p.N, 128) < 74 && p.N > 64) { plan->bn = 64; plan->cx = plan->cy = 1; }
+        else if (cdiv(p.M, BM) >= 2 && getenv("CAPB200_GEMM_NO_PAIR") == nullptr) {
+            // large problems: CTA pairs (cta_group::2, M = 256 per MMA) stage only half a W tile per CTA -- 26 % fewer operand bytes through
+            // L2 -> shared memory per FLOP and a 4-deep ring; pick the tile width with the fewest rounds over the 74 TPCs
+            const int pb[2] = {144, 128};
+            double pbest = 1e30;
+            for (int b = 0; b < 2; ++b) {
+                const long ptiles = cdiv(p.N, pb[b]) * cdiv(cdiv(p.M, BM), 2);
+                const double cost = (double)((ptiles + 73) / 74) * pb[b];
+                if (cost < pbest) { pbest = cost; plan->bn = pb[b]; }
+            }
+            plan->cx = 1; plan->cy = 2; plan->pair = 1;
+        }
         const char* force = getenv("CAPB200_GEMM_TILING");      // "<BN>x<CX>x<CY>", e.g. "144x2x1" (debug / sweeps)
         if (force != nullptr) {
             int fb = 0, fx = 0, fy = 0;
             if (sscanf(force, "%dx%dx%d", &fb, &fx, &fy) == 3 && (fb == 64 || fb == 128 || fb == 144) && (fx == 1 || fx == 2) && (fy == 1 || fy == 2)) {
-                plan->bn = fb; plan->cx = fx; plan->cy = fy;
+                plan->bn = fb; plan->cx = fx; plan->cy = fy; plan->pair = 0;
             }
             if (sscanf(force, "pair%d", &fb) == 1 && (fb == 128 || fb == 144 || fb == 192 || fb == 256) && cdiv(p.M, BM) >= 2) {
                 plan->bn = fb; plan->cx = 1; plan->cy = 2; plan->pair = 1;

@@ -20,6 +20,9 @@ for (M, N, K) in [(1280, 4000, 2000), (1280, 4000, 3000), (1280, 9488, 1000), (9
     ms = ctypes.c_float(0)
     rc = lib.capb200_bench_linear(L.ptr(xd), L.ptr(wd), L.ptr(bd), L.ptr(y), M, N, K, mode, 20, ctypes.byref(ms), L.current_stream())
     err = float((y.cpu().double() - ref).abs().max()) if rc == 0 else float('nan')
+    if rc != 0:
+        lib.capb200_last_error.restype = ctypes.c_char_p
+        print('  error:', lib.capb200_last_error().decode(), flush=True)
     print('  M=%%5d N=%%5d K=%%5d rc=%%d  %%.1f us  %%.0f TFLOP/s alg  max|err|=%%.2e' %% (M, N, K, rc, ms.value * 1e3, 2.0 * M * N * K / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0, err), flush=True)
 ''' % REPO
 

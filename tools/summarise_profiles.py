@@ -39,17 +39,16 @@ rep = 'gpurun_out/%s_gemm.ncu-rep' % tag
 if os.path.exists(rep):
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
-            'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
-            'launch__registers_per_thread', 'launch__grid_size', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
-            'sm__inst_executed_pipe_tensor.sum', 'lts__t_bytes.sum', 'l1tex__data_bank_conflicts_pipe_lsu.sum',
-            'sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active', 'launch__shared_mem_per_block_dynamic']
+            'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed',
+            'launch__registers_per_thread', 'launch__cluster_size', 'launch__shared_mem_per_block_dynamic', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+            'lts__t_bytes.sum', 'lts__t_sector_hit_rate.pct', 'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__m_xbar2l1tex_read_bytes.sum',
+            'l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed', 'l1tex__m_xbar2l1tex_read_bytes.sum.per_second', 'sm__cycles_elapsed.max',
+            'sm__cycles_elapsed.max.per_second', 'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active']
     rd = list(csv.reader(io.StringIO(raw)))
     hdr, units = rd[0], rd[1]
     with open('profiles/%s_gemm_full.md' % tag, 'w') as f:
-        f.write('# %s: `ncu --set full --clock-control none -k regex:gemm_tc_kernel -s 8 -c 4` (one timestep: att_lstm, h2att, lang_lstm, logit)\n\n' % tag)
+        f.write('# %s: `ncu --set full --clock-control none -k regex:gemm_tc_kernel -s 10 -c 6` (GEMM launches of consecutive decode steps: h2att 64-wide, att_lstm / logit <144,3,1,2>, lang_lstm <144,3,2,2>)\n\n' % tag)
         cols = [i for i, h in enumerate(hdr) if h in want or h in ('Kernel Name', 'Grid Size', 'Block Size')]
-        tens = [i for i, h in enumerate(hdr) if 'tensor' in h and 'pct' in h]
-        cols = sorted(set(cols + tens))
         for r in rd[2:]:
             f.write('## launch id %s\n\n' % r[0])
             for i in cols:
