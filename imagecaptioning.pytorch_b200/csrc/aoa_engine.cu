@@ -53,6 +53,8 @@ struct capb200_aoa_engine {
     int core_cur = 0;
     DecodeBuffers d;
     std::vector<GemmTcPlan*> plans;
+    char* tape = nullptr;          // SCST training tape (owned, grown on demand)
+    size_t tape_bytes = 0;
 };
 
 namespace {
@@ -319,6 +321,7 @@ void capb200_aoa_destroy(capb200_aoa_engine* e) {
     cudaFree(e->wblock);
     cudaFree(e->ws);
     cudaFree(e->d.slab);
+    cudaFree(e->tape);
     delete e;
 }
 
@@ -452,3 +455,274 @@ int capb200_aoa_decode_sample(capb200_aoa_engine* e, const float* att, const flo
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// SCST training step (AoANet)
+// =====================================================================================================================
+namespace {
+
+constexpr int NL = CAPB200_AOA_REFINER_LAYERS;
+
+struct ATape {
+    float *x[NL + 1], *ln[NL], *qkv[NL], *ratt[NL], *catd[NL], *t[NL], *g[NL];
+    float *att_e, *mean, *kv;
+    int* tok;
+    float *xt, *x1c, *gates, *c, *h, *qln, *qp, *probs, *att, *t2, *out, *outd;
+    float *DL, *dOUTD, *D_T2, *D_QP, *DG, *dctx, *dh, *dc, *d_out, *dX2, *d_qln, *d_hatt, *dxt, *d_x1c, *tmpH, *S, *d_mean, *d_kv, *d_att_e, *d_x, *d_g, *d_t,
+        *d_catd, *d_qkv, *d_ln, *dpre, *stats, *mask_sum, *skinny, *glp;
+    size_t skinny_floats;
+    double* scores;
+};
+
+void layout_atape(ATape& tp, Arena& a, int B, int R, int N, int T, int E, int H, int heads, int V1) {
+    const long BR = (long)B * R, TN = (long)T * N;
+    for (int l = 0; l <= NL; ++l) tp.x[l] = a.take<float>(BR * H);
+    for (int l = 0; l < NL; ++l) {
+        tp.ln[l] = a.take<float>(BR * H); tp.qkv[l] = a.take<float>(BR * 3 * H); tp.ratt[l] = a.take<float>(BR * H);
+        tp.catd[l] = a.take<float>(BR * 2 * H); tp.t[l] = a.take<float>(BR * 2 * H); tp.g[l] = a.take<float>(BR * H);
+    }
+    tp.att_e = a.take<float>(BR * H); tp.mean = a.take<float>((long)B * H); tp.kv = a.take<float>(BR * 2 * H);
+    tp.tok = a.take<int>(TN);
+    tp.xt = a.take<float>(TN * E); tp.x1c = a.take<float>(TN * H); tp.gates = a.take<float>(TN * 4 * H); tp.c = a.take<float>(TN * H);
+    tp.h = a.take<float>(TN * H); tp.qln = a.take<float>(TN * H); tp.qp = a.take<float>(TN * H); tp.probs = a.take<float>(TN * heads * R);
+    tp.att = a.take<float>(TN * H); tp.t2 = a.take<float>(TN * 2 * H); tp.out = a.take<float>(TN * H); tp.outd = a.take<float>(TN * H);
+    tp.DL = a.take<float>(TN * V1); tp.dOUTD = a.take<float>(TN * H); tp.D_T2 = a.take<float>(TN * 2 * H); tp.D_QP = a.take<float>(TN * H);
+    tp.DG = a.take<float>(TN * 4 * H);
+    const long NH = (long)N * H;
+    tp.dctx = a.take<float>(NH); tp.dh = a.take<float>(NH); tp.dc = a.take<float>(NH); tp.d_out = a.take<float>(NH); tp.dX2 = a.take<float>(2 * NH);
+    tp.d_qln = a.take<float>(NH); tp.d_hatt = a.take<float>(NH); tp.dxt = a.take<float>((long)N * E); tp.d_x1c = a.take<float>(NH); tp.tmpH = a.take<float>(NH);
+    tp.S = a.take<float>((long)B * 4 * H); tp.d_mean = a.take<float>((long)B * H); tp.d_kv = a.take<float>(BR * 2 * H); tp.d_att_e = a.take<float>(BR * H);
+    tp.d_x = a.take<float>(BR * H); tp.d_g = a.take<float>(BR * H); tp.d_t = a.take<float>(BR * 2 * H); tp.d_catd = a.take<float>(BR * 2 * H);
+    tp.d_qkv = a.take<float>(BR * 3 * H); tp.d_ln = a.take<float>(BR * H); tp.dpre = a.take<float>(BR * H);
+    tp.stats = a.take<float>(2 * (BR > N ? BR : N)); tp.mask_sum = a.take<float>(8);
+    tp.skinny_floats = (size_t)4 << 20;
+    tp.skinny = a.take<float>((long)tp.skinny_floats);
+    tp.glp = a.take<float>((long)B * T * V1);
+    tp.scores = a.take<double>((long)N + B);
+}
+
+// dW[out, in] (+)= dY[rows, out]^T * X[rows, in]
+inline int wgrad(int out_f, int in_f, int rows, const float* dY, long ld_dy, const float* X, long ld_x, float* G, long ld_g, int accumulate, cudaStream_t st) {
+    return gemm_generic_launch(1, 0, out_f, in_f, rows, dY, ld_dy, X, ld_x, G, ld_g, accumulate, nullptr, st);
+}
+
+}  // namespace
+
+extern "C" int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, int B, int R, const capb200_aoa_scst_opts* opts,
+                                     const capb200_cider_table* table, const int* refs, const int* ref_offsets, int L, const capb200_aoa_grads* grads,
+                                     long long* sample_seq, long long* greedy_seq, float* sample_logprobs, float* reward, float* loss, void* stream) {
+    if (check_ready(e)) return 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CAPB_REQUIRE(opts && att && table && refs && ref_offsets && grads && sample_seq && sample_logprobs && reward && loss, "null argument");
+    const bool greedy_baseline = opts->baseline == CAPB200_BASELINE_GREEDY;
+    CAPB_REQUIRE(greedy_baseline || opts->baseline == CAPB200_BASELINE_LEAVE_ONE_OUT, "unknown baseline");
+    CAPB_REQUIRE(!greedy_baseline || greedy_seq != nullptr, "the greedy baseline needs greedy_seq");
+    const int n = opts->sample_n, N = B * n, T = e->T, E = e->E, H = e->H, V1 = e->V1, F = e->F, heads = e->heads, dk = e->dk;
+    CAPB_REQUIRE(n >= 1 && n <= 16 && (greedy_baseline || n >= 2) && B >= 1 && R >= 1, "sample_n must be in 1..16 (>= 2 for the leave-one-out baseline)");
+    const float p_lm = opts->drop_prob_lm, p_at = opts->drop_attn, p_aoa = opts->drop_aoa, p_sub = opts->drop_sublayer;
+    CAPB_REQUIRE(p_lm >= 0.f && p_lm < 1.f && p_at >= 0.f && p_at < 1.f && p_aoa >= 0.f && p_aoa < 1.f && p_sub >= 0.f && p_sub < 1.f, "dropout rates must be in [0, 1)");
+    const float p_ctx = opts->ctx_drop ? p_lm : 0.f;
+    const float keep_lm = 1.0f / (1.0f - p_lm);
+    const unsigned long long seed = opts->seed;
+    const capb200_aoa_weights& w = e->w;
+    const capb200_aoa_grads& G = *grads;
+    const long BR = (long)B * R, NH = (long)N * H, TN = (long)T * N;
+    const long ld_lp = (long)T * V1;
+
+    {
+        Arena dry; ATape t0; layout_atape(t0, dry, B, R, N, T, E, H, heads, V1);
+        if (dry.off + 256 > e->tape_bytes) {
+            CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
+            if (e->tape) CAPB_CHECK_CUDA(cudaFree(e->tape));
+            e->tape = nullptr;
+            CAPB_CHECK_CUDA(cudaMalloc(&e->tape, dry.off + 256));
+            e->tape_bytes = dry.off + 256;
+        }
+    }
+    Arena ar; ar.base = e->tape;
+    ATape tp; layout_atape(tp, ar, B, R, N, T, E, H, heads, V1);
+
+    // ---- (1) greedy baseline, eval mode: the regular decode path
+    if (greedy_baseline) {
+        capb200_sample_opts so; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.seed = 0; so.steps = T;
+        CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, st));
+        CAPB_CHECK_CUDA(cudaMemsetAsync(greedy_seq, 0, sizeof(long long) * (size_t)B * T, st));
+        if (capb200_aoa_decode_sample(e, att, nullptr, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, stream)) return 1;
+    }
+    if (ensure_workspace(e, B, N, R, 1, st)) return 1;
+    const Skinny sk{tp.skinny, tp.skinny_floats, e->tc ? 1 : 0, st};
+    auto act = [](float* p, long ld) { ActView v; v.f = p; v.hi = nullptr; v.lo = nullptr; v.ld = ld; return v; };
+
+    // ---- (2) train-mode prologue: att_embed (+dropout), six refiner layers, final norm, mean pooling, ctx2att
+    if (sk.lin(att, F, w.att_embed_w, F, w.att_embed_b, tp.x[0], H, (int)BR, H, F, 0)) return 1;
+    if (relu_copy_launch(tp.x[0], BR * H, act(tp.x[0], H), st)) return 1;
+    if (dropout_apply_launch(tp.x[0], (int)BR, H, H, seed, 1, 0, p_lm, st)) return 1;
+    for (int l = 0; l < NL; ++l) {
+        const capb200_aoa_refiner_layer& Lw = w.refiner[l];
+        if (layer_norm_launch((int)BR, H, tp.x[l], H, Lw.ln_a, Lw.ln_b, 1e-6f, act(tp.ln[l], H), st)) return 1;
+        if (sk.lin(tp.ln[l], H, e->r_qkv_w[l], H, e->r_qkv_b[l], tp.qkv[l], 3 * H, (int)BR, 3 * H, H, 0)) return 1;
+        if (enc_attn_train_launch(B, R, heads, dk, tp.qkv[l], tp.qkv[l] + H, tp.qkv[l] + 2 * H, 3 * H, seed, 10 + l, p_at, tp.ratt[l], H, st)) return 1;
+        if (cat_dropout_launch((int)BR, H, H, tp.ratt[l], H, tp.ln[l], H, tp.catd[l], 2 * H, seed, 20 + l, 0, p_aoa, st)) return 1;
+        if (sk.lin(tp.catd[l], 2 * H, Lw.aoa_w, 2 * H, Lw.aoa_b, tp.t[l], 2 * H, (int)BR, 2 * H, 2 * H, 0)) return 1;
+        if (glu_launch((int)BR, H, tp.t[l], 2 * H, nullptr, 0, act(tp.g[l], H), st)) return 1;
+        if (add_dropout_launch((int)BR, H, tp.x[l], H, tp.g[l], H, tp.x[l + 1], H, seed, 30 + l, 0, p_sub, st)) return 1;
+        e->launches += 9;
+    }
+    if (layer_norm_launch((int)BR, H, tp.x[NL], H, w.refiner_norm_a, w.refiner_norm_b, 1e-6f, act(tp.att_e, H), st)) return 1;
+    if (masked_mean_launch(B, R, H, tp.att_e, H, nullptr, R, act(tp.mean, H), st)) return 1;
+    if (sk.lin(tp.att_e, H, w.ctx2att_w, H, w.ctx2att_b, tp.kv, 2 * H, (int)BR, 2 * H, H, 0)) return 1;
+    e->launches += 8;
+
+    // ---- (3) T sampling steps with the tape
+    CAPB_CHECK_CUDA(cudaMemsetAsync(e->d.tokens, 0, sizeof(int) * N, st));
+    for (int t = 0; t < T; ++t) {
+        int* tok = tp.tok + (long)t * N;
+        CAPB_CHECK_CUDA(cudaMemcpyAsync(tok, e->d.tokens, sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
+        float* xt = tp.xt + (long)t * N * E;
+        float* x1c = tp.x1c + (long)t * NH;
+        float* gates = tp.gates + (long)t * N * 4 * H;
+        float *c_t = tp.c + (long)t * NH, *h_t = tp.h + (long)t * NH, *qln = tp.qln + (long)t * NH, *qp = tp.qp + (long)t * NH;
+        float *att_t = tp.att + (long)t * NH, *t2 = tp.t2 + (long)t * 2 * NH, *out_t = tp.out + (long)t * NH;
+        const float* h_prev = t ? tp.h + (long)(t - 1) * NH : nullptr;
+        const float* c_prev = t ? tp.c + (long)(t - 1) * NH : nullptr;
+        if (embed_relu_dropout_launch(N, E, tok, w.embed, xt, seed, (unsigned)t, p_lm, st)) return 1;
+        // x1c = mean[img] + ctx_drop(previous context vector)
+        if (t == 0) CAPB_CHECK_CUDA(cudaMemsetAsync(tp.tmpH, 0, sizeof(float) * NH, st));
+        else if (dropout_copy_launch(tp.out + (long)(t - 1) * NH, H, tp.tmpH, H, N, H, seed, 4, (unsigned)t, p_ctx, st)) return 1;
+        if (add_row_group_launch(N, H, n, tp.tmpH, H, tp.mean, H, x1c, H, st)) return 1;
+        {
+            GemmProblem g; g.M = N; g.N = 4 * H; g.nseg = 2;
+            g.seg[0].A = xt; g.seg[0].lda = E; g.seg[0].W = w.att_lstm_w_ih; g.seg[0].ldw = E + H; g.seg[0].K = E;
+            g.seg[1].A = x1c; g.seg[1].lda = H; g.seg[1].W = w.att_lstm_w_ih + E; g.seg[1].ldw = E + H; g.seg[1].K = H;
+            if (t) { g.seg[2].A = h_prev; g.seg[2].lda = H; g.seg[2].W = w.att_lstm_w_hh; g.seg[2].ldw = H; g.seg[2].K = H; g.nseg = 3; }
+            g.epi.bias = e->bsum; g.epi.C = gates; g.epi.ldc = 4 * H;
+            if (sk.gates(g)) return 1;
+        }
+        if (lstm_pointwise_launch(N, H, gates, 4 * H, nullptr, c_prev, H, c_t, H, act(h_t, H), nullptr, 0, nullptr, st)) return 1;
+        if (layer_norm_launch(N, H, h_t, H, w.attn_norm_a, w.attn_norm_b, 1e-6f, act(qln, H), st)) return 1;
+        if (sk.lin(qln, H, w.attn_q_w, H, w.attn_q_b, qp, H, N, H, H, 0)) return 1;
+        // AoAModel.py:168 passes (query, value = p_att[..., :H], key = p_att[..., H:])
+        if (cross_attn_train_launch(N, n, heads, dk, R, qp, H, tp.kv + H, tp.kv, 2 * H, seed, 5, t, p_at, att_t, H, tp.probs + (long)t * N * heads * R, st)) return 1;
+        {
+            GemmProblem g; g.M = N; g.N = 2 * H; g.nseg = 2;
+            g.seg[0].A = att_t; g.seg[0].lda = H; g.seg[0].W = w.att2ctx_w; g.seg[0].ldw = 2 * H; g.seg[0].K = H;
+            g.seg[1].A = h_t; g.seg[1].lda = H; g.seg[1].W = w.att2ctx_w + H; g.seg[1].ldw = 2 * H; g.seg[1].K = H;
+            g.epi.bias = w.att2ctx_b; g.epi.C = t2; g.epi.ldc = 2 * H;
+            if (sk.gates(g)) return 1;
+        }
+        if (glu_launch(N, H, t2, 2 * H, nullptr, 0, act(out_t, H), st)) return 1;
+        float* outd = tp.outd + (long)t * H;                                   // [N][T][H]: batched logit backward
+        if (dropout_copy_launch(out_t, H, outd, (long)T * H, N, H, seed, 3, (unsigned)t, p_lm, st)) return 1;
+        float* logits = sample_logprobs + (long)t * V1;
+        if (sk.lin(outd, (long)T * H, w.logit_w, H, w.logit_b, logits, ld_lp, N, V1, H, 0)) return 1;
+        VocabStepArgs va;
+        va.rows = N; va.V1 = V1; va.logits = logits; va.ld = ld_lp;
+        va.select = 2; va.temperature = opts->temperature; va.seed = seed; va.step = (unsigned long long)t;
+        va.unfinished = e->d.unfinished; va.first_step = (t == 0); va.tokens_out = e->d.tokens;
+        va.seq_out = sample_seq; va.ld_seq = T; va.t = t;
+        if (vocab_step_launch(va, st)) return 1;
+        e->launches += 20;
+    }
+
+    // ---- (4) reward and loss
+    if (cider_reward_launch(table->t, sample_seq, N, greedy_baseline ? greedy_seq : nullptr, B, T, refs, ref_offsets, L, tp.scores, reward, T, T, st)) return 1;
+    if (reward_criterion_fwd_launch(sample_logprobs, ld_lp, V1, sample_seq, reward, N, T, loss, nullptr, tp.mask_sum, st)) return 1;
+
+    // ---- (5) backward through the decoder
+    if (scst_dlogits_launch(sample_logprobs, ld_lp, sample_seq, reward, tp.mask_sum, opts->upstream, N, T, V1, tp.DL, st)) return 1;
+    if (sk.dgrad((int)TN, H, V1, tp.DL, V1, w.logit_w, H, tp.dOUTD, H, 0)) return 1;
+    if (wgrad(V1, H, (int)TN, tp.DL, V1, tp.outd, H, G.logit_w, H, 0, st)) return 1;
+    if (colsum_launch((int)TN, V1, tp.DL, V1, G.logit_b, 0, st)) return 1;
+    CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dctx, 0, sizeof(float) * NH, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dh, 0, sizeof(float) * NH, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dc, 0, sizeof(float) * NH, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(tp.d_kv, 0, sizeof(float) * BR * 2 * H, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(G.embed, 0, sizeof(float) * (size_t)V1 * E, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(G.attn_norm_a, 0, sizeof(float) * H, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(G.attn_norm_b, 0, sizeof(float) * H, st));
+    for (int t = T - 1; t >= 0; --t) {
+        const float* c_prev = t ? tp.c + (long)(t - 1) * NH : nullptr;
+        float* d_t2 = tp.D_T2 + (long)t * 2 * NH;
+        float* d_qp = tp.D_QP + (long)t * NH;
+        float* dg = tp.DG + (long)t * N * 4 * H;
+        // d out_t = out_drop-masked logit gradient + what step t+1 received through its (dropped) context input
+        if (dropout_copy_launch(tp.dOUTD + (long)t * H, (long)T * H, tp.d_out, H, N, H, seed, 3, (unsigned)t, p_lm, st)) return 1;
+        if (add_inplace_launch(tp.d_out, tp.dctx, NH, st)) return 1;
+        if (glu_backward_launch(N, H, tp.t2 + (long)t * 2 * NH, 2 * H, tp.d_out, H, d_t2, 2 * H, st)) return 1;
+        if (sk.dgrad(N, 2 * H, 2 * H, d_t2, 2 * H, w.att2ctx_w, 2 * H, tp.dX2, 2 * H, 0)) return 1;             // [d att | d h_att]
+        // attention: needs a contiguous d att
+        CAPB_CHECK_CUDA(cudaMemcpy2DAsync(tp.tmpH, sizeof(float) * H, tp.dX2, sizeof(float) * 2 * H, sizeof(float) * H, N, cudaMemcpyDeviceToDevice, st));
+        if (cross_attn_backward_launch(B, n, heads, dk, R, tp.qp + (long)t * NH, H, tp.kv + H, tp.kv, 2 * H, seed, 5, t, p_at, tp.probs + (long)t * N * heads * R,
+                                       tp.tmpH, H, d_qp, H, tp.d_kv + H, tp.d_kv, 2 * H, st)) return 1;
+        if (sk.dgrad(N, H, H, d_qp, H, w.attn_q_w, H, tp.d_qln, H, 0)) return 1;
+        // d h_att = carried (from W_hh of step t+1) + att2ctx's h_att half + through the query LayerNorm
+        CAPB_CHECK_CUDA(cudaMemcpy2DAsync(tp.d_hatt, sizeof(float) * H, tp.dX2 + H, sizeof(float) * 2 * H, sizeof(float) * H, N, cudaMemcpyDeviceToDevice, st));
+        if (add_inplace_launch(tp.d_hatt, tp.dh, NH, st)) return 1;
+        if (ln_backward_launch(N, H, tp.h + (long)t * NH, H, w.attn_norm_a, tp.d_qln, H, 1e-6f, tp.d_hatt, H, 1, tp.stats, G.attn_norm_a, G.attn_norm_b, 1, st)) return 1;
+        if (lstm_cell_backward_launch(N, H, tp.gates + (long)t * N * 4 * H, c_prev, tp.c + (long)t * NH, tp.d_hatt, nullptr, 0, 0, 0, seed, 0.f, tp.dc, dg, st)) return 1;
+        if (sk.dgrad(N, E, 4 * H, dg, 4 * H, w.att_lstm_w_ih, E + H, tp.dxt, E, 0)) return 1;
+        if (sk.dgrad(N, H, 4 * H, dg, 4 * H, w.att_lstm_w_ih + E, E + H, tp.d_x1c, H, 0)) return 1;
+        if (sk.dgrad(N, H, 4 * H, dg, 4 * H, w.att_lstm_w_hh, H, tp.dh, H, 0)) return 1;                             // carried to step t-1
+        if (embed_backward_launch(N, E, tp.tok + (long)t * N, tp.xt + (long)t * N * E, tp.dxt, E, keep_lm, G.embed, st)) return 1;
+        // the context input of step t is ctx_drop(out_{t-1}): its gradient flows to out_{t-1}
+        if (t > 0 && dropout_copy_launch(tp.d_x1c, H, tp.dctx, H, N, H, seed, 4, (unsigned)t, p_ctx, st)) return 1;
+        e->launches += 22;
+    }
+    // weight gradients batched over time (K = T*N rows)
+    const int TN1 = (int)((long)(T - 1) * N);
+    int rc = 0;
+    rc |= wgrad(2 * H, H, (int)TN, tp.D_T2, 2 * H, tp.att, H, G.att2ctx_w, 2 * H, 0, st);
+    rc |= wgrad(2 * H, H, (int)TN, tp.D_T2, 2 * H, tp.h, H, G.att2ctx_w + H, 2 * H, 0, st);
+    rc |= colsum_launch((int)TN, 2 * H, tp.D_T2, 2 * H, G.att2ctx_b, 0, st);
+    rc |= wgrad(H, H, (int)TN, tp.D_QP, H, tp.qln, H, G.attn_q_w, H, 0, st);
+    rc |= colsum_launch((int)TN, H, tp.D_QP, H, G.attn_q_b, 0, st);
+    rc |= wgrad(4 * H, E, (int)TN, tp.DG, 4 * H, tp.xt, E, G.att_lstm_w_ih, E + H, 0, st);
+    rc |= wgrad(4 * H, H, (int)TN, tp.DG, 4 * H, tp.x1c, H, G.att_lstm_w_ih + E, E + H, 0, st);
+    if (TN1 > 0) rc |= wgrad(4 * H, H, TN1, tp.DG + (long)N * 4 * H, 4 * H, tp.h, H, G.att_lstm_w_hh, H, 0, st);
+    else CAPB_CHECK_CUDA(cudaMemsetAsync(G.att_lstm_w_hh, 0, sizeof(float) * 4 * H * H, st));
+    rc |= colsum_launch((int)TN, 4 * H, tp.DG, 4 * H, G.att_lstm_b_ih, 0, st);
+    rc |= colsum_launch((int)TN, 4 * H, tp.DG, 4 * H, G.att_lstm_b_hh, 0, st);
+    // mean_feats enters every step's gate input: d mean[img] = (sum over steps and the image's rows of d gates) * W_ih[:, E:]
+    rc |= per_image_sum_launch(T, N, n, 4 * H, tp.DG, tp.S, st);
+    rc |= sk.dgrad(B, H, 4 * H, tp.S, 4 * H, w.att_lstm_w_ih + E, E + H, tp.d_mean, H, 0);
+    if (rc) return 1;
+
+    // ---- (6) backward through the prologue
+    rc |= sk.dgrad((int)BR, H, 2 * H, tp.d_kv, 2 * H, w.ctx2att_w, H, tp.d_att_e, H, 0);
+    rc |= wgrad(2 * H, H, (int)BR, tp.d_kv, 2 * H, tp.att_e, H, G.ctx2att_w, H, 0, st);
+    rc |= colsum_launch((int)BR, 2 * H, tp.d_kv, 2 * H, G.ctx2att_b, 0, st);
+    rc |= mean_backward_launch(B, R, H, tp.d_mean, H, tp.d_att_e, H, st);
+    rc |= ln_backward_launch((int)BR, H, tp.x[NL], H, w.refiner_norm_a, tp.d_att_e, H, 1e-6f, tp.d_x, H, 0, tp.stats, G.refiner_norm_a, G.refiner_norm_b, 0, st);
+    if (rc) return 1;
+    for (int l = NL - 1; l >= 0; --l) {
+        const capb200_aoa_refiner_layer& Lw = w.refiner[l];
+        const capb200_aoa_refiner_layer_grads& Lg = G.refiner[l];
+        // x[l+1] = x[l] + dropout(g): d_x carries to x[l] unchanged; d g = d_x * mask
+        rc |= dropout_copy_launch(tp.d_x, H, tp.d_g, H, (int)BR, H, seed, 30 + l, 0, p_sub, st);
+        rc |= glu_backward_launch((int)BR, H, tp.t[l], 2 * H, tp.d_g, H, tp.d_t, 2 * H, st);
+        rc |= wgrad(2 * H, 2 * H, (int)BR, tp.d_t, 2 * H, tp.catd[l], 2 * H, Lg.aoa_w, 2 * H, 0, st);
+        rc |= colsum_launch((int)BR, 2 * H, tp.d_t, 2 * H, Lg.aoa_b, 0, st);
+        rc |= sk.dgrad((int)BR, 2 * H, 2 * H, tp.d_t, 2 * H, Lw.aoa_w, 2 * H, tp.d_catd, 2 * H, 0);
+        rc |= dropout_apply_launch(tp.d_catd, (int)BR, 2 * H, 2 * H, seed, 20 + l, 0, p_aoa, st);               // [d attended | d ln (query half)]
+        // self-attention backward needs a contiguous d attended
+        CAPB_CHECK_CUDA(cudaMemcpy2DAsync(tp.d_g, sizeof(float) * H, tp.d_catd, sizeof(float) * 2 * H, sizeof(float) * H, BR, cudaMemcpyDeviceToDevice, st));
+        rc |= enc_attn_backward_launch(B, R, heads, dk, tp.qkv[l], tp.qkv[l] + H, tp.qkv[l] + 2 * H, 3 * H, seed, 10 + l, p_at, tp.d_g, H, tp.d_qkv, tp.d_qkv + H,
+                                       tp.d_qkv + 2 * H, 3 * H, st);
+        rc |= wgrad(H, H, (int)BR, tp.d_qkv, 3 * H, tp.ln[l], H, Lg.q_w, H, 0, st);
+        rc |= wgrad(H, H, (int)BR, tp.d_qkv + H, 3 * H, tp.ln[l], H, Lg.k_w, H, 0, st);
+        rc |= wgrad(H, H, (int)BR, tp.d_qkv + 2 * H, 3 * H, tp.ln[l], H, Lg.v_w, H, 0, st);
+        rc |= colsum_launch((int)BR, H, tp.d_qkv, 3 * H, Lg.q_b, 0, st);
+        rc |= colsum_launch((int)BR, H, tp.d_qkv + H, 3 * H, Lg.k_b, 0, st);
+        rc |= colsum_launch((int)BR, H, tp.d_qkv + 2 * H, 3 * H, Lg.v_b, 0, st);
+        // d ln = query half of the AoA input + through the packed q|k|v projection
+        CAPB_CHECK_CUDA(cudaMemcpy2DAsync(tp.d_ln, sizeof(float) * H, tp.d_catd + H, sizeof(float) * 2 * H, sizeof(float) * H, BR, cudaMemcpyDeviceToDevice, st));
+        rc |= sk.dgrad((int)BR, H, 3 * H, tp.d_qkv, 3 * H, e->r_qkv_w[l], H, tp.d_ln, H, 1);
+        rc |= ln_backward_launch((int)BR, H, tp.x[l], H, Lw.ln_a, tp.d_ln, H, 1e-6f, tp.d_x, H, 1, tp.stats, Lg.ln_a, Lg.ln_b, 0, st);
+        if (rc) return 1;
+        e->launches += 22;
+    }
+    rc |= relu_dropout_backward_launch(BR * H, tp.x[0], tp.d_x, tp.dpre, keep_lm, st);
+    rc |= wgrad(H, F, (int)BR, tp.dpre, H, att, F, G.att_embed_w, F, 0, st);
+    rc |= colsum_launch((int)BR, H, tp.dpre, H, G.att_embed_b, 0, st);
+    return rc;
+}

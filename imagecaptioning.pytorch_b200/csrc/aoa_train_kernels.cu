@@ -1,0 +1,440 @@
+// Training-only kernels of the AoANet SCST step (forward variants with replayable dropout, and the backward passes):
+//   layer_norm backward          captioning/models/TransformerModel.py:76-87   (a*(x-mean)/(std_unbiased+eps)+b)
+//   GLU backward                 nn.GLU, AoAModel.py:41,143
+//   refiner self-attention       AoAModel.py:56-98 with TransformerModel.attention (:152-162), dropout on the probabilities
+//   decoder multi-head attention AoAModel.py:168 (single query per row over the image's K | V halves of ctx2att's output)
+//   mean-pool backward           AoAModel.py:214-216
+#include "common.cuh"
+#include "dropout.cuh"
+#include "kernels.cuh"
+
+namespace capb200 {
+
+namespace {
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// one warp per row: dx (+)= d LayerNorm / dx; stats[row] = (mean, 1/(std+eps)) for the parameter-gradient pass
+__global__ void ln_backward_kernel(int rows, int D, const float* __restrict__ x, long ld_x, const float* __restrict__ a, const float* __restrict__ dy,
+                                   long ld_dy, float eps, float* __restrict__ dx, long ld_dx, int accumulate, float2* __restrict__ stats) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* xr = x + (long)row * ld_x;
+    const float* gr = dy + (long)row * ld_dy;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) s += xr[c];
+    const float mean = wsum(s) / (float)D;
+    float q = 0.f;
+    for (int c = lane; c < D; c += 32) { const float d = xr[c] - mean; q = fmaf(d, d, q); }
+    const float stdv = sqrtf(wsum(q) / (float)(D - 1));
+    const float inv = 1.0f / (stdv + eps);
+    float g_sum = 0.f, g_dot = 0.f;                  // sum of g and of g * (x - mean), g = dy * a
+    for (int c = lane; c < D; c += 32) {
+        const float g = gr[c] * __ldg(a + c);
+        g_sum += g;
+        g_dot = fmaf(g, xr[c] - mean, g_dot);
+    }
+    g_sum = wsum(g_sum);
+    g_dot = wsum(g_dot);
+    const float g_mean = g_sum / (float)D;
+    const float k = (stdv > 0.f) ? inv * inv * g_dot / ((float)(D - 1) * stdv) : 0.f;
+    for (int c = lane; c < D; c += 32) {
+        const float v = inv * (gr[c] * __ldg(a + c) - g_mean) - k * (xr[c] - mean);
+        float* o = dx + (long)row * ld_dx + c;
+        *o = accumulate ? *o + v : v;
+    }
+    if (lane == 0 && stats != nullptr) stats[row] = make_float2(mean, inv);
+}
+
+// thread per column: da[c] (+)= sum_rows dy * xhat, db[c] (+)= sum_rows dy
+__global__ void ln_param_grad_kernel(int rows, int D, const float* __restrict__ x, long ld_x, const float* __restrict__ dy, long ld_dy,
+                                     const float2* __restrict__ stats, float* __restrict__ da, float* __restrict__ db, int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= D) return;
+    float sa = 0.f, sb = 0.f;
+    for (int r = 0; r < rows; ++r) {
+        const float2 st = stats[r];
+        const float g = dy[(long)r * ld_dy + c];
+        sa = fmaf(g, (x[(long)r * ld_x + c] - st.x) * st.y, sa);
+        sb += g;
+    }
+    da[c] = accumulate ? da[c] + sa : sa;
+    db[c] = accumulate ? db[c] + sb : sb;
+}
+
+// y = t[:, :H] * sigmoid(t[:, H:]):  dt[:, :H] = dy * s,  dt[:, H:] = dy * t[:, :H] * s * (1 - s)
+__global__ void glu_backward_kernel(int rows, int H, const float* __restrict__ t, long ld_t, const float* __restrict__ dy, long ld_dy, float* __restrict__ dt,
+                                    long ld_dt) {
+    const long total = (long)rows * H;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / H), j = (int)(i % H);
+        const float a = t[(long)r * ld_t + j], b = t[(long)r * ld_t + H + j];
+        const float s = 1.0f / (1.0f + expf(-b));
+        const float g = dy[(long)r * ld_dy + j];
+        dt[(long)r * ld_dt + j] = g * s;
+        dt[(long)r * ld_dt + H + j] = g * a * s * (1.f - s);
+    }
+}
+
+// ---- refiner self-attention, train mode: one CTA per (image, head), dropout on the probabilities ----------------------------------
+// q,k,v: [B*R, ld] with the head at columns [head*dk, (head+1)*dk).  Dropout element index = ((img*heads + head)*R + qi)*R + r.
+__global__ void __launch_bounds__(128) enc_attn_train_kernel(int R, int dk, int heads, const float* __restrict__ q, const float* __restrict__ k,
+                                                             const float* __restrict__ v, long ld, float scale, unsigned long long seed, uint32_t site,
+                                                             float p_drop, float* __restrict__ out, long ld_out) {
+    extern __shared__ float sm[];
+    float* sk = sm;                 // [R][dk+1]
+    float* sv = sk + R * (dk + 1);
+    float* sp = sv + R * (dk + 1);  // [4 warps][R]
+    const int img = blockIdx.x, head = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {
+        const int r = i / dk, c = i % dk;
+        sk[r * (dk + 1) + c] = k[((long)img * R + r) * ld + head * dk + c];
+        sv[r * (dk + 1) + c] = v[((long)img * R + r) * ld + head * dk + c];
+    }
+    __syncthreads();
+    float* p = sp + warp * R;
+    for (int qi = warp; qi < R; qi += 4) {
+        const float* qr = q + ((long)img * R + qi) * ld + head * dk;
+        float mx = -INFINITY;
+        for (int r = lane; r < R; r += 32) {
+            float s = 0.f;
+            for (int c = 0; c < dk; ++c) s = fmaf(__ldg(qr + c), sk[r * (dk + 1) + c], s);
+            s *= scale;
+            p[r] = s;
+            mx = fmaxf(mx, s);
+        }
+        mx = wmax(mx);
+        float sum = 0.f;
+        for (int r = lane; r < R; r += 32) { const float e = expf(p[r] - mx); p[r] = e; sum += e; }
+        sum = wsum(sum);
+        const float inv = 1.0f / sum;
+        for (int r = lane; r < R; r += 32) p[r] = p[r] * inv * drop_scale(seed, site, 0u, (uint32_t)((((long)img * heads + head) * R + qi) * R + r), p_drop);
+        __syncwarp();
+        for (int c = lane; c < dk; c += 32) {
+            float acc = 0.f;
+            for (int r = 0; r < R; ++r) acc = fmaf(p[r], sv[r * (dk + 1) + c], acc);
+            out[((long)img * R + qi) * ld_out + head * dk + c] = acc;
+        }
+        __syncwarp();
+    }
+}
+
+// backward: recomputes the probabilities; writes dq | dk | dv of this (image, head) slice
+__global__ void __launch_bounds__(256) enc_attn_backward_kernel(int R, int dk, int heads, const float* __restrict__ q, const float* __restrict__ k,
+                                                                const float* __restrict__ v, long ld, float scale, unsigned long long seed,
+                                                                uint32_t site, float p_drop, const float* __restrict__ d_out, long ld_do,
+                                                                float* __restrict__ dq, float* __restrict__ dk_, float* __restrict__ dv, long ld_d) {
+    extern __shared__ float sm[];
+    const int W = dk + 1;
+    float* sq = sm;                 // [R][W]
+    float* sk = sq + R * W;
+    float* sv = sk + R * W;
+    float* sd = sv + R * W;         // d_out
+    float* P = sd + R * W;          // [R][R] softmax probabilities
+    float* DS = P + R * R;          // [R][R] dropout scale, then d score
+    const int img = blockIdx.x, head = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {
+        const int r = i / dk, c = i % dk;
+        const long g = ((long)img * R + r) * ld + head * dk + c;
+        sq[r * W + c] = q[g]; sk[r * W + c] = k[g]; sv[r * W + c] = v[g];
+        sd[r * W + c] = d_out[((long)img * R + r) * ld_do + head * dk + c];
+    }
+    __syncthreads();
+    // P = softmax(q k^T * scale) row by row (one warp per query row)
+    for (int qi = warp; qi < R; qi += nw) {
+        float mx = -INFINITY;
+        for (int r = lane; r < R; r += 32) {
+            float s = 0.f;
+            for (int c = 0; c < dk; ++c) s = fmaf(sq[qi * W + c], sk[r * W + c], s);
+            s *= scale;
+            P[qi * R + r] = s;
+            mx = fmaxf(mx, s);
+        }
+        mx = wmax(mx);
+        float sum = 0.f;
+        for (int r = lane; r < R; r += 32) { const float e = expf(P[qi * R + r] - mx); P[qi * R + r] = e; sum += e; }
+        sum = wsum(sum);
+        const float inv = 1.0f / sum;
+        for (int r = lane; r < R; r += 32) {
+            P[qi * R + r] *= inv;
+            DS[qi * R + r] = drop_scale(seed, site, 0u, (uint32_t)((((long)img * heads + head) * R + qi) * R + r), p_drop);
+        }
+    }
+    __syncthreads();
+    // dV[r, c] = sum_qi P[qi, r] * D[qi, r] * dO[qi, c]
+    for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {
+        const int r = i / dk, c = i % dk;
+        float acc = 0.f;
+        for (int qi = 0; qi < R; ++qi) acc = fmaf(P[qi * R + r] * DS[qi * R + r], sd[qi * W + c], acc);
+        dv[((long)img * R + r) * ld_d + head * dk + c] = acc;
+    }
+    __syncthreads();
+    // d score: dP = (dO V^T) * D ; dS = P * (dP - sum_r P dP)
+    for (int qi = warp; qi < R; qi += nw) {
+        float dot = 0.f;
+        for (int r = lane; r < R; r += 32) {
+            float s = 0.f;
+            for (int c = 0; c < dk; ++c) s = fmaf(sd[qi * W + c], sv[r * W + c], s);
+            const float dp = s * DS[qi * R + r];
+            DS[qi * R + r] = dp;
+            dot = fmaf(P[qi * R + r], dp, dot);
+        }
+        dot = wsum(dot);
+        __syncwarp();
+        for (int r = lane; r < R; r += 32) DS[qi * R + r] = P[qi * R + r] * (DS[qi * R + r] - dot) * scale;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {
+        const int r = i / dk, c = i % dk;
+        float aq = 0.f, ak = 0.f;
+        for (int j = 0; j < R; ++j) {
+            aq = fmaf(DS[r * R + j], sk[j * W + c], aq);          // dQ[r] = sum_j dS[r, j] K[j]
+            ak = fmaf(DS[j * R + r], sq[j * W + c], ak);          // dK[r] = sum_j dS[j, r] Q[j]
+        }
+        const long g = ((long)img * R + r) * ld_d + head * dk + c;
+        dq[g] = aq;
+        dk_[g] = ak;
+    }
+}
+
+// ---- decoder attention, train mode: one warp per (row, head); probabilities (before dropout) are saved for the backward ------------
+__global__ void __launch_bounds__(128) cross_attn_train_kernel(int rows, int rpi, int heads, int dk, int R, const float* __restrict__ q, long ld_q,
+                                                               const float* __restrict__ kk, const float* __restrict__ vv, long ld_kv, float scale,
+                                                               unsigned long long seed, uint32_t site, uint32_t step, float p_drop,
+                                                               float* __restrict__ out, long ld_out, float* __restrict__ probs) {
+    extern __shared__ float sm[];       // [4 warps][R]
+    const int item = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (item >= rows * heads) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = item / heads, head = item % heads;
+    const int img = row / rpi;
+    float* p = sm + warp * R;
+    const float* qr = q + (long)row * ld_q + head * dk;
+    float mx = -INFINITY;
+    for (int r = lane; r < R; r += 32) {
+        const float* kr = kk + ((long)img * R + r) * ld_kv + head * dk;
+        float s = 0.f;
+        for (int c = 0; c < dk; ++c) s = fmaf(qr[c], __ldg(kr + c), s);
+        s *= scale;
+        p[r] = s;
+        mx = fmaxf(mx, s);
+    }
+    mx = wmax(mx);
+    float sum = 0.f;
+    for (int r = lane; r < R; r += 32) { const float e = expf(p[r] - mx); p[r] = e; sum += e; }
+    sum = wsum(sum);
+    const float inv = 1.0f / sum;
+    for (int r = lane; r < R; r += 32) {
+        const float pr = p[r] * inv;
+        probs[(long)item * R + r] = pr;
+        p[r] = pr * drop_scale(seed, site, step, (uint32_t)((long)item * R + r), p_drop);
+    }
+    __syncwarp();
+    for (int c = lane; c < dk; c += 32) {
+        float acc = 0.f;
+        for (int r = 0; r < R; ++r) acc = fmaf(p[r], __ldg(vv + ((long)img * R + r) * ld_kv + head * dk + c), acc);
+        out[(long)row * ld_out + head * dk + c] = acc;
+    }
+}
+
+// backward: one CTA per (image, head) walks the image's rpi rows; dq written, dK / dV accumulated (+=) into the per-image buffers
+__global__ void __launch_bounds__(128) cross_attn_backward_kernel(int rpi, int heads, int dk, int R, const float* __restrict__ q, long ld_q,
+                                                                  const float* __restrict__ kk, const float* __restrict__ vv, long ld_kv, float scale,
+                                                                  unsigned long long seed, uint32_t site, uint32_t step, float p_drop,
+                                                                  const float* __restrict__ probs, const float* __restrict__ d_out, long ld_do,
+                                                                  float* __restrict__ dq, long ld_dq, float* __restrict__ dkk, float* __restrict__ dvv,
+                                                                  long ld_dkv) {
+    extern __shared__ float sm[];
+    const int W = dk + 1;
+    float* sk = sm;                  // [R][W]
+    float* sv = sk + R * W;
+    float* sq = sv + R * W;          // [rpi][W]
+    float* sd = sq + rpi * W;        // [rpi][W]  d_out
+    float* PD = sd + rpi * W;        // [rpi][R]  p * D
+    float* DS = PD + rpi * R;        // [rpi][R]  d score (scaled)
+    const int img = blockIdx.x, head = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {
+        const int r = i / dk, c = i % dk;
+        sk[r * W + c] = kk[((long)img * R + r) * ld_kv + head * dk + c];
+        sv[r * W + c] = vv[((long)img * R + r) * ld_kv + head * dk + c];
+    }
+    for (int i = threadIdx.x; i < rpi * dk; i += blockDim.x) {
+        const int j = i / dk, c = i % dk;
+        const long row = (long)img * rpi + j;
+        sq[j * W + c] = q[row * ld_q + head * dk + c];
+        sd[j * W + c] = d_out[row * ld_do + head * dk + c];
+    }
+    __syncthreads();
+    for (int j = warp; j < rpi; j += nw) {
+        const long item = ((long)img * rpi + j) * heads + head;
+        float dot = 0.f;
+        for (int r = lane; r < R; r += 32) {
+            const float pr = probs[item * R + r];
+            const float D = drop_scale(seed, site, step, (uint32_t)(item * R + r), p_drop);
+            float s = 0.f;
+            for (int c = 0; c < dk; ++c) s = fmaf(sd[j * W + c], sv[r * W + c], s);
+            const float dp = s * D;
+            PD[j * R + r] = pr * D;
+            DS[j * R + r] = dp;
+            dot = fmaf(pr, dp, dot);
+        }
+        dot = wsum(dot);
+        __syncwarp();
+        for (int r = lane; r < R; r += 32) DS[j * R + r] = probs[item * R + r] * (DS[j * R + r] - dot) * scale;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {
+        const int r = i / dk, c = i % dk;
+        float av = 0.f, ak = 0.f;
+        for (int j = 0; j < rpi; ++j) {
+            av = fmaf(PD[j * R + r], sd[j * W + c], av);
+            ak = fmaf(DS[j * R + r], sq[j * W + c], ak);
+        }
+        const long g = ((long)img * R + r) * ld_dkv + head * dk + c;
+        dvv[g] += av;
+        dkk[g] += ak;
+    }
+    for (int i = threadIdx.x; i < rpi * dk; i += blockDim.x) {
+        const int j = i / dk, c = i % dk;
+        float a = 0.f;
+        for (int r = 0; r < R; ++r) a = fmaf(DS[j * R + r], sk[r * W + c], a);
+        dq[((long)img * rpi + j) * ld_dq + head * dk + c] = a;
+    }
+}
+
+// d x[img, r, :] += d mean[img, :] / R
+__global__ void mean_backward_kernel(int R, int H, const float* __restrict__ d_mean, long ld_dm, float* __restrict__ dx, long ld_dx) {
+    const int row = blockIdx.x;              // img * R + r
+    const int img = row / R;
+    const float inv = 1.0f / (float)R;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) dx[(long)row * ld_dx + c] += d_mean[(long)img * ld_dm + c] * inv;
+}
+
+// out[r, :] = a[r, :] + b[r, :] * dropmask(site, step, r*cols + c)      (SublayerConnection: x + dropout(sublayer(norm(x))))
+__global__ void add_dropout_kernel(int rows, int cols, const float* __restrict__ a, long ld_a, const float* __restrict__ b, long ld_b, float* __restrict__ out,
+                                   long ld_o, unsigned long long seed, uint32_t site, uint32_t step, float p) {
+    const long n = (long)rows * cols;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / cols;
+        const int c = (int)(i % cols);
+        out[r * ld_o + c] = a[r * ld_a + c] + b[r * ld_b + c] * drop_scale(seed, site, step, (uint32_t)i, p);
+    }
+}
+
+// out[r, c] = (c < c1 ? a[r, c] : b[r, c - c1]) * dropmask(site, step, r*(c1+c2) + c)     (dropout_aoa(cat[x, query]))
+__global__ void cat_dropout_kernel(int rows, int c1, int c2, const float* __restrict__ a, long ld_a, const float* __restrict__ b, long ld_b,
+                                   float* __restrict__ out, long ld_o, unsigned long long seed, uint32_t site, uint32_t step, float p) {
+    const int cols = c1 + c2;
+    const long n = (long)rows * cols;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / cols;
+        const int c = (int)(i % cols);
+        const float v = c < c1 ? a[r * ld_a + c] : b[r * ld_b + (c - c1)];
+        out[r * ld_o + c] = v * drop_scale(seed, site, step, (uint32_t)i, p);
+    }
+}
+
+// out[r, c] = a[r, c] + b[img(r), c]       (mean_feats + ctx_drop(ctx), AoAModel.py:165)
+__global__ void add_row_group_kernel(int rows, int cols, int rpg, const float* __restrict__ a, long ld_a, const float* __restrict__ g, long ld_g,
+                                     float* __restrict__ out, long ld_o) {
+    const long n = (long)rows * cols;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / cols;
+        const int c = (int)(i % cols);
+        out[r * ld_o + c] = a[r * ld_a + c] + g[(r / rpg) * ld_g + c];
+    }
+}
+
+int blocks_for(long n) {
+    long b = (n + 255) / 256;
+    return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
+}
+
+}  // namespace
+
+#define LAUNCH_OK() do { CAPB_CHECK_CUDA(cudaGetLastError()); return 0; } while (0)
+
+int ln_backward_launch(int rows, int D, const float* x, long ld_x, const float* a, const float* dy, long ld_dy, float eps, float* dx, long ld_dx, int accumulate,
+                       float* stats, float* da, float* db, int accumulate_params, cudaStream_t st) {
+    ln_backward_kernel<<<cdiv(rows, 4), 128, 0, st>>>(rows, D, x, ld_x, a, dy, ld_dy, eps, dx, ld_dx, accumulate, reinterpret_cast<float2*>(stats));
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    ln_param_grad_kernel<<<cdiv(D, 128), 128, 0, st>>>(rows, D, x, ld_x, dy, ld_dy, reinterpret_cast<const float2*>(stats), da, db, accumulate_params);
+    LAUNCH_OK();
+}
+int glu_backward_launch(int rows, int H, const float* t, long ld_t, const float* dy, long ld_dy, float* dt, long ld_dt, cudaStream_t st) {
+    glu_backward_kernel<<<blocks_for((long)rows * H), 256, 0, st>>>(rows, H, t, ld_t, dy, ld_dy, dt, ld_dt);
+    LAUNCH_OK();
+}
+int enc_attn_train_launch(int B, int R, int heads, int dk, const float* q, const float* k, const float* v, long ld, unsigned long long seed, int site, float p,
+                          float* out, long ld_out, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((size_t)2 * R * (dk + 1) + 4 * R);
+    CAPB_REQUIRE(smem <= 48 * 1024, "refiner attention: regions * head width too large for the training kernel");
+    enc_attn_train_kernel<<<dim3(B, heads), 128, smem, st>>>(R, dk, heads, q, k, v, ld, 1.0f / sqrtf((float)dk), seed, (uint32_t)site, p, out, ld_out);
+    LAUNCH_OK();
+}
+int enc_attn_backward_launch(int B, int R, int heads, int dk, const float* q, const float* k, const float* v, long ld, unsigned long long seed, int site, float p,
+                             const float* d_out, long ld_do, float* dq, float* dk_, float* dv, long ld_d, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((size_t)4 * R * (dk + 1) + 2 * R * R);
+    CAPB_REQUIRE(smem <= 200 * 1024, "refiner attention backward: shared-memory footprint too large");
+    static bool configured = false;
+    if (!configured) {
+        CAPB_CHECK_CUDA(cudaFuncSetAttribute(enc_attn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    enc_attn_backward_kernel<<<dim3(B, heads), 256, smem, st>>>(R, dk, heads, q, k, v, ld, 1.0f / sqrtf((float)dk), seed, (uint32_t)site, p, d_out, ld_do, dq,
+                                                                  dk_, dv, ld_d);
+    LAUNCH_OK();
+}
+int cross_attn_train_launch(int rows, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
+                            unsigned long long seed, int site, int step, float p, float* out, long ld_out, float* probs, cudaStream_t st) {
+    cross_attn_train_kernel<<<cdiv(rows * heads, 4), 128, sizeof(float) * 4 * R, st>>>(rows, rpi, heads, dk, R, q, ld_q, kk, vv, ld_kv, 1.0f / sqrtf((float)dk),
+                                                                                        seed, (uint32_t)site, (uint32_t)step, p, out, ld_out, probs);
+    LAUNCH_OK();
+}
+int cross_attn_backward_launch(int B, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
+                               unsigned long long seed, int site, int step, float p, const float* probs, const float* d_out, long ld_do, float* dq, long ld_dq,
+                               float* dkk, float* dvv, long ld_dkv, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((size_t)2 * R * (dk + 1) + 2 * rpi * (dk + 1) + 2 * rpi * R);
+    CAPB_REQUIRE(smem <= 200 * 1024, "decoder attention backward: shared-memory footprint too large");
+    static bool configured = false;
+    if (!configured) {
+        CAPB_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    cross_attn_backward_kernel<<<dim3(B, heads), 128, smem, st>>>(rpi, heads, dk, R, q, ld_q, kk, vv, ld_kv, 1.0f / sqrtf((float)dk), seed, (uint32_t)site,
+                                                                   (uint32_t)step, p, probs, d_out, ld_do, dq, ld_dq, dkk, dvv, ld_dkv);
+    LAUNCH_OK();
+}
+int mean_backward_launch(int B, int R, int H, const float* d_mean, long ld_dm, float* dx, long ld_dx, cudaStream_t st) {
+    mean_backward_kernel<<<B * R, 256, 0, st>>>(R, H, d_mean, ld_dm, dx, ld_dx);
+    LAUNCH_OK();
+}
+int add_dropout_launch(int rows, int cols, const float* a, long ld_a, const float* b, long ld_b, float* out, long ld_o, unsigned long long seed, int site, int step,
+                       float p, cudaStream_t st) {
+    add_dropout_kernel<<<blocks_for((long)rows * cols), 256, 0, st>>>(rows, cols, a, ld_a, b, ld_b, out, ld_o, seed, (uint32_t)site, (uint32_t)step, p);
+    LAUNCH_OK();
+}
+int cat_dropout_launch(int rows, int c1, int c2, const float* a, long ld_a, const float* b, long ld_b, float* out, long ld_o, unsigned long long seed, int site,
+                       int step, float p, cudaStream_t st) {
+    cat_dropout_kernel<<<blocks_for((long)rows * (c1 + c2)), 256, 0, st>>>(rows, c1, c2, a, ld_a, b, ld_b, out, ld_o, seed, (uint32_t)site, (uint32_t)step, p);
+    LAUNCH_OK();
+}
+int add_row_group_launch(int rows, int cols, int rpg, const float* a, long ld_a, const float* g, long ld_g, float* out, long ld_o, cudaStream_t st) {
+    add_row_group_kernel<<<blocks_for((long)rows * cols), 256, 0, st>>>(rows, cols, rpg, a, ld_a, g, ld_g, out, ld_o);
+    LAUNCH_OK();
+}
+
+}  // namespace capb200

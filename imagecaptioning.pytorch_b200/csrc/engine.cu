@@ -71,9 +71,6 @@ enum GemmId { G_FC = 0, G_ATT, G_CTX, G_GFC, G_LSTM1, G_H2ATT, G_LSTM2, G_LOGIT,
 
 using namespace capb200;
 
-struct capb200_cider_table {
-    CiderTable* t = nullptr;
-};
 
 struct capb200_engine {
     capb200_model_cfg cfg{};
@@ -833,28 +830,6 @@ void layout_tape(Tape& tp, Arena& a, int B, int R, int N, int T, int E, int H, i
     tp.skinny = a.take<float>((long)tp.skinny_floats);
     (void)F_att; (void)F_fc;
 }
-
-// Skinny fp32 GEMMs on the raw PyTorch weights (always current, no repack after optimizer steps); split-K partials live in the tape.
-struct Skinny {
-    float* scratch; size_t cap; int mode; cudaStream_t st;
-    // y = x * W^T (+ b)          (nn.Linear forward; W stored [N, K])
-    int lin(const float* x, long ldx, const float* w, long ldw, const float* b, float* y, long ldy, int M, int N, int K, int accumulate) const {
-        const int tb = 1;
-        return gemm_skinny_launch(M, N, 1, &x, &ldx, &w, &ldw, &K, &tb, y, ldy, b, nullptr, 0, 1, accumulate, scratch, cap, mode, st);
-    }
-    // dx = dy * W                (nn.Linear input gradient; W stored [K, N])
-    int dgrad(int M, int N, int K, const float* dy, long lddy, const float* w, long ldw, float* dx, long lddx, int accumulate) const {
-        const int tb = 0;
-        return gemm_skinny_launch(M, N, 1, &dy, &lddy, &w, &ldw, &K, &tb, dx, lddx, nullptr, nullptr, 0, 1, accumulate, scratch, cap, mode, st);
-    }
-    // the K-segmented gate GEMM of the decode path, on fp32 weights
-    int gates(const GemmProblem& g) const {
-        const float* A[3]; const float* B[3]; long lda[3], ldb[3]; int K[3], tb[3];
-        for (int i = 0; i < g.nseg; ++i) { A[i] = g.seg[i].A; lda[i] = g.seg[i].lda; B[i] = g.seg[i].W; ldb[i] = g.seg[i].ldw; K[i] = g.seg[i].K; tb[i] = 1; }
-        return gemm_skinny_launch(g.M, g.N, g.nseg, A, lda, B, ldb, K, tb, g.epi.C, g.epi.ldc, g.epi.bias, g.epi.row_bias, g.epi.ld_row_bias,
-                                  g.epi.rows_per_group, 0, scratch, cap, mode, st);
-    }
-};
 
 }  // namespace
 

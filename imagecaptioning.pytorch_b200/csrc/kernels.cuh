@@ -133,6 +133,26 @@ int per_image_sum_launch(int steps, int rows, int rpi, int cols, const float* x,
 int add_inplace_launch(float* a, const float* b, long n, cudaStream_t st);
 int add_strided_launch(float* a, const float* b, long ld_b, int rows, int cols, cudaStream_t st);
 
+// ---- aoa_train_kernels.cu (AoANet training step)
+int ln_backward_launch(int rows, int D, const float* x, long ld_x, const float* a, const float* dy, long ld_dy, float eps, float* dx, long ld_dx, int accumulate,
+                       float* stats, float* da, float* db, int accumulate_params, cudaStream_t st);
+int glu_backward_launch(int rows, int H, const float* t, long ld_t, const float* dy, long ld_dy, float* dt, long ld_dt, cudaStream_t st);
+int enc_attn_train_launch(int B, int R, int heads, int dk, const float* q, const float* k, const float* v, long ld, unsigned long long seed, int site, float p,
+                          float* out, long ld_out, cudaStream_t st);
+int enc_attn_backward_launch(int B, int R, int heads, int dk, const float* q, const float* k, const float* v, long ld, unsigned long long seed, int site, float p,
+                             const float* d_out, long ld_do, float* dq, float* dk_, float* dv, long ld_d, cudaStream_t st);
+int cross_attn_train_launch(int rows, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
+                            unsigned long long seed, int site, int step, float p, float* out, long ld_out, float* probs, cudaStream_t st);
+int cross_attn_backward_launch(int B, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
+                               unsigned long long seed, int site, int step, float p, const float* probs, const float* d_out, long ld_do, float* dq, long ld_dq,
+                               float* dkk, float* dvv, long ld_dkv, cudaStream_t st);
+int mean_backward_launch(int B, int R, int H, const float* d_mean, long ld_dm, float* dx, long ld_dx, cudaStream_t st);
+int add_dropout_launch(int rows, int cols, const float* a, long ld_a, const float* b, long ld_b, float* out, long ld_o, unsigned long long seed, int site, int step,
+                       float p, cudaStream_t st);
+int cat_dropout_launch(int rows, int c1, int c2, const float* a, long ld_a, const float* b, long ld_b, float* out, long ld_o, unsigned long long seed, int site,
+                       int step, float p, cudaStream_t st);
+int add_row_group_launch(int rows, int cols, int rpg, const float* a, long ld_a, const float* g, long ld_g, float* out, long ld_o, cudaStream_t st);
+
 // ---- reward.cu (CIDEr-D) and criterion
 struct CiderTable;   // device hash table of n-gram -> idf
 CiderTable* cider_table_create(const int* keys, const double* df, long n, double ref_len, cudaStream_t stream);

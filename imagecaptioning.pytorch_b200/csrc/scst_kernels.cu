@@ -8,32 +8,12 @@
 //   attention_backward       models/AttModel.py:728-748
 // Dropout masks are never stored: keep(seed, site, step, element) is a pure function (Philox4x32-10), re-evaluated in the backward.
 #include "common.cuh"
+#include "dropout.cuh"
 #include "kernels.cuh"
 
 namespace capb200 {
 
 namespace {
-
-__device__ __forceinline__ uint32_t philox_word(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    return c0;
-}
-
-// 0 (dropped) or 1/(1-p) (kept): inverted dropout like nn.Dropout
-__device__ __forceinline__ float drop_scale(unsigned long long seed, uint32_t site, uint32_t step, uint32_t idx, float p) {
-    if (p <= 0.f) return 1.f;
-    const uint32_t bits = philox_word(idx, site, step, 0x5C57u, (uint32_t)seed, (uint32_t)(seed >> 32));
-    const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);        // [0, 1)
-    return u < p ? 0.f : 1.0f / (1.0f - p);
-}
 
 __global__ void dropout_apply_kernel(float* x, long n, int cols, long ld, unsigned long long seed, uint32_t site, uint32_t step, float p) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {

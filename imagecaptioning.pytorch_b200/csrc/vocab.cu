@@ -258,6 +258,75 @@ __global__ void __launch_bounds__(VT) vocab_stats_kernel(const VocabStepArgs a) 
     }
 }
 
+// Register-resident variant for rows of up to VT * 4 * NV elements (16-byte aligned): the row is read from L2/HBM exactly once, with
+// all of a thread's loads in flight together; max, sum-exp, per-thread top-2 and the rare rescan then work on registers.  Same
+// arithmetic (and the same tie order) as vocab_stats_kernel.
+template <int NV>
+__global__ void __launch_bounds__(VT) vocab_stats_reg_kernel(const VocabStepArgs a) {
+    __shared__ float s_red[VT / 32];
+    __shared__ int s_idx[VT / 32];
+    const int r = blockIdx.x;
+    const int n4 = a.V1 >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(a.logits + (long)r * a.ld);
+    float4 xs[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int v = threadIdx.x + i * VT;
+        xs[i] = v < n4 ? g4[v] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) mx = fmaxf(mx, fmaxf(fmaxf(xs[i].x, xs[i].y), fmaxf(xs[i].z, xs[i].w)));
+    mx = block_max(mx, s_red);
+    float t0v = -INFINITY, t1v = -INFINITY;
+    int t0i = 0x7fffffff, t1i = 0x7fffffff;
+    float sum = 0.f;
+    auto visit = [&](float x, int v) {
+        sum += __expf(x - mx);                      // padding lanes hold -inf: exp -> 0, never a candidate
+        if (x > t1v) {                              // strict: earlier (lower) indices win ties
+            if (x > t0v) { t1v = t0v; t1i = t0i; t0v = x; t0i = v; }
+            else { t1v = x; t1i = v; }
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int v = 4 * (threadIdx.x + i * VT);
+        visit(xs[i].x, v); visit(xs[i].y, v + 1); visit(xs[i].z, v + 2); visit(xs[i].w, v + 3);
+    }
+    sum = block_sum(sum, s_red);
+    const float lsum = logf(sum);
+    const float m2 = (mx - mx) - lsum, l2 = lsum;
+    if (threadIdx.x == 0) a.stats[r] = make_float2(mx, lsum);
+    int popped = 0;
+    for (int k = 0; k < a.topk; ++k) {
+        float ov;
+        int oi;
+        block_argmax(t0v, t0i, s_red, s_idx, ov, oi);
+        if (t0i == oi && oi != 0x7fffffff) {
+            const float lastv = t0v;
+            const int lasti = t0i;
+            t0v = t1v; t0i = t1i;
+            t1v = -INFINITY; t1i = 0x7fffffff;
+            if (++popped >= 2 && t0i == 0x7fffffff) {
+                auto consider = [&](float x, int v) {
+                    const bool after = (x < lastv) || (x == lastv && v > lasti);
+                    if (after && (x > t0v || (x == t0v && v < t0i))) { t0v = x; t0i = v; }
+                };
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const int v = 4 * (threadIdx.x + i * VT);
+                    if (v < a.V1) { consider(xs[i].x, v); consider(xs[i].y, v + 1); consider(xs[i].z, v + 2); consider(xs[i].w, v + 3); }
+                }
+            }
+        }
+        if (threadIdx.x == 0) {
+            const float lp = (ov - mx) - lsum;
+            a.top_val[(long)r * a.topk + k] = a.twice ? (lp - m2) - l2 : lp;
+            a.top_idx[(long)r * a.topk + k] = oi;
+        }
+    }
+}
+
 __global__ void mask_rows_kernel(ActView x, int R, int cols, const float* __restrict__ mask, long ld_mask) {
     const int row = blockIdx.x;              // row = img * R + r
     const int img = row / R, r = row % R;
@@ -275,7 +344,10 @@ int vocab_step_launch(const VocabStepArgs& a, cudaStream_t stream) {
     CAPB_REQUIRE(a.topk <= 16, "beam size up to 16");
     if (a.stats != nullptr) {
         CAPB_REQUIRE(a.select == 0 && a.topk > 0, "stats mode is the beam-search epilogue");
-        vocab_stats_kernel<<<a.rows, VT, 0, stream>>>(a);
+        const bool vec = ((a.V1 & 3) == 0) && ((a.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.logits) & 15) == 0);
+        if (vec && a.V1 <= VT * 4 * 10) vocab_stats_reg_kernel<10><<<a.rows, VT, 0, stream>>>(a);
+        else if (vec && a.V1 <= VT * 4 * 16) vocab_stats_reg_kernel<16><<<a.rows, VT, 0, stream>>>(a);
+        else vocab_stats_kernel<<<a.rows, VT, 0, stream>>>(a);
         CAPB_CHECK_CUDA(cudaGetLastError());
         return 0;
     }

@@ -298,6 +298,46 @@ typedef struct {
 int capb200_updown_xe_step(capb200_engine* e, const float* fc, const float* att, int B, int R, const capb200_xe_opts* opts, const long long* labels,
                            const float* masks, int label_cols, const capb200_updown_grads* grads, float* logprobs, float* loss, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * One self-critical training step of the AoANet model (BASELINE configs[3]): LossWrapper.forward with sc_flag (loss_wrapper.py:56-73)
+ * over AoAModel (refiner + AoA decoder, AoAModel.py:56-226) in train mode, and its backward.  Dropout sites (replayable through
+ * capb200_dropout_mask with the same seed): 1 att_embed [B*R,H]; 2 word embedding at `step` [N,E]; 3 core output at `step` [N,H];
+ * 4 ctx_drop at `step` [N,H]; 5 decoder attention probabilities at `step` [N,heads,R]; 10+l refiner attention probabilities
+ * [B,heads,R,R]; 20+l AoA-layer input [B*R,2H]; 30+l refiner SublayerConnection [B*R,H]   (l = refiner layer 0..5).
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int sample_n;
+    float temperature;
+    unsigned long long seed;
+    float upstream;
+    int baseline;              /* CAPB200_BASELINE_* */
+    float drop_prob_lm;        /* att_embed, word embedding, ctx_drop, out_drop (opt.drop_prob_lm) */
+    float drop_attn;           /* MultiHeadedDotAttention dropout on the probabilities (0.1, AoAModel.py:18) */
+    float drop_aoa;            /* dropout_aoa (0.3) */
+    float drop_sublayer;       /* refiner SublayerConnection (0.1, AoAModel.py:119) */
+    int ctx_drop;              /* opt.ctx_drop */
+} capb200_aoa_scst_opts;
+/* Gradient buffers: the same field layout as capb200_aoa_weights (shapes of the parameters, fp32, device); every one is OVERWRITTEN. */
+typedef struct {
+    float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *aoa_w, *aoa_b, *ln_a, *ln_b;
+} capb200_aoa_refiner_layer_grads;
+typedef struct {
+    float* embed;
+    float *att_embed_w, *att_embed_b;
+    capb200_aoa_refiner_layer_grads refiner[CAPB200_AOA_REFINER_LAYERS];
+    float *refiner_norm_a, *refiner_norm_b;
+    float *ctx2att_w, *ctx2att_b;
+    float *att_lstm_w_ih, *att_lstm_w_hh, *att_lstm_b_ih, *att_lstm_b_hh;
+    float *attn_norm_a, *attn_norm_b;
+    float *attn_q_w, *attn_q_b;
+    float *att2ctx_w, *att2ctx_b;
+    float *logit_w, *logit_b;
+} capb200_aoa_grads;
+/* att[B,R,F_att] (fixed region count, att_masks = None); outputs as in capb200_updown_scst_step. */
+int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, int B, int R, const capb200_aoa_scst_opts* opts, const capb200_cider_table* table,
+                          const int* refs, const int* ref_offsets, int L, const capb200_aoa_grads* grads, long long* sample_seq, long long* greedy_seq,
+                          float* sample_logprobs, float* reward, float* loss, void* stream);
+
 /* The dropout keep/scale mask (0 or 1/(1-p)) of one site and step, for tests that replay it in the oracle:
  * site 0 = fc_embed [B,H], 1 = att_embed [B*R,H], 2 = word embedding at `step` [N,E], 3 = core output at `step` [N,H]. */
 int capb200_dropout_mask(float* mask, long n, unsigned long long seed, int site, int step, float p, void* stream);

@@ -160,11 +160,16 @@ def layer_norm(x: Tensor, a: Tensor, b: Tensor, eps: float = 1e-6) -> Tensor:
     return a * (x - mean) / (std + eps) + b
 
 
-def dot_attention(q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor]) -> Tensor:
+def dot_attention(q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor], p_drop: Optional[Tensor] = None) -> Tensor:
+    """captioning/models/TransformerModel.py:152-162; ``p_drop`` is an explicit keep/scale mask for the dropout on the
+    attention probabilities (:160-161), shaped like the probabilities [n, h, tq, tk]."""
     scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(q.shape[-1])
     if mask is not None:
         scores = scores.masked_fill(mask == 0, float('-inf'))
-    return torch.matmul(F.softmax(scores, dim=-1), v)
+    p = F.softmax(scores, dim=-1)
+    if p_drop is not None:
+        p = p * p_drop
+    return torch.matmul(p, v)
 
 
 def _heads(x: Tensor, h: int) -> Tensor:
@@ -221,8 +226,11 @@ def transformer_decode(W: Weights, memory: Tensor, src_mask: Tensor, ys: Tensor,
     return _ln(W, 'model.decoder.norm.', x)
 
 
-def aoa_mha(W: Weights, pre: str, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor], h: int, project_k_v: bool, norm_q: bool, do_aoa: bool):
-    """MultiHeadedDotAttention(query, value, key) -- note the reference's argument order is (query, value, key)."""
+def aoa_mha(W: Weights, pre: str, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor], h: int, project_k_v: bool, norm_q: bool, do_aoa: bool,
+            p_drop: Optional[Tensor] = None, aoa_drop: Optional[Tensor] = None):
+    """MultiHeadedDotAttention(query, value, key) -- note the reference's argument order is (query, value, key).
+    Train-mode replay: ``p_drop`` multiplies the attention probabilities (AoAModel.py:83-84 -> TransformerModel.py:160-161) and
+    ``aoa_drop`` the input cat[x, query] of the AoA layer (AoAModel.py:90-92)."""
     if mask is not None:
         if mask.dim() == 2:
             mask = mask.unsqueeze(-2)
@@ -238,22 +246,31 @@ def aoa_mha(W: Weights, pre: str, q: Tensor, k: Tensor, v: Tensor, mask: Optiona
         vh = _heads(linear(v, W[pre + 'linears.2.weight'], W[pre + 'linears.2.bias']), h)
     else:
         kh, vh = _heads(k, h), _heads(v, h)
-    x = dot_attention(qh, kh, vh, mask).transpose(1, 2).contiguous().view(q.shape[0], -1, qh.shape[1] * qh.shape[3])
+    x = dot_attention(qh, kh, vh, mask, p_drop).transpose(1, 2).contiguous().view(q.shape[0], -1, qh.shape[1] * qh.shape[3])
     if do_aoa:
-        x = F.glu(linear(torch.cat([x, q], -1), W[pre + 'aoa_layer.0.weight'], W[pre + 'aoa_layer.0.bias']), -1)
+        cat = torch.cat([x, q], -1)
+        if aoa_drop is not None:
+            cat = cat * aoa_drop
+        x = F.glu(linear(cat, W[pre + 'aoa_layer.0.weight'], W[pre + 'aoa_layer.0.bias']), -1)
     return x.squeeze(1) if single else x
 
 
-def aoa_prepare(W: Weights, fc: Tensor, att: Tensor, masks: Optional[Tensor], h: int):
+def aoa_prepare(W: Weights, fc: Tensor, att: Tensor, masks: Optional[Tensor], h: int, drop: Optional[Dict[str, Tensor]] = None):
+    """``drop`` (train-mode replay): 'att' [B,R,H] after att_embed (AttModel.py:77-79); per refiner layer i 'ref_p%d' [B,h,R,R] on the
+    attention probabilities, 'ref_aoa%d' [B,R,2H] on the AoA input, 'ref_sub%d' [B,R,H] in the SublayerConnection (TransformerModel.py:99-101)."""
     att, masks = clip_att(att, masks)
     x = torch.relu(linear(att, W['att_embed.0.weight'], W['att_embed.0.bias']))
+    if drop is not None:
+        x = x * drop['att']
     if masks is not None:
         x = x * masks.unsqueeze(-1).to(x)
     for i in range(6):
         pre = 'refiner.layers.%d.' % i
         y = _ln(W, pre + 'sublayer.0.norm.', x)
         # self_attn(x, x, x, mask): key = value = query source
-        x = x + aoa_mha(W, pre + 'self_attn.', y, y, y, masks, h, True, False, True)
+        sub = aoa_mha(W, pre + 'self_attn.', y, y, y, masks, h, True, False, True, drop['ref_p%d' % i] if drop else None,
+                      drop['ref_aoa%d' % i] if drop else None)
+        x = x + (sub * drop['ref_sub%d' % i] if drop else sub)
     x = _ln(W, 'refiner.norm.', x)
     if masks is None:
         mean = x.mean(1)
@@ -263,16 +280,19 @@ def aoa_prepare(W: Weights, fc: Tensor, att: Tensor, masks: Optional[Tensor], h:
     return mean, x, p_att, masks
 
 
-def aoa_core(W: Weights, xt: Tensor, mean: Tensor, att_e: Tensor, p_att: Tensor, state, masks, h: int):
+def aoa_core(W: Weights, xt: Tensor, mean: Tensor, att_e: Tensor, p_att: Tensor, state, masks, h: int, drop: Optional[Dict[str, Tensor]] = None):
+    """``drop`` (one step of a train-mode replay): 'ctx' [N,H] on the carried context vector (ctx_drop, AoAModel.py:158-165), 'p' [N,h,1,R] on
+    the attention probabilities, 'out' [N,H] on the returned output (out_drop, :186; the state keeps the un-dropped vector, :179)."""
     hs, cs = state                                  # [2, N, H]; hs[1] carries the previous context vector
     H = hs.shape[2]
-    x1 = torch.cat([xt, mean + hs[1]], 1)
+    x1 = torch.cat([xt, mean + (hs[1] * drop['ctx'] if drop else hs[1])], 1)
     h_att, c_att = lstm_cell(x1, hs[0], cs[0], W['core.att_lstm.weight_ih'], W['core.att_lstm.weight_hh'], W['core.att_lstm.bias_ih'],
                              W['core.att_lstm.bias_hh'])
     # attention(h_att, p_att[..., :H], p_att[..., H:], mask) with signature (query, value, key)
-    att = aoa_mha(W, 'core.attention.', h_att, p_att[..., H:], p_att[..., :H], masks, h, False, True, False)
+    att = aoa_mha(W, 'core.attention.', h_att, p_att[..., H:], p_att[..., :H], masks, h, False, True, False, drop['p'] if drop else None)
     out = F.glu(linear(torch.cat([att, h_att], 1), W['core.att2ctx.0.weight'], W['core.att2ctx.0.bias']), -1)
-    return out, (torch.stack([h_att, out]), torch.stack([c_att, cs[1]]))
+    state = (torch.stack([h_att, out]), torch.stack([c_att, cs[1]]))
+    return (out * drop['out'] if drop else out), state
 
 
 # --------------------------------------------------------------------------------------------------
@@ -281,7 +301,7 @@ def aoa_core(W: Weights, xt: Tensor, mean: Tensor, att_e: Tensor, p_att: Tensor,
 
 class Family:
     def __init__(self, name: str, W: Weights, seq_length: int, heads: int = 8):
-        self.drop = None          # explicit dropout masks for a train-mode replay (UpDown only)
+        self.drop = None          # explicit dropout masks for a train-mode replay (UpDown, AoA)
         self.name = name
         self.W = W
         self.seq_length = seq_length
@@ -311,7 +331,7 @@ class Family:
         if self.name == 'newfc':
             return newfc_prepare(self.W, fc, att, masks)
         if self.name == 'aoa':
-            return aoa_prepare(self.W, fc, att, masks, self.heads)
+            return aoa_prepare(self.W, fc, att, masks, self.heads, self.drop)
         return transformer_prepare(self.W, fc, att, masks, self.n_layers, self.heads)
 
     def init_state(self, n: int):
@@ -333,7 +353,11 @@ class Family:
             return (F.log_softmax(logits, dim=1) if output_logsoftmax else logits), [ys.unsqueeze(0)]
         xt = self.embed(it)
         if self.name == 'aoa':
-            out, state = aoa_core(self.W, xt, fc_e, att_e, p_att, state, masks, self.heads)
+            sd = None
+            if self.drop is not None and t is not None:       # per-step masks: 'xt', 'ctx', 'p', 'out' are stacked over the steps
+                xt = xt * self.drop['xt'][t]
+                sd = {'ctx': self.drop['ctx'][t], 'p': self.drop['p'][t], 'out': self.drop['out'][t]}
+            out, state = aoa_core(self.W, xt, fc_e, att_e, p_att, state, masks, self.heads, sd)
         elif self.name == 'updown':
             od = None
             if self.drop is not None and t is not None:
