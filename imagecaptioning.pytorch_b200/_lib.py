@@ -47,6 +47,11 @@ class ScstOpts(Structure):
 BASELINE_GREEDY, BASELINE_LEAVE_ONE_OUT = 0, 1
 
 
+class AoaScstOpts(Structure):
+    _fields_ = [('sample_n', c_int), ('temperature', c_float), ('seed', c_ulonglong), ('upstream', c_float), ('baseline', c_int),
+                ('drop_prob_lm', c_float), ('drop_attn', c_float), ('drop_aoa', c_float), ('drop_sublayer', c_float), ('ctx_drop', c_int)]
+
+
 class XeOpts(Structure):
     _fields_ = [('seq_per_img', c_int), ('steps', c_int), ('seed', c_ulonglong), ('drop_prob', c_float), ('label_smoothing', c_float),
                 ('upstream', c_float)]
@@ -144,6 +149,8 @@ SIGNATURES = {
     'capb200_aoa_beam_record_logprobs': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'capb200_aoa_decode_sample': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(SampleOpts), c_void_p, c_long, c_void_p, c_void_p, c_void_p,
                                           c_void_p]),
+    'capb200_aoa_scst_step': (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(AoaScstOpts), c_void_p, c_void_p, c_void_p, c_int, POINTER(AoaWeights),
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'capb200_aoa_launch_count': (c_long, [c_void_p]),
     'capb200_updown_scst_step': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(ScstOpts), c_void_p, c_void_p, c_void_p, c_int,
                                          POINTER(UpdownGrads), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

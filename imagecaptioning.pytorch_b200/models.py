@@ -649,6 +649,8 @@ class B200AoAModel(B200CaptionModel):
             raise NotImplementedError('out_res is outside the configs/aoa.yml configuration')
         self.num_layers = 2
         self.num_heads = opt.num_heads
+        self.dropout_aoa = getattr(opt, 'dropout_aoa', 0.3)          # AoAModel.py:117
+        self.ctx_drop = getattr(opt, 'ctx_drop', 0)                  # AoAModel.py:134
         H, E, V1 = self.rnn_size, self.input_encoding_size, self.vocab_size + 1
         self.embed = nn.Sequential(nn.Embedding(V1, E), nn.ReLU(), nn.Dropout(self.drop_prob_lm))
         self.att_embed = nn.Sequential(nn.Linear(self.att_feat_size, H), nn.ReLU(), nn.Dropout(self.drop_prob_lm))
@@ -676,6 +678,70 @@ class B200AoAModel(B200CaptionModel):
     def _tensors(self):
         return list(self.parameters())
 
+    def _slots(self):
+        """(field path in capb200_aoa_weights / capb200_aoa_grads, parameter) pairs."""
+        out = [(('embed',), self.embed[0].weight), (('att_embed_w',), self.att_embed[0].weight), (('att_embed_b',), self.att_embed[0].bias)]
+        for i, layer in enumerate(self.refiner.layers):
+            for name, lin in zip(('q', 'k', 'v'), layer.self_attn.linears):
+                out += [(('refiner', i, name + '_w'), lin.weight), (('refiner', i, name + '_b'), lin.bias)]
+            out += [(('refiner', i, 'aoa_w'), layer.self_attn.aoa_layer[0].weight), (('refiner', i, 'aoa_b'), layer.self_attn.aoa_layer[0].bias),
+                    (('refiner', i, 'ln_a'), layer.sublayer[0].norm.a_2), (('refiner', i, 'ln_b'), layer.sublayer[0].norm.b_2)]
+        c = self.core
+        out += [(('refiner_norm_a',), self.refiner.norm.a_2), (('refiner_norm_b',), self.refiner.norm.b_2),
+                (('ctx2att_w',), self.ctx2att.weight), (('ctx2att_b',), self.ctx2att.bias),
+                (('att_lstm_w_ih',), c.att_lstm.weight_ih), (('att_lstm_w_hh',), c.att_lstm.weight_hh),
+                (('att_lstm_b_ih',), c.att_lstm.bias_ih), (('att_lstm_b_hh',), c.att_lstm.bias_hh),
+                (('attn_norm_a',), c.attention.norm.a_2), (('attn_norm_b',), c.attention.norm.b_2),
+                (('attn_q_w',), c.attention.linears[0].weight), (('attn_q_b',), c.attention.linears[0].bias),
+                (('att2ctx_w',), c.att2ctx[0].weight), (('att2ctx_b',), c.att2ctx[0].bias),
+                (('logit_w',), self.logit.weight), (('logit_b',), self.logit.bias)]
+        return out
+
+    def _fill_table(self, table, tensor_of):
+        """Writes data pointers into an AoaWeights-layout ctypes struct; ``tensor_of`` maps id(parameter) -> tensor to point at."""
+        for path, prm in self._slots():
+            ptr = tensor_of[id(prm)].data_ptr()
+            if len(path) == 1:
+                setattr(table, path[0], ptr)
+            else:
+                setattr(table.refiner[path[1]], path[2], ptr)
+
+    def scst_step(self, fc_feats, att_feats, gts, table, sample_n, temperature=1.0, drop_prob=None, seed=None, upstream=1.0, baseline='greedy',
+                  drop_attn=0.1, drop_aoa=None, drop_sublayer=0.1, ctx_drop=None):
+        """One self-critical step of AoANet on the device (capb200_aoa_scst_step): eval-mode greedy baseline (or the leave-one-out baseline of
+        'new_self_critical'), train-mode samples with every dropout site of AoAModel.py active, CIDEr-D reward, RewardCriterion, BPTT through
+        the decoder and the six refiner layers.  ``fc_feats`` is unused (mean_feats=1).  Returns the dict of B200UpDownModel.scst_step."""
+        from .rewards import pack_references
+        lib = self._ensure_engine(att_feats.device)
+        att = self._f32(att_feats)
+        dev = att.device
+        B, R = att.shape[0], att.shape[1]
+        N, T, V1 = B * sample_n, self.seq_length, self.vocab_size + 1
+        refs, offsets, L = pack_references(gts, dev)
+        params = [prm for _, prm in self._slots()]
+        grads = {id(prm): torch.empty_like(prm) for prm in params}
+        g = _lib.AoaWeights()
+        self._fill_table(g, grads)
+        if baseline not in ('greedy', 'leave_one_out'):
+            raise ValueError("baseline must be 'greedy' or 'leave_one_out'")
+        loo = baseline == 'leave_one_out'
+        sample_seq = torch.zeros(N, T, dtype=torch.long, device=dev)
+        greedy_seq = torch.zeros(B, T, dtype=torch.long, device=dev)
+        logprobs = torch.zeros(N, T, V1, dtype=torch.float32, device=dev)
+        reward = torch.empty(N, T, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        p = self.drop_prob_lm if drop_prob is None else drop_prob
+        so = _lib.AoaScstOpts(sample_n, float(temperature), seed, float(upstream), _lib.BASELINE_LEAVE_ONE_OUT if loo else _lib.BASELINE_GREEDY, float(p),
+                              float(drop_attn), float(self.dropout_aoa if drop_aoa is None else drop_aoa), float(drop_sublayer),
+                              int(self.ctx_drop if ctx_drop is None else ctx_drop))
+        _lib.check(lib.capb200_aoa_scst_step(self._engine, _lib.ptr(att), B, R, ctypes.byref(so), table._h, _lib.ptr(refs), _lib.ptr(offsets), L,
+                                             ctypes.byref(g), _lib.ptr(sample_seq), None if loo else _lib.ptr(greedy_seq), _lib.ptr(logprobs),
+                                             _lib.ptr(reward), _lib.ptr(loss), _lib.current_stream()), 'aoa_scst_step')
+        return {'loss': loss[0], 'reward': reward, 'sample_seq': sample_seq, 'greedy_seq': None if loo else greedy_seq, 'sample_logprobs': logprobs,
+                'grads': {prm: grads[id(prm)] for prm in params}, 'seed': seed}
+
     def _ensure_engine(self, device):
         if device.type != 'cuda':
             raise RuntimeError('capb200: the decode engine runs on CUDA devices only (no CPU fallback); got %s' % device)
@@ -696,26 +762,8 @@ class B200AoAModel(B200CaptionModel):
             for t in tensors:
                 if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
                     raise RuntimeError('capb200: parameters must be contiguous float32 tensors on %s' % device)
-            P = lambda t: t.data_ptr()
             w = _lib.AoaWeights()
-            w.embed = P(self.embed[0].weight)
-            w.att_embed_w, w.att_embed_b = P(self.att_embed[0].weight), P(self.att_embed[0].bias)
-            for i, layer in enumerate(self.refiner.layers):
-                r = w.refiner[i]
-                for name, lin in zip(('q', 'k', 'v'), layer.self_attn.linears):
-                    setattr(r, name + '_w', P(lin.weight))
-                    setattr(r, name + '_b', P(lin.bias))
-                r.aoa_w, r.aoa_b = P(layer.self_attn.aoa_layer[0].weight), P(layer.self_attn.aoa_layer[0].bias)
-                r.ln_a, r.ln_b = P(layer.sublayer[0].norm.a_2), P(layer.sublayer[0].norm.b_2)
-            w.refiner_norm_a, w.refiner_norm_b = P(self.refiner.norm.a_2), P(self.refiner.norm.b_2)
-            w.ctx2att_w, w.ctx2att_b = P(self.ctx2att.weight), P(self.ctx2att.bias)
-            c = self.core
-            w.att_lstm_w_ih, w.att_lstm_w_hh = P(c.att_lstm.weight_ih), P(c.att_lstm.weight_hh)
-            w.att_lstm_b_ih, w.att_lstm_b_hh = P(c.att_lstm.bias_ih), P(c.att_lstm.bias_hh)
-            w.attn_norm_a, w.attn_norm_b = P(c.attention.norm.a_2), P(c.attention.norm.b_2)
-            w.attn_q_w, w.attn_q_b = P(c.attention.linears[0].weight), P(c.attention.linears[0].bias)
-            w.att2ctx_w, w.att2ctx_b = P(c.att2ctx[0].weight), P(c.att2ctx[0].bias)
-            w.logit_w, w.logit_b = P(self.logit.weight), P(self.logit.bias)
+            self._fill_table(w, {id(t): t for t in tensors})
             _lib.check(lib.capb200_aoa_bind_weights(self._engine, ctypes.byref(w), _lib.current_stream()), 'aoa_bind_weights')
             self._bound_versions = versions
         return lib

@@ -317,7 +317,7 @@ typedef struct {
     float drop_sublayer;       /* refiner SublayerConnection (0.1, AoAModel.py:119) */
     int ctx_drop;              /* opt.ctx_drop */
 } capb200_aoa_scst_opts;
-/* Gradient buffers: the same field layout as capb200_aoa_weights (shapes of the parameters, fp32, device); every one is OVERWRITTEN. */
+/* Gradient buffers, laid out field by field like the weights struct above: parameter shapes, fp32, device; every one is OVERWRITTEN. */
 typedef struct {
     float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *aoa_w, *aoa_b, *ln_a, *ln_b;
 } capb200_aoa_refiner_layer_grads;

@@ -262,3 +262,73 @@ def test_loss_wrapper_xe_and_structure_branches():
     out['loss'].backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
     b200.rewards.reset_scorer()
+
+
+AOA_CFG = dict(V=40, E=32, H=64, A=0, F_fc=32, F_att=40, T=7)
+
+
+def _aoa_masks(b200, seed, B, R, N, T, E, H, heads, p_lm, p_at, p_aoa, p_sub):
+    """Every dropout mask of one AoANet training step, regenerated from the engine's Philox streams (capb200.h lists the sites)."""
+    L, lib = b200._lib, b200._lib.load()
+
+    def mask(site, step, shape, p):
+        n = int(np.prod(shape))
+        m = torch.empty(n, device='cuda')
+        L.check(lib.capb200_dropout_mask(L.ptr(m), n, seed, site, step, p, L.current_stream()), 'dropout_mask')
+        return m.cpu().reshape(shape)
+    d = {'att': mask(1, 0, (B, R, H), p_lm)}
+    for l in range(6):
+        d['ref_p%d' % l] = mask(10 + l, 0, (B, heads, R, R), p_at)
+        d['ref_aoa%d' % l] = mask(20 + l, 0, (B, R, 2 * H), p_aoa)
+        d['ref_sub%d' % l] = mask(30 + l, 0, (B, R, H), p_sub)
+    d['xt'] = torch.stack([mask(2, t, (N, E), p_lm) for t in range(T)])
+    d['out'] = torch.stack([mask(3, t, (N, H), p_lm) for t in range(T)])
+    d['ctx'] = torch.stack([mask(4, t, (N, H), p_lm) for t in range(T)])
+    d['p'] = torch.stack([mask(5, t, (N, heads, 1, R), p_at) for t in range(T)])
+    return d
+
+
+@pytest.mark.parametrize('mode,dropout,baseline', [('tc_f16x3', False, 'greedy'), ('tc_f16x3', True, 'greedy'), ('simt_fp32', True, 'leave_one_out')])
+def test_aoa_scst_step_gradients(mode, dropout, baseline):
+    """AoANet SCST step (BASELINE configs[3]): loss, reward and every parameter gradient against torch autograd through the oracle, with
+    the engine's samples and all of its dropout masks (att_embed, refiner attention / AoA / sublayer, word, ctx, decoder attention,
+    output) replayed in the oracle."""
+    import imagecaptioning.pytorch_b200 as b200
+    from oracle import ciderd_oracle as cdo
+    heads = 4
+    model, fam = build_pair('aoa', seed=21, logit_scale=5.0, mode=mode, heads=heads, **AOA_CFG)
+    W = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    B, R, n, T = 3, 9, 3, AOA_CFG['T']
+    E, H = AOA_CFG['E'], AOA_CFG['H']
+    fc, att = co.make_inputs(B, R, AOA_CFG['F_fc'], AOA_CFG['F_att'], seed=4)
+    gts = cdo.make_refs(B, AOA_CFG['V'], seed=2)
+    df, ref_len = cdo.build_document_frequency(cdo.make_refs(200, AOA_CFG['V'], seed=4))
+    table = b200.rewards.CiderDTable(df, ref_len)
+    p_lm, p_at, p_aoa, p_sub = (0.5, 0.1, 0.3, 0.1) if dropout else (0.0, 0.0, 0.0, 0.0)
+    model.train()
+    res = model.scst_step(fc.cuda(), att.cuda(), gts, table, n, drop_prob=p_lm, seed=4321, baseline=baseline, drop_attn=p_at, drop_aoa=p_aoa,
+                          drop_sublayer=p_sub, ctx_drop=1)
+    torch.cuda.synchronize()
+    seq = res['sample_seq'].cpu()
+    Wg = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    fam_g = co.Family('aoa', Wg, T, heads=heads)
+    if dropout:
+        fam_g.drop = _aoa_masks(b200, 4321, B, R, B * n, T, E, H, heads, p_lm, p_at, p_aoa, p_sub)
+    _, lp = co.sample(fam_g, fc, att, sample_method='sample', sample_n=n, forced_tokens=seq)
+    if baseline == 'greedy':
+        og, _ = co.sample(fam, fc, att)
+        assert torch.equal(res['greedy_seq'].cpu(), og)
+        reward, _ = cdo.self_critical_reward(og.numpy(), gts, seq.numpy(), df, ref_len)
+        reward = torch.from_numpy(reward).float()
+        loss = co.reward_criterion(lp, seq, reward)
+    else:
+        scores = torch.from_numpy(cdo.get_scores(gts, seq.numpy(), df, ref_len))
+        loss = co.new_self_critical_loss(lp, seq, scores, n)
+        sc = scores.float().view(B, n)
+        reward = (sc - (sc.sum(1, keepdim=True) - sc) / (n - 1)).reshape(-1, 1).expand(-1, T)
+    loss.backward()
+    assert float((res['sample_logprobs'].cpu() - lp.detach()).abs().max()) < LOGP_TOL
+    assert float((res['reward'].cpu() - reward).abs().max()) < LOGP_TOL
+    assert abs(float(res['loss']) - float(loss)) < LOGP_TOL
+    assert float(reward.abs().max()) > 1e-3                       # the comparison is not vacuous (the leave-one-out loss itself is ~0)
+    _check_grads(model, res['grads'], {k: v.grad for k, v in Wg.items()})
