@@ -43,11 +43,11 @@ def parse():
     p.add_argument('--mode', default='tc_f16x3', choices=['tc_f16x3', 'tc_f16x1', 'simt_fp32'])
     p.add_argument('--cpu-batch', type=int, default=32, help='images per CPU-baseline step (bounded sample)')
     p.add_argument('--no-cpu-baseline', action='store_true')
-    p.add_argument('--workload', default='updown_beam', choices=['updown_beam', 'transformer_beam', 'aoa_beam', 'updown_scst'],
+    p.add_argument('--workload', default='updown_beam', choices=['updown_beam', 'transformer_beam', 'aoa_beam', 'updown_scst', 'aoa_scst'],
                    help='updown_beam = BASELINE.json configs[1] (the headline); transformer_beam = configs[2] (use --batch 64); aoa_beam = AoANet decode')
     args = p.parse_args()
     if args.batch is None:
-        args.batch = 10 if args.workload == 'updown_scst' else 256
+        args.batch = 10 if args.workload in ('updown_scst', 'aoa_scst') else 256
     return args
 
 
@@ -133,7 +133,12 @@ def bench_scst(args, rank, world, local_rank, dev):
     from oracle import caption_oracle as co
     from oracle import ciderd_oracle as cdo
     B, n, T = args.batch, 5, CFG['T']
-    model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode=args.mode, device=dev, **CFG)
+    aoa = args.workload == 'aoa_scst'
+    if aoa:       # configs/aoa.yml: E = H = 1024, 8 heads, 6 refiner layers, ctx_drop, dropout_aoa 0.3 (BASELINE configs[3])
+        model, _ = build_pair('aoa', seed=1234, logit_scale=6.0, mode=args.mode, device=dev, heads=8, **dict(CFG, E=1024, H=1024, A=0))
+    else:
+        model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode=args.mode, device=dev, **CFG)
+    fam_name = 'AoANet' if aoa else 'UpDown'
     model.train()
     df, ref_len = cdo.build_document_frequency(cdo.make_refs(1000, CFG['V'], seed=4))        # synthetic DF table (format of prepro_ngrams.py)
     b200.rewards.reset_scorer()
@@ -184,10 +189,10 @@ def bench_scst(args, rank, world, local_rank, dev):
     ms = float(ms.item())
     if rank == 0:
         value = world * B * n * args.steps / (ms / 1e3)
-        line = {'metric': 'SCST samples/sec (UpDown, train_sample_n=5, CIDEr-D reward, greedy baseline, BPTT, Adam)', 'value': value, 'unit': 'samples/s',
+        line = {'metric': 'SCST samples/sec (%s, train_sample_n=5, CIDEr-D reward, greedy baseline, BPTT, Adam)' % fam_name, 'value': value, 'unit': 'samples/s',
                 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': 'UpDown SCST step, per-GPU batch=%d images x %d samples, 36x2048 feats, seq_len=20, V=9487' % (B, n),
+                'config': {'workload': '%s SCST step, per-GPU batch=%d images x %d samples, 36x2048 feats, seq_len=20, V=9487' % (fam_name, B, n),
                            'images_per_sec': value / n, 'parallelism': 'dp%d, one gradient all-reduce of %d bytes per step' % (world, grad_bytes[0]),
                            'numeric_mode': 'greedy baseline %s (tcgen05); sampling + backward on 3xTF32 split-K tensor-core GEMMs over the fp32 weights, weight-gradient GEMMs fp32' % args.mode},
                 'clocks': sampler.summary(),
@@ -203,7 +208,8 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    names = {'updown_beam': 'UpDown', 'transformer_beam': 'Transformer 6+6/512/2048/8', 'aoa_beam': 'AoANet 1024', 'updown_scst': 'UpDown SCST'}
+    names = {'updown_beam': 'UpDown', 'transformer_beam': 'Transformer 6+6/512/2048/8', 'aoa_beam': 'AoANet 1024', 'updown_scst': 'UpDown SCST',
+             'aoa_scst': 'AoANet SCST'}
     workload = '%s beam=%d, %dx2048 bottom-up feats, batch=%d per GPU, seq_len=20, V=9487' % (names[args.workload], args.beam, R, args.batch)
 
     if args.impl == 'reference':
@@ -233,7 +239,7 @@ def main():
     from helpers import build_pair
     from oracle import caption_oracle as co
     dev = torch.device('cuda', local_rank)
-    if args.workload == 'updown_scst':
+    if args.workload in ('updown_scst', 'aoa_scst'):
         return bench_scst(args, rank, world, local_rank, dev)
     if args.workload == 'updown_beam':
         model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode=args.mode, device=dev, **CFG)
@@ -347,13 +353,19 @@ def main():
     # The dominant kernel is the persistent tcgen05 GEMM (gemm_tc_kernel): every dense contraction of the step is a launch of it.
     # achieved = algorithmic FLOPs (2*M*N*K of the contraction actually executed) of ALL its launches / their summed CUDA-event time;
     # the largest single call site (language-LSTM gates, M=B*beam, N=4000, K=3000) is listed beside it.
+    # DRAM bytes per launch of the largest call site (lang_lstm gates) from the committed `ncu --set full` capture, when present
+    traffic, traffic_src = None, None
+    tpath = os.path.join(REPO, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get('dram_bytes_per_launch'), tj.get('source')
     all_ms = sum(v[0] for v in prof.values())
     all_fl = sum(v[1] for v in prof.values())
     all_calls = sum(v[2] for v in prof.values())
     achieved = all_fl / (all_ms / 1e3) / 1e12 if all_ms > 0 else 0.0
     big_ms, big_fl, big_calls = prof['lang_lstm']
-    roofline = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel<BN,%d,CX,CY> (persistent tcgen05 GEMM, all call sites of the step)' % (3 if args.mode == 'tc_f16x3' else 1),
-                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+    roofline = {'bound': 'tensor', 'kernel': 'gemm_tc_pair_kernel<144,%d> / gemm_tc_kernel<64,..> (persistent tcgen05 GEMM, cta_group::2 pairs for the large call sites; all call sites of the step)' % (3 if args.mode == 'tc_f16x3' else 1),
+                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                 'mma_passes': 3 if args.mode == 'tc_f16x3' else 1, 'launches_timed': all_calls, 'avg_launch_ms': all_ms / max(all_calls, 1),
                 'share_of_step': (all_ms / 3) / (ms / args.steps),
                 'largest_call_site': {'name': 'lang_lstm gates M=%d N=4000 K=3000 (fused LSTM cell epilogue)' % (B * args.beam),

@@ -6,8 +6,11 @@
 //                             torch.max / Categorical(logits).sample()     CaptionModel.py:372,405
 //                             finished-row masking                         AttModel.py:340-347
 // One CTA per row; the row lives in shared memory between the passes so HBM sees one read and one write.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 namespace capb200 {
 
@@ -327,6 +330,91 @@ __global__ void __launch_bounds__(VT) vocab_stats_reg_kernel(const VocabStepArgs
     }
 }
 
+// Streaming variant: persistent CTAs walk the rows; each row (V1 * 4 bytes, 16-byte aligned) arrives in shared memory through one
+// cp.async.bulk while the previous row is being reduced (double buffer), so the L2/HBM read of row i+1 overlaps the arithmetic of
+// row i and no thread ever waits on its own global loads.  Same arithmetic and tie order as vocab_stats_kernel.
+__global__ void __launch_bounds__(VT) vocab_stats_stream_kernel(const VocabStepArgs a) {
+    extern __shared__ __align__(16) unsigned char vs_smem[];
+    __shared__ float s_red[VT / 32];
+    __shared__ int s_idx[VT / 32];
+    __shared__ __align__(8) uint64_t bar[2];
+    const int V1 = a.V1, n4 = V1 >> 2;
+    const uint32_t row_bytes = (uint32_t)V1 * 4u;
+    float* buf0 = reinterpret_cast<float*>(vs_smem);
+    float* buf1 = buf0 + V1;
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(&bar[0], 1);
+        ptx::mbar_init(&bar[1], 1);
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    int r = blockIdx.x;
+    if (threadIdx.x == 0 && r < a.rows) {
+        ptx::mbar_arrive_expect_tx(&bar[0], row_bytes);
+        ptx::bulk_load_1d(buf0, a.logits + (long)r * a.ld, row_bytes, &bar[0]);
+    }
+    for (int it = 0; r < a.rows; r += gridDim.x, ++it) {
+        const int cur = it & 1;
+        const float* g = cur ? buf1 : buf0;
+        const int rn = r + gridDim.x;
+        if (threadIdx.x == 0 && rn < a.rows) {          // the other buffer was released by the __syncthreads that ended iteration it-1
+            ptx::mbar_arrive_expect_tx(&bar[cur ^ 1], row_bytes);
+            ptx::bulk_load_1d(cur ? buf0 : buf1, a.logits + (long)rn * a.ld, row_bytes, &bar[cur ^ 1]);
+        }
+        ptx::mbar_wait(&bar[cur], (it >> 1) & 1);
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        float mx = -INFINITY;
+        for (int v = threadIdx.x; v < n4; v += VT) { const float4 x = g4[v]; mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w))); }
+        mx = block_max(mx, s_red);
+        float t0v = -INFINITY, t1v = -INFINITY;
+        int t0i = 0x7fffffff, t1i = 0x7fffffff;
+        float sum = 0.f;
+        auto visit = [&](float x, int v) {
+            sum += __expf(x - mx);
+            if (x > t1v) {
+                if (x > t0v) { t1v = t0v; t1i = t0i; t0v = x; t0i = v; }
+                else { t1v = x; t1i = v; }
+            }
+        };
+        for (int v = threadIdx.x; v < n4; v += VT) {
+            const float4 x = g4[v];
+            visit(x.x, 4 * v); visit(x.y, 4 * v + 1); visit(x.z, 4 * v + 2); visit(x.w, 4 * v + 3);
+        }
+        sum = block_sum(sum, s_red);
+        const float lsum = logf(sum);
+        const float m2 = (mx - mx) - lsum, l2 = lsum;
+        if (threadIdx.x == 0) a.stats[r] = make_float2(mx, lsum);
+        int popped = 0;
+        for (int k = 0; k < a.topk; ++k) {
+            float ov;
+            int oi;
+            block_argmax(t0v, t0i, s_red, s_idx, ov, oi);
+            if (t0i == oi && oi != 0x7fffffff) {
+                const float lastv = t0v;
+                const int lasti = t0i;
+                t0v = t1v; t0i = t1i;
+                t1v = -INFINITY; t1i = 0x7fffffff;
+                if (++popped >= 2 && t0i == 0x7fffffff) {
+                    auto consider = [&](float x, int v) {
+                        const bool after = (x < lastv) || (x == lastv && v > lasti);
+                        if (after && (x > t0v || (x == t0v && v < t0i))) { t0v = x; t0i = v; }
+                    };
+                    for (int v = threadIdx.x; v < n4; v += VT) {
+                        const float4 x = g4[v];
+                        consider(x.x, 4 * v); consider(x.y, 4 * v + 1); consider(x.z, 4 * v + 2); consider(x.w, 4 * v + 3);
+                    }
+                }
+            }
+            if (threadIdx.x == 0) {
+                const float lp = (ov - mx) - lsum;
+                a.top_val[(long)r * a.topk + k] = a.twice ? (lp - m2) - l2 : lp;
+                a.top_idx[(long)r * a.topk + k] = oi;
+            }
+        }
+        __syncthreads();                                // everyone is done with buffer `cur` before it is refilled
+    }
+}
+
 __global__ void mask_rows_kernel(ActView x, int R, int cols, const float* __restrict__ mask, long ld_mask) {
     const int row = blockIdx.x;              // row = img * R + r
     const int img = row / R, r = row % R;
@@ -345,9 +433,21 @@ int vocab_step_launch(const VocabStepArgs& a, cudaStream_t stream) {
     if (a.stats != nullptr) {
         CAPB_REQUIRE(a.select == 0 && a.topk > 0, "stats mode is the beam-search epilogue");
         const bool vec = ((a.V1 & 3) == 0) && ((a.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.logits) & 15) == 0);
-        if (vec && a.V1 <= VT * 4 * 10) vocab_stats_reg_kernel<10><<<a.rows, VT, 0, stream>>>(a);
-        else if (vec && a.V1 <= VT * 4 * 16) vocab_stats_reg_kernel<16><<<a.rows, VT, 0, stream>>>(a);
-        else vocab_stats_kernel<<<a.rows, VT, 0, stream>>>(a);
+        const size_t stream_smem = sizeof(float) * 2 * (size_t)a.V1;
+        static const char* variant = getenv("CAPB200_VOCAB_STATS");      // "reg" / "plain": the older variants, kept for A/B timing
+        if (vec && stream_smem <= 100 * 1024 && variant == nullptr) {
+            static bool configured = false;
+            if (!configured) {
+                CAPB_CHECK_CUDA(cudaFuncSetAttribute(vocab_stats_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(100 * 1024)));
+                configured = true;
+            }
+            const int grid = a.rows < 2 * 148 ? a.rows : 2 * 148;       // two resident CTAs per SM, each double-buffering one row
+            vocab_stats_stream_kernel<<<grid, VT, stream_smem, stream>>>(a);
+        } else if (vec && a.V1 <= VT * 4 * 10 && (variant == nullptr || variant[0] == 'r')) {
+            vocab_stats_reg_kernel<10><<<a.rows, VT, 0, stream>>>(a);
+        } else {
+            vocab_stats_kernel<<<a.rows, VT, 0, stream>>>(a);
+        }
         CAPB_CHECK_CUDA(cudaGetLastError());
         return 0;
     }

@@ -8,7 +8,11 @@ from helpers import build_pair
 from oracle import caption_oracle as co, ciderd_oracle as cdo
 import bench
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 10
-model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode='tc_f16x3', **bench.CFG)
+FAM = sys.argv[2] if len(sys.argv) > 2 else 'updown'
+if FAM == 'aoa':
+    model, _ = build_pair('aoa', seed=1234, logit_scale=6.0, mode='tc_f16x3', heads=8, **dict(bench.CFG, E=1024, H=1024, A=0))
+else:
+    model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode='tc_f16x3', **bench.CFG)
 model.train()
 df, ref_len = cdo.build_document_frequency(cdo.make_refs(500, 9487, seed=4))
 table = b200.rewards.CiderDTable(df, ref_len)
@@ -25,6 +29,6 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
 rows = [(e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0]
 tot = sum(r[2] for r in rows)
-print('SCST step (B=%d, n=5): total kernel time %.2f ms per step' % (B, tot / 2e3))
+print('%s SCST step (B=%d, n=5): total kernel time %.2f ms per step' % (FAM, B, tot / 2e3))
 for k, n, t in sorted(rows, key=lambda r: -r[2])[:22]:
     print('%-100s n=%5d  %9.1f us/step  %7.1f us/launch  %5.1f%%' % (k[:100], n // 2, t / 2, t / n, 100 * t / tot))
