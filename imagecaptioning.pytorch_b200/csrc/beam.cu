@@ -53,6 +53,9 @@ __global__ void __launch_bounds__(32) beam_step_kernel(BeamState s, int t, int l
     const int* hist_old = (t & 1) ? s.hist_b : s.hist_a;
     int* hist_new = (t & 1) ? s.hist_a : s.hist_b;
 
+    // ---- phase 1: the b winners in order (registers and shuffles only); lane j keeps winner j
+    float my_v = -INFINITY;
+    int my_f = 0;
     for (int j = 0; j < b; ++j) {
         // arg-max over the remaining candidates; ties -> lowest flat index
         float bv = -INFINITY;
@@ -72,46 +75,51 @@ __global__ void __launch_bounds__(32) beam_step_kernel(BeamState s, int t, int l
 #pragma unroll
             for (int u = 0; u < 8; ++u) if (u == bu) { cv[u] = -INFINITY; cf[u] = 0x7fffffff; }
         }
-        const int parent = wf / s.V1;
-        const int word = wf % s.V1;
-        float new_sum = wv;
-        const long dst = ((long)img * b + j) * T;
-        const long src = ((long)img * b + parent) * T;
-        for (int q = lane; q < t; q += 32) {
-            seq_new[dst + q] = seq_old[src + q];
-            hist_new[dst + q] = hist_old[src + q];
+        if (lane == j) { my_v = wv; my_f = wf; }
+    }
+    // ---- phase 2: all history copies in parallel (the serial per-winner version was a chain of dependent global round trips)
+    __shared__ int sh_parent[MAXB], sh_word[MAXB], sh_slot[MAXB];
+    const bool has = lane < b;
+    const int parent = has ? my_f / s.V1 : 0;
+    const int word = has ? my_f % s.V1 : 0;
+    const bool ended = has && ((word == 0) || (t == T - 1));
+    const unsigned em = __ballot_sync(0xffffffffu, ended);
+    const int cnt0 = s.done_cnt[img];
+    const int slot = cnt0 + __popc(em & ((1u << lane) - 1u));          // records are appended in winner order
+    if (has) { sh_parent[lane] = parent; sh_word[lane] = word; sh_slot[lane] = ended ? slot : -1; }
+    __syncwarp();
+    for (int idx = lane; idx < b * t; idx += 32) {
+        const int j = idx / t, q = idx - j * t;
+        const long dst = ((long)img * b + j) * T, src = ((long)img * b + sh_parent[j]) * T;
+        seq_new[dst + q] = seq_old[src + q];
+        hist_new[dst + q] = hist_old[src + q];
+    }
+    if (em != 0u) {
+        for (int idx = lane; idx < b * (t + 1); idx += 32) {
+            const int j = idx / (t + 1), q = idx - j * (t + 1);
+            if (sh_slot[j] < 0) continue;
+            const long rec = ((long)img * b * T + sh_slot[j]) * T, src = ((long)img * b + sh_parent[j]) * T;
+            s.done_seq[rec + q] = (q < t) ? seq_old[src + q] : sh_word[j];
+            s.done_hist[rec + q] = (q < t) ? hist_old[src + q] : img * live + sh_parent[j];
         }
-        if (lane == 0) {
-            seq_new[dst + t] = word;
-            hist_new[dst + t] = img * live + parent;
-        }
-        __syncwarp();
-        const bool ended = (word == 0) || (t == T - 1);
+    }
+    if (has) {
+        const long dst = ((long)img * b + lane) * T;
+        seq_new[dst + t] = word;
+        hist_new[dst + t] = img * live + parent;
+        float new_sum = my_v;
         if (ended) {
-            int slot = 0;
-            if (lane == 0) {
-                slot = s.done_cnt[img];
-                s.done_cnt[img] = slot + 1;
-                const long rec = (long)img * b * T + slot;
-                s.done_len[rec] = t + 1;
-                s.done_raw[rec] = new_sum;
-                done_p[rec] = apply_penalty(penalty_kind, penalty_alpha, t + 1, (double)new_sum);
-            }
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            const long rec = ((long)img * b * T + slot) * T;
-            for (int q = lane; q <= t; q += 32) {
-                s.done_seq[rec + q] = seq_new[dst + q];
-                s.done_hist[rec + q] = hist_new[dst + q];
-            }
+            const long rec = (long)img * b * T + slot;
+            s.done_len[rec] = t + 1;
+            s.done_raw[rec] = new_sum;
+            done_p[rec] = apply_penalty(penalty_kind, penalty_alpha, t + 1, (double)new_sum);
             new_sum -= 1000.0f;
         }
-        if (lane == 0) {
-            s.sums[(long)img * b + j] = new_sum;
-            s.tokens[(long)img * b + j] = word;
-            s.src_row[(long)img * b + j] = img * live + parent;
-        }
-        __syncwarp();
+        s.sums[(long)img * b + lane] = new_sum;
+        s.tokens[(long)img * b + lane] = word;
+        s.src_row[(long)img * b + lane] = img * live + parent;
     }
+    if (lane == 0 && em != 0u) s.done_cnt[img] = cnt0 + __popc(em);
 }
 
 // one warp per image: stable selection of the `keep` best records by penalised score (CaptionModel.py:207)

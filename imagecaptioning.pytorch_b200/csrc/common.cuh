@@ -94,6 +94,21 @@ __device__ __forceinline__ float fast_tanh(float x) {
     const float e = __expf(2.0f * x);
     return 1.0f - __fdividef(2.0f, 1.0f + e);
 }
+// Four tanh values with four ex2 and ONE reciprocal: 1/y_i is recovered from 1/(y0*y1*y2*y3) by multiplications, which moves work
+// from the 16-lane SFU to the FMA pipe (the attention score kernel is SFU-bound).  Arguments are clamped at 10 (tanh(10) rounds to 1
+// in fp32), so every y = 1 + e^(2x) stays below 4.9e8 and the product of four below 5.5e34.
+__device__ __forceinline__ void fast_tanh4(const float (&x)[4], float (&t)[4]) {
+    float y[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = 1.0f + __expf(fminf(2.0f * x[i], 20.0f));
+    const float p01 = y[0] * y[1], p23 = y[2] * y[3];
+    const float r = __fdividef(1.0f, p01 * p23);
+    const float r01 = r * p23, r23 = r * p01;
+    t[0] = fmaf(-2.0f, r01 * y[1], 1.0f);
+    t[1] = fmaf(-2.0f, r01 * y[0], 1.0f);
+    t[2] = fmaf(-2.0f, r23 * y[3], 1.0f);
+    t[3] = fmaf(-2.0f, r23 * y[2], 1.0f);
+}
 struct GemmProblem {
     int M = 0, N = 0, nseg = 0;
     GemmSeg seg[kMaxSeg];

@@ -472,6 +472,7 @@ void capb200_engine_destroy(capb200_engine* e) {
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     cudaFree(e->wblock);
     cudaFree(e->ws);
+    if (e->d.loop_exec) cudaGraphExecDestroy(e->d.loop_exec);
     cudaFree(e->d.slab);
     cudaFree(e->tape);
     delete e;
@@ -631,7 +632,7 @@ int capb200_decode_beam(capb200_engine* e, const float* fc, const float* att, co
         return core_step(e, nrows, live, tokens, src_row, logits, ld, B, R, mask, st);
     };
     return beam_decode_driver(e->d, V1, T, B, beam, keep, opts->penalty_kind, opts->penalty_alpha, seq, seq_logprobs, done_seq, done_len, done_p,
-                              done_raw, core, &e->launches, st);
+                              done_raw, core, &e->launches, st, e->profiling ? 0ull : loop_graph_key(e->ws, e->wblock, mask, R, (int)e->cfg.family));
 }
 
 int capb200_beam_record_logprobs(capb200_engine* e, int image, int rank, float* dst, void* stream) {

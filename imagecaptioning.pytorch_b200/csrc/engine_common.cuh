@@ -1,5 +1,8 @@
 // Helpers shared by the engines (UpDown/NewFC in engine.cu, Transformer in tfm_engine.cu, AoA in aoa_engine.cu).
 #pragma once
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -94,6 +97,12 @@ struct DecodeBuffers {
     size_t slab_bytes = 0;
     long slab_step_stride = 0;
     int last_B = 0, last_beam = 0;
+    // CUDA graph of the T-step beam loop (every launch of it is static for a given shape / workspace): captured the second time a
+    // configuration is seen, replayed afterwards; the launch gaps of ~180 serial kernels are ~5 % of a decode
+    cudaGraphExec_t loop_exec = nullptr;
+    unsigned long long loop_key[8] = {0, 0, 0, 0, 0, 0, 0, 0}, seen_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long loop_launches = 0;
+    bool graph_broken = false;
 
     void carve(Arena& a, int B, int rows, int beam, int T) {
         tokens = a.take<int>(rows);
@@ -139,10 +148,19 @@ int load_token_column_launch(const long long* src, long ld, int col, int n, int*
 inline const int* beam_ancestors(const BeamState& s, int t) { return ((t - 1) & 1) ? s.hist_a : s.hist_b; }
 
 // AttModel._sample_beam + CaptionModel.beam_search (see engine.cu header for the reference lines)
+// Key of everything outside the driver that the captured beam-loop launches depend on (0 disables graph capture)
+inline unsigned long long loop_graph_key(const void* ws, const void* wblock, const void* mask, int R, int family) {
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { h ^= v; h *= 1099511628211ull; };
+    mix(reinterpret_cast<uintptr_t>(ws)); mix(reinterpret_cast<uintptr_t>(wblock)); mix(reinterpret_cast<uintptr_t>(mask));
+    mix((unsigned long long)R); mix((unsigned long long)family + 17);
+    return h | 1ull;
+}
+
 template <class CoreFn>
 int beam_decode_driver(DecodeBuffers& d, int V1, int T, int B, int beam, int keep, int penalty_kind, float penalty_alpha, long long* seq,
                        float* seq_logprobs, long long* done_seq, int* done_len, float* done_p, float* done_raw, CoreFn core, long* launches,
-                       cudaStream_t st) {
+                       cudaStream_t st, unsigned long long graph_key = 0) {
     const int rows = B * beam;
     const size_t slab_need = (size_t)T * rows * V1 * sizeof(float);
     if (slab_need > d.slab_bytes) {
@@ -157,22 +175,59 @@ int beam_decode_driver(DecodeBuffers& d, int V1, int T, int B, int beam, int kee
     d.last_beam = beam;
     BeamState s = d.bs;
     s.B = B; s.beam = beam; s.T = T; s.V1 = V1;
-    CAPB_CHECK_CUDA(cudaMemsetAsync(s.sums, 0, sizeof(float) * B * beam, st));
-    CAPB_CHECK_CUDA(cudaMemsetAsync(s.done_cnt, 0, sizeof(int) * B, st));
-    CAPB_CHECK_CUDA(cudaMemsetAsync(d.tokens, 0, sizeof(int) * rows, st));      // <bos> = 0
-    for (int t = 0; t < T; ++t) {
-        const int live = (t == 0) ? 1 : beam;
-        const int nrows = B * live;
-        float* logits = d.slab + (long)t * d.slab_step_stride;
-        if (core(nrows, live, d.tokens, t == 0 ? d.neg1 : d.src_row, t, logits, (long)V1)) return 1;
-        VocabStepArgs va;
-        va.rows = nrows; va.V1 = V1; va.logits = logits; va.ld = V1;
-        va.twice = (t > 0) ? 1 : 0;      // init_logprobs went through one log_softmax only (AttModel.py:239, CaptionModel.py:204)
-        va.topk = beam; va.top_val = d.top_val; va.top_idx = d.top_idx;
-        va.stats = d.slab_stats + (long)t * rows;
-        if (vocab_step_launch(va, st)) return 1;
-        if (beam_step_launch(s, t, live, d.top_val, d.top_idx, penalty_kind, penalty_alpha, st)) return 1;
-        *launches += 2;
+    auto run_loop = [&]() -> int {
+        CAPB_CHECK_CUDA(cudaMemsetAsync(s.sums, 0, sizeof(float) * B * beam, st));
+        CAPB_CHECK_CUDA(cudaMemsetAsync(s.done_cnt, 0, sizeof(int) * B, st));
+        CAPB_CHECK_CUDA(cudaMemsetAsync(d.tokens, 0, sizeof(int) * rows, st));      // <bos> = 0
+        for (int t = 0; t < T; ++t) {
+            const int live = (t == 0) ? 1 : beam;
+            const int nrows = B * live;
+            float* logits = d.slab + (long)t * d.slab_step_stride;
+            if (core(nrows, live, d.tokens, t == 0 ? d.neg1 : d.src_row, t, logits, (long)V1)) return 1;
+            VocabStepArgs va;
+            va.rows = nrows; va.V1 = V1; va.logits = logits; va.ld = V1;
+            va.twice = (t > 0) ? 1 : 0;      // init_logprobs went through one log_softmax only (AttModel.py:239, CaptionModel.py:204)
+            va.topk = beam; va.top_val = d.top_val; va.top_idx = d.top_idx;
+            va.stats = d.slab_stats + (long)t * rows;
+            if (vocab_step_launch(va, st)) return 1;
+            if (beam_step_launch(s, t, live, d.top_val, d.top_idx, penalty_kind, penalty_alpha, st)) return 1;
+            *launches += 2;
+        }
+        return 0;
+    };
+    // graph key: everything the captured launches depend on (caller's key covers workspace / weight / mask pointers and R)
+    unsigned long long key[8] = {graph_key, (unsigned long long)B, (unsigned long long)beam, (unsigned long long)T, (unsigned long long)V1,
+                                 (unsigned long long)penalty_kind, 0ull, (unsigned long long)reinterpret_cast<uintptr_t>(d.slab)};
+    memcpy(&key[6], &penalty_alpha, sizeof(float));
+    static const bool graphs_off = getenv("CAPB200_NO_GRAPH") != nullptr;
+    const bool try_graph = graph_key != 0 && !graphs_off && !d.graph_broken;
+    if (try_graph && d.loop_exec != nullptr && memcmp(key, d.loop_key, sizeof(key)) == 0) {
+        CAPB_CHECK_CUDA(cudaGraphLaunch(d.loop_exec, st));
+        *launches += d.loop_launches;
+    } else if (try_graph && memcmp(key, d.seen_key, sizeof(key)) == 0) {
+        // second decode with this configuration: every lazy initialisation has happened, capture the loop and replay it from now on
+        if (d.loop_exec != nullptr) { cudaGraphExecDestroy(d.loop_exec); d.loop_exec = nullptr; }
+        const long l0 = *launches;
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        const int rc = ok ? run_loop() : 1;
+        if (ok) ok = cudaStreamEndCapture(st, &graph) == cudaSuccess && graph != nullptr && rc == 0;
+        if (ok) ok = cudaGraphInstantiate(&d.loop_exec, graph, 0) == cudaSuccess;
+        if (graph != nullptr) cudaGraphDestroy(graph);
+        if (!ok) {
+            (void)cudaGetLastError();
+            d.loop_exec = nullptr;
+            d.graph_broken = true;          // fall back to eager launches for good
+            *launches = l0;
+            if (run_loop()) return 1;
+        } else {
+            d.loop_launches = *launches - l0;
+            memcpy(d.loop_key, key, sizeof(key));
+            CAPB_CHECK_CUDA(cudaGraphLaunch(d.loop_exec, st));
+        }
+    } else {
+        memcpy(d.seen_key, key, sizeof(key));
+        if (run_loop()) return 1;
     }
     // all finished beams of every image, best first
     if (beam_finalize_launch(s, beam, d.rec_seq, d.rec_len, d.rec_p, d.rec_raw, d.rec_hist, st)) return 1;

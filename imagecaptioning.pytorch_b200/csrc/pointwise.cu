@@ -45,6 +45,30 @@ __global__ void state_gather_embed_kernel(int rows, const int* __restrict__ toke
         store_act(xt, r, c, v);
     }
     const int src = src_row ? src_row[r] : r;
+    const bool vec = (H & 3) == 0 && (sc0.ld_src & 3) == 0 && (sc0.dst.ld & 3) == 0 && (nstate < 2 || ((sc1.ld_src & 3) == 0 && (sc1.dst.ld & 3) == 0));
+    if (vec) {
+        // 128-bit copies with the loads of both states issued before any store (the scalar loop was latency-bound: r01f capture)
+        for (int c4 = threadIdx.x; c4 < (H >> 2); c4 += blockDim.x) {
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (src >= 0) {
+                v0 = *reinterpret_cast<const float4*>(sc0.src + (long)src * sc0.ld_src + 4 * c4);
+                if (nstate > 1) v1 = *reinterpret_cast<const float4*>(sc1.src + (long)src * sc1.ld_src + 4 * c4);
+            }
+            for (int s = 0; s < nstate; ++s) {
+                const ActView& o = (s == 0) ? sc0.dst : sc1.dst;
+                const float4 v = (s == 0) ? v0 : v1;
+                *reinterpret_cast<float4*>(o.f + (long)r * o.ld + 4 * c4) = v;
+                if (o.hi != nullptr) {
+                    __align__(8) __half h[4];
+                    __align__(8) __half l[4];
+                    split_f32(v.x, h[0], l[0]); split_f32(v.y, h[1], l[1]); split_f32(v.z, h[2], l[2]); split_f32(v.w, h[3], l[3]);
+                    *reinterpret_cast<uint2*>(o.hi + (long)r * o.ld + 4 * c4) = *reinterpret_cast<const uint2*>(h);
+                    *reinterpret_cast<uint2*>(o.lo + (long)r * o.ld + 4 * c4) = *reinterpret_cast<const uint2*>(l);
+                }
+            }
+        }
+        return;
+    }
     for (int s = 0; s < nstate; ++s) {
         const StateCopy& sc = (s == 0) ? sc0 : sc1;
         for (int c = threadIdx.x; c < H; c += blockDim.x) {
@@ -110,28 +134,34 @@ template <int NA>
 __global__ void __launch_bounds__(ATT_SW * 32) att_score_kernel(int rpi, int R, int A, const float* __restrict__ att_h, long ld_ah,
                                                                 const float* __restrict__ p_att, long ld_pa, const float* __restrict__ alpha_w,
                                                                 const float* __restrict__ alpha_b_ptr, float* __restrict__ score) {
-    extern __shared__ float s_ah[];               // [ATT_JB][NA * 32] (zero padded beyond A)
+    // tanh(x) = 1 - 2 / (1 + 2^(x * 2 log2 e)): p_att and att_h are pre-multiplied by 2 log2(e) when loaded, the sum over a of
+    // w[a] * tanh = sum(w) - 2 * sum_a w[a] / (1 + 2^z), and four reciprocals share one MUFU.RCP (1/y_i from 1/(y0 y1 y2 y3)).
+    // The r01f capture showed the earlier version issue-bound at 23 instructions per tanh; this form needs about 10.
+    extern __shared__ float s_ah[];               // [ATT_JB][NA * 32] pre-scaled (zero padded beyond A)
     constexpr int AP = NA * 32;
+    constexpr float kC = 2.885390081777927f;      // 2 * log2(e)
     const int img = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * ATT_SW + warp;
     const float alpha_b = __ldg(alpha_b_ptr);
-    float pv[NA], wv[NA];
+    float pv[NA], wv[NA];                          // element k = 4 * g + u  <->  hidden index a = 128 * g + 4 * lane + u
     const bool live = r < R;
     const float* pr = p_att + ((long)img * R + (live ? r : 0)) * ld_pa;
+    float wsum = 0.f;
 #pragma unroll
     for (int k = 0; k < NA; ++k) {
-        const int a = lane + 32 * k;
+        const int a = (NA % 4 == 0) ? 128 * (k >> 2) + 4 * lane + (k & 3) : lane + 32 * k;
         const bool ok = live && (a < A);
-        pv[k] = ok ? __ldg(pr + a) : 0.f;
+        pv[k] = ok ? __ldg(pr + a) * kC : 0.f;
         wv[k] = ok ? __ldg(alpha_w + a) : 0.f;      // zero weight kills padded lanes
+        wsum += wv[k];
     }
     for (int j0 = 0; j0 < rpi; j0 += ATT_JB) {
         const int nj = min(ATT_JB, rpi - j0);
         __syncthreads();
         for (int i = threadIdx.x; i < nj * AP; i += ATT_SW * 32) {
             const int j = i / AP, a = i - j * AP;
-            s_ah[i] = (a < A) ? att_h[((long)img * rpi + j0 + j) * ld_ah + a] : 0.f;
+            s_ah[i] = (a < A) ? att_h[((long)img * rpi + j0 + j) * ld_ah + a] * kC : 0.f;
         }
         __syncthreads();
         if (live) {
@@ -140,8 +170,37 @@ __global__ void __launch_bounds__(ATT_SW * 32) att_score_kernel(int rpi, int R, 
             for (int j = 0; j < ATT_JB; ++j) {
                 part[j] = 0.f;
                 if (j < nj) {
+                    if (NA % 4 == 0) {
+                        float acc = 0.f;
 #pragma unroll
-                    for (int k = 0; k < NA; ++k) part[j] = fmaf(wv[k], fast_tanh(pv[k] + s_ah[j * AP + lane + 32 * k]), part[j]);
+                        for (int g = 0; g < NA / 4; ++g) {
+                            const float4 ah = *reinterpret_cast<const float4*>(&s_ah[j * AP + 128 * g + 4 * lane]);
+                            const float z[4] = {pv[4 * g] + ah.x, pv[4 * g + 1] + ah.y, pv[4 * g + 2] + ah.z, pv[4 * g + 3] + ah.w};
+                            float y[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                float e;
+                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(z[u], 28.0f)));      // 2^28: tanh rounds to 1 long before
+                                y[u] = 1.0f + e;
+                            }
+                            const float p01 = y[0] * y[1], p23 = y[2] * y[3];
+                            float rr;
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rr) : "f"(p01 * p23));
+                            const float r01 = rr * p23, r23 = rr * p01;
+                            acc = fmaf(wv[4 * g], r01 * y[1], acc);
+                            acc = fmaf(wv[4 * g + 1], r01 * y[0], acc);
+                            acc = fmaf(wv[4 * g + 2], r23 * y[3], acc);
+                            acc = fmaf(wv[4 * g + 3], r23 * y[2], acc);
+                        }
+                        part[j] = fmaf(-2.0f, acc, wsum);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < NA; ++k) {
+                            float e;
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(pv[k] + s_ah[j * AP + lane + 32 * k], 28.0f)));
+                            part[j] = fmaf(wv[k], 1.0f - __fdividef(2.0f, 1.0f + e), part[j]);
+                        }
+                    }
                 }
             }
 #pragma unroll

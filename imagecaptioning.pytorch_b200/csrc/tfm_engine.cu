@@ -265,6 +265,7 @@ void capb200_tfm_destroy(capb200_tfm_engine* e) {
     destroy_plans(e);
     cudaFree(e->wblock);
     cudaFree(e->ws);
+    if (e->d.loop_exec) cudaGraphExecDestroy(e->d.loop_exec);
     cudaFree(e->d.slab);
     delete e;
 }
@@ -329,7 +330,7 @@ int capb200_tfm_decode_beam(capb200_tfm_engine* e, const float* att, const float
         return core_step(e, nrows, live, tokens, anc, nullptr, 0, t, logits, ld, R, mask, st);
     };
     return beam_decode_driver(e->d, e->V1, e->T, B, beam, keep, opts->penalty_kind, opts->penalty_alpha, seq, seq_logprobs, done_seq, done_len, done_p,
-                              done_raw, core, &e->launches, st);
+                              done_raw, core, &e->launches, st, loop_graph_key(e->ws, e->wblock, mask, R, 7));
 }
 
 int capb200_tfm_beam_record_logprobs(capb200_tfm_engine* e, int image, int rank, float* dst, void* stream) {

@@ -261,6 +261,81 @@ __global__ void __launch_bounds__(VT) vocab_stats_kernel(const VocabStepArgs a) 
     }
 }
 
+// Single-pass variant of vocab_stats_kernel (one CTA per row, loads straight from global memory, 8 CTAs per SM): per-thread online
+// softmax (running max, partial sum rescaled when the max grows) and one max-of-four test in front of the top-2 bookkeeping, so the
+// row is read once and the common path is ~5 instructions per element.
+__global__ void __launch_bounds__(VT) vocab_stats_online_kernel(const VocabStepArgs a) {
+    __shared__ float s_red[VT / 32];
+    __shared__ int s_idx[VT / 32];
+    const int r = blockIdx.x;
+    const int n4 = a.V1 >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(a.logits + (long)r * a.ld);
+    constexpr float kL2E = 1.4426950408889634f;
+    float t0v = -INFINITY, t1v = -INFINITY;
+    int t0i = 0x7fffffff, t1i = 0x7fffffff;
+    float m = -INFINITY, mL = -INFINITY, part = 0.f;
+    for (int v = threadIdx.x; v < n4; v += VT) {
+        const float4 x = g4[v];
+        const float m4 = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+        if (m4 > m) {
+            float sc;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sc) : "f"((m - m4) * kL2E));
+            part = (m == -INFINITY) ? 0.f : part * sc;
+            m = m4;
+            mL = m4 * kL2E;
+        }
+        float e0, e1, e2, e3;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(x.x, kL2E, -mL)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(x.y, kL2E, -mL)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(x.z, kL2E, -mL)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fmaf(x.w, kL2E, -mL)));
+        part += (e0 + e1) + (e2 + e3);
+        if (m4 > t1v) {                             // strict: earlier (lower) indices win ties
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (xs[u] > t1v) {
+                    if (xs[u] > t0v) { t1v = t0v; t1i = t0i; t0v = xs[u]; t0i = 4 * v + u; }
+                    else { t1v = xs[u]; t1i = 4 * v + u; }
+                }
+            }
+        }
+    }
+    const float mx = block_max(m, s_red);
+    float sum = (m == -INFINITY) ? 0.f : part * __expf(m - mx);
+    sum = block_sum(sum, s_red);
+    const float lsum = logf(sum);
+    const float m2 = (mx - mx) - lsum, l2 = lsum;
+    if (threadIdx.x == 0) a.stats[r] = make_float2(mx, lsum);
+    int popped = 0;
+    for (int k = 0; k < a.topk; ++k) {
+        float ov;
+        int oi;
+        block_argmax(t0v, t0i, s_red, s_idx, ov, oi);
+        if (t0i == oi && oi != 0x7fffffff) {
+            const float lastv = t0v;
+            const int lasti = t0i;
+            t0v = t1v; t0i = t1i;
+            t1v = -INFINITY; t1i = 0x7fffffff;
+            if (++popped >= 2 && t0i == 0x7fffffff) {
+                auto consider = [&](float x, int v) {
+                    const bool after = (x < lastv) || (x == lastv && v > lasti);
+                    if (after && (x > t0v || (x == t0v && v < t0i))) { t0v = x; t0i = v; }
+                };
+                for (int v = threadIdx.x; v < n4; v += VT) {
+                    const float4 x = g4[v];
+                    consider(x.x, 4 * v); consider(x.y, 4 * v + 1); consider(x.z, 4 * v + 2); consider(x.w, 4 * v + 3);
+                }
+            }
+        }
+        if (threadIdx.x == 0) {
+            const float lp = (ov - mx) - lsum;
+            a.top_val[(long)r * a.topk + k] = a.twice ? (lp - m2) - l2 : lp;
+            a.top_idx[(long)r * a.topk + k] = oi;
+        }
+    }
+}
+
 // Register-resident variant for rows of up to VT * 4 * NV elements (16-byte aligned): the row is read from L2/HBM exactly once, with
 // all of a thread's loads in flight together; max, sum-exp, per-thread top-2 and the rare rescan then work on registers.  Same
 // arithmetic (and the same tie order) as vocab_stats_kernel.
@@ -363,23 +438,42 @@ __global__ void __launch_bounds__(VT) vocab_stats_stream_kernel(const VocabStepA
         }
         ptx::mbar_wait(&bar[cur], (it >> 1) & 1);
         const float4* g4 = reinterpret_cast<const float4*>(g);
-        float mx = -INFINITY;
-        for (int v = threadIdx.x; v < n4; v += VT) { const float4 x = g4[v]; mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w))); }
-        mx = block_max(mx, s_red);
+        // One pass, online softmax per thread: running max m with the partial sum rescaled when it grows (rare after the first few
+        // elements), one max-of-four test guards the top-2 bookkeeping.  The r01f capture showed the two-pass form issue-bound at
+        // ~40 thread-instructions per element; this form needs about half.
+        constexpr float kL2E = 1.4426950408889634f;
         float t0v = -INFINITY, t1v = -INFINITY;
         int t0i = 0x7fffffff, t1i = 0x7fffffff;
-        float sum = 0.f;
-        auto visit = [&](float x, int v) {
-            sum += __expf(x - mx);
-            if (x > t1v) {
-                if (x > t0v) { t1v = t0v; t1i = t0i; t0v = x; t0i = v; }
-                else { t1v = x; t1i = v; }
-            }
-        };
+        float m = -INFINITY, mL = -INFINITY, part = 0.f;
         for (int v = threadIdx.x; v < n4; v += VT) {
             const float4 x = g4[v];
-            visit(x.x, 4 * v); visit(x.y, 4 * v + 1); visit(x.z, 4 * v + 2); visit(x.w, 4 * v + 3);
+            const float m4 = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+            if (m4 > m) {
+                float sc;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sc) : "f"((m - m4) * kL2E));
+                part = (m == -INFINITY) ? 0.f : part * sc;
+                m = m4;
+                mL = m4 * kL2E;
+            }
+            float e0, e1, e2, e3;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(x.x, kL2E, -mL)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(x.y, kL2E, -mL)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(x.z, kL2E, -mL)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fmaf(x.w, kL2E, -mL)));
+            part += (e0 + e1) + (e2 + e3);
+            if (m4 > t1v) {                             // strict: earlier (lower) indices win ties
+                const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (xs[u] > t1v) {
+                        if (xs[u] > t0v) { t1v = t0v; t1i = t0i; t0v = xs[u]; t0i = 4 * v + u; }
+                        else { t1v = xs[u]; t1i = 4 * v + u; }
+                    }
+                }
+            }
         }
+        const float mx = block_max(m, s_red);
+        float sum = (m == -INFINITY) ? 0.f : part * __expf(m - mx);
         sum = block_sum(sum, s_red);
         const float lsum = logf(sum);
         const float m2 = (mx - mx) - lsum, l2 = lsum;
@@ -434,8 +528,12 @@ int vocab_step_launch(const VocabStepArgs& a, cudaStream_t stream) {
         CAPB_REQUIRE(a.select == 0 && a.topk > 0, "stats mode is the beam-search epilogue");
         const bool vec = ((a.V1 & 3) == 0) && ((a.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.logits) & 15) == 0);
         const size_t stream_smem = sizeof(float) * 2 * (size_t)a.V1;
-        static const char* variant = getenv("CAPB200_VOCAB_STATS");      // "reg" / "plain": the older variants, kept for A/B timing
-        if (vec && stream_smem <= 100 * 1024 && variant == nullptr) {
+        // default: single-pass online kernel; "stream" / "reg" / "plain" select the other variants for A/B timing (profiles/)
+        static const char* variant = getenv("CAPB200_VOCAB_STATS");
+        const char vsel = variant ? variant[0] : 'o';
+        if (vec && vsel == 'o') {
+            vocab_stats_online_kernel<<<a.rows, VT, 0, stream>>>(a);
+        } else if (vec && vsel == 's' && stream_smem <= 100 * 1024) {
             static bool configured = false;
             if (!configured) {
                 CAPB_CHECK_CUDA(cudaFuncSetAttribute(vocab_stats_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(100 * 1024)));
@@ -443,7 +541,7 @@ int vocab_step_launch(const VocabStepArgs& a, cudaStream_t stream) {
             }
             const int grid = a.rows < 2 * 148 ? a.rows : 2 * 148;       // two resident CTAs per SM, each double-buffering one row
             vocab_stats_stream_kernel<<<grid, VT, stream_smem, stream>>>(a);
-        } else if (vec && a.V1 <= VT * 4 * 10 && (variant == nullptr || variant[0] == 'r')) {
+        } else if (vec && vsel == 'r' && a.V1 <= VT * 4 * 10) {
             vocab_stats_reg_kernel<10><<<a.rows, VT, 0, stream>>>(a);
         } else {
             vocab_stats_kernel<<<a.rows, VT, 0, stream>>>(a);

@@ -175,3 +175,28 @@ def test_scst_forward_values(golden_dir):
     assert abs(float(out['loss']) - float(oloss)) < LOGP_TOL
     assert abs(float(out['reward']) - float(reward[:, 0].mean())) < LOGP_TOL
     b200.rewards.reset_scorer()
+
+
+@pytest.mark.parametrize('family,seed,scale', [('updown', 11, 20.0), ('transformer', 17, 10.0), ('aoa', 6, 20.0)])
+def test_beam_loop_graph_replay(family, seed, scale):
+    """The T-step beam loop is captured into a CUDA graph the second time a configuration is decoded and replayed afterwards: the eager
+    call, the capture call and two replays (the last one on different features of the same shape) must all agree with the oracle."""
+    cfg = dict(V=60, E=32, H=32, A=16, F_fc=48, F_att=48, T=8)
+    if family == 'transformer':
+        cfg = dict(cfg, E=32, H=64, A=2)
+    model, fam = build_pair(family, seed=seed, logit_scale=scale, mode='tc_f16x3', heads=4, **cfg)
+    B, R, b = 5, 7, 3
+    opt = {'beam_size': b, 'sample_n': 1}
+    outs = []
+    with torch.no_grad():
+        for call in range(4):
+            fc, att = co.make_inputs(B, R, cfg['F_fc'], cfg['F_att'], seed=seed + (100 if call == 3 else 0))
+            seq, lp = model(fc.cuda(), att.cuda(), None, opt=opt, mode='sample')
+            outs.append((fc, att, seq.cpu().clone(), lp.cpu().clone()))
+    for call in (1, 2):
+        assert torch.equal(outs[call][2], outs[0][2]) and torch.equal(outs[call][3], outs[0][3])
+    for fc, att, seq, lp in (outs[0], outs[3]):
+        margins = []
+        oseq, olp, odone = co.sample_beam(fam, fc, att, beam_size=b, record_margin=margins)
+        check_decode(fam, fc, att, seq, lp, oseq, olp, margins)
+    assert not torch.equal(outs[3][2], outs[0][2])

@@ -8,7 +8,13 @@ from oracle import caption_oracle as co
 import bench
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 beam = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode='tc_f16x3', **bench.CFG)
+FAM = sys.argv[3] if len(sys.argv) > 3 else 'updown'
+if FAM == 'transformer':
+    model, _ = build_pair('transformer', seed=1234, logit_scale=3.0, mode='tc_f16x3', heads=8, **dict(bench.CFG, E=512, H=2048, A=6))
+elif FAM == 'aoa':
+    model, _ = build_pair('aoa', seed=1234, logit_scale=6.0, mode='tc_f16x3', heads=8, **dict(bench.CFG, E=1024, H=1024, A=0))
+else:
+    model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode='tc_f16x3', **bench.CFG)
 fc, att = co.make_inputs(B, 36, 2048, 2048, seed=1)
 fc, att = fc.cuda(), att.cuda()
 opt = {'beam_size': beam, 'sample_n': 1}
@@ -23,6 +29,6 @@ with torch.no_grad():
         torch.cuda.synchronize()
 rows = [(e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0]
 tot = sum(r[2] for r in rows)
-print('warm per-kernel table over 3 decodes (B=%d beam=%d): total kernel time %.2f ms per decode' % (B, beam, tot / 3e3))
+print('%s: warm per-kernel table over 3 decodes (B=%d beam=%d): total kernel time %.2f ms per decode' % (FAM, B, beam, tot / 3e3))
 for k, n, t in sorted(rows, key=lambda r: -r[2])[:25]:
     print('%-90s n=%5d  %8.1f us/decode  %6.1f us/launch  %5.1f%%' % (k[:90], n // 3, t / 3, t / n, 100 * t / tot))

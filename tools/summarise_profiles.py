@@ -47,7 +47,7 @@ if os.path.exists(rep):
     rd = list(csv.reader(io.StringIO(raw)))
     hdr, units = rd[0], rd[1]
     with open('profiles/%s_gemm_full.md' % tag, 'w') as f:
-        f.write('# %s: `ncu --set full --clock-control none -k regex:gemm_tc_kernel -s 10 -c 6` (GEMM launches of consecutive decode steps: h2att 64-wide, att_lstm / logit <144,3,1,2>, lang_lstm <144,3,2,2>)\n\n' % tag)
+        f.write('# %s: `ncu --set full --clock-control none -k regex:gemm_tc -s 12 -c 5` (GEMM launches of consecutive decode steps: gemm_tc_pair_kernel<144,3> = att_lstm / lang_lstm / logit, gemm_tc_kernel<64,3,1,1> = h2att)\n\n' % tag)
         cols = [i for i, h in enumerate(hdr) if h in want or h in ('Kernel Name', 'Grid Size', 'Block Size')]
         for r in rd[2:]:
             f.write('## launch id %s\n\n' % r[0])
@@ -55,3 +55,24 @@ if os.path.exists(rep):
                 f.write('- %s = %s %s\n' % (hdr[i], r[i], units[i]))
             f.write('\n')
     print(open('profiles/%s_gemm_full.md' % tag).read()[:6000])
+
+# ---- non-GEMM kernels of the step (one launch each)
+rep = 'gpurun_out/%s_small.ncu-rep' % tag
+if os.path.exists(rep):
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_sector_hit_rate.pct', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+            'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+            'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__waves_per_multiprocessor',
+            'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+            'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio']
+    rd = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rd[0], rd[1]
+    with open('profiles/%s_small_kernels.md' % tag, 'w') as f:
+        f.write('# %s: `ncu --set full --clock-control none` of the non-GEMM kernels of one decode step (B=256, beam 5)\n\n' % tag)
+        cols = [i for i, h in enumerate(hdr) if h in want or h in ('Kernel Name', 'Grid Size', 'Block Size')]
+        for r in rd[2:]:
+            f.write('## %s\n\n' % r[hdr.index('Kernel Name')].split('(')[0])
+            for i in cols:
+                if hdr[i] != 'Kernel Name':
+                    f.write('- %s = %s %s\n' % (hdr[i], r[i], units[i]))
+            f.write('\n')
