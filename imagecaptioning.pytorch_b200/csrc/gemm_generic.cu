@@ -4,6 +4,7 @@
 //   TB = 0: B stored [K, N] (pitch ldb)      TB = 1: B stored [N, K]   (nn.Linear forward: x * W^T)
 // The training shapes are skinny (M = B * sample_n = 50..60 rows, or K = T * rows ~ 1000 for the weight gradients), i.e. weight-
 // streaming bound; 64x64x16 tiles with 4x4 register blocks keep enough CTAs in flight for those shapes.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -321,6 +322,131 @@ __global__ void __launch_bounds__(256) gemm_skinny_tf32_kernel(const SkinnyParam
             }
 }
 
+// Second generation of the 3xTF32 skinny kernel: the first one kept only one 16-deep K-slice per thread in flight (two float4 loads),
+// which caps a weight-streaming GEMM at ~1 TB/s.  Here raw fp32 tiles are staged with cp.async through a 4-stage ring of 32-deep
+// K-slices (18 KB per stage, 3 CTAs per SM => ~160 KB of loads in flight per SM); the TF32 hi/lo split happens on the fragments.
+constexpr int S2_BK = 32, S2_STAGES = 4;
+constexpr int S2_ALD = S2_BK + 4;        // A / B^T rows: 36 floats (16-byte multiples, conflict-free fragment loads)
+constexpr int S2_BLD = GT + 8;           // B rows [k][n]: 72 floats
+constexpr int S2_STAGE_FLOATS = GT * S2_ALD + GT * S2_ALD;     // A tile + B tile (TB: 64 x 36; else 32 x 72 = the same 2304 floats)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+template <int TB>
+__global__ void __launch_bounds__(256) gemm_skinny_tf32_v2_kernel(const SkinnyParams p) {
+    extern __shared__ __align__(16) float s2[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;
+    const int n0 = blockIdx.x * GT, m0 = blockIdx.z * GT;
+    const int per = (p.ksteps_total + p.ksplit - 1) / p.ksplit;
+    const int ks0 = blockIdx.y * per, ks1 = min(p.ksteps_total, ks0 + per);
+    const int nsteps = ks1 > ks0 ? ks1 - ks0 : 0;
+    float acc[2][2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+
+    // issue the loads of K-step `ks` (global index) into ring slot `slot`
+    auto issue = [&](int ks, int slot) {
+        int seg = 0, first = 0;
+        while (seg < p.nseg - 1 && ks >= first + (p.K[seg] + S2_BK - 1) / S2_BK) { first += (p.K[seg] + S2_BK - 1) / S2_BK; ++seg; }
+        const int k0 = (ks - first) * S2_BK, K = p.K[seg];
+        float* As = s2 + slot * S2_STAGE_FLOATS;
+        float* Bs = As + GT * S2_ALD;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int idx = tid + 256 * u;                  // 512 float4 per operand tile
+            {   // A tile: 64 rows x 8 float4
+                const int row = idx >> 3, kq = (idx & 7) * 4;
+                const bool ok = (m0 + row < p.M) && (k0 + kq < K);
+                const float* src = ok ? p.A[seg] + (long)(m0 + row) * p.lda[seg] + k0 + kq : p.A[seg];
+                cp_async16(As + row * S2_ALD + kq, src, ok ? 16 : 0);
+            }
+            if (TB) {   // W stored [N, K]: 64 rows (n) x 8 float4 (k)
+                const int row = idx >> 3, kq = (idx & 7) * 4;
+                const bool ok = (n0 + row < p.N) && (k0 + kq < K);
+                const float* src = ok ? p.B[seg] + (long)(n0 + row) * p.ldb[seg] + k0 + kq : p.B[seg];
+                cp_async16(Bs + row * S2_ALD + kq, src, ok ? 16 : 0);
+            } else {    // W stored [K, N]: 32 rows (k) x 16 float4 (n)
+                const int row = idx >> 4, nq = (idx & 15) * 4;
+                const bool ok = (k0 + row < K) && (n0 + nq < p.N);
+                const float* src = ok ? p.B[seg] + (long)(k0 + row) * p.ldb[seg] + n0 + nq : p.B[seg];
+                cp_async16(Bs + row * S2_BLD + nq, src, ok ? 16 : 0);
+            }
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < S2_STAGES - 1; ++s) {
+        if (s < nsteps) issue(ks0 + s, s);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int it = 0; it < nsteps; ++it) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(S2_STAGES - 2) : "memory");
+        __syncthreads();                                    // slot (it-1) % STAGES is free again, slot it % STAGES has landed
+        if (it + S2_STAGES - 1 < nsteps) issue(ks0 + it + S2_STAGES - 1, (it + S2_STAGES - 1) % S2_STAGES);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const float* As = s2 + (it % S2_STAGES) * S2_STAGE_FLOATS;
+        const float* Bs = As + GT * S2_ALD;
+#pragma unroll
+        for (int kk = 0; kk < S2_BK; kk += 8) {
+            uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = wm + i * 16 + g;
+                split_tf32(As[r * S2_ALD + kk + tig], ah[i][0], al[i][0]);
+                split_tf32(As[(r + 8) * S2_ALD + kk + tig], ah[i][1], al[i][1]);
+                split_tf32(As[r * S2_ALD + kk + tig + 4], ah[i][2], al[i][2]);
+                split_tf32(As[(r + 8) * S2_ALD + kk + tig + 4], ah[i][3], al[i][3]);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = wn + j * 8 + g;
+                if (TB) {
+                    split_tf32(Bs[c * S2_ALD + kk + tig], bh[j][0], bl[j][0]);
+                    split_tf32(Bs[c * S2_ALD + kk + tig + 4], bh[j][1], bl[j][1]);
+                } else {
+                    split_tf32(Bs[(kk + tig) * S2_BLD + c], bh[j][0], bl[j][0]);
+                    split_tf32(Bs[(kk + tig + 4) * S2_BLD + c], bh[j][1], bl[j][1]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    mma_tf32(acc[i][j], ah[i], bl[j]);
+                    mma_tf32(acc[i][j], al[i], bh[j]);
+                    mma_tf32(acc[i][j], ah[i], bh[j]);
+                }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int row = m0 + wm + i * 16 + g + (q >> 1) * 8;
+                const int col = n0 + wn + j * 8 + 2 * tig + (q & 1);
+                if (row >= p.M || col >= p.N) continue;
+                float v = acc[i][j][q];
+                if (p.ksplit == 1) {
+                    if (p.bias) v += p.bias[col];
+                    if (p.row_bias) v += p.row_bias[(long)(row / p.rpg) * p.ld_rb + col];
+                    float* c = p.out + (long)row * p.ldo + col;
+                    *c = p.accumulate ? (*c + v) : v;
+                } else {
+                    p.out[((long)blockIdx.y * p.M + row) * p.N + col] = v;
+                }
+            }
+}
+
 __global__ void skinny_reduce_kernel(int M, int N, int ksplit, const float* __restrict__ part, float* __restrict__ C, long ldc, const float* __restrict__ bias,
                                      const float* __restrict__ row_bias, long ld_rb, int rpg, int accumulate) {
     const long total = (long)M * N;
@@ -345,14 +471,23 @@ int gemm_skinny_launch(int M, int N, int nseg, const float* const* A, const long
     SkinnyParams p;
     memset(&p, 0, sizeof(p));
     p.nseg = nseg; p.M = M; p.N = N;
+    // tensor-core variants need 16-byte aligned float4 rows and one storage order for all segments
+    bool tc = (mode != 0);
+    for (int s = 0; s < nseg; ++s) {
+        tc = tc && tb[s] == tb[0] && K[s] % 4 == 0 && lda[s] % 4 == 0 && ldb[s] % 4 == 0 && (reinterpret_cast<uintptr_t>(A[s]) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(B[s]) & 15) == 0 && (tb[s] || N % 4 == 0);
+    }
+    static const bool v1_only = getenv("CAPB200_SKINNY_V1") != nullptr;
+    const bool v2 = tc && !v1_only;
+    const int bk = v2 ? S2_BK : GK;
     int ksteps = 0;
     for (int s = 0; s < nseg; ++s) {
         p.A[s] = A[s]; p.B[s] = B[s]; p.lda[s] = lda[s]; p.ldb[s] = ldb[s]; p.K[s] = K[s]; p.tb[s] = tb[s];
-        ksteps += cdiv(K[s], GK);
+        ksteps += cdiv(K[s], bk);
     }
     p.ksteps_total = ksteps;
     const int tiles = cdiv(N, GT) * cdiv(M, GT);
-    int ksplit = (2 * 148 + tiles - 1) / tiles;
+    int ksplit = ((v2 ? 3 : 2) * 148 + tiles - 1) / tiles;          // CTAs resident per SM: 3 (v2, 74 KB of shared memory each) or 2
     if (ksplit > ksteps / 4) ksplit = ksteps / 4;                  // at least 4 K-steps per CTA
     if (ksplit < 1) ksplit = 1;
     while (ksplit > 1 && (size_t)ksplit * M * N > scratch_floats) --ksplit;
@@ -360,13 +495,17 @@ int gemm_skinny_launch(int M, int N, int nseg, const float* const* A, const long
     p.bias = bias; p.row_bias = row_bias; p.ld_rb = ld_rb; p.rpg = rpg < 1 ? 1 : rpg; p.accumulate = accumulate;
     if (ksplit == 1) { p.out = C; p.ldo = ldc; } else { p.out = scratch; p.ldo = N; }
     dim3 grid(cdiv(N, GT), ksplit, cdiv(M, GT));
-    // tensor-core variant needs 16-byte aligned float4 rows and one storage order for all segments
-    bool tc = (mode != 0);
-    for (int s = 0; s < nseg; ++s) {
-        tc = tc && tb[s] == tb[0] && K[s] % 4 == 0 && lda[s] % 4 == 0 && ldb[s] % 4 == 0 && (reinterpret_cast<uintptr_t>(A[s]) & 15) == 0 &&
-             (reinterpret_cast<uintptr_t>(B[s]) & 15) == 0 && (tb[s] || N % 4 == 0);
-    }
-    if (tc && tb[0]) gemm_skinny_tf32_kernel<1><<<grid, 256, 0, st>>>(p);
+    if (v2) {
+        constexpr int smem = S2_STAGES * S2_STAGE_FLOATS * (int)sizeof(float);
+        static bool configured = false;
+        if (!configured) {
+            CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_tf32_v2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_tf32_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured = true;
+        }
+        if (tb[0]) gemm_skinny_tf32_v2_kernel<1><<<grid, 256, smem, st>>>(p);
+        else gemm_skinny_tf32_v2_kernel<0><<<grid, 256, smem, st>>>(p);
+    } else if (tc && tb[0]) gemm_skinny_tf32_kernel<1><<<grid, 256, 0, st>>>(p);
     else if (tc) gemm_skinny_tf32_kernel<0><<<grid, 256, 0, st>>>(p);
     else gemm_skinny_kernel<<<grid, 256, 0, st>>>(p);
     CAPB_CHECK_CUDA(cudaGetLastError());

@@ -745,7 +745,8 @@ GemmTcPlan* gemm_tc_plan_create(const GemmProblem& p, int passes) {
         const char* force = getenv("CAPB200_GEMM_TILING");      // "<BN>x<CX>x<CY>", e.g. "144x2x1" (debug / sweeps)
         if (force != nullptr) {
             int fb = 0, fx = 0, fy = 0;
-            if (sscanf(force, "%dx%dx%d", &fb, &fx, &fy) == 3 && (fb == 64 || fb == 128 || fb == 144) && (fx == 1 || fx == 2) && (fy == 1 || fy == 2)) {
+            if (sscanf(force, "%dx%dx%d", &fb, &fx, &fy) == 3 && (fb == 32 || fb == 64 || fb == 128 || fb == 144) && (fx == 1 || fx == 2 || (fx == 4 && fy == 1 && fb <= 64)) &&
+                (fy == 1 || fy == 2)) {
                 plan->bn = fb; plan->cx = fx; plan->cy = fy; plan->pair = 0;
             }
             if (sscanf(force, "pair%d", &fb) == 1 && (fb == 128 || fb == 144 || fb == 192 || fb == 256) && cdiv(p.M, BM) >= 2) {
@@ -804,6 +805,7 @@ int gemm_tc_plan_launch(GemmTcPlan* plan, const GemmEpilogue* epi_override, int 
     case BN_ * 100 + CX_ * 10 + CY_:                                                     \
         return plan->passes == 3 ? launch_cfg<BN_, 3, CX_, CY_>(prm, stream) : launch_cfg<BN_, 1, CX_, CY_>(prm, stream);
     switch (key) {
+        CAPB_TC_CASE(32, 1, 1) CAPB_TC_CASE(32, 2, 1) CAPB_TC_CASE(32, 4, 1) CAPB_TC_CASE(64, 4, 1)
         CAPB_TC_CASE(64, 1, 1) CAPB_TC_CASE(64, 2, 1) CAPB_TC_CASE(64, 1, 2) CAPB_TC_CASE(64, 2, 2)
         CAPB_TC_CASE(128, 1, 1) CAPB_TC_CASE(128, 2, 1) CAPB_TC_CASE(128, 1, 2) CAPB_TC_CASE(128, 2, 2)
         CAPB_TC_CASE(144, 1, 1) CAPB_TC_CASE(144, 2, 1) CAPB_TC_CASE(144, 1, 2) CAPB_TC_CASE(144, 2, 2)

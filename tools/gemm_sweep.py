@@ -11,7 +11,9 @@ sys.path.insert(0, %r)
 import imagecaptioning.pytorch_b200 as b200
 L = b200._lib; lib = L.load()
 mode = L.MODES[sys.argv[1]]
-for (M, N, K) in [(1280, 4000, 2000), (1280, 4000, 3000), (1280, 9488, 1000), (9216, 1000, 2048), (1280, 512, 1000), (256, 4000, 2000)]:
+SH = os.environ.get('SHAPES')
+shapes = [tuple(int(v) for v in t.split('x')) for t in SH.split(',')] if SH else [(1280, 4000, 2000), (1280, 4000, 3000), (1280, 9488, 1000), (9216, 1000, 2048), (1280, 512, 1000), (256, 4000, 2000)]
+for (M, N, K) in shapes:
     g = torch.Generator().manual_seed(M + N + K)
     x = torch.randn(M, K, generator=g); w = (torch.rand(N, K, generator=g) * 2 - 1) / K ** 0.5; b = torch.randn(N, generator=g)
     ref = x.double() @ w.double().t() + b.double()

@@ -8,7 +8,16 @@ from helpers import build_pair
 from oracle import caption_oracle as co, ciderd_oracle as cdo
 import bench
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 10
-model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode='tc_f16x3', **bench.CFG)
+FAM = sys.argv[2] if len(sys.argv) > 2 else 'updown'
+import torch.distributed as dist
+rank, world, lrank = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
+torch.cuda.set_device(lrank)
+if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', lrank))
+if FAM == 'aoa':
+    model, _ = build_pair('aoa', seed=1234, logit_scale=6.0, mode='tc_f16x3', heads=8, device=torch.device('cuda', lrank), **dict(bench.CFG, E=1024, H=1024, A=0))
+else:
+    model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode='tc_f16x3', device=torch.device('cuda', lrank), **bench.CFG)
 model.train()
 df, ref_len = cdo.build_document_frequency(cdo.make_refs(500, 9487, seed=4))
 b200.rewards.reset_scorer(); b200.rewards.init_scorer(b200.rewards.CiderDTable(df, ref_len))
@@ -37,7 +46,11 @@ for it in range(6):
     torch.nn.utils.clip_grad_value_(model.parameters(), 0.1); t = tick('clip_grad_value_', t)
     optim.step(); t = tick('optimizer step', t)
 for k, v in acc.items():
-    print('%-55s %8.2f ms/step' % (k, v / 4 * 1e3))
+    print('rank %d  %-55s %8.2f ms/step' % (rank, k, v / 4 * 1e3), flush=True)
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0)
 # inside the wrapper: engine rebind vs the C call
 import cProfile, pstats
 pr = cProfile.Profile()
