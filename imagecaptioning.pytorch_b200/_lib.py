@@ -52,6 +52,11 @@ class AoaScstOpts(Structure):
                 ('drop_prob_lm', c_float), ('drop_attn', c_float), ('drop_aoa', c_float), ('drop_sublayer', c_float), ('ctx_drop', c_int)]
 
 
+class AoaXeOpts(Structure):
+    _fields_ = [('seq_per_img', c_int), ('steps', c_int), ('seed', c_ulonglong), ('label_smoothing', c_float), ('upstream', c_float),
+                ('drop_prob_lm', c_float), ('drop_attn', c_float), ('drop_aoa', c_float), ('drop_sublayer', c_float), ('ctx_drop', c_int)]
+
+
 class XeOpts(Structure):
     _fields_ = [('seq_per_img', c_int), ('steps', c_int), ('seed', c_ulonglong), ('drop_prob', c_float), ('label_smoothing', c_float),
                 ('upstream', c_float)]
@@ -151,6 +156,8 @@ SIGNATURES = {
                                           c_void_p]),
     'capb200_aoa_scst_step': (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(AoaScstOpts), c_void_p, c_void_p, c_void_p, c_int, POINTER(AoaWeights),
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'capb200_aoa_xe_step': (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(AoaXeOpts), c_void_p, c_void_p, c_int, POINTER(AoaWeights), c_void_p,
+                                    c_void_p, c_void_p]),
     'capb200_aoa_launch_count': (c_long, [c_void_p]),
     'capb200_updown_scst_step': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(ScstOpts), c_void_p, c_void_p, c_void_p, c_int,
                                          POINTER(UpdownGrads), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

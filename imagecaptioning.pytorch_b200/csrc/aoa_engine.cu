@@ -470,7 +470,7 @@ struct ATape {
     int* tok;
     float *xt, *x1c, *gates, *c, *h, *qln, *qp, *probs, *att, *t2, *out, *outd;
     float *DL, *dOUTD, *D_T2, *D_QP, *DG, *dctx, *dh, *dc, *d_out, *dX2, *d_qln, *d_hatt, *dxt, *d_x1c, *tmpH, *S, *d_mean, *d_kv, *d_att_e, *d_x, *d_g, *d_t,
-        *d_catd, *d_qkv, *d_ln, *dpre, *stats, *mask_sum, *skinny, *glp;
+        *d_catd, *d_qkv, *d_ln, *dpre, *stats, *mask_sum, *skinny, *glp, *item_loss;
     size_t skinny_floats;
     double* scores;
 };
@@ -499,6 +499,7 @@ void layout_atape(ATape& tp, Arena& a, int B, int R, int N, int T, int E, int H,
     tp.skinny_floats = (size_t)4 << 20;
     tp.skinny = a.take<float>((long)tp.skinny_floats);
     tp.glp = a.take<float>((long)B * T * V1);
+    tp.item_loss = a.take<float>(TN);
     tp.scores = a.take<double>((long)N + B);
 }
 
@@ -509,26 +510,39 @@ inline int wgrad(int out_f, int in_f, int rows, const float* dY, long ld_dy, con
 
 }  // namespace
 
-extern "C" int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, int B, int R, const capb200_aoa_scst_opts* opts,
-                                     const capb200_cider_table* table, const int* refs, const int* ref_offsets, int L, const capb200_aoa_grads* grads,
-                                     long long* sample_seq, long long* greedy_seq, float* sample_logprobs, float* reward, float* loss, void* stream) {
-    if (check_ready(e)) return 1;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CAPB_REQUIRE(opts && att && table && refs && ref_offsets && grads && sample_seq && sample_logprobs && reward && loss, "null argument");
-    const bool greedy_baseline = opts->baseline == CAPB200_BASELINE_GREEDY;
-    CAPB_REQUIRE(greedy_baseline || opts->baseline == CAPB200_BASELINE_LEAVE_ONE_OUT, "unknown baseline");
-    CAPB_REQUIRE(!greedy_baseline || greedy_seq != nullptr, "the greedy baseline needs greedy_seq");
-    const int n = opts->sample_n, N = B * n, T = e->T, E = e->E, H = e->H, V1 = e->V1, F = e->F, heads = e->heads, dk = e->dk;
-    CAPB_REQUIRE(n >= 1 && n <= 16 && (greedy_baseline || n >= 2) && B >= 1 && R >= 1, "sample_n must be in 1..16 (>= 2 for the leave-one-out baseline)");
-    const float p_lm = opts->drop_prob_lm, p_at = opts->drop_attn, p_aoa = opts->drop_aoa, p_sub = opts->drop_sublayer;
-    CAPB_REQUIRE(p_lm >= 0.f && p_lm < 1.f && p_at >= 0.f && p_at < 1.f && p_aoa >= 0.f && p_aoa < 1.f && p_sub >= 0.f && p_sub < 1.f, "dropout rates must be in [0, 1)");
-    const float p_ctx = opts->ctx_drop ? p_lm : 0.f;
+namespace {
+
+struct AoaTrainArgs {
+    bool xe = false;
+    int n = 1, T = 0, Tl = 0;              // rows per image, steps evaluated, log-prob columns
+    float p_lm = 0.f, p_at = 0.f, p_aoa = 0.f, p_sub = 0.f, temperature = 1.f, upstream = 1.f, smoothing = 0.f;
+    int ctx_drop = 0;
+    unsigned long long seed = 0;
+    bool greedy_baseline = true;
+    const capb200_cider_table* table = nullptr;
+    const int* refs = nullptr; const int* ref_offsets = nullptr; int L = 0;
+    long long* sample_seq = nullptr; long long* greedy_seq = nullptr; float* reward = nullptr;
+    const long long* labels = nullptr; long ld_labels = 0; const float* masks = nullptr; long ld_masks = 0;
+    float* logprobs = nullptr; float* loss = nullptr;
+};
+
+int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const AoaTrainArgs& ta, const capb200_aoa_grads* grads, cudaStream_t st) {
+    void* stream = static_cast<void*>(st);
+    const bool greedy_baseline = !ta.xe && ta.greedy_baseline;
+    const int n = ta.n, N = B * n, T = ta.T, E = e->E, H = e->H, V1 = e->V1, F = e->F, heads = e->heads, dk = e->dk;
+    const float p_lm = ta.p_lm, p_at = ta.p_at, p_aoa = ta.p_aoa, p_sub = ta.p_sub;
+    const float p_ctx = ta.ctx_drop ? p_lm : 0.f;
     const float keep_lm = 1.0f / (1.0f - p_lm);
-    const unsigned long long seed = opts->seed;
+    const unsigned long long seed = ta.seed;
     const capb200_aoa_weights& w = e->w;
     const capb200_aoa_grads& G = *grads;
     const long BR = (long)B * R, NH = (long)N * H, TN = (long)T * N;
-    const long ld_lp = (long)T * V1;
+    const long ld_lp = (long)ta.Tl * V1;
+    float* const sample_logprobs = ta.logprobs;
+    long long* const sample_seq = ta.sample_seq;
+    long long* const greedy_seq = ta.greedy_seq;
+    float* const reward = ta.reward;
+    float* const loss = ta.loss;
 
     {
         Arena dry; ATape t0; layout_atape(t0, dry, B, R, N, T, E, H, heads, V1);
@@ -578,7 +592,8 @@ extern "C" int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, in
     CAPB_CHECK_CUDA(cudaMemsetAsync(e->d.tokens, 0, sizeof(int) * N, st));
     for (int t = 0; t < T; ++t) {
         int* tok = tp.tok + (long)t * N;
-        CAPB_CHECK_CUDA(cudaMemcpyAsync(tok, e->d.tokens, sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
+        if (ta.xe) { if (load_token_column_launch(ta.labels, ta.ld_labels, t, N, tok, st)) return 1; }
+        else CAPB_CHECK_CUDA(cudaMemcpyAsync(tok, e->d.tokens, sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
         float* xt = tp.xt + (long)t * N * E;
         float* x1c = tp.x1c + (long)t * NH;
         float* gates = tp.gates + (long)t * N * 4 * H;
@@ -618,19 +633,26 @@ extern "C" int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, in
         if (sk.lin(outd, (long)T * H, w.logit_w, H, w.logit_b, logits, ld_lp, N, V1, H, 0)) return 1;
         VocabStepArgs va;
         va.rows = N; va.V1 = V1; va.logits = logits; va.ld = ld_lp;
-        va.select = 2; va.temperature = opts->temperature; va.seed = seed; va.step = (unsigned long long)t;
-        va.unfinished = e->d.unfinished; va.first_step = (t == 0); va.tokens_out = e->d.tokens;
-        va.seq_out = sample_seq; va.ld_seq = T; va.t = t;
+        if (!ta.xe) {
+            va.select = 2; va.temperature = ta.temperature; va.seed = seed; va.step = (unsigned long long)t;
+            va.unfinished = e->d.unfinished; va.first_step = (t == 0); va.tokens_out = e->d.tokens;
+            va.seq_out = sample_seq; va.ld_seq = T; va.t = t;
+        }
         if (vocab_step_launch(va, st)) return 1;
         e->launches += 20;
     }
 
     // ---- (4) reward and loss
-    if (cider_reward_launch(table->t, sample_seq, N, greedy_baseline ? greedy_seq : nullptr, B, T, refs, ref_offsets, L, tp.scores, reward, T, T, st)) return 1;
-    if (reward_criterion_fwd_launch(sample_logprobs, ld_lp, V1, sample_seq, reward, N, T, loss, nullptr, tp.mask_sum, st)) return 1;
-
-    // ---- (5) backward through the decoder
-    if (scst_dlogits_launch(sample_logprobs, ld_lp, sample_seq, reward, tp.mask_sum, opts->upstream, N, T, V1, tp.DL, st)) return 1;
+    if (ta.xe) {
+        if (xe_loss_backward_launch(sample_logprobs, ld_lp, ta.labels, ta.ld_labels, ta.masks, ta.ld_masks, N, T, ta.Tl, V1, ta.smoothing, ta.upstream,
+                                    tp.mask_sum, tp.item_loss, tp.DL, loss, st)) return 1;
+    } else {
+        if (cider_reward_launch(ta.table->t, sample_seq, N, greedy_baseline ? greedy_seq : nullptr, B, T, ta.refs, ta.ref_offsets, ta.L, tp.scores, reward, T, T,
+                                st)) return 1;
+        if (reward_criterion_fwd_launch(sample_logprobs, ld_lp, V1, sample_seq, reward, N, T, loss, nullptr, tp.mask_sum, st)) return 1;
+        // ---- (5) backward through the decoder
+        if (scst_dlogits_launch(sample_logprobs, ld_lp, sample_seq, reward, tp.mask_sum, ta.upstream, N, T, V1, tp.DL, st)) return 1;
+    }
     if (sk.dgrad((int)TN, H, V1, tp.DL, V1, w.logit_w, H, tp.dOUTD, H, 0)) return 1;
     if (wgrad(V1, H, (int)TN, tp.DL, V1, tp.outd, H, G.logit_w, H, 0, st)) return 1;
     if (colsum_launch((int)TN, V1, tp.DL, V1, G.logit_b, 0, st)) return 1;
@@ -726,4 +748,44 @@ extern "C" int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, in
     rc |= wgrad(H, F, (int)BR, tp.dpre, H, att, F, G.att_embed_w, F, 0, st);
     rc |= colsum_launch((int)BR, H, tp.dpre, H, G.att_embed_b, 0, st);
     return rc;
+}
+
+}  // namespace
+
+extern "C" int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, int B, int R, const capb200_aoa_scst_opts* opts,
+                                     const capb200_cider_table* table, const int* refs, const int* ref_offsets, int L, const capb200_aoa_grads* grads,
+                                     long long* sample_seq, long long* greedy_seq, float* sample_logprobs, float* reward, float* loss, void* stream) {
+    if (check_ready(e)) return 1;
+    CAPB_REQUIRE(opts && att && table && refs && ref_offsets && grads && sample_seq && sample_logprobs && reward && loss, "null argument");
+    const bool greedy_baseline = opts->baseline == CAPB200_BASELINE_GREEDY;
+    CAPB_REQUIRE(greedy_baseline || opts->baseline == CAPB200_BASELINE_LEAVE_ONE_OUT, "unknown baseline");
+    CAPB_REQUIRE(!greedy_baseline || greedy_seq != nullptr, "the greedy baseline needs greedy_seq");
+    const int n = opts->sample_n;
+    CAPB_REQUIRE(n >= 1 && n <= 16 && (greedy_baseline || n >= 2) && B >= 1 && R >= 1, "sample_n must be in 1..16 (>= 2 for the leave-one-out baseline)");
+    const float p_lm = opts->drop_prob_lm, p_at = opts->drop_attn, p_aoa = opts->drop_aoa, p_sub = opts->drop_sublayer;
+    CAPB_REQUIRE(p_lm >= 0.f && p_lm < 1.f && p_at >= 0.f && p_at < 1.f && p_aoa >= 0.f && p_aoa < 1.f && p_sub >= 0.f && p_sub < 1.f, "dropout rates must be in [0, 1)");
+    AoaTrainArgs ta;
+    ta.n = n; ta.T = e->T; ta.Tl = e->T; ta.p_lm = p_lm; ta.p_at = p_at; ta.p_aoa = p_aoa; ta.p_sub = p_sub; ta.temperature = opts->temperature;
+    ta.upstream = opts->upstream; ta.ctx_drop = opts->ctx_drop; ta.seed = opts->seed; ta.greedy_baseline = greedy_baseline; ta.table = table;
+    ta.refs = refs; ta.ref_offsets = ref_offsets; ta.L = L; ta.sample_seq = sample_seq; ta.greedy_seq = greedy_seq; ta.reward = reward;
+    ta.logprobs = sample_logprobs; ta.loss = loss;
+    return aoa_train_step(e, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int capb200_aoa_xe_step(capb200_aoa_engine* e, const float* att, int B, int R, const capb200_aoa_xe_opts* opts, const long long* labels,
+                                   const float* masks, int label_cols, const capb200_aoa_grads* grads, float* logprobs, float* loss, void* stream) {
+    if (check_ready(e)) return 1;
+    CAPB_REQUIRE(opts && att && labels && masks && grads && logprobs && loss, "null argument");
+    CAPB_REQUIRE(opts->seq_per_img >= 1 && opts->seq_per_img <= 16 && B >= 1 && R >= 1, "seq_per_img must be in 1..16");
+    const float p_lm = opts->drop_prob_lm, p_at = opts->drop_attn, p_aoa = opts->drop_aoa, p_sub = opts->drop_sublayer;
+    CAPB_REQUIRE(p_lm >= 0.f && p_lm < 1.f && p_at >= 0.f && p_at < 1.f && p_aoa >= 0.f && p_aoa < 1.f && p_sub >= 0.f && p_sub < 1.f, "dropout rates must be in [0, 1)");
+    CAPB_REQUIRE(opts->label_smoothing >= 0.f && opts->label_smoothing < 1.f, "label_smoothing must be in [0, 1)");
+    CAPB_REQUIRE(label_cols >= 2 && label_cols <= e->T + 2, "labels are [N, seq_length + 2] (BOS, words, EOS padding)");
+    CAPB_REQUIRE(opts->steps >= 1 && opts->steps <= label_cols - 1, "steps must be in 1..label_cols-1");
+    AoaTrainArgs ta;
+    ta.xe = true;
+    ta.n = opts->seq_per_img; ta.T = opts->steps; ta.Tl = label_cols - 1; ta.p_lm = p_lm; ta.p_at = p_at; ta.p_aoa = p_aoa; ta.p_sub = p_sub;
+    ta.upstream = opts->upstream; ta.ctx_drop = opts->ctx_drop; ta.seed = opts->seed; ta.smoothing = opts->label_smoothing;
+    ta.labels = labels; ta.ld_labels = label_cols; ta.masks = masks; ta.ld_masks = label_cols; ta.logprobs = logprobs; ta.loss = loss;
+    return aoa_train_step(e, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }

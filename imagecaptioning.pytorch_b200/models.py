@@ -742,6 +742,40 @@ class B200AoAModel(B200CaptionModel):
         return {'loss': loss[0], 'reward': reward, 'sample_seq': sample_seq, 'greedy_seq': None if loo else greedy_seq, 'sample_logprobs': logprobs,
                 'grads': {prm: grads[id(prm)] for prm in params}, 'seed': seed}
 
+    def xe_step(self, fc_feats, att_feats, labels, masks, label_smoothing=0.0, drop_prob=None, seed=None, upstream=1.0, drop_attn=0.1, drop_aoa=None,
+                drop_sublayer=0.1, ctx_drop=None):
+        """One cross-entropy step of AoANet on the device (capb200_aoa_xe_step); arguments and result as B200UpDownModel.xe_step."""
+        if self.ss_prob > 0.0:
+            raise NotImplementedError('scheduled sampling is out of scope of the B200 engine')
+        lib = self._ensure_engine(att_feats.device)
+        att = self._f32(att_feats)
+        dev = att.device
+        B, R = att.shape[0], att.shape[1]
+        if labels.dim() == 3:
+            labels = labels.reshape(-1, labels.shape[2])
+            masks = masks.reshape(-1, masks.shape[2])
+        labels = labels.detach().to(torch.long).contiguous()
+        masks = masks.detach().to(torch.float32).contiguous()
+        N, Lc = labels.shape
+        if N % B != 0 or Lc > self.seq_length + 2 or masks.shape != labels.shape:
+            raise ValueError('labels/masks must be [B * seq_per_img, <= seq_length + 2]')
+        steps = self._teacher_steps(labels[:, :-1])
+        V1 = self.vocab_size + 1
+        params = [prm for _, prm in self._slots()]
+        grads = {id(prm): torch.empty_like(prm) for prm in params}
+        g = _lib.AoaWeights()
+        self._fill_table(g, grads)
+        logprobs = torch.zeros(N, Lc - 1, V1, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        p = self.drop_prob_lm if drop_prob is None else drop_prob
+        xo = _lib.AoaXeOpts(N // B, steps, seed, float(label_smoothing), float(upstream), float(p), float(drop_attn),
+                            float(self.dropout_aoa if drop_aoa is None else drop_aoa), float(drop_sublayer), int(self.ctx_drop if ctx_drop is None else ctx_drop))
+        _lib.check(lib.capb200_aoa_xe_step(self._engine, _lib.ptr(att), B, R, ctypes.byref(xo), _lib.ptr(labels), _lib.ptr(masks), Lc, ctypes.byref(g),
+                                           _lib.ptr(logprobs), _lib.ptr(loss), _lib.current_stream()), 'aoa_xe_step')
+        return {'loss': loss[0], 'logprobs': logprobs, 'grads': {prm: grads[id(prm)] for prm in params}, 'seed': seed}
+
     def _ensure_engine(self, device):
         if device.type != 'cuda':
             raise RuntimeError('capb200: the decode engine runs on CUDA devices only (no CPU fallback); got %s' % device)

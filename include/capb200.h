@@ -338,6 +338,20 @@ int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, int B, int R,
                           const int* refs, const int* ref_offsets, int L, const capb200_aoa_grads* grads, long long* sample_seq, long long* greedy_seq,
                           float* sample_logprobs, float* reward, float* loss, void* stream);
 
+/* One cross-entropy training step of AoANet (teacher-forced AttModel._forward over AoAModel in train mode + LanguageModelCriterion /
+ * LabelSmoothing + backward); arguments as capb200_updown_xe_step, dropout sites as capb200_aoa_scst_step. */
+typedef struct {
+    int seq_per_img;
+    int steps;                 /* columns actually evaluated (early break of AttModel.py:158-159) */
+    unsigned long long seed;
+    float label_smoothing;
+    float upstream;
+    float drop_prob_lm, drop_attn, drop_aoa, drop_sublayer;
+    int ctx_drop;
+} capb200_aoa_xe_opts;
+int capb200_aoa_xe_step(capb200_aoa_engine* e, const float* att, int B, int R, const capb200_aoa_xe_opts* opts, const long long* labels,
+                        const float* masks, int label_cols, const capb200_aoa_grads* grads, float* logprobs, float* loss, void* stream);
+
 /* The dropout keep/scale mask (0 or 1/(1-p)) of one site and step, for tests that replay it in the oracle:
  * site 0 = fc_embed [B,H], 1 = att_embed [B*R,H], 2 = word embedding at `step` [N,E], 3 = core output at `step` [N,H]. */
 int capb200_dropout_mask(float* mask, long n, unsigned long long seed, int site, int step, float p, void* stream);

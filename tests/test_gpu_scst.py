@@ -332,3 +332,34 @@ def test_aoa_scst_step_gradients(mode, dropout, baseline):
     assert abs(float(res['loss']) - float(loss)) < LOGP_TOL
     assert float(reward.abs().max()) > 1e-3                       # the comparison is not vacuous (the leave-one-out loss itself is ~0)
     _check_grads(model, res['grads'], {k: v.grad for k, v in Wg.items()})
+
+
+@pytest.mark.parametrize('dropout,smoothing', [(False, 0.0), (True, 0.1)])
+def test_aoa_xe_step_gradients(dropout, smoothing):
+    """AoANet XE step: teacher-forced train-mode forward, LanguageModelCriterion / LabelSmoothing and every gradient against autograd
+    through the oracle with the engine's dropout masks replayed (labels end early: the data-dependent break is exercised)."""
+    import imagecaptioning.pytorch_b200 as b200
+    heads = 4
+    model, _ = build_pair('aoa', seed=21, logit_scale=5.0, mode='tc_f16x3', heads=heads, **AOA_CFG)
+    W = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    B, R, spi, T = 3, 9, 2, AOA_CFG['T']
+    E, H = AOA_CFG['E'], AOA_CFG['H']
+    fc, att = co.make_inputs(B, R, AOA_CFG['F_fc'], AOA_CFG['F_att'], seed=4)
+    labels, masks = _labels(B, spi, AOA_CFG['V'], T + 2, seed=12, short=True)
+    p_lm, p_at, p_aoa, p_sub = (0.5, 0.1, 0.3, 0.1) if dropout else (0.0, 0.0, 0.0, 0.0)
+    model.train()
+    res = model.xe_step(fc.cuda(), att.cuda(), labels.cuda(), masks.cuda(), label_smoothing=smoothing, drop_prob=p_lm, seed=555, drop_attn=p_at,
+                        drop_aoa=p_aoa, drop_sublayer=p_sub, ctx_drop=1)
+    torch.cuda.synchronize()
+    Wg = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    fam = co.Family('aoa', Wg, T, heads=heads)
+    if dropout:
+        fam.drop = _aoa_masks(b200, 555, B, R, B * spi, T + 1, E, H, heads, p_lm, p_at, p_aoa, p_sub)
+    lp = co.forward_teacher(fam, fc, att, labels[..., :-1])
+    assert float(lp[:, -1].abs().max()) == 0.0
+    tl, tm = labels[..., 1:].reshape(B * spi, -1), masks[..., 1:].reshape(B * spi, -1)
+    loss = co.language_model_criterion(lp, tl, tm) if smoothing == 0 else co.label_smoothing_loss(lp, tl, tm, smoothing)
+    loss.backward()
+    assert float((res['logprobs'].cpu() - lp.detach()).abs().max()) < LOGP_TOL
+    assert abs(float(res['loss']) - float(loss)) < LOGP_TOL
+    _check_grads(model, res['grads'], {k: v.grad for k, v in Wg.items()})
