@@ -233,6 +233,12 @@ def main():
     if local_rank == 0:
         ge.build()
     torch.cuda.set_device(local_rank)
+    try:        # bind this rank to the CPU cores next to its GPU (NUMA): the SCST step is ~1600 launches of host-side work per step
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
         dist.barrier()
