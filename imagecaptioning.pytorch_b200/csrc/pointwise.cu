@@ -131,30 +131,33 @@ constexpr int ATT_SW = 8;       // warps (= regions) per CTA
 // NA = ceil(A / 32) rounded up to a power of two is a template parameter so the inner loops are branch-free and the
 // independent tanh chains of different k overlap (the runtime-bound version serialised them: 61 us -> see profiles/).
 template <int NA>
-__global__ void __launch_bounds__(ATT_SW * 32) att_score_kernel(int rpi, int R, int A, const float* __restrict__ att_h, long ld_ah,
+__global__ void __launch_bounds__(ATT_SW * 32, NA <= 16 ? 5 : 2) att_score_kernel(int rpi, int R, int A, const float* __restrict__ att_h, long ld_ah,
                                                                 const float* __restrict__ p_att, long ld_pa, const float* __restrict__ alpha_w,
                                                                 const float* __restrict__ alpha_b_ptr, float* __restrict__ score) {
     // tanh(x) = 1 - 2 / (1 + 2^(x * 2 log2 e)): p_att and att_h are pre-multiplied by 2 log2(e) when loaded, the sum over a of
     // w[a] * tanh = sum(w) - 2 * sum_a w[a] / (1 + 2^z), and four reciprocals share one MUFU.RCP (1/y_i from 1/(y0 y1 y2 y3)).
     // The r01f capture showed the earlier version issue-bound at 23 instructions per tanh; this form needs about 10.
-    extern __shared__ float s_ah[];               // [ATT_JB][NA * 32] pre-scaled (zero padded beyond A)
+    // Registers: five CTAs per SM (<= 51 registers) turn the 1280-CTA grid of the headline shape from 3 rounds into 2, so the
+    // attention weights w live in shared memory instead of 16 registers per lane.
+    extern __shared__ float s_ah[];               // [ATT_JB][NA * 32] pre-scaled (zero padded beyond A), then w [NA * 32]
     constexpr int AP = NA * 32;
+    float* s_w = s_ah + ATT_JB * AP;
     constexpr float kC = 2.885390081777927f;      // 2 * log2(e)
     const int img = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * ATT_SW + warp;
     const float alpha_b = __ldg(alpha_b_ptr);
-    float pv[NA], wv[NA];                          // element k = 4 * g + u  <->  hidden index a = 128 * g + 4 * lane + u
+    float pv[NA];                                  // element k = 4 * g + u  <->  hidden index a = 128 * g + 4 * lane + u
     const bool live = r < R;
     const float* pr = p_att + ((long)img * R + (live ? r : 0)) * ld_pa;
+    for (int i = threadIdx.x; i < AP; i += ATT_SW * 32) s_w[i] = (i < A) ? __ldg(alpha_w + i) : 0.f;      // zero weight kills padded lanes
+    __syncthreads();
     float wsum = 0.f;
 #pragma unroll
     for (int k = 0; k < NA; ++k) {
         const int a = (NA % 4 == 0) ? 128 * (k >> 2) + 4 * lane + (k & 3) : lane + 32 * k;
-        const bool ok = live && (a < A);
-        pv[k] = ok ? __ldg(pr + a) * kC : 0.f;
-        wv[k] = ok ? __ldg(alpha_w + a) : 0.f;      // zero weight kills padded lanes
-        wsum += wv[k];
+        pv[k] = (live && a < A) ? __ldg(pr + a) * kC : 0.f;
+        wsum += s_w[a];
     }
     for (int j0 = 0; j0 < rpi; j0 += ATT_JB) {
         const int nj = min(ATT_JB, rpi - j0);
@@ -187,10 +190,11 @@ __global__ void __launch_bounds__(ATT_SW * 32) att_score_kernel(int rpi, int R, 
                             float rr;
                             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rr) : "f"(p01 * p23));
                             const float r01 = rr * p23, r23 = rr * p01;
-                            acc = fmaf(wv[4 * g], r01 * y[1], acc);
-                            acc = fmaf(wv[4 * g + 1], r01 * y[0], acc);
-                            acc = fmaf(wv[4 * g + 2], r23 * y[3], acc);
-                            acc = fmaf(wv[4 * g + 3], r23 * y[2], acc);
+                            const float4 w4 = *reinterpret_cast<const float4*>(&s_w[128 * g + 4 * lane]);
+                            acc = fmaf(w4.x, r01 * y[1], acc);
+                            acc = fmaf(w4.y, r01 * y[0], acc);
+                            acc = fmaf(w4.z, r23 * y[3], acc);
+                            acc = fmaf(w4.w, r23 * y[2], acc);
                         }
                         part[j] = fmaf(-2.0f, acc, wsum);
                     } else {
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(ATT_SW * 32) att_score_kernel(int rpi, int R, 
                         for (int k = 0; k < NA; ++k) {
                             float e;
                             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(pv[k] + s_ah[j * AP + lane + 32 * k], 28.0f)));
-                            part[j] = fmaf(wv[k], 1.0f - __fdividef(2.0f, 1.0f + e), part[j]);
+                            part[j] = fmaf(s_w[lane + 32 * k], 1.0f - __fdividef(2.0f, 1.0f + e), part[j]);
                         }
                     }
                 }
@@ -258,6 +262,7 @@ __global__ void __launch_bounds__(ATT_CT) att_combine_kernel(int rpi, int R, int
 #pragma unroll
             for (int j = 0; j < ATT_JB; ++j) acc[j] = 0.f;
             const float* ap = att + (long)img * R * ld_at + c;
+            // (batching several feature loads per thread was measured twice and is slower: 14.5 -> 17-20 us)
             for (int r = 0; r < R; ++r) {
                 const float v = __ldg(ap + (long)r * ld_at);
 #pragma unroll
@@ -323,7 +328,7 @@ int additive_attention_launch(int n_images, int rpi, int R, int A, int H, const 
     dim3 sgrid(cdiv(R, ATT_SW), n_images);
     const int na = cdiv(A, 32);
 #define CAPB_ATT_CASE(NA_)                                                                                                             \
-    att_score_kernel<NA_><<<sgrid, ATT_SW * 32, sizeof(float) * ATT_JB * NA_ * 32, stream>>>(rpi, R, A, att_h, ld_ah, p_att, ld_pa, alpha_w, \
+    att_score_kernel<NA_><<<sgrid, ATT_SW * 32, sizeof(float) * (ATT_JB + 1) * NA_ * 32, stream>>>(rpi, R, A, att_h, ld_ah, p_att, ld_pa, alpha_w, \
                                                                                                alpha_b, score_scratch)
     if (na <= 2) CAPB_ATT_CASE(2);
     else if (na <= 4) CAPB_ATT_CASE(4);
