@@ -389,10 +389,9 @@ int enc_attn_backward_launch(int B, int R, int heads, int dk, const float* q, co
                              const float* d_out, long ld_do, float* dq, float* dk_, float* dv, long ld_d, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)4 * R * (dk + 1) + 2 * R * R);
     CAPB_REQUIRE(smem <= 200 * 1024, "refiner attention backward: shared-memory footprint too large");
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<unsigned long long> configured{0};
+    if (first_use_on_device(configured)) {
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(enc_attn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
     }
     enc_attn_backward_kernel<<<dim3(B, heads), 256, smem, st>>>(R, dk, heads, q, k, v, ld, 1.0f / sqrtf((float)dk), seed, (uint32_t)site, p, d_out, ld_do, dq,
                                                                   dk_, dv, ld_d);
@@ -409,10 +408,9 @@ int cross_attn_backward_launch(int B, int rpi, int heads, int dk, int R, const f
                                float* dkk, float* dvv, long ld_dkv, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)2 * R * (dk + 1) + 2 * rpi * (dk + 1) + 2 * rpi * R);
     CAPB_REQUIRE(smem <= 200 * 1024, "decoder attention backward: shared-memory footprint too large");
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<unsigned long long> configured{0};
+    if (first_use_on_device(configured)) {
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
     }
     cross_attn_backward_kernel<<<dim3(B, heads), 128, smem, st>>>(rpi, heads, dk, R, q, ld_q, kk, vv, ld_kv, 1.0f / sqrtf((float)dk), seed, (uint32_t)site,
                                                                    (uint32_t)step, p, probs, d_out, ld_do, dq, ld_dq, dkk, dvv, ld_dkv);

@@ -1,5 +1,6 @@
 // Shared host/device helpers for the capb200 kernels.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -31,6 +32,15 @@ void set_error(const std::string& msg);
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline long round_up(long a, long b) { return (a + b - 1) / b * b; }
+
+// Function attributes (dynamic shared-memory opt-in) are per device: `mask` is a per-call-site bit set of the devices already configured,
+// so engines on several devices in one process (nn.DataParallel: one host thread per GPU) each configure their own.
+inline bool first_use_on_device(std::atomic<unsigned long long>& mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+    const unsigned long long bit = 1ull << dev;
+    return (mask.fetch_or(bit) & bit) == 0;
+}
 
 // ---- split-fp16 representation of an fp32 value: x ~= hi + lo, |x - hi - lo| <= 2^-22 |x| + 2^-25
 __device__ __forceinline__ void split_f32(float x, __half& hi, __half& lo) {

@@ -497,11 +497,10 @@ int gemm_skinny_launch(int M, int N, int nseg, const float* const* A, const long
     dim3 grid(cdiv(N, GT), ksplit, cdiv(M, GT));
     if (v2) {
         constexpr int smem = S2_STAGES * S2_STAGE_FLOATS * (int)sizeof(float);
-        static bool configured = false;
-        if (!configured) {
+        static std::atomic<unsigned long long> configured{0};
+        if (first_use_on_device(configured)) {
             CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_tf32_v2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_tf32_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            configured = true;
         }
         if (tb[0]) gemm_skinny_tf32_v2_kernel<1><<<grid, 256, smem, st>>>(p);
         else gemm_skinny_tf32_v2_kernel<0><<<grid, 256, smem, st>>>(p);

@@ -596,10 +596,9 @@ bool encode_plane(CUtensorMap* map, const __half* base, long rows, long K, long 
 template <int BN, int PASSES, int CX, int CY>
 int launch_cfg(const TcParams& prm, cudaStream_t stream) {
     using Cfg = TcCfg<BN, PASSES>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_set{0};
+    if (first_use_on_device(attr_set)) {
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, CX, CY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_set = true;
     }
     // grid padded to whole clusters; CTAs outside the matrix still run the pipeline (their TMA boxes are zero-filled) so
     // that their cluster peers receive the multicast slices they wait for
@@ -630,10 +629,9 @@ int launch_cfg(const TcParams& prm, cudaStream_t stream) {
 template <int BN, int PASSES>
 int launch_pair(const TcParams& prm, cudaStream_t stream) {
     using Cfg = TcPairCfg<BN, PASSES>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_set{0};
+    if (first_use_on_device(attr_set)) {
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_set = true;
     }
     TcParams prm2 = prm;
     prm2.tiles_n = (int)cdiv(prm.N, BN);

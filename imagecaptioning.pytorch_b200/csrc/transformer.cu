@@ -259,10 +259,9 @@ int enc_self_attention_launch(int B, int R, int heads, int dk, const float* q, c
     if (B <= 0) return 0;
     const size_t smem = sizeof(float) * ((size_t)2 * R * (dk + 1) + 4 * R);
     CAPB_REQUIRE(smem <= 200 * 1024, "self-attention: region count x head width too large for the shared-memory staging");
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<unsigned long long> configured{0};
+    if (first_use_on_device(configured)) {
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(enc_self_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
     }
     enc_self_attention_kernel<<<dim3(B, heads), 128, smem, st>>>(R, dk, q, k, v, ld, mask, ld_mask, 1.0f / sqrtf((float)dk), out);
     CAPB_CHECK_CUDA(cudaGetLastError());

@@ -652,10 +652,9 @@ int vocab_step_launch(const VocabStepArgs& a, cudaStream_t stream) {
         } else if (vec && vsel == 'o') {                                  // "o2": the 256-thread form
             vocab_stats_online_kernel<<<a.rows, VT, 0, stream>>>(a);
         } else if (vec && vsel == 's' && stream_smem <= 100 * 1024) {
-            static bool configured = false;
-            if (!configured) {
+            static std::atomic<unsigned long long> configured{0};
+            if (first_use_on_device(configured)) {
                 CAPB_CHECK_CUDA(cudaFuncSetAttribute(vocab_stats_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(100 * 1024)));
-                configured = true;
             }
             const int grid = a.rows < 2 * 148 ? a.rows : 2 * 148;       // two resident CTAs per SM, each double-buffering one row
             vocab_stats_stream_kernel<<<grid, VT, stream_smem, stream>>>(a);
@@ -669,12 +668,11 @@ int vocab_step_launch(const VocabStepArgs& a, cudaStream_t stream) {
     }
     const size_t smem = sizeof(float) * (size_t)a.V1;
     CAPB_REQUIRE(smem <= 200 * 1024, "vocabulary larger than 51200 entries needs the multi-pass variant");
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<unsigned long long> configured{0};
+    if (first_use_on_device(configured)) {
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(vocab_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(vocab_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(vocab_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-        configured = true;
     }
     if (a.topk <= 2) vocab_step_kernel<2><<<a.rows, VT, smem, stream>>>(a);
     else if (a.topk <= 8) vocab_step_kernel<8><<<a.rows, VT, smem, stream>>>(a);
