@@ -177,10 +177,15 @@ def bench_scst(args, rank, world, local_rank, dev):
     l0 = model.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    step_ms = []
     for i in range(args.steps):
+        t_s = time.perf_counter()
         step(args.warmup + i)
+        step_ms.append((time.perf_counter() - t_s) * 1e3)
     e1.record()
     barrier()
+    if os.environ.get('CAPB200_BENCH_STEP_TIMES'):
+        print('rank %d per-step wall ms: %s' % (rank, ' '.join('%.1f' % v for v in step_ms)), file=sys.stderr, flush=True)
     sampler.stop_flag = True
     sampler.join()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -234,6 +239,8 @@ def main():
         ge.build()
     torch.cuda.set_device(local_rank)
     try:        # bind this rank to the CPU cores next to its GPU (NUMA): the SCST step is ~1600 launches of host-side work per step
+        if os.environ.get('CAPB200_BENCH_NO_AFFINITY'):
+            raise RuntimeError('disabled')
         import pynvml
         pynvml.nvmlInit()
         pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))

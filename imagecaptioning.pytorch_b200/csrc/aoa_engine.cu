@@ -504,8 +504,9 @@ void layout_atape(ATape& tp, Arena& a, int B, int R, int N, int T, int E, int H,
 }
 
 // dW[out, in] (+)= dY[rows, out]^T * X[rows, in]
-inline int wgrad(int out_f, int in_f, int rows, const float* dY, long ld_dy, const float* X, long ld_x, float* G, long ld_g, int accumulate, cudaStream_t st) {
-    return gemm_generic_launch(1, 0, out_f, in_f, rows, dY, ld_dy, X, ld_x, G, ld_g, accumulate, nullptr, st);
+inline int wgrad_mode(int out_f, int in_f, int rows, const float* dY, long ld_dy, const float* X, long ld_x, float* G, long ld_g, int accumulate, int mode,
+                      cudaStream_t st) {
+    return gemm_wgrad_launch(out_f, in_f, rows, dY, ld_dy, X, ld_x, G, ld_g, accumulate, mode, st);
 }
 
 }  // namespace
@@ -567,6 +568,10 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     if (ensure_workspace(e, B, N, R, 1, st)) return 1;
     const Skinny sk{tp.skinny, tp.skinny_floats, e->tc ? 1 : 0, st};
     auto act = [](float* p, long ld) { ActView v; v.f = p; v.hi = nullptr; v.lo = nullptr; v.ld = ld; return v; };
+    const int wmode = e->tc ? 1 : 0;
+    auto wgrad = [&](int out_f, int in_f, int rows, const float* dY, long ld_dy, const float* X, long ld_x, float* Gp, long ld_g, int accumulate, cudaStream_t s_) {
+        return wgrad_mode(out_f, in_f, rows, dY, ld_dy, X, ld_x, Gp, ld_g, accumulate, wmode, s_);
+    };
 
     // ---- (2) train-mode prologue: att_embed (+dropout), six refiner layers, final norm, mean pooling, ctx2att
     if (sk.lin(att, F, w.att_embed_w, F, w.att_embed_b, tp.x[0], H, (int)BR, H, F, 0)) return 1;

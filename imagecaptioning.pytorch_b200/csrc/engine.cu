@@ -985,7 +985,7 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     }
     e->launches += 3;
     if (sk.dgrad((int)TN, H, V1, tp.DL, V1, w.logit_w, H, tp.dOUT, H, 0)) return 1;          // dOUT = DL * W
-    if (gemm_generic_launch(1, 0, V1, H, (int)TN, tp.DL, V1, tp.out, H, G.logit_w, H, 0, nullptr, st)) return 1;            // dW = DL^T * OUT
+    if (gemm_wgrad_launch(V1, H, (int)TN, tp.DL, V1, tp.out, H, G.logit_w, H, 0, e->tc ? 1 : 0, st)) return 1;            // dW = DL^T * OUT
     if (colsum_launch((int)TN, V1, tp.DL, V1, G.logit_b, 0, st)) return 1;
     CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dh0, 0, sizeof(float) * NH, st));
     CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dc0, 0, sizeof(float) * NH, st));
@@ -1027,30 +1027,30 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     const float* DG1s = tp.DG1 + (long)N * 4 * H;     // steps 1..T-1 pair with the previous step's hidden states
     const float* DG2s = tp.DG2 + (long)N * 4 * H;
     int rc = 0;
-    rc |= gemm_generic_launch(1, 0, 4 * H, H, (int)TN, tp.DG2, 4 * H, tp.attres, H, G.lang_lstm_w_ih, 2 * H, 0, nullptr, st);
-    rc |= gemm_generic_launch(1, 0, 4 * H, H, (int)TN, tp.DG2, 4 * H, tp.h0, H, G.lang_lstm_w_ih + H, 2 * H, 0, nullptr, st);
-    rc |= gemm_generic_launch(1, 0, 4 * H, H, TN1, DG2s, 4 * H, tp.h1, H, G.lang_lstm_w_hh, H, 0, nullptr, st);
+    rc |= gemm_wgrad_launch(4 * H, H, (int)TN, tp.DG2, 4 * H, tp.attres, H, G.lang_lstm_w_ih, 2 * H, 0, e->tc ? 1 : 0, st);
+    rc |= gemm_wgrad_launch(4 * H, H, (int)TN, tp.DG2, 4 * H, tp.h0, H, G.lang_lstm_w_ih + H, 2 * H, 0, e->tc ? 1 : 0, st);
+    rc |= gemm_wgrad_launch(4 * H, H, TN1, DG2s, 4 * H, tp.h1, H, G.lang_lstm_w_hh, H, 0, e->tc ? 1 : 0, st);
     rc |= colsum_launch((int)TN, 4 * H, tp.DG2, 4 * H, G.lang_lstm_b_ih, 0, st);
     rc |= colsum_launch((int)TN, 4 * H, tp.DG2, 4 * H, G.lang_lstm_b_hh, 0, st);
-    rc |= gemm_generic_launch(1, 0, 4 * H, H, TN1, DG1s, 4 * H, tp.h1, H, G.att_lstm_w_ih, E + 2 * H, 0, nullptr, st);
-    rc |= gemm_generic_launch(1, 0, 4 * H, E, (int)TN, tp.DG1, 4 * H, tp.xt, E, G.att_lstm_w_ih + 2 * H, E + 2 * H, 0, nullptr, st);
-    rc |= gemm_generic_launch(1, 0, 4 * H, H, TN1, DG1s, 4 * H, tp.h0, H, G.att_lstm_w_hh, H, 0, nullptr, st);
+    rc |= gemm_wgrad_launch(4 * H, H, TN1, DG1s, 4 * H, tp.h1, H, G.att_lstm_w_ih, E + 2 * H, 0, e->tc ? 1 : 0, st);
+    rc |= gemm_wgrad_launch(4 * H, E, (int)TN, tp.DG1, 4 * H, tp.xt, E, G.att_lstm_w_ih + 2 * H, E + 2 * H, 0, e->tc ? 1 : 0, st);
+    rc |= gemm_wgrad_launch(4 * H, H, TN1, DG1s, 4 * H, tp.h0, H, G.att_lstm_w_hh, H, 0, e->tc ? 1 : 0, st);
     rc |= colsum_launch((int)TN, 4 * H, tp.DG1, 4 * H, G.att_lstm_b_ih, 0, st);
     rc |= colsum_launch((int)TN, 4 * H, tp.DG1, 4 * H, G.att_lstm_b_hh, 0, st);
     rc |= per_image_sum_launch(T, N, n, 4 * H, tp.DG1, tp.S, st);
-    rc |= gemm_generic_launch(1, 0, 4 * H, H, B, tp.S, 4 * H, tp.fc_e, H, G.att_lstm_w_ih + H, E + 2 * H, 0, nullptr, st);               // fc' block
+    rc |= gemm_wgrad_launch(4 * H, H, B, tp.S, 4 * H, tp.fc_e, H, G.att_lstm_w_ih + H, E + 2 * H, 0, e->tc ? 1 : 0, st);               // fc' block
     rc |= sk.dgrad(B, H, 4 * H, tp.S, 4 * H, w.att_lstm_w_ih + H, E + 2 * H, tp.d_fc_e, H, 0);             // d fc'
-    rc |= gemm_generic_launch(1, 0, A, H, (int)TN, tp.DATTH, A, tp.h0, H, G.h2att_w, H, 0, nullptr, st);
+    rc |= gemm_wgrad_launch(A, H, (int)TN, tp.DATTH, A, tp.h0, H, G.h2att_w, H, 0, e->tc ? 1 : 0, st);
     rc |= colsum_launch((int)TN, A, tp.DATTH, A, G.h2att_b, 0, st);
     // prologue
     rc |= sk.dgrad((int)BR, H, A, tp.d_p_att, A, w.ctx2att_w, H, tp.d_att_e, H, 1);
-    rc |= gemm_generic_launch(1, 0, A, H, (int)BR, tp.d_p_att, A, tp.att_e, H, G.ctx2att_w, H, 0, nullptr, st);
+    rc |= gemm_wgrad_launch(A, H, (int)BR, tp.d_p_att, A, tp.att_e, H, G.ctx2att_w, H, 0, e->tc ? 1 : 0, st);
     rc |= colsum_launch((int)BR, A, tp.d_p_att, A, G.ctx2att_b, 0, st);
     rc |= relu_dropout_backward_launch(BR * H, tp.att_e, tp.d_att_e, tp.dpre_att, keep_scale, st);
-    rc |= gemm_generic_launch(1, 0, H, Fa, (int)BR, tp.dpre_att, H, att, Fa, G.att_embed_w, Fa, 0, nullptr, st);
+    rc |= gemm_wgrad_launch(H, Fa, (int)BR, tp.dpre_att, H, att, Fa, G.att_embed_w, Fa, 0, e->tc ? 1 : 0, st);
     rc |= colsum_launch((int)BR, H, tp.dpre_att, H, G.att_embed_b, 0, st);
     rc |= relu_dropout_backward_launch((long)B * H, tp.fc_e, tp.d_fc_e, tp.dpre_fc, keep_scale, st);
-    rc |= gemm_generic_launch(1, 0, H, Ff, B, tp.dpre_fc, H, fc, Ff, G.fc_embed_w, Ff, 0, nullptr, st);
+    rc |= gemm_wgrad_launch(H, Ff, B, tp.dpre_fc, H, fc, Ff, G.fc_embed_w, Ff, 0, e->tc ? 1 : 0, st);
     rc |= colsum_launch(B, H, tp.dpre_fc, H, G.fc_embed_b, 0, st);
     e->launches += 30;
     return rc;

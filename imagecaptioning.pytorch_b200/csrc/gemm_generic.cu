@@ -334,7 +334,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 
-template <int TB>
+// TA = 1: A stored [K, M] (the dY operand of a weight gradient dW = dY^T X): its tile is staged as [k][m] rows like a [K, N] W tile.
+template <int TB, int TA>
 __global__ void __launch_bounds__(256) gemm_skinny_tf32_v2_kernel(const SkinnyParams p) {
     extern __shared__ __align__(16) float s2[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -362,7 +363,12 @@ __global__ void __launch_bounds__(256) gemm_skinny_tf32_v2_kernel(const SkinnyPa
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int idx = tid + 256 * u;                  // 512 float4 per operand tile
-            {   // A tile: 64 rows x 8 float4
+            if (TA) {   // A stored [K, M]: 32 rows (k) x 16 float4 (m)
+                const int row = idx >> 4, mq = (idx & 15) * 4;
+                const bool ok = (k0 + row < K) && (m0 + mq < p.M);
+                const float* src = ok ? p.A[seg] + (long)(k0 + row) * p.lda[seg] + m0 + mq : p.A[seg];
+                cp_async16(As + row * S2_BLD + mq, src, ok ? 16 : 0);
+            } else {    // A tile: 64 rows x 8 float4
                 const int row = idx >> 3, kq = (idx & 7) * 4;
                 const bool ok = (m0 + row < p.M) && (k0 + kq < K);
                 const float* src = ok ? p.A[seg] + (long)(m0 + row) * p.lda[seg] + k0 + kq : p.A[seg];
@@ -399,10 +405,17 @@ __global__ void __launch_bounds__(256) gemm_skinny_tf32_v2_kernel(const SkinnyPa
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int r = wm + i * 16 + g;
-                split_tf32(As[r * S2_ALD + kk + tig], ah[i][0], al[i][0]);
-                split_tf32(As[(r + 8) * S2_ALD + kk + tig], ah[i][1], al[i][1]);
-                split_tf32(As[r * S2_ALD + kk + tig + 4], ah[i][2], al[i][2]);
-                split_tf32(As[(r + 8) * S2_ALD + kk + tig + 4], ah[i][3], al[i][3]);
+                if (TA) {
+                    split_tf32(As[(kk + tig) * S2_BLD + r], ah[i][0], al[i][0]);
+                    split_tf32(As[(kk + tig) * S2_BLD + r + 8], ah[i][1], al[i][1]);
+                    split_tf32(As[(kk + tig + 4) * S2_BLD + r], ah[i][2], al[i][2]);
+                    split_tf32(As[(kk + tig + 4) * S2_BLD + r + 8], ah[i][3], al[i][3]);
+                } else {
+                    split_tf32(As[r * S2_ALD + kk + tig], ah[i][0], al[i][0]);
+                    split_tf32(As[(r + 8) * S2_ALD + kk + tig], ah[i][1], al[i][1]);
+                    split_tf32(As[r * S2_ALD + kk + tig + 4], ah[i][2], al[i][2]);
+                    split_tf32(As[(r + 8) * S2_ALD + kk + tig + 4], ah[i][3], al[i][3]);
+                }
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -499,11 +512,11 @@ int gemm_skinny_launch(int M, int N, int nseg, const float* const* A, const long
         constexpr int smem = S2_STAGES * S2_STAGE_FLOATS * (int)sizeof(float);
         static std::atomic<unsigned long long> configured{0};
         if (first_use_on_device(configured)) {
-            CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_tf32_v2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_tf32_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_tf32_v2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_tf32_v2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         }
-        if (tb[0]) gemm_skinny_tf32_v2_kernel<1><<<grid, 256, smem, st>>>(p);
-        else gemm_skinny_tf32_v2_kernel<0><<<grid, 256, smem, st>>>(p);
+        if (tb[0]) gemm_skinny_tf32_v2_kernel<1, 0><<<grid, 256, smem, st>>>(p);
+        else gemm_skinny_tf32_v2_kernel<0, 0><<<grid, 256, smem, st>>>(p);
     } else if (tc && tb[0]) gemm_skinny_tf32_kernel<1><<<grid, 256, 0, st>>>(p);
     else if (tc) gemm_skinny_tf32_kernel<0><<<grid, 256, 0, st>>>(p);
     else gemm_skinny_kernel<<<grid, 256, 0, st>>>(p);
@@ -514,6 +527,33 @@ int gemm_skinny_launch(int M, int N, int nseg, const float* const* A, const long
         skinny_reduce_kernel<<<(int)blocks, 256, 0, st>>>(M, N, ksplit, scratch, C, ldc, bias, row_bias, ld_rb, p.rpg, accumulate);
         CAPB_CHECK_CUDA(cudaGetLastError());
     }
+    return 0;
+}
+
+// Weight gradient on the tensor cores:  G[M, N] (+)= dY[K, M]^T * X[K, N]  (3xTF32, fp32 accumulate).  Falls back to the fp32 CUDA-core
+// kernel when the operands are not 16-byte aligned or mode == 0.
+int gemm_wgrad_launch(int M, int N, int K, const float* dY, long ld_dy, const float* X, long ld_x, float* G, long ld_g, int accumulate, int mode,
+                      cudaStream_t st) {
+    if (M <= 0 || N <= 0) return 0;
+    const bool ok = mode != 0 && K > 0 && M % 4 == 0 && N % 4 == 0 && ld_dy % 4 == 0 && ld_x % 4 == 0 && (reinterpret_cast<uintptr_t>(dY) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+    static const bool v1_only = getenv("CAPB200_SKINNY_V1") != nullptr;
+    if (!ok || v1_only) return gemm_generic_launch(1, 0, M, N, K, dY, ld_dy, X, ld_x, G, ld_g, accumulate, nullptr, st);
+    SkinnyParams p;
+    memset(&p, 0, sizeof(p));
+    p.nseg = 1; p.M = M; p.N = N;
+    p.A[0] = dY; p.lda[0] = ld_dy; p.B[0] = X; p.ldb[0] = ld_x; p.K[0] = K; p.tb[0] = 0;
+    p.ksteps_total = cdiv(K, S2_BK);
+    p.ksplit = 1;
+    p.out = G; p.ldo = ld_g; p.rpg = 1; p.accumulate = accumulate;
+    constexpr int smem = S2_STAGES * S2_STAGE_FLOATS * (int)sizeof(float);
+    static std::atomic<unsigned long long> configured{0};
+    if (first_use_on_device(configured)) {
+        CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_tf32_v2_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    dim3 grid(cdiv(N, GT), 1, cdiv(M, GT));
+    gemm_skinny_tf32_v2_kernel<0, 1><<<grid, 256, smem, st>>>(p);
+    CAPB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -110,6 +110,8 @@ int gemm_generic_launch(int ta, int tb, int M, int N, int K, const float* A, lon
 int gemm_skinny_launch(int M, int N, int nseg, const float* const* A, const long* lda, const float* const* B, const long* ldb, const int* K, const int* tb,
                        float* C, long ldc, const float* bias, const float* row_bias, long ld_rb, int rpg, int accumulate, float* scratch,
                        size_t scratch_floats, int mode, cudaStream_t st);   // mode 0 = fp32 CUDA cores, 1 = 3xTF32 mma.sync
+int gemm_wgrad_launch(int M, int N, int K, const float* dY, long ld_dy, const float* X, long ld_x, float* G, long ld_g, int accumulate, int mode,
+                      cudaStream_t st);   // G[M,N] (+)= dY[K,M]^T X[K,N]; mode 1 = 3xTF32 tensor cores
 int colsum_launch(int rows, int cols, const float* x, long ld, float* out, int accumulate, cudaStream_t st);
 int dropout_apply_launch(float* x, int rows, int cols, long ld, unsigned long long seed, unsigned site, unsigned step, float p, cudaStream_t st);
 int dropout_mask_launch(float* m, long n, unsigned long long seed, unsigned site, unsigned step, float p, cudaStream_t st);
