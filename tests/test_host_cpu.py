@@ -1,0 +1,61 @@
+"""CPU tests of the host-side mirrors: the criterion modules against the live-reference goldens, the option guards, and the
+"fail loudly without CUDA" contract of the product path (no CPU fallback anywhere)."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import co, family_opt
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def test_criterion_modules_match_reference_golden():
+    """loss_wrapper.LanguageModelCriterion / LabelSmoothing (host-level torch ops) reproduce the reference's losses and gradients."""
+    from imagecaptioning.pytorch_b200.loss_wrapper import LabelSmoothing, LanguageModelCriterion
+    g = np.load(os.path.join(GOLD, 'xe_struct.npz'))
+    labels, masks = torch.from_numpy(g['crit_labels']), torch.from_numpy(g['crit_masks'])
+    for name, crit in (('lm', LanguageModelCriterion()), ('ls', LabelSmoothing(smoothing=0.2))):
+        x = torch.from_numpy(g['crit_lp']).clone().requires_grad_(True)
+        loss = crit(x, labels[:, 1:], masks[:, 1:])
+        loss.backward()
+        assert abs(float(loss.detach()) - float(g[name + '_loss'])) < 1e-6
+        assert np.abs(x.grad.numpy() - g[name + '_grad']).max() < 1e-7
+        none = crit(x.detach(), labels[:, 1:], masks[:, 1:], reduction='none')
+        assert np.abs(none.numpy() - g[name + '_loss_none']).max() < 1e-6
+
+
+@pytest.mark.parametrize('family', ['updown', 'newfc', 'transformer', 'aoa'])
+def test_product_path_refuses_cpu_tensors(family):
+    """Every family's decode raises instead of computing on the CPU (the engine has no CPU or PyTorch-op fallback)."""
+    import imagecaptioning.pytorch_b200 as b200
+    cfg = dict(V=30, E=16, H=16, A=8, F_fc=16, F_att=16, T=5)
+    if family == 'transformer':
+        cfg = dict(cfg, E=16, H=32, A=1)
+    model = b200.setup(family_opt(family, heads=2, **cfg))
+    fc, att = co.make_inputs(2, 3, 16, 16, seed=1)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        model(fc, att, None, opt={'sample_method': 'greedy', 'beam_size': 1}, mode='sample')
+
+
+def test_loss_wrapper_option_guards():
+    """Unsupported LossWrapper configurations raise NotImplementedError before any device work (structure losses other than
+    new_self_critical, PPO) and the reward needs init_scorer."""
+    import imagecaptioning.pytorch_b200 as b200
+    model = b200.setup(family_opt('updown', V=30, E=16, H=16, A=8, F_fc=16, F_att=16, T=5))
+    opt = argparse.Namespace(sc_sample_method='greedy', sc_beam_size=1, train_sample_method='sample', train_beam_size=1, train_sample_n=2,
+                             cider_reward_weight=1, bleu_reward_weight=0, label_smoothing=0.0, structure_loss_weight=1.0,
+                             structure_loss_type='softmax_margin', use_ppo=0)
+    lw = b200.B200LossWrapper(model, opt)
+    fc, att = co.make_inputs(2, 3, 16, 16, seed=1)
+    gts = [np.zeros((5, 7), np.int64)] * 2
+    with pytest.raises(NotImplementedError):
+        lw(fc, att, None, None, None, gts, torch.arange(2), False, True, False)
+    b200.rewards.reset_scorer()
+    opt.structure_loss_type = 'new_self_critical'
+    with pytest.raises(RuntimeError, match='init_scorer'):
+        lw(fc, att, None, None, None, gts, torch.arange(2), True, False, False)
+    with pytest.raises(NotImplementedError):
+        b200.loss_wrapper.StructureLosses(argparse.Namespace(structure_loss_type='risk'))

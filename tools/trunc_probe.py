@@ -12,9 +12,10 @@ for K in (256, 512, 1000, 2000, 3000):
         if dist == 'positive':
             x = x.abs(); w = w.abs()
         ref = x.double() @ w.double().t()
+        xd, wd = x.cuda(), w.cuda()              # keep the device copies alive for the asynchronous call
         for mode in ('tc_f16x3', 'simt_fp32'):
             y = torch.empty(M, N, device='cuda')
-            lib.capb200_linear(L.ptr(x.cuda()), K, L.ptr(w.cuda()), K, None, L.ptr(y), N, M, N, K, 0, L.MODES[mode], L.current_stream())
+            L.check(lib.capb200_linear(L.ptr(xd), K, L.ptr(wd), K, None, L.ptr(y), N, M, N, K, 0, L.MODES[mode], L.current_stream()), 'linear')
             torch.cuda.synchronize()
             yd = y.cpu().double()
             sel = ref.abs() > 0.25 * ref.abs().max()
