@@ -17,6 +17,7 @@ PyTorch ops: unsupported decode options raise.
 from __future__ import annotations
 
 import ctypes
+import threading
 from collections.abc import Mapping
 from typing import Optional
 
@@ -64,6 +65,44 @@ class _DoneBeam(Mapping):
         return 4
 
 
+class _EngineStore:
+    """Per-device engine handles of one model, shared BY REFERENCE between the module and the shallow replicas nn.DataParallel makes on
+    every forward (replicate() copies __dict__), so each GPU keeps its engine, workspaces and CUDA graphs across steps.  Only the
+    module that created the store frees the engines."""
+
+    def __init__(self, owner):
+        self.owner = id(owner)
+        self.lock = threading.RLock()
+        self.slots = {}
+
+    def slot(self, dev):
+        with self.lock:
+            return self.slots.setdefault(dev, {'engine': None, 'key': None, 'versions': None, 'keepalive': None})
+
+    def __deepcopy__(self, memo):
+        fresh = _EngineStore(None)
+        fresh.owner = None          # claimed by the copy at its first _ensure_engine
+        return fresh
+
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.owner, self.lock, self.slots = None, threading.RLock(), {}
+
+
+_tls = threading.local()           # device index the calling thread is decoding on (set by _ensure_engine)
+
+
+def _slot_property(field):
+    def get(self):
+        return self._store.slot(getattr(_tls, 'dev', None))[field]
+
+    def put(self, value):
+        self._store.slot(getattr(_tls, 'dev', None))[field] = value
+    return property(get, put)
+
+
 class B200CaptionModel(nn.Module):
     """Common machinery: engine life-cycle, weight binding and the three call surfaces."""
 
@@ -98,20 +137,29 @@ class B200CaptionModel(nn.Module):
         if self.numeric_mode not in _lib.MODES:
             raise ValueError('numeric_mode must be one of %s' % sorted(_lib.MODES))
         self.done_beams = []
-        self._engine = None
-        self._engine_key = None
-        self._bound_versions = None
-        self._keepalive = None
+        self._store = _EngineStore(self)
 
     # ---- engine plumbing --------------------------------------------------------------------------------------------
+    _engine = _slot_property('engine')
+    _engine_key = _slot_property('key')
+    _bound_versions = _slot_property('versions')
+    _keepalive = _slot_property('keepalive')
+
+    def _enter_device(self, device):
+        """Selects the per-device engine slot for this thread; returns the loaded library."""
+        if device.type != 'cuda':
+            raise RuntimeError('capb200: the decode engine runs on CUDA devices only (no CPU fallback); got %s' % device)
+        _tls.dev = device.index if device.index is not None else torch.cuda.current_device()
+        if self._store.owner is None:
+            self._store.owner = id(self)
+        return _lib.load()
+
     def _weight_table(self):
         raise NotImplementedError
 
     def _ensure_engine(self, device):
-        if device.type != 'cuda':
-            raise RuntimeError('capb200: the decode engine runs on CUDA devices only (no CPU fallback); got %s' % device)
-        lib = _lib.load()
-        key = (device.index, self.numeric_mode)
+        lib = self._enter_device(device)
+        key = (_tls.dev, self.numeric_mode)
         if self._engine is None or self._engine_key != key:
             self._destroy_engine()
             cfg = _lib.ModelCfg(self.family, self.vocab_size, self.input_encoding_size, self.rnn_size, self.att_hid_size, self.fc_feat_size,
@@ -137,14 +185,23 @@ class B200CaptionModel(nn.Module):
             self._bound_versions = versions
         return lib
 
+    def _free_engine(self, handle):
+        _lib.load().capb200_engine_destroy(handle)
+
     def _destroy_engine(self):
         if self._engine is not None:
-            _lib.load().capb200_engine_destroy(self._engine)
+            self._free_engine(self._engine)
             self._engine = None
 
     def __del__(self):
         try:
-            self._destroy_engine()
+            store = self.__dict__.get('_store')
+            if store is None or store.owner != id(self):
+                return                                   # DataParallel replica: the engines belong to the original module
+            for slot in store.slots.values():
+                if slot['engine'] is not None:
+                    self._free_engine(slot['engine'])
+                    slot['engine'] = None
         except Exception:
             pass
 
@@ -556,10 +613,8 @@ class B200TransformerModel(B200CaptionModel):
         return out
 
     def _ensure_engine(self, device):
-        if device.type != 'cuda':
-            raise RuntimeError('capb200: the decode engine runs on CUDA devices only (no CPU fallback); got %s' % device)
-        lib = _lib.load()
-        key = (device.index, self.numeric_mode)
+        lib = self._enter_device(device)
+        key = (_tls.dev, self.numeric_mode)
         if self._engine is None or self._engine_key != key:
             self._destroy_engine()
             cfg = _lib.TfmCfg(self.vocab_size, self.d_model, self.d_ff, self.h, self.N_enc, self.N_dec, self.att_feat_size, self.seq_length,
@@ -606,10 +661,8 @@ class B200TransformerModel(B200CaptionModel):
             self._bound_versions = versions
         return lib
 
-    def _destroy_engine(self):
-        if self._engine is not None:
-            _lib.load().capb200_tfm_destroy(self._engine)
-            self._engine = None
+    def _free_engine(self, handle):
+        _lib.load().capb200_tfm_destroy(handle)
 
     @property
     def launch_count(self) -> int:
@@ -676,7 +729,7 @@ class B200AoAModel(B200CaptionModel):
         self.core.attention.linears = nn.ModuleList([nn.Linear(H, H)])
 
     def _tensors(self):
-        return list(self.parameters())
+        return [prm for _, prm in self._slots()]          # attribute access: works on nn.DataParallel replicas too (their parameters() is empty)
 
     def _slots(self):
         """(field path in capb200_aoa_weights / capb200_aoa_grads, parameter) pairs."""
@@ -777,10 +830,8 @@ class B200AoAModel(B200CaptionModel):
         return {'loss': loss[0], 'logprobs': logprobs, 'grads': {prm: grads[id(prm)] for prm in params}, 'seed': seed}
 
     def _ensure_engine(self, device):
-        if device.type != 'cuda':
-            raise RuntimeError('capb200: the decode engine runs on CUDA devices only (no CPU fallback); got %s' % device)
-        lib = _lib.load()
-        key = (device.index, self.numeric_mode)
+        lib = self._enter_device(device)
+        key = (_tls.dev, self.numeric_mode)
         if self._engine is None or self._engine_key != key:
             self._destroy_engine()
             cfg = _lib.AoaCfg(self.vocab_size, self.input_encoding_size, self.rnn_size, self.num_heads, self.att_feat_size, self.seq_length,
@@ -802,10 +853,8 @@ class B200AoAModel(B200CaptionModel):
             self._bound_versions = versions
         return lib
 
-    def _destroy_engine(self):
-        if self._engine is not None:
-            _lib.load().capb200_aoa_destroy(self._engine)
-            self._engine = None
+    def _free_engine(self, handle):
+        _lib.load().capb200_aoa_destroy(handle)
 
     @property
     def launch_count(self) -> int:

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import os
 import pickle
+import threading
 from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
@@ -22,7 +23,8 @@ from . import _lib
 
 
 class CiderDTable:
-    """Owns the device hash table n-gram -> idf (capb200_cider_table)."""
+    """Owns the device hash tables n-gram -> idf (capb200_cider_table), one per GPU, built lazily on the device that asks (under
+    nn.DataParallel every replica scores its shard on its own GPU)."""
 
     def __init__(self, document_frequency: Dict[Tuple, float], ref_len: float, device=None):
         n = len(document_frequency)
@@ -31,14 +33,30 @@ class CiderDTable:
         for i, (k, v) in enumerate(document_frequency.items()):
             keys[i, :len(k)] = [int(t) for t in k]        # pickle keys are tuples of id strings (prepro_ngrams.py:42-45)
             vals[i] = float(v)
+        self._keys, self._vals = keys, vals
         self.ref_len = float(ref_len)
         self.entries = n
+        self._handles = {}
+        self._lock = threading.Lock()
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
-        lib = _lib.load()
-        with torch.cuda.device(self.device):
-            self._h = lib.capb200_cider_table_create(keys.ctypes.data, vals.ctypes.data, n, self.ref_len, _lib.current_stream())
-        if not self._h:
-            raise RuntimeError('capb200 cider_table_create failed: %s' % lib.capb200_last_error().decode())
+        self._handle(self.device.index if self.device.index is not None else torch.cuda.current_device())
+
+    def _handle(self, index: int):
+        with self._lock:
+            h = self._handles.get(index)
+            if h is None:
+                lib = _lib.load()
+                with torch.cuda.device(index):
+                    h = lib.capb200_cider_table_create(self._keys.ctypes.data, self._vals.ctypes.data, self.entries, self.ref_len, _lib.current_stream())
+                if not h:
+                    raise RuntimeError('capb200 cider_table_create failed: %s' % lib.capb200_last_error().decode())
+                self._handles[index] = h
+            return h
+
+    @property
+    def _h(self):
+        """Handle of the table on the calling thread's current CUDA device."""
+        return self._handle(torch.cuda.current_device())
 
     @classmethod
     def from_pickle(cls, path: str, device=None):
@@ -48,9 +66,9 @@ class CiderDTable:
 
     def __del__(self):
         try:
-            if getattr(self, '_h', None):
-                _lib.load().capb200_cider_table_destroy(self._h)
-                self._h = None
+            for h in self._handles.values():
+                _lib.load().capb200_cider_table_destroy(h)
+            self._handles = {}
         except Exception:
             pass
 
