@@ -26,7 +26,6 @@ import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
-sys.path.insert(0, os.path.join(REPO, 'tests'))
 
 CFG = dict(V=9487, E=1000, H=1000, A=512, F_fc=2048, F_att=2048, T=20)     # configs/updown/updown.yml + opts.py defaults
 R = 36
@@ -129,27 +128,25 @@ def bench_scst(args, rank, world, local_rank, dev):
     import torch
     import torch.distributed as dist
     import imagecaptioning.pytorch_b200 as b200
-    from helpers import build_pair
-    from oracle import caption_oracle as co
-    from oracle import ciderd_oracle as cdo
+    from imagecaptioning.pytorch_b200 import synthetic as syn
     B, n, T = args.batch, 5, CFG['T']
     aoa = args.workload == 'aoa_scst'
     if aoa:       # configs/aoa.yml: E = H = 1024, 8 heads, 6 refiner layers, ctx_drop, dropout_aoa 0.3 (BASELINE configs[3])
-        model, _ = build_pair('aoa', seed=1234, logit_scale=6.0, mode=args.mode, device=dev, heads=8, **dict(CFG, E=1024, H=1024, A=0))
+        model = syn.build_model('aoa', seed=1234, logit_scale=6.0, mode=args.mode, device=dev, heads=8, **dict(CFG, E=1024, H=1024, A=0))
     else:
-        model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode=args.mode, device=dev, **CFG)
+        model = syn.build_model('updown', seed=1234, logit_scale=12.0, mode=args.mode, device=dev, **CFG)
     fam_name = 'AoANet' if aoa else 'UpDown'
     model.train()
-    df, ref_len = cdo.build_document_frequency(cdo.make_refs(1000, CFG['V'], seed=4))        # synthetic DF table (format of prepro_ngrams.py)
+    df, ref_len = syn.document_frequency(syn.make_refs(1000, CFG['V'], seed=4))              # synthetic DF table (format of prepro_ngrams.py)
     b200.rewards.reset_scorer()
     b200.rewards.init_scorer(b200.rewards.CiderDTable(df, ref_len))
     opt = ap.Namespace(sc_sample_method='greedy', sc_beam_size=1, train_sample_method='sample', train_beam_size=1, train_sample_n=n,
                        cider_reward_weight=1, bleu_reward_weight=0)
     lw = b200.B200LossWrapper(model, opt)
     optim = torch.optim.Adam(model.parameters(), lr=5e-5)
-    host = [co.make_inputs(B, R, CFG['F_fc'], CFG['F_att'], seed=99 + 13 * rank + i) for i in range(3)]
+    host = [syn.make_inputs(B, R, CFG['F_fc'], CFG['F_att'], seed=99 + 13 * rank + i) for i in range(3)]
     host = [(a.pin_memory(), b.pin_memory()) for a, b in host]
-    gts = cdo.make_refs(B, CFG['V'], seed=5 + rank)
+    gts = syn.make_refs(B, CFG['V'], seed=5 + rank)
     idx = torch.arange(B)
     grad_bytes = [0]
 
@@ -249,22 +246,21 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
         dist.barrier()
-    from helpers import build_pair
-    from oracle import caption_oracle as co
+    from imagecaptioning.pytorch_b200 import synthetic as syn      # seeded random-init weights / features: the GPU arm never touches oracle/
     dev = torch.device('cuda', local_rank)
     if args.workload in ('updown_scst', 'aoa_scst'):
         return bench_scst(args, rank, world, local_rank, dev)
     if args.workload == 'updown_beam':
-        model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode=args.mode, device=dev, **CFG)
+        model = syn.build_model('updown', seed=1234, logit_scale=12.0, mode=args.mode, device=dev, **CFG)
     elif args.workload == 'transformer_beam':     # configs/transformer/transformer.yml: d_model 512, d_ff 2048, 6 + 6 layers, 8 heads
-        model, _ = build_pair('transformer', seed=1234, logit_scale=3.0, mode=args.mode, device=dev, heads=8,
-                              **dict(CFG, E=512, H=2048, A=6))
+        model = syn.build_model('transformer', seed=1234, logit_scale=3.0, mode=args.mode, device=dev, heads=8,
+                                **dict(CFG, E=512, H=2048, A=6))
     else:                                         # configs/aoa.yml: E = H = 1024, 8 heads, 6 refiner layers
-        model, _ = build_pair('aoa', seed=1234, logit_scale=6.0, mode=args.mode, device=dev, heads=8, **dict(CFG, E=1024, H=1024, A=0))
+        model = syn.build_model('aoa', seed=1234, logit_scale=6.0, mode=args.mode, device=dev, heads=8, **dict(CFG, E=1024, H=1024, A=0))
     B, T = args.batch, CFG['T']
     opt = {'beam_size': args.beam, 'sample_n': 1}
     n_rot = 3                                         # rotate input batches; per-step working set (features, weights, 1 GB slab) >> 126 MB L2
-    host = [co.make_inputs(B, R, CFG['F_fc'], CFG['F_att'], seed=1234 + 17 * rank + i) for i in range(n_rot)]
+    host = [syn.make_inputs(B, R, CFG['F_fc'], CFG['F_att'], seed=1234 + 17 * rank + i) for i in range(n_rot)]
     host = [(a.pin_memory(), b.pin_memory()) for a, b in host]
     devin = [(a.to(dev), b.to(dev)) for a, b in host]
 

@@ -597,108 +597,7 @@ def reward_criterion_grad(seq: Tensor, reward: Tensor, V1: int) -> Tensor:
 
 
 # --------------------------------------------------------------------------------------------------
-# synthetic weights (shared by tests, bench and the golden generator)
+# synthetic weights / inputs: the seeded generators live in the package (imagecaptioning.pytorch_b200.synthetic) because bench.py's
+# GPU arm needs them without importing the oracle; re-exported here for the tests and the golden generator.
 # --------------------------------------------------------------------------------------------------
-
-def _uniform(gen, shape, bound):
-    return (torch.rand(shape, generator=gen) * 2 - 1) * bound
-
-
-def make_weights(family: str, V: int, E: int, H: int, A: int, F_fc: int, F_att: int, seed: int = 1234,
-                 logit_scale: float = 12.0) -> Weights:
-    """Deterministic synthetic weights with torch-default-like ranges; ``logit.weight`` is scaled so the
-    next-word distribution is peaked (top-1/top-2 margins far above the 1e-4 log-prob tolerance)."""
-    g = torch.Generator().manual_seed(seed)
-    V1 = V + 1
-    W: Weights = {}
-
-    def lin(name, out_f, in_f, scale=1.0):
-        b = 1.0 / math.sqrt(in_f)
-        W[name + '.weight'] = _uniform(g, (out_f, in_f), b) * scale
-        W[name + '.bias'] = _uniform(g, (out_f,), b)
-
-    if family == 'updown':
-        W['embed.0.weight'] = torch.randn(V1, E, generator=g)
-        lin('fc_embed.0', H, F_fc)
-        lin('att_embed.0', H, F_att)
-        lin('logit', V1, H, logit_scale)
-        lin('ctx2att', A, H)
-        b = 1.0 / math.sqrt(H)
-        for cell, in_f in (('core.att_lstm', E + 2 * H), ('core.lang_lstm', 2 * H)):
-            W[cell + '.weight_ih'] = _uniform(g, (4 * H, in_f), b)
-            W[cell + '.weight_hh'] = _uniform(g, (4 * H, H), b)
-            W[cell + '.bias_ih'] = _uniform(g, (4 * H,), b)
-            W[cell + '.bias_hh'] = _uniform(g, (4 * H,), b)
-        lin('core.attention.h2att', A, H)
-        lin('core.attention.alpha_net', 1, A)
-    elif family == 'aoa':
-        W['embed.0.weight'] = torch.randn(V1, E, generator=g)
-        lin('att_embed.0', H, F_att)
-        lin('logit', V1, H, logit_scale)
-        lin('ctx2att', 2 * H, H)
-        for i in range(6):
-            pre = 'refiner.layers.%d.' % i
-            for j in range(3):
-                lin(pre + 'self_attn.linears.%d' % j, H, H)
-            lin(pre + 'self_attn.aoa_layer.0', 2 * H, 2 * H)
-            W[pre + 'sublayer.0.norm.a_2'] = 1 + 0.1 * torch.randn(H, generator=g)
-            W[pre + 'sublayer.0.norm.b_2'] = 0.1 * torch.randn(H, generator=g)
-        W['refiner.norm.a_2'] = 1 + 0.1 * torch.randn(H, generator=g)
-        W['refiner.norm.b_2'] = 0.1 * torch.randn(H, generator=g)
-        b = 1.0 / math.sqrt(H)
-        W['core.att_lstm.weight_ih'] = _uniform(g, (4 * H, E + H), b)
-        W['core.att_lstm.weight_hh'] = _uniform(g, (4 * H, H), b)
-        W['core.att_lstm.bias_ih'] = _uniform(g, (4 * H,), b)
-        W['core.att_lstm.bias_hh'] = _uniform(g, (4 * H,), b)
-        lin('core.att2ctx.0', 2 * H, 2 * H)
-        W['core.attention.norm.a_2'] = 1 + 0.1 * torch.randn(H, generator=g)
-        W['core.attention.norm.b_2'] = 0.1 * torch.randn(H, generator=g)
-        lin('core.attention.linears.0', H, H)
-        W['logit.bias'][0] -= 4.0          # keep EOS from winning at the first steps so the synthetic captions have some length
-    elif family == 'transformer':
-        # here E = d_model, H = d_ff, A = number of layers (both stacks)
-        D, Dff, NL = E, H, A
-
-        def xav(name, out_f, in_f, scale=1.0):
-            bnd = math.sqrt(6.0 / (in_f + out_f))
-            W[name + '.weight'] = _uniform(g, (out_f, in_f), bnd) * scale
-            W[name + '.bias'] = _uniform(g, (out_f,), 1.0 / math.sqrt(in_f))
-
-        def norm(name):
-            W[name + '.a_2'] = 1 + 0.1 * torch.randn(D, generator=g)
-            W[name + '.b_2'] = 0.1 * torch.randn(D, generator=g)
-
-        xav('att_embed.0', D, F_att)
-        for stack, n_sub in (('encoder', 2), ('decoder', 3)):
-            for i in range(NL):
-                pre = 'model.%s.layers.%d.' % (stack, i)
-                for att_name in (('self_attn',) if stack == 'encoder' else ('self_attn', 'src_attn')):
-                    for j in range(4):
-                        xav(pre + att_name + '.linears.%d' % j, D, D)
-                xav(pre + 'feed_forward.w_1', Dff, D)
-                xav(pre + 'feed_forward.w_2', D, Dff)
-                for j in range(n_sub):
-                    norm(pre + 'sublayer.%d.norm' % j)
-            norm('model.%s.norm' % stack)
-        W['model.tgt_embed.0.lut.weight'] = torch.randn(V1, D, generator=g) * (1.0 / math.sqrt(D))
-        pe = torch.zeros(5000, D)
-        position = torch.arange(0, 5000).unsqueeze(1).float()
-        div_term = torch.exp(torch.arange(0, D, 2).float() * -(math.log(10000.0) / D))
-        pe[:, 0::2] = torch.sin(position * div_term)
-        pe[:, 1::2] = torch.cos(position * div_term)
-        W['model.tgt_embed.1.pe'] = pe.unsqueeze(0)
-        xav('model.generator.proj', V1, D, logit_scale)
-    elif family == 'newfc':
-        W['embed.weight'] = torch.randn(V1, E, generator=g)
-        lin('fc_embed', E, F_fc)
-        lin('logit', V1, H, logit_scale)
-        lin('_core.i2h', 5 * H, E)
-        lin('_core.h2h', 5 * H, H)
-    else:
-        raise ValueError(family)
-    return W
-
-
-def make_inputs(B: int, R: int, F_fc: int, F_att: int, seed: int = 1234):
-    g = torch.Generator().manual_seed(seed + 1)
-    return torch.randn(B, F_fc, generator=g), torch.randn(B, R, F_att, generator=g)
+from imagecaptioning.pytorch_b200.synthetic import make_inputs, make_weights      # noqa: E402,F401

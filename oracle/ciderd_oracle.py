@@ -121,19 +121,4 @@ def get_scores(gts: Sequence[np.ndarray], sampled: np.ndarray, df: Dict[Tuple[in
     return cider_weight * ciderd_scores(hyps, [ref_tok[i // n] for i in range(S)], df, ref_len)
 
 
-def make_refs(B: int, V: int, n_refs: int = 5, L: int = 16, seed: int = 7, zipf: bool = True) -> List[np.ndarray]:
-    """Synthetic references: per image n_refs rows, lengths U[6,15], 0-padded to L.  Ids follow a Zipf-like law so
-    n-grams repeat (otherwise every similarity would be 0)."""
-    rng = np.random.RandomState(seed)
-    out = []
-    for _ in range(B):
-        rows = np.zeros((n_refs, L), dtype=np.int64)
-        for j in range(n_refs):
-            ln = rng.randint(6, 16)
-            if zipf:
-                ids = np.minimum(rng.zipf(1.3, size=ln), V).astype(np.int64)
-            else:
-                ids = rng.randint(1, V + 1, size=ln)
-            rows[j, :ln] = ids
-        out.append(rows)
-    return out
+from imagecaptioning.pytorch_b200.synthetic import make_refs      # noqa: E402,F401  (seeded synthetic references, shared with bench.py)

@@ -59,3 +59,32 @@ def test_loss_wrapper_option_guards():
         lw(fc, att, None, None, None, gts, torch.arange(2), True, False, False)
     with pytest.raises(NotImplementedError):
         b200.loss_wrapper.StructureLosses(argparse.Namespace(structure_loss_type='risk'))
+
+
+def test_bench_gpu_arm_does_not_import_the_oracle():
+    """Only bench.py's CPU-baseline leg may touch oracle/ (or the test helpers that import it); the measured GPU arms build their synthetic
+    model and inputs from the package's own generators."""
+    import ast
+    src = open(os.path.join(os.path.dirname(os.path.dirname(__file__)), 'bench.py')).read()
+    tree = ast.parse(src)
+    offenders = []
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)] + [tree]:
+        for node in ast.walk(fn):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or '']
+            for nm in names:
+                if nm.split('.')[0] in ('oracle', 'helpers') and getattr(fn, 'name', '<module>') != 'cpu_reference_rate':
+                    if isinstance(fn, ast.Module) and any(node in ast.walk(f) for f in ast.walk(tree) if isinstance(f, ast.FunctionDef)):
+                        continue                      # counted with its enclosing function
+                    offenders.append((getattr(fn, 'name', '<module>'), nm))
+    assert offenders == [], offenders
+
+
+def test_synthetic_document_frequency_matches_oracle_builder():
+    from imagecaptioning.pytorch_b200 import synthetic as syn
+    from oracle import ciderd_oracle as cdo
+    refs = syn.make_refs(40, 120, seed=4)
+    assert syn.document_frequency(refs) == cdo.build_document_frequency(refs)
