@@ -8,5 +8,8 @@ from .models import B200UpDownModel, B200NewFCModel, B200TransformerModel, B200A
 from .loss_wrapper import B200LossWrapper, RewardCriterion                        # noqa: F401
 from . import rewards                                 # noqa: F401
 from . import parallel                                # noqa: F401
+from . import utils                                   # noqa: F401
+from .utils import decode_sequence                    # noqa: F401
 
-__all__ = ['setup', 'B200UpDownModel', 'B200NewFCModel', 'B200CaptionModel', 'B200LossWrapper', 'RewardCriterion', 'rewards', 'parallel']
+__all__ = ['setup', 'B200UpDownModel', 'B200NewFCModel', 'B200TransformerModel', 'B200AoAModel', 'B200CaptionModel', 'B200LossWrapper', 'RewardCriterion',
+           'rewards', 'parallel', 'utils', 'decode_sequence']

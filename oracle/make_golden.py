@@ -273,6 +273,29 @@ def gen_xe_struct(out_dir, scratch):
           'xels', float(res['xels_loss']))
 
 
+def gen_decode_sequence(out_dir):
+    """captioning/utils/misc.py:62-84 on random id rows (with bad endings, BPE pieces, empty rows), with and without REMOVE_BAD_ENDINGS."""
+    import json
+    import captioning.utils.misc as M
+    rng = np.random.RandomState(3)
+    words = ['with', 'in', 'on', 'of', 'a', 'at', 'to', 'for', 'an', 'this', 'his', 'her', 'that', 'the', 'dog', 'cat@@', 's', 'runn@@', 'ing', 'man',
+             'sits', 'table', 'red', 'two']
+    vocab = {str(i + 1): w for i, w in enumerate(words)}
+    seq = np.zeros((40, 9), np.int64)
+    for i in range(40):
+        ln = rng.randint(0, 10)
+        seq[i, :ln] = rng.randint(1, len(words) + 1, size=ln)
+    seq[5, :3] = [1, 2, 3]                 # only bad endings
+    seq[6, :4] = [15, 21, 3, 14]           # ends with two bad endings
+    res = {}
+    for flag in ('0', '1'):
+        os.environ['REMOVE_BAD_ENDINGS'] = flag
+        res[flag] = M.decode_sequence(vocab, torch.from_numpy(seq))
+    os.environ.pop('REMOVE_BAD_ENDINGS', None)
+    json.dump({'vocab': vocab, 'seq': seq.tolist(), 'out': res}, open(os.path.join(out_dir, 'decode_sequence.json'), 'w'))
+    print('decode_sequence', res['0'][6], '|', res['1'][6])
+
+
 def gen_reward_criterion(out_dir):
     from captioning.modules.losses import RewardCriterion
     g = torch.Generator().manual_seed(3)
@@ -364,7 +387,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     scratch = _enter_scratch()
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys', 'tfm', 'aoa', 'xe']
+    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys', 'tfm', 'aoa', 'xe', 'dseq']
     if 'small' in which:
         gen_updown_small(out_dir)
     if 'newfc' in which:
@@ -375,6 +398,8 @@ def main():
         gen_ciderd(out_dir, scratch)
     if 'rc' in which:
         gen_reward_criterion(out_dir)
+    if 'dseq' in which:
+        gen_decode_sequence(out_dir)
     if 'xe' in which:
         gen_xe_struct(out_dir, scratch)            # needs the scratch pickle written by gen_ciderd in the same run
     if 'keys' in which:

@@ -88,3 +88,16 @@ def test_synthetic_document_frequency_matches_oracle_builder():
     from oracle import ciderd_oracle as cdo
     refs = syn.make_refs(40, 120, seed=4)
     assert syn.document_frequency(refs) == cdo.build_document_frequency(refs)
+
+
+def test_decode_sequence_matches_reference(monkeypatch):
+    """utils.decode_sequence against strings produced by the reference's misc.decode_sequence (incl. REMOVE_BAD_ENDINGS and BPE merges)."""
+    import json
+    from imagecaptioning.pytorch_b200.utils import decode_sequence
+    g = json.load(open(os.path.join(GOLD, 'decode_sequence.json')))
+    seq = torch.tensor(g['seq'])
+    for flag in ('0', '1'):
+        monkeypatch.setenv('REMOVE_BAD_ENDINGS', flag)
+        assert decode_sequence(g['vocab'], seq) == g['out'][flag]
+    monkeypatch.delenv('REMOVE_BAD_ENDINGS')
+    assert decode_sequence(g['vocab'], seq.numpy()) == g['out']['0']
