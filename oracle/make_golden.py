@@ -296,6 +296,58 @@ def gen_decode_sequence(out_dir):
     print('decode_sequence', res['0'][6], '|', res['1'][6])
 
 
+def gen_ciderd_pascal(out_dir, scratch):
+    """CIDEr-D of the live reference scorer on REAL captions: the first 60 images of cider/data/pascal50S.json (50 references each) and
+    their candidates from pascal_candsB.json, lower-cased and split on non-alphanumerics, words mapped to ids 1..V; the document
+    frequencies come from the reference's own compute_doc_freq over those references."""
+    import json
+    import re
+    from collections import defaultdict, OrderedDict
+    from captioning.utils import rewards as R
+    sys.path.append('cider')
+    from pyciderevalcap.ciderD.ciderD_scorer import CiderScorer
+    refs_all = json.load(open(os.path.join(REF, 'cider', 'data', 'pascal50S.json')))
+    cands_all = json.load(open(os.path.join(REF, 'cider', 'data', 'pascal_candsB.json')))
+    tok = lambda t: [w for w in re.split(r'[^a-z0-9]+', t.lower()) if w]
+    by_img = OrderedDict()
+    for r in refs_all:
+        by_img.setdefault(r['image_id'], []).append(tok(r['caption']))
+    imgs = [k for k in by_img][:60]
+    cand_of = {c['image_id']: tok(c['caption']) for c in cands_all}
+    imgs = [k for k in imgs if k in cand_of and cand_of[k]][:60]
+    vocab = {}
+    def ids(words):
+        return [vocab.setdefault(w, len(vocab) + 1) for w in words]
+    L = 40
+    refs = np.zeros((len(imgs), 50, L), np.int32)
+    cands = np.zeros((len(imgs), L), np.int64)
+    for i, k in enumerate(imgs):
+        for j, words in enumerate(by_img[k][:50]):
+            w = ids(words)[:L - 1]
+            refs[i, j, :len(w)] = w
+        w = ids(cand_of[k])[:L - 1]
+        cands[i, :len(w)] = w
+    cs = CiderScorer(df_mode='corpus')
+    for i in range(len(imgs)):
+        cs.cook_append(None, [R.array_to_str(r) for r in refs[i]])
+    cs.compute_doc_freq()
+    dd = defaultdict(float)
+    dd.update(cs.document_frequency)
+    with open(os.path.join(scratch, 'data', 'pascal-df.p'), 'wb') as f:
+        pickle.dump({'document_frequency': dd, 'ref_len': float(len(imgs))}, f, protocol=2)
+    R.CiderD_scorer = None
+    R.init_scorer('pascal-df')
+    res_ = [{'image_id': i, 'caption': [R.array_to_str(cands[i])]} for i in range(len(imgs))]
+    gts_ = {i: [R.array_to_str(r) for r in refs[i]] for i in range(len(imgs))}
+    mean, scores = R.CiderD_scorer.compute_score(gts_, res_)
+    keys = np.array([[int(t) for t in k] + [-1] * (4 - len(k)) for k in cs.document_frequency.keys()], np.int32)
+    vals = np.array(list(cs.document_frequency.values()), np.float64)
+    np.savez_compressed(os.path.join(out_dir, 'ciderd_pascal.npz'), df_keys=keys, df_vals=vals, ref_len=np.array(float(len(imgs))), refs=refs.astype(np.int16),
+                        cands=cands.astype(np.int16), scores=np.asarray(scores), mean=np.array(mean))
+    R.CiderD_scorer = None
+    print('ciderd_pascal: %d images, %d n-grams, vocabulary %d, mean CIDEr-D %.4f' % (len(imgs), len(keys), len(vocab), mean))
+
+
 def gen_reward_criterion(out_dir):
     from captioning.modules.losses import RewardCriterion
     g = torch.Generator().manual_seed(3)
@@ -387,7 +439,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     scratch = _enter_scratch()
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys', 'tfm', 'aoa', 'xe', 'dseq']
+    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys', 'tfm', 'aoa', 'xe', 'dseq', 'pascal']
     if 'small' in which:
         gen_updown_small(out_dir)
     if 'newfc' in which:
@@ -400,6 +452,8 @@ def main():
         gen_reward_criterion(out_dir)
     if 'dseq' in which:
         gen_decode_sequence(out_dir)
+    if 'pascal' in which:
+        gen_ciderd_pascal(out_dir, scratch)
     if 'xe' in which:
         gen_xe_struct(out_dir, scratch)            # needs the scratch pickle written by gen_ciderd in the same run
     if 'keys' in which:

@@ -363,3 +363,17 @@ def test_aoa_xe_step_gradients(dropout, smoothing):
     assert float((res['logprobs'].cpu() - lp.detach()).abs().max()) < LOGP_TOL
     assert abs(float(res['loss']) - float(loss)) < LOGP_TOL
     _check_grads(model, res['grads'], {k: v.grad for k, v in Wg.items()})
+
+
+def test_cider_kernel_on_real_captions(golden_dir):
+    """The CIDEr-D reward kernel on real text: 60 PASCAL-50S images with 50 references each (tests/golden/ciderd_pascal.npz, produced by
+    the live reference scorer), document-frequency table of 38 k n-grams."""
+    import os
+    import imagecaptioning.pytorch_b200 as b200
+    g = np.load(os.path.join(golden_dir, 'ciderd_pascal.npz'))
+    df = {tuple(int(t) for t in k if t >= 0): float(v) for k, v in zip(g['df_keys'], g['df_vals'])}
+    table = b200.rewards.CiderDTable(df, float(g['ref_len']))
+    refs, cands = g['refs'].astype(np.int64), torch.from_numpy(g['cands'].astype(np.int64)).cuda()
+    gts = [refs[i] for i in range(refs.shape[0])]
+    scores = b200.rewards.cider_scores(gts, cands, table).cpu().numpy()
+    assert np.abs(scores - g['scores']).max() < 1e-9

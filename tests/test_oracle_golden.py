@@ -190,3 +190,18 @@ def test_xe_step_of_the_reference_model(golden_dir, name, smoothing):
             ref = g[k]
             got = Wg[k[len(name) + 6:]].grad.numpy()
             assert np.abs(got - ref).max() < 1e-5 * max(1.0, np.abs(ref).max()), k
+
+
+def test_ciderd_on_real_captions(golden_dir):
+    """CIDEr-D restatement against the live reference scorer on real text: 60 PASCAL-50S images with 50 references each and their
+    candidate captions (cider/data/pascal50S.json, pascal_candsB.json), document frequencies from the reference's compute_doc_freq."""
+    g = _load(golden_dir, 'ciderd_pascal.npz')
+    df = _df_from_golden(g)
+    refs, cands = g['refs'].astype(np.int64), g['cands'].astype(np.int64)
+    gts = [refs[i] for i in range(refs.shape[0])]
+    scores = cdo.get_scores(gts, cands, df, float(g['ref_len']))
+    assert np.abs(scores - g['scores']).max() < 1e-9
+    assert abs(float(scores.mean()) - float(g['mean'])) < 1e-9 and float(g['mean']) > 0.3
+    # the document-frequency builder reproduces the reference's table on real text too
+    df2, n_img = cdo.build_document_frequency(gts)
+    assert df2 == df and n_img == int(g['ref_len'])
