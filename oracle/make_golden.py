@@ -105,6 +105,24 @@ def gen_updown_small(out_dir):
     print('updown_small', {k: v.shape for k, v in res.items()})
 
 
+def gen_updown_penalty(out_dir):
+    """Beam search with the length penalties of misc.penalty_builder (:133-158) on the small UpDown configuration."""
+    cfg = dict(V=60, E=32, H=32, A=16, F_fc=48, F_att=48, T=8)
+    B, R, b = 4, 7, 3
+    W = co.make_weights('updown', cfg['V'], cfg['E'], cfg['H'], cfg['A'], cfg['F_fc'], cfg['F_att'], seed=11, logit_scale=20.0)
+    fc, att = co.make_inputs(B, R, cfg['F_fc'], cfg['F_att'], seed=11)
+    m = ref_model('updown', W=W, **cfg)
+    res = {}
+    with torch.no_grad():
+        for tag, pen in (('wu', 'wu_0.5'), ('avg', 'avg_0'), ('wu2', 'wu_1.5')):
+            seq, lp = m(fc, att, None, opt={'beam_size': b, 'sample_n': 1, 'length_penalty': pen}, mode='sample')
+            res[tag + '_seq'], res[tag + '_lp'] = seq.numpy(), lp.numpy()
+            res[tag + '_done_seq'], res[tag + '_done_len'], res[tag + '_done_p'] = beams_to_arrays(m.done_beams, b, cfg['T'])
+    np.savez_compressed(os.path.join(out_dir, 'updown_penalty.npz'), cfg=np.array([cfg[k] for k in ('V', 'E', 'H', 'A', 'F_fc', 'F_att', 'T')]),
+                        meta=np.array([B, R, b, 11]), **res)
+    print('updown_penalty', res['wu_seq'][0].tolist(), res['avg_seq'][0].tolist(), np.round(res['wu2_done_p'][0], 3).tolist())
+
+
 def gen_newfc(out_dir):
     """BASELINE.json configs[0]: newfc greedy, batch 4, 2048-d fc feats, seq_len 16 (opts.py defaults E=H=512)."""
     cfg = dict(V=9487, E=512, H=512, A=512, F_fc=2048, F_att=2048, T=16)
@@ -439,11 +457,13 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     scratch = _enter_scratch()
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys', 'tfm', 'aoa', 'xe', 'dseq', 'pascal']
+    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys', 'tfm', 'aoa', 'xe', 'dseq', 'pascal', 'penalty']
     if 'small' in which:
         gen_updown_small(out_dir)
     if 'newfc' in which:
         gen_newfc(out_dir)
+    if 'penalty' in which:
+        gen_updown_penalty(out_dir)
     if 'full' in which:
         gen_updown_full(out_dir)
     if 'ciderd' in which:

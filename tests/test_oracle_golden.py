@@ -205,3 +205,18 @@ def test_ciderd_on_real_captions(golden_dir):
     # the document-frequency builder reproduces the reference's table on real text too
     df2, n_img = cdo.build_document_frequency(gts)
     assert df2 == df and n_img == int(g['ref_len'])
+
+
+@pytest.mark.parametrize('tag,pen', [('wu', 'wu_0.5'), ('avg', 'avg_0'), ('wu2', 'wu_1.5')])
+def test_beam_length_penalties(golden_dir, tag, pen):
+    """misc.penalty_builder (length_wu / length_average) only re-ranks the finished beams ('p'): ids, log-probs and penalised scores of
+    the reference's beam search with each penalty."""
+    g = _load(golden_dir, 'updown_penalty.npz')
+    V, E, H, A, F_fc, F_att, T = (int(x) for x in g['cfg'])
+    B, R, b, seed = (int(x) for x in g['meta'])
+    W = co.make_weights('updown', V, E, H, A, F_fc, F_att, seed=seed, logit_scale=20.0)
+    fc, att = co.make_inputs(B, R, F_fc, F_att, seed=seed)
+    seq, lp, done = co.sample_beam(co.Family('updown', W, T), fc, att, beam_size=b, length_penalty=pen)
+    assert np.array_equal(seq.numpy(), g[tag + '_seq'])
+    assert np.abs(lp.numpy() - g[tag + '_lp']).max() < TOL
+    assert np.abs(np.array([[r['p'] for r in d] for d in done]) - g[tag + '_done_p']).max() < 1e-3
