@@ -101,3 +101,26 @@ def test_decode_sequence_matches_reference(monkeypatch):
         assert decode_sequence(g['vocab'], seq) == g['out'][flag]
     monkeypatch.delenv('REMOVE_BAD_ENDINGS')
     assert decode_sequence(g['vocab'], seq.numpy()) == g['out']['0']
+
+
+def test_decode_option_guards():
+    """SURVEY appendix A items 2 and 15 plus the section 8(f) 'later' options: unsupported decode options raise before any device work,
+    the reference's own assertions on beam_size / sample_n hold."""
+    import imagecaptioning.pytorch_b200 as b200
+    cfg = dict(V=30, E=16, H=16, A=8, F_fc=16, F_att=16, T=5)
+    model = b200.setup(family_opt('updown', **cfg))
+    fc, att = co.make_inputs(2, 3, 16, 16, seed=1)
+    for bad in ({'group_size': 2, 'beam_size': 2}, {'decoding_constraint': 1}, {'block_trigrams': 1}, {'remove_bad_endings': 1}, {'output_logsoftmax': 0},
+                {'sample_method': 'top0.9'}, {'sample_method': 'gumbel'}):
+        with pytest.raises(NotImplementedError):
+            model(fc, att, None, opt=dict({'beam_size': 1}, **bad), mode='sample')
+    with pytest.raises(AssertionError):        # AttModel.py:223: sample_n must be 1 or beam_size when beam searching
+        model(fc, att, None, opt={'beam_size': 3, 'sample_n': 2}, mode='sample')
+    with pytest.raises(AssertionError):        # AttModel.py:228: beam_size <= vocab_size + 1
+        model(fc, att, None, opt={'beam_size': 40, 'sample_n': 1}, mode='sample')
+    opt_unk = family_opt('updown', **cfg)
+    opt_unk.vocab = dict(opt_unk.vocab)
+    opt_unk.vocab[str(cfg['V'])] = 'UNK'
+    unk_model = b200.setup(opt_unk)
+    with pytest.raises(NotImplementedError):   # CaptionModel.py:120,161-162: UNK suppression is not on the engine path
+        unk_model(fc, att, None, opt={'beam_size': 2, 'sample_n': 1, 'suppress_UNK': 1}, mode='sample')
