@@ -10,9 +10,14 @@ collective ("scaling": "weak"); the only collectives are the timing barrier and 
   value   captions/s with the step's inputs already resident in HBM (CUDA events, max over ranks)
   e2e     the same metric through the public model(...) call with HOST (pinned) inputs: H2D copy of the features and the
           D2H read of the caption ids are inside the timed region, every step
-  roofline the dominant kernel (attention-LSTM gate GEMM, tcgen05): algorithmic FLOPs / CUDA-event time vs the measured bf16
-          tensor peak in MEASURED_PEAKS.json (see DESIGN.md for why the parity-grade 3-pass kernel tops out at 1/3 of it)
+  roofline the dominant kernel (the persistent tcgen05 GEMM: CTA-pair kernel for the LSTM-gate and logit call sites): algorithmic
+          FLOPs of all its launches / their CUDA-event time vs the measured bf16 tensor peak in MEASURED_PEAKS.json, the DRAM traffic
+          of the largest call site from the committed ncu capture, and the fraction of the 3-pass ceiling
   cpu_baseline  the oracle port of the reference's CPU path, timed on this box's host cores on a bounded sample
+
+Other workloads (--workload): transformer_beam / aoa_beam (BASELINE configs[2] shape and AoANet decode), updown_scst / aoa_scst (SCST
+training step incl. H2D, the single NCCL gradient all-reduce and Adam; aoa_scst = BASELINE configs[3]).  The GPU arms build their
+seeded random-init model and features from imagecaptioning.pytorch_b200.synthetic; only cpu_reference_rate() touches oracle/.
 """
 from __future__ import annotations
 

@@ -16,21 +16,16 @@ LOGP_TOL = 1e-4      # BASELINE.json north_star: log-probs within 1e-4 (fp32)
 PARITY_MODES = ['simt_fp32', 'tc_f16x3']
 
 
-def make_opt(family, V, E, H, A, F_fc, F_att, T):
-    return argparse.Namespace(vocab_size=V, input_encoding_size=E, rnn_size=H, num_layers=1, drop_prob_lm=0.5, max_length=T, seq_length=T,
-                              fc_feat_size=F_fc, att_feat_size=F_att, att_hid_size=A, vocab={str(i): 'w%d' % i for i in range(1, V + 1)},
-                              caption_model=family, use_bn=0, logit_layers=1)
+from imagecaptioning.pytorch_b200 import synthetic as syn   # noqa: E402
 
 
 def family_opt(family, V, E, H, A, F_fc, F_att, T, heads=8):
     """opt namespace for a family; for 'transformer' E = d_model, H = d_ff, A = layers per stack (make_weights convention)."""
-    opt = make_opt(family, V, E, H, A, F_fc, F_att, T)
-    if family == 'transformer':
-        opt.num_layers, opt.N_enc, opt.N_dec, opt.d_model, opt.d_ff, opt.num_att_heads = A, A, A, E, H, heads
-    if family == 'aoa':
-        opt.num_layers, opt.refine, opt.refine_aoa, opt.use_ff, opt.decoder_type, opt.use_multi_head = 2, 1, 1, 0, 'AoA', 2
-        opt.num_heads, opt.multi_head_scale, opt.mean_feats, opt.ctx_drop = heads, 1, 1, 1
-    return opt
+    return syn.model_opt(family, V, E, H, A, F_fc, F_att, T, heads)
+
+
+def make_opt(family, V, E, H, A, F_fc, F_att, T):
+    return syn.model_opt(family, V, E, H, A, F_fc, F_att, T)
 
 
 def build_pair(family, V, E, H, A, F_fc, F_att, T, seed, logit_scale, mode, device='cuda', heads=8):
