@@ -161,10 +161,9 @@ def document_frequency(ref_rows_per_image: Sequence[Sequence[Sequence[int]]], ma
 def model_opt(family: str, V: int, E: int, H: int, A: int, F_fc: int, F_att: int, T: int, heads: int = 8):
     """argparse-style ``opt`` of the reference for one family (for 'transformer': E = d_model, H = d_ff, A = layers per stack)."""
     import argparse
-    name = {'updown': 'updown', 'newfc': 'newfc', 'transformer': 'transformer', 'aoa': 'aoa'}[family]
     opt = argparse.Namespace(vocab_size=V, input_encoding_size=E, rnn_size=H, num_layers=1, drop_prob_lm=0.5, max_length=T, seq_length=T,
                              fc_feat_size=F_fc, att_feat_size=F_att, att_hid_size=A, vocab={str(i): 'w%d' % i for i in range(1, V + 1)},
-                             caption_model=name, use_bn=0, logit_layers=1)
+                             caption_model=family, use_bn=0, logit_layers=1)
     if family == 'transformer':
         opt.num_layers, opt.N_enc, opt.N_dec, opt.d_model, opt.d_ff, opt.num_att_heads = A, A, A, E, H, heads
     if family == 'aoa':
