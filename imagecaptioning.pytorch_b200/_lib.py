@@ -41,7 +41,8 @@ class SampleOpts(Structure):
 
 
 class ScstOpts(Structure):
-    _fields_ = [('sample_n', c_int), ('temperature', c_float), ('seed', c_ulonglong), ('drop_prob', c_float), ('upstream', c_float), ('baseline', c_int)]
+    _fields_ = [('sample_n', c_int), ('temperature', c_float), ('seed', c_ulonglong), ('drop_prob', c_float), ('upstream', c_float), ('baseline', c_int),
+                ('forced_tokens', c_void_p)]
 
 
 BASELINE_GREEDY, BASELINE_LEAVE_ONE_OUT = 0, 1
@@ -49,7 +50,8 @@ BASELINE_GREEDY, BASELINE_LEAVE_ONE_OUT = 0, 1
 
 class AoaScstOpts(Structure):
     _fields_ = [('sample_n', c_int), ('temperature', c_float), ('seed', c_ulonglong), ('upstream', c_float), ('baseline', c_int),
-                ('drop_prob_lm', c_float), ('drop_attn', c_float), ('drop_aoa', c_float), ('drop_sublayer', c_float), ('ctx_drop', c_int)]
+                ('drop_prob_lm', c_float), ('drop_attn', c_float), ('drop_aoa', c_float), ('drop_sublayer', c_float), ('ctx_drop', c_int),
+                ('forced_tokens', c_void_p)]
 
 
 class AoaXeOpts(Structure):
@@ -119,6 +121,7 @@ class AoaWeights(Structure):
 SIGNATURES = {
     'capb200_last_error': (c_char_p, []),
     'capb200_abi_version': (c_int, []),
+    'capb200_range_status': (c_int, [c_int]),
     'capb200_linear': (c_int, [c_void_p, c_long, c_void_p, c_long, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'capb200_bench_linear': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'capb200_lstm_cell': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,

@@ -292,6 +292,7 @@ int core_step(capb200_aoa_engine* e, int rows, int rpi, const int* tokens, const
 int check_ready(capb200_aoa_engine* e) {
     CAPB_REQUIRE(e != nullptr, "null engine");
     CAPB_REQUIRE(e->bound, "capb200_aoa_bind_weights has not been called");
+    CAPB_CHECK_RANGE();
     return 0;
 }
 
@@ -403,6 +404,10 @@ int capb200_aoa_bind_weights(capb200_aoa_engine* e, const capb200_aoa_weights* w
         e->launches += 2;
         cudaFreeAsync(tmp, st);
         if (rc) return 1;
+    }
+    if (e->tc) {
+        CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
+        CAPB_CHECK_RANGE();
     }
     e->bound = true;
     return 0;
@@ -523,6 +528,7 @@ struct AoaTrainArgs {
     const capb200_cider_table* table = nullptr;
     const int* refs = nullptr; const int* ref_offsets = nullptr; int L = 0;
     long long* sample_seq = nullptr; long long* greedy_seq = nullptr; float* reward = nullptr;
+    const long long* forced = nullptr;
     const long long* labels = nullptr; long ld_labels = 0; const float* masks = nullptr; long ld_masks = 0;
     float* logprobs = nullptr; float* loss = nullptr;
 };
@@ -642,6 +648,10 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
             va.select = 2; va.temperature = ta.temperature; va.seed = seed; va.step = (unsigned long long)t;
             va.unfinished = e->d.unfinished; va.first_step = (t == 0); va.tokens_out = e->d.tokens;
             va.seq_out = sample_seq; va.ld_seq = T; va.t = t;
+            if (ta.forced != nullptr) {
+                if (load_token_column_launch(ta.forced, T, t, N, e->d.forced, st)) return 1;
+                va.select = 3; va.forced = e->d.forced;
+            }
         }
         if (vocab_step_launch(va, st)) return 1;
         e->launches += 20;
@@ -773,7 +783,7 @@ extern "C" int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, in
     ta.n = n; ta.T = e->T; ta.Tl = e->T; ta.p_lm = p_lm; ta.p_at = p_at; ta.p_aoa = p_aoa; ta.p_sub = p_sub; ta.temperature = opts->temperature;
     ta.upstream = opts->upstream; ta.ctx_drop = opts->ctx_drop; ta.seed = opts->seed; ta.greedy_baseline = greedy_baseline; ta.table = table;
     ta.refs = refs; ta.ref_offsets = ref_offsets; ta.L = L; ta.sample_seq = sample_seq; ta.greedy_seq = greedy_seq; ta.reward = reward;
-    ta.logprobs = sample_logprobs; ta.loss = loss;
+    ta.logprobs = sample_logprobs; ta.loss = loss; ta.forced = opts->forced_tokens;
     return aoa_train_step(e, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }
 

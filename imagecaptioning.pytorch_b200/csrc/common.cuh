@@ -144,6 +144,17 @@ int gemm_tc_plan_launch(GemmTcPlan* plan, const GemmEpilogue* epi_override, int 
 bool gemm_tc_supported(const GemmProblem& p, std::string* why);
 
 int split_planes_launch(const float* x, long ldx, int rows, int cols, __half* hi, __half* lo, long ldh, cudaStream_t stream);
+// fp16-range guard of the split conversions (gemm_simt.cu): device-visible flag pointer, host read (optionally clearing it)
+int* range_flag_ptr();
+int range_flag_read(int reset);
+#define CAPB_CHECK_RANGE()                                                                                              \
+    do {                                                                                                                \
+        if (capb200::range_flag_read(0)) {                                                                              \
+            capb200::set_error("a value with |x| >= 65504 (or inf/nan) reached a split-fp16 conversion in an earlier call: results of the "   \
+                               "tensor-core modes are invalid for such inputs/weights (DESIGN.md section 3); capb200_range_status(1) clears the flag"); \
+            return 1;                                                                                                   \
+        }                                                                                                               \
+    } while (0)
 // gate-interleaving variant for LSTM weights [4H, cols]: destination row 4*j+g <- source row g*H + j
 int split_planes_interleave_launch(const float* x, long ldx, int H, int cols, __half* hi, __half* lo, long ldh, cudaStream_t stream);
 

@@ -431,6 +431,7 @@ int core_step(capb200_engine* e, int rows, int rpi, const int* tokens, const int
 int check_ready(capb200_engine* e) {
     CAPB_REQUIRE(e != nullptr, "null engine");
     CAPB_REQUIRE(e->bound, "capb200_engine_bind_weights has not been called");
+    CAPB_CHECK_RANGE();
     return 0;
 }
 
@@ -443,6 +444,7 @@ extern "C" {
 
 const char* capb200_last_error(void) { return g_last_error.c_str(); }
 int capb200_abi_version(void) { return CAPB200_ABI_VERSION; }
+int capb200_range_status(int reset) { return range_flag_read(reset); }
 
 capb200_engine* capb200_engine_create(const capb200_model_cfg* cfg) {
     if (cfg == nullptr) { set_error("null cfg"); return nullptr; }
@@ -605,6 +607,10 @@ int capb200_engine_bind_weights(capb200_engine* e, const capb200_weights* w, voi
         e->launches += 2;
         cudaFreeAsync(tmp, st);
         if (rc) return 1;
+    }
+    if (e->tc) {   // binding is rare: wait for the conversions and refuse weights outside the fp16 range of the split planes
+        CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
+        CAPB_CHECK_RANGE();
     }
     e->bound = true;
     return 0;
@@ -854,6 +860,7 @@ struct TrainArgs {
     const capb200_cider_table* table = nullptr;
     const int* refs = nullptr; const int* ref_offsets = nullptr; int L = 0;
     long long* sample_seq = nullptr; long long* greedy_seq = nullptr; float* reward = nullptr;
+    const long long* forced = nullptr;      // replay these samples instead of drawing
     // XE
     const long long* labels = nullptr; long ld_labels = 0; const float* masks = nullptr; long ld_masks = 0;
     float* logprobs = nullptr; float* loss = nullptr;
@@ -965,6 +972,10 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
             va.select = 2; va.temperature = ta.temperature; va.seed = seed; va.step = (unsigned long long)t;
             va.unfinished = e->d.unfinished; va.first_step = (t == 0); va.tokens_out = e->d.tokens;
             va.seq_out = sample_seq; va.ld_seq = T; va.t = t;
+            if (ta.forced != nullptr) {
+                if (load_token_column_launch(ta.forced, T, t, N, e->d.forced, st)) return 1;
+                va.select = 3; va.forced = e->d.forced;
+            }
         }
         if (vocab_step_launch(va, st)) return 1;
         e->launches += 12;
@@ -1075,6 +1086,7 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
     ta.n = opts->sample_n; ta.T = e->T; ta.Tl = e->T; ta.p = opts->drop_prob; ta.temperature = opts->temperature; ta.upstream = opts->upstream;
     ta.seed = opts->seed; ta.greedy_baseline = greedy_baseline; ta.table = table; ta.refs = refs; ta.ref_offsets = ref_offsets; ta.L = L;
     ta.sample_seq = sample_seq; ta.greedy_seq = greedy_seq; ta.reward = reward; ta.logprobs = sample_logprobs; ta.loss = loss;
+    ta.forced = opts->forced_tokens;
     return updown_train_step(e, fc, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }
 

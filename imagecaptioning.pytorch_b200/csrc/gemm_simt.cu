@@ -126,39 +126,71 @@ __global__ void __launch_bounds__(256, 2) gemm_simt_kernel(const SimtParams p) {
     }
 }
 
+// Both conversion kernels also enforce the one numeric precondition of the split-fp16 scheme: |x| < 65504 and finite (fp16 range).  A
+// violation sets the process-wide flag (pinned, host-mapped) that every C-ABI entry point reports as an error (range_flag_*).
 __global__ void split_planes_kernel(const float* __restrict__ x, long ldx, int rows, int cols, __half* __restrict__ hi,
-                                    __half* __restrict__ lo, long ldh) {
+                                    __half* __restrict__ lo, long ldh, int* __restrict__ range_flag) {
     const long total = (long)rows * cols;
+    bool bad = false;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int r = (int)(i / cols), c = (int)(i % cols);
         __half h, l;
-        split_f32(__ldg(x + (long)r * ldx + c), h, l);
+        const float v = __ldg(x + (long)r * ldx + c);
+        bad |= !(fabsf(v) < 65504.0f);
+        split_f32(v, h, l);
         hi[(long)r * ldh + c] = h;
         lo[(long)r * ldh + c] = l;
     }
+    if (bad && range_flag != nullptr) *range_flag = 1;
 }
 
 __global__ void split_planes_interleave_kernel(const float* __restrict__ x, long ldx, int H, int cols, __half* __restrict__ hi,
-                                               __half* __restrict__ lo, long ldh) {
+                                               __half* __restrict__ lo, long ldh, int* __restrict__ range_flag) {
     const long total = (long)4 * H * cols;
+    bool bad = false;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int rd = (int)(i / cols), c = (int)(i % cols);          // destination row 4*j+g
         const int j = rd >> 2, g = rd & 3;
         __half h, l;
-        split_f32(__ldg(x + (long)(g * H + j) * ldx + c), h, l);
+        const float v = __ldg(x + (long)(g * H + j) * ldx + c);
+        bad |= !(fabsf(v) < 65504.0f);
+        split_f32(v, h, l);
         hi[(long)rd * ldh + c] = h;
         lo[(long)rd * ldh + c] = l;
     }
+    if (bad && range_flag != nullptr) *range_flag = 1;
 }
 
 }  // namespace
+
+// Process-wide "a value outside the fp16 range reached a split-fp16 conversion" flag: one int in pinned, host-mapped, portable memory
+// (kernels on any device write it through the unified address; the host reads it without a copy once the writing stream has been
+// synchronised by whoever consumes the results).
+static int* g_range_flag = nullptr;
+int* range_flag_ptr() {
+    static std::atomic<int> once{0};
+    int expected = 0;
+    if (g_range_flag == nullptr && once.compare_exchange_strong(expected, 1)) {
+        int* p = nullptr;
+        if (cudaHostAlloc(&p, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) { *p = 0; g_range_flag = p; }
+        else (void)cudaGetLastError();
+    }
+    return g_range_flag;
+}
+int range_flag_read(int reset) {
+    int* p = range_flag_ptr();
+    if (p == nullptr) return 0;
+    const int v = *reinterpret_cast<volatile int*>(p);
+    if (reset) *reinterpret_cast<volatile int*>(p) = 0;
+    return v;
+}
 
 int split_planes_interleave_launch(const float* x, long ldx, int H, int cols, __half* hi, __half* lo, long ldh, cudaStream_t stream) {
     const long total = (long)4 * H * cols;
     if (total <= 0) return 0;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    split_planes_interleave_kernel<<<blocks, 256, 0, stream>>>(x, ldx, H, cols, hi, lo, ldh);
+    split_planes_interleave_kernel<<<blocks, 256, 0, stream>>>(x, ldx, H, cols, hi, lo, ldh, range_flag_ptr());
     CAPB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -190,7 +222,7 @@ int split_planes_launch(const float* x, long ldx, int rows, int cols, __half* hi
     const long total = (long)rows * cols;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    split_planes_kernel<<<blocks, 256, 0, stream>>>(x, ldx, rows, cols, hi, lo, ldh);
+    split_planes_kernel<<<blocks, 256, 0, stream>>>(x, ldx, rows, cols, hi, lo, ldh, range_flag_ptr());
     CAPB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

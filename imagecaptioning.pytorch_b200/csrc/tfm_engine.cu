@@ -236,6 +236,7 @@ int core_step(capb200_tfm_engine* e, int rows, int rpi, const int* tokens, const
 int check_ready(capb200_tfm_engine* e) {
     CAPB_REQUIRE(e != nullptr, "null engine");
     CAPB_REQUIRE(e->bound, "capb200_tfm_bind_weights has not been called");
+    CAPB_CHECK_RANGE();
     return 0;
 }
 
@@ -310,6 +311,8 @@ int capb200_tfm_bind_weights(capb200_tfm_engine* e, const capb200_tfm_weights* w
             rc |= pack(e, w->dec[l].w1_w, Dff, D, e->pd_w1[l], st) | pack(e, w->dec[l].w2_w, D, Dff, e->pd_w2[l], st);
         }
         if (rc) return 1;
+        CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
+        CAPB_CHECK_RANGE();
     }
     e->bound = true;
     return 0;

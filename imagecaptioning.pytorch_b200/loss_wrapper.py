@@ -163,8 +163,8 @@ class B200LossWrapper(nn.Module):
     def _sampled_step(self, fc_feats, att_feats, gts, baseline):
         opt = self.opt
         self.model.train()
-        res = self.model.scst_step(fc_feats, att_feats, gts, self._scorer(), opt.train_sample_n, temperature=getattr(opt, 'temperature', 1.0),
-                                   baseline=baseline)
+        # the reference's training-time _sample call passes no temperature (loss_wrapper.py:63-67): 1.0, whatever opt.temperature says
+        res = self.model.scst_step(fc_feats, att_feats, gts, self._scorer(), opt.train_sample_n, temperature=1.0, baseline=baseline)
         self.last_step = res
         return res
 
@@ -199,6 +199,24 @@ class B200LossWrapper(nn.Module):
             out['loss'] = self._bridge(res)
             out['reward'] = res['reward'][:, 0].mean()
             return out
+        if torch.is_grad_enabled():
+            # a differentiable loss exists only on the fused device step: refuse up front instead of returning a detached loss that fails (or
+            # silently trains nothing) at backward()
+            why = []
+            if not hasattr(self.model, 'scst_step'):
+                why.append('model family %r has no fused SCST step (UpDown and AoANet do)' % getattr(self.model, 'family_name', type(self.model).__name__))
+            if att_masks is not None and not getattr(self.model, 'scst_masks', False):
+                why.append('att_masks is not None')
+            if drop_worst_flag:
+                why.append('drop_worst_flag')
+            if not plain_reward:
+                why.append('cider_reward_weight != 1 or bleu_reward_weight != 0')
+            if opt.train_sample_method != 'sample' or opt.train_beam_size != 1:
+                why.append('train_sample_method / train_beam_size other than multinomial sampling')
+            if opt.sc_sample_method != 'greedy' or opt.sc_beam_size != 1:
+                why.append('sc_sample_method / sc_beam_size other than a greedy baseline')
+            raise NotImplementedError('self-critical training step outside the fused B200 path: ' + '; '.join(why or ['unsupported configuration']))
+        # no-grad evaluation of the sc branch (reward monitoring): host-level composition of the engine calls, dropout off
         self.model.eval()
         with torch.no_grad():
             greedy_res, _ = self.model(fc_feats, att_feats, att_masks, mode='sample',

@@ -94,6 +94,22 @@ class _EngineStore:
 _tls = threading.local()           # device index the calling thread is decoding on (set by _ensure_engine)
 
 
+def _on_device(fn):
+    """Runs a call surface with the tensors' device current: the C ABI launches on the current device's stream and never calls
+    cudaSetDevice itself, so a model living on cuda:1 while cuda:0 is current (model.to('cuda:1') without set_device) would otherwise launch
+    on the wrong device with foreign pointers.  PyTorch modules handle that case transparently; so does this."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        dev = next((a.device for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if dev is None:
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+    return wrapped
+
+
 def _slot_property(field):
     def get(self):
         return self._store.slot(getattr(_tls, 'dev', None))[field]
@@ -157,6 +173,15 @@ class B200CaptionModel(nn.Module):
     def _weight_table(self):
         raise NotImplementedError
 
+    def _bind_key(self, tensors):
+        """What the engine's derived weight copies (fp16 planes, fused QKV blocks, gate tables) were built from.  (data_ptr, _version)
+        identifies the contents only for tensors this module owns: the parameters of an nn.DataParallel replica are fresh Broadcast outputs
+        every forward (version 0, and the caching allocator hands the same addresses back after an optimizer step), so replicas re-bind on
+        every call; the bound tensors are also kept alive so a freed-and-reused address can never look unchanged."""
+        if getattr(self, '_is_replica', False) or any(not t.is_leaf for t in tensors):
+            return None
+        return tuple((t.data_ptr(), t._version) for t in tensors)
+
     def _ensure_engine(self, device):
         lib = self._enter_device(device)
         key = (_tls.dev, self.numeric_mode)
@@ -170,8 +195,8 @@ class B200CaptionModel(nn.Module):
                 raise RuntimeError('capb200 engine_create failed: %s' % lib.capb200_last_error().decode())
             self._engine, self._engine_key, self._bound_versions = eng, key, None
         table = self._weight_table()
-        versions = tuple((t.data_ptr(), t._version) for t in table.values())
-        if versions != self._bound_versions:
+        versions = self._bind_key(list(table.values()))
+        if versions is None or versions != self._bound_versions:
             w = _lib.Weights()
             keep = []
             for name, t in table.items():
@@ -247,6 +272,7 @@ class B200CaptionModel(nn.Module):
         if opt.get('output_logsoftmax', 1) != 1:
             raise NotImplementedError('output_logsoftmax=0 is out of scope of the B200 engine')
 
+    @_on_device
     def _sample(self, fc_feats, att_feats, att_masks=None, opt={}, forced_tokens=None):
         sample_method = opt.get('sample_method', 'greedy')
         beam_size = opt.get('beam_size', 1)
@@ -297,6 +323,7 @@ class B200CaptionModel(nn.Module):
         col_empty = (seq[:, 1:].sum(0) == 0).nonzero()
         return int(col_empty[0].item()) + 1 if col_empty.numel() > 0 else seq.shape[1]
 
+    @_on_device
     def _sample_beam(self, fc_feats, att_feats, att_masks=None, opt={}):
         beam_size = opt.get('beam_size', 10)
         sample_n = opt.get('sample_n', 10)
@@ -331,6 +358,7 @@ class B200CaptionModel(nn.Module):
         _lib.check(self._call_record(_lib.load(), image, rank, dst), 'beam_record_logprobs')
         return dst
 
+    @_on_device
     def _forward(self, fc_feats, att_feats, seq, att_masks=None):
         """Teacher forcing (AttModel.py:126-164).  Scheduled sampling (ss_prob > 0) is an XE-stage feature."""
         if self.training and self.ss_prob > 0.0:
@@ -428,7 +456,9 @@ class B200UpDownModel(B200CaptionModel):
 
 
     # ---- SCST training step (UpDown): greedy baseline + sampling with dropout + CIDEr-D reward + RewardCriterion + BPTT -----
-    def scst_step(self, fc_feats, att_feats, gts, table, sample_n, temperature=1.0, drop_prob=None, seed=None, upstream=1.0, baseline='greedy'):
+    @_on_device
+    def scst_step(self, fc_feats, att_feats, gts, table, sample_n, temperature=1.0, drop_prob=None, seed=None, upstream=1.0, baseline='greedy',
+                  forced_tokens=None):
         """Runs one self-critical step entirely on the device (capb200_updown_scst_step).  Returns a dict with 'loss' (0-dim),
         'reward' [N, T], 'sample_seq', 'greedy_seq', 'sample_logprobs' and 'grads' {parameter: gradient tensor}.
         ``baseline='greedy'`` is the self-critical step (loss_wrapper.py:56-73); ``'leave_one_out'`` the 'new_self_critical' structure
@@ -458,7 +488,12 @@ class B200UpDownModel(B200CaptionModel):
         if baseline not in ('greedy', 'leave_one_out'):
             raise ValueError("baseline must be 'greedy' or 'leave_one_out'")
         loo = baseline == 'leave_one_out'
-        so = _lib.ScstOpts(sample_n, float(temperature), seed, float(p), float(upstream), _lib.BASELINE_LEAVE_ONE_OUT if loo else _lib.BASELINE_GREEDY)
+        forced = None
+        if forced_tokens is not None:       # replay a given draw (parity tests against the reference's own samples)
+            forced = forced_tokens.detach().to(device=dev, dtype=torch.long).contiguous()
+            assert forced.shape == (N, T)
+        so = _lib.ScstOpts(sample_n, float(temperature), seed, float(p), float(upstream), _lib.BASELINE_LEAVE_ONE_OUT if loo else _lib.BASELINE_GREEDY,
+                           _lib.ptr(forced))
         _lib.check(lib.capb200_updown_scst_step(self._engine, _lib.ptr(fc), _lib.ptr(att), B, R, ctypes.byref(so), table._h, _lib.ptr(refs),
                                                 _lib.ptr(offsets), L, ctypes.byref(g), _lib.ptr(sample_seq), _lib.ptr(greedy_seq), _lib.ptr(logprobs),
                                                 _lib.ptr(reward), _lib.ptr(loss), _lib.current_stream()), 'updown_scst_step')
@@ -466,6 +501,7 @@ class B200UpDownModel(B200CaptionModel):
                'grads': {table_params[k]: v for k, v in grads.items()}, 'seed': seed}
         return res
 
+    @_on_device
     def xe_step(self, fc_feats, att_feats, labels, masks, label_smoothing=0.0, drop_prob=None, seed=None, upstream=1.0):
         """One cross-entropy step on the device (capb200_updown_xe_step): teacher-forced forward over ``labels[..., :-1]`` in train mode,
         LanguageModelCriterion / LabelSmoothing against ``labels[..., 1:]``, ``masks[..., 1:]`` (reduction 'mean'), BPTT.
@@ -625,8 +661,8 @@ class B200TransformerModel(B200CaptionModel):
                 raise RuntimeError('capb200 tfm_create failed: %s' % lib.capb200_last_error().decode())
             self._engine, self._engine_key, self._bound_versions = eng, key, None
         tensors = self._tensors()
-        versions = tuple((t.data_ptr(), t._version) for t in tensors)
-        if versions != self._bound_versions:
+        versions = self._bind_key(tensors)
+        if versions is None or versions != self._bound_versions:
             for t in tensors:
                 if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
                     raise RuntimeError('capb200: parameters must be contiguous float32 tensors on %s' % device)
@@ -658,6 +694,7 @@ class B200TransformerModel(B200CaptionModel):
             w.lut, w.pe = P(self.model.tgt_embed[0].lut.weight), P(self.model.tgt_embed[1].pe)
             w.gen_w, w.gen_b = P(self.model.generator.proj.weight), P(self.model.generator.proj.bias)
             _lib.check(lib.capb200_tfm_bind_weights(self._engine, ctypes.byref(w), _lib.current_stream()), 'tfm_bind_weights')
+            self._keepalive = tensors
             self._bound_versions = versions
         return lib
 
@@ -759,8 +796,9 @@ class B200AoAModel(B200CaptionModel):
             else:
                 setattr(table.refiner[path[1]], path[2], ptr)
 
+    @_on_device
     def scst_step(self, fc_feats, att_feats, gts, table, sample_n, temperature=1.0, drop_prob=None, seed=None, upstream=1.0, baseline='greedy',
-                  drop_attn=0.1, drop_aoa=None, drop_sublayer=0.1, ctx_drop=None):
+                  drop_attn=0.1, drop_aoa=None, drop_sublayer=0.1, ctx_drop=None, forced_tokens=None):
         """One self-critical step of AoANet on the device (capb200_aoa_scst_step): eval-mode greedy baseline (or the leave-one-out baseline of
         'new_self_critical'), train-mode samples with every dropout site of AoAModel.py active, CIDEr-D reward, RewardCriterion, BPTT through
         the decoder and the six refiner layers.  ``fc_feats`` is unused (mean_feats=1).  Returns the dict of B200UpDownModel.scst_step."""
@@ -786,15 +824,20 @@ class B200AoAModel(B200CaptionModel):
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         p = self.drop_prob_lm if drop_prob is None else drop_prob
+        forced = None
+        if forced_tokens is not None:
+            forced = forced_tokens.detach().to(device=dev, dtype=torch.long).contiguous()
+            assert forced.shape == (N, T)
         so = _lib.AoaScstOpts(sample_n, float(temperature), seed, float(upstream), _lib.BASELINE_LEAVE_ONE_OUT if loo else _lib.BASELINE_GREEDY, float(p),
                               float(drop_attn), float(self.dropout_aoa if drop_aoa is None else drop_aoa), float(drop_sublayer),
-                              int(self.ctx_drop if ctx_drop is None else ctx_drop))
+                              int(self.ctx_drop if ctx_drop is None else ctx_drop), _lib.ptr(forced))
         _lib.check(lib.capb200_aoa_scst_step(self._engine, _lib.ptr(att), B, R, ctypes.byref(so), table._h, _lib.ptr(refs), _lib.ptr(offsets), L,
                                              ctypes.byref(g), _lib.ptr(sample_seq), None if loo else _lib.ptr(greedy_seq), _lib.ptr(logprobs),
                                              _lib.ptr(reward), _lib.ptr(loss), _lib.current_stream()), 'aoa_scst_step')
         return {'loss': loss[0], 'reward': reward, 'sample_seq': sample_seq, 'greedy_seq': None if loo else greedy_seq, 'sample_logprobs': logprobs,
                 'grads': {prm: grads[id(prm)] for prm in params}, 'seed': seed}
 
+    @_on_device
     def xe_step(self, fc_feats, att_feats, labels, masks, label_smoothing=0.0, drop_prob=None, seed=None, upstream=1.0, drop_attn=0.1, drop_aoa=None,
                 drop_sublayer=0.1, ctx_drop=None):
         """One cross-entropy step of AoANet on the device (capb200_aoa_xe_step); arguments and result as B200UpDownModel.xe_step."""
@@ -842,14 +885,15 @@ class B200AoAModel(B200CaptionModel):
                 raise RuntimeError('capb200 aoa_create failed: %s' % lib.capb200_last_error().decode())
             self._engine, self._engine_key, self._bound_versions = eng, key, None
         tensors = self._tensors()
-        versions = tuple((t.data_ptr(), t._version) for t in tensors)
-        if versions != self._bound_versions:
+        versions = self._bind_key(tensors)
+        if versions is None or versions != self._bound_versions:
             for t in tensors:
                 if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
                     raise RuntimeError('capb200: parameters must be contiguous float32 tensors on %s' % device)
             w = _lib.AoaWeights()
             self._fill_table(w, {id(t): t for t in tensors})
             _lib.check(lib.capb200_aoa_bind_weights(self._engine, ctypes.byref(w), _lib.current_stream()), 'aoa_bind_weights')
+            self._keepalive = tensors
             self._bound_versions = versions
         return lib
 

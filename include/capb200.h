@@ -37,6 +37,11 @@ typedef struct capb200_cider_table capb200_cider_table;
 
 const char* capb200_last_error(void);
 int capb200_abi_version(void);
+/* Numeric precondition of the tensor-core modes: every value that is converted to split-fp16 planes (weights at bind time, the fc / att
+ * feature tiles of each call) must be finite with |x| < 65504.  A violation sets a process-wide flag; bind_weights checks it synchronously,
+ * every later entry point fails with a message while it is set.  Returns the flag (valid once the stream of the offending call has been
+ * synchronised); reset != 0 clears it. */
+int capb200_range_status(int reset);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Operator level (each replaces one library call of the reference's per-timestep core; used by the parity tests)
@@ -265,6 +270,8 @@ typedef struct {
     float upstream;            /* d(total loss)/d(this loss), normally 1 */
     int baseline;              /* CAPB200_BASELINE_GREEDY (self-critical, loss_wrapper.py:56-73) or CAPB200_BASELINE_LEAVE_ONE_OUT
                                   (structure loss 'new_self_critical', losses.py:168-187: no greedy decode, greedy_seq may be NULL) */
+    const long long* forced_tokens; /* optional [B*sample_n, T] int64 device: replay these samples instead of drawing them (parity
+                                  checks against the reference's own multinomial draw); NULL = sample */
 } capb200_scst_opts;
 #define CAPB200_BASELINE_GREEDY 0
 #define CAPB200_BASELINE_LEAVE_ONE_OUT 1
@@ -316,6 +323,7 @@ typedef struct {
     float drop_aoa;            /* dropout_aoa (0.3) */
     float drop_sublayer;       /* refiner SublayerConnection (0.1, AoAModel.py:119) */
     int ctx_drop;              /* opt.ctx_drop */
+    const long long* forced_tokens; /* optional [B*sample_n, T] int64 device: replay these samples (see capb200_scst_opts) */
 } capb200_aoa_scst_opts;
 /* Gradient buffers, laid out field by field like the weights struct above: parameter shapes, fp32, device; every one is OVERWRITTEN. */
 typedef struct {

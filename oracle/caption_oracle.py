@@ -387,7 +387,8 @@ def _length_penalty(cfg: str):
 
 
 def beam_search(fam: Family, init_state, init_logprobs: Tensor, fc_e, att_e, p_att, masks, beam_size: int,
-                length_penalty: str = '', temperature: float = 1.0, eos_idx: int = 0, record_margin: Optional[list] = None):
+                length_penalty: str = '', temperature: float = 1.0, eos_idx: int = 0, record_margin: Optional[list] = None,
+                margin_rows: Optional[list] = None):
     """Classical batched beam search, one group.  Returns list[B] of list[<=beam] records.
 
     State/feature rows are image-major: row i*beam+j is beam j of image i.  The first step works on B rows
@@ -410,6 +411,10 @@ def beam_search(fam: Family, init_state, init_logprobs: Tensor, fc_e, att_e, p_a
         ys, ix = torch.sort(cand, -1, True)
         if record_margin is not None:
             record_margin.append(float((ys[:, :beam_size] - ys[:, 1:beam_size + 1]).min()))
+        if margin_rows is not None:          # per-image smallest gap among the top beam_size + 1 candidates of this step
+            gaps = ys[:, :beam_size] - ys[:, 1:beam_size + 1]
+            gaps = torch.where(ys[:, :beam_size] > -500.0, gaps, torch.full_like(gaps, 1e9))     # ended beams (sum - 1000) tie freely: ignore
+            margin_rows.append(gaps.min(1).values.clone())
         ys, ix = ys[:, :beam_size], ix[:, :beam_size]
         parent = ix // V1
         word = ix % V1
@@ -436,7 +441,7 @@ def beam_search(fam: Family, init_state, init_logprobs: Tensor, fc_e, att_e, p_a
 
 
 def sample_beam(fam: Family, fc: Tensor, att: Tensor, masks: Optional[Tensor] = None, beam_size: int = 5, sample_n: int = 1,
-                length_penalty: str = '', record_margin: Optional[list] = None):
+                length_penalty: str = '', record_margin: Optional[list] = None, margin_rows: Optional[list] = None):
     assert sample_n in (1, beam_size)
     B = fc.shape[0]
     T, V1 = fam.seq_length, fam.vocab1
@@ -445,7 +450,8 @@ def sample_beam(fam: Family, fc: Tensor, att: Tensor, masks: Optional[Tensor] = 
     it = torch.zeros(B, dtype=torch.long)
     logprobs, state = fam.logprobs_state(it, fc_e, att_e, p_att, masks, state)
     fc_r, att_r, p_att_r, masks_r = (repeat_rows(x, beam_size) for x in (fc_e, att_e, p_att, masks))
-    done = beam_search(fam, state, logprobs, fc_r, att_r, p_att_r, masks_r, beam_size, length_penalty, record_margin=record_margin)
+    done = beam_search(fam, state, logprobs, fc_r, att_r, p_att_r, masks_r, beam_size, length_penalty, record_margin=record_margin,
+                       margin_rows=margin_rows)
     seq = torch.zeros(B * sample_n, T, dtype=torch.long)
     seq_lp = torch.zeros(B * sample_n, T, V1)
     for k in range(B):

@@ -431,6 +431,151 @@ def gen_aoa_small(out_dir):
                                                                   num_heads=4, multi_head_scale=1, mean_feats=1, ctx_drop=1, dropout_aoa=0.3), 4, 20.0)
 
 
+def gen_updown_b256(out_dir):
+    """BASELINE.json configs[1] at its own shape: UpDown full dimensions, batch 256, beam 5, through the live reference.  Stores the winning
+    ids, their log-probs, the finished-beam scores, and (from the oracle port on the same inputs) each image's smallest candidate gap so
+    the GPU test can demand bit-exact ids wherever the decision is not a numerical tie."""
+    cfg = dict(V=9487, E=1000, H=1000, A=512, F_fc=2048, F_att=2048, T=20)
+    B, R, b = 256, 36, 5
+    W = co.make_weights('updown', cfg['V'], cfg['E'], cfg['H'], cfg['A'], cfg['F_fc'], cfg['F_att'], seed=1234, logit_scale=12.0)
+    fc, att = co.make_inputs(B, R, cfg['F_fc'], cfg['F_att'], seed=1234)
+    m = ref_model('updown', W=W, **cfg)
+    with torch.no_grad():
+        seqb, lpb = m(fc, att, None, opt={'beam_size': b, 'sample_n': 1}, mode='sample')
+        pickedb = lpb.gather(2, seqb.unsqueeze(2)).squeeze(2)
+        dseq, dlen, dp = beams_to_arrays(m.done_beams, b, cfg['T'])
+        rows = []
+        oseq, olp, _ = co.sample_beam(co.Family('updown', W, cfg['T']), fc, att, beam_size=b, margin_rows=rows)
+    margin = torch.stack(rows, 1).min(1).values.numpy()
+    agree = (oseq == seqb).all(1).numpy()
+    np.savez_compressed(os.path.join(out_dir, 'updown_b256.npz'), cfg=np.array([cfg[k] for k in ('V', 'E', 'H', 'A', 'F_fc', 'F_att', 'T')]),
+                        meta=np.array([B, R, b, 1234]), beam_seq=seqb.numpy().astype(np.int16), beam_picked_lp=pickedb.numpy(),
+                        done_len=dlen.astype(np.int8), done_p=dp, done_seq=dseq.astype(np.int16), image_margin=margin)
+    print('updown_b256: oracle port agrees with the reference on %d / %d images; smallest margin %.3g; %d images below 1e-3' %
+          (int(agree.sum()), B, float(margin.min()), int((margin < 1e-3).sum())))
+
+
+def gen_transformer_b64(out_dir):
+    """BASELINE.json configs[2] at its per-GPU shape: Transformer 6+6 / d_model 512 / d_ff 2048 / 8 heads, batch 64, beam 5 and greedy,
+    through the live reference (which re-runs the whole decoder every step, TransformerModel.py:351-363)."""
+    cfg = dict(V=9487, E=512, H=2048, A=6, F_fc=2048, F_att=2048, T=20)
+    B, R, b = 64, 36, 5
+    W = co.make_weights('transformer', cfg['V'], cfg['E'], cfg['H'], cfg['A'], cfg['F_fc'], cfg['F_att'], seed=1234, logit_scale=3.0)
+    fc, att = co.make_inputs(B, R, cfg['F_fc'], cfg['F_att'], seed=1234)
+    m = ref_model('transformer', W=W, **cfg, num_layers=6, N_enc=6, N_dec=6, d_model=512, d_ff=2048, num_att_heads=8, dropout=0.1)
+    with torch.no_grad():
+        seq, lp = m(fc, att, None, opt={'sample_method': 'greedy', 'beam_size': 1}, mode='sample')
+        picked = lp.gather(2, seq.unsqueeze(2)).squeeze(2)
+        top2 = lp.topk(2, dim=2).values
+        gmargin = (top2[..., 0] - top2[..., 1])
+        live = torch.cat([torch.ones(B, 1, dtype=torch.bool), (seq[:, :-1] > 0)], 1)
+        gmargin = torch.where(live, gmargin, torch.full_like(gmargin, 1e9)).min(1).values
+        seqb, lpb = m(fc, att, None, opt={'beam_size': b, 'sample_n': 1}, mode='sample')
+        pickedb = lpb.gather(2, seqb.unsqueeze(2)).squeeze(2)
+        dseq, dlen, dp = beams_to_arrays(m.done_beams, b, cfg['T'])
+        rows = []
+        oseq, _, _ = co.sample_beam(co.Family('transformer', W, cfg['T'], heads=8), fc, att, beam_size=b, margin_rows=rows)
+    margin = torch.stack(rows, 1).min(1).values.numpy()
+    np.savez_compressed(os.path.join(out_dir, 'transformer_b64.npz'), cfg=np.array([cfg[k] for k in ('V', 'E', 'H', 'A', 'F_fc', 'F_att', 'T')]),
+                        meta=np.array([B, R, b, 1234, 8]), greedy_seq=seq.numpy().astype(np.int16), greedy_picked_lp=picked.numpy(),
+                        greedy_margin=gmargin.numpy(), beam_seq=seqb.numpy().astype(np.int16), beam_picked_lp=pickedb.numpy(), done_len=dlen.astype(np.int8),
+                        done_p=dp, image_margin=margin)
+    print('transformer_b64: oracle port agrees on %d / %d images; smallest beam margin %.3g, smallest greedy margin %.3g' %
+          (int((oseq == seqb).all(1).sum()), B, float(margin.min()), float(gmargin.min())))
+
+
+def _subsample(t):
+    """Compact fingerprint of a gradient tensor: every entry when small, else a strided sub-grid; plus sum / abs-sum / Frobenius norm."""
+    a = t.detach().numpy()
+    if a.size <= 8192:
+        sub, step = a.copy(), (1, 1)
+    elif a.ndim == 1:
+        sub, step = a[::7].copy(), (7, 1)
+    else:
+        sr, sc = max(1, a.shape[0] // 96), max(1, a.shape[1] // 80)
+        sub, step = a[::sr, ::sc].copy(), (sr, sc)
+    stats = np.array([a.sum(dtype=np.float64), np.abs(a).sum(dtype=np.float64), np.sqrt((a.astype(np.float64) ** 2).sum()), np.abs(a).max()])
+    return sub, np.array(step), stats
+
+
+def gen_aoa_scst_full(out_dir, scratch):
+    """BASELINE.json configs[3] at its own shape: AoANet (configs/aoa.yml: E = H = 1024, 8 heads, 6 refiner layers), V = 9487, per-GPU batch 10,
+    train_sample_n 5, one LossWrapper(sc_flag=True) step + loss.backward() of the LIVE reference (loss_wrapper.py:56-73).  Every dropout
+    probability is set to 0 so no RNG stream has to be shared; the reference's own multinomial samples are stored and the engine replays them
+    as forced tokens.  Gradients: a fingerprint (sub-grid + sums + norm) of every parameter."""
+    from captioning.modules.loss_wrapper import LossWrapper
+    from captioning.utils import rewards as R
+    cfg = dict(V=9487, E=1024, H=1024, A=512, F_fc=2048, F_att=2048, T=20)
+    B, Rr, n, heads = 10, 36, 5, 8
+    W = co.make_weights('aoa', cfg['V'], cfg['E'], cfg['H'], cfg['A'], cfg['F_fc'], cfg['F_att'], seed=1234, logit_scale=6.0)
+    fc, att = co.make_inputs(B, Rr, cfg['F_fc'], cfg['F_att'], seed=1234)
+    extra = dict(num_layers=2, refine=1, refine_aoa=1, use_ff=0, decoder_type='AoA', use_multi_head=2, num_heads=heads, multi_head_scale=1, mean_feats=1,
+                 ctx_drop=1, dropout_aoa=0.3)
+    m = ref_model('aoa', W=W, **cfg, **extra)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+        if isinstance(getattr(mod, 'drop_prob_lm', None), float):
+            mod.drop_prob_lm = 0.0
+    # Random references share no n-grams with the model's captions at V = 9487 (all rewards ~ 0).  The references are therefore corrupted
+    # copies of the model's own greedy caption of each image (30 % of the tokens replaced, three of the five truncated), which gives CIDEr-D
+    # scores of O(1) for the greedy baseline and a spread of rewards for the samples.
+    with torch.no_grad():
+        g0, _ = m(fc, att, None, opt={'sample_method': 'greedy', 'beam_size': 1}, mode='sample')
+    rng = np.random.RandomState(5)
+    gts = []
+    for i in range(B):
+        rows = np.zeros((5, 16), np.int64)
+        for j in range(5):
+            ln = 16 if j < 2 else int(rng.randint(6, 15))
+            row = g0[i, :ln].numpy().copy()
+            flip = rng.rand(ln) < 0.3
+            row[flip] = rng.randint(1, cfg['V'] + 1, size=int(flip.sum()))
+            rows[j, :ln] = row
+        gts.append(rows)
+    df, ref_len = cdo.build_document_frequency(cdo.make_refs(1000, cfg['V'], seed=4) + gts)
+    from collections import defaultdict
+    dd = defaultdict(float)
+    dd.update({tuple(str(t) for t in k): v for k, v in df.items()})
+    with open(os.path.join(scratch, 'data', 'aoa-full-df.p'), 'wb') as f:
+        pickle.dump({'document_frequency': dd, 'ref_len': ref_len}, f, protocol=2)
+    R.CiderD_scorer = None
+    R.Cider_scorer = None
+    R.init_scorer('aoa-full-df')
+    opt = argparse.Namespace(label_smoothing=0, structure_loss_type='seqnll', structure_loss_weight=1, train_sample_method='sample', train_beam_size=1,
+                             train_sample_n=n, sc_sample_method='greedy', sc_beam_size=1, cider_reward_weight=1.0, bleu_reward_weight=0.0, use_ppo=0,
+                             struc_use_logsoftmax=1)
+    lw = LossWrapper(m, opt)
+    captured = {}
+    orig = m._sample
+
+    def spy(*a, **k):
+        out = orig(*a, **k)
+        captured.setdefault('calls', []).append(out[0].detach().clone())
+        return out
+    m._sample = spy
+    torch.manual_seed(77)
+    m.zero_grad()
+    out = lw(fc, att, None, None, None, gts, torch.arange(B), True, False, False)
+    out['loss'].backward()
+    greedy_seq, sample_seq = captured['calls'][0], captured['calls'][1]
+    assert greedy_seq.shape == (B, cfg['T']) and sample_seq.shape == (B * n, cfg['T'])
+    reward = R.get_self_critical_reward(greedy_seq, gts, sample_seq, opt)
+    res = {'greedy_seq': greedy_seq.numpy().astype(np.int16), 'sample_seq': sample_seq.numpy().astype(np.int16), 'loss': out['loss'].detach().numpy(),
+           'reward_mean': out['reward'].numpy(), 'reward': reward[:, 0].astype(np.float64), 'gts': np.stack(gts).astype(np.int16)}
+    names = []
+    for k, prm in m.named_parameters():
+        sub, step, stats = _subsample(prm.grad)
+        res['g_' + k], res['s_' + k], res['t_' + k] = sub, step, stats
+        names.append(k)
+    keys = np.array([list(k) + [-1] * (4 - len(k)) for k in df.keys()], np.int32)
+    vals = np.array(list(df.values()), np.float64)
+    np.savez_compressed(os.path.join(out_dir, 'aoa_scst_full.npz'), cfg=np.array([cfg[k] for k in ('V', 'E', 'H', 'A', 'F_fc', 'F_att', 'T')]),
+                        meta=np.array([B, Rr, n, 1234, heads]), df_keys=keys, df_vals=vals, ref_len=np.array(ref_len), names=np.array(names), **res)
+    print('aoa_scst_full: loss %.6g, mean reward %.4g, max |reward| %.4g, %d gradient tensors, sample lengths %s' %
+          (float(out['loss']), float(out['reward']), float(np.abs(reward).max()), len(names), (sample_seq > 0).sum(1)[:8].tolist()))
+
+
 def gen_state_dict_keys(out_dir):
     """Names and shapes of the reference modules' parameters: the drop-in must expose exactly these."""
     import json
@@ -457,7 +602,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     scratch = _enter_scratch()
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys', 'tfm', 'aoa', 'xe', 'dseq', 'pascal', 'penalty']
+    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys', 'tfm', 'aoa', 'xe', 'dseq', 'pascal', 'penalty', 'b256', 'tfm64', 'aoafull']
     if 'small' in which:
         gen_updown_small(out_dir)
     if 'newfc' in which:
@@ -482,6 +627,12 @@ def main():
         gen_transformer_small(out_dir)
     if 'aoa' in which:
         gen_aoa_small(out_dir)
+    if 'b256' in which:
+        gen_updown_b256(out_dir)
+    if 'tfm64' in which:
+        gen_transformer_b64(out_dir)
+    if 'aoafull' in which:
+        gen_aoa_scst_full(out_dir, scratch)
 
 
 if __name__ == '__main__':

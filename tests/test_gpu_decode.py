@@ -202,7 +202,6 @@ def test_beam_loop_graph_replay(family, seed, scale):
     assert not torch.equal(outs[3][2], outs[0][2])
 
 
-@pytest.mark.xfail(strict=False, reason='added after the round-1 GPU budget was spent: first hardware run happens at round end')
 @pytest.mark.parametrize('tag,pen', [('wu', 'wu_0.5'), ('avg', 'avg_0'), ('wu2', 'wu_1.5')])
 def test_beam_length_penalties_golden(golden_dir, tag, pen):
     """Beam search with opt['length_penalty'] (misc.penalty_builder) against the reference's output (tests/golden/updown_penalty.npz)."""

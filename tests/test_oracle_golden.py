@@ -220,3 +220,32 @@ def test_beam_length_penalties(golden_dir, tag, pen):
     assert np.array_equal(seq.numpy(), g[tag + '_seq'])
     assert np.abs(lp.numpy() - g[tag + '_lp']).max() < TOL
     assert np.abs(np.array([[r['p'] for r in d] for d in done]) - g[tag + '_done_p']).max() < 1e-3
+
+
+def test_aoa_scst_step_at_config_dims(golden_dir):
+    """The oracle at BASELINE configs[3]'s own size (AoANet H = 1024, V = 9487, 10 images x 5 samples): loss, reward and the gradient
+    fingerprints of the reference's LossWrapper(sc_flag=True) step (tests/golden/aoa_scst_full.npz), with the reference's samples replayed."""
+    g = _load(golden_dir, 'aoa_scst_full.npz')
+    V, E, H, A, F_fc, F_att, T = (int(x) for x in g['cfg'])
+    B, R, n, seed, heads = (int(x) for x in g['meta'])
+    W = co.make_weights('aoa', V, E, H, A, F_fc, F_att, seed=seed, logit_scale=6.0)
+    fc, att = co.make_inputs(B, R, F_fc, F_att, seed=seed)
+    og, _ = co.sample(co.Family('aoa', W, T, heads=heads), fc, att)
+    assert np.array_equal(og.numpy(), g['greedy_seq'].astype(np.int64))
+    df = {tuple(int(t) for t in k if t >= 0): float(v) for k, v in zip(g['df_keys'], g['df_vals'])}
+    gts = [g['gts'][i].astype(np.int64) for i in range(B)]
+    sample_seq = torch.from_numpy(g['sample_seq'].astype(np.int64))
+    reward, _ = cdo.self_critical_reward(og.numpy(), gts, sample_seq.numpy(), df, float(g['ref_len']))
+    assert np.abs(reward[:, 0] - g['reward']).max() < 1e-9
+    Wg = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    fam = co.Family('aoa', Wg, T, heads=heads)
+    _, lp = co.sample(fam, fc, att, sample_method='sample', sample_n=n, forced_tokens=sample_seq)
+    loss = co.reward_criterion(lp, sample_seq, torch.from_numpy(reward).float())
+    loss.backward()
+    assert abs(float(loss) - float(g['loss'])) < TOL * abs(float(g['loss']))
+    largest = max(float(g['t_' + k][3]) for k in g['names'])
+    for k in g['names']:
+        a = Wg[str(k)].grad.numpy()
+        step, stats = g['s_' + k], g['t_' + k]
+        sub = a if a.size <= 8192 else (a[::int(step[0])] if a.ndim == 1 else a[::int(step[0]), ::int(step[1])])
+        assert np.abs(sub - g['g_' + k]).max() <= 2e-4 * float(stats[3]) + 1e-7 * largest, k
