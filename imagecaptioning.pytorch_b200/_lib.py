@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(PKG, 'libcapb200.so')
 MODE_SIMT_FP32, MODE_TC_F16X3, MODE_TC_F16X1 = 0, 1, 2
 MODES = {'simt_fp32': MODE_SIMT_FP32, 'tc_f16x3': MODE_TC_F16X3, 'tc_f16x1': MODE_TC_F16X1}
 # capb200_linear additionally exposes the training step's split-K GEMM variants
-OP_MODES = dict(MODES, skinny_tf32x3=3, skinny_fp32=4)
+OP_MODES = dict(MODES, skinny_tf32x3=3, skinny_fp32=4, tf32x3_tc=5, tf32x3_tc_dgrad=6, tf32x3_tc_wgrad=7)
 FAMILY_UPDOWN, FAMILY_NEWFC = 0, 1
 SAMPLE_GREEDY, SAMPLE_MULTINOMIAL, SAMPLE_FORCED, SAMPLE_TEACHER = 0, 1, 2, 3
 

@@ -55,6 +55,7 @@ struct capb200_aoa_engine {
     std::vector<GemmTcPlan*> plans;
     char* tape = nullptr;          // SCST training tape (owned, grown on demand)
     size_t tape_bytes = 0;
+    Tf32Context* tf32 = nullptr;   // tensor maps + transposed operands of the training GEMMs (tensor-core modes)
 };
 
 namespace {
@@ -324,6 +325,7 @@ void capb200_aoa_destroy(capb200_aoa_engine* e) {
     if (e->d.loop_exec) cudaGraphExecDestroy(e->d.loop_exec);
     cudaFree(e->d.slab);
     cudaFree(e->tape);
+    tf32_context_destroy(e->tf32);
     delete e;
 }
 
@@ -572,12 +574,17 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
         if (capb200_aoa_decode_sample(e, att, nullptr, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, stream)) return 1;
     }
     if (ensure_workspace(e, B, N, R, 1, st)) return 1;
-    const Skinny sk{tp.skinny, tp.skinny_floats, e->tc ? 1 : 0, st};
+    if (e->tc && e->tf32 == nullptr) e->tf32 = tf32_context_create();
+    tf32_context_new_step(e->tf32);
+    const long tf32_l0 = tf32_context_launches(e->tf32);
+    Skinny sk{tp.skinny, tp.skinny_floats, e->tc ? 1 : 0, st};
+    sk.ctx = e->tf32;
     auto act = [](float* p, long ld) { ActView v; v.f = p; v.hi = nullptr; v.lo = nullptr; v.ld = ld; return v; };
     const int wmode = e->tc ? 1 : 0;
-    auto wgrad = [&](int out_f, int in_f, int rows, const float* dY, long ld_dy, const float* X, long ld_x, float* Gp, long ld_g, int accumulate, cudaStream_t s_) {
-        return wgrad_mode(out_f, in_f, rows, dY, ld_dy, X, ld_x, Gp, ld_g, accumulate, wmode, s_);
+    auto wgrad = [&](int out_f, int in_f, int rows, const float* dY, long ld_dy, const float* X, long ld_x, float* Gp, long ld_g, int accumulate, cudaStream_t) {
+        return sk.wgrad(out_f, in_f, rows, dY, ld_dy, X, ld_x, Gp, ld_g, accumulate);
     };
+    (void)wmode;
 
     // ---- (2) train-mode prologue: att_embed (+dropout), six refiner layers, final norm, mean pooling, ctx2att
     if (sk.lin(att, F, w.att_embed_w, F, w.att_embed_b, tp.x[0], H, (int)BR, H, F, 0)) return 1;
@@ -762,6 +769,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     rc |= relu_dropout_backward_launch(BR * H, tp.x[0], tp.d_x, tp.dpre, keep_lm, st);
     rc |= wgrad(H, F, (int)BR, tp.dpre, H, att, F, G.att_embed_w, F, 0, st);
     rc |= colsum_launch((int)BR, H, tp.dpre, H, G.att_embed_b, 0, st);
+    e->launches += tf32_context_launches(e->tf32) - tf32_l0;
     return rc;
 }
 

@@ -109,6 +109,7 @@ struct capb200_engine {
     // SCST training tape (owned, grown on demand)
     char* tape = nullptr;
     size_t tape_bytes = 0;
+    Tf32Context* tf32 = nullptr;       // tensor maps + transposed operands of the training GEMMs (tensor-core modes)
 
     // optional per-GEMM device timing (cudaEvent pairs on the launching stream), off by default
     bool profiling = false;
@@ -477,6 +478,7 @@ void capb200_engine_destroy(capb200_engine* e) {
     if (e->d.loop_exec) cudaGraphExecDestroy(e->d.loop_exec);
     cudaFree(e->d.slab);
     cudaFree(e->tape);
+    tf32_context_destroy(e->tf32);
     delete e;
 }
 
@@ -700,6 +702,24 @@ int capb200_linear(const float* x, long ldx, const float* w, long ldw, const flo
         cudaFreeAsync(part, st);
         return rc;
     }
+    if (mode == CAPB200_MODE_TF32X3_TC || mode == CAPB200_MODE_TF32X3_TC_DGRAD || mode == CAPB200_MODE_TF32X3_TC_WGRAD) {
+        // the training steps' tcgen05 kind::tf32 kernel (gemm_tf32.cu) through the same helper the engines use:
+        //   TF32X3_TC        y[M,N]  = x[M,K] w[N,K]^T + b                         (forward)
+        //   TF32X3_TC_DGRAD  y[M,N]  = x[M,K] w'[K,N]       with w' passed as `w`  (input gradient: W stored [out = K, in = N], cached transpose)
+        //   TF32X3_TC_WGRAD  y[M,N]  = x'[K,M]^T w'[K,N]    with x', w' row-major   (weight gradient: dY = x', X = w', transposed per call)
+        CAPB_REQUIRE(!relu, "the tf32 GEMM has no relu epilogue");
+        Tf32Context* ctx = tf32_context_create();
+        Skinny sk{nullptr, 0, 1, st};
+        sk.ctx = ctx;
+        int rc;
+        if (mode == CAPB200_MODE_TF32X3_TC) rc = sk.lin(x, ldx, w, ldw, b, y, ldy, M, N, K, 0);
+        else if (mode == CAPB200_MODE_TF32X3_TC_DGRAD) rc = sk.dgrad(M, N, K, x, ldx, w, ldw, y, ldy, 0);
+        else rc = sk.wgrad(M, N, K, x, ldx, w, ldw, y, ldy, 0);
+        if (tf32_context_launches(ctx) == 0 && !rc) { set_error("capb200_linear: the operands are not TMA-compatible, the tcgen05 tf32 kernel did not run"); rc = 1; }
+        cudaStreamSynchronize(st);
+        tf32_context_destroy(ctx);
+        return rc;
+    }
     CAPB_REQUIRE(mode == CAPB200_MODE_TC_F16X3 || mode == CAPB200_MODE_TC_F16X1, "unknown mode");
     const long ldh = round_up(K, 64);
     __half* scratch = nullptr;
@@ -902,7 +922,11 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
         if (capb200_decode_sample(e, fc, att, nullptr, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, stream)) return 1;
     }
     if (ensure_workspace(e, B, N, R, 1, st)) return 1;        // DecodeBuffers (tokens, unfinished, ...) for N rows
-    const Skinny sk{tp.skinny, tp.skinny_floats, e->tc ? 1 : 0, st};        // 3xTF32 tensor-core GEMMs unless the engine is in simt_fp32 mode
+    if (e->tc && e->tf32 == nullptr) e->tf32 = tf32_context_create();
+    tf32_context_new_step(e->tf32);                                          // the weights may have changed since the last step
+    const long tf32_l0 = tf32_context_launches(e->tf32);
+    Skinny sk{tp.skinny, tp.skinny_floats, e->tc ? 1 : 0, st};              // tcgen05 3xTF32 GEMMs unless the engine is in simt_fp32 mode
+    sk.ctx = e->tf32;
 
     // ---- (2) train-mode prologue: fc_embed / att_embed with dropout, ctx2att, per-image gate term
     const long BR = (long)B * R;
@@ -996,7 +1020,7 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     }
     e->launches += 3;
     if (sk.dgrad((int)TN, H, V1, tp.DL, V1, w.logit_w, H, tp.dOUT, H, 0)) return 1;          // dOUT = DL * W
-    if (gemm_wgrad_launch(V1, H, (int)TN, tp.DL, V1, tp.out, H, G.logit_w, H, 0, e->tc ? 1 : 0, st)) return 1;            // dW = DL^T * OUT
+    if (sk.wgrad(V1, H, (int)TN, tp.DL, V1, tp.out, H, G.logit_w, H, 0)) return 1;            // dW = DL^T * OUT
     if (colsum_launch((int)TN, V1, tp.DL, V1, G.logit_b, 0, st)) return 1;
     CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dh0, 0, sizeof(float) * NH, st));
     CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dc0, 0, sizeof(float) * NH, st));
@@ -1038,32 +1062,32 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     const float* DG1s = tp.DG1 + (long)N * 4 * H;     // steps 1..T-1 pair with the previous step's hidden states
     const float* DG2s = tp.DG2 + (long)N * 4 * H;
     int rc = 0;
-    rc |= gemm_wgrad_launch(4 * H, H, (int)TN, tp.DG2, 4 * H, tp.attres, H, G.lang_lstm_w_ih, 2 * H, 0, e->tc ? 1 : 0, st);
-    rc |= gemm_wgrad_launch(4 * H, H, (int)TN, tp.DG2, 4 * H, tp.h0, H, G.lang_lstm_w_ih + H, 2 * H, 0, e->tc ? 1 : 0, st);
-    rc |= gemm_wgrad_launch(4 * H, H, TN1, DG2s, 4 * H, tp.h1, H, G.lang_lstm_w_hh, H, 0, e->tc ? 1 : 0, st);
+    rc |= sk.wgrad(4 * H, H, (int)TN, tp.DG2, 4 * H, tp.attres, H, G.lang_lstm_w_ih, 2 * H, 0);
+    rc |= sk.wgrad(4 * H, H, (int)TN, tp.DG2, 4 * H, tp.h0, H, G.lang_lstm_w_ih + H, 2 * H, 0);
+    rc |= sk.wgrad(4 * H, H, TN1, DG2s, 4 * H, tp.h1, H, G.lang_lstm_w_hh, H, 0);
     rc |= colsum_launch((int)TN, 4 * H, tp.DG2, 4 * H, G.lang_lstm_b_ih, 0, st);
     rc |= colsum_launch((int)TN, 4 * H, tp.DG2, 4 * H, G.lang_lstm_b_hh, 0, st);
-    rc |= gemm_wgrad_launch(4 * H, H, TN1, DG1s, 4 * H, tp.h1, H, G.att_lstm_w_ih, E + 2 * H, 0, e->tc ? 1 : 0, st);
-    rc |= gemm_wgrad_launch(4 * H, E, (int)TN, tp.DG1, 4 * H, tp.xt, E, G.att_lstm_w_ih + 2 * H, E + 2 * H, 0, e->tc ? 1 : 0, st);
-    rc |= gemm_wgrad_launch(4 * H, H, TN1, DG1s, 4 * H, tp.h0, H, G.att_lstm_w_hh, H, 0, e->tc ? 1 : 0, st);
+    rc |= sk.wgrad(4 * H, H, TN1, DG1s, 4 * H, tp.h1, H, G.att_lstm_w_ih, E + 2 * H, 0);
+    rc |= sk.wgrad(4 * H, E, (int)TN, tp.DG1, 4 * H, tp.xt, E, G.att_lstm_w_ih + 2 * H, E + 2 * H, 0);
+    rc |= sk.wgrad(4 * H, H, TN1, DG1s, 4 * H, tp.h0, H, G.att_lstm_w_hh, H, 0);
     rc |= colsum_launch((int)TN, 4 * H, tp.DG1, 4 * H, G.att_lstm_b_ih, 0, st);
     rc |= colsum_launch((int)TN, 4 * H, tp.DG1, 4 * H, G.att_lstm_b_hh, 0, st);
     rc |= per_image_sum_launch(T, N, n, 4 * H, tp.DG1, tp.S, st);
-    rc |= gemm_wgrad_launch(4 * H, H, B, tp.S, 4 * H, tp.fc_e, H, G.att_lstm_w_ih + H, E + 2 * H, 0, e->tc ? 1 : 0, st);               // fc' block
+    rc |= sk.wgrad(4 * H, H, B, tp.S, 4 * H, tp.fc_e, H, G.att_lstm_w_ih + H, E + 2 * H, 0);               // fc' block
     rc |= sk.dgrad(B, H, 4 * H, tp.S, 4 * H, w.att_lstm_w_ih + H, E + 2 * H, tp.d_fc_e, H, 0);             // d fc'
-    rc |= gemm_wgrad_launch(A, H, (int)TN, tp.DATTH, A, tp.h0, H, G.h2att_w, H, 0, e->tc ? 1 : 0, st);
+    rc |= sk.wgrad(A, H, (int)TN, tp.DATTH, A, tp.h0, H, G.h2att_w, H, 0);
     rc |= colsum_launch((int)TN, A, tp.DATTH, A, G.h2att_b, 0, st);
     // prologue
     rc |= sk.dgrad((int)BR, H, A, tp.d_p_att, A, w.ctx2att_w, H, tp.d_att_e, H, 1);
-    rc |= gemm_wgrad_launch(A, H, (int)BR, tp.d_p_att, A, tp.att_e, H, G.ctx2att_w, H, 0, e->tc ? 1 : 0, st);
+    rc |= sk.wgrad(A, H, (int)BR, tp.d_p_att, A, tp.att_e, H, G.ctx2att_w, H, 0);
     rc |= colsum_launch((int)BR, A, tp.d_p_att, A, G.ctx2att_b, 0, st);
     rc |= relu_dropout_backward_launch(BR * H, tp.att_e, tp.d_att_e, tp.dpre_att, keep_scale, st);
-    rc |= gemm_wgrad_launch(H, Fa, (int)BR, tp.dpre_att, H, att, Fa, G.att_embed_w, Fa, 0, e->tc ? 1 : 0, st);
+    rc |= sk.wgrad(H, Fa, (int)BR, tp.dpre_att, H, att, Fa, G.att_embed_w, Fa, 0);
     rc |= colsum_launch((int)BR, H, tp.dpre_att, H, G.att_embed_b, 0, st);
     rc |= relu_dropout_backward_launch((long)B * H, tp.fc_e, tp.d_fc_e, tp.dpre_fc, keep_scale, st);
-    rc |= gemm_wgrad_launch(H, Ff, B, tp.dpre_fc, H, fc, Ff, G.fc_embed_w, Ff, 0, e->tc ? 1 : 0, st);
+    rc |= sk.wgrad(H, Ff, B, tp.dpre_fc, H, fc, Ff, G.fc_embed_w, Ff, 0);
     rc |= colsum_launch(B, H, tp.dpre_fc, H, G.fc_embed_b, 0, st);
-    e->launches += 30;
+    e->launches += 30 + (tf32_context_launches(e->tf32) - tf32_l0);     // + transposes of the tcgen05 path
     return rc;
 }
 

@@ -294,16 +294,30 @@ int sample_decode_driver(DecodeBuffers& d, int V1, int T, int rows, int method, 
     return 0;
 }
 
-// Skinny fp32 GEMMs on the raw PyTorch weights (always current, no repack after optimizer steps); split-K partials live in the tape.
+// Training-step GEMMs on the raw fp32 PyTorch weights (always current, no repack after optimizer steps).  With a Tf32Context (tensor-core
+// engines) every call runs on the tcgen05 kind::tf32 3-pass kernel of gemm_tf32.cu; operands that are not K-major in HBM (W for the input
+// gradients, dY / X for the weight gradients) go through cached transposes.  Without a context (simt_fp32 engines), when an operand is not
+// TMA-compatible (rows not 16-byte aligned: tiny test shapes), or with CAPB200_SKINNY_LEGACY set, the split-K kernels of gemm_generic.cu run.
 struct Skinny {
     float* scratch; size_t cap; int mode; cudaStream_t st;
+    Tf32Context* ctx = nullptr;
+    static bool legacy() { static const bool v = getenv("CAPB200_SKINNY_LEGACY") != nullptr; return v; }
+    bool tc() const { return ctx != nullptr && mode != 0 && !legacy(); }
     // y = x * W^T (+ b)          (nn.Linear forward; W stored [N, K])
     int lin(const float* x, long ldx, const float* w, long ldw, const float* b, float* y, long ldy, int M, int N, int K, int accumulate) const {
+        if (tc() && gemm_tf32_supported(1, &x, &ldx, &w, &ldw, &K))
+            return gemm_tf32_launch(ctx, M, N, 1, &x, &ldx, &w, &ldw, &K, y, ldy, b, nullptr, 0, 1, accumulate, st);
         const int tb = 1;
         return gemm_skinny_launch(M, N, 1, &x, &ldx, &w, &ldw, &K, &tb, y, ldy, b, nullptr, 0, 1, accumulate, scratch, cap, mode, st);
     }
-    // dx = dy * W                (nn.Linear input gradient; W stored [K, N])
+    // dx = dy * W                (nn.Linear input gradient; W stored [K, N] = [out, in])
     int dgrad(int M, int N, int K, const float* dy, long lddy, const float* w, long ldw, float* dx, long lddx, int accumulate) const {
+        if (tc() && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (lddy & 3) == 0) {
+            long ldt = 0;
+            const float* wt = tf32_transposed(ctx, w, ldw, K, N, true, &ldt, st);          // W^T [N, K]: rebuilt once per training step
+            if (wt == nullptr) return 1;
+            return gemm_tf32_launch(ctx, M, N, 1, &dy, &lddy, &wt, &ldt, &K, dx, lddx, nullptr, nullptr, 0, 1, accumulate, st);
+        }
         const int tb = 0;
         return gemm_skinny_launch(M, N, 1, &dy, &lddy, &w, &ldw, &K, &tb, dx, lddx, nullptr, nullptr, 0, 1, accumulate, scratch, cap, mode, st);
     }
@@ -311,8 +325,22 @@ struct Skinny {
     int gates(const GemmProblem& g) const {
         const float* A[3]; const float* B[3]; long lda[3], ldb[3]; int K[3], tb[3];
         for (int i = 0; i < g.nseg; ++i) { A[i] = g.seg[i].A; lda[i] = g.seg[i].lda; B[i] = g.seg[i].W; ldb[i] = g.seg[i].ldw; K[i] = g.seg[i].K; tb[i] = 1; }
+        if (tc() && gemm_tf32_supported(g.nseg, A, lda, B, ldb, K))
+            return gemm_tf32_launch(ctx, g.M, g.N, g.nseg, A, lda, B, ldb, K, g.epi.C, g.epi.ldc, g.epi.bias, g.epi.row_bias, g.epi.ld_row_bias,
+                                    g.epi.rows_per_group, 0, st);
         return gemm_skinny_launch(g.M, g.N, g.nseg, A, lda, B, ldb, K, tb, g.epi.C, g.epi.ldc, g.epi.bias, g.epi.row_bias, g.epi.ld_row_bias,
                                   g.epi.rows_per_group, 0, scratch, cap, mode, st);
+    }
+    // dW[out, in] (+)= dY[rows, out]^T * X[rows, in]      (weight gradient, batched over time: rows = T * N)
+    int wgrad(int out_f, int in_f, int rows, const float* dY, long ld_dy, const float* X, long ld_x, float* G, long ld_g, int accumulate) const {
+        if (tc() && rows >= 64) {
+            long ld_a = 0, ld_b = 0;
+            const float* dyt = tf32_transposed(ctx, dY, ld_dy, rows, out_f, false, &ld_a, st);     // [out, rows]
+            const float* xt = dyt ? tf32_transposed(ctx, X, ld_x, rows, in_f, false, &ld_b, st) : nullptr;     // [in, rows]
+            if (xt == nullptr) return 1;
+            return gemm_tf32_launch(ctx, out_f, in_f, 1, &dyt, &ld_a, &xt, &ld_b, &rows, G, ld_g, nullptr, nullptr, 0, 1, accumulate, st);
+        }
+        return gemm_wgrad_launch(out_f, in_f, rows, dY, ld_dy, X, ld_x, G, ld_g, accumulate, mode, st);
     }
 };
 

@@ -113,6 +113,16 @@ int gemm_skinny_launch(int M, int N, int nseg, const float* const* A, const long
 int gemm_wgrad_launch(int M, int N, int K, const float* dY, long ld_dy, const float* X, long ld_x, float* G, long ld_g, int accumulate, int mode,
                       cudaStream_t st);   // G[M,N] (+)= dY[K,M]^T X[K,N]; mode 1 = 3xTF32 tensor cores
 int colsum_launch(int rows, int cols, const float* x, long ld, float* out, int accumulate, cudaStream_t st);
+// ---- gemm_tf32.cu: tcgen05 kind::tf32 3-pass GEMM on fp32 operands (in-kernel hi/lo split), split-K over a cluster with a DSMEM reduction
+struct Tf32Context;      // per-engine cache of encoded tensor maps and transposed operands
+Tf32Context* tf32_context_create();
+void tf32_context_destroy(Tf32Context* c);
+void tf32_context_new_step(Tf32Context* c);          // weights may have changed: per-step transposes are rebuilt on next use
+long tf32_context_launches(const Tf32Context* c);
+bool gemm_tf32_supported(int nseg, const float* const* X, const long* ldx, const float* const* W, const long* ldw, const int* K);
+int gemm_tf32_launch(Tf32Context* ctx, int M, int N, int nseg, const float* const* X, const long* ldx, const float* const* W, const long* ldw, const int* K,
+                     float* C, long ldc, const float* bias, const float* row_bias, long ld_rb, int rpg, int accumulate, cudaStream_t st);
+const float* tf32_transposed(Tf32Context* ctx, const float* src, long ld_src, int rows, int cols, bool per_step, long* ld_dst, cudaStream_t st);
 int dropout_apply_launch(float* x, int rows, int cols, long ld, unsigned long long seed, unsigned site, unsigned step, float p, cudaStream_t st);
 int dropout_mask_launch(float* m, long n, unsigned long long seed, unsigned site, unsigned step, float p, cudaStream_t st);
 int dropout_copy_launch(const float* x, long ld_x, float* y, long ld_y, int rows, int cols, unsigned long long seed, unsigned site, unsigned step, float p,

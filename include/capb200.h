@@ -28,6 +28,9 @@ extern "C" {
 #define CAPB200_MODE_TC_F16X1 2  /* tcgen05 kind::f16, single pass (throughput mode, not parity grade) */
 #define CAPB200_MODE_SKINNY_TF32X3 3 /* capb200_linear only: the training step's split-K GEMM, 3xTF32 mma.sync on the fp32 weights */
 #define CAPB200_MODE_SKINNY_FP32 4   /* capb200_linear only: same split-K GEMM on CUDA cores */
+#define CAPB200_MODE_TF32X3_TC 5       /* capb200_linear only: the training steps' tcgen05 kind::tf32 3-pass GEMM on fp32 operands (gemm_tf32.cu) */
+#define CAPB200_MODE_TF32X3_TC_DGRAD 6 /* same kernel, input-gradient form: y[M,N] = x[M,K] * w[K,N]  (w row-major [K,N], transposed internally) */
+#define CAPB200_MODE_TF32X3_TC_WGRAD 7 /* same kernel, weight-gradient form: y[M,N] = x[K,M]^T * w[K,N] (both row-major, transposed internally) */
 
 #define CAPB200_FAMILY_UPDOWN 0 /* UpDownModel  captioning/models/AttModel.py:868 */
 #define CAPB200_FAMILY_NEWFC 1  /* NewFCModel   captioning/models/AttModel.py:904 */

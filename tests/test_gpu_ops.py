@@ -69,6 +69,57 @@ def test_skinny_linear_matches_fp64(L, mode, shape):
     assert rel < (4e-6 if mode == 'skinny_tf32x3' else 2e-6), (mode, shape, rel)
 
 
+@pytest.mark.parametrize('shape', [(50, 4096, 3072), (50, 9488, 1024), (50, 1000, 4000), (12, 41, 48), (64, 256, 96), (200, 520, 1000), (360, 3072, 1024),
+                                   (1000, 1024, 9488), (257, 130, 36)])
+def test_tf32x3_tcgen05_linear_matches_fp64(L, shape):
+    """The training steps' tcgen05 kind::tf32 kernel (gemm_tf32.cu: raw fp32 tiles by TMA, hi/lo split in shared memory, 3 MMAs per K-block,
+    split-K over a cluster with a DSMEM reduction), swapped (M <= 256) and normal orientation, ragged M / N / K, against float64.  Half of
+    the rows are gradient-like (1e-7): they must not be flushed."""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M * 13 + N)
+    x = torch.randn(M, K, generator=g)
+    x[M // 2:] *= 1e-7
+    w = (torch.rand(N, K, generator=g) * 2 - 1) / K ** 0.5
+    b = torch.randn(N, generator=g) * 1e-3
+    ref = x.double() @ w.double().t() + b.double()
+    y = _linear(L, x.cuda(), w.cuda(), b.cuda(), False, 'tf32x3_tc').cpu().double()
+    scale = (x.double().abs() @ w.double().abs().t() + b.double().abs())
+    rel = float(((y - ref).abs() / scale).max())
+    assert rel < 4e-6, (shape, rel)
+
+
+@pytest.mark.parametrize('shape', [(50, 2048, 4096), (50, 1000, 9488), (360, 1024, 3072), (1000, 1024, 9488), (20, 48, 164)])
+def test_tf32x3_tcgen05_input_gradient(L, shape):
+    """dx[M, in] = dy[M, out] * W[out, in] through the cached transpose of W."""
+    M, N, K = shape                       # N = in features, K = out features
+    g = torch.Generator().manual_seed(M + N)
+    dy = torch.randn(M, K, generator=g) * 1e-6
+    w = (torch.rand(K, N, generator=g) * 2 - 1) / K ** 0.5
+    ref = dy.double() @ w.double()
+    y = torch.empty(M, N, device='cuda')
+    L.check(L.load().capb200_linear(L.ptr(dy.cuda()), K, L.ptr(w.cuda()), N, None, L.ptr(y), N, M, N, K, 0, L.OP_MODES['tf32x3_tc_dgrad'], L.current_stream()),
+            'linear dgrad')
+    torch.cuda.synchronize()
+    scale = dy.double().abs() @ w.double().abs()
+    assert float(((y.cpu().double() - ref).abs() / scale).max()) < 4e-6
+
+
+@pytest.mark.parametrize('shape', [(4096, 1024, 1000), (9488, 1024, 1000), (2048, 2048, 360), (512, 1000, 950), (96, 40, 135)])
+def test_tf32x3_tcgen05_weight_gradient(L, shape):
+    """dW[out, in] = dY[rows, out]^T * X[rows, in], batched over time (rows = T * N), through per-call transposes."""
+    M, N, K = shape                       # M = out features, N = in features, K = rows
+    g = torch.Generator().manual_seed(M + K)
+    dy = torch.randn(K, M, generator=g) * 1e-6
+    x = torch.randn(K, N, generator=g)
+    ref = dy.double().t() @ x.double()
+    y = torch.empty(M, N, device='cuda')
+    L.check(L.load().capb200_linear(L.ptr(dy.cuda()), M, L.ptr(x.cuda()), N, None, L.ptr(y), N, M, N, K, 0, L.OP_MODES['tf32x3_tc_wgrad'], L.current_stream()),
+            'linear wgrad')
+    torch.cuda.synchronize()
+    scale = dy.double().abs().t() @ x.double().abs()
+    assert float(((y.cpu().double() - ref).abs() / scale).max()) < 4e-6
+
+
 @pytest.mark.parametrize('mode', ['simt_fp32', 'tc_f16x3'])
 def test_lstm_cell(L, mode):
     g = torch.Generator().manual_seed(3)
