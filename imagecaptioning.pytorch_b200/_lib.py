@@ -165,6 +165,8 @@ SIGNATURES = {
     'capb200_updown_scst_step': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(ScstOpts), c_void_p, c_void_p, c_void_p, c_int,
                                          POINTER(UpdownGrads), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'capb200_dropout_mask': (c_int, [c_void_p, c_long, c_ulonglong, c_int, c_int, c_float, c_void_p]),
+    'capb200_engine_set_grad_events': (c_int, [c_void_p, c_void_p, c_int]),
+    'capb200_aoa_set_grad_events': (c_int, [c_void_p, c_void_p, c_int]),
     'capb200_cider_table_create': (c_void_p, [c_void_p, c_void_p, c_long, c_double, c_void_p]),
     'capb200_cider_table_destroy': (None, [c_void_p]),
     'capb200_cider_scores': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

@@ -56,6 +56,7 @@ struct capb200_aoa_engine {
     char* tape = nullptr;          // SCST training tape (owned, grown on demand)
     size_t tape_bytes = 0;
     Tf32Context* tf32 = nullptr;   // tensor maps + transposed operands of the training GEMMs (tensor-core modes)
+    cudaEvent_t grad_events[10] = {};   // caller-owned: recorded when a gradient group is complete (capb200_aoa_set_grad_events)
 };
 
 namespace {
@@ -678,6 +679,11 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     if (sk.dgrad((int)TN, H, V1, tp.DL, V1, w.logit_w, H, tp.dOUTD, H, 0)) return 1;
     if (wgrad(V1, H, (int)TN, tp.DL, V1, tp.outd, H, G.logit_w, H, 0, st)) return 1;
     if (colsum_launch((int)TN, V1, tp.DL, V1, G.logit_b, 0, st)) return 1;
+    auto group_done = [&](int k) -> int {
+        if (e->grad_events[k]) CAPB_CHECK_CUDA(cudaEventRecord(e->grad_events[k], st));
+        return 0;
+    };
+    if (group_done(0)) return 1;                                        // logit
     CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dctx, 0, sizeof(float) * NH, st));
     CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dh, 0, sizeof(float) * NH, st));
     CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dc, 0, sizeof(float) * NH, st));
@@ -731,6 +737,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     rc |= per_image_sum_launch(T, N, n, 4 * H, tp.DG, tp.S, st);
     rc |= sk.dgrad(B, H, 4 * H, tp.S, 4 * H, w.att_lstm_w_ih + E, E + H, tp.d_mean, H, 0);
     if (rc) return 1;
+    if (group_done(1)) return 1;                                        // decoder + embed
 
     // ---- (6) backward through the prologue
     rc |= sk.dgrad((int)BR, H, 2 * H, tp.d_kv, 2 * H, w.ctx2att_w, H, tp.d_att_e, H, 0);
@@ -739,6 +746,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     rc |= mean_backward_launch(B, R, H, tp.d_mean, H, tp.d_att_e, H, st);
     rc |= ln_backward_launch((int)BR, H, tp.x[NL], H, w.refiner_norm_a, tp.d_att_e, H, 1e-6f, tp.d_x, H, 0, tp.stats, G.refiner_norm_a, G.refiner_norm_b, 0, st);
     if (rc) return 1;
+    if (group_done(2)) return 1;                                        // ctx2att + refiner.norm
     for (int l = NL - 1; l >= 0; --l) {
         const capb200_aoa_refiner_layer& Lw = w.refiner[l];
         const capb200_aoa_refiner_layer_grads& Lg = G.refiner[l];
@@ -764,12 +772,14 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
         rc |= sk.dgrad((int)BR, H, 3 * H, tp.d_qkv, 3 * H, e->r_qkv_w[l], H, tp.d_ln, H, 1);
         rc |= ln_backward_launch((int)BR, H, tp.x[l], H, Lw.ln_a, tp.d_ln, H, 1e-6f, tp.d_x, H, 1, tp.stats, Lg.ln_a, Lg.ln_b, 0, st);
         if (rc) return 1;
+        if (group_done(3 + (NL - 1 - l))) return 1;                     // refiner layer l (layers finish 5 -> 0)
         e->launches += 22;
     }
     rc |= relu_dropout_backward_launch(BR * H, tp.x[0], tp.d_x, tp.dpre, keep_lm, st);
     rc |= wgrad(H, F, (int)BR, tp.dpre, H, att, F, G.att_embed_w, F, 0, st);
     rc |= colsum_launch((int)BR, H, tp.dpre, H, G.att_embed_b, 0, st);
     e->launches += tf32_context_launches(e->tf32) - tf32_l0;
+    if (!rc && group_done(9)) return 1;                                 // att_embed
     return rc;
 }
 
@@ -793,6 +803,12 @@ extern "C" int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, in
     ta.refs = refs; ta.ref_offsets = ref_offsets; ta.L = L; ta.sample_seq = sample_seq; ta.greedy_seq = greedy_seq; ta.reward = reward;
     ta.logprobs = sample_logprobs; ta.loss = loss; ta.forced = opts->forced_tokens;
     return aoa_train_step(e, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int capb200_aoa_set_grad_events(capb200_aoa_engine* e, void* const* events, int n) {
+    CAPB_REQUIRE(e != nullptr && n >= 0 && n <= 10, "AoANet has 10 gradient groups");
+    for (int i = 0; i < 10; ++i) e->grad_events[i] = (events != nullptr && i < n) ? static_cast<cudaEvent_t>(events[i]) : nullptr;
+    return 0;
 }
 
 extern "C" int capb200_aoa_xe_step(capb200_aoa_engine* e, const float* att, int B, int R, const capb200_aoa_xe_opts* opts, const long long* labels,

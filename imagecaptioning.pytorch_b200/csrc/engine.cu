@@ -110,6 +110,7 @@ struct capb200_engine {
     char* tape = nullptr;
     size_t tape_bytes = 0;
     Tf32Context* tf32 = nullptr;       // tensor maps + transposed operands of the training GEMMs (tensor-core modes)
+    cudaEvent_t grad_events[2] = {nullptr, nullptr};   // caller-owned: recorded when a gradient group is complete (capb200_engine_set_grad_events)
 
     // optional per-GEMM device timing (cudaEvent pairs on the launching stream), off by default
     bool profiling = false;
@@ -1022,6 +1023,7 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     if (sk.dgrad((int)TN, H, V1, tp.DL, V1, w.logit_w, H, tp.dOUT, H, 0)) return 1;          // dOUT = DL * W
     if (sk.wgrad(V1, H, (int)TN, tp.DL, V1, tp.out, H, G.logit_w, H, 0)) return 1;            // dW = DL^T * OUT
     if (colsum_launch((int)TN, V1, tp.DL, V1, G.logit_b, 0, st)) return 1;
+    if (e->grad_events[0]) CAPB_CHECK_CUDA(cudaEventRecord(e->grad_events[0], st));          // group 0 (logit) is final
     CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dh0, 0, sizeof(float) * NH, st));
     CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dc0, 0, sizeof(float) * NH, st));
     CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dh1, 0, sizeof(float) * NH, st));
@@ -1088,6 +1090,7 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     rc |= sk.wgrad(H, Ff, B, tp.dpre_fc, H, fc, Ff, G.fc_embed_w, Ff, 0);
     rc |= colsum_launch(B, H, tp.dpre_fc, H, G.fc_embed_b, 0, st);
     e->launches += 30 + (tf32_context_launches(e->tf32) - tf32_l0);     // + transposes of the tcgen05 path
+    if (!rc && e->grad_events[1]) CAPB_CHECK_CUDA(cudaEventRecord(e->grad_events[1], st));
     return rc;
 }
 
@@ -1112,6 +1115,12 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
     ta.sample_seq = sample_seq; ta.greedy_seq = greedy_seq; ta.reward = reward; ta.logprobs = sample_logprobs; ta.loss = loss;
     ta.forced = opts->forced_tokens;
     return updown_train_step(e, fc, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int capb200_engine_set_grad_events(capb200_engine* e, void* const* events, int n) {
+    CAPB_REQUIRE(e != nullptr && n >= 0 && n <= 2, "UpDown has 2 gradient groups");
+    for (int i = 0; i < 2; ++i) e->grad_events[i] = (events != nullptr && i < n) ? static_cast<cudaEvent_t>(events[i]) : nullptr;
+    return 0;
 }
 
 extern "C" int capb200_updown_xe_step(capb200_engine* e, const float* fc, const float* att, int B, int R, const capb200_xe_opts* opts,

@@ -114,17 +114,32 @@ class StructureLosses(nn.Module):
 
 class _ScstLoss(torch.autograd.Function):
     """Connects the engine-computed loss to the parameters: the gradients were produced by the engine's own BPTT during the forward
-    call; backward hands them (scaled by the upstream gradient) to autograd, so loss.backward(), DDP hooks, clip_grad_value_ and the
-    optimizers of tools/train.py:189-196 work unchanged."""
+    call (into the model's persistent flat gradient buffer); backward hands them (scaled by the upstream gradient) to autograd, so
+    loss.backward(), DDP hooks, clip_grad_value_ and the optimizers of tools/train.py:189-196 work unchanged.
+
+    With B200LossWrapper.enable_gradient_sync() the wrapper itself plays DDP's role: the flat buffer has been all-reduced in chunks while
+    the step was still running; backward waits for that, scales the buffer in place and makes ``param.grad`` VIEWS of it (no copy; a second
+    backward before zero_grad accumulates like autograd would)."""
 
     @staticmethod
-    def forward(ctx, loss_value, grad_list, *params):
+    def forward(ctx, loss_value, grad_list, sync, *params):
         ctx.grad_list = grad_list
+        ctx.sync = sync
+        ctx.params = params
         return loss_value.clone()
 
     @staticmethod
     def backward(ctx, grad_out):
-        return (None, None) + tuple(g * grad_out for g in ctx.grad_list)
+        if ctx.sync is None:
+            return (None, None, None) + tuple(g * grad_out for g in ctx.grad_list)
+        ctx.sync.wait()
+        torch._foreach_mul_(list(ctx.grad_list), grad_out)
+        for p_, g in zip(ctx.params, ctx.grad_list):
+            if p_.grad is None:
+                p_.grad = g
+            else:
+                p_.grad.add_(g)
+        return (None, None, None) + tuple(None for _ in ctx.params)
 
 
 class B200LossWrapper(nn.Module):
@@ -136,11 +151,33 @@ class B200LossWrapper(nn.Module):
         self.crit = LabelSmoothing(smoothing=smoothing) if smoothing > 0 else LanguageModelCriterion()      # loss_wrapper.py:10-13
         self.rl_crit = RewardCriterion()
         self.struc_crit = None
+        self._sync = None
+        self.last_sync_bytes = 0
+
+    # -- data-parallel gradient synchronisation (the role DDP plays for the reference, tools/train_pl.py:479) -------------------------
+    def enable_gradient_sync(self, process_group=None):
+        """One process per GPU: after every fused training step the engine's flat gradient buffer is averaged over the ranks with one NCCL
+        all-reduce per gradient group, issued on a communication stream as soon as the engine has finished that group (logit first, then the
+        decoder, then the refiner layers), i.e. overlapped with the rest of the backward pass.  ``loss.backward()`` then waits for the
+        reduced buffer and points ``param.grad`` at it."""
+        from .grad_sync import GradSync
+        self._sync = GradSync(process_group)
+        return self
+
+    @property
+    def last_sync_exposed_ms(self):
+        """Device time the last backward() spent waiting for the all-reduce (the part that did not overlap); synchronises."""
+        return 0.0 if self._sync is None else self._sync.exposed_ms()
 
     # -- fused device steps ------------------------------------------------------------------------------------------
     def _bridge(self, res):
         params = list(res['grads'].keys())
-        return _ScstLoss.apply(res['loss'], [res['grads'][p_] for p_ in params], *params)
+        sync = None
+        if self._sync is not None and res.get('flat') is not None:
+            self._sync.launch(res['flat'])
+            self.last_sync_bytes = self._sync.bytes
+            sync = self._sync
+        return _ScstLoss.apply(res['loss'], [res['grads'][p_] for p_ in params], sync, *params)
 
     def _scorer(self):
         from . import rewards as _rw
@@ -148,12 +185,14 @@ class B200LossWrapper(nn.Module):
             raise RuntimeError('init_scorer(cached_tokens) must be called before the SCST reward (tools/train.py:150-152)')
         return _rw.CiderD_scorer
 
-    def _xe_loss(self, fc_feats, att_feats, labels, masks, att_masks, drop_worst_flag):
+    def _xe_loss(self, fc_feats, att_feats, labels, masks, att_masks, drop_worst_flag, snapshot=False):
         """loss_wrapper.py:54-55: crit(model(fc, att, labels[..., :-1], att_masks), labels[..., 1:], masks[..., 1:])."""
         if torch.is_grad_enabled() and self.model.training:
             if not hasattr(self.model, 'xe_step') or att_masks is not None or drop_worst_flag:
                 raise NotImplementedError('the fused XE step covers the UpDown family with att_masks=None and reduction="mean"')
             res = self.model.xe_step(fc_feats, att_feats, labels, masks, label_smoothing=getattr(self.opt, 'label_smoothing', 0))
+            if snapshot:        # another fused step will reuse the model's flat gradient buffer before this loss is back-propagated
+                res = dict(res, grads={p_: g.clone() for p_, g in res['grads'].items()}, flat=None)
             self.last_step = res
             return self._bridge(res)
         # evaluation (no gradients): the teacher-forced forward of the engine plus the criterion as host-level ops
@@ -177,7 +216,8 @@ class B200LossWrapper(nn.Module):
                     opt.train_sample_method == 'sample' and opt.train_beam_size == 1)
         if struc_flag:
             w = opt.structure_loss_weight
-            lm_loss = self._xe_loss(fc_feats, att_feats, labels, masks, att_masks, drop_worst_flag) if w < 1 else torch.zeros((), device=fc_feats.device)
+            lm_loss = self._xe_loss(fc_feats, att_feats, labels, masks, att_masks, drop_worst_flag, snapshot=w > 0) if w < 1 else \
+                torch.zeros((), device=fc_feats.device)
             if w > 0:
                 if getattr(opt, 'use_ppo', 0) or opt.structure_loss_type != 'new_self_critical' or not can_fuse:
                     raise NotImplementedError("the structure-loss branch covers structure_loss_type='new_self_critical' on the fused UpDown step")

@@ -77,7 +77,7 @@ class _EngineStore:
 
     def slot(self, dev):
         with self.lock:
-            return self.slots.setdefault(dev, {'engine': None, 'key': None, 'versions': None, 'keepalive': None})
+            return self.slots.setdefault(dev, {'engine': None, 'key': None, 'versions': None, 'keepalive': None, 'flat': None, 'bufs': {}})
 
     def __deepcopy__(self, memo):
         fresh = _EngineStore(None)
@@ -160,6 +160,33 @@ class B200CaptionModel(nn.Module):
     _engine_key = _slot_property('key')
     _bound_versions = _slot_property('versions')
     _keepalive = _slot_property('keepalive')
+    _flat = _slot_property('flat')            # grad_sync.FlatGrads of this device (persistent flat gradient buffer of the fused training steps)
+    _bufs = _slot_property('bufs')            # persistent per-shape output buffers of the fused training steps
+
+    def _grad_groups(self):
+        """[(name, parameter)] lists in the order the engine completes the gradients (include/capb200.h: *_set_grad_events)."""
+        raise NotImplementedError
+
+    def _flat_grads(self, device):
+        """The persistent flat gradient buffer of this device, its {name: view} table and the engine-recorded group events.  Keyed by name:
+        nn.DataParallel replicas carry different Parameter objects every forward but the same names and shapes."""
+        from .grad_sync import FlatGrads
+        groups = self._grad_groups()
+        sig = tuple((n, tuple(p.shape)) for g in groups for n, p in g)
+        fg = self._flat
+        if fg is None or fg.sig != sig:
+            fg = FlatGrads([[p for _, p in g] for g in groups], device)
+            fg.sig = sig
+            fg.by_name = {n: fg.view(p) for g in groups for n, p in g}
+            self._flat = fg
+        return fg
+
+    def _buffers(self, key, make):
+        bufs = self._bufs
+        if key not in bufs:
+            bufs.clear()            # one live shape at a time: the buffers are large (the [N, T, V+1] log-prob block)
+            bufs[key] = make()
+        return bufs[key]
 
     def _enter_device(self, device):
         """Selects the per-device engine slot for this thread; returns the loaded library."""
@@ -455,6 +482,21 @@ class B200UpDownModel(B200CaptionModel):
         }
 
 
+    def _grad_groups(self):
+        t = self._weight_table()
+        first = ('logit_w', 'logit_b')
+        return [[(k, t[k]) for k in first], [(k, v) for k, v in t.items() if k not in first]]
+
+    def _grad_table(self, lib, device):
+        """capb200_updown_grads pointing into the persistent flat buffer, the group events registered with the engine."""
+        fg = self._flat_grads(device)
+        g = _lib.UpdownGrads()
+        for name in _lib.GRAD_FIELDS:
+            setattr(g, name, fg.by_name[name].data_ptr())
+        table, n = fg.event_table()
+        _lib.check(lib.capb200_engine_set_grad_events(self._engine, table, n), 'set_grad_events')
+        return fg, g
+
     # ---- SCST training step (UpDown): greedy baseline + sampling with dropout + CIDEr-D reward + RewardCriterion + BPTT -----
     @_on_device
     def scst_step(self, fc_feats, att_feats, gts, table, sample_n, temperature=1.0, drop_prob=None, seed=None, upstream=1.0, baseline='greedy',
@@ -473,15 +515,13 @@ class B200UpDownModel(B200CaptionModel):
         N, T, V1 = B * sample_n, self.seq_length, self.vocab_size + 1
         refs, offsets, L = pack_references(gts, dev)
         table_params = self._weight_table()
-        grads = {name: torch.empty_like(t) for name, t in table_params.items()}
-        g = _lib.UpdownGrads()
-        for name, t in grads.items():
-            setattr(g, name, t.data_ptr())
-        sample_seq = torch.zeros(N, T, dtype=torch.long, device=dev)
-        greedy_seq = torch.zeros(B, T, dtype=torch.long, device=dev)
-        logprobs = torch.zeros(N, T, V1, dtype=torch.float32, device=dev)
-        reward = torch.empty(N, T, dtype=torch.float32, device=dev)
-        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        fg, g = self._grad_table(lib, dev)
+        grads = fg.by_name
+        # outputs live in persistent buffers (overwritten by the next step of the same shape): the step writes every row of every one
+        sample_seq, greedy_seq, logprobs, reward, loss = self._buffers(('scst', B, sample_n), lambda: (
+            torch.zeros(N, T, dtype=torch.long, device=dev), torch.zeros(B, T, dtype=torch.long, device=dev),
+            torch.zeros(N, T, V1, dtype=torch.float32, device=dev), torch.empty(N, T, dtype=torch.float32, device=dev),
+            torch.empty(1, dtype=torch.float32, device=dev)))
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         p = self.drop_prob_lm if drop_prob is None else drop_prob
@@ -498,7 +538,7 @@ class B200UpDownModel(B200CaptionModel):
                                                 _lib.ptr(offsets), L, ctypes.byref(g), _lib.ptr(sample_seq), _lib.ptr(greedy_seq), _lib.ptr(logprobs),
                                                 _lib.ptr(reward), _lib.ptr(loss), _lib.current_stream()), 'updown_scst_step')
         res = {'loss': loss[0], 'reward': reward, 'sample_seq': sample_seq, 'greedy_seq': None if loo else greedy_seq, 'sample_logprobs': logprobs,
-               'grads': {table_params[k]: v for k, v in grads.items()}, 'seed': seed}
+               'grads': {table_params[k]: grads[k] for k in table_params}, 'seed': seed, 'flat': fg}
         return res
 
     @_on_device
@@ -524,10 +564,8 @@ class B200UpDownModel(B200CaptionModel):
         steps = self._teacher_steps(labels[:, :-1])
         V1 = self.vocab_size + 1
         table_params = self._weight_table()
-        grads = {name: torch.empty_like(t) for name, t in table_params.items()}
-        g = _lib.UpdownGrads()
-        for name, t in grads.items():
-            setattr(g, name, t.data_ptr())
+        fg, g = self._grad_table(lib, dev)
+        grads = fg.by_name
         logprobs = torch.zeros(N, Lc - 1, V1, dtype=torch.float32, device=dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         if seed is None:
@@ -536,7 +574,7 @@ class B200UpDownModel(B200CaptionModel):
         xo = _lib.XeOpts(N // B, steps, seed, float(p), float(label_smoothing), float(upstream))
         _lib.check(lib.capb200_updown_xe_step(self._engine, _lib.ptr(fc), _lib.ptr(att), B, R, ctypes.byref(xo), _lib.ptr(labels), _lib.ptr(masks), Lc,
                                               ctypes.byref(g), _lib.ptr(logprobs), _lib.ptr(loss), _lib.current_stream()), 'updown_xe_step')
-        return {'loss': loss[0], 'logprobs': logprobs, 'grads': {table_params[k]: v for k, v in grads.items()}, 'seed': seed}
+        return {'loss': loss[0], 'logprobs': logprobs, 'grads': {table_params[k]: grads[k] for k in table_params}, 'seed': seed, 'flat': fg}
 
 
 class _MaxoutCoreParams(nn.Module):
@@ -787,6 +825,32 @@ class B200AoAModel(B200CaptionModel):
                 (('logit_w',), self.logit.weight), (('logit_b',), self.logit.bias)]
         return out
 
+    def _grad_groups(self):
+        slots = {'/'.join(str(x) for x in path): prm for path, prm in self._slots()}
+        pick = lambda names: [(n, slots[n]) for n in names]
+        groups = [pick(['logit_w', 'logit_b']),
+                  pick(['att2ctx_w', 'att2ctx_b', 'attn_q_w', 'attn_q_b', 'att_lstm_w_ih', 'att_lstm_w_hh', 'att_lstm_b_ih', 'att_lstm_b_hh', 'attn_norm_a',
+                        'attn_norm_b', 'embed']),
+                  pick(['ctx2att_w', 'ctx2att_b', 'refiner_norm_a', 'refiner_norm_b'])]
+        for l in reversed(range(_lib.AOA_REFINER_LAYERS)):
+            groups.append(pick(['refiner/%d/%s' % (l, f) for f in ('q_w', 'q_b', 'k_w', 'k_b', 'v_w', 'v_b', 'aoa_w', 'aoa_b', 'ln_a', 'ln_b')]))
+        groups.append(pick(['att_embed_w', 'att_embed_b']))
+        assert sum(len(g) for g in groups) == len(slots)
+        return groups
+
+    def _grad_table(self, lib, device):
+        fg = self._flat_grads(device)
+        g = _lib.AoaWeights()
+        for path, _ in self._slots():
+            ptr = fg.by_name['/'.join(str(x) for x in path)].data_ptr()
+            if len(path) == 1:
+                setattr(g, path[0], ptr)
+            else:
+                setattr(g.refiner[path[1]], path[2], ptr)
+        table, n = fg.event_table()
+        _lib.check(lib.capb200_aoa_set_grad_events(self._engine, table, n), 'aoa_set_grad_events')
+        return fg, g
+
     def _fill_table(self, table, tensor_of):
         """Writes data pointers into an AoaWeights-layout ctypes struct; ``tensor_of`` maps id(parameter) -> tensor to point at."""
         for path, prm in self._slots():
@@ -809,18 +873,15 @@ class B200AoAModel(B200CaptionModel):
         B, R = att.shape[0], att.shape[1]
         N, T, V1 = B * sample_n, self.seq_length, self.vocab_size + 1
         refs, offsets, L = pack_references(gts, dev)
-        params = [prm for _, prm in self._slots()]
-        grads = {id(prm): torch.empty_like(prm) for prm in params}
-        g = _lib.AoaWeights()
-        self._fill_table(g, grads)
+        slots = self._slots()
+        fg, g = self._grad_table(lib, dev)
         if baseline not in ('greedy', 'leave_one_out'):
             raise ValueError("baseline must be 'greedy' or 'leave_one_out'")
         loo = baseline == 'leave_one_out'
-        sample_seq = torch.zeros(N, T, dtype=torch.long, device=dev)
-        greedy_seq = torch.zeros(B, T, dtype=torch.long, device=dev)
-        logprobs = torch.zeros(N, T, V1, dtype=torch.float32, device=dev)
-        reward = torch.empty(N, T, dtype=torch.float32, device=dev)
-        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        sample_seq, greedy_seq, logprobs, reward, loss = self._buffers(('scst', B, sample_n), lambda: (
+            torch.zeros(N, T, dtype=torch.long, device=dev), torch.zeros(B, T, dtype=torch.long, device=dev),
+            torch.zeros(N, T, V1, dtype=torch.float32, device=dev), torch.empty(N, T, dtype=torch.float32, device=dev),
+            torch.empty(1, dtype=torch.float32, device=dev)))
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         p = self.drop_prob_lm if drop_prob is None else drop_prob
@@ -835,7 +896,7 @@ class B200AoAModel(B200CaptionModel):
                                              ctypes.byref(g), _lib.ptr(sample_seq), None if loo else _lib.ptr(greedy_seq), _lib.ptr(logprobs),
                                              _lib.ptr(reward), _lib.ptr(loss), _lib.current_stream()), 'aoa_scst_step')
         return {'loss': loss[0], 'reward': reward, 'sample_seq': sample_seq, 'greedy_seq': None if loo else greedy_seq, 'sample_logprobs': logprobs,
-                'grads': {prm: grads[id(prm)] for prm in params}, 'seed': seed}
+                'grads': {prm: fg.by_name['/'.join(str(x) for x in path)] for path, prm in slots}, 'seed': seed, 'flat': fg}
 
     @_on_device
     def xe_step(self, fc_feats, att_feats, labels, masks, label_smoothing=0.0, drop_prob=None, seed=None, upstream=1.0, drop_attn=0.1, drop_aoa=None,
@@ -857,10 +918,8 @@ class B200AoAModel(B200CaptionModel):
             raise ValueError('labels/masks must be [B * seq_per_img, <= seq_length + 2]')
         steps = self._teacher_steps(labels[:, :-1])
         V1 = self.vocab_size + 1
-        params = [prm for _, prm in self._slots()]
-        grads = {id(prm): torch.empty_like(prm) for prm in params}
-        g = _lib.AoaWeights()
-        self._fill_table(g, grads)
+        slots = self._slots()
+        fg, g = self._grad_table(lib, dev)
         logprobs = torch.zeros(N, Lc - 1, V1, dtype=torch.float32, device=dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         if seed is None:
@@ -870,7 +929,8 @@ class B200AoAModel(B200CaptionModel):
                             float(self.dropout_aoa if drop_aoa is None else drop_aoa), float(drop_sublayer), int(self.ctx_drop if ctx_drop is None else ctx_drop))
         _lib.check(lib.capb200_aoa_xe_step(self._engine, _lib.ptr(att), B, R, ctypes.byref(xo), _lib.ptr(labels), _lib.ptr(masks), Lc, ctypes.byref(g),
                                            _lib.ptr(logprobs), _lib.ptr(loss), _lib.current_stream()), 'aoa_xe_step')
-        return {'loss': loss[0], 'logprobs': logprobs, 'grads': {prm: grads[id(prm)] for prm in params}, 'seed': seed}
+        return {'loss': loss[0], 'logprobs': logprobs, 'grads': {prm: fg.by_name['/'.join(str(x) for x in path)] for path, prm in slots}, 'seed': seed,
+                'flat': fg}
 
     def _ensure_engine(self, device):
         lib = self._enter_device(device)

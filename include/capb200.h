@@ -363,6 +363,16 @@ typedef struct {
 int capb200_aoa_xe_step(capb200_aoa_engine* e, const float* att, int B, int R, const capb200_aoa_xe_opts* opts, const long long* labels,
                         const float* masks, int label_cols, const capb200_aoa_grads* grads, float* logprobs, float* loss, void* stream);
 
+/* Gradient-group events for an overlapped data-parallel all-reduce (tools/train_pl.py:479: DDP buckets the reference's gradients the
+ * same way).  A training step finishes its gradient buffers in a fixed order of groups; after the last write of group k it records
+ * events[k] (cudaEvent_t, caller-owned) on the step's stream, so a communication stream can all-reduce group k while the rest of the
+ * backward pass still runs.  n = 0 or events = NULL switches the recording off.  Groups:
+ *   UpDown (capb200_engine_set_grad_events, n <= 2): 0 logit.{weight,bias}; 1 every other parameter.
+ *   AoANet (capb200_aoa_set_grad_events, n <= 10):  0 logit; 1 decoder (att2ctx, attention q-projection and norm, att_lstm) + embed;
+ *           2 ctx2att + refiner.norm; 3..8 refiner layers 5..0; 9 att_embed. */
+int capb200_engine_set_grad_events(capb200_engine* e, void* const* events, int n);
+int capb200_aoa_set_grad_events(capb200_aoa_engine* e, void* const* events, int n);
+
 /* The dropout keep/scale mask (0 or 1/(1-p)) of one site and step, for tests that replay it in the oracle:
  * site 0 = fc_embed [B,H], 1 = att_embed [B*R,H], 2 = word embedding at `step` [N,E], 3 = core output at `step` [N,H]. */
 int capb200_dropout_mask(float* mask, long n, unsigned long long seed, int site, int step, float p, void* stream);
