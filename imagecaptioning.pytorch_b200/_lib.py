@@ -15,7 +15,7 @@ MODES = {'simt_fp32': MODE_SIMT_FP32, 'tc_f16x3': MODE_TC_F16X3, 'tc_f16x1': MOD
 # capb200_linear additionally exposes the training step's split-K GEMM variants
 OP_MODES = dict(MODES, skinny_tf32x3=3, skinny_fp32=4, tf32x3_tc=5, tf32x3_tc_dgrad=6, tf32x3_tc_wgrad=7)
 FAMILY_UPDOWN, FAMILY_NEWFC = 0, 1
-SAMPLE_GREEDY, SAMPLE_MULTINOMIAL, SAMPLE_FORCED, SAMPLE_TEACHER = 0, 1, 2, 3
+SAMPLE_GREEDY, SAMPLE_MULTINOMIAL, SAMPLE_FORCED, SAMPLE_TEACHER, SAMPLE_TOPK, SAMPLE_TOPP = 0, 1, 2, 3, 4, 5
 
 
 class ModelCfg(Structure):
@@ -32,12 +32,29 @@ class Weights(Structure):
     _fields_ = [(f, c_void_p) for f in WEIGHT_FIELDS]
 
 
+class DecodeEdits(Structure):
+    _fields_ = [('decoding_constraint', c_int), ('unk_col', c_int), ('n_bad_endings', c_int), ('bad_endings', c_void_p), ('block_trigrams', c_int),
+                ('trigram_rows', c_int)]
+
+    @classmethod
+    def none(cls):
+        return cls(0, -1, 0, None, 0, 0)
+
+
 class BeamOpts(Structure):
-    _fields_ = [('beam_size', c_int), ('sample_n', c_int), ('penalty_kind', c_int), ('penalty_alpha', c_float)]
+    _fields_ = [('beam_size', c_int), ('sample_n', c_int), ('penalty_kind', c_int), ('penalty_alpha', c_float), ('temperature', c_float),
+                ('edits', DecodeEdits)]
+
+    def __init__(self, beam_size, sample_n, penalty_kind=0, penalty_alpha=0.0, temperature=1.0, edits=None):
+        super().__init__(beam_size, sample_n, penalty_kind, penalty_alpha, temperature, edits if edits is not None else DecodeEdits.none())
 
 
 class SampleOpts(Structure):
-    _fields_ = [('sample_n', c_int), ('method', c_int), ('temperature', c_float), ('seed', c_ulonglong), ('steps', c_int)]
+    _fields_ = [('sample_n', c_int), ('method', c_int), ('temperature', c_float), ('seed', c_ulonglong), ('steps', c_int), ('top', c_float),
+                ('edits', DecodeEdits)]
+
+    def __init__(self, sample_n, method, temperature=1.0, seed=0, steps=0, top=0.0, edits=None):
+        super().__init__(sample_n, method, temperature, seed, steps, top, edits if edits is not None else DecodeEdits.none())
 
 
 class ScstOpts(Structure):

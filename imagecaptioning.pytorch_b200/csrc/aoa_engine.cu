@@ -431,7 +431,7 @@ int capb200_aoa_decode_beam(capb200_aoa_engine* e, const float* att, const float
         return core_step(e, nrows, live, tokens, src_row, logits, ld, B, R, mask, st);
     };
     return beam_decode_driver(e->d, e->V1, e->T, B, beam, keep, opts->penalty_kind, opts->penalty_alpha, seq, seq_logprobs, done_seq, done_len, done_p,
-                              done_raw, core, &e->launches, st, loop_graph_key(e->ws, e->wblock, mask, R, 9));
+                              done_raw, core, &e->launches, st, loop_graph_key(e->ws, e->wblock, mask, R, 9), to_edits(opts->edits), opts->temperature);
 }
 
 int capb200_aoa_beam_record_logprobs(capb200_aoa_engine* e, int image, int rank, float* dst, void* stream) {
@@ -445,7 +445,7 @@ int capb200_aoa_decode_sample(capb200_aoa_engine* e, const float* att, const flo
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CAPB_REQUIRE(opts != nullptr && att != nullptr && seq_logprobs != nullptr && B >= 1 && R >= 1, "bad argument");
     const int n = opts->sample_n, method = opts->method;
-    CAPB_REQUIRE(n >= 1 && method >= 0 && method <= 3, "bad sampling options");
+    CAPB_REQUIRE(n >= 1 && method >= 0 && method <= 5, "bad sampling options");
     if (method == CAPB200_SAMPLE_FORCED || method == CAPB200_SAMPLE_TEACHER) CAPB_REQUIRE(tokens_in != nullptr && ld_tok >= 1, "token matrix required");
     if (method != CAPB200_SAMPLE_TEACHER) CAPB_REQUIRE(seq != nullptr, "seq output required");
     if (method == CAPB200_SAMPLE_MULTINOMIAL) CAPB_REQUIRE(opts->temperature > 0.f, "temperature must be positive");
@@ -460,7 +460,7 @@ int capb200_aoa_decode_sample(capb200_aoa_engine* e, const float* att, const flo
         return core_step(e, nrows, n, tokens, src_row, logits, ld, B, R, mask, st);
     };
     return sample_decode_driver(e->d, e->V1, e->T, rows, method, opts->temperature, opts->seed, steps, tokens_in, ld_tok, seq, seq_logprobs, picked,
-                                core, &e->launches, st);
+                                core, &e->launches, st, to_edits(opts->edits), opts->top);
 }
 
 }  // extern "C"
@@ -569,7 +569,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
 
     // ---- (1) greedy baseline, eval mode: the regular decode path
     if (greedy_baseline) {
-        capb200_sample_opts so; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.seed = 0; so.steps = T;
+        capb200_sample_opts so; memset(&so, 0, sizeof(so)); so.edits.unk_col = -1; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.seed = 0; so.steps = T;
         CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, st));
         CAPB_CHECK_CUDA(cudaMemsetAsync(greedy_seq, 0, sizeof(long long) * (size_t)B * T, st));
         if (capb200_aoa_decode_sample(e, att, nullptr, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, stream)) return 1;

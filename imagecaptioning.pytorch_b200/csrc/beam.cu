@@ -169,8 +169,51 @@ __global__ void __launch_bounds__(32) beam_finalize_kernel(BeamState s, int keep
     }
 }
 
+// Decode edits on a per-row candidate list (beam search): the vocabulary kernel delivered the k_in best raw candidates of every row;
+// drop / lower the edited ones exactly as the reference edits the log-prob row (CaptionModel.py:154-162) and keep the `beam` best.
+// k_in = beam + (number of active edit kinds) guarantees that `beam` unedited candidates remain.  One thread per row.
+__global__ void beam_edit_kernel(int rows, int k_in, int beam, int t, DecodeEdits ed, const int* __restrict__ prev_tokens,
+                                 const float* __restrict__ val_in, const int* __restrict__ idx_in, float* __restrict__ val_out, int* __restrict__ idx_out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float v[MAXB];
+    int ix[MAXB];
+    const int prev = (t > 0 && prev_tokens != nullptr) ? prev_tokens[r] : -1;
+    bool prev_bad = false;
+    if (t > 0 && ed.n_bad > 0)
+        for (int i = 0; i < ed.n_bad; ++i) prev_bad |= (ed.bad[i] == prev);
+    for (int k = 0; k < k_in; ++k) {
+        float x = val_in[(long)r * k_in + k];
+        const int w = idx_in[(long)r * k_in + k];
+        if (ed.constraint && t > 0 && w == prev) x = -INFINITY;
+        if (prev_bad && w == 0) x = -INFINITY;
+        if (w == ed.unk_col) x -= 1000.0f;
+        v[k] = x;
+        ix[k] = w;
+    }
+    // selection sort of the first `beam` (value descending, word index ascending on ties: the order the unedited list came in)
+    for (int j = 0; j < beam; ++j) {
+        int best = j;
+        for (int k = j + 1; k < k_in; ++k)
+            if (v[k] > v[best] || (v[k] == v[best] && ix[k] < ix[best])) best = k;
+        const float tv = v[j]; v[j] = v[best]; v[best] = tv;
+        const int ti = ix[j]; ix[j] = ix[best]; ix[best] = ti;
+        val_out[(long)r * beam + j] = v[j];
+        idx_out[(long)r * beam + j] = ix[j];
+    }
+}
+
+__global__ void scale_rows_kernel(float* __restrict__ x, long ld, int rows, int cols, float f) {
+    const long total = (long)rows * cols;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / cols, c = i % cols;
+        x[r * ld + c] *= f;
+    }
+}
+
 __global__ void gather_rows_kernel(const float* __restrict__ slab, long step_stride, long ld_slab, const int* __restrict__ hist, int T, int V1,
-                                   float* __restrict__ dst, const float2* __restrict__ stats, long stats_stride) {
+                                   float* __restrict__ dst, const float2* __restrict__ stats, long stats_stride, const long long* __restrict__ seqs,
+                                   DecodeEdits ed) {
     const long item = blockIdx.x;          // item = k * T + s
     const int sidx = (int)(item % T);
     const int row = hist[item];
@@ -179,6 +222,19 @@ __global__ void gather_rows_kernel(const float* __restrict__ slab, long step_str
         for (int v = threadIdx.x; v < V1; v += blockDim.x) d[v] = 0.f;
         return;
     }
+    // the edits the search applied to this row before choosing word `sidx` of this sequence (same stream order: after the row is written)
+    auto apply_edits = [&]() {
+        if (seqs == nullptr || !ed.any()) return;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int prev = sidx > 0 ? (int)seqs[item - 1] : -1;
+            if (ed.unk_col >= 0 && ed.unk_col < V1) d[ed.unk_col] -= 1000.0f;
+            if (ed.constraint && prev >= 0 && prev < V1) d[prev] = -INFINITY;
+            bool prev_bad = false;
+            for (int i = 0; i < ed.n_bad; ++i) prev_bad |= (sidx > 0 && ed.bad[i] == prev);
+            if (prev_bad) d[0] = -INFINITY;
+        }
+    };
     const float* src = slab + (long)sidx * step_stride + (long)row * ld_slab;
     if (stats != nullptr) {
         // raw logits -> log-probs with the row statistics of the search step (second log_softmax from step 1 on)
@@ -190,6 +246,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ slab, long step_str
             const float lp = (src[v] - mx) - lsum;
             d[v] = twice ? (lp - m2) - l2 : lp;
         }
+        apply_edits();
         return;
     }
     const bool vec = ((V1 & 3) == 0) && ((ld_slab & 3) == 0) && ((step_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(slab) & 15) == 0) &&
@@ -201,9 +258,28 @@ __global__ void gather_rows_kernel(const float* __restrict__ slab, long step_str
     } else {
         for (int v = threadIdx.x; v < V1; v += blockDim.x) d[v] = src[v];
     }
+    apply_edits();
 }
 
 }  // namespace
+
+int beam_edit_launch(int rows, int k_in, int beam, int t, const DecodeEdits& ed, const int* prev_tokens, const float* val_in, const int* idx_in,
+                     float* val_out, int* idx_out, cudaStream_t stream) {
+    CAPB_REQUIRE(k_in >= beam && k_in <= MAXB, "beam_size + number of active decode edits must be <= 16");
+    if (rows <= 0) return 0;
+    beam_edit_kernel<<<cdiv(rows, 128), 128, 0, stream>>>(rows, k_in, beam, t, ed, prev_tokens, val_in, idx_in, val_out, idx_out);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scale_rows_launch(float* x, long ld, int rows, int cols, float factor, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    long blocks = ((long)rows * cols + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    scale_rows_kernel<<<(int)blocks, 256, 0, stream>>>(x, ld, rows, cols, factor);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int beam_step_launch(const BeamState& s, int t, int live, const float* top_val, const int* top_idx, int penalty_kind, float penalty_alpha,
                      cudaStream_t stream) {
@@ -223,9 +299,9 @@ int beam_finalize_launch(const BeamState& s, int keep, long long* out_seq, int* 
 }
 
 int gather_logprob_rows_launch(const float* slab, long step_stride, long ld_slab, const int* hist, int nseq, int T, int V1, float* dst,
-                               const float2* stats, long stats_stride, cudaStream_t stream) {
+                               const float2* stats, long stats_stride, cudaStream_t stream, const long long* seqs, const DecodeEdits* ed) {
     if (nseq <= 0) return 0;
-    gather_rows_kernel<<<nseq * T, 256, 0, stream>>>(slab, step_stride, ld_slab, hist, T, V1, dst, stats, stats_stride);
+    gather_rows_kernel<<<nseq * T, 256, 0, stream>>>(slab, step_stride, ld_slab, hist, T, V1, dst, stats, stats_stride, seqs, ed ? *ed : DecodeEdits());
     CAPB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -641,7 +641,8 @@ int capb200_decode_beam(capb200_engine* e, const float* fc, const float* att, co
         return core_step(e, nrows, live, tokens, src_row, logits, ld, B, R, mask, st);
     };
     return beam_decode_driver(e->d, V1, T, B, beam, keep, opts->penalty_kind, opts->penalty_alpha, seq, seq_logprobs, done_seq, done_len, done_p,
-                              done_raw, core, &e->launches, st, e->profiling ? 0ull : loop_graph_key(e->ws, e->wblock, mask, R, (int)e->cfg.family));
+                              done_raw, core, &e->launches, st, e->profiling ? 0ull : loop_graph_key(e->ws, e->wblock, mask, R, (int)e->cfg.family),
+                              to_edits(opts->edits), opts->temperature);
 }
 
 int capb200_beam_record_logprobs(capb200_engine* e, int image, int rank, float* dst, void* stream) {
@@ -660,10 +661,10 @@ int capb200_decode_sample(capb200_engine* e, const float* fc, const float* att, 
     if (updown) CAPB_REQUIRE(att != nullptr && R >= 1, "attention features required");
     if (!updown) R = 1;
     const int method = opts->method;
-    CAPB_REQUIRE(method >= 0 && method <= 3, "unknown sampling method");
+    CAPB_REQUIRE(method >= 0 && method <= 5, "unknown sampling method");
     if (method == CAPB200_SAMPLE_FORCED || method == CAPB200_SAMPLE_TEACHER) CAPB_REQUIRE(tokens_in != nullptr && ld_tok >= 1, "token matrix required");
     if (method != CAPB200_SAMPLE_TEACHER) CAPB_REQUIRE(seq != nullptr, "seq output required");
-    if (method == CAPB200_SAMPLE_MULTINOMIAL) CAPB_REQUIRE(opts->temperature > 0.f, "temperature must be positive");
+    if (method == CAPB200_SAMPLE_MULTINOMIAL || method >= CAPB200_SAMPLE_TOPK) CAPB_REQUIRE(opts->temperature > 0.f, "temperature must be positive");
     const int T = e->T, V1 = e->V1;
     const int rows = B * n;
     const int steps = (method == CAPB200_SAMPLE_TEACHER) ? opts->steps : T;
@@ -677,7 +678,7 @@ int capb200_decode_sample(capb200_engine* e, const float* fc, const float* att, 
         return core_step(e, nrows, n, tokens, src_row, logits, ld, B, R, mask, st);
     };
     return sample_decode_driver(e->d, V1, T, rows, method, opts->temperature, opts->seed, steps, tokens_in, ld_tok, seq, seq_logprobs, picked, core,
-                                &e->launches, st);
+                                &e->launches, st, to_edits(opts->edits), opts->top);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -917,7 +918,7 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     Arena ar; ar.base = e->tape;
     Tape tp; layout_tape(tp, ar, B, R, N, T, E, H, A, V1, Fa, Ff);
     if (!ta.xe && ta.greedy_baseline) {
-        capb200_sample_opts so; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.seed = 0; so.steps = T;
+        capb200_sample_opts so; memset(&so, 0, sizeof(so)); so.edits.unk_col = -1; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.seed = 0; so.steps = T;
         CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, st));
         CAPB_CHECK_CUDA(cudaMemsetAsync(greedy_seq, 0, sizeof(long long) * (size_t)B * T, st));
         if (capb200_decode_sample(e, fc, att, nullptr, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, stream)) return 1;

@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "../../include/capb200.h"
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -46,6 +47,17 @@ struct Act {
     }
 };
 
+inline DecodeEdits to_edits(const capb200_decode_edits& c) {
+    DecodeEdits e;
+    e.constraint = c.decoding_constraint;
+    e.unk_col = c.unk_col;
+    e.n_bad = (c.bad_endings != nullptr && c.n_bad_endings > 0) ? c.n_bad_endings : 0;
+    e.bad = c.bad_endings;
+    e.trigrams = c.block_trigrams;
+    e.trigram_rows = c.trigram_rows;
+    return e;
+}
+
 inline Planes carve_planes(Arena& a, long rows, long cols) {
     Planes p;
     p.ld = round_up(cols, 64);
@@ -88,6 +100,8 @@ struct DecodeBuffers {
     int *tokens = nullptr, *src_row = nullptr, *neg1 = nullptr, *unfinished = nullptr, *forced = nullptr;
     float* top_val = nullptr;
     int* top_idx = nullptr;
+    float* top_val_e = nullptr;       // [rows, 16] candidate lists after the decode edits (beam search with options)
+    int* top_idx_e = nullptr;
     float2* slab_stats = nullptr;     // [T, rows]
     BeamState bs;
     long long* rec_seq = nullptr;     // [B, beam, T] sorted records of the last beam decode
@@ -97,6 +111,7 @@ struct DecodeBuffers {
     size_t slab_bytes = 0;
     long slab_step_stride = 0;
     int last_B = 0, last_beam = 0;
+    DecodeEdits last_edits;           // edits of the last beam decode (re-applied when a finished beam's rows are materialised later)
     // CUDA graph of the T-step beam loop (every launch of it is static for a given shape / workspace): captured the second time a
     // configuration is seen, replayed afterwards; the launch gaps of ~180 serial kernels are ~5 % of a decode
     cudaGraphExec_t loop_exec = nullptr;
@@ -112,6 +127,8 @@ struct DecodeBuffers {
         forced = a.take<int>(rows);
         top_val = a.take<float>((long)rows * 16);
         top_idx = a.take<int>((long)rows * 16);
+        top_val_e = a.take<float>((long)rows * 16);
+        top_idx_e = a.take<int>((long)rows * 16);
         slab_stats = a.take<float2>((long)rows * T);
         const long rec = (long)B * beam * T;
         bs.sums = a.take<float>((long)B * beam);
@@ -160,8 +177,14 @@ inline unsigned long long loop_graph_key(const void* ws, const void* wblock, con
 template <class CoreFn>
 int beam_decode_driver(DecodeBuffers& d, int V1, int T, int B, int beam, int keep, int penalty_kind, float penalty_alpha, long long* seq,
                        float* seq_logprobs, long long* done_seq, int* done_len, float* done_p, float* done_raw, CoreFn core, long* launches,
-                       cudaStream_t st, unsigned long long graph_key = 0) {
+                       cudaStream_t st, unsigned long long graph_key = 0, const DecodeEdits& ed = DecodeEdits(), float temperature = 1.0f) {
     const int rows = B * beam;
+    const bool edits = ed.any();
+    const int k_in = beam + ed.kinds();
+    CAPB_REQUIRE(!ed.trigrams, "block_trigrams applies to _sample only (AttModel.py:306)");
+    CAPB_REQUIRE(k_in <= 16, "beam_size + number of active decode edits (decoding_constraint, remove_bad_endings, UNK suppression) must be <= 16");
+    if (temperature == 0.f) temperature = 1.0f;
+    CAPB_REQUIRE(temperature > 0.f, "temperature must be positive");
     const size_t slab_need = (size_t)T * rows * V1 * sizeof(float);
     if (slab_need > d.slab_bytes) {
         CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -184,13 +207,24 @@ int beam_decode_driver(DecodeBuffers& d, int V1, int T, int B, int beam, int kee
             const int nrows = B * live;
             float* logits = d.slab + (long)t * d.slab_step_stride;
             if (core(nrows, live, d.tokens, t == 0 ? d.neg1 : d.src_row, t, logits, (long)V1)) return 1;
+            if (t > 0 && temperature != 1.0f) {      // log_softmax(logprobs / temperature) = log_softmax(logits / temperature)  (CaptionModel.py:204)
+                if (scale_rows_launch(logits, V1, nrows, V1, 1.0f / temperature, st)) return 1;
+                *launches += 1;
+            }
             VocabStepArgs va;
             va.rows = nrows; va.V1 = V1; va.logits = logits; va.ld = V1;
             va.twice = (t > 0) ? 1 : 0;      // init_logprobs went through one log_softmax only (AttModel.py:239, CaptionModel.py:204)
-            va.topk = beam; va.top_val = d.top_val; va.top_idx = d.top_idx;
+            va.topk = edits ? k_in : beam; va.top_val = d.top_val; va.top_idx = d.top_idx;
             va.stats = d.slab_stats + (long)t * rows;
             if (vocab_step_launch(va, st)) return 1;
-            if (beam_step_launch(s, t, live, d.top_val, d.top_idx, penalty_kind, penalty_alpha, st)) return 1;
+            const float* tv = d.top_val;
+            const int* ti = d.top_idx;
+            if (edits) {      // drop / lower the edited candidates, keep the `beam` best (the edits of CaptionModel.py:154-162)
+                if (beam_edit_launch(nrows, k_in, beam, t, ed, d.tokens, d.top_val, d.top_idx, d.top_val_e, d.top_idx_e, st)) return 1;
+                tv = d.top_val_e; ti = d.top_idx_e;
+                *launches += 1;
+            }
+            if (beam_step_launch(s, t, live, tv, ti, penalty_kind, penalty_alpha, st)) return 1;
             *launches += 2;
         }
         return 0;
@@ -199,6 +233,11 @@ int beam_decode_driver(DecodeBuffers& d, int V1, int T, int B, int beam, int kee
     unsigned long long key[8] = {graph_key, (unsigned long long)B, (unsigned long long)beam, (unsigned long long)T, (unsigned long long)V1,
                                  (unsigned long long)penalty_kind, 0ull, (unsigned long long)reinterpret_cast<uintptr_t>(d.slab)};
     memcpy(&key[6], &penalty_alpha, sizeof(float));
+    memcpy(reinterpret_cast<char*>(&key[6]) + 4, &temperature, sizeof(float));
+    // decode edits are baked into the captured launches too
+    key[5] ^= ((unsigned long long)(ed.constraint & 1) << 8) ^ ((unsigned long long)(unsigned)(ed.unk_col + 1) << 16) ^ ((unsigned long long)ed.n_bad << 48);
+    key[0] ^= (unsigned long long)reinterpret_cast<uintptr_t>(ed.bad) * 0x9E3779B97F4A7C15ull;
+    d.last_edits = ed;
     static const bool graphs_off = getenv("CAPB200_NO_GRAPH") != nullptr;
     const bool try_graph = graph_key != 0 && !graphs_off && !d.graph_broken;
     if (try_graph && d.loop_exec != nullptr && memcmp(key, d.loop_key, sizeof(key)) == 0) {
@@ -236,14 +275,14 @@ int beam_decode_driver(DecodeBuffers& d, int V1, int T, int B, int beam, int kee
         CAPB_CHECK_CUDA(cudaMemcpyAsync(seq, d.rec_seq, sizeof(long long) * B * beam * T, cudaMemcpyDeviceToDevice, st));
         if (seq_logprobs) {
             *launches += 1;
-            if (gather_logprob_rows_launch(d.slab, d.slab_step_stride, V1, d.rec_hist, B * beam, T, V1, seq_logprobs, d.slab_stats, rows, st)) return 1;
+            if (gather_logprob_rows_launch(d.slab, d.slab_step_stride, V1, d.rec_hist, B * beam, T, V1, seq_logprobs, d.slab_stats, rows, st, d.rec_seq, &ed)) return 1;
         }
     } else {
         *launches += 1;
         if (beam_finalize_launch(s, 1, seq, d.tmp_len, d.tmp_p, d.tmp_raw, d.out_hist, st)) return 1;
         if (seq_logprobs) {
             *launches += 1;
-            if (gather_logprob_rows_launch(d.slab, d.slab_step_stride, V1, d.out_hist, B, T, V1, seq_logprobs, d.slab_stats, rows, st)) return 1;
+            if (gather_logprob_rows_launch(d.slab, d.slab_step_stride, V1, d.out_hist, B, T, V1, seq_logprobs, d.slab_stats, rows, st, seq, &ed)) return 1;
         }
     }
     if (done_seq) CAPB_CHECK_CUDA(cudaMemcpyAsync(done_seq, d.rec_seq, sizeof(long long) * B * beam * T, cudaMemcpyDeviceToDevice, st));
@@ -256,15 +295,18 @@ int beam_decode_driver(DecodeBuffers& d, int V1, int T, int B, int beam, int kee
 inline int beam_record_logprobs(DecodeBuffers& d, int V1, int T, int image, int rank, float* dst, cudaStream_t st) {
     CAPB_REQUIRE(d.slab != nullptr && image >= 0 && image < d.last_B && rank >= 0 && rank < d.last_beam, "no such finished beam");
     return gather_logprob_rows_launch(d.slab, d.slab_step_stride, V1, d.rec_hist + ((long)image * d.last_beam + rank) * T, 1, T, V1, dst,
-                                      d.slab_stats, (long)d.last_B * d.last_beam, st);
+                                      d.slab_stats, (long)d.last_B * d.last_beam, st, d.rec_seq + ((long)image * d.last_beam + rank) * T, &d.last_edits);
 }
 
 // AttModel._sample (greedy / multinomial / forced replay) and AttModel._forward (teacher forcing); method codes = CAPB200_SAMPLE_*
 template <class CoreFn>
 int sample_decode_driver(DecodeBuffers& d, int V1, int T, int rows, int method, float temperature, unsigned long long seed, int steps,
                          const long long* tokens_in, long ld_tok, long long* seq, float* seq_logprobs, float* picked, CoreFn core, long* launches,
-                         cudaStream_t st) {
+                         cudaStream_t st, const DecodeEdits& ed = DecodeEdits(), float top = 0.f) {
     const bool teacher = method == 3, forced = method == 2;
+    CAPB_REQUIRE(ed.unk_col < 0, "UNK suppression is a beam-search option (CaptionModel.py:159-162)");
+    if (method == 4) CAPB_REQUIRE(top >= 1.f, "top-k sampling needs k >= 1");
+    if (method == 5) CAPB_REQUIRE(top > 0.f && top < 1.f, "nucleus sampling needs 0 < p < 1");
     const long t_out = teacher ? ld_tok : T;
     CAPB_CHECK_CUDA(cudaMemsetAsync(d.tokens, 0, sizeof(int) * rows, st));
     for (int t = 0; t < steps; ++t) {
@@ -276,7 +318,10 @@ int sample_decode_driver(DecodeBuffers& d, int V1, int T, int rows, int method, 
         va.rows = rows; va.V1 = V1; va.logits = logits; va.ld = t_out * V1;
         va.twice = 0;
         if (!teacher) {
-            va.select = (method == 0) ? 1 : (method == 1 ? 2 : 3);
+            va.select = (method == 0) ? 1 : (method == 1 ? 2 : (method == 2 ? 3 : method));      // 4 top-k, 5 nucleus
+            va.top = top;
+            va.edits = ed;
+            va.prev_tokens = d.tokens;        // the word fed into this step (read before tokens_out is rewritten at the end of the kernel)
             va.temperature = temperature;
             va.seed = seed;
             va.step = (unsigned long long)t;

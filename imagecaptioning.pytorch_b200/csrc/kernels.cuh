@@ -33,6 +33,18 @@ int additive_attention_launch(int n_images, int rpi, int R, int A, int H, const 
                               float* score_scratch /*[rows, R]*/, ActView out, cudaStream_t stream, float* alpha_out = nullptr /*[rows, R]*/);
 int mask_rows_launch(ActView x, int n_images, int R, int cols, const float* mask, long ld_mask, cudaStream_t stream);
 
+// Edits of a log-prob row before the next word is chosen (capb200_decode_edits in include/capb200.h)
+struct DecodeEdits {
+    int constraint = 0;
+    int unk_col = -1;
+    int n_bad = 0;
+    const int* bad = nullptr;
+    int trigrams = 0;
+    int trigram_rows = 0;
+    __host__ __device__ bool any() const { return constraint != 0 || unk_col >= 0 || n_bad > 0 || trigrams != 0; }
+    __host__ __device__ int kinds() const { return (constraint ? 1 : 0) + (unk_col >= 0 ? 1 : 0) + (n_bad > 0 ? 1 : 0); }
+};
+
 // ---- vocab.cu : log-softmax over the vocabulary + candidate selection
 struct VocabStepArgs {
     int rows = 0;
@@ -46,7 +58,11 @@ struct VocabStepArgs {
     float* top_val = nullptr;     // [rows, topk]
     int* top_idx = nullptr;       // [rows, topk]
     // greedy / multinomial selection for _sample
-    int select = 0;               // 0 none, 1 greedy argmax, 2 multinomial (Gumbel-max on logp / temperature), 3 forced tokens
+    int select = 0;               // 0 none, 1 greedy argmax, 2 multinomial (Gumbel-max on logp / temperature), 3 forced tokens,
+                                  // 4 top-k sampling, 5 nucleus (top-p) sampling
+    float top = 0.f;              // k (select 4) or p (select 5)
+    DecodeEdits edits;            // applied after the log-softmax, before the selection; the edited row is what is stored
+    const int* prev_tokens = nullptr;   // [rows] the word fed into this step (for the edits; only read when t > 0)
     float temperature = 1.0f;
     unsigned long long seed = 0;
     unsigned long long step = 0;  // Philox offset: one independent stream per (row, step)
@@ -61,6 +77,10 @@ struct VocabStepArgs {
     long ld_picked = 1;
 };
 int vocab_step_launch(const VocabStepArgs& a, cudaStream_t stream);
+// beam search with decode edits: the per-row candidate list [rows, k_in] (k_in = beam + edits.kinds()) is edited and cut to [rows, beam]
+int beam_edit_launch(int rows, int k_in, int beam, int t, const DecodeEdits& ed, const int* prev_tokens, const float* val_in, const int* idx_in,
+                     float* val_out, int* idx_out, cudaStream_t stream);
+int scale_rows_launch(float* x, long ld, int rows, int cols, float factor, cudaStream_t stream);
 
 // ---- beam.cu
 struct BeamState {
@@ -88,8 +108,10 @@ int beam_finalize_launch(const BeamState& s, int keep, long long* out_seq, int* 
 // dst[k, s, :] = slab[s][hist[k, s], :] (zeros where hist < 0); slab step stride `step_stride` elements
 // `stats` (optional): the slab holds raw logits and stats[s * stats_stride + row] = (max, log-sum-exp); rows are normalised on the fly
 // (log_softmax once at s == 0, twice afterwards, exactly as the search scored them).
+// `seqs` ([nseq, T] int64, the sequences the rows belong to) + `ed`: re-apply the decode edits the search made to each row (optional)
 int gather_logprob_rows_launch(const float* slab, long step_stride, long ld_slab, const int* hist, int nseq, int T, int V1, float* dst,
-                               const float2* stats, long stats_stride, cudaStream_t stream);
+                               const float2* stats, long stats_stride, cudaStream_t stream, const long long* seqs = nullptr,
+                               const DecodeEdits* ed = nullptr);
 
 // ---- transformer.cu
 int layer_norm_launch(int rows, int D, const float* x, long ld_x, const float* a, const float* b, float eps, ActView out, cudaStream_t st);

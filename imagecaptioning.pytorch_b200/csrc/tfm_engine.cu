@@ -333,7 +333,7 @@ int capb200_tfm_decode_beam(capb200_tfm_engine* e, const float* att, const float
         return core_step(e, nrows, live, tokens, anc, nullptr, 0, t, logits, ld, R, mask, st);
     };
     return beam_decode_driver(e->d, e->V1, e->T, B, beam, keep, opts->penalty_kind, opts->penalty_alpha, seq, seq_logprobs, done_seq, done_len, done_p,
-                              done_raw, core, &e->launches, st, loop_graph_key(e->ws, e->wblock, mask, R, 7));
+                              done_raw, core, &e->launches, st, loop_graph_key(e->ws, e->wblock, mask, R, 7), to_edits(opts->edits), opts->temperature);
 }
 
 int capb200_tfm_beam_record_logprobs(capb200_tfm_engine* e, int image, int rank, float* dst, void* stream) {
@@ -347,7 +347,7 @@ int capb200_tfm_decode_sample(capb200_tfm_engine* e, const float* att, const flo
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CAPB_REQUIRE(opts != nullptr && att != nullptr && seq_logprobs != nullptr && B >= 1 && R >= 1, "bad argument");
     const int n = opts->sample_n, method = opts->method;
-    CAPB_REQUIRE(n >= 1 && method >= 0 && method <= 3, "bad sampling options");
+    CAPB_REQUIRE(n >= 1 && method >= 0 && method <= 5, "bad sampling options");
     if (method == CAPB200_SAMPLE_FORCED || method == CAPB200_SAMPLE_TEACHER) CAPB_REQUIRE(tokens_in != nullptr && ld_tok >= 1, "token matrix required");
     if (method != CAPB200_SAMPLE_TEACHER) CAPB_REQUIRE(seq != nullptr, "seq output required");
     if (method == CAPB200_SAMPLE_MULTINOMIAL) CAPB_REQUIRE(opts->temperature > 0.f, "temperature must be positive");
@@ -362,7 +362,7 @@ int capb200_tfm_decode_sample(capb200_tfm_engine* e, const float* att, const flo
         return core_step(e, nrows, n, tokens, nullptr, labels, ld_tok, t, logits, ld, R, mask, st);
     };
     return sample_decode_driver(e->d, e->V1, e->T, rows, method, opts->temperature, opts->seed, steps, tokens_in, ld_tok, seq, seq_logprobs, picked,
-                                core, &e->launches, st);
+                                core, &e->launches, st, to_edits(opts->edits), opts->top);
 }
 
 }  // extern "C"

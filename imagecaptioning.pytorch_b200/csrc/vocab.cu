@@ -113,9 +113,7 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
     int ti[KMAX];
 #pragma unroll
     for (int q = 0; q < KMAX; ++q) { tv[q] = -INFINITY; ti[q] = 0x7fffffff; }
-    for (int v = threadIdx.x; v < V1; v += VT) {
-        const float lp = (row[v] - mx) - lsum;
-        row[v] = lp;
+    auto consider = [&](float lp, int v) {
         if (k_eff > 0 && lp > tv[KMAX - 1]) {
             float cv = lp;
             int ci = v;
@@ -124,6 +122,41 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
                 if (cv > tv[q]) { const float t0 = tv[q]; const int t1 = ti[q]; tv[q] = cv; ti[q] = ci; cv = t0; ci = t1; }
             }
         }
+    };
+    const bool edit = a.edits.any();
+    for (int v = threadIdx.x; v < V1; v += VT) {
+        const float lp = (row[v] - mx) - lsum;
+        row[v] = lp;
+        if (!edit) consider(lp, v);
+    }
+    if (edit) {
+        // The reference's decode options edit the log-prob row AFTER the log-softmax, and the edited row is both what the next word is
+        // chosen from and what is stored (AttModel.py:294-332).  A handful of columns change: one thread applies them to the shared copy.
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int t = a.t;
+            const int prev = (t > 0 && a.prev_tokens != nullptr) ? a.prev_tokens[r] : -1;
+            if (a.edits.constraint && prev >= 0 && prev < V1) row[prev] = -INFINITY;                   // never repeat the previous word
+            bool prev_bad = false;
+            for (int i = 0; i < a.edits.n_bad; ++i) prev_bad |= (t > 0 && a.edits.bad[i] == prev);
+            if (prev_bad) row[0] = -INFINITY;                                                          // no end token after a bad ending
+            if (a.edits.trigrams && t >= 3 && r < a.edits.trigram_rows && a.seq_out != nullptr) {
+                const long long* sq = a.seq_out + (long)r * a.ld_seq;
+                const long long p0 = sq[t - 2], p1 = sq[t - 1];
+                for (int j = 0; j + 2 <= t - 1; ++j) {
+                    if (sq[j] != p0 || sq[j + 1] != p1) continue;
+                    const long long w = sq[j + 2];
+                    bool first = true;
+                    int count = 0;
+                    for (int i = 0; i + 2 <= t - 1; ++i) {
+                        if (sq[i] == p0 && sq[i + 1] == p1 && sq[i + 2] == w) { if (i < j) first = false; ++count; }
+                    }
+                    if (first && w >= 0 && w < V1) row[w] += ((float)count * -0.693f) * 2.0f;          // mask * -0.693 * alpha, alpha = 2 (AttModel.py:330-332)
+                }
+            }
+        }
+        __syncthreads();
+        for (int v = threadIdx.x; v < V1; v += VT) consider(row[v], v);
     }
     // Second log_softmax (beam search, CaptionModel.py:204): its max is m2 = -lsum, so exp(lp - m2) = exp(x - mx) term by term and
     // its normaliser is the first pass's `sum` again (up to one rounding, ~1e-7 on the log-prob); no second exp pass is needed.
@@ -160,11 +193,50 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
             tok = greedy_tok;
         } else {
             __syncthreads();
+            const float inv_t = 1.0f / a.temperature;
+            // order-preserving map float -> uint32 (for the threshold searches of the truncated samplers)
+            auto okey = [](float x) { const uint32_t u = __float_as_uint(x); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); };
+            uint32_t keep_from = 0;                    // sample among the words whose key is >= keep_from
+            if (a.select == 4) {
+                // top-k (CaptionModel.py:398-402): threshold = k-th largest log-prob, by bisection on the key bits (exact; ties at the threshold are all kept)
+                const float kf = floorf(a.top);
+                for (int bit = 31; bit >= 0; --bit) {
+                    const uint32_t cand = keep_from | (1u << bit);
+                    float cnt = 0.f;
+                    for (int v = threadIdx.x; v < V1; v += VT) cnt += (okey(row[v]) >= cand) ? 1.f : 0.f;
+                    cnt = block_sum(cnt, s_red);
+                    if (cnt >= kf) keep_from = cand;
+                }
+            } else if (a.select == 5) {
+                // nucleus (CaptionModel.py:388-397): a word is kept iff the probability mass of the strictly more likely words is < p
+                float mxl = -INFINITY;
+                for (int v = threadIdx.x; v < V1; v += VT) mxl = fmaxf(mxl, row[v]);
+                mxl = block_max(mxl, s_red);
+                float z = 0.f;
+                for (int v = threadIdx.x; v < V1; v += VT) z += __expf((row[v] - mxl) * inv_t);
+                z = block_sum(z, s_red);
+                const float target = a.top * z;
+                auto mass_above = [&](uint32_t key) {   // sum over the words with key > `key`
+                    float m = 0.f;
+                    for (int v = threadIdx.x; v < V1; v += VT) m += (okey(row[v]) > key) ? __expf((row[v] - mxl) * inv_t) : 0.f;
+                    return block_sum(m, s_red);
+                };
+                // largest key F with mass_above(F) >= target; everything above F is kept (the most likely word always is)
+                uint32_t F = 0;
+                if (mass_above(0u) < target) keep_from = 0;
+                else {
+                    for (int bit = 31; bit >= 0; --bit) {
+                        const uint32_t cand = F | (1u << bit);
+                        if (mass_above(cand) >= target) F = cand;
+                    }
+                    keep_from = F + 1u;
+                }
+            }
             float bv = -INFINITY;
             int bi = 0x7fffffff;
-            const float inv_t = 1.0f / a.temperature;
             const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
             for (int v = threadIdx.x; v < V1; v += VT) {
+                if (okey(row[v]) < keep_from) continue;
                 const uint32_t bits = philox_first((uint32_t)v, (uint32_t)r, (uint32_t)a.step, (uint32_t)(a.step >> 32), k0, k1);
                 const float u = ((float)(bits >> 9) + 0.5f) * (1.0f / 8388608.0f);      // (0,1), 23 bits
                 const float x = row[v] * inv_t - logf(-logf(u));                         // Gumbel-max sample of softmax(logp / T)

@@ -293,11 +293,28 @@ class B200CaptionModel(nn.Module):
     def _check_opts(self, opt):
         if opt.get('group_size', 1) != 1:
             raise NotImplementedError('diverse beam search (group_size > 1) is out of scope of the B200 engine (SURVEY.md section 8f)')
-        for k in ('decoding_constraint', 'block_trigrams', 'remove_bad_endings'):
-            if opt.get(k, 0):
-                raise NotImplementedError('%s is out of scope of the B200 engine (SURVEY.md section 8f)' % k)
         if opt.get('output_logsoftmax', 1) != 1:
             raise NotImplementedError('output_logsoftmax=0 is out of scope of the B200 engine')
+
+    def _decode_edits(self, opt, device, beam, batch_size=0):
+        """The reference's per-step log-prob edits as a capb200_decode_edits (CaptionModel.py:118-120,154-162; AttModel.py:265-332)."""
+        ed = _lib.DecodeEdits.none()
+        keep = None
+        ed.decoding_constraint = 1 if opt.get('decoding_constraint', 0) else 0
+        if opt.get('remove_bad_endings', 0) and self.bad_endings_ix:
+            keep = torch.tensor(sorted(set(self.bad_endings_ix)), dtype=torch.int32, device=device)
+            ed.n_bad_endings, ed.bad_endings = keep.numel(), keep.data_ptr()
+        if beam:
+            # CaptionModel.py:120 reads opt.get('suppress_UNK', 0); the elif branch lowers unk_idx whatever the flag says (:161-162)
+            if opt.get('suppress_UNK', 0) and self.vocab.get(str(self.vocab_size)) == 'UNK':
+                ed.unk_col = self.vocab_size
+            elif self.unk_idx is not None:
+                ed.unk_col = int(self.unk_idx)
+            if opt.get('block_trigrams', 0):
+                pass                                 # beam search ignores it (the option is only read by _sample, AttModel.py:267)
+        elif opt.get('block_trigrams', 0):
+            ed.block_trigrams, ed.trigram_rows = 1, int(batch_size)
+        return ed, keep
 
     @_on_device
     def _sample(self, fc_feats, att_feats, att_masks=None, opt={}, forced_tokens=None):
@@ -308,14 +325,23 @@ class B200CaptionModel(nn.Module):
         self._check_opts(opt)
         if beam_size > 1 and sample_method in ('greedy', 'beam_search'):
             return self._sample_beam(fc_feats, att_feats, att_masks, opt)
+        top = 0.0
         if forced_tokens is not None:
             method = _lib.SAMPLE_FORCED
         elif sample_method == 'greedy':
             method = _lib.SAMPLE_GREEDY
         elif sample_method == 'sample':
             method = _lib.SAMPLE_MULTINOMIAL
+        elif sample_method == 'gumbel':
+            # argmax(logprobs + Gumbel noise) / temperature-free: a multinomial draw at temperature 1 (CaptionModel.py:375-385)
+            method, temperature = _lib.SAMPLE_MULTINOMIAL, 1.0
+        elif sample_method.startswith('top'):
+            top = float(sample_method[3:])           # CaptionModel.py:387-402: 0 < x < 1 nucleus, else top-k
+            if top <= 0:
+                raise ValueError('sample_method %r: top-k needs k >= 1, nucleus sampling 0 < p < 1' % sample_method)
+            method = _lib.SAMPLE_TOPP if top < 1 else _lib.SAMPLE_TOPK
         else:
-            raise NotImplementedError("sample_method %r is out of scope of the B200 engine (greedy / sample / beam search)" % sample_method)
+            raise NotImplementedError("sample_method %r is out of scope of the B200 engine" % sample_method)
         lib = self._ensure_engine(fc_feats.device)
         fc = self._f32(fc_feats)
         att, masks = self._clip(att_feats, att_masks)
@@ -324,8 +350,10 @@ class B200CaptionModel(nn.Module):
         N, T, V1 = B * sample_n, self.seq_length, self.vocab_size + 1
         seq = torch.zeros(N, T, dtype=torch.long, device=fc.device)
         logprobs = torch.zeros(N, T, V1, dtype=torch.float32, device=fc.device)
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if method == _lib.SAMPLE_MULTINOMIAL else 0   # follows torch.manual_seed
-        so = _lib.SampleOpts(sample_n, method, temperature, seed, T)
+        draws = method in (_lib.SAMPLE_MULTINOMIAL, _lib.SAMPLE_TOPK, _lib.SAMPLE_TOPP)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if draws else 0   # follows torch.manual_seed
+        edits, keep_bad = self._decode_edits(opt, fc.device, beam=False, batch_size=B)
+        so = _lib.SampleOpts(sample_n, method, temperature, seed, T, top, edits)
         tok = None
         if forced_tokens is not None:
             tok = forced_tokens.detach().to(torch.long).contiguous()
@@ -355,10 +383,12 @@ class B200CaptionModel(nn.Module):
         beam_size = opt.get('beam_size', 10)
         sample_n = opt.get('sample_n', 10)
         self._check_opts(opt)
-        if opt.get('suppress_UNK', 0) and self.vocab.get(str(self.vocab_size)) == 'UNK' or self.unk_idx is not None:
-            raise NotImplementedError('UNK suppression is out of scope of the B200 engine')
         assert sample_n == 1 or sample_n == beam_size, 'when beam search, sample_n == 1 or beam search'
         assert beam_size <= self.vocab_size + 1
+        n_kinds = int(bool(opt.get('decoding_constraint', 0))) + int(bool(opt.get('remove_bad_endings', 0)) and bool(self.bad_endings_ix)) + \
+            int((bool(opt.get('suppress_UNK', 0)) and self.vocab.get(str(self.vocab_size)) == 'UNK') or self.unk_idx is not None)
+        if beam_size + n_kinds > 16:
+            raise NotImplementedError('beam_size + number of active decode edits must be <= 16 on the B200 engine')
         cfg = opt.get('length_penalty', '')
         kind, alpha = (cfg.split('_') + ['0'])[:2] if cfg else ('', '0')
         lib = self._ensure_engine(fc_feats.device)
@@ -374,7 +404,8 @@ class B200CaptionModel(nn.Module):
         d_len = torch.zeros(B, beam_size, dtype=torch.int32, device=dev)
         d_p = torch.zeros(B, beam_size, dtype=torch.float32, device=dev)
         d_raw = torch.zeros(B, beam_size, dtype=torch.float32, device=dev)
-        bo = _lib.BeamOpts(beam_size, sample_n, _PENALTY[kind], float(alpha))
+        edits, keep_bad = self._decode_edits(opt, dev, beam=True)
+        bo = _lib.BeamOpts(beam_size, sample_n, _PENALTY[kind], float(alpha), float(opt.get('temperature', 1.0)), edits)
         _lib.check(self._call_beam(lib, fc, att, masks, B, R, bo, seq, logprobs, d_seq, d_len, d_p, d_raw), 'decode_beam')
         self._last_beam = (d_seq, d_len, d_p, d_raw)
         self.done_beams = _LazyDoneBeams(self, B, beam_size)

@@ -108,11 +108,26 @@ void capb200_engine_destroy(capb200_engine* e);
 /* (Re)binds the parameter tensors; call again after every optimizer step.  Tensor-core modes repack the fp16 planes here. */
 int capb200_engine_bind_weights(capb200_engine* e, const capb200_weights* w, void* stream);
 
+/* Per-step edits of the log-prob rows before the next word is chosen (the reference's decode options; the edited row is also what the
+ * reference stores in seqLogprobs / done_beams[...]['logps'], and so do we).  All zero / -1 / NULL = none. */
 typedef struct {
-    int beam_size;      /* b, 1..16 */
+    int decoding_constraint;   /* t > 0: log-prob of the previous word = -inf (CaptionModel.py:154-155, AttModel.py:294-297) */
+    int unk_col;               /* beam search: this column's log-prob is lowered by 1000 at every step (suppress_UNK with 'UNK' as the last
+                                  word, or unk_idx: CaptionModel.py:159-162); -1 = none */
+    int n_bad_endings;         /* remove_bad_endings: t > 0 and previous word in the list -> log-prob of the end token (column 0) = -inf
+                                  (CaptionModel.py:156-157, AttModel.py:299-304) */
+    const int* bad_endings;    /* device, n_bad_endings word ids (model.bad_endings_ix) */
+    int block_trigrams;        /* _sample only, t >= 3: every earlier occurrence of (w[t-2], w[t-1], x) lowers x by 2 ln 2 (AttModel.py:306-332) */
+    int trigram_rows;          /* rows 0 .. trigram_rows-1 get it (the reference loops over batch_size rows, also when sample_n > 1) */
+} capb200_decode_edits;
+
+typedef struct {
+    int beam_size;      /* b, 1..16 (with edits: b + number of active edit kinds <= 16) */
     int sample_n;       /* 1 or beam_size (AttModel.py:223) */
     int penalty_kind;   /* 0 '' (identity), 1 'wu_<alpha>', 2 'avg_<alpha>'   captioning/utils/misc.py:133-151 */
     float penalty_alpha;
+    float temperature;  /* log_softmax(logprobs / temperature) from the second step on (CaptionModel.py:204); 0 is read as 1 */
+    capb200_decode_edits edits;
 } capb200_beam_opts;
 
 /* AttModel._sample_beam + CaptionModel.beam_search (group_size 1).
@@ -129,12 +144,17 @@ int capb200_beam_record_logprobs(capb200_engine* e, int image, int rank, float* 
 #define CAPB200_SAMPLE_MULTINOMIAL 1
 #define CAPB200_SAMPLE_FORCED 2  /* replay given tokens (parity checks against another sampler's draw) */
 #define CAPB200_SAMPLE_TEACHER 3 /* AttModel._forward: feed labels[:, t] at step t, no finished-row masking */
+#define CAPB200_SAMPLE_TOPK 4    /* sample_method 'top<k>', k >= 1: multinomial over the k most likely words of logprobs / temperature
+                                    (CaptionModel.py:398-402); `top` = k */
+#define CAPB200_SAMPLE_TOPP 5    /* sample_method 'top<p>', 0 < p < 1: nucleus sampling (CaptionModel.py:388-397); `top` = p */
 typedef struct {
     int sample_n;             /* rows per image */
     int method;               /* CAPB200_SAMPLE_* */
     float temperature;
-    unsigned long long seed;  /* Philox key for CAPB200_SAMPLE_MULTINOMIAL */
+    unsigned long long seed;  /* Philox key for the sampling methods */
     int steps;                /* TEACHER: number of label columns to run (<= the label width) */
+    float top;                /* TOPK: k, TOPP: p */
+    capb200_decode_edits edits;
 } capb200_sample_opts;
 
 /* AttModel._sample (greedy / multinomial) and AttModel._forward (teacher forcing).

@@ -576,6 +576,49 @@ def gen_aoa_scst_full(out_dir, scratch):
           (float(out['loss']), float(out['reward']), float(np.abs(reward).max()), len(names), (sample_seq > 0).sum(1)[:8].tolist()))
 
 
+def gen_updown_options(out_dir):
+    """Decode options of the reference on the small UpDown configuration: decoding_constraint, remove_bad_endings, block_trigrams (greedy
+    _sample, AttModel.py:294-332) and suppress_UNK / decoding_constraint / remove_bad_endings / temperature in beam search
+    (CaptionModel.py:118-120,154-162,204).  The vocabulary carries 'UNK' as its last word and a few bad-ending words."""
+    cfg = dict(V=60, E=32, H=32, A=16, F_fc=48, F_att=48, T=10)
+    B, R, b = 5, 7, 3
+    W = co.make_weights('updown', cfg['V'], cfg['E'], cfg['H'], cfg['A'], cfg['F_fc'], cfg['F_att'], seed=23, logit_scale=8.0)
+    fc, att = co.make_inputs(B, R, cfg['F_fc'], cfg['F_att'], seed=23)
+    m = ref_model('updown', W=W, **cfg)
+    vocab = {str(i): 'w%d' % i for i in range(1, cfg['V'] + 1)}
+    vocab[str(cfg['V'])] = 'UNK'
+    # make the model's favourite words bad endings so that the option changes something
+    with torch.no_grad():
+        g0, _ = m(fc, att, None, opt={'sample_method': 'greedy', 'beam_size': 1}, mode='sample')
+    fav = [int(t) for t in torch.bincount(g0[g0 > 0].flatten(), minlength=cfg['V'] + 1).argsort(descending=True)[:3] if int(t) != cfg['V']]
+    for w, name in zip(fav, ('the', 'a', 'with')):
+        vocab[str(w)] = name
+    m.vocab = vocab
+    m.bad_endings_ix = [int(k) for k, v in vocab.items() if v in ('a', 'an', 'the', 'in', 'for', 'at', 'of', 'with', 'before', 'after', 'on', 'upon', 'near', 'to', 'is', 'are', 'am')]
+    res = {'bad_words': np.array(fav), 'vocab_unk': np.array(cfg['V'])}
+    with torch.no_grad():
+        # (remove_bad_endings in _sample indexes with a uint8 mask, AttModel.py:303, which current torch rejects: the reference itself cannot
+        # run that option there, so it has no golden; in beam search the mask is boolean and it works)
+        for tag, opt in (('g_plain', {}), ('g_con', {'decoding_constraint': 1}), ('g_tri', {'block_trigrams': 1}),
+                         ('g_all', {'decoding_constraint': 1, 'block_trigrams': 1})):
+            seq, lp = m(fc, att, None, opt=dict({'sample_method': 'greedy', 'beam_size': 1}, **opt), mode='sample')
+            res[tag + '_seq'], res[tag + '_lp'] = seq.numpy(), lp.numpy()
+        # block_trigrams with sample_n > 1 only touches the first batch_size rows (the reference loops over range(batch_size))
+        torch.manual_seed(3)
+        seq, lp = m(fc, att, None, opt={'sample_method': 'sample', 'beam_size': 1, 'sample_n': 2, 'block_trigrams': 1, 'decoding_constraint': 1}, mode='sample')
+        res['s_tri_seq'], res['s_tri_lp'] = seq.numpy(), lp.numpy()
+        for tag, opt in (('b_unk', {'suppress_UNK': 1}), ('b_temp', {'temperature': 0.7}), ('b_con', {'decoding_constraint': 1}),
+                         ('b_bad', {'remove_bad_endings': 1}),
+                         ('b_all', {'suppress_UNK': 1, 'decoding_constraint': 1, 'remove_bad_endings': 1, 'temperature': 1.3})):
+            seq, lp = m(fc, att, None, opt=dict({'beam_size': b, 'sample_n': 1}, **opt), mode='sample')
+            res[tag + '_seq'], res[tag + '_lp'] = seq.numpy(), lp.numpy()
+            res[tag + '_done_seq'], res[tag + '_done_len'], res[tag + '_done_p'] = beams_to_arrays(m.done_beams, b, cfg['T'])
+    np.savez_compressed(os.path.join(out_dir, 'updown_options.npz'), cfg=np.array([cfg[k] for k in ('V', 'E', 'H', 'A', 'F_fc', 'F_att', 'T')]),
+                        meta=np.array([B, R, b, 23]), **res)
+    print('updown_options: greedy plain', res['g_plain_seq'][0].tolist(), 'constraint', res['g_con_seq'][0].tolist(), 'all', res['g_all_seq'][0].tolist(),
+          '| beam all', res['b_all_seq'][0].tolist(), 'bad words', fav)
+
+
 def gen_state_dict_keys(out_dir):
     """Names and shapes of the reference modules' parameters: the drop-in must expose exactly these."""
     import json
@@ -602,7 +645,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     scratch = _enter_scratch()
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys', 'tfm', 'aoa', 'xe', 'dseq', 'pascal', 'penalty', 'b256', 'tfm64', 'aoafull']
+    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys', 'tfm', 'aoa', 'xe', 'dseq', 'pascal', 'penalty', 'b256', 'tfm64', 'aoafull', 'options']
     if 'small' in which:
         gen_updown_small(out_dir)
     if 'newfc' in which:
@@ -627,6 +670,8 @@ def main():
         gen_transformer_small(out_dir)
     if 'aoa' in which:
         gen_aoa_small(out_dir)
+    if 'options' in which:
+        gen_updown_options(out_dir)
     if 'b256' in which:
         gen_updown_b256(out_dir)
     if 'tfm64' in which:

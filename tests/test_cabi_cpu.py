@@ -62,9 +62,14 @@ def test_unsupported_options_raise():
     import imagecaptioning.pytorch_b200 as b200
     m = b200.setup(make_opt('updown', 60, 32, 32, 16, 48, 48, 8))
     fc, att = torch.zeros(2, 48), torch.zeros(2, 3, 48)
-    for bad in ({'group_size': 2, 'beam_size': 2}, {'block_trigrams': 1}, {'sample_method': 'top5'}, {'decoding_constraint': 1}):
+    for bad in ({'group_size': 2, 'beam_size': 2}, {'output_logsoftmax': 0}, {'sample_method': 'dbs'}):
         with pytest.raises(NotImplementedError):
             m(fc, att, None, opt=bad, mode='sample')
+    # options the engine implements get past the guards and stop at the no-CPU-fallback check
+    for ok in ({'block_trigrams': 1}, {'sample_method': 'top5'}, {'sample_method': 'top0.9'}, {'sample_method': 'gumbel'}, {'decoding_constraint': 1},
+               {'remove_bad_endings': 1, 'beam_size': 2, 'sample_n': 1}, {'suppress_UNK': 1, 'beam_size': 2, 'sample_n': 1, 'temperature': 0.7}):
+        with pytest.raises(RuntimeError, match='CUDA'):
+            m(fc, att, None, opt=ok, mode='sample')
     with pytest.raises(NotImplementedError):
         b200.setup(make_opt('adaatt', 60, 32, 32, 16, 48, 48, 8))
 

@@ -110,10 +110,11 @@ def test_decode_option_guards():
     cfg = dict(V=30, E=16, H=16, A=8, F_fc=16, F_att=16, T=5)
     model = b200.setup(family_opt('updown', **cfg))
     fc, att = co.make_inputs(2, 3, 16, 16, seed=1)
-    for bad in ({'group_size': 2, 'beam_size': 2}, {'decoding_constraint': 1}, {'block_trigrams': 1}, {'remove_bad_endings': 1}, {'output_logsoftmax': 0},
-                {'sample_method': 'top0.9'}, {'sample_method': 'gumbel'}):
+    for bad in ({'group_size': 2, 'beam_size': 2}, {'output_logsoftmax': 0}, {'sample_method': 'nonsense'}):
         with pytest.raises(NotImplementedError):
             model(fc, att, None, opt=dict({'beam_size': 1}, **bad), mode='sample')
+    with pytest.raises(ValueError):
+        model(fc, att, None, opt={'beam_size': 1, 'sample_method': 'top0'}, mode='sample')
     with pytest.raises(AssertionError):        # AttModel.py:223: sample_n must be 1 or beam_size when beam searching
         model(fc, att, None, opt={'beam_size': 3, 'sample_n': 2}, mode='sample')
     with pytest.raises(AssertionError):        # AttModel.py:228: beam_size <= vocab_size + 1
@@ -122,5 +123,7 @@ def test_decode_option_guards():
     opt_unk.vocab = dict(opt_unk.vocab)
     opt_unk.vocab[str(cfg['V'])] = 'UNK'
     unk_model = b200.setup(opt_unk)
-    with pytest.raises(NotImplementedError):   # CaptionModel.py:120,161-162: UNK suppression is not on the engine path
+    with pytest.raises(RuntimeError, match='CUDA'):   # CaptionModel.py:120,161-162: UNK suppression runs on the engine (stops at the no-CPU check)
         unk_model(fc, att, None, opt={'beam_size': 2, 'sample_n': 1, 'suppress_UNK': 1}, mode='sample')
+    with pytest.raises(NotImplementedError):           # 15 beams + 2 edit kinds exceed the 16 candidates a row keeps
+        unk_model(fc, att, None, opt={'beam_size': 15, 'sample_n': 1, 'suppress_UNK': 1, 'decoding_constraint': 1}, mode='sample')
