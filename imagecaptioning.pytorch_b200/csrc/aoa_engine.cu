@@ -532,6 +532,7 @@ struct AoaTrainArgs {
     const int* refs = nullptr; const int* ref_offsets = nullptr; int L = 0;
     long long* sample_seq = nullptr; long long* greedy_seq = nullptr; float* reward = nullptr;
     const long long* forced = nullptr;
+    const float* mask = nullptr;           // [B, R] region mask or null
     const long long* labels = nullptr; long ld_labels = 0; const float* masks = nullptr; long ld_masks = 0;
     float* logprobs = nullptr; float* loss = nullptr;
 };
@@ -572,7 +573,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
         capb200_sample_opts so; memset(&so, 0, sizeof(so)); so.edits.unk_col = -1; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.seed = 0; so.steps = T;
         CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, st));
         CAPB_CHECK_CUDA(cudaMemsetAsync(greedy_seq, 0, sizeof(long long) * (size_t)B * T, st));
-        if (capb200_aoa_decode_sample(e, att, nullptr, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, stream)) return 1;
+        if (capb200_aoa_decode_sample(e, att, ta.mask, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, stream)) return 1;
     }
     if (ensure_workspace(e, B, N, R, 1, st)) return 1;
     if (e->tc && e->tf32 == nullptr) e->tf32 = tf32_context_create();
@@ -591,11 +592,15 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     if (sk.lin(att, F, w.att_embed_w, F, w.att_embed_b, tp.x[0], H, (int)BR, H, F, 0)) return 1;
     if (relu_copy_launch(tp.x[0], BR * H, act(tp.x[0], H), st)) return 1;
     if (dropout_apply_launch(tp.x[0], (int)BR, H, H, seed, 1, 0, p_lm, st)) return 1;
+    if (ta.mask != nullptr) {      // pack_wrapper(att_embed): padded regions embed to exactly zero (AoAModel.py:211, AttModel.py:44-49)
+        if (mask_rows_launch(act(tp.x[0], H), B, R, H, ta.mask, R, st)) return 1;
+        e->launches++;
+    }
     for (int l = 0; l < NL; ++l) {
         const capb200_aoa_refiner_layer& Lw = w.refiner[l];
         if (layer_norm_launch((int)BR, H, tp.x[l], H, Lw.ln_a, Lw.ln_b, 1e-6f, act(tp.ln[l], H), st)) return 1;
         if (sk.lin(tp.ln[l], H, e->r_qkv_w[l], H, e->r_qkv_b[l], tp.qkv[l], 3 * H, (int)BR, 3 * H, H, 0)) return 1;
-        if (enc_attn_train_launch(B, R, heads, dk, tp.qkv[l], tp.qkv[l] + H, tp.qkv[l] + 2 * H, 3 * H, seed, 10 + l, p_at, tp.ratt[l], H, st)) return 1;
+        if (enc_attn_train_launch(B, R, heads, dk, tp.qkv[l], tp.qkv[l] + H, tp.qkv[l] + 2 * H, 3 * H, seed, 10 + l, p_at, tp.ratt[l], H, st, ta.mask, R)) return 1;
         if (cat_dropout_launch((int)BR, H, H, tp.ratt[l], H, tp.ln[l], H, tp.catd[l], 2 * H, seed, 20 + l, 0, p_aoa, st)) return 1;
         if (sk.lin(tp.catd[l], 2 * H, Lw.aoa_w, 2 * H, Lw.aoa_b, tp.t[l], 2 * H, (int)BR, 2 * H, 2 * H, 0)) return 1;
         if (glu_launch((int)BR, H, tp.t[l], 2 * H, nullptr, 0, act(tp.g[l], H), st)) return 1;
@@ -603,7 +608,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
         e->launches += 9;
     }
     if (layer_norm_launch((int)BR, H, tp.x[NL], H, w.refiner_norm_a, w.refiner_norm_b, 1e-6f, act(tp.att_e, H), st)) return 1;
-    if (masked_mean_launch(B, R, H, tp.att_e, H, nullptr, R, act(tp.mean, H), st)) return 1;
+    if (masked_mean_launch(B, R, H, tp.att_e, H, ta.mask, R, act(tp.mean, H), st)) return 1;
     if (sk.lin(tp.att_e, H, w.ctx2att_w, H, w.ctx2att_b, tp.kv, 2 * H, (int)BR, 2 * H, H, 0)) return 1;
     e->launches += 8;
 
@@ -637,7 +642,8 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
         if (layer_norm_launch(N, H, h_t, H, w.attn_norm_a, w.attn_norm_b, 1e-6f, act(qln, H), st)) return 1;
         if (sk.lin(qln, H, w.attn_q_w, H, w.attn_q_b, qp, H, N, H, H, 0)) return 1;
         // AoAModel.py:168 passes (query, value = p_att[..., :H], key = p_att[..., H:])
-        if (cross_attn_train_launch(N, n, heads, dk, R, qp, H, tp.kv + H, tp.kv, 2 * H, seed, 5, t, p_at, att_t, H, tp.probs + (long)t * N * heads * R, st)) return 1;
+        if (cross_attn_train_launch(N, n, heads, dk, R, qp, H, tp.kv + H, tp.kv, 2 * H, seed, 5, t, p_at, att_t, H, tp.probs + (long)t * N * heads * R, st,
+                                    ta.mask, R)) return 1;
         {
             GemmProblem g; g.M = N; g.N = 2 * H; g.nseg = 2;
             g.seg[0].A = att_t; g.seg[0].lda = H; g.seg[0].W = w.att2ctx_w; g.seg[0].ldw = 2 * H; g.seg[0].K = H;
@@ -743,7 +749,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     rc |= sk.dgrad((int)BR, H, 2 * H, tp.d_kv, 2 * H, w.ctx2att_w, H, tp.d_att_e, H, 0);
     rc |= wgrad(2 * H, H, (int)BR, tp.d_kv, 2 * H, tp.att_e, H, G.ctx2att_w, H, 0, st);
     rc |= colsum_launch((int)BR, 2 * H, tp.d_kv, 2 * H, G.ctx2att_b, 0, st);
-    rc |= mean_backward_launch(B, R, H, tp.d_mean, H, tp.d_att_e, H, st);
+    rc |= mean_backward_launch(B, R, H, tp.d_mean, H, tp.d_att_e, H, st, ta.mask, R);
     rc |= ln_backward_launch((int)BR, H, tp.x[NL], H, w.refiner_norm_a, tp.d_att_e, H, 1e-6f, tp.d_x, H, 0, tp.stats, G.refiner_norm_a, G.refiner_norm_b, 0, st);
     if (rc) return 1;
     if (group_done(2)) return 1;                                        // ctx2att + refiner.norm
@@ -760,7 +766,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
         // self-attention backward needs a contiguous d attended
         CAPB_CHECK_CUDA(cudaMemcpy2DAsync(tp.d_g, sizeof(float) * H, tp.d_catd, sizeof(float) * 2 * H, sizeof(float) * H, BR, cudaMemcpyDeviceToDevice, st));
         rc |= enc_attn_backward_launch(B, R, heads, dk, tp.qkv[l], tp.qkv[l] + H, tp.qkv[l] + 2 * H, 3 * H, seed, 10 + l, p_at, tp.d_g, H, tp.d_qkv, tp.d_qkv + H,
-                                       tp.d_qkv + 2 * H, 3 * H, st);
+                                       tp.d_qkv + 2 * H, 3 * H, st, ta.mask, R);
         rc |= wgrad(H, H, (int)BR, tp.d_qkv, 3 * H, tp.ln[l], H, Lg.q_w, H, 0, st);
         rc |= wgrad(H, H, (int)BR, tp.d_qkv + H, 3 * H, tp.ln[l], H, Lg.k_w, H, 0, st);
         rc |= wgrad(H, H, (int)BR, tp.d_qkv + 2 * H, 3 * H, tp.ln[l], H, Lg.v_w, H, 0, st);
@@ -801,7 +807,7 @@ extern "C" int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, in
     ta.n = n; ta.T = e->T; ta.Tl = e->T; ta.p_lm = p_lm; ta.p_at = p_at; ta.p_aoa = p_aoa; ta.p_sub = p_sub; ta.temperature = opts->temperature;
     ta.upstream = opts->upstream; ta.ctx_drop = opts->ctx_drop; ta.seed = opts->seed; ta.greedy_baseline = greedy_baseline; ta.table = table;
     ta.refs = refs; ta.ref_offsets = ref_offsets; ta.L = L; ta.sample_seq = sample_seq; ta.greedy_seq = greedy_seq; ta.reward = reward;
-    ta.logprobs = sample_logprobs; ta.loss = loss; ta.forced = opts->forced_tokens;
+    ta.logprobs = sample_logprobs; ta.loss = loss; ta.forced = opts->forced_tokens; ta.mask = opts->att_masks;
     return aoa_train_step(e, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }
 
@@ -826,5 +832,6 @@ extern "C" int capb200_aoa_xe_step(capb200_aoa_engine* e, const float* att, int 
     ta.n = opts->seq_per_img; ta.T = opts->steps; ta.Tl = label_cols - 1; ta.p_lm = p_lm; ta.p_at = p_at; ta.p_aoa = p_aoa; ta.p_sub = p_sub;
     ta.upstream = opts->upstream; ta.ctx_drop = opts->ctx_drop; ta.seed = opts->seed; ta.smoothing = opts->label_smoothing;
     ta.labels = labels; ta.ld_labels = label_cols; ta.masks = masks; ta.ld_masks = label_cols; ta.logprobs = logprobs; ta.loss = loss;
+    ta.mask = opts->att_masks;
     return aoa_train_step(e, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }

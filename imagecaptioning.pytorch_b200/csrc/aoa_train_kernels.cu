@@ -90,7 +90,8 @@ __global__ void glu_backward_kernel(int rows, int H, const float* __restrict__ t
 // q,k,v: [B*R, ld] with the head at columns [head*dk, (head+1)*dk).  Dropout element index = ((img*heads + head)*R + qi)*R + r.
 __global__ void __launch_bounds__(128) enc_attn_train_kernel(int R, int dk, int heads, const float* __restrict__ q, const float* __restrict__ k,
                                                              const float* __restrict__ v, long ld, float scale, unsigned long long seed, uint32_t site,
-                                                             float p_drop, float* __restrict__ out, long ld_out) {
+                                                             float p_drop, float* __restrict__ out, long ld_out, const float* __restrict__ mask,
+                                                             long ld_mask) {
     extern __shared__ float sm[];
     float* sk = sm;                 // [R][dk+1]
     float* sv = sk + R * (dk + 1);
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(128) enc_attn_train_kernel(int R, int dk, int 
             float s = 0.f;
             for (int c = 0; c < dk; ++c) s = fmaf(__ldg(qr + c), sk[r * (dk + 1) + c], s);
             s *= scale;
+            if (mask != nullptr && mask[(long)img * ld_mask + r] == 0.f) s = -INFINITY;     // scores.masked_fill(mask == 0, -inf)  (TransformerModel.py:157-158)
             p[r] = s;
             mx = fmaxf(mx, s);
         }
@@ -134,7 +136,8 @@ __global__ void __launch_bounds__(128) enc_attn_train_kernel(int R, int dk, int 
 __global__ void __launch_bounds__(256) enc_attn_backward_kernel(int R, int dk, int heads, const float* __restrict__ q, const float* __restrict__ k,
                                                                 const float* __restrict__ v, long ld, float scale, unsigned long long seed,
                                                                 uint32_t site, float p_drop, const float* __restrict__ d_out, long ld_do,
-                                                                float* __restrict__ dq, float* __restrict__ dk_, float* __restrict__ dv, long ld_d) {
+                                                                float* __restrict__ dq, float* __restrict__ dk_, float* __restrict__ dv, long ld_d,
+                                                                const float* __restrict__ mask, long ld_mask) {
     extern __shared__ float sm[];
     const int W = dk + 1;
     float* sq = sm;                 // [R][W]
@@ -159,6 +162,7 @@ __global__ void __launch_bounds__(256) enc_attn_backward_kernel(int R, int dk, i
             float s = 0.f;
             for (int c = 0; c < dk; ++c) s = fmaf(sq[qi * W + c], sk[r * W + c], s);
             s *= scale;
+            if (mask != nullptr && mask[(long)img * ld_mask + r] == 0.f) s = -INFINITY;
             P[qi * R + r] = s;
             mx = fmaxf(mx, s);
         }
@@ -213,7 +217,8 @@ __global__ void __launch_bounds__(256) enc_attn_backward_kernel(int R, int dk, i
 __global__ void __launch_bounds__(128) cross_attn_train_kernel(int rows, int rpi, int heads, int dk, int R, const float* __restrict__ q, long ld_q,
                                                                const float* __restrict__ kk, const float* __restrict__ vv, long ld_kv, float scale,
                                                                unsigned long long seed, uint32_t site, uint32_t step, float p_drop,
-                                                               float* __restrict__ out, long ld_out, float* __restrict__ probs) {
+                                                               float* __restrict__ out, long ld_out, float* __restrict__ probs,
+                                                               const float* __restrict__ mask, long ld_mask) {
     extern __shared__ float sm[];       // [4 warps][R]
     const int item = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (item >= rows * heads) return;
@@ -228,6 +233,7 @@ __global__ void __launch_bounds__(128) cross_attn_train_kernel(int rows, int rpi
         float s = 0.f;
         for (int c = 0; c < dk; ++c) s = fmaf(qr[c], __ldg(kr + c), s);
         s *= scale;
+        if (mask != nullptr && mask[(long)img * ld_mask + r] == 0.f) s = -INFINITY;
         p[r] = s;
         mx = fmaxf(mx, s);
     }
@@ -315,11 +321,17 @@ __global__ void __launch_bounds__(128) cross_attn_backward_kernel(int rpi, int h
     }
 }
 
-// d x[img, r, :] += d mean[img, :] / R
-__global__ void mean_backward_kernel(int R, int H, const float* __restrict__ d_mean, long ld_dm, float* __restrict__ dx, long ld_dx) {
+// d x[img, r, :] += d mean[img, :] / R        (masked: mean over the valid regions, AoAModel.py:216-219 -> += mask[r] * d mean / sum(mask))
+__global__ void mean_backward_kernel(int R, int H, const float* __restrict__ d_mean, long ld_dm, float* __restrict__ dx, long ld_dx,
+                                     const float* __restrict__ mask, long ld_mask) {
     const int row = blockIdx.x;              // img * R + r
-    const int img = row / R;
-    const float inv = 1.0f / (float)R;
+    const int img = row / R, r = row % R;
+    float inv = 1.0f / (float)R;
+    if (mask != nullptr) {
+        float cnt = 0.f;
+        for (int j = 0; j < R; ++j) cnt += mask[(long)img * ld_mask + j];
+        inv = mask[(long)img * ld_mask + r] / cnt;
+    }
     for (int c = threadIdx.x; c < H; c += blockDim.x) dx[(long)row * ld_dx + c] += d_mean[(long)img * ld_dm + c] * inv;
 }
 
@@ -379,14 +391,14 @@ int glu_backward_launch(int rows, int H, const float* t, long ld_t, const float*
     LAUNCH_OK();
 }
 int enc_attn_train_launch(int B, int R, int heads, int dk, const float* q, const float* k, const float* v, long ld, unsigned long long seed, int site, float p,
-                          float* out, long ld_out, cudaStream_t st) {
+                          float* out, long ld_out, cudaStream_t st, const float* mask, long ld_mask) {
     const size_t smem = sizeof(float) * ((size_t)2 * R * (dk + 1) + 4 * R);
     CAPB_REQUIRE(smem <= 48 * 1024, "refiner attention: regions * head width too large for the training kernel");
-    enc_attn_train_kernel<<<dim3(B, heads), 128, smem, st>>>(R, dk, heads, q, k, v, ld, 1.0f / sqrtf((float)dk), seed, (uint32_t)site, p, out, ld_out);
+    enc_attn_train_kernel<<<dim3(B, heads), 128, smem, st>>>(R, dk, heads, q, k, v, ld, 1.0f / sqrtf((float)dk), seed, (uint32_t)site, p, out, ld_out, mask, ld_mask);
     LAUNCH_OK();
 }
 int enc_attn_backward_launch(int B, int R, int heads, int dk, const float* q, const float* k, const float* v, long ld, unsigned long long seed, int site, float p,
-                             const float* d_out, long ld_do, float* dq, float* dk_, float* dv, long ld_d, cudaStream_t st) {
+                             const float* d_out, long ld_do, float* dq, float* dk_, float* dv, long ld_d, cudaStream_t st, const float* mask, long ld_mask) {
     const size_t smem = sizeof(float) * ((size_t)4 * R * (dk + 1) + 2 * R * R);
     CAPB_REQUIRE(smem <= 200 * 1024, "refiner attention backward: shared-memory footprint too large");
     static std::atomic<unsigned long long> configured{0};
@@ -394,13 +406,14 @@ int enc_attn_backward_launch(int B, int R, int heads, int dk, const float* q, co
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(enc_attn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     enc_attn_backward_kernel<<<dim3(B, heads), 256, smem, st>>>(R, dk, heads, q, k, v, ld, 1.0f / sqrtf((float)dk), seed, (uint32_t)site, p, d_out, ld_do, dq,
-                                                                  dk_, dv, ld_d);
+                                                                  dk_, dv, ld_d, mask, ld_mask);
     LAUNCH_OK();
 }
 int cross_attn_train_launch(int rows, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
-                            unsigned long long seed, int site, int step, float p, float* out, long ld_out, float* probs, cudaStream_t st) {
+                            unsigned long long seed, int site, int step, float p, float* out, long ld_out, float* probs, cudaStream_t st, const float* mask,
+                            long ld_mask) {
     cross_attn_train_kernel<<<cdiv(rows * heads, 4), 128, sizeof(float) * 4 * R, st>>>(rows, rpi, heads, dk, R, q, ld_q, kk, vv, ld_kv, 1.0f / sqrtf((float)dk),
-                                                                                        seed, (uint32_t)site, (uint32_t)step, p, out, ld_out, probs);
+                                                                                        seed, (uint32_t)site, (uint32_t)step, p, out, ld_out, probs, mask, ld_mask);
     LAUNCH_OK();
 }
 int cross_attn_backward_launch(int B, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
@@ -416,8 +429,8 @@ int cross_attn_backward_launch(int B, int rpi, int heads, int dk, int R, const f
                                                                    (uint32_t)step, p, probs, d_out, ld_do, dq, ld_dq, dkk, dvv, ld_dkv);
     LAUNCH_OK();
 }
-int mean_backward_launch(int B, int R, int H, const float* d_mean, long ld_dm, float* dx, long ld_dx, cudaStream_t st) {
-    mean_backward_kernel<<<B * R, 256, 0, st>>>(R, H, d_mean, ld_dm, dx, ld_dx);
+int mean_backward_launch(int B, int R, int H, const float* d_mean, long ld_dm, float* dx, long ld_dx, cudaStream_t st, const float* mask, long ld_mask) {
+    mean_backward_kernel<<<B * R, 256, 0, st>>>(R, H, d_mean, ld_dm, dx, ld_dx, mask, ld_mask);
     LAUNCH_OK();
 }
 int add_dropout_launch(int rows, int cols, const float* a, long ld_a, const float* b, long ld_b, float* out, long ld_o, unsigned long long seed, int site, int step,

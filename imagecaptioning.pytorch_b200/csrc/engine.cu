@@ -883,6 +883,7 @@ struct TrainArgs {
     const int* refs = nullptr; const int* ref_offsets = nullptr; int L = 0;
     long long* sample_seq = nullptr; long long* greedy_seq = nullptr; float* reward = nullptr;
     const long long* forced = nullptr;      // replay these samples instead of drawing
+    const float* mask = nullptr;            // [B, R] region mask or null
     // XE
     const long long* labels = nullptr; long ld_labels = 0; const float* masks = nullptr; long ld_masks = 0;
     float* logprobs = nullptr; float* loss = nullptr;
@@ -921,7 +922,7 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
         capb200_sample_opts so; memset(&so, 0, sizeof(so)); so.edits.unk_col = -1; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.seed = 0; so.steps = T;
         CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, st));
         CAPB_CHECK_CUDA(cudaMemsetAsync(greedy_seq, 0, sizeof(long long) * (size_t)B * T, st));
-        if (capb200_decode_sample(e, fc, att, nullptr, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, stream)) return 1;
+        if (capb200_decode_sample(e, fc, att, ta.mask, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, stream)) return 1;
     }
     if (ensure_workspace(e, B, N, R, 1, st)) return 1;        // DecodeBuffers (tokens, unfinished, ...) for N rows
     if (e->tc && e->tf32 == nullptr) e->tf32 = tf32_context_create();
@@ -938,6 +939,10 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     if (sk.lin(att, Fa, w.att_embed_w, Fa, w.att_embed_b, tp.att_e, H, (int)BR, H, Fa, 0)) return 1;
     if (relu_copy_launch(tp.att_e, BR * H, ActView{tp.att_e, nullptr, nullptr, H}, st)) return 1;
     if (dropout_apply_launch(tp.att_e, (int)BR, H, H, seed, 1, 0, p, st)) return 1;
+    if (ta.mask != nullptr) {      // pack_wrapper: the embedding of a padded region is exactly zero (AttModel.py:44-49); relu'(0) = 0 keeps its gradient zero
+        if (mask_rows_launch(ActView{tp.att_e, nullptr, nullptr, H}, B, R, H, ta.mask, R, st)) return 1;
+        e->launches++;
+    }
     if (sk.lin(tp.att_e, H, w.ctx2att_w, H, w.ctx2att_b, tp.p_att, A, (int)BR, A, H, 0)) return 1;
     if (sk.lin(tp.fc_e, H, w.att_lstm_w_ih + H, E + 2 * H, e->bsum_att, tp.g_fc, 4 * H, B, 4 * H, H, 0)) return 1;
     e->launches += 8;
@@ -975,7 +980,7 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
         float* atth = tp.atth + (long)t * N * A;
         if (sk.lin(h0, H, w.h2att_w, H, w.h2att_b, atth, A, N, A, H, 0)) return 1;
         float* attres = tp.attres + (long)t * NH;
-        if (additive_attention_launch(B, n, R, A, H, atth, A, tp.p_att, A, tp.att_e, H, nullptr, R, w.alpha_w, w.alpha_b, e->att_score,
+        if (additive_attention_launch(B, n, R, A, H, atth, A, tp.p_att, A, tp.att_e, H, ta.mask, R, w.alpha_w, w.alpha_b, e->att_score,
                                       ActView{attres, nullptr, nullptr, H}, st, tp.alpha + (long)t * N * R)) return 1;
         {
             GemmProblem g; g.M = N; g.N = 4 * H; g.nseg = 2;
@@ -1114,7 +1119,7 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
     ta.n = opts->sample_n; ta.T = e->T; ta.Tl = e->T; ta.p = opts->drop_prob; ta.temperature = opts->temperature; ta.upstream = opts->upstream;
     ta.seed = opts->seed; ta.greedy_baseline = greedy_baseline; ta.table = table; ta.refs = refs; ta.ref_offsets = ref_offsets; ta.L = L;
     ta.sample_seq = sample_seq; ta.greedy_seq = greedy_seq; ta.reward = reward; ta.logprobs = sample_logprobs; ta.loss = loss;
-    ta.forced = opts->forced_tokens;
+    ta.forced = opts->forced_tokens; ta.mask = opts->att_masks;
     return updown_train_step(e, fc, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }
 
@@ -1140,6 +1145,7 @@ extern "C" int capb200_updown_xe_step(capb200_engine* e, const float* fc, const 
     ta.n = opts->seq_per_img; ta.T = opts->steps; ta.Tl = label_cols - 1; ta.p = opts->drop_prob; ta.upstream = opts->upstream; ta.seed = opts->seed;
     ta.smoothing = opts->label_smoothing;
     ta.labels = labels; ta.ld_labels = label_cols; ta.masks = masks; ta.ld_masks = label_cols; ta.logprobs = logprobs; ta.loss = loss;
+    ta.mask = opts->att_masks;
     return updown_train_step(e, fc, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }
 

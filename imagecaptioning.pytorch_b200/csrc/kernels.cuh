@@ -172,15 +172,18 @@ int ln_backward_launch(int rows, int D, const float* x, long ld_x, const float* 
                        float* stats, float* da, float* db, int accumulate_params, cudaStream_t st);
 int glu_backward_launch(int rows, int H, const float* t, long ld_t, const float* dy, long ld_dy, float* dt, long ld_dt, cudaStream_t st);
 int enc_attn_train_launch(int B, int R, int heads, int dk, const float* q, const float* k, const float* v, long ld, unsigned long long seed, int site, float p,
-                          float* out, long ld_out, cudaStream_t st);
+                          float* out, long ld_out, cudaStream_t st, const float* mask = nullptr, long ld_mask = 0);
 int enc_attn_backward_launch(int B, int R, int heads, int dk, const float* q, const float* k, const float* v, long ld, unsigned long long seed, int site, float p,
-                             const float* d_out, long ld_do, float* dq, float* dk_, float* dv, long ld_d, cudaStream_t st);
+                             const float* d_out, long ld_do, float* dq, float* dk_, float* dv, long ld_d, cudaStream_t st, const float* mask = nullptr,
+                             long ld_mask = 0);
 int cross_attn_train_launch(int rows, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
-                            unsigned long long seed, int site, int step, float p, float* out, long ld_out, float* probs, cudaStream_t st);
+                            unsigned long long seed, int site, int step, float p, float* out, long ld_out, float* probs, cudaStream_t st,
+                            const float* mask = nullptr, long ld_mask = 0);
 int cross_attn_backward_launch(int B, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
                                unsigned long long seed, int site, int step, float p, const float* probs, const float* d_out, long ld_do, float* dq, long ld_dq,
                                float* dkk, float* dvv, long ld_dkv, cudaStream_t st);
-int mean_backward_launch(int B, int R, int H, const float* d_mean, long ld_dm, float* dx, long ld_dx, cudaStream_t st);
+int mean_backward_launch(int B, int R, int H, const float* d_mean, long ld_dm, float* dx, long ld_dx, cudaStream_t st, const float* mask = nullptr,
+                         long ld_mask = 0);
 int add_dropout_launch(int rows, int cols, const float* a, long ld_a, const float* b, long ld_b, float* out, long ld_o, unsigned long long seed, int site, int step,
                        float p, cudaStream_t st);
 int cat_dropout_launch(int rows, int c1, int c2, const float* a, long ld_a, const float* b, long ld_b, float* out, long ld_o, unsigned long long seed, int site,

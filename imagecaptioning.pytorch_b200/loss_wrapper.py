@@ -188,9 +188,9 @@ class B200LossWrapper(nn.Module):
     def _xe_loss(self, fc_feats, att_feats, labels, masks, att_masks, drop_worst_flag, snapshot=False):
         """loss_wrapper.py:54-55: crit(model(fc, att, labels[..., :-1], att_masks), labels[..., 1:], masks[..., 1:])."""
         if torch.is_grad_enabled() and self.model.training:
-            if not hasattr(self.model, 'xe_step') or att_masks is not None or drop_worst_flag:
-                raise NotImplementedError('the fused XE step covers the UpDown family with att_masks=None and reduction="mean"')
-            res = self.model.xe_step(fc_feats, att_feats, labels, masks, label_smoothing=getattr(self.opt, 'label_smoothing', 0))
+            if not hasattr(self.model, 'xe_step') or drop_worst_flag:
+                raise NotImplementedError('the fused XE step covers the UpDown and AoANet families with reduction="mean" (no drop_worst)')
+            res = self.model.xe_step(fc_feats, att_feats, labels, masks, label_smoothing=getattr(self.opt, 'label_smoothing', 0), att_masks=att_masks)
             if snapshot:        # another fused step will reuse the model's flat gradient buffer before this loss is back-propagated
                 res = dict(res, grads={p_: g.clone() for p_, g in res['grads'].items()}, flat=None)
             self.last_step = res
@@ -199,11 +199,11 @@ class B200LossWrapper(nn.Module):
         reduction = 'none' if drop_worst_flag else 'mean'
         return self.crit(self.model(fc_feats, att_feats, labels[..., :-1], att_masks), labels[..., 1:], masks[..., 1:], reduction=reduction)
 
-    def _sampled_step(self, fc_feats, att_feats, gts, baseline):
+    def _sampled_step(self, fc_feats, att_feats, gts, baseline, att_masks=None):
         opt = self.opt
         self.model.train()
         # the reference's training-time _sample call passes no temperature (loss_wrapper.py:63-67): 1.0, whatever opt.temperature says
-        res = self.model.scst_step(fc_feats, att_feats, gts, self._scorer(), opt.train_sample_n, temperature=1.0, baseline=baseline)
+        res = self.model.scst_step(fc_feats, att_feats, gts, self._scorer(), opt.train_sample_n, temperature=1.0, baseline=baseline, att_masks=att_masks)
         self.last_step = res
         return res
 
@@ -212,7 +212,7 @@ class B200LossWrapper(nn.Module):
         out = {}
         reduction = 'none' if drop_worst_flag else 'mean'
         plain_reward = getattr(opt, 'bleu_reward_weight', 0) == 0 and getattr(opt, 'cider_reward_weight', 1) == 1
-        can_fuse = (hasattr(self.model, 'scst_step') and att_masks is None and not drop_worst_flag and torch.is_grad_enabled() and plain_reward and
+        can_fuse = (hasattr(self.model, 'scst_step') and not drop_worst_flag and torch.is_grad_enabled() and plain_reward and
                     opt.train_sample_method == 'sample' and opt.train_beam_size == 1)
         if struc_flag:
             w = opt.structure_loss_weight
@@ -222,7 +222,7 @@ class B200LossWrapper(nn.Module):
                 if getattr(opt, 'use_ppo', 0) or opt.structure_loss_type != 'new_self_critical' or not can_fuse:
                     raise NotImplementedError("the structure-loss branch covers structure_loss_type='new_self_critical' on the fused UpDown step")
                 gts = [gts[_] for _ in gt_indices.tolist()]
-                res = self._sampled_step(fc_feats, att_feats, gts, 'leave_one_out')
+                res = self._sampled_step(fc_feats, att_feats, gts, 'leave_one_out', att_masks)
                 struc = {'loss': self._bridge(res), 'reward': cider_scores(gts, res['sample_seq']).float().view(-1, opt.train_sample_n)}
             else:
                 struc = {'loss': torch.zeros((), device=fc_feats.device), 'reward': torch.zeros((), device=fc_feats.device)}
@@ -235,7 +235,7 @@ class B200LossWrapper(nn.Module):
         if can_fuse and opt.sc_sample_method == 'greedy' and opt.sc_beam_size == 1:
             # whole step on the device incl. back-propagation through time (UpDown); dropout as in model.train()
             gts = [gts[_] for _ in gt_indices.tolist()]
-            res = self._sampled_step(fc_feats, att_feats, gts, 'greedy')
+            res = self._sampled_step(fc_feats, att_feats, gts, 'greedy', att_masks)
             out['loss'] = self._bridge(res)
             out['reward'] = res['reward'][:, 0].mean()
             return out
@@ -245,8 +245,6 @@ class B200LossWrapper(nn.Module):
             why = []
             if not hasattr(self.model, 'scst_step'):
                 why.append('model family %r has no fused SCST step (UpDown and AoANet do)' % getattr(self.model, 'family_name', type(self.model).__name__))
-            if att_masks is not None and not getattr(self.model, 'scst_masks', False):
-                why.append('att_masks is not None')
             if drop_worst_flag:
                 why.append('drop_worst_flag')
             if not plain_reward:

@@ -295,6 +295,8 @@ typedef struct {
                                   (structure loss 'new_self_critical', losses.py:168-187: no greedy decode, greedy_seq may be NULL) */
     const long long* forced_tokens; /* optional [B*sample_n, T] int64 device: replay these samples instead of drawing them (parity
                                   checks against the reference's own multinomial draw); NULL = sample */
+    const float* att_masks;    /* optional [B, R] fp32 device (1 = valid region): variable region counts (AttModel.py:44-49,106-112,742-744;
+                                  dataloader.py:230-241); the caller has clipped R to the longest valid length; NULL = all regions valid */
 } capb200_scst_opts;
 #define CAPB200_BASELINE_GREEDY 0
 #define CAPB200_BASELINE_LEAVE_ONE_OUT 1
@@ -305,7 +307,7 @@ typedef struct {
     float *att_lstm_w_ih, *att_lstm_w_hh, *att_lstm_b_ih, *att_lstm_b_hh, *lang_lstm_w_ih, *lang_lstm_w_hh, *lang_lstm_b_ih, *lang_lstm_b_hh;
     float *h2att_w, *h2att_b, *alpha_w, *alpha_b;
 } capb200_updown_grads;
-/* fc[B,F_fc], att[B,R,F_att] (fixed region count: att_masks = None, dataloader.py:239-241); refs as in capb200_self_critical_reward.
+/* fc[B,F_fc], att[B,R,F_att] (opts->att_masks for variable region counts); refs as in capb200_self_critical_reward.
  * Outputs: sample_seq[B*n,T] int64, greedy_seq[B,T] int64, sample_logprobs[B*n,T,V+1] (caller zero-fills), reward[B*n,T], loss[1]. */
 int capb200_updown_scst_step(capb200_engine* e, const float* fc, const float* att, int B, int R, const capb200_scst_opts* opts,
                              const capb200_cider_table* table, const int* refs, const int* ref_offsets, int L, const capb200_updown_grads* grads,
@@ -322,6 +324,7 @@ typedef struct {
     float drop_prob;
     float label_smoothing;     /* 0 = LanguageModelCriterion, > 0 = LabelSmoothing(smoothing) */
     float upstream;
+    const float* att_masks;    /* optional [B, R] region mask, see capb200_scst_opts */
 } capb200_xe_opts;
 /* labels[N, label_cols] int64 (column 0 = BOS = 0), masks[N, label_cols] fp32, N = B * seq_per_img.
  * Outputs: logprobs[N, label_cols-1, V+1] (caller zero-fills; columns >= steps stay zero), loss[1], every grads buffer overwritten. */
@@ -347,6 +350,8 @@ typedef struct {
     float drop_sublayer;       /* refiner SublayerConnection (0.1, AoAModel.py:119) */
     int ctx_drop;              /* opt.ctx_drop */
     const long long* forced_tokens; /* optional [B*sample_n, T] int64 device: replay these samples (see capb200_scst_opts) */
+    const float* att_masks;    /* optional [B, R] region mask (refiner self-attention keys, masked mean pooling AoAModel.py:216-219, decoder
+                                  attention keys) */
 } capb200_aoa_scst_opts;
 /* Gradient buffers, laid out field by field like the weights struct above: parameter shapes, fp32, device; every one is OVERWRITTEN. */
 typedef struct {
@@ -364,7 +369,7 @@ typedef struct {
     float *att2ctx_w, *att2ctx_b;
     float *logit_w, *logit_b;
 } capb200_aoa_grads;
-/* att[B,R,F_att] (fixed region count, att_masks = None); outputs as in capb200_updown_scst_step. */
+/* att[B,R,F_att] (opts->att_masks for variable region counts); outputs as in capb200_updown_scst_step. */
 int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, int B, int R, const capb200_aoa_scst_opts* opts, const capb200_cider_table* table,
                           const int* refs, const int* ref_offsets, int L, const capb200_aoa_grads* grads, long long* sample_seq, long long* greedy_seq,
                           float* sample_logprobs, float* reward, float* loss, void* stream);
@@ -379,6 +384,7 @@ typedef struct {
     float upstream;
     float drop_prob_lm, drop_attn, drop_aoa, drop_sublayer;
     int ctx_drop;
+    const float* att_masks;    /* optional [B, R] region mask */
 } capb200_aoa_xe_opts;
 int capb200_aoa_xe_step(capb200_aoa_engine* e, const float* att, int B, int R, const capb200_aoa_xe_opts* opts, const long long* labels,
                         const float* masks, int label_cols, const capb200_aoa_grads* grads, float* logprobs, float* loss, void* stream);

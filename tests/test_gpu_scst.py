@@ -377,3 +377,107 @@ def test_cider_kernel_on_real_captions(golden_dir):
     gts = [refs[i] for i in range(refs.shape[0])]
     scores = b200.rewards.cider_scores(gts, cands, table).cpu().numpy()
     assert np.abs(scores - g['scores']).max() < 1e-9
+
+
+def _region_masks(B, R, clip):
+    """Prefix masks (the collate format of dataloader.py:230-241); with ``clip`` no image uses all R regions, so clip_att shortens the axis."""
+    lens = [R - 2 - (i % 3) if clip else (R if i == 0 else R - 1 - (2 * i) % (R - 2)) for i in range(B)]
+    m = torch.zeros(B, R)
+    for i, ln in enumerate(lens):
+        m[i, :max(ln, 1)] = 1
+    return m
+
+
+@pytest.mark.parametrize('clip', [False, True])
+@pytest.mark.parametrize('mode', ['tc_f16x3', 'simt_fp32'])
+def test_scst_step_gradients_with_region_masks(mode, clip):
+    """variable region counts in the fused UpDown SCST step (pack_wrapper zero rows, masked-renormalised attention,
+    AttModel.py:44-49,742-744) against autograd through the oracle, dropout replayed."""
+    import imagecaptioning.pytorch_b200 as b200
+    from oracle import ciderd_oracle as cdo
+    model, fam = build_pair('updown', seed=31, logit_scale=5.0, mode=mode, **CFG)
+    W = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    B, R, n, T = 5, 11, 4, CFG['T']
+    fc, att = co.make_inputs(B, R, CFG['F_fc'], CFG['F_att'], seed=4)
+    masks = _region_masks(B, R, clip)
+    Rc = int(masks.sum(1).max())
+    gts = cdo.make_refs(B, CFG['V'], seed=2)
+    df, ref_len = cdo.build_document_frequency(cdo.make_refs(200, CFG['V'], seed=4))
+    table = b200.rewards.CiderDTable(df, ref_len)
+    model.train()
+    res = model.scst_step(fc.cuda(), att.cuda(), gts, table, n, drop_prob=0.5, seed=77, att_masks=masks.cuda())
+    torch.cuda.synchronize()
+    sample_seq, greedy_seq = res['sample_seq'].cpu(), res['greedy_seq'].cpu()
+    og, _ = co.sample(fam, fc, att, masks)
+    assert torch.equal(greedy_seq, og)
+    Wg = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    fam_g = co.Family('updown', Wg, T)
+    fam_g.drop = _dropout_masks(b200, 77, 0.5, B, Rc, B * n, T, CFG['E'], CFG['H'])
+    _, lp = co.sample(fam_g, fc, att, masks, sample_method='sample', sample_n=n, forced_tokens=sample_seq)
+    reward, _ = cdo.self_critical_reward(greedy_seq.numpy(), gts, sample_seq.numpy(), df, ref_len)
+    loss = co.reward_criterion(lp, sample_seq, torch.from_numpy(reward).float())
+    loss.backward()
+    assert float((res['sample_logprobs'].cpu() - lp.detach()).abs().max()) < LOGP_TOL
+    assert abs(float(res['loss']) - float(loss)) < LOGP_TOL
+    _check_grads(model, res['grads'], {k: v.grad for k, v in Wg.items()})
+
+
+def test_xe_step_gradients_with_region_masks():
+    import imagecaptioning.pytorch_b200 as b200
+    model, _ = build_pair('updown', seed=31, logit_scale=5.0, mode='tc_f16x3', **CFG)
+    W = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    B, R, spi, T = 4, 9, 3, CFG['T']
+    fc, att = co.make_inputs(B, R, CFG['F_fc'], CFG['F_att'], seed=6)
+    masks = _region_masks(B, R, True)
+    Rc = int(masks.sum(1).max())
+    labels, lmasks = _labels(B, spi, CFG['V'], T + 2, seed=9, short=True)
+    model.train()
+    res = model.xe_step(fc.cuda(), att.cuda(), labels.cuda(), lmasks.cuda(), label_smoothing=0.1, drop_prob=0.5, seed=78, att_masks=masks.cuda())
+    torch.cuda.synchronize()
+    Wg = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    fam = co.Family('updown', Wg, T)
+    fam.drop = _dropout_masks(b200, 78, 0.5, B, Rc, B * spi, T + 1, CFG['E'], CFG['H'])
+    lp = co.forward_teacher(fam, fc, att, labels[..., :-1], masks)
+    tl, tm = labels[..., 1:].reshape(B * spi, -1), lmasks[..., 1:].reshape(B * spi, -1)
+    loss = co.label_smoothing_loss(lp, tl, tm, 0.1)
+    loss.backward()
+    assert float((res['logprobs'].cpu() - lp.detach()).abs().max()) < LOGP_TOL
+    assert abs(float(res['loss']) - float(loss)) < LOGP_TOL
+    _check_grads(model, res['grads'], {k: v.grad for k, v in Wg.items()})
+
+
+@pytest.mark.parametrize('clip', [False, True])
+def test_aoa_scst_step_gradients_with_region_masks(clip):
+    """AoANet with variable region counts: masked refiner self-attention keys, masked mean pooling (AoAModel.py:216-219) and masked decoder
+    attention keys, every gradient against autograd through the oracle with all dropout masks replayed."""
+    import imagecaptioning.pytorch_b200 as b200
+    from oracle import ciderd_oracle as cdo
+    heads = 4
+    model, fam = build_pair('aoa', seed=21, logit_scale=5.0, mode='tc_f16x3', heads=heads, **AOA_CFG)
+    W = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    B, R, n, T = 3, 9, 3, AOA_CFG['T']
+    E, H = AOA_CFG['E'], AOA_CFG['H']
+    fc, att = co.make_inputs(B, R, AOA_CFG['F_fc'], AOA_CFG['F_att'], seed=4)
+    masks = _region_masks(B, R, clip)
+    Rc = int(masks.sum(1).max())
+    gts = cdo.make_refs(B, AOA_CFG['V'], seed=2)
+    df, ref_len = cdo.build_document_frequency(cdo.make_refs(200, AOA_CFG['V'], seed=4))
+    table = b200.rewards.CiderDTable(df, ref_len)
+    p_lm, p_at, p_aoa, p_sub = 0.5, 0.1, 0.3, 0.1
+    model.train()
+    res = model.scst_step(fc.cuda(), att.cuda(), gts, table, n, drop_prob=p_lm, seed=4322, drop_attn=p_at, drop_aoa=p_aoa, drop_sublayer=p_sub, ctx_drop=1,
+                          att_masks=masks.cuda())
+    torch.cuda.synchronize()
+    seq = res['sample_seq'].cpu()
+    og, _ = co.sample(fam, fc, att, masks)
+    assert torch.equal(res['greedy_seq'].cpu(), og)
+    Wg = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    fam_g = co.Family('aoa', Wg, T, heads=heads)
+    fam_g.drop = _aoa_masks(b200, 4322, B, Rc, B * n, T, E, H, heads, p_lm, p_at, p_aoa, p_sub)
+    _, lp = co.sample(fam_g, fc, att, masks, sample_method='sample', sample_n=n, forced_tokens=seq)
+    reward, _ = cdo.self_critical_reward(og.numpy(), gts, seq.numpy(), df, ref_len)
+    loss = co.reward_criterion(lp, seq, torch.from_numpy(reward).float())
+    loss.backward()
+    assert float((res['sample_logprobs'].cpu() - lp.detach()).abs().max()) < LOGP_TOL
+    assert abs(float(res['loss']) - float(loss)) < LOGP_TOL
+    _check_grads(model, res['grads'], {k: v.grad for k, v in Wg.items()})
