@@ -533,6 +533,8 @@ struct AoaTrainArgs {
     long long* sample_seq = nullptr; long long* greedy_seq = nullptr; float* reward = nullptr;
     const long long* forced = nullptr;
     const float* mask = nullptr;           // [B, R] region mask or null
+    float ss_prob = 0.f;
+    long long* tokens_used = nullptr;
     const long long* labels = nullptr; long ld_labels = 0; const float* masks = nullptr; long ld_masks = 0;
     float* logprobs = nullptr; float* loss = nullptr;
 };
@@ -616,7 +618,12 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     CAPB_CHECK_CUDA(cudaMemsetAsync(e->d.tokens, 0, sizeof(int) * N, st));
     for (int t = 0; t < T; ++t) {
         int* tok = tp.tok + (long)t * N;
-        if (ta.xe) { if (load_token_column_launch(ta.labels, ta.ld_labels, t, N, tok, st)) return 1; }
+        if (ta.xe) {
+            if (t >= 1 && ta.ss_prob > 0.f) {      // scheduled sampling (AttModel.py:145-154)
+                if (ss_select_launch(N, V1, sample_logprobs + (long)(t - 1) * V1, ld_lp, ta.labels, ta.ld_labels, t, seed, ta.ss_prob, tok, st)) return 1;
+            } else if (load_token_column_launch(ta.labels, ta.ld_labels, t, N, tok, st)) return 1;
+            if (ta.tokens_used != nullptr && store_token_column_launch(tok, N, ta.tokens_used, ta.Tl, t, st)) return 1;
+        }
         else CAPB_CHECK_CUDA(cudaMemcpyAsync(tok, e->d.tokens, sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
         float* xt = tp.xt + (long)t * N * E;
         float* x1c = tp.x1c + (long)t * NH;
@@ -832,6 +839,7 @@ extern "C" int capb200_aoa_xe_step(capb200_aoa_engine* e, const float* att, int 
     ta.n = opts->seq_per_img; ta.T = opts->steps; ta.Tl = label_cols - 1; ta.p_lm = p_lm; ta.p_at = p_at; ta.p_aoa = p_aoa; ta.p_sub = p_sub;
     ta.upstream = opts->upstream; ta.ctx_drop = opts->ctx_drop; ta.seed = opts->seed; ta.smoothing = opts->label_smoothing;
     ta.labels = labels; ta.ld_labels = label_cols; ta.masks = masks; ta.ld_masks = label_cols; ta.logprobs = logprobs; ta.loss = loss;
-    ta.mask = opts->att_masks;
+    ta.mask = opts->att_masks; ta.ss_prob = opts->ss_prob; ta.tokens_used = opts->tokens_used;
+    CAPB_REQUIRE(ta.ss_prob >= 0.f && ta.ss_prob <= 1.f, "ss_prob must be in [0, 1]");
     return aoa_train_step(e, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }

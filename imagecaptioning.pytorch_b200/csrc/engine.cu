@@ -34,6 +34,16 @@ __global__ void capb_load_token_column_kernel(const long long* src, long ld, int
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = (int)src[(long)i * ld + col];
 }
+__global__ void capb_store_token_column_kernel(const int* src, int n, long long* dst, long ld, int col) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[(long)i * ld + col] = src[i];
+}
+int store_token_column_launch(const int* src, int n, long long* dst, long ld, int col, cudaStream_t st) {
+    if (n <= 0) return 0;
+    capb_store_token_column_kernel<<<cdiv(n, 256), 256, 0, st>>>(src, n, dst, ld, col);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 int fill_int_launch(int* p, int n, int v, cudaStream_t st) {
     if (n <= 0) return 0;
     capb_fill_int_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, n, v);
@@ -884,6 +894,8 @@ struct TrainArgs {
     long long* sample_seq = nullptr; long long* greedy_seq = nullptr; float* reward = nullptr;
     const long long* forced = nullptr;      // replay these samples instead of drawing
     const float* mask = nullptr;            // [B, R] region mask or null
+    float ss_prob = 0.f;                    // XE: scheduled sampling probability
+    long long* tokens_used = nullptr;       // XE: optional [N, Tl] record of the words fed
     // XE
     const long long* labels = nullptr; long ld_labels = 0; const float* masks = nullptr; long ld_masks = 0;
     float* logprobs = nullptr; float* loss = nullptr;
@@ -952,7 +964,12 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     CAPB_CHECK_CUDA(cudaMemsetAsync(e->d.tokens, 0, sizeof(int) * N, st));
     for (int t = 0; t < T; ++t) {
         int* tok = tp.tok + (long)t * N;
-        if (ta.xe) { if (load_token_column_launch(ta.labels, ta.ld_labels, t, N, tok, st)) return 1; }
+        if (ta.xe) {
+            if (t >= 1 && ta.ss_prob > 0.f) {      // scheduled sampling: draw from the model's own previous prediction (AttModel.py:145-154)
+                if (ss_select_launch(N, V1, sample_logprobs + (long)(t - 1) * V1, ld_lp, ta.labels, ta.ld_labels, t, seed, ta.ss_prob, tok, st)) return 1;
+            } else if (load_token_column_launch(ta.labels, ta.ld_labels, t, N, tok, st)) return 1;
+            if (ta.tokens_used != nullptr && store_token_column_launch(tok, N, ta.tokens_used, ta.Tl, t, st)) return 1;
+        }
         else CAPB_CHECK_CUDA(cudaMemcpyAsync(tok, e->d.tokens, sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
         float* xt = tp.xt + (long)t * N * E;
         float* g1 = tp.g1 + (long)t * N * 4 * H;
@@ -1145,7 +1162,8 @@ extern "C" int capb200_updown_xe_step(capb200_engine* e, const float* fc, const 
     ta.n = opts->seq_per_img; ta.T = opts->steps; ta.Tl = label_cols - 1; ta.p = opts->drop_prob; ta.upstream = opts->upstream; ta.seed = opts->seed;
     ta.smoothing = opts->label_smoothing;
     ta.labels = labels; ta.ld_labels = label_cols; ta.masks = masks; ta.ld_masks = label_cols; ta.logprobs = logprobs; ta.loss = loss;
-    ta.mask = opts->att_masks;
+    ta.mask = opts->att_masks; ta.ss_prob = opts->ss_prob; ta.tokens_used = opts->tokens_used;
+    CAPB_REQUIRE(ta.ss_prob >= 0.f && ta.ss_prob <= 1.f, "ss_prob must be in [0, 1]");
     return updown_train_step(e, fc, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }
 

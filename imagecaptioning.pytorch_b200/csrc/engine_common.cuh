@@ -160,6 +160,7 @@ __global__ void capb_fill_int_kernel(int* p, int n, int v);
 __global__ void capb_load_token_column_kernel(const long long* src, long ld, int col, int n, int* dst);
 int fill_int_launch(int* p, int n, int v, cudaStream_t st);
 int load_token_column_launch(const long long* src, long ld, int col, int n, int* dst, cudaStream_t st);
+int store_token_column_launch(const int* src, int n, long long* dst, long ld, int col, cudaStream_t st);
 
 // ancestors of the current rows at step t of a beam search (valid for positions < t): the table beam_step(t-1) wrote
 inline const int* beam_ancestors(const BeamState& s, int t) { return ((t - 1) & 1) ? s.hist_a : s.hist_b; }

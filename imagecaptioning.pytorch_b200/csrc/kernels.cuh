@@ -32,6 +32,9 @@ int additive_attention_launch(int n_images, int rpi, int R, int A, int H, const 
                               const float* att, long ld_at, const float* mask, long ld_mask, const float* alpha_w, const float* alpha_b,
                               float* score_scratch /*[rows, R]*/, ActView out, cudaStream_t stream, float* alpha_out = nullptr /*[rows, R]*/);
 int mask_rows_launch(ActView x, int n_images, int R, int cols, const float* mask, long ld_mask, cudaStream_t stream);
+// scheduled sampling: tok_out[r] = label[r, col] or, with probability prob, a draw from exp(prev_logp[r, :])
+int ss_select_launch(int rows, int V1, const float* prev_logp, long ld, const long long* labels, long ld_labels, int col, unsigned long long seed, float prob,
+                     int* tok_out, cudaStream_t stream);
 
 // Edits of a log-prob row before the next word is chosen (capb200_decode_edits in include/capb200.h)
 struct DecodeEdits {

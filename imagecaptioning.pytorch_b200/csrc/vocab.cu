@@ -697,6 +697,36 @@ __global__ void __launch_bounds__(VT) vocab_stats_stream_kernel(const VocabStepA
     }
 }
 
+// Scheduled sampling (AttModel.py:145-154): with probability `prob` the word fed into step `col` is drawn from the model's own previous
+// prediction exp(logprobs[:, col-1]) instead of the label.  One CTA per row; per-row uniform and the Gumbel-max draw come from the Philox
+// stream (seed, site 6, step col).  Non-differentiable by construction (the reference samples from a detached tensor).
+__global__ void __launch_bounds__(VT) ss_select_kernel(int V1, const float* __restrict__ prev_logp, long ld, const long long* __restrict__ labels,
+                                                      long ld_labels, int col, unsigned long long seed, float prob, int* __restrict__ tok_out) {
+    __shared__ float s_red[VT / 32];
+    __shared__ int s_idx[VT / 32];
+    const int r = blockIdx.x;
+    const uint32_t k0 = (uint32_t)seed ^ 0x6a09e667u, k1 = (uint32_t)(seed >> 32) ^ 0xbb67ae85u;
+    const uint32_t ubits = philox_first(0xffffffffu, (uint32_t)r, (uint32_t)col, 6u, k0, k1);
+    const float u_row = ((float)(ubits >> 9) + 0.5f) * (1.0f / 8388608.0f);
+    if (!(u_row < prob)) {                       // keep the label (uniform over the whole CTA: no divergence at the barriers below)
+        if (threadIdx.x == 0) tok_out[r] = (int)labels[(long)r * ld_labels + col];
+        return;
+    }
+    const float* g = prev_logp + (long)r * ld;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int v = threadIdx.x; v < V1; v += VT) {
+        const uint32_t bits = philox_first((uint32_t)v, (uint32_t)r, (uint32_t)col, 6u, k0, k1);
+        const float u = ((float)(bits >> 9) + 0.5f) * (1.0f / 8388608.0f);
+        const float x = g[v] - logf(-logf(u));                  // Gumbel-max draw from softmax(logp) = exp(logp)
+        if (x > bv) { bv = x; bi = v; }
+    }
+    float ov;
+    int tok;
+    block_argmax(bv, bi, s_red, s_idx, ov, tok);
+    if (threadIdx.x == 0) tok_out[r] = tok;
+}
+
 __global__ void mask_rows_kernel(ActView x, int R, int cols, const float* __restrict__ mask, long ld_mask) {
     const int row = blockIdx.x;              // row = img * R + r
     const int img = row / R, r = row % R;
@@ -749,6 +779,14 @@ int vocab_step_launch(const VocabStepArgs& a, cudaStream_t stream) {
     if (a.topk <= 2) vocab_step_kernel<2><<<a.rows, VT, smem, stream>>>(a);
     else if (a.topk <= 8) vocab_step_kernel<8><<<a.rows, VT, smem, stream>>>(a);
     else vocab_step_kernel<16><<<a.rows, VT, smem, stream>>>(a);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ss_select_launch(int rows, int V1, const float* prev_logp, long ld, const long long* labels, long ld_labels, int col, unsigned long long seed, float prob,
+                     int* tok_out, cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    ss_select_kernel<<<rows, VT, 0, stream>>>(V1, prev_logp, ld, labels, ld_labels, col, seed, prob, tok_out);
     CAPB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -418,9 +418,10 @@ class B200CaptionModel(nn.Module):
 
     @_on_device
     def _forward(self, fc_feats, att_feats, seq, att_masks=None):
-        """Teacher forcing (AttModel.py:126-164).  Scheduled sampling (ss_prob > 0) is an XE-stage feature."""
-        if self.training and self.ss_prob > 0.0:
-            raise NotImplementedError('scheduled sampling is out of scope of the B200 engine')
+        """Teacher forcing (AttModel.py:126-164).  Scheduled sampling (training with ss_prob > 0) lives in the fused XE step (xe_step /
+        B200LossWrapper), which is what trains; this inference-style call is plain teacher forcing."""
+        if self.training and self.ss_prob > 0.0 and torch.is_grad_enabled():
+            raise NotImplementedError('scheduled sampling runs inside the fused XE step (B200LossWrapper / model.xe_step), not in a bare _forward call')
         lib = self._ensure_engine(fc_feats.device)
         fc = self._f32(fc_feats)
         att, masks = self._clip(att_feats, att_masks)
@@ -577,8 +578,6 @@ class B200UpDownModel(B200CaptionModel):
         """One cross-entropy step on the device (capb200_updown_xe_step): teacher-forced forward over ``labels[..., :-1]`` in train mode,
         LanguageModelCriterion / LabelSmoothing against ``labels[..., 1:]``, ``masks[..., 1:]`` (reduction 'mean'), BPTT.
         Returns {'loss', 'logprobs' [N, L-1, V+1], 'grads' {parameter: gradient}, 'seed'}."""
-        if self.ss_prob > 0.0:
-            raise NotImplementedError('scheduled sampling is out of scope of the B200 engine')
         lib = self._ensure_engine(fc_feats.device)
         fc = self._f32(fc_feats)
         att, region_masks = self._clip(att_feats, att_masks)
@@ -602,10 +601,14 @@ class B200UpDownModel(B200CaptionModel):
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         p = self.drop_prob_lm if drop_prob is None else drop_prob
-        xo = _lib.XeOpts(N // B, steps, seed, float(p), float(label_smoothing), float(upstream), _lib.ptr(region_masks))
+        # scheduled sampling (self.ss_prob, set by the trainer: tools/train.py:147-148): the words actually fed are returned as 'tokens_used'
+        tokens_used = torch.zeros(N, Lc - 1, dtype=torch.long, device=dev) if self.ss_prob > 0.0 else None
+        xo = _lib.XeOpts(N // B, steps, seed, float(p), float(label_smoothing), float(upstream), _lib.ptr(region_masks), float(self.ss_prob),
+                         _lib.ptr(tokens_used))
         _lib.check(lib.capb200_updown_xe_step(self._engine, _lib.ptr(fc), _lib.ptr(att), B, R, ctypes.byref(xo), _lib.ptr(labels), _lib.ptr(masks), Lc,
                                               ctypes.byref(g), _lib.ptr(logprobs), _lib.ptr(loss), _lib.current_stream()), 'updown_xe_step')
-        return {'loss': loss[0], 'logprobs': logprobs, 'grads': {table_params[k]: grads[k] for k in table_params}, 'seed': seed, 'flat': fg}
+        return {'loss': loss[0], 'logprobs': logprobs, 'grads': {table_params[k]: grads[k] for k in table_params}, 'seed': seed, 'flat': fg,
+                'tokens_used': tokens_used}
 
 
 class _MaxoutCoreParams(nn.Module):
@@ -933,8 +936,6 @@ class B200AoAModel(B200CaptionModel):
     def xe_step(self, fc_feats, att_feats, labels, masks, label_smoothing=0.0, drop_prob=None, seed=None, upstream=1.0, drop_attn=0.1, drop_aoa=None,
                 drop_sublayer=0.1, ctx_drop=None, att_masks=None):
         """One cross-entropy step of AoANet on the device (capb200_aoa_xe_step); arguments and result as B200UpDownModel.xe_step."""
-        if self.ss_prob > 0.0:
-            raise NotImplementedError('scheduled sampling is out of scope of the B200 engine')
         lib = self._ensure_engine(att_feats.device)
         att, region_masks = self._clip(att_feats, att_masks)
         dev = att.device
@@ -956,13 +957,14 @@ class B200AoAModel(B200CaptionModel):
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         p = self.drop_prob_lm if drop_prob is None else drop_prob
+        tokens_used = torch.zeros(N, Lc - 1, dtype=torch.long, device=dev) if self.ss_prob > 0.0 else None
         xo = _lib.AoaXeOpts(N // B, steps, seed, float(label_smoothing), float(upstream), float(p), float(drop_attn),
                             float(self.dropout_aoa if drop_aoa is None else drop_aoa), float(drop_sublayer), int(self.ctx_drop if ctx_drop is None else ctx_drop),
-                            _lib.ptr(region_masks))
+                            _lib.ptr(region_masks), float(self.ss_prob), _lib.ptr(tokens_used))
         _lib.check(lib.capb200_aoa_xe_step(self._engine, _lib.ptr(att), B, R, ctypes.byref(xo), _lib.ptr(labels), _lib.ptr(masks), Lc, ctypes.byref(g),
                                            _lib.ptr(logprobs), _lib.ptr(loss), _lib.current_stream()), 'aoa_xe_step')
         return {'loss': loss[0], 'logprobs': logprobs, 'grads': {prm: fg.by_name['/'.join(str(x) for x in path)] for path, prm in slots}, 'seed': seed,
-                'flat': fg}
+                'flat': fg, 'tokens_used': tokens_used}
 
     def _ensure_engine(self, device):
         lib = self._enter_device(device)

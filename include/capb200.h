@@ -325,6 +325,9 @@ typedef struct {
     float label_smoothing;     /* 0 = LanguageModelCriterion, > 0 = LabelSmoothing(smoothing) */
     float upstream;
     const float* att_masks;    /* optional [B, R] region mask, see capb200_scst_opts */
+    float ss_prob;             /* scheduled sampling (AttModel.py:145-154): from the second step on, each row's input word is drawn from the model's
+                                  previous prediction with this probability; 0 = teacher forcing */
+    long long* tokens_used;    /* optional [N, label_cols-1] int64: the words actually fed (labels, or the draws where scheduled sampling hit) */
 } capb200_xe_opts;
 /* labels[N, label_cols] int64 (column 0 = BOS = 0), masks[N, label_cols] fp32, N = B * seq_per_img.
  * Outputs: logprobs[N, label_cols-1, V+1] (caller zero-fills; columns >= steps stay zero), loss[1], every grads buffer overwritten. */
@@ -385,6 +388,8 @@ typedef struct {
     float drop_prob_lm, drop_attn, drop_aoa, drop_sublayer;
     int ctx_drop;
     const float* att_masks;    /* optional [B, R] region mask */
+    float ss_prob;             /* scheduled sampling, see capb200_xe_opts */
+    long long* tokens_used;
 } capb200_aoa_xe_opts;
 int capb200_aoa_xe_step(capb200_aoa_engine* e, const float* att, int B, int R, const capb200_aoa_xe_opts* opts, const long long* labels,
                         const float* masks, int label_cols, const capb200_aoa_grads* grads, float* logprobs, float* loss, void* stream);

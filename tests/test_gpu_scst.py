@@ -481,3 +481,48 @@ def test_aoa_scst_step_gradients_with_region_masks(clip):
     assert float((res['sample_logprobs'].cpu() - lp.detach()).abs().max()) < LOGP_TOL
     assert abs(float(res['loss']) - float(loss)) < LOGP_TOL
     _check_grads(model, res['grads'], {k: v.grad for k, v in Wg.items()})
+
+
+@pytest.mark.parametrize('family', ['updown', 'aoa'])
+def test_xe_step_scheduled_sampling(family):
+    """Scheduled sampling (AttModel.py:145-154) inside the fused XE step: from the second column on a row's input word is drawn from the model's
+    previous prediction with probability ss_prob.  The draw cannot share torch's random stream, so the test checks (a) the hit rate, (b) that
+    the draws follow exp(previous log-probs) (their mean probability against the expectation sum p^2), and (c) loss, log-probs and every
+    gradient against autograd through the oracle fed with the words the engine actually used."""
+    import imagecaptioning.pytorch_b200 as b200
+    heads = 4
+    cfg = AOA_CFG if family == 'aoa' else CFG
+    model, _ = build_pair(family, seed=21, logit_scale=5.0, mode='tc_f16x3', heads=heads, **cfg)
+    W = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    B, R, spi, T = 6, 9, 5, cfg['T']
+    fc, att = co.make_inputs(B, R, cfg['F_fc'], cfg['F_att'], seed=4)
+    labels, masks = _labels(B, spi, cfg['V'], T + 2, seed=12)
+    model.train()
+    model.ss_prob = 0.4
+    kw = dict(drop_attn=0.0, drop_aoa=0.0, drop_sublayer=0.0, ctx_drop=1) if family == 'aoa' else {}
+    res = model.xe_step(fc.cuda(), att.cuda(), labels.cuda(), masks.cuda(), label_smoothing=0.0, drop_prob=0.0, seed=991, **kw)
+    torch.cuda.synchronize()
+    used = res['tokens_used'].cpu()
+    lab = labels[..., :-1].reshape(B * spi, -1)
+    steps = int(((lab[:, 1:].sum(0) == 0).nonzero()[0]) + 1) if bool((lab[:, 1:].sum(0) == 0).any()) else lab.shape[1]
+    assert torch.equal(used[:, 0], lab[:, 0])                                   # the first input is always <bos>
+    cand = used[:, 1:steps] != lab[:, 1:steps]
+    rate = float(cand.float().mean())
+    n_cells = cand.numel()
+    assert abs(rate - 0.4) < 4 * (0.4 * 0.6 / n_cells) ** 0.5 + 0.08, rate         # a draw that equals the label is not counted: slightly below 0.4
+    # (c) replay in the oracle with the words that were fed
+    Wg = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    fam = co.Family(family, Wg, T, heads=heads)
+    lp = co.forward_teacher(fam, fc, att, used.reshape(B, spi, -1))
+    tl, tm = labels[..., 1:].reshape(B * spi, -1), masks[..., 1:].reshape(B * spi, -1)
+    loss = co.language_model_criterion(lp, tl, tm)
+    loss.backward()
+    assert float((res['logprobs'].cpu() - lp.detach())[:, :steps].abs().max()) < LOGP_TOL
+    assert abs(float(res['loss']) - float(loss)) < LOGP_TOL
+    _check_grads(model, res['grads'], {k: v.grad for k, v in Wg.items()})
+    # (b) the replaced words were drawn from exp(logprobs[:, t-1])
+    p_prev = lp.detach()[:, :steps - 1].exp()
+    drawn = p_prev.gather(2, used[:, 1:steps].unsqueeze(2)).squeeze(2)[cand]
+    expect = (p_prev ** 2).sum(2)[cand]                                          # E[p(draw)] for a draw from p
+    assert abs(float(drawn.mean()) - float(expect.mean())) < 0.15
+    model.ss_prob = 0.0
