@@ -74,7 +74,8 @@ __global__ void iota_div_kernel(int* p, int n, int div) {
 }
 
 
-enum GemmId { G_FC = 0, G_ATT, G_CTX, G_GFC, G_LSTM1, G_H2ATT, G_LSTM2, G_LOGIT, G_CORE, G_COUNT };
+enum GemmId { G_FC = 0, G_ATT, G_CTX, G_GFC, G_LSTM1, G_H2ATT, G_LSTM2, G_LOGIT, G_CORE, G_LSTM2A, G_LSTM2B, G_COUNT };
+constexpr int G_REPORTED = 9;      // ids exposed through capb200_engine_read_profile (the split language-LSTM launches are folded into G_LSTM2)
 
 }  // namespace
 }  // namespace capb200
@@ -121,6 +122,11 @@ struct capb200_engine {
     size_t tape_bytes = 0;
     Tf32Context* tf32 = nullptr;       // tensor maps + transposed operands of the training GEMMs (tensor-core modes)
     cudaEvent_t grad_events[2] = {nullptr, nullptr};   // caller-owned: recorded when a gradient group is complete (capb200_engine_set_grad_events)
+    // Optional overlap of the additive attention (SFU / FMA pipes) with the tensor-core work of the language LSTM that does not depend on it:
+    // gates = W_h h_att + W_hh h_lang_prev (side stream, while the attention runs) and then + W_a att_res with the fused cell (main stream).
+    bool split_lang = false;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     // optional per-GEMM device timing (cudaEvent pairs on the launching stream), off by default
     bool profiling = false;
@@ -371,10 +377,34 @@ int core_step(capb200_engine* e, int rows, int rpi, const int* tokens, const int
             g.epi.C = e->att_h.v.f; g.epi.ldc = e->att_h.v.ld;
             if (run_gemm(e, G_H2ATT, g, e->capRows, st)) return 1;
         }
+        const bool split = e->split_lang && e->tc && e->side != nullptr;
+        if (split) {   // fork: the part of the language-LSTM gates that does not need the attention result, on the side stream
+            CAPB_CHECK_CUDA(cudaEventRecord(e->ev_fork, st));
+            CAPB_CHECK_CUDA(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+            GemmProblem g;
+            g.M = rows; g.N = 4 * H; g.nseg = 2;
+            g.seg[0] = seg_of(e->h0_out.v, w.lang_lstm_w_ih + H, 2 * H, e->p_l_ih_h, H);
+            g.seg[1] = seg_of(e->h1_in.v, w.lang_lstm_w_hh, H, e->p_l_hh, H);
+            g.epi.bias = e->bsum_lang_il;
+            g.epi.C = e->gates.v.f; g.epi.ldc = e->gates.v.ld;          // gate-interleaved partial sums [rows, 4H]
+            if (run_gemm(e, G_LSTM2A, g, e->capRows, e->side)) return 1;
+            CAPB_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
+        }
         e->launches += 2;
         if (additive_attention_launch(n_images, rpi, R, A, H, e->att_h.v.f, e->att_h.v.ld, e->p_att.v.f, e->p_att.v.ld, e->att_e.v.f, e->att_e.v.ld,
                                       mask, R, w.alpha_w, w.alpha_b, e->att_score, e->att_res.v, st)) return 1;
-        {   // language LSTM gates: [att_res | h_att | h_lang_prev]
+        if (split) {   // join: add the attention term and apply the cell
+            CAPB_CHECK_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
+            GemmProblem g;
+            g.M = rows; g.N = 4 * H; g.nseg = 1;
+            g.seg[0] = seg_of(e->att_res.v, w.lang_lstm_w_ih, 2 * H, e->p_l_ih_a, H);
+            g.epi.residual = e->gates.v.f; g.epi.ld_res = e->gates.v.ld;
+            g.epi.lstm = 1; g.epi.H = H;
+            g.epi.c_prev = e->c1[cur]; g.epi.ld_cprev = e->ld_c; g.epi.src_row = src_row;
+            g.epi.c_out = e->c1[nxt]; g.epi.ld_cout = e->ld_c;
+            g.epi.h_f = e->h1_out.v.f; g.epi.h_hi = e->h1_out.v.hi; g.epi.h_lo = e->h1_out.v.lo; g.epi.ld_h = e->h1_out.v.ld;
+            if (run_gemm(e, G_LSTM2B, g, e->capRows, st)) return 1;
+        } else {   // language LSTM gates: [att_res | h_att | h_lang_prev]
             GemmProblem g;
             g.M = rows; g.N = 4 * H; g.nseg = 3;
             g.seg[0] = seg_of(e->att_res.v, w.lang_lstm_w_ih, 2 * H, e->p_l_ih_a, H);
@@ -477,6 +507,12 @@ capb200_engine* capb200_engine_create(const capb200_model_cfg* cfg) {
     e->T = cfg->seq_length;
     e->mode = cfg->numeric_mode;
     e->tc = cfg->numeric_mode != CAPB200_MODE_SIMT_FP32;
+    if (e->tc && getenv("CAPB200_SPLIT_LANG") != nullptr && atoi(getenv("CAPB200_SPLIT_LANG")) != 0) {
+        if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) == cudaSuccess) e->split_lang = true;
+        else (void)cudaGetLastError();
+    }
     return e;
 }
 
@@ -490,6 +526,9 @@ void capb200_engine_destroy(capb200_engine* e) {
     cudaFree(e->d.slab);
     cudaFree(e->tape);
     tf32_context_destroy(e->tf32);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->side) cudaStreamDestroy(e->side);
     delete e;
 }
 
@@ -502,7 +541,7 @@ int capb200_engine_set_profiling(capb200_engine* e, int enable) {
 }
 
 int capb200_engine_read_profile(capb200_engine* e, int reset, double* ms, double* flops, long* calls, int n) {
-    CAPB_REQUIRE(e != nullptr && n >= G_COUNT, "need room for 9 GEMM ids");
+    CAPB_REQUIRE(e != nullptr && n >= G_REPORTED, "need room for 9 GEMM ids");
     CAPB_CHECK_CUDA(cudaDeviceSynchronize());
     for (size_t i = 0; i < e->ev_ids.size(); ++i) {
         float t = 0.f;
@@ -514,7 +553,11 @@ int capb200_engine_read_profile(capb200_engine* e, int reset, double* ms, double
     e->ev_ids.clear();
     e->ev_flops.clear();
     e->ev_used = 0;
-    for (int i = 0; i < G_COUNT; ++i) {
+    for (int i = G_LSTM2A; i <= G_LSTM2B; ++i) {       // the split language-LSTM launches report under the language-LSTM id
+        e->prof_ms[G_LSTM2] += e->prof_ms[i]; e->prof_flops[G_LSTM2] += e->prof_flops[i]; e->prof_calls[G_LSTM2] += e->prof_calls[i];
+        e->prof_ms[i] = 0; e->prof_flops[i] = 0; e->prof_calls[i] = 0;
+    }
+    for (int i = 0; i < G_REPORTED; ++i) {
         if (ms) ms[i] = e->prof_ms[i];
         if (flops) flops[i] = e->prof_flops[i];
         if (calls) calls[i] = e->prof_calls[i];

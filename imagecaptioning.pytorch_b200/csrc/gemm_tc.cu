@@ -9,13 +9,13 @@
 // one fp32 TMEM accumulator:  hi*lo + lo*hi + hi*hi  (the lo*lo term, <= 2^-22 relative, is dropped).
 // PASSES == 1 is the throughput mode (hi plane only) and is never used for parity claims.
 //
-// Structure (one 128 x BN output tile per CTA, 256 threads):
+// Structure (one 128 x BN output tile per CTA, 384 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes [64 k x 128 rows] (128B swizzle) for A_hi, A_lo, W_hi,
 //               W_lo of the current K-block into a STAGES-deep shared-memory ring, mbarrier complete_tx signalling.
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) straight from
 //               shared-memory descriptors; tcgen05.commit releases ring slots and finally signals the epilogue.
 //   warp 2      allocates / frees the TMEM accumulator columns.
-//   warps 4..7  epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused bias / row-bias / ReLU, fp32 store and
+//   warps 4..11 epilogue (two warps per TMEM lane quadrant, half of the columns each): tcgen05.ld, fused bias / row-bias / ReLU, fp32 store and
 //               (optionally) a split-fp16 copy so the next GEMM can consume the result without a conversion pass.
 // K-segments (up to 3 activation/weight pairs) are walked back to back so concatenated LSTM inputs are never built.
 #include <cstdlib>
@@ -29,6 +29,11 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;   // fp16 elements: one 128-byte swizzle row
+// Two epilogue warps per TMEM lane quadrant (warps 4..7 drain the lower half of the accumulator columns, warps 8..11 the upper half): the
+// epilogue of the LAST tile of a CTA cannot overlap a main loop, and the fused LSTM-cell epilogue is LSU-bound (one row per thread), so
+// doubling the threads that drain it halves the exposed tail of every GEMM launch.
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + 32 * kEpiWarps;
 
 struct TcParams {
     CUtensorMap a_hi[kMaxSeg];
@@ -83,7 +88,8 @@ struct TcCfg {
 
 // Drains one 128 x BN accumulator (TMEM columns tmem_acc .. tmem_acc + BN) into global memory: thread (q, lane) owns tile row q*32 + lane.
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_acc, int m0, int n0, int q, int lane, bool vec4, bool vec2h, bool lstm_vec) {
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_acc, int m0, int n0, int q, int lane, bool vec4, bool vec2h, bool lstm_vec,
+                                              int c_begin, int c_end) {
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < p.M;
     const float* rb = (p.row_bias != nullptr && row_ok) ? p.row_bias + (long)(row / p.rows_per_group) * p.ld_row_bias : nullptr;
@@ -96,7 +102,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
                         (p.gather_bias == nullptr || ((reinterpret_cast<uintptr_t>(p.gather_bias) & 15) == 0 && (p.ld_gb & 3) == 0)) &&
                         (p.residual == nullptr || ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 && (p.ld_res & 3) == 0));
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
+    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
         uint32_t r[16];
         __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the guarded stores of the previous chunk
         ptx::tmem_ld_32x32b_x16(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
@@ -227,7 +233,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
 // single-CTA kernel).  Stage release is the mirror image: tcgen05.commit multicasts the "slot free" arrival to every CTA
 // that writes into this CTA's slot.
 template <int BN, int PASSES, int CX, int CY>
-__global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
     using Cfg = TcCfg<BN, PASSES>;
     constexpr bool kCluster = (CX * CY) > 1;
     extern __shared__ uint8_t smem_raw[];
@@ -271,7 +277,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tmem_full_bar[i], 1);
-            ptx::mbar_init(&tmem_empty_bar[i], 128);         // every epilogue thread releases the accumulator
+            ptx::mbar_init(&tmem_empty_bar[i], 32 * kEpiWarps);   // every epilogue thread releases the accumulator
         }
         ptx::fence_mbar_init();
     }
@@ -381,7 +387,12 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             const int n0 = ((ct / cl_m) * CX + cx) * BN;
             ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
             ptx::tc_fence_after_sync();
-            epilogue_tile<BN>(p, tmem_base + buf * BN, m0, n0, q, lane, vec4, vec2h, lstm_vec);
+            // column split between the two warps of a lane quadrant, in 16-column chunks
+            constexpr int kChunks = BN / 16, kLow = (kChunks + 1) / 2;
+            const int grp = (warp - 4) >> 2;
+            const int c_begin = (kEpiWarps == 8 && grp == 1) ? kLow * 16 : 0;
+            const int c_end = (kEpiWarps == 8 && grp == 0) ? kLow * 16 : BN;
+            epilogue_tile<BN>(p, tmem_base + buf * BN, m0, n0, q, lane, vec4, vec2h, lstm_vec, c_begin, c_end);
             __syncwarp();
             ptx::tc_fence_before_sync();
             ptx::mbar_arrive(&tmem_empty_bar[buf]);            // accumulator drained: the MMA warp may reuse it
@@ -418,7 +429,7 @@ struct TcPairCfg {
 };
 
 template <int BN, int PASSES>
-__global__ void __launch_bounds__(256, 1) gemm_tc_pair_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_pair_kernel(const __grid_constant__ TcParams p) {
     using Cfg = TcPairCfg<BN, PASSES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -453,7 +464,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_pair_kernel(const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tmem_full_bar[i], 1);
-            ptx::mbar_init(&tmem_empty_bar[i], 256);           // 128 epilogue threads of each CTA
+            ptx::mbar_init(&tmem_empty_bar[i], 2 * 32 * kEpiWarps);   // the epilogue threads of both CTAs
         }
         ptx::fence_mbar_init();
     }
@@ -547,7 +558,12 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_pair_kernel(const __grid_const
             const int n0 = (pt / cl_m) * BN;
             ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
             ptx::tc_fence_after_sync();
-            epilogue_tile<BN>(p, tmem_base + buf * BN, m0, n0, q, lane, vec4, vec2h, lstm_vec);
+            // column split between the two warps of a lane quadrant, in 16-column chunks
+            constexpr int kChunks = BN / 16, kLow = (kChunks + 1) / 2;
+            const int grp = (warp - 4) >> 2;
+            const int c_begin = (kEpiWarps == 8 && grp == 1) ? kLow * 16 : 0;
+            const int c_end = (kEpiWarps == 8 && grp == 0) ? kLow * 16 : BN;
+            epilogue_tile<BN>(p, tmem_base + buf * BN, m0, n0, q, lane, vec4, vec2h, lstm_vec, c_begin, c_end);
             __syncwarp();
             ptx::tc_fence_before_sync();
             ptx::mbar_arrive_leader(&tmem_empty_bar[buf]);
@@ -611,7 +627,7 @@ int launch_cfg(const TcParams& prm, cudaStream_t stream) {
     dim3 grid(CX * P, CY);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -640,7 +656,7 @@ int launch_pair(const TcParams& prm, cudaStream_t stream) {
     const int P = n_ptiles < 74 ? n_ptiles : 74;                       // one pair per TPC
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * P, 1);                                      // the pair must be adjacent in x (clusterDim.x = 2)
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
