@@ -155,6 +155,7 @@ int pack_gates(capb200_aoa_engine* e, const float* w, long ldw, int H, int cols,
 }
 
 int prepare(capb200_aoa_engine* e, const float* att, const float* mask, int B, int R, cudaStream_t st) {
+    CAPB_NVTX("capb200 aoa prepare_feature (att_embed, refiner, ctx2att)");
     const int H = e->H, E = e->E, BR = B * R, capBR = e->capB * e->capR;
     const capb200_aoa_weights& w = e->w;
     ActView in; in.f = const_cast<float*>(att); in.ld = e->F;
@@ -572,6 +573,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
 
     // ---- (1) greedy baseline, eval mode: the regular decode path
     if (greedy_baseline) {
+        CAPB_NVTX("capb200 aoa scst: greedy baseline (eval mode)");
         capb200_sample_opts so; memset(&so, 0, sizeof(so)); so.edits.unk_col = -1; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.seed = 0; so.steps = T;
         CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, st));
         CAPB_CHECK_CUDA(cudaMemsetAsync(greedy_seq, 0, sizeof(long long) * (size_t)B * T, st));
@@ -591,6 +593,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     (void)wmode;
 
     // ---- (2) train-mode prologue: att_embed (+dropout), six refiner layers, final norm, mean pooling, ctx2att
+    nvtxRangePushA("capb200 aoa train step: forward on the tape");
     if (sk.lin(att, F, w.att_embed_w, F, w.att_embed_b, tp.x[0], H, (int)BR, H, F, 0)) return 1;
     if (relu_copy_launch(tp.x[0], BR * H, act(tp.x[0], H), st)) return 1;
     if (dropout_apply_launch(tp.x[0], (int)BR, H, H, seed, 1, 0, p_lm, st)) return 1;
@@ -679,6 +682,8 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     }
 
     // ---- (4) reward and loss
+    nvtxRangePop();
+    CAPB_NVTX("capb200 aoa train step: reward, loss, backward, weight gradients");
     if (ta.xe) {
         if (xe_loss_backward_launch(sample_logprobs, ld_lp, ta.labels, ta.ld_labels, ta.masks, ta.ld_masks, N, T, ta.Tl, V1, ta.smoothing, ta.upstream,
                                     tp.mask_sum, tp.item_loss, tp.DL, loss, st)) return 1;

@@ -276,6 +276,7 @@ int run_gemm(capb200_engine* e, int id, GemmProblem& g, int plan_rows, cudaStrea
 
 // ---- prologue: _prepare_feature ---------------------------------------------------------------------------------------
 int prepare(capb200_engine* e, const float* fc, const float* att, const float* mask, int B, int R, cudaStream_t st) {
+    CAPB_NVTX("capb200 prepare_feature (fc_embed, att_embed, ctx2att)");
     const int H = e->H, E = e->E, A = e->A;
     const bool updown = e->cfg.family == CAPB200_FAMILY_UPDOWN;
     const capb200_weights& w = e->w;
@@ -974,6 +975,7 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     Arena ar; ar.base = e->tape;
     Tape tp; layout_tape(tp, ar, B, R, N, T, E, H, A, V1, Fa, Ff);
     if (!ta.xe && ta.greedy_baseline) {
+        CAPB_NVTX("capb200 scst: greedy baseline (eval mode)");
         capb200_sample_opts so; memset(&so, 0, sizeof(so)); so.edits.unk_col = -1; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.seed = 0; so.steps = T;
         CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, st));
         CAPB_CHECK_CUDA(cudaMemsetAsync(greedy_seq, 0, sizeof(long long) * (size_t)B * T, st));
@@ -987,6 +989,7 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     sk.ctx = e->tf32;
 
     // ---- (2) train-mode prologue: fc_embed / att_embed with dropout, ctx2att, per-image gate term
+    nvtxRangePushA("capb200 train step: forward on the tape");
     const long BR = (long)B * R;
     if (sk.lin(fc, Ff, w.fc_embed_w, Ff, w.fc_embed_b, tp.fc_e, H, B, H, Ff, 0)) return 1;
     if (relu_copy_launch(tp.fc_e, (long)B * H, ActView{tp.fc_e, nullptr, nullptr, H}, st)) return 1;
@@ -1073,6 +1076,8 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     }
 
     // ---- (4) reward and loss
+    nvtxRangePop();
+    CAPB_NVTX("capb200 train step: reward, loss, backward through time, weight gradients");
     const long TN = (long)T * N;
     const capb200_updown_grads& G = *grads;
     if (ta.xe) {

@@ -6,6 +6,7 @@
 #include "../../include/capb200.h"
 #include "common.cuh"
 #include "kernels.cuh"
+#include "nvtx.cuh"
 
 // opaque C handle of the CIDEr-D document-frequency table (shared by the UpDown and AoA training steps)
 struct capb200_cider_table {
@@ -200,6 +201,7 @@ int beam_decode_driver(DecodeBuffers& d, int V1, int T, int B, int beam, int kee
     BeamState s = d.bs;
     s.B = B; s.beam = beam; s.T = T; s.V1 = V1;
     auto run_loop = [&]() -> int {
+        CAPB_NVTX("capb200 beam loop (T steps: core, vocab stats, beam step)");
         CAPB_CHECK_CUDA(cudaMemsetAsync(s.sums, 0, sizeof(float) * B * beam, st));
         CAPB_CHECK_CUDA(cudaMemsetAsync(s.done_cnt, 0, sizeof(int) * B, st));
         CAPB_CHECK_CUDA(cudaMemsetAsync(d.tokens, 0, sizeof(int) * rows, st));      // <bos> = 0
@@ -270,6 +272,7 @@ int beam_decode_driver(DecodeBuffers& d, int V1, int T, int B, int beam, int kee
         if (run_loop()) return 1;
     }
     // all finished beams of every image, best first
+    CAPB_NVTX("capb200 beam finalize + log-prob rows");
     if (beam_finalize_launch(s, beam, d.rec_seq, d.rec_len, d.rec_p, d.rec_raw, d.rec_hist, st)) return 1;
     *launches += 1;
     if (keep == beam) {
@@ -305,6 +308,7 @@ int sample_decode_driver(DecodeBuffers& d, int V1, int T, int rows, int method, 
                          const long long* tokens_in, long ld_tok, long long* seq, float* seq_logprobs, float* picked, CoreFn core, long* launches,
                          cudaStream_t st, const DecodeEdits& ed = DecodeEdits(), float top = 0.f) {
     const bool teacher = method == 3, forced = method == 2;
+    CAPB_NVTX("capb200 sample / teacher-forcing loop");
     CAPB_REQUIRE(ed.unk_col < 0, "UNK suppression is a beam-search option (CaptionModel.py:159-162)");
     if (method == 4) CAPB_REQUIRE(top >= 1.f, "top-k sampling needs k >= 1");
     if (method == 5) CAPB_REQUIRE(top > 0.f && top < 1.f, "nucleus sampling needs 0 < p < 1");
