@@ -57,6 +57,8 @@ struct capb200_aoa_engine {
     size_t tape_bytes = 0;
     Tf32Context* tf32 = nullptr;   // tensor maps + transposed operands of the training GEMMs (tensor-core modes)
     cudaEvent_t grad_events[10] = {};   // caller-owned: recorded when a gradient group is complete (capb200_aoa_set_grad_events)
+    cudaStream_t side = nullptr;        // the greedy baseline of the SCST step runs here, concurrently with the sampling forward
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -328,6 +330,9 @@ void capb200_aoa_destroy(capb200_aoa_engine* e) {
     cudaFree(e->d.slab);
     cudaFree(e->tape);
     tf32_context_destroy(e->tf32);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->side) cudaStreamDestroy(e->side);
     delete e;
 }
 
@@ -482,6 +487,7 @@ struct ATape {
         *d_catd, *d_qkv, *d_ln, *dpre, *stats, *mask_sum, *skinny, *glp, *item_loss;
     size_t skinny_floats;
     double* scores;
+    int *s_tokens, *s_unfinished, *s_forced;   // sampling-loop state (own copies: the greedy baseline runs concurrently on the decode workspace)
 };
 
 void layout_atape(ATape& tp, Arena& a, int B, int R, int N, int T, int E, int H, int heads, int V1) {
@@ -510,6 +516,7 @@ void layout_atape(ATape& tp, Arena& a, int B, int R, int N, int T, int E, int H,
     tp.glp = a.take<float>((long)B * T * V1);
     tp.item_loss = a.take<float>(TN);
     tp.scores = a.take<double>((long)N + B);
+    tp.s_tokens = a.take<int>(N); tp.s_unfinished = a.take<int>(N); tp.s_forced = a.take<int>(N);
 }
 
 // dW[out, in] (+)= dY[rows, out]^T * X[rows, in]
@@ -571,15 +578,32 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     Arena ar; ar.base = e->tape;
     ATape tp; layout_atape(tp, ar, B, R, N, T, E, H, heads, V1);
 
-    // ---- (1) greedy baseline, eval mode: the regular decode path
+    // ---- (1) greedy baseline, eval mode: the regular decode path, on a side stream (joins before the reward): it and the train-mode
+    // sampling forward are independent chains of small latency-bound kernels
+    if (ensure_workspace(e, B, N, R, 1, st)) return 1;         // decode workspace sized before anything is in flight
+    bool greedy_on_side = false;
     if (greedy_baseline) {
-        CAPB_NVTX("capb200 aoa scst: greedy baseline (eval mode)");
+        CAPB_NVTX("capb200 aoa scst: greedy baseline (eval mode, side stream)");
         capb200_sample_opts so; memset(&so, 0, sizeof(so)); so.edits.unk_col = -1; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.seed = 0; so.steps = T;
-        CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, st));
-        CAPB_CHECK_CUDA(cudaMemsetAsync(greedy_seq, 0, sizeof(long long) * (size_t)B * T, st));
-        if (capb200_aoa_decode_sample(e, att, ta.mask, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, stream)) return 1;
+        cudaStream_t gs = st;
+        static const bool serial = getenv("CAPB200_SCST_SERIAL_GREEDY") != nullptr;
+        if (!serial) {
+            bool ok = true;
+            if (e->side == nullptr) ok = cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) == cudaSuccess;
+            if (ok && e->ev_fork == nullptr) ok = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+            if (ok && e->ev_join == nullptr) ok = cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) == cudaSuccess;
+            if (ok) {
+                CAPB_CHECK_CUDA(cudaEventRecord(e->ev_fork, st));
+                CAPB_CHECK_CUDA(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+                gs = e->side;
+                greedy_on_side = true;
+            } else (void)cudaGetLastError();
+        }
+        CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, gs));
+        CAPB_CHECK_CUDA(cudaMemsetAsync(greedy_seq, 0, sizeof(long long) * (size_t)B * T, gs));
+        if (capb200_aoa_decode_sample(e, att, ta.mask, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, static_cast<void*>(gs))) return 1;
+        if (greedy_on_side) CAPB_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
     }
-    if (ensure_workspace(e, B, N, R, 1, st)) return 1;
     if (e->tc && e->tf32 == nullptr) e->tf32 = tf32_context_create();
     tf32_context_new_step(e->tf32);
     const long tf32_l0 = tf32_context_launches(e->tf32);
@@ -618,7 +642,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     e->launches += 8;
 
     // ---- (3) T sampling steps with the tape
-    CAPB_CHECK_CUDA(cudaMemsetAsync(e->d.tokens, 0, sizeof(int) * N, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(tp.s_tokens, 0, sizeof(int) * N, st));
     for (int t = 0; t < T; ++t) {
         int* tok = tp.tok + (long)t * N;
         if (ta.xe) {
@@ -627,7 +651,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
             } else if (load_token_column_launch(ta.labels, ta.ld_labels, t, N, tok, st)) return 1;
             if (ta.tokens_used != nullptr && store_token_column_launch(tok, N, ta.tokens_used, ta.Tl, t, st)) return 1;
         }
-        else CAPB_CHECK_CUDA(cudaMemcpyAsync(tok, e->d.tokens, sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
+        else CAPB_CHECK_CUDA(cudaMemcpyAsync(tok, tp.s_tokens, sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
         float* xt = tp.xt + (long)t * N * E;
         float* x1c = tp.x1c + (long)t * NH;
         float* gates = tp.gates + (long)t * N * 4 * H;
@@ -670,11 +694,11 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
         va.rows = N; va.V1 = V1; va.logits = logits; va.ld = ld_lp;
         if (!ta.xe) {
             va.select = 2; va.temperature = ta.temperature; va.seed = seed; va.step = (unsigned long long)t;
-            va.unfinished = e->d.unfinished; va.first_step = (t == 0); va.tokens_out = e->d.tokens;
+            va.unfinished = tp.s_unfinished; va.first_step = (t == 0); va.tokens_out = tp.s_tokens;
             va.seq_out = sample_seq; va.ld_seq = T; va.t = t;
             if (ta.forced != nullptr) {
-                if (load_token_column_launch(ta.forced, T, t, N, e->d.forced, st)) return 1;
-                va.select = 3; va.forced = e->d.forced;
+                if (load_token_column_launch(ta.forced, T, t, N, tp.s_forced, st)) return 1;
+                va.select = 3; va.forced = tp.s_forced;
             }
         }
         if (vocab_step_launch(va, st)) return 1;
@@ -688,6 +712,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
         if (xe_loss_backward_launch(sample_logprobs, ld_lp, ta.labels, ta.ld_labels, ta.masks, ta.ld_masks, N, T, ta.Tl, V1, ta.smoothing, ta.upstream,
                                     tp.mask_sum, tp.item_loss, tp.DL, loss, st)) return 1;
     } else {
+        if (greedy_on_side) CAPB_CHECK_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));      // join: the reward needs the baseline captions
         if (cider_reward_launch(ta.table->t, sample_seq, N, greedy_baseline ? greedy_seq : nullptr, B, T, ta.refs, ta.ref_offsets, ta.L, tp.scores, reward, T, T,
                                 st)) return 1;
         if (reward_criterion_fwd_launch(sample_logprobs, ld_lp, V1, sample_seq, reward, N, T, loss, nullptr, tp.mask_sum, st)) return 1;

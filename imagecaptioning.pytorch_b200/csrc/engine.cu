@@ -127,6 +127,7 @@ struct capb200_engine {
     bool split_lang = false;
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_gfork = nullptr, ev_gjoin = nullptr;     // fork / join of the SCST step's concurrent greedy baseline
 
     // optional per-GEMM device timing (cudaEvent pairs on the launching stream), off by default
     bool profiling = false;
@@ -471,6 +472,16 @@ int core_step(capb200_engine* e, int rows, int rpi, const int* tokens, const int
     return run_gemm(e, G_LOGIT, g, e->capRows, st);
 }
 
+bool ensure_side(capb200_engine* e) {
+    if (e->side != nullptr && e->ev_fork != nullptr && e->ev_join != nullptr && e->ev_gfork != nullptr && e->ev_gjoin != nullptr) return true;
+    if (e->side == nullptr && cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); e->side = nullptr; return false; }
+    if (e->ev_fork == nullptr && cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); e->ev_fork = nullptr; return false; }
+    if (e->ev_join == nullptr && cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); e->ev_join = nullptr; return false; }
+    if (e->ev_gfork == nullptr && cudaEventCreateWithFlags(&e->ev_gfork, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); e->ev_gfork = nullptr; return false; }
+    if (e->ev_gjoin == nullptr && cudaEventCreateWithFlags(&e->ev_gjoin, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); e->ev_gjoin = nullptr; return false; }
+    return true;
+}
+
 int check_ready(capb200_engine* e) {
     CAPB_REQUIRE(e != nullptr, "null engine");
     CAPB_REQUIRE(e->bound, "capb200_engine_bind_weights has not been called");
@@ -529,6 +540,8 @@ void capb200_engine_destroy(capb200_engine* e) {
     tf32_context_destroy(e->tf32);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->ev_gfork) cudaEventDestroy(e->ev_gfork);
+    if (e->ev_gjoin) cudaEventDestroy(e->ev_gjoin);
     if (e->side) cudaStreamDestroy(e->side);
     delete e;
 }
@@ -890,6 +903,8 @@ struct Tape {
     size_t skinny_floats;
     double* scores;
     long long* gseq_dummy;
+    int *s_tokens, *s_unfinished, *s_forced;   // sampling-loop state of the train step (its own copies: the greedy baseline runs concurrently)
+    float* s_att_score;
 };
 
 void layout_tape(Tape& tp, Arena& a, int B, int R, int N, int T, int E, int H, int A, int V1, int F_att, int F_fc) {
@@ -911,6 +926,8 @@ void layout_tape(Tape& tp, Arena& a, int B, int R, int N, int T, int E, int H, i
     tp.item_loss = a.take<float>(TN);
     tp.skinny_floats = (size_t)4 << 20;                       // split-K partial sums (16 MB)
     tp.skinny = a.take<float>((long)tp.skinny_floats);
+    tp.s_tokens = a.take<int>(N); tp.s_unfinished = a.take<int>(N); tp.s_forced = a.take<int>(N);
+    tp.s_att_score = a.take<float>((long)N * R);
     (void)F_att; (void)F_fc;
 }
 
@@ -974,14 +991,26 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     }
     Arena ar; ar.base = e->tape;
     Tape tp; layout_tape(tp, ar, B, R, N, T, E, H, A, V1, Fa, Ff);
+    if (ensure_workspace(e, B, N, R, 1, st)) return 1;        // decode workspace sized before anything is in flight
+    bool greedy_on_side = false;
     if (!ta.xe && ta.greedy_baseline) {
-        CAPB_NVTX("capb200 scst: greedy baseline (eval mode)");
+        // The eval-mode greedy baseline (B rows, the regular decode path with its own workspace) and the train-mode sampling forward (B*n rows,
+        // on the tape) are independent chains of small, latency-bound kernels: the baseline runs on a side stream and joins before the reward.
+        CAPB_NVTX("capb200 scst: greedy baseline (eval mode, side stream)");
         capb200_sample_opts so; memset(&so, 0, sizeof(so)); so.edits.unk_col = -1; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.seed = 0; so.steps = T;
-        CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, st));
-        CAPB_CHECK_CUDA(cudaMemsetAsync(greedy_seq, 0, sizeof(long long) * (size_t)B * T, st));
-        if (capb200_decode_sample(e, fc, att, ta.mask, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, stream)) return 1;
+        cudaStream_t gs = st;
+        static const bool serial = getenv("CAPB200_SCST_SERIAL_GREEDY") != nullptr;
+        if (!serial && ensure_side(e)) {
+            CAPB_CHECK_CUDA(cudaEventRecord(e->ev_gfork, st));
+            CAPB_CHECK_CUDA(cudaStreamWaitEvent(e->side, e->ev_gfork, 0));
+            gs = e->side;
+            greedy_on_side = true;
+        }
+        CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, gs));
+        CAPB_CHECK_CUDA(cudaMemsetAsync(greedy_seq, 0, sizeof(long long) * (size_t)B * T, gs));
+        if (capb200_decode_sample(e, fc, att, ta.mask, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, static_cast<void*>(gs))) return 1;
+        if (greedy_on_side) CAPB_CHECK_CUDA(cudaEventRecord(e->ev_gjoin, e->side));
     }
-    if (ensure_workspace(e, B, N, R, 1, st)) return 1;        // DecodeBuffers (tokens, unfinished, ...) for N rows
     if (e->tc && e->tf32 == nullptr) e->tf32 = tf32_context_create();
     tf32_context_new_step(e->tf32);                                          // the weights may have changed since the last step
     const long tf32_l0 = tf32_context_launches(e->tf32);
@@ -1007,7 +1036,7 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
 
     // ---- (3) T sampling steps with the tape
     const long NH = (long)N * H;
-    CAPB_CHECK_CUDA(cudaMemsetAsync(e->d.tokens, 0, sizeof(int) * N, st));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(tp.s_tokens, 0, sizeof(int) * N, st));
     for (int t = 0; t < T; ++t) {
         int* tok = tp.tok + (long)t * N;
         if (ta.xe) {
@@ -1016,7 +1045,7 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
             } else if (load_token_column_launch(ta.labels, ta.ld_labels, t, N, tok, st)) return 1;
             if (ta.tokens_used != nullptr && store_token_column_launch(tok, N, ta.tokens_used, ta.Tl, t, st)) return 1;
         }
-        else CAPB_CHECK_CUDA(cudaMemcpyAsync(tok, e->d.tokens, sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
+        else CAPB_CHECK_CUDA(cudaMemcpyAsync(tok, tp.s_tokens, sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
         float* xt = tp.xt + (long)t * N * E;
         float* g1 = tp.g1 + (long)t * N * 4 * H;
         float* g2 = tp.g2 + (long)t * N * 4 * H;
@@ -1043,7 +1072,7 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
         float* atth = tp.atth + (long)t * N * A;
         if (sk.lin(h0, H, w.h2att_w, H, w.h2att_b, atth, A, N, A, H, 0)) return 1;
         float* attres = tp.attres + (long)t * NH;
-        if (additive_attention_launch(B, n, R, A, H, atth, A, tp.p_att, A, tp.att_e, H, ta.mask, R, w.alpha_w, w.alpha_b, e->att_score,
+        if (additive_attention_launch(B, n, R, A, H, atth, A, tp.p_att, A, tp.att_e, H, ta.mask, R, w.alpha_w, w.alpha_b, tp.s_att_score,
                                       ActView{attres, nullptr, nullptr, H}, st, tp.alpha + (long)t * N * R)) return 1;
         {
             GemmProblem g; g.M = N; g.N = 4 * H; g.nseg = 2;
@@ -1064,11 +1093,11 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
         va.rows = N; va.V1 = V1; va.logits = logits; va.ld = ld_lp;
         if (!ta.xe) {
             va.select = 2; va.temperature = ta.temperature; va.seed = seed; va.step = (unsigned long long)t;
-            va.unfinished = e->d.unfinished; va.first_step = (t == 0); va.tokens_out = e->d.tokens;
+            va.unfinished = tp.s_unfinished; va.first_step = (t == 0); va.tokens_out = tp.s_tokens;
             va.seq_out = sample_seq; va.ld_seq = T; va.t = t;
             if (ta.forced != nullptr) {
-                if (load_token_column_launch(ta.forced, T, t, N, e->d.forced, st)) return 1;
-                va.select = 3; va.forced = e->d.forced;
+                if (load_token_column_launch(ta.forced, T, t, N, tp.s_forced, st)) return 1;
+                va.select = 3; va.forced = tp.s_forced;
             }
         }
         if (vocab_step_launch(va, st)) return 1;
@@ -1084,6 +1113,7 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
         if (xe_loss_backward_launch(sample_logprobs, ld_lp, ta.labels, ta.ld_labels, ta.masks, ta.ld_masks, N, T, ta.Tl, V1, ta.smoothing, ta.upstream,
                                     tp.mask_sum, tp.item_loss, tp.DL, loss, st)) return 1;
     } else {
+        if (greedy_on_side) CAPB_CHECK_CUDA(cudaStreamWaitEvent(st, e->ev_gjoin, 0));     // join: the reward needs the baseline captions
         if (cider_reward_launch(ta.table->t, sample_seq, N, ta.greedy_baseline ? greedy_seq : nullptr, B, T, ta.refs, ta.ref_offsets, ta.L, tp.scores, reward,
                                 T, T, st)) return 1;
         if (reward_criterion_fwd_launch(sample_logprobs, ld_lp, V1, sample_seq, reward, N, T, loss, nullptr, tp.mask_sum, st)) return 1;
