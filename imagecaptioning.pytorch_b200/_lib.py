@@ -59,7 +59,7 @@ class SampleOpts(Structure):
 
 class ScstOpts(Structure):
     _fields_ = [('sample_n', c_int), ('temperature', c_float), ('seed', c_ulonglong), ('drop_prob', c_float), ('upstream', c_float), ('baseline', c_int),
-                ('forced_tokens', c_void_p), ('att_masks', c_void_p)]
+                ('forced_tokens', c_void_p), ('att_masks', c_void_p), ('keep_rows', c_int), ('row_loss', c_void_p)]
 
 
 BASELINE_GREEDY, BASELINE_LEAVE_ONE_OUT = 0, 1
@@ -68,18 +68,18 @@ BASELINE_GREEDY, BASELINE_LEAVE_ONE_OUT = 0, 1
 class AoaScstOpts(Structure):
     _fields_ = [('sample_n', c_int), ('temperature', c_float), ('seed', c_ulonglong), ('upstream', c_float), ('baseline', c_int),
                 ('drop_prob_lm', c_float), ('drop_attn', c_float), ('drop_aoa', c_float), ('drop_sublayer', c_float), ('ctx_drop', c_int),
-                ('forced_tokens', c_void_p), ('att_masks', c_void_p)]
+                ('forced_tokens', c_void_p), ('att_masks', c_void_p), ('keep_rows', c_int), ('row_loss', c_void_p)]
 
 
 class AoaXeOpts(Structure):
     _fields_ = [('seq_per_img', c_int), ('steps', c_int), ('seed', c_ulonglong), ('label_smoothing', c_float), ('upstream', c_float),
                 ('drop_prob_lm', c_float), ('drop_attn', c_float), ('drop_aoa', c_float), ('drop_sublayer', c_float), ('ctx_drop', c_int),
-                ('att_masks', c_void_p), ('ss_prob', c_float), ('tokens_used', c_void_p)]
+                ('att_masks', c_void_p), ('ss_prob', c_float), ('tokens_used', c_void_p), ('keep_rows', c_int), ('row_loss', c_void_p)]
 
 
 class XeOpts(Structure):
     _fields_ = [('seq_per_img', c_int), ('steps', c_int), ('seed', c_ulonglong), ('drop_prob', c_float), ('label_smoothing', c_float),
-                ('upstream', c_float), ('att_masks', c_void_p), ('ss_prob', c_float), ('tokens_used', c_void_p)]
+                ('upstream', c_float), ('att_masks', c_void_p), ('ss_prob', c_float), ('tokens_used', c_void_p), ('keep_rows', c_int), ('row_loss', c_void_p)]
 
 
 GRAD_FIELDS = ['embed', 'fc_embed_w', 'fc_embed_b', 'att_embed_w', 'att_embed_b', 'ctx2att_w', 'ctx2att_b', 'logit_w', 'logit_b',

@@ -488,6 +488,7 @@ struct ATape {
     size_t skinny_floats;
     double* scores;
     int *s_tokens, *s_unfinished, *s_forced;   // sampling-loop state (own copies: the greedy baseline runs concurrently on the decode workspace)
+    float *row_loss, *row_msum, *row_coef;     // drop_worst
 };
 
 void layout_atape(ATape& tp, Arena& a, int B, int R, int N, int T, int E, int H, int heads, int V1) {
@@ -517,6 +518,7 @@ void layout_atape(ATape& tp, Arena& a, int B, int R, int N, int T, int E, int H,
     tp.item_loss = a.take<float>(TN);
     tp.scores = a.take<double>((long)N + B);
     tp.s_tokens = a.take<int>(N); tp.s_unfinished = a.take<int>(N); tp.s_forced = a.take<int>(N);
+    tp.row_loss = a.take<float>(N); tp.row_msum = a.take<float>(N); tp.row_coef = a.take<float>(N);
 }
 
 // dW[out, in] (+)= dY[rows, out]^T * X[rows, in]
@@ -543,6 +545,8 @@ struct AoaTrainArgs {
     const float* mask = nullptr;           // [B, R] region mask or null
     float ss_prob = 0.f;
     long long* tokens_used = nullptr;
+    int keep = 0;
+    float* row_loss = nullptr;
     const long long* labels = nullptr; long ld_labels = 0; const float* masks = nullptr; long ld_masks = 0;
     float* logprobs = nullptr; float* loss = nullptr;
 };
@@ -710,14 +714,16 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     CAPB_NVTX("capb200 aoa train step: reward, loss, backward, weight gradients");
     if (ta.xe) {
         if (xe_loss_backward_launch(sample_logprobs, ld_lp, ta.labels, ta.ld_labels, ta.masks, ta.ld_masks, N, T, ta.Tl, V1, ta.smoothing, ta.upstream,
-                                    tp.mask_sum, tp.item_loss, tp.DL, loss, st)) return 1;
+                                    tp.mask_sum, tp.item_loss, tp.DL, loss, st, ta.keep, ta.row_loss ? ta.row_loss : tp.row_loss, tp.row_msum, tp.row_coef)) return 1;
     } else {
         if (greedy_on_side) CAPB_CHECK_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));      // join: the reward needs the baseline captions
         if (cider_reward_launch(ta.table->t, sample_seq, N, greedy_baseline ? greedy_seq : nullptr, B, T, ta.refs, ta.ref_offsets, ta.L, tp.scores, reward, T, T,
                                 st)) return 1;
-        if (reward_criterion_fwd_launch(sample_logprobs, ld_lp, V1, sample_seq, reward, N, T, loss, nullptr, tp.mask_sum, st)) return 1;
+        float* rl = ta.keep > 0 ? (ta.row_loss ? ta.row_loss : tp.row_loss) : nullptr;
+        if (reward_criterion_fwd_launch(sample_logprobs, ld_lp, V1, sample_seq, reward, N, T, loss, rl, tp.mask_sum, st)) return 1;
+        if (ta.keep > 0 && scst_drop_worst_launch(sample_seq, rl, N, T, ta.keep, ta.upstream, tp.row_msum, tp.row_coef, loss, st)) return 1;
         // ---- (5) backward through the decoder
-        if (scst_dlogits_launch(sample_logprobs, ld_lp, sample_seq, reward, tp.mask_sum, ta.upstream, N, T, V1, tp.DL, st)) return 1;
+        if (scst_dlogits_launch(sample_logprobs, ld_lp, sample_seq, reward, tp.mask_sum, ta.upstream, N, T, V1, tp.DL, st, ta.keep > 0 ? tp.row_coef : nullptr)) return 1;
     }
     if (sk.dgrad((int)TN, H, V1, tp.DL, V1, w.logit_w, H, tp.dOUTD, H, 0)) return 1;
     if (wgrad(V1, H, (int)TN, tp.DL, V1, tp.outd, H, G.logit_w, H, 0, st)) return 1;
@@ -844,7 +850,8 @@ extern "C" int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, in
     ta.n = n; ta.T = e->T; ta.Tl = e->T; ta.p_lm = p_lm; ta.p_at = p_at; ta.p_aoa = p_aoa; ta.p_sub = p_sub; ta.temperature = opts->temperature;
     ta.upstream = opts->upstream; ta.ctx_drop = opts->ctx_drop; ta.seed = opts->seed; ta.greedy_baseline = greedy_baseline; ta.table = table;
     ta.refs = refs; ta.ref_offsets = ref_offsets; ta.L = L; ta.sample_seq = sample_seq; ta.greedy_seq = greedy_seq; ta.reward = reward;
-    ta.logprobs = sample_logprobs; ta.loss = loss; ta.forced = opts->forced_tokens; ta.mask = opts->att_masks;
+    ta.logprobs = sample_logprobs; ta.loss = loss; ta.forced = opts->forced_tokens; ta.mask = opts->att_masks; ta.keep = opts->keep_rows; ta.row_loss = opts->row_loss;
+    CAPB_REQUIRE(ta.keep >= 0 && ta.keep <= B * n, "keep_rows must be in 0..rows");
     return aoa_train_step(e, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }
 
@@ -869,7 +876,8 @@ extern "C" int capb200_aoa_xe_step(capb200_aoa_engine* e, const float* att, int 
     ta.n = opts->seq_per_img; ta.T = opts->steps; ta.Tl = label_cols - 1; ta.p_lm = p_lm; ta.p_at = p_at; ta.p_aoa = p_aoa; ta.p_sub = p_sub;
     ta.upstream = opts->upstream; ta.ctx_drop = opts->ctx_drop; ta.seed = opts->seed; ta.smoothing = opts->label_smoothing;
     ta.labels = labels; ta.ld_labels = label_cols; ta.masks = masks; ta.ld_masks = label_cols; ta.logprobs = logprobs; ta.loss = loss;
-    ta.mask = opts->att_masks; ta.ss_prob = opts->ss_prob; ta.tokens_used = opts->tokens_used;
+    ta.mask = opts->att_masks; ta.ss_prob = opts->ss_prob; ta.tokens_used = opts->tokens_used; ta.keep = opts->keep_rows; ta.row_loss = opts->row_loss;
     CAPB_REQUIRE(ta.ss_prob >= 0.f && ta.ss_prob <= 1.f, "ss_prob must be in [0, 1]");
+    CAPB_REQUIRE(ta.keep >= 0 && ta.keep <= B * opts->seq_per_img, "keep_rows must be in 0..rows");
     return aoa_train_step(e, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }

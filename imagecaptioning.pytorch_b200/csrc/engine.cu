@@ -905,6 +905,7 @@ struct Tape {
     long long* gseq_dummy;
     int *s_tokens, *s_unfinished, *s_forced;   // sampling-loop state of the train step (its own copies: the greedy baseline runs concurrently)
     float* s_att_score;
+    float *row_loss, *row_msum, *row_coef;     // drop_worst: per-row loss, mask count and gradient coefficient
 };
 
 void layout_tape(Tape& tp, Arena& a, int B, int R, int N, int T, int E, int H, int A, int V1, int F_att, int F_fc) {
@@ -928,6 +929,7 @@ void layout_tape(Tape& tp, Arena& a, int B, int R, int N, int T, int E, int H, i
     tp.skinny = a.take<float>((long)tp.skinny_floats);
     tp.s_tokens = a.take<int>(N); tp.s_unfinished = a.take<int>(N); tp.s_forced = a.take<int>(N);
     tp.s_att_score = a.take<float>((long)N * R);
+    tp.row_loss = a.take<float>(N); tp.row_msum = a.take<float>(N); tp.row_coef = a.take<float>(N);
     (void)F_att; (void)F_fc;
 }
 
@@ -957,6 +959,8 @@ struct TrainArgs {
     const float* mask = nullptr;            // [B, R] region mask or null
     float ss_prob = 0.f;                    // XE: scheduled sampling probability
     long long* tokens_used = nullptr;       // XE: optional [N, Tl] record of the words fed
+    int keep = 0;                           // drop_worst: rows kept (0 = reduction 'mean')
+    float* row_loss = nullptr;              // drop_worst: optional per-row loss output
     // XE
     const long long* labels = nullptr; long ld_labels = 0; const float* masks = nullptr; long ld_masks = 0;
     float* logprobs = nullptr; float* loss = nullptr;
@@ -1111,14 +1115,16 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     const capb200_updown_grads& G = *grads;
     if (ta.xe) {
         if (xe_loss_backward_launch(sample_logprobs, ld_lp, ta.labels, ta.ld_labels, ta.masks, ta.ld_masks, N, T, ta.Tl, V1, ta.smoothing, ta.upstream,
-                                    tp.mask_sum, tp.item_loss, tp.DL, loss, st)) return 1;
+                                    tp.mask_sum, tp.item_loss, tp.DL, loss, st, ta.keep, ta.row_loss ? ta.row_loss : tp.row_loss, tp.row_msum, tp.row_coef)) return 1;
     } else {
         if (greedy_on_side) CAPB_CHECK_CUDA(cudaStreamWaitEvent(st, e->ev_gjoin, 0));     // join: the reward needs the baseline captions
         if (cider_reward_launch(ta.table->t, sample_seq, N, ta.greedy_baseline ? greedy_seq : nullptr, B, T, ta.refs, ta.ref_offsets, ta.L, tp.scores, reward,
                                 T, T, st)) return 1;
-        if (reward_criterion_fwd_launch(sample_logprobs, ld_lp, V1, sample_seq, reward, N, T, loss, nullptr, tp.mask_sum, st)) return 1;
+        float* rl = ta.keep > 0 ? (ta.row_loss ? ta.row_loss : tp.row_loss) : nullptr;
+        if (reward_criterion_fwd_launch(sample_logprobs, ld_lp, V1, sample_seq, reward, N, T, loss, rl, tp.mask_sum, st)) return 1;
+        if (ta.keep > 0 && scst_drop_worst_launch(sample_seq, rl, N, T, ta.keep, ta.upstream, tp.row_msum, tp.row_coef, loss, st)) return 1;
         // ---- (5) backward: logit layer, batched over all (n, t)
-        if (scst_dlogits_launch(sample_logprobs, ld_lp, sample_seq, reward, tp.mask_sum, ta.upstream, N, T, V1, tp.DL, st)) return 1;
+        if (scst_dlogits_launch(sample_logprobs, ld_lp, sample_seq, reward, tp.mask_sum, ta.upstream, N, T, V1, tp.DL, st, ta.keep > 0 ? tp.row_coef : nullptr)) return 1;
     }
     e->launches += 3;
     if (sk.dgrad((int)TN, H, V1, tp.DL, V1, w.logit_w, H, tp.dOUT, H, 0)) return 1;          // dOUT = DL * W
@@ -1214,7 +1220,8 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
     ta.n = opts->sample_n; ta.T = e->T; ta.Tl = e->T; ta.p = opts->drop_prob; ta.temperature = opts->temperature; ta.upstream = opts->upstream;
     ta.seed = opts->seed; ta.greedy_baseline = greedy_baseline; ta.table = table; ta.refs = refs; ta.ref_offsets = ref_offsets; ta.L = L;
     ta.sample_seq = sample_seq; ta.greedy_seq = greedy_seq; ta.reward = reward; ta.logprobs = sample_logprobs; ta.loss = loss;
-    ta.forced = opts->forced_tokens; ta.mask = opts->att_masks;
+    ta.forced = opts->forced_tokens; ta.mask = opts->att_masks; ta.keep = opts->keep_rows; ta.row_loss = opts->row_loss;
+    CAPB_REQUIRE(ta.keep >= 0 && ta.keep <= B * opts->sample_n, "keep_rows must be in 0..rows");
     return updown_train_step(e, fc, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }
 
@@ -1240,8 +1247,9 @@ extern "C" int capb200_updown_xe_step(capb200_engine* e, const float* fc, const 
     ta.n = opts->seq_per_img; ta.T = opts->steps; ta.Tl = label_cols - 1; ta.p = opts->drop_prob; ta.upstream = opts->upstream; ta.seed = opts->seed;
     ta.smoothing = opts->label_smoothing;
     ta.labels = labels; ta.ld_labels = label_cols; ta.masks = masks; ta.ld_masks = label_cols; ta.logprobs = logprobs; ta.loss = loss;
-    ta.mask = opts->att_masks; ta.ss_prob = opts->ss_prob; ta.tokens_used = opts->tokens_used;
+    ta.mask = opts->att_masks; ta.ss_prob = opts->ss_prob; ta.tokens_used = opts->tokens_used; ta.keep = opts->keep_rows; ta.row_loss = opts->row_loss;
     CAPB_REQUIRE(ta.ss_prob >= 0.f && ta.ss_prob <= 1.f, "ss_prob must be in [0, 1]");
+    CAPB_REQUIRE(ta.keep >= 0 && ta.keep <= B * opts->seq_per_img, "keep_rows must be in 0..rows");
     return updown_train_step(e, fc, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }
 

@@ -155,9 +155,13 @@ int dropout_copy_launch(const float* x, long ld_x, float* y, long ld_y, int rows
 int embed_relu_dropout_launch(int rows, int E, const int* tokens, const float* emb, float* xt, unsigned long long seed, unsigned step, float p,
                               cudaStream_t st);
 int scst_dlogits_launch(const float* logp, long ld_row, const long long* seq, const float* reward, const float* mask_sum, float upstream, int N, int T, int V1,
-                        float* dl, cudaStream_t st);
+                        float* dl, cudaStream_t st, const float* row_coef = nullptr);
+// drop_worst on the sampled-loss rows: row_msum / row_coef [N] scratch; loss[0] = mean of the `keep` smallest row losses
+int scst_drop_worst_launch(const long long* seq, const float* row_loss, int N, int T, int keep, float upstream, float* row_msum, float* row_coef, float* loss,
+                           cudaStream_t st);
 int xe_loss_backward_launch(const float* logp, long ld_row, const long long* labels, long ld_l, const float* masks, long ld_m, int N, int steps, int Ls, int V1,
-                            float smoothing, float upstream, float* mask_sum, float* item_loss, float* dl, float* loss, cudaStream_t st);
+                            float smoothing, float upstream, float* mask_sum, float* item_loss, float* dl, float* loss, cudaStream_t st, int keep = 0,
+                            float* row_loss = nullptr, float* row_msum = nullptr, float* row_coef = nullptr);
 int lstm_cell_backward_launch(int rows, int H, const float* gates, const float* c_prev, const float* c_new, const float* dh, const float* dh_extra,
                               long ld_extra, unsigned drop_site, unsigned drop_step, unsigned long long seed, float p, float* dc_carry, float* dgates,
                               cudaStream_t st);

@@ -49,12 +49,14 @@ __global__ void embed_relu_dropout_kernel(int rows, int E, const int* __restrict
 // d logits of  loss = sum_{n,t} -logp[n,t,seq] * reward[n] * mask[n,t] / sum(mask)  through log_softmax:
 //   dl[n,t,v] = coef * (1[v == seq] - exp(logp[n,t,v])),  coef = -reward[n,t] * mask[n,t] / mask_sum * upstream
 __global__ void scst_dlogits_kernel(const float* __restrict__ logp, long ld_row, const long long* __restrict__ seq, const float* __restrict__ reward,
-                                    const float* __restrict__ mask_sum, float upstream, int T, int V1, float* __restrict__ dl) {
+                                    const float* __restrict__ mask_sum, float upstream, int T, int V1, float* __restrict__ dl,
+                                    const float* __restrict__ row_coef) {
     const long item = blockIdx.x;                 // n * T + t
     const int t = (int)(item % T);
     const long n = item / T;
     const float m = (t == 0 || seq[n * T + t - 1] > 0) ? 1.f : 0.f;
-    const float coef = -reward[item] * m / (*mask_sum) * upstream;
+    // reduction 'mean': upstream / (all mask entries); drop_worst: upstream / (k * this row's mask entries) for kept rows, 0 for dropped ones
+    const float coef = -reward[item] * m * (row_coef != nullptr ? row_coef[n] : upstream / (*mask_sum));
     const long long tok = seq[item];
     const float* lp = logp + n * ld_row + (long)t * V1;
     float* d = dl + item * V1;
@@ -83,14 +85,15 @@ __global__ void xe_mask_sum_kernel(const float* __restrict__ masks, long ld_m, i
 // one CTA per (n, t < steps): d logits = coef * (softmax - target_dist), coef = mask / mask_sum * upstream; item_loss = un-normalised loss term
 __global__ void __launch_bounds__(256) xe_dlogits_kernel(const float* __restrict__ logp, long ld_row, const long long* __restrict__ labels, long ld_l,
                                                          const float* __restrict__ masks, long ld_m, const float* __restrict__ mask_sum, float upstream,
-                                                         float smoothing, int steps, int V1, float* __restrict__ dl, float* __restrict__ item_loss) {
+                                                         float smoothing, int steps, int V1, float* __restrict__ dl, float* __restrict__ item_loss,
+                                                         const float* __restrict__ row_coef) {
     __shared__ float sh[256];
     const long item = blockIdx.x;                 // n * steps + t
     const int t = (int)(item % steps);
     const long n = item / steps;
     const float m = masks[n * ld_m + t + 1];
     const long long tgt = labels[n * ld_l + t + 1];
-    const float coef = m / (*mask_sum) * upstream;
+    const float coef = m * (row_coef != nullptr ? row_coef[n] : upstream / (*mask_sum));
     const float* lp = logp + n * ld_row + (long)t * V1;
     float* d = dl + item * V1;
     const float off = smoothing > 0.f ? smoothing / (float)(V1 - 1) : 0.f, conf = 1.f - smoothing;
@@ -129,6 +132,58 @@ __global__ void xe_loss_kernel(const float* __restrict__ item_loss, int N, int s
         __syncthreads();
     }
     if (threadIdx.x == 0) *loss = sh[0] / (*mask_sum);
+}
+
+// ---- drop_worst (tools/train.py:187-191): the criterion runs with reduction 'none' (one loss per caption row, normalised by that row's mask
+// entries) and the trainer averages the k rows with the SMALLEST loss.  The selection happens on the device between the forward and the
+// backward of the fused step: row_coef[n] = upstream / (k * row_mask[n]) for kept rows, 0 for dropped ones; loss = mean over the kept rows.
+__global__ void xe_row_loss_kernel(const float* __restrict__ item_loss, int N, int steps, int Ls, const float* __restrict__ masks, long ld_m, float smoothing,
+                                   int V1, float* __restrict__ row_loss, float* __restrict__ row_msum) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f, ms = 0.f;
+    for (int t = 0; t < steps; ++t) s += item_loss[(long)n * steps + t];
+    for (int t = 0; t < Ls; ++t) ms += masks[(long)n * ld_m + t + 1];
+    if (smoothing > 0.f && steps < Ls) {          // never-evaluated columns: their log-prob rows are zero (AttModel.py:158-159)
+        const float off = smoothing / (float)(V1 - 1), conf = 1.f - smoothing;
+        const float zero_row = (float)(V1 - 1) * off * logf(off) + (conf > 0.f ? conf * logf(conf) : 0.f);
+        for (int t = steps; t < Ls; ++t) s += zero_row * masks[(long)n * ld_m + t + 1];
+    }
+    row_loss[n] = s / ms;
+    row_msum[n] = ms;
+}
+
+__global__ void scst_row_mask_kernel(const long long* __restrict__ seq, int N, int T, float* __restrict__ row_msum) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float ms = 0.f;
+    for (int t = 0; t < T; ++t) ms += (t == 0 || seq[(long)n * T + t - 1] > 0) ? 1.f : 0.f;
+    row_msum[n] = ms;
+}
+
+// single CTA: rank every row among all rows (ties: lower index first), keep the k smallest
+__global__ void __launch_bounds__(256) drop_worst_select_kernel(const float* __restrict__ row_loss, const float* __restrict__ row_msum, int N, int k,
+                                                                float upstream, float* __restrict__ row_coef, float* __restrict__ loss) {
+    __shared__ float sh[256];
+    float acc = 0.f;
+    for (int n = threadIdx.x; n < N; n += 256) {
+        const float l = row_loss[n];
+        int rank = 0;
+        for (int j = 0; j < N; ++j) {
+            const float lj = row_loss[j];
+            rank += (lj < l || (lj == l && j < n)) ? 1 : 0;
+        }
+        const bool kept = rank < k;
+        row_coef[n] = kept ? upstream / ((float)k * row_msum[n]) : 0.f;
+        if (kept) acc += l;
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss = sh[0] / (float)k;
 }
 
 // nn.LSTMCell backward (gate pre-activations saved): dgates [rows, 4H] (i,f,g,o) and dc_prev from dh, dc
@@ -331,16 +386,34 @@ int embed_relu_dropout_launch(int rows, int E, const int* tokens, const float* e
     LAUNCH_OK();
 }
 int scst_dlogits_launch(const float* logp, long ld_row, const long long* seq, const float* reward, const float* mask_sum, float upstream, int N, int T, int V1,
-                        float* dl, cudaStream_t st) {
-    scst_dlogits_kernel<<<N * T, 256, 0, st>>>(logp, ld_row, seq, reward, mask_sum, upstream, T, V1, dl);
+                        float* dl, cudaStream_t st, const float* row_coef) {
+    scst_dlogits_kernel<<<N * T, 256, 0, st>>>(logp, ld_row, seq, reward, mask_sum, upstream, T, V1, dl, row_coef);
+    LAUNCH_OK();
+}
+int scst_drop_worst_launch(const long long* seq, const float* row_loss, int N, int T, int keep, float upstream, float* row_msum, float* row_coef, float* loss,
+                           cudaStream_t st) {
+    CAPB_REQUIRE(keep >= 1 && keep <= N, "drop_worst: the number of kept rows must be in 1..rows");
+    scst_row_mask_kernel<<<cdiv(N, 128), 128, 0, st>>>(seq, N, T, row_msum);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    drop_worst_select_kernel<<<1, 256, 0, st>>>(row_loss, row_msum, N, keep, upstream, row_coef, loss);
     LAUNCH_OK();
 }
 int xe_loss_backward_launch(const float* logp, long ld_row, const long long* labels, long ld_l, const float* masks, long ld_m, int N, int steps, int Ls, int V1,
-                            float smoothing, float upstream, float* mask_sum, float* item_loss, float* dl, float* loss, cudaStream_t st) {
+                            float smoothing, float upstream, float* mask_sum, float* item_loss, float* dl, float* loss, cudaStream_t st, int keep,
+                            float* row_loss, float* row_msum, float* row_coef) {
     xe_mask_sum_kernel<<<1, 256, 0, st>>>(masks, ld_m, N, Ls, mask_sum);
     CAPB_CHECK_CUDA(cudaGetLastError());
-    xe_dlogits_kernel<<<N * steps, 256, 0, st>>>(logp, ld_row, labels, ld_l, masks, ld_m, mask_sum, upstream, smoothing, steps, V1, dl, item_loss);
+    xe_dlogits_kernel<<<N * steps, 256, 0, st>>>(logp, ld_row, labels, ld_l, masks, ld_m, mask_sum, upstream, smoothing, steps, V1, dl, item_loss, nullptr);
     CAPB_CHECK_CUDA(cudaGetLastError());
+    if (keep > 0) {      // drop_worst: per-row losses, selection, then the gradient pass again with the per-row coefficients
+        CAPB_REQUIRE(keep <= N && row_loss && row_msum && row_coef, "drop_worst: bad arguments");
+        xe_row_loss_kernel<<<cdiv(N, 128), 128, 0, st>>>(item_loss, N, steps, Ls, masks, ld_m, smoothing, V1, row_loss, row_msum);
+        CAPB_CHECK_CUDA(cudaGetLastError());
+        drop_worst_select_kernel<<<1, 256, 0, st>>>(row_loss, row_msum, N, keep, upstream, row_coef, loss);
+        CAPB_CHECK_CUDA(cudaGetLastError());
+        xe_dlogits_kernel<<<N * steps, 256, 0, st>>>(logp, ld_row, labels, ld_l, masks, ld_m, mask_sum, upstream, smoothing, steps, V1, dl, item_loss, row_coef);
+        LAUNCH_OK();
+    }
     xe_loss_kernel<<<1, 256, 0, st>>>(item_loss, N, steps, Ls, masks, ld_m, smoothing, V1, mask_sum, loss);
     LAUNCH_OK();
 }

@@ -142,6 +142,40 @@ class _ScstLoss(torch.autograd.Function):
         return (None, None, None) + tuple(None for _ in ctx.params)
 
 
+class _DropWorstLoss(torch.autograd.Function):
+    """drop_worst (tools/train.py:187-191): LossWrapper returns one loss per caption row (reduction 'none') and the TRAINER averages the
+    k = int(rows * (1 - drop_worst_rate)) smallest.  The fused step has already applied exactly that selection on the device (its gradients
+    are those of the mean over the kept rows); backward checks that the upstream gradient is the selection the step assumed -- 1/k on the
+    kept rows, 0 elsewhere -- and refuses anything else instead of handing out gradients of a different objective."""
+
+    @staticmethod
+    def forward(ctx, row_loss, keep, grad_list, sync, *params):
+        ctx.grad_list, ctx.sync, ctx.params, ctx.keep = grad_list, sync, params, keep
+        ctx.save_for_backward(row_loss)
+        return row_loss.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (row_loss,) = ctx.saved_tensors
+        k = ctx.keep
+        kept = torch.zeros_like(row_loss)
+        kept[torch.topk(row_loss, k, largest=False).indices] = 1.0 / k
+        scale = grad_out.sum()                         # the trainer may multiply the mean by a constant
+        if not torch.allclose(grad_out, kept * scale, rtol=1e-4, atol=1e-8):
+            raise NotImplementedError('drop_worst: the fused step computed the gradients of the mean over the %d smallest row losses '
+                                      '(tools/train.py:191); a different reduction of out[\'loss\'] is not supported' % k)
+        if ctx.sync is None:
+            return (None, None, None, None) + tuple(g * scale for g in ctx.grad_list)
+        ctx.sync.wait()
+        torch._foreach_mul_(list(ctx.grad_list), scale)
+        for p_, g in zip(ctx.params, ctx.grad_list):
+            if p_.grad is None:
+                p_.grad = g
+            else:
+                p_.grad.add_(g)
+        return (None, None, None, None) + tuple(None for _ in ctx.params)
+
+
 class B200LossWrapper(nn.Module):
     def __init__(self, model, opt):
         super().__init__()
@@ -177,7 +211,18 @@ class B200LossWrapper(nn.Module):
             self._sync.launch(res['flat'])
             self.last_sync_bytes = self._sync.bytes
             sync = self._sync
+        if res.get('row_loss') is not None:          # drop_worst: the per-row vector is what the reference returns as out['loss']
+            return _DropWorstLoss.apply(res['row_loss'], int(res['keep_rows']), [res['grads'][p_] for p_ in params], sync, *params)
         return _ScstLoss.apply(res['loss'], [res['grads'][p_] for p_ in params], sync, *params)
+
+    def _keep_rows(self, rows, drop_worst_flag):
+        """int(loss.shape[0] * (1 - opt.drop_worst_rate)), the trainer's own arithmetic (tools/train.py:191); 0 when the flag is off."""
+        if not drop_worst_flag:
+            return 0
+        k = int(rows * (1 - float(getattr(self.opt, 'drop_worst_rate', 0))))
+        if k < 1:
+            raise ValueError('drop_worst_rate leaves no caption rows')
+        return k
 
     def _scorer(self):
         from . import rewards as _rw
@@ -188,9 +233,13 @@ class B200LossWrapper(nn.Module):
     def _xe_loss(self, fc_feats, att_feats, labels, masks, att_masks, drop_worst_flag, snapshot=False):
         """loss_wrapper.py:54-55: crit(model(fc, att, labels[..., :-1], att_masks), labels[..., 1:], masks[..., 1:])."""
         if torch.is_grad_enabled() and self.model.training:
-            if not hasattr(self.model, 'xe_step') or drop_worst_flag:
-                raise NotImplementedError('the fused XE step covers the UpDown and AoANet families with reduction="mean" (no drop_worst)')
-            res = self.model.xe_step(fc_feats, att_feats, labels, masks, label_smoothing=getattr(self.opt, 'label_smoothing', 0), att_masks=att_masks)
+            if not hasattr(self.model, 'xe_step'):
+                raise NotImplementedError('the fused XE step covers the UpDown and AoANet families')
+            rows = labels.shape[0] * (labels.shape[1] if labels.dim() == 3 else 1)
+            keep = self._keep_rows(rows, drop_worst_flag)
+            res = self.model.xe_step(fc_feats, att_feats, labels, masks, label_smoothing=getattr(self.opt, 'label_smoothing', 0), att_masks=att_masks,
+                                     keep_rows=keep)
+            res['keep_rows'] = keep
             if snapshot:        # another fused step will reuse the model's flat gradient buffer before this loss is back-propagated
                 res = dict(res, grads={p_: g.clone() for p_, g in res['grads'].items()}, flat=None)
             self.last_step = res
@@ -199,11 +248,14 @@ class B200LossWrapper(nn.Module):
         reduction = 'none' if drop_worst_flag else 'mean'
         return self.crit(self.model(fc_feats, att_feats, labels[..., :-1], att_masks), labels[..., 1:], masks[..., 1:], reduction=reduction)
 
-    def _sampled_step(self, fc_feats, att_feats, gts, baseline, att_masks=None):
+    def _sampled_step(self, fc_feats, att_feats, gts, baseline, att_masks=None, drop_worst_flag=False):
         opt = self.opt
         self.model.train()
+        keep = self._keep_rows(len(gts) * opt.train_sample_n, drop_worst_flag)
         # the reference's training-time _sample call passes no temperature (loss_wrapper.py:63-67): 1.0, whatever opt.temperature says
-        res = self.model.scst_step(fc_feats, att_feats, gts, self._scorer(), opt.train_sample_n, temperature=1.0, baseline=baseline, att_masks=att_masks)
+        res = self.model.scst_step(fc_feats, att_feats, gts, self._scorer(), opt.train_sample_n, temperature=1.0, baseline=baseline, att_masks=att_masks,
+                                   keep_rows=keep)
+        res['keep_rows'] = keep
         self.last_step = res
         return res
 
@@ -212,7 +264,7 @@ class B200LossWrapper(nn.Module):
         out = {}
         reduction = 'none' if drop_worst_flag else 'mean'
         plain_reward = getattr(opt, 'bleu_reward_weight', 0) == 0 and getattr(opt, 'cider_reward_weight', 1) == 1
-        can_fuse = (hasattr(self.model, 'scst_step') and not drop_worst_flag and torch.is_grad_enabled() and plain_reward and
+        can_fuse = (hasattr(self.model, 'scst_step') and torch.is_grad_enabled() and plain_reward and
                     opt.train_sample_method == 'sample' and opt.train_beam_size == 1)
         if struc_flag:
             w = opt.structure_loss_weight
@@ -222,7 +274,9 @@ class B200LossWrapper(nn.Module):
                 if getattr(opt, 'use_ppo', 0) or opt.structure_loss_type != 'new_self_critical' or not can_fuse:
                     raise NotImplementedError("the structure-loss branch covers structure_loss_type='new_self_critical' on the fused UpDown step")
                 gts = [gts[_] for _ in gt_indices.tolist()]
-                res = self._sampled_step(fc_feats, att_feats, gts, 'leave_one_out', att_masks)
+                if drop_worst_flag and 0 < w < 1:
+                    raise NotImplementedError('drop_worst with a mixed XE / structure loss: the two fused steps would select rows independently')
+                res = self._sampled_step(fc_feats, att_feats, gts, 'leave_one_out', att_masks, drop_worst_flag)
                 struc = {'loss': self._bridge(res), 'reward': cider_scores(gts, res['sample_seq']).float().view(-1, opt.train_sample_n)}
             else:
                 struc = {'loss': torch.zeros((), device=fc_feats.device), 'reward': torch.zeros((), device=fc_feats.device)}
@@ -235,7 +289,7 @@ class B200LossWrapper(nn.Module):
         if can_fuse and opt.sc_sample_method == 'greedy' and opt.sc_beam_size == 1:
             # whole step on the device incl. back-propagation through time (UpDown); dropout as in model.train()
             gts = [gts[_] for _ in gt_indices.tolist()]
-            res = self._sampled_step(fc_feats, att_feats, gts, 'greedy', att_masks)
+            res = self._sampled_step(fc_feats, att_feats, gts, 'greedy', att_masks, drop_worst_flag)
             out['loss'] = self._bridge(res)
             out['reward'] = res['reward'][:, 0].mean()
             return out
@@ -245,8 +299,6 @@ class B200LossWrapper(nn.Module):
             why = []
             if not hasattr(self.model, 'scst_step'):
                 why.append('model family %r has no fused SCST step (UpDown and AoANet do)' % getattr(self.model, 'family_name', type(self.model).__name__))
-            if drop_worst_flag:
-                why.append('drop_worst_flag')
             if not plain_reward:
                 why.append('cider_reward_weight != 1 or bleu_reward_weight != 0')
             if opt.train_sample_method != 'sample' or opt.train_beam_size != 1:

@@ -532,7 +532,7 @@ class B200UpDownModel(B200CaptionModel):
     # ---- SCST training step (UpDown): greedy baseline + sampling with dropout + CIDEr-D reward + RewardCriterion + BPTT -----
     @_on_device
     def scst_step(self, fc_feats, att_feats, gts, table, sample_n, temperature=1.0, drop_prob=None, seed=None, upstream=1.0, baseline='greedy',
-                  forced_tokens=None, att_masks=None):
+                  forced_tokens=None, att_masks=None, keep_rows=0):
         """Runs one self-critical step entirely on the device (capb200_updown_scst_step).  Returns a dict with 'loss' (0-dim),
         'reward' [N, T], 'sample_seq', 'greedy_seq', 'sample_logprobs' and 'grads' {parameter: gradient tensor}.
         ``baseline='greedy'`` is the self-critical step (loss_wrapper.py:56-73); ``'leave_one_out'`` the 'new_self_critical' structure
@@ -564,17 +564,18 @@ class B200UpDownModel(B200CaptionModel):
         if forced_tokens is not None:       # replay a given draw (parity tests against the reference's own samples)
             forced = forced_tokens.detach().to(device=dev, dtype=torch.long).contiguous()
             assert forced.shape == (N, T)
+        row_loss = torch.empty(N, dtype=torch.float32, device=dev) if keep_rows else None      # drop_worst: per-row losses (reduction 'none')
         so = _lib.ScstOpts(sample_n, float(temperature), seed, float(p), float(upstream), _lib.BASELINE_LEAVE_ONE_OUT if loo else _lib.BASELINE_GREEDY,
-                           _lib.ptr(forced), _lib.ptr(masks))
+                           _lib.ptr(forced), _lib.ptr(masks), int(keep_rows), _lib.ptr(row_loss))
         _lib.check(lib.capb200_updown_scst_step(self._engine, _lib.ptr(fc), _lib.ptr(att), B, R, ctypes.byref(so), table._h, _lib.ptr(refs),
                                                 _lib.ptr(offsets), L, ctypes.byref(g), _lib.ptr(sample_seq), _lib.ptr(greedy_seq), _lib.ptr(logprobs),
                                                 _lib.ptr(reward), _lib.ptr(loss), _lib.current_stream()), 'updown_scst_step')
         res = {'loss': loss[0], 'reward': reward, 'sample_seq': sample_seq, 'greedy_seq': None if loo else greedy_seq, 'sample_logprobs': logprobs,
-               'grads': {table_params[k]: grads[k] for k in table_params}, 'seed': seed, 'flat': fg}
+               'grads': {table_params[k]: grads[k] for k in table_params}, 'seed': seed, 'flat': fg, 'row_loss': row_loss}
         return res
 
     @_on_device
-    def xe_step(self, fc_feats, att_feats, labels, masks, label_smoothing=0.0, drop_prob=None, seed=None, upstream=1.0, att_masks=None):
+    def xe_step(self, fc_feats, att_feats, labels, masks, label_smoothing=0.0, drop_prob=None, seed=None, upstream=1.0, att_masks=None, keep_rows=0):
         """One cross-entropy step on the device (capb200_updown_xe_step): teacher-forced forward over ``labels[..., :-1]`` in train mode,
         LanguageModelCriterion / LabelSmoothing against ``labels[..., 1:]``, ``masks[..., 1:]`` (reduction 'mean'), BPTT.
         Returns {'loss', 'logprobs' [N, L-1, V+1], 'grads' {parameter: gradient}, 'seed'}."""
@@ -603,12 +604,13 @@ class B200UpDownModel(B200CaptionModel):
         p = self.drop_prob_lm if drop_prob is None else drop_prob
         # scheduled sampling (self.ss_prob, set by the trainer: tools/train.py:147-148): the words actually fed are returned as 'tokens_used'
         tokens_used = torch.zeros(N, Lc - 1, dtype=torch.long, device=dev) if self.ss_prob > 0.0 else None
+        row_loss = torch.empty(N, dtype=torch.float32, device=dev) if keep_rows else None
         xo = _lib.XeOpts(N // B, steps, seed, float(p), float(label_smoothing), float(upstream), _lib.ptr(region_masks), float(self.ss_prob),
-                         _lib.ptr(tokens_used))
+                         _lib.ptr(tokens_used), int(keep_rows), _lib.ptr(row_loss))
         _lib.check(lib.capb200_updown_xe_step(self._engine, _lib.ptr(fc), _lib.ptr(att), B, R, ctypes.byref(xo), _lib.ptr(labels), _lib.ptr(masks), Lc,
                                               ctypes.byref(g), _lib.ptr(logprobs), _lib.ptr(loss), _lib.current_stream()), 'updown_xe_step')
         return {'loss': loss[0], 'logprobs': logprobs, 'grads': {table_params[k]: grads[k] for k in table_params}, 'seed': seed, 'flat': fg,
-                'tokens_used': tokens_used}
+                'tokens_used': tokens_used, 'row_loss': row_loss}
 
 
 class _MaxoutCoreParams(nn.Module):
@@ -896,7 +898,7 @@ class B200AoAModel(B200CaptionModel):
 
     @_on_device
     def scst_step(self, fc_feats, att_feats, gts, table, sample_n, temperature=1.0, drop_prob=None, seed=None, upstream=1.0, baseline='greedy',
-                  drop_attn=0.1, drop_aoa=None, drop_sublayer=0.1, ctx_drop=None, forced_tokens=None, att_masks=None):
+                  drop_attn=0.1, drop_aoa=None, drop_sublayer=0.1, ctx_drop=None, forced_tokens=None, att_masks=None, keep_rows=0):
         """One self-critical step of AoANet on the device (capb200_aoa_scst_step): eval-mode greedy baseline (or the leave-one-out baseline of
         'new_self_critical'), train-mode samples with every dropout site of AoAModel.py active, CIDEr-D reward, RewardCriterion, BPTT through
         the decoder and the six refiner layers.  ``fc_feats`` is unused (mean_feats=1).  Returns the dict of B200UpDownModel.scst_step."""
@@ -923,18 +925,19 @@ class B200AoAModel(B200CaptionModel):
         if forced_tokens is not None:
             forced = forced_tokens.detach().to(device=dev, dtype=torch.long).contiguous()
             assert forced.shape == (N, T)
+        row_loss = torch.empty(N, dtype=torch.float32, device=dev) if keep_rows else None
         so = _lib.AoaScstOpts(sample_n, float(temperature), seed, float(upstream), _lib.BASELINE_LEAVE_ONE_OUT if loo else _lib.BASELINE_GREEDY, float(p),
                               float(drop_attn), float(self.dropout_aoa if drop_aoa is None else drop_aoa), float(drop_sublayer),
-                              int(self.ctx_drop if ctx_drop is None else ctx_drop), _lib.ptr(forced), _lib.ptr(masks))
+                              int(self.ctx_drop if ctx_drop is None else ctx_drop), _lib.ptr(forced), _lib.ptr(masks), int(keep_rows), _lib.ptr(row_loss))
         _lib.check(lib.capb200_aoa_scst_step(self._engine, _lib.ptr(att), B, R, ctypes.byref(so), table._h, _lib.ptr(refs), _lib.ptr(offsets), L,
                                              ctypes.byref(g), _lib.ptr(sample_seq), None if loo else _lib.ptr(greedy_seq), _lib.ptr(logprobs),
                                              _lib.ptr(reward), _lib.ptr(loss), _lib.current_stream()), 'aoa_scst_step')
         return {'loss': loss[0], 'reward': reward, 'sample_seq': sample_seq, 'greedy_seq': None if loo else greedy_seq, 'sample_logprobs': logprobs,
-                'grads': {prm: fg.by_name['/'.join(str(x) for x in path)] for path, prm in slots}, 'seed': seed, 'flat': fg}
+                'grads': {prm: fg.by_name['/'.join(str(x) for x in path)] for path, prm in slots}, 'seed': seed, 'flat': fg, 'row_loss': row_loss}
 
     @_on_device
     def xe_step(self, fc_feats, att_feats, labels, masks, label_smoothing=0.0, drop_prob=None, seed=None, upstream=1.0, drop_attn=0.1, drop_aoa=None,
-                drop_sublayer=0.1, ctx_drop=None, att_masks=None):
+                drop_sublayer=0.1, ctx_drop=None, att_masks=None, keep_rows=0):
         """One cross-entropy step of AoANet on the device (capb200_aoa_xe_step); arguments and result as B200UpDownModel.xe_step."""
         lib = self._ensure_engine(att_feats.device)
         att, region_masks = self._clip(att_feats, att_masks)
@@ -958,13 +961,14 @@ class B200AoAModel(B200CaptionModel):
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         p = self.drop_prob_lm if drop_prob is None else drop_prob
         tokens_used = torch.zeros(N, Lc - 1, dtype=torch.long, device=dev) if self.ss_prob > 0.0 else None
+        row_loss = torch.empty(N, dtype=torch.float32, device=dev) if keep_rows else None
         xo = _lib.AoaXeOpts(N // B, steps, seed, float(label_smoothing), float(upstream), float(p), float(drop_attn),
                             float(self.dropout_aoa if drop_aoa is None else drop_aoa), float(drop_sublayer), int(self.ctx_drop if ctx_drop is None else ctx_drop),
-                            _lib.ptr(region_masks), float(self.ss_prob), _lib.ptr(tokens_used))
+                            _lib.ptr(region_masks), float(self.ss_prob), _lib.ptr(tokens_used), int(keep_rows), _lib.ptr(row_loss))
         _lib.check(lib.capb200_aoa_xe_step(self._engine, _lib.ptr(att), B, R, ctypes.byref(xo), _lib.ptr(labels), _lib.ptr(masks), Lc, ctypes.byref(g),
                                            _lib.ptr(logprobs), _lib.ptr(loss), _lib.current_stream()), 'aoa_xe_step')
         return {'loss': loss[0], 'logprobs': logprobs, 'grads': {prm: fg.by_name['/'.join(str(x) for x in path)] for path, prm in slots}, 'seed': seed,
-                'flat': fg, 'tokens_used': tokens_used}
+                'flat': fg, 'tokens_used': tokens_used, 'row_loss': row_loss}
 
     def _ensure_engine(self, device):
         lib = self._enter_device(device)

@@ -297,6 +297,9 @@ typedef struct {
                                   checks against the reference's own multinomial draw); NULL = sample */
     const float* att_masks;    /* optional [B, R] fp32 device (1 = valid region): variable region counts (AttModel.py:44-49,106-112,742-744;
                                   dataloader.py:230-241); the caller has clipped R to the longest valid length; NULL = all regions valid */
+    int keep_rows;             /* drop_worst (tools/train.py:187-191): 0 = reduction 'mean'; k > 0 = the criterion runs with reduction 'none' (one loss per
+                                  caption row) and the k rows with the smallest loss are averaged: loss[0] = that mean, gradients accordingly */
+    float* row_loss;           /* optional [rows] output of the per-row losses (what LossWrapper returns as out['loss'] under drop_worst_flag) */
 } capb200_scst_opts;
 #define CAPB200_BASELINE_GREEDY 0
 #define CAPB200_BASELINE_LEAVE_ONE_OUT 1
@@ -328,6 +331,9 @@ typedef struct {
     float ss_prob;             /* scheduled sampling (AttModel.py:145-154): from the second step on, each row's input word is drawn from the model's
                                   previous prediction with this probability; 0 = teacher forcing */
     long long* tokens_used;    /* optional [N, label_cols-1] int64: the words actually fed (labels, or the draws where scheduled sampling hit) */
+    int keep_rows;             /* drop_worst (tools/train.py:187-191): 0 = reduction 'mean'; k > 0 = the criterion runs with reduction 'none' (one loss per
+                                  caption row) and the k rows with the smallest loss are averaged: loss[0] = that mean, gradients accordingly */
+    float* row_loss;           /* optional [rows] output of the per-row losses (what LossWrapper returns as out['loss'] under drop_worst_flag) */
 } capb200_xe_opts;
 /* labels[N, label_cols] int64 (column 0 = BOS = 0), masks[N, label_cols] fp32, N = B * seq_per_img.
  * Outputs: logprobs[N, label_cols-1, V+1] (caller zero-fills; columns >= steps stay zero), loss[1], every grads buffer overwritten. */
@@ -355,6 +361,9 @@ typedef struct {
     const long long* forced_tokens; /* optional [B*sample_n, T] int64 device: replay these samples (see capb200_scst_opts) */
     const float* att_masks;    /* optional [B, R] region mask (refiner self-attention keys, masked mean pooling AoAModel.py:216-219, decoder
                                   attention keys) */
+    int keep_rows;             /* drop_worst (tools/train.py:187-191): 0 = reduction 'mean'; k > 0 = the criterion runs with reduction 'none' (one loss per
+                                  caption row) and the k rows with the smallest loss are averaged: loss[0] = that mean, gradients accordingly */
+    float* row_loss;           /* optional [rows] output of the per-row losses (what LossWrapper returns as out['loss'] under drop_worst_flag) */
 } capb200_aoa_scst_opts;
 /* Gradient buffers, laid out field by field like the weights struct above: parameter shapes, fp32, device; every one is OVERWRITTEN. */
 typedef struct {
@@ -390,6 +399,9 @@ typedef struct {
     const float* att_masks;    /* optional [B, R] region mask */
     float ss_prob;             /* scheduled sampling, see capb200_xe_opts */
     long long* tokens_used;
+    int keep_rows;             /* drop_worst (tools/train.py:187-191): 0 = reduction 'mean'; k > 0 = the criterion runs with reduction 'none' (one loss per
+                                  caption row) and the k rows with the smallest loss are averaged: loss[0] = that mean, gradients accordingly */
+    float* row_loss;           /* optional [rows] output of the per-row losses (what LossWrapper returns as out['loss'] under drop_worst_flag) */
 } capb200_aoa_xe_opts;
 int capb200_aoa_xe_step(capb200_aoa_engine* e, const float* att, int B, int R, const capb200_aoa_xe_opts* opts, const long long* labels,
                         const float* masks, int label_cols, const capb200_aoa_grads* grads, float* logprobs, float* loss, void* stream);

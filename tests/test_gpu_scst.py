@@ -526,3 +526,58 @@ def test_xe_step_scheduled_sampling(family):
     expect = (p_prev ** 2).sum(2)[cand]                                          # E[p(draw)] for a draw from p
     assert abs(float(drawn.mean()) - float(expect.mean())) < 0.15
     model.ss_prob = 0.0
+
+
+@pytest.mark.parametrize('branch', ['xe', 'sc'])
+def test_drop_worst_through_the_loss_wrapper(branch):
+    """drop_worst_flag (tools/train.py:187-191): LossWrapper returns one loss per caption row, the trainer averages the
+    k = int(rows * (1 - drop_worst_rate)) smallest and back-propagates; loss vector and every parameter gradient against autograd through
+    the oracle doing literally that."""
+    import imagecaptioning.pytorch_b200 as b200
+    from oracle import ciderd_oracle as cdo
+    model, fam = build_pair('updown', seed=31, logit_scale=5.0, mode='tc_f16x3', **CFG)
+    W = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    B, R, n, spi, T = 5, 9, 4, 3, CFG['T']
+    fc, att = co.make_inputs(B, R, CFG['F_fc'], CFG['F_att'], seed=5)
+    labels, masks = _labels(B, spi, CFG['V'], T + 2, seed=3)
+    gts = cdo.make_refs(B, CFG['V'], seed=3)
+    df, ref_len = cdo.build_document_frequency(cdo.make_refs(100, CFG['V'], seed=4))
+    b200.rewards.reset_scorer()
+    b200.rewards.init_scorer(b200.rewards.CiderDTable(df, ref_len))
+    rate = 0.3
+    opt = argparse.Namespace(sc_sample_method='greedy', sc_beam_size=1, train_sample_method='sample', train_beam_size=1, train_sample_n=n,
+                             cider_reward_weight=1, bleu_reward_weight=0, label_smoothing=0.0, drop_worst_rate=rate)
+    lw = b200.B200LossWrapper(model, opt)
+    model.train()
+    model.drop_prob_lm = 0.0
+    sc = branch == 'sc'
+    out = lw(fc.cuda(), att.cuda(), labels.cuda(), masks.cuda(), None, gts, torch.arange(B), sc, False, True)
+    rows = out['loss']
+    k = int(rows.shape[0] * (1 - rate))
+    assert rows.dim() == 1 and rows.shape[0] == (B * n if sc else B * spi) and rows.requires_grad
+    loss = torch.topk(rows, k=k, largest=False)[0].mean()
+    loss.backward()
+    Wg = {k_: v.clone().requires_grad_(True) for k_, v in W.items()}
+    fam_g = co.Family('updown', Wg, T)
+    if sc:
+        seq = lw.last_step['sample_seq'].cpu()
+        greedy = lw.last_step['greedy_seq'].cpu()
+        _, lp = co.sample(fam_g, fc, att, sample_method='sample', sample_n=n, forced_tokens=seq)
+        reward, _ = cdo.self_critical_reward(greedy.numpy(), gts, seq.numpy(), df, ref_len)
+        m = torch.cat([torch.ones(seq.shape[0], 1), (seq[:, :-1] > 0).float()], 1)
+        orow = (-lp.gather(2, seq.unsqueeze(2)).squeeze(2) * torch.from_numpy(reward).float() * m).sum(1) / m.sum(1)
+    else:
+        lp = co.forward_teacher(fam_g, fc, att, labels[..., :-1])
+        tl, tm = labels[..., 1:].reshape(B * spi, -1), masks[..., 1:].reshape(B * spi, -1)
+        orow = (-lp.gather(2, tl.unsqueeze(2)).squeeze(2) * tm).sum(1) / tm.sum(1)
+    oloss = torch.topk(orow, k=k, largest=False)[0].mean()
+    oloss.backward()
+    assert float((rows.detach().cpu() - orow.detach()).abs().max()) < LOGP_TOL
+    assert abs(float(loss) - float(oloss)) < LOGP_TOL
+    grads = {p: p.grad for p in model.parameters()}
+    _check_grads(model, grads, {k_: v.grad for k_, v in Wg.items()})
+    # any other reduction of the row vector is refused instead of silently mis-trained
+    out = lw(fc.cuda(), att.cuda(), labels.cuda(), masks.cuda(), None, gts, torch.arange(B), sc, False, True)
+    with pytest.raises(NotImplementedError):
+        out['loss'].mean().backward()
+    b200.rewards.reset_scorer()
