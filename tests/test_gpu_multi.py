@@ -52,3 +52,31 @@ def test_data_parallel_decode_and_scst():
     assert all(g is not None and torch.isfinite(g).all() for g in grads)
     assert sum(float(g.abs().max()) > 0 for g in grads) >= 15
     b200.rewards.reset_scorer()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+@pytest.mark.parametrize('family', ['aoa', 'transformer'])
+def test_data_parallel_replicas_see_updated_weights(family):
+    """nn.DataParallel replicas are fresh Broadcast outputs every forward (version 0) and the caching allocator hands the same addresses back
+    after an optimizer step, so (data_ptr, _version) cannot tell a replica's weights changed: the engines on GPU >= 1 must re-bind on every
+    call.  decode -> in-place weight update (what optimizer.step does) -> decode: both GPUs must follow the new weights (checked per shard
+    against the oracle built from the updated state dict)."""
+    heads = 4
+    cfg = dict(V=40, E=32, H=64, A=0, F_fc=32, F_att=40, T=7) if family == 'aoa' else dict(V=40, E=32, H=64, A=2, F_fc=32, F_att=40, T=7)
+    model, fam = build_pair(family, seed=21, logit_scale=8.0, mode='tc_f16x3', device='cuda:0', heads=heads, **cfg)
+    dp = torch.nn.DataParallel(model, device_ids=[0, 1])
+    B, R = 6, 7
+    fc, att = co.make_inputs(B, R, cfg['F_fc'], cfg['F_att'], seed=5)
+    opt = {'sample_method': 'greedy', 'beam_size': 1}
+    with torch.no_grad():
+        seq0, _ = dp(fc.cuda(0), att.cuda(0), None, opt=opt, mode='sample')
+        g = torch.Generator(device='cuda:0').manual_seed(1)
+        for p in model.parameters():                        # an "optimizer step": in-place update of the master parameters
+            p.add_(torch.randn(p.shape, generator=g, device='cuda:0') * 0.05 * p.abs().mean())
+        seq1, lp1 = dp(fc.cuda(0), att.cuda(0), None, opt=opt, mode='sample')
+    W1 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    fam1 = co.Family(family, W1, cfg['T'], heads=heads)
+    margins = []
+    oseq, olp = co.sample(fam1, fc, att, record_margin=margins)
+    check_decode(fam1, fc, att, seq1, lp1, oseq, olp, margins)          # covers the second half of the batch = the GPU-1 replica
+    assert not torch.equal(seq0.cpu(), seq1.cpu())                       # the update did change the captions
