@@ -227,16 +227,33 @@ __global__ void __launch_bounds__(128) cross_attn_train_kernel(int rows, int rpi
     const int img = row / rpi;
     float* p = sm + warp * R;
     const float* qr = q + (long)row * ld_q + head * dk;
-    float mx = -INFINITY;
-    for (int r = lane; r < R; r += 32) {
-        const float* kr = kk + ((long)img * R + r) * ld_kv + head * dk;
-        float s = 0.f;
-        for (int c = 0; c < dk; ++c) s = fmaf(qr[c], __ldg(kr + c), s);
-        s *= scale;
-        if (mask != nullptr && mask[(long)img * ld_mask + r] == 0.f) s = -INFINITY;
-        p[r] = s;
-        mx = fmaxf(mx, s);
+    // lanes across the head's dk columns: coalesced key reads, four regions in flight (see cross_attention_kernel in transformer.cu)
+    {
+        const float* kb = kk + (long)img * R * ld_kv + head * dk;
+        constexpr int NQ = 8;
+        float qv[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) { const int c = lane + 32 * i; qv[i] = (c < dk) ? qr[c] : 0.f; }
+        for (int r0 = 0; r0 < R; r0 += 4) {
+            float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (r0 + u < R) {
+                    const float* kr = kb + (long)(r0 + u) * ld_kv;
+#pragma unroll
+                    for (int i = 0; i < NQ; ++i) { const int c = lane + 32 * i; if (c < dk) part[u] = fmaf(qv[i], __ldg(kr + c), part[u]); }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float s = wsum(part[u]) * scale;
+                if (lane == 0 && r0 + u < R) p[r0 + u] = (mask != nullptr && mask[(long)img * ld_mask + r0 + u] == 0.f) ? -INFINITY : s;
+            }
+        }
+        __syncwarp();
     }
+    float mx = -INFINITY;
+    for (int r = lane; r < R; r += 32) mx = fmaxf(mx, p[r]);
     mx = wmax(mx);
     float sum = 0.f;
     for (int r = lane; r < R; r += 32) { const float e = expf(p[r] - mx); p[r] = e; sum += e; }

@@ -25,3 +25,6 @@ CAPB200_SKINNY_LEGACY=1 CAPB200_SCST_SERIAL_GREEDY=1 timeout 600 python bench.py
 echo "legacy scst rc=$?"; tail -c 900 gpurun_out/r02a_bench_scst_legacy.json
 CAPB200_SPLIT_LANG=1 CAPB200_BENCH_NO_SCST=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02a_bench_split.json 2> gpurun_out/r02a_bench_split.err
 echo "split-lang rc=$?"; tail -c 1500 gpurun_out/r02a_bench_split.json | cut -c1-700
+# warm per-kernel tables (CUPTI) of the AoANet SCST step and the headline decode
+timeout 600 python tools/scst_table.py 10 aoa > gpurun_out/r02a_scst_table_aoa.txt 2>&1; echo "scst table rc=$?"; head -30 gpurun_out/r02a_scst_table_aoa.txt
+timeout 600 python tools/kernel_table.py 256 5 updown > gpurun_out/r02a_kernel_table.txt 2>&1; echo "decode table rc=$?"; head -16 gpurun_out/r02a_kernel_table.txt
