@@ -242,9 +242,23 @@ __global__ void gather_rows_kernel(const float* __restrict__ slab, long step_str
         const float mx = st.x, lsum = st.y;
         const float m2 = (mx - mx) - lsum, l2 = lsum;
         const bool twice = sidx > 0;
-        for (int v = threadIdx.x; v < V1; v += blockDim.x) {
-            const float lp = (src[v] - mx) - lsum;
-            d[v] = twice ? (lp - m2) - l2 : lp;
+        const bool vec4 = ((V1 & 3) == 0) && ((ld_slab & 3) == 0) && ((step_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(slab) & 15) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+        if (vec4) {      // 194 MB of winner rows per decode: 128-bit loads and stores
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(d);
+            for (int v = threadIdx.x; v < V1 / 4; v += blockDim.x) {
+                const float4 x = __ldg(s4 + v);
+                float4 o;
+                o.x = (x.x - mx) - lsum; o.y = (x.y - mx) - lsum; o.z = (x.z - mx) - lsum; o.w = (x.w - mx) - lsum;
+                if (twice) { o.x = (o.x - m2) - l2; o.y = (o.y - m2) - l2; o.z = (o.z - m2) - l2; o.w = (o.w - m2) - l2; }
+                d4[v] = o;
+            }
+        } else {
+            for (int v = threadIdx.x; v < V1; v += blockDim.x) {
+                const float lp = (src[v] - mx) - lsum;
+                d[v] = twice ? (lp - m2) - l2 : lp;
+            }
         }
         apply_edits();
         return;

@@ -144,6 +144,26 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long ldx, int r
     if (bad && range_flag != nullptr) *range_flag = 1;
 }
 
+// 128-bit variant for 16-byte aligned rows (the 75.5 MB bottom-up feature tile of every decode goes through here): one float4 in, two 8-byte
+// stores out per thread and no integer division per element.
+__global__ void split_planes_vec4_kernel(const float* __restrict__ x, long ldx, int rows, int cols4, __half* __restrict__ hi, __half* __restrict__ lo,
+                                         long ldh, int* __restrict__ range_flag) {
+    const long total = (long)rows * cols4;
+    bool bad = false;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / cols4;
+        const int c = (int)(i - r * cols4) * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ldx + c));
+        bad |= !(fabsf(v.x) < 65504.0f) || !(fabsf(v.y) < 65504.0f) || !(fabsf(v.z) < 65504.0f) || !(fabsf(v.w) < 65504.0f);
+        __align__(8) __half h[4];
+        __align__(8) __half l[4];
+        split_f32(v.x, h[0], l[0]); split_f32(v.y, h[1], l[1]); split_f32(v.z, h[2], l[2]); split_f32(v.w, h[3], l[3]);
+        *reinterpret_cast<uint2*>(hi + r * ldh + c) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(lo + r * ldh + c) = *reinterpret_cast<const uint2*>(l);
+    }
+    if (bad && range_flag != nullptr) *range_flag = 1;
+}
+
 __global__ void split_planes_interleave_kernel(const float* __restrict__ x, long ldx, int H, int cols, __half* __restrict__ hi,
                                                __half* __restrict__ lo, long ldh, int* __restrict__ range_flag) {
     const long total = (long)4 * H * cols;
@@ -220,6 +240,15 @@ int gemm_simt_launch(const GemmProblem& g, cudaStream_t stream) {
 int split_planes_launch(const float* x, long ldx, int rows, int cols, __half* hi, __half* lo, long ldh, cudaStream_t stream) {
     if (rows <= 0 || cols <= 0) return 0;
     const long total = (long)rows * cols;
+    const bool vec = (cols & 3) == 0 && (ldx & 3) == 0 && (ldh & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(lo) & 7) == 0;
+    if (vec) {
+        int vb = (int)((total / 4 + 255) / 256);
+        if (vb > 148 * 16) vb = 148 * 16;
+        split_planes_vec4_kernel<<<vb, 256, 0, stream>>>(x, ldx, rows, cols / 4, hi, lo, ldh, range_flag_ptr());
+        CAPB_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     split_planes_kernel<<<blocks, 256, 0, stream>>>(x, ldx, rows, cols, hi, lo, ldh, range_flag_ptr());

@@ -181,7 +181,7 @@ class B200CaptionModel(nn.Module):
             self._flat = fg
         return fg
 
-    def _buffers(self, key, make):
+    def _step_buffers(self, key, make):      # (nn.Module owns the name _buffers)
         bufs = self._bufs
         if key not in bufs:
             bufs.clear()            # one live shape at a time: the buffers are large (the [N, T, V+1] log-prob block)
@@ -348,8 +348,9 @@ class B200CaptionModel(nn.Module):
         B = fc.shape[0]
         R = att.shape[1] if att is not None and att.dim() == 3 else 1
         N, T, V1 = B * sample_n, self.seq_length, self.vocab_size + 1
-        seq = torch.zeros(N, T, dtype=torch.long, device=fc.device)
-        logprobs = torch.zeros(N, T, V1, dtype=torch.float32, device=fc.device)
+        # every (row, step) of both outputs is written by the engine (finished rows get pad / zero rows): no memset of the [N, T, V+1] block
+        seq = torch.empty(N, T, dtype=torch.long, device=fc.device)
+        logprobs = torch.empty(N, T, V1, dtype=torch.float32, device=fc.device)
         draws = method in (_lib.SAMPLE_MULTINOMIAL, _lib.SAMPLE_TOPK, _lib.SAMPLE_TOPP)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if draws else 0   # follows torch.manual_seed
         edits, keep_bad = self._decode_edits(opt, fc.device, beam=False, batch_size=B)
@@ -398,12 +399,13 @@ class B200CaptionModel(nn.Module):
         R = att.shape[1] if att is not None and att.dim() == 3 else 1
         T, V1 = self.seq_length, self.vocab_size + 1
         dev = fc.device
-        seq = torch.zeros(B * sample_n, T, dtype=torch.long, device=dev)
-        logprobs = torch.zeros(B * sample_n, T, V1, dtype=torch.float32, device=dev)
-        d_seq = torch.zeros(B, beam_size, T, dtype=torch.long, device=dev)
-        d_len = torch.zeros(B, beam_size, dtype=torch.int32, device=dev)
-        d_p = torch.zeros(B, beam_size, dtype=torch.float32, device=dev)
-        d_raw = torch.zeros(B, beam_size, dtype=torch.float32, device=dev)
+        # all six outputs are written in full by the engine (zero rows / pad beyond each caption's length): no 194 MB memset per call
+        seq = torch.empty(B * sample_n, T, dtype=torch.long, device=dev)
+        logprobs = torch.empty(B * sample_n, T, V1, dtype=torch.float32, device=dev)
+        d_seq = torch.empty(B, beam_size, T, dtype=torch.long, device=dev)
+        d_len = torch.empty(B, beam_size, dtype=torch.int32, device=dev)
+        d_p = torch.empty(B, beam_size, dtype=torch.float32, device=dev)
+        d_raw = torch.empty(B, beam_size, dtype=torch.float32, device=dev)
         edits, keep_bad = self._decode_edits(opt, dev, beam=True)
         bo = _lib.BeamOpts(beam_size, sample_n, _PENALTY[kind], float(alpha), float(opt.get('temperature', 1.0)), edits)
         _lib.check(self._call_beam(lib, fc, att, masks, B, R, bo, seq, logprobs, d_seq, d_len, d_p, d_raw), 'decode_beam')
@@ -550,7 +552,7 @@ class B200UpDownModel(B200CaptionModel):
         fg, g = self._grad_table(lib, dev)
         grads = fg.by_name
         # outputs live in persistent buffers (overwritten by the next step of the same shape): the step writes every row of every one
-        sample_seq, greedy_seq, logprobs, reward, loss = self._buffers(('scst', B, sample_n), lambda: (
+        sample_seq, greedy_seq, logprobs, reward, loss = self._step_buffers(('scst', B, sample_n), lambda: (
             torch.zeros(N, T, dtype=torch.long, device=dev), torch.zeros(B, T, dtype=torch.long, device=dev),
             torch.zeros(N, T, V1, dtype=torch.float32, device=dev), torch.empty(N, T, dtype=torch.float32, device=dev),
             torch.empty(1, dtype=torch.float32, device=dev)))
@@ -914,7 +916,7 @@ class B200AoAModel(B200CaptionModel):
         if baseline not in ('greedy', 'leave_one_out'):
             raise ValueError("baseline must be 'greedy' or 'leave_one_out'")
         loo = baseline == 'leave_one_out'
-        sample_seq, greedy_seq, logprobs, reward, loss = self._buffers(('scst', B, sample_n), lambda: (
+        sample_seq, greedy_seq, logprobs, reward, loss = self._step_buffers(('scst', B, sample_n), lambda: (
             torch.zeros(N, T, dtype=torch.long, device=dev), torch.zeros(B, T, dtype=torch.long, device=dev),
             torch.zeros(N, T, V1, dtype=torch.float32, device=dev), torch.empty(N, T, dtype=torch.float32, device=dev),
             torch.empty(1, dtype=torch.float32, device=dev)))

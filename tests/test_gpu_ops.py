@@ -97,7 +97,8 @@ def test_tf32x3_tcgen05_input_gradient(L, shape):
     w = (torch.rand(K, N, generator=g) * 2 - 1) / K ** 0.5
     ref = dy.double() @ w.double()
     y = torch.empty(M, N, device='cuda')
-    L.check(L.load().capb200_linear(L.ptr(dy.cuda()), K, L.ptr(w.cuda()), N, None, L.ptr(y), N, M, N, K, 0, L.OP_MODES['tf32x3_tc_dgrad'], L.current_stream()),
+    dyd, wd = dy.cuda(), w.cuda()               # keep the device tensors alive across the asynchronous call
+    L.check(L.load().capb200_linear(L.ptr(dyd), K, L.ptr(wd), N, None, L.ptr(y), N, M, N, K, 0, L.OP_MODES['tf32x3_tc_dgrad'], L.current_stream()),
             'linear dgrad')
     torch.cuda.synchronize()
     scale = dy.double().abs() @ w.double().abs()
@@ -113,7 +114,8 @@ def test_tf32x3_tcgen05_weight_gradient(L, shape):
     x = torch.randn(K, N, generator=g)
     ref = dy.double().t() @ x.double()
     y = torch.empty(M, N, device='cuda')
-    L.check(L.load().capb200_linear(L.ptr(dy.cuda()), M, L.ptr(x.cuda()), N, None, L.ptr(y), N, M, N, K, 0, L.OP_MODES['tf32x3_tc_wgrad'], L.current_stream()),
+    dyd, xd = dy.cuda(), x.cuda()
+    L.check(L.load().capb200_linear(L.ptr(dyd), M, L.ptr(xd), N, None, L.ptr(y), N, M, N, K, 0, L.OP_MODES['tf32x3_tc_wgrad'], L.current_stream()),
             'linear wgrad')
     torch.cuda.synchronize()
     scale = dy.double().abs().t() @ x.double().abs()
