@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "dropout.cuh"
 #include "kernels.cuh"
+#include "attn.cuh"
 
 namespace capb200 {
 
@@ -23,53 +24,72 @@ __device__ __forceinline__ float wmax(float v) {
     return v;
 }
 
-// one warp per row: dx (+)= d LayerNorm / dx; stats[row] = (mean, 1/(std+eps)) for the parameter-gradient pass
-__global__ void ln_backward_kernel(int rows, int D, const float* __restrict__ x, long ld_x, const float* __restrict__ a, const float* __restrict__ dy,
-                                   long ld_dy, float eps, float* __restrict__ dx, long ld_dx, int accumulate, float2* __restrict__ stats) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const int lane = threadIdx.x & 31;
+// one CTA of 128 threads per row: dx (+)= d LayerNorm / dx; stats[row] = (mean, 1/(std+eps)) for the parameter-gradient pass
+__device__ __forceinline__ float bsum128(float v, float* sh) {
+    v = wsum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return (sh[0] + sh[1]) + (sh[2] + sh[3]);
+}
+__global__ void __launch_bounds__(128) ln_backward_kernel(int rows, int D, const float* __restrict__ x, long ld_x, const float* __restrict__ a,
+                                                          const float* __restrict__ dy, long ld_dy, float eps, float* __restrict__ dx, long ld_dx,
+                                                          int accumulate, float2* __restrict__ stats) {
+    __shared__ float sh[4];
+    const int row = blockIdx.x;
     const float* xr = x + (long)row * ld_x;
     const float* gr = dy + (long)row * ld_dy;
     float s = 0.f;
-    for (int c = lane; c < D; c += 32) s += xr[c];
-    const float mean = wsum(s) / (float)D;
+    for (int c = threadIdx.x; c < D; c += 128) s += xr[c];
+    const float mean = bsum128(s, sh) / (float)D;
     float q = 0.f;
-    for (int c = lane; c < D; c += 32) { const float d = xr[c] - mean; q = fmaf(d, d, q); }
-    const float stdv = sqrtf(wsum(q) / (float)(D - 1));
+    for (int c = threadIdx.x; c < D; c += 128) { const float d = xr[c] - mean; q = fmaf(d, d, q); }
+    const float stdv = sqrtf(bsum128(q, sh) / (float)(D - 1));
     const float inv = 1.0f / (stdv + eps);
     float g_sum = 0.f, g_dot = 0.f;                  // sum of g and of g * (x - mean), g = dy * a
-    for (int c = lane; c < D; c += 32) {
+    for (int c = threadIdx.x; c < D; c += 128) {
         const float g = gr[c] * __ldg(a + c);
         g_sum += g;
         g_dot = fmaf(g, xr[c] - mean, g_dot);
     }
-    g_sum = wsum(g_sum);
-    g_dot = wsum(g_dot);
+    g_sum = bsum128(g_sum, sh);
+    g_dot = bsum128(g_dot, sh);
     const float g_mean = g_sum / (float)D;
     const float k = (stdv > 0.f) ? inv * inv * g_dot / ((float)(D - 1) * stdv) : 0.f;
-    for (int c = lane; c < D; c += 32) {
+    for (int c = threadIdx.x; c < D; c += 128) {
         const float v = inv * (gr[c] * __ldg(a + c) - g_mean) - k * (xr[c] - mean);
         float* o = dx + (long)row * ld_dx + c;
         *o = accumulate ? *o + v : v;
     }
-    if (lane == 0 && stats != nullptr) stats[row] = make_float2(mean, inv);
+    if (threadIdx.x == 0 && stats != nullptr) stats[row] = make_float2(mean, inv);
 }
 
 // thread per column: da[c] (+)= sum_rows dy * xhat, db[c] (+)= sum_rows dy
 __global__ void ln_param_grad_kernel(int rows, int D, const float* __restrict__ x, long ld_x, const float* __restrict__ dy, long ld_dy,
                                      const float2* __restrict__ stats, float* __restrict__ da, float* __restrict__ db, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= D) return;
+    // block = 32 columns x 8 row groups (see colsum_kernel): coalesced row segments, eight independent partial sums per column
+    __shared__ float sha[8][33], shb[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     float sa = 0.f, sb = 0.f;
-    for (int r = 0; r < rows; ++r) {
-        const float2 st = stats[r];
-        const float g = dy[(long)r * ld_dy + c];
-        sa = fmaf(g, (x[(long)r * ld_x + c] - st.x) * st.y, sa);
-        sb += g;
+    if (c < D) {
+        for (int r = ty; r < rows; r += 8) {
+            const float2 st = stats[r];
+            const float g = dy[(long)r * ld_dy + c];
+            sa = fmaf(g, (x[(long)r * ld_x + c] - st.x) * st.y, sa);
+            sb += g;
+        }
     }
-    da[c] = accumulate ? da[c] + sa : sa;
-    db[c] = accumulate ? db[c] + sb : sb;
+    sha[ty][tx] = sa;
+    shb[ty][tx] = sb;
+    __syncthreads();
+    if (ty == 0 && c < D) {
+        float ta = 0.f, tb = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) { ta += sha[g][tx]; tb += shb[g][tx]; }
+        da[c] = accumulate ? da[c] + ta : ta;
+        db[c] = accumulate ? db[c] + tb : tb;
+    }
 }
 
 // y = t[:, :H] * sigmoid(t[:, H:]):  dt[:, :H] = dy * s,  dt[:, H:] = dy * t[:, :H] * s * (1 - s)
@@ -88,24 +108,25 @@ __global__ void glu_backward_kernel(int rows, int H, const float* __restrict__ t
 
 // ---- refiner self-attention, train mode: one CTA per (image, head), dropout on the probabilities ----------------------------------
 // q,k,v: [B*R, ld] with the head at columns [head*dk, (head+1)*dk).  Dropout element index = ((img*heads + head)*R + qi)*R + r.
-__global__ void __launch_bounds__(128) enc_attn_train_kernel(int R, int dk, int heads, const float* __restrict__ q, const float* __restrict__ k,
+__global__ void __launch_bounds__(256) enc_attn_train_kernel(int R, int dk, int heads, const float* __restrict__ q, const float* __restrict__ k,
                                                              const float* __restrict__ v, long ld, float scale, unsigned long long seed, uint32_t site,
                                                              float p_drop, float* __restrict__ out, long ld_out, const float* __restrict__ mask,
                                                              long ld_mask) {
     extern __shared__ float sm[];
     float* sk = sm;                 // [R][dk+1]
     float* sv = sk + R * (dk + 1);
-    float* sp = sv + R * (dk + 1);  // [4 warps][R]
+    float* sp = sv + R * (dk + 1);  // [warps][R]
     const int img = blockIdx.x, head = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {       // independent coalesced loads, four in flight per thread
         const int r = i / dk, c = i % dk;
         sk[r * (dk + 1) + c] = k[((long)img * R + r) * ld + head * dk + c];
         sv[r * (dk + 1) + c] = v[((long)img * R + r) * ld + head * dk + c];
     }
     __syncthreads();
     float* p = sp + warp * R;
-    for (int qi = warp; qi < R; qi += 4) {
+    for (int qi = warp; qi < R; qi += nw) {
         const float* qr = q + ((long)img * R + qi) * ld + head * dk;
         float mx = -INFINITY;
         for (int r = lane; r < R; r += 32) {
@@ -148,6 +169,7 @@ __global__ void __launch_bounds__(256) enc_attn_backward_kernel(int R, int dk, i
     float* DS = P + R * R;          // [R][R] dropout scale, then d score
     const int img = blockIdx.x, head = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+#pragma unroll 2
     for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {
         const int r = i / dk, c = i % dk;
         const long g = ((long)img * R + r) * ld + head * dk + c;
@@ -213,67 +235,33 @@ __global__ void __launch_bounds__(256) enc_attn_backward_kernel(int R, int dk, i
     }
 }
 
-// ---- decoder attention, train mode: one warp per (row, head); probabilities (before dropout) are saved for the backward ------------
+// ---- decoder attention, train mode: one CTA per (row, head) (attn.cuh); probabilities (before dropout) are saved for the backward ------------
 __global__ void __launch_bounds__(128) cross_attn_train_kernel(int rows, int rpi, int heads, int dk, int R, const float* __restrict__ q, long ld_q,
                                                                const float* __restrict__ kk, const float* __restrict__ vv, long ld_kv, float scale,
                                                                unsigned long long seed, uint32_t site, uint32_t step, float p_drop,
                                                                float* __restrict__ out, long ld_out, float* __restrict__ probs,
                                                                const float* __restrict__ mask, long ld_mask) {
-    extern __shared__ float sm[];       // [4 warps][R]
-    const int item = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (item >= rows * heads) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    extern __shared__ float sm[];       // [R] scores -> exp -> dropped probabilities
+    __shared__ float sh_inv;
+    const int item = blockIdx.x;
     const int row = item / heads, head = item % heads;
     const int img = row / rpi;
-    float* p = sm + warp * R;
     const float* qr = q + (long)row * ld_q + head * dk;
-    // lanes across the head's dk columns: coalesced key reads, four regions in flight (see cross_attention_kernel in transformer.cu)
-    {
-        const float* kb = kk + (long)img * R * ld_kv + head * dk;
-        constexpr int NQ = 8;
-        float qv[NQ];
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) { const int c = lane + 32 * i; qv[i] = (c < dk) ? qr[c] : 0.f; }
-        for (int r0 = 0; r0 < R; r0 += 4) {
-            float part[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (r0 + u < R) {
-                    const float* kr = kb + (long)(r0 + u) * ld_kv;
-#pragma unroll
-                    for (int i = 0; i < NQ; ++i) { const int c = lane + 32 * i; if (c < dk) part[u] = fmaf(qv[i], __ldg(kr + c), part[u]); }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float s = wsum(part[u]) * scale;
-                if (lane == 0 && r0 + u < R) p[r0 + u] = (mask != nullptr && mask[(long)img * ld_mask + r0 + u] == 0.f) ? -INFINITY : s;
-            }
-        }
-        __syncwarp();
-    }
-    float mx = -INFINITY;
-    for (int r = lane; r < R; r += 32) mx = fmaxf(mx, p[r]);
-    mx = wmax(mx);
-    float sum = 0.f;
-    for (int r = lane; r < R; r += 32) { const float e = expf(p[r] - mx); p[r] = e; sum += e; }
-    sum = wsum(sum);
-    const float inv = 1.0f / sum;
-    for (int r = lane; r < R; r += 32) {
-        const float pr = p[r] * inv;
+    const float* kb = kk + (long)img * R * ld_kv + head * dk;
+    const float* vb = vv + (long)img * R * ld_kv + head * dk;
+    sq_attention_scores(qr, kb, ld_kv, R, dk, scale, mask != nullptr ? mask + (long)img * ld_mask : nullptr, sm);
+    const float inv = sq_attention_softmax(sm, R, &sh_inv);
+    for (int r = threadIdx.x; r < R; r += 128) {
+        const float pr = sm[r] * inv;
         probs[(long)item * R + r] = pr;
-        p[r] = pr * drop_scale(seed, site, step, (uint32_t)((long)item * R + r), p_drop);
+        sm[r] = pr * drop_scale(seed, site, step, (uint32_t)((long)item * R + r), p_drop);
     }
-    __syncwarp();
-    for (int c = lane; c < dk; c += 32) {
-        float acc = 0.f;
-        for (int r = 0; r < R; ++r) acc = fmaf(p[r], __ldg(vv + ((long)img * R + r) * ld_kv + head * dk + c), acc);
-        out[(long)row * ld_out + head * dk + c] = acc;
-    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < dk; c += 128) out[(long)row * ld_out + head * dk + c] = sq_attention_column(sm, vb, ld_kv, R, c);
 }
 
 // backward: one CTA per (image, head) walks the image's rpi rows; dq written, dK / dV accumulated (+=) into the per-image buffers
-__global__ void __launch_bounds__(128) cross_attn_backward_kernel(int rpi, int heads, int dk, int R, const float* __restrict__ q, long ld_q,
+__global__ void __launch_bounds__(256) cross_attn_backward_kernel(int rpi, int heads, int dk, int R, const float* __restrict__ q, long ld_q,
                                                                   const float* __restrict__ kk, const float* __restrict__ vv, long ld_kv, float scale,
                                                                   unsigned long long seed, uint32_t site, uint32_t step, float p_drop,
                                                                   const float* __restrict__ probs, const float* __restrict__ d_out, long ld_do,
@@ -289,7 +277,8 @@ __global__ void __launch_bounds__(128) cross_attn_backward_kernel(int rpi, int h
     float* DS = PD + rpi * R;        // [rpi][R]  d score (scaled)
     const int img = blockIdx.x, head = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {
+#pragma unroll 4
+    for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {       // independent coalesced loads, several in flight per thread
         const int r = i / dk, c = i % dk;
         sk[r * W + c] = kk[((long)img * R + r) * ld_kv + head * dk + c];
         sv[r * W + c] = vv[((long)img * R + r) * ld_kv + head * dk + c];
@@ -321,14 +310,15 @@ __global__ void __launch_bounds__(128) cross_attn_backward_kernel(int rpi, int h
     __syncthreads();
     for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {
         const int r = i / dk, c = i % dk;
+        const long g = ((long)img * R + r) * ld_dkv + head * dk + c;
+        const float ov = dvv[g], ok = dkk[g];            // the read-modify-write's loads are issued before the reduction over the rows
         float av = 0.f, ak = 0.f;
         for (int j = 0; j < rpi; ++j) {
             av = fmaf(PD[j * R + r], sd[j * W + c], av);
             ak = fmaf(DS[j * R + r], sq[j * W + c], ak);
         }
-        const long g = ((long)img * R + r) * ld_dkv + head * dk + c;
-        dvv[g] += av;
-        dkk[g] += ak;
+        dvv[g] = ov + av;
+        dkk[g] = ok + ak;
     }
     for (int i = threadIdx.x; i < rpi * dk; i += blockDim.x) {
         const int j = i / dk, c = i % dk;
@@ -398,9 +388,9 @@ int blocks_for(long n) {
 
 int ln_backward_launch(int rows, int D, const float* x, long ld_x, const float* a, const float* dy, long ld_dy, float eps, float* dx, long ld_dx, int accumulate,
                        float* stats, float* da, float* db, int accumulate_params, cudaStream_t st) {
-    ln_backward_kernel<<<cdiv(rows, 4), 128, 0, st>>>(rows, D, x, ld_x, a, dy, ld_dy, eps, dx, ld_dx, accumulate, reinterpret_cast<float2*>(stats));
+    ln_backward_kernel<<<rows, 128, 0, st>>>(rows, D, x, ld_x, a, dy, ld_dy, eps, dx, ld_dx, accumulate, reinterpret_cast<float2*>(stats));
     CAPB_CHECK_CUDA(cudaGetLastError());
-    ln_param_grad_kernel<<<cdiv(D, 128), 128, 0, st>>>(rows, D, x, ld_x, dy, ld_dy, reinterpret_cast<const float2*>(stats), da, db, accumulate_params);
+    ln_param_grad_kernel<<<cdiv(D, 32), 256, 0, st>>>(rows, D, x, ld_x, dy, ld_dy, reinterpret_cast<const float2*>(stats), da, db, accumulate_params);
     LAUNCH_OK();
 }
 int glu_backward_launch(int rows, int H, const float* t, long ld_t, const float* dy, long ld_dy, float* dt, long ld_dt, cudaStream_t st) {
@@ -409,9 +399,9 @@ int glu_backward_launch(int rows, int H, const float* t, long ld_t, const float*
 }
 int enc_attn_train_launch(int B, int R, int heads, int dk, const float* q, const float* k, const float* v, long ld, unsigned long long seed, int site, float p,
                           float* out, long ld_out, cudaStream_t st, const float* mask, long ld_mask) {
-    const size_t smem = sizeof(float) * ((size_t)2 * R * (dk + 1) + 4 * R);
+    const size_t smem = sizeof(float) * ((size_t)2 * R * (dk + 1) + 8 * R);
     CAPB_REQUIRE(smem <= 48 * 1024, "refiner attention: regions * head width too large for the training kernel");
-    enc_attn_train_kernel<<<dim3(B, heads), 128, smem, st>>>(R, dk, heads, q, k, v, ld, 1.0f / sqrtf((float)dk), seed, (uint32_t)site, p, out, ld_out, mask, ld_mask);
+    enc_attn_train_kernel<<<dim3(B, heads), 256, smem, st>>>(R, dk, heads, q, k, v, ld, 1.0f / sqrtf((float)dk), seed, (uint32_t)site, p, out, ld_out, mask, ld_mask);
     LAUNCH_OK();
 }
 int enc_attn_backward_launch(int B, int R, int heads, int dk, const float* q, const float* k, const float* v, long ld, unsigned long long seed, int site, float p,
@@ -429,7 +419,8 @@ int enc_attn_backward_launch(int B, int R, int heads, int dk, const float* q, co
 int cross_attn_train_launch(int rows, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
                             unsigned long long seed, int site, int step, float p, float* out, long ld_out, float* probs, cudaStream_t st, const float* mask,
                             long ld_mask) {
-    cross_attn_train_kernel<<<cdiv(rows * heads, 4), 128, sizeof(float) * 4 * R, st>>>(rows, rpi, heads, dk, R, q, ld_q, kk, vv, ld_kv, 1.0f / sqrtf((float)dk),
+    CAPB_REQUIRE(dk <= 256, "attention: head width above 256");
+    cross_attn_train_kernel<<<rows * heads, 128, sizeof(float) * R, st>>>(rows, rpi, heads, dk, R, q, ld_q, kk, vv, ld_kv, 1.0f / sqrtf((float)dk),
                                                                                         seed, (uint32_t)site, (uint32_t)step, p, out, ld_out, probs, mask, ld_mask);
     LAUNCH_OK();
 }
@@ -442,7 +433,7 @@ int cross_attn_backward_launch(int B, int rpi, int heads, int dk, int R, const f
     if (first_use_on_device(configured)) {
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
-    cross_attn_backward_kernel<<<dim3(B, heads), 128, smem, st>>>(rpi, heads, dk, R, q, ld_q, kk, vv, ld_kv, 1.0f / sqrtf((float)dk), seed, (uint32_t)site,
+    cross_attn_backward_kernel<<<dim3(B, heads), 256, smem, st>>>(rpi, heads, dk, R, q, ld_q, kk, vv, ld_kv, 1.0f / sqrtf((float)dk), seed, (uint32_t)site,
                                                                    (uint32_t)step, p, probs, d_out, ld_do, dq, ld_dq, dkk, dvv, ld_dkv);
     LAUNCH_OK();
 }

@@ -96,6 +96,7 @@ struct GemmEpilogue {
     __half* h_hi = nullptr;
     __half* h_lo = nullptr;
     long ld_h = 0;
+    unsigned long long* trace = nullptr;    // optional phase time stamps of the pair kernel ([CTAs][16] %globaltimer values), tools/gemm_trace.py
 };
 
 // SFU-based transcendental forms (ex2.approx + fast reciprocal): absolute error < 3e-7 on outputs in [-1, 1].

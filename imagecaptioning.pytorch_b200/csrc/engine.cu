@@ -811,6 +811,32 @@ int capb200_bench_linear(const float* x, const float* w, const float* b, float* 
                          void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CAPB_REQUIRE(x && w && y && ms_per_launch && M > 0 && N > 0 && K > 0 && iters > 0, "bad argument");
+    if (mode == CAPB200_MODE_TF32X3_TC || mode == CAPB200_MODE_SKINNY_TF32X3) {
+        // the training GEMMs: tcgen05 kind::tf32 kernel (gemm_tf32.cu) or the mma.sync split-K kernel it replaced, timed back to back
+        Tf32Context* ctx = mode == CAPB200_MODE_TF32X3_TC ? tf32_context_create() : nullptr;
+        float* scratch = nullptr;
+        const size_t cap = (size_t)4 << 20;
+        CAPB_CHECK_CUDA(cudaMalloc(&scratch, cap * sizeof(float)));
+        Skinny sk{scratch, cap, 1, st};
+        sk.ctx = ctx;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        int rc = 0;
+        for (int i = 0; i < 3 + iters && !rc; ++i) {
+            if (i == 3) cudaEventRecord(e0, st);
+            rc = sk.lin(x, K, w, K, b, y, N, M, N, K, 0);
+        }
+        cudaEventRecord(e1, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("bench_linear: ") + cudaGetErrorString(cudaGetLastError())); rc = 1; }
+        float ms = 0.f;
+        if (!rc) { cudaEventElapsedTime(&ms, e0, e1); *ms_per_launch = ms / iters; }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaFree(scratch);
+        tf32_context_destroy(ctx);
+        return rc;
+    }
     GemmProblem g;
     g.M = M; g.N = N; g.nseg = 1;
     g.seg[0].A = x; g.seg[0].lda = K; g.seg[0].W = w; g.seg[0].ldw = K; g.seg[0].K = K;
@@ -844,6 +870,41 @@ int capb200_bench_linear(const float* x, const float* w, const float* b, float* 
     cudaEventDestroy(e1);
     if (plan) gemm_tc_plan_destroy(plan);
     if (scratch) cudaFree(scratch);
+    return rc;
+}
+
+int capb200_gemm_trace(const float* x, const float* w, float* y, int M, int N, int K, unsigned long long* trace_host, int n_slots, void* stream) {
+    // one traced launch of the decode GEMM (3-pass tcgen05, CTA pairs) after three warm launches: trace_host[296][16] %globaltimer stamps
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CAPB_REQUIRE(x && w && y && trace_host && n_slots >= 296 * 16, "bad argument");
+    GemmProblem g;
+    g.M = M; g.N = N; g.nseg = 1;
+    g.seg[0].A = x; g.seg[0].lda = K; g.seg[0].W = w; g.seg[0].ldw = K; g.seg[0].K = K;
+    g.epi.C = y; g.epi.ldc = N;
+    const long ldh = round_up(K, 64);
+    __half* scratch = nullptr;
+    unsigned long long* trace = nullptr;
+    CAPB_CHECK_CUDA(cudaMalloc(&scratch, (size_t)(M + N) * ldh * 2 * sizeof(__half)));
+    CAPB_CHECK_CUDA(cudaMalloc(&trace, sizeof(unsigned long long) * 296 * 16));
+    CAPB_CHECK_CUDA(cudaMemsetAsync(trace, 0, sizeof(unsigned long long) * 296 * 16, st));
+    __half* xh = scratch; __half* xl = xh + (size_t)M * ldh;
+    __half* wh = xl + (size_t)M * ldh; __half* wl = wh + (size_t)N * ldh;
+    int rc = split_planes_launch(x, K, M, K, xh, xl, ldh, st) | split_planes_launch(w, K, N, K, wh, wl, ldh, st);
+    g.seg[0].A_hi = xh; g.seg[0].A_lo = xl; g.seg[0].lda_h = ldh;
+    g.seg[0].W_hi = wh; g.seg[0].W_lo = wl; g.seg[0].ldw_h = ldh;
+    GemmTcPlan* plan = rc ? nullptr : gemm_tc_plan_create(g, 3);
+    if (plan == nullptr) rc = 1;
+    for (int i = 0; i < 3 && !rc; ++i) rc = gemm_tc_plan_launch(plan, nullptr, 0, st);
+    if (!rc) {
+        GemmEpilogue ep = g.epi;
+        ep.trace = trace;
+        rc = gemm_tc_plan_launch(plan, &ep, 0, st);
+    }
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { set_error("gemm_trace: kernel failed"); rc = 1; }
+    if (!rc) CAPB_CHECK_CUDA(cudaMemcpy(trace_host, trace, sizeof(unsigned long long) * 296 * 16, cudaMemcpyDeviceToHost));
+    if (plan) gemm_tc_plan_destroy(plan);
+    cudaFree(scratch);
+    cudaFree(trace);
     return rc;
 }
 

@@ -70,7 +70,15 @@ struct TcParams {
     __half* h_hi;
     __half* h_lo;
     long ld_h;
+    unsigned long long* trace;  // optional [CTAs][16] %globaltimer stamps of the pair kernel's phases (tools/gemm_trace.py); nullptr = off
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define CAPB_TRACE(slot) do { if (p.trace != nullptr) p.trace[(long)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
 
 template <int BN, int PASSES>
 struct TcCfg {
@@ -477,6 +485,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_pair_kernel(const __grid_
     ptx::cluster_sync_all();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_holder;
+    if (threadIdx.x == 0) CAPB_TRACE(0);                 // set-up done (barriers, TMEM, cluster sync)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -521,6 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_pair_kernel(const __grid_
                     for (int kb = 0; kb < p.kblocks[s]; ++kb) {
                         ptx::mbar_wait(&full_bar[stage], phase);
                         ptx::tc_fence_after_sync();
+                        if (it == 0 && s == 0 && kb == 0) CAPB_TRACE(1);      // first operands landed
                         const uint32_t st = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
                         const uint32_t a_hi = st;
                         const uint32_t a_lo = st + Cfg::kABytes;
@@ -543,6 +553,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_pair_kernel(const __grid_
                     }
                 }
                 ptx::umma_commit_pair(&tmem_full_bar[buf]);
+                if (it < 2) CAPB_TRACE(2 + it);                   // all MMAs of tile `it` issued
             }
         }
     } else if (warp >= 4) {
@@ -558,6 +569,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_pair_kernel(const __grid_
             const int n0 = (pt / cl_m) * BN;
             ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
             ptx::tc_fence_after_sync();
+            if (threadIdx.x == 128 && it < 2) CAPB_TRACE(4 + it);       // accumulator of tile `it` complete: epilogue starts
             // column split between the two warps of a lane quadrant, in 16-column chunks
             constexpr int kChunks = BN / 16, kLow = (kChunks + 1) / 2;
             const int grp = (warp - 4) >> 2;
@@ -565,6 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_pair_kernel(const __grid_
             const int c_end = (kEpiWarps == 8 && grp == 0) ? kLow * 16 : BN;
             epilogue_tile<BN>(p, tmem_base + buf * BN, m0, n0, q, lane, vec4, vec2h, lstm_vec, c_begin, c_end);
             __syncwarp();
+            if (threadIdx.x == 128 && it < 2) CAPB_TRACE(6 + it);       // this warp's share of the epilogue of tile `it` done
             ptx::tc_fence_before_sync();
             ptx::mbar_arrive_leader(&tmem_empty_bar[buf]);
         }
@@ -573,6 +586,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_pair_kernel(const __grid_
     __syncthreads();
     ptx::cluster_sync_all();
     ptx::tc_fence_after_sync();
+    if (threadIdx.x == 0) CAPB_TRACE(8);                 // every role of the pair is done
     if (warp == 2) ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
 }
 
@@ -704,6 +718,7 @@ static void fill_epilogue(TcParams& t, const GemmEpilogue& e) {
     t.c_out = e.c_out; t.ld_cout = e.ld_cout;
     t.gather_bias = e.gather_bias; t.ld_gb = e.ld_gb; t.gather_idx = e.gather_idx;
     t.h_f = e.h_f; t.h_hi = e.h_hi; t.h_lo = e.h_lo; t.ld_h = e.ld_h;
+    t.trace = e.trace;
 }
 
 bool gemm_tc_supported(const GemmProblem& p, std::string* why) {

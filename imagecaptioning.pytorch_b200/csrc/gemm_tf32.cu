@@ -111,7 +111,12 @@ __device__ __forceinline__ void split_keep_tf32(float x, float& hi, float& lo) {
     lo = x - hi;
 }
 
-template <int BN>
+// TRUNC = true: the raw fp32 tile is left in place as the hi operand (the tensor core reads its top 19 bits, i.e. truncates) and only
+// lo = x - trunc(x) is written: one third less shared-memory traffic in the converter.  Valid only if the hardware's fp32 -> tf32 operand
+// conversion is a truncation; CAPB200_TF32_TRUNC=1 selects it so the accuracy tests can decide (tests/test_gpu_ops.py).
+__device__ __forceinline__ void split_trunc_tf32(float x, float& lo) { lo = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+template <int BN, bool TRUNC>
 __global__ void __launch_bounds__(256, 1) gemm_tf32x3_kernel(const __grid_constant__ Tf32Params p) {
     using Cfg = Tf32Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -217,16 +222,22 @@ __global__ void __launch_bounds__(256, 1) gemm_tf32x3_kernel(const __grid_consta
             for (int i = ct; i < kAVec; i += 128) {
                 const float4 x = a_hi[i];
                 float4 h, l;
-                split_keep_tf32(x.x, h.x, l.x); split_keep_tf32(x.y, h.y, l.y); split_keep_tf32(x.z, h.z, l.z); split_keep_tf32(x.w, h.w, l.w);
-                a_hi[i] = h;
+                if (TRUNC) { split_trunc_tf32(x.x, l.x); split_trunc_tf32(x.y, l.y); split_trunc_tf32(x.z, l.z); split_trunc_tf32(x.w, l.w); }
+                else {
+                    split_keep_tf32(x.x, h.x, l.x); split_keep_tf32(x.y, h.y, l.y); split_keep_tf32(x.z, h.z, l.z); split_keep_tf32(x.w, h.w, l.w);
+                    a_hi[i] = h;
+                }
                 a_lo[i] = l;
             }
 #pragma unroll 4
             for (int i = ct; i < kBVec; i += 128) {
                 const float4 x = b_hi[i];
                 float4 h, l;
-                split_keep_tf32(x.x, h.x, l.x); split_keep_tf32(x.y, h.y, l.y); split_keep_tf32(x.z, h.z, l.z); split_keep_tf32(x.w, h.w, l.w);
-                b_hi[i] = h;
+                if (TRUNC) { split_trunc_tf32(x.x, l.x); split_trunc_tf32(x.y, l.y); split_trunc_tf32(x.z, l.z); split_trunc_tf32(x.w, l.w); }
+                else {
+                    split_keep_tf32(x.x, h.x, l.x); split_keep_tf32(x.y, h.y, l.y); split_keep_tf32(x.z, h.z, l.z); split_keep_tf32(x.w, h.w, l.w);
+                    b_hi[i] = h;
+                }
                 b_lo[i] = l;
             }
             ptx::fence_proxy_async_smem();              // generic-proxy writes -> visible to the tensor core's async-proxy reads
@@ -397,12 +408,12 @@ const CUtensorMap* get_map(Tf32Context* ctx, const float* base, long rows, long 
     return &(ctx->maps[key] = m);
 }
 
-template <int BN>
-int launch_tf32(const Tf32Params& prm, int ksplit, int tiles_a, int tiles_b, cudaStream_t st) {
+template <int BN, bool TRUNC>
+int launch_tf32_v(const Tf32Params& prm, int ksplit, int tiles_a, int tiles_b, cudaStream_t st) {
     using Cfg = Tf32Cfg<BN>;
     static std::atomic<unsigned long long> attr_set{0};
     if (first_use_on_device(attr_set)) {
-        CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, TRUNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ksplit, tiles_a, tiles_b);
@@ -416,8 +427,13 @@ int launch_tf32(const Tf32Params& prm, int ksplit, int tiles_a, int tiles_b, cud
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = ksplit > 1 ? 1 : 0;
-    CAPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN>, prm));
+    CAPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, TRUNC>, prm));
     return 0;
+}
+template <int BN>
+int launch_tf32(const Tf32Params& prm, int ksplit, int tiles_a, int tiles_b, cudaStream_t st) {
+    static const bool trunc = getenv("CAPB200_TF32_TRUNC") != nullptr && atoi(getenv("CAPB200_TF32_TRUNC")) != 0;
+    return trunc ? launch_tf32_v<BN, true>(prm, ksplit, tiles_a, tiles_b, st) : launch_tf32_v<BN, false>(prm, ksplit, tiles_a, tiles_b, st);
 }
 
 bool tma_ok(const float* p, long pitch, int K) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (pitch & 3) == 0 && K >= 1; }

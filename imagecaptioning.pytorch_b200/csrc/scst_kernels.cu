@@ -337,14 +337,19 @@ __global__ void embed_backward_kernel(int rows, int E, const int* __restrict__ t
 }
 
 // out[img, c] (+)= sum over the image's rows and all steps of x[step][row, c]
+// grid (images, column slices of 256): one column per thread, the steps x rpi terms of a column four loads at a time
+// (the first version ran one CTA per image over all columns: 10 CTAs on 148 SMs, 196 us for [20 x 50 x 4096])
 __global__ void per_image_sum_kernel(int steps, int rows, int rpi, int cols, const float* __restrict__ x, float* __restrict__ out) {
     const int img = blockIdx.x;
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-        float s = 0.f;
-        for (int t = 0; t < steps; ++t)
-            for (int j = 0; j < rpi; ++j) s += x[((long)t * rows + (long)img * rpi + j) * cols + c];
-        out[(long)img * cols + c] = s;
-    }
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const int n = steps * rpi;
+    int i = 0;
+    auto at = [&](int k) { return x[((long)(k / rpi) * rows + (long)img * rpi + (k % rpi)) * cols + c]; };
+    for (; i + 4 <= n; i += 4) { s0 += at(i); s1 += at(i + 1); s2 += at(i + 2); s3 += at(i + 3); }
+    for (; i < n; ++i) s0 += at(i);
+    out[(long)img * cols + c] = (s0 + s1) + (s2 + s3);
 }
 
 __global__ void add_inplace_kernel(float* a, const float* b, long n) {
@@ -446,7 +451,7 @@ int embed_backward_launch(int rows, int E, const int* tokens, const float* xt, c
     LAUNCH_OK();
 }
 int per_image_sum_launch(int steps, int rows, int rpi, int cols, const float* x, float* out, cudaStream_t st) {
-    per_image_sum_kernel<<<rows / rpi, 256, 0, st>>>(steps, rows, rpi, cols, x, out);
+    per_image_sum_kernel<<<dim3(rows / rpi, cdiv(cols, 256)), 256, 0, st>>>(steps, rows, rpi, cols, x, out);
     LAUNCH_OK();
 }
 int add_inplace_launch(float* a, const float* b, long n, cudaStream_t st) {

@@ -10,6 +10,7 @@
 //   cross_attention     src_attn over the image's encoder memory; K/V are per IMAGE, rows index them by row / rows_per_image
 #include "common.cuh"
 #include "kernels.cuh"
+#include "attn.cuh"
 
 namespace capb200 {
 
@@ -37,20 +38,27 @@ __device__ __forceinline__ void store_act2(const ActView& o, long row, int col, 
 }
 
 // one warp per row
-__global__ void layer_norm_kernel(int rows, int D, const float* __restrict__ x, long ld_x, const float* __restrict__ a, const float* __restrict__ b,
-                                  float eps, ActView out) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const int lane = threadIdx.x & 31;
+// One CTA of 128 threads per row (the rows are few -- 10 .. 1280 -- and a single warp walking a 1024-wide row three times was latency bound).
+__device__ __forceinline__ float block_sum128(float v, float* sh) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return (sh[0] + sh[1]) + (sh[2] + sh[3]);
+}
+__global__ void __launch_bounds__(128) layer_norm_kernel(int rows, int D, const float* __restrict__ x, long ld_x, const float* __restrict__ a,
+                                                         const float* __restrict__ b, float eps, ActView out) {
+    __shared__ float sh[4];
+    const int row = blockIdx.x;
     const float* xr = x + (long)row * ld_x;
     float s = 0.f;
-    for (int c = lane; c < D; c += 32) s += xr[c];
-    const float mean = warp_sum(s) / (float)D;
+    for (int c = threadIdx.x; c < D; c += 128) s += xr[c];
+    const float mean = block_sum128(s, sh) / (float)D;
     float q = 0.f;
-    for (int c = lane; c < D; c += 32) { const float d = xr[c] - mean; q = fmaf(d, d, q); }
-    const float stdv = sqrtf(warp_sum(q) / (float)(D - 1));      // torch.std: unbiased
+    for (int c = threadIdx.x; c < D; c += 128) { const float d = xr[c] - mean; q = fmaf(d, d, q); }
+    const float stdv = sqrtf(block_sum128(q, sh) / (float)(D - 1));      // torch.std: unbiased
     const float inv = 1.0f / (stdv + eps);
-    for (int c = lane; c < D; c += 32) store_act2(out, row, c, __ldg(a + c) * (xr[c] - mean) * inv + __ldg(b + c));
+    for (int c = threadIdx.x; c < D; c += 128) store_act2(out, row, c, __ldg(a + c) * (xr[c] - mean) * inv + __ldg(b + c));
 }
 
 __global__ void embed_pe_kernel(int rows, int D, const int* __restrict__ tokens, const float* __restrict__ lut, const float* __restrict__ pe_row,
@@ -62,23 +70,24 @@ __global__ void embed_pe_kernel(int rows, int D, const int* __restrict__ tokens,
 
 // Encoder / refiner self-attention: one CTA per (image, head); K and V head slices staged in shared memory.
 // q,k,v: [B*R, ld] with the head at columns [head*dk, (head+1)*dk).  mask[B, R] (1 = valid key) or nullptr.
-__global__ void __launch_bounds__(128) enc_self_attention_kernel(int R, int dk, const float* __restrict__ q, const float* __restrict__ k,
+__global__ void __launch_bounds__(256) enc_self_attention_kernel(int R, int dk, const float* __restrict__ q, const float* __restrict__ k,
                                                                  const float* __restrict__ v, long ld, const float* __restrict__ mask, long ld_mask,
                                                                  float scale, ActView out) {
     extern __shared__ float sm[];
     float* sk = sm;                 // [R][dk+1]
     float* sv = sk + R * (dk + 1);  // [R][dk+1]
-    float* sp = sv + R * (dk + 1);  // [4 warps][R]
+    float* sp = sv + R * (dk + 1);  // [warps][R]
     const int img = blockIdx.x, head = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {       // independent coalesced loads, four in flight per thread
         const int r = i / dk, c = i % dk;
         sk[r * (dk + 1) + c] = k[((long)img * R + r) * ld + head * dk + c];
         sv[r * (dk + 1) + c] = v[((long)img * R + r) * ld + head * dk + c];
     }
     __syncthreads();
     float* p = sp + warp * R;
-    for (int qi = warp; qi < R; qi += 4) {
+    for (int qi = warp; qi < R; qi += nw) {
         const float* qr = q + ((long)img * R + qi) * ld + head * dk;
         float mx = -INFINITY;
         for (int r = lane; r < R; r += 32) {
@@ -159,58 +168,22 @@ __global__ void __launch_bounds__(128) dec_self_attention_kernel(int rows, int h
     }
 }
 
-// Single-query multi-head attention over per-image keys / values: one warp per (row, head).
+// Single-query multi-head attention over per-image keys / values: one CTA per (row, head) (attn.cuh).
 //   q [rows, ld_q]; kk, vv [B*R, ld_kv] (+ column offsets k_off / v_off); mask [B, R] or nullptr
-// The warp's lanes run ACROSS the head's dk columns (coalesced 128-byte reads of every key / value row, four regions in flight per
-// iteration); the earlier lane-per-region form read each key with a stride of a whole row per lane and a dk-long dependent FMA chain
-// (37 us per launch at 50 rows x 8 heads x 36 regions x 128 columns: 0.75 ms of every AoANet training step and as much of its decode).
 __global__ void __launch_bounds__(128) cross_attention_kernel(int rows, int rpi, int heads, int dk, int R, const float* __restrict__ q, long ld_q,
                                                               const float* __restrict__ kk, const float* __restrict__ vv, long ld_kv,
                                                               const float* __restrict__ mask, long ld_mask, float scale, ActView out) {
-    extern __shared__ float sm[];       // [4 warps][R]
-    const int item = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (item >= rows * heads) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    extern __shared__ float sm[];       // [R] scores -> exp
+    __shared__ float sh_inv;
+    const int item = blockIdx.x;
     const int row = item / heads, head = item % heads;
     const int img = row / rpi;
-    float* p = sm + warp * R;
     const float* qr = q + (long)row * ld_q + head * dk;
     const float* kb = kk + (long)img * R * ld_kv + head * dk;
     const float* vb = vv + (long)img * R * ld_kv + head * dk;
-    constexpr int NQ = 8;               // dk <= 256
-    float qv[NQ];
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) { const int c = lane + 32 * i; qv[i] = (c < dk) ? qr[c] : 0.f; }
-    for (int r0 = 0; r0 < R; r0 += 4) {
-        float part[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (r0 + u < R) {
-                const float* kr = kb + (long)(r0 + u) * ld_kv;
-#pragma unroll
-                for (int i = 0; i < NQ; ++i) { const int c = lane + 32 * i; if (c < dk) part[u] = fmaf(qv[i], __ldg(kr + c), part[u]); }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float s = warp_sum(part[u]) * scale;
-            if (lane == 0 && r0 + u < R) p[r0 + u] = (mask != nullptr && mask[(long)img * ld_mask + r0 + u] == 0.f) ? -INFINITY : s;
-        }
-    }
-    __syncwarp();
-    float mx = -INFINITY;
-    for (int r = lane; r < R; r += 32) mx = fmaxf(mx, p[r]);
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int r = lane; r < R; r += 32) { const float e = expf(p[r] - mx); p[r] = e; sum += e; }
-    sum = warp_sum(sum);
-    __syncwarp();
-    const float inv = 1.0f / sum;
-    for (int c = lane; c < dk; c += 32) {
-        float acc = 0.f;
-        for (int r = 0; r < R; ++r) acc = fmaf(p[r], __ldg(vb + (long)r * ld_kv + c), acc);
-        store_act2(out, row, head * dk + c, acc * inv);
-    }
+    sq_attention_scores(qr, kb, ld_kv, R, dk, scale, mask != nullptr ? mask + (long)img * ld_mask : nullptr, sm);
+    const float inv = sq_attention_softmax(sm, R, &sh_inv);
+    for (int c = threadIdx.x; c < dk; c += 128) store_act2(out, row, head * dk + c, sq_attention_column(sm, vb, ld_kv, R, c) * inv);
 }
 
 // GLU over the last dimension (nn.GLU, AoAModel.py:41,143): out[r, j] = t[r, j] * sigmoid(t[r, H + j]) (+ residual[r, j])
@@ -260,7 +233,7 @@ int masked_mean_launch(int B, int R, int H, const float* x, long ld_x, const flo
 
 int layer_norm_launch(int rows, int D, const float* x, long ld_x, const float* a, const float* b, float eps, ActView out, cudaStream_t st) {
     if (rows <= 0) return 0;
-    layer_norm_kernel<<<cdiv(rows, 8), 256, 0, st>>>(rows, D, x, ld_x, a, b, eps, out);
+    layer_norm_kernel<<<rows, 128, 0, st>>>(rows, D, x, ld_x, a, b, eps, out);
     CAPB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -275,13 +248,13 @@ int embed_pe_launch(int rows, int D, const int* tokens, const float* lut, const 
 int enc_self_attention_launch(int B, int R, int heads, int dk, const float* q, const float* k, const float* v, long ld, const float* mask,
                               long ld_mask, ActView out, cudaStream_t st) {
     if (B <= 0) return 0;
-    const size_t smem = sizeof(float) * ((size_t)2 * R * (dk + 1) + 4 * R);
+    const size_t smem = sizeof(float) * ((size_t)2 * R * (dk + 1) + 8 * R);
     CAPB_REQUIRE(smem <= 200 * 1024, "self-attention: region count x head width too large for the shared-memory staging");
     static std::atomic<unsigned long long> configured{0};
     if (first_use_on_device(configured)) {
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(enc_self_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
-    enc_self_attention_kernel<<<dim3(B, heads), 128, smem, st>>>(R, dk, q, k, v, ld, mask, ld_mask, 1.0f / sqrtf((float)dk), out);
+    enc_self_attention_kernel<<<dim3(B, heads), 256, smem, st>>>(R, dk, q, k, v, ld, mask, ld_mask, 1.0f / sqrtf((float)dk), out);
     CAPB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -299,8 +272,9 @@ int dec_self_attention_launch(int rows, int heads, int dk, int t, const float* q
 int cross_attention_launch(int rows, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
                            const float* mask, long ld_mask, ActView out, cudaStream_t st) {
     if (rows <= 0) return 0;
-    const size_t smem = sizeof(float) * 4 * R;
-    cross_attention_kernel<<<cdiv(rows * heads, 4), 128, smem, st>>>(rows, rpi, heads, dk, R, q, ld_q, kk, vv, ld_kv, mask, ld_mask,
+    const size_t smem = sizeof(float) * R;
+    CAPB_REQUIRE(dk <= 256, "attention: head width above 256");
+    cross_attention_kernel<<<rows * heads, 128, smem, st>>>(rows, rpi, heads, dk, R, q, ld_q, kk, vv, ld_kv, mask, ld_mask,
                                                                       1.0f / sqrtf((float)dk), out);
     CAPB_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -60,6 +60,11 @@ int capb200_linear(const float* x, long ldx, const float* w, long ldw, const flo
 int capb200_bench_linear(const float* x, const float* w, const float* b, float* y, int M, int N, int K, int mode, int iters, float* ms_per_launch,
                          void* stream);
 
+/* Diagnostics: one traced launch of the decode GEMM y[M,N] = x[M,K] w[N,K]^T (tc_f16x3, CTA-pair kernel).  trace_host receives 296 x 16
+ * %globaltimer stamps (ns), one row per CTA: 0 set-up done, 1 first operands landed, 2/3 all MMAs of the CTA pair's first / second tile
+ * issued, 4/5 accumulator of tile 0 / 1 complete (epilogue starts), 6/7 epilogue of tile 0 / 1 done, 8 kernel end (tools/gemm_trace.py). */
+int capb200_gemm_trace(const float* x, const float* w, float* y, int M, int N, int K, unsigned long long* trace_host, int n_slots, void* stream);
+
 /* nn.LSTMCell: gates = x*w_ih^T + b_ih + h*w_hh^T + b_hh; (i,f,g,o)           AttModel.py:628,635
  * x[M,Kx], h/c[M,H] -> h_out/c_out[M,H] */
 int capb200_lstm_cell(const float* x, int Kx, const float* h, const float* c, const float* w_ih, const float* w_hh, const float* b_ih,
