@@ -299,6 +299,7 @@ def bench_scst(args, rank, world, local_rank, dev, workload, batch):
            'images_per_sec': value / n, 'n_gpus': world, 'steps': args.steps, 'ms_per_step': ms / args.steps, 'per_rank_ms_per_step': [v / args.steps for v in per_rank],
            'allreduce_ms': allreduce_ms, 'allreduce_bytes': grad_bytes[0], 'allreduce': 'chunked, overlapped with the backward pass' if fused_sync else ('one flat all-reduce after backward' if world > 1 else 'none (1 GPU)'),
            'launches': (model.launch_count - l0) // max(args.steps, 1), 'scaling': 'weak',
+           'step_wall_ms': {'min': min(step_ms), 'median': statistics.median(step_ms), 'max': max(step_ms)},
            'config': {'workload': '%s SCST step (BASELINE configs[3]), per-GPU batch=%d images x %d samples, 36x2048 feats, seq_len=20, V=9487' % (fam_name, B, n),
                       'numeric_mode': 'greedy baseline %s (tcgen05 kind::f16 x3); sampling, backward and weight gradients on 3xTF32 tensor-core GEMMs over the fp32 weights' % args.mode},
            'clocks': sampler.summary(),
