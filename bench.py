@@ -228,7 +228,7 @@ def bench_scst(args, rank, world, local_rank, dev, workload, batch):
     opt = ap.Namespace(sc_sample_method='greedy', sc_beam_size=1, train_sample_method='sample', train_beam_size=1, train_sample_n=n,
                        cider_reward_weight=1, bleu_reward_weight=0)
     lw = b200.B200LossWrapper(model, opt)
-    fused_sync = world > 1 and hasattr(lw, 'enable_gradient_sync')
+    fused_sync = world > 1 and hasattr(lw, 'enable_gradient_sync') and not os.environ.get('CAPB200_SCST_NO_OVERLAP')     # A/B switch
     if fused_sync:
         lw.enable_gradient_sync()            # the engine's flat gradient buffer is all-reduced in chunks while the backward pass still runs
     optim = torch.optim.Adam(model.parameters(), lr=5e-5)
