@@ -231,7 +231,8 @@ def bench_scst(args, rank, world, local_rank, dev, workload, batch):
     fused_sync = world > 1 and hasattr(lw, 'enable_gradient_sync') and not os.environ.get('CAPB200_SCST_NO_OVERLAP')     # A/B switch
     if fused_sync:
         lw.enable_gradient_sync()            # the engine's flat gradient buffer is all-reduced in chunks while the backward pass still runs
-    optim = torch.optim.Adam(model.parameters(), lr=5e-5)
+    # tools/train.py:193-196: utils.clip_gradient(optimizer, 0.1) + Adam.step(), one launch of the engine's fused kernel (optim.py)
+    optim = b200.optim.FusedAdam(model.parameters(), lr=5e-5, clip_value=0.1)
     host = [syn.make_inputs(B, R, CFG['F_fc'], CFG['F_att'], seed=99 + 13 * rank + i) for i in range(3)]
     host = [(a.pin_memory(), b.pin_memory()) for a, b in host]
     gts = syn.make_refs(B, CFG['V'], seed=5 + rank)
@@ -255,9 +256,8 @@ def bench_scst(args, rank, world, local_rank, dev, workload, batch):
             if timed and world > 1:
                 a1.record()
                 ar_events.append((a0, a1))
-        torch.nn.utils.clip_grad_value_(model.parameters(), 0.1)
         optim.step()
-        return float(out['loss'])                                                        # D2H read of the loss
+        return float(out['loss'].detach())                                                        # D2H read of the loss
 
     def barrier():
         if world > 1:

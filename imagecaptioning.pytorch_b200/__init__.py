@@ -12,6 +12,7 @@ from . import parallel                                # noqa: F401
 from . import utils                                   # noqa: F401
 from . import eval_utils                              # noqa: F401
 from . import grad_sync                               # noqa: F401
+from . import optim                                   # noqa: F401
 from .utils import decode_sequence                    # noqa: F401
 
 __all__ = ['setup', 'B200UpDownModel', 'B200NewFCModel', 'B200TransformerModel', 'B200AoAModel', 'B200CaptionModel', 'B200LossWrapper', 'RewardCriterion',

@@ -184,6 +184,8 @@ SIGNATURES = {
     'capb200_updown_scst_step': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(ScstOpts), c_void_p, c_void_p, c_void_p, c_int,
                                          POINTER(UpdownGrads), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'capb200_dropout_mask': (c_int, [c_void_p, c_long, c_ulonglong, c_int, c_int, c_float, c_void_p]),
+    'capb200_adam_chunk_elems': (c_int, []),
+    'capb200_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_float, c_float, c_long, c_float, c_int, c_void_p]),
     'capb200_engine_set_grad_events': (c_int, [c_void_p, c_void_p, c_int]),
     'capb200_aoa_set_grad_events': (c_int, [c_void_p, c_void_p, c_int]),
     'capb200_cider_table_create': (c_void_p, [c_void_p, c_void_p, c_long, c_double, c_void_p]),

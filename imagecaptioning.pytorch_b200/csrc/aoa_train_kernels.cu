@@ -106,85 +106,115 @@ __global__ void glu_backward_kernel(int rows, int H, const float* __restrict__ t
     }
 }
 
-// ---- refiner self-attention, train mode: one CTA per (image, head), dropout on the probabilities ----------------------------------
-// q,k,v: [B*R, ld] with the head at columns [head*dk, (head+1)*dk).  Dropout element index = ((img*heads + head)*R + qi)*R + r.
-__global__ void __launch_bounds__(256) enc_attn_train_kernel(int R, int dk, int heads, const float* __restrict__ q, const float* __restrict__ k,
-                                                             const float* __restrict__ v, long ld, float scale, unsigned long long seed, uint32_t site,
-                                                             float p_drop, float* __restrict__ out, long ld_out, const float* __restrict__ mask,
-                                                             long ld_mask) {
+// ---- sequence self-attention, train mode (dropout on the probabilities) --------------------------------------------------------------
+// Shared by the AoANet refiner / Transformer encoder (all regions attend to all regions, rows image-major) and the Transformer decoder
+// (causal, rows TIME-major so that the same buffers serve the step-by-step sampling pass and the batched teacher-forced pass).
+//   row(b, pos) = b * b_stride + pos * p_stride;  q, k, v: [rows, ld] with the head at columns [head*dk, (head+1)*dk)
+//   queries [q_lo, q_hi) of every sequence; keys [0, n_keys) (causal: key r is visible to query qi iff r <= qi)
+//   key_mask [b, ld_mask] (0 = masked) or nullptr;  dropout element index = ((b*heads + head)*idx_L + qi)*idx_L + r
+// Grid (sequences, heads, query chunks): the chunks split the query range (forward) or the output elements (backward) so that a
+// 10-image batch still fills the machine (80 CTAs of 148 SMs took 65-72 us per launch, profiles/r02c_scst_table_aoa.txt).
+struct SeqAttn {
+    int n_keys, dk, heads, q_lo, q_hi, causal, idx_L;
+    long b_stride, p_stride, ld;
+    float scale, p_drop;
+    unsigned long long seed;
+    uint32_t site;
+    const float* key_mask;
+    long ld_mask;
+};
+
+__global__ void __launch_bounds__(256) seq_attn_train_kernel(SeqAttn a, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                                                             float* __restrict__ out, long ld_out) {
     extern __shared__ float sm[];
-    float* sk = sm;                 // [R][dk+1]
-    float* sv = sk + R * (dk + 1);
-    float* sp = sv + R * (dk + 1);  // [warps][R]
-    const int img = blockIdx.x, head = blockIdx.y;
+    const int R = a.n_keys, dk = a.dk, W = dk + 1;
+    float* sk = sm;                 // [R][W]
+    float* sv = sk + R * W;
+    float* sp = sv + R * W;         // [warps][R]
+    float* sq = sp + 8 * R;         // [warps][dk]
+    const int b = blockIdx.x, head = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int nq = a.q_hi - a.q_lo;
+    const int c_lo = a.q_lo + (int)(((long)nq * blockIdx.z) / gridDim.z), c_hi = a.q_lo + (int)(((long)nq * (blockIdx.z + 1)) / gridDim.z);
+    if (c_lo >= c_hi) return;
+    const int need = a.causal ? (c_hi < R ? c_hi : R) : R;      // keys this chunk can see
 #pragma unroll 4
-    for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {       // independent coalesced loads, four in flight per thread
+    for (int i = threadIdx.x; i < need * dk; i += blockDim.x) {       // independent coalesced loads, four in flight per thread
         const int r = i / dk, c = i % dk;
-        sk[r * (dk + 1) + c] = k[((long)img * R + r) * ld + head * dk + c];
-        sv[r * (dk + 1) + c] = v[((long)img * R + r) * ld + head * dk + c];
+        const long g = ((long)b * a.b_stride + (long)r * a.p_stride) * a.ld + head * dk + c;
+        sk[r * W + c] = k[g];
+        sv[r * W + c] = v[g];
     }
     __syncthreads();
     float* p = sp + warp * R;
-    for (int qi = warp; qi < R; qi += nw) {
-        const float* qr = q + ((long)img * R + qi) * ld + head * dk;
+    float* qs = sq + warp * dk;
+    for (int qi = c_lo + warp; qi < c_hi; qi += nw) {
+        const long qrow = (long)b * a.b_stride + (long)qi * a.p_stride;
+        for (int c = lane; c < dk; c += 32) qs[c] = q[qrow * a.ld + head * dk + c];
+        __syncwarp();
+        const int vis = a.causal ? (qi + 1 < need ? qi + 1 : need) : need;
         float mx = -INFINITY;
-        for (int r = lane; r < R; r += 32) {
+        for (int r = lane; r < vis; r += 32) {
             float s = 0.f;
-            for (int c = 0; c < dk; ++c) s = fmaf(__ldg(qr + c), sk[r * (dk + 1) + c], s);
-            s *= scale;
-            if (mask != nullptr && mask[(long)img * ld_mask + r] == 0.f) s = -INFINITY;     // scores.masked_fill(mask == 0, -inf)  (TransformerModel.py:157-158)
+            for (int c = 0; c < dk; ++c) s = fmaf(qs[c], sk[r * W + c], s);
+            s *= a.scale;
+            if (a.key_mask != nullptr && a.key_mask[(long)b * a.ld_mask + r] == 0.f) s = -INFINITY;     // scores.masked_fill(mask == 0, -inf)  (TransformerModel.py:157-158)
             p[r] = s;
             mx = fmaxf(mx, s);
         }
         mx = wmax(mx);
         float sum = 0.f;
-        for (int r = lane; r < R; r += 32) { const float e = expf(p[r] - mx); p[r] = e; sum += e; }
+        for (int r = lane; r < vis; r += 32) { const float e = expf(p[r] - mx); p[r] = e; sum += e; }
         sum = wsum(sum);
         const float inv = 1.0f / sum;
-        for (int r = lane; r < R; r += 32) p[r] = p[r] * inv * drop_scale(seed, site, 0u, (uint32_t)((((long)img * heads + head) * R + qi) * R + r), p_drop);
+        for (int r = lane; r < vis; r += 32)
+            p[r] = p[r] * inv * drop_scale(a.seed, a.site, 0u, (uint32_t)((((long)b * a.heads + head) * a.idx_L + qi) * a.idx_L + r), a.p_drop);
         __syncwarp();
         for (int c = lane; c < dk; c += 32) {
             float acc = 0.f;
-            for (int r = 0; r < R; ++r) acc = fmaf(p[r], sv[r * (dk + 1) + c], acc);
-            out[((long)img * R + qi) * ld_out + head * dk + c] = acc;
+            for (int r = 0; r < vis; ++r) acc = fmaf(p[r], sv[r * W + c], acc);
+            out[qrow * ld_out + head * dk + c] = acc;
         }
         __syncwarp();
     }
 }
 
-// backward: recomputes the probabilities; writes dq | dk | dv of this (image, head) slice
-__global__ void __launch_bounds__(256) enc_attn_backward_kernel(int R, int dk, int heads, const float* __restrict__ q, const float* __restrict__ k,
-                                                                const float* __restrict__ v, long ld, float scale, unsigned long long seed,
-                                                                uint32_t site, float p_drop, const float* __restrict__ d_out, long ld_do,
-                                                                float* __restrict__ dq, float* __restrict__ dk_, float* __restrict__ dv, long ld_d,
-                                                                const float* __restrict__ mask, long ld_mask) {
+// backward over ALL queries [0, n_keys) of a sequence: recomputes the probabilities; every chunk CTA rebuilds P and dS (cheap) and writes
+// its share of the dq | dk | dv elements of this (sequence, head) slice
+__global__ void __launch_bounds__(256) seq_attn_backward_kernel(SeqAttn a, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                                                                const float* __restrict__ d_out, long ld_do, float* __restrict__ dq, float* __restrict__ dk_,
+                                                                float* __restrict__ dv, long ld_d) {
     extern __shared__ float sm[];
-    const int W = dk + 1;
+    const int R = a.n_keys, dk = a.dk, W = dk + 1;
     float* sq = sm;                 // [R][W]
     float* sk = sq + R * W;
     float* sv = sk + R * W;
     float* sd = sv + R * W;         // d_out
     float* P = sd + R * W;          // [R][R] softmax probabilities
     float* DS = P + R * R;          // [R][R] dropout scale, then d score
-    const int img = blockIdx.x, head = blockIdx.y;
+    const int b = blockIdx.x, head = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
 #pragma unroll 2
     for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {
         const int r = i / dk, c = i % dk;
-        const long g = ((long)img * R + r) * ld + head * dk + c;
+        const long row = (long)b * a.b_stride + (long)r * a.p_stride;
+        const long g = row * a.ld + head * dk + c;
         sq[r * W + c] = q[g]; sk[r * W + c] = k[g]; sv[r * W + c] = v[g];
-        sd[r * W + c] = d_out[((long)img * R + r) * ld_do + head * dk + c];
+        sd[r * W + c] = d_out[row * ld_do + head * dk + c];
     }
     __syncthreads();
-    // P = softmax(q k^T * scale) row by row (one warp per query row)
+    // P = softmax(q k^T * scale) row by row (one warp per query row); invisible keys get probability 0
     for (int qi = warp; qi < R; qi += nw) {
+        const int vis = a.causal ? qi + 1 : R;
         float mx = -INFINITY;
         for (int r = lane; r < R; r += 32) {
-            float s = 0.f;
-            for (int c = 0; c < dk; ++c) s = fmaf(sq[qi * W + c], sk[r * W + c], s);
-            s *= scale;
-            if (mask != nullptr && mask[(long)img * ld_mask + r] == 0.f) s = -INFINITY;
+            float s = -INFINITY;
+            if (r < vis) {
+                s = 0.f;
+                for (int c = 0; c < dk; ++c) s = fmaf(sq[qi * W + c], sk[r * W + c], s);
+                s *= a.scale;
+                if (a.key_mask != nullptr && a.key_mask[(long)b * a.ld_mask + r] == 0.f) s = -INFINITY;
+            }
             P[qi * R + r] = s;
             mx = fmaxf(mx, s);
         }
@@ -195,41 +225,47 @@ __global__ void __launch_bounds__(256) enc_attn_backward_kernel(int R, int dk, i
         const float inv = 1.0f / sum;
         for (int r = lane; r < R; r += 32) {
             P[qi * R + r] *= inv;
-            DS[qi * R + r] = drop_scale(seed, site, 0u, (uint32_t)((((long)img * heads + head) * R + qi) * R + r), p_drop);
+            DS[qi * R + r] = drop_scale(a.seed, a.site, 0u, (uint32_t)((((long)b * a.heads + head) * a.idx_L + qi) * a.idx_L + r), a.p_drop);
         }
     }
     __syncthreads();
+    const int total = R * dk;
+    const int e_lo = (int)(((long)total * blockIdx.z) / gridDim.z), e_hi = (int)(((long)total * (blockIdx.z + 1)) / gridDim.z);
     // dV[r, c] = sum_qi P[qi, r] * D[qi, r] * dO[qi, c]
-    for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {
+    for (int i = e_lo + threadIdx.x; i < e_hi; i += blockDim.x) {
         const int r = i / dk, c = i % dk;
         float acc = 0.f;
-        for (int qi = 0; qi < R; ++qi) acc = fmaf(P[qi * R + r] * DS[qi * R + r], sd[qi * W + c], acc);
-        dv[((long)img * R + r) * ld_d + head * dk + c] = acc;
+        for (int qi = a.causal ? r : 0; qi < R; ++qi) acc = fmaf(P[qi * R + r] * DS[qi * R + r], sd[qi * W + c], acc);
+        dv[((long)b * a.b_stride + (long)r * a.p_stride) * ld_d + head * dk + c] = acc;
     }
     __syncthreads();
     // d score: dP = (dO V^T) * D ; dS = P * (dP - sum_r P dP)
     for (int qi = warp; qi < R; qi += nw) {
+        const int vis = a.causal ? qi + 1 : R;
         float dot = 0.f;
         for (int r = lane; r < R; r += 32) {
-            float s = 0.f;
-            for (int c = 0; c < dk; ++c) s = fmaf(sd[qi * W + c], sv[r * W + c], s);
-            const float dp = s * DS[qi * R + r];
+            float dp = 0.f;
+            if (r < vis) {
+                float s = 0.f;
+                for (int c = 0; c < dk; ++c) s = fmaf(sd[qi * W + c], sv[r * W + c], s);
+                dp = s * DS[qi * R + r];
+            }
             DS[qi * R + r] = dp;
             dot = fmaf(P[qi * R + r], dp, dot);
         }
         dot = wsum(dot);
         __syncwarp();
-        for (int r = lane; r < R; r += 32) DS[qi * R + r] = P[qi * R + r] * (DS[qi * R + r] - dot) * scale;
+        for (int r = lane; r < R; r += 32) DS[qi * R + r] = P[qi * R + r] * (DS[qi * R + r] - dot) * a.scale;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {
+    for (int i = e_lo + threadIdx.x; i < e_hi; i += blockDim.x) {
         const int r = i / dk, c = i % dk;
         float aq = 0.f, ak = 0.f;
         for (int j = 0; j < R; ++j) {
             aq = fmaf(DS[r * R + j], sk[j * W + c], aq);          // dQ[r] = sum_j dS[r, j] K[j]
             ak = fmaf(DS[j * R + r], sq[j * W + c], ak);          // dK[r] = sum_j dS[j, r] Q[j]
         }
-        const long g = ((long)img * R + r) * ld_d + head * dk + c;
+        const long g = ((long)b * a.b_stride + (long)r * a.p_stride) * ld_d + head * dk + c;
         dq[g] = aq;
         dk_[g] = ak;
     }
@@ -397,24 +433,52 @@ int glu_backward_launch(int rows, int H, const float* t, long ld_t, const float*
     glu_backward_kernel<<<blocks_for((long)rows * H), 256, 0, st>>>(rows, H, t, ld_t, dy, ld_dy, dt, ld_dt);
     LAUNCH_OK();
 }
+inline int attn_chunks(int seqs, int heads, int units) {      // query chunks so that the grid reaches about two CTAs per SM
+    int z = (296 + seqs * heads - 1) / (seqs * heads);
+    if (z > 4) z = 4;
+    if (z > units) z = units;
+    return z < 1 ? 1 : z;
+}
+int seq_attn_train_launch(int seqs, int n_keys, int q_lo, int q_hi, int heads, int dk, int causal, int idx_L, long b_stride, long p_stride, const float* q,
+                          const float* k, const float* v, long ld, unsigned long long seed, int site, float p, float* out, long ld_out, const float* key_mask,
+                          long ld_mask, cudaStream_t st) {
+    if (seqs <= 0 || q_hi <= q_lo) return 0;
+    const size_t smem = sizeof(float) * ((size_t)2 * n_keys * (dk + 1) + 8 * n_keys + 8 * dk);
+    CAPB_REQUIRE(smem <= 200 * 1024, "self-attention (train): keys * head width too large for the shared-memory staging");
+    static std::atomic<unsigned long long> configured{0};
+    if (first_use_on_device(configured)) {
+        CAPB_CHECK_CUDA(cudaFuncSetAttribute(seq_attn_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
+    SeqAttn a;
+    a.n_keys = n_keys; a.dk = dk; a.heads = heads; a.q_lo = q_lo; a.q_hi = q_hi; a.causal = causal; a.idx_L = idx_L; a.b_stride = b_stride; a.p_stride = p_stride;
+    a.ld = ld; a.scale = 1.0f / sqrtf((float)dk); a.p_drop = p; a.seed = seed; a.site = (uint32_t)site; a.key_mask = key_mask; a.ld_mask = ld_mask;
+    seq_attn_train_kernel<<<dim3(seqs, heads, attn_chunks(seqs, heads, q_hi - q_lo)), 256, smem, st>>>(a, q, k, v, out, ld_out);
+    LAUNCH_OK();
+}
+int seq_attn_backward_launch(int seqs, int n_keys, int heads, int dk, int causal, int idx_L, long b_stride, long p_stride, const float* q, const float* k,
+                             const float* v, long ld, unsigned long long seed, int site, float p, const float* d_out, long ld_do, float* dq, float* dk_,
+                             float* dv, long ld_d, const float* key_mask, long ld_mask, cudaStream_t st) {
+    if (seqs <= 0) return 0;
+    const size_t smem = sizeof(float) * ((size_t)4 * n_keys * (dk + 1) + 2 * n_keys * n_keys);
+    CAPB_REQUIRE(smem <= 200 * 1024, "self-attention backward: shared-memory footprint too large");
+    static std::atomic<unsigned long long> configured{0};
+    if (first_use_on_device(configured)) {
+        CAPB_CHECK_CUDA(cudaFuncSetAttribute(seq_attn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
+    SeqAttn a;
+    a.n_keys = n_keys; a.dk = dk; a.heads = heads; a.q_lo = 0; a.q_hi = n_keys; a.causal = causal; a.idx_L = idx_L; a.b_stride = b_stride; a.p_stride = p_stride;
+    a.ld = ld; a.scale = 1.0f / sqrtf((float)dk); a.p_drop = p; a.seed = seed; a.site = (uint32_t)site; a.key_mask = key_mask; a.ld_mask = ld_mask;
+    seq_attn_backward_kernel<<<dim3(seqs, heads, attn_chunks(seqs, heads, n_keys)), 256, smem, st>>>(a, q, k, v, d_out, ld_do, dq, dk_, dv, ld_d);
+    LAUNCH_OK();
+}
+// the refiner / encoder form: sequences = images, keys = queries = the R regions, rows image-major
 int enc_attn_train_launch(int B, int R, int heads, int dk, const float* q, const float* k, const float* v, long ld, unsigned long long seed, int site, float p,
                           float* out, long ld_out, cudaStream_t st, const float* mask, long ld_mask) {
-    const size_t smem = sizeof(float) * ((size_t)2 * R * (dk + 1) + 8 * R);
-    CAPB_REQUIRE(smem <= 48 * 1024, "refiner attention: regions * head width too large for the training kernel");
-    enc_attn_train_kernel<<<dim3(B, heads), 256, smem, st>>>(R, dk, heads, q, k, v, ld, 1.0f / sqrtf((float)dk), seed, (uint32_t)site, p, out, ld_out, mask, ld_mask);
-    LAUNCH_OK();
+    return seq_attn_train_launch(B, R, 0, R, heads, dk, 0, R, R, 1, q, k, v, ld, seed, site, p, out, ld_out, mask, ld_mask, st);
 }
 int enc_attn_backward_launch(int B, int R, int heads, int dk, const float* q, const float* k, const float* v, long ld, unsigned long long seed, int site, float p,
                              const float* d_out, long ld_do, float* dq, float* dk_, float* dv, long ld_d, cudaStream_t st, const float* mask, long ld_mask) {
-    const size_t smem = sizeof(float) * ((size_t)4 * R * (dk + 1) + 2 * R * R);
-    CAPB_REQUIRE(smem <= 200 * 1024, "refiner attention backward: shared-memory footprint too large");
-    static std::atomic<unsigned long long> configured{0};
-    if (first_use_on_device(configured)) {
-        CAPB_CHECK_CUDA(cudaFuncSetAttribute(enc_attn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    }
-    enc_attn_backward_kernel<<<dim3(B, heads), 256, smem, st>>>(R, dk, heads, q, k, v, ld, 1.0f / sqrtf((float)dk), seed, (uint32_t)site, p, d_out, ld_do, dq,
-                                                                  dk_, dv, ld_d, mask, ld_mask);
-    LAUNCH_OK();
+    return seq_attn_backward_launch(B, R, heads, dk, 0, R, R, 1, q, k, v, ld, seed, site, p, d_out, ld_do, dq, dk_, dv, ld_d, mask, ld_mask, st);
 }
 int cross_attn_train_launch(int rows, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
                             unsigned long long seed, int site, int step, float p, float* out, long ld_out, float* probs, cudaStream_t st, const float* mask,

@@ -10,14 +10,16 @@
 //   lo = x - hi           (exact in fp32; the tensor core keeps its top 11 bits: relative error <= 2^-21 of x)
 // and every K-block issues three kind::tf32 MMAs into one fp32 TMEM accumulator: hi*lo + lo*hi + hi*hi (3xTF32, dropped lo*lo <= 2^-22).
 //
-// Structure (one 128 x BN accumulator tile per CTA, 256 threads, split-K across a thread-block cluster):
+// Structure (one 128 x BN accumulator tile per CTA, 384 threads, split-K across a thread-block cluster):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes of RAW fp32 [32 k x 128 rows] (A side) and [32 k x BN rows] (B side), 128B swizzle,
 //               into a STAGES-deep ring (mbarrier complete_tx).
-//   warps 4..7  converters: read the raw tiles from shared memory, write hi in place and lo next to it (element-wise, so the swizzle
-//               pattern is preserved), fence.proxy.async, arrive on the stage's "converted" barrier.
+//   warps 4..11 converters: read the raw tiles from shared memory, write hi in place and lo next to it (element-wise, so the swizzle
+//               pattern is preserved), fence.proxy.async, arrive on the stage's "converted" barrier.  Eight warps: one K-block is a chain
+//               of wait -> 128-bit loads -> subtract -> stores -> fence -> arrive per thread, and with four warps that chain (not the TMA
+//               or the MMAs) set the K-block rate (profiles/r02c_tf32_sweep*.txt: 2.2 TB/s at 50 rows).
 //   warp 1      MMA issuer: one thread, 12 tcgen05.mma.kind::tf32 (M = 128, N = BN, K = 8) per K-block, tcgen05.commit releases the slot.
 //   warp 2      TMEM allocation.
-//   epilogue    warps 4..7 drain the accumulator into a shared-memory staging tile laid out like the OUTPUT (so global stores are
+//   epilogue    warps 4..11 (two per TMEM lane quadrant) drain the accumulator into a shared-memory staging tile laid out like the OUTPUT (so global stores are
 //               coalesced); with split-K the CTAs of the cluster (cluster dim = ksplit <= 8, K-ranges side by side) then add their tiles
 //               through distributed shared memory in rank order (deterministic, no atomics, no second kernel) and each stores a slice.
 // Operand roles: the A side always supplies 128 accumulator rows, the B side BN columns.  Skinny problems (M <= 256 activation rows:
@@ -39,6 +41,8 @@ namespace {
 constexpr int TM = 128;          // accumulator rows per CTA (A-side rows)
 constexpr int TK = 32;           // fp32 elements per K-block: one 128-byte swizzle row
 constexpr int kMaxSegT = 3;
+constexpr int kConvThreads = 256;   // warps 4..11
+constexpr int kThreadsT = 128 + kConvThreads;
 
 struct Tf32Params {
     CUtensorMap a_map[kMaxSegT];
@@ -119,7 +123,7 @@ __device__ __forceinline__ void split_keep_tf32(float x, float& hi, float& lo) {
 __device__ __forceinline__ void split_trunc_tf32(float x, float& lo) { lo = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 template <int BN, bool TRUNC>
-__global__ void __launch_bounds__(256, 1) gemm_tf32x3_kernel(const __grid_constant__ Tf32Params p) {
+__global__ void __launch_bounds__(kThreadsT, 1) gemm_tf32x3_kernel(const __grid_constant__ Tf32Params p) {
     using Cfg = Tf32Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tf32x3_kernel(const __grid_consta
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < Cfg::kStages; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&conv_bar[i], 128);
+            ptx::mbar_init(&conv_bar[i], kConvThreads);
             ptx::mbar_init(&empty_bar[i], 1);
         }
         ptx::mbar_init(tmem_full_bar, 1);
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tf32x3_kernel(const __grid_consta
             float4* b_hi = reinterpret_cast<float4*>(st + 2 * Cfg::kABytes);
             float4* b_lo = reinterpret_cast<float4*>(st + 2 * Cfg::kABytes + Cfg::kBBytes);
 #pragma unroll 4
-            for (int i = ct; i < kAVec; i += 128) {
+            for (int i = ct; i < kAVec; i += kConvThreads) {
                 const float4 x = a_hi[i];
                 float4 h, l;
                 if (TRUNC) { split_trunc_tf32(x.x, l.x); split_trunc_tf32(x.y, l.y); split_trunc_tf32(x.z, l.z); split_trunc_tf32(x.w, l.w); }
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tf32x3_kernel(const __grid_consta
                 a_lo[i] = l;
             }
 #pragma unroll 4
-            for (int i = ct; i < kBVec; i += 128) {
+            for (int i = ct; i < kBVec; i += kConvThreads) {
                 const float4 x = b_hi[i];
                 float4 h, l;
                 if (TRUNC) { split_trunc_tf32(x.x, l.x); split_trunc_tf32(x.y, l.y); split_trunc_tf32(x.z, l.z); split_trunc_tf32(x.w, l.w); }
@@ -252,8 +256,10 @@ __global__ void __launch_bounds__(256, 1) gemm_tf32x3_kernel(const __grid_consta
         float* S = reinterpret_cast<float*>(smem);
         const int q = warp & 3;
         const int arow = q * 32 + lane;                 // accumulator row (A-side row inside the tile) owned by this thread
+        const int half = (warp - 4) >> 2;               // two warps share a lane quadrant and split its columns
+        constexpr int kColsPerWarp = BN >= 32 ? BN / 2 : BN;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int c0 = (BN >= 32 ? half * kColsPerWarp : 0); c0 < (BN >= 32 ? (half + 1) * kColsPerWarp : (half == 0 ? BN : 0)); c0 += 16) {
             uint32_t r[16];
             __syncwarp();
             ptx::tmem_ld_32x32b_x16(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tf32x3_kernel(const __grid_consta
         const uint32_t s_base = ptx::smem_u32(smem);
         const int vec_per_row = cols_out / 4;
         const bool vec_ok = (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (n_base & 3) == 0;
-        for (int idx = threadIdx.x; idx < (r_hi - r_lo) * vec_per_row; idx += 256) {
+        for (int idx = threadIdx.x; idx < (r_hi - r_lo) * vec_per_row; idx += kThreadsT) {
             const int ro = r_lo + idx / vec_per_row, co = (idx % vec_per_row) * 4;
             const int m = m_base + ro, n = n_base + co;
             if (m >= p.M || n >= p.N) continue;
@@ -419,7 +425,7 @@ int launch_tf32_v(const Tf32Params& prm, int ksplit, int tiles_a, int tiles_b, c
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ksplit, tiles_a, tiles_b);
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(kThreadsT);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

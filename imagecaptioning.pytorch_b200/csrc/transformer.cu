@@ -87,12 +87,16 @@ __global__ void __launch_bounds__(256) enc_self_attention_kernel(int R, int dk, 
     }
     __syncthreads();
     float* p = sp + warp * R;
-    for (int qi = warp; qi < R; qi += nw) {
+    float* qs = sp + nw * R + warp * dk;                        // this warp's query row
+    const int q_lo = (int)(((long)R * blockIdx.z) / gridDim.z), q_hi = (int)(((long)R * (blockIdx.z + 1)) / gridDim.z);   // query chunk of this CTA
+    for (int qi = q_lo + warp; qi < q_hi; qi += nw) {
         const float* qr = q + ((long)img * R + qi) * ld + head * dk;
+        for (int c = lane; c < dk; c += 32) qs[c] = qr[c];
+        __syncwarp();
         float mx = -INFINITY;
         for (int r = lane; r < R; r += 32) {
             float s = 0.f;
-            for (int c = 0; c < dk; ++c) s = fmaf(__ldg(qr + c), sk[r * (dk + 1) + c], s);
+            for (int c = 0; c < dk; ++c) s = fmaf(qs[c], sk[r * (dk + 1) + c], s);
             s *= scale;
             if (mask != nullptr && mask[(long)img * ld_mask + r] == 0.f) s = -INFINITY;
             p[r] = s;
@@ -248,13 +252,16 @@ int embed_pe_launch(int rows, int D, const int* tokens, const float* lut, const 
 int enc_self_attention_launch(int B, int R, int heads, int dk, const float* q, const float* k, const float* v, long ld, const float* mask,
                               long ld_mask, ActView out, cudaStream_t st) {
     if (B <= 0) return 0;
-    const size_t smem = sizeof(float) * ((size_t)2 * R * (dk + 1) + 8 * R);
+    const size_t smem = sizeof(float) * ((size_t)2 * R * (dk + 1) + 8 * R + 8 * dk);
     CAPB_REQUIRE(smem <= 200 * 1024, "self-attention: region count x head width too large for the shared-memory staging");
+    int chunks = (296 + B * heads - 1) / (B * heads);           // query chunks: about two CTAs per SM even for a 10-image batch
+    chunks = chunks > 4 ? 4 : (chunks < 1 ? 1 : chunks);
+    if (chunks > R) chunks = R;
     static std::atomic<unsigned long long> configured{0};
     if (first_use_on_device(configured)) {
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(enc_self_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
-    enc_self_attention_kernel<<<dim3(B, heads), 256, smem, st>>>(R, dk, q, k, v, ld, mask, ld_mask, 1.0f / sqrtf((float)dk), out);
+    enc_self_attention_kernel<<<dim3(B, heads, chunks), 256, smem, st>>>(R, dk, q, k, v, ld, mask, ld_mask, 1.0f / sqrtf((float)dk), out);
     CAPB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

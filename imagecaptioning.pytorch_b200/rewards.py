@@ -95,18 +95,58 @@ def reset_scorer():
     CiderD_scorer = None
 
 
+class _Staging:
+    """Round-robin pinned host buffers for the per-step reference upload: one pinned block holds the padded reference rows and the offsets,
+    so the step pays ONE asynchronous H2D copy instead of two pageable ones (each of which blocks the host until the driver has staged
+    it).  A slot is reused only after the copy that read it has completed (event per slot)."""
+    SLOTS = 4
+
+    def __init__(self):
+        self.slots = {}
+        self.turn = 0
+
+    def upload(self, host_rows: np.ndarray, offs: np.ndarray, device):
+        dev = torch.device(device)
+        n = host_rows.size + offs.size
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), self.turn % self.SLOTS)
+        self.turn += 1
+        slot = self.slots.get(key)
+        if slot is None or slot[0].numel() < n:
+            slot = [torch.empty(max(n, 1 << 14), dtype=torch.int32).pin_memory(), torch.empty(max(n, 1 << 14), dtype=torch.int32, device=dev), None]
+            self.slots[key] = slot
+        pinned, devbuf, ev = slot
+        if ev is not None:
+            ev.synchronize()
+        flat = pinned.numpy()
+        flat[:host_rows.size] = host_rows.reshape(-1)
+        flat[host_rows.size:n] = offs
+        devbuf[:n].copy_(pinned[:n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        slot[2] = ev
+        refs = devbuf[:host_rows.size].view(host_rows.shape)
+        return refs, devbuf[host_rows.size:n]
+
+
+_staging = _Staging()
+
+
 def pack_references(data_gts: Sequence, device) -> Tuple[torch.Tensor, torch.Tensor, int]:
-    """list[B] of int arrays [n_refs_i, L] (dataloader.py:213) -> (refs int32 [total, L], offsets int32 [B+1], L) on the device."""
+    """list[B] of int arrays [n_refs_i, L] (dataloader.py:213) -> (refs int32 [total, L], offsets int32 [B+1], L) on the device.
+    The returned tensors are views of a staging buffer that is reused four uploads later: consume them in the step they were packed for."""
     L = max(int(np.asarray(g).shape[1]) for g in data_gts)
-    rows, offs = [], [0]
-    for g in data_gts:
+    total = sum(int(np.asarray(g).shape[0]) for g in data_gts)
+    rows = np.zeros((total, L), dtype=np.int32)
+    offs = np.zeros(len(data_gts) + 1, dtype=np.int32)
+    at = 0
+    for i, g in enumerate(data_gts):
         g = np.asarray(g)
-        pad = np.zeros((g.shape[0], L), dtype=np.int32)
-        pad[:, :g.shape[1]] = g
-        rows.append(pad)
-        offs.append(offs[-1] + g.shape[0])
-    refs = torch.from_numpy(np.concatenate(rows, 0)).to(device, non_blocking=True)
-    offsets = torch.tensor(offs, dtype=torch.int32).to(device, non_blocking=True)
+        rows[at:at + g.shape[0], :g.shape[1]] = g
+        at += g.shape[0]
+        offs[i + 1] = at
+    if torch.device(device).type != 'cuda':
+        return torch.from_numpy(rows), torch.from_numpy(offs), L
+    refs, offsets = _staging.upload(rows, offs, device)
     return refs, offsets, L
 
 

@@ -425,6 +425,19 @@ int capb200_aoa_set_grad_events(capb200_aoa_engine* e, void* const* events, int 
  * site 0 = fc_embed [B,H], 1 = att_embed [B*R,H], 2 = word embedding at `step` [N,E], 3 = core output at `step` [N,H]. */
 int capb200_dropout_mask(float* mask, long n, unsigned long long seed, int site, int step, float p, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Optimizer step of the training loop: utils.clip_gradient(optimizer, grad_clip_value) (captioning/utils/misc.py:156-160, called at
+ * tools/train.py:193) + torch.optim.Adam.step() (built by build_optimizer, misc.py:186-205; tools/train.py:196) in ONE launch.
+ *   table  [n_tensors][4] device pointers {param, grad, exp_avg, exp_avg_sq} (fp32, contiguous), itself in device memory
+ *   numel  [n_tensors] element counts (device)
+ *   chunks [n_chunks][2] int32 {tensor index, chunk index}; a chunk is capb200_adam_chunk_elems() elements (device)
+ *   step   the 1-based step count AFTER this update (bias corrections 1 - beta^step);  clip_value <= 0 disables the clamp;
+ *   write_clamped != 0 stores the clamped gradient back (clip_gradient's in-place side effect).  weight_decay is Adam's L2 term.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int capb200_adam_chunk_elems(void);
+int capb200_adam_step(const unsigned long long* table, const long long* numel, const int* chunks, int n_chunks, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, long step, float clip_value, int write_clamped, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

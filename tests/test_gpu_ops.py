@@ -223,3 +223,39 @@ def test_reward_criterion_matches_golden(golden_dir):
     assert np.abs(crit(lp, seq, reward, reduction='none').cpu().numpy() - g['loss_none']).max() < 1e-6
     grad = crit.backward_logprobs(seq, reward, lp.shape[2])
     assert np.abs(grad.cpu().numpy() - g['grad']).max() < 1e-7
+
+
+@pytest.mark.parametrize('clip,wd', [(None, 0.0), (0.05, 0.0), (0.05, 0.01)])
+def test_fused_adam_matches_torch_adam(clip, wd):
+    """capb200_adam_step (clamp + Adam in one launch; tools/train.py:193-196) against utils.clip_gradient's clamp + torch.optim.Adam over four
+    steps: parameters, both moment buffers and the clamped gradients; odd sizes and a misaligned view exercise the scalar tails; the state
+    dict written by one loads into the other."""
+    import imagecaptioning.pytorch_b200 as b200
+    g = torch.Generator(device='cuda').manual_seed(3)
+    shapes = [(1000, 37), (4097,), (3, 5, 7), (1,), (8192 * 2 + 5,)]
+    mine = [torch.nn.Parameter(torch.randn(s, generator=g, device='cuda')) for s in shapes]
+    mine.append(torch.nn.Parameter(torch.randn(1001, generator=g, device='cuda')[1:]))      # a view that is only 4-byte aligned
+    ref = [torch.nn.Parameter(t.detach().clone()) for t in mine]
+    o_mine = b200.optim.FusedAdam(mine, lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd, clip_value=clip)
+    o_ref = torch.optim.Adam(ref, lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+    for it in range(4):
+        for a, b in zip(mine, ref):
+            gr = torch.randn(a.shape, generator=g, device='cuda') * (0.1 if it % 2 else 1.0)
+            a.grad = gr.clone()
+            b.grad = gr.clone()
+        if clip:
+            for b in ref:
+                b.grad.data.clamp_(-clip, clip)             # captioning/utils/misc.py:156-160
+        o_mine.step()
+        o_ref.step()
+        for a, b in zip(mine, ref):
+            scale = float(b.abs().max()) + 1e-6
+            assert float((a - b).abs().max()) <= 2e-6 * scale
+            assert torch.equal(a.grad, b.grad)
+            sa, sb = o_mine.state[a], o_ref.state[b]
+            assert float((sa['exp_avg'] - sb['exp_avg']).abs().max()) <= 1e-6 * (float(sb['exp_avg'].abs().max()) + 1e-12)
+            assert float((sa['exp_avg_sq'] - sb['exp_avg_sq']).abs().max()) <= 1e-6 * (float(sb['exp_avg_sq'].abs().max()) + 1e-12)
+            assert float(sa['step']) == float(sb['step']) == it + 1
+    assert o_mine.launches == 4
+    o_ref.load_state_dict(o_mine.state_dict())              # same layout: optimizer.pth is interchangeable (tools/train.py:74-77)
+    o_mine.load_state_dict(o_ref.state_dict())
