@@ -117,6 +117,17 @@ class TfmWeights(Structure):
                 ('lut', c_void_p), ('pe', c_void_p), ('gen_w', c_void_p), ('gen_b', c_void_p)]
 
 
+class TfmXeOpts(Structure):
+    _fields_ = [('seq_per_img', c_int), ('seed', c_ulonglong), ('label_smoothing', c_float), ('upstream', c_float), ('drop_prob_lm', c_float),
+                ('dropout', c_float), ('att_masks', c_void_p), ('keep_rows', c_int), ('row_loss', c_void_p)]
+
+
+class TfmScstOpts(Structure):
+    _fields_ = [('sample_n', c_int), ('temperature', c_float), ('seed', c_ulonglong), ('upstream', c_float), ('baseline', c_int),
+                ('drop_prob_lm', c_float), ('dropout', c_float), ('forced_tokens', c_void_p), ('att_masks', c_void_p), ('keep_rows', c_int),
+                ('row_loss', c_void_p)]
+
+
 AOA_REFINER_LAYERS = 6
 
 
@@ -184,8 +195,13 @@ SIGNATURES = {
     'capb200_updown_scst_step': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(ScstOpts), c_void_p, c_void_p, c_void_p, c_int,
                                          POINTER(UpdownGrads), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'capb200_dropout_mask': (c_int, [c_void_p, c_long, c_ulonglong, c_int, c_int, c_float, c_void_p]),
+    'capb200_tfm_xe_step': (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(TfmXeOpts), c_void_p, c_void_p, c_int, POINTER(TfmWeights), c_void_p, c_void_p,
+                                    c_void_p]),
+    'capb200_tfm_scst_step': (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(TfmScstOpts), c_void_p, c_void_p, c_void_p, c_int, POINTER(TfmWeights),
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'capb200_tfm_set_grad_events': (c_int, [c_void_p, c_void_p, c_int]),
     'capb200_adam_chunk_elems': (c_int, []),
-    'capb200_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_float, c_float, c_long, c_float, c_int, c_void_p]),
+    'capb200_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double, c_double, c_long, c_double, c_int, c_void_p]),
     'capb200_engine_set_grad_events': (c_int, [c_void_p, c_void_p, c_int]),
     'capb200_aoa_set_grad_events': (c_int, [c_void_p, c_void_p, c_int]),
     'capb200_cider_table_create': (c_void_p, [c_void_p, c_void_p, c_long, c_double, c_void_p]),

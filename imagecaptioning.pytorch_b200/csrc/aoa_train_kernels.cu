@@ -276,12 +276,17 @@ __global__ void __launch_bounds__(128) cross_attn_train_kernel(int rows, int rpi
                                                                const float* __restrict__ kk, const float* __restrict__ vv, long ld_kv, float scale,
                                                                unsigned long long seed, uint32_t site, uint32_t step, float p_drop,
                                                                float* __restrict__ out, long ld_out, float* __restrict__ probs,
-                                                               const float* __restrict__ mask, long ld_mask) {
+                                                               const float* __restrict__ mask, long ld_mask, int row_mod) {
+    // rows may be TIME-major blocks of row_mod rows each (Transformer training: row = t * row_mod + n): the image is (row % row_mod) / rpi and the
+    // dropout stream is keyed by (step + t, n), so a batched call over all t and a step-by-step sequence of calls draw the same masks
     extern __shared__ float sm[];       // [R] scores -> exp -> dropped probabilities
     __shared__ float sh_inv;
     const int item = blockIdx.x;
     const int row = item / heads, head = item % heads;
-    const int img = row / rpi;
+    const int local = row % row_mod;
+    const uint32_t tstep = step + (uint32_t)(row / row_mod);
+    const int img = local / rpi;
+    const long item_local = (long)local * heads + head;
     const float* qr = q + (long)row * ld_q + head * dk;
     const float* kb = kk + (long)img * R * ld_kv + head * dk;
     const float* vb = vv + (long)img * R * ld_kv + head * dk;
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(128) cross_attn_train_kernel(int rows, int rpi
     for (int r = threadIdx.x; r < R; r += 128) {
         const float pr = sm[r] * inv;
         probs[(long)item * R + r] = pr;
-        sm[r] = pr * drop_scale(seed, site, step, (uint32_t)((long)item * R + r), p_drop);
+        sm[r] = pr * drop_scale(seed, site, tstep, (uint32_t)(item_local * R + r), p_drop);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < dk; c += 128) out[(long)row * ld_out + head * dk + c] = sq_attention_column(sm, vb, ld_kv, R, c);
@@ -302,7 +307,8 @@ __global__ void __launch_bounds__(256) cross_attn_backward_kernel(int rpi, int h
                                                                   unsigned long long seed, uint32_t site, uint32_t step, float p_drop,
                                                                   const float* __restrict__ probs, const float* __restrict__ d_out, long ld_do,
                                                                   float* __restrict__ dq, long ld_dq, float* __restrict__ dkk, float* __restrict__ dvv,
-                                                                  long ld_dkv) {
+                                                                  long ld_dkv, int rpi1, int row_mod) {
+    // rpi = rows of this image in the launch = n_steps * rpi1 (rpi1 rows per image per time block; time blocks are row_mod rows apart)
     extern __shared__ float sm[];
     const int W = dk + 1;
     float* sk = sm;                  // [R][W]
@@ -312,6 +318,7 @@ __global__ void __launch_bounds__(256) cross_attn_backward_kernel(int rpi, int h
     float* PD = sd + rpi * W;        // [rpi][R]  p * D
     float* DS = PD + rpi * R;        // [rpi][R]  d score (scaled)
     const int img = blockIdx.x, head = blockIdx.y;
+    auto row_of = [&](int j) -> long { return (long)(j / rpi1) * row_mod + (long)img * rpi1 + (j % rpi1); };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
 #pragma unroll 4
     for (int i = threadIdx.x; i < R * dk; i += blockDim.x) {       // independent coalesced loads, several in flight per thread
@@ -321,17 +328,19 @@ __global__ void __launch_bounds__(256) cross_attn_backward_kernel(int rpi, int h
     }
     for (int i = threadIdx.x; i < rpi * dk; i += blockDim.x) {
         const int j = i / dk, c = i % dk;
-        const long row = (long)img * rpi + j;
+        const long row = row_of(j);
         sq[j * W + c] = q[row * ld_q + head * dk + c];
         sd[j * W + c] = d_out[row * ld_do + head * dk + c];
     }
     __syncthreads();
     for (int j = warp; j < rpi; j += nw) {
-        const long item = ((long)img * rpi + j) * heads + head;
+        const long item = row_of(j) * heads + head;
+        const long item_local = ((long)img * rpi1 + (j % rpi1)) * heads + head;
+        const uint32_t tstep = step + (uint32_t)(j / rpi1);
         float dot = 0.f;
         for (int r = lane; r < R; r += 32) {
             const float pr = probs[item * R + r];
-            const float D = drop_scale(seed, site, step, (uint32_t)(item * R + r), p_drop);
+            const float D = drop_scale(seed, site, tstep, (uint32_t)(item_local * R + r), p_drop);
             float s = 0.f;
             for (int c = 0; c < dk; ++c) s = fmaf(sd[j * W + c], sv[r * W + c], s);
             const float dp = s * D;
@@ -360,7 +369,7 @@ __global__ void __launch_bounds__(256) cross_attn_backward_kernel(int rpi, int h
         const int j = i / dk, c = i % dk;
         float a = 0.f;
         for (int r = 0; r < R; ++r) a = fmaf(DS[j * R + r], sk[r * W + c], a);
-        dq[((long)img * rpi + j) * ld_dq + head * dk + c] = a;
+        dq[row_of(j) * ld_dq + head * dk + c] = a;
     }
 }
 
@@ -482,15 +491,19 @@ int enc_attn_backward_launch(int B, int R, int heads, int dk, const float* q, co
 }
 int cross_attn_train_launch(int rows, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
                             unsigned long long seed, int site, int step, float p, float* out, long ld_out, float* probs, cudaStream_t st, const float* mask,
-                            long ld_mask) {
+                            long ld_mask, int row_mod) {
     CAPB_REQUIRE(dk <= 256, "attention: head width above 256");
+    if (rows <= 0) return 0;
     cross_attn_train_kernel<<<rows * heads, 128, sizeof(float) * R, st>>>(rows, rpi, heads, dk, R, q, ld_q, kk, vv, ld_kv, 1.0f / sqrtf((float)dk),
-                                                                                        seed, (uint32_t)site, (uint32_t)step, p, out, ld_out, probs, mask, ld_mask);
+                                                                                        seed, (uint32_t)site, (uint32_t)step, p, out, ld_out, probs, mask, ld_mask,
+                                                                                        row_mod > 0 ? row_mod : rows);
     LAUNCH_OK();
 }
 int cross_attn_backward_launch(int B, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
                                unsigned long long seed, int site, int step, float p, const float* probs, const float* d_out, long ld_do, float* dq, long ld_dq,
-                               float* dkk, float* dvv, long ld_dkv, cudaStream_t st) {
+                               float* dkk, float* dvv, long ld_dkv, cudaStream_t st, int n_steps, int row_mod) {
+    const int rpi1 = rpi;
+    rpi = rpi1 * (n_steps > 0 ? n_steps : 1);          // all of the image's rows in this launch
     const size_t smem = sizeof(float) * ((size_t)2 * R * (dk + 1) + 2 * rpi * (dk + 1) + 2 * rpi * R);
     CAPB_REQUIRE(smem <= 200 * 1024, "decoder attention backward: shared-memory footprint too large");
     static std::atomic<unsigned long long> configured{0};
@@ -498,7 +511,7 @@ int cross_attn_backward_launch(int B, int rpi, int heads, int dk, int R, const f
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     cross_attn_backward_kernel<<<dim3(B, heads), 256, smem, st>>>(rpi, heads, dk, R, q, ld_q, kk, vv, ld_kv, 1.0f / sqrtf((float)dk), seed, (uint32_t)site,
-                                                                   (uint32_t)step, p, probs, d_out, ld_do, dq, ld_dq, dkk, dvv, ld_dkv);
+                                                                   (uint32_t)step, p, probs, d_out, ld_do, dq, ld_dq, dkk, dvv, ld_dkv, rpi1, row_mod > 0 ? row_mod : B * rpi1);
     LAUNCH_OK();
 }
 int mean_backward_launch(int B, int R, int H, const float* d_mean, long ld_dm, float* dx, long ld_dx, cudaStream_t st, const float* mask, long ld_mask) {

@@ -178,6 +178,19 @@ int add_strided_launch(float* a, const float* b, long ld_b, int rows, int cols, 
 int ln_backward_launch(int rows, int D, const float* x, long ld_x, const float* a, const float* dy, long ld_dy, float eps, float* dx, long ld_dx, int accumulate,
                        float* stats, float* da, float* db, int accumulate_params, cudaStream_t st);
 int glu_backward_launch(int rows, int H, const float* t, long ld_t, const float* dy, long ld_dy, float* dt, long ld_dt, cudaStream_t st);
+// ---- tfm_train_kernels.cu: element-wise pieces of the Transformer training steps on TIME-major rows (row = t * rps + n; dropout keyed by (t, n))
+int embed_pe_dropout_launch(int rows, int rps, int D, const int* tok, const float* lut, const float* pe, float scale, int t0, unsigned long long seed, int site,
+                            float p, float* x, long ld, cudaStream_t st);
+int embed_pe_backward_launch(int rows, int rps, int D, const int* tok, float scale, int t0, unsigned long long seed, int site, float p, const float* dx, long ld,
+                             float* dlut, cudaStream_t st);
+int add_dropout_rows_launch(int rows, int rps, int cols, int t0, const float* a, long ld_a, const float* b, long ld_b, float* out, long ld_o, unsigned long long seed,
+                            int site, float p, cudaStream_t st);
+int dropout_rows_copy_launch(int rows, int rps, int cols, int t0, const float* src, long ld_s, float* dst, long ld_d, unsigned long long seed, int site, float p,
+                             const float* relu_of, long ld_r, cudaStream_t st);
+int relu_dropout_rows_launch(int rows, int rps, int cols, int t0, float* h, long ld, unsigned long long seed, int site, float p, cudaStream_t st);
+int permute_rows_launch(int L, int N, int D, const float* src, long ld_s, float* dst, long ld_d, int to_seq_major, cudaStream_t st);
+int load_tokens_tm_launch(const long long* labels, long ld, int N, int L, int* tok, float* key_mask, long ld_m, cudaStream_t st);
+int add_rows_launch(int rows, int cols, float* x, long ld_x, const float* y, long ld_y, cudaStream_t st);
 // sequence self-attention with replayable dropout (aoa_train_kernels.cu): row(b, pos) = b * b_stride + pos * p_stride
 int seq_attn_train_launch(int seqs, int n_keys, int q_lo, int q_hi, int heads, int dk, int causal, int idx_L, long b_stride, long p_stride, const float* q,
                           const float* k, const float* v, long ld, unsigned long long seed, int site, float p, float* out, long ld_out, const float* key_mask,
@@ -192,10 +205,10 @@ int enc_attn_backward_launch(int B, int R, int heads, int dk, const float* q, co
                              long ld_mask = 0);
 int cross_attn_train_launch(int rows, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
                             unsigned long long seed, int site, int step, float p, float* out, long ld_out, float* probs, cudaStream_t st,
-                            const float* mask = nullptr, long ld_mask = 0);
+                            const float* mask = nullptr, long ld_mask = 0, int row_mod = 0);
 int cross_attn_backward_launch(int B, int rpi, int heads, int dk, int R, const float* q, long ld_q, const float* kk, const float* vv, long ld_kv,
                                unsigned long long seed, int site, int step, float p, const float* probs, const float* d_out, long ld_do, float* dq, long ld_dq,
-                               float* dkk, float* dvv, long ld_dkv, cudaStream_t st);
+                               float* dkk, float* dvv, long ld_dkv, cudaStream_t st, int n_steps = 1, int row_mod = 0);
 int mean_backward_launch(int B, int R, int H, const float* d_mean, long ld_dm, float* dx, long ld_dx, cudaStream_t st, const float* mask = nullptr,
                          long ld_mask = 0);
 int add_dropout_launch(int rows, int cols, const float* a, long ld_a, const float* b, long ld_b, float* out, long ld_o, unsigned long long seed, int site, int step,

@@ -16,7 +16,7 @@ namespace {
 constexpr int kChunk = 8192;        // elements per CTA (256 threads x 8 float4)
 
 struct AdamScalars {
-    float lr_over_bias1, bias2_sqrt, beta1, beta2, eps, weight_decay, clip;
+    float lr_over_bias1, bias2_sqrt, beta1, beta2, omb1, omb2, eps, weight_decay, clip;      // omb = 1 - beta, rounded from double like torch's python scalars
     int write_clamped;
 };
 
@@ -24,8 +24,8 @@ __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v,
     if (s.clip > 0.f) g = fminf(fmaxf(g, -s.clip), s.clip);
     float gg = g;
     if (s.weight_decay != 0.f) gg = fmaf(s.weight_decay, p, gg);
-    m = m + (gg - m) * (1.0f - s.beta1);                       // exp_avg.lerp_(grad, 1 - beta1)
-    v = v * s.beta2 + (1.0f - s.beta2) * gg * gg;              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
+    m = m + (gg - m) * s.omb1;                                // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * s.beta2 + s.omb2 * gg * gg;                       // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
     const float denom = sqrtf(v) / s.bias2_sqrt + s.eps;
     p = p - s.lr_over_bias1 * (m / denom);                     // param.addcdiv_(exp_avg, denom, value = -lr / bias1)
 }
@@ -76,17 +76,19 @@ using namespace capb200;
 
 extern "C" int capb200_adam_chunk_elems(void) { return kChunk; }
 
-extern "C" int capb200_adam_step(const unsigned long long* table, const long long* numel, const int* chunks, int n_chunks, float lr, float beta1,
-                                 float beta2, float eps, float weight_decay, long step, float clip_value, int write_clamped, void* stream) {
+extern "C" int capb200_adam_step(const unsigned long long* table, const long long* numel, const int* chunks, int n_chunks, double lr, double beta1,
+                                 double beta2, double eps, double weight_decay, long step, double clip_value, int write_clamped, void* stream) {
     CAPB_REQUIRE(table != nullptr && numel != nullptr && chunks != nullptr && n_chunks >= 0, "null argument");
-    CAPB_REQUIRE(step >= 1 && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "bad Adam hyper-parameters");
+    CAPB_REQUIRE(step >= 1 && beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0, "bad Adam hyper-parameters");
     if (n_chunks == 0) return 0;
     AdamScalars s;
-    const double bias1 = 1.0 - pow((double)beta1, (double)step);
-    const double bias2 = 1.0 - pow((double)beta2, (double)step);
-    s.lr_over_bias1 = (float)((double)lr / bias1);
+    // the scalars are python floats (doubles) in torch's Adam and reach its kernels rounded once to fp32: same here
+    const double bias1 = 1.0 - pow(beta1, (double)step);
+    const double bias2 = 1.0 - pow(beta2, (double)step);
+    s.lr_over_bias1 = (float)(lr / bias1);
     s.bias2_sqrt = (float)sqrt(bias2);
-    s.beta1 = beta1; s.beta2 = beta2; s.eps = eps; s.weight_decay = weight_decay; s.clip = clip_value; s.write_clamped = write_clamped;
+    s.beta1 = (float)beta1; s.beta2 = (float)beta2; s.omb1 = (float)(1.0 - beta1); s.omb2 = (float)(1.0 - beta2); s.eps = (float)eps;
+    s.weight_decay = (float)weight_decay; s.clip = (float)clip_value; s.write_clamped = write_clamped;
     adam_kernel<<<n_chunks, 256, 0, static_cast<cudaStream_t>(stream)>>>(table, numel, reinterpret_cast<const int2*>(chunks), s);
     CAPB_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -122,24 +122,38 @@ class _ScstLoss(torch.autograd.Function):
     backward before zero_grad accumulates like autograd would)."""
 
     @staticmethod
-    def forward(ctx, loss_value, grad_list, sync, *params):
+    def forward(ctx, loss_value, grad_list, sync, flat, *params):
         ctx.grad_list = grad_list
         ctx.sync = sync
+        ctx.flat = flat
         ctx.params = params
         return loss_value.clone()
 
     @staticmethod
     def backward(ctx, grad_out):
-        if ctx.sync is None:
-            return (None, None, None) + tuple(g * grad_out for g in ctx.grad_list)
+        if ctx.flat is None:
+            # through autograd (nn.DataParallel replicas, torch DDP hooks): one new tensor per parameter
+            return (None, None, None, None) + tuple(g * grad_out for g in ctx.grad_list)
+        _deliver_views(ctx, grad_out)
+        return (None, None, None, None) + tuple(None for _ in ctx.params)
+
+
+def _deliver_views(ctx, scale):
+    """The direct path of the fused steps: the engine's flat gradient buffer is scaled in place by the upstream gradient (ONE launch) and
+    every ``param.grad`` becomes a view of it -- no per-parameter kernels, no allocation, and stable gradient addresses from step to step
+    (what lets optim.FusedAdam keep its pointer table).  Gradient accumulation over several fused steps is refused: the next step
+    overwrites the buffer the views point into."""
+    if ctx.sync is not None:
         ctx.sync.wait()
-        torch._foreach_mul_(list(ctx.grad_list), grad_out)
-        for p_, g in zip(ctx.params, ctx.grad_list):
-            if p_.grad is None:
-                p_.grad = g
-            else:
-                p_.grad.add_(g)
-        return (None, None, None) + tuple(None for _ in ctx.params)
+    ctx.flat.mul_(scale)
+    for p_, g in zip(ctx.params, ctx.grad_list):
+        if p_.grad is None:
+            p_.grad = g
+        elif p_.grad.data_ptr() == g.data_ptr():
+            raise RuntimeError('capb200: param.grad still views the engine\'s gradient buffer of an earlier fused step; call optimizer.zero_grad() between '
+                               'steps (gradient accumulation needs B200LossWrapper.direct_grads = False)')
+        else:
+            p_.grad.add_(g)
 
 
 class _DropWorstLoss(torch.autograd.Function):
@@ -149,8 +163,8 @@ class _DropWorstLoss(torch.autograd.Function):
     kept rows, 0 elsewhere -- and refuses anything else instead of handing out gradients of a different objective."""
 
     @staticmethod
-    def forward(ctx, row_loss, keep, grad_list, sync, *params):
-        ctx.grad_list, ctx.sync, ctx.params, ctx.keep = grad_list, sync, params, keep
+    def forward(ctx, row_loss, keep, grad_list, sync, flat, *params):
+        ctx.grad_list, ctx.sync, ctx.flat, ctx.params, ctx.keep = grad_list, sync, flat, params, keep
         ctx.save_for_backward(row_loss)
         return row_loss.clone()
 
@@ -164,16 +178,10 @@ class _DropWorstLoss(torch.autograd.Function):
         if not torch.allclose(grad_out, kept * scale, rtol=1e-4, atol=1e-8):
             raise NotImplementedError('drop_worst: the fused step computed the gradients of the mean over the %d smallest row losses '
                                       '(tools/train.py:191); a different reduction of out[\'loss\'] is not supported' % k)
-        if ctx.sync is None:
-            return (None, None, None, None) + tuple(g * scale for g in ctx.grad_list)
-        ctx.sync.wait()
-        torch._foreach_mul_(list(ctx.grad_list), scale)
-        for p_, g in zip(ctx.params, ctx.grad_list):
-            if p_.grad is None:
-                p_.grad = g
-            else:
-                p_.grad.add_(g)
-        return (None, None, None, None) + tuple(None for _ in ctx.params)
+        if ctx.flat is None:
+            return (None, None, None, None, None) + tuple(g * scale for g in ctx.grad_list)
+        _deliver_views(ctx, scale)
+        return (None, None, None, None, None) + tuple(None for _ in ctx.params)
 
 
 class B200LossWrapper(nn.Module):
@@ -187,6 +195,9 @@ class B200LossWrapper(nn.Module):
         self.struc_crit = None
         self._sync = None
         self.last_sync_bytes = 0
+        # True: backward() points param.grad at views of the engine's flat gradient buffer (fast path).  Set False under torch DDP (its
+        # reducer listens to autograd's per-parameter hooks) or for gradient accumulation; nn.DataParallel replicas always go through autograd.
+        self.direct_grads = True
 
     # -- data-parallel gradient synchronisation (the role DDP plays for the reference, tools/train_pl.py:479) -------------------------
     def enable_gradient_sync(self, process_group=None):
@@ -206,14 +217,17 @@ class B200LossWrapper(nn.Module):
     # -- fused device steps ------------------------------------------------------------------------------------------
     def _bridge(self, res):
         params = list(res['grads'].keys())
+        fg = res.get('flat')
         sync = None
-        if self._sync is not None and res.get('flat') is not None:
-            self._sync.launch(res['flat'])
+        if self._sync is not None and fg is not None:
+            self._sync.launch(fg)
             self.last_sync_bytes = self._sync.bytes
             sync = self._sync
+        direct = fg is not None and (sync is not None or (self.direct_grads and all(p_.is_leaf for p_ in params)))
+        flat = fg.flat if direct else None
         if res.get('row_loss') is not None:          # drop_worst: the per-row vector is what the reference returns as out['loss']
-            return _DropWorstLoss.apply(res['row_loss'], int(res['keep_rows']), [res['grads'][p_] for p_ in params], sync, *params)
-        return _ScstLoss.apply(res['loss'], [res['grads'][p_] for p_ in params], sync, *params)
+            return _DropWorstLoss.apply(res['row_loss'], int(res['keep_rows']), [res['grads'][p_] for p_ in params], sync, flat, *params)
+        return _ScstLoss.apply(res['loss'], [res['grads'][p_] for p_ in params], sync, flat, *params)
 
     def _keep_rows(self, rows, drop_worst_flag):
         """int(loss.shape[0] * (1 - opt.drop_worst_rate)), the trainer's own arithmetic (tools/train.py:191); 0 when the flag is off."""
@@ -234,7 +248,7 @@ class B200LossWrapper(nn.Module):
         """loss_wrapper.py:54-55: crit(model(fc, att, labels[..., :-1], att_masks), labels[..., 1:], masks[..., 1:])."""
         if torch.is_grad_enabled() and self.model.training:
             if not hasattr(self.model, 'xe_step'):
-                raise NotImplementedError('the fused XE step covers the UpDown and AoANet families')
+                raise NotImplementedError('the fused XE step covers the UpDown, AoANet and Transformer families')
             rows = labels.shape[0] * (labels.shape[1] if labels.dim() == 3 else 1)
             keep = self._keep_rows(rows, drop_worst_flag)
             res = self.model.xe_step(fc_feats, att_feats, labels, masks, label_smoothing=getattr(self.opt, 'label_smoothing', 0), att_masks=att_masks,
@@ -298,7 +312,7 @@ class B200LossWrapper(nn.Module):
             # silently trains nothing) at backward()
             why = []
             if not hasattr(self.model, 'scst_step'):
-                why.append('model family %r has no fused SCST step (UpDown and AoANet do)' % getattr(self.model, 'family_name', type(self.model).__name__))
+                why.append('model family %r has no fused SCST step (UpDown, AoANet and Transformer do)' % getattr(self.model, 'family_name', type(self.model).__name__))
             if not plain_reward:
                 why.append('cider_reward_weight != 1 or bleu_reward_weight != 0')
             if opt.train_sample_method != 'sample' or opt.train_beam_size != 1:

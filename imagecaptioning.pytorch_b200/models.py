@@ -690,6 +690,7 @@ class B200TransformerModel(B200CaptionModel):
         self.d_model = getattr(opt, 'd_model', opt.input_encoding_size)
         self.d_ff = getattr(opt, 'd_ff', opt.rnn_size)
         self.h = getattr(opt, 'num_att_heads', 8)
+        self.dropout = getattr(opt, 'dropout', 0.1)             # every nn.Dropout inside make_model (TransformerModel.py:240-253)
         if self.N_enc > _lib.TFM_MAX_LAYERS or self.N_dec > _lib.TFM_MAX_LAYERS:
             raise NotImplementedError('at most %d layers per stack' % _lib.TFM_MAX_LAYERS)
         V1, D = self.vocab_size + 1, self.d_model
@@ -795,6 +796,127 @@ class B200TransformerModel(B200CaptionModel):
 
     def _teacher_steps(self, seq):
         return seq.shape[1]            # one parallel pass in the reference: every position is computed (TransformerModel.py:340-348)
+
+    # ---- training steps (capb200_tfm_xe_step / capb200_tfm_scst_step) ---------------------------------------------------------------
+    def _slots(self):
+        """[(path into capb200_tfm_weights / capb200_tfm_grads, parameter)]: path = (field,) | ('enc'|'dec', layer, field) | ('enc'|'dec', layer, attn, field)."""
+        out = [(('att_embed_w',), self.att_embed[0].weight), (('att_embed_b',), self.att_embed[0].bias)]
+
+        def layer_slots(kind, i, layer, attns, n_sub):
+            for an in attns:
+                for name, lin in zip(('q', 'k', 'v', 'o'), getattr(layer, an).linears):
+                    out.append(((kind, i, an, name + '_w'), lin.weight))
+                    out.append(((kind, i, an, name + '_b'), lin.bias))
+            out.append(((kind, i, 'w1_w'), layer.feed_forward.w_1.weight)); out.append(((kind, i, 'w1_b'), layer.feed_forward.w_1.bias))
+            out.append(((kind, i, 'w2_w'), layer.feed_forward.w_2.weight)); out.append(((kind, i, 'w2_b'), layer.feed_forward.w_2.bias))
+            for j in range(n_sub):
+                out.append(((kind, i, 'ln%d_a' % j), layer.sublayer[j].norm.a_2)); out.append(((kind, i, 'ln%d_b' % j), layer.sublayer[j].norm.b_2))
+
+        for i, layer in enumerate(self.model.encoder.layers):
+            layer_slots('enc', i, layer, ('self_attn',), 2)
+        out += [(('enc_norm_a',), self.model.encoder.norm.a_2), (('enc_norm_b',), self.model.encoder.norm.b_2)]
+        for i, layer in enumerate(self.model.decoder.layers):
+            layer_slots('dec', i, layer, ('self_attn', 'src_attn'), 3)
+        out += [(('dec_norm_a',), self.model.decoder.norm.a_2), (('dec_norm_b',), self.model.decoder.norm.b_2),
+                (('lut',), self.model.tgt_embed[0].lut.weight), (('gen_w',), self.model.generator.proj.weight), (('gen_b',), self.model.generator.proj.bias)]
+        return out
+
+    @staticmethod
+    def _slot_name(path):
+        return '/'.join(str(x) for x in path)
+
+    def _grad_groups(self):
+        slots = [(self._slot_name(path), prm) for path, prm in self._slots()]
+        late = [s for s in slots if s[0].startswith(('enc', 'att_embed'))]              # encoder + att_embed finish last
+        early = [s for s in slots if not s[0].startswith(('enc', 'att_embed'))]
+        return [early, late]
+
+    def _grad_table(self, lib, device):
+        fg = self._flat_grads(device)
+        g = _lib.TfmWeights()
+        for path, _ in self._slots():
+            ptr = fg.by_name[self._slot_name(path)].data_ptr()
+            dst = g
+            for key in path[:-1]:
+                dst = getattr(dst, key) if isinstance(key, str) else dst[key]
+            setattr(dst, path[-1], ptr)
+        table, n = fg.event_table()
+        _lib.check(lib.capb200_tfm_set_grad_events(self._engine, table, n), 'tfm_set_grad_events')
+        return fg, g
+
+    def _result_grads(self, fg):
+        return {prm: fg.by_name[self._slot_name(path)] for path, prm in self._slots()}
+
+    @_on_device
+    def xe_step(self, fc_feats, att_feats, labels, masks, label_smoothing=0.0, drop_prob=None, seed=None, upstream=1.0, dropout=None, att_masks=None,
+                keep_rows=0):
+        """One cross-entropy step of the Transformer on the device (capb200_tfm_xe_step): the teacher-forced pass over every position
+        (TransformerModel.py:340-348), LanguageModelCriterion / LabelSmoothing, backward through decoder and encoder.  ``drop_prob`` is
+        att_embed's dropout (drop_prob_lm), ``dropout`` the Transformer's own rate.  Result as B200UpDownModel.xe_step."""
+        lib = self._ensure_engine(att_feats.device)
+        att, region_masks = self._clip(att_feats, att_masks)
+        dev = att.device
+        B, R = att.shape[0], att.shape[1]
+        if labels.dim() == 3:
+            labels = labels.reshape(-1, labels.shape[2])
+            masks = masks.reshape(-1, masks.shape[2])
+        labels = labels.detach().to(torch.long).contiguous()
+        masks = masks.detach().to(torch.float32).contiguous()
+        N, Lc = labels.shape
+        if N % B != 0 or Lc > self.seq_length + 2 or masks.shape != labels.shape:
+            raise ValueError('labels/masks must be [B * seq_per_img, <= seq_length + 2]')
+        # self.ss_prob is ignored, as in the reference: TransformerModel._forward is one parallel pass with no scheduled-sampling branch
+        V1 = self.vocab_size + 1
+        fg, g = self._grad_table(lib, dev)
+        logprobs = torch.empty(N, Lc - 1, V1, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        p_lm = self.drop_prob_lm if drop_prob is None else drop_prob
+        p = self.dropout if dropout is None else dropout
+        row_loss = torch.empty(N, dtype=torch.float32, device=dev) if keep_rows else None
+        xo = _lib.TfmXeOpts(N // B, seed, float(label_smoothing), float(upstream), float(p_lm), float(p), _lib.ptr(region_masks), int(keep_rows), _lib.ptr(row_loss))
+        _lib.check(lib.capb200_tfm_xe_step(self._engine, _lib.ptr(att), B, R, ctypes.byref(xo), _lib.ptr(labels), _lib.ptr(masks), Lc, ctypes.byref(g),
+                                           _lib.ptr(logprobs), _lib.ptr(loss), _lib.current_stream()), 'tfm_xe_step')
+        return {'loss': loss[0], 'logprobs': logprobs, 'grads': self._result_grads(fg), 'seed': seed, 'flat': fg, 'tokens_used': None, 'row_loss': row_loss}
+
+    @_on_device
+    def scst_step(self, fc_feats, att_feats, gts, table, sample_n, temperature=1.0, drop_prob=None, seed=None, upstream=1.0, baseline='greedy', dropout=None,
+                  forced_tokens=None, att_masks=None, keep_rows=0):
+        """One self-critical step of the Transformer on the device (capb200_tfm_scst_step): eval-mode greedy baseline (or leave-one-out),
+        train-mode samples drawn position by position on the K/V tape, CIDEr-D reward, RewardCriterion, batched backward.  Result as
+        B200UpDownModel.scst_step."""
+        from .rewards import pack_references
+        lib = self._ensure_engine(att_feats.device)
+        att, masks = self._clip(att_feats, att_masks)
+        dev = att.device
+        B, R = att.shape[0], att.shape[1]
+        N, T, V1 = B * sample_n, self.seq_length, self.vocab_size + 1
+        refs, offsets, L = pack_references(gts, dev)
+        fg, g = self._grad_table(lib, dev)
+        if baseline not in ('greedy', 'leave_one_out'):
+            raise ValueError("baseline must be 'greedy' or 'leave_one_out'")
+        loo = baseline == 'leave_one_out'
+        sample_seq, greedy_seq, logprobs, reward, loss = self._step_buffers(('scst', B, sample_n), lambda: (
+            torch.zeros(N, T, dtype=torch.long, device=dev), torch.zeros(B, T, dtype=torch.long, device=dev),
+            torch.zeros(N, T, V1, dtype=torch.float32, device=dev), torch.empty(N, T, dtype=torch.float32, device=dev),
+            torch.empty(1, dtype=torch.float32, device=dev)))
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        p_lm = self.drop_prob_lm if drop_prob is None else drop_prob
+        p = self.dropout if dropout is None else dropout
+        forced = None
+        if forced_tokens is not None:
+            forced = forced_tokens.detach().to(device=dev, dtype=torch.long).contiguous()
+            assert forced.shape == (N, T)
+        row_loss = torch.empty(N, dtype=torch.float32, device=dev) if keep_rows else None
+        so = _lib.TfmScstOpts(sample_n, float(temperature), seed, float(upstream), _lib.BASELINE_LEAVE_ONE_OUT if loo else _lib.BASELINE_GREEDY, float(p_lm),
+                              float(p), _lib.ptr(forced), _lib.ptr(masks), int(keep_rows), _lib.ptr(row_loss))
+        _lib.check(lib.capb200_tfm_scst_step(self._engine, _lib.ptr(att), B, R, ctypes.byref(so), table._h, _lib.ptr(refs), _lib.ptr(offsets), L,
+                                             ctypes.byref(g), _lib.ptr(sample_seq), None if loo else _lib.ptr(greedy_seq), _lib.ptr(logprobs),
+                                             _lib.ptr(reward), _lib.ptr(loss), _lib.current_stream()), 'tfm_scst_step')
+        return {'loss': loss[0], 'reward': reward, 'sample_seq': sample_seq, 'greedy_seq': None if loo else greedy_seq, 'sample_logprobs': logprobs,
+                'grads': self._result_grads(fg), 'seed': seed, 'flat': fg, 'row_loss': row_loss}
 
 
 class B200AoAModel(B200CaptionModel):

@@ -67,14 +67,15 @@ class FusedAdam(torch.optim.Adam):
                     st['step'] = torch.tensor(0.0, dtype=torch.float32)         # torch.optim.Adam's default (host scalar tensor)
                     st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st['step'] += 1
-                by_dev.setdefault((p.device, int(st['step'].item())), []).append(p)
+                by_dev.setdefault((p.device, float(st['step'])), []).append(p)
             beta1, beta2 = group['betas']
-            for (dev, step), ps in by_dev.items():
+            for (dev, step0), ps in by_dev.items():
+                step = int(step0) + 1
+                torch._foreach_add_([self.state[p]['step'] for p in ps], 1)
                 grads = [p.grad for p in ps]
                 ms = [self.state[p]['exp_avg'] for p in ps]
                 vs = [self.state[p]['exp_avg_sq'] for p in ps]
-                table, numel, chunks, n_chunks = self._table((gi, str(dev), step), ps, grads, ms, vs) if len(by_dev) > 1 else self._table((gi, str(dev)), ps, grads, ms, vs)
+                table, numel, chunks, n_chunks = self._table((gi, str(dev), len(by_dev) > 1 and step), ps, grads, ms, vs)
                 with torch.cuda.device(dev):
                     _lib.check(lib.capb200_adam_step(_lib.ptr(table), _lib.ptr(numel), _lib.ptr(chunks), n_chunks, float(group['lr']), float(beta1),
                                                      float(beta2), float(group['eps']), float(group['weight_decay']), step,

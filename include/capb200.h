@@ -426,6 +426,70 @@ int capb200_aoa_set_grad_events(capb200_aoa_engine* e, void* const* events, int 
 int capb200_dropout_mask(float* mask, long n, unsigned long long seed, int site, int step, float p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Training steps of the Transformer captioner (TransformerModel.py:262-363 under LossWrapper, loss_wrapper.py:25-73, + loss.backward()).
+ *   capb200_tfm_xe_step    the teacher-forced TransformerModel._forward (:340-348: one pass over all label_cols - 1 positions; keys that
+ *                          are pad / eos are masked, position 0 never, :323-328) + LanguageModelCriterion / LabelSmoothing + backward;
+ *                          labels / masks / logprobs / loss as capb200_updown_xe_step (logprobs [N, label_cols - 1, V+1], all positions)
+ *   capb200_tfm_scst_step  eval-mode greedy baseline (or leave-one-out), train-mode multinomial samples, CIDEr-D reward, RewardCriterion,
+ *                          backward; arguments as capb200_aoa_scst_step
+ * The gradient table has the field layout of the weight table (every pointer is written; `pe` is a buffer and is ignored).
+ * dropout = the Transformer's own rate (attention probabilities, SublayerConnections, feed-forward, positional encoding: 0.1);
+ * drop_prob_lm = att_embed's Dropout.  Replayable through capb200_dropout_mask(seed, site, step, ...) with, per site, step = the position t
+ * and the element index n * cols + c for decoder tensors [N, cols] (encoder tensors [B*R, cols]: step 0): 1 att_embed; 2 target embedding;
+ * encoder layer l: 10+l attention probabilities [B, heads, R, R], 20+l / 40+l SublayerConnections, 30+l feed-forward hidden;
+ * decoder layer l: 50+l self-attention probabilities (step 0, index ((n*heads + h)*(T+2) + t)*(T+2) + s), 60+l / 80+l / 100+l
+ * SublayerConnections, 70+l source-attention probabilities [N, heads, R] at step t, 90+l feed-forward hidden.
+ * The encoder runs once per image (the reference's _forward runs it once per caption: same values, seq_per_img x the work).
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct { float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b; } capb200_mha_grads;
+typedef struct {
+    capb200_mha_grads self_attn;
+    float *w1_w, *w1_b, *w2_w, *w2_b;
+    float *ln0_a, *ln0_b, *ln1_a, *ln1_b;
+} capb200_tfm_enc_layer_grads;
+typedef struct {
+    capb200_mha_grads self_attn, src_attn;
+    float *w1_w, *w1_b, *w2_w, *w2_b;
+    float *ln0_a, *ln0_b, *ln1_a, *ln1_b, *ln2_a, *ln2_b;
+} capb200_tfm_dec_layer_grads;
+typedef struct {
+    float *att_embed_w, *att_embed_b;
+    capb200_tfm_enc_layer_grads enc[CAPB200_TFM_MAX_LAYERS];
+    float *enc_norm_a, *enc_norm_b;
+    capb200_tfm_dec_layer_grads dec[CAPB200_TFM_MAX_LAYERS];
+    float *dec_norm_a, *dec_norm_b;
+    float *lut, *pe;
+    float *gen_w, *gen_b;
+} capb200_tfm_grads;
+typedef struct {
+    int seq_per_img;
+    unsigned long long seed;
+    float label_smoothing, upstream, drop_prob_lm, dropout;
+    const float* att_masks;        /* [B, R] or NULL */
+    int keep_rows;                 /* drop_worst: > 0 keeps the `keep_rows` rows with the smallest loss (loss_wrapper.py:47-49, 75-77) */
+    float* row_loss;               /* [N] or NULL */
+} capb200_tfm_xe_opts;
+typedef struct {
+    int sample_n;
+    float temperature;
+    unsigned long long seed;
+    float upstream;
+    int baseline;                  /* CAPB200_BASELINE_GREEDY / CAPB200_BASELINE_LEAVE_ONE_OUT */
+    float drop_prob_lm, dropout;
+    const long long* forced_tokens;   /* [N, T] or NULL: replay these samples instead of drawing (tests) */
+    const float* att_masks;
+    int keep_rows;
+    float* row_loss;
+} capb200_tfm_scst_opts;
+int capb200_tfm_xe_step(capb200_tfm_engine* e, const float* att, int B, int R, const capb200_tfm_xe_opts* opts, const long long* labels, const float* masks,
+                        int label_cols, const capb200_tfm_grads* grads, float* logprobs, float* loss, void* stream);
+int capb200_tfm_scst_step(capb200_tfm_engine* e, const float* att, int B, int R, const capb200_tfm_scst_opts* opts, const capb200_cider_table* table,
+                          const int* refs, const int* ref_offsets, int L, const capb200_tfm_grads* grads, long long* sample_seq, long long* greedy_seq,
+                          float* sample_logprobs, float* reward, float* loss, void* stream);
+/* gradient groups (see capb200_engine_set_grad_events), n <= 2: 0 generator + decoder + target embedding; 1 encoder + att_embed */
+int capb200_tfm_set_grad_events(capb200_tfm_engine* e, void* const* events, int n);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Optimizer step of the training loop: utils.clip_gradient(optimizer, grad_clip_value) (captioning/utils/misc.py:156-160, called at
  * tools/train.py:193) + torch.optim.Adam.step() (built by build_optimizer, misc.py:186-205; tools/train.py:196) in ONE launch.
  *   table  [n_tensors][4] device pointers {param, grad, exp_avg, exp_avg_sq} (fp32, contiguous), itself in device memory
@@ -435,8 +499,8 @@ int capb200_dropout_mask(float* mask, long n, unsigned long long seed, int site,
  *   write_clamped != 0 stores the clamped gradient back (clip_gradient's in-place side effect).  weight_decay is Adam's L2 term.
  * ---------------------------------------------------------------------------------------------------------------- */
 int capb200_adam_chunk_elems(void);
-int capb200_adam_step(const unsigned long long* table, const long long* numel, const int* chunks, int n_chunks, float lr, float beta1, float beta2,
-                      float eps, float weight_decay, long step, float clip_value, int write_clamped, void* stream);
+int capb200_adam_step(const unsigned long long* table, const long long* numel, const int* chunks, int n_chunks, double lr, double beta1, double beta2,
+                      double eps, double weight_decay, long step, double clip_value, int write_clamped, void* stream);
 
 #ifdef __cplusplus
 }

@@ -177,25 +177,36 @@ def _heads(x: Tensor, h: int) -> Tensor:
     return x.view(n, t, h, d // h).transpose(1, 2)
 
 
-def mha4(W: Weights, pre: str, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor], h: int) -> Tensor:
+def mha4(W: Weights, pre: str, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor], h: int, p_drop: Optional[Tensor] = None) -> Tensor:
     if mask is not None:
         mask = mask.unsqueeze(1)
     qh, kh, vh = (_heads(linear(x, W[pre + 'linears.%d.weight' % i], W[pre + 'linears.%d.bias' % i]), h) for i, x in enumerate((q, k, v)))
-    x = dot_attention(qh, kh, vh, mask).transpose(1, 2).contiguous().view(q.shape[0], -1, q.shape[2])
+    x = dot_attention(qh, kh, vh, mask, p_drop).transpose(1, 2).contiguous().view(q.shape[0], -1, q.shape[2])
     return linear(x, W[pre + 'linears.3.weight'], W[pre + 'linears.3.bias'])
 
 
-def _ffn(W: Weights, pre: str, x: Tensor) -> Tensor:
-    return linear(torch.relu(linear(x, W[pre + 'w_1.weight'], W[pre + 'w_1.bias'])), W[pre + 'w_2.weight'], W[pre + 'w_2.bias'])
+def _ffn(W: Weights, pre: str, x: Tensor, h_drop: Optional[Tensor] = None) -> Tensor:
+    """PositionwiseFeedForward (TransformerModel.py:197-206); ``h_drop`` = explicit keep/scale mask of the dropout between w_1 and w_2."""
+    hdn = torch.relu(linear(x, W[pre + 'w_1.weight'], W[pre + 'w_1.bias']))
+    if h_drop is not None:
+        hdn = hdn * h_drop
+    return linear(hdn, W[pre + 'w_2.weight'], W[pre + 'w_2.bias'])
+
+
+def _dm(drop, key, x: Tensor) -> Tensor:
+    """x * drop[key] when a train-mode replay supplies that mask (explicit keep/scale masks stand in for nn.Dropout)."""
+    return x if drop is None or key not in drop else x * drop[key]
 
 
 def _ln(W: Weights, pre: str, x: Tensor) -> Tensor:
     return layer_norm(x, W[pre + 'a_2'], W[pre + 'b_2'])
 
 
-def transformer_prepare(W: Weights, fc: Tensor, att: Tensor, masks: Optional[Tensor], n_layers: int, h: int):
+def transformer_prepare(W: Weights, fc: Tensor, att: Tensor, masks: Optional[Tensor], n_layers: int, h: int, drop=None):
+    """TransformerModel._prepare_feature (:305-338).  ``drop`` (train-mode replay): 'att_embed' [B,R,D], per encoder layer i 'enc_p%d' [B,h,R,R]
+    (attention probabilities), 'enc_sub0_%d' / 'enc_sub1_%d' [B,R,D] (SublayerConnection, :89-101), 'enc_ffn%d' [B,R,d_ff]."""
     att, masks = clip_att(att, masks)
-    x = torch.relu(linear(att, W['att_embed.0.weight'], W['att_embed.0.bias']))
+    x = _dm(drop, 'att_embed', torch.relu(linear(att, W['att_embed.0.weight'], W['att_embed.0.bias'])))
     if masks is not None:
         x = x * masks.unsqueeze(-1).to(x)
     else:
@@ -204,25 +215,28 @@ def transformer_prepare(W: Weights, fc: Tensor, att: Tensor, masks: Optional[Ten
     for i in range(n_layers):
         pre = 'model.encoder.layers.%d.' % i
         y = _ln(W, pre + 'sublayer.0.norm.', x)
-        x = x + mha4(W, pre + 'self_attn.', y, y, y, m3, h)
-        x = x + _ffn(W, pre + 'feed_forward.', _ln(W, pre + 'sublayer.1.norm.', x))
+        x = x + _dm(drop, 'enc_sub0_%d' % i, mha4(W, pre + 'self_attn.', y, y, y, m3, h, None if drop is None else drop.get('enc_p%d' % i)))
+        x = x + _dm(drop, 'enc_sub1_%d' % i, _ffn(W, pre + 'feed_forward.', _ln(W, pre + 'sublayer.1.norm.', x), None if drop is None else drop.get('enc_ffn%d' % i)))
     memory = _ln(W, 'model.encoder.norm.', x)
     return fc[..., :0], att[..., :0], memory, m3
 
 
-def transformer_decode(W: Weights, memory: Tensor, src_mask: Tensor, ys: Tensor, n_layers: int, h: int, tgt_mask: Optional[Tensor] = None) -> Tensor:
+def transformer_decode(W: Weights, memory: Tensor, src_mask: Tensor, ys: Tensor, n_layers: int, h: int, tgt_mask: Optional[Tensor] = None, drop=None) -> Tensor:
+    """EncoderDecoder.decode (:46-47) + Decoder / DecoderLayer (:113-144).  ``drop`` (train-mode replay): 'emb' [N,t,D] (PositionalEncoding's
+    dropout), per layer i 'dec_p%d' [N,h,t,t], 'dec_src%d' [N,h,t,R], 'dec_sub0_%d' / 'dec_sub1_%d' / 'dec_sub2_%d' [N,t,D], 'dec_ffn%d' [N,t,d_ff]."""
     d = memory.shape[-1]
     t = ys.shape[1]
-    x = W['model.tgt_embed.0.lut.weight'][ys] * math.sqrt(d) + W['model.tgt_embed.1.pe'][:, :t]
+    x = _dm(drop, 'emb', W['model.tgt_embed.0.lut.weight'][ys] * math.sqrt(d) + W['model.tgt_embed.1.pe'][:, :t])
     if tgt_mask is None:
         tgt_mask = torch.tril(torch.ones(1, t, t, dtype=torch.bool))
+    g = (lambda k: None) if drop is None else drop.get
     for i in range(n_layers):
         pre = 'model.decoder.layers.%d.' % i
         y = _ln(W, pre + 'sublayer.0.norm.', x)
-        x = x + mha4(W, pre + 'self_attn.', y, y, y, tgt_mask, h)
+        x = x + _dm(drop, 'dec_sub0_%d' % i, mha4(W, pre + 'self_attn.', y, y, y, tgt_mask, h, g('dec_p%d' % i)))
         y = _ln(W, pre + 'sublayer.1.norm.', x)
-        x = x + mha4(W, pre + 'src_attn.', y, memory, memory, src_mask, h)
-        x = x + _ffn(W, pre + 'feed_forward.', _ln(W, pre + 'sublayer.2.norm.', x))
+        x = x + _dm(drop, 'dec_sub1_%d' % i, mha4(W, pre + 'src_attn.', y, memory, memory, src_mask, h, g('dec_src%d' % i)))
+        x = x + _dm(drop, 'dec_sub2_%d' % i, _ffn(W, pre + 'feed_forward.', _ln(W, pre + 'sublayer.2.norm.', x), g('dec_ffn%d' % i)))
     return _ln(W, 'model.decoder.norm.', x)
 
 
@@ -332,7 +346,7 @@ class Family:
             return newfc_prepare(self.W, fc, att, masks)
         if self.name == 'aoa':
             return aoa_prepare(self.W, fc, att, masks, self.heads, self.drop)
-        return transformer_prepare(self.W, fc, att, masks, self.n_layers, self.heads)
+        return transformer_prepare(self.W, fc, att, masks, self.n_layers, self.heads, self.drop)
 
     def init_state(self, n: int):
         if self.name == 'transformer':
@@ -513,7 +527,9 @@ def sample(fam: Family, fc: Tensor, att: Tensor, masks: Optional[Tensor] = None,
 # teacher forcing and the SCST criterion
 # --------------------------------------------------------------------------------------------------
 
-def forward_teacher(fam: Family, fc: Tensor, att: Tensor, seq: Tensor, masks: Optional[Tensor] = None):
+def forward_teacher(fam: Family, fc: Tensor, att: Tensor, seq: Tensor, masks: Optional[Tensor] = None, pad_keys_masked: bool = True):
+    """``pad_keys_masked=False`` (transformer): causal mask only -- what core() applies while sampling (TransformerModel.py:351-363), so the one-pass
+    result equals the step-by-step log-probs of a sampled prefix."""
     B = fc.shape[0]
     if seq.dim() == 3:
         seq = seq.reshape(-1, seq.shape[2])
@@ -525,8 +541,10 @@ def forward_teacher(fam: Family, fc: Tensor, att: Tensor, seq: Tensor, masks: Op
         seq_mask = (seq != 0)
         seq_mask[:, 0] = True
         t = seq.shape[1]
-        tgt_mask = seq_mask.unsqueeze(-2) & torch.tril(torch.ones(1, t, t, dtype=torch.bool))
-        out = transformer_decode(fam.W, memory, m3, seq, fam.n_layers, fam.heads, tgt_mask)
+        tgt_mask = torch.tril(torch.ones(1, t, t, dtype=torch.bool))
+        if pad_keys_masked:
+            tgt_mask = seq_mask.unsqueeze(-2) & tgt_mask
+        out = transformer_decode(fam.W, memory, m3, seq, fam.n_layers, fam.heads, tgt_mask, fam.drop)
         return F.log_softmax(linear(out, fam.W['model.generator.proj.weight'], fam.W['model.generator.proj.bias']), dim=-1)
     fc_e, att_e, p_att, masks = fam.prepare(fc, att, masks)
     fc_e, att_e, p_att, masks = (repeat_rows(x, spi) for x in (fc_e, att_e, p_att, masks))

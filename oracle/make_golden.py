@@ -484,15 +484,15 @@ def gen_transformer_b64(out_dir):
           (int((oseq == seqb).all(1).sum()), B, float(margin.min()), float(gmargin.min())))
 
 
-def _subsample(t):
+def _subsample(t, grid=(96, 80), whole=8192):
     """Compact fingerprint of a gradient tensor: every entry when small, else a strided sub-grid; plus sum / abs-sum / Frobenius norm."""
     a = t.detach().numpy()
-    if a.size <= 8192:
+    if a.size <= whole:
         sub, step = a.copy(), (1, 1)
     elif a.ndim == 1:
         sub, step = a[::7].copy(), (7, 1)
     else:
-        sr, sc = max(1, a.shape[0] // 96), max(1, a.shape[1] // 80)
+        sr, sc = max(1, a.shape[0] // grid[0]), max(1, a.shape[1] // grid[1])
         sub, step = a[::sr, ::sc].copy(), (sr, sc)
     stats = np.array([a.sum(dtype=np.float64), np.abs(a).sum(dtype=np.float64), np.sqrt((a.astype(np.float64) ** 2).sum()), np.abs(a).max()])
     return sub, np.array(step), stats
@@ -576,6 +576,124 @@ def gen_aoa_scst_full(out_dir, scratch):
           (float(out['loss']), float(out['reward']), float(np.abs(reward).max()), len(names), (sample_seq > 0).sum(1)[:8].tolist()))
 
 
+def _gen_transformer_train(out_dir, scratch, name, cfg, layers, heads, B, Rr, n, spi, logit_scale, seed, full_grads):
+    """Transformer under the LIVE reference's LossWrapper: (a) the XE branch (teacher-forced _forward + LanguageModelCriterion / LabelSmoothing) and
+    (b) the sc branch (greedy baseline, train-mode multinomial samples, CIDEr-D reward, RewardCriterion), each followed by loss.backward().
+    Every dropout probability is 0 (no RNG stream to share); the reference's own samples are stored and the engine replays them as forced
+    tokens.  Gradients: every tensor in full for the small model, a fingerprint (sub-grid + sums + norm) at BASELINE size."""
+    from captioning.modules.loss_wrapper import LossWrapper
+    from captioning.modules import losses as RL
+    from captioning.utils import rewards as R
+    T, V = cfg['T'], cfg['V']
+    W = co.make_weights('transformer', V, cfg['E'], cfg['H'], cfg['A'], cfg['F_fc'], cfg['F_att'], seed=seed, logit_scale=logit_scale)
+    fc, att = co.make_inputs(B, Rr, cfg['F_fc'], cfg['F_att'], seed=seed)
+    m = ref_model('transformer', W=W, **cfg, num_layers=layers, N_enc=layers, N_dec=layers, d_model=cfg['E'], d_ff=cfg['H'], num_att_heads=heads, dropout=0.0)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    res = {}
+
+    def store(prefix):
+        for k, prm in m.named_parameters():
+            if full_grads:
+                res[prefix + 'g_' + k] = prm.grad.numpy().copy()
+            else:
+                res[prefix + 'g_' + k], res[prefix + 's_' + k], res[prefix + 't_' + k] = _subsample(prm.grad, grid=(40, 32), whole=2048)
+
+    # ---- (a) XE: labels [B, spi, T + 2]: BOS, words, EOS / padding; captions of different lengths, some ending early
+    g = torch.Generator().manual_seed(seed + 1)
+    xl = torch.zeros(B, spi, T + 2, dtype=torch.long)
+    xm = torch.zeros(B, spi, T + 2)
+    for i in range(B):
+        for j in range(spi):
+            ln = int(torch.randint(2, T + 1, (1,), generator=g))
+            xl[i, j, 1:1 + ln] = torch.randint(1, V + 1, (ln,), generator=g)
+            xm[i, j, :ln + 2] = 1
+    m.train()
+    for tag, crit in (('xe_', RL.LanguageModelCriterion()), ('xels_', RL.LabelSmoothing(smoothing=0.1))):
+        if tag == 'xels_' and not full_grads:
+            res['xels_loss'] = np.array(0.0)
+            continue                                # the BASELINE-size fixture stays small: one XE criterion
+        m.zero_grad()
+        lpm = m(fc, att, xl[..., :-1], None)
+        loss = crit(lpm, xl[..., 1:].reshape(B * spi, -1), xm[..., 1:].reshape(B * spi, -1))
+        loss.backward()
+        res[tag + 'loss'] = loss.detach().numpy()
+        store(tag)
+        if tag == 'xe_' and full_grads:
+            res['xe_logprobs'] = lpm.detach().numpy()
+    res['xe_labels'], res['xe_masks'] = xl.numpy().astype(np.int16), xm.numpy()
+    # ---- (b) SCST; references = corrupted copies of the greedy captions (see gen_aoa_scst_full)
+    m.eval()
+    with torch.no_grad():
+        g0, _ = m(fc, att, None, opt={'sample_method': 'greedy', 'beam_size': 1}, mode='sample')
+    rng = np.random.RandomState(seed + 2)
+    gts = []
+    Lr = min(16, T)
+    for i in range(B):
+        rows = np.zeros((5, Lr), np.int64)
+        for j in range(5):
+            ln = Lr if j < 2 else int(rng.randint(max(2, Lr // 3), Lr))
+            row = g0[i, :ln].numpy().copy()
+            flip = rng.rand(ln) < 0.3
+            row[flip] = rng.randint(1, V + 1, size=int(flip.sum()))
+            rows[j, :ln] = row
+        gts.append(rows)
+    df, ref_len = cdo.build_document_frequency(cdo.make_refs(300 if full_grads else 1000, V, seed=4) + gts)
+    from collections import defaultdict
+    dd = defaultdict(float)
+    dd.update({tuple(str(t) for t in k): v for k, v in df.items()})
+    dfname = 'tfm-train-df-%s' % name.replace('.npz', '')
+    with open(os.path.join(scratch, 'data', dfname + '.p'), 'wb') as f:
+        pickle.dump({'document_frequency': dd, 'ref_len': ref_len}, f, protocol=2)
+    R.CiderD_scorer = None
+    R.Cider_scorer = None
+    R.init_scorer(dfname)
+    opt = argparse.Namespace(label_smoothing=0, structure_loss_type='seqnll', structure_loss_weight=1, train_sample_method='sample', train_beam_size=1,
+                             train_sample_n=n, sc_sample_method='greedy', sc_beam_size=1, cider_reward_weight=1.0, bleu_reward_weight=0.0, use_ppo=0,
+                             struc_use_logsoftmax=1)
+    lw = LossWrapper(m, opt)
+    captured = {}
+    orig = m._sample
+
+    def spy(*a, **k):
+        out = orig(*a, **k)
+        captured.setdefault('calls', []).append(out[0].detach().clone())
+        return out
+    m._sample = spy
+    m.train()
+    torch.manual_seed(77)
+    m.zero_grad()
+    out = lw(fc, att, None, None, None, gts, torch.arange(B), True, False, False)
+    out['loss'].backward()
+    greedy_seq, sample_seq = captured['calls'][0], captured['calls'][1]
+    assert greedy_seq.shape == (B, T) and sample_seq.shape == (B * n, T)
+    reward = R.get_self_critical_reward(greedy_seq, gts, sample_seq, opt)
+    res.update({'greedy_seq': greedy_seq.numpy().astype(np.int16), 'sample_seq': sample_seq.numpy().astype(np.int16), 'sc_loss': out['loss'].detach().numpy(),
+                'reward_mean': out['reward'].numpy(), 'reward': reward[:, 0].astype(np.float64), 'gts': np.stack(gts).astype(np.int16)})
+    store('sc_')
+    names = [k for k, _ in m.named_parameters()]
+    keys = np.array([list(k) + [-1] * (4 - len(k)) for k in df.keys()], np.int32)
+    vals = np.array(list(df.values()), np.float64)
+    np.savez_compressed(os.path.join(out_dir, name), cfg=np.array([cfg[k] for k in ('V', 'E', 'H', 'A', 'F_fc', 'F_att', 'T')]),
+                        meta=np.array([B, Rr, n, seed, heads, spi, int(full_grads)]), logit_scale=np.array(logit_scale), df_keys=keys, df_vals=vals,
+                        ref_len=np.array(ref_len), names=np.array(names), **res)
+    print('%s: xe %.6g, xels %.6g, sc loss %.6g, mean reward %.4g, max |reward| %.4g, %d gradient tensors, sample lengths %s' %
+          (name, float(res['xe_loss']), float(res['xels_loss']), float(out['loss']), float(out['reward']), float(np.abs(reward).max()), len(names),
+           (sample_seq > 0).sum(1)[:8].tolist()))
+
+
+def gen_transformer_train(out_dir, scratch):
+    _gen_transformer_train(out_dir, scratch, 'transformer_train_small.npz', dict(V=60, E=32, H=64, A=2, F_fc=48, F_att=48, T=8), 2, 4, B=3, Rr=7, n=3, spi=2,
+                           logit_scale=10.0, seed=23, full_grads=True)
+
+
+def gen_transformer_train_full(out_dir, scratch):
+    """BASELINE.json configs[2]'s architecture (6+6 layers, d_model 512, d_ff 2048, 8 heads, V = 9487) at configs[3]'s training shape (10 images x 5)."""
+    _gen_transformer_train(out_dir, scratch, 'transformer_train_full.npz', dict(V=9487, E=512, H=2048, A=6, F_fc=2048, F_att=2048, T=20), 6, 8, B=10, Rr=36, n=5,
+                           spi=5, logit_scale=3.0, seed=1234, full_grads=False)
+
+
 def gen_updown_options(out_dir):
     """Decode options of the reference on the small UpDown configuration: decoding_constraint, remove_bad_endings, block_trigrams (greedy
     _sample, AttModel.py:294-332) and suppress_UNK / decoding_constraint / remove_bad_endings / temperature in beam search
@@ -645,7 +763,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     scratch = _enter_scratch()
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys', 'tfm', 'aoa', 'xe', 'dseq', 'pascal', 'penalty', 'b256', 'tfm64', 'aoafull', 'options']
+    which = sys.argv[1:] or ['small', 'newfc', 'full', 'ciderd', 'rc', 'keys', 'tfm', 'aoa', 'xe', 'dseq', 'pascal', 'penalty', 'b256', 'tfm64', 'aoafull', 'options', 'tfmtrain', 'tfmtrainfull']
     if 'small' in which:
         gen_updown_small(out_dir)
     if 'newfc' in which:
@@ -678,6 +796,10 @@ def main():
         gen_transformer_b64(out_dir)
     if 'aoafull' in which:
         gen_aoa_scst_full(out_dir, scratch)
+    if 'tfmtrain' in which:
+        gen_transformer_train(out_dir, scratch)
+    if 'tfmtrainfull' in which:
+        gen_transformer_train_full(out_dir, scratch)
 
 
 if __name__ == '__main__':

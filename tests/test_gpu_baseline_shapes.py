@@ -131,3 +131,59 @@ def test_aoa_scst_step_at_config_dims_matches_reference(golden_dir):
     assert checked == len(g['names']) == 79
     print('AoA H=1024 SCST step: loss %.6f (reference %.6f), worst relative gradient error %.2e over %d tensors' %
           (float(res['loss']), float(g['loss']), worst, checked))
+
+
+def test_transformer_training_at_config_dims_matches_reference(golden_dir):
+    """BASELINE configs[2]'s architecture (6 + 6 layers, d_model 512, d_ff 2048, 8 heads, V = 9487) at configs[3]'s training shape (10 images x 5):
+    the golden holds what the reference's LossWrapper + loss.backward() produced for the XE branch and for the sc branch (dropout 0, its own
+    multinomial draw); the engine replays the draw, so losses, rewards and the fingerprints of all 261 gradient tensors compare one to one."""
+    import imagecaptioning.pytorch_b200 as b200
+    g, cfg = _load(golden_dir, 'transformer_train_full.npz')
+    B, R, n, seed, heads, spi, _ = (int(x) for x in g['meta'])
+    model, _ = build_pair('transformer', seed=seed, logit_scale=float(g['logit_scale']), mode='tc_f16x3', heads=heads, **cfg)
+    fc, att = co.make_inputs(B, R, cfg['F_fc'], cfg['F_att'], seed=seed)
+    name_of = {id(p): k for k, p in model.state_dict(keep_vars=True).items()}
+    model.train()
+
+    def check(res, prefix):
+        largest = max(float(g[prefix + 't_' + k][3]) for k in g['names'])
+        worst = 0.0
+        for p, grad in res['grads'].items():
+            key = name_of[id(p)]
+            ref, step, stats = g[prefix + 'g_' + key], g[prefix + 's_' + key], g[prefix + 't_' + key]
+            a = grad.detach().cpu().numpy()
+            if tuple(step) == (1, 1):
+                sub = a
+            elif a.ndim == 1:
+                sub = a[::int(step[0])]
+            else:
+                sub = a[::int(step[0]), ::int(step[1])]
+            assert sub.shape == ref.shape, (key, sub.shape, ref.shape)
+            scale = float(stats[3])
+            err = float(np.abs(sub - ref).max())
+            assert err <= 5e-4 * scale + 2e-7 * largest, (prefix, key, err, scale)
+            fro = float(np.sqrt((a.astype(np.float64) ** 2).sum()))
+            assert abs(fro - float(stats[2])) <= 1e-3 * float(stats[2]) + 1e-6 * largest, (prefix, key, fro, float(stats[2]))
+            if scale > 1e-3 * largest:
+                worst = max(worst, err / scale)
+        assert len(res['grads']) == len(g['names']) == 261
+        return worst
+
+    labels, masks = torch.from_numpy(g['xe_labels'].astype(np.int64)), torch.from_numpy(g['xe_masks'])
+    res = model.xe_step(fc.cuda(), att.cuda(), labels.cuda(), masks.cuda(), label_smoothing=0.0, drop_prob=0.0, dropout=0.0, seed=1)
+    torch.cuda.synchronize()
+    assert abs(float(res['loss']) - float(g['xe_loss'])) < LOGP_TOL * max(1.0, abs(float(g['xe_loss'])))
+    w_xe = check(res, 'xe_')
+    df = {tuple(int(t) for t in k if t >= 0): float(v) for k, v in zip(g['df_keys'], g['df_vals'])}
+    table = b200.rewards.CiderDTable(df, float(g['ref_len']))
+    gts = [g['gts'][i].astype(np.int64) for i in range(B)]
+    forced = torch.from_numpy(g['sample_seq'].astype(np.int64))
+    res = model.scst_step(fc.cuda(), att.cuda(), gts, table, n, drop_prob=0.0, dropout=0.0, seed=1, forced_tokens=forced.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(res['sample_seq'].cpu(), forced)
+    assert np.array_equal(res['greedy_seq'].cpu().numpy(), g['greedy_seq'].astype(np.int64))
+    assert np.abs(res['reward'][:, 0].double().cpu().numpy() - g['reward']).max() < LOGP_TOL
+    assert abs(float(res['loss']) - float(g['sc_loss'])) < LOGP_TOL * max(1.0, abs(float(g['sc_loss'])))
+    w_sc = check(res, 'sc_')
+    print('Transformer 6+6/512 training steps: XE loss %.5f, sc loss %.5f; worst relative gradient error XE %.2e, sc %.2e over 261 tensors' %
+          (float(g['xe_loss']), float(res['loss']), w_xe, w_sc))

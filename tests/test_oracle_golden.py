@@ -249,3 +249,51 @@ def test_aoa_scst_step_at_config_dims(golden_dir):
         step, stats = g['s_' + k], g['t_' + k]
         sub = a if a.size <= 8192 else (a[::int(step[0])] if a.ndim == 1 else a[::int(step[0]), ::int(step[1])])
         assert np.abs(sub - g['g_' + k]).max() <= 2e-4 * float(stats[3]) + 1e-7 * largest, k
+
+
+def test_transformer_training_steps_of_the_reference(golden_dir):
+    """The oracle's Transformer training path (teacher-forced pass with the pad/eos + causal mask; sampled prefixes with the causal mask only)
+    against the LIVE reference's LossWrapper + backward() (transformer_train_small.npz: XE with both criteria, the sc branch with the
+    reference's own draw): losses, log-probs, rewards and all 93 gradients."""
+    g = np.load(os.path.join(golden_dir, 'transformer_train_small.npz'))
+    cfg = dict(zip(('V', 'E', 'H', 'A', 'F_fc', 'F_att', 'T'), (int(v) for v in g['cfg'])))
+    B, R, n, seed, heads, spi, _ = (int(x) for x in g['meta'])
+    W = co.make_weights('transformer', cfg['V'], cfg['E'], cfg['H'], cfg['A'], cfg['F_fc'], cfg['F_att'], seed=seed, logit_scale=float(g['logit_scale']))
+    fc, att = co.make_inputs(B, R, cfg['F_fc'], cfg['F_att'], seed=seed)
+    labels, masks = torch.from_numpy(g['xe_labels'].astype(np.int64)), torch.from_numpy(g['xe_masks'])
+    N = B * spi
+
+    def grads_of(loss, Wg, prefix):
+        loss.backward()
+        largest = max(float(np.abs(g[prefix + 'g_' + k]).max()) for k in g['names'])
+        for k in g['names']:
+            ref = g[prefix + 'g_' + k]
+            # key biases have a true gradient of zero (softmax is shift invariant): held to 1e-6 of the step's largest gradient
+            assert np.abs(Wg[k].grad.numpy() - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-6 * largest, (prefix, k)
+
+    for prefix, smoothing in (('xe_', 0.0), ('xels_', 0.1)):
+        Wg = {k: (v.clone().requires_grad_(True) if k in set(g['names']) else v) for k, v in W.items()}
+        fam = co.Family('transformer', Wg, cfg['T'], heads=heads)
+        lp = co.forward_teacher(fam, fc, att, labels[..., :-1])
+        fl, fm = labels.reshape(N, -1), masks.reshape(N, -1)
+        loss = co.label_smoothing_loss(lp, fl[:, 1:], fm[:, 1:], smoothing) if smoothing > 0 else co.language_model_criterion(lp, fl[:, 1:], fm[:, 1:])
+        assert abs(float(loss) - float(g[prefix + 'loss'])) < 1e-5 * max(1.0, abs(float(loss)))
+        if prefix == 'xe_':
+            assert np.abs(lp.detach().numpy() - g['xe_logprobs']).max() < 1e-5
+        grads_of(loss, Wg, prefix)
+    Wg = {k: (v.clone().requires_grad_(True) if k in set(g['names']) else v) for k, v in W.items()}
+    fam = co.Family('transformer', Wg, cfg['T'], heads=heads)
+    seq = torch.from_numpy(g['sample_seq'].astype(np.int64))
+    seq_in = torch.cat([torch.zeros(seq.shape[0], 1, dtype=torch.long), seq[:, :-1]], 1)
+    lp = co.forward_teacher(fam, fc, att, seq_in, None, pad_keys_masked=False)          # one causal pass == the reference's step-by-step prefixes
+    lp = lp * torch.cat([torch.ones(seq.shape[0], 1, dtype=torch.bool), seq[:, :-1] > 0], 1).unsqueeze(2)
+    df = _df_from_golden(g)
+    gts = [g['gts'][i].astype(np.int64) for i in range(B)]
+    with torch.no_grad():
+        og, _ = co.sample(co.Family('transformer', W, cfg['T'], heads=heads), fc, att)
+    assert np.array_equal(og.numpy(), g['greedy_seq'].astype(np.int64))
+    reward, _ = cdo.self_critical_reward(og.numpy(), gts, seq.numpy(), df, float(g['ref_len']))
+    assert np.abs(reward[:, 0] - g['reward']).max() < 1e-9
+    loss = co.reward_criterion(lp, seq, torch.from_numpy(reward).float())
+    assert abs(float(loss) - float(g['sc_loss'])) < 1e-5
+    grads_of(loss, Wg, 'sc_')
