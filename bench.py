@@ -49,11 +49,11 @@ def parse():
     p.add_argument('--mode', default='tc_f16x3', choices=['tc_f16x3', 'tc_f16x1', 'simt_fp32'])
     p.add_argument('--cpu-batch', type=int, default=32, help='images per CPU-baseline step (bounded sample)')
     p.add_argument('--no-cpu-baseline', action='store_true')
-    p.add_argument('--workload', default='updown_beam', choices=['updown_beam', 'transformer_beam', 'aoa_beam', 'updown_scst', 'aoa_scst'],
+    p.add_argument('--workload', default='updown_beam', choices=['updown_beam', 'transformer_beam', 'aoa_beam', 'updown_scst', 'aoa_scst', 'transformer_scst'],
                    help='updown_beam = BASELINE.json configs[1] (the headline); transformer_beam = configs[2] (use --batch 64); aoa_beam = AoANet decode')
     args = p.parse_args()
     if args.batch is None:
-        args.batch = 10 if args.workload in ('updown_scst', 'aoa_scst') else 256
+        args.batch = 10 if args.workload in ('updown_scst', 'aoa_scst', 'transformer_scst') else 256
     return args
 
 
@@ -218,9 +218,11 @@ def bench_scst(args, rank, world, local_rank, dev, workload, batch):
     aoa = workload == 'aoa_scst'
     if aoa:       # configs/aoa.yml: E = H = 1024, 8 heads, 6 refiner layers, ctx_drop, dropout_aoa 0.3 (BASELINE configs[3])
         model = syn.build_model('aoa', seed=1234, logit_scale=6.0, mode=args.mode, device=dev, heads=8, **dict(CFG, E=1024, H=1024, A=0))
+    elif workload == 'transformer_scst':    # configs/transformer/transformer.yml: 6 + 6 layers, d_model 512, d_ff 2048, 8 heads
+        model = syn.build_model('transformer', seed=1234, logit_scale=3.0, mode=args.mode, device=dev, heads=8, **dict(CFG, E=512, H=2048, A=6))
     else:
         model = syn.build_model('updown', seed=1234, logit_scale=12.0, mode=args.mode, device=dev, **CFG)
-    fam_name = 'AoANet' if aoa else 'UpDown'
+    fam_name = 'AoANet' if aoa else ('Transformer' if workload == 'transformer_scst' else 'UpDown')
     model.train()
     df, ref_len = syn.document_frequency(syn.make_refs(1000, CFG['V'], seed=4))              # synthetic DF table (format of prepro_ngrams.py)
     b200.rewards.reset_scorer()
@@ -319,7 +321,7 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     names = {'updown_beam': 'UpDown', 'transformer_beam': 'Transformer 6+6/512/2048/8', 'aoa_beam': 'AoANet 1024', 'updown_scst': 'UpDown SCST',
-             'aoa_scst': 'AoANet SCST'}
+             'aoa_scst': 'AoANet SCST', 'transformer_scst': 'Transformer 6+6/512/2048/8 SCST'}
     workload = '%s beam=%d, %dx2048 bottom-up feats, batch=%d per GPU, seq_len=20, V=9487' % (names[args.workload], args.beam, R, args.batch)
 
     if args.impl == 'reference':
@@ -363,7 +365,7 @@ def main():
         dist.barrier()
     from imagecaptioning.pytorch_b200 import synthetic as syn      # seeded random-init weights / features: the GPU arm never touches oracle/
     dev = torch.device('cuda', local_rank)
-    if args.workload in ('updown_scst', 'aoa_scst'):
+    if args.workload in ('updown_scst', 'aoa_scst', 'transformer_scst'):
         res = bench_scst(args, rank, world, local_rank, dev, args.workload, args.batch)
         if rank == 0:
             line = dict(res, warmup=args.warmup, higher_is_better=True, vs_baseline=None, dtype='f32', data='synthetic', gpu_launches=res['launches'] * args.steps)

@@ -593,7 +593,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
         static const bool serial = getenv("CAPB200_SCST_SERIAL_GREEDY") != nullptr;
         if (!serial) {
             bool ok = true;
-            if (e->side == nullptr) ok = cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) == cudaSuccess;
+            if (e->side == nullptr) ok = create_side_stream(&e->side) == cudaSuccess;
             if (ok && e->ev_fork == nullptr) ok = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
             if (ok && e->ev_join == nullptr) ok = cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) == cudaSuccess;
             if (ok) {
@@ -810,12 +810,22 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
         CAPB_CHECK_CUDA(cudaMemcpy2DAsync(tp.d_g, sizeof(float) * H, tp.d_catd, sizeof(float) * 2 * H, sizeof(float) * H, BR, cudaMemcpyDeviceToDevice, st));
         rc |= enc_attn_backward_launch(B, R, heads, dk, tp.qkv[l], tp.qkv[l] + H, tp.qkv[l] + 2 * H, 3 * H, seed, 10 + l, p_at, tp.d_g, H, tp.d_qkv, tp.d_qkv + H,
                                        tp.d_qkv + 2 * H, 3 * H, st, ta.mask, R);
-        rc |= wgrad(H, H, (int)BR, tp.d_qkv, 3 * H, tp.ln[l], H, Lg.q_w, H, 0, st);
-        rc |= wgrad(H, H, (int)BR, tp.d_qkv + H, 3 * H, tp.ln[l], H, Lg.k_w, H, 0, st);
-        rc |= wgrad(H, H, (int)BR, tp.d_qkv + 2 * H, 3 * H, tp.ln[l], H, Lg.v_w, H, 0, st);
-        rc |= colsum_launch((int)BR, H, tp.d_qkv, 3 * H, Lg.q_b, 0, st);
-        rc |= colsum_launch((int)BR, H, tp.d_qkv + H, 3 * H, Lg.k_b, 0, st);
-        rc |= colsum_launch((int)BR, H, tp.d_qkv + 2 * H, 3 * H, Lg.v_b, 0, st);
+        // q | k | v gradients: one GEMM / one column reduction when the caller laid the three tensors out back to back (the Python
+        // mirror's flat gradient buffer does), else three
+        if (Lg.k_w == Lg.q_w + (long)H * H && Lg.v_w == Lg.k_w + (long)H * H) {
+            rc |= wgrad(3 * H, H, (int)BR, tp.d_qkv, 3 * H, tp.ln[l], H, Lg.q_w, H, 0, st);
+        } else {
+            rc |= wgrad(H, H, (int)BR, tp.d_qkv, 3 * H, tp.ln[l], H, Lg.q_w, H, 0, st);
+            rc |= wgrad(H, H, (int)BR, tp.d_qkv + H, 3 * H, tp.ln[l], H, Lg.k_w, H, 0, st);
+            rc |= wgrad(H, H, (int)BR, tp.d_qkv + 2 * H, 3 * H, tp.ln[l], H, Lg.v_w, H, 0, st);
+        }
+        if (Lg.k_b == Lg.q_b + H && Lg.v_b == Lg.k_b + H) {
+            rc |= colsum_launch((int)BR, 3 * H, tp.d_qkv, 3 * H, Lg.q_b, 0, st);
+        } else {
+            rc |= colsum_launch((int)BR, H, tp.d_qkv, 3 * H, Lg.q_b, 0, st);
+            rc |= colsum_launch((int)BR, H, tp.d_qkv + H, 3 * H, Lg.k_b, 0, st);
+            rc |= colsum_launch((int)BR, H, tp.d_qkv + 2 * H, 3 * H, Lg.v_b, 0, st);
+        }
         // d ln = query half of the AoA input + through the packed q|k|v projection
         CAPB_CHECK_CUDA(cudaMemcpy2DAsync(tp.d_ln, sizeof(float) * H, tp.d_catd + H, sizeof(float) * 2 * H, sizeof(float) * H, BR, cudaMemcpyDeviceToDevice, st));
         rc |= sk.dgrad((int)BR, H, 3 * H, tp.d_qkv, 3 * H, e->r_qkv_w[l], H, tp.d_ln, H, 1);

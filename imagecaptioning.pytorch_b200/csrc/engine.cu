@@ -474,7 +474,7 @@ int core_step(capb200_engine* e, int rows, int rpi, const int* tokens, const int
 
 bool ensure_side(capb200_engine* e) {
     if (e->side != nullptr && e->ev_fork != nullptr && e->ev_join != nullptr && e->ev_gfork != nullptr && e->ev_gjoin != nullptr) return true;
-    if (e->side == nullptr && cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); e->side = nullptr; return false; }
+    if (e->side == nullptr && create_side_stream(&e->side) != cudaSuccess) { (void)cudaGetLastError(); e->side = nullptr; return false; }
     if (e->ev_fork == nullptr && cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); e->ev_fork = nullptr; return false; }
     if (e->ev_join == nullptr && cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); e->ev_join = nullptr; return false; }
     if (e->ev_gfork == nullptr && cudaEventCreateWithFlags(&e->ev_gfork, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); e->ev_gfork = nullptr; return false; }
@@ -520,7 +520,7 @@ capb200_engine* capb200_engine_create(const capb200_model_cfg* cfg) {
     e->mode = cfg->numeric_mode;
     e->tc = cfg->numeric_mode != CAPB200_MODE_SIMT_FP32;
     if (e->tc && getenv("CAPB200_SPLIT_LANG") != nullptr && atoi(getenv("CAPB200_SPLIT_LANG")) != 0) {
-        if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) == cudaSuccess &&
+        if (create_side_stream(&e->side) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) == cudaSuccess) e->split_lang = true;
         else (void)cudaGetLastError();

@@ -348,6 +348,16 @@ int sample_decode_driver(DecodeBuffers& d, int V1, int T, int rows, int method, 
 // engines) every call runs on the tcgen05 kind::tf32 3-pass kernel of gemm_tf32.cu; operands that are not K-major in HBM (W for the input
 // gradients, dY / X for the weight gradients) go through cached transposes.  Without a context (simt_fp32 engines), when an operand is not
 // TMA-compatible (rows not 16-byte aligned: tiny test shapes), or with CAPB200_SKINNY_LEGACY set, the split-K kernels of gemm_generic.cu run.
+// Side stream of the SCST steps (the eval-mode greedy baseline runs on it while the train-mode sampling pass runs on the caller's stream).
+// Lowest priority by default: both chains are latency-bound and compete for SMs (a persistent GEMM CTA owns its SM's shared memory), and
+// the sampling pass is the critical path -- its pending CTAs should be placed first.  CAPB200_SIDE_PRIORITY=0 gives both equal priority.
+inline cudaError_t create_side_stream(cudaStream_t* s) {
+    static const bool equal = getenv("CAPB200_SIDE_PRIORITY") != nullptr && atoi(getenv("CAPB200_SIDE_PRIORITY")) == 0;
+    int least = 0, greatest = 0;
+    if (!equal && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, least);
+    return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+}
+
 struct Skinny {
     float* scratch; size_t cap; int mode; cudaStream_t st;
     Tf32Context* ctx = nullptr;

@@ -504,7 +504,7 @@ int tfm_train_step(capb200_tfm_engine* e, const float* att, int B, int R, const 
         static const bool serial = getenv("CAPB200_SCST_SERIAL_GREEDY") != nullptr;
         if (!serial) {
             bool ok = true;
-            if (e->side == nullptr) ok = cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) == cudaSuccess;
+            if (e->side == nullptr) ok = create_side_stream(&e->side) == cudaSuccess;
             if (ok && e->ev_fork == nullptr) ok = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
             if (ok && e->ev_join == nullptr) ok = cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) == cudaSuccess;
             if (ok) {
@@ -629,6 +629,24 @@ int tfm_train_step(capb200_tfm_engine* e, const float* att, int B, int R, const 
 
     // ---- backward: generator and the final LayerNorm
     auto colsum = [&](int rows, int cols, const float* x, long ld, float* out) { nl++; return colsum_launch(rows, cols, x, ld, out, 0, st); };
+    // q | k | v gradients of a self-attention block: one GEMM / one column reduction when the caller laid the three tensors out back to back
+    // (the Python mirror's flat gradient buffer does), else three
+    auto qkv_grads = [&](int rows, const float* x, const capb200_mha_grads& ag) -> int {
+        int r = 0;
+        if (ag.k_w == ag.q_w + (long)D * D && ag.v_w == ag.k_w + (long)D * D) r |= sk.wgrad(3 * D, D, rows, tp.d_qkv, 3 * D, x, D, ag.q_w, D, 0);
+        else {
+            r |= sk.wgrad(D, D, rows, tp.d_qkv, 3 * D, x, D, ag.q_w, D, 0);
+            r |= sk.wgrad(D, D, rows, tp.d_qkv + D, 3 * D, x, D, ag.k_w, D, 0);
+            r |= sk.wgrad(D, D, rows, tp.d_qkv + 2 * D, 3 * D, x, D, ag.v_w, D, 0);
+        }
+        if (ag.k_b == ag.q_b + D && ag.v_b == ag.k_b + D) r |= colsum(rows, 3 * D, tp.d_qkv, 3 * D, ag.q_b);
+        else {
+            r |= colsum(rows, D, tp.d_qkv, 3 * D, ag.q_b);
+            r |= colsum(rows, D, tp.d_qkv + D, 3 * D, ag.k_b);
+            r |= colsum(rows, D, tp.d_qkv + 2 * D, 3 * D, ag.v_b);
+        }
+        return r;
+    };
     rc |= sk.dgrad(LNr, D, V1, tp.DL, V1, w.gen_w, D, tp.d_yln_nm, D, 0);
     rc |= sk.wgrad(V1, D, LNr, tp.DL, V1, tp.yln_nm, D, G.gen_w, D, 0);
     rc |= colsum(LNr, V1, tp.DL, V1, G.gen_b);
@@ -668,12 +686,7 @@ int tfm_train_step(capb200_tfm_engine* e, const float* att, int B, int R, const 
         rc |= sk.dgrad(LNr, D, D, tp.d_tmp, D, Lw.self_attn.o_w, D, tp.d_att, D, 0);
         rc |= seq_attn_backward_launch(N, L, heads, dk, 1, idxL, 1, N, tp.dqkv[l], tp.dqkv[l] + D, tp.dqkv[l] + 2 * D, 3 * D, seed, 50 + l, p, tp.d_att, D, tp.d_qkv,
                                        tp.d_qkv + D, tp.d_qkv + 2 * D, 3 * D, key_mask, L, st);
-        rc |= sk.wgrad(D, D, LNr, tp.d_qkv, 3 * D, tp.dln0[l], D, Lg.self_attn.q_w, D, 0);
-        rc |= sk.wgrad(D, D, LNr, tp.d_qkv + D, 3 * D, tp.dln0[l], D, Lg.self_attn.k_w, D, 0);
-        rc |= sk.wgrad(D, D, LNr, tp.d_qkv + 2 * D, 3 * D, tp.dln0[l], D, Lg.self_attn.v_w, D, 0);
-        rc |= colsum(LNr, D, tp.d_qkv, 3 * D, Lg.self_attn.q_b);
-        rc |= colsum(LNr, D, tp.d_qkv + D, 3 * D, Lg.self_attn.k_b);
-        rc |= colsum(LNr, D, tp.d_qkv + 2 * D, 3 * D, Lg.self_attn.v_b);
+        rc |= qkv_grads(LNr, tp.dln0[l], Lg.self_attn);
         rc |= sk.dgrad(LNr, D, 3 * D, tp.d_qkv, 3 * D, e->dec_qkv_w[l], D, tp.d_ln, D, 0);
         rc |= ln_backward_launch(LNr, D, tp.Y[l], D, Lw.ln0_a, tp.d_ln, D, 1e-6f, tp.dY, D, 1, tp.stats, Lg.ln0_a, Lg.ln0_b, 0, st);
         nl += 14;
@@ -685,10 +698,16 @@ int tfm_train_step(capb200_tfm_engine* e, const float* att, int B, int R, const 
     for (int l = 0; l < ND; ++l) {
         const capb200_tfm_dec_layer_grads& Lg = G.dec[l];
         rc |= sk.dgrad(BR, D, 2 * D, tp.d_skv[l], 2 * D, e->dec_skv_w[l], D, tp.d_mem, D, l > 0 ? 1 : 0);
-        rc |= sk.wgrad(D, D, BR, tp.d_skv[l], 2 * D, tp.mem, D, Lg.src_attn.k_w, D, 0);
-        rc |= sk.wgrad(D, D, BR, tp.d_skv[l] + D, 2 * D, tp.mem, D, Lg.src_attn.v_w, D, 0);
-        rc |= colsum(BR, D, tp.d_skv[l], 2 * D, Lg.src_attn.k_b);
-        rc |= colsum(BR, D, tp.d_skv[l] + D, 2 * D, Lg.src_attn.v_b);
+        if (Lg.src_attn.v_w == Lg.src_attn.k_w + (long)D * D) rc |= sk.wgrad(2 * D, D, BR, tp.d_skv[l], 2 * D, tp.mem, D, Lg.src_attn.k_w, D, 0);
+        else {
+            rc |= sk.wgrad(D, D, BR, tp.d_skv[l], 2 * D, tp.mem, D, Lg.src_attn.k_w, D, 0);
+            rc |= sk.wgrad(D, D, BR, tp.d_skv[l] + D, 2 * D, tp.mem, D, Lg.src_attn.v_w, D, 0);
+        }
+        if (Lg.src_attn.v_b == Lg.src_attn.k_b + D) rc |= colsum(BR, 2 * D, tp.d_skv[l], 2 * D, Lg.src_attn.k_b);
+        else {
+            rc |= colsum(BR, D, tp.d_skv[l], 2 * D, Lg.src_attn.k_b);
+            rc |= colsum(BR, D, tp.d_skv[l] + D, 2 * D, Lg.src_attn.v_b);
+        }
     }
     if (rc) return 1;
     if (e->grad_events[0]) CAPB_CHECK_CUDA(cudaEventRecord(e->grad_events[0], st));            // generator + decoder + target embedding
@@ -711,12 +730,7 @@ int tfm_train_step(capb200_tfm_engine* e, const float* att, int B, int R, const 
         rc |= sk.dgrad(BR, D, D, tp.d_tmp, D, Lw.self_attn.o_w, D, tp.d_att, D, 0);
         rc |= seq_attn_backward_launch(B, R, heads, dk, 0, R, R, 1, tp.eqkv[l], tp.eqkv[l] + D, tp.eqkv[l] + 2 * D, 3 * D, seed, 10 + l, p, tp.d_att, D, tp.d_qkv,
                                        tp.d_qkv + D, tp.d_qkv + 2 * D, 3 * D, ta.mask, R, st);
-        rc |= sk.wgrad(D, D, BR, tp.d_qkv, 3 * D, tp.eln0[l], D, Lg.self_attn.q_w, D, 0);
-        rc |= sk.wgrad(D, D, BR, tp.d_qkv + D, 3 * D, tp.eln0[l], D, Lg.self_attn.k_w, D, 0);
-        rc |= sk.wgrad(D, D, BR, tp.d_qkv + 2 * D, 3 * D, tp.eln0[l], D, Lg.self_attn.v_w, D, 0);
-        rc |= colsum(BR, D, tp.d_qkv, 3 * D, Lg.self_attn.q_b);
-        rc |= colsum(BR, D, tp.d_qkv + D, 3 * D, Lg.self_attn.k_b);
-        rc |= colsum(BR, D, tp.d_qkv + 2 * D, 3 * D, Lg.self_attn.v_b);
+        rc |= qkv_grads(BR, tp.eln0[l], Lg.self_attn);
         rc |= sk.dgrad(BR, D, 3 * D, tp.d_qkv, 3 * D, e->enc_qkv_w[l], D, tp.d_ln, D, 0);
         rc |= ln_backward_launch(BR, D, tp.X[l], D, Lw.ln0_a, tp.d_ln, D, 1e-6f, tp.dX, D, 1, tp.stats, Lg.ln0_a, Lg.ln0_b, 0, st);
         nl += 8;

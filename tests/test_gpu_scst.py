@@ -91,10 +91,28 @@ def test_loss_wrapper_backward_sets_param_grads():
     lw = b200.B200LossWrapper(model, opt)
     out = lw(fc.cuda(), att.cuda(), None, None, None, gts, torch.arange(B), True, False, False)
     assert out['loss'].requires_grad
-    (2.0 * out['loss']).backward()
     step = lw.last_step
+    engine_grads = {p: g.clone() for p, g in step['grads'].items()}
+    (2.0 * out['loss']).backward()
     for p, g in step['grads'].items():
-        assert p.grad is not None and torch.allclose(p.grad, 2.0 * g)
+        # direct path (default): the flat buffer was scaled in place by the upstream gradient and param.grad is a VIEW of it
+        assert p.grad is not None and p.grad.data_ptr() == g.data_ptr() and torch.allclose(p.grad, 2.0 * engine_grads[p])
+    # zero_grad(set_to_none=False) (the default of the torch versions the reference targets) keeps the views: the next step's gradients land in them
+    model.zero_grad(set_to_none=False)
+    out_b = lw(fc.cuda(), att.cuda(), None, None, None, gts, torch.arange(B), True, False, False)
+    engine_grads = {p: g.clone() for p, g in lw.last_step['grads'].items()}
+    out_b['loss'].backward()
+    for p, g in lw.last_step['grads'].items():
+        assert p.grad.data_ptr() == g.data_ptr() and torch.allclose(p.grad, engine_grads[p])
+    # through autograd (what torch DDP / gradient accumulation need): fresh tensors, accumulated like any other gradient
+    model.zero_grad(set_to_none=True)
+    lw.direct_grads = False
+    out_c = lw(fc.cuda(), att.cuda(), None, None, None, gts, torch.arange(B), True, False, False)
+    engine_grads = {p: g.clone() for p, g in lw.last_step['grads'].items()}
+    (3.0 * out_c['loss']).backward()
+    for p, g in lw.last_step['grads'].items():
+        assert p.grad.data_ptr() != g.data_ptr() and torch.allclose(p.grad, 3.0 * engine_grads[p])
+    lw.direct_grads = True
     # an optimizer step changes the weights, the next call re-binds them (version counters) and still works
     torch.optim.SGD(model.parameters(), lr=1e-3).step()
     out2 = lw(fc.cuda(), att.cuda(), None, None, None, gts, torch.arange(B), True, False, False)
