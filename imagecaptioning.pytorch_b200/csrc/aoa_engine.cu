@@ -59,6 +59,7 @@ struct capb200_aoa_engine {
     cudaEvent_t grad_events[10] = {};   // caller-owned: recorded when a gradient group is complete (capb200_aoa_set_grad_events)
     cudaStream_t side = nullptr;        // the greedy baseline of the SCST step runs here, concurrently with the sampling forward
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    StepGraph sg;                       // CUDA graph of the whole SCST step (engine_common.cuh)
 };
 
 namespace {
@@ -329,6 +330,7 @@ void capb200_aoa_destroy(capb200_aoa_engine* e) {
     if (e->d.loop_exec) cudaGraphExecDestroy(e->d.loop_exec);
     cudaFree(e->d.slab);
     cudaFree(e->tape);
+    e->sg.destroy();
     tf32_context_destroy(e->tf32);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
@@ -414,7 +416,7 @@ int capb200_aoa_bind_weights(capb200_aoa_engine* e, const capb200_aoa_weights* w
         cudaFreeAsync(tmp, st);
         if (rc) return 1;
     }
-    if (e->tc) {
+    if (e->tc && !e->bound) {        // first binding only: a re-binding must not stall the training loop (see capb200_engine_bind_weights)
         CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
         CAPB_CHECK_RANGE();
     }
@@ -586,9 +588,11 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     // sampling forward are independent chains of small latency-bound kernels
     if (ensure_workspace(e, B, N, R, 1, st)) return 1;         // decode workspace sized before anything is in flight
     bool greedy_on_side = false;
+    cudaStream_t gs_enqueue = st;
+    capb200_sample_opts so;
     if (greedy_baseline) {
         CAPB_NVTX("capb200 aoa scst: greedy baseline (eval mode, side stream)");
-        capb200_sample_opts so; memset(&so, 0, sizeof(so)); so.edits.unk_col = -1; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.seed = 0; so.steps = T;
+        memset(&so, 0, sizeof(so)); so.edits.unk_col = -1; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.seed = 0; so.steps = T;
         cudaStream_t gs = st;
         static const bool serial = getenv("CAPB200_SCST_SERIAL_GREEDY") != nullptr;
         if (!serial) {
@@ -603,10 +607,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
                 greedy_on_side = true;
             } else (void)cudaGetLastError();
         }
-        CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, gs));
-        CAPB_CHECK_CUDA(cudaMemsetAsync(greedy_seq, 0, sizeof(long long) * (size_t)B * T, gs));
-        if (capb200_aoa_decode_sample(e, att, ta.mask, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, static_cast<void*>(gs))) return 1;
-        if (greedy_on_side) CAPB_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
+        gs_enqueue = gs;
     }
     if (e->tc && e->tf32 == nullptr) e->tf32 = tf32_context_create();
     tf32_context_new_step(e->tf32);
@@ -645,6 +646,15 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     if (sk.lin(tp.att_e, H, w.ctx2att_w, H, w.ctx2att_b, tp.kv, 2 * H, (int)BR, 2 * H, H, 0)) return 1;
     e->launches += 8;
 
+    // ---- the greedy baseline's ~220 launches are enqueued only now: the side stream forked at the top of the step (it does not wait for the
+    // prologue), but the host needs ~0.7 ms to enqueue them, and the main stream should be busy with the prologue meanwhile, not idle
+    if (greedy_baseline) {
+        CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, gs_enqueue));
+        CAPB_CHECK_CUDA(cudaMemsetAsync(greedy_seq, 0, sizeof(long long) * (size_t)B * T, gs_enqueue));
+        if (capb200_aoa_decode_sample(e, att, ta.mask, B, R, &so, nullptr, 0, greedy_seq, tp.glp, nullptr, static_cast<void*>(gs_enqueue))) return 1;
+        if (greedy_on_side) CAPB_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
+    
+    }
     // ---- (3) T sampling steps with the tape
     CAPB_CHECK_CUDA(cudaMemsetAsync(tp.s_tokens, 0, sizeof(int) * N, st));
     for (int t = 0; t < T; ++t) {
@@ -862,7 +872,61 @@ extern "C" int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, in
     ta.refs = refs; ta.ref_offsets = ref_offsets; ta.L = L; ta.sample_seq = sample_seq; ta.greedy_seq = greedy_seq; ta.reward = reward;
     ta.logprobs = sample_logprobs; ta.loss = loss; ta.forced = opts->forced_tokens; ta.mask = opts->att_masks; ta.keep = opts->keep_rows; ta.row_loss = opts->row_loss;
     CAPB_REQUIRE(ta.keep >= 0 && ta.keep <= B * n, "keep_rows must be in 0..rows");
-    return aoa_train_step(e, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // ---- the step as ONE CUDA graph.  Its ~1100 kernels are 5-30 us each and every launch boundary costs ~2 us on the stream, the host
+    // needs ~3 ms to enqueue them, and nothing about the sequence depends on data: captured the second time a configuration is seen,
+    // replayed afterwards with a fresh seed (dropout.cuh: seed salt).  The features are copied to an engine-owned buffer first so that the
+    // graph reads a stable address.  Not used while a caller listens to the gradient-group events (overlapped all-reduce: an event recorded
+    // inside a graph cannot be waited on from outside before it has executed) or replays forced tokens.
+    bool listening = false;
+    for (int i = 0; i < 10; ++i) listening = listening || e->grad_events[i] != nullptr;
+    if (!StepGraph::enabled() || !e->tc || listening || ta.forced != nullptr || e->sg.broken) {
+        if (dropout_salt_set_all(0ull, st)) return 1;
+        return aoa_train_step(e, att, B, R, ta, grads, st);
+    }
+    const size_t att_bytes = sizeof(float) * (size_t)B * R * e->F, mask_bytes = ta.mask ? sizeof(float) * (size_t)B * R : 0;
+    if (e->sg.stage_inputs(att, att_bytes, ta.mask, mask_bytes, st)) return 1;
+    const float* att_s = reinterpret_cast<const float*>(e->sg.stage);
+    if (ta.mask) ta.mask = reinterpret_cast<const float*>(e->sg.stage + ((att_bytes + 255) & ~size_t(255)));
+    unsigned long long key = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t nbytes) { const unsigned char* c = static_cast<const unsigned char*>(p); for (size_t i = 0; i < nbytes; ++i) { key ^= c[i]; key *= 1099511628211ull; } };
+    capb200_aoa_scst_opts o2 = *opts; o2.seed = 0; o2.att_masks = ta.mask;
+    mix(&o2, sizeof(o2)); mix(grads, sizeof(*grads)); mix(&e->w, sizeof(e->w));
+    const void* ptrs[] = {table, refs, ref_offsets, sample_seq, greedy_seq, sample_logprobs, reward, loss, e->tape, e->ws, e->wblock, e->sg.stage, stream};
+    mix(ptrs, sizeof(ptrs));
+    const int dims[] = {B, R, L};
+    mix(dims, sizeof(dims));
+    StepGraph& sg = e->sg;
+    if (sg.exec != nullptr && sg.key == key) {
+        if (dropout_salt_set_all(sg.cap_seed ^ opts->seed, st)) return 1;
+        CAPB_CHECK_CUDA(cudaGraphLaunch(sg.exec, st));
+        e->launches += sg.launches;
+        return 0;
+    }
+    if (dropout_salt_set_all(0ull, st)) return 1;
+    if (sg.seen != key) {               // first sighting: eager (it also performs every first-use allocation)
+        sg.seen = key;
+        return aoa_train_step(e, att_s, B, R, ta, grads, st);
+    }
+    sg.reset();
+    const long l0 = e->launches;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { (void)cudaGetLastError(); sg.broken = true; return aoa_train_step(e, att_s, B, R, ta, grads, st); }
+    const int rc = aoa_train_step(e, att_s, B, R, ta, grads, st);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
+        (void)cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        sg.broken = true;               // something in the step is not capturable here: stay eager from now on
+        e->launches = l0;
+        return aoa_train_step(e, att_s, B, R, ta, grads, st);
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&sg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { (void)cudaGetLastError(); sg.exec = nullptr; sg.broken = true; e->launches = l0; return aoa_train_step(e, att_s, B, R, ta, grads, st); }
+    sg.key = key; sg.cap_seed = opts->seed; sg.launches = e->launches - l0;
+    CAPB_CHECK_CUDA(cudaGraphLaunch(sg.exec, st));
+    return 0;
 }
 
 extern "C" int capb200_aoa_set_grad_events(capb200_aoa_engine* e, void* const* events, int n) {
@@ -889,5 +953,6 @@ extern "C" int capb200_aoa_xe_step(capb200_aoa_engine* e, const float* att, int 
     ta.mask = opts->att_masks; ta.ss_prob = opts->ss_prob; ta.tokens_used = opts->tokens_used; ta.keep = opts->keep_rows; ta.row_loss = opts->row_loss;
     CAPB_REQUIRE(ta.ss_prob >= 0.f && ta.ss_prob <= 1.f, "ss_prob must be in [0, 1]");
     CAPB_REQUIRE(ta.keep >= 0 && ta.keep <= B * opts->seq_per_img, "keep_rows must be in 0..rows");
+    if (dropout_salt_set_all(0ull, static_cast<cudaStream_t>(stream))) return 1;      // eager step: the seed arguments are the effective seeds
     return aoa_train_step(e, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }

@@ -533,4 +533,6 @@ int add_row_group_launch(int rows, int cols, int rpg, const float* a, long ld_a,
     LAUNCH_OK();
 }
 
+CAPB_DEFINE_SALT_SETTER(dropout_salt_set_aoa)
+
 }  // namespace capb200

@@ -678,7 +678,9 @@ int capb200_engine_bind_weights(capb200_engine* e, const capb200_weights* w, voi
         cudaFreeAsync(tmp, st);
         if (rc) return 1;
     }
-    if (e->tc) {   // binding is rare: wait for the conversions and refuse weights outside the fp16 range of the split planes
+    if (e->tc && !e->bound) {   // first binding: wait for the conversions and refuse weights outside the fp16 range of the split planes.
+        // Re-bindings (a training loop changes the weights every step) must not stall the host: the range flag is host-mapped and every later
+        // entry point checks it (check_ready), so an overflow introduced by an optimizer step is reported by the next call instead.
         CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
         CAPB_CHECK_RANGE();
     }
@@ -998,6 +1000,7 @@ void layout_tape(Tape& tp, Arena& a, int B, int R, int N, int T, int E, int H, i
 
 extern "C" int capb200_dropout_mask(float* mask, long n, unsigned long long seed, int site, int step, float p, void* stream) {
     CAPB_REQUIRE(mask != nullptr && n > 0, "bad argument");
+    if (dropout_salt_set_all(0ull, static_cast<cudaStream_t>(stream))) return 1;      // a graph replay of an SCST step may have left a salt behind
     return dropout_mask_launch(mask, n, seed, (unsigned)site, (unsigned)step, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -1283,6 +1286,7 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
     ta.sample_seq = sample_seq; ta.greedy_seq = greedy_seq; ta.reward = reward; ta.logprobs = sample_logprobs; ta.loss = loss;
     ta.forced = opts->forced_tokens; ta.mask = opts->att_masks; ta.keep = opts->keep_rows; ta.row_loss = opts->row_loss;
     CAPB_REQUIRE(ta.keep >= 0 && ta.keep <= B * opts->sample_n, "keep_rows must be in 0..rows");
+    if (dropout_salt_set_all(0ull, static_cast<cudaStream_t>(stream))) return 1;      // eager step: the seed arguments are the effective seeds
     return updown_train_step(e, fc, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }
 
@@ -1311,6 +1315,7 @@ extern "C" int capb200_updown_xe_step(capb200_engine* e, const float* fc, const 
     ta.mask = opts->att_masks; ta.ss_prob = opts->ss_prob; ta.tokens_used = opts->tokens_used; ta.keep = opts->keep_rows; ta.row_loss = opts->row_loss;
     CAPB_REQUIRE(ta.ss_prob >= 0.f && ta.ss_prob <= 1.f, "ss_prob must be in [0, 1]");
     CAPB_REQUIRE(ta.keep >= 0 && ta.keep <= B * opts->seq_per_img, "keep_rows must be in 0..rows");
+    if (dropout_salt_set_all(0ull, static_cast<cudaStream_t>(stream))) return 1;      // eager step: the seed arguments are the effective seeds
     return updown_train_step(e, fc, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }
 

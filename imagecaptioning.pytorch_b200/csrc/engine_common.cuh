@@ -348,6 +348,35 @@ int sample_decode_driver(DecodeBuffers& d, int V1, int T, int rows, int method, 
 // engines) every call runs on the tcgen05 kind::tf32 3-pass kernel of gemm_tf32.cu; operands that are not K-major in HBM (W for the input
 // gradients, dY / X for the weight gradients) go through cached transposes.  Without a context (simt_fp32 engines), when an operand is not
 // TMA-compatible (rows not 16-byte aligned: tiny test shapes), or with CAPB200_SKINNY_LEGACY set, the split-K kernels of gemm_generic.cu run.
+// CUDA graph of a whole fused training step (see capb200_aoa_scst_step) + the engine-owned staging buffer that gives the graph stable input
+// addresses.  CAPB200_SCST_GRAPH=0 keeps the steps eager.
+struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long key = 0, seen = 0, cap_seed = 0;
+    long launches = 0;
+    char* stage = nullptr;
+    size_t stage_bytes = 0;
+    bool broken = false;
+    static bool enabled() { static const bool v = !(getenv("CAPB200_SCST_GRAPH") != nullptr && atoi(getenv("CAPB200_SCST_GRAPH")) == 0); return v; }
+    void reset() { if (exec) cudaGraphExecDestroy(exec); exec = nullptr; key = 0; }
+    void destroy() { reset(); if (stage) cudaFree(stage); stage = nullptr; stage_bytes = 0; }
+    // copies a (and b behind it, 256-byte aligned) into the staging buffer in stream order
+    int stage_inputs(const void* a, size_t a_bytes, const void* b, size_t b_bytes, cudaStream_t st) {
+        const size_t a_pad = (a_bytes + 255) & ~size_t(255), need = a_pad + b_bytes + 256;
+        if (need > stage_bytes) {
+            CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
+            reset();
+            if (stage) CAPB_CHECK_CUDA(cudaFree(stage));
+            stage = nullptr;
+            CAPB_CHECK_CUDA(cudaMalloc(&stage, need));
+            stage_bytes = need;
+        }
+        CAPB_CHECK_CUDA(cudaMemcpyAsync(stage, a, a_bytes, cudaMemcpyDeviceToDevice, st));
+        if (b != nullptr && b_bytes) CAPB_CHECK_CUDA(cudaMemcpyAsync(stage + a_pad, b, b_bytes, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+};
+
 // Side stream of the SCST steps (the eval-mode greedy baseline runs on it while the train-mode sampling pass runs on the caller's stream).
 // Lowest priority by default: both chains are latency-bound and compete for SMs (a persistent GEMM CTA owns its SM's shared memory), and
 // the sampling pass is the critical path -- its pending CTAs should be placed first.  CAPB200_SIDE_PRIORITY=0 gives both equal priority.

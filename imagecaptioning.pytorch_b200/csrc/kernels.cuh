@@ -178,6 +178,14 @@ int add_strided_launch(float* a, const float* b, long ld_b, int rows, int cols, 
 int ln_backward_launch(int rows, int D, const float* x, long ld_x, const float* a, const float* dy, long ld_dy, float eps, float* dx, long ld_dx, int accumulate,
                        float* stats, float* da, float* db, int accumulate_params, cudaStream_t st);
 int glu_backward_launch(int rows, int H, const float* t, long ld_t, const float* dy, long ld_dy, float* dt, long ld_dt, cudaStream_t st);
+// ---- seed salt (dropout.cuh): effective seed of every dropout / sampling kernel = seed argument XOR salt; uploaded in stream order
+int dropout_salt_set_scst(unsigned long long salt, cudaStream_t st);
+int dropout_salt_set_aoa(unsigned long long salt, cudaStream_t st);
+int dropout_salt_set_tfm(unsigned long long salt, cudaStream_t st);
+int dropout_salt_set_vocab(unsigned long long salt, cudaStream_t st);
+inline int dropout_salt_set_all(unsigned long long salt, cudaStream_t st) {
+    return dropout_salt_set_scst(salt, st) | dropout_salt_set_aoa(salt, st) | dropout_salt_set_tfm(salt, st) | dropout_salt_set_vocab(salt, st);
+}
 // ---- tfm_train_kernels.cu: element-wise pieces of the Transformer training steps on TIME-major rows (row = t * rps + n; dropout keyed by (t, n))
 int embed_pe_dropout_launch(int rows, int rps, int D, const int* tok, const float* lut, const float* pe, float scale, int t0, unsigned long long seed, int site,
                             float p, float* x, long ld, cudaStream_t st);

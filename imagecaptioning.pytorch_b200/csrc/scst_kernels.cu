@@ -463,4 +463,6 @@ int add_strided_launch(float* a, const float* b, long ld_b, int rows, int cols, 
     LAUNCH_OK();
 }
 
+CAPB_DEFINE_SALT_SETTER(dropout_salt_set_scst)
+
 }  // namespace capb200

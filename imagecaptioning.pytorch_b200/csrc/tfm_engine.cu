@@ -324,8 +324,10 @@ int capb200_tfm_bind_weights(capb200_tfm_engine* e, const capb200_tfm_weights* w
             rc |= pack(e, w->dec[l].w1_w, Dff, D, e->pd_w1[l], st) | pack(e, w->dec[l].w2_w, D, Dff, e->pd_w2[l], st);
         }
         if (rc) return 1;
-        CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
-        CAPB_CHECK_RANGE();
+        if (!e->bound) {        // first binding only: a re-binding must not stall the training loop (see capb200_engine_bind_weights)
+            CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
+            CAPB_CHECK_RANGE();
+        }
     }
     e->bound = true;
     return 0;
@@ -497,9 +499,11 @@ int tfm_train_step(capb200_tfm_engine* e, const float* att, int B, int R, const 
     // ---- greedy baseline (eval mode): the regular K/V-cached decode on a side stream, joined before the reward
     const bool greedy_baseline = !ta.xe && ta.greedy_baseline;
     bool greedy_on_side = false;
+    cudaStream_t gs_enqueue = st;
+    capb200_sample_opts so;
     if (greedy_baseline) {
         if (ensure_workspace(e, B, B, R, 1, st)) return 1;
-        capb200_sample_opts so; memset(&so, 0, sizeof(so)); so.edits.unk_col = -1; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.steps = T;
+        memset(&so, 0, sizeof(so)); so.edits.unk_col = -1; so.sample_n = 1; so.method = CAPB200_SAMPLE_GREEDY; so.temperature = 1.f; so.steps = T;
         cudaStream_t gs = st;
         static const bool serial = getenv("CAPB200_SCST_SERIAL_GREEDY") != nullptr;
         if (!serial) {
@@ -514,10 +518,7 @@ int tfm_train_step(capb200_tfm_engine* e, const float* att, int B, int R, const 
                 greedy_on_side = true;
             } else (void)cudaGetLastError();
         }
-        CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, gs));
-        CAPB_CHECK_CUDA(cudaMemsetAsync(ta.greedy_seq, 0, sizeof(long long) * (size_t)B * T, gs));
-        if (capb200_tfm_decode_sample(e, att, ta.mask, B, R, &so, nullptr, 0, ta.greedy_seq, tp.glp, nullptr, static_cast<void*>(gs))) return 1;
-        if (greedy_on_side) CAPB_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
+        gs_enqueue = gs;
     }
     if (e->tc && e->tf32 == nullptr) e->tf32 = tf32_context_create();
     tf32_context_new_step(e->tf32);
@@ -551,6 +552,15 @@ int tfm_train_step(capb200_tfm_engine* e, const float* att, int B, int R, const 
     for (int l = 0; l < ND; ++l) rc |= sk.lin(tp.mem, D, e->dec_skv_w[l], D, e->dec_skv_b[l], tp.skv[l], 2 * D, BR, 2 * D, D, 0);
     nl += 1 + ND;
     if (rc) return 1;
+
+    // ---- the greedy baseline's launches are enqueued only now: its stream forked at the top of the step, and while the host enqueues
+    // them the main stream is busy with the encoder instead of idle
+    if (greedy_baseline) {
+        CAPB_CHECK_CUDA(cudaMemsetAsync(tp.glp, 0, sizeof(float) * (size_t)B * T * V1, gs_enqueue));
+        CAPB_CHECK_CUDA(cudaMemsetAsync(ta.greedy_seq, 0, sizeof(long long) * (size_t)B * T, gs_enqueue));
+        if (capb200_tfm_decode_sample(e, att, ta.mask, B, R, &so, nullptr, 0, ta.greedy_seq, tp.glp, nullptr, static_cast<void*>(gs_enqueue))) return 1;
+        if (greedy_on_side) CAPB_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
+    }
 
     // ---- decoder forward over positions [t0, t1)
     const float* key_mask = ta.xe ? tp.key_mask : nullptr;
@@ -764,6 +774,7 @@ extern "C" int capb200_tfm_xe_step(capb200_tfm_engine* e, const float* att, int 
     ta.seed = opts->seed; ta.smoothing = opts->label_smoothing; ta.labels = labels; ta.ld_labels = label_cols; ta.masks = masks; ta.ld_masks = label_cols;
     ta.logprobs = logprobs; ta.loss = loss; ta.mask = opts->att_masks; ta.keep = opts->keep_rows; ta.row_loss = opts->row_loss;
     CAPB_REQUIRE(ta.keep >= 0 && ta.keep <= B * ta.n, "keep_rows must be in 0..rows");
+    if (dropout_salt_set_all(0ull, static_cast<cudaStream_t>(stream))) return 1;      // eager step: the seed arguments are the effective seeds
     return tfm_train_step(e, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }
 
@@ -785,5 +796,6 @@ extern "C" int capb200_tfm_scst_step(capb200_tfm_engine* e, const float* att, in
     ta.greedy_seq = greedy_seq; ta.reward = reward; ta.logprobs = sample_logprobs; ta.loss = loss; ta.forced = opts->forced_tokens; ta.mask = opts->att_masks;
     ta.keep = opts->keep_rows; ta.row_loss = opts->row_loss;
     CAPB_REQUIRE(ta.keep >= 0 && ta.keep <= B * n, "keep_rows must be in 0..rows");
+    if (dropout_salt_set_all(0ull, static_cast<cudaStream_t>(stream))) return 1;      // eager step: the seed arguments are the effective seeds
     return tfm_train_step(e, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
 }

@@ -157,4 +157,6 @@ int add_rows_launch(int rows, int cols, float* x, long ld_x, const float* y, lon
     LAUNCH_OK();
 }
 
+CAPB_DEFINE_SALT_SETTER(dropout_salt_set_tfm)
+
 }  // namespace capb200

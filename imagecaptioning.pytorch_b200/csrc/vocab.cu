@@ -14,6 +14,12 @@
 
 namespace capb200 {
 
+// seed salt of the sampling kernels (see dropout.cuh: lets a captured CUDA graph of the SCST step draw fresh samples on every replay)
+static __device__ unsigned long long g_vocab_seed_salt = 0ull;
+int dropout_salt_set_vocab(unsigned long long salt, cudaStream_t st) {
+    return cudaMemcpyToSymbolAsync(g_vocab_seed_salt, &salt, sizeof(salt), 0, cudaMemcpyHostToDevice, st) == cudaSuccess ? 0 : 1;
+}
+
 namespace {
 
 constexpr int VT = 256;   // threads per row
@@ -234,7 +240,8 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
             }
             float bv = -INFINITY;
             int bi = 0x7fffffff;
-            const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+            const unsigned long long sd = a.seed ^ g_vocab_seed_salt;           // see dropout.cuh: graph replays of the SCST step
+            const uint32_t k0 = (uint32_t)sd, k1 = (uint32_t)(sd >> 32);
             for (int v = threadIdx.x; v < V1; v += VT) {
                 if (okey(row[v]) < keep_from) continue;
                 const uint32_t bits = philox_first((uint32_t)v, (uint32_t)r, (uint32_t)a.step, (uint32_t)(a.step >> 32), k0, k1);
@@ -705,6 +712,7 @@ __global__ void __launch_bounds__(VT) ss_select_kernel(int V1, const float* __re
     __shared__ float s_red[VT / 32];
     __shared__ int s_idx[VT / 32];
     const int r = blockIdx.x;
+    seed ^= g_vocab_seed_salt;
     const uint32_t k0 = (uint32_t)seed ^ 0x6a09e667u, k1 = (uint32_t)(seed >> 32) ^ 0xbb67ae85u;
     const uint32_t ubits = philox_first(0xffffffffu, (uint32_t)r, (uint32_t)col, 6u, k0, k1);
     const float u_row = ((float)(ubits >> 9) + 0.5f) * (1.0f / 8388608.0f);

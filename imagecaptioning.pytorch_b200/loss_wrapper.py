@@ -207,6 +207,7 @@ class B200LossWrapper(nn.Module):
         reduced buffer and points ``param.grad`` at it."""
         from .grad_sync import GradSync
         self._sync = GradSync(process_group)
+        self.model._grad_sync_on = True            # the engine now records an event per finished gradient group
         return self
 
     @property

@@ -527,7 +527,8 @@ class B200UpDownModel(B200CaptionModel):
         g = _lib.UpdownGrads()
         for name in _lib.GRAD_FIELDS:
             setattr(g, name, fg.by_name[name].data_ptr())
-        table, n = fg.event_table()
+        # the engine records the group events only for a listener (B200LossWrapper.enable_gradient_sync); without one the whole step may run as a CUDA graph
+        table, n = fg.event_table() if getattr(self, '_grad_sync_on', False) else (None, 0)
         _lib.check(lib.capb200_engine_set_grad_events(self._engine, table, n), 'set_grad_events')
         return fg, g
 
@@ -843,7 +844,8 @@ class B200TransformerModel(B200CaptionModel):
             for key in path[:-1]:
                 dst = getattr(dst, key) if isinstance(key, str) else dst[key]
             setattr(dst, path[-1], ptr)
-        table, n = fg.event_table()
+        # the engine records the group events only for a listener (B200LossWrapper.enable_gradient_sync); without one the whole step may run as a CUDA graph
+        table, n = fg.event_table() if getattr(self, '_grad_sync_on', False) else (None, 0)
         _lib.check(lib.capb200_tfm_set_grad_events(self._engine, table, n), 'tfm_set_grad_events')
         return fg, g
 
@@ -1011,7 +1013,8 @@ class B200AoAModel(B200CaptionModel):
                 setattr(g, path[0], ptr)
             else:
                 setattr(g.refiner[path[1]], path[2], ptr)
-        table, n = fg.event_table()
+        # the engine records the group events only for a listener (B200LossWrapper.enable_gradient_sync); without one the whole step may run as a CUDA graph
+        table, n = fg.event_table() if getattr(self, '_grad_sync_on', False) else (None, 0)
         _lib.check(lib.capb200_aoa_set_grad_events(self._engine, table, n), 'aoa_set_grad_events')
         return fg, g
 

@@ -96,36 +96,44 @@ def reset_scorer():
 
 
 class _Staging:
-    """Round-robin pinned host buffers for the per-step reference upload: one pinned block holds the padded reference rows and the offsets,
-    so the step pays ONE asynchronous H2D copy instead of two pageable ones (each of which blocks the host until the driver has staged
-    it).  A slot is reused only after the copy that read it has completed (event per slot)."""
+    """Per-step reference upload: round-robin PINNED host blocks (a block is reused only after the copy that read it has completed) feeding ONE
+    device buffer per GPU -- the padded reference rows and the offsets travel in a single asynchronous H2D copy, and the device addresses stay
+    the same from step to step (copies and the kernels that read them are ordered on the stream), which is what lets the engine replay the
+    SCST step as a CUDA graph."""
     SLOTS = 4
 
     def __init__(self):
-        self.slots = {}
+        self.host = {}
+        self.dev = {}
         self.turn = 0
 
     def upload(self, host_rows: np.ndarray, offs: np.ndarray, device):
         dev = torch.device(device)
-        n = host_rows.size + offs.size
-        key = (dev.index if dev.index is not None else torch.cuda.current_device(), self.turn % self.SLOTS)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        head = (offs.size + 1023) // 1024 * 1024          # offsets first, in a fixed-size head: both device addresses are independent of the row count
+        n = head + host_rows.size
+        cap = max(n, 1 << 14)
+        key = (idx, self.turn % self.SLOTS)
         self.turn += 1
-        slot = self.slots.get(key)
+        slot = self.host.get(key)
         if slot is None or slot[0].numel() < n:
-            slot = [torch.empty(max(n, 1 << 14), dtype=torch.int32).pin_memory(), torch.empty(max(n, 1 << 14), dtype=torch.int32, device=dev), None]
-            self.slots[key] = slot
-        pinned, devbuf, ev = slot
+            slot = [torch.empty(cap, dtype=torch.int32).pin_memory(), None]
+            self.host[key] = slot
+        pinned, ev = slot
         if ev is not None:
             ev.synchronize()
+        devbuf = self.dev.get(idx)
+        if devbuf is None or devbuf.numel() < n:
+            devbuf = torch.empty(cap, dtype=torch.int32, device=dev)
+            self.dev[idx] = devbuf
         flat = pinned.numpy()
-        flat[:host_rows.size] = host_rows.reshape(-1)
-        flat[host_rows.size:n] = offs
+        flat[:offs.size] = offs
+        flat[head:n] = host_rows.reshape(-1)
         devbuf[:n].copy_(pinned[:n], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
-        slot[2] = ev
-        refs = devbuf[:host_rows.size].view(host_rows.shape)
-        return refs, devbuf[host_rows.size:n]
+        slot[1] = ev
+        return devbuf[head:n].view(host_rows.shape), devbuf[:offs.size]
 
 
 _staging = _Staging()
@@ -133,7 +141,8 @@ _staging = _Staging()
 
 def pack_references(data_gts: Sequence, device) -> Tuple[torch.Tensor, torch.Tensor, int]:
     """list[B] of int arrays [n_refs_i, L] (dataloader.py:213) -> (refs int32 [total, L], offsets int32 [B+1], L) on the device.
-    The returned tensors are views of a staging buffer that is reused four uploads later: consume them in the step they were packed for."""
+    The returned tensors are views of the device staging buffer, overwritten by the next upload (in stream order): consume them in the step
+    they were packed for."""
     L = max(int(np.asarray(g).shape[1]) for g in data_gts)
     total = sum(int(np.asarray(g).shape[0]) for g in data_gts)
     rows = np.zeros((total, L), dtype=np.int32)

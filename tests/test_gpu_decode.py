@@ -215,3 +215,42 @@ def test_beam_length_penalties_golden(golden_dir, tag, pen):
     for i in range(B):
         for j in range(b):
             assert abs(model.done_beams[i][j]['p'] - g[tag + '_done_p'][i, j]) < 1e-3
+
+
+def test_fp16_range_guard():
+    """The tensor-core decode path keeps every operand as two fp16 planes: weights or features with |x| >= 65504 (or inf / nan) must be refused, not
+    silently saturated.  First binding: checked synchronously.  Re-binding after an in-place weight change (what an optimizer step
+    does): the conversion kernels raise a host-mapped flag and the NEXT entry point fails; capb200_range_status(1) clears it."""
+    import imagecaptioning.pytorch_b200 as b200
+    lib = b200._lib.load()
+    cfg = dict(V=40, E=32, H=48, A=24, F_fc=32, F_att=40, T=6)
+    model, _ = build_pair('updown', seed=3, logit_scale=5.0, mode='tc_f16x3', **cfg)
+    fc, att = co.make_inputs(2, 5, cfg['F_fc'], cfg['F_att'], seed=1)
+    opt = {'sample_method': 'greedy', 'beam_size': 1}
+    with torch.no_grad():
+        model.logit.weight[3, 4] = 1.0e5
+        with pytest.raises(RuntimeError, match='65504'):
+            model(fc.cuda(), att.cuda(), None, opt=opt, mode='sample')            # first binding: synchronous check
+        assert lib.capb200_range_status(1) == 1 and lib.capb200_range_status(0) == 0
+        model.logit.weight[3, 4] = 0.5
+        seq, _ = model(fc.cuda(), att.cuda(), None, opt=opt, mode='sample')       # binds cleanly now
+        model.logit.weight[3, 4] = float('inf')                                    # in-place change -> re-binding, not synchronised
+        try:
+            model(fc.cuda(), att.cuda(), None, opt=opt, mode='sample')
+        except RuntimeError:
+            pass
+        torch.cuda.synchronize()
+        with pytest.raises(RuntimeError, match='65504'):
+            model(fc.cuda(), att.cuda(), None, opt=opt, mode='sample')            # the flag raised by the re-binding stops the next call
+        assert lib.capb200_range_status(1) == 1
+        model.logit.weight[3, 4] = 0.5
+        seq2, _ = model(fc.cuda(), att.cuda(), None, opt=opt, mode='sample')
+        assert torch.equal(seq, seq2)
+        bad = att.clone()
+        bad[0, 0, 0] = 7.0e4                                                       # features go through the same planes
+        try:
+            model(fc.cuda(), bad.cuda(), None, opt=opt, mode='sample')
+        except RuntimeError:
+            pass
+        torch.cuda.synchronize()
+        assert lib.capb200_range_status(1) == 1
