@@ -884,49 +884,20 @@ extern "C" int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, in
         if (dropout_salt_set_all(0ull, st)) return 1;
         return aoa_train_step(e, att, B, R, ta, grads, st);
     }
-    const size_t att_bytes = sizeof(float) * (size_t)B * R * e->F, mask_bytes = ta.mask ? sizeof(float) * (size_t)B * R : 0;
-    if (e->sg.stage_inputs(att, att_bytes, ta.mask, mask_bytes, st)) return 1;
-    const float* att_s = reinterpret_cast<const float*>(e->sg.stage);
-    if (ta.mask) ta.mask = reinterpret_cast<const float*>(e->sg.stage + ((att_bytes + 255) & ~size_t(255)));
+    const void* srcs[2] = {att, ta.mask};
+    const size_t bytes[2] = {sizeof(float) * (size_t)B * R * e->F, ta.mask ? sizeof(float) * (size_t)B * R : 0};
+    size_t off[2];
+    if (e->sg.stage_inputs(2, srcs, bytes, off, st)) return 1;
+    const float* att_s = reinterpret_cast<const float*>(e->sg.stage + off[0]);
+    if (ta.mask) ta.mask = reinterpret_cast<const float*>(e->sg.stage + off[1]);
     unsigned long long key = 1469598103934665603ull;
-    auto mix = [&](const void* p, size_t nbytes) { const unsigned char* c = static_cast<const unsigned char*>(p); for (size_t i = 0; i < nbytes; ++i) { key ^= c[i]; key *= 1099511628211ull; } };
     capb200_aoa_scst_opts o2 = *opts; o2.seed = 0; o2.att_masks = ta.mask;
-    mix(&o2, sizeof(o2)); mix(grads, sizeof(*grads)); mix(&e->w, sizeof(e->w));
+    StepGraph::mix(key, &o2, sizeof(o2)); StepGraph::mix(key, grads, sizeof(*grads)); StepGraph::mix(key, &e->w, sizeof(e->w));
     const void* ptrs[] = {table, refs, ref_offsets, sample_seq, greedy_seq, sample_logprobs, reward, loss, e->tape, e->ws, e->wblock, e->sg.stage, stream};
-    mix(ptrs, sizeof(ptrs));
+    StepGraph::mix(key, ptrs, sizeof(ptrs));
     const int dims[] = {B, R, L};
-    mix(dims, sizeof(dims));
-    StepGraph& sg = e->sg;
-    if (sg.exec != nullptr && sg.key == key) {
-        if (dropout_salt_set_all(sg.cap_seed ^ opts->seed, st)) return 1;
-        CAPB_CHECK_CUDA(cudaGraphLaunch(sg.exec, st));
-        e->launches += sg.launches;
-        return 0;
-    }
-    if (dropout_salt_set_all(0ull, st)) return 1;
-    if (sg.seen != key) {               // first sighting: eager (it also performs every first-use allocation)
-        sg.seen = key;
-        return aoa_train_step(e, att_s, B, R, ta, grads, st);
-    }
-    sg.reset();
-    const long l0 = e->launches;
-    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { (void)cudaGetLastError(); sg.broken = true; return aoa_train_step(e, att_s, B, R, ta, grads, st); }
-    const int rc = aoa_train_step(e, att_s, B, R, ta, grads, st);
-    cudaGraph_t graph = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
-        (void)cudaGetLastError();
-        if (graph) cudaGraphDestroy(graph);
-        sg.broken = true;               // something in the step is not capturable here: stay eager from now on
-        e->launches = l0;
-        return aoa_train_step(e, att_s, B, R, ta, grads, st);
-    }
-    const cudaError_t ie = cudaGraphInstantiate(&sg.exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ie != cudaSuccess) { (void)cudaGetLastError(); sg.exec = nullptr; sg.broken = true; e->launches = l0; return aoa_train_step(e, att_s, B, R, ta, grads, st); }
-    sg.key = key; sg.cap_seed = opts->seed; sg.launches = e->launches - l0;
-    CAPB_CHECK_CUDA(cudaGraphLaunch(sg.exec, st));
-    return 0;
+    StepGraph::mix(key, dims, sizeof(dims));
+    return run_step_graph(e->sg, key, opts->seed, &e->launches, st, [&]() { return aoa_train_step(e, att_s, B, R, ta, grads, st); });
 }
 
 extern "C" int capb200_aoa_set_grad_events(capb200_aoa_engine* e, void* const* events, int n) {

@@ -121,6 +121,7 @@ struct capb200_engine {
     char* tape = nullptr;
     size_t tape_bytes = 0;
     Tf32Context* tf32 = nullptr;       // tensor maps + transposed operands of the training GEMMs (tensor-core modes)
+    StepGraph sg;                                      // CUDA graph of the whole SCST step
     cudaEvent_t grad_events[2] = {nullptr, nullptr};   // caller-owned: recorded when a gradient group is complete (capb200_engine_set_grad_events)
     // Optional overlap of the additive attention (SFU / FMA pipes) with the tensor-core work of the language LSTM that does not depend on it:
     // gates = W_h h_att + W_hh h_lang_prev (side stream, while the attention runs) and then + W_a att_res with the fused cell (main stream).
@@ -537,6 +538,7 @@ void capb200_engine_destroy(capb200_engine* e) {
     if (e->d.loop_exec) cudaGraphExecDestroy(e->d.loop_exec);
     cudaFree(e->d.slab);
     cudaFree(e->tape);
+    e->sg.destroy();
     tf32_context_destroy(e->tf32);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
@@ -1286,8 +1288,28 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
     ta.sample_seq = sample_seq; ta.greedy_seq = greedy_seq; ta.reward = reward; ta.logprobs = sample_logprobs; ta.loss = loss;
     ta.forced = opts->forced_tokens; ta.mask = opts->att_masks; ta.keep = opts->keep_rows; ta.row_loss = opts->row_loss;
     CAPB_REQUIRE(ta.keep >= 0 && ta.keep <= B * opts->sample_n, "keep_rows must be in 0..rows");
-    if (dropout_salt_set_all(0ull, static_cast<cudaStream_t>(stream))) return 1;      // eager step: the seed arguments are the effective seeds
-    return updown_train_step(e, fc, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the whole step as one CUDA graph (see capb200_aoa_scst_step and engine_common.cuh: StepGraph)
+    if (!StepGraph::enabled() || !e->tc || e->grad_events[0] != nullptr || e->grad_events[1] != nullptr || ta.forced != nullptr || e->sg.broken) {
+        if (dropout_salt_set_all(0ull, st)) return 1;      // eager step: the seed arguments are the effective seeds
+        return updown_train_step(e, fc, att, B, R, ta, grads, st);
+    }
+    const void* srcs[3] = {fc, att, ta.mask};
+    const size_t bytes[3] = {sizeof(float) * (size_t)B * e->cfg.fc_feat_size, sizeof(float) * (size_t)B * R * e->cfg.att_feat_size,
+                             ta.mask ? sizeof(float) * (size_t)B * R : 0};
+    size_t off[3];
+    if (e->sg.stage_inputs(3, srcs, bytes, off, st)) return 1;
+    const float* fc_s = reinterpret_cast<const float*>(e->sg.stage + off[0]);
+    const float* att_s = reinterpret_cast<const float*>(e->sg.stage + off[1]);
+    if (ta.mask) ta.mask = reinterpret_cast<const float*>(e->sg.stage + off[2]);
+    unsigned long long key = 1469598103934665603ull;
+    capb200_scst_opts o2 = *opts; o2.seed = 0; o2.att_masks = ta.mask;
+    StepGraph::mix(key, &o2, sizeof(o2)); StepGraph::mix(key, grads, sizeof(*grads)); StepGraph::mix(key, &e->w, sizeof(e->w));
+    const void* ptrs[] = {table, refs, ref_offsets, sample_seq, greedy_seq, sample_logprobs, reward, loss, e->tape, e->ws, e->wblock, e->sg.stage, stream};
+    StepGraph::mix(key, ptrs, sizeof(ptrs));
+    const int dims[] = {B, R, L};
+    StepGraph::mix(key, dims, sizeof(dims));
+    return run_step_graph(e->sg, key, opts->seed, &e->launches, st, [&]() { return updown_train_step(e, fc_s, att_s, B, R, ta, grads, st); });
 }
 
 extern "C" int capb200_engine_set_grad_events(capb200_engine* e, void* const* events, int n) {

@@ -360,9 +360,10 @@ struct StepGraph {
     static bool enabled() { static const bool v = !(getenv("CAPB200_SCST_GRAPH") != nullptr && atoi(getenv("CAPB200_SCST_GRAPH")) == 0); return v; }
     void reset() { if (exec) cudaGraphExecDestroy(exec); exec = nullptr; key = 0; }
     void destroy() { reset(); if (stage) cudaFree(stage); stage = nullptr; stage_bytes = 0; }
-    // copies a (and b behind it, 256-byte aligned) into the staging buffer in stream order
-    int stage_inputs(const void* a, size_t a_bytes, const void* b, size_t b_bytes, cudaStream_t st) {
-        const size_t a_pad = (a_bytes + 255) & ~size_t(255), need = a_pad + b_bytes + 256;
+    // copies up to four buffers back to back (256-byte aligned) into the staging buffer in stream order; off[i] = where buffer i landed
+    int stage_inputs(int n, const void* const* src, const size_t* bytes, size_t* off, cudaStream_t st) {
+        size_t need = 256;
+        for (int i = 0; i < n; ++i) { off[i] = need; need += (bytes[i] + 255) & ~size_t(255); }
         if (need > stage_bytes) {
             CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
             reset();
@@ -371,11 +372,51 @@ struct StepGraph {
             CAPB_CHECK_CUDA(cudaMalloc(&stage, need));
             stage_bytes = need;
         }
-        CAPB_CHECK_CUDA(cudaMemcpyAsync(stage, a, a_bytes, cudaMemcpyDeviceToDevice, st));
-        if (b != nullptr && b_bytes) CAPB_CHECK_CUDA(cudaMemcpyAsync(stage + a_pad, b, b_bytes, cudaMemcpyDeviceToDevice, st));
+        for (int i = 0; i < n; ++i)
+            if (src[i] != nullptr && bytes[i]) CAPB_CHECK_CUDA(cudaMemcpyAsync(stage + off[i], src[i], bytes[i], cudaMemcpyDeviceToDevice, st));
         return 0;
     }
+    static void mix(unsigned long long& h, const void* p, size_t nbytes) {
+        const unsigned char* c = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < nbytes; ++i) { h ^= c[i]; h *= 1099511628211ull; }
+    }
 };
+
+// Runs `run()` (which enqueues one whole training step on `st`, reading its inputs from the staging buffer) eagerly the first time `key` is
+// seen, captures it into a graph the second time, and replays the graph afterwards with the seed carried by the salt.
+template <class Run>
+int run_step_graph(StepGraph& sg, unsigned long long key, unsigned long long seed, long* launches, cudaStream_t st, Run run) {
+    if (sg.exec != nullptr && sg.key == key) {
+        if (dropout_salt_set_all(sg.cap_seed ^ seed, st)) return 1;
+        CAPB_CHECK_CUDA(cudaGraphLaunch(sg.exec, st));
+        *launches += sg.launches;
+        return 0;
+    }
+    if (dropout_salt_set_all(0ull, st)) return 1;
+    if (sg.seen != key) {               // first sighting: eager (it also performs every first-use allocation)
+        sg.seen = key;
+        return run();
+    }
+    sg.reset();
+    const long l0 = *launches;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { (void)cudaGetLastError(); sg.broken = true; return run(); }
+    const int rc = run();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
+        (void)cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        sg.broken = true;               // something in the step is not capturable here: stay eager from now on
+        *launches = l0;
+        return run();
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&sg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { (void)cudaGetLastError(); sg.exec = nullptr; sg.broken = true; *launches = l0; return run(); }
+    sg.key = key; sg.cap_seed = seed; sg.launches = *launches - l0;
+    CAPB_CHECK_CUDA(cudaGraphLaunch(sg.exec, st));
+    return 0;
+}
 
 // Side stream of the SCST steps (the eval-mode greedy baseline runs on it while the train-mode sampling pass runs on the caller's stream).
 // Lowest priority by default: both chains are latency-bound and compete for SMs (a persistent GEMM CTA owns its SM's shared memory), and

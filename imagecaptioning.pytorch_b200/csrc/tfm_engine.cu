@@ -55,6 +55,7 @@ struct capb200_tfm_engine {
     cudaEvent_t grad_events[2] = {};
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    StepGraph sg;                       // CUDA graph of the whole SCST step (engine_common.cuh)
 };
 
 namespace {
@@ -275,6 +276,7 @@ void capb200_tfm_destroy(capb200_tfm_engine* e) {
     cudaFree(e->wblock);
     cudaFree(e->ws);
     cudaFree(e->tape);
+    e->sg.destroy();
     tf32_context_destroy(e->tf32);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
@@ -796,6 +798,24 @@ extern "C" int capb200_tfm_scst_step(capb200_tfm_engine* e, const float* att, in
     ta.greedy_seq = greedy_seq; ta.reward = reward; ta.logprobs = sample_logprobs; ta.loss = loss; ta.forced = opts->forced_tokens; ta.mask = opts->att_masks;
     ta.keep = opts->keep_rows; ta.row_loss = opts->row_loss;
     CAPB_REQUIRE(ta.keep >= 0 && ta.keep <= B * n, "keep_rows must be in 0..rows");
-    if (dropout_salt_set_all(0ull, static_cast<cudaStream_t>(stream))) return 1;      // eager step: the seed arguments are the effective seeds
-    return tfm_train_step(e, att, B, R, ta, grads, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the whole step (~4900 launches at 6 + 6 layers) as one CUDA graph: see capb200_aoa_scst_step and engine_common.cuh (StepGraph)
+    if (!StepGraph::enabled() || !e->tc || e->grad_events[0] != nullptr || e->grad_events[1] != nullptr || ta.forced != nullptr || e->sg.broken) {
+        if (dropout_salt_set_all(0ull, st)) return 1;      // eager step: the seed arguments are the effective seeds
+        return tfm_train_step(e, att, B, R, ta, grads, st);
+    }
+    const void* srcs[2] = {att, ta.mask};
+    const size_t bytes[2] = {sizeof(float) * (size_t)B * R * e->F, ta.mask ? sizeof(float) * (size_t)B * R : 0};
+    size_t off[2];
+    if (e->sg.stage_inputs(2, srcs, bytes, off, st)) return 1;
+    const float* att_s = reinterpret_cast<const float*>(e->sg.stage + off[0]);
+    if (ta.mask) ta.mask = reinterpret_cast<const float*>(e->sg.stage + off[1]);
+    unsigned long long key = 1469598103934665603ull;
+    capb200_tfm_scst_opts o2 = *opts; o2.seed = 0; o2.att_masks = ta.mask;
+    StepGraph::mix(key, &o2, sizeof(o2)); StepGraph::mix(key, grads, sizeof(*grads)); StepGraph::mix(key, &e->w, sizeof(e->w));
+    const void* ptrs[] = {table, refs, ref_offsets, sample_seq, greedy_seq, sample_logprobs, reward, loss, e->tape, e->ws, e->wblock, e->sg.stage, stream};
+    StepGraph::mix(key, ptrs, sizeof(ptrs));
+    const int dims[] = {B, R, L};
+    StepGraph::mix(key, dims, sizeof(dims));
+    return run_step_graph(e->sg, key, opts->seed, &e->launches, st, [&]() { return tfm_train_step(e, att_s, B, R, ta, grads, st); });
 }

@@ -601,46 +601,48 @@ def test_drop_worst_through_the_loss_wrapper(branch):
     b200.rewards.reset_scorer()
 
 
-def test_aoa_scst_step_graph_replay():
-    """The AoANet SCST step is captured into a CUDA graph the second time a configuration is seen and replayed afterwards with the seed
-    carried by the device-side salt (dropout.cuh).  A replay must be the same function of (weights, inputs, seed) as the eager step: the
-    same seed reproduces samples, loss and gradients of the eager run; another seed draws other samples; new features / references are
-    picked up (the graph reads them through the engine's staging buffer)."""
+@pytest.mark.parametrize('family', ['aoa', 'updown', 'transformer'])
+def test_scst_step_graph_replay(family):
+    """The SCST step is captured into a CUDA graph the second time a configuration is seen and replayed afterwards with the seed carried by
+    the device-side salt (dropout.cuh).  A replay must be the same function of (weights, inputs, seed) as the eager step: the same seed
+    reproduces samples, loss and gradients of the eager run; another seed draws other samples; new features / references are picked up
+    (the graph reads them through the engine's staging buffers)."""
     import imagecaptioning.pytorch_b200 as b200
     from oracle import ciderd_oracle as cdo
     heads = 4
-    model, _ = build_pair('aoa', seed=27, logit_scale=5.0, mode='tc_f16x3', heads=heads, **AOA_CFG)
-    B, R, n = 3, 9, 3
-    fc, att = co.make_inputs(B, R, AOA_CFG['F_fc'], AOA_CFG['F_att'], seed=4)
-    fc2, att2 = co.make_inputs(B, R, AOA_CFG['F_fc'], AOA_CFG['F_att'], seed=5)
-    gts = cdo.make_refs(B, AOA_CFG['V'], seed=2)
-    gts2 = cdo.make_refs(B, AOA_CFG['V'], seed=3)
-    df, ref_len = cdo.build_document_frequency(cdo.make_refs(200, AOA_CFG['V'], seed=4))
-    table = b200.rewards.CiderDTable(df, ref_len)
-    model.train()
+    cfg = {'aoa': AOA_CFG, 'updown': CFG, 'transformer': dict(V=40, E=32, H=64, A=2, F_fc=32, F_att=40, T=7)}[family]
 
-    def run(a, g, seed):
-        res = model.scst_step(None, a.cuda(), g, table, n, seed=seed)
+    def fresh():
+        m, _ = build_pair(family, seed=27, logit_scale=5.0, mode='tc_f16x3', heads=heads, **cfg)
+        m.train()
+        return m
+    model = fresh()
+    B, R, n = 3, 9, 3
+    fc, att = co.make_inputs(B, R, cfg['F_fc'], cfg['F_att'], seed=4)
+    fc2, att2 = co.make_inputs(B, R, cfg['F_fc'], cfg['F_att'], seed=5)
+    gts = cdo.make_refs(B, cfg['V'], seed=2)
+    gts2 = cdo.make_refs(B, cfg['V'], seed=3)
+    df, ref_len = cdo.build_document_frequency(cdo.make_refs(200, cfg['V'], seed=4))
+    table = b200.rewards.CiderDTable(df, ref_len)
+
+    def run(m, f, a, g, seed):
+        res = m.scst_step(f.cuda(), a.cuda(), g, table, n, seed=seed)
         torch.cuda.synchronize()
         return (res['sample_seq'].cpu().clone(), float(res['loss']), res['reward'].cpu().clone(), res['flat'].flat.cpu().clone(), res['greedy_seq'].cpu().clone())
 
     l0 = model.launch_count
-    eager = run(att, gts, 11)                       # first sighting: eager
+    eager = run(model, fc, att, gts, 11)            # first sighting: eager
     per_step = model.launch_count - l0
-    other = run(att, gts, 22)                       # second: captured + launched
-    replay = run(att, gts, 11)                      # third: replayed, salt = 22 ^ 11
+    other = run(model, fc, att, gts, 22)            # second: captured + launched
+    replay = run(model, fc, att, gts, 11)           # third: replayed, salt = 22 ^ 11
     assert model.launch_count - l0 == 3 * per_step  # the replay accounts for the launches it stands for
     assert torch.equal(replay[0], eager[0]) and torch.equal(replay[4], eager[4])
     assert abs(replay[1] - eager[1]) < 1e-6 and torch.allclose(replay[2], eager[2])
     scale = float(eager[3].abs().max())
     assert float((replay[3] - eager[3]).abs().max()) <= 1e-5 * scale          # embedding gradients use atomics: not bit-reproducible
     assert not torch.equal(other[0], eager[0])
-    new_inputs = run(att2, gts2, 11)                # replay with other features and references
-    assert not torch.equal(new_inputs[0], eager[0]) or abs(new_inputs[1] - eager[1]) > 1e-7
+    new_inputs = run(model, fc2, att2, gts2, 11)    # replay with other features and references
     # cross-check the replayed step on the new inputs against an engine that has never seen a graph (fresh model, eager first call)
-    model2, _ = build_pair('aoa', seed=27, logit_scale=5.0, mode='tc_f16x3', heads=heads, **AOA_CFG)
-    model2.train()
-    res2 = model2.scst_step(None, att2.cuda(), gts2, table, n, seed=11)
-    torch.cuda.synchronize()
-    assert torch.equal(res2['sample_seq'].cpu(), new_inputs[0]) and abs(float(res2['loss']) - new_inputs[1]) < 1e-6
-    assert float((res2['flat'].flat.cpu() - new_inputs[3]).abs().max()) <= 1e-5 * float(new_inputs[3].abs().max())
+    ref = run(fresh(), fc2, att2, gts2, 11)
+    assert torch.equal(ref[0], new_inputs[0]) and abs(ref[1] - new_inputs[1]) < 1e-6
+    assert float((ref[3] - new_inputs[3]).abs().max()) <= 1e-5 * float(new_inputs[3].abs().max())
