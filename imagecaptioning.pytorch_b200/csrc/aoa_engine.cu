@@ -739,7 +739,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
     if (wgrad(V1, H, (int)TN, tp.DL, V1, tp.outd, H, G.logit_w, H, 0, st)) return 1;
     if (colsum_launch((int)TN, V1, tp.DL, V1, G.logit_b, 0, st)) return 1;
     auto group_done = [&](int k) -> int {
-        if (e->grad_events[k]) CAPB_CHECK_CUDA(cudaEventRecord(e->grad_events[k], st));
+        if (record_group_event(e->grad_events[k], st)) return 1;
         return 0;
     };
     if (group_done(0)) return 1;                                        // logit
@@ -876,11 +876,12 @@ extern "C" int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, in
     // ---- the step as ONE CUDA graph.  Its ~1100 kernels are 5-30 us each and every launch boundary costs ~2 us on the stream, the host
     // needs ~3 ms to enqueue them, and nothing about the sequence depends on data: captured the second time a configuration is seen,
     // replayed afterwards with a fresh seed (dropout.cuh: seed salt).  The features are copied to an engine-owned buffer first so that the
-    // graph reads a stable address.  Not used while a caller listens to the gradient-group events (overlapped all-reduce: an event recorded
-    // inside a graph cannot be waited on from outside before it has executed) or replays forced tokens.
+    // graph reads a stable address.  The gradient-group events a data-parallel caller listens to (overlapped all-reduce) become external
+    // event-record nodes of the graph (record_group_event); the event handles are part of the key.  Not used when forced tokens are replayed.
+    static const bool graph_with_listener = !(getenv("CAPB200_SCST_GRAPH_SYNC") != nullptr && atoi(getenv("CAPB200_SCST_GRAPH_SYNC")) == 0);
     bool listening = false;
     for (int i = 0; i < 10; ++i) listening = listening || e->grad_events[i] != nullptr;
-    if (!StepGraph::enabled() || !e->tc || listening || ta.forced != nullptr || e->sg.broken) {
+    if (!StepGraph::enabled() || !e->tc || (listening && !graph_with_listener) || ta.forced != nullptr || e->sg.broken) {
         if (dropout_salt_set_all(0ull, st)) return 1;
         return aoa_train_step(e, att, B, R, ta, grads, st);
     }
@@ -895,6 +896,7 @@ extern "C" int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, in
     StepGraph::mix(key, &o2, sizeof(o2)); StepGraph::mix(key, grads, sizeof(*grads)); StepGraph::mix(key, &e->w, sizeof(e->w));
     const void* ptrs[] = {table, refs, ref_offsets, sample_seq, greedy_seq, sample_logprobs, reward, loss, e->tape, e->ws, e->wblock, e->sg.stage, stream};
     StepGraph::mix(key, ptrs, sizeof(ptrs));
+    StepGraph::mix(key, e->grad_events, sizeof(e->grad_events));
     const int dims[] = {B, R, L};
     StepGraph::mix(key, dims, sizeof(dims));
     return run_step_graph(e->sg, key, opts->seed, &e->launches, st, [&]() { return aoa_train_step(e, att_s, B, R, ta, grads, st); });

@@ -1196,7 +1196,7 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     if (sk.dgrad((int)TN, H, V1, tp.DL, V1, w.logit_w, H, tp.dOUT, H, 0)) return 1;          // dOUT = DL * W
     if (sk.wgrad(V1, H, (int)TN, tp.DL, V1, tp.out, H, G.logit_w, H, 0)) return 1;            // dW = DL^T * OUT
     if (colsum_launch((int)TN, V1, tp.DL, V1, G.logit_b, 0, st)) return 1;
-    if (e->grad_events[0]) CAPB_CHECK_CUDA(cudaEventRecord(e->grad_events[0], st));          // group 0 (logit) is final
+    if (record_group_event(e->grad_events[0], st)) return 1;                                  // group 0 (logit) is final
     CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dh0, 0, sizeof(float) * NH, st));
     CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dc0, 0, sizeof(float) * NH, st));
     CAPB_CHECK_CUDA(cudaMemsetAsync(tp.dh1, 0, sizeof(float) * NH, st));
@@ -1263,7 +1263,7 @@ int updown_train_step(capb200_engine* e, const float* fc, const float* att, int 
     rc |= sk.wgrad(H, Ff, B, tp.dpre_fc, H, fc, Ff, G.fc_embed_w, Ff, 0);
     rc |= colsum_launch(B, H, tp.dpre_fc, H, G.fc_embed_b, 0, st);
     e->launches += 30 + (tf32_context_launches(e->tf32) - tf32_l0);     // + transposes of the tcgen05 path
-    if (!rc && e->grad_events[1]) CAPB_CHECK_CUDA(cudaEventRecord(e->grad_events[1], st));
+    if (!rc && record_group_event(e->grad_events[1], st)) return 1;
     return rc;
 }
 
@@ -1290,7 +1290,7 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
     CAPB_REQUIRE(ta.keep >= 0 && ta.keep <= B * opts->sample_n, "keep_rows must be in 0..rows");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // the whole step as one CUDA graph (see capb200_aoa_scst_step and engine_common.cuh: StepGraph)
-    if (!StepGraph::enabled() || !e->tc || e->grad_events[0] != nullptr || e->grad_events[1] != nullptr || ta.forced != nullptr || e->sg.broken) {
+    if (!StepGraph::enabled() || !e->tc || ta.forced != nullptr || e->sg.broken) {
         if (dropout_salt_set_all(0ull, st)) return 1;      // eager step: the seed arguments are the effective seeds
         return updown_train_step(e, fc, att, B, R, ta, grads, st);
     }
@@ -1307,6 +1307,7 @@ extern "C" int capb200_updown_scst_step(capb200_engine* e, const float* fc, cons
     StepGraph::mix(key, &o2, sizeof(o2)); StepGraph::mix(key, grads, sizeof(*grads)); StepGraph::mix(key, &e->w, sizeof(e->w));
     const void* ptrs[] = {table, refs, ref_offsets, sample_seq, greedy_seq, sample_logprobs, reward, loss, e->tape, e->ws, e->wblock, e->sg.stage, stream};
     StepGraph::mix(key, ptrs, sizeof(ptrs));
+    StepGraph::mix(key, e->grad_events, sizeof(e->grad_events));
     const int dims[] = {B, R, L};
     StepGraph::mix(key, dims, sizeof(dims));
     return run_step_graph(e->sg, key, opts->seed, &e->launches, st, [&]() { return updown_train_step(e, fc_s, att_s, B, R, ta, grads, st); });

@@ -418,6 +418,17 @@ int run_step_graph(StepGraph& sg, unsigned long long key, unsigned long long see
     return 0;
 }
 
+// Records a caller-owned "gradient group complete" event.  Inside a stream capture (the step is being turned into a graph) the record
+// becomes an EXTERNAL event-record node: every replay records the event when the node's dependencies have executed, and a
+// cudaStreamWaitEvent issued on another stream after cudaGraphLaunch waits for exactly that (the overlapped all-reduce of grad_sync.py).
+inline int record_group_event(cudaEvent_t ev, cudaStream_t st) {
+    if (ev == nullptr) return 0;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    CAPB_CHECK_CUDA(cudaStreamIsCapturing(st, &cs));
+    CAPB_CHECK_CUDA(cudaEventRecordWithFlags(ev, st, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+    return 0;
+}
+
 // Side stream of the SCST steps (the eval-mode greedy baseline runs on it while the train-mode sampling pass runs on the caller's stream).
 // Lowest priority by default: both chains are latency-bound and compete for SMs (a persistent GEMM CTA owns its SM's shared memory), and
 // the sampling pass is the critical path -- its pending CTAs should be placed first.  CAPB200_SIDE_PRIORITY=0 gives both equal priority.

@@ -722,7 +722,7 @@ int tfm_train_step(capb200_tfm_engine* e, const float* att, int B, int R, const 
         }
     }
     if (rc) return 1;
-    if (e->grad_events[0]) CAPB_CHECK_CUDA(cudaEventRecord(e->grad_events[0], st));            // generator + decoder + target embedding
+    if (record_group_event(e->grad_events[0], st)) return 1;                                    // generator + decoder + target embedding
     rc |= ln_backward_launch(BR, D, tp.X[NE], D, w.enc_norm_a, tp.d_mem, D, 1e-6f, tp.dX, D, 0, tp.stats, G.enc_norm_a, G.enc_norm_b, 0, st);
     for (int l = NE - 1; l >= 0 && !rc; --l) {
         const capb200_tfm_enc_layer& Lw = w.enc[l];
@@ -751,7 +751,7 @@ int tfm_train_step(capb200_tfm_engine* e, const float* att, int B, int R, const 
     rc |= sk.wgrad(D, F, BR, tp.d_tmp, D, att, F, G.att_embed_w, F, 0);
     rc |= colsum(BR, D, tp.d_tmp, D, G.att_embed_b);
     nl += 2 + tf32_context_launches(e->tf32) - tf32_l0;
-    if (!rc && e->grad_events[1]) CAPB_CHECK_CUDA(cudaEventRecord(e->grad_events[1], st));     // encoder + att_embed
+    if (!rc && record_group_event(e->grad_events[1], st)) return 1;                             // encoder + att_embed
     return rc;
 }
 
@@ -800,7 +800,7 @@ extern "C" int capb200_tfm_scst_step(capb200_tfm_engine* e, const float* att, in
     CAPB_REQUIRE(ta.keep >= 0 && ta.keep <= B * n, "keep_rows must be in 0..rows");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // the whole step (~4900 launches at 6 + 6 layers) as one CUDA graph: see capb200_aoa_scst_step and engine_common.cuh (StepGraph)
-    if (!StepGraph::enabled() || !e->tc || e->grad_events[0] != nullptr || e->grad_events[1] != nullptr || ta.forced != nullptr || e->sg.broken) {
+    if (!StepGraph::enabled() || !e->tc || ta.forced != nullptr || e->sg.broken) {
         if (dropout_salt_set_all(0ull, st)) return 1;      // eager step: the seed arguments are the effective seeds
         return tfm_train_step(e, att, B, R, ta, grads, st);
     }
@@ -815,6 +815,7 @@ extern "C" int capb200_tfm_scst_step(capb200_tfm_engine* e, const float* att, in
     StepGraph::mix(key, &o2, sizeof(o2)); StepGraph::mix(key, grads, sizeof(*grads)); StepGraph::mix(key, &e->w, sizeof(e->w));
     const void* ptrs[] = {table, refs, ref_offsets, sample_seq, greedy_seq, sample_logprobs, reward, loss, e->tape, e->ws, e->wblock, e->sg.stage, stream};
     StepGraph::mix(key, ptrs, sizeof(ptrs));
+    StepGraph::mix(key, e->grad_events, sizeof(e->grad_events));
     const int dims[] = {B, R, L};
     StepGraph::mix(key, dims, sizeof(dims));
     return run_step_graph(e->sg, key, opts->seed, &e->launches, st, [&]() { return tfm_train_step(e, att_s, B, R, ta, grads, st); });

@@ -80,3 +80,18 @@ def test_data_parallel_replicas_see_updated_weights(family):
     oseq, olp = co.sample(fam1, fc, att, record_margin=margins)
     check_decode(fam1, fc, att, seq1, lp1, oseq, olp, margins)          # covers the second half of the batch = the GPU-1 replica
     assert not torch.equal(seq0.cpu(), seq1.cpu())                       # the update did change the captions
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+@pytest.mark.parametrize('family', ['aoa', 'updown', 'transformer'])
+def test_overlapped_gradient_sync_two_ranks(family):
+    """One process per GPU (torchrun, NCCL): see tests/gpu_sync_check.py."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    port = 29600 + {'aoa': 1, 'updown': 2, 'transformer': 3}[family]
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1', '--master-port', str(port),
+           os.path.join(here, 'gpu_sync_check.py'), family]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(here))
+    assert r.returncode == 0 and 'SYNC-OK' in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])

@@ -630,12 +630,12 @@ def test_scst_step_graph_replay(family):
         torch.cuda.synchronize()
         return (res['sample_seq'].cpu().clone(), float(res['loss']), res['reward'].cpu().clone(), res['flat'].flat.cpu().clone(), res['greedy_seq'].cpu().clone())
 
-    l0 = model.launch_count
-    eager = run(model, fc, att, gts, 11)            # first sighting: eager
-    per_step = model.launch_count - l0
+    eager = run(model, fc, att, gts, 11)            # first sighting: eager (this call also binds the weights)
+    l1 = model.launch_count
     other = run(model, fc, att, gts, 22)            # second: captured + launched
+    l2 = model.launch_count
     replay = run(model, fc, att, gts, 11)           # third: replayed, salt = 22 ^ 11
-    assert model.launch_count - l0 == 3 * per_step  # the replay accounts for the launches it stands for
+    assert model.launch_count - l2 == l2 - l1 > 100 # the replay accounts for the launches it stands for
     assert torch.equal(replay[0], eager[0]) and torch.equal(replay[4], eager[4])
     assert abs(replay[1] - eager[1]) < 1e-6 and torch.allclose(replay[2], eager[2])
     scale = float(eager[3].abs().max())
