@@ -665,7 +665,6 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
             } else if (load_token_column_launch(ta.labels, ta.ld_labels, t, N, tok, st)) return 1;
             if (ta.tokens_used != nullptr && store_token_column_launch(tok, N, ta.tokens_used, ta.Tl, t, st)) return 1;
         }
-        else CAPB_CHECK_CUDA(cudaMemcpyAsync(tok, tp.s_tokens, sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
         float* xt = tp.xt + (long)t * N * E;
         float* x1c = tp.x1c + (long)t * NH;
         float* gates = tp.gates + (long)t * N * 4 * H;
@@ -673,11 +672,9 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
         float *att_t = tp.att + (long)t * NH, *t2 = tp.t2 + (long)t * 2 * NH, *out_t = tp.out + (long)t * NH;
         const float* h_prev = t ? tp.h + (long)(t - 1) * NH : nullptr;
         const float* c_prev = t ? tp.c + (long)(t - 1) * NH : nullptr;
-        if (embed_relu_dropout_launch(N, E, tok, w.embed, xt, seed, (unsigned)t, p_lm, st)) return 1;
-        // x1c = mean[img] + ctx_drop(previous context vector)
-        if (t == 0) CAPB_CHECK_CUDA(cudaMemsetAsync(tp.tmpH, 0, sizeof(float) * NH, st));
-        else if (dropout_copy_launch(tp.out + (long)(t - 1) * NH, H, tp.tmpH, H, N, H, seed, 4, (unsigned)t, p_ctx, st)) return 1;
-        if (add_row_group_launch(N, H, n, tp.tmpH, H, tp.mean, H, x1c, H, st)) return 1;
+        // one launch: the step's tokens (sampling: the previous step's draw), xt = dropout(relu(embed)), x1c = mean[img] + ctx_drop(previous context)
+        if (aoa_step_inputs_launch(N, E, H, n, ta.xe ? tok : tp.s_tokens, ta.xe ? nullptr : tok, w.embed, xt, tp.mean, H, t ? tp.out + (long)(t - 1) * NH : nullptr, x1c,
+                                   seed, t, p_lm, p_ctx, st)) return 1;
         {
             GemmProblem g; g.M = N; g.N = 4 * H; g.nseg = 2;
             g.seg[0].A = xt; g.seg[0].lda = E; g.seg[0].W = w.att_lstm_w_ih; g.seg[0].ldw = E + H; g.seg[0].K = E;
@@ -699,9 +696,8 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
             g.epi.bias = w.att2ctx_b; g.epi.C = t2; g.epi.ldc = 2 * H;
             if (sk.gates(g)) return 1;
         }
-        if (glu_launch(N, H, t2, 2 * H, nullptr, 0, act(out_t, H), st)) return 1;
         float* outd = tp.outd + (long)t * H;                                   // [N][T][H]: batched logit backward
-        if (dropout_copy_launch(out_t, H, outd, (long)T * H, N, H, seed, 3, (unsigned)t, p_lm, st)) return 1;
+        if (glu_dropout_launch(N, H, t2, 2 * H, out_t, H, outd, (long)T * H, seed, t, p_lm, st)) return 1;
         float* logits = sample_logprobs + (long)t * V1;
         if (sk.lin(outd, (long)T * H, w.logit_w, H, w.logit_b, logits, ld_lp, N, V1, H, 0)) return 1;
         VocabStepArgs va;
@@ -716,7 +712,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
             }
         }
         if (vocab_step_launch(va, st)) return 1;
-        e->launches += 20;
+        e->launches += 16;
     }
 
     // ---- (4) reward and loss
@@ -756,19 +752,15 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
         float* d_qp = tp.D_QP + (long)t * NH;
         float* dg = tp.DG + (long)t * N * 4 * H;
         // d out_t = out_drop-masked logit gradient + what step t+1 received through its (dropped) context input
-        if (dropout_copy_launch(tp.dOUTD + (long)t * H, (long)T * H, tp.d_out, H, N, H, seed, 3, (unsigned)t, p_lm, st)) return 1;
-        if (add_inplace_launch(tp.d_out, tp.dctx, NH, st)) return 1;
-        if (glu_backward_launch(N, H, tp.t2 + (long)t * 2 * NH, 2 * H, tp.d_out, H, d_t2, 2 * H, st)) return 1;
+        if (glu_backward_fused_launch(N, H, tp.t2 + (long)t * 2 * NH, 2 * H, tp.dOUTD + (long)t * H, (long)T * H, tp.dctx, d_t2, 2 * H, seed, t, p_lm, st)) return 1;
         if (sk.dgrad(N, 2 * H, 2 * H, d_t2, 2 * H, w.att2ctx_w, 2 * H, tp.dX2, 2 * H, 0)) return 1;             // [d att | d h_att]
-        // attention: needs a contiguous d att
-        CAPB_CHECK_CUDA(cudaMemcpy2DAsync(tp.tmpH, sizeof(float) * H, tp.dX2, sizeof(float) * 2 * H, sizeof(float) * H, N, cudaMemcpyDeviceToDevice, st));
+        // attention: d att is the first half of dX2's rows (pitch 2H)
         if (cross_attn_backward_launch(B, n, heads, dk, R, tp.qp + (long)t * NH, H, tp.kv + H, tp.kv, 2 * H, seed, 5, t, p_at, tp.probs + (long)t * N * heads * R,
-                                       tp.tmpH, H, d_qp, H, tp.d_kv + H, tp.d_kv, 2 * H, st)) return 1;
+                                       tp.dX2, 2 * H, d_qp, H, tp.d_kv + H, tp.d_kv, 2 * H, st)) return 1;
         if (sk.dgrad(N, H, H, d_qp, H, w.attn_q_w, H, tp.d_qln, H, 0)) return 1;
         // d h_att = carried (from W_hh of step t+1) + att2ctx's h_att half + through the query LayerNorm
-        CAPB_CHECK_CUDA(cudaMemcpy2DAsync(tp.d_hatt, sizeof(float) * H, tp.dX2 + H, sizeof(float) * 2 * H, sizeof(float) * H, N, cudaMemcpyDeviceToDevice, st));
-        if (add_inplace_launch(tp.d_hatt, tp.dh, NH, st)) return 1;
-        if (ln_backward_launch(N, H, tp.h + (long)t * NH, H, w.attn_norm_a, tp.d_qln, H, 1e-6f, tp.d_hatt, H, 1, tp.stats, G.attn_norm_a, G.attn_norm_b, 1, st)) return 1;
+        if (ln_backward_launch(N, H, tp.h + (long)t * NH, H, w.attn_norm_a, tp.d_qln, H, 1e-6f, tp.d_hatt, H, 0, tp.stats, G.attn_norm_a, G.attn_norm_b, 1, st,
+                               tp.dX2 + H, 2 * H, tp.dh, H)) return 1;
         if (lstm_cell_backward_launch(N, H, tp.gates + (long)t * N * 4 * H, c_prev, tp.c + (long)t * NH, tp.d_hatt, nullptr, 0, 0, 0, seed, 0.f, tp.dc, dg, st)) return 1;
         if (sk.dgrad(N, E, 4 * H, dg, 4 * H, w.att_lstm_w_ih, E + H, tp.dxt, E, 0)) return 1;
         if (sk.dgrad(N, H, 4 * H, dg, 4 * H, w.att_lstm_w_ih + E, E + H, tp.d_x1c, H, 0)) return 1;
@@ -776,7 +768,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
         if (embed_backward_launch(N, E, tp.tok + (long)t * N, tp.xt + (long)t * N * E, tp.dxt, E, keep_lm, G.embed, st)) return 1;
         // the context input of step t is ctx_drop(out_{t-1}): its gradient flows to out_{t-1}
         if (t > 0 && dropout_copy_launch(tp.d_x1c, H, tp.dctx, H, N, H, seed, 4, (unsigned)t, p_ctx, st)) return 1;
-        e->launches += 22;
+        e->launches += 17;
     }
     // weight gradients batched over time (K = T*N rows)
     const int TN1 = (int)((long)(T - 1) * N);

@@ -32,9 +32,12 @@ __device__ __forceinline__ float bsum128(float v, float* sh) {
     __syncthreads();
     return (sh[0] + sh[1]) + (sh[2] + sh[3]);
 }
+// add1 / add2 (optional): two more addends of the output row (the other branches that reach the LayerNorm input), folded in here instead
+// of separate copy / add launches:  dx = [dx +] add1 + add2 + dLN
 __global__ void __launch_bounds__(128) ln_backward_kernel(int rows, int D, const float* __restrict__ x, long ld_x, const float* __restrict__ a,
                                                           const float* __restrict__ dy, long ld_dy, float eps, float* __restrict__ dx, long ld_dx,
-                                                          int accumulate, float2* __restrict__ stats) {
+                                                          int accumulate, float2* __restrict__ stats, const float* __restrict__ add1, long ld_a1,
+                                                          const float* __restrict__ add2, long ld_a2) {
     __shared__ float sh[4];
     const int row = blockIdx.x;
     const float* xr = x + (long)row * ld_x;
@@ -57,7 +60,9 @@ __global__ void __launch_bounds__(128) ln_backward_kernel(int rows, int D, const
     const float g_mean = g_sum / (float)D;
     const float k = (stdv > 0.f) ? inv * inv * g_dot / ((float)(D - 1) * stdv) : 0.f;
     for (int c = threadIdx.x; c < D; c += 128) {
-        const float v = inv * (gr[c] * __ldg(a + c) - g_mean) - k * (xr[c] - mean);
+        float v = inv * (gr[c] * __ldg(a + c) - g_mean) - k * (xr[c] - mean);
+        if (add1 != nullptr) v += add1[(long)row * ld_a1 + c];
+        if (add2 != nullptr) v += add2[(long)row * ld_a2 + c];
         float* o = dx + (long)row * ld_dx + c;
         *o = accumulate ? *o + v : v;
     }
@@ -103,6 +108,52 @@ __global__ void glu_backward_kernel(int rows, int H, const float* __restrict__ t
         const float g = dy[(long)r * ld_dy + j];
         dt[(long)r * ld_dt + j] = g * s;
         dt[(long)r * ld_dt + H + j] = g * a * s * (1.f - s);
+    }
+}
+
+// ---- fused element-wise steps of the AoANet decoder loop (each replaces two to four launches of ~2 us + a launch boundary) --------------------
+// inputs of step t, one CTA per row:  tok_dst[r] = tok_src[r];  xt[r] = dropout_2(relu(embed[tok]));  x1c[r] = mean[img] + dropout_4(out_prev[r])
+__global__ void __launch_bounds__(256) aoa_step_inputs_kernel(int E, int H, int rpi, const int* __restrict__ tok_src, int* __restrict__ tok_dst,
+                                                              const float* __restrict__ emb, float* __restrict__ xt, const float* __restrict__ mean, long ld_mean,
+                                                              const float* __restrict__ out_prev, float* __restrict__ x1c, unsigned long long seed,
+                                                              uint32_t step, float p_lm, float p_ctx) {
+    const int r = blockIdx.x;
+    const int tok = tok_src[r];
+    if (tok_dst != nullptr && threadIdx.x == 0) tok_dst[r] = tok;
+    const float* e = emb + (long)tok * E;
+    for (int c = threadIdx.x; c < E; c += 256) xt[(long)r * E + c] = fmaxf(__ldg(e + c), 0.f) * drop_scale(seed, 2u, step, (uint32_t)(r * E + c), p_lm);
+    const float* m = mean + (long)(r / rpi) * ld_mean;
+    for (int c = threadIdx.x; c < H; c += 256) {
+        float v = m[c];
+        if (out_prev != nullptr) v += out_prev[(long)r * H + c] * drop_scale(seed, 4u, step, (uint32_t)(r * H + c), p_ctx);
+        x1c[(long)r * H + c] = v;
+    }
+}
+
+// out[r, j] = t[r, j] * sigmoid(t[r, H + j]);  outd[r, j] = dropout_3(out[r, j])        (GLU + the output dropout, AoAModel.py:143,181)
+__global__ void glu_dropout_kernel(int rows, int H, const float* __restrict__ t, long ld_t, float* __restrict__ out, long ld_o, float* __restrict__ outd, long ld_d,
+                                   unsigned long long seed, uint32_t step, float p) {
+    const long total = (long)rows * H;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / H), j = (int)(i % H);
+        const float a = t[(long)r * ld_t + j], b = t[(long)r * ld_t + H + j];
+        const float v = a * (1.0f / (1.0f + expf(-b)));
+        out[(long)r * ld_o + j] = v;
+        outd[(long)r * ld_d + j] = v * drop_scale(seed, 3u, step, (uint32_t)i, p);
+    }
+}
+
+// d out = dropout_3(d outd) + d ctx (what step t+1 received through its context input);  then the GLU backward of glu_backward_kernel
+__global__ void glu_backward_fused_kernel(int rows, int H, const float* __restrict__ t, long ld_t, const float* __restrict__ d_outd, long ld_dd,
+                                          const float* __restrict__ dctx, float* __restrict__ dt, long ld_dt, unsigned long long seed, uint32_t step, float p) {
+    const long total = (long)rows * H;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / H), j = (int)(i % H);
+        const float g = d_outd[(long)r * ld_dd + j] * drop_scale(seed, 3u, step, (uint32_t)i, p) + dctx[i];
+        const float a = t[(long)r * ld_t + j], b = t[(long)r * ld_t + H + j];
+        const float sg = 1.0f / (1.0f + expf(-b));
+        dt[(long)r * ld_dt + j] = g * sg;
+        dt[(long)r * ld_dt + H + j] = g * a * sg * (1.f - sg);
     }
 }
 
@@ -432,8 +483,8 @@ int blocks_for(long n) {
 #define LAUNCH_OK() do { CAPB_CHECK_CUDA(cudaGetLastError()); return 0; } while (0)
 
 int ln_backward_launch(int rows, int D, const float* x, long ld_x, const float* a, const float* dy, long ld_dy, float eps, float* dx, long ld_dx, int accumulate,
-                       float* stats, float* da, float* db, int accumulate_params, cudaStream_t st) {
-    ln_backward_kernel<<<rows, 128, 0, st>>>(rows, D, x, ld_x, a, dy, ld_dy, eps, dx, ld_dx, accumulate, reinterpret_cast<float2*>(stats));
+                       float* stats, float* da, float* db, int accumulate_params, cudaStream_t st, const float* add1, long ld_a1, const float* add2, long ld_a2) {
+    ln_backward_kernel<<<rows, 128, 0, st>>>(rows, D, x, ld_x, a, dy, ld_dy, eps, dx, ld_dx, accumulate, reinterpret_cast<float2*>(stats), add1, ld_a1, add2, ld_a2);
     CAPB_CHECK_CUDA(cudaGetLastError());
     ln_param_grad_kernel<<<cdiv(D, 32), 256, 0, st>>>(rows, D, x, ld_x, dy, ld_dy, reinterpret_cast<const float2*>(stats), da, db, accumulate_params);
     LAUNCH_OK();
@@ -530,6 +581,25 @@ int cat_dropout_launch(int rows, int c1, int c2, const float* a, long ld_a, cons
 }
 int add_row_group_launch(int rows, int cols, int rpg, const float* a, long ld_a, const float* g, long ld_g, float* out, long ld_o, cudaStream_t st) {
     add_row_group_kernel<<<blocks_for((long)rows * cols), 256, 0, st>>>(rows, cols, rpg, a, ld_a, g, ld_g, out, ld_o);
+    LAUNCH_OK();
+}
+
+int aoa_step_inputs_launch(int rows, int E, int H, int rpi, const int* tok_src, int* tok_dst, const float* emb, float* xt, const float* mean, long ld_mean,
+                           const float* out_prev, float* x1c, unsigned long long seed, int step, float p_lm, float p_ctx, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    aoa_step_inputs_kernel<<<rows, 256, 0, st>>>(E, H, rpi, tok_src, tok_dst, emb, xt, mean, ld_mean, out_prev, x1c, seed, (uint32_t)step, p_lm, p_ctx);
+    LAUNCH_OK();
+}
+int glu_dropout_launch(int rows, int H, const float* t, long ld_t, float* out, long ld_o, float* outd, long ld_d, unsigned long long seed, int step, float p,
+                       cudaStream_t st) {
+    if (rows <= 0) return 0;
+    glu_dropout_kernel<<<blocks_for((long)rows * H), 256, 0, st>>>(rows, H, t, ld_t, out, ld_o, outd, ld_d, seed, (uint32_t)step, p);
+    LAUNCH_OK();
+}
+int glu_backward_fused_launch(int rows, int H, const float* t, long ld_t, const float* d_outd, long ld_dd, const float* dctx, float* dt, long ld_dt,
+                              unsigned long long seed, int step, float p, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    glu_backward_fused_kernel<<<blocks_for((long)rows * H), 256, 0, st>>>(rows, H, t, ld_t, d_outd, ld_dd, dctx, dt, ld_dt, seed, (uint32_t)step, p);
     LAUNCH_OK();
 }
 

@@ -1,5 +1,6 @@
 // Helpers shared by the engines (UpDown/NewFC in engine.cu, Transformer in tfm_engine.cu, AoA in aoa_engine.cu).
 #pragma once
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -353,13 +354,16 @@ int sample_decode_driver(DecodeBuffers& d, int V1, int T, int rows, int method, 
 struct StepGraph {
     cudaGraphExec_t exec = nullptr;
     unsigned long long key = 0, seen = 0, cap_seed = 0;
-    long launches = 0;
+    long launches = 0, replays = 0;
     char* stage = nullptr;
     size_t stage_bytes = 0;
     bool broken = false;
     static bool enabled() { static const bool v = !(getenv("CAPB200_SCST_GRAPH") != nullptr && atoi(getenv("CAPB200_SCST_GRAPH")) == 0); return v; }
     void reset() { if (exec) cudaGraphExecDestroy(exec); exec = nullptr; key = 0; }
-    void destroy() { reset(); if (stage) cudaFree(stage); stage = nullptr; stage_bytes = 0; }
+    void destroy() {
+        if (getenv("CAPB200_GRAPH_DEBUG") != nullptr && (exec || replays)) fprintf(stderr, "capb200: step graph replayed %ld times\n", replays);
+        reset(); if (stage) cudaFree(stage); stage = nullptr; stage_bytes = 0;
+    }
     // copies up to four buffers back to back (256-byte aligned) into the staging buffer in stream order; off[i] = where buffer i landed
     int stage_inputs(int n, const void* const* src, const size_t* bytes, size_t* off, cudaStream_t st) {
         size_t need = 256;
@@ -387,6 +391,7 @@ struct StepGraph {
 template <class Run>
 int run_step_graph(StepGraph& sg, unsigned long long key, unsigned long long seed, long* launches, cudaStream_t st, Run run) {
     if (sg.exec != nullptr && sg.key == key) {
+        sg.replays++;
         if (dropout_salt_set_all(sg.cap_seed ^ seed, st)) return 1;
         CAPB_CHECK_CUDA(cudaGraphLaunch(sg.exec, st));
         *launches += sg.launches;
@@ -414,6 +419,7 @@ int run_step_graph(StepGraph& sg, unsigned long long key, unsigned long long see
     cudaGraphDestroy(graph);
     if (ie != cudaSuccess) { (void)cudaGetLastError(); sg.exec = nullptr; sg.broken = true; *launches = l0; return run(); }
     sg.key = key; sg.cap_seed = seed; sg.launches = *launches - l0;
+    if (getenv("CAPB200_GRAPH_DEBUG") != nullptr) fprintf(stderr, "capb200: training step captured into a CUDA graph (%ld launches)\n", sg.launches);
     CAPB_CHECK_CUDA(cudaGraphLaunch(sg.exec, st));
     return 0;
 }

@@ -78,7 +78,8 @@ __device__ __forceinline__ unsigned long long gtimer() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define CAPB_TRACE(slot) do { if (p.trace != nullptr) p.trace[(long)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
+// compiled in only for the TRACE = true instantiation of the pair kernel (tools/gemm_trace.py): the production kernels carry no trace branches
+#define CAPB_TRACE(slot) do { if (TRACE && p.trace != nullptr) p.trace[(long)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
 
 template <int BN, int PASSES>
 struct TcCfg {
@@ -436,7 +437,7 @@ struct TcPairCfg {
     static_assert(kStages >= 2, "need at least a double buffer");
 };
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, bool TRACE = false>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_pair_kernel(const __grid_constant__ TcParams p) {
     using Cfg = TcPairCfg<BN, PASSES>;
     extern __shared__ uint8_t smem_raw[];
@@ -656,12 +657,12 @@ int launch_cfg(const TcParams& prm, cudaStream_t stream) {
 }
 
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, bool TRACE = false>
 int launch_pair(const TcParams& prm, cudaStream_t stream) {
     using Cfg = TcPairCfg<BN, PASSES>;
     static std::atomic<unsigned long long> attr_set{0};
     if (first_use_on_device(attr_set)) {
-        CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        CAPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<BN, PASSES, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     }
     TcParams prm2 = prm;
     prm2.tiles_n = (int)cdiv(prm.N, BN);
@@ -680,7 +681,7 @@ int launch_pair(const TcParams& prm, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CAPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BN, PASSES>, prm2));
+    CAPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BN, PASSES, TRACE>, prm2));
     return 0;
 }
 
@@ -822,7 +823,9 @@ int gemm_tc_plan_launch(GemmTcPlan* plan, const GemmEpilogue* epi_override, int 
     if (plan->pair) {
         switch (plan->bn) {
             case 128: return plan->passes == 3 ? launch_pair<128, 3>(prm, stream) : launch_pair<128, 1>(prm, stream);
-            case 144: return plan->passes == 3 ? launch_pair<144, 3>(prm, stream) : launch_pair<144, 1>(prm, stream);
+            case 144:
+                if (prm.trace != nullptr && plan->passes == 3) return launch_pair<144, 3, true>(prm, stream);      // capb200_gemm_trace only
+                return plan->passes == 3 ? launch_pair<144, 3>(prm, stream) : launch_pair<144, 1>(prm, stream);
             case 192: return plan->passes == 3 ? launch_pair<192, 3>(prm, stream) : launch_pair<192, 1>(prm, stream);
             case 256: return plan->passes == 3 ? launch_pair<256, 3>(prm, stream) : launch_pair<256, 1>(prm, stream);
         }

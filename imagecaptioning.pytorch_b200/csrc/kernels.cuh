@@ -176,7 +176,15 @@ int add_strided_launch(float* a, const float* b, long ld_b, int rows, int cols, 
 
 // ---- aoa_train_kernels.cu (AoANet training step)
 int ln_backward_launch(int rows, int D, const float* x, long ld_x, const float* a, const float* dy, long ld_dy, float eps, float* dx, long ld_dx, int accumulate,
-                       float* stats, float* da, float* db, int accumulate_params, cudaStream_t st);
+                       float* stats, float* da, float* db, int accumulate_params, cudaStream_t st, const float* add1 = nullptr, long ld_a1 = 0,
+                       const float* add2 = nullptr, long ld_a2 = 0);
+// fused element-wise steps of the AoANet decoder loop (aoa_train_kernels.cu)
+int aoa_step_inputs_launch(int rows, int E, int H, int rpi, const int* tok_src, int* tok_dst, const float* emb, float* xt, const float* mean, long ld_mean,
+                           const float* out_prev, float* x1c, unsigned long long seed, int step, float p_lm, float p_ctx, cudaStream_t st);
+int glu_dropout_launch(int rows, int H, const float* t, long ld_t, float* out, long ld_o, float* outd, long ld_d, unsigned long long seed, int step, float p,
+                       cudaStream_t st);
+int glu_backward_fused_launch(int rows, int H, const float* t, long ld_t, const float* d_outd, long ld_dd, const float* dctx, float* dt, long ld_dt,
+                              unsigned long long seed, int step, float p, cudaStream_t st);
 int glu_backward_launch(int rows, int H, const float* t, long ld_t, const float* dy, long ld_dy, float* dt, long ld_dt, cudaStream_t st);
 // ---- seed salt (dropout.cuh): effective seed of every dropout / sampling kernel = seed argument XOR salt; uploaded in stream order
 int dropout_salt_set_scst(unsigned long long salt, cudaStream_t st);
