@@ -877,21 +877,24 @@ extern "C" int capb200_aoa_scst_step(capb200_aoa_engine* e, const float* att, in
         if (dropout_salt_set_all(0ull, st)) return 1;
         return aoa_train_step(e, att, B, R, ta, grads, st);
     }
+    cudaStream_t gst = e->sg.enter(st);             // a capturable engine-owned stream, ordered after the caller's stream
     const void* srcs[2] = {att, ta.mask};
     const size_t bytes[2] = {sizeof(float) * (size_t)B * R * e->F, ta.mask ? sizeof(float) * (size_t)B * R : 0};
     size_t off[2];
-    if (e->sg.stage_inputs(2, srcs, bytes, off, st)) return 1;
+    if (e->sg.stage_inputs(2, srcs, bytes, off, gst)) return 1;
     const float* att_s = reinterpret_cast<const float*>(e->sg.stage + off[0]);
     if (ta.mask) ta.mask = reinterpret_cast<const float*>(e->sg.stage + off[1]);
     unsigned long long key = 1469598103934665603ull;
     capb200_aoa_scst_opts o2 = *opts; o2.seed = 0; o2.att_masks = ta.mask;
     StepGraph::mix(key, &o2, sizeof(o2)); StepGraph::mix(key, grads, sizeof(*grads)); StepGraph::mix(key, &e->w, sizeof(e->w));
-    const void* ptrs[] = {table, refs, ref_offsets, sample_seq, greedy_seq, sample_logprobs, reward, loss, e->tape, e->ws, e->wblock, e->sg.stage, stream};
+    const void* ptrs[] = {table, refs, ref_offsets, sample_seq, greedy_seq, sample_logprobs, reward, loss, e->tape, e->ws, e->wblock, e->sg.stage, gst};
     StepGraph::mix(key, ptrs, sizeof(ptrs));
     StepGraph::mix(key, e->grad_events, sizeof(e->grad_events));
     const int dims[] = {B, R, L};
     StepGraph::mix(key, dims, sizeof(dims));
-    return run_step_graph(e->sg, key, opts->seed, &e->launches, st, [&]() { return aoa_train_step(e, att_s, B, R, ta, grads, st); });
+    const int rc_graph = run_step_graph(e->sg, key, opts->seed, &e->launches, gst, [&]() { return aoa_train_step(e, att_s, B, R, ta, grads, gst); });
+    if (e->sg.leave(st, gst)) return 1;
+    return rc_graph;
 }
 
 extern "C" int capb200_aoa_set_grad_events(capb200_aoa_engine* e, void* const* events, int n) {

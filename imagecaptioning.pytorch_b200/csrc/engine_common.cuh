@@ -358,11 +358,33 @@ struct StepGraph {
     char* stage = nullptr;
     size_t stage_bytes = 0;
     bool broken = false;
+    // The caller's stream is usually torch's legacy default stream, which cannot be captured: the step runs on an engine-owned stream that
+    // waits for the caller's stream on entry (enter) and that the caller's stream waits for on exit (leave).
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    cudaStream_t enter(cudaStream_t caller) {
+        if (stream == nullptr) {
+            if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); broken = true; return caller; }
+        }
+        if (cudaEventRecord(ev_in, caller) != cudaSuccess || cudaStreamWaitEvent(stream, ev_in, 0) != cudaSuccess) { (void)cudaGetLastError(); broken = true; return caller; }
+        return stream;
+    }
+    int leave(cudaStream_t caller, cudaStream_t used) {
+        if (used == caller) return 0;
+        CAPB_CHECK_CUDA(cudaEventRecord(ev_out, used));
+        CAPB_CHECK_CUDA(cudaStreamWaitEvent(caller, ev_out, 0));
+        return 0;
+    }
     static bool enabled() { static const bool v = !(getenv("CAPB200_SCST_GRAPH") != nullptr && atoi(getenv("CAPB200_SCST_GRAPH")) == 0); return v; }
     void reset() { if (exec) cudaGraphExecDestroy(exec); exec = nullptr; key = 0; }
     void destroy() {
         if (getenv("CAPB200_GRAPH_DEBUG") != nullptr && (exec || replays)) fprintf(stderr, "capb200: step graph replayed %ld times\n", replays);
         reset(); if (stage) cudaFree(stage); stage = nullptr; stage_bytes = 0;
+        if (ev_in) cudaEventDestroy(ev_in);
+        if (ev_out) cudaEventDestroy(ev_out);
+        if (stream) cudaStreamDestroy(stream);
+        ev_in = ev_out = nullptr; stream = nullptr;
     }
     // copies up to four buffers back to back (256-byte aligned) into the staging buffer in stream order; off[i] = where buffer i landed
     int stage_inputs(int n, const void* const* src, const size_t* bytes, size_t* off, cudaStream_t st) {
