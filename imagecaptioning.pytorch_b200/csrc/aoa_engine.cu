@@ -683,8 +683,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
             g.epi.bias = e->bsum; g.epi.C = gates; g.epi.ldc = 4 * H;
             if (sk.gates(g)) return 1;
         }
-        if (lstm_pointwise_launch(N, H, gates, 4 * H, nullptr, c_prev, H, c_t, H, act(h_t, H), nullptr, 0, nullptr, st)) return 1;
-        if (layer_norm_launch(N, H, h_t, H, w.attn_norm_a, w.attn_norm_b, 1e-6f, act(qln, H), st)) return 1;
+        if (lstm_ln_launch(N, H, gates, 4 * H, c_prev, H, c_t, H, h_t, H, w.attn_norm_a, w.attn_norm_b, 1e-6f, qln, H, st)) return 1;      // cell + attention.norm
         if (sk.lin(qln, H, w.attn_q_w, H, w.attn_q_b, qp, H, N, H, H, 0)) return 1;
         // AoAModel.py:168 passes (query, value = p_att[..., :H], key = p_att[..., H:])
         if (cross_attn_train_launch(N, n, heads, dk, R, qp, H, tp.kv + H, tp.kv, 2 * H, seed, 5, t, p_at, att_t, H, tp.probs + (long)t * N * heads * R, st,
@@ -712,7 +711,7 @@ int aoa_train_step(capb200_aoa_engine* e, const float* att, int B, int R, const 
             }
         }
         if (vocab_step_launch(va, st)) return 1;
-        e->launches += 16;
+        e->launches += 15;
     }
 
     // ---- (4) reward and loss

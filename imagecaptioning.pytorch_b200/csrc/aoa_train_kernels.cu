@@ -175,14 +175,19 @@ struct SeqAttn {
     long ld_mask;
 };
 
+// Shared-memory rows are padded to W = dk + 4 floats: rows stay 16-byte aligned, so every inner product walks them with 128-bit loads
+// (one LDS.128 per four multiply-adds instead of two or three LDS.32 per multiply-add; the scalar form was shared-memory-bandwidth
+// bound: 72 us per backward launch at 36 regions x 128 columns), and W/4 = 33 chunks per row keeps the per-lane row starts on distinct banks.
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float s) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, s)))); }
+
 __global__ void __launch_bounds__(256) seq_attn_train_kernel(SeqAttn a, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                                                              float* __restrict__ out, long ld_out) {
-    extern __shared__ float sm[];
-    const int R = a.n_keys, dk = a.dk, W = dk + 1;
+    extern __shared__ __align__(16) float sm[];
+    const int R = a.n_keys, dk = a.dk, W = dk + 4, dk4 = dk >> 2;
     float* sk = sm;                 // [R][W]
     float* sv = sk + R * W;
-    float* sp = sv + R * W;         // [warps][R]
-    float* sq = sp + 8 * R;         // [warps][dk]
+    float* sq = sv + R * W;         // [warps][dk]
+    float* sp = sq + 8 * dk;        // [warps][R]
     const int b = blockIdx.x, head = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const int nq = a.q_hi - a.q_lo;
@@ -207,7 +212,9 @@ __global__ void __launch_bounds__(256) seq_attn_train_kernel(SeqAttn a, const fl
         float mx = -INFINITY;
         for (int r = lane; r < vis; r += 32) {
             float s = 0.f;
-            for (int c = 0; c < dk; ++c) s = fmaf(qs[c], sk[r * W + c], s);
+            const float4* kr = reinterpret_cast<const float4*>(sk + r * W);
+            const float4* q4 = reinterpret_cast<const float4*>(qs);
+            for (int c = 0; c < dk4; ++c) s = dot4(q4[c], kr[c], s);
             s *= a.scale;
             if (a.key_mask != nullptr && a.key_mask[(long)b * a.ld_mask + r] == 0.f) s = -INFINITY;     // scores.masked_fill(mask == 0, -inf)  (TransformerModel.py:157-158)
             p[r] = s;
@@ -221,22 +228,27 @@ __global__ void __launch_bounds__(256) seq_attn_train_kernel(SeqAttn a, const fl
         for (int r = lane; r < vis; r += 32)
             p[r] = p[r] * inv * drop_scale(a.seed, a.site, 0u, (uint32_t)((((long)b * a.heads + head) * a.idx_L + qi) * a.idx_L + r), a.p_drop);
         __syncwarp();
-        for (int c = lane; c < dk; c += 32) {
-            float acc = 0.f;
-            for (int r = 0; r < vis; ++r) acc = fmaf(p[r], sv[r * W + c], acc);
-            out[qrow * ld_out + head * dk + c] = acc;
+        for (int c4 = lane; c4 < dk4; c4 += 32) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < vis; ++r) {
+                const float w = p[r];
+                const float4 x = *reinterpret_cast<const float4*>(sv + r * W + 4 * c4);
+                acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y); acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
+            }
+            float* o = out + qrow * ld_out + head * dk + 4 * c4;
+            o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
         }
         __syncwarp();
     }
 }
 
-// backward over ALL queries [0, n_keys) of a sequence: recomputes the probabilities; every chunk CTA rebuilds P and dS (cheap) and writes
-// its share of the dq | dk | dv elements of this (sequence, head) slice
+// backward over ALL queries [0, n_keys) of a sequence: recomputes the probabilities; every chunk CTA rebuilds P and dS and writes its share
+// of the dq | dk | dv elements of this (sequence, head) slice
 __global__ void __launch_bounds__(256) seq_attn_backward_kernel(SeqAttn a, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                                                                 const float* __restrict__ d_out, long ld_do, float* __restrict__ dq, float* __restrict__ dk_,
                                                                 float* __restrict__ dv, long ld_d) {
-    extern __shared__ float sm[];
-    const int R = a.n_keys, dk = a.dk, W = dk + 1;
+    extern __shared__ __align__(16) float sm[];
+    const int R = a.n_keys, dk = a.dk, W = dk + 4, dk4 = dk >> 2;
     float* sq = sm;                 // [R][W]
     float* sk = sq + R * W;
     float* sv = sk + R * W;
@@ -257,12 +269,14 @@ __global__ void __launch_bounds__(256) seq_attn_backward_kernel(SeqAttn a, const
     // P = softmax(q k^T * scale) row by row (one warp per query row); invisible keys get probability 0
     for (int qi = warp; qi < R; qi += nw) {
         const int vis = a.causal ? qi + 1 : R;
+        const float4* q4 = reinterpret_cast<const float4*>(sq + qi * W);
         float mx = -INFINITY;
         for (int r = lane; r < R; r += 32) {
             float s = -INFINITY;
             if (r < vis) {
                 s = 0.f;
-                for (int c = 0; c < dk; ++c) s = fmaf(sq[qi * W + c], sk[r * W + c], s);
+                const float4* kr = reinterpret_cast<const float4*>(sk + r * W);
+                for (int c = 0; c < dk4; ++c) s = dot4(q4[c], kr[c], s);
                 s *= a.scale;
                 if (a.key_mask != nullptr && a.key_mask[(long)b * a.ld_mask + r] == 0.f) s = -INFINITY;
             }
@@ -280,25 +294,32 @@ __global__ void __launch_bounds__(256) seq_attn_backward_kernel(SeqAttn a, const
         }
     }
     __syncthreads();
-    const int total = R * dk;
+    const int total = R * dk4;          // output elements in units of four columns
     const int e_lo = (int)(((long)total * blockIdx.z) / gridDim.z), e_hi = (int)(((long)total * (blockIdx.z + 1)) / gridDim.z);
-    // dV[r, c] = sum_qi P[qi, r] * D[qi, r] * dO[qi, c]
+    // dV[r, c..c+3] = sum_qi P[qi, r] * D[qi, r] * dO[qi, c..c+3]
     for (int i = e_lo + threadIdx.x; i < e_hi; i += blockDim.x) {
-        const int r = i / dk, c = i % dk;
-        float acc = 0.f;
-        for (int qi = a.causal ? r : 0; qi < R; ++qi) acc = fmaf(P[qi * R + r] * DS[qi * R + r], sd[qi * W + c], acc);
-        dv[((long)b * a.b_stride + (long)r * a.p_stride) * ld_d + head * dk + c] = acc;
+        const int r = i / dk4, c = 4 * (i % dk4);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int qi = a.causal ? r : 0; qi < R; ++qi) {
+            const float w = P[qi * R + r] * DS[qi * R + r];
+            const float4 x = *reinterpret_cast<const float4*>(sd + qi * W + c);
+            acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y); acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
+        }
+        float* o = dv + ((long)b * a.b_stride + (long)r * a.p_stride) * ld_d + head * dk + c;
+        o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
     }
     __syncthreads();
     // d score: dP = (dO V^T) * D ; dS = P * (dP - sum_r P dP)
     for (int qi = warp; qi < R; qi += nw) {
         const int vis = a.causal ? qi + 1 : R;
+        const float4* d4 = reinterpret_cast<const float4*>(sd + qi * W);
         float dot = 0.f;
         for (int r = lane; r < R; r += 32) {
             float dp = 0.f;
             if (r < vis) {
                 float s = 0.f;
-                for (int c = 0; c < dk; ++c) s = fmaf(sd[qi * W + c], sv[r * W + c], s);
+                const float4* vr = reinterpret_cast<const float4*>(sv + r * W);
+                for (int c = 0; c < dk4; ++c) s = dot4(d4[c], vr[c], s);
                 dp = s * DS[qi * R + r];
             }
             DS[qi * R + r] = dp;
@@ -310,15 +331,18 @@ __global__ void __launch_bounds__(256) seq_attn_backward_kernel(SeqAttn a, const
     }
     __syncthreads();
     for (int i = e_lo + threadIdx.x; i < e_hi; i += blockDim.x) {
-        const int r = i / dk, c = i % dk;
-        float aq = 0.f, ak = 0.f;
+        const int r = i / dk4, c = 4 * (i % dk4);
+        float4 aq = make_float4(0.f, 0.f, 0.f, 0.f), ak = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int j = 0; j < R; ++j) {
-            aq = fmaf(DS[r * R + j], sk[j * W + c], aq);          // dQ[r] = sum_j dS[r, j] K[j]
-            ak = fmaf(DS[j * R + r], sq[j * W + c], ak);          // dK[r] = sum_j dS[j, r] Q[j]
+            const float w1 = DS[r * R + j], w2 = DS[j * R + r];
+            const float4 kk = *reinterpret_cast<const float4*>(sk + j * W + c);          // dQ[r] = sum_j dS[r, j] K[j]
+            const float4 qq = *reinterpret_cast<const float4*>(sq + j * W + c);          // dK[r] = sum_j dS[j, r] Q[j]
+            aq.x = fmaf(w1, kk.x, aq.x); aq.y = fmaf(w1, kk.y, aq.y); aq.z = fmaf(w1, kk.z, aq.z); aq.w = fmaf(w1, kk.w, aq.w);
+            ak.x = fmaf(w2, qq.x, ak.x); ak.y = fmaf(w2, qq.y, ak.y); ak.z = fmaf(w2, qq.z, ak.z); ak.w = fmaf(w2, qq.w, ak.w);
         }
         const long g = ((long)b * a.b_stride + (long)r * a.p_stride) * ld_d + head * dk + c;
-        dq[g] = aq;
-        dk_[g] = ak;
+        dq[g] = aq.x; dq[g + 1] = aq.y; dq[g + 2] = aq.z; dq[g + 3] = aq.w;
+        dk_[g] = ak.x; dk_[g + 1] = ak.y; dk_[g + 2] = ak.z; dk_[g + 3] = ak.w;
     }
 }
 
@@ -353,7 +377,7 @@ __global__ void __launch_bounds__(128) cross_attn_train_kernel(int rows, int rpi
 }
 
 // backward: one CTA per (image, head) walks the image's rpi rows; dq written, dK / dV accumulated (+=) into the per-image buffers
-__global__ void __launch_bounds__(256) cross_attn_backward_kernel(int rpi, int heads, int dk, int R, const float* __restrict__ q, long ld_q,
+__global__ void __launch_bounds__(512) cross_attn_backward_kernel(int rpi, int heads, int dk, int R, const float* __restrict__ q, long ld_q,
                                                                   const float* __restrict__ kk, const float* __restrict__ vv, long ld_kv, float scale,
                                                                   unsigned long long seed, uint32_t site, uint32_t step, float p_drop,
                                                                   const float* __restrict__ probs, const float* __restrict__ d_out, long ld_do,
@@ -503,7 +527,8 @@ int seq_attn_train_launch(int seqs, int n_keys, int q_lo, int q_hi, int heads, i
                           const float* k, const float* v, long ld, unsigned long long seed, int site, float p, float* out, long ld_out, const float* key_mask,
                           long ld_mask, cudaStream_t st) {
     if (seqs <= 0 || q_hi <= q_lo) return 0;
-    const size_t smem = sizeof(float) * ((size_t)2 * n_keys * (dk + 1) + 8 * n_keys + 8 * dk);
+    CAPB_REQUIRE((dk & 3) == 0, "self-attention (train): the head width must be a multiple of 4");
+    const size_t smem = sizeof(float) * ((size_t)2 * n_keys * (dk + 4) + 8 * n_keys + 8 * dk);
     CAPB_REQUIRE(smem <= 200 * 1024, "self-attention (train): keys * head width too large for the shared-memory staging");
     static std::atomic<unsigned long long> configured{0};
     if (first_use_on_device(configured)) {
@@ -519,7 +544,8 @@ int seq_attn_backward_launch(int seqs, int n_keys, int heads, int dk, int causal
                              const float* v, long ld, unsigned long long seed, int site, float p, const float* d_out, long ld_do, float* dq, float* dk_,
                              float* dv, long ld_d, const float* key_mask, long ld_mask, cudaStream_t st) {
     if (seqs <= 0) return 0;
-    const size_t smem = sizeof(float) * ((size_t)4 * n_keys * (dk + 1) + 2 * n_keys * n_keys);
+    CAPB_REQUIRE((dk & 3) == 0, "self-attention backward: the head width must be a multiple of 4");
+    const size_t smem = sizeof(float) * ((size_t)4 * n_keys * (dk + 4) + 2 * n_keys * n_keys);
     CAPB_REQUIRE(smem <= 200 * 1024, "self-attention backward: shared-memory footprint too large");
     static std::atomic<unsigned long long> configured{0};
     if (first_use_on_device(configured)) {
@@ -528,7 +554,11 @@ int seq_attn_backward_launch(int seqs, int n_keys, int heads, int dk, int causal
     SeqAttn a;
     a.n_keys = n_keys; a.dk = dk; a.heads = heads; a.q_lo = 0; a.q_hi = n_keys; a.causal = causal; a.idx_L = idx_L; a.b_stride = b_stride; a.p_stride = p_stride;
     a.ld = ld; a.scale = 1.0f / sqrtf((float)dk); a.p_drop = p; a.seed = seed; a.site = (uint32_t)site; a.key_mask = key_mask; a.ld_mask = ld_mask;
-    seq_attn_backward_kernel<<<dim3(seqs, heads, attn_chunks(seqs, heads, n_keys)), 256, smem, st>>>(a, q, k, v, d_out, ld_do, dq, dk_, dv, ld_d);
+    // every chunk CTA rebuilds P and dS (half of the kernel's work) and owns a whole SM (up to 150 KB of shared memory): chunks only help while
+    // the grid stays within one wave (measured: 4 chunks at 80 (image, head) pairs = 320 CTAs took 108 us, 1 chunk 72 us)
+    int z = 148 / (seqs * heads);
+    z = z < 1 ? 1 : (z > 4 ? 4 : z);
+    seq_attn_backward_kernel<<<dim3(seqs, heads, z), 256, smem, st>>>(a, q, k, v, d_out, ld_do, dq, dk_, dv, ld_d);
     LAUNCH_OK();
 }
 // the refiner / encoder form: sequences = images, keys = queries = the R regions, rows image-major
@@ -561,7 +591,8 @@ int cross_attn_backward_launch(int B, int rpi, int heads, int dk, int R, const f
     if (first_use_on_device(configured)) {
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
-    cross_attn_backward_kernel<<<dim3(B, heads), 256, smem, st>>>(rpi, heads, dk, R, q, ld_q, kk, vv, ld_kv, 1.0f / sqrtf((float)dk), seed, (uint32_t)site,
+    // 512 threads: the kernel is a chain of global-load rounds (K, V, q, d_out, the dK / dV read-modify-write) on only B x heads CTAs
+    cross_attn_backward_kernel<<<dim3(B, heads), 512, smem, st>>>(rpi, heads, dk, R, q, ld_q, kk, vv, ld_kv, 1.0f / sqrtf((float)dk), seed, (uint32_t)site,
                                                                    (uint32_t)step, p, probs, d_out, ld_do, dq, ld_dq, dkk, dvv, ld_dkv, rpi1, row_mod > 0 ? row_mod : B * rpi1);
     LAUNCH_OK();
 }

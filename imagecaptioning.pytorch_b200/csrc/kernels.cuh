@@ -26,6 +26,8 @@ int lstm_pointwise_launch(int rows, int H, const float* gates, long ld_g, const 
                           float* c_out, long ld_co, ActView h_out, const float* gather_bias, long ld_gb, const int* gather_idx,
                           cudaStream_t stream);
 int relu_copy_launch(const float* x, long n, ActView out_flat, cudaStream_t stream);   // out = relu(x) (+ split planes), flat
+int lstm_ln_launch(int rows, int H, const float* gates, long ld_g, const float* c_prev, long ld_cp, float* c_out, long ld_co, float* h_out, long ld_h,
+                   const float* ln_a, const float* ln_b, float eps, float* ln_out, long ld_ln, cudaStream_t stream);   // LSTM cell + LayerNorm of h
 int maxout_pointwise_launch(int rows, int H, const float* sums, long ld_s, const int* src_row, const float* c_prev, long ld_cp,
                             float* c_out, long ld_co, ActView h_out, cudaStream_t stream);
 int additive_attention_launch(int n_images, int rpi, int R, int A, int H, const float* att_h, long ld_ah, const float* p_att, long ld_pa,

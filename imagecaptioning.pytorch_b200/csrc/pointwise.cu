@@ -101,6 +101,50 @@ __global__ void lstm_pointwise_kernel(int rows, int H, const float* __restrict__
     }
 }
 
+// LSTM cell + the LayerNorm of its output in one launch (AoANet decoder: core.attention.norm(h_att) follows the cell, AoAModel.py:166-168),
+// one CTA of 256 threads per row, H <= 2048: the cell of lstm_pointwise_kernel (same expressions), h kept in registers for the two
+// reductions of TransformerModel.LayerNorm (unbiased std, eps added to std).
+__global__ void __launch_bounds__(256) lstm_ln_kernel(int H, const float* __restrict__ gates, long ld_g, const float* __restrict__ c_prev, long ld_cp,
+                                                      float* __restrict__ c_out, long ld_co, float* __restrict__ h_out, long ld_h, const float* __restrict__ ln_a,
+                                                      const float* __restrict__ ln_b, float eps, float* __restrict__ ln_out, long ld_ln) {
+    __shared__ float sh[8];
+    const int r = blockIdx.x;
+    const float* g = gates + (long)r * ld_g;
+    float hv[8];
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int c = threadIdx.x + 256 * u;
+        hv[u] = 0.f;
+        if (c < H) {
+            const float gi = g[c], gf = g[H + c], gg = g[2 * H + c], go = g[3 * H + c];
+            const float cp = c_prev == nullptr ? 0.f : c_prev[(long)r * ld_cp + c];
+            const float cn = sigmoidf_(gf) * cp + sigmoidf_(gi) * fast_tanh(gg);
+            const float hn = sigmoidf_(go) * fast_tanh(cn);
+            c_out[(long)r * ld_co + c] = cn;
+            h_out[(long)r * ld_h + c] = hn;
+            hv[u] = hn;
+            s += hn;
+        }
+    }
+    auto bsum = [&](float v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+        __syncthreads();
+        return ((sh[0] + sh[1]) + (sh[2] + sh[3])) + ((sh[4] + sh[5]) + (sh[6] + sh[7]));
+    };
+    const float mean = bsum(s) / (float)H;
+    float q = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int c = threadIdx.x + 256 * u; if (c < H) { const float d = hv[u] - mean; q = fmaf(d, d, q); } }
+    const float stdv = sqrtf(bsum(q) / (float)(H - 1));
+    const float inv = 1.0f / (stdv + eps);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int c = threadIdx.x + 256 * u; if (c < H) ln_out[(long)r * ld_ln + c] = __ldg(ln_a + c) * (hv[u] - mean) * inv + __ldg(ln_b + c); }
+}
+
 // sums [rows, 5H]: sigmoid(i), sigmoid(f), sigmoid(o), then two candidates whose max is the cell input.
 __global__ void maxout_pointwise_kernel(int rows, int H, const float* __restrict__ sums, long ld_s, const int* __restrict__ src_row,
                                         const float* __restrict__ c_prev, long ld_cp, float* __restrict__ c_out, long ld_co, ActView h_out) {
@@ -307,6 +351,15 @@ int lstm_pointwise_launch(int rows, int H, const float* gates, long ld_g, const 
     if (rows <= 0) return 0;
     lstm_pointwise_kernel<<<pw_blocks((long)rows * H), 256, 0, stream>>>(rows, H, gates, ld_g, src_row, c_prev, ld_cp, c_out, ld_co, h_out,
                                                                           gather_bias, ld_gb, gather_idx);
+    CAPB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int lstm_ln_launch(int rows, int H, const float* gates, long ld_g, const float* c_prev, long ld_cp, float* c_out, long ld_co, float* h_out, long ld_h,
+                   const float* ln_a, const float* ln_b, float eps, float* ln_out, long ld_ln, cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    CAPB_REQUIRE(H <= 2048, "lstm_ln: hidden size above 2048");
+    lstm_ln_kernel<<<rows, 256, 0, stream>>>(H, gates, ld_g, c_prev, ld_cp, c_out, ld_co, h_out, ld_h, ln_a, ln_b, eps, ln_out, ld_ln);
     CAPB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

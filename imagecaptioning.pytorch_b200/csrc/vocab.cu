@@ -24,6 +24,7 @@ namespace {
 
 constexpr int VT = 256;   // threads per row
 
+template <int NT = VT>
 __device__ __forceinline__ float block_max(float v, float* scratch) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -32,10 +33,11 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
     __syncthreads();
     float r = scratch[0];
 #pragma unroll
-    for (int w = 1; w < VT / 32; ++w) r = fmaxf(r, scratch[w]);
+    for (int w = 1; w < NT / 32; ++w) r = fmaxf(r, scratch[w]);
     return r;
 }
 
+template <int NT = VT>
 __device__ __forceinline__ float block_sum(float v, float* scratch) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -44,11 +46,12 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
     __syncthreads();
     float r = 0.f;
 #pragma unroll
-    for (int w = 0; w < VT / 32; ++w) r += scratch[w];
+    for (int w = 0; w < NT / 32; ++w) r += scratch[w];
     return r;
 }
 
 // arg-max with lowest-index tie-break; result broadcast to all threads
+template <int NT = VT>
 __device__ __forceinline__ void block_argmax(float v, int i, float* sval, int* sidx, float& out_v, int& out_i) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -62,7 +65,7 @@ __device__ __forceinline__ void block_argmax(float v, int i, float* sval, int* s
     out_v = sval[0];
     out_i = sidx[0];
 #pragma unroll
-    for (int w = 1; w < VT / 32; ++w) {
+    for (int w = 1; w < NT / 32; ++w) {
         const float ov = sval[w];
         const int oi = sidx[w];
         if (ov > out_v || (ov == out_v && oi < out_i)) { out_v = ov; out_i = oi; }
@@ -86,18 +89,20 @@ __device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint3
 // Passes over the shared-memory copy of the row: (1) load + max, (2) sum exp, (3) log-probs + second-normalisation sum +
 // per-thread sorted top-KMAX, (4) final values to HBM; then k block-wide arg-max rounds over the per-thread list heads.
 // The second log_softmax only shifts the row by a constant, so candidates are ranked on the first-pass values.
-template <int KMAX>
-__global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
+// NT threads per row: 256 in general; 1024 for the few-row sampling / greedy steps of the training loops, where one CTA per row leaves the
+// machine nearly empty and the row passes (37 elements per thread at 256 threads, a Philox draw each) are the whole cost
+template <int KMAX, int NT = VT>
+__global__ void __launch_bounds__(NT) vocab_step_kernel(const VocabStepArgs a) {
     extern __shared__ float row[];                // [V1]
-    __shared__ float s_red[VT / 32];
-    __shared__ int s_idx[VT / 32];
+    __shared__ float s_red[NT / 32];
+    __shared__ int s_idx[NT / 32];
     const int r = blockIdx.x;
     const int V1 = a.V1;
     float* g = a.logits + (long)r * a.ld;
 
     if (a.unfinished != nullptr && !a.first_step && a.unfinished[r] == 0) {
         // sequence already ended: emit pad and a zero log-prob row (AttModel.py:342-344)
-        for (int v = threadIdx.x; v < V1; v += VT) g[v] = 0.f;
+        for (int v = threadIdx.x; v < V1; v += NT) g[v] = 0.f;
         if (threadIdx.x == 0) {
             if (a.tokens_out) a.tokens_out[r] = 0;
             if (a.seq_out) a.seq_out[(long)r * a.ld_seq + a.t] = 0;
@@ -107,11 +112,11 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
     }
 
     float mx = -INFINITY;
-    for (int v = threadIdx.x; v < V1; v += VT) { const float x = g[v]; row[v] = x; mx = fmaxf(mx, x); }
-    mx = block_max(mx, s_red);
+    for (int v = threadIdx.x; v < V1; v += NT) { const float x = g[v]; row[v] = x; mx = fmaxf(mx, x); }
+    mx = block_max<NT>(mx, s_red);
     float sum = 0.f;
-    for (int v = threadIdx.x; v < V1; v += VT) sum += __expf(row[v] - mx);      // ex2.approx path: relative error ~1e-7 on the sum
-    sum = block_sum(sum, s_red);
+    for (int v = threadIdx.x; v < V1; v += NT) sum += __expf(row[v] - mx);      // ex2.approx path: relative error ~1e-7 on the sum
+    sum = block_sum<NT>(sum, s_red);
     const float lsum = logf(sum);
     const float m2 = (mx - mx) - lsum;            // max of the log-probs (second log_softmax)
     const int k_eff = a.topk > 0 ? a.topk : (a.select == 1 ? 1 : 0);
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
         }
     };
     const bool edit = a.edits.any();
-    for (int v = threadIdx.x; v < V1; v += VT) {
+    for (int v = threadIdx.x; v < V1; v += NT) {
         const float lp = (row[v] - mx) - lsum;
         row[v] = lp;
         if (!edit) consider(lp, v);
@@ -162,22 +167,22 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
             }
         }
         __syncthreads();
-        for (int v = threadIdx.x; v < V1; v += VT) consider(row[v], v);
+        for (int v = threadIdx.x; v < V1; v += NT) consider(row[v], v);
     }
     // Second log_softmax (beam search, CaptionModel.py:204): its max is m2 = -lsum, so exp(lp - m2) = exp(x - mx) term by term and
     // its normaliser is the first pass's `sum` again (up to one rounding, ~1e-7 on the log-prob); no second exp pass is needed.
     const float l2 = lsum;
     if (a.twice) {
-        for (int v = threadIdx.x; v < V1; v += VT) g[v] = (row[v] - m2) - l2;
+        for (int v = threadIdx.x; v < V1; v += NT) g[v] = (row[v] - m2) - l2;
     } else {
-        for (int v = threadIdx.x; v < V1; v += VT) g[v] = row[v];
+        for (int v = threadIdx.x; v < V1; v += NT) g[v] = row[v];
     }
 
     int greedy_tok = 0;
     for (int k = 0; k < k_eff; ++k) {
         float ov;
         int oi;
-        block_argmax(tv[0], ti[0], s_red, s_idx, ov, oi);
+        block_argmax<NT>(tv[0], ti[0], s_red, s_idx, ov, oi);
         if (ti[0] == oi) {                        // the owner pops its head
 #pragma unroll
             for (int q = 0; q + 1 < KMAX; ++q) { tv[q] = tv[q + 1]; ti[q] = ti[q + 1]; }
@@ -209,23 +214,23 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
                 for (int bit = 31; bit >= 0; --bit) {
                     const uint32_t cand = keep_from | (1u << bit);
                     float cnt = 0.f;
-                    for (int v = threadIdx.x; v < V1; v += VT) cnt += (okey(row[v]) >= cand) ? 1.f : 0.f;
-                    cnt = block_sum(cnt, s_red);
+                    for (int v = threadIdx.x; v < V1; v += NT) cnt += (okey(row[v]) >= cand) ? 1.f : 0.f;
+                    cnt = block_sum<NT>(cnt, s_red);
                     if (cnt >= kf) keep_from = cand;
                 }
             } else if (a.select == 5) {
                 // nucleus (CaptionModel.py:388-397): a word is kept iff the probability mass of the strictly more likely words is < p
                 float mxl = -INFINITY;
-                for (int v = threadIdx.x; v < V1; v += VT) mxl = fmaxf(mxl, row[v]);
-                mxl = block_max(mxl, s_red);
+                for (int v = threadIdx.x; v < V1; v += NT) mxl = fmaxf(mxl, row[v]);
+                mxl = block_max<NT>(mxl, s_red);
                 float z = 0.f;
-                for (int v = threadIdx.x; v < V1; v += VT) z += __expf((row[v] - mxl) * inv_t);
-                z = block_sum(z, s_red);
+                for (int v = threadIdx.x; v < V1; v += NT) z += __expf((row[v] - mxl) * inv_t);
+                z = block_sum<NT>(z, s_red);
                 const float target = a.top * z;
                 auto mass_above = [&](uint32_t key) {   // sum over the words with key > `key`
                     float m = 0.f;
-                    for (int v = threadIdx.x; v < V1; v += VT) m += (okey(row[v]) > key) ? __expf((row[v] - mxl) * inv_t) : 0.f;
-                    return block_sum(m, s_red);
+                    for (int v = threadIdx.x; v < V1; v += NT) m += (okey(row[v]) > key) ? __expf((row[v] - mxl) * inv_t) : 0.f;
+                    return block_sum<NT>(m, s_red);
                 };
                 // largest key F with mass_above(F) >= target; everything above F is kept (the most likely word always is)
                 uint32_t F = 0;
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
             int bi = 0x7fffffff;
             const unsigned long long sd = a.seed ^ g_vocab_seed_salt;           // see dropout.cuh: graph replays of the SCST step
             const uint32_t k0 = (uint32_t)sd, k1 = (uint32_t)(sd >> 32);
-            for (int v = threadIdx.x; v < V1; v += VT) {
+            for (int v = threadIdx.x; v < V1; v += NT) {
                 if (okey(row[v]) < keep_from) continue;
                 const uint32_t bits = philox_first((uint32_t)v, (uint32_t)r, (uint32_t)a.step, (uint32_t)(a.step >> 32), k0, k1);
                 const float u = ((float)(bits >> 9) + 0.5f) * (1.0f / 8388608.0f);      // (0,1), 23 bits
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(VT) vocab_step_kernel(const VocabStepArgs a) {
                 if (x > bv) { bv = x; bi = v; }
             }
             float ov;
-            block_argmax(bv, bi, s_red, s_idx, ov, tok);
+            block_argmax<NT>(bv, bi, s_red, s_idx, ov, tok);
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -784,7 +789,14 @@ int vocab_step_launch(const VocabStepArgs& a, cudaStream_t stream) {
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(vocab_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
         CAPB_CHECK_CUDA(cudaFuncSetAttribute(vocab_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     }
-    if (a.topk <= 2) vocab_step_kernel<2><<<a.rows, VT, smem, stream>>>(a);
+    if (a.topk <= 2 && a.select != 0 && a.rows <= 2 * 148) {
+        static std::atomic<unsigned long long> configured2{0};
+        if (first_use_on_device(configured2)) {
+            CAPB_CHECK_CUDA(cudaFuncSetAttribute(vocab_step_kernel<2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        }
+        vocab_step_kernel<2, 1024><<<a.rows, 1024, smem, stream>>>(a);
+    }
+    else if (a.topk <= 2) vocab_step_kernel<2><<<a.rows, VT, smem, stream>>>(a);
     else if (a.topk <= 8) vocab_step_kernel<8><<<a.rows, VT, smem, stream>>>(a);
     else vocab_step_kernel<16><<<a.rows, VT, smem, stream>>>(a);
     CAPB_CHECK_CUDA(cudaGetLastError());

@@ -168,10 +168,10 @@ def test_transformer_training_at_config_dims_matches_reference(golden_dir):
             # discontinuous function of the forward pass: an activation within rounding distance of zero (a handful of the 14 M hidden units
             # of this step) is "on" in one fp32 implementation and "off" in the other, which moves a few entries of the tensors behind it by
             # a full upstream-gradient value (for a bias gradient that can be a tenth of the entry itself).  Those are tolerated as long as
-            # they stay rare (<= 0.2 % of a tensor's entries), bounded (0.1 of the tensor's scale + 1e-3 of the step's largest) and
+            # they stay rare (<= 0.2 % of a tensor's entries, or three of them), bounded (0.1 of the tensor's scale + 1e-3 of the step's largest) and
             # invisible in the norm (last assertion).
             bar = 2e-3 * scale + 4e-6 * largest
-            assert float((diff > bar).mean()) <= 2e-3, (prefix, key, err, scale, float((diff > bar).mean()))
+            assert int((diff > bar).sum()) <= max(3, int(2e-3 * diff.size)), (prefix, key, err, scale, int((diff > bar).sum()), diff.size)
             assert err <= 0.1 * scale + 1e-3 * largest, (prefix, key, err, scale)
             assert float(np.sqrt((diff.astype(np.float64) ** 2).sum())) <= 2e-3 * float(np.sqrt((ref.astype(np.float64) ** 2).sum())) + 4e-6 * largest * np.sqrt(diff.size), (prefix, key)
             fro = float(np.sqrt((a.astype(np.float64) ** 2).sum()))
