@@ -59,6 +59,10 @@ struct Tf32Params {
     long ld_rb;
     int rpg;
     int accumulate;
+    // split-K without a cluster (finer splits than 8, no co-scheduling constraint): every K-rank writes its tile to `scratch`, the last CTA
+    // of a tile to arrive (per-tile counter) adds the ranks in rank order -- deterministic -- and applies the epilogue.  nullptr = cluster / DSMEM.
+    float* scratch;
+    unsigned int* counters;
 };
 
 template <int BN>
@@ -279,20 +283,44 @@ __global__ void __launch_bounds__(kThreadsT, 1) gemm_tf32x3_kernel(const __grid_
         ptx::tc_fence_before_sync();
     }
     __syncthreads();
-    if (ksplit > 1) ptx::cluster_sync_all();            // every K-rank's staging tile is complete and visible cluster-wide
+    const bool via_scratch = ksplit > 1 && p.scratch != nullptr;
+    if (ksplit > 1 && !via_scratch) ptx::cluster_sync_all();            // every K-rank's staging tile is complete and visible cluster-wide
 
-    // ---- reduce across the K-ranks (fixed order) and store: rank r owns output-tile rows [r * rows / ksplit, (r + 1) * rows / ksplit)
+    // ---- reduce across the K-ranks (fixed order) and store
     {
         const int rows_out = p.swapped ? BN : TM;
         const int cols_out = p.swapped ? TM : BN;
         const int pitch = cols_out + Cfg::kPad;
-        const int r_lo = rows_out * krank / ksplit, r_hi = rows_out * (krank + 1) / ksplit;
+        const int vec_per_row = cols_out / 4;
+        const int tile_vecs = rows_out * vec_per_row;
+        int r_lo = rows_out * krank / ksplit, r_hi = rows_out * (krank + 1) / ksplit;      // cluster form: rank r owns a slice of the tile's rows
+        const float4* part = nullptr;
+        bool active = true;
+        if (via_scratch) {
+            __shared__ int s_last;
+            const long tile_id = (long)blockIdx.y * gridDim.z + blockIdx.z;
+            float4* mine = reinterpret_cast<float4*>(p.scratch) + (tile_id * ksplit + krank) * tile_vecs;
+            for (int idx = threadIdx.x; idx < tile_vecs; idx += kThreadsT) {
+                const int ro = idx / vec_per_row, co = (idx % vec_per_row) * 4;
+                __stcg(mine + idx, *reinterpret_cast<const float4*>(smem + (ro * pitch + co) * 4));
+            }
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) s_last = (atomicAdd(p.counters + tile_id, 1u) == (unsigned)(ksplit - 1)) ? 1 : 0;
+            __syncthreads();
+            active = s_last != 0;                                   // the last K-rank to arrive finishes the tile
+            if (active) {
+                __threadfence();
+                if (threadIdx.x == 0) p.counters[tile_id] = 0u;     // ready for the next launch (stream order)
+                part = reinterpret_cast<const float4*>(p.scratch) + tile_id * ksplit * tile_vecs;
+                r_lo = 0; r_hi = rows_out;
+            }
+        }
         const int m_base = p.swapped ? b_row0 : a_row0;
         const int n_base = p.swapped ? a_row0 : b_row0;
         const uint32_t s_base = ptx::smem_u32(smem);
-        const int vec_per_row = cols_out / 4;
         const bool vec_ok = (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (n_base & 3) == 0;
-        for (int idx = threadIdx.x; idx < (r_hi - r_lo) * vec_per_row; idx += kThreadsT) {
+        for (int idx = threadIdx.x; active && idx < (r_hi - r_lo) * vec_per_row; idx += kThreadsT) {
             const int ro = r_lo + idx / vec_per_row, co = (idx % vec_per_row) * 4;
             const int m = m_base + ro, n = n_base + co;
             if (m >= p.M || n >= p.N) continue;
@@ -300,6 +328,11 @@ __global__ void __launch_bounds__(kThreadsT, 1) gemm_tf32x3_kernel(const __grid_
             const uint32_t off = s_base + static_cast<uint32_t>((ro * pitch + co) * 4);
             if (ksplit == 1) {
                 acc = *reinterpret_cast<const float4*>(smem + (ro * pitch + co) * 4);
+            } else if (via_scratch) {
+                for (int kr = 0; kr < ksplit; ++kr) {
+                    const float4 v = __ldcg(part + (long)kr * tile_vecs + ro * vec_per_row + co / 4);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
             } else {
                 for (int kr = 0; kr < ksplit; ++kr) {
                     const float4 v = ld_dsmem_f4(mapa_shared(off, (uint32_t)kr));
@@ -328,7 +361,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) gemm_tf32x3_kernel(const __grid_
     }
     ptx::tc_fence_before_sync();
     __syncthreads();
-    if (ksplit > 1) ptx::cluster_sync_all();            // nobody leaves while a peer may still read its staging tile
+    if (ksplit > 1 && !via_scratch) ptx::cluster_sync_all();            // nobody leaves while a peer may still read its staging tile
     ptx::tc_fence_after_sync();
     if (warp == 2) ptx::tmem_dealloc(tmem_acc, Cfg::kTmemCols);
 }
@@ -386,12 +419,18 @@ struct Tf32Context {
     std::unordered_map<MapKey, TEntry, MapKeyHash> transposed;        // key: (src, rows, cols, ld_src)
     unsigned long long stamp = 1;                                      // bumped per training step: weight transposes are rebuilt once per step
     long launches = 0;
+    float* scratch = nullptr;          // split-K partial tiles [tile][K-rank][rows][cols]
+    size_t scratch_floats = 0;
+    unsigned int* counters = nullptr;  // per-tile arrival counters (zero between launches)
+    int n_counters = 0;
 };
 
 Tf32Context* tf32_context_create() { return new Tf32Context(); }
 void tf32_context_destroy(Tf32Context* c) {
     if (c == nullptr) return;
     for (auto& kv : c->transposed) cudaFree(kv.second.buf);
+    cudaFree(c->scratch);
+    cudaFree(c->counters);
     delete c;
 }
 void tf32_context_new_step(Tf32Context* c) { if (c) c->stamp++; }
@@ -434,7 +473,7 @@ int launch_tf32_v(const Tf32Params& prm, int ksplit, int tiles_a, int tiles_b, c
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = ksplit > 1 ? 1 : 0;
+    cfg.numAttrs = (ksplit > 1 && prm.scratch == nullptr) ? 1 : 0;
     CAPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, TRUNC>, prm));
     return 0;
 }
@@ -488,9 +527,46 @@ int gemm_tf32_launch(Tf32Context* ctx, int M, int N, int nseg, const float* cons
     }
     p.ksteps_total = ksteps;
     const int tiles_a = (int)cdiv((int)a_rows, TM), tiles_b = (int)cdiv((int)b_rows, bn);
-    // split-K across a cluster so that ~all 148 SMs stream disjoint slices: largest power of two with tiles * ksplit <= 148, >= 2 K-blocks each
+    // split-K so that ~all 148 SMs stream disjoint K-slices.
+    //  * default: as many K-ranks as it takes to reach one wave (up to 24, >= 2 K-blocks each), partial tiles through a global scratch buffer and
+    //    a last-arriver reduction in rank order.  The cluster form is limited to 8 ranks (N = 1024 outputs: 8 tiles x 8 = 64 CTAs, each a
+    //    chain of 8+ dependent K-blocks: profiles/r02k_gemm_full.md shows those launches at 11 % of the DRAM bandwidth) and needs the 8 SMs of
+    //    a cluster free at the same time.
+    //  * CAPB200_TF32_CLUSTER=1: split-K across a thread-block cluster with the DSMEM reduction (largest power of two <= 8).
+    static const bool use_cluster = getenv("CAPB200_TF32_CLUSTER") != nullptr && atoi(getenv("CAPB200_TF32_CLUSTER")) != 0;
+    const long tiles = (long)tiles_a * tiles_b;
     int ksplit = 1;
-    while (ksplit < 8 && (long)tiles_a * tiles_b * (ksplit * 2) <= 148 && ksteps / (ksplit * 2) >= 2) ksplit *= 2;
+    if (use_cluster) {
+        while (ksplit < 8 && tiles * (ksplit * 2) <= 148 && ksteps / (ksplit * 2) >= 2) ksplit *= 2;
+    } else {
+        ksplit = (int)(148 / tiles);
+        if (ksplit > ksteps / 2) ksplit = ksteps / 2;
+        if (ksplit > 24) ksplit = 24;
+        if (ksplit < 1) ksplit = 1;
+        if (ksplit > 1) {
+            const size_t need = (size_t)tiles * ksplit * TM * bn;
+            if (need > ctx->scratch_floats || tiles > ctx->n_counters) {
+                CAPB_CHECK_CUDA(cudaStreamSynchronize(st));
+                if (need > ctx->scratch_floats) {
+                    if (ctx->scratch) CAPB_CHECK_CUDA(cudaFree(ctx->scratch));
+                    ctx->scratch = nullptr;
+                    const size_t grow = need > ((size_t)8 << 20) ? need : ((size_t)8 << 20);
+                    CAPB_CHECK_CUDA(cudaMalloc(&ctx->scratch, grow * sizeof(float)));
+                    ctx->scratch_floats = grow;
+                }
+                if (tiles > ctx->n_counters) {
+                    if (ctx->counters) CAPB_CHECK_CUDA(cudaFree(ctx->counters));
+                    ctx->counters = nullptr;
+                    const int nc = tiles > 4096 ? (int)tiles : 4096;
+                    CAPB_CHECK_CUDA(cudaMalloc(&ctx->counters, nc * sizeof(unsigned int)));
+                    CAPB_CHECK_CUDA(cudaMemsetAsync(ctx->counters, 0, nc * sizeof(unsigned int), st));
+                    ctx->n_counters = nc;
+                }
+            }
+            p.scratch = ctx->scratch;
+            p.counters = ctx->counters;
+        }
+    }
     ctx->launches++;
     switch (bn) {
         case 32: return launch_tf32<32>(p, ksplit, tiles_a, tiles_b, st);

@@ -138,10 +138,13 @@ def test_lstm_cell(L, mode):
     assert float((ho.cpu() - h_ref).abs().max()) < 2e-6 and float((c_o.cpu() - c_ref).abs().max()) < 2e-6
 
 
-@pytest.mark.parametrize('rpi,masked', [(1, False), (5, False), (7, True), (10, False)])
-def test_additive_attention(L, rpi, masked):
+@pytest.mark.parametrize('rpi,masked,B,A,H', [(1, False, 3, 64, 100), (5, False, 3, 64, 100), (7, True, 3, 64, 100), (10, False, 3, 64, 100),
+                                               (5, False, 130, 512, 1000), (3, True, 121, 200, 300), (1, False, 150, 128, 64)])
+def test_additive_attention(L, rpi, masked, B, A, H):
+    """The last three cases (>= 120 images, <= 5 rows per image) run the fused one-launch kernel of the decode path, the others the
+    score / combine pair."""
     g = torch.Generator().manual_seed(rpi)
-    B, R, A, H = 3, 36, 64, 100
+    R = 36
     N = B * rpi
     W = {'core.attention.h2att.weight': torch.zeros(A, H), 'core.attention.h2att.bias': torch.zeros(A),
          'core.attention.alpha_net.weight': torch.randn(1, A, generator=g), 'core.attention.alpha_net.bias': torch.randn(1, generator=g)}
@@ -153,6 +156,7 @@ def test_additive_attention(L, rpi, masked):
         mask = torch.ones(B, R)
         mask[0, 20:] = 0
         mask[2, 5:] = 0
+        mask[B - 1, 1:] = 0
     # oracle: feed att_h through a zero h2att by adding it to p_att rows
     rep = lambda t: co.repeat_rows(t, rpi)
     dot = torch.tanh(rep(p_att) + att_h.unsqueeze(1))
