@@ -60,7 +60,7 @@ struct Tf32Params {
     int rpg;
     int accumulate;
     // split-K without a cluster (finer splits than 8, no co-scheduling constraint): every K-rank writes its tile to `scratch`, the last CTA
-    // of a tile to arrive (per-tile counter) adds the ranks in rank order -- deterministic -- and applies the epilogue.  nullptr = cluster / DSMEM.
+    // of a tile to arrive (per-tile counter) adds the ranks in rank order -- deterministic -- and applies the epilogue.  nullptr = cluster / DSMEM (the default; see gemm_tf32_launch).
     float* scratch;
     unsigned int* counters;
 };
@@ -528,12 +528,12 @@ int gemm_tf32_launch(Tf32Context* ctx, int M, int N, int nseg, const float* cons
     p.ksteps_total = ksteps;
     const int tiles_a = (int)cdiv((int)a_rows, TM), tiles_b = (int)cdiv((int)b_rows, bn);
     // split-K so that ~all 148 SMs stream disjoint K-slices.
-    //  * default: as many K-ranks as it takes to reach one wave (up to 24, >= 2 K-blocks each), partial tiles through a global scratch buffer and
-    //    a last-arriver reduction in rank order.  The cluster form is limited to 8 ranks (N = 1024 outputs: 8 tiles x 8 = 64 CTAs, each a
-    //    chain of 8+ dependent K-blocks: profiles/r02k_gemm_full.md shows those launches at 11 % of the DRAM bandwidth) and needs the 8 SMs of
-    //    a cluster free at the same time.
-    //  * CAPB200_TF32_CLUSTER=1: split-K across a thread-block cluster with the DSMEM reduction (largest power of two <= 8).
-    static const bool use_cluster = getenv("CAPB200_TF32_CLUSTER") != nullptr && atoi(getenv("CAPB200_TF32_CLUSTER")) != 0;
+    //  * default: across a thread-block cluster with the DSMEM reduction (largest power of two <= 8 with tiles * ksplit <= 148).
+    //  * CAPB200_TF32_SCRATCH=1: finer splits (up to 24 K-ranks, >= 2 K-blocks each) with the partial tiles in a global scratch buffer and a
+    //    last-arriver reduction in rank order.  Measured (profiles/r02p_tf32_sweep*.txt): it helps where the cluster form tops out at 64 CTAs on a
+    //    large K (att2ctx 22.6 -> 18.5 us) but loses elsewhere (q-projection 10.3 -> 14.3 us: the last CTA re-reads 16 partial tiles; gates
+    //    22.8 -> 26.1 us) and on the whole step (AoANet SCST 10.8 -> 11.2 ms), so the cluster form stays the default.
+    static const bool use_cluster = !(getenv("CAPB200_TF32_SCRATCH") != nullptr && atoi(getenv("CAPB200_TF32_SCRATCH")) != 0);
     const long tiles = (long)tiles_a * tiles_b;
     int ksplit = 1;
     if (use_cluster) {

@@ -262,120 +262,9 @@ __global__ void __launch_bounds__(ATT_SW * 32, NA <= 16 ? 5 : 2) att_score_kerne
     }
 }
 
-// The two launches above fused for the decode shapes (rows per image <= ATT_JB, no attention weights to keep): ONE CTA of 16 warps per image.
-//   scores   warp w scores regions w, w + 16, ...: the same exp2 / shared-reciprocal tanh as att_score_kernel, all rows of the image per region
-//   softmax  one warp per row over the R scores in shared memory (+ mask renormalisation)
-//   combine  thread c walks the image's R feature rows once for all its rows (beams): out[row, c] = sum_r a[row, r] * att[img, r, c]
-// The split version costs two launches and a round trip of the scores through HBM (18.6 + 14.4 us per step at 256 images x 5 beams,
-// profiles/r02a_kernel_table_decode.txt); every image's work is independent, and 256 images on 148 SMs with two resident CTAs each is one wave.
-template <int NA>
-__global__ void __launch_bounds__(512, 2) att_fused_kernel(int rpi, int R, int A, int H, const float* __restrict__ att_h, long ld_ah,
-                                                           const float* __restrict__ p_att, long ld_pa, const float* __restrict__ att, long ld_at,
-                                                           const float* __restrict__ mask, long ld_mask, const float* __restrict__ alpha_w,
-                                                           const float* __restrict__ alpha_b_ptr, ActView out) {
-    static_assert(NA % 4 == 0, "the fused kernel uses the 128-bit path");
-    extern __shared__ __align__(16) float s_all[];
-    constexpr int AP = NA * 32;
-    constexpr float kC = 2.885390081777927f;      // 2 * log2(e)
-    float* s_ah = s_all;                          // [ATT_JB][AP] pre-scaled att_h rows (zero padded)
-    float* s_w = s_ah + ATT_JB * AP;              // [AP] attention weights (zero padded)
-    float* s_sc = s_w + AP;                       // [ATT_JB][R] scores -> softmax weights
-    const int img = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float alpha_b = __ldg(alpha_b_ptr);
-    for (int i = threadIdx.x; i < AP; i += 512) s_w[i] = (i < A) ? __ldg(alpha_w + i) : 0.f;
-    for (int i = threadIdx.x; i < ATT_JB * AP; i += 512) {
-        const int j = i / AP, a = i - j * AP;
-        s_ah[i] = (j < rpi && a < A) ? att_h[((long)img * rpi + j) * ld_ah + a] * kC : 0.f;
-    }
-    __syncthreads();
-    float wsum = 0.f;
-#pragma unroll
-    for (int k = 0; k < NA; ++k) wsum += s_w[128 * (k >> 2) + 4 * lane + (k & 3)];
-    for (int r = warp; r < R; r += 16) {
-        const float* pr = p_att + ((long)img * R + r) * ld_pa;
-        float pv[NA];
-#pragma unroll
-        for (int g = 0; g < NA / 4; ++g) {
-            const int a = 128 * g + 4 * lane;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a + 3 < A) v = __ldg(reinterpret_cast<const float4*>(pr + a));
-            else { if (a < A) v.x = __ldg(pr + a); if (a + 1 < A) v.y = __ldg(pr + a + 1); if (a + 2 < A) v.z = __ldg(pr + a + 2); }
-            pv[4 * g] = v.x * kC; pv[4 * g + 1] = v.y * kC; pv[4 * g + 2] = v.z * kC; pv[4 * g + 3] = v.w * kC;
-        }
-#pragma unroll
-        for (int j = 0; j < ATT_JB; ++j) {
-            if (j >= rpi) break;
-            float acc = 0.f;
-#pragma unroll
-            for (int g = 0; g < NA / 4; ++g) {
-                const float4 ah = *reinterpret_cast<const float4*>(&s_ah[j * AP + 128 * g + 4 * lane]);
-                const float z[4] = {pv[4 * g] + ah.x, pv[4 * g + 1] + ah.y, pv[4 * g + 2] + ah.z, pv[4 * g + 3] + ah.w};
-                float y[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    float e;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(z[u], 28.0f)));
-                    y[u] = 1.0f + e;
-                }
-                const float p01 = y[0] * y[1], p23 = y[2] * y[3];
-                float rr;
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rr) : "f"(p01 * p23));
-                const float r01 = rr * p23, r23 = rr * p01;
-                const float4 w4 = *reinterpret_cast<const float4*>(&s_w[128 * g + 4 * lane]);
-                acc = fmaf(w4.x, r01 * y[1], acc);
-                acc = fmaf(w4.y, r01 * y[0], acc);
-                acc = fmaf(w4.z, r23 * y[3], acc);
-                acc = fmaf(w4.w, r23 * y[2], acc);
-            }
-            float v = fmaf(-2.0f, acc, wsum);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) s_sc[j * R + r] = v + alpha_b;
-        }
-    }
-    __syncthreads();
-    if (warp < rpi) {                             // softmax over the regions of one row per warp (att_combine_kernel's arithmetic)
-        float* w = s_sc + warp * R;
-        float mx = -INFINITY;
-        for (int r = lane; r < R; r += 32) mx = fmaxf(mx, w[r]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float sum = 0.f;
-        for (int r = lane; r < R; r += 32) { const float e = expf(w[r] - mx); w[r] = e; sum += e; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float inv = 1.0f / sum;
-        float msum = 0.f;
-        for (int r = lane; r < R; r += 32) {
-            float v = w[r] * inv;
-            if (mask != nullptr) { v *= mask[(long)img * ld_mask + r]; msum += v; }
-            w[r] = v;
-        }
-        if (mask != nullptr) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
-            for (int r = lane; r < R; r += 32) w[r] = w[r] / msum;
-        }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < H; c += 512) {
-        float acc[ATT_JB];
-#pragma unroll
-        for (int j = 0; j < ATT_JB; ++j) acc[j] = 0.f;
-        const float* ap = att + (long)img * R * ld_at + c;
-        for (int r = 0; r < R; ++r) {
-            const float v = __ldg(ap + (long)r * ld_at);
-#pragma unroll
-            for (int j = 0; j < ATT_JB; ++j)
-                if (j < rpi) acc[j] = fmaf(s_sc[j * R + r], v, acc[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < ATT_JB; ++j)
-            if (j < rpi) store_act(out, (long)img * rpi + j, c, acc[j]);
-    }
-}
-
+// (A one-launch fusion of the two kernels -- one CTA of 16 warps per image: scores, softmax, weighted sum -- was measured in round 2: no faster
+// than the pair at 256 images x 5 beams (6.08 vs 6.08 ms per batch; 36 regions on 16 warps leave the score phase at 75 % utilisation and the
+// image count, not the chip, sets the parallelism), so the split form stays.)
 constexpr int ATT_CT = 256;
 __global__ void __launch_bounds__(ATT_CT) att_combine_kernel(int rpi, int R, int H, const float* __restrict__ score, const float* __restrict__ att,
                                                              long ld_at, const float* __restrict__ mask, long ld_mask, ActView out,
@@ -493,28 +382,6 @@ int additive_attention_launch(int n_images, int rpi, int R, int A, int H, const 
     CAPB_REQUIRE(A <= 1024, "attention: att_hid_size above 1024");
     CAPB_REQUIRE(score_scratch != nullptr, "attention: score scratch missing");
     const int na = cdiv(A, 32);
-    {   // decode shapes: one fused launch (CAPB200_ATT_SPLIT=1 keeps the two-kernel form for A/B timing)
-        static const bool split = getenv("CAPB200_ATT_SPLIT") != nullptr && atoi(getenv("CAPB200_ATT_SPLIT")) != 0;
-        const int na4 = na <= 4 ? 4 : (na <= 8 ? 8 : (na <= 16 ? 16 : 32));
-        const size_t fsmem = sizeof(float) * ((size_t)(ATT_JB + 1) * na4 * 32 + (size_t)ATT_JB * R);
-        const bool aligned = (ld_pa & 3) == 0 && (reinterpret_cast<uintptr_t>(p_att) & 15) == 0;
-        if (!split && alpha_out == nullptr && rpi <= ATT_JB && n_images >= 120 && na > 2 && na4 <= 16 && aligned && fsmem <= 100 * 1024) {
-#define CAPB_ATTF_CASE(NA_)                                                                                                              \
-    do {                                                                                                                                 \
-        static std::atomic<unsigned long long> cfg_##NA_{0};                                                                             \
-        if (first_use_on_device(cfg_##NA_))                                                                                              \
-            CAPB_CHECK_CUDA(cudaFuncSetAttribute(att_fused_kernel<NA_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));       \
-        att_fused_kernel<NA_><<<n_images, 512, fsmem, stream>>>(rpi, R, A, H, att_h, ld_ah, p_att, ld_pa, att, ld_at, mask, ld_mask, alpha_w, alpha_b, out); \
-    } while (0)
-            if (na4 == 4) CAPB_ATTF_CASE(4);
-            else if (na4 == 8) CAPB_ATTF_CASE(8);
-            else if (na4 == 16) CAPB_ATTF_CASE(16);
-            else CAPB_ATTF_CASE(32);
-#undef CAPB_ATTF_CASE
-            CAPB_CHECK_CUDA(cudaGetLastError());
-            return 0;
-        }
-    }
     dim3 sgrid(cdiv(R, ATT_SW), n_images);
 #define CAPB_ATT_CASE(NA_)                                                                                                             \
     att_score_kernel<NA_><<<sgrid, ATT_SW * 32, sizeof(float) * (ATT_JB + 1) * NA_ * 32, stream>>>(rpi, R, A, att_h, ld_ah, p_att, ld_pa, alpha_w, \

@@ -141,8 +141,8 @@ def test_lstm_cell(L, mode):
 @pytest.mark.parametrize('rpi,masked,B,A,H', [(1, False, 3, 64, 100), (5, False, 3, 64, 100), (7, True, 3, 64, 100), (10, False, 3, 64, 100),
                                                (5, False, 130, 512, 1000), (3, True, 121, 200, 300), (1, False, 150, 128, 64)])
 def test_additive_attention(L, rpi, masked, B, A, H):
-    """The last three cases (>= 120 images, <= 5 rows per image) run the fused one-launch kernel of the decode path, the others the
-    score / combine pair."""
+    """Small cases and decode-sized ones (>= 120 images, att_hid_size up to the config's 512: the score is a sum of A approximated tanh terms,
+    so the bar scales with A)."""
     g = torch.Generator().manual_seed(rpi)
     R = 36
     N = B * rpi
@@ -171,7 +171,7 @@ def test_additive_attention(L, rpi, masked, B, A, H):
     L.check(L.load().capb200_additive_attention(L.ptr(d[0]), L.ptr(d[1]), L.ptr(d[2]), L.ptr(d[3]), L.ptr(d[4]), L.ptr(d[5]), L.ptr(out), B, rpi, R, A, H,
                                                 L.current_stream()), 'attention')
     torch.cuda.synchronize()
-    assert float((out.cpu() - ref).abs().max()) < 5e-6
+    assert float((out.cpu() - ref).abs().max()) < (5e-6 if A <= 64 else 3e-5)
 
 
 @pytest.mark.parametrize('V1,twice,k', [(61, 0, 3), (9488, 1, 5), (9488, 0, 10), (1000, 1, 1)])
