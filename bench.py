@@ -484,7 +484,8 @@ def main():
     # The dominant kernel is the persistent tcgen05 GEMM (gemm_tc_kernel): every dense contraction of the step is a launch of it.
     # achieved = algorithmic FLOPs (2*M*N*K of the contraction actually executed) of ALL its launches / their summed CUDA-event time;
     # the largest single call site (language-LSTM gates, M=B*beam, N=4000, K=3000) is listed beside it.
-    # DRAM bytes per launch of the largest call site (lang_lstm gates) from the committed `ncu --set full` capture, when present
+    # DRAM bytes per launch of one of the three large call sites (the capture's own `kernel` field says which) from the committed
+    # `ncu --set full` capture, when present
     traffic, traffic_src = None, None
     tpath = os.path.join(REPO, 'profiles', 'roofline_traffic.json')
     if os.path.exists(tpath):
@@ -497,7 +498,7 @@ def main():
     big_ms, big_fl, big_calls = prof['lang_lstm']
     passes = 3 if args.mode == 'tc_f16x3' else 1
     roofline = {'bound': 'tensor', 'kernel': 'gemm_tc_pair_kernel<144,%d> / gemm_tc_kernel<64,..> (persistent tcgen05 GEMM, cta_group::2 pairs for the large call sites; all call sites of the step)' % passes,
-                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
+                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'traffic_kernel': tj.get('kernel') if traffic is not None else None, 'peak_source': peak_src,
                 'mma_passes': passes,
                 'frac_of_pass_ceiling': achieved / (peak / passes),       # fp32-grade results cost 3 MMA passes per product
                 'launches_timed': all_calls, 'avg_launch_ms': all_ms / max(all_calls, 1),
