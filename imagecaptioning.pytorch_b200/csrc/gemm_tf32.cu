@@ -528,17 +528,20 @@ int gemm_tf32_launch(Tf32Context* ctx, int M, int N, int nseg, const float* cons
     p.ksteps_total = ksteps;
     const int tiles_a = (int)cdiv((int)a_rows, TM), tiles_b = (int)cdiv((int)b_rows, bn);
     // split-K so that ~all 148 SMs stream disjoint K-slices.
-    //  * default: across a thread-block cluster with the DSMEM reduction (largest power of two <= 8 with tiles * ksplit <= 148).
-    //  * CAPB200_TF32_SCRATCH=1: finer splits (up to 24 K-ranks, >= 2 K-blocks each) with the partial tiles in a global scratch buffer and a
+    //  * default: across a thread-block cluster with the DSMEM reduction (largest power of two <= 8 with tiles * ksplit <= 148), except
+    //    for the shape class named below.
+    //  * CAPB200_TF32_SCRATCH=1 (0 = never): finer splits (up to 24 K-ranks, >= 2 K-blocks each) with the partial tiles in a global scratch buffer and a
     //    last-arriver reduction in rank order.  Measured (profiles/r02p_tf32_sweep*.txt): it helps where the cluster form tops out at 64 CTAs on a
     //    large K (att2ctx 22.6 -> 18.5 us) but loses elsewhere (q-projection 10.3 -> 14.3 us: the last CTA re-reads 16 partial tiles; gates
     //    22.8 -> 26.1 us) and on the whole step (AoANet SCST 10.8 -> 11.2 ms), so the cluster form stays the default.
-    static const bool use_cluster = !(getenv("CAPB200_TF32_SCRATCH") != nullptr && atoi(getenv("CAPB200_TF32_SCRATCH")) != 0);
+    static const int scratch_mode = getenv("CAPB200_TF32_SCRATCH") != nullptr ? atoi(getenv("CAPB200_TF32_SCRATCH")) : -1;     // 1 always, 0 never, unset: hybrid
     const long tiles = (long)tiles_a * tiles_b;
     int ksplit = 1;
-    if (use_cluster) {
-        while (ksplit < 8 && tiles * (ksplit * 2) <= 148 && ksteps / (ksplit * 2) >= 2) ksplit *= 2;
-    } else {
+    while (ksplit < 8 && tiles * (ksplit * 2) <= 148 && ksteps / (ksplit * 2) >= 2) ksplit *= 2;
+    // hybrid default: the one shape class where the cluster form loses is 16 clusters of 8 (att2ctx and its input gradient, 2048 x 2048:
+    // 22.6 us as clusters, 18.5 us with 9 independent K-ranks per tile)
+    bool use_scratch = scratch_mode == 1 || (scratch_mode != 0 && ksplit == 8 && tiles >= 16);
+    if (use_scratch) {
         ksplit = (int)(148 / tiles);
         if (ksplit > ksteps / 2) ksplit = ksteps / 2;
         if (ksplit > 24) ksplit = 24;

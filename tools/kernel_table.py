@@ -2,20 +2,19 @@
 import os, sys
 import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, 'tests'))
-from helpers import build_pair
-from oracle import caption_oracle as co
+sys.path.insert(0, REPO)
+from imagecaptioning.pytorch_b200 import synthetic as syn       # seeded synthetic weights / inputs (profiling tools never touch oracle/)
 import bench
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 beam = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 FAM = sys.argv[3] if len(sys.argv) > 3 else 'updown'
 if FAM == 'transformer':
-    model, _ = build_pair('transformer', seed=1234, logit_scale=3.0, mode='tc_f16x3', heads=8, **dict(bench.CFG, E=512, H=2048, A=6))
+    model = syn.build_model('transformer', seed=1234, logit_scale=3.0, mode='tc_f16x3', heads=8, **dict(bench.CFG, E=512, H=2048, A=6))
 elif FAM == 'aoa':
-    model, _ = build_pair('aoa', seed=1234, logit_scale=6.0, mode='tc_f16x3', heads=8, **dict(bench.CFG, E=1024, H=1024, A=0))
+    model = syn.build_model('aoa', seed=1234, logit_scale=6.0, mode='tc_f16x3', heads=8, **dict(bench.CFG, E=1024, H=1024, A=0))
 else:
-    model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode='tc_f16x3', **bench.CFG)
-fc, att = co.make_inputs(B, 36, 2048, 2048, seed=1)
+    model = syn.build_model('updown', seed=1234, logit_scale=12.0, mode='tc_f16x3', **bench.CFG)
+fc, att = syn.make_inputs(B, 36, 2048, 2048, seed=1)
 fc, att = fc.cuda(), att.cuda()
 opt = {'beam_size': beam, 'sample_n': 1}
 with torch.no_grad():

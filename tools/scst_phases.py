@@ -2,10 +2,9 @@
 import argparse, os, sys, time
 import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, 'tests'))
+sys.path.insert(0, REPO)
 import imagecaptioning.pytorch_b200 as b200
-from helpers import build_pair
-from oracle import caption_oracle as co, ciderd_oracle as cdo
+from imagecaptioning.pytorch_b200 import synthetic as syn       # seeded synthetic weights / inputs (profiling tools never touch oracle/)
 import bench
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 FAM = sys.argv[2] if len(sys.argv) > 2 else 'updown'
@@ -15,19 +14,19 @@ torch.cuda.set_device(lrank)
 if world > 1:
     dist.init_process_group('nccl', device_id=torch.device('cuda', lrank))
 if FAM == 'aoa':
-    model, _ = build_pair('aoa', seed=1234, logit_scale=6.0, mode='tc_f16x3', heads=8, device=torch.device('cuda', lrank), **dict(bench.CFG, E=1024, H=1024, A=0))
+    model = syn.build_model('aoa', seed=1234, logit_scale=6.0, mode='tc_f16x3', heads=8, device=torch.device('cuda', lrank), **dict(bench.CFG, E=1024, H=1024, A=0))
 else:
-    model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode='tc_f16x3', device=torch.device('cuda', lrank), **bench.CFG)
+    model = syn.build_model('updown', seed=1234, logit_scale=12.0, mode='tc_f16x3', device=torch.device('cuda', lrank), **bench.CFG)
 model.train()
-df, ref_len = cdo.build_document_frequency(cdo.make_refs(500, 9487, seed=4))
+df, ref_len = syn.document_frequency(syn.make_refs(500, 9487, seed=4))
 b200.rewards.reset_scorer(); b200.rewards.init_scorer(b200.rewards.CiderDTable(df, ref_len))
 opt = argparse.Namespace(sc_sample_method='greedy', sc_beam_size=1, train_sample_method='sample', train_beam_size=1, train_sample_n=5,
                          cider_reward_weight=1, bleu_reward_weight=0)
 lw = b200.B200LossWrapper(model, opt)
 optim = torch.optim.Adam(model.parameters(), lr=5e-5)
-fc, att = co.make_inputs(B, 36, 2048, 2048, seed=1)
+fc, att = syn.make_inputs(B, 36, 2048, 2048, seed=1)
 fc, att = fc.cuda(), att.cuda()
-gts = cdo.make_refs(B, 9487, seed=5)
+gts = syn.make_refs(B, 9487, seed=5)
 idx = torch.arange(B)
 acc = {}
 def tick(name, t0):

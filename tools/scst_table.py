@@ -2,23 +2,22 @@
 import argparse, os, sys
 import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, 'tests'))
+sys.path.insert(0, REPO)
 import imagecaptioning.pytorch_b200 as b200
-from helpers import build_pair
-from oracle import caption_oracle as co, ciderd_oracle as cdo
+from imagecaptioning.pytorch_b200 import synthetic as syn       # seeded synthetic weights / inputs (profiling tools never touch oracle/)
 import bench
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 FAM = sys.argv[2] if len(sys.argv) > 2 else 'updown'
 if FAM == 'aoa':
-    model, _ = build_pair('aoa', seed=1234, logit_scale=6.0, mode='tc_f16x3', heads=8, **dict(bench.CFG, E=1024, H=1024, A=0))
+    model = syn.build_model('aoa', seed=1234, logit_scale=6.0, mode='tc_f16x3', heads=8, **dict(bench.CFG, E=1024, H=1024, A=0))
 else:
-    model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode='tc_f16x3', **bench.CFG)
+    model = syn.build_model('updown', seed=1234, logit_scale=12.0, mode='tc_f16x3', **bench.CFG)
 model.train()
-df, ref_len = cdo.build_document_frequency(cdo.make_refs(500, 9487, seed=4))
+df, ref_len = syn.document_frequency(syn.make_refs(500, 9487, seed=4))
 table = b200.rewards.CiderDTable(df, ref_len)
-fc, att = co.make_inputs(B, 36, 2048, 2048, seed=1)
+fc, att = syn.make_inputs(B, 36, 2048, 2048, seed=1)
 fc, att = fc.cuda(), att.cuda()
-gts = cdo.make_refs(B, 9487, seed=5)
+gts = syn.make_refs(B, 9487, seed=5)
 for _ in range(2):
     model.scst_step(fc, att, gts, table, 5)
 torch.cuda.synchronize()

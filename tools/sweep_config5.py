@@ -3,10 +3,9 @@ tensor roofline the GEMM launches reach at each point.  Writes gpurun_out/<tag>_
 import json, os, sys
 import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, 'tests'))
+sys.path.insert(0, REPO)
 import bench
-from helpers import build_pair
-from oracle import caption_oracle as co
+from imagecaptioning.pytorch_b200 import synthetic as syn       # seeded synthetic weights / inputs (profiling tools never touch oracle/)
 
 tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
 mode = sys.argv[2] if len(sys.argv) > 2 else 'tc_f16x3'
@@ -14,11 +13,11 @@ peak = 1442.4
 pp = os.path.join(REPO, 'MEASURED_PEAKS.json')
 if os.path.exists(pp):
     peak = float(json.load(open(pp))['bf16_tflops_sustained'])
-model, _ = build_pair('updown', seed=1234, logit_scale=12.0, mode=mode, **bench.CFG)
+model = syn.build_model('updown', seed=1234, logit_scale=12.0, mode=mode, **bench.CFG)
 rows = []
 for beam in (1, 3, 5, 10):
     for B in (64, 128, 256, 512, 1024):
-        ins = [co.make_inputs(B, 36, 2048, 2048, seed=7 + i) for i in range(2)]
+        ins = [syn.make_inputs(B, 36, 2048, 2048, seed=7 + i) for i in range(2)]
         ins = [(a.cuda(), b.cuda()) for a, b in ins]
         opt = {'beam_size': beam, 'sample_n': 1}
         with torch.no_grad():
