@@ -83,6 +83,30 @@ def test_bench_gpu_arm_does_not_import_the_oracle():
     assert offenders == [], offenders
 
 
+def test_product_and_tools_never_import_the_oracle():
+    """The package (the product path) and the profiling tools must not import oracle/ or the test helpers: the oracle is test infrastructure."""
+    import ast
+    root = os.path.dirname(os.path.dirname(__file__))
+    files = []
+    for sub in ('imagecaptioning.pytorch_b200', 'tools'):
+        d = os.path.join(root, sub)
+        files += [os.path.join(d, f) for f in os.listdir(d) if f.endswith('.py')]
+    files.append(os.path.join(root, '__graft_entry__.py'))
+    offenders = []
+    for path in files:
+        tree = ast.parse(open(path).read())
+        scopes = [tree] if not path.endswith('__graft_entry__.py') else [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name != 'smoke'] + [
+            ast.Module(body=[n for n in tree.body if not isinstance(n, ast.FunctionDef)], type_ignores=[])]
+        for scope in scopes:
+            for node in ast.walk(scope):
+                names = [a.name for a in node.names] if isinstance(node, ast.Import) else ([node.module or ''] if isinstance(node, ast.ImportFrom) else [])
+                for nm in names:
+                    # __graft_entry__.build() may compile the oracle's reference copy (oracle.build_ref): building the checker is not using it
+                    if nm.split('.')[0] in ('oracle', 'helpers') and not (path.endswith('__graft_entry__.py') and nm.endswith('build_ref')):
+                        offenders.append((os.path.relpath(path, root), nm))
+    assert offenders == [], offenders
+
+
 def test_synthetic_document_frequency_matches_oracle_builder():
     from imagecaptioning.pytorch_b200 import synthetic as syn
     from oracle import ciderd_oracle as cdo
