@@ -485,7 +485,7 @@ struct ATape {
     float *att_e, *mean, *kv;
     int* tok;
     float *xt, *x1c, *gates, *c, *h, *qln, *qp, *probs, *att, *t2, *out, *outd;
-    float *DL, *dOUTD, *D_T2, *D_QP, *DG, *dctx, *dh, *dc, *d_out, *dX2, *d_qln, *d_hatt, *dxt, *d_x1c, *tmpH, *S, *d_mean, *d_kv, *d_att_e, *d_x, *d_g, *d_t,
+    float *DL, *dOUTD, *D_T2, *D_QP, *DG, *dctx, *dh, *dc, *dX2, *d_qln, *d_hatt, *dxt, *d_x1c, *S, *d_mean, *d_kv, *d_att_e, *d_x, *d_g, *d_t,
         *d_catd, *d_qkv, *d_ln, *dpre, *stats, *mask_sum, *skinny, *glp, *item_loss;
     size_t skinny_floats;
     double* scores;
@@ -508,8 +508,8 @@ void layout_atape(ATape& tp, Arena& a, int B, int R, int N, int T, int E, int H,
     tp.DL = a.take<float>(TN * V1); tp.dOUTD = a.take<float>(TN * H); tp.D_T2 = a.take<float>(TN * 2 * H); tp.D_QP = a.take<float>(TN * H);
     tp.DG = a.take<float>(TN * 4 * H);
     const long NH = (long)N * H;
-    tp.dctx = a.take<float>(NH); tp.dh = a.take<float>(NH); tp.dc = a.take<float>(NH); tp.d_out = a.take<float>(NH); tp.dX2 = a.take<float>(2 * NH);
-    tp.d_qln = a.take<float>(NH); tp.d_hatt = a.take<float>(NH); tp.dxt = a.take<float>((long)N * E); tp.d_x1c = a.take<float>(NH); tp.tmpH = a.take<float>(NH);
+    tp.dctx = a.take<float>(NH); tp.dh = a.take<float>(NH); tp.dc = a.take<float>(NH); tp.dX2 = a.take<float>(2 * NH);
+    tp.d_qln = a.take<float>(NH); tp.d_hatt = a.take<float>(NH); tp.dxt = a.take<float>((long)N * E); tp.d_x1c = a.take<float>(NH);
     tp.S = a.take<float>((long)B * 4 * H); tp.d_mean = a.take<float>((long)B * H); tp.d_kv = a.take<float>(BR * 2 * H); tp.d_att_e = a.take<float>(BR * H);
     tp.d_x = a.take<float>(BR * H); tp.d_g = a.take<float>(BR * H); tp.d_t = a.take<float>(BR * 2 * H); tp.d_catd = a.take<float>(BR * 2 * H);
     tp.d_qkv = a.take<float>(BR * 3 * H); tp.d_ln = a.take<float>(BR * H); tp.dpre = a.take<float>(BR * H);

@@ -486,17 +486,6 @@ __global__ void cat_dropout_kernel(int rows, int c1, int c2, const float* __rest
     }
 }
 
-// out[r, c] = a[r, c] + b[img(r), c]       (mean_feats + ctx_drop(ctx), AoAModel.py:165)
-__global__ void add_row_group_kernel(int rows, int cols, int rpg, const float* __restrict__ a, long ld_a, const float* __restrict__ g, long ld_g,
-                                     float* __restrict__ out, long ld_o) {
-    const long n = (long)rows * cols;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        const long r = i / cols;
-        const int c = (int)(i % cols);
-        out[r * ld_o + c] = a[r * ld_a + c] + g[(r / rpg) * ld_g + c];
-    }
-}
-
 int blocks_for(long n) {
     long b = (n + 255) / 256;
     return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
@@ -610,11 +599,6 @@ int cat_dropout_launch(int rows, int c1, int c2, const float* a, long ld_a, cons
     cat_dropout_kernel<<<blocks_for((long)rows * (c1 + c2)), 256, 0, st>>>(rows, c1, c2, a, ld_a, b, ld_b, out, ld_o, seed, (uint32_t)site, (uint32_t)step, p);
     LAUNCH_OK();
 }
-int add_row_group_launch(int rows, int cols, int rpg, const float* a, long ld_a, const float* g, long ld_g, float* out, long ld_o, cudaStream_t st) {
-    add_row_group_kernel<<<blocks_for((long)rows * cols), 256, 0, st>>>(rows, cols, rpg, a, ld_a, g, ld_g, out, ld_o);
-    LAUNCH_OK();
-}
-
 int aoa_step_inputs_launch(int rows, int E, int H, int rpi, const int* tok_src, int* tok_dst, const float* emb, float* xt, const float* mean, long ld_mean,
                            const float* out_prev, float* x1c, unsigned long long seed, int step, float p_lm, float p_ctx, cudaStream_t st) {
     if (rows <= 0) return 0;

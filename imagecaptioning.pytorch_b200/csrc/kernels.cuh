@@ -173,7 +173,6 @@ int attention_backward_launch(int n_images, int rpi, int R, int A, int H, const 
 int relu_dropout_backward_launch(long n, const float* x, const float* dy, float* dx, float scale, cudaStream_t st);
 int embed_backward_launch(int rows, int E, const int* tokens, const float* xt, const float* dxt, long ld_dxt, float scale, float* d_emb, cudaStream_t st);
 int per_image_sum_launch(int steps, int rows, int rpi, int cols, const float* x, float* out, cudaStream_t st);
-int add_inplace_launch(float* a, const float* b, long n, cudaStream_t st);
 int add_strided_launch(float* a, const float* b, long ld_b, int rows, int cols, cudaStream_t st);
 
 // ---- aoa_train_kernels.cu (AoANet training step)
@@ -208,7 +207,6 @@ int dropout_rows_copy_launch(int rows, int rps, int cols, int t0, const float* s
 int relu_dropout_rows_launch(int rows, int rps, int cols, int t0, float* h, long ld, unsigned long long seed, int site, float p, cudaStream_t st);
 int permute_rows_launch(int L, int N, int D, const float* src, long ld_s, float* dst, long ld_d, int to_seq_major, cudaStream_t st);
 int load_tokens_tm_launch(const long long* labels, long ld, int N, int L, int* tok, float* key_mask, long ld_m, cudaStream_t st);
-int add_rows_launch(int rows, int cols, float* x, long ld_x, const float* y, long ld_y, cudaStream_t st);
 // sequence self-attention with replayable dropout (aoa_train_kernels.cu): row(b, pos) = b * b_stride + pos * p_stride
 int seq_attn_train_launch(int seqs, int n_keys, int q_lo, int q_hi, int heads, int dk, int causal, int idx_L, long b_stride, long p_stride, const float* q,
                           const float* k, const float* v, long ld, unsigned long long seed, int site, float p, float* out, long ld_out, const float* key_mask,
@@ -233,7 +231,6 @@ int add_dropout_launch(int rows, int cols, const float* a, long ld_a, const floa
                        float p, cudaStream_t st);
 int cat_dropout_launch(int rows, int c1, int c2, const float* a, long ld_a, const float* b, long ld_b, float* out, long ld_o, unsigned long long seed, int site,
                        int step, float p, cudaStream_t st);
-int add_row_group_launch(int rows, int cols, int rpg, const float* a, long ld_a, const float* g, long ld_g, float* out, long ld_o, cudaStream_t st);
 
 // ---- reward.cu (CIDEr-D) and criterion
 struct CiderTable;   // device hash table of n-gram -> idf

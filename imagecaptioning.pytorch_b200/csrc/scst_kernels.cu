@@ -352,9 +352,6 @@ __global__ void per_image_sum_kernel(int steps, int rows, int rpi, int cols, con
     out[(long)img * cols + c] = (s0 + s1) + (s2 + s3);
 }
 
-__global__ void add_inplace_kernel(float* a, const float* b, long n) {
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) a[i] += b[i];
-}
 __global__ void add_strided_kernel(float* a, const float* b, long ld_b, int rows, int cols) {
     const long n = (long)rows * cols;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) a[i] += b[(i / cols) * ld_b + (i % cols)];
@@ -452,10 +449,6 @@ int embed_backward_launch(int rows, int E, const int* tokens, const float* xt, c
 }
 int per_image_sum_launch(int steps, int rows, int rpi, int cols, const float* x, float* out, cudaStream_t st) {
     per_image_sum_kernel<<<dim3(rows / rpi, cdiv(cols, 256)), 256, 0, st>>>(steps, rows, rpi, cols, x, out);
-    LAUNCH_OK();
-}
-int add_inplace_launch(float* a, const float* b, long n, cudaStream_t st) {
-    add_inplace_kernel<<<nblocks(n), 256, 0, st>>>(a, b, n);
     LAUNCH_OK();
 }
 int add_strided_launch(float* a, const float* b, long ld_b, int rows, int cols, cudaStream_t st) {

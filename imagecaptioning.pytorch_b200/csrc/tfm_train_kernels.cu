@@ -99,15 +99,6 @@ __global__ void load_tokens_tm_kernel(const long long* __restrict__ labels, long
     if (key_mask != nullptr) key_mask[(long)n * ld_m + t] = (t == 0 || v != 0) ? 1.f : 0.f;
 }
 
-// x += y (strided rows)
-__global__ void add_rows_kernel(int rows, int cols, float* __restrict__ x, long ld_x, const float* __restrict__ y, long ld_y) {
-    const long total = (long)rows * cols;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int r = (int)(i / cols), c = (int)(i % cols);
-        x[(long)r * ld_x + c] += y[(long)r * ld_y + c];
-    }
-}
-
 }  // namespace
 
 #define LAUNCH_OK() do { CAPB_CHECK_CUDA(cudaGetLastError()); return 0; } while (0)
@@ -151,12 +142,6 @@ int load_tokens_tm_launch(const long long* labels, long ld, int N, int L, int* t
     load_tokens_tm_kernel<<<(N * L + 255) / 256, 256, 0, st>>>(labels, ld, N, L, tok, key_mask, ld_m);
     LAUNCH_OK();
 }
-int add_rows_launch(int rows, int cols, float* x, long ld_x, const float* y, long ld_y, cudaStream_t st) {
-    if (rows <= 0) return 0;
-    add_rows_kernel<<<blocks_for((long)rows * cols), 256, 0, st>>>(rows, cols, x, ld_x, y, ld_y);
-    LAUNCH_OK();
-}
-
 CAPB_DEFINE_SALT_SETTER(dropout_salt_set_tfm)
 
 }  // namespace capb200
