@@ -316,7 +316,14 @@ typedef struct {
     float *h2att_w, *h2att_b, *alpha_w, *alpha_b;
 } capb200_updown_grads;
 /* fc[B,F_fc], att[B,R,F_att] (opts->att_masks for variable region counts); refs as in capb200_self_critical_reward.
- * Outputs: sample_seq[B*n,T] int64, greedy_seq[B,T] int64, sample_logprobs[B*n,T,V+1] (caller zero-fills), reward[B*n,T], loss[1]. */
+ * Outputs: sample_seq[B*n,T] int64, greedy_seq[B,T] int64, sample_logprobs[B*n,T,V+1] (caller zero-fills), reward[B*n,T], loss[1].
+ * Execution: the whole step (~900-4900 launches, none of them data dependent) is captured into ONE CUDA graph the second time a configuration
+ * -- shapes, every pointer argument, every option except the seed -- is seen, and replayed afterwards (the *_scst_step entry points of all
+ * three families; CAPB200_SCST_GRAPH=0 disables it).  For that the step runs on an engine-owned stream that first waits for `stream` and that
+ * `stream` is made to wait for before the call returns; the features (and the region mask) are copied into an engine-owned staging buffer, so
+ * they may live anywhere, while refs / ref_offsets / the output and gradient buffers should keep their addresses from step to step (a changed
+ * address is a new configuration: one eager step, one capture).  A replay draws new samples and masks from opts->seed exactly as the eager
+ * step would (the seed reaches the kernels through a device-side salt), so results do not depend on whether a step was replayed. */
 int capb200_updown_scst_step(capb200_engine* e, const float* fc, const float* att, int B, int R, const capb200_scst_opts* opts,
                              const capb200_cider_table* table, const int* refs, const int* ref_offsets, int L, const capb200_updown_grads* grads,
                              long long* sample_seq, long long* greedy_seq, float* sample_logprobs, float* reward, float* loss, void* stream);

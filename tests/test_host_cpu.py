@@ -151,3 +151,43 @@ def test_decode_option_guards():
         unk_model(fc, att, None, opt={'beam_size': 2, 'sample_n': 1, 'suppress_UNK': 1}, mode='sample')
     with pytest.raises(NotImplementedError):           # 15 beams + 2 edit kinds exceed the 16 candidates a row keeps
         unk_model(fc, att, None, opt={'beam_size': 15, 'sample_n': 1, 'suppress_UNK': 1, 'decoding_constraint': 1}, mode='sample')
+
+
+def test_documented_switches_exist_in_the_sources():
+    """Every CAPB200_* environment variable INTEGRATION.md documents is read somewhere in the package or bench.py (no stale documentation)."""
+    import re
+    root = os.path.dirname(os.path.dirname(__file__))
+    doc = open(os.path.join(root, 'INTEGRATION.md')).read()
+    documented = set(re.findall(r'`(CAPB200_[A-Z0-9_]+)', doc))
+    assert len(documented) >= 8
+    blob = open(os.path.join(root, 'bench.py')).read()
+    pkg = os.path.join(root, 'imagecaptioning.pytorch_b200')
+    for d, _, files in os.walk(pkg):
+        if os.path.basename(d) == 'build':
+            continue
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                blob += open(os.path.join(d, f)).read()
+    missing = sorted(v for v in documented if v not in blob)
+    assert missing == [], missing
+
+
+def test_fused_adam_is_a_torch_adam():
+    """FusedAdam keeps torch.optim.Adam's constructor, param groups and state_dict layout (optimizer.pth round-trips, tools/train.py:74-77), and
+    refuses CPU tensors instead of falling back."""
+    import imagecaptioning.pytorch_b200 as b200
+    ps = [torch.nn.Parameter(torch.randn(7, 3)), torch.nn.Parameter(torch.randn(5))]
+    ref = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in ps], lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    for p in ref.param_groups[0]['params']:
+        p.grad = torch.randn_like(p)
+    ref.step()
+    opt = b200.optim.FusedAdam(ps, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, clip_value=0.1)
+    assert isinstance(opt, torch.optim.Adam) and opt.defaults['lr'] == 5e-4 and opt.clip_value == 0.1
+    opt.load_state_dict(ref.state_dict())                     # a checkpoint written by the stock optimizer loads
+    sd = opt.state_dict()
+    assert set(sd['state'][0]) == {'step', 'exp_avg', 'exp_avg_sq'} and float(sd['state'][0]['step']) == 1.0
+    ref.load_state_dict(sd)                                   # and the other way round
+    for p in ps:
+        p.grad = torch.randn_like(p)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        opt.step()
