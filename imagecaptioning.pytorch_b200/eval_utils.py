@@ -83,6 +83,52 @@ def caption_stats(seq: torch.Tensor, seq_logprobs: torch.Tensor):
     return perplexity, entropy
 
 
+def eval_split_n(model, n_predictions, input_data, eval_kwargs: Dict[str, Any] = {}):
+    """Contract of captioning/utils/eval_utils.py:230-283: ``sample_n`` captions per image, appended to ``n_predictions``.
+    ``sample_n_method`` 'bs' (the sample_n best beams), 'sample' / 'gumbel' / 'top<k>' / 'top<p>' (sample_n draws, with their perplexity:
+    read back with ONE transfer for the batch instead of one .item() per caption).  'dbs' and the remaining branch are diverse beam
+    search (group_size > 1), which the engine refuses; the model's own NotImplementedError surfaces."""
+    verbose = eval_kwargs.get('verbose', True)
+    beam_size = eval_kwargs.get('beam_size', 1)
+    sample_n = eval_kwargs.get('sample_n', 1)
+    sample_n_method = eval_kwargs.get('sample_n_method', 'sample')
+    fc_feats, att_feats, att_masks, data = input_data
+    kw = dict(eval_kwargs)
+    n_images = fc_feats.shape[0]
+    if sample_n_method == 'bs':
+        kw.update({'sample_n': 1, 'beam_size': sample_n, 'group_size': 1})
+        with torch.no_grad():
+            model(fc_feats, att_feats, att_masks, opt=kw, mode='sample')
+        for k in range(n_images):
+            sents = decode_sequence(model.vocab, torch.stack([model.done_beams[k][_]['seq'] for _ in range(sample_n)]))
+            for sent in sents:
+                n_predictions.append({'image_id': data['infos'][k]['id'], 'caption': sent})
+    elif sample_n_method in ('sample', 'gumbel') or sample_n_method.startswith('top'):
+        kw.update({'sample_n': sample_n, 'sample_method': sample_n_method, 'beam_size': 1})
+        with torch.no_grad():
+            seq, logprobs = model(fc_feats, att_feats, att_masks, opt=kw, mode='sample')
+        perplexity = (-logprobs.gather(2, seq.unsqueeze(2)).squeeze(2).sum(1) / ((seq > 0).to(logprobs).sum(1) + 1)).cpu().tolist()
+        for k, sent in enumerate(decode_sequence(model.vocab, seq)):
+            n_predictions.append({'image_id': data['infos'][k // sample_n]['id'], 'caption': sent, 'perplexity': perplexity[k]})
+    elif sample_n_method == 'dbs':
+        kw.update({'beam_size': sample_n * beam_size, 'group_size': sample_n})
+        with torch.no_grad():
+            model(fc_feats, att_feats, att_masks, opt=kw, mode='sample')
+        for k in range(n_images):
+            sents = decode_sequence(model.vocab, torch.stack([model.done_beams[k][_]['seq'] for _ in range(0, sample_n * beam_size, beam_size)]))
+            for sent in sents:
+                n_predictions.append({'image_id': data['infos'][k]['id'], 'caption': sent})
+    else:
+        kw.update({'sample_method': sample_n_method[1:], 'group_size': sample_n, 'beam_size': 1})
+        with torch.no_grad():
+            seq, _ = model(fc_feats, att_feats, att_masks, opt=kw, mode='sample')
+        for k, sent in enumerate(decode_sequence(model.vocab, seq)):
+            n_predictions.append({'image_id': data['infos'][k // sample_n]['id'], 'caption': sent})
+    if verbose:
+        for entry in sorted(n_predictions[-n_images * sample_n:], key=lambda x: x['image_id']):
+            print('image %s: %s' % (entry['image_id'], entry['caption']))
+
+
 def eval_split(model, crit, loader, eval_kwargs: Dict[str, Any] = {}):
     """Contract of captioning/utils/eval_utils.py:129-213.  ``crit`` is the XE criterion (LanguageModelCriterion / LabelSmoothing)."""
     verbose = eval_kwargs.get('verbose', True)
@@ -97,9 +143,6 @@ def eval_split(model, crit, loader, eval_kwargs: Dict[str, Any] = {}):
     remove_bad_endings = eval_kwargs.get('remove_bad_endings', 0)
     os.environ['REMOVE_BAD_ENDINGS'] = str(remove_bad_endings)      # same global configuration channel as the reference (eval_utils.py:139)
     device = eval_kwargs.get('device', 'cuda')
-    if sample_n > 1:
-        raise NotImplementedError('eval_split_n (sample_n > 1: eval_utils.py:216-283) is not on the B200 evaluation path')
-
     model.eval()
     loader.reset_iterator(split)
     n, loss, loss_sum, loss_evals = 0, 0.0, 0.0, 1e-8
@@ -140,6 +183,8 @@ def eval_split(model, crit, loader, eval_kwargs: Dict[str, Any] = {}):
             predictions.append(entry)
             if verbose:
                 print('image %s: %s' % (entry['image_id'], entry['caption']))
+        if sample_n > 1:
+            eval_split_n(model, n_predictions, [fc_feats, att_feats, att_masks, data], eval_kwargs)
         ix1 = data['bounds']['it_max']
         if num_images != -1:
             ix1 = min(ix1, num_images)
@@ -153,6 +198,11 @@ def eval_split(model, crit, loader, eval_kwargs: Dict[str, Any] = {}):
             break
 
     lang_stats = None
+    if len(n_predictions) > 0 and 'perplexity' in n_predictions[0]:
+        n_predictions = sorted(n_predictions, key=lambda x: x['perplexity'])
+    if 'id' in eval_kwargs:         # the reference's side effect (eval_utils.py:217-219): language_eval and tools/eval.py read this file back
+        os.makedirs('eval_results', exist_ok=True)
+        torch.save((predictions, n_predictions), os.path.join('eval_results/', '.saved_pred_' + eval_kwargs['id'] + '_' + split + '.pth'))
     if callable(lang_eval):
         lang_stats = lang_eval(dataset, predictions, n_predictions, eval_kwargs, split)
     elif lang_eval == 1:

@@ -46,9 +46,18 @@ class _StubModel(torch.nn.Module):
     def forward(self, fc_feats, att_feats, third, *rest, **kw):
         lp = torch.log_softmax((fc_feats @ self.w).view(-1, self.T, self.V1) * 3, 2)
         if kw.get('mode', 'forward') == 'sample':
-            seq = lp.argmax(2)
+            opt = kw.get('opt', {})
+            n, beam = opt.get('sample_n', 1), opt.get('beam_size', 1)
+            if n > 1:                                       # sample_n captions per image: the j-th is the (j+1)-th best word at every step
+                lp = lp.repeat_interleave(n, 0)
+                seq = torch.stack([lp[i].topk(n, 1).indices[:, i % n] for i in range(lp.shape[0])])
+            else:
+                seq = lp.argmax(2)
             ended = (seq == 0).cumsum(1) > 0
             seq = seq.masked_fill(ended, 0)
+            if beam > 1:                                    # done_beams[i][j]['seq']: j-th candidate of image i
+                cand = lp.topk(beam, 2).indices             # [B, T, beam]
+                self.done_beams = [[{'seq': cand[i, :, j]} for j in range(beam)] for i in range(lp.shape[0])]
             return seq, lp
         return lp[:, :third.shape[-1]]            # teacher forcing: third = labels[..., :-1]
 
@@ -92,3 +101,39 @@ def test_prefetch_loader_is_one_batch_ahead_and_stops_at_wrap():
     loader = _StubLoader(10, 4, 5, 9)
     seen = [d['infos'][0]['id'] for d in PrefetchLoader(loader, 'val', 'cpu')]
     assert seen == [0, 4, 8] and loader.calls == 3             # the wrapped batch is the last one fetched
+
+
+@pytest.mark.parametrize('method', ['sample', 'bs', 'top3'])
+def test_eval_split_n_matches_the_reference_loop(tmp_path, monkeypatch, method):
+    """sample_n > 1 (eval_utils.py:196-197 -> eval_split_n): sample_n captions per image through 'bs' (the best beams) and the sampling
+    methods, n_predictions sorted by perplexity and saved beside the predictions like the reference does."""
+    from imagecaptioning.pytorch_b200 import eval_utils as EU
+    T, V1 = 6, 12
+    kwargs = {'verbose': False, 'verbose_loss': 1, 'split': 'val', 'language_eval': 0, 'dataset': 'coco', 'beam_size': 1, 'sample_n': 3,
+              'sample_n_method': method, 'device': 'cpu', 'id': 'stubn', 'num_images': -1}
+    monkeypatch.chdir(tmp_path)
+    loss, preds, _ = EU.eval_split(_StubModel(T, V1), _crit, _StubLoader(10, 4, T, V1), dict(kwargs))
+    saved_preds, saved_n = torch.load(os.path.join('eval_results', '.saved_pred_stubn_val.pth'), weights_only=False)
+    assert len(saved_preds) == 10 and len(saved_n) == 3 * 12          # three batches of four images reach eval_split_n (the loop's own bookkeeping)
+    if method != 'bs':
+        ps = [e['perplexity'] for e in saved_n]
+        assert ps == sorted(ps)
+    from oracle import ref_runtime as rr
+    if rr.available():
+        cwd = os.getcwd()
+        rr.enter()
+        try:
+            import captioning.utils.eval_utils as REF
+        except Exception as exc:
+            os.chdir(cwd)
+            pytest.skip('reference eval_utils not importable here: %r' % (exc,))
+        ref_dir = tmp_path / 'ref'
+        ref_dir.mkdir()
+        os.chdir(str(ref_dir))
+        rloss, rpreds, _ = REF.eval_split(_StubModel(T, V1), _crit, _StubLoader(10, 4, T, V1), dict(kwargs))
+        _, rn = torch.load(os.path.join('eval_results', '.saved_pred_stubn_val.pth'), weights_only=False)
+        os.chdir(cwd)
+        assert abs(loss - rloss) < 1e-6 and [p['caption'] for p in preds] == [p['caption'] for p in rpreds]
+        assert [(e['image_id'], e['caption']) for e in saved_n] == [(e['image_id'], e['caption']) for e in rn]
+        if method != 'bs':
+            assert np.allclose([e['perplexity'] for e in saved_n], [e['perplexity'] for e in rn], atol=1e-5)
