@@ -191,3 +191,83 @@ def test_fused_adam_is_a_torch_adam():
         p.grad = torch.randn_like(p)
     with pytest.raises(RuntimeError, match='CUDA'):
         opt.step()
+
+
+def test_loss_wrapper_gradient_delivery_paths(monkeypatch):
+    """B200LossWrapper's bridge between a fused step and autograd, on a stand-in model (CPU tensors, no engine): the direct path scales the
+    flat gradient buffer once and makes param.grad views of it; direct_grads = False (and non-leaf parameters, i.e. DataParallel replicas)
+    hand fresh tensors to autograd so that hooks and accumulation work; drop_worst checks the upstream selection."""
+    import imagecaptioning.pytorch_b200 as b200
+
+    class Flat:
+        def __init__(self, params):
+            self.flat = torch.zeros(sum(p.numel() for p in params))
+            self.views, off = {}, 0
+            for p in params:
+                self.views[p] = self.flat[off:off + p.numel()].view(p.shape)
+                off += p.numel()
+
+    class Fake(torch.nn.Module):
+        family_name = 'fake'
+
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Parameter(torch.randn(3, 4))
+            self.b = torch.nn.Parameter(torch.randn(5))
+            self.fg = Flat([self.a, self.b])
+            self.calls = 0
+
+        def scst_step(self, fc, att, gts, table, n, temperature=1.0, baseline='greedy', att_masks=None, keep_rows=0):
+            self.calls += 1
+            g = torch.Generator().manual_seed(self.calls)
+            self.fg.flat.copy_(torch.randn(self.fg.flat.shape, generator=g))
+            rows = len(gts) * n
+            res = {'loss': torch.tensor(0.25 * self.calls), 'reward': torch.ones(rows, 4), 'sample_seq': torch.ones(rows, 4, dtype=torch.long),
+                   'grads': dict(self.fg.views), 'flat': self.fg, 'seed': 1, 'row_loss': torch.arange(rows, dtype=torch.float32) if keep_rows else None}
+            return res
+
+    monkeypatch.setattr(b200.rewards, 'CiderD_scorer', object())
+    opt = argparse.Namespace(sc_sample_method='greedy', sc_beam_size=1, train_sample_method='sample', train_beam_size=1, train_sample_n=2, cider_reward_weight=1,
+                             bleu_reward_weight=0, label_smoothing=0.0, drop_worst_rate=0.5)
+    model = Fake()
+    lw = b200.B200LossWrapper(model, opt)
+    fc, att, gts = torch.zeros(2, 4), torch.zeros(2, 3, 4), [np.zeros((1, 4), dtype=np.int64)] * 2
+    args = (fc, att, None, None, None, gts, torch.arange(2), True, False)
+    # direct path: views of the flat buffer, scaled in place by the upstream gradient
+    out = lw(*args, False)
+    engine = {p: g.clone() for p, g in lw.last_step['grads'].items()}
+    (2.0 * out['loss']).backward()
+    for p, g in lw.last_step['grads'].items():
+        assert p.grad.data_ptr() == g.data_ptr() and torch.allclose(p.grad, 2.0 * engine[p])
+    # the next step's gradients land in the same views (zero_grad(set_to_none=False) keeps them attached)
+    model.zero_grad(set_to_none=False)
+    out = lw(*args, False)
+    engine = {p: g.clone() for p, g in lw.last_step['grads'].items()}
+    out['loss'].backward()
+    assert all(torch.allclose(p.grad, engine[p]) for p in engine)
+    # through autograd: fresh tensors, accumulated over two steps, hooks fire
+    model.zero_grad(set_to_none=True)
+    lw.direct_grads = False
+    fired = []
+    h = model.a.register_hook(lambda g_: fired.append(g_.clone()))
+    total = {p: torch.zeros_like(p) for p in model.parameters()}
+    for k in (1.0, 3.0):
+        out = lw(*args, False)
+        for p, g in lw.last_step['grads'].items():
+            total[p] += k * g
+        (k * out['loss']).backward()
+    h.remove()
+    assert len(fired) == 2 and all(p.grad.data_ptr() != lw.last_step['grads'][p].data_ptr() and torch.allclose(p.grad, total[p]) for p in total)
+    # drop_worst: the per-row loss vector goes out, the trainer's top-k mean must be the selection the step assumed
+    lw.direct_grads = True
+    model.zero_grad(set_to_none=True)
+    out = lw(*args, True)
+    rows = out['loss']
+    assert rows.shape == (4,) and lw.last_step['keep_rows'] == 2
+    engine = {p: g.clone() for p, g in lw.last_step['grads'].items()}
+    torch.topk(rows, k=2, largest=False)[0].mean().backward()             # tools/train.py:191
+    assert all(torch.allclose(p.grad, engine[p]) for p in engine)
+    out = lw(*args, True)
+    model.zero_grad(set_to_none=True)
+    with pytest.raises(NotImplementedError, match='drop_worst'):
+        out['loss'].mean().backward()                                        # a different reduction than the step's selection
