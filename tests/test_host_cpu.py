@@ -271,3 +271,24 @@ def test_loss_wrapper_gradient_delivery_paths(monkeypatch):
     model.zero_grad(set_to_none=True)
     with pytest.raises(NotImplementedError, match='drop_worst'):
         out['loss'].mean().backward()                                        # a different reduction than the step's selection
+
+
+def test_fused_adam_pointer_table_layout():
+    """The device table capb200_adam_step walks: one row of four pointers per tensor, its element count, and one (tensor, chunk) pair per
+    capb200_adam_chunk_elems() elements; cached while every address stays the same (the flat gradient buffer guarantees that for the grads)."""
+    import imagecaptioning.pytorch_b200 as b200
+    chunk = b200._lib.load().capb200_adam_chunk_elems()
+    sizes = [2 * chunk + 5, 1, 100, chunk]
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in sizes]
+    opt = b200.optim.FusedAdam(ps, lr=1e-3)
+    gs = [torch.zeros(n) for n in sizes]
+    ms = [torch.zeros(n) for n in sizes]
+    vs = [torch.zeros(n) for n in sizes]
+    table, numel, chunks, n_chunks = opt._table((0, 'cpu'), ps, gs, ms, vs)
+    assert table.shape == (4, 4) and numel.tolist() == sizes and n_chunks == 3 + 1 + 1 + 1
+    assert table[:, 0].tolist() == [p.data_ptr() for p in ps] and table[:, 1].tolist() == [g.data_ptr() for g in gs]
+    assert chunks.tolist() == [[0, 0], [0, 1], [0, 2], [1, 0], [2, 0], [3, 0]]
+    again = opt._table((0, 'cpu'), ps, gs, ms, vs)
+    assert again[0] is table                                   # cache hit: nothing is rebuilt or uploaded
+    gs[1] = torch.zeros(1)                                     # one gradient moved: the table is rebuilt
+    assert opt._table((0, 'cpu'), ps, gs, ms, vs)[0] is not table
