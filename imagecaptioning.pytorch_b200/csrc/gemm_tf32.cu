@@ -14,9 +14,10 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes of RAW fp32 [32 k x 128 rows] (A side) and [32 k x BN rows] (B side), 128B swizzle,
 //               into a STAGES-deep ring (mbarrier complete_tx).
 //   warps 4..11 converters: read the raw tiles from shared memory, write hi in place and lo next to it (element-wise, so the swizzle
-//               pattern is preserved), fence.proxy.async, arrive on the stage's "converted" barrier.  Eight warps: one K-block is a chain
-//               of wait -> 128-bit loads -> subtract -> stores -> fence -> arrive per thread, and with four warps that chain (not the TMA
-//               or the MMAs) set the K-block rate (profiles/r02c_tf32_sweep*.txt: 2.2 TB/s at 50 rows).
+//               pattern is preserved), fence.proxy.async, arrive on the stage's "converted" barrier.  Eight warps (the same warps drain
+//               the accumulator, two per TMEM lane quadrant); going from four to eight converter warps did not change the per-call times
+//               (profiles/r02c_tf32_sweep_trunc.txt vs r02f_tf32_sweep.txt): at the skinny shapes a launch is bound by its fixed costs and
+//               the depth of its K chain, not by the conversion (profiles/r02k_gemm_full.md).
 //   warp 1      MMA issuer: one thread, 12 tcgen05.mma.kind::tf32 (M = 128, N = BN, K = 8) per K-block, tcgen05.commit releases the slot.
 //   warp 2      TMEM allocation.
 //   epilogue    warps 4..11 (two per TMEM lane quadrant) drain the accumulator into a shared-memory staging tile laid out like the OUTPUT (so global stores are
