@@ -7,7 +7,7 @@ sc_flag=True follows loss_wrapper.py:56-73 exactly: eval-mode greedy baseline, t
 self-critical reward and RewardCriterion -- every stage on the device through the C ABI.  sc_flag=False is the XE stage
 (loss_wrapper.py:54-55: teacher-forced forward + LanguageModelCriterion / LabelSmoothing) and struc_flag=True the structure-loss
 branch (loss_wrapper.py:25-53) with ``structure_loss_type='new_self_critical'`` (losses.py:168-187), the recipe of the reference's
-best models; both run as one fused device step incl. back-propagation through time (UpDown).
+best models; both run as one fused device step incl. the backward pass (UpDown, AoANet, Transformer).
 """
 from __future__ import annotations
 
@@ -55,7 +55,7 @@ def _shifted_mask(seq):
 
 class LanguageModelCriterion(nn.Module):
     """losses.py:204-225: masked negative log-likelihood of the target tokens (host-level torch ops; the training path uses the fused
-    kernel of capb200_updown_xe_step, this module serves evaluation and the parity tests)."""
+    kernels of the capb200_*_xe_step entry points, this module serves evaluation and the parity tests)."""
 
     def forward(self, input, target, mask, reduction='mean'):
         if target.ndim == 3:
@@ -287,7 +287,7 @@ class B200LossWrapper(nn.Module):
                 torch.zeros((), device=fc_feats.device)
             if w > 0:
                 if getattr(opt, 'use_ppo', 0) or opt.structure_loss_type != 'new_self_critical' or not can_fuse:
-                    raise NotImplementedError("the structure-loss branch covers structure_loss_type='new_self_critical' on the fused UpDown step")
+                    raise NotImplementedError("the structure-loss branch covers structure_loss_type='new_self_critical' on the fused SCST steps")
                 gts = [gts[_] for _ in gt_indices.tolist()]
                 if drop_worst_flag and 0 < w < 1:
                     raise NotImplementedError('drop_worst with a mixed XE / structure loss: the two fused steps would select rows independently')
@@ -302,7 +302,7 @@ class B200LossWrapper(nn.Module):
             out['loss'] = self._xe_loss(fc_feats, att_feats, labels, masks, att_masks, drop_worst_flag)
             return out
         if can_fuse and opt.sc_sample_method == 'greedy' and opt.sc_beam_size == 1:
-            # whole step on the device incl. back-propagation through time (UpDown); dropout as in model.train()
+            # whole step on the device incl. the backward pass; dropout as in model.train()
             gts = [gts[_] for _ in gt_indices.tolist()]
             res = self._sampled_step(fc_feats, att_feats, gts, 'greedy', att_masks, drop_worst_flag)
             out['loss'] = self._bridge(res)
