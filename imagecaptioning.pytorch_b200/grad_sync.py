@@ -37,11 +37,14 @@ class FlatGrads:
         self.flat = torch.zeros(total, dtype=torch.float32, device=device)
         self.views = {id(p): self.flat[o:o + p.numel()].view(p.shape) for p, o in offs}
         self.params = [p for p, _ in offs]
-        # one event per group, recorded by the engine when the group's last gradient has been written
-        self.events = [torch.cuda.Event() for _ in self.groups]
-        with torch.cuda.device(device):
-            for ev in self.events:
-                ev.record()          # creates the underlying cudaEvent_t (torch creates it lazily on first record)
+        # one event per group, recorded by the engine when the group's last gradient has been written (a CPU buffer -- the layout tests --
+        # has none)
+        self.events = []
+        if torch.device(device).type == 'cuda':
+            self.events = [torch.cuda.Event() for _ in self.groups]
+            with torch.cuda.device(device):
+                for ev in self.events:
+                    ev.record()          # creates the underlying cudaEvent_t (torch creates it lazily on first record)
         self._event_table = (ctypes.c_void_p * len(self.events))(*[ev.cuda_event for ev in self.events])
 
     def event_table(self):
